@@ -1,0 +1,158 @@
+/*
+ * klampt_b200.h -- C ABI of the B200 batched configuration-feasibility engine.
+ *
+ * This is the drop-in boundary for ONE hot path of Klamp't: forward kinematics -> self collision ->
+ * robot-vs-environment collision / distance -> discretised edge checks, for N configurations (or N
+ * edges) at once.  Plain C: opaque handle, int status codes (0 = ok, <0 = error; text from
+ * kb_last_error()), caller-owned buffers, no exceptions across the boundary, no torch types.
+ * One CUDA device and one CUDA stream per engine handle; calls on one handle are not re-entrant
+ * (the reference path is not thread-safe either: Cpp/Planning/RobotCSpace.cpp:632-637).
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the Klamp't tree).
+ * The arithmetic below Klamp't's call sites lives in KrisLibrary (absent from the reference tree);
+ * those rows cite the Klamp't call site.
+ *
+ * Conventions
+ *   - rigid transforms: 12 doubles, row-major 3x3 rotation then translation
+ *     (file-format convention, Cpp/docs/Manual-FileTypes.md:35-37);
+ *   - configurations: row-major N x L doubles, L = number of robot links (Config = Vector of L Reals);
+ *   - world IDs: terrains [0,T), rigid objects [T,T+O), robot id T+O, links T+O+1+j
+ *     (Cpp/Modeling/World.cpp:47-53,110-180);
+ *   - "host" entry points take host pointers and include the H2D / D2H copies;
+ *     "_device" entry points take device pointers resident on the engine's device and enqueue on the
+ *     engine's stream (kb_set_stream) without synchronising the host.
+ */
+#ifndef KLAMPT_B200_H
+#define KLAMPT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kb_engine kb_engine;
+
+/* link types: .rob "jointtype r|p" (Cpp/Modeling/Robot.cpp:326-336) */
+enum { KB_REVOLUTE = 0, KB_PRISMATIC = 1 };
+/* RobotModelJoint::Type (Cpp/Modeling/Robot.h:28) */
+enum { KB_JOINT_WELD = 0, KB_JOINT_NORMAL = 1, KB_JOINT_SPIN = 2, KB_JOINT_FLOATING = 3,
+       KB_JOINT_FLOATINGPLANAR = 4, KB_JOINT_BALLANDSOCKET = 5, KB_JOINT_CLOSED = 6 };
+/* geometric primitives supported so far (subset of GeometricPrimitive3D, Cpp/docs/Manual-Geometry.md:22) */
+enum { KB_PRIM_POINT = 0, KB_PRIM_SPHERE = 1 };
+
+enum { KB_OK = 0, KB_ERR_INVALID = -1, KB_ERR_STATE = -2, KB_ERR_CUDA = -3, KB_ERR_UNSUPPORTED = -4,
+       KB_ERR_NOMEM = -5 };
+
+/* counters since kb_finalize / kb_reset_stats; the getStats-style dictionary of the Python adapter is built
+ * from these (Python/klampt/src/motionplanning.cpp:1031-1055) */
+typedef struct {
+  int64_t configs_checked;      /* configurations through the feasibility kernels                     */
+  int64_t configs_feasible;
+  int64_t edges_checked;
+  int64_t edges_visible;
+  int64_t edge_config_checks;   /* configurations checked on behalf of edges                           */
+  int64_t recheck_pairs;        /* element pairs sent to the fp64 recheck kernel                       */
+  int64_t recheck_overflow;     /* element pairs rechecked inline because the recheck queue was full   */
+  int64_t kernel_launches;      /* launches of this library's kernels                                  */
+  double  gpu_ms;               /* device time of those launches as measured with CUDA events          */
+} kb_stats;
+
+/* ---- lifetime ---------------------------------------------------------------------------------------- */
+int  kb_engine_create(kb_engine** out);
+void kb_engine_destroy(kb_engine* e);
+/* thread-local text of the last error raised by any call on this thread */
+const char* kb_last_error(void);
+/* library version string and the CUDA arch it was built for ("sm_100a") */
+const char* kb_version(void);
+
+/* ---- geometry (AnyCollisionGeometry3D: local data + margin; Python/klampt/src/geometry.h:17-19,140-148) */
+/* replaces Geometry3D.setTriangleMesh + setCollisionMargin; returns the geometry index (>=0) */
+int kb_add_trimesh(kb_engine* e, const double* verts, int nv, const int32_t* tris, int nt, double margin);
+/* replaces Geometry3D.setPointCloud; radius may be NULL (all zero) */
+int kb_add_pointcloud(kb_engine* e, const double* pts, int n, const double* radius, double margin);
+/* replaces Geometry3D.setGeometricPrimitive; params: point x,y,z / sphere cx,cy,cz,r */
+int kb_add_primitive(kb_engine* e, int type, const double* params, double margin);
+
+/* ---- world entities (WorldModel terrains / rigidObjects / robots, Cpp/Modeling/World.cpp:47-196) ------ */
+int kb_add_terrain(kb_engine* e, int geom);                         /* geom = -1: empty geometry */
+int kb_add_rigid_object(kb_engine* e, int geom, const double T[12]);
+/* RobotKinematics3D data model: parents[i] < i, T0_Parent with the base transform already multiplied into
+ * root links (Cpp/Modeling/Robot.cpp:971-975), unit axes, inclusive joint limits */
+int kb_robot_create(kb_engine* e, int L, const int32_t* parents, const uint8_t* linktype,
+                    const double* axis, const double* T0_parent, const double* qmin, const double* qmax);
+int kb_robot_set_link_geometry(kb_engine* e, int link, int geom);
+/* RobotModel::joints; default = one Normal joint per link */
+int kb_robot_set_joints(kb_engine* e, int nj, const uint8_t* jtype, const int32_t* jlink);
+/* RobotModelDriver limits as read by CheckJointLimits (Cpp/Modeling/Robot.cpp:2166-2187):
+ * value = mean_k (q[links[k]] - offset[k]) / scale[k];  scale/offset may be NULL (1 / 0) */
+int kb_robot_add_driver(kb_engine* e, int n, const int32_t* links, const double* scale, const double* offset,
+                        double dmin, double dmax);
+/* RobotWithGeometry::InitSelfCollisionPair / delete (Cpp/Modeling/Robot.cpp:1274-1313; robotsim.cpp:5504-5527).
+ * Default when never called = InitAllSelfCollisions: all i<j, both non-empty, neither the other's parent. */
+int kb_robot_set_self_collision(kb_engine* e, int i, int j, int enabled);
+/* WorldPlannerSettings::collisionEnabled (n_ids x n_ids, row-major).  Default when never called =
+ * WorldPlannerSettings::InitializeDefault (Cpp/Planning/PlannerSettings.cpp:16-41). */
+int kb_set_pair_mask(kb_engine* e, const uint8_t* mask, int n_ids);
+int kb_num_ids(const kb_engine* e);
+/* writes the n_ids x n_ids mask in effect after kb_finalize */
+int kb_get_pair_mask(const kb_engine* e, uint8_t* mask_out);
+
+/* WorldModel::InitCollisions + SingleRobotCSpace::Init (Cpp/Modeling/World.cpp:266-274,
+ * Cpp/Planning/RobotCSpace.cpp:668-754): builds the BVHs, flattens them and uploads everything to `device`. */
+int kb_finalize(kb_engine* e, int device);
+/* use an existing CUDA stream (cudaStream_t) for all later work; NULL = the engine's own stream */
+int kb_set_stream(kb_engine* e, void* cuda_stream);
+int kb_synchronize(kb_engine* e);
+/* tuning / instrumentation knobs: "collect_stats" (0|1: count node / element tests and fp64 rechecks in the kernels),
+ * "chunk" (configurations per kernel launch; the default keeps one chunk's transforms resident in L2) */
+int kb_set_option(kb_engine* e, const char* name, int64_t value);
+
+/* ---- the hot path ------------------------------------------------------------------------------------- */
+/* RobotKinematics3D::UpdateConfig/UpdateFrames for N configurations (call sites Cpp/Planning/RobotCSpace.cpp:612,634).
+ * T_out: N x L x 12 doubles. */
+int kb_fk_batch(kb_engine* e, const double* Q, int64_t N, double* T_out);
+
+/* SingleRobotCSpace::IsFeasible for N configurations (Cpp/Planning/RobotCSpace.cpp:786-823):
+ * out[c] = 1 iff joint/driver limits hold and no enabled pair collides.
+ * first_pair (optional, N x 2 int32): world ids of one colliding pair, or -1,-1 (which pair is reported first is
+ * traversal-order dependent in the reference as well). */
+int kb_feasible_batch(kb_engine* e, const double* Q, int64_t N, uint8_t* out, int32_t* first_pair);
+int kb_feasible_batch_device(kb_engine* e, const double* dQ, int64_t N, uint8_t* d_out, int32_t* d_first_pair);
+
+/* SingleRobotCSpace::PathChecker(a,b)->IsVisible() = EpsilonEdgeChecker with RobotCSpace::Distance / Interpolate
+ * (Cpp/Planning/RobotCSpace.cpp:835-838, Cpp/Modeling/Interpolate.cpp:10-71,208-343) for N edges.
+ * weights: per-joint metric weights or NULL.  out[e] = 1 iff every bisection midpoint is feasible (endpoints are not
+ * re-checked).  nchecks (optional): number of feasibility checks the sequential early-exit checker performs. */
+int kb_edges_visible_batch(kb_engine* e, const double* A, const double* B, int64_t N, double eps,
+                           const double* weights, uint8_t* out, int32_t* nchecks);
+int kb_edges_visible_batch_device(kb_engine* e, const double* dA, const double* dB, int64_t N, double eps,
+                                  const double* weights_host, uint8_t* d_out, int32_t* d_nchecks);
+
+/* WorldPlannerSettings::DistanceLowerBound(world, {robot}, {environment}, eps=0, bound) for N configurations
+ * (Cpp/Planning/PlannerSettings.cpp:570-620): min over enabled pairs of (geometric distance - margins), capped at
+ * upper_bound; include_self adds the enabled self pairs.  out_pair optional (N x 2 world ids, -1 if capped). */
+int kb_distance_batch(kb_engine* e, const double* Q, int64_t N, double upper_bound, int include_self,
+                      double* out_d, int32_t* out_pair);
+int kb_distance_batch_device(kb_engine* e, const double* dQ, int64_t N, double upper_bound, int include_self,
+                             double* d_out_d, int32_t* d_out_pair);
+
+/* AnyCollisionQuery between two registered geometries at explicit transforms, N transform pairs at once
+ * (Geometry3D.collides / withinDistance / distance, Python/klampt/src/robotsim.cpp:1656-1819).
+ * Ta, Tb: N x 12.  tol = 0 -> Collide(), tol > 0 -> WithinDistance(tol).  */
+int kb_geom_collides_batch(kb_engine* e, int ga, const double* Ta, int gb, const double* Tb, int64_t N, double tol,
+                           uint8_t* out);
+int kb_geom_distance_batch(kb_engine* e, int ga, const double* Ta, int gb, const double* Tb, int64_t N,
+                           double upper_bound, double* out_d);
+
+/* ---- introspection ------------------------------------------------------------------------------------ */
+int kb_get_stats(kb_engine* e, kb_stats* out);
+int kb_reset_stats(kb_engine* e);
+/* sizes of the device-resident static data: [0] bvh nodes, [1] elements, [2] bytes, [3] work items per config,
+ * [4] merged environment groups, [5] max BVH depth sum */
+int kb_get_layout(const kb_engine* e, int64_t out[6]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,909 @@
+// kb_engine.cu -- host side of the C ABI declared in include/klampt_b200.h: world description, BVH build and
+// flattening (kb_finalize), per-batch orchestration of the kernels in kb_kernels.cu.
+//
+// There is no CPU fallback: every query entry point runs the CUDA kernels or returns KB_ERR_CUDA.
+#include "../../include/klampt_b200.h"
+#include "kb_kernels.h"
+#include "kb_types.h"
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return fail(KB_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); } while (0)
+
+struct Xf { double R[9]; double t[3]; };
+inline void xf_from12(const double* a, Xf& T) { memcpy(T.R, a, 72); memcpy(T.t, a + 9, 24); }
+// same operation order as a scalar fp64 R*p+t so baked world-frame vertices match a query-time transform bit for bit
+inline void xf_apply(const Xf& T, const double* p, double* o) {
+  double x = p[0], y = p[1], z = p[2];
+  o[0] = T.R[0] * x + T.R[1] * y + T.R[2] * z + T.t[0];
+  o[1] = T.R[3] * x + T.R[4] * y + T.R[5] * z + T.t[1];
+  o[2] = T.R[6] * x + T.R[7] * y + T.R[8] * z + T.t[2];
+}
+
+enum { G_EMPTY = 0, G_MESH = 1, G_CLOUD = 2, G_PRIM = 3 };
+
+struct Geom {
+  int kind = G_EMPTY;
+  double margin = 0;
+  std::vector<double> tri;     // 9 per triangle (expanded), local frame
+  std::vector<double> sph;     // 4 per sphere (x,y,z,r), local frame
+  int nelem() const { return kind == G_MESH ? (int)(tri.size() / 9) : (int)(sph.size() / 4); }
+  bool empty() const { return kind == G_EMPTY || nelem() == 0; }
+};
+
+struct Driver { std::vector<int32_t> links; std::vector<double> scale, offset; double dmin, dmax; };
+
+// ------------------------------------------------------------------------------------------------- BVH build
+struct BNode { double lo[3], hi[3]; int left; int first, count; };   // left >= 0: children left,left+1 ; left < 0: leaf
+
+struct Bvh {
+  std::vector<BNode> nodes;
+  std::vector<int> perm;       // leaf order -> input element index
+  int depth = 0;
+};
+
+// Binned-SAH top-down build (16 bins, 3 axes), siblings adjacent, median split once a branch gets deeper than 48.
+void build_bvh(const std::vector<double>& elo, const std::vector<double>& ehi, int n, int leaf_size, Bvh& out) {
+  out.nodes.clear(); out.perm.resize(n); out.depth = 0;
+  if (n <= 0) return;
+  std::iota(out.perm.begin(), out.perm.end(), 0);
+  std::vector<double> cen(3 * (size_t)n);
+  for (int i = 0; i < n; i++) for (int k = 0; k < 3; k++) cen[3 * (size_t)i + k] = 0.5 * (elo[3 * (size_t)i + k] + ehi[3 * (size_t)i + k]);
+  out.nodes.reserve(2 * (size_t)n);
+  struct Task { int node, first, count, depth; };
+  std::vector<Task> todo;
+  out.nodes.push_back(BNode());
+  todo.push_back({0, 0, n, 0});
+  const int NB = 16;
+  while (!todo.empty()) {
+    Task t = todo.back(); todo.pop_back();
+    if (t.depth > out.depth) out.depth = t.depth;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, clo[3] = {1e300, 1e300, 1e300}, chi[3] = {-1e300, -1e300, -1e300};
+    for (int i = t.first; i < t.first + t.count; i++) {
+      int e = out.perm[i];
+      for (int k = 0; k < 3; k++) {
+        lo[k] = std::min(lo[k], elo[3 * (size_t)e + k]); hi[k] = std::max(hi[k], ehi[3 * (size_t)e + k]);
+        clo[k] = std::min(clo[k], cen[3 * (size_t)e + k]); chi[k] = std::max(chi[k], cen[3 * (size_t)e + k]);
+      }
+    }
+    {
+      BNode& nd = out.nodes[t.node];
+      memcpy(nd.lo, lo, 24); memcpy(nd.hi, hi, 24); nd.first = t.first; nd.count = t.count; nd.left = -1;
+    }
+    if (t.count <= leaf_size) continue;
+    int mid = -1;
+    if (t.depth < 48) {
+      double bestc = 1e300; int bax = -1, bsplit = -1;
+      for (int ax = 0; ax < 3; ax++) {
+        double ext = chi[ax] - clo[ax];
+        if (!(ext > 0)) continue;
+        int cnt[NB]; double blo[NB][3], bhi[NB][3];
+        for (int b = 0; b < NB; b++) { cnt[b] = 0; for (int k = 0; k < 3; k++) { blo[b][k] = 1e300; bhi[b][k] = -1e300; } }
+        double sc = NB / ext;
+        for (int i = t.first; i < t.first + t.count; i++) {
+          int e = out.perm[i];
+          int b = (int)((cen[3 * (size_t)e + ax] - clo[ax]) * sc); if (b >= NB) b = NB - 1; if (b < 0) b = 0;
+          cnt[b]++;
+          for (int k = 0; k < 3; k++) { blo[b][k] = std::min(blo[b][k], elo[3 * (size_t)e + k]); bhi[b][k] = std::max(bhi[b][k], ehi[3 * (size_t)e + k]); }
+        }
+        double ra[NB]; int rc[NB];
+        double l3[3] = {1e300, 1e300, 1e300}, h3[3] = {-1e300, -1e300, -1e300}; int c = 0;
+        for (int b = NB - 1; b > 0; b--) {
+          c += cnt[b];
+          for (int k = 0; k < 3; k++) { l3[k] = std::min(l3[k], blo[b][k]); h3[k] = std::max(h3[k], bhi[b][k]); }
+          double dx = h3[0] - l3[0], dy = h3[1] - l3[1], dz = h3[2] - l3[2];
+          ra[b] = c ? 2 * (dx * dy + dy * dz + dz * dx) : 0; rc[b] = c;
+        }
+        for (int k = 0; k < 3; k++) { l3[k] = 1e300; h3[k] = -1e300; } c = 0;
+        for (int b = 0; b < NB - 1; b++) {
+          c += cnt[b];
+          for (int k = 0; k < 3; k++) { l3[k] = std::min(l3[k], blo[b][k]); h3[k] = std::max(h3[k], bhi[b][k]); }
+          if (c == 0 || rc[b + 1] == 0) continue;
+          double dx = h3[0] - l3[0], dy = h3[1] - l3[1], dz = h3[2] - l3[2];
+          double cost = 2 * (dx * dy + dy * dz + dz * dx) * c + ra[b + 1] * rc[b + 1];
+          if (cost < bestc) { bestc = cost; bax = ax; bsplit = b; }
+        }
+      }
+      if (bax >= 0) {
+        double ext = chi[bax] - clo[bax], sc = NB / ext;
+        auto it = std::partition(out.perm.begin() + t.first, out.perm.begin() + t.first + t.count, [&](int e) {
+          int b = (int)((cen[3 * (size_t)e + bax] - clo[bax]) * sc); if (b >= NB) b = NB - 1; if (b < 0) b = 0; return b <= bsplit; });
+        mid = (int)(it - out.perm.begin());
+        if (mid == t.first || mid == t.first + t.count) mid = -1;
+      }
+    }
+    if (mid < 0) {   // median split on the longest axis (deterministic tie break on the element index)
+      int ax = 0; double ext = hi[0] - lo[0];
+      for (int k = 1; k < 3; k++) if (hi[k] - lo[k] > ext) { ext = hi[k] - lo[k]; ax = k; }
+      mid = t.first + t.count / 2;
+      std::nth_element(out.perm.begin() + t.first, out.perm.begin() + mid, out.perm.begin() + t.first + t.count, [&](int a, int b) {
+        double ca = cen[3 * (size_t)a + ax], cb = cen[3 * (size_t)b + ax]; return ca < cb || (ca == cb && a < b); });
+    }
+    int l = (int)out.nodes.size();
+    out.nodes.push_back(BNode()); out.nodes.push_back(BNode());
+    out.nodes[t.node].left = l;
+    todo.push_back({l + 1, mid, t.first + t.count - mid, t.depth + 1});
+    todo.push_back({l, t.first, mid - t.first, t.depth + 1});
+  }
+}
+
+inline float f_down(double x) { float f = (float)x; if ((double)f > x) f = nextafterf(f, -INFINITY); return f; }
+inline float f_up(double x) { float f = (float)x; if ((double)f < x) f = nextafterf(f, INFINITY); return f; }
+inline float i2f(int32_t i) { float f; memcpy(&f, &i, 4); return f; }
+
+// device-side geometry: a flattened BVH + elements in leaf order
+struct DevGeom { int node_base = 0, nnodes = 0, elem_base = 0, nelem = 0, kind = KB_ELEM_TRI, depth = 0; double margin = 0; bool empty = true; double lo[3], hi[3]; };
+
+struct ItemSet { std::vector<KbItem> items; KbItem* d_items = nullptr; int nxf = 0; int maxdepth = 0; };
+
+}  // namespace
+
+struct kb_engine {
+  // ---- description
+  std::vector<Geom> geoms;
+  std::vector<int> terrains;
+  std::vector<int> objects; std::vector<Xf> objT;
+  int L = 0;
+  std::vector<int32_t> parents; std::vector<uint8_t> linktype; std::vector<double> axis, T0, qmin, qmax;
+  std::vector<int> linkgeom;
+  std::vector<uint8_t> jtype; std::vector<int32_t> jlink;
+  std::vector<Driver> drivers;
+  std::vector<uint8_t> selfcol; bool selfcol_default = true;
+  std::vector<uint8_t> mask; int nids = 0; bool mask_user = false;
+  bool finalized = false;
+  // ---- device
+  int device = -1, num_sms = 148;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  std::vector<float> h_nodes;               // 8 floats per node
+  std::vector<float> h_tris32; std::vector<double> h_tris64; std::vector<int32_t> h_triown;
+  std::vector<float> h_sph32; std::vector<double> h_sph64; std::vector<int32_t> h_sphown;
+  std::vector<DevGeom> dgeoms;              // per registered geometry (local frame)
+  std::vector<DevGeom> groups;              // merged environment groups (world frame)
+  KbScene scene{};
+  float4* d_nodes = nullptr; float4* d_tris32 = nullptr; double* d_tris64 = nullptr; float4* d_sph32 = nullptr; double* d_sph64 = nullptr;
+  int32_t* d_triown = nullptr; int32_t* d_sphown = nullptr;
+  KbRobotDev* d_robot = nullptr; KbDriverDev* d_drv = nullptr; int32_t* d_drv_link = nullptr; double* d_drv_scale = nullptr; double* d_drv_off = nullptr;
+  ItemSet feas_items, env_items;            // env + self ; env only (distance without self)
+  int64_t static_bytes = 0;
+  // ---- per-batch scratch (grown on demand)
+  int64_t chunk = 65536;
+  double* d_xf = nullptr; int64_t xf_cap = 0;
+  uint8_t* d_state = nullptr; int32_t* d_hit = nullptr; int32_t* d_hit_elem = nullptr; int64_t cfg_cap = 0;
+  uint32_t* d_work = nullptr; unsigned long long* d_counters = nullptr;   // counters: [0] recheck [1] node [2] leaf [3] feasible [4] visible
+  double* d_Q = nullptr; int64_t q_cap = 0;             // staging for host entry points
+  uint8_t* d_out = nullptr; int64_t out_cap = 0;
+  int32_t* d_pair = nullptr; int64_t pair_cap = 0;
+  double* d_dist = nullptr; int64_t dist_cap = 0;
+  // edges
+  double* d_A = nullptr; double* d_B = nullptr; int64_t ab_cap = 0;
+  int32_t* d_nlev = nullptr; uint8_t* d_alive = nullptr; int32_t* d_nchecks = nullptr; int32_t* d_firstbad = nullptr; int32_t* d_list = nullptr; int64_t edge_cap = 0;
+  double* d_eQ = nullptr; uint8_t* d_efeas = nullptr; int64_t eq_cap = 0;
+  int32_t* d_scalars = nullptr;             // [0] maxlev, [1] list count
+  double* d_weights = nullptr; int64_t w_cap = 0;
+  // generic transform-pair queries
+  double* d_T = nullptr; int64_t t_cap = 0;
+  // ---- stats
+  kb_stats stats{};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool collect_stats = false;
+};
+
+namespace {
+
+int robot_id(const kb_engine* e) { return (int)e->terrains.size() + (int)e->objects.size(); }
+int link_id(const kb_engine* e, int j) { return robot_id(e) + 1 + j; }
+int num_ids(const kb_engine* e) { return (int)e->terrains.size() + (int)e->objects.size() + (e->L ? 1 + e->L : 0); }
+bool geom_empty(const kb_engine* e, int g) { return g < 0 || g >= (int)e->geoms.size() || e->geoms[g].empty(); }
+
+void init_all_self_collisions(kb_engine* e) {
+  int L = e->L;
+  for (int i = 0; i < L; i++) for (int j = i + 1; j < L; j++)
+    e->selfcol[i * L + j] = !geom_empty(e, e->linkgeom[i]) && !geom_empty(e, e->linkgeom[j]) && e->parents[j] != i && e->parents[i] != j;
+}
+
+// WorldPlannerSettings::InitializeDefault (reference Cpp/Planning/PlannerSettings.cpp:16-41)
+void init_default_mask(kb_engine* e) {
+  int n = num_ids(e); e->nids = n;
+  e->mask.assign((size_t)n * n, 1);
+  for (int i = 0; i < n; i++) e->mask[(size_t)i * n + i] = 0;
+  if (e->L) {
+    int k = robot_id(e), base = k + 1, L = e->L, T = (int)e->terrains.size();
+    e->mask[(size_t)k * n + k] = 1;
+    for (int j = 0; j < L; j++) { e->mask[(size_t)(base + j) * n + k] = 0; e->mask[(size_t)k * n + base + j] = 0; }
+    for (int j = 0; j < L; j++) for (int m = 0; m < L; m++) e->mask[(size_t)(base + j) * n + base + m] = (j < m) ? e->selfcol[j * L + m] : 0;
+    for (int j = 0; j < L; j++) if (e->parents[j] == -1)
+      for (int t = 0; t < T; t++) { e->mask[(size_t)(base + j) * n + t] = 0; e->mask[(size_t)t * n + base + j] = 0; }
+  }
+}
+inline bool mask_en(const kb_engine* e, int a, int b) { return e->mask[(size_t)a * e->nids + b] != 0; }
+
+// appends one geometry (elements given in some frame) to the host arrays: builds its BVH, writes nodes + elements
+int append_geom(kb_engine* e, int kind, const std::vector<double>& elems, const std::vector<int32_t>& owners, double margin, DevGeom& dg) {
+  const int stride = kind == G_MESH ? 9 : 4;
+  const int n = (int)(elems.size() / stride);
+  dg = DevGeom(); dg.margin = margin; dg.kind = kind == G_MESH ? KB_ELEM_TRI : KB_ELEM_SPHERE; dg.nelem = n; dg.empty = n == 0;
+  if (n == 0) return KB_OK;
+  std::vector<double> elo(3 * (size_t)n), ehi(3 * (size_t)n);
+  for (int i = 0; i < n; i++) {
+    const double* p = &elems[(size_t)stride * i];
+    for (int k = 0; k < 3; k++) {
+      if (kind == G_MESH) { elo[3 * (size_t)i + k] = std::min(p[k], std::min(p[3 + k], p[6 + k])); ehi[3 * (size_t)i + k] = std::max(p[k], std::max(p[3 + k], p[6 + k])); }
+      else { elo[3 * (size_t)i + k] = p[k] - p[3]; ehi[3 * (size_t)i + k] = p[k] + p[3]; }
+    }
+  }
+  Bvh bvh; build_bvh(elo, ehi, n, kind == G_MESH ? 1 : 8, bvh);
+  dg.node_base = (int)(e->h_nodes.size() / 8); dg.nnodes = (int)bvh.nodes.size(); dg.depth = bvh.depth;
+  dg.elem_base = kind == G_MESH ? (int)(e->h_tris64.size() / 9) : (int)(e->h_sph64.size() / 4);
+  memcpy(dg.lo, bvh.nodes[0].lo, 24); memcpy(dg.hi, bvh.nodes[0].hi, 24);
+  for (const BNode& nd : bvh.nodes) {
+    float v[8] = {f_down(nd.lo[0]), f_down(nd.lo[1]), f_down(nd.lo[2]), 0.f, f_up(nd.hi[0]), f_up(nd.hi[1]), f_up(nd.hi[2]), 0.f};
+    if (nd.left >= 0) { v[3] = i2f(nd.left); v[7] = i2f(0); }
+    else { v[3] = i2f(~nd.first); v[7] = i2f(nd.count); }
+    e->h_nodes.insert(e->h_nodes.end(), v, v + 8);
+  }
+  for (int i = 0; i < n; i++) {
+    int src = bvh.perm[i];
+    const double* p = &elems[(size_t)stride * src];
+    int32_t own = owners.empty() ? -1 : owners[src];
+    if (kind == G_MESH) {
+      e->h_tris64.insert(e->h_tris64.end(), p, p + 9);
+      for (int v = 0; v < 3; v++) { float f[4] = {(float)p[3 * v], (float)p[3 * v + 1], (float)p[3 * v + 2], v == 0 ? i2f(own) : 0.f}; e->h_tris32.insert(e->h_tris32.end(), f, f + 4); }
+      e->h_triown.push_back(own);
+    } else {
+      e->h_sph64.insert(e->h_sph64.end(), p, p + 4);
+      float f[4] = {(float)p[0], (float)p[1], (float)p[2], (float)p[3]}; e->h_sph32.insert(e->h_sph32.end(), f, f + 4);
+      e->h_sphown.push_back(own);
+    }
+  }
+  return KB_OK;
+}
+
+KbItem make_item(const DevGeom& A, int xfA, int idA, const DevGeom& B, int xfB, int idB, bool self) {
+  KbItem it; memset(&it, 0, sizeof it);
+  it.nodeA = A.node_base; it.nodeB = B.node_base; it.elemA = A.elem_base; it.elemB = B.elem_base;
+  it.xfA = (int16_t)xfA; it.xfB = (int16_t)xfB; it.kindA = (uint8_t)A.kind; it.kindB = (uint8_t)B.kind; it.flags = self ? 1 : 0;
+  it.idA = idA; it.idB = idB; it.thr = A.margin + B.margin; it.marg = A.margin + B.margin;
+  return it;
+}
+// the A side of an item is limited to 2^20 nodes (stack entry packing); put the smaller hierarchy there
+int add_item(ItemSet& set, const DevGeom& A, int xfA, int idA, const DevGeom& B, int xfB, int idB, bool self) {
+  if (A.empty || B.empty) return KB_OK;
+  const bool swap = A.nnodes > B.nnodes;
+  const DevGeom& a = swap ? B : A; const DevGeom& b = swap ? A : B;
+  if (a.nnodes >= KB_MAX_NODES_A) return fail(KB_ERR_UNSUPPORTED, "both geometries of a pair have more than %d BVH nodes", KB_MAX_NODES_A);
+  if ((int)set.items.size() >= KB_MAX_ITEMS) return fail(KB_ERR_UNSUPPORTED, "more than %d geometry pairs per configuration", KB_MAX_ITEMS);
+  set.items.push_back(swap ? make_item(B, xfB, idB, A, xfA, idA, self) : make_item(A, xfA, idA, B, xfB, idB, self));
+  set.maxdepth = std::max(set.maxdepth, a.depth + b.depth);
+  return KB_OK;
+}
+
+template <class T> int upload(T*& dptr, const void* src, size_t bytes, int64_t* total) {
+  dptr = nullptr;
+  if (bytes == 0) { CK(cudaMalloc((void**)&dptr, 16)); return KB_OK; }
+  CK(cudaMalloc((void**)&dptr, bytes));
+  CK(cudaMemcpy(dptr, src, bytes, cudaMemcpyHostToDevice));
+  if (total) *total += (int64_t)bytes;
+  return KB_OK;
+}
+template <class T> int grow(T*& p, int64_t& cap, int64_t need) {
+  if (need <= cap) return KB_OK;
+  if (p) cudaFree(p);
+  p = nullptr; cap = 0;
+  CK(cudaMalloc((void**)&p, (size_t)need * sizeof(T)));
+  cap = need;
+  return KB_OK;
+}
+template <class T> int grow_plain(T*& p, int64_t need_elems, int64_t& cap_elems) { return grow(p, cap_elems, need_elems); }
+
+int ensure_cfg_scratch(kb_engine* e, int nxf) {
+  int64_t ch = e->chunk;
+  int64_t need_xf = ch * nxf * 12;
+  if (need_xf > e->xf_cap) { if (e->d_xf) cudaFree(e->d_xf); e->d_xf = nullptr; e->xf_cap = 0; CK(cudaMalloc((void**)&e->d_xf, (size_t)need_xf * 8)); e->xf_cap = need_xf; }
+  if (ch > e->cfg_cap) {
+    if (e->d_state) cudaFree(e->d_state); if (e->d_hit) cudaFree(e->d_hit); if (e->d_hit_elem) cudaFree(e->d_hit_elem);
+    e->cfg_cap = 0;
+    CK(cudaMalloc((void**)&e->d_state, (size_t)ch)); CK(cudaMalloc((void**)&e->d_hit, (size_t)ch * 4)); CK(cudaMalloc((void**)&e->d_hit_elem, (size_t)ch * 8));
+    e->cfg_cap = ch;
+  }
+  return KB_OK;
+}
+
+void begin_timing(kb_engine* e) { cudaEventRecord(e->ev0, e->stream); }
+void end_timing(kb_engine* e, bool sync) {
+  cudaEventRecord(e->ev1, e->stream);
+  if (sync) { cudaEventSynchronize(e->ev1); float ms = 0; if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->stats.gpu_ms += ms; }
+}
+
+KbTraverseParams make_params(kb_engine* e, const ItemSet& set, const double* xf, int64_t n, const uint8_t* state) {
+  KbTraverseParams p; memset(&p, 0, sizeof p);
+  p.scene = e->scene; p.items = set.d_items; p.nitems = (int)set.items.size(); p.nxf = set.nxf; p.xf64 = xf; p.N = n; p.state = state;
+  p.hit = e->d_hit; p.hit_elem = e->d_hit_elem; p.work_counter = e->d_work; p.counters = e->d_counters;
+  p.wide_limit = KB_STACK_CAP - 32 - set.maxdepth - 2; p.collect_stats = e->collect_stats ? 1 : 0;
+  return p;
+}
+
+// feasibility of n configurations resident on the device: FK -> traversal -> finish, chunk by chunk
+int run_feasible_device(kb_engine* e, const double* dQ, int64_t N, uint8_t* d_out, int32_t* d_first_pair, unsigned long long* d_nfeas) {
+  int rc = ensure_cfg_scratch(e, e->feas_items.nxf); if (rc) return rc;
+  for (int64_t off = 0; off < N; off += e->chunk) {
+    int64_t n = std::min(e->chunk, N - off);
+    CK(kb_launch_fk(e->d_robot, e->d_drv, e->d_drv_link, e->d_drv_scale, e->d_drv_off, dQ + off * e->L, n, e->d_xf, e->feas_items.nxf, e->d_state, nullptr, e->d_hit, e->stream));
+    e->stats.kernel_launches++;
+    if (!e->feas_items.items.empty()) {
+      KbTraverseParams p = make_params(e, e->feas_items, e->d_xf, n, e->d_state);
+      CK(kb_launch_traverse(p, 0, nullptr, 0.0, e->num_sms, e->stream));
+      e->stats.kernel_launches++;
+    }
+    CK(kb_launch_finish(e->d_state, e->d_hit, e->d_hit_elem, e->feas_items.d_items, e->d_triown, e->d_sphown, n, d_out + off,
+                        d_first_pair ? d_first_pair + 2 * off : nullptr, d_nfeas, e->stream));
+    e->stats.kernel_launches++;
+  }
+  return KB_OK;
+}
+
+int upload_itemset(ItemSet& s, int64_t* total) {
+  if (s.d_items) { cudaFree(s.d_items); s.d_items = nullptr; }
+  return upload(s.d_items, s.items.data(), s.items.size() * sizeof(KbItem), total);
+}
+
+}  // namespace
+
+// =================================================================================================== C ABI
+extern "C" {
+
+const char* kb_last_error(void) { return g_err.c_str(); }
+const char* kb_version(void) { return "klampt_b200 0.1 (sm_100a)"; }
+
+int kb_engine_create(kb_engine** out) {
+  if (!out) return fail(KB_ERR_INVALID, "null out pointer");
+  *out = new kb_engine();
+  return KB_OK;
+}
+
+void kb_engine_destroy(kb_engine* e) {
+  if (!e) return;
+  if (e->device >= 0) {
+    cudaSetDevice(e->device);
+    void* ptrs[] = {e->d_nodes, e->d_tris32, e->d_tris64, e->d_sph32, e->d_sph64, e->d_triown, e->d_sphown, e->d_robot, e->d_drv, e->d_drv_link,
+                    e->d_drv_scale, e->d_drv_off, e->feas_items.d_items, e->env_items.d_items, e->d_xf, e->d_state, e->d_hit, e->d_hit_elem, e->d_work,
+                    e->d_counters, e->d_Q, e->d_out, e->d_pair, e->d_dist, e->d_A, e->d_B, e->d_nlev, e->d_alive, e->d_nchecks, e->d_firstbad, e->d_list,
+                    e->d_eQ, e->d_efeas, e->d_scalars, e->d_weights, e->d_T};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  }
+  delete e;
+}
+
+int kb_add_trimesh(kb_engine* e, const double* verts, int nv, const int32_t* tris, int nt, double margin) {
+  if (!e || e->finalized) return fail(KB_ERR_STATE, "engine is null or already finalized");
+  if (nt < 0 || nv < 0 || margin < 0) return fail(KB_ERR_INVALID, "negative size or margin");
+  Geom g; g.kind = nt > 0 ? G_MESH : G_EMPTY; g.margin = margin; g.tri.resize(9 * (size_t)nt);
+  for (int t = 0; t < nt; t++) for (int v = 0; v < 3; v++) {
+    int idx = tris[3 * t + v];
+    if (idx < 0 || idx >= nv) return fail(KB_ERR_INVALID, "triangle %d references vertex %d of %d", t, idx, nv);
+    for (int k = 0; k < 3; k++) g.tri[9 * (size_t)t + 3 * v + k] = verts[3 * (size_t)idx + k];
+  }
+  e->geoms.push_back(std::move(g));
+  return (int)e->geoms.size() - 1;
+}
+
+int kb_add_pointcloud(kb_engine* e, const double* pts, int n, const double* radius, double margin) {
+  if (!e || e->finalized) return fail(KB_ERR_STATE, "engine is null or already finalized");
+  if (n < 0 || margin < 0) return fail(KB_ERR_INVALID, "negative size or margin");
+  Geom g; g.kind = n > 0 ? G_CLOUD : G_EMPTY; g.margin = margin; g.sph.resize(4 * (size_t)n);
+  for (int i = 0; i < n; i++) { for (int k = 0; k < 3; k++) g.sph[4 * (size_t)i + k] = pts[3 * (size_t)i + k]; g.sph[4 * (size_t)i + 3] = radius ? radius[i] : 0.0; }
+  e->geoms.push_back(std::move(g));
+  return (int)e->geoms.size() - 1;
+}
+
+int kb_add_primitive(kb_engine* e, int type, const double* params, double margin) {
+  if (!e || e->finalized) return fail(KB_ERR_STATE, "engine is null or already finalized");
+  if (type != KB_PRIM_POINT && type != KB_PRIM_SPHERE) return fail(KB_ERR_UNSUPPORTED, "primitive type %d is not supported (point and sphere are)", type);
+  Geom g; g.kind = G_PRIM; g.margin = margin; g.sph = {params[0], params[1], params[2], type == KB_PRIM_SPHERE ? params[3] : 0.0};
+  e->geoms.push_back(std::move(g));
+  return (int)e->geoms.size() - 1;
+}
+
+int kb_add_terrain(kb_engine* e, int geom) {
+  if (!e || e->finalized) return fail(KB_ERR_STATE, "engine is null or already finalized");
+  if (geom >= (int)e->geoms.size()) return fail(KB_ERR_INVALID, "unknown geometry %d", geom);
+  e->terrains.push_back(geom); return (int)e->terrains.size() - 1;
+}
+
+int kb_add_rigid_object(kb_engine* e, int geom, const double T[12]) {
+  if (!e || e->finalized) return fail(KB_ERR_STATE, "engine is null or already finalized");
+  if (geom >= (int)e->geoms.size()) return fail(KB_ERR_INVALID, "unknown geometry %d", geom);
+  Xf x; xf_from12(T, x); e->objects.push_back(geom); e->objT.push_back(x); return (int)e->objects.size() - 1;
+}
+
+int kb_robot_create(kb_engine* e, int L, const int32_t* parents, const uint8_t* linktype, const double* axis, const double* T0,
+                    const double* qmin, const double* qmax) {
+  if (!e || e->finalized) return fail(KB_ERR_STATE, "engine is null or already finalized");
+  if (e->L) return fail(KB_ERR_STATE, "the engine already has its active robot");
+  if (L <= 0 || L > KB_MAX_LINKS) return fail(KB_ERR_UNSUPPORTED, "robot has %d links; supported: 1..%d", L, KB_MAX_LINKS);
+  for (int i = 0; i < L; i++) if (parents[i] >= i || parents[i] < -1) return fail(KB_ERR_INVALID, "parents[%d]=%d must be -1 or < %d", i, parents[i], i);
+  e->L = L;
+  e->parents.assign(parents, parents + L); e->linktype.assign(linktype, linktype + L);
+  e->axis.assign(axis, axis + 3 * L); e->T0.assign(T0, T0 + 12 * L); e->qmin.assign(qmin, qmin + L); e->qmax.assign(qmax, qmax + L);
+  e->linkgeom.assign(L, -1);
+  e->jtype.assign(L, KB_JOINT_NORMAL); e->jlink.resize(L); std::iota(e->jlink.begin(), e->jlink.end(), 0);
+  e->selfcol.assign((size_t)L * L, 0);
+  return KB_OK;
+}
+
+int kb_robot_set_link_geometry(kb_engine* e, int link, int geom) {
+  if (!e || e->finalized) return fail(KB_ERR_STATE, "engine is null or already finalized");
+  if (link < 0 || link >= e->L || geom >= (int)e->geoms.size()) return fail(KB_ERR_INVALID, "bad link %d or geometry %d", link, geom);
+  e->linkgeom[link] = geom; return KB_OK;
+}
+
+int kb_robot_set_joints(kb_engine* e, int nj, const uint8_t* jtype, const int32_t* jlink) {
+  if (!e || e->finalized) return fail(KB_ERR_STATE, "engine is null or already finalized");
+  if (nj < 0 || nj > KB_MAX_LINKS) return fail(KB_ERR_INVALID, "bad joint count %d", nj);
+  for (int i = 0; i < nj; i++) {
+    if (jlink[i] < 0 || jlink[i] >= e->L) return fail(KB_ERR_INVALID, "joint %d references link %d", i, jlink[i]);
+    if (jtype[i] == KB_JOINT_FLOATING || jtype[i] == KB_JOINT_FLOATINGPLANAR || jtype[i] == KB_JOINT_BALLANDSOCKET)
+      return fail(KB_ERR_UNSUPPORTED, "floating / ball-and-socket joints are not supported by the batched metric and interpolation yet");
+  }
+  e->jtype.assign(jtype, jtype + nj); e->jlink.assign(jlink, jlink + nj); return KB_OK;
+}
+
+int kb_robot_add_driver(kb_engine* e, int n, const int32_t* links, const double* scale, const double* offset, double dmin, double dmax) {
+  if (!e || e->finalized) return fail(KB_ERR_STATE, "engine is null or already finalized");
+  if (n <= 0) return fail(KB_ERR_INVALID, "driver needs at least one link");
+  Driver d; d.dmin = dmin; d.dmax = dmax;
+  for (int i = 0; i < n; i++) {
+    if (links[i] < 0 || links[i] >= e->L) return fail(KB_ERR_INVALID, "driver references link %d", links[i]);
+    d.links.push_back(links[i]); d.scale.push_back(scale ? scale[i] : 1.0); d.offset.push_back(offset ? offset[i] : 0.0);
+  }
+  e->drivers.push_back(d); return (int)e->drivers.size() - 1;
+}
+
+int kb_robot_set_self_collision(kb_engine* e, int i, int j, int enabled) {
+  if (!e || e->finalized) return fail(KB_ERR_STATE, "engine is null or already finalized");
+  if (i > j) std::swap(i, j);
+  if (i == j || i < 0 || j >= e->L) return fail(KB_ERR_INVALID, "bad self-collision pair %d,%d", i, j);
+  if (e->selfcol_default) { init_all_self_collisions(e); e->selfcol_default = false; }
+  if (enabled && (geom_empty(e, e->linkgeom[i]) || geom_empty(e, e->linkgeom[j]))) enabled = 0;
+  e->selfcol[i * e->L + j] = enabled != 0; return KB_OK;
+}
+
+int kb_set_pair_mask(kb_engine* e, const uint8_t* mask, int n_ids) {
+  if (!e || e->finalized) return fail(KB_ERR_STATE, "engine is null or already finalized");
+  if (n_ids != num_ids(e)) return fail(KB_ERR_INVALID, "mask is %d x %d but the world has %d ids", n_ids, n_ids, num_ids(e));
+  e->mask.assign(mask, mask + (size_t)n_ids * n_ids); e->nids = n_ids; e->mask_user = true; return KB_OK;
+}
+
+int kb_num_ids(const kb_engine* e) { return e ? num_ids(e) : 0; }
+
+int kb_get_pair_mask(const kb_engine* e, uint8_t* out) {
+  if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
+  memcpy(out, e->mask.data(), e->mask.size()); return e->nids;
+}
+
+int kb_finalize(kb_engine* e, int device) {
+  if (!e || e->finalized) return fail(KB_ERR_STATE, "engine is null or already finalized");
+  if (!e->L) return fail(KB_ERR_STATE, "no robot: call kb_robot_create first");
+  if (e->selfcol_default) { init_all_self_collisions(e); e->selfcol_default = false; }
+  if (!e->mask_user) init_default_mask(e);
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) return fail(KB_ERR_CUDA, "no CUDA device available (%s); this engine has no CPU fallback", cudaGetErrorString(ce));
+  if (device < 0 || device >= ndev) return fail(KB_ERR_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+  CK(cudaSetDevice(device));
+  e->device = device;
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
+  e->num_sms = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+  e->stream = e->own_stream;
+  CK(cudaEventCreate(&e->ev0)); CK(cudaEventCreate(&e->ev1));
+
+  // ---- 1. per-geometry local-frame BVHs (links, and every geometry for explicit pair queries)
+  e->dgeoms.resize(e->geoms.size());
+  std::vector<int32_t> none;
+  for (size_t g = 0; g < e->geoms.size(); g++) {
+    const Geom& G = e->geoms[g];
+    int rc = append_geom(e, G.kind == G_MESH ? G_MESH : G_CLOUD, G.kind == G_MESH ? G.tri : G.sph, none, G.margin, e->dgeoms[g]);
+    if (rc) return rc;
+    if (G.kind == G_EMPTY) e->dgeoms[g].empty = true;
+  }
+  // ---- 2. merged world-frame environment groups: static objects with the same (element kind, margin, link mask)
+  const int L = e->L, T = (int)e->terrains.size(), O = (int)e->objects.size();
+  struct Grp { int kind; double margin; std::string sig; std::vector<double> elems; std::vector<int32_t> owners; };
+  std::vector<Grp> grp;
+  std::map<std::string, int> grp_index;
+  double extent = 0;
+  for (int s = 0; s < T + O; s++) {
+    int gi = s < T ? e->terrains[s] : e->objects[s - T];
+    if (geom_empty(e, gi)) continue;
+    const Geom& G = e->geoms[gi];
+    std::string sig((size_t)L, '0'); bool any = false;
+    for (int j = 0; j < L; j++) if (!geom_empty(e, e->linkgeom[j]) && (mask_en(e, link_id(e, j), s) || mask_en(e, s, link_id(e, j)))) { sig[j] = '1'; any = true; }
+    if (!any) continue;
+    int kind = G.kind == G_MESH ? G_MESH : G_CLOUD;
+    char key[64]; snprintf(key, sizeof key, "%d:%.17g:", kind, G.margin);
+    std::string k = std::string(key) + sig;
+    auto it = grp_index.find(k);
+    if (it == grp_index.end()) { grp_index[k] = (int)grp.size(); grp.push_back({kind, G.margin, sig, {}, {}}); it = grp_index.find(k); }
+    Grp& gr = grp[it->second];
+    Xf X; if (s < T) { memset(&X, 0, sizeof X); X.R[0] = X.R[4] = X.R[8] = 1; } else X = e->objT[s - T];
+    if (kind == G_MESH) {
+      int nt = (int)(G.tri.size() / 9);
+      for (int t = 0; t < nt; t++) {
+        double w[9];
+        for (int v = 0; v < 3; v++) { if (s < T) memcpy(w + 3 * v, &G.tri[9 * (size_t)t + 3 * v], 24); else xf_apply(X, &G.tri[9 * (size_t)t + 3 * v], w + 3 * v); }
+        gr.elems.insert(gr.elems.end(), w, w + 9); gr.owners.push_back(s);
+        for (int k2 = 0; k2 < 9; k2++) extent = std::max(extent, std::fabs(w[k2]));
+      }
+    } else {
+      int np = (int)(G.sph.size() / 4);
+      for (int i = 0; i < np; i++) {
+        double w[4];
+        if (s < T) memcpy(w, &G.sph[4 * (size_t)i], 24); else xf_apply(X, &G.sph[4 * (size_t)i], w);
+        w[3] = G.sph[4 * (size_t)i + 3];
+        gr.elems.insert(gr.elems.end(), w, w + 4); gr.owners.push_back(s);
+        for (int k2 = 0; k2 < 3; k2++) extent = std::max(extent, std::fabs(w[k2]) + w[3]);
+      }
+    }
+  }
+  e->groups.resize(grp.size());
+  for (size_t g = 0; g < grp.size(); g++) {
+    int rc = append_geom(e, grp[g].kind, grp[g].elems, grp[g].owners, grp[g].margin, e->groups[g]);
+    if (rc) return rc;
+    std::vector<double>().swap(grp[g].elems);
+  }
+  // ---- 3. work items per configuration: links vs groups (environment first, as CheckCollisionFree does), then self pairs
+  e->feas_items = ItemSet(); e->env_items = ItemSet();
+  e->feas_items.nxf = e->env_items.nxf = L;
+  for (size_t g = 0; g < grp.size(); g++)
+    for (int j = 0; j < L; j++) if (grp[g].sig[j] == '1') {
+      const DevGeom& lg = e->dgeoms[e->linkgeom[j]];
+      int rc = add_item(e->feas_items, lg, j, link_id(e, j), e->groups[g], -1, -1, false); if (rc) return rc;
+      rc = add_item(e->env_items, lg, j, link_id(e, j), e->groups[g], -1, -1, false); if (rc) return rc;
+    }
+  for (int i = 0; i < L; i++) for (int j = i + 1; j < L; j++) {
+    if (geom_empty(e, e->linkgeom[i]) || geom_empty(e, e->linkgeom[j])) continue;
+    // WorldPlannerSettings::CheckCollision(world, ids): enabled(i,j) || enabled(i,i); the second term is the diagonal (always false
+    // for links under InitializeDefault, but honoured if a caller's mask sets it)
+    if (!(mask_en(e, link_id(e, i), link_id(e, j)) || mask_en(e, link_id(e, i), link_id(e, i)))) continue;
+    int rc = add_item(e->feas_items, e->dgeoms[e->linkgeom[i]], i, link_id(e, i), e->dgeoms[e->linkgeom[j]], j, link_id(e, j), true); if (rc) return rc;
+  }
+  if (e->feas_items.maxdepth + 64 + 34 > KB_STACK_CAP) return fail(KB_ERR_UNSUPPORTED, "BVH depth sum %d exceeds the traversal stack model", e->feas_items.maxdepth);
+  // ---- 4. fp32 coordinate error bound: scene extent + robot reach
+  double reach = 0;
+  for (int j = 0; j < L; j++) {
+    double t = std::sqrt(e->T0[12 * j + 9] * e->T0[12 * j + 9] + e->T0[12 * j + 10] * e->T0[12 * j + 10] + e->T0[12 * j + 11] * e->T0[12 * j + 11]);
+    if (e->linktype[j] == KB_PRISMATIC) t += std::max(std::fabs(e->qmin[j]), std::fabs(e->qmax[j]));
+    reach += t;
+  }
+  double lmax = 0;
+  for (const DevGeom& dg : e->dgeoms) if (!dg.empty) for (int k = 0; k < 3; k++) lmax = std::max(lmax, std::max(std::fabs(dg.lo[k]), std::fabs(dg.hi[k])));
+  double S = std::max(extent, reach + lmax) + lmax;
+  if (!(S > 0)) S = 1;
+  e->scene.eps_abs = (float)(8.0 * 5.9604645e-8 * S);
+  // ---- 5. upload
+  e->static_bytes = 0;
+  int rc;
+  if ((rc = upload(e->d_nodes, e->h_nodes.data(), e->h_nodes.size() * 4, &e->static_bytes))) return rc;
+  if ((rc = upload(e->d_tris32, e->h_tris32.data(), e->h_tris32.size() * 4, &e->static_bytes))) return rc;
+  if ((rc = upload(e->d_tris64, e->h_tris64.data(), e->h_tris64.size() * 8, &e->static_bytes))) return rc;
+  if ((rc = upload(e->d_sph32, e->h_sph32.data(), e->h_sph32.size() * 4, &e->static_bytes))) return rc;
+  if ((rc = upload(e->d_sph64, e->h_sph64.data(), e->h_sph64.size() * 8, &e->static_bytes))) return rc;
+  if ((rc = upload(e->d_triown, e->h_triown.data(), e->h_triown.size() * 4, &e->static_bytes))) return rc;
+  if ((rc = upload(e->d_sphown, e->h_sphown.data(), e->h_sphown.size() * 4, &e->static_bytes))) return rc;
+  e->scene.nodes = e->d_nodes; e->scene.tris32 = e->d_tris32; e->scene.tris64 = e->d_tris64; e->scene.sph32 = e->d_sph32; e->scene.sph64 = e->d_sph64;
+  e->scene.triown = e->d_triown; e->scene.sphown = e->d_sphown;
+  if ((rc = upload_itemset(e->feas_items, &e->static_bytes))) return rc;
+  if ((rc = upload_itemset(e->env_items, &e->static_bytes))) return rc;
+  KbRobotDev* R = new KbRobotDev(); memset(R, 0, sizeof(KbRobotDev));
+  R->L = L; R->nj = (int)e->jtype.size(); R->ndrv = (int)e->drivers.size();
+  for (int i = 0; i < L; i++) { R->parents[i] = e->parents[i]; R->linktype[i] = e->linktype[i]; R->qmin[i] = e->qmin[i]; R->qmax[i] = e->qmax[i]; }
+  memcpy(R->axis, e->axis.data(), sizeof(double) * 3 * L); memcpy(R->T0, e->T0.data(), sizeof(double) * 12 * L);
+  for (int i = 0; i < R->nj; i++) { R->jtype[i] = e->jtype[i]; R->jlink[i] = e->jlink[i]; }
+  std::vector<KbDriverDev> dd; std::vector<int32_t> dl; std::vector<double> ds, dofs;
+  for (const Driver& d : e->drivers) {
+    KbDriverDev x; x.first = (int)dl.size(); x.n = (int)d.links.size(); x.dmin = d.dmin; x.dmax = d.dmax; dd.push_back(x);
+    dl.insert(dl.end(), d.links.begin(), d.links.end()); ds.insert(ds.end(), d.scale.begin(), d.scale.end()); dofs.insert(dofs.end(), d.offset.begin(), d.offset.end());
+  }
+  R->ndrv_terms = (int)dl.size();
+  rc = upload(e->d_robot, R, sizeof(KbRobotDev), &e->static_bytes); delete R; if (rc) return rc;
+  if ((rc = upload(e->d_drv, dd.data(), dd.size() * sizeof(KbDriverDev), &e->static_bytes))) return rc;
+  if ((rc = upload(e->d_drv_link, dl.data(), dl.size() * 4, &e->static_bytes))) return rc;
+  if ((rc = upload(e->d_drv_scale, ds.data(), ds.size() * 8, &e->static_bytes))) return rc;
+  if ((rc = upload(e->d_drv_off, dofs.data(), dofs.size() * 8, &e->static_bytes))) return rc;
+  CK(cudaMalloc((void**)&e->d_work, 64)); CK(cudaMalloc((void**)&e->d_counters, 64)); CK(cudaMemset(e->d_counters, 0, 64));
+  CK(cudaMalloc((void**)&e->d_scalars, 64));
+  // the host copies of the big arrays are no longer needed
+  std::vector<float>().swap(e->h_tris32); std::vector<double>().swap(e->h_tris64); std::vector<float>().swap(e->h_sph32); std::vector<double>().swap(e->h_sph64);
+  std::vector<float>().swap(e->h_nodes);
+  // keep the L2 warm with whole chunks: ~96 B per link per configuration of transform traffic
+  int64_t per_cfg = (int64_t)L * 96 + 16;
+  int64_t ch = (48ll << 20) / per_cfg; ch = std::max<int64_t>(8192, std::min<int64_t>(ch, 262144)); e->chunk = (ch / 1024) * 1024;
+  e->finalized = true;
+  return KB_OK;
+}
+
+int kb_set_stream(kb_engine* e, void* s) {
+  if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
+  e->stream = s ? (cudaStream_t)s : e->own_stream; return KB_OK;
+}
+
+int kb_set_option(kb_engine* e, const char* name, int64_t value) {
+  if (!e || !name) return fail(KB_ERR_INVALID, "null argument");
+  if (!strcmp(name, "collect_stats")) { e->collect_stats = value != 0; return KB_OK; }
+  if (!strcmp(name, "chunk")) {
+    if (value < 256 || value > (1 << 22)) return fail(KB_ERR_INVALID, "chunk must be in [256, 4194304]");
+    e->chunk = value; return KB_OK;
+  }
+  return fail(KB_ERR_INVALID, "unknown option '%s'", name);
+}
+
+int kb_synchronize(kb_engine* e) {
+  if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
+  CK(cudaSetDevice(e->device)); CK(cudaStreamSynchronize(e->stream)); return KB_OK;
+}
+
+int kb_fk_batch(kb_engine* e, const double* Q, int64_t N, double* T_out) {
+  if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
+  if (N < 0 || (N > 0 && (!Q || !T_out))) return fail(KB_ERR_INVALID, "bad arguments");
+  CK(cudaSetDevice(e->device));
+  int rc = ensure_cfg_scratch(e, e->L); if (rc) return rc;
+  if ((rc = grow(e->d_Q, e->q_cap, std::min(N, e->chunk) * e->L))) return rc;
+  for (int64_t off = 0; off < N; off += e->chunk) {
+    int64_t n = std::min(e->chunk, N - off);
+    CK(cudaMemcpyAsync(e->d_Q, Q + off * e->L, (size_t)n * e->L * 8, cudaMemcpyHostToDevice, e->stream));
+    CK(kb_launch_fk(e->d_robot, e->d_drv, e->d_drv_link, e->d_drv_scale, e->d_drv_off, e->d_Q, n, e->d_xf, e->L, nullptr, nullptr, nullptr, e->stream));
+    e->stats.kernel_launches++;
+    CK(cudaMemcpyAsync(T_out + off * e->L * 12, e->d_xf, (size_t)n * e->L * 96, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+  }
+  return KB_OK;
+}
+
+int kb_feasible_batch_device(kb_engine* e, const double* dQ, int64_t N, uint8_t* d_out, int32_t* d_first_pair) {
+  if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
+  if (N < 0 || (N > 0 && (!dQ || !d_out))) return fail(KB_ERR_INVALID, "bad arguments");
+  CK(cudaSetDevice(e->device));
+  int rc = run_feasible_device(e, dQ, N, d_out, d_first_pair, e->d_counters + 3);
+  if (rc) return rc;
+  e->stats.configs_checked += N;
+  return KB_OK;
+}
+
+int kb_feasible_batch(kb_engine* e, const double* Q, int64_t N, uint8_t* out, int32_t* first_pair) {
+  if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
+  if (N < 0 || (N > 0 && (!Q || !out))) return fail(KB_ERR_INVALID, "bad arguments");
+  if (N == 0) return KB_OK;
+  CK(cudaSetDevice(e->device));
+  int rc;
+  if ((rc = grow(e->d_Q, e->q_cap, N * e->L))) return rc;
+  if ((rc = grow(e->d_out, e->out_cap, N))) return rc;
+  if (first_pair && (rc = grow(e->d_pair, e->pair_cap, 2 * N))) return rc;
+  begin_timing(e);
+  CK(cudaMemcpyAsync(e->d_Q, Q, (size_t)N * e->L * 8, cudaMemcpyHostToDevice, e->stream));
+  if ((rc = run_feasible_device(e, e->d_Q, N, e->d_out, first_pair ? e->d_pair : nullptr, e->d_counters + 3))) return rc;
+  CK(cudaMemcpyAsync(out, e->d_out, (size_t)N, cudaMemcpyDeviceToHost, e->stream));
+  if (first_pair) CK(cudaMemcpyAsync(first_pair, e->d_pair, (size_t)N * 8, cudaMemcpyDeviceToHost, e->stream));
+  end_timing(e, true);
+  CK(cudaStreamSynchronize(e->stream));
+  e->stats.configs_checked += N;
+  return KB_OK;
+}
+
+int kb_edges_visible_batch_device(kb_engine* e, const double* dA, const double* dB, int64_t N, double eps, const double* weights_host,
+                                  uint8_t* d_out, int32_t* d_nchecks) {
+  if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
+  if (N < 0 || (N > 0 && (!dA || !dB || !d_out)) || !(eps > 0)) return fail(KB_ERR_INVALID, "bad arguments (eps must be > 0)");
+  if (N == 0) return KB_OK;
+  if (N > 0x7fffffff) return fail(KB_ERR_UNSUPPORTED, "more than 2^31 edges per call");
+  CK(cudaSetDevice(e->device));
+  int rc;
+  if (N > e->edge_cap) {
+    void* olds[] = {e->d_nlev, e->d_alive, e->d_nchecks, e->d_firstbad, e->d_list};
+    for (void* p : olds) if (p) cudaFree(p);
+    e->d_nlev = e->d_nchecks = e->d_firstbad = e->d_list = nullptr; e->d_alive = nullptr; e->edge_cap = 0;
+    CK(cudaMalloc((void**)&e->d_nlev, (size_t)N * 4)); CK(cudaMalloc((void**)&e->d_alive, (size_t)N)); CK(cudaMalloc((void**)&e->d_nchecks, (size_t)N * 4));
+    CK(cudaMalloc((void**)&e->d_firstbad, (size_t)N * 4)); CK(cudaMalloc((void**)&e->d_list, (size_t)N * 4));
+    e->edge_cap = N;
+  }
+  if (e->chunk > e->eq_cap) {
+    if (e->d_eQ) cudaFree(e->d_eQ); if (e->d_efeas) cudaFree(e->d_efeas); e->d_eQ = nullptr; e->d_efeas = nullptr; e->eq_cap = 0;
+    CK(cudaMalloc((void**)&e->d_eQ, (size_t)e->chunk * e->L * 8)); CK(cudaMalloc((void**)&e->d_efeas, (size_t)e->chunk));
+    e->eq_cap = e->chunk;
+  }
+  const double* d_w = nullptr;
+  if (weights_host) {
+    if ((rc = grow(e->d_weights, e->w_cap, (int64_t)e->jtype.size()))) return rc;
+    CK(cudaMemcpyAsync(e->d_weights, weights_host, e->jtype.size() * 8, cudaMemcpyHostToDevice, e->stream));
+    d_w = e->d_weights;
+  }
+  CK(cudaMemsetAsync(e->d_scalars, 0, 64, e->stream));
+  CK(kb_launch_edge_setup(e->d_robot, dA, dB, d_w, N, eps, e->d_nlev, e->d_alive, e->d_nchecks, e->d_scalars, e->stream)); e->stats.kernel_launches++;
+  CK(kb_launch_fill_i32(e->d_firstbad, N, 0x7fffffff, e->stream)); e->stats.kernel_launches++;
+  int32_t maxlev = 0;
+  CK(cudaMemcpyAsync(&maxlev, e->d_scalars, 4, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  int64_t cfg_checks = 0;
+  for (int lev = 1; lev <= maxlev; lev++) {
+    CK(cudaMemsetAsync(e->d_scalars + 1, 0, 4, e->stream));
+    CK(kb_launch_edge_count(e->d_nlev, e->d_alive, N, lev, e->d_list, (unsigned int*)(e->d_scalars + 1), e->stream)); e->stats.kernel_launches++;
+    uint32_t nlist = 0;
+    CK(cudaMemcpyAsync(&nlist, e->d_scalars + 1, 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (nlist == 0) break;
+    const int64_t per = (int64_t)1 << (lev - 1), total = (int64_t)nlist * per;
+    for (int64_t off = 0; off < total; off += e->chunk) {
+      int64_t n = std::min(e->chunk, total - off);
+      CK(kb_launch_edge_expand(e->d_robot, dA, dB, e->d_list, off, n, lev, e->d_eQ, e->stream)); e->stats.kernel_launches++;
+      if ((rc = run_feasible_device(e, e->d_eQ, n, e->d_efeas, nullptr, nullptr))) return rc;
+      CK(kb_launch_edge_reduce(e->d_efeas, e->d_list, off, n, lev, e->d_firstbad, e->stream)); e->stats.kernel_launches++;
+    }
+    CK(kb_launch_edge_level_end(e->d_list, nlist, lev, e->d_firstbad, e->d_alive, e->d_nchecks, e->stream)); e->stats.kernel_launches++;
+    cfg_checks += total;
+  }
+  CK(kb_launch_copy_u8(e->d_alive, d_out, N, e->d_counters + 4, e->stream)); e->stats.kernel_launches++;
+  if (d_nchecks) CK(cudaMemcpyAsync(d_nchecks, e->d_nchecks, (size_t)N * 4, cudaMemcpyDeviceToDevice, e->stream));
+  e->stats.edges_checked += N; e->stats.edge_config_checks += cfg_checks;
+  return KB_OK;
+}
+
+int kb_edges_visible_batch(kb_engine* e, const double* A, const double* B, int64_t N, double eps, const double* weights, uint8_t* out, int32_t* nchecks) {
+  if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
+  if (N < 0 || (N > 0 && (!A || !B || !out))) return fail(KB_ERR_INVALID, "bad arguments");
+  if (N == 0) return KB_OK;
+  CK(cudaSetDevice(e->device));
+  int rc;
+  if (N * e->L > e->ab_cap) {
+    if (e->d_A) cudaFree(e->d_A); if (e->d_B) cudaFree(e->d_B); e->d_A = e->d_B = nullptr; e->ab_cap = 0;
+    CK(cudaMalloc((void**)&e->d_A, (size_t)N * e->L * 8)); CK(cudaMalloc((void**)&e->d_B, (size_t)N * e->L * 8)); e->ab_cap = N * e->L;
+  }
+  if ((rc = grow(e->d_out, e->out_cap, N))) return rc;
+  if ((rc = grow(e->d_pair, e->pair_cap, 2 * N))) return rc;
+  begin_timing(e);
+  CK(cudaMemcpyAsync(e->d_A, A, (size_t)N * e->L * 8, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpyAsync(e->d_B, B, (size_t)N * e->L * 8, cudaMemcpyHostToDevice, e->stream));
+  if ((rc = kb_edges_visible_batch_device(e, e->d_A, e->d_B, N, eps, weights, e->d_out, nchecks ? e->d_pair : nullptr))) return rc;
+  CK(cudaMemcpyAsync(out, e->d_out, (size_t)N, cudaMemcpyDeviceToHost, e->stream));
+  if (nchecks) CK(cudaMemcpyAsync(nchecks, e->d_pair, (size_t)N * 4, cudaMemcpyDeviceToHost, e->stream));
+  end_timing(e, true);
+  CK(cudaStreamSynchronize(e->stream));
+  return KB_OK;
+}
+
+int kb_distance_batch_device(kb_engine* e, const double* dQ, int64_t N, double upper_bound, int include_self, double* d_out_d, int32_t* d_out_pair) {
+  if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
+  if (N < 0 || (N > 0 && (!dQ || !d_out_d))) return fail(KB_ERR_INVALID, "bad arguments");
+  CK(cudaSetDevice(e->device));
+  const ItemSet& set = include_self ? e->feas_items : e->env_items;
+  int rc = ensure_cfg_scratch(e, set.nxf); if (rc) return rc;
+  if (std::isinf(upper_bound) || upper_bound > 1e300) upper_bound = 1e300;
+  for (int64_t off = 0; off < N; off += e->chunk) {
+    int64_t n = std::min(e->chunk, N - off);
+    CK(kb_launch_fk(e->d_robot, e->d_drv, e->d_drv_link, e->d_drv_scale, e->d_drv_off, dQ + off * e->L, n, e->d_xf, set.nxf, nullptr, nullptr, e->d_hit, e->stream));
+    e->stats.kernel_launches++;
+    KbTraverseParams p = make_params(e, set, e->d_xf, n, nullptr);
+    if (p.nitems > 0) { CK(kb_launch_traverse(p, 1, d_out_d + off, upper_bound, e->num_sms, e->stream)); e->stats.kernel_launches++; }
+    else return fail(KB_ERR_STATE, "no enabled geometry pairs to measure");
+    if (d_out_pair) { CK(kb_launch_pair_ids(e->d_hit, e->d_hit_elem, set.d_items, e->d_triown, e->d_sphown, n, d_out_pair + 2 * off, e->stream)); e->stats.kernel_launches++; }
+  }
+  return KB_OK;
+}
+
+int kb_distance_batch(kb_engine* e, const double* Q, int64_t N, double upper_bound, int include_self, double* out_d, int32_t* out_pair) {
+  if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
+  if (N < 0 || (N > 0 && (!Q || !out_d))) return fail(KB_ERR_INVALID, "bad arguments");
+  if (N == 0) return KB_OK;
+  CK(cudaSetDevice(e->device));
+  int rc;
+  if ((rc = grow(e->d_Q, e->q_cap, N * e->L))) return rc;
+  if ((rc = grow(e->d_dist, e->dist_cap, N))) return rc;
+  if (out_pair && (rc = grow(e->d_pair, e->pair_cap, 2 * N))) return rc;
+  begin_timing(e);
+  CK(cudaMemcpyAsync(e->d_Q, Q, (size_t)N * e->L * 8, cudaMemcpyHostToDevice, e->stream));
+  if ((rc = kb_distance_batch_device(e, e->d_Q, N, upper_bound, include_self, e->d_dist, out_pair ? e->d_pair : nullptr))) return rc;
+  CK(cudaMemcpyAsync(out_d, e->d_dist, (size_t)N * 8, cudaMemcpyDeviceToHost, e->stream));
+  if (out_pair) CK(cudaMemcpyAsync(out_pair, e->d_pair, (size_t)N * 8, cudaMemcpyDeviceToHost, e->stream));
+  end_timing(e, true);
+  CK(cudaStreamSynchronize(e->stream));
+  if (std::isinf(upper_bound)) for (int64_t i = 0; i < N; i++) if (out_d[i] >= 1e300) out_d[i] = INFINITY;
+  return KB_OK;
+}
+
+// explicit geometry pair at N transform pairs: a 1-item work list over a 2-slot transform table
+static int geom_pair_query(kb_engine* e, int ga, const double* Ta, int gb, const double* Tb, int64_t N, double tol, int mode, double upper_bound,
+                           uint8_t* out, double* out_d) {
+  if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
+  if (ga < 0 || gb < 0 || ga >= (int)e->dgeoms.size() || gb >= (int)e->dgeoms.size()) return fail(KB_ERR_INVALID, "unknown geometry");
+  if (N < 0 || (N > 0 && (!Ta || !Tb))) return fail(KB_ERR_INVALID, "bad arguments");
+  if (N == 0) return KB_OK;
+  CK(cudaSetDevice(e->device));
+  const DevGeom& A = e->dgeoms[ga]; const DevGeom& B = e->dgeoms[gb];
+  if (A.empty || B.empty) {   // null geometry: no collision / infinite distance (PlannerSettings.cpp:96-115)
+    for (int64_t i = 0; i < N; i++) { if (out) out[i] = 0; if (out_d) out_d[i] = INFINITY; }
+    return KB_OK;
+  }
+  ItemSet set; set.nxf = 2;
+  int rc = add_item(set, A, 0, ga, B, 1, gb, false); if (rc) return rc;
+  set.items[0].thr += tol;
+  if ((rc = upload_itemset(set, nullptr))) return rc;
+  std::vector<double> host((size_t)N * 24);
+  for (int64_t i = 0; i < N; i++) { memcpy(&host[24 * (size_t)i], Ta + 12 * i, 96); memcpy(&host[24 * (size_t)i + 12], Tb + 12 * i, 96); }
+  if ((rc = grow(e->d_T, e->t_cap, N * 24))) { cudaFree(set.d_items); return rc; }
+  if ((rc = grow(e->d_dist, e->dist_cap, N))) { cudaFree(set.d_items); return rc; }
+  int64_t save_chunk = e->chunk;
+  if (N > e->cfg_cap) { e->chunk = std::max(e->chunk, N); if ((rc = ensure_cfg_scratch(e, 2))) { e->chunk = save_chunk; cudaFree(set.d_items); return rc; } e->chunk = save_chunk; }
+  else if ((rc = ensure_cfg_scratch(e, 2))) { cudaFree(set.d_items); return rc; }
+  cudaError_t ce = cudaMemcpyAsync(e->d_T, host.data(), host.size() * 8, cudaMemcpyHostToDevice, e->stream);
+  if (ce == cudaSuccess) ce = kb_launch_fill_i32(e->d_hit, N, -1, e->stream);
+  KbTraverseParams p = make_params(e, set, e->d_T, N, nullptr);
+  if (std::isinf(upper_bound) || upper_bound > 1e300) upper_bound = 1e300;
+  if (ce == cudaSuccess) ce = kb_launch_traverse(p, mode, e->d_dist, upper_bound, e->num_sms, e->stream);
+  e->stats.kernel_launches += 2;
+  std::vector<int32_t> hit((size_t)N);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(hit.data(), e->d_hit, (size_t)N * 4, cudaMemcpyDeviceToHost, e->stream);
+  if (ce == cudaSuccess && out_d) ce = cudaMemcpyAsync(out_d, e->d_dist, (size_t)N * 8, cudaMemcpyDeviceToHost, e->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+  cudaFree(set.d_items);
+  if (ce != cudaSuccess) return fail(KB_ERR_CUDA, "geometry pair query: %s", cudaGetErrorString(ce));
+  if (out) for (int64_t i = 0; i < N; i++) out[i] = hit[i] >= 0;
+  if (out_d) for (int64_t i = 0; i < N; i++) if (out_d[i] >= 1e300) out_d[i] = INFINITY;
+  return KB_OK;
+}
+
+int kb_geom_collides_batch(kb_engine* e, int ga, const double* Ta, int gb, const double* Tb, int64_t N, double tol, uint8_t* out) {
+  if (!out || tol < 0) return fail(KB_ERR_INVALID, "bad arguments");
+  return geom_pair_query(e, ga, Ta, gb, Tb, N, tol, 0, 0.0, out, nullptr);
+}
+
+int kb_geom_distance_batch(kb_engine* e, int ga, const double* Ta, int gb, const double* Tb, int64_t N, double upper_bound, double* out_d) {
+  if (!out_d) return fail(KB_ERR_INVALID, "bad arguments");
+  return geom_pair_query(e, ga, Ta, gb, Tb, N, 0.0, 1, upper_bound, nullptr, out_d);
+}
+
+int kb_get_stats(kb_engine* e, kb_stats* out) {
+  if (!e || !out) return fail(KB_ERR_INVALID, "null argument");
+  if (e->finalized) {
+    CK(cudaSetDevice(e->device)); CK(cudaStreamSynchronize(e->stream));
+    unsigned long long c[8]; CK(cudaMemcpy(c, e->d_counters, 64, cudaMemcpyDeviceToHost));
+    e->stats.recheck_pairs = (int64_t)c[0]; e->stats.configs_feasible = (int64_t)c[3]; e->stats.edges_visible = (int64_t)c[4];
+  }
+  *out = e->stats; return KB_OK;
+}
+
+int kb_reset_stats(kb_engine* e) {
+  if (!e) return fail(KB_ERR_INVALID, "null argument");
+  memset(&e->stats, 0, sizeof e->stats);
+  if (e->finalized) { CK(cudaSetDevice(e->device)); CK(cudaMemsetAsync(e->d_counters, 0, 64, e->stream)); }
+  return KB_OK;
+}
+
+int kb_get_layout(const kb_engine* e, int64_t out[6]) {
+  if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
+  int64_t nodes = 0, elems = 0;
+  for (const DevGeom& g : e->dgeoms) { nodes += g.nnodes; elems += g.nelem; }
+  for (const DevGeom& g : e->groups) { nodes += g.nnodes; elems += g.nelem; }
+  out[0] = nodes; out[1] = elems; out[2] = e->static_bytes; out[3] = (int64_t)e->feas_items.items.size(); out[4] = (int64_t)e->groups.size(); out[5] = e->feas_items.maxdepth;
+  return KB_OK;
+}
+
+}  // extern "C"

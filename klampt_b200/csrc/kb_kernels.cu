@@ -1,0 +1,712 @@
+// kb_kernels.cu -- hand-written sm_100a kernels of the batched configuration-feasibility path.
+//
+//   kb_fk_kernel          K1+K2  batched forward kinematics over SoA joint arrays + joint / driver limits
+//                                 (replaces RobotKinematics3D::UpdateFrames + RobotWithGeometry::UpdateGeometry and
+//                                 SingleRobotCSpace::CheckJointLimits; call sites Cpp/Planning/RobotCSpace.cpp:610-637)
+//   kb_traverse_kernel    K3-K7  warp-cooperative dual-BVH traversal for every enabled geometry pair of one
+//                                 configuration: fp32 OBB tests, fp32 filtered element tests, inline fp64 recheck
+//                                 (replaces WorldPlannerSettings::CheckCollision -> AnyCollisionQuery::Collide /
+//                                 WithinDistance / Distance; Cpp/Planning/PlannerSettings.cpp:96-115,241-331,570-620)
+//   kb_edge_* kernels     K8     edge expansion in bisection order, level by level, with per-edge early exit
+//                                 (replaces EpsilonEdgeChecker::IsVisible; Cpp/Planning/RobotCSpace.cpp:835-838)
+//
+// No tensor cores: no stage of this path is a dense contraction.  The bound is L2/HBM latency and bandwidth on
+// BVH nodes, so the design keeps all 32 lanes of a warp on one configuration's frontier of node pairs.
+#include "kb_types.h"
+#include "kb_geom.cuh"
+#include "kb_kernels.h"
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#define FULL 0xffffffffu
+
+// =============================================================================================== FK (fp64)
+// One thread per configuration.  All products use explicitly rounded fp64 operations (no FMA contraction) so the
+// result follows the same arithmetic as the reference's scalar fp64 code up to the last ulp of sin/cos.
+struct Xf64 { ExactD r[9]; ExactD t[3]; };
+
+__device__ __forceinline__ void xf_mul(const Xf64& A, const Xf64& B, Xf64& C) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) C.r[3 * i + j] = A.r[3 * i] * B.r[j] + A.r[3 * i + 1] * B.r[3 + j] + A.r[3 * i + 2] * B.r[6 + j];
+    C.t[i] = A.r[3 * i] * B.t[0] + A.r[3 * i + 1] * B.t[1] + A.r[3 * i + 2] * B.t[2] + A.t[i];
+  }
+}
+
+__global__ void __launch_bounds__(128)
+kb_fk_kernel(const KbRobotDev* __restrict__ robot, const KbDriverDev* __restrict__ drv, const int32_t* __restrict__ drv_link,
+             const double* __restrict__ drv_scale, const double* __restrict__ drv_off,
+             const double* __restrict__ Q, int64_t N, double* __restrict__ xf64, int nxf,
+             uint8_t* __restrict__ state, const uint8_t* __restrict__ alive, int32_t* __restrict__ hit) {
+  __shared__ KbRobotDev R;
+  {
+    const int* src = (const int*)robot; int* dst = (int*)&R;
+    for (int i = threadIdx.x; i < (int)(sizeof(KbRobotDev) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  const int L = R.L;
+  const double* q = Q + c * L;
+  if (hit) hit[c] = -1;
+  if (alive && !alive[c]) { if (state) state[c] = 0; return; }
+  // K2: joint limits (closed interval, Normal / Weld joints only) and driver limits
+  bool ok = true;
+  for (int j = 0; j < R.nj; j++) {
+    int t = R.jtype[j];
+    if (t == 1 || t == 0) { int k = R.jlink[j]; double v = q[k]; if (v < R.qmin[k] || v > R.qmax[k]) ok = false; }
+  }
+  for (int d = 0; d < R.ndrv; d++) {
+    ExactD v(0.0);
+    for (int k = drv[d].first; k < drv[d].first + drv[d].n; k++) v = v + (ExactD(q[drv_link[k]]) - ExactD(drv_off[k])) / ExactD(drv_scale[k]);
+    v = v / ExactD((double)drv[d].n);
+    if (v.v < drv[d].dmin || v.v > drv[d].dmax) ok = false;
+  }
+  if (state) state[c] = ok ? 1 : 0;
+  if (!ok && state) return;          // infeasible by limits: the traversal skips it, no transforms needed
+  // K1: T_World[i] = T_World[parent] * (T0_Parent[i] * T_loc(q_i))
+  double* out = xf64 + c * (int64_t)nxf * 12;
+  Xf64 prev;                          // transform of link i-1 stays in registers (chains)
+  for (int i = 0; i < L; i++) {
+    Xf64 T0, loc, rel, W;
+#pragma unroll
+    for (int k = 0; k < 9; k++) T0.r[k] = ExactD(R.T0[12 * i + k]);
+#pragma unroll
+    for (int k = 0; k < 3; k++) T0.t[k] = ExactD(R.T0[12 * i + 9 + k]);
+    ExactD wx(R.axis[3 * i]), wy(R.axis[3 * i + 1]), wz(R.axis[3 * i + 2]), qi(q[i]);
+    if (R.linktype[i] == 1) {
+      loc.r[0] = loc.r[4] = loc.r[8] = ExactD(1.0);
+      loc.r[1] = loc.r[2] = loc.r[3] = loc.r[5] = loc.r[6] = loc.r[7] = ExactD(0.0);
+      loc.t[0] = qi * wx; loc.t[1] = qi * wy; loc.t[2] = qi * wz;
+    } else {
+      double sn, cs; sincos(qi.v, &sn, &cs);
+      ExactD s(sn), co(cs), v = ExactD(1.0) - co;
+      loc.r[0] = co + v * wx * wx;      loc.r[1] = v * wx * wy - s * wz; loc.r[2] = v * wx * wz + s * wy;
+      loc.r[3] = v * wy * wx + s * wz;  loc.r[4] = co + v * wy * wy;     loc.r[5] = v * wy * wz - s * wx;
+      loc.r[6] = v * wz * wx - s * wy;  loc.r[7] = v * wz * wy + s * wx; loc.r[8] = co + v * wz * wz;
+      loc.t[0] = loc.t[1] = loc.t[2] = ExactD(0.0);
+    }
+    xf_mul(T0, loc, rel);
+    int par = R.parents[i];
+    if (par < 0) W = rel;
+    else if (par == i - 1) xf_mul(prev, rel, W);
+    else {
+      Xf64 P;
+#pragma unroll
+      for (int k = 0; k < 9; k++) P.r[k] = ExactD(out[12 * par + k]);
+#pragma unroll
+      for (int k = 0; k < 3; k++) P.t[k] = ExactD(out[12 * par + 9 + k]);
+      xf_mul(P, rel, W);
+    }
+#pragma unroll
+    for (int k = 0; k < 9; k++) out[12 * i + k] = W.r[k].v;
+#pragma unroll
+    for (int k = 0; k < 3; k++) out[12 * i + 9 + k] = W.t[k].v;
+    prev = W;
+  }
+}
+
+// =============================================================================================== traversal helpers
+struct XfF { float r[9]; float t[3]; };
+
+// T = A^-1 * B for two slots of the per-warp fp32 transform table; slot < 0 = identity
+__device__ __forceinline__ void rel_xf(const float* __restrict__ xfw, int sa, int sb, XfF& T) {
+  if (sa < 0 && sb < 0) {
+    T.r[0] = T.r[4] = T.r[8] = 1.f; T.r[1] = T.r[2] = T.r[3] = T.r[5] = T.r[6] = T.r[7] = 0.f; T.t[0] = T.t[1] = T.t[2] = 0.f;
+    return;
+  }
+  if (sa < 0) {
+    const float4* b = (const float4*)(xfw + 12 * sb);
+    float4 b0 = b[0], b1 = b[1], b2 = b[2];
+    T.r[0] = b0.x; T.r[1] = b0.y; T.r[2] = b0.z; T.r[3] = b0.w; T.r[4] = b1.x; T.r[5] = b1.y; T.r[6] = b1.z; T.r[7] = b1.w; T.r[8] = b2.x;
+    T.t[0] = b2.y; T.t[1] = b2.z; T.t[2] = b2.w;
+    return;
+  }
+  const float4* a = (const float4*)(xfw + 12 * sa);
+  float4 a0 = a[0], a1 = a[1], a2 = a[2];
+  float A[9] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x};
+  float ta[3] = {a2.y, a2.z, a2.w};
+  if (sb < 0) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+#pragma unroll
+      for (int j = 0; j < 3; j++) T.r[3 * i + j] = A[3 * j + i];
+      T.t[i] = -(A[i] * ta[0] + A[3 + i] * ta[1] + A[6 + i] * ta[2]);
+    }
+    return;
+  }
+  const float4* b = (const float4*)(xfw + 12 * sb);
+  float4 b0 = b[0], b1 = b[1], b2 = b[2];
+  float B[9] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x};
+  float d[3] = {b2.y - ta[0], b2.z - ta[1], b2.w - ta[2]};
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) T.r[3 * i + j] = A[i] * B[j] + A[3 + i] * B[3 + j] + A[6 + i] * B[6 + j];
+    T.t[i] = A[i] * d[0] + A[3 + i] * d[1] + A[6 + i] * d[2];
+  }
+}
+
+// 15-axis separating-axis test between box A (its own frame) and box B mapped into A's frame by T.
+// infl = collision threshold + fp32 slack, added to A's half extents (conservative).
+__device__ __forceinline__ bool obb_overlap(const float4& alo, const float4& ahi, const float4& blo, const float4& bhi,
+                                            const XfF& T, float infl) {
+  float ha[3] = {0.5f * (ahi.x - alo.x) + infl, 0.5f * (ahi.y - alo.y) + infl, 0.5f * (ahi.z - alo.z) + infl};
+  float ca[3] = {0.5f * (ahi.x + alo.x), 0.5f * (ahi.y + alo.y), 0.5f * (ahi.z + alo.z)};
+  float hb[3] = {0.5f * (bhi.x - blo.x), 0.5f * (bhi.y - blo.y), 0.5f * (bhi.z - blo.z)};
+  float cb[3] = {0.5f * (bhi.x + blo.x), 0.5f * (bhi.y + blo.y), 0.5f * (bhi.z + blo.z)};
+  float t[3], AR[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++) t[i] = T.r[3 * i] * cb[0] + T.r[3 * i + 1] * cb[1] + T.r[3 * i + 2] * cb[2] + T.t[i] - ca[i];
+#pragma unroll
+  for (int i = 0; i < 9; i++) AR[i] = fabsf(T.r[i]) + 1e-6f;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+    if (fabsf(t[i]) > ha[i] + hb[0] * AR[3 * i] + hb[1] * AR[3 * i + 1] + hb[2] * AR[3 * i + 2]) return false;
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+    if (fabsf(t[0] * T.r[j] + t[1] * T.r[3 + j] + t[2] * T.r[6 + j]) > hb[j] + ha[0] * AR[j] + ha[1] * AR[3 + j] + ha[2] * AR[6 + j]) return false;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      float ra = ha[i1] * AR[3 * i2 + j] + ha[i2] * AR[3 * i1 + j];
+      float rb = hb[j1] * AR[3 * i + j2] + hb[j2] * AR[3 * i + j1];
+      if (fabsf(t[i2] * T.r[3 * i1 + j] - t[i1] * T.r[3 * i2 + j]) > ra + rb) return false;
+    }
+  }
+  return true;
+}
+
+// lower bound on the distance between the two boxes: per-axis gaps in A's frame and in B's frame
+__device__ __forceinline__ float obb_dist_lb(const float4& alo, const float4& ahi, const float4& blo, const float4& bhi, const XfF& T) {
+  float ha[3] = {0.5f * (ahi.x - alo.x), 0.5f * (ahi.y - alo.y), 0.5f * (ahi.z - alo.z)};
+  float ca[3] = {0.5f * (ahi.x + alo.x), 0.5f * (ahi.y + alo.y), 0.5f * (ahi.z + alo.z)};
+  float hb[3] = {0.5f * (bhi.x - blo.x), 0.5f * (bhi.y - blo.y), 0.5f * (bhi.z - blo.z)};
+  float cb[3] = {0.5f * (bhi.x + blo.x), 0.5f * (bhi.y + blo.y), 0.5f * (bhi.z + blo.z)};
+  float t[3], g2a = 0.f, g2b = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; i++) t[i] = T.r[3 * i] * cb[0] + T.r[3 * i + 1] * cb[1] + T.r[3 * i + 2] * cb[2] + T.t[i] - ca[i];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    float e = hb[0] * fabsf(T.r[3 * i]) + hb[1] * fabsf(T.r[3 * i + 1]) + hb[2] * fabsf(T.r[3 * i + 2]);
+    float g = fabsf(t[i]) - ha[i] - e; g = fmaxf(g, 0.f); g2a += g * g;
+  }
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    float e = ha[0] * fabsf(T.r[j]) + ha[1] * fabsf(T.r[3 + j]) + ha[2] * fabsf(T.r[6 + j]);
+    float g = fabsf(t[0] * T.r[j] + t[1] * T.r[3 + j] + t[2] * T.r[6 + j]) - hb[j] - e; g = fmaxf(g, 0.f); g2b += g * g;
+  }
+  return sqrtf(fmaxf(g2a, g2b));
+}
+
+__device__ __forceinline__ V3<float> xform(const XfF& T, const float4& p) {
+  return mk3<float>(T.r[0] * p.x + T.r[1] * p.y + T.r[2] * p.z + T.t[0],
+                    T.r[3] * p.x + T.r[4] * p.y + T.r[5] * p.z + T.t[1],
+                    T.r[6] * p.x + T.r[7] * p.y + T.r[8] * p.z + T.t[2]);
+}
+
+// fp64 world-frame element fetch for the exact recheck; same operation order as a scalar fp64 R*p+t
+__device__ __forceinline__ V3<ExactD> xform64(const double* __restrict__ xf, int slot, const double* __restrict__ p) {
+  ExactD x(p[0]), y(p[1]), z(p[2]);
+  if (slot < 0) return mk3<ExactD>(x, y, z);
+  const double* T = xf + 12 * slot;
+  return mk3<ExactD>(ExactD(T[0]) * x + ExactD(T[1]) * y + ExactD(T[2]) * z + ExactD(T[9]),
+                     ExactD(T[3]) * x + ExactD(T[4]) * y + ExactD(T[5]) * z + ExactD(T[10]),
+                     ExactD(T[6]) * x + ExactD(T[7]) * y + ExactD(T[8]) * z + ExactD(T[11]));
+}
+
+// exact (fp64) distance between two elements in the world frame, minus sphere radii; 0 when triangles intersect
+__device__ __noinline__ double exact_elem_distance(const KbScene& sc, const KbItem& it, const double* __restrict__ xf,
+                                                   int ea, int eb) {
+  if (it.kindA == KB_ELEM_TRI && it.kindB == KB_ELEM_TRI) {
+    V3<ExactD> A[3], B[3];
+#pragma unroll
+    for (int v = 0; v < 3; v++) { A[v] = xform64(xf, it.xfA, sc.tris64 + 9 * (size_t)ea + 3 * v); B[v] = xform64(xf, it.xfB, sc.tris64 + 9 * (size_t)eb + 3 * v); }
+    V3<ExactD> A2[3] = {A[0], A[1], A[2]}, B2[3] = {B[0], B[1], B[2]};
+    if (tri_tri_intersect<ExactD, FiltE>(A2, B2, FiltE()) == KB_YES) return 0.0;
+    return kb_sqrt(tri_tri_dist2_disjoint<ExactD>(A, B)).v;
+  }
+  if (it.kindA == KB_ELEM_TRI) {
+    V3<ExactD> A[3];
+#pragma unroll
+    for (int v = 0; v < 3; v++) A[v] = xform64(xf, it.xfA, sc.tris64 + 9 * (size_t)ea + 3 * v);
+    V3<ExactD> p = xform64(xf, it.xfB, sc.sph64 + 4 * (size_t)eb);
+    return (kb_sqrt(point_tri_dist2<ExactD>(p, A[0], A[1], A[2])) - ExactD(sc.sph64[4 * (size_t)eb + 3])).v;
+  }
+  if (it.kindB == KB_ELEM_TRI) {
+    V3<ExactD> B[3];
+#pragma unroll
+    for (int v = 0; v < 3; v++) B[v] = xform64(xf, it.xfB, sc.tris64 + 9 * (size_t)eb + 3 * v);
+    V3<ExactD> p = xform64(xf, it.xfA, sc.sph64 + 4 * (size_t)ea);
+    return (kb_sqrt(point_tri_dist2<ExactD>(p, B[0], B[1], B[2])) - ExactD(sc.sph64[4 * (size_t)ea + 3])).v;
+  }
+  V3<ExactD> p = xform64(xf, it.xfA, sc.sph64 + 4 * (size_t)ea), s = xform64(xf, it.xfB, sc.sph64 + 4 * (size_t)eb), d = p - s;
+  return (kb_sqrt(dot(d, d)) - ExactD(sc.sph64[4 * (size_t)ea + 3]) - ExactD(sc.sph64[4 * (size_t)eb + 3])).v;
+}
+
+// exact boolean: elements within thr of each other (thr == 0 and two triangles: surfaces intersect)
+__device__ __noinline__ bool exact_elem_collide(const KbScene& sc, const KbItem& it, const double* __restrict__ xf, int ea, int eb) {
+  if (it.kindA == KB_ELEM_TRI && it.kindB == KB_ELEM_TRI) {
+    V3<ExactD> A[3], B[3];
+#pragma unroll
+    for (int v = 0; v < 3; v++) { A[v] = xform64(xf, it.xfA, sc.tris64 + 9 * (size_t)ea + 3 * v); B[v] = xform64(xf, it.xfB, sc.tris64 + 9 * (size_t)eb + 3 * v); }
+    V3<ExactD> A2[3] = {A[0], A[1], A[2]}, B2[3] = {B[0], B[1], B[2]};
+    if (tri_tri_intersect<ExactD, FiltE>(A2, B2, FiltE()) == KB_YES) return true;
+    if (it.thr == 0.0) return false;
+    ExactD d2 = tri_tri_dist2_disjoint<ExactD>(A, B);
+    return d2.v <= (ExactD(it.thr) * ExactD(it.thr)).v;
+  }
+  // sphere cases: compare squared centre distance with (radius + thr)^2 like the scalar fp64 code does
+  if (it.kindA == KB_ELEM_TRI || it.kindB == KB_ELEM_TRI) {
+    bool aTri = it.kindA == KB_ELEM_TRI;
+    int et = aTri ? ea : eb, es = aTri ? eb : ea, st = aTri ? it.xfA : it.xfB, ss = aTri ? it.xfB : it.xfA;
+    V3<ExactD> Tt[3];
+#pragma unroll
+    for (int v = 0; v < 3; v++) Tt[v] = xform64(xf, st, sc.tris64 + 9 * (size_t)et + 3 * v);
+    V3<ExactD> p = xform64(xf, ss, sc.sph64 + 4 * (size_t)es);
+    ExactD r = ExactD(sc.sph64[4 * (size_t)es + 3]) + ExactD(it.thr);
+    return point_tri_dist2<ExactD>(p, Tt[0], Tt[1], Tt[2]).v <= (r * r).v;
+  }
+  V3<ExactD> p = xform64(xf, it.xfA, sc.sph64 + 4 * (size_t)ea), s = xform64(xf, it.xfB, sc.sph64 + 4 * (size_t)eb), d = p - s;
+  ExactD r = ExactD(sc.sph64[4 * (size_t)ea + 3]) + ExactD(sc.sph64[4 * (size_t)eb + 3]) + ExactD(it.thr);
+  return dot(d, d).v <= (r * r).v;
+}
+
+// fp32 filtered boolean for one element pair in A's frame.  Returns KB_NO / KB_YES / KB_UNCERTAIN.
+__device__ __forceinline__ int fast_elem_collide(const KbScene& sc, const KbItem& it, const XfF& T, int ea, int eb, float thr) {
+  const float delta = sc.eps_abs;
+  const float band = 16.f * delta;
+  if (it.kindA == KB_ELEM_TRI && it.kindB == KB_ELEM_TRI) {
+    const float4* ta = sc.tris32 + 3 * (size_t)ea; const float4* tb = sc.tris32 + 3 * (size_t)eb;
+    float4 a0 = __ldg(ta), a1 = __ldg(ta + 1), a2 = __ldg(ta + 2), b0 = __ldg(tb), b1 = __ldg(tb + 1), b2 = __ldg(tb + 2);
+    V3<float> A[3] = {mk3<float>(a0.x, a0.y, a0.z), mk3<float>(a1.x, a1.y, a1.z), mk3<float>(a2.x, a2.y, a2.z)};
+    V3<float> B[3] = {xform(T, b0), xform(T, b1), xform(T, b2)};
+    FiltF f; f.filt = 64.f * delta;
+    if (thr == 0.f) return tri_tri_intersect<float, FiltF>(A, B, f);
+    V3<float> A2[3] = {A[0], A[1], A[2]}, B2[3] = {B[0], B[1], B[2]};
+    int r = tri_tri_intersect<float, FiltF>(A2, B2, f);
+    if (r != KB_NO) return r;
+    float d = sqrtf(tri_tri_dist2_disjoint<float>(A, B));
+    return d < thr - band ? KB_YES : (d > thr + band ? KB_NO : KB_UNCERTAIN);
+  }
+  if (it.kindA == KB_ELEM_TRI) {          // triangle (A frame) vs sphere of B
+    const float4* ta = sc.tris32 + 3 * (size_t)ea;
+    float4 a0 = __ldg(ta), a1 = __ldg(ta + 1), a2 = __ldg(ta + 2), s = __ldg(sc.sph32 + eb);
+    V3<float> p = xform(T, s);
+    float d = sqrtf(point_tri_dist2<float>(p, mk3<float>(a0.x, a0.y, a0.z), mk3<float>(a1.x, a1.y, a1.z), mk3<float>(a2.x, a2.y, a2.z)));
+    float r = s.w + thr;
+    return d < r - band ? KB_YES : (d > r + band ? KB_NO : KB_UNCERTAIN);
+  }
+  if (it.kindB == KB_ELEM_TRI) {          // sphere of A vs triangle of B (mapped into A's frame)
+    const float4* tb = sc.tris32 + 3 * (size_t)eb;
+    float4 b0 = __ldg(tb), b1 = __ldg(tb + 1), b2 = __ldg(tb + 2), s = __ldg(sc.sph32 + ea);
+    float d = sqrtf(point_tri_dist2<float>(mk3<float>(s.x, s.y, s.z), xform(T, b0), xform(T, b1), xform(T, b2)));
+    float r = s.w + thr;
+    return d < r - band ? KB_YES : (d > r + band ? KB_NO : KB_UNCERTAIN);
+  }
+  float4 sa = __ldg(sc.sph32 + ea), sb = __ldg(sc.sph32 + eb);
+  V3<float> p = xform(T, sb), q = mk3<float>(sa.x, sa.y, sa.z), dv = p - q;
+  float d = sqrtf(dot(dv, dv)), r = sa.w + sb.w + thr;
+  return d < r - band ? KB_YES : (d > r + band ? KB_NO : KB_UNCERTAIN);
+}
+
+__device__ __forceinline__ float box_size2(const float4& lo, const float4& hi) {
+  float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z; return dx * dx + dy * dy + dz * dz; }
+
+// =============================================================================================== traversal
+// One warp per configuration.  The warp keeps a LIFO frontier of (item, nodeA, nodeB) pairs in shared memory; every
+// iteration the 32 lanes pop up to 32 pairs, run the OBB test, and push the children of the overlapping pairs
+// (descend the larger box) with a ballot/popc compaction.  Leaf pairs go to a second queue that is drained 32 at a
+// time so the expensive element tests also run on full warps.  Any certain hit ends the configuration for all lanes
+// (__ballot_sync early exit).  MODE 0: boolean collide / within-threshold.  MODE 1: branch-and-bound distance.
+template <int MODE>
+__global__ void __launch_bounds__(KB_WARPS_PER_BLOCK * 32)
+kb_traverse_kernel(const KbTraverseParams p, double* __restrict__ out_dist, double upper_bound) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int xf_floats = (p.nxf * 12 + 3) & ~3;
+  const size_t per_warp = (size_t)KB_STACK_CAP * 8 + (size_t)KB_LEAFQ_CAP * 8 + (size_t)xf_floats * 4;
+  unsigned char* base = smem_raw + warp * per_warp;
+  uint2* stack = (uint2*)base;
+  uint2* leafq = (uint2*)(base + (size_t)KB_STACK_CAP * 8);
+  float* xfw = (float*)(base + (size_t)KB_STACK_CAP * 8 + (size_t)KB_LEAFQ_CAP * 8);
+  const KbScene& sc = p.scene;
+  const float slack = 4.f * sc.eps_abs;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  unsigned long long st_node = 0, st_leaf = 0, st_re = 0;
+
+  for (;;) {
+    unsigned int c0 = 0;
+    if (lane == 0) c0 = atomicAdd(p.work_counter, 8u);
+    c0 = __shfl_sync(FULL, c0, 0);
+    if ((int64_t)c0 >= p.N) break;
+    const int64_t cend = ((int64_t)c0 + 8 < p.N) ? (int64_t)c0 + 8 : p.N;
+    for (int64_t c = c0; c < cend; c++) {
+      if (p.state && p.state[c] == 0) continue;
+      const double* xf = p.xf64 + c * (int64_t)p.nxf * 12;
+      __syncwarp();
+      for (int i = lane; i < p.nxf * 12; i += 32) xfw[i] = (float)xf[i];
+      __syncwarp();
+      int sp = 0, nleaf = 0, cursor = 0;
+      int found = -1, found_ea = -1, found_eb = -1;
+      double best = upper_bound;                     // MODE 1: running minimum (already including margins per item)
+      int best_item = -1, best_ea = -1, best_eb = -1;
+      for (;;) {
+        if (sp < 32 && cursor < p.nitems) {          // feed root pairs of the next work items
+          int k = p.nitems - cursor; if (k > 32) k = 32;
+          if (lane < k) stack[sp + lane] = make_uint2(((unsigned)(cursor + lane) << KB_NODEA_BITS), 0u);
+          sp += k; cursor += k;
+          __syncwarp();
+        }
+        if (sp == 0 && nleaf == 0) break;
+        if (nleaf >= 32 || sp == 0) {
+          // ---------------------------------------------------------------- element phase
+          int m = nleaf < 32 ? nleaf : 32;
+          int res = KB_NO, ea = -1, eb = -1, item = 0;
+          double dmin = 1e300;
+          if (lane < m) {
+            uint2 e = leafq[nleaf - 1 - lane];
+            item = (int)(e.x >> KB_NODEA_BITS);
+            const KbItem it = p.items[item];
+            int na = (int)(e.x & (KB_MAX_NODES_A - 1)), nb = (int)e.y;
+            float4 a0 = __ldg(sc.nodes + 2 * (size_t)(it.nodeA + na)), a1 = __ldg(sc.nodes + 2 * (size_t)(it.nodeA + na) + 1);
+            float4 b0 = __ldg(sc.nodes + 2 * (size_t)(it.nodeB + nb)), b1 = __ldg(sc.nodes + 2 * (size_t)(it.nodeB + nb) + 1);
+            int fa = it.elemA + ~__float_as_int(a0.w), ca = __float_as_int(a1.w);
+            int fb = it.elemB + ~__float_as_int(b0.w), cb = __float_as_int(b1.w);
+            XfF T; rel_xf(xfw, it.xfA, it.xfB, T);
+            if (MODE == 0) {
+              const float thr = (float)it.thr;
+              for (int i = 0; i < ca && res != KB_YES; i++)
+                for (int j = 0; j < cb && res != KB_YES; j++) {
+                  int r = fast_elem_collide(sc, it, T, fa + i, fb + j, thr);
+                  st_leaf++;
+                  if (r == KB_UNCERTAIN) { st_re++; r = exact_elem_collide(sc, it, xf, fa + i, fb + j) ? KB_YES : KB_NO; }
+                  if (r == KB_YES) { res = KB_YES; ea = fa + i; eb = fb + j; }
+                }
+            } else {
+              for (int i = 0; i < ca; i++)
+                for (int j = 0; j < cb; j++) {
+                  double d = exact_elem_distance(sc, it, xf, fa + i, fb + j) - it.marg;
+                  st_leaf++;
+                  if (d < dmin) { dmin = d; ea = fa + i; eb = fb + j; }
+                }
+            }
+          }
+          nleaf -= m;
+          if (MODE == 0) {
+            unsigned hm = __ballot_sync(FULL, res == KB_YES);
+            if (hm) {
+              int src = __ffs(hm) - 1;
+              found = __shfl_sync(FULL, item, src); found_ea = __shfl_sync(FULL, ea, src); found_eb = __shfl_sync(FULL, eb, src);
+              break;
+            }
+          } else {
+            double wmin = dmin;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { double x = __shfl_xor_sync(FULL, wmin, o); wmin = x < wmin ? x : wmin; }
+            if (wmin < best) {
+              unsigned who = __ballot_sync(FULL, dmin == wmin);
+              int src = __ffs(who) - 1;
+              best = wmin; best_item = __shfl_sync(FULL, item, src); best_ea = __shfl_sync(FULL, ea, src); best_eb = __shfl_sync(FULL, eb, src);
+            }
+          }
+          __syncwarp();
+          continue;
+        }
+        // ------------------------------------------------------------------ node phase
+        int m = (sp <= p.wide_limit) ? (sp < 32 ? sp : 32) : 1;
+        const bool act = lane < m;
+        uint2 e = make_uint2(0u, 0u);
+        if (act) e = stack[sp - 1 - lane];
+        sp -= m;
+        __syncwarp();
+        bool push2 = false, leafpair = false;
+        uint2 c0e = e, c1e = e;
+        if (act) {
+          const int item = (int)(e.x >> KB_NODEA_BITS);
+          const KbItem* itp = p.items + item;
+          const int nodeA = itp->nodeA, nodeB = itp->nodeB, sa = itp->xfA, sb = itp->xfB;
+          const int na = (int)(e.x & (KB_MAX_NODES_A - 1)), nb = (int)e.y;
+          float4 a0 = __ldg(sc.nodes + 2 * (size_t)(nodeA + na)), a1 = __ldg(sc.nodes + 2 * (size_t)(nodeA + na) + 1);
+          float4 b0 = __ldg(sc.nodes + 2 * (size_t)(nodeB + nb)), b1 = __ldg(sc.nodes + 2 * (size_t)(nodeB + nb) + 1);
+          XfF T; rel_xf(xfw, sa, sb, T);
+          st_node++;
+          bool ov;
+          if (MODE == 0) ov = obb_overlap(a0, a1, b0, b1, T, (float)itp->thr + slack);
+          else ov = (double)obb_dist_lb(a0, a1, b0, b1, T) - (double)slack - itp->marg < best;
+          if (ov) {
+            const int la = __float_as_int(a0.w), lb = __float_as_int(b0.w);
+            if (la < 0 && lb < 0) leafpair = true;
+            else {
+              push2 = true;
+              if (lb < 0 || (la >= 0 && box_size2(a0, a1) >= box_size2(b0, b1))) {
+                c0e = make_uint2((e.x & ~(unsigned)(KB_MAX_NODES_A - 1)) | (unsigned)la, e.y);
+                c1e = make_uint2(c0e.x + 1u, e.y);
+              } else {
+                c0e = make_uint2(e.x, (unsigned)lb);
+                c1e = make_uint2(e.x, (unsigned)lb + 1u);
+              }
+            }
+          }
+        }
+        const unsigned pm = __ballot_sync(FULL, push2), lm = __ballot_sync(FULL, leafpair);
+        if (push2) { int off = sp + 2 * __popc(pm & lt_mask); stack[off] = c1e; stack[off + 1] = c0e; }
+        if (leafpair) leafq[nleaf + __popc(lm & lt_mask)] = e;
+        sp += 2 * __popc(pm); nleaf += __popc(lm);
+        __syncwarp();
+      }
+      if (lane == 0) {
+        if (MODE == 0) {
+          p.hit[c] = found;
+          if (p.hit_elem) { p.hit_elem[2 * c] = found_ea; p.hit_elem[2 * c + 1] = found_eb; }
+        } else {
+          out_dist[c] = best;
+          p.hit[c] = best_item;
+          if (p.hit_elem) { p.hit_elem[2 * c] = best_ea; p.hit_elem[2 * c + 1] = best_eb; }
+        }
+      }
+    }
+  }
+  if (p.collect_stats && p.counters) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      st_node += __shfl_xor_sync(FULL, st_node, o); st_leaf += __shfl_xor_sync(FULL, st_leaf, o); st_re += __shfl_xor_sync(FULL, st_re, o);
+    }
+    if (lane == 0) { atomicAdd(p.counters + 0, st_re); atomicAdd(p.counters + 1, st_node); atomicAdd(p.counters + 2, st_leaf); }
+  }
+}
+
+// =============================================================================================== result kernels
+// feasible[c] = limits ok && no hit ; first_pair = world ids of the reported pair
+__global__ void kb_finish_kernel(const uint8_t* __restrict__ state, const int32_t* __restrict__ hit, const int32_t* __restrict__ hit_elem,
+                                 const KbItem* __restrict__ items, const int32_t* __restrict__ triown, const int32_t* __restrict__ sphown,
+                                 int64_t N, uint8_t* __restrict__ out, int32_t* __restrict__ first_pair, unsigned long long* nfeasible) {
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool feas = false;
+  if (c < N) {
+    int h = hit[c];
+    feas = state[c] != 0 && h < 0;
+    if (out) out[c] = feas ? 1 : 0;
+    if (first_pair) {
+      int ia = -1, ib = -1;
+      if (state[c] != 0 && h >= 0) {
+        const KbItem it = items[h];
+        ia = it.idA; ib = it.idB;
+        if (ia < 0) ia = (it.kindA == KB_ELEM_TRI ? triown : sphown)[hit_elem[2 * c]];
+        if (ib < 0) ib = (it.kindB == KB_ELEM_TRI ? triown : sphown)[hit_elem[2 * c + 1]];
+      }
+      first_pair[2 * c] = ia; first_pair[2 * c + 1] = ib;
+    }
+  }
+  if (nfeasible) {
+    unsigned m = __ballot_sync(FULL, feas);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(nfeasible, (unsigned long long)__popc(m));
+  }
+}
+
+__global__ void kb_pair_ids_kernel(const int32_t* __restrict__ hit, const int32_t* __restrict__ hit_elem, const KbItem* __restrict__ items,
+                                   const int32_t* __restrict__ triown, const int32_t* __restrict__ sphown, int64_t N, int32_t* __restrict__ pair) {
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  int h = hit[c], ia = -1, ib = -1;
+  if (h >= 0) {
+    const KbItem it = items[h];
+    ia = it.idA; ib = it.idB;
+    if (ia < 0) ia = (it.kindA == KB_ELEM_TRI ? triown : sphown)[hit_elem[2 * c]];
+    if (ib < 0) ib = (it.kindB == KB_ELEM_TRI ? triown : sphown)[hit_elem[2 * c + 1]];
+  }
+  pair[2 * c] = ia; pair[2 * c + 1] = ib;
+}
+
+// =============================================================================================== edges (K8)
+// Edge e of C-space length len needs nlev = number of halvings until len/2^nlev <= eps.  Level l (1-based) holds the
+// 2^(l-1) odd multiples k/2^l.  All alive edges are expanded level by level; an edge dies at the first level that
+// holds an infeasible midpoint, and the sequential checker's check count is recovered from the lowest failing k.
+__global__ void kb_edge_setup_kernel(const KbRobotDev* __restrict__ robot, const double* __restrict__ A, const double* __restrict__ B,
+                                     const double* __restrict__ weights, int64_t N, double eps, int32_t* __restrict__ nlev,
+                                     uint8_t* __restrict__ alive, int32_t* __restrict__ nchecks, int32_t* maxlev) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N) return;
+  const int L = robot->L;
+  ExactD s(0.0);
+  for (int j = 0; j < robot->nj; j++) {
+    int t = robot->jtype[j]; int k = robot->jlink[j];
+    ExactD w(weights ? weights[j] : 1.0), d(0.0);
+    if (t == 1) d = ExactD(A[e * L + k]) - ExactD(B[e * L + k]);
+    else if (t == 2) {
+      double x = fmod(A[e * L + k], 6.283185307179586476925286766559); if (x < 0) x += 6.283185307179586476925286766559;
+      double y = fmod(B[e * L + k], 6.283185307179586476925286766559); if (y < 0) y += 6.283185307179586476925286766559;
+      double dd = x - y; if (dd > 3.14159265358979323846) dd -= 6.283185307179586476925286766559; else if (dd < -3.14159265358979323846) dd += 6.283185307179586476925286766559;
+      d = ExactD(dd);
+    } else continue;
+    s = s + w * d * d;
+  }
+  double len = kb_sqrt(s).v;
+  int n = 0;
+  while (len > eps && n < 30) { len *= 0.5; n++; }
+  nlev[e] = n; alive[e] = 1; nchecks[e] = 0;
+  if (n > 0) atomicMax(maxlev, n);
+}
+
+// compacts the edges that are alive and reach level `lev`, and gives each its slot offset in this level's batch
+__global__ void kb_edge_count_kernel(const int32_t* __restrict__ nlev, const uint8_t* __restrict__ alive, int64_t N, int lev,
+                                     int32_t* __restrict__ list, unsigned int* __restrict__ count) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool on = e < N && alive[e] && nlev[e] >= lev;
+  unsigned m = __ballot_sync(FULL, on);
+  int lane = threadIdx.x & 31;
+  unsigned base = 0;
+  if (lane == 0 && m) base = atomicAdd(count, (unsigned)__popc(m));
+  base = __shfl_sync(FULL, base, 0);
+  if (on) list[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)e;
+}
+
+// writes the midpoints of level `lev` for the listed edges: slot = i * per + j, k = 2j+1, u = k / 2^lev.
+// Klampt::Interpolate (Cpp/Modeling/Interpolate.cpp:10-71): out = x*(1-u); out += y*u; Spin joints take the short arc.
+__global__ void kb_edge_expand_kernel(const KbRobotDev* __restrict__ robot, const double* __restrict__ A, const double* __restrict__ B,
+                                      const int32_t* __restrict__ list, int64_t first_slot, int64_t nslots, int lev, double* __restrict__ Q) {
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nslots) return;
+  const int L = robot->L;
+  const int64_t per = (int64_t)1 << (lev - 1);
+  int64_t g = first_slot + s;
+  int64_t i = g / per, j = g % per;
+  int64_t e = list[i];
+  ExactD u((double)(2 * j + 1) / (double)((int64_t)1 << lev));
+  ExactD um = ExactD(1.0) - u;
+  double* q = Q + s * L;
+  for (int k = 0; k < L; k++) q[k] = (ExactD(A[e * L + k]) * um + ExactD(B[e * L + k]) * u).v;
+  for (int jn = 0; jn < robot->nj; jn++) if (robot->jtype[jn] == 2) {
+    int k = robot->jlink[jn];
+    const double tp = 6.283185307179586476925286766559;
+    double x = fmod(A[e * L + k], tp); if (x < 0) x += tp;
+    double y = fmod(B[e * L + k], tp); if (y < 0) y += tp;
+    double d = y - x; if (d > 3.14159265358979323846) d -= tp; else if (d < -3.14159265358979323846) d += tp;
+    double r = fmod((ExactD(x) + u * ExactD(d)).v, tp); if (r < 0) r += tp;
+    q[k] = r;
+  }
+}
+
+// folds the feasibility bytes of one level chunk back into the edges: lowest infeasible j per edge
+__global__ void kb_edge_reduce_kernel(const uint8_t* __restrict__ feas, const int32_t* __restrict__ list, int64_t first_slot, int64_t nslots,
+                                      int lev, int32_t* __restrict__ firstbad) {
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nslots) return;
+  if (feas[s]) return;
+  const int64_t per = (int64_t)1 << (lev - 1);
+  int64_t g = first_slot + s;
+  atomicMin(firstbad + list[g / per], (int32_t)(g % per));
+}
+
+__global__ void kb_edge_level_end_kernel(const int32_t* __restrict__ list, unsigned int nlist, int lev, int32_t* __restrict__ firstbad,
+                                         uint8_t* __restrict__ alive, int32_t* __restrict__ nchecks) {
+  unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlist) return;
+  int e = list[i];
+  int fb = firstbad[e];
+  int per = 1 << (lev - 1);
+  if (fb < per) { alive[e] = 0; nchecks[e] += fb + 1; firstbad[e] = 0x7fffffff; }
+  else nchecks[e] += per;
+}
+
+__global__ void kb_fill_i32_kernel(int32_t* p, int64_t n, int32_t v) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
+
+__global__ void kb_copy_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int64_t n, unsigned long long* ones) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool v = false;
+  if (i < n) { v = src[i] != 0; dst[i] = src[i]; }
+  if (ones) { unsigned m = __ballot_sync(FULL, v); if ((threadIdx.x & 31) == 0 && m) atomicAdd(ones, (unsigned long long)__popc(m)); }
+}
+
+// =============================================================================================== launchers
+static inline unsigned int nblocks(int64_t n, int bs) { return (unsigned int)((n + bs - 1) / bs); }
+
+size_t kb_traverse_smem_bytes(int nxf) {
+  size_t xf_floats = ((size_t)nxf * 12 + 3) & ~(size_t)3;
+  return (size_t)KB_WARPS_PER_BLOCK * ((size_t)KB_STACK_CAP * 8 + (size_t)KB_LEAFQ_CAP * 8 + xf_floats * 4);
+}
+
+cudaError_t kb_launch_fk(const KbRobotDev* robot, const KbDriverDev* drv, const int32_t* drv_link, const double* drv_scale,
+                         const double* drv_off, const double* Q, int64_t N, double* xf64, int nxf, uint8_t* state,
+                         const uint8_t* alive, int32_t* hit, cudaStream_t s) {
+  if (N <= 0) return cudaSuccess;
+  kb_fk_kernel<<<nblocks(N, 128), 128, 0, s>>>(robot, drv, drv_link, drv_scale, drv_off, Q, N, xf64, nxf, state, alive, hit);
+  return cudaGetLastError();
+}
+
+cudaError_t kb_launch_traverse(const KbTraverseParams& p, int mode, double* out_dist, double upper_bound, int num_sms, cudaStream_t s) {
+  if (p.N <= 0) return cudaSuccess;
+  size_t smem = kb_traverse_smem_bytes(p.nxf);
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[mode]) {
+    cudaError_t e = mode == 0 ? cudaFuncSetAttribute(kb_traverse_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
+                              : cudaFuncSetAttribute(kb_traverse_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set[mode] = true;
+  }
+  int per_sm = (int)((220 * 1024) / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > 12) per_sm = 12;
+  int64_t want = (p.N + 8 * KB_WARPS_PER_BLOCK - 1) / (8 * KB_WARPS_PER_BLOCK);
+  int64_t grid = (int64_t)num_sms * per_sm; if (grid > want) grid = want; if (grid < 1) grid = 1;
+  cudaError_t e = cudaMemsetAsync(p.work_counter, 0, sizeof(uint32_t), s);
+  if (e != cudaSuccess) return e;
+  if (mode == 0) kb_traverse_kernel<0><<<(unsigned)grid, KB_WARPS_PER_BLOCK * 32, smem, s>>>(p, out_dist, upper_bound);
+  else kb_traverse_kernel<1><<<(unsigned)grid, KB_WARPS_PER_BLOCK * 32, smem, s>>>(p, out_dist, upper_bound);
+  return cudaGetLastError();
+}
+
+cudaError_t kb_launch_finish(const uint8_t* state, const int32_t* hit, const int32_t* hit_elem, const KbItem* items, const int32_t* triown,
+                             const int32_t* sphown, int64_t N, uint8_t* out, int32_t* first_pair, unsigned long long* nfeasible, cudaStream_t s) {
+  if (N <= 0) return cudaSuccess;
+  kb_finish_kernel<<<nblocks(N, 256), 256, 0, s>>>(state, hit, hit_elem, items, triown, sphown, N, out, first_pair, nfeasible);
+  return cudaGetLastError();
+}
+
+cudaError_t kb_launch_pair_ids(const int32_t* hit, const int32_t* hit_elem, const KbItem* items, const int32_t* triown, const int32_t* sphown,
+                               int64_t N, int32_t* pair, cudaStream_t s) {
+  if (N <= 0) return cudaSuccess;
+  kb_pair_ids_kernel<<<nblocks(N, 256), 256, 0, s>>>(hit, hit_elem, items, triown, sphown, N, pair);
+  return cudaGetLastError();
+}
+
+cudaError_t kb_launch_edge_setup(const KbRobotDev* robot, const double* A, const double* B, const double* w, int64_t N, double eps,
+                                 int32_t* nlev, uint8_t* alive, int32_t* nchecks, int32_t* maxlev, cudaStream_t s) {
+  if (N <= 0) return cudaSuccess;
+  kb_edge_setup_kernel<<<nblocks(N, 256), 256, 0, s>>>(robot, A, B, w, N, eps, nlev, alive, nchecks, maxlev);
+  return cudaGetLastError();
+}
+cudaError_t kb_launch_edge_count(const int32_t* nlev, const uint8_t* alive, int64_t N, int lev, int32_t* list, unsigned int* count, cudaStream_t s) {
+  if (N <= 0) return cudaSuccess;
+  kb_edge_count_kernel<<<nblocks(N, 256), 256, 0, s>>>(nlev, alive, N, lev, list, count);
+  return cudaGetLastError();
+}
+cudaError_t kb_launch_edge_expand(const KbRobotDev* robot, const double* A, const double* B, const int32_t* list, int64_t first_slot,
+                                  int64_t nslots, int lev, double* Q, cudaStream_t s) {
+  if (nslots <= 0) return cudaSuccess;
+  kb_edge_expand_kernel<<<nblocks(nslots, 256), 256, 0, s>>>(robot, A, B, list, first_slot, nslots, lev, Q);
+  return cudaGetLastError();
+}
+cudaError_t kb_launch_edge_reduce(const uint8_t* feas, const int32_t* list, int64_t first_slot, int64_t nslots, int lev, int32_t* firstbad, cudaStream_t s) {
+  if (nslots <= 0) return cudaSuccess;
+  kb_edge_reduce_kernel<<<nblocks(nslots, 256), 256, 0, s>>>(feas, list, first_slot, nslots, lev, firstbad);
+  return cudaGetLastError();
+}
+cudaError_t kb_launch_edge_level_end(const int32_t* list, unsigned int nlist, int lev, int32_t* firstbad, uint8_t* alive, int32_t* nchecks, cudaStream_t s) {
+  if (nlist == 0) return cudaSuccess;
+  kb_edge_level_end_kernel<<<nblocks(nlist, 256), 256, 0, s>>>(list, nlist, lev, firstbad, alive, nchecks);
+  return cudaGetLastError();
+}
+cudaError_t kb_launch_fill_i32(int32_t* p, int64_t n, int32_t v, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  kb_fill_i32_kernel<<<nblocks(n, 256), 256, 0, s>>>(p, n, v);
+  return cudaGetLastError();
+}
+cudaError_t kb_launch_copy_u8(const uint8_t* src, uint8_t* dst, int64_t n, unsigned long long* ones, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  kb_copy_u8_kernel<<<nblocks(n, 256), 256, 0, s>>>(src, dst, n, ones);
+  return cudaGetLastError();
+}

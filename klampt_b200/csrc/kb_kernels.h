@@ -1,0 +1,25 @@
+// kb_kernels.h -- host-side launch wrappers of the sm_100a kernels in kb_kernels.cu
+#pragma once
+#include "kb_types.h"
+#include <cuda_runtime.h>
+
+size_t kb_traverse_smem_bytes(int nxf);
+
+cudaError_t kb_launch_fk(const KbRobotDev* robot, const KbDriverDev* drv, const int32_t* drv_link, const double* drv_scale,
+                         const double* drv_off, const double* Q, int64_t N, double* xf64, int nxf, uint8_t* state,
+                         const uint8_t* alive, int32_t* hit, cudaStream_t s);
+// mode 0: boolean collide, mode 1: branch-and-bound distance (out_dist, upper_bound)
+cudaError_t kb_launch_traverse(const KbTraverseParams& p, int mode, double* out_dist, double upper_bound, int num_sms, cudaStream_t s);
+cudaError_t kb_launch_finish(const uint8_t* state, const int32_t* hit, const int32_t* hit_elem, const KbItem* items, const int32_t* triown,
+                             const int32_t* sphown, int64_t N, uint8_t* out, int32_t* first_pair, unsigned long long* nfeasible, cudaStream_t s);
+cudaError_t kb_launch_pair_ids(const int32_t* hit, const int32_t* hit_elem, const KbItem* items, const int32_t* triown, const int32_t* sphown,
+                               int64_t N, int32_t* pair, cudaStream_t s);
+cudaError_t kb_launch_edge_setup(const KbRobotDev* robot, const double* A, const double* B, const double* w, int64_t N, double eps,
+                                 int32_t* nlev, uint8_t* alive, int32_t* nchecks, int32_t* maxlev, cudaStream_t s);
+cudaError_t kb_launch_edge_count(const int32_t* nlev, const uint8_t* alive, int64_t N, int lev, int32_t* list, unsigned int* count, cudaStream_t s);
+cudaError_t kb_launch_edge_expand(const KbRobotDev* robot, const double* A, const double* B, const int32_t* list, int64_t first_slot,
+                                  int64_t nslots, int lev, double* Q, cudaStream_t s);
+cudaError_t kb_launch_edge_reduce(const uint8_t* feas, const int32_t* list, int64_t first_slot, int64_t nslots, int lev, int32_t* firstbad, cudaStream_t s);
+cudaError_t kb_launch_edge_level_end(const int32_t* list, unsigned int nlist, int lev, int32_t* firstbad, uint8_t* alive, int32_t* nchecks, cudaStream_t s);
+cudaError_t kb_launch_fill_i32(int32_t* p, int64_t n, int32_t v, cudaStream_t s);
+cudaError_t kb_launch_copy_u8(const uint8_t* src, uint8_t* dst, int64_t n, unsigned long long* ones, cudaStream_t s);

@@ -1,0 +1,86 @@
+// kb_types.h -- data layout shared by the host engine and the sm_100a kernels.
+//
+// HBM layout (all static data is uploaded once at kb_finalize and then read-only):
+//   nodes    float4[2*n]   flattened BVHs of every geometry, one after the other.  Node i of a geometry =
+//                          { lo.xyz, as_float(left) } { hi.xyz, as_float(count) }.  left >= 0: inner node,
+//                          children at left and left+1 (siblings adjacent, indices relative to the geometry's
+//                          node base).  left < 0: leaf, first element = ~left (relative to the geometry's element
+//                          base), count elements.  Boxes are fp32, rounded outwards from the fp64 build.
+//   tris32   float4[3*n]   triangle vertices (fp32, local frame; merged environment groups: world frame);
+//                          .w of vertex 0 = as_float(owner world id)
+//   tris64   double[9*n]   the same triangles in fp64 for the exact recheck
+//   sph32    float4[n]     point-cloud points / sphere primitives: xyz, radius ; sph64 double[4*n]
+//   sphown   int[n]        owner world id per sphere element
+//   items    KbItem[]      the per-configuration work list: one entry per enabled geometry pair
+//                          (link vs merged environment group, link vs link)
+//   robot    KbRobotDev    SoA joint arrays for FK
+// Per batch: Q (N x L f64, caller), xf64 (chunk x nxf x 12 f64, written by FK, read by the traversal),
+// state/hit arrays (1-4 B per configuration).
+#pragma once
+#include <stdint.h>
+
+#define KB_MAX_LINKS 128          // links per robot supported by the FK kernel's shared-memory model
+#define KB_STACK_CAP 1024         // node-pair stack entries per warp
+#define KB_LEAFQ_CAP 64           // leaf-pair queue entries per warp
+#define KB_ITEM_BITS 12
+#define KB_NODEA_BITS 20
+#define KB_MAX_ITEMS (1 << KB_ITEM_BITS)
+#define KB_MAX_NODES_A (1 << KB_NODEA_BITS)
+#define KB_WARPS_PER_BLOCK 4
+
+enum { KB_ELEM_TRI = 0, KB_ELEM_SPHERE = 1 };
+
+struct KbItem {                   // 48 bytes
+  int32_t nodeA, nodeB;           // global node index of the two roots
+  int32_t elemA, elemB;           // global element base (into tris* or sph* according to kind)
+  int16_t xfA, xfB;               // transform slot in the per-configuration table, -1 = identity (static world frame)
+  uint8_t kindA, kindB;           // KB_ELEM_*
+  uint16_t flags;                 // bit 0: self pair (link vs link)
+  int32_t idA, idB;               // world ids; -1 = look the owner up per element (merged environment group)
+  double thr;                     // collision threshold: margin_A + margin_B (+ tolerance); 0 = surfaces must intersect
+  double marg;                    // margin_A + margin_B, subtracted from reported distances
+};
+
+struct KbRobotDev {
+  int32_t L;
+  int32_t nj, ndrv_terms, ndrv;
+  int32_t parents[KB_MAX_LINKS];
+  uint8_t linktype[KB_MAX_LINKS];
+  double axis[KB_MAX_LINKS * 3];
+  double T0[KB_MAX_LINKS * 12];
+  double qmin[KB_MAX_LINKS], qmax[KB_MAX_LINKS];
+  uint8_t jtype[KB_MAX_LINKS];
+  int32_t jlink[KB_MAX_LINKS];
+};
+
+struct KbDriverDev {              // flattened affine drivers: driver d covers terms [first, first+n)
+  int32_t first, n;
+  double dmin, dmax;
+};
+
+struct KbScene {                  // device pointers to the static data
+  const float4* nodes;
+  const float4* tris32;
+  const double* tris64;
+  const float4* sph32;
+  const double* sph64;
+  const int32_t* triown;
+  const int32_t* sphown;
+  float eps_abs;                  // absolute fp32 coordinate error bound for this scene (metres)
+};
+
+struct KbTraverseParams {
+  KbScene scene;
+  const KbItem* items;
+  int32_t nitems;
+  int32_t nxf;                    // transform slots per configuration
+  const double* xf64;             // N x nxf x 12
+  int64_t N;
+  const uint8_t* state;           // per configuration: 1 = run, 0 = skip (limits failed / edge already dead); may be null
+  int32_t* hit;                   // per configuration: -1 none, else item index of a colliding pair
+  int32_t* hit_elem;              // per configuration: elemA / elemB (2 ints) of that pair; may be null
+  uint32_t* work_counter;         // dynamic work distribution
+  unsigned long long* counters;   // [0] rechecks, [1] node tests, [2] leaf tests (optional statistics)
+  int32_t wide_limit;             // stack size up to which 32-wide pops are allowed
+  int32_t collect_stats;
+};

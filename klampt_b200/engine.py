@@ -1,0 +1,212 @@
+"""Python face of the C ABI: builds one engine handle from a WorldSpec and exposes the batched hot path.
+
+Host entry points take / return numpy arrays (H2D and D2H copies happen inside the library).  The
+``*_device`` entry points take raw device pointers (ints, or anything with ``data_ptr()`` such as a torch
+tensor) and enqueue on the engine's stream: PyTorch is only plumbing for device memory and streams here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _capi
+from ._capi import KbStats, check
+from .worldspec import WorldSpec
+
+
+def _ptr(x):
+    """device / host pointer of a numpy array, torch tensor, int or None"""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return C.c_void_p(x)
+    if isinstance(x, np.ndarray):
+        return C.c_void_p(x.ctypes.data)
+    if hasattr(x, "data_ptr"):
+        return C.c_void_p(x.data_ptr())
+    raise TypeError("cannot take a pointer of %r" % type(x))
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a if shape is None else a.reshape(shape)
+
+
+class Engine:
+    """One kb_engine handle = static world + one active robot, resident on one GPU."""
+
+    def __init__(self, spec: WorldSpec, device: int = 0):
+        self.lib = _capi.load()
+        self.spec = spec
+        self.h = C.c_void_p()
+        check(self.lib.kb_engine_create(C.byref(self.h)))
+        try:
+            self._describe(spec)
+            check(self.lib.kb_finalize(self.h, int(device)))
+        except Exception:
+            self.close()
+            raise
+        self.device = int(device)
+        self.L = spec.robot.L
+
+    # ------------------------------------------------------------------ construction
+    def _describe(self, spec: WorldSpec):
+        lib, h = self.lib, self.h
+        dp, ip, up = _capi.c_double_p, _capi.c_int32_p, _capi.c_uint8_p
+        for g in spec.geoms:
+            if g.kind == "mesh":
+                v = _f64(g.verts)
+                t = np.ascontiguousarray(g.tris, dtype=np.int32)
+                check(lib.kb_add_trimesh(h, v.ctypes.data_as(dp), len(v), t.ctypes.data_as(ip), len(t), g.margin))
+            elif g.kind == "cloud":
+                p = _f64(g.points)
+                r = None if g.radius is None else _f64(g.radius)
+                check(lib.kb_add_pointcloud(h, p.ctypes.data_as(dp), len(p), None if r is None else r.ctypes.data_as(dp), g.margin))
+            elif g.kind in ("sphere", "point"):
+                p = _f64(g.params)
+                check(lib.kb_add_primitive(h, 1 if g.kind == "sphere" else 0, p.ctypes.data_as(dp), g.margin))
+            elif g.kind == "empty":
+                check(lib.kb_add_trimesh(h, None, 0, None, 0, 0.0))
+            else:
+                raise ValueError("unsupported geometry kind %r" % g.kind)
+        for gi in spec.terrains:
+            check(lib.kb_add_terrain(h, int(gi)))
+        for gi, T in spec.objects:
+            T = _f64(T, (12,))
+            check(lib.kb_add_rigid_object(h, int(gi), T.ctypes.data_as(dp)))
+        r = spec.robot
+        if r is None:
+            raise ValueError("WorldSpec has no robot")
+        par = np.ascontiguousarray(r.parents, dtype=np.int32)
+        lt = np.ascontiguousarray(r.linktype, dtype=np.uint8)
+        ax, T0, qmin, qmax = _f64(r.axis), _f64(r.T0), _f64(r.qmin), _f64(r.qmax)
+        check(lib.kb_robot_create(h, r.L, par.ctypes.data_as(ip), lt.ctypes.data_as(up), ax.ctypes.data_as(dp), T0.ctypes.data_as(dp),
+                                  qmin.ctypes.data_as(dp), qmax.ctypes.data_as(dp)))
+        for j, gi in enumerate(r.link_geom):
+            check(lib.kb_robot_set_link_geometry(h, j, int(gi)))
+        if r.joint_type is not None:
+            jt = np.ascontiguousarray(r.joint_type, dtype=np.uint8)
+            jl = np.ascontiguousarray(r.joint_link, dtype=np.int32)
+            check(lib.kb_robot_set_joints(h, len(jt), jt.ctypes.data_as(up), jl.ctypes.data_as(ip)))
+        for d in r.drivers:
+            li = np.ascontiguousarray(d.links, dtype=np.int32)
+            sc, of = _f64(d.scale), _f64(d.offset)
+            check(lib.kb_robot_add_driver(h, len(li), li.ctypes.data_as(ip), sc.ctypes.data_as(dp), of.ctypes.data_as(dp), d.qmin, d.qmax))
+        for (i, j, en) in r.self_collision_edits:
+            check(lib.kb_robot_set_self_collision(h, int(i), int(j), int(bool(en))))
+        if spec.pair_mask is not None:
+            m = np.ascontiguousarray(spec.pair_mask, dtype=np.uint8)
+            check(lib.kb_set_pair_mask(h, m.ctypes.data_as(up), m.shape[0]))
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.kb_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ plumbing
+    def set_stream(self, stream_ptr: Optional[int]):
+        check(self.lib.kb_set_stream(self.h, C.c_void_p(stream_ptr) if stream_ptr else None))
+
+    def synchronize(self):
+        check(self.lib.kb_synchronize(self.h))
+
+    def set_option(self, name: str, value: int):
+        check(self.lib.kb_set_option(self.h, name.encode(), int(value)))
+
+    def num_ids(self) -> int:
+        return int(self.lib.kb_num_ids(self.h))
+
+    def pair_mask(self) -> np.ndarray:
+        n = self.num_ids()
+        m = np.zeros((n, n), dtype=np.uint8)
+        check(self.lib.kb_get_pair_mask(self.h, m.ctypes.data_as(_capi.c_uint8_p)))
+        return m
+
+    def stats(self) -> dict:
+        s = KbStats()
+        check(self.lib.kb_get_stats(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in KbStats._fields_}
+
+    def reset_stats(self):
+        check(self.lib.kb_reset_stats(self.h))
+
+    def layout(self) -> dict:
+        a = (C.c_int64 * 6)()
+        check(self.lib.kb_get_layout(self.h, a))
+        return {"nodes": a[0], "elements": a[1], "static_bytes": a[2], "items_per_config": a[3], "env_groups": a[4], "max_depth_sum": a[5]}
+
+    # ------------------------------------------------------------------ hot path, host buffers
+    def _Q(self, Q):
+        Q = np.ascontiguousarray(Q, dtype=np.float64)
+        if Q.ndim == 1:
+            Q = Q.reshape(1, -1)
+        if Q.ndim != 2 or Q.shape[1] != self.L:
+            raise ValueError("configurations must be (N, %d), got %r" % (self.L, Q.shape))
+        return Q
+
+    def fk_batch(self, Q) -> np.ndarray:
+        Q = self._Q(Q)
+        T = np.empty((Q.shape[0], self.L, 12), dtype=np.float64)
+        check(self.lib.kb_fk_batch(self.h, _ptr(Q), Q.shape[0], _ptr(T)))
+        return T
+
+    def feasible_batch(self, Q, return_pairs: bool = False, out: Optional[np.ndarray] = None):
+        Q = self._Q(Q)
+        N = Q.shape[0]
+        if out is None:
+            out = np.empty(N, dtype=np.uint8)
+        pairs = np.empty((N, 2), dtype=np.int32) if return_pairs else None
+        check(self.lib.kb_feasible_batch(self.h, _ptr(Q), N, _ptr(out), _ptr(pairs)))
+        return (out, pairs) if return_pairs else out
+
+    def edges_visible_batch(self, A, B, eps: float = 0.01, weights=None, return_nchecks: bool = True):
+        A, B = self._Q(A), self._Q(B)
+        if A.shape != B.shape:
+            raise ValueError("A and B must have the same shape")
+        N = A.shape[0]
+        out = np.empty(N, dtype=np.uint8)
+        nchecks = np.empty(N, dtype=np.int32) if return_nchecks else None
+        w = None if weights is None else _f64(weights)
+        check(self.lib.kb_edges_visible_batch(self.h, _ptr(A), _ptr(B), N, float(eps), _ptr(w), _ptr(out), _ptr(nchecks)))
+        return (out, nchecks) if return_nchecks else out
+
+    def distance_batch(self, Q, upper_bound: float = np.inf, include_self: bool = False, return_pairs: bool = False):
+        Q = self._Q(Q)
+        N = Q.shape[0]
+        d = np.empty(N, dtype=np.float64)
+        pairs = np.empty((N, 2), dtype=np.int32) if return_pairs else None
+        check(self.lib.kb_distance_batch(self.h, _ptr(Q), N, float(upper_bound), int(include_self), _ptr(d), _ptr(pairs)))
+        return (d, pairs) if return_pairs else d
+
+    def geom_collides_batch(self, ga: int, Ta, gb: int, Tb, tol: float = 0.0) -> np.ndarray:
+        Ta, Tb = _f64(Ta).reshape(-1, 12), _f64(Tb).reshape(-1, 12)
+        N = Ta.shape[0]
+        out = np.empty(N, dtype=np.uint8)
+        check(self.lib.kb_geom_collides_batch(self.h, int(ga), _ptr(Ta), int(gb), _ptr(Tb), N, float(tol), _ptr(out)))
+        return out
+
+    def geom_distance_batch(self, ga: int, Ta, gb: int, Tb, upper_bound: float = np.inf) -> np.ndarray:
+        Ta, Tb = _f64(Ta).reshape(-1, 12), _f64(Tb).reshape(-1, 12)
+        N = Ta.shape[0]
+        out = np.empty(N, dtype=np.float64)
+        check(self.lib.kb_geom_distance_batch(self.h, int(ga), _ptr(Ta), int(gb), _ptr(Tb), N, float(upper_bound), _ptr(out)))
+        return out
+
+    # ------------------------------------------------------------------ hot path, device buffers
+    def feasible_batch_device(self, dQ, N: int, d_out, d_first_pair=None):
+        check(self.lib.kb_feasible_batch_device(self.h, _ptr(dQ), int(N), _ptr(d_out), _ptr(d_first_pair)))
+
+    def edges_visible_batch_device(self, dA, dB, N: int, eps: float, d_out, d_nchecks=None, weights=None):
+        w = None if weights is None else _f64(weights)
+        check(self.lib.kb_edges_visible_batch_device(self.h, _ptr(dA), _ptr(dB), int(N), float(eps), _ptr(w), _ptr(d_out), _ptr(d_nchecks)))
+
+    def distance_batch_device(self, dQ, N: int, upper_bound: float, include_self: bool, d_out_d, d_out_pair=None):
+        check(self.lib.kb_distance_batch_device(self.h, _ptr(dQ), int(N), float(upper_bound), int(include_self), _ptr(d_out_d), _ptr(d_out_pair)))

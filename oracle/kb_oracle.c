@@ -1,0 +1,834 @@
+/*
+ * kb_oracle.c -- CPU oracle (plain C, fp64) for the batched configuration-feasibility path.
+ *
+ * TEST INFRASTRUCTURE ONLY -- see kb_oracle.h.  PARITY UNPINNED (KrisLibrary absent; no golden
+ * vectors in the reference).  Deliberately simple: fp64 everywhere, median-split AABB trees with
+ * one element per leaf (8 for point clouds), exhaustive minima, no FMA contraction
+ * (-ffp-contract=off in the Makefile).
+ *
+ * Reference anchors (relative to /root/reference):
+ *   FK recurrence ............ Python/klampt/math/autodiff/kinematics_ad.py:434-457,
+ *                              Cpp/docs/Manual-Modeling.md:94,107-117
+ *   joint / driver limits .... Cpp/Planning/RobotCSpace.cpp:610-630, Cpp/Modeling/Robot.cpp:2166-2187
+ *   IsFeasible ............... Cpp/Planning/RobotCSpace.cpp:786-823
+ *   pair mask ................ Cpp/Planning/PlannerSettings.cpp:16-41
+ *   self-collision defaults .. Cpp/docs/Manual-FileTypes.md:212, Cpp/Modeling/Robot.cpp:1274-1313
+ *   broad phase .............. Cpp/Planning/PlannerSettings.cpp:241-331
+ *   pair query ............... Cpp/Planning/PlannerSettings.cpp:96-115
+ *   margin semantics ......... Cpp/docs/Manual-Geometry.md:17, Python/klampt/src/geometry.h:1006-1108
+ *   edge checker ............. Cpp/Planning/RobotCSpace.cpp:835-838 (EpsilonEdgeChecker, eps from
+ *                              PlannerSettings.cpp:86-87), metric/interp Cpp/Modeling/Interpolate.cpp:10-71,208-343
+ *   distance lower bound ..... Cpp/Planning/PlannerSettings.cpp:570-620
+ */
+#include "kb_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#include <float.h>
+#include <alloca.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------ small vector math */
+typedef struct { double R[9]; double t[3]; } xf_t;
+
+static inline void v_sub(const double* a, const double* b, double* o) { o[0]=a[0]-b[0]; o[1]=a[1]-b[1]; o[2]=a[2]-b[2]; }
+static inline void v_add(const double* a, const double* b, double* o) { o[0]=a[0]+b[0]; o[1]=a[1]+b[1]; o[2]=a[2]+b[2]; }
+static inline double v_dot(const double* a, const double* b) { return a[0]*b[0]+a[1]*b[1]+a[2]*b[2]; }
+static inline void v_cross(const double* a, const double* b, double* o) {
+  o[0]=a[1]*b[2]-a[2]*b[1]; o[1]=a[2]*b[0]-a[0]*b[2]; o[2]=a[0]*b[1]-a[1]*b[0]; }
+static inline void v_madd(const double* a, const double* d, double s, double* o) { o[0]=a[0]+s*d[0]; o[1]=a[1]+s*d[1]; o[2]=a[2]+s*d[2]; }
+static inline double v_dist2(const double* a, const double* b) { double d[3]; v_sub(a,b,d); return v_dot(d,d); }
+
+static void xf_identity(xf_t* T) { memset(T,0,sizeof(*T)); T->R[0]=T->R[4]=T->R[8]=1.0; }
+static void xf_from12(const double* a, xf_t* T) { memcpy(T->R,a,9*sizeof(double)); memcpy(T->t,a+9,3*sizeof(double)); }
+static void xf_to12(const xf_t* T, double* a) { memcpy(a,T->R,9*sizeof(double)); memcpy(a+9,T->t,3*sizeof(double)); }
+static inline void xf_apply(const xf_t* T, const double* p, double* o) {
+  double x=p[0],y=p[1],z=p[2];
+  o[0]=T->R[0]*x+T->R[1]*y+T->R[2]*z+T->t[0];
+  o[1]=T->R[3]*x+T->R[4]*y+T->R[5]*z+T->t[1];
+  o[2]=T->R[6]*x+T->R[7]*y+T->R[8]*z+T->t[2];
+}
+/* C = A*B */
+static void xf_mul(const xf_t* A, const xf_t* B, xf_t* C) {
+  xf_t o;
+  for (int i=0;i<3;i++) for (int j=0;j<3;j++)
+    o.R[3*i+j]=A->R[3*i]*B->R[j]+A->R[3*i+1]*B->R[3+j]+A->R[3*i+2]*B->R[6+j];
+  for (int i=0;i<3;i++) o.t[i]=A->R[3*i]*B->t[0]+A->R[3*i+1]*B->t[1]+A->R[3*i+2]*B->t[2]+A->t[i];
+  *C=o;
+}
+/* C = A^-1 * B */
+static void xf_mul_inv_a(const xf_t* A, const xf_t* B, xf_t* C) {
+  xf_t o; double d[3]; v_sub(B->t,A->t,d);
+  for (int i=0;i<3;i++) for (int j=0;j<3;j++)
+    o.R[3*i+j]=A->R[i]*B->R[j]+A->R[3+i]*B->R[3+j]+A->R[6+i]*B->R[6+j];
+  for (int i=0;i<3;i++) o.t[i]=A->R[i]*d[0]+A->R[3+i]*d[1]+A->R[6+i]*d[2];
+  *C=o;
+}
+
+/* ------------------------------------------------------------------ geometry containers */
+enum { G_EMPTY=0, G_MESH=1, G_CLOUD=2, G_PRIM=3 };
+#define CLOUD_LEAF 8
+
+typedef struct { double lo[3], hi[3]; int left, right; int first; int count; } node_t; /* left<0 => leaf [first,first+count) */
+
+typedef struct {
+  int kind;
+  double margin;
+  int nv, nt;           /* mesh */
+  double* verts;        /* nv*3 */
+  int32_t* tris;        /* nt*3 */
+  double* tv;           /* nt*9 expanded triangle vertices, BVH order */
+  int np;               /* cloud / prim (sphere): points + radius */
+  double* pts;          /* np*3, BVH order */
+  double* rad;          /* np (may be all zeros) */
+  int* perm;            /* element permutation (BVH order -> original index) */
+  node_t* nodes; int nnodes;
+  double lo[3], hi[3];  /* local AABB */
+} geom_t;
+
+typedef struct { int n; int32_t* links; double* scale; double* offset; double dmin, dmax; } driver_t;
+
+struct ko_world {
+  geom_t* geoms; int ngeoms, capgeoms;
+  int* terrains; int nterr;
+  int* objects; xf_t* objT; int nobj;
+  int L; int32_t* parents; uint8_t* linktype; double* axis; xf_t* T0; double* qmin; double* qmax;
+  int* linkgeom;
+  int nj; uint8_t* jtype; int32_t* jlink;
+  driver_t* drivers; int ndrv;
+  uint8_t* selfcol;     /* L*L upper triangular (i<j) */
+  int selfcol_default;
+  uint8_t* mask; int nids; int mask_user;
+  int finalized;
+};
+
+/* ------------------------------------------------------------------ element predicates */
+static inline double orient3d(const double* a, const double* b, const double* c, const double* d) {
+  double ad[3],bd[3],cd[3],bc[3];
+  v_sub(a,d,ad); v_sub(b,d,bd); v_sub(c,d,cd);
+  v_cross(bd,cd,bc);
+  return v_dot(ad,bc);
+}
+
+static inline double orient2d(const double* a, const double* b, const double* c) {
+  return (b[0]-a[0])*(c[1]-a[1]) - (b[1]-a[1])*(c[0]-a[0]);
+}
+static int on_seg2d(const double* a, const double* b, const double* p) {
+  return p[0] >= fmin(a[0],b[0]) && p[0] <= fmax(a[0],b[0]) && p[1] >= fmin(a[1],b[1]) && p[1] <= fmax(a[1],b[1]);
+}
+static int seg_seg_2d(const double* a, const double* b, const double* c, const double* d) {
+  double o1=orient2d(a,b,c), o2=orient2d(a,b,d), o3=orient2d(c,d,a), o4=orient2d(c,d,b);
+  if (((o1>0&&o2<0)||(o1<0&&o2>0)) && ((o3>0&&o4<0)||(o3<0&&o4>0))) return 1;
+  if (o1==0 && on_seg2d(a,b,c)) return 1;
+  if (o2==0 && on_seg2d(a,b,d)) return 1;
+  if (o3==0 && on_seg2d(c,d,a)) return 1;
+  if (o4==0 && on_seg2d(c,d,b)) return 1;
+  return 0;
+}
+static int point_in_tri_2d(const double* p, const double* a, const double* b, const double* c) {
+  double o1=orient2d(a,b,p), o2=orient2d(b,c,p), o3=orient2d(c,a,p);
+  return (o1>=0&&o2>=0&&o3>=0)||(o1<=0&&o2<=0&&o3<=0);
+}
+/* coplanar triangles: project on the dominant plane of the normal n */
+static int tri_tri_coplanar(const double* A, const double* B, const double* n) {
+  int ax=0; double m=fabs(n[0]);
+  if (fabs(n[1])>m) { ax=1; m=fabs(n[1]); }
+  if (fabs(n[2])>m) { ax=2; }
+  int i0=(ax+1)%3, i1=(ax+2)%3;
+  double a[3][2], b[3][2];
+  for (int k=0;k<3;k++) { a[k][0]=A[3*k+i0]; a[k][1]=A[3*k+i1]; b[k][0]=B[3*k+i0]; b[k][1]=B[3*k+i1]; }
+  for (int i=0;i<3;i++) for (int j=0;j<3;j++)
+    if (seg_seg_2d(a[i],a[(i+1)%3],b[j],b[(j+1)%3])) return 1;
+  if (point_in_tri_2d(a[0],b[0],b[1],b[2])) return 1;
+  if (point_in_tri_2d(b[0],a[0],a[1],a[2])) return 1;
+  return 0;
+}
+/* closed segment pq vs closed triangle abc, pq not coplanar with abc as a whole */
+static int seg_tri(const double* p, const double* q, const double* a, const double* b, const double* c, double sp, double sq) {
+  if ((sp>0&&sq>0)||(sp<0&&sq<0)) return 0;
+  if (sp==0 && sq==0) return 0; /* segment inside the plane: caught by the other triangle's edges or coplanar path */
+  double s1=orient3d(p,q,a,b), s2=orient3d(p,q,b,c), s3=orient3d(p,q,c,a);
+  return (s1>=0&&s2>=0&&s3>=0)||(s1<=0&&s2<=0&&s3<=0);
+}
+
+/* Two closed triangles share a point?  Edge-vs-triangle formulation (any exact tri-tri overlap test is
+ * acceptable because the boolean is a geometric fact). */
+int ko_tri_tri_intersect(const double A[9], const double B[9]) {
+  const double *a0=A,*a1=A+3,*a2=A+6,*b0=B,*b1=B+3,*b2=B+6;
+  double da[3], db[3];
+  da[0]=orient3d(b0,b1,b2,a0); da[1]=orient3d(b0,b1,b2,a1); da[2]=orient3d(b0,b1,b2,a2);
+  if ((da[0]>0&&da[1]>0&&da[2]>0)||(da[0]<0&&da[1]<0&&da[2]<0)) return 0;
+  db[0]=orient3d(a0,a1,a2,b0); db[1]=orient3d(a0,a1,a2,b1); db[2]=orient3d(a0,a1,a2,b2);
+  if ((db[0]>0&&db[1]>0&&db[2]>0)||(db[0]<0&&db[1]<0&&db[2]<0)) return 0;
+  if (da[0]==0&&da[1]==0&&da[2]==0) {
+    double e1[3],e2[3],n[3]; v_sub(b1,b0,e1); v_sub(b2,b0,e2); v_cross(e1,e2,n);
+    if (n[0]==0&&n[1]==0&&n[2]==0) { v_sub(a1,a0,e1); v_sub(a2,a0,e2); v_cross(e1,e2,n); }
+    return tri_tri_coplanar(A,B,n);
+  }
+  /* edges of A against B */
+  if (seg_tri(a0,a1,b0,b1,b2,da[0],da[1])) return 1;
+  if (seg_tri(a1,a2,b0,b1,b2,da[1],da[2])) return 1;
+  if (seg_tri(a2,a0,b0,b1,b2,da[2],da[0])) return 1;
+  if (seg_tri(b0,b1,a0,a1,a2,db[0],db[1])) return 1;
+  if (seg_tri(b1,b2,a0,a1,a2,db[1],db[2])) return 1;
+  if (seg_tri(b2,b0,a0,a1,a2,db[2],db[0])) return 1;
+  return 0;
+}
+
+/* closest point on triangle to p (region walk), returns squared distance */
+static double point_tri_dist2(const double* p, const double* a, const double* b, const double* c) {
+  double ab[3],ac[3],ap[3]; v_sub(b,a,ab); v_sub(c,a,ac); v_sub(p,a,ap);
+  double d1=v_dot(ab,ap), d2=v_dot(ac,ap);
+  if (d1<=0 && d2<=0) return v_dot(ap,ap);
+  double bp[3]; v_sub(p,b,bp);
+  double d3=v_dot(ab,bp), d4=v_dot(ac,bp);
+  if (d3>=0 && d4<=d3) return v_dot(bp,bp);
+  double vc=d1*d4-d3*d2;
+  if (vc<=0 && d1>=0 && d3<=0) { double v=d1/(d1-d3); double q[3]; v_madd(a,ab,v,q); return v_dist2(p,q); }
+  double cp[3]; v_sub(p,c,cp);
+  double d5=v_dot(ab,cp), d6=v_dot(ac,cp);
+  if (d6>=0 && d5<=d6) return v_dot(cp,cp);
+  double vb=d5*d2-d1*d6;
+  if (vb<=0 && d2>=0 && d6<=0) { double w=d2/(d2-d6); double q[3]; v_madd(a,ac,w,q); return v_dist2(p,q); }
+  double va=d3*d6-d5*d4;
+  if (va<=0 && (d4-d3)>=0 && (d5-d6)>=0) {
+    double w=(d4-d3)/((d4-d3)+(d5-d6)); double bc[3],q[3]; v_sub(c,b,bc); v_madd(b,bc,w,q); return v_dist2(p,q); }
+  /* interior: distance to plane */
+  double n[3]; v_cross(ab,ac,n);
+  double nn=v_dot(n,n);
+  if (nn==0) { /* degenerate triangle: min over edges handled by callers via seg tests; fall back to vertices */
+    double m=v_dot(ap,ap), t=v_dot(bp,bp); if (t<m) m=t; t=v_dot(cp,cp); if (t<m) m=t; return m; }
+  double h=v_dot(ap,n);
+  return h*h/nn;
+}
+double ko_point_tri_distance(const double p[3], const double t[9]) { return sqrt(point_tri_dist2(p,t,t+3,t+6)); }
+
+/* closest points between two segments, squared distance */
+static double seg_seg_dist2(const double* p1, const double* q1, const double* p2, const double* q2) {
+  double d1[3],d2[3],r[3]; v_sub(q1,p1,d1); v_sub(q2,p2,d2); v_sub(p1,p2,r);
+  double a=v_dot(d1,d1), e=v_dot(d2,d2), f=v_dot(d2,r);
+  double s,t;
+  if (a==0 && e==0) return v_dot(r,r);
+  if (a==0) { s=0; t=f/e; if (t<0) t=0; if (t>1) t=1; }
+  else {
+    double c=v_dot(d1,r);
+    if (e==0) { t=0; s=-c/a; if (s<0) s=0; if (s>1) s=1; }
+    else {
+      double b=v_dot(d1,d2), denom=a*e-b*b;
+      if (denom>0) { s=(b*f-c*e)/denom; if (s<0) s=0; if (s>1) s=1; } else s=0;
+      t=(b*s+f)/e;
+      if (t<0) { t=0; s=-c/a; if (s<0) s=0; if (s>1) s=1; }
+      else if (t>1) { t=1; s=(b-c)/a; if (s<0) s=0; if (s>1) s=1; }
+    }
+  }
+  double c1[3],c2[3]; v_madd(p1,d1,s,c1); v_madd(p2,d2,t,c2);
+  return v_dist2(c1,c2);
+}
+double ko_seg_seg_distance(const double p0[3], const double p1[3], const double q0[3], const double q1[3]) {
+  return sqrt(seg_seg_dist2(p0,p1,q0,q1)); }
+
+/* distance between two closed triangles: 0 if they intersect, else min over 9 edge pairs and 6 vertex-face pairs */
+static double tri_tri_dist2(const double* A, const double* B) {
+  if (ko_tri_tri_intersect(A,B)) return 0.0;
+  double m=DBL_MAX, d;
+  for (int i=0;i<3;i++) for (int j=0;j<3;j++) {
+    d=seg_seg_dist2(A+3*i,A+3*((i+1)%3),B+3*j,B+3*((j+1)%3)); if (d<m) m=d; }
+  for (int i=0;i<3;i++) { d=point_tri_dist2(A+3*i,B,B+3,B+6); if (d<m) m=d; }
+  for (int i=0;i<3;i++) { d=point_tri_dist2(B+3*i,A,A+3,A+6); if (d<m) m=d; }
+  return m;
+}
+double ko_tri_tri_distance(const double a[9], const double b[9]) { return sqrt(tri_tri_dist2(a,b)); }
+
+/* ------------------------------------------------------------------ BVH build (median split, canonical) */
+typedef struct { double c[3]; int idx; } cent_t;
+static int g_sort_axis;
+static int cent_cmp(const void* a, const void* b) {
+  const cent_t* x=(const cent_t*)a; const cent_t* y=(const cent_t*)b;
+  if (x->c[g_sort_axis]<y->c[g_sort_axis]) return -1;
+  if (x->c[g_sort_axis]>y->c[g_sort_axis]) return 1;
+  return (x->idx>y->idx)-(x->idx<y->idx);
+}
+typedef struct { node_t* nodes; int nnodes; cent_t* cents; const double* elo; const double* ehi; int leafsize; } build_t;
+
+static int build_rec(build_t* b, int first, int count) {
+  int me=b->nnodes++;
+  node_t* nd=&b->nodes[me];
+  for (int k=0;k<3;k++) { nd->lo[k]=DBL_MAX; nd->hi[k]=-DBL_MAX; }
+  for (int i=first;i<first+count;i++) { int e=b->cents[i].idx;
+    for (int k=0;k<3;k++) { if (b->elo[3*e+k]<nd->lo[k]) nd->lo[k]=b->elo[3*e+k]; if (b->ehi[3*e+k]>nd->hi[k]) nd->hi[k]=b->ehi[3*e+k]; } }
+  nd->first=first; nd->count=count;
+  if (count<=b->leafsize) { nd->left=-1; nd->right=-1; return me; }
+  int ax=0; double ext=nd->hi[0]-nd->lo[0];
+  for (int k=1;k<3;k++) if (nd->hi[k]-nd->lo[k]>ext) { ext=nd->hi[k]-nd->lo[k]; ax=k; }
+  g_sort_axis=ax;
+  qsort(b->cents+first,count,sizeof(cent_t),cent_cmp);
+  int half=count/2;
+  int l=build_rec(b,first,half);
+  int r=build_rec(b,first+half,count-half);
+  b->nodes[me].left=l; b->nodes[me].right=r;
+  return me;
+}
+
+static void geom_build_bvh(geom_t* g) {
+  int n = (g->kind==G_MESH) ? g->nt : g->np;
+  if (n<=0) { g->nodes=NULL; g->nnodes=0; return; }
+  double* elo=(double*)malloc(sizeof(double)*3*n); double* ehi=(double*)malloc(sizeof(double)*3*n);
+  cent_t* cents=(cent_t*)malloc(sizeof(cent_t)*n);
+  for (int e=0;e<n;e++) {
+    cents[e].idx=e;
+    if (g->kind==G_MESH) {
+      for (int k=0;k<3;k++) {
+        double a=g->verts[3*g->tris[3*e]+k], b=g->verts[3*g->tris[3*e+1]+k], c=g->verts[3*g->tris[3*e+2]+k];
+        elo[3*e+k]=fmin(a,fmin(b,c)); ehi[3*e+k]=fmax(a,fmax(b,c));
+        cents[e].c[k]=(a+b+c)/3.0; }
+    } else {
+      for (int k=0;k<3;k++) { elo[3*e+k]=g->pts[3*e+k]-g->rad[e]; ehi[3*e+k]=g->pts[3*e+k]+g->rad[e]; cents[e].c[k]=g->pts[3*e+k]; }
+    }
+  }
+  build_t b; b.leafsize=(g->kind==G_MESH)?1:CLOUD_LEAF;
+  b.nodes=(node_t*)malloc(sizeof(node_t)*(2*(size_t)n)); b.nnodes=0; b.cents=cents; b.elo=elo; b.ehi=ehi;
+  build_rec(&b,0,n);
+  g->nodes=b.nodes; g->nnodes=b.nnodes;
+  g->perm=(int*)malloc(sizeof(int)*n);
+  for (int i=0;i<n;i++) g->perm[i]=cents[i].idx;
+  if (g->kind==G_MESH) {
+    g->tv=(double*)malloc(sizeof(double)*9*(size_t)n);
+    for (int i=0;i<n;i++) { int e=g->perm[i];
+      for (int v=0;v<3;v++) for (int k=0;k<3;k++) g->tv[9*(size_t)i+3*v+k]=g->verts[3*g->tris[3*e+v]+k]; }
+  } else {
+    double* p2=(double*)malloc(sizeof(double)*3*(size_t)n); double* r2=(double*)malloc(sizeof(double)*n);
+    for (int i=0;i<n;i++) { int e=g->perm[i]; memcpy(p2+3*(size_t)i,g->pts+3*(size_t)e,3*sizeof(double)); r2[i]=g->rad[e]; }
+    free(g->pts); free(g->rad); g->pts=p2; g->rad=r2;
+  }
+  memcpy(g->lo,g->nodes[0].lo,sizeof(g->lo)); memcpy(g->hi,g->nodes[0].hi,sizeof(g->hi));
+  free(elo); free(ehi); free(cents);
+}
+static inline int node_right(const geom_t* g, int i) { return g->nodes[i].right; }
+
+/* ------------------------------------------------------------------ world construction */
+ko_world* ko_create(void) { ko_world* w=(ko_world*)calloc(1,sizeof(ko_world)); w->selfcol_default=1; return w; }
+
+static void geom_free(geom_t* g) { free(g->verts); free(g->tris); free(g->tv); free(g->pts); free(g->rad); free(g->perm); free(g->nodes); }
+void ko_destroy(ko_world* w) {
+  if (!w) return;
+  for (int i=0;i<w->ngeoms;i++) geom_free(&w->geoms[i]);
+  free(w->geoms); free(w->terrains); free(w->objects); free(w->objT);
+  free(w->parents); free(w->linktype); free(w->axis); free(w->T0); free(w->qmin); free(w->qmax); free(w->linkgeom);
+  free(w->jtype); free(w->jlink);
+  for (int i=0;i<w->ndrv;i++) { free(w->drivers[i].links); free(w->drivers[i].scale); free(w->drivers[i].offset); }
+  free(w->drivers); free(w->selfcol); free(w->mask);
+  free(w);
+}
+static geom_t* new_geom(ko_world* w) {
+  if (w->ngeoms==w->capgeoms) { w->capgeoms=w->capgeoms? 2*w->capgeoms:16; w->geoms=(geom_t*)realloc(w->geoms,sizeof(geom_t)*w->capgeoms); }
+  geom_t* g=&w->geoms[w->ngeoms++]; memset(g,0,sizeof(*g)); return g;
+}
+int ko_add_trimesh(ko_world* w, const double* verts, int nv, const int32_t* tris, int nt, double margin) {
+  geom_t* g=new_geom(w); g->kind=(nt>0)?G_MESH:G_EMPTY; g->margin=margin; g->nv=nv; g->nt=nt;
+  g->verts=(double*)malloc(sizeof(double)*3*(nv>0?nv:1)); memcpy(g->verts,verts,sizeof(double)*3*nv);
+  g->tris=(int32_t*)malloc(sizeof(int32_t)*3*(nt>0?nt:1)); memcpy(g->tris,tris,sizeof(int32_t)*3*nt);
+  geom_build_bvh(g);
+  return w->ngeoms-1;
+}
+int ko_add_pointcloud(ko_world* w, const double* pts, int n, const double* radius, double margin) {
+  geom_t* g=new_geom(w); g->kind=(n>0)?G_CLOUD:G_EMPTY; g->margin=margin; g->np=n;
+  g->pts=(double*)malloc(sizeof(double)*3*(n>0?n:1)); memcpy(g->pts,pts,sizeof(double)*3*n);
+  g->rad=(double*)calloc(n>0?n:1,sizeof(double)); if (radius) memcpy(g->rad,radius,sizeof(double)*n);
+  geom_build_bvh(g);
+  return w->ngeoms-1;
+}
+int ko_add_primitive(ko_world* w, int type, const double* params, double margin) {
+  double r = (type==KO_PRIM_SPHERE) ? params[3] : 0.0;
+  if (type!=KO_PRIM_POINT && type!=KO_PRIM_SPHERE) return -1;
+  int gi=ko_add_pointcloud(w,params,1,&r,margin);
+  w->geoms[gi].kind=G_PRIM;
+  return gi;
+}
+int ko_add_terrain(ko_world* w, int geom) {
+  w->terrains=(int*)realloc(w->terrains,sizeof(int)*(w->nterr+1)); w->terrains[w->nterr]=geom; return w->nterr++; }
+int ko_add_rigid_object(ko_world* w, int geom, const double T[12]) {
+  w->objects=(int*)realloc(w->objects,sizeof(int)*(w->nobj+1)); w->objT=(xf_t*)realloc(w->objT,sizeof(xf_t)*(w->nobj+1));
+  w->objects[w->nobj]=geom; xf_from12(T,&w->objT[w->nobj]); return w->nobj++; }
+int ko_robot_create(ko_world* w, int L, const int32_t* parents, const uint8_t* linktype,
+                    const double* axis, const double* T0, const double* qmin, const double* qmax) {
+  if (w->L) return -1;
+  w->L=L;
+  w->parents=(int32_t*)malloc(sizeof(int32_t)*L); memcpy(w->parents,parents,sizeof(int32_t)*L);
+  w->linktype=(uint8_t*)malloc(L); memcpy(w->linktype,linktype,L);
+  w->axis=(double*)malloc(sizeof(double)*3*L); memcpy(w->axis,axis,sizeof(double)*3*L);
+  w->T0=(xf_t*)malloc(sizeof(xf_t)*L); for (int i=0;i<L;i++) xf_from12(T0+12*i,&w->T0[i]);
+  w->qmin=(double*)malloc(sizeof(double)*L); memcpy(w->qmin,qmin,sizeof(double)*L);
+  w->qmax=(double*)malloc(sizeof(double)*L); memcpy(w->qmax,qmax,sizeof(double)*L);
+  w->linkgeom=(int*)malloc(sizeof(int)*L); for (int i=0;i<L;i++) w->linkgeom[i]=-1;
+  /* default joints: one Normal joint per link (Robot.cpp default when no "joint" lines) */
+  w->nj=L; w->jtype=(uint8_t*)malloc(L); w->jlink=(int32_t*)malloc(sizeof(int32_t)*L);
+  for (int i=0;i<L;i++) { w->jtype[i]=KO_JOINT_NORMAL; w->jlink[i]=i; }
+  w->selfcol=(uint8_t*)calloc((size_t)L*L,1);
+  for (int i=0;i<L;i++) if (parents[i]>=i) return -2;
+  return 0;
+}
+int ko_robot_set_link_geometry(ko_world* w, int link, int geom) { if (link<0||link>=w->L) return -1; w->linkgeom[link]=geom; return 0; }
+int ko_robot_set_joints(ko_world* w, int nj, const uint8_t* jtype, const int32_t* jlink) {
+  free(w->jtype); free(w->jlink); w->nj=nj;
+  w->jtype=(uint8_t*)malloc(nj>0?nj:1); memcpy(w->jtype,jtype,nj);
+  w->jlink=(int32_t*)malloc(sizeof(int32_t)*(nj>0?nj:1)); memcpy(w->jlink,jlink,sizeof(int32_t)*nj); return 0; }
+int ko_robot_add_affine_driver(ko_world* w, int n, const int32_t* links, const double* scale, const double* offset, double dmin, double dmax) {
+  w->drivers=(driver_t*)realloc(w->drivers,sizeof(driver_t)*(w->ndrv+1));
+  driver_t* d=&w->drivers[w->ndrv++]; d->n=n; d->dmin=dmin; d->dmax=dmax;
+  d->links=(int32_t*)malloc(sizeof(int32_t)*n); memcpy(d->links,links,sizeof(int32_t)*n);
+  d->scale=(double*)malloc(sizeof(double)*n); d->offset=(double*)malloc(sizeof(double)*n);
+  for (int i=0;i<n;i++) { d->scale[i]=scale?scale[i]:1.0; d->offset[i]=offset?offset[i]:0.0; }
+  return w->ndrv-1;
+}
+static int geom_empty(const ko_world* w, int g) { return g<0 || w->geoms[g].kind==G_EMPTY; }
+
+/* a7: default self-collision set = all i<j, both non-empty, neither the other's parent */
+static void init_all_self_collisions(ko_world* w) {
+  int L=w->L;
+  for (int i=0;i<L;i++) for (int j=i+1;j<L;j++) {
+    int en = !geom_empty(w,w->linkgeom[i]) && !geom_empty(w,w->linkgeom[j]) && w->parents[j]!=i && w->parents[i]!=j;
+    w->selfcol[i*L+j]=(uint8_t)en; }
+}
+int ko_robot_set_self_collision(ko_world* w, int i, int j, int enabled) {
+  if (i>j) { int t=i; i=j; j=t; }
+  if (i==j || i<0 || j>=w->L) return -1;
+  if (w->selfcol_default) { init_all_self_collisions(w); w->selfcol_default=0; }
+  if (enabled && (geom_empty(w,w->linkgeom[i])||geom_empty(w,w->linkgeom[j]))) enabled=0;
+  w->selfcol[i*w->L+j]=(uint8_t)(enabled!=0); return 0;
+}
+int ko_num_ids(const ko_world* w) { return w->nterr+w->nobj+(w->L?1+w->L:0); }
+int ko_set_pair_mask(ko_world* w, const uint8_t* mask, int n_ids) {
+  if (n_ids!=ko_num_ids(w)) return -1;
+  free(w->mask); w->mask=(uint8_t*)malloc((size_t)n_ids*n_ids); memcpy(w->mask,mask,(size_t)n_ids*n_ids);
+  w->nids=n_ids; w->mask_user=1; return 0;
+}
+/* a6: WorldPlannerSettings::InitializeDefault, PlannerSettings.cpp:16-41 */
+static void init_default_mask(ko_world* w) {
+  int n=ko_num_ids(w); w->nids=n;
+  w->mask=(uint8_t*)malloc((size_t)n*n); memset(w->mask,1,(size_t)n*n);
+  for (int i=0;i<n;i++) w->mask[i*n+i]=0;
+  if (w->L) {
+    int k=w->nterr+w->nobj, base=k+1, L=w->L;
+    w->mask[k*n+k]=1;
+    for (int j=0;j<L;j++) { w->mask[(base+j)*n+k]=0; w->mask[k*n+base+j]=0; }
+    for (int j=0;j<L;j++) for (int m=0;m<L;m++)
+      w->mask[(base+j)*n+base+m] = (j<m) ? w->selfcol[j*L+m] : 0;   /* selfCollisions(j,k) upper triangular */
+    for (int j=0;j<L;j++) if (w->parents[j]==-1)
+      for (int t=0;t<w->nterr;t++) { w->mask[(base+j)*n+t]=0; w->mask[t*n+base+j]=0; }
+  }
+}
+int ko_finalize(ko_world* w) {
+  if (w->L && w->selfcol_default) { init_all_self_collisions(w); w->selfcol_default=0; }
+  if (!w->mask_user) { free(w->mask); init_default_mask(w); }
+  w->finalized=1; return 0;
+}
+int ko_get_pair_mask(const ko_world* w, uint8_t* out) { memcpy(out,w->mask,(size_t)w->nids*w->nids); return w->nids; }
+
+/* ------------------------------------------------------------------ FK, limits */
+static void axis_angle(const double* w, double th, double* R) {
+  double c=cos(th), s=sin(th), v=1.0-c;
+  R[0]=c+v*w[0]*w[0];      R[1]=v*w[0]*w[1]-s*w[2]; R[2]=v*w[0]*w[2]+s*w[1];
+  R[3]=v*w[1]*w[0]+s*w[2]; R[4]=c+v*w[1]*w[1];      R[5]=v*w[1]*w[2]-s*w[0];
+  R[6]=v*w[2]*w[0]-s*w[1]; R[7]=v*w[2]*w[1]+s*w[0]; R[8]=c+v*w[2]*w[2];
+}
+static void fk_links(const ko_world* w, const double* q, xf_t* T) {
+  for (int i=0;i<w->L;i++) {
+    xf_t loc; xf_identity(&loc);
+    if (w->linktype[i]==KO_PRISMATIC) { loc.t[0]=q[i]*w->axis[3*i]; loc.t[1]=q[i]*w->axis[3*i+1]; loc.t[2]=q[i]*w->axis[3*i+2]; }
+    else axis_angle(w->axis+3*i,q[i],loc.R);
+    xf_t rel; xf_mul(&w->T0[i],&loc,&rel);
+    if (w->parents[i]<0) T[i]=rel; else xf_mul(&T[w->parents[i]],&rel,&T[i]);
+  }
+}
+void ko_fk(const ko_world* w, const double* q, double* T_out) {
+  xf_t* T=(xf_t*)malloc(sizeof(xf_t)*w->L); fk_links(w,q,T);
+  for (int i=0;i<w->L;i++) xf_to12(&T[i],T_out+12*i);
+  free(T);
+}
+int ko_check_joint_limits(const ko_world* w, const double* q) {
+  for (int i=0;i<w->nj;i++) if (w->jtype[i]==KO_JOINT_NORMAL || w->jtype[i]==KO_JOINT_WELD) {
+    int k=w->jlink[i]; if (q[k]<w->qmin[k] || q[k]>w->qmax[k]) return 0; }
+  for (int i=0;i<w->ndrv;i++) { const driver_t* d=&w->drivers[i];
+    double v=0; for (int j=0;j<d->n;j++) v+=(q[d->links[j]]-d->offset[j])/d->scale[j];
+    v/=d->n; if (v<d->dmin || v>d->dmax) return 0; }
+  return 1;
+}
+
+/* ------------------------------------------------------------------ BV tests and traversals */
+/* world AABB of a transformed local box, inflated by margin: AnyCollisionGeometry3D::GetAABB (O(1), loose) */
+static void box_world_aabb(const double* lo, const double* hi, const xf_t* T, double m, double* bmin, double* bmax) {
+  double c[3]={0.5*(lo[0]+hi[0]),0.5*(lo[1]+hi[1]),0.5*(lo[2]+hi[2])}, h[3]={0.5*(hi[0]-lo[0]),0.5*(hi[1]-lo[1]),0.5*(hi[2]-lo[2])};
+  double wc[3]; xf_apply(T,c,wc);
+  for (int i=0;i<3;i++) { double e=fabs(T->R[3*i])*h[0]+fabs(T->R[3*i+1])*h[1]+fabs(T->R[3*i+2])*h[2]+m; bmin[i]=wc[i]-e; bmax[i]=wc[i]+e; }
+}
+void ko_geom_aabb(const ko_world* w, int g, const double T12[12], double bmin[3], double bmax[3]) {
+  xf_t T; xf_from12(T12,&T); const geom_t* G=&w->geoms[g];
+  box_world_aabb(G->lo,G->hi,&T,G->margin,bmin,bmax);
+}
+static inline int aabb_overlap(const double* alo, const double* ahi, const double* blo, const double* bhi) {
+  return alo[0]<=bhi[0] && blo[0]<=ahi[0] && alo[1]<=bhi[1] && blo[1]<=ahi[1] && alo[2]<=bhi[2] && blo[2]<=ahi[2]; }
+
+/* OBB-OBB separating-axis test; box B is expressed in A's frame by Tab; A half-extents inflated by tol. */
+static int obb_overlap(const node_t* a, const node_t* b, const xf_t* Tab, double tol) {
+  double ca[3],ha[3],cb[3],hb[3];
+  for (int i=0;i<3;i++) { ca[i]=0.5*(a->lo[i]+a->hi[i]); ha[i]=0.5*(a->hi[i]-a->lo[i])+tol; cb[i]=0.5*(b->lo[i]+b->hi[i]); hb[i]=0.5*(b->hi[i]-b->lo[i]); }
+  double cbA[3]; xf_apply(Tab,cb,cbA);
+  double t[3]; v_sub(cbA,ca,t);
+  const double* R=Tab->R; double AR[9];
+  for (int i=0;i<9;i++) AR[i]=fabs(R[i])+1e-12;
+  for (int i=0;i<3;i++) if (fabs(t[i]) > ha[i]+hb[0]*AR[3*i]+hb[1]*AR[3*i+1]+hb[2]*AR[3*i+2]) return 0;
+  for (int j=0;j<3;j++) if (fabs(t[0]*R[j]+t[1]*R[3+j]+t[2]*R[6+j]) > hb[j]+ha[0]*AR[j]+ha[1]*AR[3+j]+ha[2]*AR[6+j]) return 0;
+  for (int i=0;i<3;i++) { int i1=(i+1)%3, i2=(i+2)%3;
+    for (int j=0;j<3;j++) { int j1=(j+1)%3, j2=(j+2)%3;
+      double ra=ha[i1]*AR[3*i2+j]+ha[i2]*AR[3*i1+j];
+      double rb=hb[j1]*AR[3*i+j2]+hb[j2]*AR[3*i+j1];
+      if (fabs(t[i2]*R[3*i1+j]-t[i1]*R[3*i2+j]) > ra+rb) return 0; } }
+  return 1;
+}
+/* lower bound on the distance between two boxes (B in A's frame): max over the 6 face axes of the gap */
+static double obb_dist_lb(const node_t* a, const node_t* b, const xf_t* Tab) {
+  double ca[3],ha[3],cb[3],hb[3];
+  for (int i=0;i<3;i++) { ca[i]=0.5*(a->lo[i]+a->hi[i]); ha[i]=0.5*(a->hi[i]-a->lo[i]); cb[i]=0.5*(b->lo[i]+b->hi[i]); hb[i]=0.5*(b->hi[i]-b->lo[i]); }
+  double cbA[3]; xf_apply(Tab,cb,cbA); double t[3]; v_sub(cbA,ca,t);
+  const double* R=Tab->R; double g2=0, best=0;
+  /* A's axes: per-axis gaps combine in quadrature (AABB-AABB distance with B's AABB in A's frame) */
+  for (int i=0;i<3;i++) { double e=hb[0]*fabs(R[3*i])+hb[1]*fabs(R[3*i+1])+hb[2]*fabs(R[3*i+2]);
+    double g=fabs(t[i])-ha[i]-e; if (g>0) g2+=g*g; }
+  best=sqrt(g2); g2=0;
+  for (int j=0;j<3;j++) { double e=ha[0]*fabs(R[j])+ha[1]*fabs(R[3+j])+ha[2]*fabs(R[6+j]);
+    double g=fabs(t[0]*R[j]+t[1]*R[3+j]+t[2]*R[6+j])-hb[j]-e; if (g>0) g2+=g*g; }
+  double b2=sqrt(g2); return b2>best?b2:best;
+}
+static inline double node_size2(const node_t* n) { double d[3]; v_sub(n->hi,n->lo,d); return v_dot(d,d); }
+
+typedef struct { const geom_t* A; const geom_t* B; xf_t Ta, Tb, Tab; double tol; ko_counts* cnt; } pairq_t;
+
+/* leaf-vs-leaf: returns 1 if any element pair is within tol (tol==0: intersects) */
+static int leaf_collide(pairq_t* q, const node_t* a, const node_t* b) {
+  const geom_t *A=q->A, *B=q->B;
+  if (A->kind==G_MESH && B->kind==G_MESH) {
+    double ta[9], tb[9];
+    for (int v=0;v<3;v++) { xf_apply(&q->Ta,A->tv+9*(size_t)a->first+3*v,ta+3*v); xf_apply(&q->Tb,B->tv+9*(size_t)b->first+3*v,tb+3*v); }
+    if (q->cnt) q->cnt->n_tri++;
+    if (q->tol==0) return ko_tri_tri_intersect(ta,tb);
+    return tri_tri_dist2(ta,tb) <= q->tol*q->tol;
+  }
+  if (A->kind==G_MESH) { /* triangle vs point-spheres */
+    double ta[9]; for (int v=0;v<3;v++) xf_apply(&q->Ta,A->tv+9*(size_t)a->first+3*v,ta+3*v);
+    for (int i=b->first;i<b->first+b->count;i++) { double p[3]; xf_apply(&q->Tb,B->pts+3*(size_t)i,p);
+      if (q->cnt) q->cnt->n_pt++;
+      double r=B->rad[i]+q->tol; if (point_tri_dist2(p,ta,ta+3,ta+6) <= r*r) return 1; }
+    return 0;
+  }
+  if (B->kind==G_MESH) {
+    double tb[9]; for (int v=0;v<3;v++) xf_apply(&q->Tb,B->tv+9*(size_t)b->first+3*v,tb+3*v);
+    for (int i=a->first;i<a->first+a->count;i++) { double p[3]; xf_apply(&q->Ta,A->pts+3*(size_t)i,p);
+      if (q->cnt) q->cnt->n_pt++;
+      double r=A->rad[i]+q->tol; if (point_tri_dist2(p,tb,tb+3,tb+6) <= r*r) return 1; }
+    return 0;
+  }
+  for (int i=a->first;i<a->first+a->count;i++) { double p[3]; xf_apply(&q->Ta,A->pts+3*(size_t)i,p);
+    for (int j=b->first;j<b->first+b->count;j++) { double s[3]; xf_apply(&q->Tb,B->pts+3*(size_t)j,s);
+      if (q->cnt) q->cnt->n_pt++;
+      double r=A->rad[i]+B->rad[j]+q->tol; if (v_dist2(p,s) <= r*r) return 1; } }
+  return 0;
+}
+/* leaf-vs-leaf signed-for-spheres distance (geometric distance minus radii) */
+static double leaf_distance(pairq_t* q, const node_t* a, const node_t* b) {
+  const geom_t *A=q->A, *B=q->B; double best=DBL_MAX;
+  if (A->kind==G_MESH && B->kind==G_MESH) {
+    double ta[9], tb[9];
+    for (int v=0;v<3;v++) { xf_apply(&q->Ta,A->tv+9*(size_t)a->first+3*v,ta+3*v); xf_apply(&q->Tb,B->tv+9*(size_t)b->first+3*v,tb+3*v); }
+    if (q->cnt) q->cnt->n_tri++;
+    return sqrt(tri_tri_dist2(ta,tb));
+  }
+  if (A->kind==G_MESH || B->kind==G_MESH) {
+    const geom_t* M = A->kind==G_MESH?A:B; const geom_t* C = A->kind==G_MESH?B:A;
+    const node_t* mn = A->kind==G_MESH?a:b; const node_t* cn = A->kind==G_MESH?b:a;
+    const xf_t* Tm = A->kind==G_MESH?&q->Ta:&q->Tb; const xf_t* Tc = A->kind==G_MESH?&q->Tb:&q->Ta;
+    double t[9]; for (int v=0;v<3;v++) xf_apply(Tm,M->tv+9*(size_t)mn->first+3*v,t+3*v);
+    for (int i=cn->first;i<cn->first+cn->count;i++) { double p[3]; xf_apply(Tc,C->pts+3*(size_t)i,p);
+      if (q->cnt) q->cnt->n_pt++;
+      double d=sqrt(point_tri_dist2(p,t,t+3,t+6))-C->rad[i]; if (d<best) best=d; }
+    return best;
+  }
+  for (int i=a->first;i<a->first+a->count;i++) { double p[3]; xf_apply(&q->Ta,A->pts+3*(size_t)i,p);
+    for (int j=b->first;j<b->first+b->count;j++) { double s[3]; xf_apply(&q->Tb,B->pts+3*(size_t)j,s);
+      if (q->cnt) q->cnt->n_pt++;
+      double d=sqrt(v_dist2(p,s))-A->rad[i]-B->rad[j]; if (d<best) best=d; } }
+  return best;
+}
+
+/* canonical boolean traversal: simultaneous descent, descend-larger-first, first-contact exit */
+static int collide_rec(pairq_t* q, int ia, int ib) {
+  const node_t* a=&q->A->nodes[ia]; const node_t* b=&q->B->nodes[ib];
+  if (q->cnt) q->cnt->n_node++;
+  if (!obb_overlap(a,b,&q->Tab,q->tol)) return 0;
+  int la=a->left<0, lb=b->left<0;
+  if (la && lb) return leaf_collide(q,a,b);
+  if (lb || (!la && node_size2(a)>=node_size2(b))) {
+    int l=a->left; if (collide_rec(q,l,ib)) return 1;
+    return collide_rec(q,node_right(q->A,ia),ib);
+  } else {
+    int l=b->left; if (collide_rec(q,ia,l)) return 1;
+    return collide_rec(q,ia,node_right(q->B,ib));
+  }
+}
+/* branch and bound distance; *best is the running minimum (starts at the upper bound) */
+static void distance_rec(pairq_t* q, int ia, int ib, double* best) {
+  const node_t* a=&q->A->nodes[ia]; const node_t* b=&q->B->nodes[ib];
+  if (q->cnt) q->cnt->n_node++;
+  /* elements may be spheres: their radius is already inside the node boxes */
+  if (obb_dist_lb(a,b,&q->Tab) >= *best) return;
+  int la=a->left<0, lb=b->left<0;
+  if (la && lb) { double d=leaf_distance(q,a,b); if (d<*best) *best=d; return; }
+  if (lb || (!la && node_size2(a)>=node_size2(b))) {
+    int l=a->left, r=node_right(q->A,ia);
+    double dl=obb_dist_lb(&q->A->nodes[l],b,&q->Tab), dr=obb_dist_lb(&q->A->nodes[r],b,&q->Tab);
+    if (dl<=dr) { distance_rec(q,l,ib,best); distance_rec(q,r,ib,best); } else { distance_rec(q,r,ib,best); distance_rec(q,l,ib,best); }
+  } else {
+    int l=b->left, r=node_right(q->B,ib);
+    double dl=obb_dist_lb(a,&q->B->nodes[l],&q->Tab), dr=obb_dist_lb(a,&q->B->nodes[r],&q->Tab);
+    if (dl<=dr) { distance_rec(q,ia,l,best); distance_rec(q,ia,r,best); } else { distance_rec(q,ia,r,best); distance_rec(q,ia,l,best); }
+  }
+}
+static void pairq_init(pairq_t* q, const geom_t* A, const xf_t* Ta, const geom_t* B, const xf_t* Tb, double tol, ko_counts* cnt) {
+  q->A=A; q->B=B; q->Ta=*Ta; q->Tb=*Tb; xf_mul_inv_a(Ta,Tb,&q->Tab); q->tol=tol; q->cnt=cnt; }
+
+/* a11/a13: AnyCollisionQuery::Collide / WithinDistance(tol).  Margins add to the threshold (a12). */
+static int geom_pair_collide(const geom_t* A, const xf_t* Ta, const geom_t* B, const xf_t* Tb, double tol, ko_counts* cnt) {
+  if (A->kind==G_EMPTY || B->kind==G_EMPTY) return 0;
+  pairq_t q; pairq_init(&q,A,Ta,B,Tb,tol+A->margin+B->margin,cnt);
+  return collide_rec(&q,0,0);
+}
+/* AnyCollisionQuery::Distance(0,0,bound): geometric distance minus margins; returns bound if nothing closer */
+static double geom_pair_distance(const geom_t* A, const xf_t* Ta, const geom_t* B, const xf_t* Tb, double bound, ko_counts* cnt) {
+  if (A->kind==G_EMPTY || B->kind==G_EMPTY) return INFINITY;
+  double m=A->margin+B->margin;
+  pairq_t q; pairq_init(&q,A,Ta,B,Tb,0.0,cnt);
+  double best = isinf(bound)? DBL_MAX : bound+m;
+  double best0=best;
+  distance_rec(&q,0,0,&best);
+  if (best>=best0) return bound;
+  return best-m;
+}
+int ko_geom_collides(const ko_world* w, int ga, const double Ta[12], int gb, const double Tb[12]) {
+  xf_t A,B; xf_from12(Ta,&A); xf_from12(Tb,&B); return geom_pair_collide(&w->geoms[ga],&A,&w->geoms[gb],&B,0.0,NULL); }
+int ko_geom_within_distance(const ko_world* w, int ga, const double Ta[12], int gb, const double Tb[12], double tol) {
+  xf_t A,B; xf_from12(Ta,&A); xf_from12(Tb,&B); return geom_pair_collide(&w->geoms[ga],&A,&w->geoms[gb],&B,tol,NULL); }
+double ko_geom_distance(const ko_world* w, int ga, const double Ta[12], int gb, const double Tb[12], double ub) {
+  xf_t A,B; xf_from12(Ta,&A); xf_from12(Tb,&B); return geom_pair_distance(&w->geoms[ga],&A,&w->geoms[gb],&B,ub,NULL); }
+
+/* exhaustive distance over all element pairs (second, independent method for the BVH path) */
+static double geom_pair_distance_brute(const geom_t* A, const xf_t* Ta, const geom_t* B, const xf_t* Tb) {
+  if (A->kind==G_EMPTY || B->kind==G_EMPTY) return INFINITY;
+  double best=DBL_MAX;
+  int na=(A->kind==G_MESH)?A->nt:A->np, nb=(B->kind==G_MESH)?B->nt:B->np;
+  for (int i=0;i<na;i++) {
+    double ea[9]; double ra=0;
+    if (A->kind==G_MESH) { for (int v=0;v<3;v++) xf_apply(Ta,A->tv+9*(size_t)i+3*v,ea+3*v); }
+    else { xf_apply(Ta,A->pts+3*(size_t)i,ea); ra=A->rad[i]; }
+    for (int j=0;j<nb;j++) {
+      double eb[9]; double rb=0, d;
+      if (B->kind==G_MESH) { for (int v=0;v<3;v++) xf_apply(Tb,B->tv+9*(size_t)j+3*v,eb+3*v); }
+      else { xf_apply(Tb,B->pts+3*(size_t)j,eb); rb=B->rad[j]; }
+      if (A->kind==G_MESH && B->kind==G_MESH) d=sqrt(tri_tri_dist2(ea,eb));
+      else if (A->kind==G_MESH) d=sqrt(point_tri_dist2(eb,ea,ea+3,ea+6))-rb;
+      else if (B->kind==G_MESH) d=sqrt(point_tri_dist2(ea,eb,eb+3,eb+6))-ra;
+      else d=sqrt(v_dist2(ea,eb))-ra-rb;
+      if (d<best) best=d;
+    }
+  }
+  return best-A->margin-B->margin;
+}
+double ko_geom_distance_brute(const ko_world* w, int ga, const double Ta[12], int gb, const double Tb[12]) {
+  xf_t A,B; xf_from12(Ta,&A); xf_from12(Tb,&B); return geom_pair_distance_brute(&w->geoms[ga],&A,&w->geoms[gb],&B); }
+
+/* ------------------------------------------------------------------ IsFeasible */
+typedef struct { const geom_t* g; xf_t T; int id; double lo[3], hi[3]; } active_t;
+
+static int id_robot(const ko_world* w) { return w->nterr+w->nobj; }
+static int id_link(const ko_world* w, int j) { return w->nterr+w->nobj+1+j; }
+static inline int mask_en(const ko_world* w, int a, int b) { return w->mask[(size_t)a*w->nids+b]; }
+
+/* GetGeometries (PlannerSettings.cpp:214-239) for the robot and for {terrains, rigid objects} */
+static int gather_links(const ko_world* w, const xf_t* T, active_t* out) {
+  int n=0;
+  for (int j=0;j<w->L;j++) { int g=w->linkgeom[j]; if (geom_empty(w,g)) continue;
+    out[n].g=&w->geoms[g]; out[n].T=T[j]; out[n].id=id_link(w,j); n++; }
+  return n;
+}
+static int gather_env(const ko_world* w, active_t* out) {
+  int n=0; xf_t I; xf_identity(&I);
+  for (int i=0;i<w->nterr;i++) { int g=w->terrains[i]; if (geom_empty(w,g)) continue; out[n].g=&w->geoms[g]; out[n].T=I; out[n].id=i; n++; }
+  for (int i=0;i<w->nobj;i++) { int g=w->objects[i]; if (geom_empty(w,g)) continue; out[n].g=&w->geoms[g]; out[n].T=w->objT[i]; out[n].id=w->nterr+i; n++; }
+  return n;
+}
+static void compute_bbs(active_t* a, int n, double tol) {
+  for (int i=0;i<n;i++) { box_world_aabb(a[i].g->lo,a[i].g->hi,&a[i].T,a[i].g->margin,a[i].lo,a[i].hi);
+    for (int k=0;k<3;k++) { a[i].lo[k]-=0.5*tol; a[i].hi[k]+=0.5*tol; } }
+}
+/* env check, PlannerSettings.cpp:269-331 (two group-AABB quick rejects, then pair loop) */
+static int check_env(const ko_world* w, active_t* s1, int n1, active_t* s2, int n2, double tol, int32_t* pair, ko_counts* cnt) {
+  compute_bbs(s1,n1,tol); compute_bbs(s2,n2,tol);
+  double lo[3]={DBL_MAX,DBL_MAX,DBL_MAX}, hi[3]={-DBL_MAX,-DBL_MAX,-DBL_MAX};
+  for (int i=0;i<n1;i++) for (int k=0;k<3;k++) { if (s1[i].lo[k]<lo[k]) lo[k]=s1[i].lo[k]; if (s1[i].hi[k]>hi[k]) hi[k]=s1[i].hi[k]; }
+  for (int i=0;i<n2;i++) { if (cnt) cnt->n_box++; if (!aabb_overlap(s2[i].lo,s2[i].hi,lo,hi)) { s2[i]=s2[n2-1]; n2--; i--; } }
+  for (int k=0;k<3;k++) { lo[k]=DBL_MAX; hi[k]=-DBL_MAX; }
+  for (int i=0;i<n2;i++) for (int k=0;k<3;k++) { if (s2[i].lo[k]<lo[k]) lo[k]=s2[i].lo[k]; if (s2[i].hi[k]>hi[k]) hi[k]=s2[i].hi[k]; }
+  for (int i=0;i<n1;i++) { if (cnt) cnt->n_box++; if (!aabb_overlap(s1[i].lo,s1[i].hi,lo,hi)) { s1[i]=s1[n1-1]; n1--; i--; } }
+  for (int i=0;i<n1;i++) for (int j=0;j<n2;j++) {
+    if (mask_en(w,s1[i].id,s2[j].id) || mask_en(w,s2[j].id,s1[i].id)) {
+      if (cnt) cnt->n_box++;
+      if (aabb_overlap(s1[i].lo,s1[i].hi,s2[j].lo,s2[j].hi))
+        if (geom_pair_collide(s1[i].g,&s1[i].T,s2[j].g,&s2[j].T,tol,cnt)) { if (pair) { pair[0]=s1[i].id; pair[1]=s2[j].id; } return 1; }
+    } }
+  return 0;
+}
+/* self check, PlannerSettings.cpp:241-267 (second mask term indexes the diagonal: always false for links) */
+static int check_self(const ko_world* w, active_t* s, int n, double tol, int32_t* pair, ko_counts* cnt) {
+  compute_bbs(s,n,tol);
+  for (int i=0;i<n;i++) for (int j=i+1;j<n;j++) {
+    if (mask_en(w,s[i].id,s[j].id) || mask_en(w,s[i].id,s[i].id)) {
+      if (cnt) cnt->n_box++;
+      if (aabb_overlap(s[i].lo,s[i].hi,s[j].lo,s[j].hi))
+        if (geom_pair_collide(s[i].g,&s[i].T,s[j].g,&s[j].T,tol,cnt)) { if (pair) { pair[0]=s[i].id; pair[1]=s[j].id; } return 1; }
+    } }
+  return 0;
+}
+static int check_collision_free(const ko_world* w, const double* q, int32_t* pair, ko_counts* cnt) {
+  int L=w->L;
+  int big = (L+w->nterr+w->nobj) > 2048;
+  size_t b1=sizeof(xf_t)*L, b2=sizeof(active_t)*(L+1), b3=sizeof(active_t)*(w->nterr+w->nobj+1);
+  xf_t* T=(xf_t*)(big?malloc(b1):alloca(b1)); fk_links(w,q,T);
+  active_t* s1=(active_t*)(big?malloc(b2):alloca(b2));
+  active_t* s2=(active_t*)(big?malloc(b3):alloca(b3));
+  int n1=gather_links(w,T,s1), n2=gather_env(w,s2), hit;
+  hit=check_env(w,s1,n1,s2,n2,0.0,pair,cnt);
+  if (!hit) { n1=gather_links(w,T,s1); hit=check_self(w,s1,n1,0.0,pair,cnt); }
+  if (big) { free(T); free(s1); free(s2); }
+  return !hit;
+}
+int ko_feasible(const ko_world* w, const double* q, int32_t* pair, ko_counts* cnt) {
+  if (pair) { pair[0]=-1; pair[1]=-1; }
+  if (!ko_check_joint_limits(w,q)) return 0;
+  return check_collision_free(w,q,pair,cnt);
+}
+/* all element pairs of all enabled geometry pairs; no BVH, no AABB reject */
+int ko_feasible_brute(const ko_world* w, const double* q) {
+  if (!ko_check_joint_limits(w,q)) return 0;
+  int L=w->L; xf_t* T=(xf_t*)malloc(sizeof(xf_t)*L); fk_links(w,q,T);
+  active_t* s1=(active_t*)malloc(sizeof(active_t)*(L+1));
+  active_t* s2=(active_t*)malloc(sizeof(active_t)*(w->nterr+w->nobj+1));
+  int n1=gather_links(w,T,s1), n2=gather_env(w,s2), hit=0;
+  for (int i=0;i<n1&&!hit;i++) for (int j=0;j<n2&&!hit;j++)
+    if (mask_en(w,s1[i].id,s2[j].id)||mask_en(w,s2[j].id,s1[i].id))
+      hit = geom_pair_distance_brute(s1[i].g,&s1[i].T,s2[j].g,&s2[j].T) <= 0.0;
+  for (int i=0;i<n1&&!hit;i++) for (int j=i+1;j<n1&&!hit;j++)
+    if (mask_en(w,s1[i].id,s1[j].id))
+      hit = geom_pair_distance_brute(s1[i].g,&s1[i].T,s1[j].g,&s1[j].T) <= 0.0;
+  free(T); free(s1); free(s2);
+  return !hit;
+}
+int ko_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+void ko_feasible_batch(const ko_world* w, const double* Q, int64_t N, uint8_t* out, int32_t* first_pair, ko_counts* cpc, int nthreads) {
+  int L=w->L;
+  if (nthreads<=0) nthreads=ko_max_threads();
+  #pragma omp parallel for schedule(dynamic,64) num_threads(nthreads)
+  for (int64_t c=0;c<N;c++) {
+    int32_t pr[2]; ko_counts cnt={0,0,0,0};
+    out[c]=(uint8_t)ko_feasible(w,Q+c*L,pr,cpc?&cnt:NULL);
+    if (first_pair) { first_pair[2*c]=pr[0]; first_pair[2*c+1]=pr[1]; }
+    if (cpc) cpc[c]=cnt;
+  }
+}
+
+/* ------------------------------------------------------------------ edges */
+static double angle_normalize(double a) { a=fmod(a,2*M_PI); if (a<0) a+=2*M_PI; return a; }
+static double angle_diff(double a, double b) { /* signed CCW difference a-b in (-pi,pi] */
+  double d=a-b; if (d>M_PI) return d-2*M_PI; if (d<-M_PI) return d+2*M_PI; return d; }
+/* RobotCSpace::Distance -> Klampt::Distance, Interpolate.cpp:208-343, norm=2 (RobotCSpace.cpp:48).
+ * Weld joints are skipped; Normal joints collect (a-b) (times weight).  Spin uses AngleDiff.
+ * Floating / BallAndSocket bases are not part of this path's configs (C1-C5) and are rejected at build. */
+double ko_cspace_distance(const ko_world* w, const double* a, const double* b, const double* weights) {
+  double s=0;
+  for (int i=0;i<w->nj;i++) { int k=w->jlink[i]; double wt=weights?weights[i]:1.0, d;
+    switch (w->jtype[i]) {
+      case KO_JOINT_WELD: continue;
+      case KO_JOINT_NORMAL: d=a[k]-b[k]; break;
+      case KO_JOINT_SPIN: d=angle_diff(angle_normalize(a[k]),angle_normalize(b[k])); break;
+      default: continue; }
+    s+=wt*d*d; }   /* NormAccumulator<Real>(2).collect(x,w): sum w*x^2, then sqrt */
+  return sqrt(s);
+}
+/* Klampt::Interpolate, Interpolate.cpp:10-71: out = x*(1-u); out += y*u; Spin joints use the shortest arc */
+void ko_interpolate(const ko_world* w, const double* a, const double* b, double u, double* out) {
+  for (int k=0;k<w->L;k++) { out[k]=a[k]*(1.0-u); out[k]+=b[k]*u; }
+  for (int i=0;i<w->nj;i++) if (w->jtype[i]==KO_JOINT_SPIN) { int k=w->jlink[i];
+    double x=angle_normalize(a[k]), y=angle_normalize(b[k]); double d=angle_diff(y,x);
+    out[k]=angle_normalize(x+u*d); }
+}
+/* EpsilonEdgeChecker::IsVisible: bisect until segment length <= eps, midpoints in
+ * coarse-to-fine order, endpoints not re-checked, false at the first infeasible midpoint. */
+int ko_edge_visible(const ko_world* w, const double* a, const double* b, double eps, const double* weights, int32_t* nchecks, ko_counts* cnt) {
+  double len=ko_cspace_distance(w,a,b,weights);
+  double* m=(double*)malloc(sizeof(double)*w->L);
+  int32_t n=0; int vis=1; long segs=1;
+  while (len>eps && vis) {
+    segs*=2; len*=0.5;
+    for (long k=1;k<segs;k+=2) {
+      ko_interpolate(w,a,b,(double)k/(double)segs,m);
+      n++;
+      if (!ko_feasible(w,m,NULL,cnt)) { vis=0; break; }
+    }
+  }
+  free(m); if (nchecks) *nchecks=n; return vis;
+}
+void ko_edges_visible_batch(const ko_world* w, const double* A, const double* B, int64_t N, double eps,
+                            const double* weights, uint8_t* out, int32_t* nchecks, int nthreads) {
+  int L=w->L; if (nthreads<=0) nthreads=ko_max_threads();
+  #pragma omp parallel for schedule(dynamic,8) num_threads(nthreads)
+  for (int64_t e=0;e<N;e++) { int32_t n; out[e]=(uint8_t)ko_edge_visible(w,A+e*L,B+e*L,eps,weights,&n,NULL); if (nchecks) nchecks[e]=n; }
+}
+
+/* ------------------------------------------------------------------ distance */
+static double aabb_dist(const double* alo, const double* ahi, const double* blo, const double* bhi) {
+  double s=0; for (int k=0;k<3;k++) { double g=fmax(alo[k]-bhi[k],blo[k]-ahi[k]); if (g>0) s+=g*g; } return sqrt(s); }
+/* WorldPlannerSettings::DistanceLowerBound with eps=0 (PlannerSettings.cpp:570-620): min over enabled pairs of the
+ * pair distance, capped at upper_bound; candidates skipped when their AABB distance exceeds the running bound.
+ * (The reference orders candidates by AABB distance; the minimum does not depend on the order.) */
+double ko_distance(const ko_world* w, const double* q, double ub, int include_self, int32_t* pair, ko_counts* cnt) {
+  int L=w->L; xf_t* T=(xf_t*)malloc(sizeof(xf_t)*L); fk_links(w,q,T);
+  active_t* s1=(active_t*)malloc(sizeof(active_t)*(L+1));
+  active_t* s2=(active_t*)malloc(sizeof(active_t)*(w->nterr+w->nobj+1));
+  int n1=gather_links(w,T,s1), n2=gather_env(w,s2);
+  compute_bbs(s1,n1,0.0); compute_bbs(s2,n2,0.0);
+  double best=ub; if (pair) { pair[0]=-1; pair[1]=-1; }
+  for (int i=0;i<n1;i++) for (int j=0;j<n2;j++) if (mask_en(w,s1[i].id,s2[j].id)||mask_en(w,s2[j].id,s1[i].id)) {
+    if (cnt) cnt->n_box++;
+    if (aabb_dist(s1[i].lo,s1[i].hi,s2[j].lo,s2[j].hi) >= best) continue;
+    double d=geom_pair_distance(s1[i].g,&s1[i].T,s2[j].g,&s2[j].T,best,cnt);
+    if (d<best) { best=d; if (pair) { pair[0]=s1[i].id; pair[1]=s2[j].id; } } }
+  if (include_self) for (int i=0;i<n1;i++) for (int j=i+1;j<n1;j++) if (mask_en(w,s1[i].id,s1[j].id)) {
+    if (cnt) cnt->n_box++;
+    if (aabb_dist(s1[i].lo,s1[i].hi,s1[j].lo,s1[j].hi) >= best) continue;
+    double d=geom_pair_distance(s1[i].g,&s1[i].T,s1[j].g,&s1[j].T,best,cnt);
+    if (d<best) { best=d; if (pair) { pair[0]=s1[i].id; pair[1]=s1[j].id; } } }
+  free(T); free(s1); free(s2);
+  return best;
+}
+void ko_distance_batch(const ko_world* w, const double* Q, int64_t N, double ub, int include_self, double* out_d, int32_t* out_pair, int nthreads) {
+  int L=w->L; if (nthreads<=0) nthreads=ko_max_threads();
+  #pragma omp parallel for schedule(dynamic,16) num_threads(nthreads)
+  for (int64_t c=0;c<N;c++) { int32_t pr[2]; out_d[c]=ko_distance(w,Q+c*L,ub,include_self,pr,NULL);
+    if (out_pair) { out_pair[2*c]=pr[0]; out_pair[2*c+1]=pr[1]; } }
+}

@@ -1,0 +1,219 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): feasible / visible booleans bit-exact outside a 1e-6 m clearance band,
+distances within 1e-5 relative.  A boolean mismatch is tolerated only if the oracle's own clearance for that
+configuration is inside the band."""
+import numpy as np
+import pytest
+
+from klampt_b200 import synth
+from klampt_b200.worldspec import GeomSpec, WorldSpec
+
+pytestmark = pytest.mark.gpu
+
+BAND = 1e-6
+
+
+@pytest.fixture(scope="module")
+def c1(built):
+    from klampt_b200.engine import Engine
+    from oracle.oracle import OracleWorld
+    w = synth.world_c1()
+    return w, Engine(w), OracleWorld(w)
+
+
+@pytest.fixture(scope="module")
+def c2small(built):
+    from klampt_b200.engine import Engine
+    from oracle.oracle import OracleWorld
+    w = synth.world_c2(2, n_obstacles=60)
+    return w, Engine(w), OracleWorld(w)
+
+
+@pytest.fixture(scope="module")
+def c3(built):
+    from klampt_b200.engine import Engine
+    from oracle.oracle import OracleWorld
+    w = synth.world_c3()
+    return w, Engine(w), OracleWorld(w)
+
+
+def assert_bool_parity(got, want, Q, orc, include_self=True):
+    bad = np.nonzero(np.asarray(got) != np.asarray(want))[0]
+    for i in bad:
+        d, _ = orc.distance(Q[i], upper_bound=1.0, include_self=include_self)
+        assert d <= BAND, "config %d: gpu=%d oracle=%d but oracle clearance is %g m (> band)" % (i, got[i], want[i], d)
+    return len(bad)
+
+
+def test_fk_matches_oracle(c1):
+    w, eng, orc = c1
+    Q = synth.sample_configs(w.robot, 512, 11)
+    T = eng.fk_batch(Q)
+    To = orc.fk_batch(Q)
+    assert T.shape == To.shape
+    np.testing.assert_allclose(T, To, rtol=0, atol=1e-12)
+
+
+def test_fk_dualarm_branching_tree(c3):
+    w, eng, orc = c3
+    Q = synth.sample_configs(w.robot, 256, 12)
+    np.testing.assert_allclose(eng.fk_batch(Q), orc.fk_batch(Q), rtol=0, atol=1e-12)
+
+
+def test_feasible_c1(c1):
+    w, eng, orc = c1
+    Q = synth.sample_configs(w.robot, 10000, 1)
+    got, pairs = eng.feasible_batch(Q, return_pairs=True)
+    want, opairs = orc.feasible_batch(Q, want_pairs=True)
+    assert_bool_parity(got, want, Q, orc)
+    assert 0.2 < got.mean() < 0.9
+    # the reported pair must be a pair the mask enables, and -1,-1 exactly for feasible / limit-violating configurations
+    mask = eng.pair_mask()
+    hit = pairs[:, 0] >= 0
+    assert not (hit & (got == 1)).any()
+    for a, b in pairs[hit][:500]:
+        assert mask[a, b] or mask[b, a]
+
+
+def test_joint_limits_closed_interval(c1):
+    w, eng, orc = c1
+    r = w.robot
+    Q = np.tile(0.5 * (r.qmin + r.qmax), (6, 1))
+    Q[0, 2] = r.qmax[2]                      # on the bound: allowed
+    Q[1, 2] = np.nextafter(r.qmax[2], 10)    # one ulp outside: infeasible
+    Q[2, 3] = r.qmin[3]
+    Q[3, 3] = np.nextafter(r.qmin[3], -10)
+    Q[4, 0] = 1e-9                           # welded base joint has qmin=qmax=0
+    got = eng.feasible_batch(Q)
+    want = orc.feasible_batch(Q)
+    assert list(got) == list(want)
+    assert got[1] == 0 and got[3] == 0 and got[4] == 0
+
+
+def test_feasible_c2_small(c2small):
+    w, eng, orc = c2small
+    Q = synth.sample_configs(w.robot, 20000, 2)
+    got = eng.feasible_batch(Q)
+    want = orc.feasible_batch(Q)
+    assert_bool_parity(got, want, Q, orc)
+
+
+def test_feasible_c3_self_collision(c3):
+    w, eng, orc = c3
+    Q = synth.sample_configs(w.robot, 20000, 3)
+    got = eng.feasible_batch(Q)
+    want = orc.feasible_batch(Q)
+    assert_bool_parity(got, want, Q, orc)
+    assert 0.05 < got.mean() < 0.95
+
+
+def test_empty_and_ragged_batches(c1):
+    w, eng, orc = c1
+    assert eng.feasible_batch(np.zeros((0, w.robot.L))).shape == (0,)
+    for n in (1, 7, 33, 4097):
+        Q = synth.sample_configs(w.robot, n, 40 + n)
+        assert (eng.feasible_batch(Q) == orc.feasible_batch(Q)).all()
+
+
+def test_idempotent_and_order_independent(c1):
+    w, eng, orc = c1
+    Q = synth.sample_configs(w.robot, 5000, 5)
+    a = eng.feasible_batch(Q)
+    b = eng.feasible_batch(Q)
+    assert (a == b).all()
+    perm = np.random.default_rng(0).permutation(len(Q))
+    c = eng.feasible_batch(Q[perm])
+    assert (c == a[perm]).all()
+
+
+def test_edges_c1(c1):
+    w, eng, orc = c1
+    A, B = synth.sample_edges(w.robot, lambda Q: orc.feasible_batch(Q), 1500, 4)
+    vis, nchk = eng.edges_visible_batch(A, B, eps=0.01)
+    ovis, onchk = orc.edges_visible_batch(A, B, eps=0.01)
+    assert (vis == ovis).all()
+    assert (nchk == onchk).all()
+    assert 0.05 < vis.mean() < 0.95
+
+
+def test_edges_weighted_metric(c1):
+    w, eng, orc = c1
+    A, B = synth.sample_edges(w.robot, lambda Q: orc.feasible_batch(Q), 300, 6)
+    wts = np.array([1.0, 2.0, 1.5, 1.0, 0.5, 0.25, 0.1])
+    vis, nchk = eng.edges_visible_batch(A, B, eps=0.02, weights=wts)
+    ovis, onchk = orc.edges_visible_batch(A, B, eps=0.02, weights=wts)
+    assert (vis == ovis).all() and (nchk == onchk).all()
+
+
+def test_distance_c1(c1):
+    w, eng, orc = c1
+    Q = synth.sample_configs(w.robot, 1500, 7)
+    d, pairs = eng.distance_batch(Q, upper_bound=0.5, include_self=False, return_pairs=True)
+    do, _ = orc.distance_batch(Q, upper_bound=0.5, include_self=False)
+    np.testing.assert_allclose(d, do, rtol=1e-5, atol=1e-9)
+    assert (d <= 0.5).all() and (d >= 0).all()
+    assert ((pairs[:, 0] < 0) == (d >= 0.5)).all()
+
+
+def test_distance_with_self_pairs(c3):
+    w, eng, orc = c3
+    Q = synth.sample_configs(w.robot, 600, 8)
+    d = eng.distance_batch(Q, upper_bound=0.3, include_self=True)
+    do, _ = orc.distance_batch(Q, upper_bound=0.3, include_self=True)
+    np.testing.assert_allclose(d, do, rtol=1e-5, atol=1e-9)
+
+
+def test_margins_add_to_threshold(built):
+    """A,B collide iff dist(A,B) <= margin_A + margin_B (reference Cpp/docs/Manual-Geometry.md:17)."""
+    from klampt_b200.engine import Engine
+    from oracle.oracle import OracleWorld
+    w = synth.world_c1()
+    for gi, _ in w.objects:
+        w.geoms[gi].margin = 0.01
+    for gi in w.robot.link_geom:
+        w.geoms[gi].margin = 0.005
+    eng, orc = Engine(w), OracleWorld(w)
+    Q = synth.sample_configs(w.robot, 6000, 9)
+    got, want = eng.feasible_batch(Q), orc.feasible_batch(Q)
+    bad = np.nonzero(got != want)[0]
+    for i in bad:
+        d, _ = orc.distance(Q[i], upper_bound=1.0, include_self=True)
+        assert abs(d) <= BAND
+    w0 = synth.world_c1()
+    base = OracleWorld(w0).feasible_batch(Q)
+    assert want.sum() < base.sum()            # margins make the world strictly tighter
+
+
+def test_geometry_pair_queries(built):
+    """Geometry3D.collides / withinDistance / distance on two unit cubes (tests/objects/cube.off solid)."""
+    from klampt_b200.engine import Engine
+    from oracle.oracle import OracleWorld
+    v, t = synth.unit_cube()
+    w = WorldSpec()
+    ga = w.add_geom(GeomSpec.mesh(v, t))
+    gb = w.add_geom(GeomSpec.mesh(v, t))
+    gs = w.add_geom(GeomSpec.sphere([0.5, 0.5, 0.5], 0.25))
+    w.robot = synth.make_planar_nR(w, 2)
+    eng, orc = Engine(w), OracleWorld(w)
+    rng = np.random.default_rng(3)
+    N = 400
+    Ta = np.tile(synth.IDENTITY12, (N, 1))
+    Tb = np.stack([synth.make_T(synth._random_rotation(rng), rng.uniform(-1.6, 1.6, size=3)) for _ in range(N)])
+    got = eng.geom_collides_batch(ga, Ta, gb, Tb)
+    want = np.array([orc.geom_collides(ga, Ta[i], gb, Tb[i]) for i in range(N)])
+    assert (got == want).all()
+    d = eng.geom_distance_batch(ga, Ta, gb, Tb)
+    do = np.array([orc.geom_distance(ga, Ta[i], gb, Tb[i]) for i in range(N)])
+    np.testing.assert_allclose(d, do, rtol=1e-5, atol=1e-12)
+    assert ((d == 0) == want).all()
+    wd = eng.geom_collides_batch(ga, Ta, gb, Tb, tol=0.2)
+    assert (wd == (do <= 0.2)).all()
+    # sphere primitive vs mesh: distance = dist(centre, surface) - r, negative when the surface cuts the ball
+    ds = eng.geom_distance_batch(gs, Ta, gb, Tb)
+    dso = np.array([orc.geom_distance(gs, Ta[i], gb, Tb[i]) for i in range(N)])
+    np.testing.assert_allclose(ds, dso, rtol=1e-5, atol=1e-12)
+    # analytic: cubes offset by 1.5 along x -> gap 0.5; offset 0.5 -> faces cross
+    Tx = np.tile(synth.IDENTITY12, (2, 1)); Tx[0, 9] = 1.5; Tx[1, 9] = 0.5; Tx[1, 10] = 0.25; Tx[1, 11] = 0.25
+    dd = eng.geom_distance_batch(ga, Ta[:2], gb, Tx)
+    assert abs(dd[0] - 0.5) < 1e-12 and dd[1] == 0.0
