@@ -101,7 +101,8 @@ int kb_get_pair_mask(const kb_engine* e, uint8_t* mask_out);
 /* WorldModel::InitCollisions + SingleRobotCSpace::Init (Cpp/Modeling/World.cpp:266-274,
  * Cpp/Planning/RobotCSpace.cpp:668-754): builds the BVHs, flattens them and uploads everything to `device`. */
 int kb_finalize(kb_engine* e, int device);
-/* use an existing CUDA stream (cudaStream_t) for all later work; NULL = the engine's own stream */
+/* use an existing CUDA stream (cudaStream_t) for all later work; NULL = the engine's own non-blocking stream.
+ * The legacy default stream must be named explicitly as cudaStreamLegacy ((void*)0x1). */
 int kb_set_stream(kb_engine* e, void* cuda_stream);
 int kb_synchronize(kb_engine* e);
 /* tuning / instrumentation knobs: "collect_stats" (0|1: count node / element tests and fp64 rechecks in the kernels),

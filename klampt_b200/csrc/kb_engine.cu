@@ -150,7 +150,7 @@ inline float f_up(double x) { float f = (float)x; if ((double)f < x) f = nextaft
 inline float i2f(int32_t i) { float f; memcpy(&f, &i, 4); return f; }
 
 // device-side geometry: a flattened BVH + elements in leaf order
-struct DevGeom { int node_base = 0, nnodes = 0, elem_base = 0, nelem = 0, kind = KB_ELEM_TRI, depth = 0; double margin = 0; bool empty = true; double lo[3], hi[3]; };
+struct DevGeom { int node_base = 0, nnodes = 0, elem_base = 0, nelem = 0, kind = KB_ELEM_TRI, depth = 0; double margin = 0, rmax = 0; bool empty = true; double lo[3], hi[3]; };
 
 struct ItemSet { std::vector<KbItem> items; KbItem* d_items = nullptr; int nxf = 0; int maxdepth = 0; };
 
@@ -248,6 +248,7 @@ int append_geom(kb_engine* e, int kind, const std::vector<double>& elems, const 
       if (kind == G_MESH) { elo[3 * (size_t)i + k] = std::min(p[k], std::min(p[3 + k], p[6 + k])); ehi[3 * (size_t)i + k] = std::max(p[k], std::max(p[3 + k], p[6 + k])); }
       else { elo[3 * (size_t)i + k] = p[k] - p[3]; ehi[3 * (size_t)i + k] = p[k] + p[3]; }
     }
+    if (kind != G_MESH) dg.rmax = std::max(dg.rmax, p[3]);
   }
   Bvh bvh; build_bvh(elo, ehi, n, kind == G_MESH ? 1 : 8, bvh);
   dg.node_base = (int)(e->h_nodes.size() / 8); dg.nnodes = (int)bvh.nodes.size(); dg.depth = bvh.depth;
@@ -280,7 +281,7 @@ KbItem make_item(const DevGeom& A, int xfA, int idA, const DevGeom& B, int xfB, 
   KbItem it; memset(&it, 0, sizeof it);
   it.nodeA = A.node_base; it.nodeB = B.node_base; it.elemA = A.elem_base; it.elemB = B.elem_base;
   it.xfA = (int16_t)xfA; it.xfB = (int16_t)xfB; it.kindA = (uint8_t)A.kind; it.kindB = (uint8_t)B.kind; it.flags = self ? 1 : 0;
-  it.idA = idA; it.idB = idB; it.thr = A.margin + B.margin; it.marg = A.margin + B.margin;
+  it.idA = idA; it.idB = idB; it.thr = A.margin + B.margin; it.marg = A.margin + B.margin; it.rsum = A.rmax + B.rmax;
   return it;
 }
 // the A side of an item is limited to 2^20 nodes (stack entry packing); put the smaller hierarchy there
@@ -645,6 +646,7 @@ int kb_finalize(kb_engine* e, int device) {
 
 int kb_set_stream(kb_engine* e, void* s) {
   if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
+  // NULL = the engine's own non-blocking stream; cudaStreamLegacy (0x1) / cudaStreamPerThread (0x2) select the default streams
   e->stream = s ? (cudaStream_t)s : e->own_stream; return KB_OK;
 }
 

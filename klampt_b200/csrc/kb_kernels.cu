@@ -437,7 +437,10 @@ kb_traverse_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
           st_node++;
           bool ov;
           if (MODE == 0) ov = obb_overlap(a0, a1, b0, b1, T, (float)itp->thr + slack);
-          else ov = (double)obb_dist_lb(a0, a1, b0, b1, T) - (double)slack - itp->marg < best;
+          else {
+            float lb = obb_dist_lb(a0, a1, b0, b1, T) - slack;
+            ov = (lb > 0.f ? (double)lb : -itp->rsum) - itp->marg < best;
+          }
           if (ov) {
             const int la = __float_as_int(a0.w), lb = __float_as_int(b0.w);
             if (la < 0 && lb < 0) leafpair = true;

@@ -30,7 +30,7 @@
 
 enum { KB_ELEM_TRI = 0, KB_ELEM_SPHERE = 1 };
 
-struct KbItem {                   // 48 bytes
+struct KbItem {                   // 56 bytes
   int32_t nodeA, nodeB;           // global node index of the two roots
   int32_t elemA, elemB;           // global element base (into tris* or sph* according to kind)
   int16_t xfA, xfB;               // transform slot in the per-configuration table, -1 = identity (static world frame)
@@ -39,6 +39,7 @@ struct KbItem {                   // 48 bytes
   int32_t idA, idB;               // world ids; -1 = look the owner up per element (merged environment group)
   double thr;                     // collision threshold: margin_A + margin_B (+ tolerance); 0 = surfaces must intersect
   double marg;                    // margin_A + margin_B, subtracted from reported distances
+  double rsum;                    // largest sphere radius of A + of B: bound on how far two touching boxes' elements can interpenetrate
 };
 
 struct KbRobotDev {

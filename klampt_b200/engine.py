@@ -113,7 +113,12 @@ class Engine:
 
     # ------------------------------------------------------------------ plumbing
     def set_stream(self, stream_ptr: Optional[int]):
-        check(self.lib.kb_set_stream(self.h, C.c_void_p(stream_ptr) if stream_ptr else None))
+        """stream_ptr: a cudaStream_t as int (e.g. torch.cuda.current_stream().cuda_stream).  0 means CUDA's legacy
+        default stream (passed to the library as cudaStreamLegacy); None restores the engine's own stream."""
+        if stream_ptr is None:
+            check(self.lib.kb_set_stream(self.h, None))
+        else:
+            check(self.lib.kb_set_stream(self.h, C.c_void_p(stream_ptr if stream_ptr else 1)))
 
     def synchronize(self):
         check(self.lib.kb_synchronize(self.h))

@@ -87,6 +87,7 @@ typedef struct {
   int* perm;            /* element permutation (BVH order -> original index) */
   node_t* nodes; int nnodes;
   double lo[3], hi[3];  /* local AABB */
+  double rmax;          /* largest element radius (0 for meshes) */
 } geom_t;
 
 typedef struct { int n; int32_t* links; double* scale; double* offset; double dmin, dmax; } driver_t;
@@ -304,6 +305,7 @@ static void geom_build_bvh(geom_t* g) {
     free(g->pts); free(g->rad); g->pts=p2; g->rad=r2;
   }
   memcpy(g->lo,g->nodes[0].lo,sizeof(g->lo)); memcpy(g->hi,g->nodes[0].hi,sizeof(g->hi));
+  g->rmax=0; if (g->kind!=G_MESH) for (int i=0;i<n;i++) if (g->rad[i]>g->rmax) g->rmax=g->rad[i];
   free(elo); free(ehi); free(cents);
 }
 static inline int node_right(const geom_t* g, int i) { return g->nodes[i].right; }
@@ -502,9 +504,12 @@ static double obb_dist_lb(const node_t* a, const node_t* b, const xf_t* Tab) {
     double g=fabs(t[0]*R[j]+t[1]*R[3+j]+t[2]*R[6+j])-hb[j]-e; if (g>0) g2+=g*g; }
   double b2=sqrt(g2); return b2>best?b2:best;
 }
+/* Lower bound on the signed element distance below two nodes.  Sphere radii are inside the node boxes, so a positive
+ * box gap bounds the ball distance; when the boxes touch the balls may interpenetrate by at most the radii. */
+static inline double signed_lb(double box_lb, double rsum) { return box_lb>0 ? box_lb : -rsum; }
 static inline double node_size2(const node_t* n) { double d[3]; v_sub(n->hi,n->lo,d); return v_dot(d,d); }
 
-typedef struct { const geom_t* A; const geom_t* B; xf_t Ta, Tb, Tab; double tol; ko_counts* cnt; } pairq_t;
+typedef struct { const geom_t* A; const geom_t* B; xf_t Ta, Tb, Tab; double tol; double rsum; ko_counts* cnt; } pairq_t;
 
 /* leaf-vs-leaf: returns 1 if any element pair is within tol (tol==0: intersects) */
 static int leaf_collide(pairq_t* q, const node_t* a, const node_t* b) {
@@ -582,7 +587,7 @@ static void distance_rec(pairq_t* q, int ia, int ib, double* best) {
   const node_t* a=&q->A->nodes[ia]; const node_t* b=&q->B->nodes[ib];
   if (q->cnt) q->cnt->n_node++;
   /* elements may be spheres: their radius is already inside the node boxes */
-  if (obb_dist_lb(a,b,&q->Tab) >= *best) return;
+  if (signed_lb(obb_dist_lb(a,b,&q->Tab),q->rsum) >= *best) return;
   int la=a->left<0, lb=b->left<0;
   if (la && lb) { double d=leaf_distance(q,a,b); if (d<*best) *best=d; return; }
   if (lb || (!la && node_size2(a)>=node_size2(b))) {
@@ -596,7 +601,7 @@ static void distance_rec(pairq_t* q, int ia, int ib, double* best) {
   }
 }
 static void pairq_init(pairq_t* q, const geom_t* A, const xf_t* Ta, const geom_t* B, const xf_t* Tb, double tol, ko_counts* cnt) {
-  q->A=A; q->B=B; q->Ta=*Ta; q->Tb=*Tb; xf_mul_inv_a(Ta,Tb,&q->Tab); q->tol=tol; q->cnt=cnt; }
+  q->A=A; q->B=B; q->Ta=*Ta; q->Tb=*Tb; xf_mul_inv_a(Ta,Tb,&q->Tab); q->tol=tol; q->rsum=A->rmax+B->rmax; q->cnt=cnt; }
 
 /* a11/a13: AnyCollisionQuery::Collide / WithinDistance(tol).  Margins add to the threshold (a12). */
 static int geom_pair_collide(const geom_t* A, const xf_t* Ta, const geom_t* B, const xf_t* Tb, double tol, ko_counts* cnt) {
