@@ -52,10 +52,13 @@ typedef struct {
   int64_t edges_checked;
   int64_t edges_visible;
   int64_t edge_config_checks;   /* configurations checked on behalf of edges                           */
-  int64_t recheck_pairs;        /* element pairs sent to the fp64 recheck kernel                       */
-  int64_t recheck_overflow;     /* element pairs rechecked inline because the recheck queue was full   */
+  int64_t node_tests;           /* BV-pair tests        } counted only while option "collect_stats" = 1 */
+  int64_t elem_tests;           /* element-pair tests   }                                              */
+  int64_t recheck_pairs;        /* element pairs re-run in fp64 because the fp32 filter was uncertain  */
   int64_t kernel_launches;      /* launches of this library's kernels                                  */
-  double  gpu_ms;               /* device time of those launches as measured with CUDA events          */
+  int64_t traverse_launches;    /* launches of the traversal kernel timed while option "time_kernels" = 1 */
+  double  traverse_ms;          /* their summed device time (CUDA events on the engine's stream)        */
+  double  gpu_ms;               /* device time of the host-buffer entry points, copies included         */
 } kb_stats;
 
 /* ---- lifetime ---------------------------------------------------------------------------------------- */
@@ -106,6 +109,7 @@ int kb_finalize(kb_engine* e, int device);
 int kb_set_stream(kb_engine* e, void* cuda_stream);
 int kb_synchronize(kb_engine* e);
 /* tuning / instrumentation knobs: "collect_stats" (0|1: count node / element tests and fp64 rechecks in the kernels),
+ * "time_kernels" (0|1: bracket every traversal launch with CUDA events on the engine's stream, summed into kb_stats),
  * "chunk" (configurations per kernel launch; the default keeps one chunk's transforms resident in L2) */
 int kb_set_option(kb_engine* e, const char* name, int64_t value);
 

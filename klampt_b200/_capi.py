@@ -20,8 +20,9 @@ c_int64_p = C.POINTER(C.c_int64)
 
 class KbStats(C.Structure):
     _fields_ = [("configs_checked", C.c_int64), ("configs_feasible", C.c_int64), ("edges_checked", C.c_int64),
-                ("edges_visible", C.c_int64), ("edge_config_checks", C.c_int64), ("recheck_pairs", C.c_int64),
-                ("recheck_overflow", C.c_int64), ("kernel_launches", C.c_int64), ("gpu_ms", C.c_double)]
+                ("edges_visible", C.c_int64), ("edge_config_checks", C.c_int64), ("node_tests", C.c_int64),
+                ("elem_tests", C.c_int64), ("recheck_pairs", C.c_int64), ("kernel_launches", C.c_int64),
+                ("traverse_launches", C.c_int64), ("traverse_ms", C.c_double), ("gpu_ms", C.c_double)]
 
 
 # every symbol include/klampt_b200.h declares: name -> (restype, argtypes)

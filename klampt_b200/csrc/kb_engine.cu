@@ -145,7 +145,7 @@ void build_bvh(const std::vector<double>& elo, const std::vector<double>& ehi, i
   }
 }
 
-inline float f_down(double x) { float f = (float)x; if ((double)f > x) f = nextafterf(f, -INFINITY); return f; }
+
 inline float f_up(double x) { float f = (float)x; if ((double)f < x) f = nextafterf(f, INFINITY); return f; }
 inline float i2f(int32_t i) { float f; memcpy(&f, &i, 4); return f; }
 
@@ -203,7 +203,9 @@ struct kb_engine {
   // ---- stats
   kb_stats stats{};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  bool collect_stats = false;
+  bool collect_stats = false, time_kernels = false;
+  std::vector<cudaEvent_t> tev;             // event pairs around traversal launches (time_kernels)
+  size_t tev_used = 0;
 };
 
 namespace {
@@ -255,7 +257,12 @@ int append_geom(kb_engine* e, int kind, const std::vector<double>& elems, const 
   dg.elem_base = kind == G_MESH ? (int)(e->h_tris64.size() / 9) : (int)(e->h_sph64.size() / 4);
   memcpy(dg.lo, bvh.nodes[0].lo, 24); memcpy(dg.hi, bvh.nodes[0].hi, 24);
   for (const BNode& nd : bvh.nodes) {
-    float v[8] = {f_down(nd.lo[0]), f_down(nd.lo[1]), f_down(nd.lo[2]), 0.f, f_up(nd.hi[0]), f_up(nd.hi[1]), f_up(nd.hi[2]), 0.f};
+    float v[8];
+    for (int k = 0; k < 3; k++) {   // centre / half extent; the fp32 box must contain the fp64 one
+      float c = (float)(0.5 * (nd.lo[k] + nd.hi[k]));
+      v[k] = c; v[4 + k] = f_up(std::max(nd.hi[k] - (double)c, (double)c - nd.lo[k]));
+    }
+    v[3] = v[7] = 0.f;
     if (nd.left >= 0) { v[3] = i2f(nd.left); v[7] = i2f(0); }
     else { v[3] = i2f(~nd.first); v[7] = i2f(nd.count); }
     e->h_nodes.insert(e->h_nodes.end(), v, v + 8);
@@ -333,6 +340,28 @@ void end_timing(kb_engine* e, bool sync) {
   if (sync) { cudaEventSynchronize(e->ev1); float ms = 0; if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->stats.gpu_ms += ms; }
 }
 
+// resolves the pending traversal event pairs into stats.traverse_ms (needs the stream to have drained)
+void fold_kernel_times(kb_engine* e) {
+  for (size_t i = 0; i + 1 < e->tev_used; i += 2) {
+    float ms = 0;
+    if (cudaEventSynchronize(e->tev[i + 1]) == cudaSuccess && cudaEventElapsedTime(&ms, e->tev[i], e->tev[i + 1]) == cudaSuccess) {
+      e->stats.traverse_ms += ms; e->stats.traverse_launches++;
+    }
+  }
+  e->tev_used = 0;
+}
+cudaError_t timed_traverse(kb_engine* e, const KbTraverseParams& p, int mode, double* out_dist, double ub) {
+  if (!e->time_kernels) return kb_launch_traverse(p, mode, out_dist, ub, e->num_sms, e->stream);
+  if (e->tev_used + 2 > 8192) fold_kernel_times(e);
+  while (e->tev.size() < e->tev_used + 2) { cudaEvent_t ev; cudaError_t ce = cudaEventCreate(&ev); if (ce != cudaSuccess) return ce; e->tev.push_back(ev); }
+  // the work-counter memset is part of kb_launch_traverse: keep it outside the bracket by issuing a no-op ordering point first
+  cudaEventRecord(e->tev[e->tev_used], e->stream);
+  cudaError_t ce = kb_launch_traverse(p, mode, out_dist, ub, e->num_sms, e->stream);
+  cudaEventRecord(e->tev[e->tev_used + 1], e->stream);
+  e->tev_used += 2;
+  return ce;
+}
+
 KbTraverseParams make_params(kb_engine* e, const ItemSet& set, const double* xf, int64_t n, const uint8_t* state) {
   KbTraverseParams p; memset(&p, 0, sizeof p);
   p.scene = e->scene; p.items = set.d_items; p.nitems = (int)set.items.size(); p.nxf = set.nxf; p.xf64 = xf; p.N = n; p.state = state;
@@ -350,7 +379,7 @@ int run_feasible_device(kb_engine* e, const double* dQ, int64_t N, uint8_t* d_ou
     e->stats.kernel_launches++;
     if (!e->feas_items.items.empty()) {
       KbTraverseParams p = make_params(e, e->feas_items, e->d_xf, n, e->d_state);
-      CK(kb_launch_traverse(p, 0, nullptr, 0.0, e->num_sms, e->stream));
+      CK(timed_traverse(e, p, 0, nullptr, 0.0));
       e->stats.kernel_launches++;
     }
     CK(kb_launch_finish(e->d_state, e->d_hit, e->d_hit_elem, e->feas_items.d_items, e->d_triown, e->d_sphown, n, d_out + off,
@@ -390,6 +419,7 @@ void kb_engine_destroy(kb_engine* e) {
     for (void* p : ptrs) if (p) cudaFree(p);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
+    for (cudaEvent_t ev : e->tev) cudaEventDestroy(ev);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
   }
   delete e;
@@ -653,6 +683,7 @@ int kb_set_stream(kb_engine* e, void* s) {
 int kb_set_option(kb_engine* e, const char* name, int64_t value) {
   if (!e || !name) return fail(KB_ERR_INVALID, "null argument");
   if (!strcmp(name, "collect_stats")) { e->collect_stats = value != 0; return KB_OK; }
+  if (!strcmp(name, "time_kernels")) { e->time_kernels = value != 0; return KB_OK; }
   if (!strcmp(name, "chunk")) {
     if (value < 256 || value > (1 << 22)) return fail(KB_ERR_INVALID, "chunk must be in [256, 4194304]");
     e->chunk = value; return KB_OK;
@@ -804,7 +835,7 @@ int kb_distance_batch_device(kb_engine* e, const double* dQ, int64_t N, double u
     CK(kb_launch_fk(e->d_robot, e->d_drv, e->d_drv_link, e->d_drv_scale, e->d_drv_off, dQ + off * e->L, n, e->d_xf, set.nxf, nullptr, nullptr, e->d_hit, e->stream));
     e->stats.kernel_launches++;
     KbTraverseParams p = make_params(e, set, e->d_xf, n, nullptr);
-    if (p.nitems > 0) { CK(kb_launch_traverse(p, 1, d_out_d + off, upper_bound, e->num_sms, e->stream)); e->stats.kernel_launches++; }
+    if (p.nitems > 0) { CK(timed_traverse(e, p, 1, d_out_d + off, upper_bound)); e->stats.kernel_launches++; }
     else return fail(KB_ERR_STATE, "no enabled geometry pairs to measure");
     if (d_out_pair) { CK(kb_launch_pair_ids(e->d_hit, e->d_hit_elem, set.d_items, e->d_triown, e->d_sphown, n, d_out_pair + 2 * off, e->stream)); e->stats.kernel_launches++; }
   }
@@ -887,7 +918,9 @@ int kb_get_stats(kb_engine* e, kb_stats* out) {
   if (e->finalized) {
     CK(cudaSetDevice(e->device)); CK(cudaStreamSynchronize(e->stream));
     unsigned long long c[8]; CK(cudaMemcpy(c, e->d_counters, 64, cudaMemcpyDeviceToHost));
-    e->stats.recheck_pairs = (int64_t)c[0]; e->stats.configs_feasible = (int64_t)c[3]; e->stats.edges_visible = (int64_t)c[4];
+    e->stats.recheck_pairs = (int64_t)c[0]; e->stats.node_tests = (int64_t)c[1]; e->stats.elem_tests = (int64_t)c[2];
+    e->stats.configs_feasible = (int64_t)c[3]; e->stats.edges_visible = (int64_t)c[4];
+    fold_kernel_times(e);
   }
   *out = e->stats; return KB_OK;
 }
@@ -895,6 +928,7 @@ int kb_get_stats(kb_engine* e, kb_stats* out) {
 int kb_reset_stats(kb_engine* e) {
   if (!e) return fail(KB_ERR_INVALID, "null argument");
   memset(&e->stats, 0, sizeof e->stats);
+  e->tev_used = 0;
   if (e->finalized) { CK(cudaSetDevice(e->device)); CK(cudaMemsetAsync(e->d_counters, 0, 64, e->stream)); }
   return KB_OK;
 }

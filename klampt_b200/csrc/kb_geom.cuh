@@ -62,24 +62,25 @@ template <class T> __device__ __forceinline__ T maxabs(const V3<T>& a) { return 
 // ---------------------------------------------------------------------------------------------------------------
 // Filtered sign.  side(a,b,c,d) = (d-a).((b-a)x(c-a)) > 0  iff d lies on the side of plane abc its normal points to.
 // fp32 error model: every coordinate of the six vertices carries an absolute error <= delta (transform rounding,
-// kb_finalize derives delta from the scene extent), so each difference carries 2*delta (+ half an ulp); with M the
-// largest |component| of the three difference vectors the determinant moves by at most 9 cofactors * 2M^2 * 2*delta
-// = 36 delta M^2, and rounding of the 3x3 expansion adds < 4e-6 M^3.  filt = 64*delta leaves a 1.7x safety factor.
-struct FiltF { float filt; };   // fp32: filt = 64 * delta
+// kb_finalize derives delta from the scene extent), so each difference carries 2*delta (+ half an ulp).  With
+// Mu, Mv, Mw the largest |component| of the three difference vectors u, v, w, every cofactor of an entry of row u is
+// bounded by 2*Mv*Mw (and cyclically), so perturbing the 9 entries by 2*delta moves the determinant by at most
+// 3*2*delta*2*(MvMw + MuMw + MuMv) = 12 delta (MuMv + MvMw + MwMu); rounding of the 3x3 expansion adds
+// < 4e-6 Mu Mv Mw.  filt = 24*delta leaves a 2x safety factor.
+struct FiltF { float filt; };   // fp32: filt = 24 * delta
 struct FiltE {};                // exact: sign of the fp64 value, zero is zero
 
-__device__ __forceinline__ int kb_sign(float det, float M, const FiltF& f) {
-  float thr = M * M * (f.filt + 4e-6f * M);
+__device__ __forceinline__ int kb_sign(float det, float Mu, float Mv, float Mw, const FiltF& f) {
+  float thr = f.filt * (Mu * Mv + Mv * Mw + Mw * Mu) + 4e-6f * Mu * Mv * Mw;
   return det > thr ? 1 : (det < -thr ? -1 : KB_UNCERTAIN);
 }
-__device__ __forceinline__ int kb_sign(ExactD det, ExactD, const FiltE&) { return det.v > 0.0 ? 1 : (det.v < 0.0 ? -1 : 0); }
+__device__ __forceinline__ int kb_sign(ExactD det, ExactD, ExactD, ExactD, const FiltE&) { return det.v > 0.0 ? 1 : (det.v < 0.0 ? -1 : 0); }
 
 template <class T, class F>
 __device__ __forceinline__ int side_sign(const V3<T>& a, const V3<T>& b, const V3<T>& c, const V3<T>& d, const F& f) {
   V3<T> u = b - a, v = c - a, w = d - a;
   T det = dot(w, cross(u, v));
-  T M = kb_max(maxabs(u), kb_max(maxabs(v), maxabs(w)));
-  return kb_sign(det, M, f);
+  return kb_sign(det, maxabs(u), maxabs(v), maxabs(w), f);
 }
 
 // exact 2D helpers for the coplanar case (fp64 only)

@@ -2,10 +2,10 @@
 //
 // HBM layout (all static data is uploaded once at kb_finalize and then read-only):
 //   nodes    float4[2*n]   flattened BVHs of every geometry, one after the other.  Node i of a geometry =
-//                          { lo.xyz, as_float(left) } { hi.xyz, as_float(count) }.  left >= 0: inner node,
+//                          { centre.xyz, as_float(left) } { half_extent.xyz, as_float(count) }.  left >= 0: inner node,
 //                          children at left and left+1 (siblings adjacent, indices relative to the geometry's
 //                          node base).  left < 0: leaf, first element = ~left (relative to the geometry's element
-//                          base), count elements.  Boxes are fp32, rounded outwards from the fp64 build.
+//                          base), count elements.  Boxes are fp32; half extents are rounded up so the fp32 box contains the fp64 one.
 //   tris32   float4[3*n]   triangle vertices (fp32, local frame; merged environment groups: world frame);
 //                          .w of vertex 0 = as_float(owner world id)
 //   tris64   double[9*n]   the same triangles in fp64 for the exact recheck
@@ -20,7 +20,7 @@
 #include <stdint.h>
 
 #define KB_MAX_LINKS 128          // links per robot supported by the FK kernel's shared-memory model
-#define KB_STACK_CAP 1024         // node-pair stack entries per warp
+#define KB_STACK_CAP 512          // node-pair stack entries per warp
 #define KB_LEAFQ_CAP 64           // leaf-pair queue entries per warp
 #define KB_ITEM_BITS 12
 #define KB_NODEA_BITS 20

@@ -19,7 +19,8 @@ print("oracle %d threads: %.0f cfg/s, feasible %.3f" % (max_threads(), ns / dt, 
 eng.set_option("collect_stats", 1)
 got = eng.feasible_batch(Q[:ns])
 bad = np.nonzero(got != want)[0]
-print("mismatches:", len(bad), "stats", eng.stats())
+st = eng.stats()
+print("mismatches:", len(bad), "per config: node %.1f elem %.1f recheck %.2f" % (st["node_tests"] / ns, st["elem_tests"] / ns, st["recheck_pairs"] / ns))
 for i in bad[:10]:
     print("  cfg", i, "gpu", got[i], "oracle", want[i], "clearance", orc.distance(Q[i], 1.0, True))
 eng.set_option("collect_stats", 0)
