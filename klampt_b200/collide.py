@@ -1,0 +1,188 @@
+"""Mirror of ``klampt.model.collide.WorldCollider`` (reference Python/klampt/model/collide.py:246-362,531-698): the
+mask of geometry pairs that planning code wants checked, plus the group iterators.  The mask semantics restated:
+terrain-object; terrain-link only if the link has a parent (fixed base links rest on the terrain); object-object;
+object-link; links of different robots; self pairs from ``selfCollisionEnabled``; ``ignoreCollision`` edits.
+
+``to_pair_mask()`` turns the mask into the dense ``collisionEnabled`` matrix over world IDs that the engine's
+``kb_set_pair_mask`` takes, so ignored pairs are honoured by the batched kernels.
+"""
+from __future__ import annotations
+
+from typing import Iterator, List, Tuple
+
+import numpy as np
+
+from .robotsim import WorldModel, RobotModel, RobotModelLink, RigidObjectModel, TerrainModel
+
+
+def bb_intersect(a, b) -> bool:
+    """axis-aligned boxes (bmin,bmax) overlap, closed intervals"""
+    amin, amax = a
+    bmin, bmax = b
+    return not any(q < u or v < p for (p, q, u, v) in zip(amin, amax, bmin, bmax))
+
+
+def bb_union(*bbs):
+    return [min(*x) for x in zip(*[b[0] for b in bbs])], [max(*x) for x in zip(*[b[1] for b in bbs])]
+
+
+class WorldCollider:
+    def __init__(self, world: WorldModel, ignore=()):
+        self.world = world
+        self.geomList: List[Tuple[object, object]] = []
+        self.mask: List[set] = []
+        self.terrains: List[int] = []
+        self.rigidObjects: List[int] = []
+        self.robots: List[List[int]] = []
+        self._ids: List[int] = []                       # world id of each geomList entry
+
+        def add(obj, wid) -> int:
+            g = obj.geometry()
+            if g is None or g.type() == "":
+                return -1
+            self.geomList.append((obj, g))
+            self._ids.append(wid)
+            return len(self.geomList) - 1
+
+        for i in range(world.numTerrains()):
+            self.terrains.append(add(world.terrain(i), world.terrainID(i)))
+        for i in range(world.numRigidObjects()):
+            self.rigidObjects.append(add(world.rigidObject(i), world.rigidObjectID(i)))
+        for r in range(world.numRobots()):
+            rob = world.robot(r)
+            self.robots.append([add(rob.link(j), world.robotLinkID(r, j)) for j in range(rob.numLinks())])
+        self.mask = [set() for _ in self.geomList]
+
+        def on(a, b):
+            if a >= 0 and b >= 0:
+                self.mask[a].add(b)
+                self.mask[b].add(a)
+
+        for t in self.terrains:
+            for o in self.rigidObjects:
+                on(t, o)
+            for links in self.robots:
+                for l in links:
+                    if l >= 0 and self.geomList[l][0].getParent() >= 0:    # fixed links are allowed to touch the terrain
+                        on(t, l)
+        for k, o in enumerate(self.rigidObjects):
+            for o2 in self.rigidObjects[:k]:
+                on(o, o2)
+            for links in self.robots:
+                for l in links:
+                    on(o, l)
+        for r, links in enumerate(self.robots):
+            for other in self.robots[:r]:
+                for l1 in links:
+                    for l2 in other:
+                        on(l1, l2)
+            rob = world.robot(r)
+            for i in range(rob.numLinks()):
+                for j in range(i):
+                    if rob.selfCollisionEnabled(i, j):
+                        on(links[i], links[j])
+        for item in ignore:
+            self.ignoreCollision(item)
+
+    # ------------------------------------------------------------------ mask edits
+    def _getGeomIndex(self, obj) -> int:
+        if isinstance(obj, int):
+            return obj
+        for i, (o, g) in enumerate(self.geomList):
+            if o is obj:
+                return i
+        return -1
+
+    def ignoreCollision(self, ign):
+        """ign: an object (all its pairs are dropped) or a pair of objects"""
+        if isinstance(ign, (tuple, list)) and len(ign) == 2:
+            a, b = self._getGeomIndex(ign[0]), self._getGeomIndex(ign[1])
+            if a < 0 or b < 0:
+                raise ValueError("Invalid ignore collision item, must be a pair of bodies in the world")
+            self.mask[a].discard(b)
+            self.mask[b].discard(a)
+        else:
+            a = self._getGeomIndex(ign)
+            if a < 0:
+                raise ValueError("Invalid ignore collision item, must be a body in the world")
+            for b in list(self.mask[a]):
+                self.mask[b].discard(a)
+            self.mask[a] = set()
+
+    def isCollisionEnabled(self, obj_or_pair) -> bool:
+        if isinstance(obj_or_pair, (tuple, list)) and len(obj_or_pair) == 2:
+            a, b = self._getGeomIndex(obj_or_pair[0]), self._getGeomIndex(obj_or_pair[1])
+            return a >= 0 and b >= 0 and b in self.mask[a]
+        a = self._getGeomIndex(obj_or_pair)
+        return a >= 0 and len(self.mask[a]) > 0
+
+    def to_pair_mask(self) -> np.ndarray:
+        """dense collisionEnabled matrix over world IDs (row-major, symmetric) for kb_set_pair_mask"""
+        n = self.world.numIDs()
+        m = np.zeros((n, n), dtype=np.uint8)
+        for a, s in enumerate(self.mask):
+            for b in s:
+                ia, ib = self._ids[a], self._ids[b]
+                m[min(ia, ib), max(ia, ib)] = 1          # upper triangular like selfCollisions(j,k), j<k ...
+                if not (self._is_link(a) and self._is_link(b)):
+                    m[max(ia, ib), min(ia, ib)] = 1      # ... and symmetric for robot-vs-environment entries
+        return m
+
+    def _is_link(self, a) -> bool:
+        return isinstance(self.geomList[a][0], RobotModelLink)
+
+    # ------------------------------------------------------------------ iterators (pairs that collide right now)
+    def _colliding(self, a: int, b: int) -> bool:
+        return self.geomList[a][1].collides(self.geomList[b][1])
+
+    def collisionTests(self, filter1=None, filter2=None, bb_reject=True) -> Iterator[Tuple[tuple, tuple]]:
+        for a, s in enumerate(self.mask):
+            for b in s:
+                if a < b:
+                    A, B = self.geomList[a], self.geomList[b]
+                    if filter1 is not None and not filter1(A[0]):
+                        continue
+                    if filter2 is not None and not filter2(B[0]):
+                        continue
+                    if bb_reject and not bb_intersect(A[1].getBB(), B[1].getBB()):
+                        continue
+                    yield A, B
+
+    def collisions(self, filter1=None, filter2=None):
+        for A, B in self.collisionTests(filter1, filter2):
+            if A[1].collides(B[1]):
+                yield A[0], B[0]
+
+    def robotSelfCollisions(self, robot=0):
+        if isinstance(robot, RobotModel):
+            robot = robot.index
+        links = self.robots[robot]
+        for i, a in enumerate(links):
+            for b in links[:i]:
+                if a >= 0 and b >= 0 and b in self.mask[a] and bb_intersect(self.geomList[a][1].getBB(), self.geomList[b][1].getBB()) \
+                        and self._colliding(a, b):
+                    yield self.geomList[b][0], self.geomList[a][0]
+
+    def robotObjectCollisions(self, robot, object=None):
+        if isinstance(robot, RobotModel):
+            robot = robot.index
+        objs = range(len(self.rigidObjects)) if object is None else [object.index if isinstance(object, RigidObjectModel) else object]
+        for o in objs:
+            b = self.rigidObjects[o]
+            if b < 0:
+                continue
+            for a in self.robots[robot]:
+                if a >= 0 and b in self.mask[a] and bb_intersect(self.geomList[a][1].getBB(), self.geomList[b][1].getBB()) and self._colliding(a, b):
+                    yield self.geomList[a][0], self.geomList[b][0]
+
+    def robotTerrainCollisions(self, robot, terrain=None):
+        if isinstance(robot, RobotModel):
+            robot = robot.index
+        ters = range(len(self.terrains)) if terrain is None else [terrain.index if isinstance(terrain, TerrainModel) else terrain]
+        for t in ters:
+            b = self.terrains[t]
+            if b < 0:
+                continue
+            for a in self.robots[robot]:
+                if a >= 0 and b in self.mask[a] and bb_intersect(self.geomList[a][1].getBB(), self.geomList[b][1].getBB()) and self._colliding(a, b):
+                    yield self.geomList[a][0], self.geomList[b][0]

@@ -1,0 +1,146 @@
+"""Mirror of ``klampt.plan.cspace.CSpace`` (reference Python/klampt/plan/cspace.py:76-214) for the members the
+feasibility / visibility path uses: ``eps``, ``bound``, ``properties``, ``addFeasibilityTest(func,name,dependencies)``,
+``feasible``, ``isFeasible``, ``isVisible``, ``getStats``, ``setup``, ``close``.  The reference forwards
+``isFeasible`` / ``isVisible`` to the C++ ``CSpaceInterface`` (per-test timing, bisection edge checker,
+Python/klampt/src/motionplanning.cpp:163-175,383-401,1031-1055); here the same bookkeeping is kept on the host and
+subclasses (``RobotCSpace``) route the actual tests to the GPU engine, one configuration or a batch at a time."""
+from __future__ import annotations
+
+import random
+import time
+from typing import Callable, List, Optional, Sequence, Tuple, Union
+
+
+class CSpace:
+    def __init__(self):
+        self.cspace = None
+        self.feasibilityTests: Optional[List[Callable]] = None
+        self.feasibilityTestNames: Optional[List[str]] = None
+        self.feasibilityTestDependencies: Optional[List[Tuple[str, str]]] = None
+        self.eps = 1e-3
+        self.bound: List[Tuple[float, float]] = [(0, 1)]
+        self.properties = {}
+        self._stats = {"feasible_count": 0, "feasible_true": 0, "feasible_time": 0.0,
+                       "visible_count": 0, "visible_true": 0, "visible_time": 0.0, "visible_length": 0.0}
+        self._test_stats = {}
+
+    # ------------------------------------------------------------------ bounds / sampling
+    def setBounds(self, bound: Sequence[Tuple[float, float]]):
+        self.bound = list(bound)
+        self.properties["minimum"] = [b[0] for b in bound]
+        self.properties["maximum"] = [b[1] for b in bound]
+        volume = 1
+        for b in self.bound:
+            if b[0] != b[1]:
+                volume *= b[1] - b[0]
+        self.properties["volume"] = volume
+
+    def sample(self):
+        return [random.uniform(*b) for b in self.bound]
+
+    def sampleneighborhood(self, c, r):
+        return [random.uniform(max(b[0], ci - r), min(b[1], ci + r)) for ci, b in zip(c, self.bound)]
+
+    def inBounds(self, x) -> bool:
+        return all(a <= xi <= b for (xi, (a, b)) in zip(x, self.bound))
+
+    # ------------------------------------------------------------------ tests
+    def addFeasibilityTest(self, func: Callable, name: Optional[str] = None, dependencies: Optional[Union[str, List[str]]] = None):
+        if self.feasibilityTests is None:
+            self.feasibilityTests, self.feasibilityTestNames, self.feasibilityTestDependencies = [], [], []
+        assert name is None or isinstance(name, str), "Name argument 'name' must be a string"
+        assert callable(func), "Feasibility test 'func' must be a callable object"
+        self.feasibilityTests.append(func)
+        if name is None:
+            name = "test_" + str(len(self.feasibilityTests) - 1)
+        self.feasibilityTestNames.append(name)
+        if dependencies is not None:
+            for d in (dependencies if isinstance(dependencies, (list, tuple)) else [dependencies]):
+                self.feasibilityTestDependencies.append((name, d))
+
+    def feasible(self, x) -> bool:
+        if self.feasibilityTests is None:
+            return self.inBounds(x)
+        for test in self.feasibilityTests:
+            if not test(x):
+                return False
+        return True
+
+    def feasibilityFailures(self, x) -> List[str]:
+        """names of the tests that fail at x (CSpaceInterface::feasibilityFailures)"""
+        if self.feasibilityTests is None:
+            return [] if self.inBounds(x) else ["bounds"]
+        return [n for n, t in zip(self.feasibilityTestNames, self.feasibilityTests) if not t(x)]
+
+    def distance(self, a, b) -> float:
+        return sum((p - q) ** 2 for p, q in zip(a, b)) ** 0.5
+
+    def interpolate(self, a, b, u):
+        return [p * (1.0 - u) + q * u for p, q in zip(a, b)]
+
+    # ------------------------------------------------------------------ the CSpaceInterface face
+    def setup(self, reinit: bool = False):
+        self.cspace = self
+
+    def close(self):
+        self.cspace = None
+
+    def isFeasible(self, x) -> bool:
+        t0 = time.perf_counter()
+        if self.feasibilityTests is None:
+            ok = self.feasible(x)
+        else:
+            ok = True
+            for n, test in zip(self.feasibilityTestNames, self.feasibilityTests):
+                t1 = time.perf_counter()
+                r = bool(test(x))
+                s = self._test_stats.setdefault(n, [0, 0, 0.0])
+                s[0] += 1
+                s[1] += int(r)
+                s[2] += time.perf_counter() - t1
+                if not r:
+                    ok = False
+                    break
+        self._stats["feasible_count"] += 1
+        self._stats["feasible_true"] += int(ok)
+        self._stats["feasible_time"] += time.perf_counter() - t0
+        return ok
+
+    def isVisible(self, a, b) -> bool:
+        """EpsilonEdgeChecker on this space's own distance / interpolate / feasible: bisect until the segment length is
+        <= eps, midpoints coarse to fine, endpoints not re-checked (reference SURVEY 3.2; resolution ``self.eps``)."""
+        t0 = time.perf_counter()
+        if hasattr(self, "visible"):
+            ok = bool(self.visible(a, b))
+        else:
+            ok = True
+            length = self.distance(a, b)
+            segs = 1
+            while length > self.eps and ok:
+                segs *= 2
+                length *= 0.5
+                for k in range(1, segs, 2):
+                    if not self.feasible(self.interpolate(a, b, float(k) / segs)):
+                        ok = False
+                        break
+        self._stats["visible_count"] += 1
+        self._stats["visible_true"] += int(ok)
+        self._stats["visible_time"] += time.perf_counter() - t0
+        self._stats["visible_length"] += self.distance(a, b)
+        return ok
+
+    def getStats(self) -> dict:
+        """same keys as CSpaceInterface::getStats (motionplanning.cpp:1031-1055)"""
+        s = self._stats
+        out = {"feasible_count": s["feasible_count"],
+               "feasible_probability": s["feasible_true"] / s["feasible_count"] if s["feasible_count"] else 0.0,
+               "feasible_time": s["feasible_time"] / s["feasible_count"] if s["feasible_count"] else 0.0,
+               "visible_count": s["visible_count"],
+               "visible_probability": s["visible_true"] / s["visible_count"] if s["visible_count"] else 0.0,
+               "visible_time": s["visible_time"] / s["visible_count"] if s["visible_count"] else 0.0,
+               "average_visible_length": s["visible_length"] / s["visible_count"] if s["visible_count"] else 0.0}
+        for n, (cnt, tr, tm) in self._test_stats.items():
+            out[n + "_count"] = cnt
+            out[n + "_probability"] = tr / cnt if cnt else 0.0
+            out[n + "_time"] = tm / cnt if cnt else 0.0
+        return out

@@ -1,0 +1,120 @@
+"""Mirror of ``klampt.plan.robotcspace.RobotCSpace`` (reference Python/klampt/plan/robotcspace.py:11-130) and of the
+C++ ``SingleRobotCSpace`` batch entry points the north star adds (``IsFeasibleBatch`` / ``IsVisibleBatch``).
+
+The reference evaluates, per configuration and through several Python<->C++ crossings, the named tests
+"joint limits" -> "setconfig" -> "calcbb" -> "self collision" -> "obj collision i" -> "terrain collision i".
+Here one engine call evaluates the conjunction of all of them for a whole batch on the GPU:
+
+    space = RobotCSpace(robot, collider)
+    ok  = space.feasible_batch(Q)            # (N,) uint8, SingleRobotCSpace::IsFeasible per row
+    vis = space.visible_batch(A, B)          # (N,) uint8, EpsilonEdgeChecker(a,b,eps).IsVisible per row
+
+``feasible(q)`` / ``isVisible(a,b)`` stay available for planners that call one configuration at a time."""
+from __future__ import annotations
+
+import math
+import random
+from typing import Optional
+
+import numpy as np
+
+from . import collide
+from .cspace import CSpace
+from .engine import Engine
+from .robotsim import RobotModel
+
+
+class RobotCSpace(CSpace):
+    def __init__(self, robot: RobotModel, collider: Optional[collide.WorldCollider] = None, device: int = 0):
+        CSpace.__init__(self)
+        self.robot = robot
+        self.collider = collider
+        self.setBounds(list(zip(*robot.getJointLimits())))
+        self.eps = 1e-2                                  # robotplanning.make_space(edgeCheckResolution=1e-2)
+        self.properties["geodesic"] = 1
+        self.joint_limit_failures = [0] * len(self.bound)
+        if collider is not None:
+            spec = collider.world.to_spec(robot.index, pair_mask=collider.to_pair_mask())
+        else:                                            # self-collisions only
+            from .worldspec import WorldSpec
+            spec = WorldSpec()
+            spec.robot = robot.to_spec(spec)
+        self.spec = spec
+        self.engine = Engine(spec, device=device)
+        # the named tests of the reference, each answered by the engine for one configuration
+        self.addFeasibilityTest(lambda x: self.inJointLimits(x), "joint limits")
+        self.addFeasibilityTest(lambda x: bool(self.engine.feasible_batch(np.asarray(x, dtype=np.float64))[0]), "collision free")
+
+    # ------------------------------------------------------------------ batch entry points
+    def feasible_batch(self, Q, return_pairs: bool = False):
+        return self.engine.feasible_batch(Q, return_pairs=return_pairs)
+
+    def visible_batch(self, A, B, eps: Optional[float] = None, return_nchecks: bool = False):
+        return self.engine.edges_visible_batch(A, B, eps=self.eps if eps is None else eps, return_nchecks=return_nchecks)
+
+    def distance_batch(self, Q, upper_bound: float = float("inf"), include_self: bool = False):
+        return self.engine.distance_batch(Q, upper_bound=upper_bound, include_self=include_self)
+
+    # ------------------------------------------------------------------ single-configuration face
+    def feasible(self, x) -> bool:
+        return bool(self.engine.feasible_batch(np.asarray(x, dtype=np.float64))[0])
+
+    def visible(self, a, b) -> bool:
+        return bool(self.engine.edges_visible_batch(np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64), eps=self.eps,
+                                                    return_nchecks=False)[0])
+
+    def addConstraint(self, checker, name=None):
+        self.addFeasibilityTest(checker, name)
+
+    def sample(self):
+        res = CSpace.sample(self)
+        for i, x in enumerate(res):
+            if math.isnan(x) or math.isinf(x):
+                res[i] = random.uniform(0, math.pi * 2.0)
+        return res
+
+    def inJointLimits(self, x) -> bool:
+        for i, (xi, bi) in enumerate(zip(x, self.bound)):
+            if xi < bi[0] or xi > bi[1]:
+                self.joint_limit_failures[i] += 1
+                return False
+        return True
+
+    def selfCollision(self, x=None) -> bool:
+        if x is not None:
+            self.robot.setConfig(x)
+        return self.robot.selfCollides()
+
+    def envCollision(self, x=None) -> bool:
+        if self.collider is None:
+            return False
+        q = np.asarray(self.robot.getConfig() if x is None else x, dtype=np.float64)
+        return self._env_hit(q)
+
+    def _env_hit(self, q) -> bool:
+        ok, pair = self.engine.feasible_batch(q, return_pairs=True)
+        if ok[0]:
+            return False
+        rid = self.spec.robot_id()
+        if pair[0, 0] < 0:
+            return False                                  # infeasible by limits only
+        return not (pair[0, 0] > rid and pair[0, 1] > rid) or self._env_only_hit(q)
+
+    def _env_only_hit(self, q) -> bool:
+        # the reported pair was a self pair: ask for the environment clearance explicitly
+        d = self.engine.distance_batch(q, upper_bound=1e-12, include_self=False)
+        return bool(d[0] <= 0.0)
+
+    def interpolate(self, a, b, u):
+        return self.robot.interpolate(a, b, u)
+
+    def distance(self, a, b):
+        return self.robot.distance(a, b)
+
+    def executablePath(self, path):
+        return path
+
+    def getStats(self) -> dict:
+        out = CSpace.getStats(self)
+        out.update({"engine_" + k: v for k, v in self.engine.stats().items()})
+        return out

@@ -1,0 +1,102 @@
+"""Host logic of the reference-facing adapters that does not need a GPU: WorldCollider mask semantics against the
+oracle's InitializeDefault mask, CSpace bookkeeping, world <-> spec round trip, sharding arithmetic."""
+import numpy as np
+import pytest
+
+from klampt_b200 import synth
+from klampt_b200.collide import WorldCollider, bb_intersect
+from klampt_b200.cspace import CSpace
+from klampt_b200.robotsim import WorldModel, Geometry3D, TriangleMesh
+from klampt_b200.shard import shard_range, interleaved_indices
+from oracle.oracle import OracleWorld
+
+
+def test_world_spec_round_trip():
+    spec = synth.world_c1()
+    world = WorldModel.from_spec(spec)
+    assert world.numTerrains() == 1 and world.numRigidObjects() == 10 and world.numRobots() == 1
+    assert world.numIDs() == spec.num_ids() and world.robotLinkID(0, 3) == spec.robot_link_id(3)
+    back = world.to_spec()
+    assert back.total_tris() == spec.total_tris()
+    for (g0, T0), (g1, T1) in zip(spec.objects, back.objects):
+        assert np.allclose(T0, T1)
+        assert np.array_equal(spec.geoms[g0].tris, back.geoms[g1].tris)
+    r = world.robot(0)
+    assert r.numLinks() == 7 and r.link(2).getParent() == 1 and not r.link(2).isPrismatic()
+    R, t = r.link(3).getParentTransform()
+    assert np.allclose(t, spec.robot.T0[3, 9:]) and len(R) == 9
+    assert r.selfCollisionEnabled(0, 2) and not r.selfCollisionEnabled(2, 3) and r.selfCollisionEnabled(3, 1)
+    r.enableSelfCollision(0, 2, False)
+    assert not r.selfCollisionEnabled(2, 0)
+
+
+def test_world_collider_mask_matches_initialize_default():
+    """collide.py:326-359 restates PlannerSettings.cpp:16-41; both must enable exactly the same robot pairs"""
+    spec = synth.world_c1()
+    world = WorldModel.from_spec(spec)
+    col = WorldCollider(world)
+    m = col.to_pair_mask()
+    ref = OracleWorld(spec).pair_mask()
+    rid, base, L = spec.robot_id(), spec.robot_link_id(0), spec.robot.L
+    for j in range(L):
+        for s in range(rid):                                   # link vs terrain / object
+            assert bool(m[base + j, s] or m[s, base + j]) == bool(ref[base + j, s] or ref[s, base + j])
+        for k in range(j + 1, L):                              # self pairs, upper triangular
+            assert m[base + j, base + k] == ref[base + j, base + k]
+    # ignoreCollision of one pair and of a whole body
+    col.ignoreCollision((world.robot(0).link(6), world.rigidObject(0)))
+    col.ignoreCollision(world.rigidObject(1))
+    m2 = col.to_pair_mask()
+    assert m2[base + 6, spec.rigid_object_id(0)] == 0 and m2[spec.rigid_object_id(0), base + 6] == 0
+    assert not m2[:, spec.rigid_object_id(1)].any() and not m2[spec.rigid_object_id(1), :].any()
+    assert m2[base + 5, spec.rigid_object_id(0)] == 1
+    assert not col.isCollisionEnabled(world.rigidObject(1)) and col.isCollisionEnabled((world.robot(0).link(5), world.rigidObject(0)))
+
+
+def test_geometry_bb_is_loose_but_conservative():
+    v, t = synth.unit_cube()
+    g = Geometry3D(TriangleMesh(v, t))
+    R = synth.rot_axis_angle([0, 0, 1], 0.7)
+    g.setCurrentTransform(list(R.T.reshape(-1)), [1, 2, 3])
+    lo, hi = g.getBB()
+    lt, ht = g.getBBTight()
+    assert all(a <= b + 1e-12 for a, b in zip(lo, lt)) and all(a >= b - 1e-12 for a, b in zip(hi, ht))
+    g.setCollisionMargin(0.1)
+    lo2, _ = g.getBB()
+    assert np.allclose(np.array(lo) - np.array(lo2), 0.1)
+    assert bb_intersect((lo, hi), (lt, ht)) and not bb_intersect((lo, hi), ([9, 9, 9], [10, 10, 10]))
+
+
+def test_cspace_bookkeeping_and_edge_checker():
+    class Disk(CSpace):
+        def __init__(self):
+            CSpace.__init__(self)
+            self.setBounds([(0, 1), (0, 1)])
+            self.eps = 0.01
+            self.addFeasibilityTest(lambda q: self.inBounds(q), "bounds")
+            self.addFeasibilityTest(lambda q: (q[0] - 0.5) ** 2 + (q[1] - 0.5) ** 2 > 0.09, "disk", dependencies="bounds")
+
+    s = Disk()
+    s.setup()
+    assert s.properties["volume"] == 1 and s.feasibilityTestDependencies == [("disk", "bounds")]
+    assert s.isFeasible([0.1, 0.1]) and not s.isFeasible([0.5, 0.5]) and not s.isFeasible([1.5, 0.5])
+    assert s.feasibilityFailures([0.5, 0.5]) == ["disk"]
+    assert s.isVisible([0.1, 0.1], [0.9, 0.1]) and not s.isVisible([0.1, 0.5], [0.9, 0.5])
+    st = s.getStats()
+    assert st["feasible_count"] == 3 and st["visible_count"] == 2 and st["visible_probability"] == 0.5
+    assert st["disk_count"] == 2 and st["bounds_count"] == 3 and st["average_visible_length"] == pytest.approx(0.8)
+    s.close()
+    assert s.cspace is None
+
+
+def test_shard_arithmetic():
+    for n in (0, 1, 7, 8, 1000003):
+        for world in (1, 2, 3, 8):
+            blocks = [shard_range(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            assert sum(hi - lo for lo, hi in blocks) == n
+            idx = np.concatenate([interleaved_indices(n, r, world, 16) for r in range(world)])
+            assert sorted(idx) == list(range(n))
+    with pytest.raises(ValueError):
+        shard_range(10, 3, 2)

@@ -1,0 +1,387 @@
+"""Pins the CPU oracle: analytic known-answer tests, an independent second method (numpy / scipy brute force), and
+the only fixtures the reference itself offers for this path: the unit cube of tests/objects/cube.off,
+the so3 known-answer of tests/test_math_so3.py:14-19 and the planar nR arm of model/create/planar_robot.py."""
+import math
+
+import numpy as np
+import pytest
+
+from klampt_b200 import so3, synth
+from klampt_b200.worldspec import GeomSpec, WorldSpec, DriverSpec, JOINT_SPIN, JOINT_NORMAL
+from oracle import oracle as ko
+from oracle.oracle import OracleWorld
+
+I12 = synth.IDENTITY12
+
+
+# ------------------------------------------------------------------------------------------ so3 (reference KAT)
+def test_so3_rpy_reference_kat():
+    R = so3.from_quaternion((-4.32978e-17, -0.707107, 4.32978e-17, 0.707107))
+    r, p, y = so3.rpy(R)
+    assert r == pytest.approx(0.0, abs=5e-8)
+    assert p == pytest.approx(1.5707963267948966, abs=5e-8)
+    assert y == pytest.approx(3.141592653589793, abs=5e-8)
+
+
+def test_so3_column_major_convention():
+    R = so3.from_axis_angle(((0, 0, 1), math.pi / 2))
+    # column-major: first three entries are the first COLUMN = image of the x axis = +y
+    assert np.allclose(R[:3], [0, 1, 0]) and np.allclose(so3.apply(R, [1, 0, 0]), [0, 1, 0])
+    T = so3.to_rowmajor12(R, [1, 2, 3])
+    assert np.allclose(T[:9].reshape(3, 3) @ [1, 0, 0], [0, 1, 0]) and np.allclose(T[9:], [1, 2, 3])
+    R2, t2 = so3.from_rowmajor12(T)
+    assert np.allclose(R2, R) and np.allclose(t2, [1, 2, 3])
+
+
+# ------------------------------------------------------------------------------------------ element predicates
+def tri(*p):
+    return np.array(p, dtype=np.float64).reshape(9)
+
+
+def test_tri_tri_known_answers():
+    A = tri([0, 0, 0], [1, 0, 0], [0, 1, 0])
+    assert ko.tri_tri_intersect(A, tri([0.2, 0.2, -1], [0.2, 0.2, 1], [0.8, 0.8, 1]))            # pierces
+    assert not ko.tri_tri_intersect(A, tri([0.2, 0.2, 0.1], [0.3, 0.2, 1], [0.8, 0.8, 1]))        # above
+    assert not ko.tri_tri_intersect(A, tri([2, 2, -1], [2, 2, 1], [3, 3, 1]))                     # crosses the plane far away
+    assert ko.tri_tri_intersect(A, tri([0.25, 0.25, 0], [0.3, 0.25, 0], [0.25, 0.3, 0]))          # coplanar, contained
+    assert ko.tri_tri_intersect(A, tri([0.5, 0.5, 0], [2, 2, 0], [2, 0.5, 0]))                    # coplanar, touching the hypotenuse
+    assert not ko.tri_tri_intersect(A, tri([0.6, 0.6, 0], [2, 2, 0], [2, 0.6, 0]))                # coplanar, disjoint
+    assert ko.tri_tri_intersect(A, tri([1, 0, 0], [2, 0, 1], [2, 0, -1]))                         # shares a vertex
+    assert ko.tri_tri_intersect(A, tri([0.5, 0, 0], [0.5, -1, 1], [0.5, -1, -1]))                 # vertex on an edge
+    assert ko.tri_tri_distance(A, tri([0, 0, 2], [1, 0, 2], [0, 1, 2])) == pytest.approx(2.0)
+    assert ko.tri_tri_distance(A, tri([2, 0, 0], [3, 0, 0], [2, 1, 0])) == pytest.approx(1.0)     # vertex-vertex in plane
+    assert ko.tri_tri_distance(A, tri([0.2, 0.2, -1], [0.2, 0.2, 1], [0.8, 0.8, 1])) == 0.0
+
+
+def test_point_tri_and_seg_seg_known_answers():
+    T = tri([0, 0, 0], [2, 0, 0], [0, 2, 0])
+    assert ko.point_tri_distance([0.5, 0.5, 3], T) == pytest.approx(3.0)                # face region
+    assert ko.point_tri_distance([-1, -1, 0], T) == pytest.approx(math.sqrt(2))         # vertex region
+    assert ko.point_tri_distance([1, -2, 0], T) == pytest.approx(2.0)                   # edge region
+    assert ko.point_tri_distance([2, 2, 0], T) == pytest.approx(math.sqrt(2))           # hypotenuse
+    assert ko.seg_seg_distance([0, 0, 0], [1, 0, 0], [0, 1, 1], [1, 1, 1]) == pytest.approx(math.sqrt(2))
+    assert ko.seg_seg_distance([0, 0, 0], [1, 0, 0], [0.5, -1, 0.5], [0.5, 1, 0.5]) == pytest.approx(0.5)   # crossing, skew
+    assert ko.seg_seg_distance([0, 0, 0], [1, 0, 0], [2, 0, 0], [3, 0, 0]) == pytest.approx(1.0)           # collinear
+    assert ko.seg_seg_distance([0, 0, 0], [0, 0, 0], [1, 1, 0], [1, 1, 0]) == pytest.approx(math.sqrt(2))   # degenerate
+
+
+def _np_seg_tri(p, q, a, b, c):
+    """independent restatement: Moller-Trumbore on the closed segment"""
+    d, e1, e2 = q - p, b - a, c - a
+    h = np.cross(d, e2)
+    det = e1 @ h
+    if abs(det) < 1e-14:
+        return None
+    s = p - a
+    u = (s @ h) / det
+    qv = np.cross(s, e1)
+    v = (d @ qv) / det
+    t = (e2 @ qv) / det
+    return u >= 0 and v >= 0 and u + v <= 1 and 0 <= t <= 1
+
+
+def test_tri_tri_against_numpy_second_method():
+    rng = np.random.default_rng(11)
+    n_hit = 0
+    for _ in range(4000):
+        A = rng.uniform(-1, 1, size=(3, 3))
+        B = rng.uniform(-1, 1, size=(3, 3)) * rng.uniform(0.2, 1.5)
+        want = False
+        for X, Y in ((A, B), (B, A)):
+            for i in range(3):
+                r = _np_seg_tri(X[i], X[(i + 1) % 3], Y[0], Y[1], Y[2])
+                want = want or bool(r)
+        got = ko.tri_tri_intersect(A.reshape(9), B.reshape(9))
+        assert got == want
+        n_hit += got
+    assert 400 < n_hit < 3600
+
+
+def test_tri_tri_distance_against_sampling():
+    rng = np.random.default_rng(12)
+    w = rng.dirichlet(np.ones(3), size=4000)
+    for _ in range(60):
+        A = rng.uniform(-1, 1, size=(3, 3))
+        B = rng.uniform(-1, 1, size=(3, 3)) + rng.uniform(-2, 2, size=3)
+        d = ko.tri_tri_distance(A.reshape(9), B.reshape(9))
+        pa, pb = w @ A, w @ B
+        # every sampled point of A is at least d away from triangle B and vice versa, and some sample gets close
+        dm = min(min(ko.point_tri_distance(p, B.reshape(9)) for p in pa[:300]), min(ko.point_tri_distance(p, A.reshape(9)) for p in pb[:300]))
+        assert dm >= d - 1e-12
+        assert dm <= d + 0.25
+
+
+# ------------------------------------------------------------------------------------------ cube - cube analytic
+@pytest.fixture(scope="module")
+def cubes():
+    v, t = synth.unit_cube()
+    w = WorldSpec()
+    ga = w.add_geom(GeomSpec.mesh(v, t))
+    gb = w.add_geom(GeomSpec.mesh(v, t, margin=0.0))
+    gm = w.add_geom(GeomSpec.mesh(v, t, margin=0.1))
+    gs = w.add_geom(GeomSpec.sphere([0, 0, 0], 0.25))
+    w.robot = synth.make_planar_nR(w, 1)
+    return OracleWorld(w), ga, gb, gm, gs
+
+
+def T_at(x, y=0.0, z=0.0, R=None):
+    return synth.make_T(R, [x, y, z])
+
+
+def test_cube_cube_analytic(cubes):
+    o, ga, gb, gm, gs = cubes
+    assert o.geom_distance(ga, I12, gb, T_at(1.5)) == pytest.approx(0.5, abs=1e-15)
+    assert o.geom_distance(ga, I12, gb, T_at(2.0, 2.0)) == pytest.approx(math.sqrt(2), abs=1e-15)     # edge - edge
+    assert o.geom_distance(ga, I12, gb, T_at(2.0, 2.0, 2.0)) == pytest.approx(math.sqrt(3), abs=1e-15)  # corner - corner
+    assert not o.geom_collides(ga, I12, gb, T_at(1.5))
+    assert o.geom_collides(ga, I12, gb, T_at(0.5, 0.25, 0.25))
+    assert o.geom_distance(ga, I12, gb, T_at(0.5, 0.25, 0.25)) == 0.0
+    # surfaces only: a small cube strictly inside the big one does NOT collide (src/geometry.h:1082-1085)
+    S = np.concatenate([(0.2 * np.eye(3)).reshape(-1), [0.4, 0.4, 0.4]])
+    assert not o.geom_collides(ga, I12, gb, S)
+    assert o.geom_distance(ga, I12, gb, S) == pytest.approx(0.4, abs=1e-15)
+    # rotated 45 deg about z, corner pointing at the face x = 1
+    R = synth.rot_axis_angle([0, 0, 1], math.pi / 4)
+    gap = o.geom_distance(ga, I12, gb, T_at(1.0 + math.sqrt(0.5) + 0.3, -0.2, 0.0, R))   # B rotates about its origin corner: x spans [c - sqrt(.5), c + sqrt(.5)], nearest edge at y = 0.507
+    assert gap == pytest.approx(0.3, abs=1e-12)
+
+
+def test_margin_semantics(cubes):
+    o, ga, gb, gm, gs = cubes
+    # A,B collide iff dist <= margin_A + margin_B; reported distance = geometric distance - margins (Manual-Geometry.md:17)
+    assert o.geom_distance(ga, I12, gm, T_at(1.5)) == pytest.approx(0.4, abs=1e-15)
+    assert not o.geom_collides(ga, I12, gm, T_at(1.11))
+    assert o.geom_collides(ga, I12, gm, T_at(1.09))
+    assert o.geom_within_distance(ga, I12, gb, T_at(1.5), 0.5)        # closed: dist == tol counts
+    assert not o.geom_within_distance(ga, I12, gb, T_at(1.5), 0.499)
+    assert o.geom_distance(ga, I12, gb, T_at(3.0), upper_bound=0.5) == 0.5   # capped at the bound
+
+
+def test_sphere_primitive_signed_distance(cubes):
+    o, ga, gb, gm, gs = cubes
+    assert o.geom_distance(gs, T_at(2.0, 0.5, 0.5), ga, I12) == pytest.approx(0.75, abs=1e-15)
+    assert o.geom_distance(gs, T_at(1.1, 0.5, 0.5), ga, I12) == pytest.approx(-0.15, abs=1e-15)   # surface cuts the ball
+    assert o.geom_collides(gs, T_at(1.1, 0.5, 0.5), ga, I12)
+    assert not o.geom_collides(gs, T_at(0.5, 0.5, 0.5), ga, I12)     # ball strictly inside the hollow cube
+    assert o.geom_distance(gs, T_at(0, 0, 0), gs, T_at(1, 0, 0)) == pytest.approx(0.5, abs=1e-15)
+
+
+def test_bvh_distance_equals_brute_force():
+    rng = np.random.default_rng(5)
+    w = WorldSpec()
+    ga = w.add_geom(GeomSpec.mesh(*synth.blob_mesh(rng, 2, 0.3)))
+    gb = w.add_geom(GeomSpec.mesh(*synth.capsule_mesh(0.1, 0, 0.4, nseg=10, ncap=3, nbody=3)))
+    gc = w.add_geom(GeomSpec.cloud(rng.normal(size=(500, 3)) * 0.2, rng.uniform(0, 0.02, size=500)))
+    w.robot = synth.make_planar_nR(w, 1)
+    o = OracleWorld(w)
+    for _ in range(25):
+        Ta = synth.make_T(synth._random_rotation(rng), rng.uniform(-0.5, 0.5, size=3))
+        Tb = synth.make_T(synth._random_rotation(rng), rng.uniform(-0.5, 0.5, size=3))
+        for g1, g2 in ((ga, gb), (ga, gc), (gc, gc), (gb, gc)):
+            d, db = o.geom_distance(g1, Ta, g2, Tb), o.geom_distance_brute(g1, Ta, g2, Tb)
+            assert d == pytest.approx(db, abs=1e-13)
+            assert o.geom_collides(g1, Ta, g2, Tb) == (db <= 0)
+
+
+def test_point_cloud_distance_against_ckdtree():
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(6)
+    P, Qp = rng.uniform(-1, 1, size=(3000, 3)), rng.uniform(-1, 1, size=(200, 3)) + [2.5, 0, 0]
+    w = WorldSpec()
+    gp, gq = w.add_geom(GeomSpec.cloud(P)), w.add_geom(GeomSpec.cloud(Qp))
+    w.robot = synth.make_planar_nR(w, 1)
+    o = OracleWorld(w)
+    T = synth.make_T(synth._random_rotation(rng), [0.1, -0.2, 0.3])
+    Qw = synth.transform_points(T, Qp)
+    want = cKDTree(P).query(Qw)[0].min()
+    assert o.geom_distance(gp, I12, gq, T) == pytest.approx(want, abs=1e-13)
+
+
+# ------------------------------------------------------------------------------------------ FK
+def test_planar_nR_closed_form_fk():
+    w = WorldSpec()
+    n, Llen = 5, 0.7
+    w.robot = synth.make_planar_nR(w, n, Llen)
+    o = OracleWorld(w)
+    rng = np.random.default_rng(2)
+    for _ in range(20):
+        q = rng.uniform(0, 6.28, size=n)
+        T = o.fk(q)
+        x = z = 0.0
+        th = 0.0
+        for i in range(n):
+            if i > 0:
+                x += Llen * math.cos(th)
+                z += -Llen * math.sin(th)        # rotation about +y takes +x towards -z
+            th += q[i]
+            R = T[i, :9].reshape(3, 3)
+            assert np.allclose(T[i, 9:], [x, 0, z], atol=1e-12)
+            assert np.allclose(R, synth.rot_axis_angle([0, 1, 0], th), atol=1e-12)
+
+
+def test_fk_prismatic_and_branching():
+    w = WorldSpec()
+    r = synth.make_planar_nR(w, 3)
+    r.linktype = np.array([0, 1, 0], dtype=np.uint8)
+    r.parents = np.array([-1, 0, 0], dtype=np.int32)
+    r.axis[1] = [0, 0, 1]
+    w.robot = r
+    o = OracleWorld(w)
+    T = o.fk([math.pi / 2, 0.25, 0.1])
+    # link 1: prismatic along its local z after the parent's rotation about y and the 1 m offset along x
+    assert np.allclose(T[1, 9:], synth.rot_axis_angle([0, 1, 0], math.pi / 2) @ [1, 0, 0.25], atol=1e-12)
+    assert np.allclose(T[1, :9].reshape(3, 3), synth.rot_axis_angle([0, 1, 0], math.pi / 2), atol=1e-12)
+    assert np.allclose(T[2, :9].reshape(3, 3), synth.rot_axis_angle([0, 1, 0], math.pi / 2 + 0.1), atol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------ limits, mask, feasibility
+def test_joint_and_driver_limits():
+    w = synth.world_c1()
+    w.robot.drivers.append(DriverSpec(links=[2, 3], scale=[1.0, -1.0], offset=[0.0, 0.0], qmin=-0.5, qmax=0.5))
+    o = OracleWorld(w)
+    q = np.zeros(7)
+    assert o.check_joint_limits(q)
+    q[1] = w.robot.qmax[1]
+    assert o.check_joint_limits(q)                         # closed interval
+    q[1] = np.nextafter(w.robot.qmax[1], 10)
+    assert not o.check_joint_limits(q)
+    q[1] = 0
+    q[2], q[3] = 0.6, -0.6                                 # driver value = mean(0.6/1, -0.6/-1) = 0.6 > 0.5
+    assert not o.check_joint_limits(q)
+    q[2], q[3] = 0.6, 0.2                                  # mean(0.6, -0.2) = 0.2
+    assert o.check_joint_limits(q)
+    q[0] = 1e-12                                           # welded base: qmin = qmax = 0
+    assert not o.check_joint_limits(q)
+
+
+def test_default_pair_mask_quirks():
+    """WorldPlannerSettings::InitializeDefault (Cpp/Planning/PlannerSettings.cpp:16-41)"""
+    w = synth.world_c1()
+    o = OracleWorld(w)
+    m = o.pair_mask()
+    n = w.num_ids()
+    assert m.shape == (n, n)
+    rid, base = w.robot_id(), w.robot_link_id(0)
+    assert m[rid, rid] == 1                                               # robot can self collide
+    assert all(m[i, i] == 0 for i in range(n) if i != rid)
+    assert not m[base:base + 7, rid].any() and not m[rid, base:base + 7].any()
+    assert m[base + 0, 0] == 0 and m[0, base + 0] == 0                     # root link vs terrain
+    assert m[base + 1, 0] == 1                                            # other links vs terrain
+    assert m[base + 1, 1] == 1 and m[1, base + 1] == 1                     # link vs rigid object
+    L = 7
+    for i in range(L):
+        for j in range(L):
+            want = 1 if (i < j and j != i + 1) else 0                      # upper triangular, parent-child excluded
+            assert m[base + i, base + j] == want
+    # 15 default self pairs for the 7-link chain: C(7,2) - 6
+    assert m[base:base + L, base:base + L].sum() == 15
+
+
+def test_self_collision_edits_and_empty_links():
+    w = synth.world_c3()
+    r = w.robot
+    assert r.link_geom.count(-1) == 2                                      # the two welded mounting frames carry no geometry
+    r.self_collision_edits += [(1, 3, False), (1, 2, True)]
+    o = OracleWorld(w)
+    m = o.pair_mask()
+    base = w.robot_link_id(0)
+    assert m[base + 1, base + 3] == 0 and m[base + 1, base + 2] == 0       # (1,2): link 2 has no geometry -> cannot be enabled
+    mount = [i for i, g in enumerate(r.link_geom) if g < 0]
+    assert not m[base + mount[0], :].any()
+
+
+def test_bvh_feasibility_equals_brute_force():
+    """full IsFeasible (mask + AABB broad phase + BVH descent) against all-pairs brute force on a coarse world"""
+    rng = np.random.default_rng(9)
+    w = WorldSpec()
+    v, t = synth.box_mesh([-2, -2, -0.6], [2, 2, -0.5], div=2)
+    w.terrains.append(w.add_geom(GeomSpec.mesh(v, t)))
+    for _ in range(6):
+        d = rng.uniform(0.1, 0.4, size=3)
+        v, t = synth.box_mesh(-d, d, div=2)
+        w.objects.append((w.add_geom(GeomSpec.mesh(v, t)), synth.make_T(synth._random_rotation(rng), rng.uniform(-2.5, 2.5, size=3) * [1, 0.3, 1])))
+    w.robot = synth.make_planar_nR(w, 5, 0.8)
+    o = OracleWorld(w)
+    Q = synth.sample_configs(w.robot, 400, 77)
+    got = np.array([o.feasible(q) for q in Q])
+    want = np.array([o.feasible_brute(q) for q in Q])
+    assert (got == want).all()
+    assert 0.1 < got.mean() < 0.9
+    # and a handful of configurations of the full-resolution C1 world
+    w1 = synth.world_c1()
+    o1 = OracleWorld(w1)
+    for q in synth.sample_configs(w1.robot, 3, 79):
+        assert o1.feasible(q) == o1.feasible_brute(q)
+
+
+def test_traversal_counts_definition():
+    """the roofline's algorithmic bytes use these counters: they must be deterministic and non-trivial"""
+    w = synth.world_c1()
+    o = OracleWorld(w)
+    Q = synth.sample_configs(w.robot, 200, 78)
+    out, pairs, cnt = o.feasible_batch(Q, nthreads=1, want_pairs=True, want_counts=True)
+    out2, cnt2 = o.feasible_batch(Q, nthreads=0, want_counts=True)
+    assert (out == out2).all() and (cnt == cnt2).all()
+    assert cnt["n_box"].min() >= 7 and cnt["n_node"].sum() > 0 and cnt["n_pt"].sum() == 0
+    assert ((pairs[:, 0] >= 0) == ((out == 0) & np.array([o.check_joint_limits(q) for q in Q]))).all()
+
+
+# ------------------------------------------------------------------------------------------ edges
+def _py_edge(o, a, b, eps):
+    length = o.cspace_distance(a, b)
+    segs, n = 1, 0
+    while length > eps:
+        segs *= 2
+        length *= 0.5
+        for k in range(1, segs, 2):
+            n += 1
+            if not o.feasible(o.interpolate(a, b, k / segs)):
+                return False, n
+    return True, n
+
+
+def test_edge_checker_order_and_counts():
+    w = synth.world_c1()
+    o = OracleWorld(w)
+    A, B = synth.sample_edges(w.robot, lambda Q: o.feasible_batch(Q), 40, 3)
+    vis, n = o.edges_visible_batch(A, B, eps=0.05)
+    for i in range(len(A)):
+        v2, n2 = _py_edge(o, A[i], B[i], 0.05)
+        assert bool(vis[i]) == v2 and n[i] == n2
+    # a free edge of length l costs 2^ceil(log2(l/eps)) - 1 checks
+    free = np.nonzero(vis)[0]
+    assert len(free) > 0
+    for i in free[:5]:
+        l = o.cspace_distance(A[i], B[i])
+        assert n[i] == 2 ** max(0, math.ceil(math.log2(l / 0.05))) - 1
+    # zero-length edge: visible with no checks; endpoints are never re-checked
+    v, k = o.edge_visible(A[0], A[0], 0.01)
+    assert v and k == 0
+
+
+def test_metric_and_interpolation_spin_joint():
+    w = WorldSpec()
+    r = synth.make_planar_nR(w, 2)
+    r.joint_type = np.array([JOINT_SPIN, JOINT_NORMAL], dtype=np.uint8)
+    w.robot = r
+    o = OracleWorld(w)
+    a, b = np.array([0.1, 1.0]), np.array([2 * math.pi - 0.1, 2.0])
+    assert o.cspace_distance(a, b) == pytest.approx(math.hypot(0.2, 1.0))      # short way round for the spin joint
+    m = o.interpolate(a, b, 0.5)
+    assert m[1] == pytest.approx(1.5)
+    assert min(m[0], 2 * math.pi - m[0]) == pytest.approx(0.0, abs=1e-12)
+    assert o.cspace_distance(a, b, weights=[4.0, 1.0]) == pytest.approx(math.sqrt(4 * 0.04 + 1.0))
+
+
+def test_robot_distance_lower_bound():
+    w = synth.world_c1()
+    o = OracleWorld(w)
+    Q = synth.sample_configs(w.robot, 30, 5)
+    for q in Q:
+        d, pair = o.distance(q, upper_bound=0.4, include_self=False)
+        assert 0 <= d <= 0.4
+        feas_env = d > 0
+        if not feas_env:
+            assert not o.feasible(q) or not o.check_joint_limits(q)
+        if d < 0.4:
+            assert pair[0] >= w.robot_link_id(0) and 0 <= pair[1] < w.robot_id()
