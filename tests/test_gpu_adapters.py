@@ -98,3 +98,46 @@ def test_robotsim_setconfig_selfcollides_and_geometry_queries(setup):
     hits = list(collider.robotObjectCollisions(0))
     robot.setConfig(list(Q[0]))
     assert isinstance(hits, list)
+
+
+def test_cpp_batch_single_robot_cspace(built, tmp_path):
+    """include/klampt_b200/BatchSingleRobotCSpace.h (the C++ face of SingleRobotCSpace) compiled with g++ against the C ABI"""
+    import os
+    import shutil
+    import struct
+    import subprocess
+    from oracle.oracle import OracleWorld
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    exe = str(tmp_path / "test_batch_cspace")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "cpp", "test_batch_cspace.cpp"),
+                           "-o", exe, "-L", os.path.join(root, "klampt_b200"), "-lklampt_b200", "-Wl,-rpath," + os.path.join(root, "klampt_b200")])
+    spec = synth.world_c1()
+    orc = OracleWorld(spec)
+    Q = synth.sample_configs(spec.robot, 2000, 31)
+    A, B = synth.sample_edges(spec.robot, lambda X: orc.feasible_batch(X), 200, 32)
+
+    def blob(a, dt):
+        a = np.ascontiguousarray(a, dtype=dt).reshape(-1)
+        return struct.pack("<q", a.size) + a.tobytes()
+
+    r = spec.robot
+    with open(tmp_path / "world.bin", "wb") as f:
+        f.write(blob([len(spec.geoms)], np.int64))
+        for g in spec.geoms:
+            f.write(blob(g.verts, np.float64) + blob(g.tris, np.int32))
+        f.write(blob(spec.terrains, np.int32))
+        f.write(blob([g for g, _ in spec.objects], np.int32) + blob(np.array([T for _, T in spec.objects]), np.float64))
+        f.write(blob(r.parents, np.int32) + blob(r.linktype, np.uint8) + blob(r.axis, np.float64) + blob(r.T0, np.float64) + blob(r.qmin, np.float64)
+                + blob(r.qmax, np.float64) + blob(r.link_geom, np.int32) + blob(r.joint_type, np.uint8) + blob(r.joint_link, np.int32))
+        f.write(blob(Q, np.float64) + blob(A, np.float64) + blob(B, np.float64))
+    res = subprocess.run([exe, str(tmp_path / "world.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    raw = open(tmp_path / "out.bin", "rb").read()
+    feas = np.frombuffer(raw[:2000], dtype=np.uint8)
+    vis = np.frombuffer(raw[2000:2200], dtype=np.uint8)
+    nchk = np.frombuffer(raw[2200:], dtype=np.int32)
+    assert np.array_equal(feas, orc.feasible_batch(Q))
+    ovis, on = orc.edges_visible_batch(A, B, eps=0.01)
+    assert np.array_equal(vis, ovis) and np.array_equal(nchk, on)
