@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libklampt_b200.so")
+LIB_PATH = os.environ.get("KLAMPT_B200_LIB", os.path.join(_HERE, "libklampt_b200.so"))
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)

@@ -71,6 +71,7 @@ void build_bvh(const std::vector<double>& elo, const std::vector<double>& ehi, i
   struct Task { int node, first, count, depth; };
   std::vector<Task> todo;
   out.nodes.push_back(BNode());
+  { BNode pad; memset(&pad, 0, sizeof pad); pad.left = -1; pad.first = 0; pad.count = 0; out.nodes.push_back(pad); }   // keeps sibling pairs even-aligned
   todo.push_back({0, 0, n, 0});
   const int NB = 16;
   while (!todo.empty()) {
@@ -253,6 +254,7 @@ int append_geom(kb_engine* e, int kind, const std::vector<double>& elems, const 
     if (kind != G_MESH) dg.rmax = std::max(dg.rmax, p[3]);
   }
   Bvh bvh; build_bvh(elo, ehi, n, kind == G_MESH ? 1 : 8, bvh);
+  if ((e->h_nodes.size() / 8) & 1) e->h_nodes.insert(e->h_nodes.end(), 8, 0.f);                // even node base: sibling pairs share a 64 B line
   dg.node_base = (int)(e->h_nodes.size() / 8); dg.nnodes = (int)bvh.nodes.size(); dg.depth = bvh.depth;
   dg.elem_base = kind == G_MESH ? (int)(e->h_tris64.size() / 9) : (int)(e->h_sph64.size() / 4);
   memcpy(dg.lo, bvh.nodes[0].lo, 24); memcpy(dg.hi, bvh.nodes[0].hi, 24);

@@ -346,7 +346,7 @@ __device__ __forceinline__ void load_itc(const float* __restrict__ itc, int item
 }
 
 template <int MODE, bool ITC>
-__global__ void __launch_bounds__(KB_WARPS_PER_BLOCK * 32, 4)
+__global__ void __launch_bounds__(KB_WARPS_PER_BLOCK * 32, KB_BLOCKS_PER_SM)
 kb_traverse_kernel(const KbTraverseParams p, double* __restrict__ out_dist, double upper_bound) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -717,7 +717,7 @@ static cudaError_t launch_traverse_t(const KbTraverseParams& p, double* out_dist
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  int per_sm = (int)((224 * 1024) / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > 4) per_sm = 4;
+  int per_sm = (int)((224 * 1024) / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > KB_BLOCKS_PER_SM) per_sm = KB_BLOCKS_PER_SM;
   int64_t want = (p.N + 8 * KB_WARPS_PER_BLOCK - 1) / (8 * KB_WARPS_PER_BLOCK);
   int64_t grid = (int64_t)num_sms * per_sm; if (grid > want) grid = want; if (grid < 1) grid = 1;
   kb_traverse_kernel<MODE, ITC><<<(unsigned)grid, KB_WARPS_PER_BLOCK * 32, smem, s>>>(p, out_dist, upper_bound);

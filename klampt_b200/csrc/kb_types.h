@@ -3,7 +3,7 @@
 // HBM layout (all static data is uploaded once at kb_finalize and then read-only):
 //   nodes    float4[2*n]   flattened BVHs of every geometry, one after the other.  Node i of a geometry =
 //                          { centre.xyz, as_float(left) } { half_extent.xyz, as_float(count) }.  left >= 0: inner node,
-//                          children at left and left+1 (siblings adjacent, indices relative to the geometry's
+//                          children at left and left+1 (siblings adjacent and even-aligned: one 64 B line; indices relative to the geometry's
 //                          node base).  left < 0: leaf, first element = ~left (relative to the geometry's element
 //                          base), count elements.  Boxes are fp32; half extents are rounded up so the fp32 box contains the fp64 one.
 //   tris32   float4[3*n]   triangle vertices (fp32, local frame; merged environment groups: world frame);
@@ -21,12 +21,15 @@
 
 #define KB_MAX_LINKS 128          // links per robot supported by the FK kernel's shared-memory model
 #define KB_STACK_CAP 512          // node-pair stack entries per warp
-#define KB_LEAFQ_CAP 64           // leaf-pair queue entries per warp
+#define KB_LEAFQ_CAP 96           // leaf-pair queue entries per warp
 #define KB_ITEM_BITS 12
 #define KB_NODEA_BITS 20
 #define KB_MAX_ITEMS (1 << KB_ITEM_BITS)
 #define KB_MAX_NODES_A (1 << KB_NODEA_BITS)
 #define KB_WARPS_PER_BLOCK 4
+#ifndef KB_BLOCKS_PER_SM
+#define KB_BLOCKS_PER_SM 4         // resident CTAs per SM the traversal kernel is compiled for (register cap = 65536 / (128 * this))
+#endif
 
 enum { KB_ELEM_TRI = 0, KB_ELEM_SPHERE = 1 };
 
