@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--configs", type=int, default=0, help="configurations (or edges) per step per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     return ap.parse_args()
@@ -53,6 +53,8 @@ WORKLOADS = {
                     "uniform random configurations", n=1_000_000),
     "c3": dict(name="C3 dual-arm 15-DOF (18 links) self-collision only, uniform random configurations", n=1_000_000),
     "c4": dict(name="C4 straight-line edges in the C2 world at eps=0.01 (EpsilonEdgeChecker)", n=100_000),
+    "c5": dict(name="C5 arm6 meshes vs 5M-point cloud (points on the C2 obstacle surfaces + 5 mm noise, margin 5 mm): collide bit + "
+                    "min distance with upperBound 0.5 m per configuration", n=200_000),
 }
 
 
@@ -62,6 +64,8 @@ def make_world(which):
         return synth.world_c1()
     if which in ("c2", "c4"):
         return synth.world_c2()
+    if which == "c5":
+        return synth.world_c5()
     return synth.world_c3()
 
 
@@ -114,7 +118,7 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_leg(orc, gen_batch, budget_s, edges=False, slice_n=100_000):
+def cpu_leg(orc, gen_batch, budget_s, edges=False, slice_n=100_000, with_dist=False):
     """oracle with all host threads on successive slices of the workload until the time budget is spent"""
     from oracle.oracle import max_threads
     done, t_used, feas = 0, 0.0, 0
@@ -126,6 +130,8 @@ def cpu_leg(orc, gen_batch, budget_s, edges=False, slice_n=100_000):
             out, _ = orc.edges_visible_batch(data[0], data[1], eps=0.01, nthreads=0)
         else:
             out = orc.feasible_batch(data, nthreads=0)
+            if with_dist:
+                orc.distance_batch(data, upper_bound=0.5, include_self=False, nthreads=0)
         t_used += time.perf_counter() - t0
         done += len(out)
         feas += int(out.sum())
@@ -157,7 +163,7 @@ def main():
             return
         from oracle.oracle import OracleWorld
         orc = OracleWorld(spec)
-        per_step = min(M, 200_000 if not edges else 2_000)
+        per_step = min(M, 2_000 if edges else (10_000 if args.workload == "c5" else 200_000))
         if edges:
             A0, B0 = synth.sample_edges(robot, lambda Q: orc.feasible_batch(Q), per_step, 4)
             gen = lambda k, n: (A0, B0)
@@ -171,6 +177,8 @@ def main():
                 orc.edges_visible_batch(data[0], data[1], eps=0.01, nthreads=0)
             else:
                 orc.feasible_batch(data, nthreads=0)
+                if args.workload == "c5":
+                    orc.distance_batch(data, upper_bound=0.5, include_self=False, nthreads=0)
             dt = time.perf_counter() - t0
             if s >= args.warmup:
                 times.append(dt)
@@ -219,6 +227,9 @@ def main():
         devQ = [q.cuda(non_blocking=True) for q in hostQ]
         host_out = torch.empty(M, dtype=torch.uint8).pin_memory()
     dev_out = torch.empty(M, dtype=torch.uint8, device="cuda")
+    with_dist = args.workload == "c5"
+    dev_dist = torch.empty(M, dtype=torch.float64, device="cuda") if with_dist else None
+    host_dist = torch.empty(M, dtype=torch.float64).pin_memory() if with_dist else None
     torch.cuda.synchronize()
 
     def step_device(k):
@@ -226,6 +237,8 @@ def main():
             eng.edges_visible_batch_device(devA[k % NB], devB[k % NB], M, 0.01, dev_out)
         else:
             eng.feasible_batch_device(devQ[k % NB], M, dev_out)
+            if with_dist:
+                eng.distance_batch_device(devQ[k % NB], M, 0.5, False, dev_dist)
 
     def step_host(k):
         lib, h = eng.lib, eng.h
@@ -236,6 +249,8 @@ def main():
                                              C.c_void_p(host_out.data_ptr()), None))
         else:
             check(lib.kb_feasible_batch(h, C.c_void_p(hostQ[k % NB].data_ptr()), M, C.c_void_p(host_out.data_ptr()), None))
+            if with_dist:
+                check(lib.kb_distance_batch(h, C.c_void_p(hostQ[k % NB].data_ptr()), M, 0.5, 0, C.c_void_p(host_dist.data_ptr()), None))
 
     def barrier():
         torch.cuda.synchronize()
@@ -293,8 +308,8 @@ def main():
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     e2e_value = world * M * args.steps / float(tt.item())
-    h2d = (2 if edges else 1) * M * L * 8
-    d2h = M
+    h2d = (2 if edges or with_dist else 1) * M * L * 8
+    d2h = M + (8 * M if with_dist else 0)
 
     if rank != 0:
         if world > 1:
@@ -328,7 +343,7 @@ def main():
         A0, B0 = synth.sample_edges(robot, lambda Q: eng.feasible_batch(Q), 4000, 99)
         cv, cores, cdone, cused, cfeas = cpu_leg(orc, lambda k, n: (A0, B0), args.cpu_seconds, edges=True)
     else:
-        cv, cores, cdone, cused, cfeas = cpu_leg(orc, gen_configs, args.cpu_seconds)
+        cv, cores, cdone, cused, cfeas = cpu_leg(orc, gen_configs, args.cpu_seconds, slice_n=(10_000 if with_dist else 100_000), with_dist=with_dist)
     t1 = time.perf_counter()
     n1 = 20000 if not edges else 500
     if edges:

@@ -810,7 +810,9 @@ static double aabb_dist(const double* alo, const double* ahi, const double* blo,
   double s=0; for (int k=0;k<3;k++) { double g=fmax(alo[k]-bhi[k],blo[k]-ahi[k]); if (g>0) s+=g*g; } return sqrt(s); }
 /* WorldPlannerSettings::DistanceLowerBound with eps=0 (PlannerSettings.cpp:570-620): min over enabled pairs of the
  * pair distance, capped at upper_bound; candidates skipped when their AABB distance exceeds the running bound.
- * (The reference orders candidates by AABB distance; the minimum does not depend on the order.) */
+ * (The reference orders candidates by AABB distance and stops at the first candidate whose AABB distance exceeds the running
+ * bound; once the bound is negative -- geometries inside each other's margins -- that makes its value order dependent.  The
+ * oracle returns the order-independent quantity: the exact minimum over all enabled pairs.) */
 double ko_distance(const ko_world* w, const double* q, double ub, int include_self, int32_t* pair, ko_counts* cnt) {
   int L=w->L; xf_t* T=(xf_t*)malloc(sizeof(xf_t)*L); fk_links(w,q,T);
   active_t* s1=(active_t*)malloc(sizeof(active_t)*(L+1));
@@ -820,12 +822,12 @@ double ko_distance(const ko_world* w, const double* q, double ub, int include_se
   double best=ub; if (pair) { pair[0]=-1; pair[1]=-1; }
   for (int i=0;i<n1;i++) for (int j=0;j<n2;j++) if (mask_en(w,s1[i].id,s2[j].id)||mask_en(w,s2[j].id,s1[i].id)) {
     if (cnt) cnt->n_box++;
-    if (aabb_dist(s1[i].lo,s1[i].hi,s2[j].lo,s2[j].hi) >= best) continue;
+    { double ad=aabb_dist(s1[i].lo,s1[i].hi,s2[j].lo,s2[j].hi); if (ad>0 && ad>=best) continue; }  /* touching boxes bound nothing: margins / radii can make the distance negative */
     double d=geom_pair_distance(s1[i].g,&s1[i].T,s2[j].g,&s2[j].T,best,cnt);
     if (d<best) { best=d; if (pair) { pair[0]=s1[i].id; pair[1]=s2[j].id; } } }
   if (include_self) for (int i=0;i<n1;i++) for (int j=i+1;j<n1;j++) if (mask_en(w,s1[i].id,s1[j].id)) {
     if (cnt) cnt->n_box++;
-    if (aabb_dist(s1[i].lo,s1[i].hi,s1[j].lo,s1[j].hi) >= best) continue;
+    { double ad=aabb_dist(s1[i].lo,s1[i].hi,s1[j].lo,s1[j].hi); if (ad>0 && ad>=best) continue; }
     double d=geom_pair_distance(s1[i].g,&s1[i].T,s1[j].g,&s1[j].T,best,cnt);
     if (d<best) { best=d; if (pair) { pair[0]=s1[i].id; pair[1]=s1[j].id; } } }
   free(T); free(s1); free(s2);

@@ -217,3 +217,57 @@ def test_geometry_pair_queries(built):
     Tx = np.tile(synth.IDENTITY12, (2, 1)); Tx[0, 9] = 1.5; Tx[1, 9] = 0.5; Tx[1, 10] = 0.25; Tx[1, 11] = 0.25
     dd = eng.geom_distance_batch(ga, Ta[:2], gb, Tx)
     assert abs(dd[0] - 0.5) < 1e-12 and dd[1] == 0.0
+
+
+@pytest.fixture(scope="module")
+def c5small(built):
+    from klampt_b200.engine import Engine
+    from oracle.oracle import OracleWorld
+    w = synth.world_c5(n_points=60000, n_obstacles=60)
+    return w, Engine(w), OracleWorld(w)
+
+
+def test_point_cloud_collide_with_margin(c5small):
+    """robot meshes vs point cloud (points as spheres of radius = margin 5 mm): CollisionPointCloud semantics"""
+    w, eng, orc = c5small
+    Q = synth.sample_configs(w.robot, 8000, 51)
+    got, want = eng.feasible_batch(Q), orc.feasible_batch(Q)
+    bad = np.nonzero(got != want)[0]
+    for i in bad:
+        d, _ = orc.distance(Q[i], upper_bound=1.0, include_self=True)
+        assert abs(d) <= BAND
+    assert 0.2 < got.mean() < 0.9
+
+
+def test_point_cloud_distance(c5small):
+    """mesh - cloud distance is unsigned geometric distance minus margins, capped at upperBound"""
+    w, eng, orc = c5small
+    Q = synth.sample_configs(w.robot, 1200, 52)
+    d, pairs = eng.distance_batch(Q, upper_bound=0.5, include_self=False, return_pairs=True)
+    do, po = orc.distance_batch(Q, upper_bound=0.5, include_self=False)
+    np.testing.assert_allclose(d, do, rtol=1e-5, atol=1e-9)
+    assert (d >= -0.005 - 1e-12).all()            # margin 5 mm is subtracted: touching points report -0.005
+    assert ((pairs[:, 1] == 0) | (pairs[:, 1] == -1)).all()    # the cloud is terrain 0
+
+
+def test_point_cloud_with_radii_and_cloud_cloud(built):
+    from klampt_b200.engine import Engine
+    from oracle.oracle import OracleWorld
+    rng = np.random.default_rng(8)
+    w = WorldSpec()
+    ga = w.add_geom(GeomSpec.cloud(rng.normal(size=(3000, 3)) * 0.3, rng.uniform(0.0, 0.03, size=3000)))
+    gb = w.add_geom(GeomSpec.cloud(rng.normal(size=(500, 3)) * 0.2, None, margin=0.01))
+    gm = w.add_geom(GeomSpec.mesh(*synth.blob_mesh(rng, 2, 0.25)))
+    w.robot = synth.make_planar_nR(w, 2)
+    eng, orc = Engine(w), OracleWorld(w)
+    N = 300
+    Ta = np.stack([synth.make_T(synth._random_rotation(rng), rng.uniform(-0.2, 0.2, size=3)) for _ in range(N)])
+    Tb = np.stack([synth.make_T(synth._random_rotation(rng), rng.uniform(-1.2, 1.2, size=3)) for _ in range(N)])
+    for g1, g2 in ((ga, gb), (ga, gm), (gm, gb)):
+        d = eng.geom_distance_batch(g1, Ta, g2, Tb)
+        do = np.array([orc.geom_distance(g1, Ta[i], g2, Tb[i]) for i in range(N)])
+        np.testing.assert_allclose(d, do, rtol=1e-5, atol=1e-12)
+        c = eng.geom_collides_batch(g1, Ta, g2, Tb)
+        co = np.array([orc.geom_collides(g1, Ta[i], g2, Tb[i]) for i in range(N)])
+        assert (c == co).all()
+        assert (c == (do <= 0)).all()

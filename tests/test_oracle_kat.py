@@ -385,3 +385,19 @@ def test_robot_distance_lower_bound():
             assert not o.feasible(q) or not o.check_joint_limits(q)
         if d < 0.4:
             assert pair[0] >= w.robot_link_id(0) and 0 <= pair[1] < w.robot_id()
+
+
+def test_robot_distance_with_margins_is_the_exact_minimum():
+    """inside the margins distances go negative; the robot-level minimum must still be the minimum over ALL enabled pairs
+    (an AABB distance of 0 bounds nothing there)"""
+    w = synth.world_c5(n_points=4000, n_obstacles=20, margin=0.02)
+    o = OracleWorld(w)
+    Q = synth.sample_configs(w.robot, 300, 52)
+    d, _ = o.distance_batch(Q, upper_bound=0.5, include_self=False)
+    cloud = w.terrains[0]
+    neg = np.nonzero(d < 0)[0][:12]
+    assert len(neg) > 3
+    for i in neg:
+        T = o.fk(Q[i])
+        best = min(o.geom_distance_brute(g, T[j], cloud, I12) for j, g in enumerate(w.robot.link_geom) if j > 0)
+        assert d[i] == pytest.approx(best, abs=1e-13)
