@@ -33,6 +33,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# all host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which would silently serialise the CPU arm)
+NTHREADS = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
 
 def parse():
@@ -127,16 +129,16 @@ def cpu_leg(orc, gen_batch, budget_s, edges=False, slice_n=100_000, with_dist=Fa
         data = gen_batch(k, slice_n)
         t0 = time.perf_counter()
         if edges:
-            out, _ = orc.edges_visible_batch(data[0], data[1], eps=0.01, nthreads=0)
+            out, _ = orc.edges_visible_batch(data[0], data[1], eps=0.01, nthreads=NTHREADS)
         else:
-            out = orc.feasible_batch(data, nthreads=0)
+            out = orc.feasible_batch(data, nthreads=NTHREADS)
             if with_dist:
-                orc.distance_batch(data, upper_bound=0.5, include_self=False, nthreads=0)
+                orc.distance_batch(data, upper_bound=0.5, include_self=False, nthreads=NTHREADS)
         t_used += time.perf_counter() - t0
         done += len(out)
         feas += int(out.sum())
         k += 1
-    return done / t_used, max_threads(), done, t_used, feas / max(1, done)
+    return done / t_used, NTHREADS, done, t_used, feas / max(1, done)
 
 
 def main():
@@ -174,11 +176,11 @@ def main():
             data = gen(s, per_step)
             t0 = time.perf_counter()
             if edges:
-                orc.edges_visible_batch(data[0], data[1], eps=0.01, nthreads=0)
+                orc.edges_visible_batch(data[0], data[1], eps=0.01, nthreads=NTHREADS)
             else:
-                orc.feasible_batch(data, nthreads=0)
+                orc.feasible_batch(data, nthreads=NTHREADS)
                 if args.workload == "c5":
-                    orc.distance_batch(data, upper_bound=0.5, include_self=False, nthreads=0)
+                    orc.distance_batch(data, upper_bound=0.5, include_self=False, nthreads=NTHREADS)
             dt = time.perf_counter() - t0
             if s >= args.warmup:
                 times.append(dt)
@@ -187,7 +189,7 @@ def main():
         line = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": {"workload": wl["name"], "per_step": per_step},
-                "cpu_baseline": {"value": v, "unit": unit, "cores": max_threads(), "kind": "port",
+                "cpu_baseline": {"value": v, "unit": unit, "cores": NTHREADS, "kind": "port",
                                  "sample": "%d %s per step (bounded sample of the %d-per-step workload), oracle with OpenMP over all host threads"
                                            % (per_step, "edges" if edges else "configurations", M)},
                 "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -324,7 +326,7 @@ def main():
     peak, peak_src = peaks()
     ns = 20000
     Qs = gen_configs(0, ns)
-    _, cnt = orc.feasible_batch(Qs, nthreads=0, want_counts=True)
+    _, cnt = orc.feasible_batch(Qs, nthreads=NTHREADS, want_counts=True)
     bytes_per_cfg = 4 * L + 0.125 + 32 * cnt["n_box"].mean() + 64 * cnt["n_node"].mean() + 72 * cnt["n_tri"].mean() + 16 * cnt["n_pt"].mean()
     roofline = None
     # traverse_ms / traverse_launches were captured in `st` (device-resident run) before the e2e leg reset the statistics
@@ -338,19 +340,27 @@ def main():
                     "avg_launch_ms": avg_ms, "kernel_share_of_step": tms / ms_dev, "peak_source": peak_src,
                     "counts_per_config": {k: float(cnt[k].mean()) for k in cnt.dtype.names}}
 
-    # ---- CPU baseline on this box's host cores (bounded sample)
-    if edges:
-        A0, B0 = synth.sample_edges(robot, lambda Q: eng.feasible_batch(Q), 4000, 99)
-        cv, cores, cdone, cused, cfeas = cpu_leg(orc, lambda k, n: (A0, B0), args.cpu_seconds, edges=True)
-    else:
-        cv, cores, cdone, cused, cfeas = cpu_leg(orc, gen_configs, args.cpu_seconds, slice_n=(10_000 if with_dist else 100_000), with_dist=with_dist)
-    t1 = time.perf_counter()
-    n1 = 20000 if not edges else 500
-    if edges:
-        orc.edges_visible_batch(A0[:n1], B0[:n1], eps=0.01, nthreads=1)
-    else:
-        orc.feasible_batch(gen_configs(0, n1), nthreads=1)
-    single = n1 / (time.perf_counter() - t1)
+    # ---- CPU baseline on this box's host cores (bounded sample; rank 0 at N=1 only)
+    cpu_baseline = None
+    if world == 1:
+        if edges:
+            A0, B0 = synth.sample_edges(robot, lambda Q: eng.feasible_batch(Q), 4000, 99)
+            cv, cores, cdone, cused, cfeas = cpu_leg(orc, lambda k, n: (A0, B0), args.cpu_seconds, edges=True)
+        else:
+            cv, cores, cdone, cused, cfeas = cpu_leg(orc, gen_configs, args.cpu_seconds, slice_n=(10_000 if with_dist else 100_000), with_dist=with_dist)
+        t1 = time.perf_counter()
+        n1 = 20000 if not edges else 500
+        if edges:
+            orc.edges_visible_batch(A0[:n1], B0[:n1], eps=0.01, nthreads=1)
+        else:
+            orc.feasible_batch(gen_configs(0, n1), nthreads=1)
+            if with_dist:
+                orc.distance_batch(gen_configs(0, n1), upper_bound=0.5, include_self=False, nthreads=1)
+        single = n1 / (time.perf_counter() - t1)
+        cpu_baseline = {"value": cv, "unit": unit, "cores": cores, "kind": "port",
+                        "sample": "%d %s in %.1f s (successive slices of the same workload), oracle + OpenMP on all host threads; single thread: %.0f %s"
+                                  % (cdone, "edges" if edges else "configurations", cused, single, unit),
+                        "single_core": single, "feasible_fraction": cfeas}
 
     line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 traversal + f64 FK/recheck",
@@ -361,10 +371,7 @@ def main():
                        "parallelism": "configs sharded, geometry replicated" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": {"value": cv, "unit": unit, "cores": cores, "kind": "port",
-                             "sample": "%d %s in %.1f s (successive 100k slices of the same workload), oracle + OpenMP on all host threads; single thread: %.0f %s"
-                                       % (cdone, "edges" if edges else "configurations", cused, single, unit),
-                             "single_core": single, "feasible_fraction": cfeas}}
+            "cpu_baseline": cpu_baseline}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
