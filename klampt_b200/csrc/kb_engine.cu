@@ -323,8 +323,9 @@ template <class T> int grow(T*& p, int64_t& cap, int64_t need) {
 }
 template <class T> int grow_plain(T*& p, int64_t need_elems, int64_t& cap_elems) { return grow(p, cap_elems, need_elems); }
 
-int ensure_cfg_scratch(kb_engine* e, int nxf) {
-  int64_t ch = e->chunk;
+// per-configuration scratch for `n` configurations per launch (grown on demand, never shrunk)
+int ensure_cfg_scratch(kb_engine* e, int nxf, int64_t n) {
+  int64_t ch = std::max<int64_t>(1024, std::min(e->chunk, n));
   int64_t need_xf = ch * nxf * 12;
   if (need_xf > e->xf_cap) { if (e->d_xf) cudaFree(e->d_xf); e->d_xf = nullptr; e->xf_cap = 0; CK(cudaMalloc((void**)&e->d_xf, (size_t)need_xf * 8)); e->xf_cap = need_xf; }
   if (ch > e->cfg_cap) {
@@ -374,7 +375,7 @@ KbTraverseParams make_params(kb_engine* e, const ItemSet& set, const double* xf,
 
 // feasibility of n configurations resident on the device: FK -> traversal -> finish, chunk by chunk
 int run_feasible_device(kb_engine* e, const double* dQ, int64_t N, uint8_t* d_out, int32_t* d_first_pair, unsigned long long* d_nfeas) {
-  int rc = ensure_cfg_scratch(e, e->feas_items.nxf); if (rc) return rc;
+  int rc = ensure_cfg_scratch(e, e->feas_items.nxf, N); if (rc) return rc;
   for (int64_t off = 0; off < N; off += e->chunk) {
     int64_t n = std::min(e->chunk, N - off);
     CK(kb_launch_fk(e->d_robot, e->d_drv, e->d_drv_link, e->d_drv_scale, e->d_drv_off, dQ + off * e->L, n, e->d_xf, e->feas_items.nxf, e->d_state, nullptr, e->d_hit, e->stream));
@@ -669,9 +670,11 @@ int kb_finalize(kb_engine* e, int device) {
   // the host copies of the big arrays are no longer needed
   std::vector<float>().swap(e->h_tris32); std::vector<double>().swap(e->h_tris64); std::vector<float>().swap(e->h_sph32); std::vector<double>().swap(e->h_sph64);
   std::vector<float>().swap(e->h_nodes);
-  // keep the L2 warm with whole chunks: ~96 B per link per configuration of transform traffic
+  // Configurations per launch.  Configuration cost varies by two orders of magnitude, so every launch ends with a tail of
+  // idle SMs; measured on C2 a 71 k chunk (transforms L2-resident) runs 26 % slower than a 1 M chunk (transforms through
+  // HBM: 2 x 96 L bytes per configuration, ~2 % of the step).  Use up to 1 M per launch within a 2 GB scratch budget.
   int64_t per_cfg = (int64_t)L * 96 + 16;
-  int64_t ch = (48ll << 20) / per_cfg; ch = std::max<int64_t>(8192, std::min<int64_t>(ch, 262144)); e->chunk = (ch / 1024) * 1024;
+  int64_t ch = (2048ll << 20) / per_cfg; ch = std::max<int64_t>(8192, std::min<int64_t>(ch, 1 << 20)); e->chunk = (ch / 1024) * 1024;
   e->finalized = true;
   return KB_OK;
 }
@@ -702,7 +705,7 @@ int kb_fk_batch(kb_engine* e, const double* Q, int64_t N, double* T_out) {
   if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
   if (N < 0 || (N > 0 && (!Q || !T_out))) return fail(KB_ERR_INVALID, "bad arguments");
   CK(cudaSetDevice(e->device));
-  int rc = ensure_cfg_scratch(e, e->L); if (rc) return rc;
+  int rc = ensure_cfg_scratch(e, e->L, N); if (rc) return rc;
   if ((rc = grow(e->d_Q, e->q_cap, std::min(N, e->chunk) * e->L))) return rc;
   for (int64_t off = 0; off < N; off += e->chunk) {
     int64_t n = std::min(e->chunk, N - off);
@@ -830,7 +833,7 @@ int kb_distance_batch_device(kb_engine* e, const double* dQ, int64_t N, double u
   if (N < 0 || (N > 0 && (!dQ || !d_out_d))) return fail(KB_ERR_INVALID, "bad arguments");
   CK(cudaSetDevice(e->device));
   const ItemSet& set = include_self ? e->feas_items : e->env_items;
-  int rc = ensure_cfg_scratch(e, set.nxf); if (rc) return rc;
+  int rc = ensure_cfg_scratch(e, set.nxf, N); if (rc) return rc;
   if (std::isinf(upper_bound) || upper_bound > 1e300) upper_bound = 1e300;
   for (int64_t off = 0; off < N; off += e->chunk) {
     int64_t n = std::min(e->chunk, N - off);
@@ -886,8 +889,10 @@ static int geom_pair_query(kb_engine* e, int ga, const double* Ta, int gb, const
   if ((rc = grow(e->d_T, e->t_cap, N * 24))) { cudaFree(set.d_items); return rc; }
   if ((rc = grow(e->d_dist, e->dist_cap, N))) { cudaFree(set.d_items); return rc; }
   int64_t save_chunk = e->chunk;
-  if (N > e->cfg_cap) { e->chunk = std::max(e->chunk, N); if ((rc = ensure_cfg_scratch(e, 2))) { e->chunk = save_chunk; cudaFree(set.d_items); return rc; } e->chunk = save_chunk; }
-  else if ((rc = ensure_cfg_scratch(e, 2))) { cudaFree(set.d_items); return rc; }
+  e->chunk = std::max(e->chunk, N);            // the explicit-pair query runs as one launch
+  rc = ensure_cfg_scratch(e, 2, N);
+  e->chunk = save_chunk;
+  if (rc) { cudaFree(set.d_items); return rc; }
   cudaError_t ce = cudaMemcpyAsync(e->d_T, host.data(), host.size() * 8, cudaMemcpyHostToDevice, e->stream);
   if (ce == cudaSuccess) ce = kb_launch_fill_i32(e->d_hit, N, -1, e->stream);
   KbTraverseParams p = make_params(e, set, e->d_T, N, nullptr);

@@ -307,6 +307,15 @@ __device__ __forceinline__ void drain_rechecks(const KbTraverseParams& p, uint4*
 // lanes (__ballot_sync early exit).  Per configuration the relative transform of every work item is computed once
 // into shared memory (ITC), so a node test is 2 LDS.64/128 + 4 LDG.128 + ~60 FP instructions.
 // MODE 0: boolean collide / within-threshold.  MODE 1: branch-and-bound distance.
+// one 32-byte node = one 256-bit load (LDG.E.256 on sm_100): a scattered node fetch then costs one L1 wavefront per
+// lane instead of two -- the traversal is bound by L1 wavefronts, not by bytes (profiles/r01_*).
+__device__ __forceinline__ void load_node(const float4* __restrict__ nodes, size_t idx, float4& n0, float4& n1) {
+  unsigned long long x0, x1, x2, x3;
+  asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(x0), "=l"(x1), "=l"(x2), "=l"(x3) : "l"(nodes + 2 * idx));
+  n0.x = __uint_as_float((unsigned)x0); n0.y = __uint_as_float((unsigned)(x0 >> 32)); n0.z = __uint_as_float((unsigned)x1); n0.w = __uint_as_float((unsigned)(x1 >> 32));
+  n1.x = __uint_as_float((unsigned)x2); n1.y = __uint_as_float((unsigned)(x2 >> 32)); n1.z = __uint_as_float((unsigned)x3); n1.w = __uint_as_float((unsigned)(x3 >> 32));
+}
+
 struct ItemS { int32_t nodeA, nodeB; float infl; int32_t xf; };   // 16 B static per-item record cached per block
 
 __device__ __forceinline__ bool sat6_overlap(const float4& ac, const float4& ah, const float4& bc, const float4& bh, const XfF& T, float infl) {
@@ -376,12 +385,21 @@ kb_traverse_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
   const unsigned lt_mask = (1u << lane) - 1u;
   unsigned long long st_node = 0, st_leaf = 0, st_re = 0;
 
+  // guided self-scheduling: 8 configurations per grab while work is plentiful, down to 1 near the end of the launch, so
+  // the tail is one configuration long (configuration cost varies by two orders of magnitude)
+  const unsigned total_warps = gridDim.x * KB_WARPS_PER_BLOCK;
+  unsigned grab = 8;
   for (;;) {
     unsigned int c0 = 0;
-    if (lane == 0) c0 = atomicAdd(p.work_counter, 8u);
+    if (lane == 0) c0 = atomicAdd(p.work_counter, grab);
     c0 = __shfl_sync(FULL, c0, 0);
     if ((int64_t)c0 >= p.N) break;
-    const int64_t cend = ((int64_t)c0 + 8 < p.N) ? (int64_t)c0 + 8 : p.N;
+    const int64_t cend = ((int64_t)c0 + grab < p.N) ? (int64_t)c0 + grab : p.N;
+    {
+      const int64_t rem = p.N - cend;
+      const int64_t g = rem / (4 * (int64_t)total_warps);
+      grab = g >= 8 ? 8u : (g < 1 ? 1u : (unsigned)g);
+    }
     for (int64_t c = c0; c < cend; c++) {
       if (p.state && p.state[c] == 0) continue;
       const double* xf = p.xf64 + c * (int64_t)p.nxf * 12;
@@ -419,8 +437,9 @@ kb_traverse_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
             item = (int)(e.x >> KB_NODEA_BITS);
             const KbItem it = p.items[item];
             int na = (int)(e.x & (KB_MAX_NODES_A - 1)), nb = (int)e.y;
-            float4 a0 = __ldg(sc.nodes + 2 * (size_t)(it.nodeA + na)), a1 = __ldg(sc.nodes + 2 * (size_t)(it.nodeA + na) + 1);
-            float4 b0 = __ldg(sc.nodes + 2 * (size_t)(it.nodeB + nb)), b1 = __ldg(sc.nodes + 2 * (size_t)(it.nodeB + nb) + 1);
+            float4 a0, a1, b0, b1;
+            load_node(sc.nodes, (size_t)(it.nodeA + na), a0, a1);
+            load_node(sc.nodes, (size_t)(it.nodeB + nb), b0, b1);
             int fa = it.elemA + ~__float_as_int(a0.w), ca = __float_as_int(a1.w);
             int fb = it.elemB + ~__float_as_int(b0.w), cb = __float_as_int(b1.w);
             if (MODE == 0) {
@@ -495,8 +514,9 @@ kb_traverse_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
             if (MODE == 1) { marg = itp->marg; rsum = itp->rsum; }
           }
           const int na = (int)(e.x & (KB_MAX_NODES_A - 1)), nb = (int)e.y;
-          const float4 a0 = __ldg(sc.nodes + 2 * (size_t)(nodeA + na)), a1 = __ldg(sc.nodes + 2 * (size_t)(nodeA + na) + 1);
-          const float4 b0 = __ldg(sc.nodes + 2 * (size_t)(nodeB + nb)), b1 = __ldg(sc.nodes + 2 * (size_t)(nodeB + nb) + 1);
+          float4 a0, a1, b0, b1;
+          load_node(sc.nodes, (size_t)(nodeA + na), a0, a1);
+          load_node(sc.nodes, (size_t)(nodeB + nb), b0, b1);
           st_node++;
           bool ov;
           if (MODE == 0) ov = sat6_overlap(a0, a1, b0, b1, T, infl);

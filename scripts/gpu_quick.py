@@ -24,6 +24,8 @@ print("mismatches:", len(bad), "per config: node %.1f elem %.1f recheck %.2f" % 
 for i in bad[:10]:
     print("  cfg", i, "gpu", got[i], "oracle", want[i], "clearance", orc.distance(Q[i], 1.0, True))
 eng.set_option("collect_stats", 0)
+if len(sys.argv) > 3:
+    eng.set_option("chunk", int(sys.argv[3]))
 dQ = torch.from_numpy(Q).cuda()
 dout = torch.empty(N, dtype=torch.uint8, device="cuda")
 eng.set_stream(torch.cuda.current_stream().cuda_stream)
