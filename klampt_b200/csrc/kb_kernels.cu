@@ -279,7 +279,7 @@ __device__ __forceinline__ void drain_rechecks(const KbTraverseParams& p, uint4*
       const int64_t c = (int64_t)e.x;
       const bool moot = (c == cur_c) ? (found >= 0) : (p.hit[c] >= 0);
       if (!moot) {
-        const KbItem it = p.items[e.y];
+        const KbItem& it = p.items[e.y];
         yes = exact_elem_collide(p.scene, it, p.xf64 + c * (int64_t)p.nxf * 12, (int)e.z, (int)e.w);
       }
     }
@@ -354,8 +354,8 @@ __device__ __forceinline__ void load_itc(const float* __restrict__ itc, int item
   T.t[0] = q2.y; T.t[1] = q2.z; T.t[2] = q2.w;
 }
 
-template <int MODE, bool ITC>
-__global__ void __launch_bounds__(KB_WARPS_PER_BLOCK * 32, KB_BLOCKS_PER_SM)
+template <int MODE, bool ITC, bool STATS, int BPS>
+__global__ void __launch_bounds__(KB_WARPS_PER_BLOCK * 32, BPS)
 kb_traverse_kernel(const KbTraverseParams p, double* __restrict__ out_dist, double upper_bound) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -382,8 +382,9 @@ kb_traverse_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
   }
   if (lane == 0) *rq_count = 0;
   __syncthreads();
-  const unsigned lt_mask = (1u << lane) - 1u;
-  unsigned long long st_node = 0, st_leaf = 0, st_re = 0;
+  unsigned lt_mask;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
+  unsigned st_node = 0, st_leaf = 0, st_re = 0;   // only maintained when STATS
 
   // guided self-scheduling: 8 configurations per grab while work is plentiful, down to 1 near the end of the launch, so
   // the tail is one configuration long (configuration cost varies by two orders of magnitude)
@@ -394,15 +395,15 @@ kb_traverse_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
     if (lane == 0) c0 = atomicAdd(p.work_counter, grab);
     c0 = __shfl_sync(FULL, c0, 0);
     if ((int64_t)c0 >= p.N) break;
-    const int64_t cend = ((int64_t)c0 + grab < p.N) ? (int64_t)c0 + grab : p.N;
+    const unsigned nN = (unsigned)p.N;
+    const unsigned cend = (c0 + grab < nN) ? c0 + grab : nN;
     {
-      const int64_t rem = p.N - cend;
-      const int64_t g = rem / (4 * (int64_t)total_warps);
-      grab = g >= 8 ? 8u : (g < 1 ? 1u : (unsigned)g);
+      const unsigned g = (nN - cend) / (4u * total_warps);
+      grab = g >= 8u ? 8u : (g < 1u ? 1u : g);
     }
-    for (int64_t c = c0; c < cend; c++) {
+    for (unsigned c = c0; c < cend; c++) {
       if (p.state && p.state[c] == 0) continue;
-      const double* xf = p.xf64 + c * (int64_t)p.nxf * 12;
+      const double* xf = p.xf64 + (size_t)c * (size_t)p.nxf * 12;
       __syncwarp();
       for (int i = lane; i < p.nxf * 12; i += 32) xfw[i] = (float)xf[i];
       __syncwarp();
@@ -435,7 +436,7 @@ kb_traverse_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
           if (lane < m) {
             uint2 e = leafq[nleaf - 1 - lane];
             item = (int)(e.x >> KB_NODEA_BITS);
-            const KbItem it = p.items[item];
+            const KbItem& it = p.items[item];
             int na = (int)(e.x & (KB_MAX_NODES_A - 1)), nb = (int)e.y;
             float4 a0, a1, b0, b1;
             load_node(sc.nodes, (size_t)(it.nodeA + na), a0, a1);
@@ -449,9 +450,9 @@ kb_traverse_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
               for (int i = 0; i < ca && res != KB_YES; i++)
                 for (int j = 0; j < cb && res != KB_YES; j++) {
                   int r = fast_elem_collide(sc, it, T, fa + i, fb + j, thr);
-                  st_leaf++;
+                  if (STATS) st_leaf++;
                   if (r == KB_UNCERTAIN) {
-                    st_re++;
+                    if (STATS) st_re++;
                     const int slot = atomicAdd(rq_count, 1);
                     if (slot < KB_RQ_CAP) { rq[slot] = make_uint4((unsigned)c, (unsigned)item, (unsigned)(fa + i), (unsigned)(fb + j)); r = KB_NO; }
                     else r = exact_elem_collide(sc, it, xf, fa + i, fb + j) ? KB_YES : KB_NO;   // queue full: recheck in place
@@ -462,7 +463,7 @@ kb_traverse_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
               for (int i = 0; i < ca; i++)
                 for (int j = 0; j < cb; j++) {
                   double d = exact_elem_distance(sc, it, xf, fa + i, fb + j) - it.marg;
-                  st_leaf++;
+                  if (STATS) st_leaf++;
                   if (d < dmin) { dmin = d; ea = fa + i; eb = fb + j; }
                 }
             }
@@ -475,7 +476,7 @@ kb_traverse_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
               found = __shfl_sync(FULL, item, src); found_ea = __shfl_sync(FULL, ea, src); found_eb = __shfl_sync(FULL, eb, src);
               break;
             }
-            drain_rechecks(p, rq, rq_count, lane, c, found, found_ea, found_eb, false);
+            drain_rechecks(p, rq, rq_count, lane, (int64_t)c, found, found_ea, found_eb, false);
             if (found >= 0) break;
           } else {
             double wmin = dmin;
@@ -517,7 +518,7 @@ kb_traverse_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
           float4 a0, a1, b0, b1;
           load_node(sc.nodes, (size_t)(nodeA + na), a0, a1);
           load_node(sc.nodes, (size_t)(nodeB + nb), b0, b1);
-          st_node++;
+          if (STATS) st_node++;
           bool ov;
           if (MODE == 0) ov = sat6_overlap(a0, a1, b0, b1, T, infl);
           else {
@@ -546,25 +547,31 @@ kb_traverse_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
         sp += 2 * __popc(pm); nleaf += __popc(lm);
         __syncwarp();
       }
+      if (STATS) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          st_node += __shfl_xor_sync(FULL, st_node, o); st_leaf += __shfl_xor_sync(FULL, st_leaf, o); st_re += __shfl_xor_sync(FULL, st_re, o);
+        }
+        if (lane == 0 && p.counters) {
+          atomicAdd(p.counters + 0, (unsigned long long)st_re); atomicAdd(p.counters + 1, (unsigned long long)st_node); atomicAdd(p.counters + 2, (unsigned long long)st_leaf);
+        }
+        st_node = st_leaf = st_re = 0;
+      }
       if (lane == 0) {
         if (MODE == 0) {
           p.hit[c] = found;
-          if (p.hit_elem) { p.hit_elem[2 * c] = found_ea; p.hit_elem[2 * c + 1] = found_eb; }
+          if (p.hit_elem) { p.hit_elem[2 * (size_t)c] = found_ea; p.hit_elem[2 * (size_t)c + 1] = found_eb; }
         } else {
           out_dist[c] = best;
           p.hit[c] = best_item;
-          if (p.hit_elem) { p.hit_elem[2 * c] = best_ea; p.hit_elem[2 * c + 1] = best_eb; }
+          if (p.hit_elem) { p.hit_elem[2 * (size_t)c] = best_ea; p.hit_elem[2 * (size_t)c + 1] = best_eb; }
         }
       }
     }
   }
   if (MODE == 0) { int f = 0, fa = 0, fb = 0; drain_rechecks(p, rq, rq_count, lane, (int64_t)-1, f, fa, fb, true); }
-  if (p.collect_stats && p.counters) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      st_node += __shfl_xor_sync(FULL, st_node, o); st_leaf += __shfl_xor_sync(FULL, st_leaf, o); st_re += __shfl_xor_sync(FULL, st_re, o);
-    }
-    if (lane == 0) { atomicAdd(p.counters + 0, st_re); atomicAdd(p.counters + 1, st_node); atomicAdd(p.counters + 2, st_leaf); }
+  if (STATS && p.counters) {
+    // per-lane 32-bit counters are flushed per configuration (see below); nothing left to do here
   }
 }
 
@@ -729,18 +736,18 @@ cudaError_t kb_launch_fk(const KbRobotDev* robot, const KbDriverDev* drv, const 
   return cudaGetLastError();
 }
 
-template <int MODE, bool ITC>
+template <int MODE, bool ITC, bool STATS, int BPS>
 static cudaError_t launch_traverse_t(const KbTraverseParams& p, double* out_dist, double upper_bound, int num_sms, size_t smem, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kb_traverse_kernel<MODE, ITC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(kb_traverse_kernel<MODE, ITC, STATS, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  int per_sm = (int)((224 * 1024) / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > KB_BLOCKS_PER_SM) per_sm = KB_BLOCKS_PER_SM;
+  int per_sm = (int)((224 * 1024) / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > BPS) per_sm = BPS;
   int64_t want = (p.N + 8 * KB_WARPS_PER_BLOCK - 1) / (8 * KB_WARPS_PER_BLOCK);
   int64_t grid = (int64_t)num_sms * per_sm; if (grid > want) grid = want; if (grid < 1) grid = 1;
-  kb_traverse_kernel<MODE, ITC><<<(unsigned)grid, KB_WARPS_PER_BLOCK * 32, smem, s>>>(p, out_dist, upper_bound);
+  kb_traverse_kernel<MODE, ITC, STATS, BPS><<<(unsigned)grid, KB_WARPS_PER_BLOCK * 32, smem, s>>>(p, out_dist, upper_bound);
   return cudaGetLastError();
 }
 
@@ -751,8 +758,19 @@ cudaError_t kb_launch_traverse(const KbTraverseParams& p, int mode, double* out_
   cudaError_t e = cudaMemsetAsync(p.work_counter, 0, sizeof(uint32_t), s);
   if (e != cudaSuccess) return e;
   const bool itc = p.nitems <= KB_ITC_MAX_ITEMS;
-  if (mode == 0) return itc ? launch_traverse_t<0, true>(p, out_dist, upper_bound, num_sms, smem, s) : launch_traverse_t<0, false>(p, out_dist, upper_bound, num_sms, smem, s);
-  return itc ? launch_traverse_t<1, true>(p, out_dist, upper_bound, num_sms, smem, s) : launch_traverse_t<1, false>(p, out_dist, upper_bound, num_sms, smem, s);
+  if (p.N > 0xfffffff0ll) return cudaErrorInvalidValue;
+  // two register budgets are compiled: 4 CTAs/SM (128 registers, a few spills) wins when the per-CTA shared memory is
+  // small (few work items per configuration, C2: 8.9 vs 9.2 ms), 3 CTAs/SM (168 registers, no spills) wins when the
+  // item cache is large (C3, 107 pairs: 10.5 vs 11.8 ms).  Measured on B200, profiles/r01_experiments.md.
+  const bool four = smem <= 40 * 1024;
+#define KB_LT(M, I, S) (four ? launch_traverse_t<M, I, S, 4>(p, out_dist, upper_bound, num_sms, smem, s) : launch_traverse_t<M, I, S, 3>(p, out_dist, upper_bound, num_sms, smem, s))
+  if (p.collect_stats) {
+    if (mode == 0) return itc ? KB_LT(0, true, true) : KB_LT(0, false, true);
+    return itc ? KB_LT(1, true, true) : KB_LT(1, false, true);
+  }
+  if (mode == 0) return itc ? KB_LT(0, true, false) : KB_LT(0, false, false);
+  return itc ? KB_LT(1, true, false) : KB_LT(1, false, false);
+#undef KB_LT
 }
 
 cudaError_t kb_launch_finish(const uint8_t* state, const int32_t* hit, const int32_t* hit_elem, const KbItem* items, const int32_t* triown,
