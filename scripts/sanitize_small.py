@@ -1,0 +1,21 @@
+"""small end-to-end pass for compute-sanitizer (memcheck / racecheck): feasibility, edges, distance, pair queries"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from klampt_b200 import synth
+from klampt_b200.engine import Engine
+w = synth.world_c2(2, n_obstacles=20)
+eng = Engine(w)
+Q = synth.sample_configs(w.robot, 3000, 1)
+f, pairs = eng.feasible_batch(Q, return_pairs=True)
+A, B = Q[f == 1][:64], Q[f == 1][64:128]
+v, n = eng.edges_visible_batch(A, B, eps=0.02)
+d = eng.distance_batch(Q[:300], upper_bound=0.3, include_self=True)
+w3 = synth.world_c3()
+e3 = Engine(w3)
+f3 = e3.feasible_batch(synth.sample_configs(w3.robot, 2000, 3))
+w5 = synth.world_c5(n_points=20000, n_obstacles=20)
+e5 = Engine(w5)
+f5 = e5.feasible_batch(synth.sample_configs(w5.robot, 1500, 5))
+d5 = e5.distance_batch(synth.sample_configs(w5.robot, 200, 5), upper_bound=0.5)
+print("ok", f.mean(), v.mean(), float(d.min()), f3.mean(), f5.mean(), float(d5.min()))
