@@ -575,6 +575,220 @@ kb_traverse_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
   }
 }
 
+// =============================================================================================== distance traversal
+// Branch and bound over the same flattened BVHs (replaces AnyCollisionQuery::Distance behind
+// WorldPlannerSettings::DistanceLowerBound, reference Cpp/Planning/PlannerSettings.cpp:109-115,570-620).  One warp per
+// configuration, LIFO frontier in shared memory like the boolean kernel, but organised for pruning instead of early exit:
+//   * test-before-push: a lane pops one pair, loads the two children of the side chosen for splitting (one 64 B line)
+//     and the other side's node, computes both box-distance lower bounds and pushes the survivors FARTHER FIRST, so the
+//     nearer child is on top of the stack -- a greedy descent that reaches a small distance quickly;
+//   * every entry carries its lower bound and is re-checked against the running minimum when popped;
+//   * narrow pops (8) until the first element distance has tightened the bound, then 32-wide;
+//   * leaf pairs are evaluated eagerly while no bound is known; element distances are fp64 throughout.
+#define KB_SPLIT_B 0x80000000u
+
+__device__ __forceinline__ void classify_pair(unsigned itembits, int na, int nb, const float4& a0, const float4& a1, const float4& b0, const float4& b1,
+                                              bool& leaf, uint2& e) {
+  const int la = __float_as_int(a0.w), lb = __float_as_int(b0.w);
+  if (la < 0 && lb < 0) { leaf = true; e = make_uint2(itembits | (unsigned)na, (unsigned)nb); return; }
+  leaf = false;
+  const float sa2 = a1.x * a1.x + a1.y * a1.y + a1.z * a1.z, sb2 = b1.x * b1.x + b1.y * b1.y + b1.z * b1.z;
+  if (lb < 0 || (la >= 0 && sa2 >= sb2)) e = make_uint2(itembits | (unsigned)la, (unsigned)nb);          // split A: slot A holds A's first child
+  else e = make_uint2(itembits | (unsigned)na, (unsigned)lb | KB_SPLIT_B);                                // split B: slot B holds B's first child
+}
+
+template <bool ITC, bool STATS>
+__global__ void __launch_bounds__(KB_WARPS_PER_BLOCK * 32, 3)
+kb_distance_kernel(const KbTraverseParams p, double* __restrict__ out_dist, double upper_bound) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int xf_floats = (p.nxf * 12 + 3) & ~3;
+  const int nit_c = ITC ? p.nitems : 0;
+  ItemS* s_items = (ItemS*)smem_raw;
+  const size_t per_warp = (size_t)KB_STACK_CAP * 12 + (size_t)KB_LEAFQ_CAP * 12 + (size_t)xf_floats * 4 + (size_t)nit_c * 48;
+  unsigned char* base = smem_raw + (size_t)nit_c * 16 + warp * per_warp;
+  uint2* stack = (uint2*)base;
+  uint2* leafq = (uint2*)(base + (size_t)KB_STACK_CAP * 8);
+  float* stack_lb = (float*)(base + (size_t)KB_STACK_CAP * 8 + (size_t)KB_LEAFQ_CAP * 8);
+  float* leaf_lb = stack_lb + KB_STACK_CAP;
+  float* xfw = leaf_lb + KB_LEAFQ_CAP;
+  float* itc = xfw + xf_floats;
+  const KbScene& sc = p.scene;
+  const float slack = 4.f * sc.eps_abs;
+  if (ITC) {
+    for (int i = threadIdx.x; i < p.nitems; i += blockDim.x) {
+      const KbItem* it = p.items + i;
+      ItemS s; s.nodeA = it->nodeA; s.nodeB = it->nodeB; s.infl = (float)(it->marg);      // infl slot reused: margin sum
+      s.xf = (int)((unsigned)(unsigned short)it->xfA | ((unsigned)(unsigned short)it->xfB << 16));
+      s_items[i] = s;
+    }
+  }
+  __syncthreads();
+  unsigned lt_mask;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
+  unsigned st_node = 0, st_leaf = 0;
+  const unsigned total_warps = gridDim.x * KB_WARPS_PER_BLOCK;
+  unsigned grab = 4;
+  for (;;) {
+    unsigned int c0 = 0;
+    if (lane == 0) c0 = atomicAdd(p.work_counter, grab);
+    c0 = __shfl_sync(FULL, c0, 0);
+    if ((int64_t)c0 >= p.N) break;
+    const unsigned nN = (unsigned)p.N;
+    const unsigned cend = (c0 + grab < nN) ? c0 + grab : nN;
+    { const unsigned g = (nN - cend) / (4u * total_warps); grab = g >= 4u ? 4u : (g < 1u ? 1u : g); }
+    for (unsigned c = c0; c < cend; c++) {
+      const double* xf = p.xf64 + (size_t)c * (size_t)p.nxf * 12;
+      __syncwarp();
+      for (int i = lane; i < p.nxf * 12; i += 32) xfw[i] = (float)xf[i];
+      __syncwarp();
+      if (ITC) {
+        for (int i = lane; i < p.nitems; i += 32) {
+          const int xfp = s_items[i].xf;
+          XfF T; rel_xf(xfw, (int)(short)(xfp & 0xffff), (int)(short)(xfp >> 16), T);
+          float4* q = (float4*)(itc + 12 * i);
+          q[0] = make_float4(T.r[0], T.r[1], T.r[2], T.r[3]); q[1] = make_float4(T.r[4], T.r[5], T.r[6], T.r[7]); q[2] = make_float4(T.r[8], T.t[0], T.t[1], T.t[2]);
+        }
+        __syncwarp();
+      }
+      int sp = 0, nleaf = 0, cursor = 0;
+      double best = upper_bound;                       // running minimum, margins already subtracted
+      float bestf = (float)fmin(upper_bound, 3.0e38);  // fp32 copy rounded up, for the box tests
+      if ((double)bestf < best) bestf = nextafterf(bestf, INFINITY);
+      int best_item = -1, best_ea = -1, best_eb = -1;
+      bool have_bound = false;
+      for (;;) {
+        const bool feed = sp < 32 && nleaf < 32 && cursor < p.nitems;
+        if (!feed) {
+          if (sp == 0 && nleaf == 0) break;
+          if (nleaf >= 16 || sp == 0 || (nleaf > 0 && !have_bound)) {
+            // -------------------------------------------------------------- element phase (fp64)
+            const int m = nleaf < 32 ? nleaf : 32;
+            int ea = -1, eb = -1, item = 0;
+            double dmin = 1e300;
+            if (lane < m && leaf_lb[nleaf - 1 - lane] < bestf) {
+              const uint2 e = leafq[nleaf - 1 - lane];
+              item = (int)(e.x >> KB_NODEA_BITS);
+              const KbItem& it = p.items[item];
+              const int na = (int)(e.x & (KB_MAX_NODES_A - 1)), nb = (int)e.y;
+              float4 a0, a1, b0, b1;
+              load_node(sc.nodes, (size_t)(it.nodeA + na), a0, a1);
+              load_node(sc.nodes, (size_t)(it.nodeB + nb), b0, b1);
+              const int fa = it.elemA + ~__float_as_int(a0.w), ca = __float_as_int(a1.w);
+              const int fb = it.elemB + ~__float_as_int(b0.w), cb = __float_as_int(b1.w);
+              const double marg = it.marg;
+              for (int i = 0; i < ca; i++)
+                for (int j = 0; j < cb; j++) {
+                  const double d = exact_elem_distance(sc, it, xf, fa + i, fb + j) - marg;
+                  if (STATS) st_leaf++;
+                  if (d < dmin) { dmin = d; ea = fa + i; eb = fb + j; }
+                }
+            }
+            nleaf -= m;
+            double wmin = dmin;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { const double x = __shfl_xor_sync(FULL, wmin, o); wmin = x < wmin ? x : wmin; }
+            if (wmin < best) {
+              const unsigned who = __ballot_sync(FULL, dmin == wmin);
+              const int src = __ffs(who) - 1;
+              best = wmin; best_item = __shfl_sync(FULL, item, src); best_ea = __shfl_sync(FULL, ea, src); best_eb = __shfl_sync(FULL, eb, src);
+              bestf = (float)best; if ((double)bestf < best) bestf = nextafterf(bestf, INFINITY);
+              have_bound = true;
+            }
+            __syncwarp();
+            continue;
+          }
+        }
+        // ------------------------------------------------------------------ node phase (or root feed)
+        int m;
+        uint2 e = make_uint2(0u, 0u);
+        bool live = false;
+        if (feed) { m = p.nitems - cursor; if (m > 32) m = 32; live = lane < m; }
+        else {
+          const int width = have_bound ? 32 : 8;
+          m = (sp <= p.wide_limit) ? (sp < width ? sp : width) : 1;
+          if (lane < m) { e = stack[sp - 1 - lane]; live = stack_lb[sp - 1 - lane] < bestf; }   // re-check against the current minimum
+          sp -= m;
+          __syncwarp();
+        }
+        bool ok0 = false, ok1 = false, leaf0 = false, leaf1 = false;
+        uint2 e0 = e, e1 = e;
+        float lb0 = 0.f, lb1 = 0.f;
+        if (live) {
+          const int item = feed ? cursor + lane : (int)(e.x >> KB_NODEA_BITS);
+          const unsigned itembits = (unsigned)item << KB_NODEA_BITS;
+          int nodeA, nodeB; float marg, rsum; XfF T;
+          if (ITC) {
+            const ItemS s = s_items[item];
+            nodeA = s.nodeA; nodeB = s.nodeB; marg = s.infl;
+            load_itc(itc, item, T);
+            rsum = (float)p.items[item].rsum;
+          } else {
+            const KbItem* itp = p.items + item;
+            nodeA = itp->nodeA; nodeB = itp->nodeB; marg = (float)itp->marg; rsum = (float)itp->rsum;
+            rel_xf(xfw, itp->xfA, itp->xfB, T);
+          }
+          // conservative fp32 bound on (element distance - margins): box gap minus slack; touching boxes only bound by -radii
+          const float margu = marg * (1.f + 2.4e-7f) + 1e-30f;
+          if (feed) {
+            float4 a0, a1, b0, b1;
+            load_node(sc.nodes, (size_t)nodeA, a0, a1);
+            load_node(sc.nodes, (size_t)nodeB, b0, b1);
+            if (STATS) st_node++;
+            const float g = box_dist_lb(a0, a1, b0, b1, T) - slack;
+            lb0 = (g > 0.f ? g * (1.f - 4e-7f) : -rsum * (1.f + 2.4e-7f)) - margu;
+            ok0 = lb0 < bestf;
+            if (ok0) classify_pair(itembits, 0, 0, a0, a1, b0, b1, leaf0, e0);
+          } else {
+            const bool splitB = (e.y & KB_SPLIT_B) != 0;
+            const int ra = (int)(e.x & (KB_MAX_NODES_A - 1)), rb = (int)(e.y & ~KB_SPLIT_B);
+            float4 c00, c01, c10, c11, o0, o1;
+            if (splitB) { load_node(sc.nodes, (size_t)(nodeB + rb), c00, c01); load_node(sc.nodes, (size_t)(nodeB + rb + 1), c10, c11); load_node(sc.nodes, (size_t)(nodeA + ra), o0, o1); }
+            else { load_node(sc.nodes, (size_t)(nodeA + ra), c00, c01); load_node(sc.nodes, (size_t)(nodeA + ra + 1), c10, c11); load_node(sc.nodes, (size_t)(nodeB + rb), o0, o1); }
+            if (STATS) st_node += 2;
+            float g0, g1;
+            if (splitB) { g0 = box_dist_lb(o0, o1, c00, c01, T) - slack; g1 = box_dist_lb(o0, o1, c10, c11, T) - slack; }
+            else { g0 = box_dist_lb(c00, c01, o0, o1, T) - slack; g1 = box_dist_lb(c10, c11, o0, o1, T) - slack; }
+            lb0 = (g0 > 0.f ? g0 * (1.f - 4e-7f) : -rsum * (1.f + 2.4e-7f)) - margu;
+            lb1 = (g1 > 0.f ? g1 * (1.f - 4e-7f) : -rsum * (1.f + 2.4e-7f)) - margu;
+            ok0 = lb0 < bestf; ok1 = lb1 < bestf;
+            if (splitB) {
+              if (ok0) classify_pair(itembits, ra, rb, o0, o1, c00, c01, leaf0, e0);
+              if (ok1) classify_pair(itembits, ra, rb + 1, o0, o1, c10, c11, leaf1, e1);
+            } else {
+              if (ok0) classify_pair(itembits, ra, rb, c00, c01, o0, o1, leaf0, e0);
+              if (ok1) classify_pair(itembits, ra + 1, rb, c10, c11, o0, o1, leaf1, e1);
+            }
+            if (ok0 && ok1 && lb0 < lb1) {              // candidate 1 is pushed last = on top: make it the nearer one
+              const uint2 te = e0; e0 = e1; e1 = te; const bool tl = leaf0; leaf0 = leaf1; leaf1 = tl; const float tf = lb0; lb0 = lb1; lb1 = tf;
+            }
+          }
+        }
+        if (feed) cursor += m;
+        const unsigned pm0 = __ballot_sync(FULL, ok0 && !leaf0), pm1 = __ballot_sync(FULL, ok1 && !leaf1);
+        const unsigned lm0 = __ballot_sync(FULL, ok0 && leaf0), lm1 = __ballot_sync(FULL, ok1 && leaf1);
+        if (ok0 && !leaf0) { const int o = sp + __popc(pm0 & lt_mask); stack[o] = e0; stack_lb[o] = lb0; }
+        if (ok1 && !leaf1) { const int o = sp + __popc(pm0) + __popc(pm1 & lt_mask); stack[o] = e1; stack_lb[o] = lb1; }
+        if (ok0 && leaf0) { const int o = nleaf + __popc(lm0 & lt_mask); leafq[o] = e0; leaf_lb[o] = lb0; }
+        if (ok1 && leaf1) { const int o = nleaf + __popc(lm0) + __popc(lm1 & lt_mask); leafq[o] = e1; leaf_lb[o] = lb1; }
+        sp += __popc(pm0) + __popc(pm1); nleaf += __popc(lm0) + __popc(lm1);
+        __syncwarp();
+      }
+      if (STATS) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { st_node += __shfl_xor_sync(FULL, st_node, o); st_leaf += __shfl_xor_sync(FULL, st_leaf, o); }
+        if (lane == 0 && p.counters) { atomicAdd(p.counters + 1, (unsigned long long)st_node); atomicAdd(p.counters + 2, (unsigned long long)st_leaf); }
+        st_node = st_leaf = 0;
+      }
+      if (lane == 0) {
+        out_dist[c] = best;
+        p.hit[c] = best_item;
+        if (p.hit_elem) { p.hit_elem[2 * (size_t)c] = best_ea; p.hit_elem[2 * (size_t)c + 1] = best_eb; }
+      }
+    }
+  }
+}
+
 // =============================================================================================== result kernels
 // feasible[c] = limits ok && no hit ; first_pair = world ids of the reported pair
 __global__ void kb_finish_kernel(const uint8_t* __restrict__ state, const int32_t* __restrict__ hit, const int32_t* __restrict__ hit_elem,
@@ -722,6 +936,27 @@ __global__ void kb_copy_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __re
 static inline unsigned int nblocks(int64_t n, int bs) { return (unsigned int)((n + bs - 1) / bs); }
 
 #define KB_ITC_MAX_ITEMS 256
+size_t kb_distance_smem_bytes(int nxf, int nitems) {
+  size_t xf_floats = ((size_t)nxf * 12 + 3) & ~(size_t)3;
+  size_t nit = nitems <= KB_ITC_MAX_ITEMS ? (size_t)nitems : 0;
+  return nit * 16 + (size_t)KB_WARPS_PER_BLOCK * ((size_t)KB_STACK_CAP * 12 + (size_t)KB_LEAFQ_CAP * 12 + xf_floats * 4 + nit * 48);
+}
+
+template <bool ITC, bool STATS>
+static cudaError_t launch_distance_t(const KbTraverseParams& p, double* out_dist, double upper_bound, int num_sms, size_t smem, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kb_distance_kernel<ITC, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  int per_sm = (int)((224 * 1024) / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > 3) per_sm = 3;
+  int64_t want = (p.N + KB_WARPS_PER_BLOCK - 1) / KB_WARPS_PER_BLOCK;
+  int64_t grid = (int64_t)num_sms * per_sm; if (grid > want) grid = want; if (grid < 1) grid = 1;
+  kb_distance_kernel<ITC, STATS><<<(unsigned)grid, KB_WARPS_PER_BLOCK * 32, smem, s>>>(p, out_dist, upper_bound);
+  return cudaGetLastError();
+}
+
 size_t kb_traverse_smem_bytes(int nxf, int nitems) {
   size_t xf_floats = ((size_t)nxf * 12 + 3) & ~(size_t)3;
   size_t nit = nitems <= KB_ITC_MAX_ITEMS ? (size_t)nitems : 0;
@@ -753,23 +988,24 @@ static cudaError_t launch_traverse_t(const KbTraverseParams& p, double* out_dist
 
 cudaError_t kb_launch_traverse(const KbTraverseParams& p, int mode, double* out_dist, double upper_bound, int num_sms, cudaStream_t s) {
   if (p.N <= 0) return cudaSuccess;
-  const size_t smem = kb_traverse_smem_bytes(p.nxf, p.nitems);
+  const size_t smem = mode == 0 ? kb_traverse_smem_bytes(p.nxf, p.nitems) : kb_distance_smem_bytes(p.nxf, p.nitems);
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
   cudaError_t e = cudaMemsetAsync(p.work_counter, 0, sizeof(uint32_t), s);
   if (e != cudaSuccess) return e;
   const bool itc = p.nitems <= KB_ITC_MAX_ITEMS;
+  if (p.N > 0xfffffff0ll) return cudaErrorInvalidValue;
+  if (mode == 1) {
+    if (p.collect_stats) return itc ? launch_distance_t<true, true>(p, out_dist, upper_bound, num_sms, smem, s) : launch_distance_t<false, true>(p, out_dist, upper_bound, num_sms, smem, s);
+    return itc ? launch_distance_t<true, false>(p, out_dist, upper_bound, num_sms, smem, s) : launch_distance_t<false, false>(p, out_dist, upper_bound, num_sms, smem, s);
+  }
   if (p.N > 0xfffffff0ll) return cudaErrorInvalidValue;
   // two register budgets are compiled: 4 CTAs/SM (128 registers, a few spills) wins when the per-CTA shared memory is
   // small (few work items per configuration, C2: 8.9 vs 9.2 ms), 3 CTAs/SM (168 registers, no spills) wins when the
   // item cache is large (C3, 107 pairs: 10.5 vs 11.8 ms).  Measured on B200, profiles/r01_experiments.md.
   const bool four = smem <= 40 * 1024;
 #define KB_LT(M, I, S) (four ? launch_traverse_t<M, I, S, 4>(p, out_dist, upper_bound, num_sms, smem, s) : launch_traverse_t<M, I, S, 3>(p, out_dist, upper_bound, num_sms, smem, s))
-  if (p.collect_stats) {
-    if (mode == 0) return itc ? KB_LT(0, true, true) : KB_LT(0, false, true);
-    return itc ? KB_LT(1, true, true) : KB_LT(1, false, true);
-  }
-  if (mode == 0) return itc ? KB_LT(0, true, false) : KB_LT(0, false, false);
-  return itc ? KB_LT(1, true, false) : KB_LT(1, false, false);
+  if (p.collect_stats) return itc ? KB_LT(0, true, true) : KB_LT(0, false, true);
+  return itc ? KB_LT(0, true, false) : KB_LT(0, false, false);
 #undef KB_LT
 }
 
