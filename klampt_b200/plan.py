@@ -1,0 +1,195 @@
+"""Batch-aware planner front end.
+
+The reference's planners call ``CSpace::IsFeasible`` once per sample and ``PathChecker(a,b)->IsVisible()`` once per
+candidate edge (Python/klampt/src/motionplanning.cpp:1327-1334); on a GPU engine that leaves the device idle.  This
+module keeps the user-facing shape of ``klampt.plan.cspace.MotionPlan`` (reference Python/klampt/plan/cspace.py:216-427:
+``MotionPlan(space, type, **options)``, ``setEndpoints``, ``addMilestone``, ``planMore``, ``getPath``, ``getRoadmap``,
+``getStats``, ``close``) but runs roadmap planners whose inner loops are the two batch calls:
+
+  'prm'       every round: sample a batch -> feasible_batch -> k nearest neighbours -> visible_batch on all candidate edges
+  'lazyprm*'  same sampling, but edges are only checked (in batches) when they lie on the current best path
+
+Options (MotionPlan.setOptions keys that apply): ``knn``, ``connectionThreshold``; plus ``batch`` (samples per planMore
+iteration).  The planners need a space with ``feasible_batch(Q)`` and ``visible_batch(A, B)`` (``RobotCSpace``), and use
+its ``distance`` metric restricted to the L2 form the engine implements.
+"""
+from __future__ import annotations
+
+import heapq
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+
+class MotionPlan:
+    _next_options: Dict[str, float] = {}
+
+    @staticmethod
+    def setOptions(**opts):
+        MotionPlan._next_options.update(opts)
+
+    def __init__(self, space, type: Optional[str] = None, **options):
+        if not (hasattr(space, "feasible_batch") and hasattr(space, "visible_batch")):
+            raise TypeError("MotionPlan needs a space with feasible_batch / visible_batch (klampt_b200.robotcspace.RobotCSpace)")
+        opts = dict(MotionPlan._next_options)
+        opts.update(options)
+        MotionPlan._next_options = {}
+        self.space = space
+        self.type = (type or "prm").lower()
+        if self.type not in ("prm", "prm*", "lazyprm*", "lazyprm"):
+            raise ValueError("planner type %r is not batched here; available: prm, prm*, lazyprm*" % type)
+        self.lazy = self.type.startswith("lazy")
+        self.knn = int(opts.get("knn", 10))
+        self.connectionThreshold = float(opts.get("connectionThreshold", float("inf")))
+        self.batch = int(opts.get("batch", 2048))
+        self.rng = np.random.default_rng(int(opts.get("seed", 0)))
+        lo, hi = np.array([b[0] for b in space.bound], dtype=np.float64), np.array([b[1] for b in space.bound], dtype=np.float64)
+        self._lo, self._hi = lo, np.where(np.isfinite(hi), hi, 2 * np.pi)
+        self._lo = np.where(np.isfinite(lo), lo, 0.0)
+        self.V = np.zeros((0, len(lo)))                    # milestones
+        self.adj: List[Dict[int, Tuple[float, bool]]] = []  # neighbour -> (length, checked)
+        self.start = self.goal = None
+        self.stats = {"samples": 0, "feasible_samples": 0, "edges_checked": 0, "edges_visible": 0, "iterations": 0}
+
+    # ------------------------------------------------------------------ roadmap primitives
+    def addMilestone(self, q: Sequence[float]) -> int:
+        q = np.asarray(q, dtype=np.float64).reshape(1, -1)
+        if not bool(self.space.feasible_batch(q)[0]):
+            raise RuntimeError("milestone is infeasible")
+        return self._add_vertices(q)[0]
+
+    def _add_vertices(self, Q: np.ndarray) -> List[int]:
+        base = len(self.V)
+        self.V = np.vstack([self.V, Q])
+        self.adj.extend({} for _ in range(len(Q)))
+        return list(range(base, base + len(Q)))
+
+    def setEndpoints(self, start: Sequence[float], goal: Sequence[float]):
+        ends = np.array([start, goal], dtype=np.float64)
+        ok = self.space.feasible_batch(ends)
+        if not ok[0]:
+            raise RuntimeError("Start configuration is infeasible")
+        if not ok[1]:
+            raise RuntimeError("Goal configuration is infeasible")
+        self.start, self.goal = self._add_vertices(ends)
+        self._connect([self.start, self.goal])
+
+    def _dist(self, A: np.ndarray, B: np.ndarray) -> np.ndarray:
+        return np.sqrt(((A - B) ** 2).sum(axis=-1))
+
+    def _candidates(self, new: List[int]) -> np.ndarray:
+        """k nearest neighbours of every new vertex among all vertices (brute-force on the host: the roadmap is small next to
+        the collision work)"""
+        from scipy.spatial import cKDTree
+        if len(self.V) < 2:
+            return np.zeros((0, 2), dtype=np.int64)
+        tree = cKDTree(self.V)
+        k = min(self.knn + 1, len(self.V))
+        d, idx = tree.query(self.V[new], k=k)
+        d, idx = np.atleast_2d(d), np.atleast_2d(idx)
+        pairs = set()
+        for row, i in enumerate(new):
+            for dist, j in zip(d[row], idx[row]):
+                if j != i and np.isfinite(dist) and dist <= self.connectionThreshold and int(j) not in self.adj[i]:
+                    pairs.add((min(i, int(j)), max(i, int(j))))
+        return np.array(sorted(pairs), dtype=np.int64).reshape(-1, 2)
+
+    def _connect(self, new: List[int]):
+        cand = self._candidates(new)
+        if len(cand) == 0:
+            return
+        A, B = self.V[cand[:, 0]], self.V[cand[:, 1]]
+        length = self._dist(A, B)
+        if self.lazy:
+            for (i, j), l in zip(cand, length):
+                self.adj[i][int(j)] = (float(l), False)
+                self.adj[j][int(i)] = (float(l), False)
+            return
+        vis = np.asarray(self.space.visible_batch(A, B)).astype(bool)
+        self.stats["edges_checked"] += len(cand)
+        self.stats["edges_visible"] += int(vis.sum())
+        for (i, j), l, v in zip(cand, length, vis):
+            if v:
+                self.adj[i][int(j)] = (float(l), True)
+                self.adj[j][int(i)] = (float(l), True)
+
+    # ------------------------------------------------------------------ planning
+    def planMore(self, iterations: int):
+        for _ in range(int(iterations)):
+            Q = self.rng.uniform(self._lo, self._hi, size=(self.batch, len(self._lo)))
+            ok = np.asarray(self.space.feasible_batch(Q)).astype(bool)
+            self.stats["samples"] += len(Q)
+            self.stats["feasible_samples"] += int(ok.sum())
+            self.stats["iterations"] += 1
+            if ok.any():
+                self._connect(self._add_vertices(Q[ok]))
+
+    def _shortest(self, src: int, dst: int) -> Optional[List[int]]:
+        dist = {src: 0.0}
+        prev: Dict[int, int] = {}
+        heap = [(0.0, src)]
+        while heap:
+            d, u = heapq.heappop(heap)
+            if u == dst:
+                path = [u]
+                while path[-1] != src:
+                    path.append(prev[path[-1]])
+                return path[::-1]
+            if d > dist.get(u, float("inf")):
+                continue
+            for v, (l, _) in self.adj[u].items():
+                nd = d + l
+                if nd < dist.get(v, float("inf")):
+                    dist[v] = nd
+                    prev[v] = u
+                    heapq.heappush(heap, (nd, v))
+        return None
+
+    def getPath(self, milestone1: Optional[int] = None, milestone2: Optional[int] = None) -> Optional[List[List[float]]]:
+        src = self.start if milestone1 is None else milestone1
+        dst = self.goal if milestone2 is None else milestone2
+        if src is None or dst is None:
+            raise RuntimeError("setEndpoints (or two milestones) first")
+        while True:
+            path = self._shortest(src, dst)
+            if path is None:
+                return None
+            if not self.lazy:
+                return [list(self.V[i]) for i in path]
+            # lazy: validate the unchecked edges of the candidate path in one batch, drop the blocked ones, search again
+            todo = [(a, b) for a, b in zip(path[:-1], path[1:]) if not self.adj[a][b][1]]
+            if not todo:
+                return [list(self.V[i]) for i in path]
+            A, B = self.V[[a for a, _ in todo]], self.V[[b for _, b in todo]]
+            vis = np.asarray(self.space.visible_batch(A, B)).astype(bool)
+            self.stats["edges_checked"] += len(todo)
+            self.stats["edges_visible"] += int(vis.sum())
+            for (a, b), v in zip(todo, vis):
+                if v:
+                    l = self.adj[a][b][0]
+                    self.adj[a][b] = (l, True)
+                    self.adj[b][a] = (l, True)
+                else:
+                    del self.adj[a][b]
+                    del self.adj[b][a]
+
+    def getSolutionPath(self):
+        return self.getPath()
+
+    def getRoadmap(self) -> Tuple[List[List[float]], List[Tuple[int, int]]]:
+        E = [(i, j) for i, nb in enumerate(self.adj) for j in nb if i < j]
+        return [list(v) for v in self.V], E
+
+    def pathCost(self, path) -> float:
+        P = np.asarray(path, dtype=np.float64)
+        return float(self._dist(P[:-1], P[1:]).sum())
+
+    def getStats(self) -> dict:
+        out = dict(self.stats)
+        out["milestones"] = len(self.V)
+        out["edges"] = sum(len(a) for a in self.adj) // 2
+        return out
+
+    def close(self):
+        self.V = np.zeros((0, self.V.shape[1]))
+        self.adj = []

@@ -141,3 +141,31 @@ def test_cpp_batch_single_robot_cspace(built, tmp_path):
     assert np.array_equal(feas, orc.feasible_batch(Q))
     ovis, on = orc.edges_visible_batch(A, B, eps=0.01)
     assert np.array_equal(vis, ovis) and np.array_equal(nchk, on)
+
+
+def test_batch_roadmap_planner_on_the_engine(setup):
+    """klampt_b200.plan.MotionPlan (PRM / Lazy-PRM* over feasible_batch + visible_batch): the returned path is verified
+    milestone by milestone and edge by edge with the CPU oracle"""
+    from klampt_b200.plan import MotionPlan
+    spec, world, collider, space, orc = setup
+    Q = synth.sample_configs(spec.robot, 400, 61)
+    feas = Q[orc.feasible_batch(Q) == 1]
+    start, goal = feas[0], feas[7]
+    for kind in ("prm", "lazyprm*"):
+        plan = MotionPlan(space, kind, knn=10, batch=1500, seed=5)
+        plan.setEndpoints(list(start), list(goal))
+        path = None
+        for _ in range(6):
+            plan.planMore(1)
+            path = plan.getPath()
+            if path:
+                break
+        assert path is not None, kind
+        P = np.array(path)
+        assert np.allclose(P[0], start) and np.allclose(P[-1], goal)
+        assert orc.feasible_batch(P).all()
+        vis, _ = orc.edges_visible_batch(P[:-1], P[1:], eps=space.eps)
+        assert vis.all(), kind
+        st = plan.getStats()
+        assert st["feasible_samples"] > 0 and st["edges_checked"] > 0
+        plan.close()

@@ -1,0 +1,63 @@
+"""Roadmap planner logic on a stand-in batch space (numpy predicates): no GPU needed."""
+import numpy as np
+import pytest
+
+from klampt_b200.plan import MotionPlan
+
+
+class DiskSpace:
+    """unit square with a disk obstacle; exposes the two batch calls the planners need"""
+    def __init__(self):
+        self.bound = [(0.0, 1.0), (0.0, 1.0)]
+        self.eps = 0.01
+        self.n_feas = self.n_vis = 0
+
+    def feasible_batch(self, Q):
+        Q = np.atleast_2d(Q)
+        self.n_feas += 1
+        return (((Q - 0.5) ** 2).sum(axis=1) > 0.3 ** 2).astype(np.uint8)
+
+    def visible_batch(self, A, B):
+        self.n_vis += 1
+        out = np.ones(len(A), dtype=np.uint8)
+        for u in np.linspace(0, 1, 101)[1:-1]:
+            out &= self.feasible_batch(A * (1 - u) + B * u)
+        return out
+
+
+@pytest.mark.parametrize("kind", ["prm", "lazyprm*"])
+def test_roadmap_planner_finds_a_valid_path(kind):
+    sp = DiskSpace()
+    MotionPlan.setOptions(knn=8, batch=200, seed=3)
+    plan = MotionPlan(sp, kind)
+    plan.setEndpoints([0.05, 0.5], [0.95, 0.5])
+    path = None
+    for _ in range(10):
+        plan.planMore(1)
+        path = plan.getPath()
+        if path:
+            break
+    assert path is not None and path[0] == [0.05, 0.5] and path[-1] == [0.95, 0.5]
+    P = np.array(path)
+    assert sp.visible_batch(P[:-1], P[1:]).all()                  # every edge of the answer is collision free
+    assert plan.pathCost(path) > 0.9 + 0.05                       # must go round the disk
+    st = plan.getStats()
+    assert st["milestones"] >= 2 and st["samples"] == 200 * st["iterations"]
+    V, E = plan.getRoadmap()
+    assert len(V) == st["milestones"] and len(E) == st["edges"]
+    if kind.startswith("lazy"):
+        assert st["edges_checked"] < st["edges"]                  # only edges on candidate paths were validated
+    plan.close()
+
+
+def test_endpoints_must_be_feasible_and_type_checked():
+    sp = DiskSpace()
+    plan = MotionPlan(sp, "prm")
+    with pytest.raises(RuntimeError, match="Start"):
+        plan.setEndpoints([0.5, 0.5], [0.9, 0.9])
+    with pytest.raises(RuntimeError, match="Goal"):
+        plan.setEndpoints([0.1, 0.1], [0.5, 0.45])
+    with pytest.raises(ValueError):
+        MotionPlan(sp, "rrt")
+    with pytest.raises(TypeError):
+        MotionPlan(object(), "prm")
