@@ -428,7 +428,7 @@ kb_traverse_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
           __syncwarp();
         }
         if (sp == 0 && nleaf == 0) break;
-        if (nleaf >= 32 || sp == 0) {
+        if (nleaf >= KB_LEAF_TRIGGER || sp == 0) {
           // ---------------------------------------------------------------- element phase
           int m = nleaf < 32 ? nleaf : 32;
           int res = KB_NO, ea = -1, eb = -1, item = 0;
@@ -944,11 +944,12 @@ size_t kb_distance_smem_bytes(int nxf, int nitems) {
 
 template <bool ITC, bool STATS>
 static cudaError_t launch_distance_t(const KbTraverseParams& p, double* out_dist, double upper_bound, int num_sms, size_t smem, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};      // the attribute is per device
+  int dev = 0; cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kb_distance_kernel<ITC, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   int per_sm = (int)((224 * 1024) / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > 3) per_sm = 3;
   int64_t want = (p.N + KB_WARPS_PER_BLOCK - 1) / KB_WARPS_PER_BLOCK;
@@ -973,11 +974,12 @@ cudaError_t kb_launch_fk(const KbRobotDev* robot, const KbDriverDev* drv, const 
 
 template <int MODE, bool ITC, bool STATS, int BPS>
 static cudaError_t launch_traverse_t(const KbTraverseParams& p, double* out_dist, double upper_bound, int num_sms, size_t smem, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};      // the attribute is per device
+  int dev = 0; cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kb_traverse_kernel<MODE, ITC, STATS, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   int per_sm = (int)((224 * 1024) / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > BPS) per_sm = BPS;
   int64_t want = (p.N + 8 * KB_WARPS_PER_BLOCK - 1) / (8 * KB_WARPS_PER_BLOCK);

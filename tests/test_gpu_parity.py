@@ -271,3 +271,28 @@ def test_point_cloud_with_radii_and_cloud_cloud(built):
         co = np.array([orc.geom_collides(g1, Ta[i], g2, Tb[i]) for i in range(N)])
         assert (c == co).all()
         assert (c == (do <= 0)).all()
+
+
+def test_multi_chunk_batches(c1):
+    """a batch larger than the per-launch chunk is split across launches (and fp64 rechecks parked in one launch are
+    resolved before it ends)"""
+    w, eng, orc = c1
+    Q = synth.sample_configs(w.robot, 5000, 71)
+    want = orc.feasible_batch(Q)
+    eng.set_option("chunk", 512)
+    try:
+        got, pairs = eng.feasible_batch(Q, return_pairs=True)
+        assert (got == want).all()
+        A, B = Q[want == 1][:300], Q[want == 1][300:600]
+        vis, n = eng.edges_visible_batch(A, B, eps=0.02)
+        ovis, on = orc.edges_visible_batch(A, B, eps=0.02)
+        assert (vis == ovis).all() and (n == on).all()
+        d = eng.distance_batch(Q[:1500], upper_bound=0.4)
+        do, _ = orc.distance_batch(Q[:1500], upper_bound=0.4)
+        np.testing.assert_allclose(d, do, rtol=1e-5, atol=1e-9)
+    finally:
+        eng.set_option("chunk", 1 << 20)
+    with pytest.raises(Exception):
+        eng.set_option("chunk", 3)
+    with pytest.raises(Exception):
+        eng.set_option("no_such_option", 1)
