@@ -491,7 +491,9 @@ kb_traverse_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
           __syncwarp();
           continue;
         }
-        // ------------------------------------------------------------------ node phase
+        // ------------------------------------------------------------------ node phase: a tight inner loop that runs until leaf pairs
+        // are due, the stack runs dry or new root pairs must be fed (keeps the loop state in registers)
+        do {
         int m = (sp <= p.wide_limit) ? (sp < 32 ? sp : 32) : 1;
         const bool act = lane < m;
         uint2 e = make_uint2(0u, 0u);
@@ -546,6 +548,7 @@ kb_traverse_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
         if (leafpair) leafq[nleaf + __popc(lm & lt_mask)] = e;
         sp += 2 * __popc(pm); nleaf += __popc(lm);
         __syncwarp();
+        } while (sp > 0 && nleaf < KB_LEAF_TRIGGER && !(sp < 32 && cursor < p.nitems));
       }
       if (STATS) {
 #pragma unroll
