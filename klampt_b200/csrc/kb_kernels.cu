@@ -493,12 +493,19 @@ kb_traverse_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
         }
         // ------------------------------------------------------------------ node phase: a tight inner loop that runs until leaf pairs
         // are due, the stack runs dry or new root pairs must be fed (keeps the loop state in registers)
+        {
+        // loop state in fresh variables: the allocator keeps them in registers for the loop instead of in the spill slots the
+        // element phase forces on the outer copies
+        int sp_l = sp, nleaf_l = nleaf;
+        const float* itc_l = itc;
+        const bool more_items = cursor < p.nitems;
+        const int lane_l = lane;
         do {
-        int m = (sp <= p.wide_limit) ? (sp < 32 ? sp : 32) : 1;
-        const bool act = lane < m;
+        int m = (sp_l <= p.wide_limit) ? (sp_l < 32 ? sp_l : 32) : 1;
+        const bool act = lane_l < m;
         uint2 e = make_uint2(0u, 0u);
-        if (act) e = stack[sp - 1 - lane];
-        sp -= m;
+        if (act) e = stack[sp_l - 1 - lane_l];
+        sp_l -= m;
         __syncwarp();
         bool push2 = false, leafpair = false;
         uint2 c0e = e, c1e = e;
@@ -508,7 +515,7 @@ kb_traverse_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
           if (ITC) {
             const ItemS s = s_items[item];
             nodeA = s.nodeA; nodeB = s.nodeB; infl = s.infl;
-            load_itc(itc, item, T);
+            load_itc(itc_l, item, T);
             if (MODE == 1) { marg = p.items[item].marg; rsum = p.items[item].rsum; }
           } else {
             const KbItem* itp = p.items + item;
@@ -544,11 +551,13 @@ kb_traverse_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
           }
         }
         const unsigned pm = __ballot_sync(FULL, push2), lm = __ballot_sync(FULL, leafpair);
-        if (push2) { int off = sp + 2 * __popc(pm & lt_mask); stack[off] = c1e; stack[off + 1] = c0e; }
-        if (leafpair) leafq[nleaf + __popc(lm & lt_mask)] = e;
-        sp += 2 * __popc(pm); nleaf += __popc(lm);
+        if (push2) { int off = sp_l + 2 * __popc(pm & lt_mask); stack[off] = c1e; stack[off + 1] = c0e; }
+        if (leafpair) leafq[nleaf_l + __popc(lm & lt_mask)] = e;
+        sp_l += 2 * __popc(pm); nleaf_l += __popc(lm);
         __syncwarp();
-        } while (sp > 0 && nleaf < KB_LEAF_TRIGGER && !(sp < 32 && cursor < p.nitems));
+        } while (sp_l > 0 && nleaf_l < KB_LEAF_TRIGGER && !(sp_l < 32 && more_items));
+        sp = sp_l; nleaf = nleaf_l;
+        }
       }
       if (STATS) {
 #pragma unroll
