@@ -110,7 +110,9 @@ int kb_set_stream(kb_engine* e, void* cuda_stream);
 int kb_synchronize(kb_engine* e);
 /* tuning / instrumentation knobs: "collect_stats" (0|1: count node / element tests and fp64 rechecks in the kernels),
  * "time_kernels" (0|1: bracket every traversal launch with CUDA events on the engine's stream, summed into kb_stats),
- * "chunk" (configurations per kernel launch; the default keeps one chunk's transforms resident in L2) */
+ * "chunk" (configurations per kernel launch, default up to 1 M within a 2 GB scratch budget),
+ * "pipeline" (0 = fused traversal kernel, default; 1 = split pipeline: lean node kernel -> global leaf-pair list -> leaf kernel ->
+ * fused kernel on requeued configurations; same results, measured slower on C2/C3), "leaf_budget" (split pipeline only) */
 int kb_set_option(kb_engine* e, const char* name, int64_t value);
 
 /* ---- the hot path ------------------------------------------------------------------------------------- */

@@ -188,6 +188,10 @@ struct kb_engine {
   int64_t chunk = 65536;
   double* d_xf = nullptr; int64_t xf_cap = 0;
   uint8_t* d_state = nullptr; int32_t* d_hit = nullptr; int32_t* d_hit_elem = nullptr; int64_t cfg_cap = 0;
+  uint4* d_leaf_list = nullptr; int64_t leaf_cap = 0; uint8_t* d_flagged = nullptr; uint8_t* d_state2 = nullptr; int64_t split_cap = 0;
+  int pipeline = 0;                        // 0 = fused kernel (default, faster on every measured workload); 1 = split pipeline (node kernel ->
+                                           // global leaf-pair list -> leaf kernel -> fused kernel on the requeued configurations)
+  int leaf_budget = 64; int leaf_slots = 40;
   uint32_t* d_work = nullptr; unsigned long long* d_counters = nullptr;   // counters: [0] recheck [1] node [2] leaf [3] feasible [4] visible
   double* d_Q = nullptr; int64_t q_cap = 0;             // staging for host entry points
   uint8_t* d_out = nullptr; int64_t out_cap = 0;
@@ -337,6 +341,19 @@ int ensure_cfg_scratch(kb_engine* e, int nxf, int64_t n) {
   return KB_OK;
 }
 
+int ensure_split_scratch(kb_engine* e, int64_t n) {
+  int64_t ch = std::max<int64_t>(1024, std::min(e->chunk, n));
+  if (ch > e->split_cap) {
+    if (e->d_flagged) cudaFree(e->d_flagged); if (e->d_state2) cudaFree(e->d_state2); if (e->d_leaf_list) cudaFree(e->d_leaf_list);
+    e->d_flagged = e->d_state2 = nullptr; e->d_leaf_list = nullptr; e->split_cap = 0;
+    CK(cudaMalloc((void**)&e->d_flagged, (size_t)ch)); CK(cudaMalloc((void**)&e->d_state2, (size_t)ch));
+    e->leaf_cap = std::min<int64_t>(ch * e->leaf_slots, 0x7fffffff);
+    CK(cudaMalloc((void**)&e->d_leaf_list, (size_t)e->leaf_cap * 16));
+    e->split_cap = ch;
+  }
+  return KB_OK;
+}
+
 void begin_timing(kb_engine* e) { cudaEventRecord(e->ev0, e->stream); }
 void end_timing(kb_engine* e, bool sync) {
   cudaEventRecord(e->ev1, e->stream);
@@ -365,6 +382,23 @@ cudaError_t timed_traverse(kb_engine* e, const KbTraverseParams& p, int mode, do
   return ce;
 }
 
+// split pipeline + fused fallback on the requeued configurations, bracketed like one traversal launch
+cudaError_t timed_split(kb_engine* e, const KbTraverseParams& p, const KbSplitParams& q) {
+  const bool timed = e->time_kernels;
+  if (timed) {
+    if (e->tev_used + 2 > 8192) fold_kernel_times(e);
+    while (e->tev.size() < e->tev_used + 2) { cudaEvent_t ev; cudaError_t ce = cudaEventCreate(&ev); if (ce != cudaSuccess) return ce; e->tev.push_back(ev); }
+    cudaEventRecord(e->tev[e->tev_used], e->stream);
+  }
+  cudaError_t ce = kb_launch_split(p, q, e->num_sms, e->stream);
+  if (ce == cudaSuccess) {
+    KbTraverseParams p2 = p; p2.state = q.state2;
+    ce = kb_launch_traverse(p2, 0, nullptr, 0.0, e->num_sms, e->stream);
+  }
+  if (timed) { cudaEventRecord(e->tev[e->tev_used + 1], e->stream); e->tev_used += 2; }
+  return ce;
+}
+
 KbTraverseParams make_params(kb_engine* e, const ItemSet& set, const double* xf, int64_t n, const uint8_t* state) {
   KbTraverseParams p; memset(&p, 0, sizeof p);
   p.scene = e->scene; p.items = set.d_items; p.nitems = (int)set.items.size(); p.nxf = set.nxf; p.xf64 = xf; p.N = n; p.state = state;
@@ -382,8 +416,18 @@ int run_feasible_device(kb_engine* e, const double* dQ, int64_t N, uint8_t* d_ou
     e->stats.kernel_launches++;
     if (!e->feas_items.items.empty()) {
       KbTraverseParams p = make_params(e, e->feas_items, e->d_xf, n, e->d_state);
-      CK(timed_traverse(e, p, 0, nullptr, 0.0));
-      e->stats.kernel_launches++;
+      if (e->pipeline == 1) {
+        if ((rc = ensure_split_scratch(e, N))) return rc;
+        KbSplitParams q; memset(&q, 0, sizeof q);
+        q.leaf_list = e->d_leaf_list; q.leaf_count = e->d_counters + 6; q.leaf_cap = (unsigned)e->leaf_cap; q.flagged = e->d_flagged; q.state2 = e->d_state2;
+        q.requeued = e->d_counters + 5; q.leaf_budget = e->leaf_budget;
+        q.stack_cap = e->feas_items.maxdepth <= 96 ? 256 : KB_STACK_CAP; q.wide_limit = q.stack_cap - 32 - e->feas_items.maxdepth - 2;
+        CK(timed_split(e, p, q));
+        e->stats.kernel_launches += 4;
+      } else {
+        CK(timed_traverse(e, p, 0, nullptr, 0.0));
+        e->stats.kernel_launches++;
+      }
     }
     CK(kb_launch_finish(e->d_state, e->d_hit, e->d_hit_elem, e->feas_items.d_items, e->d_triown, e->d_sphown, n, d_out + off,
                         d_first_pair ? d_first_pair + 2 * off : nullptr, d_nfeas, e->stream));
@@ -416,7 +460,7 @@ void kb_engine_destroy(kb_engine* e) {
   if (e->device >= 0) {
     cudaSetDevice(e->device);
     void* ptrs[] = {e->d_nodes, e->d_tris32, e->d_tris64, e->d_sph32, e->d_sph64, e->d_triown, e->d_sphown, e->d_robot, e->d_drv, e->d_drv_link,
-                    e->d_drv_scale, e->d_drv_off, e->feas_items.d_items, e->env_items.d_items, e->d_xf, e->d_state, e->d_hit, e->d_hit_elem, e->d_work,
+                    e->d_drv_scale, e->d_drv_off, e->feas_items.d_items, e->env_items.d_items, e->d_xf, e->d_state, e->d_hit, e->d_hit_elem, e->d_leaf_list, e->d_flagged, e->d_state2, e->d_work,
                     e->d_counters, e->d_Q, e->d_out, e->d_pair, e->d_dist, e->d_A, e->d_B, e->d_nlev, e->d_alive, e->d_nchecks, e->d_firstbad, e->d_list,
                     e->d_eQ, e->d_efeas, e->d_scalars, e->d_weights, e->d_T};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -689,6 +733,8 @@ int kb_set_option(kb_engine* e, const char* name, int64_t value) {
   if (!e || !name) return fail(KB_ERR_INVALID, "null argument");
   if (!strcmp(name, "collect_stats")) { e->collect_stats = value != 0; return KB_OK; }
   if (!strcmp(name, "time_kernels")) { e->time_kernels = value != 0; return KB_OK; }
+  if (!strcmp(name, "pipeline")) { if (value != 0 && value != 1) return fail(KB_ERR_INVALID, "pipeline must be 0 (fused) or 1 (split)"); e->pipeline = (int)value; return KB_OK; }
+  if (!strcmp(name, "leaf_budget")) { if (value < 1 || value > 100000) return fail(KB_ERR_INVALID, "leaf_budget out of range"); e->leaf_budget = (int)value; return KB_OK; }
   if (!strcmp(name, "chunk")) {
     if (value < 256 || value > (1 << 22)) return fail(KB_ERR_INVALID, "chunk must be in [256, 4194304]");
     e->chunk = value; return KB_OK;

@@ -587,6 +587,213 @@ kb_traverse_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
   }
 }
 
+// =============================================================================================== split pipeline
+// The fused kernel above carries the element tests (fp32 filtered tri-tri + fp64 recheck) in the same kernel as the
+// node loop; their register demand (166 natural) caps the whole kernel at 16 warps per SM although the node loop itself
+// lives in ~50 registers.  The split pipeline re-queues between phases instead:
+//   kb_nodes_kernel    lean (<= 64 registers, 32 warps / SM): the same warp-cooperative node traversal, but leaf pairs
+//                      are appended to a global list (config, item, nodeA, nodeB) instead of being tested in place.
+//                      A configuration that has emitted `leaf_budget` pairs stops traversing (it is almost surely in
+//                      collision) and is flagged; so is one whose pairs did not fit the list.
+//   kb_leaves_kernel   fat: one thread per listed leaf pair, fp32 filtered element tests + inline fp64 recheck; the first
+//                      hit of a configuration is recorded with an atomicCAS.
+//   kb_requeue_kernel  flagged configurations without a hit are marked for the fused kernel, which re-runs them from
+//                      scratch (rare: a configuration needs >= leaf_budget candidate pairs none of which intersects).
+// Early exit inside a configuration is given up; measured on C2 it only matters for configurations with more than 32
+// candidate pairs, which the budget covers.
+#define KB_NSTAGE_CAP 64
+
+template <bool ITC, bool STATS>
+__global__ void __launch_bounds__(KB_WARPS_PER_BLOCK * 32, 8)
+kb_nodes_kernel(const KbTraverseParams p, const KbSplitParams q) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int xf_floats = (p.nxf * 12 + 3) & ~3;
+  const int nit_c = ITC ? p.nitems : 0;
+  ItemS* s_items = (ItemS*)smem_raw;
+  const size_t per_warp = (size_t)q.stack_cap * 8 + (size_t)KB_NSTAGE_CAP * 8 + (size_t)xf_floats * 4 + (size_t)nit_c * 48;
+  unsigned char* base = smem_raw + (size_t)nit_c * 16 + warp * per_warp;
+  uint2* stack = (uint2*)base;
+  uint2* stage = (uint2*)(base + (size_t)q.stack_cap * 8);
+  float* xfw = (float*)(base + (size_t)q.stack_cap * 8 + (size_t)KB_NSTAGE_CAP * 8);
+  float* itc = xfw + xf_floats;
+  const KbScene& sc = p.scene;
+  const float slack = 4.f * sc.eps_abs;
+  if (ITC) {
+    for (int i = threadIdx.x; i < p.nitems; i += blockDim.x) {
+      const KbItem* it = p.items + i;
+      ItemS s; s.nodeA = it->nodeA; s.nodeB = it->nodeB; s.infl = (float)it->thr + slack;
+      s.xf = (int)((unsigned)(unsigned short)it->xfA | ((unsigned)(unsigned short)it->xfB << 16));
+      s_items[i] = s;
+    }
+  }
+  __syncthreads();
+  unsigned lt_mask;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
+  unsigned st_node = 0;
+  const unsigned total_warps = gridDim.x * KB_WARPS_PER_BLOCK;
+  unsigned grab = 8;
+  for (;;) {
+    unsigned int c0 = 0;
+    if (lane == 0) c0 = atomicAdd(p.work_counter, grab);
+    c0 = __shfl_sync(FULL, c0, 0);
+    if ((int64_t)c0 >= p.N) break;
+    const unsigned nN = (unsigned)p.N;
+    const unsigned cend = (c0 + grab < nN) ? c0 + grab : nN;
+    { const unsigned g = (nN - cend) / (4u * total_warps); grab = g >= 8u ? 8u : (g < 1u ? 1u : g); }
+    for (unsigned c = c0; c < cend; c++) {
+      if (p.state && p.state[c] == 0) continue;
+      const double* xf = p.xf64 + (size_t)c * (size_t)p.nxf * 12;
+      __syncwarp();
+      for (int i = lane; i < p.nxf * 12; i += 32) xfw[i] = (float)xf[i];
+      __syncwarp();
+      if (ITC) {
+        for (int i = lane; i < p.nitems; i += 32) {
+          const int xfp = s_items[i].xf;
+          XfF T; rel_xf(xfw, (int)(short)(xfp & 0xffff), (int)(short)(xfp >> 16), T);
+          float4* qv = (float4*)(itc + 12 * i);
+          qv[0] = make_float4(T.r[0], T.r[1], T.r[2], T.r[3]); qv[1] = make_float4(T.r[4], T.r[5], T.r[6], T.r[7]); qv[2] = make_float4(T.r[8], T.t[0], T.t[1], T.t[2]);
+        }
+        __syncwarp();
+      }
+      int sp = 0, nstage = 0, cursor = 0, emitted = 0;
+      bool flagged = false;
+      for (;;) {
+        if (sp < 32 && cursor < p.nitems && emitted < q.leaf_budget) {   // feed root pairs of the next work items
+          int k = p.nitems - cursor; if (k > 32) k = 32;
+          if (lane < k) stack[sp + lane] = make_uint2(((unsigned)(cursor + lane) << KB_NODEA_BITS), 0u);
+          sp += k; cursor += k;
+          __syncwarp();
+        }
+        const bool done = sp == 0 || emitted >= q.leaf_budget;
+        if (nstage >= 32 || (done && nstage > 0)) {  // append up to 32 staged leaf pairs to the global list
+          const int n = nstage < 32 ? nstage : 32;
+          unsigned long long b = 0;
+          if (lane == 0) b = atomicAdd(q.leaf_count, (unsigned long long)n);
+          b = __shfl_sync(FULL, b, 0);
+          if (b + (unsigned long long)n <= (unsigned long long)q.leaf_cap) {
+            if (lane < n) { const uint2 e = stage[nstage - 1 - lane]; q.leaf_list[b + lane] = make_uint4(c, e.x, e.y, 0u); }
+          } else flagged = true;                     // list full: this configuration is re-run by the fused kernel
+          nstage -= n;
+          __syncwarp();
+          continue;
+        }
+        if (done) { if (sp > 0 || cursor < p.nitems) flagged = true; break; }
+        do {
+          const int m = (sp <= q.wide_limit) ? (sp < 32 ? sp : 32) : 1;
+          const bool act = lane < m;
+          uint2 e = make_uint2(0u, 0u);
+          if (act) e = stack[sp - 1 - lane];
+          sp -= m;
+          __syncwarp();
+          bool push2 = false, leafpair = false;
+          uint2 c0e = e, c1e = e;
+          if (act) {
+            const int item = (int)(e.x >> KB_NODEA_BITS);
+            int nodeA, nodeB; float infl; XfF T;
+            if (ITC) {
+              const ItemS s = s_items[item];
+              nodeA = s.nodeA; nodeB = s.nodeB; infl = s.infl;
+              load_itc(itc, item, T);
+            } else {
+              const KbItem* itp = p.items + item;
+              nodeA = itp->nodeA; nodeB = itp->nodeB; infl = (float)itp->thr + slack;
+              rel_xf(xfw, itp->xfA, itp->xfB, T);
+            }
+            const int na = (int)(e.x & (KB_MAX_NODES_A - 1)), nb = (int)e.y;
+            float4 a0, a1, b0, b1;
+            load_node(sc.nodes, (size_t)(nodeA + na), a0, a1);
+            load_node(sc.nodes, (size_t)(nodeB + nb), b0, b1);
+            if (STATS) st_node++;
+            if (sat6_overlap(a0, a1, b0, b1, T, infl)) {
+              const int la = __float_as_int(a0.w), lb = __float_as_int(b0.w);
+              if (la < 0 && lb < 0) leafpair = true;
+              else {
+                push2 = true;
+                const float sa2 = a1.x * a1.x + a1.y * a1.y + a1.z * a1.z, sb2 = b1.x * b1.x + b1.y * b1.y + b1.z * b1.z;
+                if (lb < 0 || (la >= 0 && sa2 >= sb2)) {
+                  c0e = make_uint2((e.x & ~(unsigned)(KB_MAX_NODES_A - 1)) | (unsigned)la, e.y);
+                  c1e = make_uint2(c0e.x + 1u, e.y);
+                } else {
+                  c0e = make_uint2(e.x, (unsigned)lb);
+                  c1e = make_uint2(e.x, (unsigned)lb + 1u);
+                }
+              }
+            }
+          }
+          const unsigned pm = __ballot_sync(FULL, push2), lm = __ballot_sync(FULL, leafpair);
+          if (push2) { const int off = sp + 2 * __popc(pm & lt_mask); stack[off] = c1e; stack[off + 1] = c0e; }
+          if (leafpair) stage[nstage + __popc(lm & lt_mask)] = e;
+          sp += 2 * __popc(pm); nstage += __popc(lm); emitted += __popc(lm);
+          __syncwarp();
+        } while (sp > 0 && nstage < 32 && emitted < q.leaf_budget && !(sp < 32 && cursor < p.nitems));
+      }
+      if (lane == 0) q.flagged[c] = flagged ? 1 : 0;
+      if (STATS) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) st_node += __shfl_xor_sync(FULL, st_node, o);
+        if (lane == 0 && p.counters) atomicAdd(p.counters + 1, (unsigned long long)st_node);
+        st_node = 0;
+      }
+    }
+  }
+}
+
+// one thread per listed leaf pair
+template <bool STATS>
+__global__ void __launch_bounds__(256)
+kb_leaves_kernel(const KbTraverseParams p, const KbSplitParams q) {
+  const KbScene& sc = p.scene;
+  unsigned long long n = *q.leaf_count;
+  if (n > (unsigned long long)q.leaf_cap) n = q.leaf_cap;
+  unsigned n_leaf = 0, n_re = 0;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint4 e = q.leaf_list[i];
+    const unsigned c = e.x;
+    if (p.hit[c] >= 0) continue;                       // already decided by another pair
+    const int item = (int)(e.y >> KB_NODEA_BITS);
+    const KbItem& it = p.items[item];
+    const int na = (int)(e.y & (KB_MAX_NODES_A - 1)), nb = (int)e.z;
+    float4 a0, a1, b0, b1;
+    load_node(sc.nodes, (size_t)(it.nodeA + na), a0, a1);
+    load_node(sc.nodes, (size_t)(it.nodeB + nb), b0, b1);
+    const int fa = it.elemA + ~__float_as_int(a0.w), ca = __float_as_int(a1.w);
+    const int fb = it.elemB + ~__float_as_int(b0.w), cb = __float_as_int(b1.w);
+    const double* xf = p.xf64 + (size_t)c * (size_t)p.nxf * 12;
+    // relative transform from the fp64 table, rounded once (the same values the node kernel used)
+    __align__(16) float loc[24];
+    const int sa = it.xfA, sb = it.xfB;
+#pragma unroll
+    for (int k = 0; k < 12; k++) { loc[k] = sa >= 0 ? (float)xf[12 * sa + k] : 0.f; loc[12 + k] = sb >= 0 ? (float)xf[12 * sb + k] : 0.f; }
+    XfF T; rel_xf(loc, sa >= 0 ? 0 : -1, sb >= 0 ? 1 : -1, T);
+    const float thr = (float)it.thr;
+    bool hit = false; int ea = -1, eb = -1;
+    for (int ii = 0; ii < ca && !hit; ii++)
+      for (int jj = 0; jj < cb && !hit; jj++) {
+        int r = fast_elem_collide(sc, it, T, fa + ii, fb + jj, thr);
+        if (STATS) n_leaf++;
+        if (r == KB_UNCERTAIN) { if (STATS) n_re++; r = exact_elem_collide(sc, it, xf, fa + ii, fb + jj) ? KB_YES : KB_NO; }
+        if (r == KB_YES) { hit = true; ea = fa + ii; eb = fb + jj; }
+      }
+    if (hit && atomicCAS(p.hit + c, -1, item) == -1 && p.hit_elem) { p.hit_elem[2 * (size_t)c] = ea; p.hit_elem[2 * (size_t)c + 1] = eb; }
+  }
+  if (STATS && p.counters) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { n_leaf += __shfl_xor_sync(FULL, n_leaf, o); n_re += __shfl_xor_sync(FULL, n_re, o); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(p.counters + 2, (unsigned long long)n_leaf); atomicAdd(p.counters + 0, (unsigned long long)n_re); }
+  }
+}
+
+// state2[c] = 1 for the configurations the fused kernel has to redo: flagged by the node kernel and still without a hit
+__global__ void kb_requeue_kernel(const uint8_t* __restrict__ state, const uint8_t* __restrict__ flagged, const int32_t* __restrict__ hit,
+                                  int64_t N, uint8_t* __restrict__ state2, unsigned long long* requeued) {
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool r = false;
+  if (c < N) { r = (!state || state[c] != 0) && flagged[c] != 0 && hit[c] < 0; state2[c] = r ? 1 : 0; }
+  unsigned m = __ballot_sync(FULL, r);
+  if (requeued && (threadIdx.x & 31) == 0 && m) atomicAdd(requeued, (unsigned long long)__popc(m));
+}
+
 // =============================================================================================== distance traversal
 // Branch and bound over the same flattened BVHs (replaces AnyCollisionQuery::Distance behind
 // WorldPlannerSettings::DistanceLowerBound, reference Cpp/Planning/PlannerSettings.cpp:109-115,570-620).  One warp per
@@ -1021,6 +1228,50 @@ cudaError_t kb_launch_traverse(const KbTraverseParams& p, int mode, double* out_
   if (p.collect_stats) return itc ? KB_LT(0, true, true) : KB_LT(0, false, true);
   return itc ? KB_LT(0, true, false) : KB_LT(0, false, false);
 #undef KB_LT
+}
+
+size_t kb_nodes_smem_bytes(int nxf, int nitems, int stack_cap) {
+  size_t xf_floats = ((size_t)nxf * 12 + 3) & ~(size_t)3;
+  size_t nit = nitems <= KB_ITC_MAX_ITEMS ? (size_t)nitems : 0;
+  return nit * 16 + (size_t)KB_WARPS_PER_BLOCK * ((size_t)stack_cap * 8 + (size_t)KB_NSTAGE_CAP * 8 + xf_floats * 4 + nit * 48);
+}
+
+template <bool ITC, bool STATS>
+static cudaError_t launch_nodes_t(const KbTraverseParams& p, const KbSplitParams& q, int num_sms, size_t smem, cudaStream_t s) {
+  static bool attr_set[64] = {false};
+  int dev = 0; cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kb_nodes_kernel<ITC, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  int per_sm = (int)((224 * 1024) / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > 8) per_sm = 8;
+  int64_t want = (p.N + 8 * KB_WARPS_PER_BLOCK - 1) / (8 * KB_WARPS_PER_BLOCK);
+  int64_t grid = (int64_t)num_sms * per_sm; if (grid > want) grid = want; if (grid < 1) grid = 1;
+  kb_nodes_kernel<ITC, STATS><<<(unsigned)grid, KB_WARPS_PER_BLOCK * 32, smem, s>>>(p, q);
+  return cudaGetLastError();
+}
+
+// split pipeline, stages 1-3 (node traversal -> leaf tests -> requeue mask); the caller then runs the fused kernel on q.state2
+cudaError_t kb_launch_split(const KbTraverseParams& p, const KbSplitParams& q, int num_sms, cudaStream_t s) {
+  if (p.N <= 0) return cudaSuccess;
+  if (p.N > 0xfffffff0ll) return cudaErrorInvalidValue;
+  const size_t smem = kb_nodes_smem_bytes(p.nxf, p.nitems, q.stack_cap);
+  if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+  cudaError_t e = cudaMemsetAsync(p.work_counter, 0, sizeof(uint32_t), s);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(q.leaf_count, 0, sizeof(unsigned long long), s);
+  if (e != cudaSuccess) return e;
+  const bool itc = p.nitems <= KB_ITC_MAX_ITEMS;
+  if (p.collect_stats) e = itc ? launch_nodes_t<true, true>(p, q, num_sms, smem, s) : launch_nodes_t<false, true>(p, q, num_sms, smem, s);
+  else e = itc ? launch_nodes_t<true, false>(p, q, num_sms, smem, s) : launch_nodes_t<false, false>(p, q, num_sms, smem, s);
+  if (e != cudaSuccess) return e;
+  const unsigned lgrid = (unsigned)num_sms * 8;
+  if (p.collect_stats) kb_leaves_kernel<true><<<lgrid, 256, 0, s>>>(p, q); else kb_leaves_kernel<false><<<lgrid, 256, 0, s>>>(p, q);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  kb_requeue_kernel<<<nblocks(p.N, 256), 256, 0, s>>>(p.state, q.flagged, p.hit, p.N, q.state2, q.requeued);
+  return cudaGetLastError();
 }
 
 cudaError_t kb_launch_finish(const uint8_t* state, const int32_t* hit, const int32_t* hit_elem, const KbItem* items, const int32_t* triown,

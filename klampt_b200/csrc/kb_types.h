@@ -91,3 +91,16 @@ struct KbTraverseParams {
   int32_t wide_limit;             // stack size up to which 32-wide pops are allowed
   int32_t collect_stats;
 };
+
+// split pipeline (node traversal kernel -> global leaf-pair list -> leaf kernel -> requeue for the fused kernel)
+struct KbSplitParams {
+  uint4* leaf_list;               // (configuration, item | nodeA, nodeB, 0)
+  unsigned long long* leaf_count; // entries appended (may exceed leaf_cap: the surplus was not written)
+  unsigned int leaf_cap;
+  uint8_t* flagged;               // per configuration: stopped on the leaf budget with work left, or list full
+  uint8_t* state2;                // per configuration: re-run by the fused kernel
+  unsigned long long* requeued;   // statistics: configurations re-run
+  int32_t leaf_budget;            // leaf pairs after which a configuration stops traversing
+  int32_t stack_cap;              // node-pair stack entries per warp of the node kernel
+  int32_t wide_limit;
+};

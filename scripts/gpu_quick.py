@@ -17,6 +17,8 @@ ns = min(N, 20000)
 t = time.time(); want = orc.feasible_batch(Q[:ns], nthreads=0); dt = time.time() - t
 print("oracle %d threads: %.0f cfg/s, feasible %.3f" % (max_threads(), ns / dt, want.mean()))
 eng.set_option("collect_stats", 1)
+if len(sys.argv) > 4:
+    eng.set_option("pipeline", int(sys.argv[4]))
 got = eng.feasible_batch(Q[:ns])
 bad = np.nonzero(got != want)[0]
 st = eng.stats()
@@ -24,8 +26,12 @@ print("mismatches:", len(bad), "per config: node %.1f elem %.1f recheck %.2f" % 
 for i in bad[:10]:
     print("  cfg", i, "gpu", got[i], "oracle", want[i], "clearance", orc.distance(Q[i], 1.0, True))
 eng.set_option("collect_stats", 0)
-if len(sys.argv) > 3:
+if len(sys.argv) > 3 and int(sys.argv[3]) > 0:
     eng.set_option("chunk", int(sys.argv[3]))
+if len(sys.argv) > 4:
+    eng.set_option("pipeline", int(sys.argv[4]))
+if len(sys.argv) > 5:
+    eng.set_option("leaf_budget", int(sys.argv[5]))
 dQ = torch.from_numpy(Q).cuda()
 dout = torch.empty(N, dtype=torch.uint8, device="cuda")
 eng.set_stream(torch.cuda.current_stream().cuda_stream)

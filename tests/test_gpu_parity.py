@@ -296,3 +296,23 @@ def test_multi_chunk_batches(c1):
         eng.set_option("chunk", 3)
     with pytest.raises(Exception):
         eng.set_option("no_such_option", 1)
+
+
+def test_split_pipeline_gives_identical_results(c2small, c3):
+    """option pipeline=1 (node kernel -> leaf-pair list -> leaf kernel -> requeue) against the oracle and the fused kernel,
+    including a tiny leaf budget that forces most colliding configurations through the requeue path"""
+    for (w, eng, orc), seed in ((c2small, 81), (c3, 82)):
+        Q = synth.sample_configs(w.robot, 12000, seed)
+        fused, fpairs = eng.feasible_batch(Q, return_pairs=True)
+        want = orc.feasible_batch(Q)
+        try:
+            for budget in (64, 2):
+                eng.set_option("pipeline", 1)
+                eng.set_option("leaf_budget", budget)
+                got, pairs = eng.feasible_batch(Q, return_pairs=True)
+                assert (got == fused).all()
+                assert_bool_parity(got, want, Q, orc)
+                assert ((pairs[:, 0] >= 0) == (fpairs[:, 0] >= 0)).all()
+        finally:
+            eng.set_option("pipeline", 0)
+            eng.set_option("leaf_budget", 64)
