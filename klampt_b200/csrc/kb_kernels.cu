@@ -298,17 +298,19 @@ __device__ __forceinline__ void drain_rechecks(const KbTraverseParams& p, uint4*
   __syncwarp();
 }
 
-// =============================================================================================== traversal
-// One warp per configuration.  The warp keeps a LIFO frontier of (item, nodeA, nodeB) pairs in shared memory; every
-// iteration the 32 lanes pop up to 32 pairs, run a 6-axis separating-axis test (the face normals of both boxes;
-// conservative, ~3x cheaper than the 15-axis test and only ~17 % more node visits), and push the children of the
-// overlapping pairs (descend the larger box) with a ballot/popc compaction.  Leaf pairs go to a second queue that is
-// drained 32 at a time so the element tests also run on full warps.  Any certain hit ends the configuration for all
-// lanes (__ballot_sync early exit).  Per configuration the relative transform of every work item is computed once
-// into shared memory (ITC), so a node test is 2 LDS.64/128 + 4 LDG.128 + ~60 FP instructions.
-// MODE 0: boolean collide / within-threshold.  MODE 1: branch-and-bound distance.
-// one 32-byte node = one 256-bit load (LDG.E.256 on sm_100): a scattered node fetch then costs one L1 wavefront per
-// lane instead of two -- the traversal is bound by L1 wavefronts, not by bytes (profiles/r01_*).
+// =============================================================================================== traversal (boolean)
+// kb_traverse_kernel -- collide / within-threshold for every enabled geometry pair of one configuration.
+// One warp per configuration (persistent CTAs, configurations handed out by an atomic counter with guided chunk sizes).
+// The warp keeps a LIFO frontier of (item, nodeA, nodeB) pairs in shared memory; every iteration of the tight inner
+// loop the 32 lanes pop up to 32 pairs, load both nodes (one 256-bit load each), run a 6-axis separating-axis test
+// (the face normals of both boxes; conservative, ~3x cheaper than the 15-axis test for +4 % node visits on C2) and push
+// the two children of every overlapping pair (descend the larger box) with ballot/popc compaction.  Leaf pairs go to a
+// second queue drained 32 at a time so the element tests also run on full warps; any certain hit ends the
+// configuration for all lanes (__ballot_sync early exit).  Per configuration the relative transform of every work item
+// is computed once into shared memory (ITC) and a 16 B static record per item is cached per CTA, so a node test is
+// LDS.64 + 4 x LDS.128 + 2 x LDG.256 + ~56 FP instructions (165 SASS instructions per 32-pair iteration in total).
+
+// one 32-byte node = one 256-bit load (LDG.E.ENL2.256 on sm_100) instead of two 128-bit ones
 __device__ __forceinline__ void load_node(const float4* __restrict__ nodes, size_t idx, float4& n0, float4& n1) {
   unsigned long long x0, x1, x2, x3;
   asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(x0), "=l"(x1), "=l"(x2), "=l"(x3) : "l"(nodes + 2 * idx));
@@ -354,9 +356,9 @@ __device__ __forceinline__ void load_itc(const float* __restrict__ itc, int item
   T.t[0] = q2.y; T.t[1] = q2.z; T.t[2] = q2.w;
 }
 
-template <int MODE, bool ITC, bool STATS, int BPS>
+template <bool ITC, bool STATS, int BPS>
 __global__ void __launch_bounds__(KB_WARPS_PER_BLOCK * 32, BPS)
-kb_traverse_kernel(const KbTraverseParams p, double* __restrict__ out_dist, double upper_bound) {
+kb_traverse_kernel(const KbTraverseParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int xf_floats = (p.nxf * 12 + 3) & ~3;
@@ -418,8 +420,6 @@ kb_traverse_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
       }
       int sp = 0, nleaf = 0, cursor = 0;
       int found = -1, found_ea = -1, found_eb = -1;
-      double best = upper_bound;                     // MODE 1: running minimum (already including margins per item)
-      int best_item = -1, best_ea = -1, best_eb = -1;
       for (;;) {
         if (sp < 32 && cursor < p.nitems) {          // feed root pairs of the next work items
           int k = p.nitems - cursor; if (k > 32) k = 32;
@@ -432,7 +432,6 @@ kb_traverse_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
           // ---------------------------------------------------------------- element phase
           int m = nleaf < 32 ? nleaf : 32;
           int res = KB_NO, ea = -1, eb = -1, item = 0;
-          double dmin = 1e300;
           if (lane < m) {
             uint2 e = leafq[nleaf - 1 - lane];
             item = (int)(e.x >> KB_NODEA_BITS);
@@ -443,7 +442,7 @@ kb_traverse_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
             load_node(sc.nodes, (size_t)(it.nodeB + nb), b0, b1);
             int fa = it.elemA + ~__float_as_int(a0.w), ca = __float_as_int(a1.w);
             int fb = it.elemB + ~__float_as_int(b0.w), cb = __float_as_int(b1.w);
-            if (MODE == 0) {
+            {
               XfF T;
               if (ITC) load_itc(itc, item, T); else rel_xf(xfw, it.xfA, it.xfB, T);
               const float thr = (float)it.thr;
@@ -459,17 +458,10 @@ kb_traverse_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
                   }
                   if (r == KB_YES) { res = KB_YES; ea = fa + i; eb = fb + j; }
                 }
-            } else {
-              for (int i = 0; i < ca; i++)
-                for (int j = 0; j < cb; j++) {
-                  double d = exact_elem_distance(sc, it, xf, fa + i, fb + j) - it.marg;
-                  if (STATS) st_leaf++;
-                  if (d < dmin) { dmin = d; ea = fa + i; eb = fb + j; }
-                }
             }
           }
           nleaf -= m;
-          if (MODE == 0) {
+          {
             unsigned hm = __ballot_sync(FULL, res == KB_YES);
             if (hm) {
               int src = __ffs(hm) - 1;
@@ -478,15 +470,6 @@ kb_traverse_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
             }
             drain_rechecks(p, rq, rq_count, lane, (int64_t)c, found, found_ea, found_eb, false);
             if (found >= 0) break;
-          } else {
-            double wmin = dmin;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { double x = __shfl_xor_sync(FULL, wmin, o); wmin = x < wmin ? x : wmin; }
-            if (wmin < best) {
-              unsigned who = __ballot_sync(FULL, dmin == wmin);
-              int src = __ffs(who) - 1;
-              best = wmin; best_item = __shfl_sync(FULL, item, src); best_ea = __shfl_sync(FULL, ea, src); best_eb = __shfl_sync(FULL, eb, src);
-            }
           }
           __syncwarp();
           continue;
@@ -511,30 +494,22 @@ kb_traverse_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
         uint2 c0e = e, c1e = e;
         if (act) {
           const int item = (int)(e.x >> KB_NODEA_BITS);
-          int nodeA, nodeB; float infl; XfF T; double marg = 0.0, rsum = 0.0;
+          int nodeA, nodeB; float infl; XfF T;
           if (ITC) {
             const ItemS s = s_items[item];
             nodeA = s.nodeA; nodeB = s.nodeB; infl = s.infl;
             load_itc(itc_l, item, T);
-            if (MODE == 1) { marg = p.items[item].marg; rsum = p.items[item].rsum; }
           } else {
             const KbItem* itp = p.items + item;
             nodeA = itp->nodeA; nodeB = itp->nodeB; infl = (float)itp->thr + slack;
             rel_xf(xfw, itp->xfA, itp->xfB, T);
-            if (MODE == 1) { marg = itp->marg; rsum = itp->rsum; }
           }
           const int na = (int)(e.x & (KB_MAX_NODES_A - 1)), nb = (int)e.y;
           float4 a0, a1, b0, b1;
           load_node(sc.nodes, (size_t)(nodeA + na), a0, a1);
           load_node(sc.nodes, (size_t)(nodeB + nb), b0, b1);
           if (STATS) st_node++;
-          bool ov;
-          if (MODE == 0) ov = sat6_overlap(a0, a1, b0, b1, T, infl);
-          else {
-            float lb = box_dist_lb(a0, a1, b0, b1, T) - slack;
-            ov = (lb > 0.f ? (double)lb : -rsum) - marg < best;
-          }
-          if (ov) {
+          if (sat6_overlap(a0, a1, b0, b1, T, infl)) {
             const int la = __float_as_int(a0.w), lb = __float_as_int(b0.w);
             if (la < 0 && lb < 0) leafpair = true;
             else {
@@ -570,21 +545,13 @@ kb_traverse_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
         st_node = st_leaf = st_re = 0;
       }
       if (lane == 0) {
-        if (MODE == 0) {
-          p.hit[c] = found;
-          if (p.hit_elem) { p.hit_elem[2 * (size_t)c] = found_ea; p.hit_elem[2 * (size_t)c + 1] = found_eb; }
-        } else {
-          out_dist[c] = best;
-          p.hit[c] = best_item;
-          if (p.hit_elem) { p.hit_elem[2 * (size_t)c] = best_ea; p.hit_elem[2 * (size_t)c + 1] = best_eb; }
-        }
+        p.hit[c] = found;
+        if (p.hit_elem) { p.hit_elem[2 * (size_t)c] = found_ea; p.hit_elem[2 * (size_t)c + 1] = found_eb; }
       }
     }
   }
-  if (MODE == 0) { int f = 0, fa = 0, fb = 0; drain_rechecks(p, rq, rq_count, lane, (int64_t)-1, f, fa, fb, true); }
-  if (STATS && p.counters) {
-    // per-lane 32-bit counters are flushed per configuration (see below); nothing left to do here
-  }
+  // pairs still parked for the fp64 recheck belong to configurations already written as "no hit": resolve them now
+  { int f = 0, fa = 0, fb = 0; drain_rechecks(p, rq, rq_count, lane, (int64_t)-1, f, fa, fb, true); }
 }
 
 // =============================================================================================== split pipeline
@@ -1191,19 +1158,19 @@ cudaError_t kb_launch_fk(const KbRobotDev* robot, const KbDriverDev* drv, const 
   return cudaGetLastError();
 }
 
-template <int MODE, bool ITC, bool STATS, int BPS>
-static cudaError_t launch_traverse_t(const KbTraverseParams& p, double* out_dist, double upper_bound, int num_sms, size_t smem, cudaStream_t s) {
+template <bool ITC, bool STATS, int BPS>
+static cudaError_t launch_traverse_t(const KbTraverseParams& p, int num_sms, size_t smem, cudaStream_t s) {
   static bool attr_set[64] = {false};      // the attribute is per device
   int dev = 0; cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(kb_traverse_kernel<MODE, ITC, STATS, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(kb_traverse_kernel<ITC, STATS, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   int per_sm = (int)((224 * 1024) / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > BPS) per_sm = BPS;
   int64_t want = (p.N + 8 * KB_WARPS_PER_BLOCK - 1) / (8 * KB_WARPS_PER_BLOCK);
   int64_t grid = (int64_t)num_sms * per_sm; if (grid > want) grid = want; if (grid < 1) grid = 1;
-  kb_traverse_kernel<MODE, ITC, STATS, BPS><<<(unsigned)grid, KB_WARPS_PER_BLOCK * 32, smem, s>>>(p, out_dist, upper_bound);
+  kb_traverse_kernel<ITC, STATS, BPS><<<(unsigned)grid, KB_WARPS_PER_BLOCK * 32, smem, s>>>(p);
   return cudaGetLastError();
 }
 
@@ -1224,9 +1191,9 @@ cudaError_t kb_launch_traverse(const KbTraverseParams& p, int mode, double* out_
   // small (few work items per configuration, C2: 8.9 vs 9.2 ms), 3 CTAs/SM (168 registers, no spills) wins when the
   // item cache is large (C3, 107 pairs: 10.5 vs 11.8 ms).  Measured on B200, profiles/r01_experiments.md.
   const bool four = smem <= 40 * 1024;
-#define KB_LT(M, I, S) (four ? launch_traverse_t<M, I, S, 4>(p, out_dist, upper_bound, num_sms, smem, s) : launch_traverse_t<M, I, S, 3>(p, out_dist, upper_bound, num_sms, smem, s))
-  if (p.collect_stats) return itc ? KB_LT(0, true, true) : KB_LT(0, false, true);
-  return itc ? KB_LT(0, true, false) : KB_LT(0, false, false);
+#define KB_LT(I, S) (four ? launch_traverse_t<I, S, 4>(p, num_sms, smem, s) : launch_traverse_t<I, S, 3>(p, num_sms, smem, s))
+  if (p.collect_stats) return itc ? KB_LT(true, true) : KB_LT(false, true);
+  return itc ? KB_LT(true, false) : KB_LT(false, false);
 #undef KB_LT
 }
 
