@@ -356,6 +356,45 @@ __device__ __forceinline__ void load_itc(const float* __restrict__ itc, int item
   T.t[0] = q2.y; T.t[1] = q2.z; T.t[2] = q2.w;
 }
 
+// one popped frontier entry: fetch its item record + relative transform + both nodes, 6-axis SAT, and on overlap either
+// mark a leaf pair or produce the two child entries (descend the larger box)
+template <bool ITC>
+__device__ __forceinline__ void node_test(const KbTraverseParams& p, const ItemS* __restrict__ s_items, const float* __restrict__ itc,
+                                          const float* __restrict__ xfw, float slack, const uint2 e,
+                                          bool& push2, bool& leafpair, uint2& c0e, uint2& c1e) {
+  const KbScene& sc = p.scene;
+  const int item = (int)(e.x >> KB_NODEA_BITS);
+  int nodeA, nodeB; float infl; XfF T;
+  if (ITC) {
+    const ItemS s = s_items[item];
+    nodeA = s.nodeA; nodeB = s.nodeB; infl = s.infl;
+    load_itc(itc, item, T);
+  } else {
+    const KbItem* itp = p.items + item;
+    nodeA = itp->nodeA; nodeB = itp->nodeB; infl = (float)itp->thr + slack;
+    rel_xf(xfw, itp->xfA, itp->xfB, T);
+  }
+  const int na = (int)(e.x & (KB_MAX_NODES_A - 1)), nb = (int)e.y;
+  float4 a0, a1, b0, b1;
+  load_node(sc.nodes, (size_t)(nodeA + na), a0, a1);
+  load_node(sc.nodes, (size_t)(nodeB + nb), b0, b1);
+  if (sat6_overlap(a0, a1, b0, b1, T, infl)) {
+    const int la = __float_as_int(a0.w), lb = __float_as_int(b0.w);
+    if (la < 0 && lb < 0) leafpair = true;
+    else {
+      push2 = true;
+      const float sa2 = a1.x * a1.x + a1.y * a1.y + a1.z * a1.z, sb2 = b1.x * b1.x + b1.y * b1.y + b1.z * b1.z;
+      if (lb < 0 || (la >= 0 && sa2 >= sb2)) {
+        c0e = make_uint2((e.x & ~(unsigned)(KB_MAX_NODES_A - 1)) | (unsigned)la, e.y);
+        c1e = make_uint2(c0e.x + 1u, e.y);
+      } else {
+        c0e = make_uint2(e.x, (unsigned)lb);
+        c1e = make_uint2(e.x, (unsigned)lb + 1u);
+      }
+    }
+  }
+}
+
 template <bool ITC, bool STATS, int BPS>
 __global__ void __launch_bounds__(KB_WARPS_PER_BLOCK * 32, BPS)
 kb_traverse_kernel(const KbTraverseParams p) {
@@ -493,37 +532,8 @@ kb_traverse_kernel(const KbTraverseParams p) {
         bool push2 = false, leafpair = false;
         uint2 c0e = e, c1e = e;
         if (act) {
-          const int item = (int)(e.x >> KB_NODEA_BITS);
-          int nodeA, nodeB; float infl; XfF T;
-          if (ITC) {
-            const ItemS s = s_items[item];
-            nodeA = s.nodeA; nodeB = s.nodeB; infl = s.infl;
-            load_itc(itc_l, item, T);
-          } else {
-            const KbItem* itp = p.items + item;
-            nodeA = itp->nodeA; nodeB = itp->nodeB; infl = (float)itp->thr + slack;
-            rel_xf(xfw, itp->xfA, itp->xfB, T);
-          }
-          const int na = (int)(e.x & (KB_MAX_NODES_A - 1)), nb = (int)e.y;
-          float4 a0, a1, b0, b1;
-          load_node(sc.nodes, (size_t)(nodeA + na), a0, a1);
-          load_node(sc.nodes, (size_t)(nodeB + nb), b0, b1);
+          node_test<ITC>(p, s_items, itc_l, xfw, slack, e, push2, leafpair, c0e, c1e);
           if (STATS) st_node++;
-          if (sat6_overlap(a0, a1, b0, b1, T, infl)) {
-            const int la = __float_as_int(a0.w), lb = __float_as_int(b0.w);
-            if (la < 0 && lb < 0) leafpair = true;
-            else {
-              push2 = true;
-              const float sa2 = a1.x * a1.x + a1.y * a1.y + a1.z * a1.z, sb2 = b1.x * b1.x + b1.y * b1.y + b1.z * b1.z;
-              if (lb < 0 || (la >= 0 && sa2 >= sb2)) {
-                c0e = make_uint2((e.x & ~(unsigned)(KB_MAX_NODES_A - 1)) | (unsigned)la, e.y);
-                c1e = make_uint2(c0e.x + 1u, e.y);
-              } else {
-                c0e = make_uint2(e.x, (unsigned)lb);
-                c1e = make_uint2(e.x, (unsigned)lb + 1u);
-              }
-            }
-          }
         }
         const unsigned pm = __ballot_sync(FULL, push2), lm = __ballot_sync(FULL, leafpair);
         if (push2) { int off = sp_l + 2 * __popc(pm & lt_mask); stack[off] = c1e; stack[off + 1] = c0e; }
