@@ -523,7 +523,7 @@ kb_traverse_kernel(const KbTraverseParams p) {
         const bool more_items = cursor < p.nitems;
         const int lane_l = lane;
         do {
-        int m = (sp_l <= p.wide_limit) ? (sp_l < 32 ? sp_l : 32) : 1;
+        int m = (sp_l <= p.wide_limit) ? (sp_l < KB_POP_WIDTH ? sp_l : KB_POP_WIDTH) : 1;
         const bool act = lane_l < m;
         uint2 e = make_uint2(0u, 0u);
         if (act) e = stack[sp_l - 1 - lane_l];

@@ -27,6 +27,9 @@
 #define KB_MAX_ITEMS (1 << KB_ITEM_BITS)
 #define KB_MAX_NODES_A (1 << KB_NODEA_BITS)
 #define KB_WARPS_PER_BLOCK 4
+#ifndef KB_POP_WIDTH
+#define KB_POP_WIDTH 32           // frontier entries popped per iteration of the boolean kernel (<= 32)
+#endif
 #ifndef KB_LEAF_TRIGGER
 #define KB_LEAF_TRIGGER 32        // leaf pairs queued before the element phase runs (it also runs whenever the node stack is empty)
 #endif
