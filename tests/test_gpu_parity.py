@@ -316,3 +316,54 @@ def test_split_pipeline_gives_identical_results(c2small, c3):
         finally:
             eng.set_option("pipeline", 0)
             eng.set_option("leaf_budget", 64)
+
+
+def test_prismatic_spin_driver_and_custom_mask(built):
+    """the less common corners of the data model in one world: prismatic links, a branching tree, a Spin joint (metric and
+    interpolation take the short arc), an affine driver limit, a self-collision edit and a user pair mask"""
+    from klampt_b200.engine import Engine
+    from klampt_b200.worldspec import DriverSpec, JOINT_SPIN, JOINT_NORMAL, JOINT_WELD, PRISMATIC
+    from oracle.oracle import OracleWorld
+    rng = np.random.default_rng(17)
+    w = WorldSpec()
+    v, t = synth.box_mesh([-1.5, -1.5, -0.4], [1.5, 1.5, -0.3], div=3)
+    w.terrains.append(w.add_geom(GeomSpec.mesh(v, t)))
+    for _ in range(8):
+        d = rng.uniform(0.05, 0.2, size=3)
+        bv, bt = synth.box_mesh(-d, d, div=2)
+        w.objects.append((w.add_geom(GeomSpec.mesh(bv, bt)), synth.make_T(synth._random_rotation(rng), rng.uniform(-1.2, 1.2, size=3))))
+    r = synth.make_planar_nR(w, 6, 0.35)
+    r.parents = np.array([-1, 0, 1, 1, 3, 4], dtype=np.int32)           # branch at link 1
+    r.linktype[2] = PRISMATIC
+    r.axis[2] = [1.0, 0.0, 0.0]
+    r.qmin[:] = [-np.inf, -2.0, -0.3, -2.0, -2.0, -2.0]
+    r.qmax[:] = [np.inf, 2.0, 0.4, 2.0, 2.0, 2.0]
+    r.joint_type = np.array([JOINT_SPIN, JOINT_NORMAL, JOINT_NORMAL, JOINT_NORMAL, JOINT_NORMAL, JOINT_NORMAL], dtype=np.uint8)
+    r.drivers.append(DriverSpec(links=[3, 4], scale=[1.0, 2.0], offset=[0.1, 0.0], qmin=-0.8, qmax=0.8))
+    r.self_collision_edits += [(0, 2, False), (2, 3, False), (2, 5, True)]      # siblings 2 and 3 share their joint origin
+    w.robot = r
+    n = w.num_ids()
+    base = OracleWorld(w).pair_mask()
+    mask = base.copy()
+    lid = w.robot_link_id(5)
+    mask[lid, w.rigid_object_id(0)] = 0
+    mask[w.rigid_object_id(0), lid] = 0                                   # IgnoreCollisions(link 5, object 0)
+    mask[w.robot_link_id(4), w.rigid_object_id(1)] = 0                     # one direction only: still enabled via the OR
+    w.pair_mask = mask
+    eng, orc = Engine(w), OracleWorld(w)
+    assert np.array_equal(eng.pair_mask(), orc.pair_mask()) and eng.num_ids() == n
+    Q = rng.uniform([-7, -2.1, -0.32, -2.1, -2.1, -2.1], [7, 2.1, 0.42, 2.1, 2.1, 2.1], size=(20000, 6))
+    np.testing.assert_allclose(eng.fk_batch(Q[:200]), orc.fk_batch(Q[:200]), rtol=0, atol=1e-12)
+    got, want = eng.feasible_batch(Q), orc.feasible_batch(Q)
+    assert_bool_parity(got, want, Q, orc)
+    lim = np.array([orc.check_joint_limits(q) for q in Q[:2000]])
+    assert 0.2 < lim.mean() < 0.9 and not got[:2000][~lim].any()
+    ok = Q[want == 1]
+    assert len(ok) >= 400
+    A, B = ok[:200], ok[200:400]
+    vis, nchk = eng.edges_visible_batch(A, B, eps=0.02)
+    ovis, on = orc.edges_visible_batch(A, B, eps=0.02)
+    assert (vis == ovis).all() and (nchk == on).all()
+    d = eng.distance_batch(Q[:500], upper_bound=0.3, include_self=True)
+    do, _ = orc.distance_batch(Q[:500], upper_bound=0.3, include_self=True)
+    np.testing.assert_allclose(d, do, rtol=1e-5, atol=1e-9)
