@@ -136,6 +136,12 @@ int kb_edges_visible_batch(kb_engine* e, const double* A, const double* B, int64
 int kb_edges_visible_batch_device(kb_engine* e, const double* dA, const double* dB, int64_t N, double eps,
                                   const double* weights_host, uint8_t* d_out, int32_t* d_nchecks);
 
+/* Every colliding pair of each configuration: SingleRobotCSpace::Init's per-pair CollisionFreeSet constraints
+ * (Cpp/Planning/RobotCSpace.cpp:697-747) evaluated together, as CSpaceInterface::feasibilityFailures needs them
+ * (Python/klampt/src/motionplanning.h:122-171).  out_pairs: N x max_pairs x 2 world ids, -1 padded (1 <= max_pairs <= 32);
+ * out_count: pairs found (may exceed max_pairs; the surplus is not stored), -1 where the joint / driver limits fail. */
+int kb_colliding_pairs_batch(kb_engine* e, const double* Q, int64_t N, int max_pairs, int32_t* out_pairs, int32_t* out_count);
+
 /* WorldPlannerSettings::DistanceLowerBound(world, {robot}, {environment}, eps=0, bound) for N configurations
  * (Cpp/Planning/PlannerSettings.cpp:570-620): min over enabled pairs of (geometric distance - margins), capped at
  * upper_bound; include_self adds the enabled self pairs.  out_pair optional (N x 2 world ids, -1 if capped). */

@@ -54,6 +54,7 @@ SIGNATURES = {
     "kb_feasible_batch_device": (C.c_int, [_VP, _VP, C.c_int64, _VP, _VP]),
     "kb_edges_visible_batch": (C.c_int, [_VP, _VP, _VP, C.c_int64, C.c_double, _VP, _VP, _VP]),
     "kb_edges_visible_batch_device": (C.c_int, [_VP, _VP, _VP, C.c_int64, C.c_double, _VP, _VP, _VP]),
+    "kb_colliding_pairs_batch": (C.c_int, [_VP, _VP, C.c_int64, C.c_int, _VP, _VP]),
     "kb_distance_batch": (C.c_int, [_VP, _VP, C.c_int64, C.c_double, C.c_int, _VP, _VP]),
     "kb_distance_batch_device": (C.c_int, [_VP, _VP, C.c_int64, C.c_double, C.c_int, _VP, _VP]),
     "kb_geom_collides_batch": (C.c_int, [_VP, C.c_int, _VP, C.c_int, _VP, C.c_int64, C.c_double, _VP]),

@@ -874,6 +874,31 @@ int kb_edges_visible_batch(kb_engine* e, const double* A, const double* B, int64
   return KB_OK;
 }
 
+int kb_colliding_pairs_batch(kb_engine* e, const double* Q, int64_t N, int max_pairs, int32_t* out_pairs, int32_t* out_count) {
+  if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
+  if (N < 0 || (N > 0 && (!Q || !out_pairs || !out_count)) || max_pairs < 1 || max_pairs > 32) return fail(KB_ERR_INVALID, "bad arguments (1 <= max_pairs <= 32)");
+  if (N == 0) return KB_OK;
+  CK(cudaSetDevice(e->device));
+  int rc;
+  if ((rc = grow(e->d_Q, e->q_cap, N * e->L))) return rc;
+  if ((rc = grow(e->d_pair, e->pair_cap, std::max<int64_t>(2 * N, N * max_pairs * 2 + N)))) return rc;
+  if ((rc = ensure_cfg_scratch(e, e->feas_items.nxf, N))) return rc;
+  int32_t* d_pairs = e->d_pair; int32_t* d_count = e->d_pair + N * max_pairs * 2;
+  CK(cudaMemcpyAsync(e->d_Q, Q, (size_t)N * e->L * 8, cudaMemcpyHostToDevice, e->stream));
+  for (int64_t off = 0; off < N; off += e->chunk) {
+    int64_t n = std::min(e->chunk, N - off);
+    CK(kb_launch_fk(e->d_robot, e->d_drv, e->d_drv_link, e->d_drv_scale, e->d_drv_off, e->d_Q + off * e->L, n, e->d_xf, e->feas_items.nxf, e->d_state, nullptr, e->d_hit, e->stream));
+    KbTraverseParams p = make_params(e, e->feas_items, e->d_xf, n, e->d_state);
+    if (p.nitems > 0) CK(kb_launch_allpairs(p, max_pairs, d_pairs + off * max_pairs * 2, d_count + off, e->num_sms, e->stream));
+    else { CK(cudaMemsetAsync(d_pairs + off * max_pairs * 2, 0xff, (size_t)n * max_pairs * 8, e->stream)); CK(cudaMemsetAsync(d_count + off, 0, (size_t)n * 4, e->stream)); }
+    e->stats.kernel_launches += 2;
+  }
+  CK(cudaMemcpyAsync(out_pairs, d_pairs, (size_t)N * max_pairs * 8, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(out_count, d_count, (size_t)N * 4, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return KB_OK;
+}
+
 int kb_distance_batch_device(kb_engine* e, const double* dQ, int64_t N, double upper_bound, int include_self, double* d_out_d, int32_t* d_out_pair) {
   if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
   if (N < 0 || (N > 0 && (!dQ || !d_out_d))) return fail(KB_ERR_INVALID, "bad arguments");

@@ -600,6 +600,142 @@ kb_traverse_kernel(const KbTraverseParams p) {
   { int f = 0, fa = 0, fb = 0; drain_rechecks(p, rq, rq_count, lane, (int64_t)-1, f, fa, fb, true); }
 }
 
+// =============================================================================================== all colliding pairs
+// kb_allpairs_kernel -- no early exit: lists every colliding (idA, idB) world-id pair of a configuration, up to max_pairs.
+// Replaces evaluating SingleRobotCSpace's per-pair CollisionFreeSet constraints one by one (reference
+// Cpp/Planning/RobotCSpace.cpp:697-747; CSpaceInterface::feasibilityFailures, Python/klampt/src/motionplanning.h:122-171).
+// Same warp-cooperative node traversal; leaf pairs whose id pair is already listed are skipped, and items that map to a
+// single id pair (link vs link, link vs a one-object group) stop traversing once found.  Uncertain fp32 results are
+// re-run in fp64 in place (this is a diagnostic query, not the hot loop).
+#define KB_AP_MAX 32
+template <bool ITC>
+__global__ void __launch_bounds__(KB_WARPS_PER_BLOCK * 32, 3)
+kb_allpairs_kernel(const KbTraverseParams p, int max_pairs, int32_t* __restrict__ out_pairs, int32_t* __restrict__ out_count) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int xf_floats = (p.nxf * 12 + 3) & ~3;
+  const int nit_c = ITC ? p.nitems : 0;
+  ItemS* s_items = (ItemS*)smem_raw;
+  const size_t per_warp = (size_t)KB_STACK_CAP * 8 + (size_t)KB_LEAFQ_CAP * 8 + (size_t)KB_AP_MAX * 8 + (size_t)xf_floats * 4 + (size_t)nit_c * 48;
+  unsigned char* base = smem_raw + (size_t)nit_c * 16 + warp * per_warp;
+  uint2* stack = (uint2*)base;
+  uint2* leafq = (uint2*)(base + (size_t)KB_STACK_CAP * 8);
+  int2* foundp = (int2*)(base + (size_t)KB_STACK_CAP * 8 + (size_t)KB_LEAFQ_CAP * 8);
+  float* xfw = (float*)(base + (size_t)KB_STACK_CAP * 8 + (size_t)KB_LEAFQ_CAP * 8 + (size_t)KB_AP_MAX * 8);
+  float* itc = xfw + xf_floats;
+  const KbScene& sc = p.scene;
+  const float slack = 4.f * sc.eps_abs;
+  if (ITC) {
+    for (int i = threadIdx.x; i < p.nitems; i += blockDim.x) {
+      const KbItem* it = p.items + i;
+      ItemS s; s.nodeA = it->nodeA; s.nodeB = it->nodeB; s.infl = (float)it->thr + slack;
+      s.xf = (int)((unsigned)(unsigned short)it->xfA | ((unsigned)(unsigned short)it->xfB << 16));
+      s_items[i] = s;
+    }
+  }
+  __syncthreads();
+  unsigned lt_mask;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
+  for (;;) {
+    unsigned int c = 0;
+    if (lane == 0) c = atomicAdd(p.work_counter, 1u);
+    c = __shfl_sync(FULL, c, 0);
+    if ((int64_t)c >= p.N) break;
+    if (p.state && p.state[c] == 0) { if (lane == 0) out_count[c] = -1; continue; }
+    const double* xf = p.xf64 + (size_t)c * (size_t)p.nxf * 12;
+    __syncwarp();
+    for (int i = lane; i < p.nxf * 12; i += 32) xfw[i] = (float)xf[i];
+    __syncwarp();
+    if (ITC) {
+      for (int i = lane; i < p.nitems; i += 32) {
+        const int xfp = s_items[i].xf;
+        XfF T; rel_xf(xfw, (int)(short)(xfp & 0xffff), (int)(short)(xfp >> 16), T);
+        float4* qv = (float4*)(itc + 12 * i);
+        qv[0] = make_float4(T.r[0], T.r[1], T.r[2], T.r[3]); qv[1] = make_float4(T.r[4], T.r[5], T.r[6], T.r[7]); qv[2] = make_float4(T.r[8], T.t[0], T.t[1], T.t[2]);
+      }
+      __syncwarp();
+    }
+    int sp = 0, nleaf = 0, cursor = 0, nfound = 0;
+    for (;;) {
+      if (sp < 32 && cursor < p.nitems) {
+        int k = p.nitems - cursor; if (k > 32) k = 32;
+        if (lane < k) stack[sp + lane] = make_uint2(((unsigned)(cursor + lane) << KB_NODEA_BITS), 0u);
+        sp += k; cursor += k;
+        __syncwarp();
+      }
+      if (sp == 0 && nleaf == 0) break;
+      if (nleaf >= 32 || sp == 0) {
+        const int m = nleaf < 32 ? nleaf : 32;
+        bool hit = false; int ia = -1, ib = -1;
+        if (lane < m) {
+          const uint2 e = leafq[nleaf - 1 - lane];
+          const int item = (int)(e.x >> KB_NODEA_BITS);
+          const KbItem& it = p.items[item];
+          const int na = (int)(e.x & (KB_MAX_NODES_A - 1)), nb = (int)e.y;
+          float4 a0, a1, b0, b1;
+          load_node(sc.nodes, (size_t)(it.nodeA + na), a0, a1);
+          load_node(sc.nodes, (size_t)(it.nodeB + nb), b0, b1);
+          const int fa = it.elemA + ~__float_as_int(a0.w), ca = __float_as_int(a1.w);
+          const int fb = it.elemB + ~__float_as_int(b0.w), cb = __float_as_int(b1.w);
+          XfF T;
+          if (ITC) load_itc(itc, item, T); else rel_xf(xfw, it.xfA, it.xfB, T);
+          const float thr = (float)it.thr;
+          for (int i = 0; i < ca && !hit; i++)
+            for (int j = 0; j < cb && !hit; j++) {
+              int pa = it.idA, pb = it.idB;
+              if (pa < 0) pa = (it.kindA == KB_ELEM_TRI ? sc.triown : sc.sphown)[fa + i];
+              if (pb < 0) pb = (it.kindB == KB_ELEM_TRI ? sc.triown : sc.sphown)[fb + j];
+              bool known = false;
+              for (int k = 0; k < nfound && k < KB_AP_MAX; k++) known |= (foundp[k].x == pa && foundp[k].y == pb);
+              if (known) continue;
+              int r = fast_elem_collide(sc, it, T, fa + i, fb + j, thr);
+              if (r == KB_UNCERTAIN) r = exact_elem_collide(sc, it, xf, fa + i, fb + j) ? KB_YES : KB_NO;
+              if (r == KB_YES) { hit = true; ia = pa; ib = pb; }
+            }
+        }
+        nleaf -= m;
+        unsigned hm = __ballot_sync(FULL, hit);
+        while (hm) {                                   // append the new id pairs one by one (warp-uniform)
+          const int src = __ffs(hm) - 1; hm &= hm - 1;
+          const int pa = __shfl_sync(FULL, ia, src), pb = __shfl_sync(FULL, ib, src);
+          bool known = false;
+          for (int k = 0; k < nfound && k < KB_AP_MAX; k++) known |= (foundp[k].x == pa && foundp[k].y == pb);
+          if (!known) { if (lane == 0 && nfound < KB_AP_MAX) foundp[nfound] = make_int2(pa, pb); nfound++; __syncwarp(); }
+        }
+        __syncwarp();
+        continue;
+      }
+      const int m = (sp <= p.wide_limit) ? (sp < 32 ? sp : 32) : 1;
+      const bool act = lane < m;
+      uint2 e = make_uint2(0u, 0u);
+      if (act) e = stack[sp - 1 - lane];
+      sp -= m;
+      __syncwarp();
+      bool push2 = false, leafpair = false;
+      uint2 c0e = e, c1e = e;
+      if (act) {
+        // an item that names one id pair is finished once that pair is listed
+        const KbItem* itp = p.items + (e.x >> KB_NODEA_BITS);
+        bool skip = false;
+        if (itp->idA >= 0 && itp->idB >= 0)
+          for (int k = 0; k < nfound && k < KB_AP_MAX; k++) skip |= (foundp[k].x == itp->idA && foundp[k].y == itp->idB);
+        if (!skip) node_test<ITC>(p, s_items, itc, xfw, slack, e, push2, leafpair, c0e, c1e);
+      }
+      const unsigned pm = __ballot_sync(FULL, push2), lm = __ballot_sync(FULL, leafpair);
+      if (push2) { const int off = sp + 2 * __popc(pm & lt_mask); stack[off] = c1e; stack[off + 1] = c0e; }
+      if (leafpair) leafq[nleaf + __popc(lm & lt_mask)] = e;
+      sp += 2 * __popc(pm); nleaf += __popc(lm);
+      __syncwarp();
+    }
+    if (lane == 0) out_count[c] = nfound;
+    for (int k = lane; k < max_pairs; k += 32) {
+      const int2 v = (k < nfound && k < KB_AP_MAX) ? foundp[k] : make_int2(-1, -1);
+      out_pairs[((size_t)c * max_pairs + k) * 2] = v.x; out_pairs[((size_t)c * max_pairs + k) * 2 + 1] = v.y;
+    }
+    __syncwarp();
+  }
+}
+
 // =============================================================================================== split pipeline
 // The fused kernel above carries the element tests (fp32 filtered tri-tri + fp64 recheck) in the same kernel as the
 // node loop; their register demand (166 natural) caps the whole kernel at 16 warps per SM although the node loop itself
@@ -1290,6 +1426,26 @@ cudaError_t kb_launch_split(const KbTraverseParams& p, const KbSplitParams& q, i
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   kb_requeue_kernel<<<nblocks(p.N, 256), 256, 0, s>>>(p.state, q.flagged, p.hit, p.N, q.state2, q.requeued);
+  return cudaGetLastError();
+}
+
+cudaError_t kb_launch_allpairs(const KbTraverseParams& p, int max_pairs, int32_t* out_pairs, int32_t* out_count, int num_sms, cudaStream_t s) {
+  if (p.N <= 0) return cudaSuccess;
+  if (p.N > 0xfffffff0ll || max_pairs < 1 || max_pairs > KB_AP_MAX) return cudaErrorInvalidValue;
+  const bool itc = p.nitems <= KB_ITC_MAX_ITEMS;
+  const size_t xf_floats = ((size_t)p.nxf * 12 + 3) & ~(size_t)3, nit = itc ? (size_t)p.nitems : 0;
+  const size_t smem = nit * 16 + (size_t)KB_WARPS_PER_BLOCK * ((size_t)KB_STACK_CAP * 8 + (size_t)KB_LEAFQ_CAP * 8 + (size_t)KB_AP_MAX * 8 + xf_floats * 4 + nit * 48);
+  if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+  cudaError_t e = cudaMemsetAsync(p.work_counter, 0, sizeof(uint32_t), s);
+  if (e != cudaSuccess) return e;
+  e = itc ? cudaFuncSetAttribute(kb_allpairs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
+          : cudaFuncSetAttribute(kb_allpairs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) return e;
+  int per_sm = (int)((224 * 1024) / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > 3) per_sm = 3;
+  int64_t want = (p.N + KB_WARPS_PER_BLOCK - 1) / KB_WARPS_PER_BLOCK;
+  int64_t grid = (int64_t)num_sms * per_sm; if (grid > want) grid = want; if (grid < 1) grid = 1;
+  if (itc) kb_allpairs_kernel<true><<<(unsigned)grid, KB_WARPS_PER_BLOCK * 32, smem, s>>>(p, max_pairs, out_pairs, out_count);
+  else kb_allpairs_kernel<false><<<(unsigned)grid, KB_WARPS_PER_BLOCK * 32, smem, s>>>(p, max_pairs, out_pairs, out_count);
   return cudaGetLastError();
 }
 

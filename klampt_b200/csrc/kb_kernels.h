@@ -26,3 +26,5 @@ cudaError_t kb_launch_copy_u8(const uint8_t* src, uint8_t* dst, int64_t n, unsig
 
 size_t kb_nodes_smem_bytes(int nxf, int nitems, int stack_cap);
 cudaError_t kb_launch_split(const KbTraverseParams& p, const KbSplitParams& q, int num_sms, cudaStream_t s);
+// every colliding world-id pair per configuration, up to max_pairs (<= 32); out_count = -1 where state == 0
+cudaError_t kb_launch_allpairs(const KbTraverseParams& p, int max_pairs, int32_t* out_pairs, int32_t* out_count, int num_sms, cudaStream_t s);

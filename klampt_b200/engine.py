@@ -191,6 +191,16 @@ class Engine:
         check(self.lib.kb_distance_batch(self.h, _ptr(Q), N, float(upper_bound), int(include_self), _ptr(d), _ptr(pairs)))
         return (d, pairs) if return_pairs else d
 
+    def colliding_pairs_batch(self, Q, max_pairs: int = 8):
+        """every colliding (idA, idB) world-id pair per configuration: (pairs (N, max_pairs, 2) padded with -1, count (N,));
+        count = -1 where the joint / driver limits already fail"""
+        Q = self._Q(Q)
+        N = Q.shape[0]
+        pairs = np.empty((N, max_pairs, 2), dtype=np.int32)
+        count = np.empty(N, dtype=np.int32)
+        check(self.lib.kb_colliding_pairs_batch(self.h, _ptr(Q), N, int(max_pairs), _ptr(pairs), _ptr(count)))
+        return pairs, count
+
     def geom_collides_batch(self, ga: int, Ta, gb: int, Tb, tol: float = 0.0) -> np.ndarray:
         Ta, Tb = _f64(Ta).reshape(-1, 12), _f64(Tb).reshape(-1, 12)
         N = Ta.shape[0]

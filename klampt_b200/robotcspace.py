@@ -105,6 +105,32 @@ class RobotCSpace(CSpace):
         d = self.engine.distance_batch(q, upper_bound=1e-12, include_self=False)
         return bool(d[0] <= 0.0)
 
+    def colliding_pairs_batch(self, Q, max_pairs: int = 8):
+        """all colliding world-id pairs per configuration (no early exit); see Engine.colliding_pairs_batch"""
+        return self.engine.colliding_pairs_batch(Q, max_pairs=max_pairs)
+
+    def feasibilityFailures(self, x):
+        """names of the reference's feasibility tests that fail at x (CSpaceInterface::feasibilityFailures with the test names of
+        plan/robotcspace.py:62-75): 'joint limits', 'self collision', 'obj collision i name', 'terrain collision i name'"""
+        if not self.inJointLimits(x):
+            return ["joint limits"]
+        pairs, count = self.engine.colliding_pairs_batch(np.asarray(x, dtype=np.float64), max_pairs=32)
+        names = []
+        T, O = len(self.spec.terrains), len(self.spec.objects)
+        for a, b in pairs[0]:
+            if a < 0:
+                continue
+            lo = min(int(a), int(b))
+            if lo < T:
+                n = "terrain collision %d %s" % (lo, self.collider.world.terrain(lo).getName() if self.collider else "")
+            elif lo < T + O:
+                n = "obj collision %d %s" % (lo - T, self.collider.world.rigidObject(lo - T).getName() if self.collider else "")
+            else:
+                n = "self collision"
+            if n not in names:
+                names.append(n)
+        return names
+
     def interpolate(self, a, b, u):
         return self.robot.interpolate(a, b, u)
 

@@ -328,3 +328,34 @@ class OracleWorld:
         lo, hi = np.zeros(3), np.zeros(3)
         self.L.ko_geom_aabb(self.h, g, Tp, lo.ctypes.data_as(C.POINTER(C.c_double)), hi.ctypes.data_as(C.POINTER(C.c_double)))
         return lo, hi
+
+
+def colliding_pairs(orc: "OracleWorld", q):
+    """every enabled (idA, idB) world-id pair that collides at q, by explicit per-pair queries (test helper for
+    kb_colliding_pairs_batch); None if the joint / driver limits fail"""
+    spec = orc.spec
+    if not orc.check_joint_limits(q):
+        return None
+    T = orc.fk(q)
+    mask = orc.pair_mask()
+    r = spec.robot
+    out = set()
+    I12 = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], dtype=np.float64)
+    env = [(spec.terrain_id(i), g, I12) for i, g in enumerate(spec.terrains)] + [(spec.rigid_object_id(i), g, Tm) for i, (g, Tm) in enumerate(spec.objects)]
+    for j, gj in enumerate(r.link_geom):
+        if gj < 0 or spec.geoms[gj].num_elements() == 0:
+            continue
+        lid = spec.robot_link_id(j)
+        for (eid, ge, Te) in env:
+            if ge < 0 or spec.geoms[ge].num_elements() == 0:
+                continue
+            if (mask[lid, eid] or mask[eid, lid]) and orc.geom_collides(gj, T[j], ge, Te):
+                out.add((lid, eid))
+        for k in range(j + 1, r.L):
+            gk = r.link_geom[k]
+            if gk < 0 or spec.geoms[gk].num_elements() == 0:
+                continue
+            kid = spec.robot_link_id(k)
+            if (mask[lid, kid] or mask[lid, lid]) and orc.geom_collides(gj, T[j], gk, T[k]):
+                out.add((lid, kid))
+    return out

@@ -367,3 +367,30 @@ def test_prismatic_spin_driver_and_custom_mask(built):
     d = eng.distance_batch(Q[:500], upper_bound=0.3, include_self=True)
     do, _ = orc.distance_batch(Q[:500], upper_bound=0.3, include_self=True)
     np.testing.assert_allclose(d, do, rtol=1e-5, atol=1e-9)
+
+
+def test_all_colliding_pairs(c1):
+    """kb_colliding_pairs_batch lists every colliding id pair (the per-pair constraints of SingleRobotCSpace::Init evaluated
+    together); checked against explicit per-pair oracle queries with set semantics"""
+    from oracle.oracle import colliding_pairs
+    w, eng, orc = c1
+    Q = synth.sample_configs(w.robot, 400, 91)
+    Q[5, 2] = w.robot.qmax[2] + 1.0                                    # limits fail -> count -1
+    pairs, count = eng.colliding_pairs_batch(Q, max_pairs=8)
+    feas = eng.feasible_batch(Q)
+    multi = 0
+    for i in range(len(Q)):
+        want = colliding_pairs(orc, Q[i])
+        if want is None:
+            assert count[i] == -1 and (pairs[i] == -1).all()
+            continue
+        got = {(int(a), int(b)) for a, b in pairs[i] if a >= 0}
+        assert count[i] == len(want) and got == want, (i, got, want)
+        assert (count[i] == 0) == bool(feas[i])
+        multi += len(want) > 1
+    assert multi > 5                                                  # the early-exit query would have reported one of these only
+    # max_pairs smaller than the number found: count still reports all, the stored prefix is a subset
+    p1, c1_ = eng.colliding_pairs_batch(Q, max_pairs=1)
+    assert np.array_equal(c1_, count)
+    for i in np.nonzero(count > 0)[0][:50]:
+        assert (int(p1[i, 0, 0]), int(p1[i, 0, 1])) in {(int(a), int(b)) for a, b in pairs[i] if a >= 0}
