@@ -108,6 +108,13 @@ kb_fk_kernel(const KbRobotDev* __restrict__ robot, const KbDriverDev* __restrict
 }
 
 // =============================================================================================== traversal helpers
+// reported id pairs follow the reference's order: (link, environment id) for robot-vs-environment pairs (ids1 = {robot}, ids2 =
+// {terrains, objects} in CheckCollisionFree), (lower link, higher link) for self pairs -- whichever side the engine put first
+__device__ __forceinline__ void kb_order_pair(unsigned flags, int& a, int& b) {
+  const bool self = (flags & 1u) != 0;
+  if (self ? (a > b) : (a < b)) { const int t = a; a = b; b = t; }
+}
+
 struct XfF { float r[9]; float t[3]; };
 
 // T = A^-1 * B for two slots of the per-warp fp32 transform table; slot < 0 = identity
@@ -641,7 +648,11 @@ kb_allpairs_kernel(const KbTraverseParams p, int max_pairs, int32_t* __restrict_
     if (lane == 0) c = atomicAdd(p.work_counter, 1u);
     c = __shfl_sync(FULL, c, 0);
     if ((int64_t)c >= p.N) break;
-    if (p.state && p.state[c] == 0) { if (lane == 0) out_count[c] = -1; continue; }
+    if (p.state && p.state[c] == 0) {
+      if (lane == 0) out_count[c] = -1;
+      for (int k = lane; k < 2 * max_pairs; k += 32) out_pairs[(size_t)c * max_pairs * 2 + k] = -1;
+      continue;
+    }
     const double* xf = p.xf64 + (size_t)c * (size_t)p.nxf * 12;
     __syncwarp();
     for (int i = lane; i < p.nxf * 12; i += 32) xfw[i] = (float)xf[i];
@@ -685,6 +696,7 @@ kb_allpairs_kernel(const KbTraverseParams p, int max_pairs, int32_t* __restrict_
               int pa = it.idA, pb = it.idB;
               if (pa < 0) pa = (it.kindA == KB_ELEM_TRI ? sc.triown : sc.sphown)[fa + i];
               if (pb < 0) pb = (it.kindB == KB_ELEM_TRI ? sc.triown : sc.sphown)[fb + j];
+              kb_order_pair(it.flags, pa, pb);
               bool known = false;
               for (int k = 0; k < nfound && k < KB_AP_MAX; k++) known |= (foundp[k].x == pa && foundp[k].y == pb);
               if (known) continue;
@@ -717,8 +729,11 @@ kb_allpairs_kernel(const KbTraverseParams p, int max_pairs, int32_t* __restrict_
         // an item that names one id pair is finished once that pair is listed
         const KbItem* itp = p.items + (e.x >> KB_NODEA_BITS);
         bool skip = false;
-        if (itp->idA >= 0 && itp->idB >= 0)
-          for (int k = 0; k < nfound && k < KB_AP_MAX; k++) skip |= (foundp[k].x == itp->idA && foundp[k].y == itp->idB);
+        if (itp->idA >= 0 && itp->idB >= 0) {
+          int qa = itp->idA, qb = itp->idB;
+          kb_order_pair(itp->flags, qa, qb);
+          for (int k = 0; k < nfound && k < KB_AP_MAX; k++) skip |= (foundp[k].x == qa && foundp[k].y == qb);
+        }
         if (!skip) node_test<ITC>(p, s_items, itc, xfw, slack, e, push2, leafpair, c0e, c1e);
       }
       const unsigned pm = __ballot_sync(FULL, push2), lm = __ballot_sync(FULL, leafpair);
@@ -1181,6 +1196,8 @@ __global__ void kb_finish_kernel(const uint8_t* __restrict__ state, const int32_
         ia = it.idA; ib = it.idB;
         if (ia < 0) ia = (it.kindA == KB_ELEM_TRI ? triown : sphown)[hit_elem[2 * c]];
         if (ib < 0) ib = (it.kindB == KB_ELEM_TRI ? triown : sphown)[hit_elem[2 * c + 1]];
+    kb_order_pair(it.flags, ia, ib);
+        kb_order_pair(it.flags, ia, ib);
       }
       first_pair[2 * c] = ia; first_pair[2 * c + 1] = ib;
     }
@@ -1201,6 +1218,7 @@ __global__ void kb_pair_ids_kernel(const int32_t* __restrict__ hit, const int32_
     ia = it.idA; ib = it.idB;
     if (ia < 0) ia = (it.kindA == KB_ELEM_TRI ? triown : sphown)[hit_elem[2 * c]];
     if (ib < 0) ib = (it.kindB == KB_ELEM_TRI ? triown : sphown)[hit_elem[2 * c + 1]];
+    kb_order_pair(it.flags, ia, ib);
   }
   pair[2 * c] = ia; pair[2 * c + 1] = ib;
 }
