@@ -53,6 +53,9 @@ class WorldBuilder {
     if (!r.jointType.empty()) kbCheck(kb_robot_set_joints(e_, (int)r.jointType.size(), r.jointType.data(), r.jointLink.data()));
     robot_ = r;
   }
+  // RobotModelDriver limits read by CheckJointLimits: value = mean_k (q[links[k]] - offset[k]) / scale[k]
+  void AddDriver(const std::vector<int32_t>& links, const std::vector<double>* scale, const std::vector<double>* offset, double dmin, double dmax) {
+    kbCheck(kb_robot_add_driver(e_, (int)links.size(), links.data(), scale ? scale->data() : nullptr, offset ? offset->data() : nullptr, dmin, dmax)); }
   void EnableSelfCollision(int i, int j, bool on) { kbCheck(kb_robot_set_self_collision(e_, i, j, on ? 1 : 0)); }
   // WorldPlannerSettings::collisionEnabled over world ids (row-major n x n)
   void SetCollisionEnabled(const std::vector<uint8_t>& mask, int n) { kbCheck(kb_set_pair_mask(e_, mask.data(), n)); }
@@ -151,6 +154,8 @@ class BatchSingleRobotCSpace {
   void IsFeasibleBatch(const double* Q, int64_t N, uint8_t* out, int32_t* firstPair = nullptr) { kbCheck(kb_feasible_batch(engine_, Q, N, out, firstPair)); }
   void IsVisibleBatch(const double* A, const double* B, int64_t N, double eps, uint8_t* out, int32_t* nchecks = nullptr) {
     kbCheck(kb_edges_visible_batch(engine_, A, B, N, eps, jointWeights.empty() ? nullptr : jointWeights.data(), out, nchecks)); }
+  // every colliding (idA, idB) pair per configuration: the per-pair CollisionFreeSet constraints of Init() evaluated together
+  void CollidingPairsBatch(const double* Q, int64_t N, int maxPairs, int32_t* outPairs, int32_t* outCount) { kbCheck(kb_colliding_pairs_batch(engine_, Q, N, maxPairs, outPairs, outCount)); }
   void DistanceBatch(const double* Q, int64_t N, double upperBound, bool includeSelf, double* out) { kbCheck(kb_distance_batch(engine_, Q, N, upperBound, includeSelf ? 1 : 0, out, nullptr)); }
   kb_stats GetStats() { kb_stats s; kbCheck(kb_get_stats(engine_, &s)); return s; }
   kb_engine* engine() { return engine_; }
