@@ -682,7 +682,35 @@ int kb_finalize(kb_engine* e, int device) {
   // ---- 5. upload
   e->static_bytes = 0;
   int rc;
+#ifdef KB_QNODES
+  {   // experimental: re-encode the fp32 nodes as 16-byte quantised nodes on one scene-wide grid (conservative: boxes only grow)
+    const size_t nn = e->h_nodes.size() / 8;
+    double qlo[3] = {1e300, 1e300, 1e300}, qhi[3] = {-1e300, -1e300, -1e300};
+    for (size_t i = 0; i < nn; i++) for (int k = 0; k < 3; k++) {
+      const double c = e->h_nodes[8 * i + k], h = e->h_nodes[8 * i + 4 + k];
+      qlo[k] = std::min(qlo[k], c - h); qhi[k] = std::max(qhi[k], c + h);
+    }
+    for (int k = 0; k < 3; k++) { if (!(qhi[k] > qlo[k])) qhi[k] = qlo[k] + 1.0; e->scene.qo[k] = (float)qlo[k]; e->scene.qs[k] = (float)((qhi[k] - qlo[k]) / 65000.0); }
+    std::vector<uint32_t> q(4 * nn);
+    for (size_t i = 0; i < nn; i++) {
+      uint32_t cq[3], hq[3];
+      for (int k = 0; k < 3; k++) {
+        const double c = e->h_nodes[8 * i + k], h = e->h_nodes[8 * i + 4 + k], o = e->scene.qo[k], st = e->scene.qs[k];
+        double cc = std::floor((c - o) / st + 0.5); cc = std::min(65535.0, std::max(0.0, cc));
+        const double cdeq = o + st * cc;
+        double hh = std::ceil((h + std::fabs(c - cdeq)) / st) + 1.0; hh = std::min(65535.0, std::max(0.0, hh));
+        cq[k] = (uint32_t)cc; hq[k] = (uint32_t)hh;
+      }
+      int32_t left, count; memcpy(&left, &e->h_nodes[8 * i + 3], 4); memcpy(&count, &e->h_nodes[8 * i + 7], 4);
+      int32_t ref = left;
+      if (left < 0) { const int32_t first = ~left; if (count < 1) count = 1; if (count > 8 || first >= (1 << 28)) return fail(KB_ERR_UNSUPPORTED, "leaf not encodable in a quantised node"); ref = -1 - (first * 8 + (count - 1)); }
+      q[4 * i] = cq[0] | (cq[1] << 16); q[4 * i + 1] = cq[2] | (hq[0] << 16); q[4 * i + 2] = hq[1] | (hq[2] << 16); memcpy(&q[4 * i + 3], &ref, 4);
+    }
+    if ((rc = upload(e->d_nodes, q.data(), q.size() * 4, &e->static_bytes))) return rc;
+  }
+#else
   if ((rc = upload(e->d_nodes, e->h_nodes.data(), e->h_nodes.size() * 4, &e->static_bytes))) return rc;
+#endif
   if ((rc = upload(e->d_tris32, e->h_tris32.data(), e->h_tris32.size() * 4, &e->static_bytes))) return rc;
   if ((rc = upload(e->d_tris64, e->h_tris64.data(), e->h_tris64.size() * 8, &e->static_bytes))) return rc;
   if ((rc = upload(e->d_sph32, e->h_sph32.data(), e->h_sph32.size() * 4, &e->static_bytes))) return rc;

@@ -354,12 +354,27 @@ __device__ __forceinline__ void drain_rechecks(const KbTraverseParams& p, uint4*
 // LDS.64 + 4 x LDS.128 + 2 x LDG.256 + ~56 FP instructions (165 SASS instructions per 32-pair iteration in total).
 
 // one 32-byte node = one 256-bit load (LDG.E.ENL2.256 on sm_100) instead of two 128-bit ones
+#ifdef KB_QNODES
+// experimental 16-byte quantised node: u16 centre[3], u16 half[3] on one scene-wide grid, i32 ref (inner: left child; leaf:
+// -1 - (first*8 + count-1)).  Needs the scene for the grid, so it is a macro-selected overload.
+#define load_node(nodes, idx, n0, n1) load_node_q(sc, nodes, idx, n0, n1)
+__device__ __forceinline__ void load_node_q(const KbScene& sc, const float4* __restrict__ nodes, size_t idx, float4& n0, float4& n1) {
+  const uint4 w = __ldg((const uint4*)nodes + idx);
+  n0.x = fmaf(__uint2float_rn(w.x & 0xffffu), sc.qs[0], sc.qo[0]); n0.y = fmaf(__uint2float_rn(w.x >> 16), sc.qs[1], sc.qo[1]);
+  n0.z = fmaf(__uint2float_rn(w.y & 0xffffu), sc.qs[2], sc.qo[2]);
+  n1.x = __uint2float_rn(w.y >> 16) * sc.qs[0]; n1.y = __uint2float_rn(w.z & 0xffffu) * sc.qs[1]; n1.z = __uint2float_rn(w.z >> 16) * sc.qs[2];
+  const int ref = (int)w.w;
+  if (ref >= 0) { n0.w = __int_as_float(ref); n1.w = __int_as_float(0); }
+  else { const int code = -1 - ref; n0.w = __int_as_float(~(code >> 3)); n1.w = __int_as_float((code & 7) + 1); }
+}
+#else
 __device__ __forceinline__ void load_node(const float4* __restrict__ nodes, size_t idx, float4& n0, float4& n1) {
   unsigned long long x0, x1, x2, x3;
   asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(x0), "=l"(x1), "=l"(x2), "=l"(x3) : "l"(nodes + 2 * idx));
   n0.x = __uint_as_float((unsigned)x0); n0.y = __uint_as_float((unsigned)(x0 >> 32)); n0.z = __uint_as_float((unsigned)x1); n0.w = __uint_as_float((unsigned)(x1 >> 32));
   n1.x = __uint_as_float((unsigned)x2); n1.y = __uint_as_float((unsigned)(x2 >> 32)); n1.z = __uint_as_float((unsigned)x3); n1.w = __uint_as_float((unsigned)(x3 >> 32));
 }
+#endif
 
 struct ItemS { int32_t nodeA, nodeB; float infl; int32_t xf; };   // 16 B static per-item record cached per block
 

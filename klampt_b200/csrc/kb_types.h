@@ -77,6 +77,7 @@ struct KbScene {                  // device pointers to the static data
   const int32_t* triown;
   const int32_t* sphown;
   float eps_abs;                  // absolute fp32 coordinate error bound for this scene (metres)
+  float qo[3], qs[3];             // KB_QNODES builds only: origin and step of the 16-bit node quantisation grid
 };
 
 struct KbTraverseParams {
