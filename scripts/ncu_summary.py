@@ -50,6 +50,15 @@ def rep(path, out, title):
         for k, label in KEYS:
             if k in col:
                 f.write("| %s (`%s`) | " % (label, k) + " | ".join(r[col[k]] for r in data) + " | %s |\n" % units[col[k]])
+        # derived absolute rates against the B200 peaks (HBM 6544.3 GB/s measured copy; SM issue: 4 schedulers x 148 SMs)
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}
+        def val(r, k):
+            return float(r[col[k]]) * scale.get(units[col[k]], 1.0)
+        if all(k in col for k in ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum")):
+            f.write("\n| derived | " + " | ".join("launch %d" % i for i in range(len(data))) + " |\n|---|" + "---|" * len(data) + "\n")
+            f.write("| achieved HBM GB/s (of 6544.3 measured peak) | " + " | ".join("%.1f (%.1f %%)" % ((val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")) / val(r, "gpu__time_duration.sum") / 1e9,
+                    100 * (val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")) / val(r, "gpu__time_duration.sum") / 6544.3e9) for r in data) + " |\n")
+            f.write("| achieved L2 GB/s | " + " | ".join("%.1f" % (val(r, "lts__t_bytes.sum") / val(r, "gpu__time_duration.sum") / 1e9) for r in data) + " |\n")
 
 
 def launches(path, out, title):
