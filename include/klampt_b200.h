@@ -59,6 +59,8 @@ typedef struct {
   int64_t traverse_launches;    /* launches of the traversal kernel timed while option "time_kernels" = 1 */
   double  traverse_ms;          /* their summed device time (CUDA events on the engine's stream)        */
   double  gpu_ms;               /* device time of the host-buffer entry points, copies included         */
+  int64_t items_dropped;        /* (link, static group) pairs ruled out by the clearance grids ("collect_stats") */
+  int64_t node_iterations;      /* warp-wide iterations of the node loop ("collect_stats")              */
 } kb_stats;
 
 /* ---- lifetime ---------------------------------------------------------------------------------------- */

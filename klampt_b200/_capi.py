@@ -22,7 +22,8 @@ class KbStats(C.Structure):
     _fields_ = [("configs_checked", C.c_int64), ("configs_feasible", C.c_int64), ("edges_checked", C.c_int64),
                 ("edges_visible", C.c_int64), ("edge_config_checks", C.c_int64), ("node_tests", C.c_int64),
                 ("elem_tests", C.c_int64), ("recheck_pairs", C.c_int64), ("kernel_launches", C.c_int64),
-                ("traverse_launches", C.c_int64), ("traverse_ms", C.c_double), ("gpu_ms", C.c_double)]
+                ("traverse_launches", C.c_int64), ("traverse_ms", C.c_double), ("gpu_ms", C.c_double),
+                ("items_dropped", C.c_int64), ("node_iterations", C.c_int64)]
 
 
 # every symbol include/klampt_b200.h declares: name -> (restype, argtypes)

@@ -12,9 +12,11 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -151,9 +153,153 @@ inline float f_up(double x) { float f = (float)x; if ((double)f < x) f = nextaft
 inline float i2f(int32_t i) { float f; memcpy(&f, &i, 4); return f; }
 
 // device-side geometry: a flattened BVH + elements in leaf order
-struct DevGeom { int node_base = 0, nnodes = 0, elem_base = 0, nelem = 0, kind = KB_ELEM_TRI, depth = 0; double margin = 0, rmax = 0; bool empty = true; double lo[3], hi[3]; };
+struct DevGeom {
+  int node_base = 0, nnodes = 0, elem_base = 0, nelem = 0, kind = KB_ELEM_TRI, depth = 0; double margin = 0, rmax = 0; bool empty = true; double lo[3], hi[3];
+  int ncover = 0; double cover[KB_COVER_MAX][4];   // covering spheres (local frame) for the clearance-grid broad phase
+};
 
-struct ItemSet { std::vector<KbItem> items; KbItem* d_items = nullptr; int nxf = 0; int maxdepth = 0; };
+struct ItemSet {
+  std::vector<KbItem> items; KbItem* d_items = nullptr; int nxf = 0; int maxdepth = 0;
+  std::vector<KbProbe> probes; std::vector<uint32_t> always_on; KbProbe* d_probes = nullptr; uint32_t* d_always_on = nullptr;
+};
+
+// ------------------------------------------------------------------------------------------------- clearance grid
+// Conservative distance field of one static environment group on a uniform grid.  Voxels touched by an element are
+// "occupied"; an exact Euclidean distance transform in index space gives D(v) = distance (in voxels) from v to the nearest
+// occupied voxel.  For a point p in voxel a and a surface point s in occupied voxel b, |p - s| >= h * |max(|a - b| - 1, 0)|
+// >= h * (|a - b| - sqrt 3) >= h * (D(a) - sqrt 3): the stored value floor(4 * (D - sqrt 3 - 0.02)) is a lower bound on
+// the clearance of every point of the voxel, in quarter voxels.
+struct HostGrid { double o[3]; double h = 0; int dims[3] = {0, 0, 0}; std::vector<uint8_t> q; };
+
+void parallel_for(int n, const std::function<void(int, int)>& fn) {
+  int nt = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+  if (nt > n) nt = n < 1 ? 1 : n;
+  if (nt <= 1) { fn(0, n); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; t++) { int a = (int)((int64_t)n * t / nt), b = (int)((int64_t)n * (t + 1) / nt); th.emplace_back([=, &fn] { fn(a, b); }); }
+  for (auto& x : th) x.join();
+}
+
+// 1-D squared distance transform of f (lower envelope of parabolas); v / z are scratch of size n and n + 1
+void edt_1d(const int32_t* f, int n, int32_t* d, int* v, double* z) {
+  const int32_t INF = 1000000000;
+  int k = 0; v[0] = 0; z[0] = -1e30; z[1] = 1e30;
+  for (int q = 1; q < n; q++) {
+    double s;
+    for (;;) {                                   // z[0] = -1e30 is never reached: all values are finite
+      const int r = v[k];
+      s = (((double)f[q] + (double)q * q) - ((double)f[r] + (double)r * r)) / (2.0 * q - 2.0 * r);
+      if (s <= z[k]) k--; else break;
+    }
+    k++; v[k] = q; z[k] = s; z[k + 1] = 1e30;
+  }
+  k = 0;
+  for (int q = 0; q < n; q++) {
+    while (z[k + 1] < q) k++;
+    const int r = v[k];
+    const double val = (double)(q - r) * (q - r) + (double)f[r];
+    d[q] = val >= INF ? INF : (int32_t)val;
+  }
+}
+
+void build_clear_grid(int kind, const std::vector<double>& elems, const double glo[3], const double ghi[3], double pad, int res, HostGrid& G) {
+  double ext = 0;
+  for (int k = 0; k < 3; k++) ext = std::max(ext, ghi[k] - glo[k] + 2 * pad);
+  if (!(ext > 0)) ext = 1;
+  G.h = ext / res;
+  for (int k = 0; k < 3; k++) {
+    G.o[k] = glo[k] - pad;
+    G.dims[k] = std::max(1, std::min(res, (int)std::ceil((ghi[k] - glo[k] + 2 * pad) / G.h)));
+  }
+  const int nx = G.dims[0], ny = G.dims[1], nz = G.dims[2];
+  const size_t nvox = (size_t)nx * ny * nz;
+  const int32_t INF = 1000000000;
+  std::vector<int32_t> D(nvox, INF);
+  const double ih = 1.0 / G.h;
+  auto mark_box = [&](const double* lo, const double* hi) {
+    int a[3], b[3];
+    for (int k = 0; k < 3; k++) {
+      a[k] = (int)std::floor((lo[k] - G.o[k]) * ih - 1e-6); b[k] = (int)std::floor((hi[k] - G.o[k]) * ih + 1e-6);
+      a[k] = std::max(0, std::min(G.dims[k] - 1, a[k])); b[k] = std::max(0, std::min(G.dims[k] - 1, b[k]));
+    }
+    for (int z = a[2]; z <= b[2]; z++) for (int y = a[1]; y <= b[1]; y++) for (int x = a[0]; x <= b[0]; x++) D[((size_t)z * ny + y) * nx + x] = 0;
+  };
+  if (kind == G_MESH) {
+    // triangles larger than a few voxels are split (longest edge) until their boxes are small, so a big tilted triangle
+    // does not occupy its whole bounding box
+    struct Tri { double p[9]; int depth; };
+    std::vector<Tri> st;
+    const size_t nt = elems.size() / 9;
+    for (size_t t = 0; t < nt; t++) {
+      Tri r; memcpy(r.p, &elems[9 * t], 72); r.depth = 0; st.push_back(r);
+      while (!st.empty()) {
+        Tri c = st.back(); st.pop_back();
+        double lo[3], hi[3]; double cells = 1;
+        for (int k = 0; k < 3; k++) {
+          lo[k] = std::min(c.p[k], std::min(c.p[3 + k], c.p[6 + k])); hi[k] = std::max(c.p[k], std::max(c.p[3 + k], c.p[6 + k]));
+          cells *= std::floor((hi[k] - lo[k]) * ih) + 2;
+        }
+        if (cells <= 27 || c.depth >= 24) { mark_box(lo, hi); continue; }
+        int le = 0; double best = -1;
+        for (int e2 = 0; e2 < 3; e2++) {
+          const double* a = c.p + 3 * e2; const double* b = c.p + 3 * ((e2 + 1) % 3);
+          double l2 = (a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]) + (a[2] - b[2]) * (a[2] - b[2]);
+          if (l2 > best) { best = l2; le = e2; }
+        }
+        const int i0 = le, i1 = (le + 1) % 3, i2 = (le + 2) % 3;
+        double m[3]; for (int k = 0; k < 3; k++) m[k] = 0.5 * (c.p[3 * i0 + k] + c.p[3 * i1 + k]);
+        Tri x, y2; x.depth = y2.depth = c.depth + 1;
+        memcpy(x.p, c.p + 3 * i0, 24); memcpy(x.p + 3, m, 24); memcpy(x.p + 6, c.p + 3 * i2, 24);
+        memcpy(y2.p, m, 24); memcpy(y2.p + 3, c.p + 3 * i1, 24); memcpy(y2.p + 6, c.p + 3 * i2, 24);
+        st.push_back(x); st.push_back(y2);
+      }
+    }
+  } else {
+    const size_t np = elems.size() / 4;
+    for (size_t i = 0; i < np; i++) {
+      const double* s = &elems[4 * i];
+      double lo[3] = {s[0] - s[3], s[1] - s[3], s[2] - s[3]}, hi[3] = {s[0] + s[3], s[1] + s[3], s[2] + s[3]};
+      mark_box(lo, hi);
+    }
+  }
+  // pass x: two scans per row
+  parallel_for(ny * nz, [&](int r0, int r1) {
+    for (int r = r0; r < r1; r++) {
+      int32_t* row = &D[(size_t)r * nx];
+      int last = -1000000;
+      for (int x = 0; x < nx; x++) { if (row[x] == 0) last = x; else { const int64_t d = x - last; row[x] = d * d >= INF ? INF : (int32_t)(d * d); } }
+      last = 1000000 + nx;
+      for (int x = nx - 1; x >= 0; x--) { if (row[x] == 0) last = x; else { const int64_t d = last - x; if (d * d < row[x]) row[x] = (int32_t)(d * d); } }
+    }
+  });
+  // pass y (stride nx) and pass z (stride nx*ny): lower envelopes
+  parallel_for(nz, [&](int z0, int z1) {
+    std::vector<int32_t> f(ny), d(ny); std::vector<int> v(ny); std::vector<double> zz(ny + 1);
+    for (int z = z0; z < z1; z++) for (int x = 0; x < nx; x++) {
+      int32_t* col = &D[(size_t)z * ny * nx + x];
+      for (int y = 0; y < ny; y++) f[y] = col[(size_t)y * nx];
+      edt_1d(f.data(), ny, d.data(), v.data(), zz.data());
+      for (int y = 0; y < ny; y++) col[(size_t)y * nx] = d[y];
+    }
+  });
+  parallel_for(ny, [&](int y0, int y1) {
+    std::vector<int32_t> f(nz), d(nz); std::vector<int> v(nz); std::vector<double> zz(nz + 1);
+    const size_t sz = (size_t)nx * ny;
+    for (int y = y0; y < y1; y++) for (int x = 0; x < nx; x++) {
+      int32_t* col = &D[(size_t)y * nx + x];
+      for (int z = 0; z < nz; z++) f[z] = col[(size_t)z * sz];
+      edt_1d(f.data(), nz, d.data(), v.data(), zz.data());
+      for (int z = 0; z < nz; z++) col[(size_t)z * sz] = d[z];
+    }
+  });
+  G.q.resize(nvox);
+  parallel_for(nz, [&](int z0, int z1) {
+    for (size_t i = (size_t)z0 * nx * ny; i < (size_t)z1 * nx * ny; i++) {
+      const double c = std::sqrt((double)D[i]) - 1.7320508075688772 - 0.02;
+      G.q[i] = (uint8_t)(c <= 0 ? 0 : std::min(255.0, std::floor(4.0 * c)));
+    }
+  });
+}
 
 }  // namespace
 
@@ -183,6 +329,9 @@ struct kb_engine {
   int32_t* d_triown = nullptr; int32_t* d_sphown = nullptr;
   KbRobotDev* d_robot = nullptr; KbDriverDev* d_drv = nullptr; int32_t* d_drv_link = nullptr; double* d_drv_scale = nullptr; double* d_drv_off = nullptr;
   ItemSet feas_items, env_items;            // env + self ; env only (distance without self)
+  std::vector<HostGrid> hgrids; uint8_t* d_grid[KB_MAX_GRIDS] = {nullptr, nullptr, nullptr, nullptr};
+  int both_limit = 0;                        // experiment: frontier size up to which comparable inner pairs descend both trees at once
+  int grid_res = 256; bool use_grids = false; // clearance-grid broad phase of the boolean query (options grid_res, clear_grid)
   int64_t static_bytes = 0;
   // ---- per-batch scratch (grown on demand)
   int64_t chunk = 65536;
@@ -243,7 +392,7 @@ void init_default_mask(kb_engine* e) {
 inline bool mask_en(const kb_engine* e, int a, int b) { return e->mask[(size_t)a * e->nids + b] != 0; }
 
 // appends one geometry (elements given in some frame) to the host arrays: builds its BVH, writes nodes + elements
-int append_geom(kb_engine* e, int kind, const std::vector<double>& elems, const std::vector<int32_t>& owners, double margin, DevGeom& dg) {
+int append_geom(kb_engine* e, int kind, const std::vector<double>& elems, const std::vector<int32_t>& owners, double margin, DevGeom& dg, bool want_cover) {
   const int stride = kind == G_MESH ? 9 : 4;
   const int n = (int)(elems.size() / stride);
   dg = DevGeom(); dg.margin = margin; dg.kind = kind == G_MESH ? KB_ELEM_TRI : KB_ELEM_SPHERE; dg.nelem = n; dg.empty = n == 0;
@@ -272,6 +421,37 @@ int append_geom(kb_engine* e, int kind, const std::vector<double>& elems, const 
     if (nd.left >= 0) { v[3] = i2f(nd.left); v[7] = i2f(0); }
     else { v[3] = i2f(~nd.first); v[7] = i2f(nd.count); }
     e->h_nodes.insert(e->h_nodes.end(), v, v + 8);
+  }
+  if (want_cover) {
+    // up to KB_COVER_MAX spheres that together contain the geometry: a cut of the BVH grown by always splitting the
+    // node with the largest sphere; sphere = box centre + the farthest element point
+    struct CS { int node; double c[3], r; };
+    auto sphere_of = [&](int node) {
+      const BNode& nd = bvh.nodes[node];
+      CS s; s.node = node; s.r = 0;
+      for (int k = 0; k < 3; k++) s.c[k] = 0.5 * (nd.lo[k] + nd.hi[k]);
+      for (int i = nd.first; i < nd.first + nd.count; i++) {
+        const double* p = &elems[(size_t)stride * bvh.perm[i]];
+        if (kind == G_MESH) {
+          for (int v = 0; v < 3; v++) { double d2 = 0; for (int k = 0; k < 3; k++) d2 += (p[3 * v + k] - s.c[k]) * (p[3 * v + k] - s.c[k]); s.r = std::max(s.r, std::sqrt(d2)); }
+        } else { double d2 = 0; for (int k = 0; k < 3; k++) d2 += (p[k] - s.c[k]) * (p[k] - s.c[k]); s.r = std::max(s.r, std::sqrt(d2) + p[3]); }
+      }
+      return s;
+    };
+    std::vector<CS> cut; cut.push_back(sphere_of(0));
+    while ((int)cut.size() < KB_COVER_MAX) {
+      int best = -1;
+      for (int i = 0; i < (int)cut.size(); i++) if (bvh.nodes[cut[i].node].left >= 0 && (best < 0 || cut[i].r > cut[best].r)) best = i;
+      if (best < 0) break;
+      // stop once the largest sphere is itself a leaf-sized one
+      bool any_larger_leaf = false;
+      for (const CS& c : cut) if (bvh.nodes[c.node].left < 0 && c.r >= cut[best].r) any_larger_leaf = true;
+      if (any_larger_leaf) break;
+      const int l = bvh.nodes[cut[best].node].left;
+      cut[best] = sphere_of(l); cut.push_back(sphere_of(l + 1));
+    }
+    dg.ncover = (int)cut.size();
+    for (int i = 0; i < dg.ncover; i++) { memcpy(dg.cover[i], cut[i].c, 24); dg.cover[i][3] = cut[i].r * (1 + 1e-12) + 1e-300; }
   }
   for (int i = 0; i < n; i++) {
     int src = bvh.perm[i];
@@ -404,6 +584,8 @@ KbTraverseParams make_params(kb_engine* e, const ItemSet& set, const double* xf,
   p.scene = e->scene; p.items = set.d_items; p.nitems = (int)set.items.size(); p.nxf = set.nxf; p.xf64 = xf; p.N = n; p.state = state;
   p.hit = e->d_hit; p.hit_elem = e->d_hit_elem; p.work_counter = e->d_work; p.counters = e->d_counters;
   p.wide_limit = KB_STACK_CAP - 32 - set.maxdepth - 2; p.collect_stats = e->collect_stats ? 1 : 0;
+  p.both_limit = e->both_limit;
+  if (e->use_grids && set.d_probes && !set.probes.empty()) { p.probes = set.d_probes; p.nprobes = (int)set.probes.size(); p.always_on = set.d_always_on; }
   return p;
 }
 
@@ -438,6 +620,12 @@ int run_feasible_device(kb_engine* e, const double* dQ, int64_t N, uint8_t* d_ou
 
 int upload_itemset(ItemSet& s, int64_t* total) {
   if (s.d_items) { cudaFree(s.d_items); s.d_items = nullptr; }
+  if (s.d_probes) { cudaFree(s.d_probes); s.d_probes = nullptr; }
+  if (s.d_always_on) { cudaFree(s.d_always_on); s.d_always_on = nullptr; }
+  if (!s.probes.empty()) {
+    int rc = upload(s.d_probes, s.probes.data(), s.probes.size() * sizeof(KbProbe), total); if (rc) return rc;
+    if ((rc = upload(s.d_always_on, s.always_on.data(), s.always_on.size() * 4, total))) return rc;
+  }
   return upload(s.d_items, s.items.data(), s.items.size() * sizeof(KbItem), total);
 }
 
@@ -462,7 +650,8 @@ void kb_engine_destroy(kb_engine* e) {
     void* ptrs[] = {e->d_nodes, e->d_tris32, e->d_tris64, e->d_sph32, e->d_sph64, e->d_triown, e->d_sphown, e->d_robot, e->d_drv, e->d_drv_link,
                     e->d_drv_scale, e->d_drv_off, e->feas_items.d_items, e->env_items.d_items, e->d_xf, e->d_state, e->d_hit, e->d_hit_elem, e->d_leaf_list, e->d_flagged, e->d_state2, e->d_work,
                     e->d_counters, e->d_Q, e->d_out, e->d_pair, e->d_dist, e->d_A, e->d_B, e->d_nlev, e->d_alive, e->d_nchecks, e->d_firstbad, e->d_list,
-                    e->d_eQ, e->d_efeas, e->d_scalars, e->d_weights, e->d_T};
+                    e->d_eQ, e->d_efeas, e->d_scalars, e->d_weights, e->d_T, e->feas_items.d_probes, e->feas_items.d_always_on,
+                    e->d_grid[0], e->d_grid[1], e->d_grid[2], e->d_grid[3]};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -601,7 +790,7 @@ int kb_finalize(kb_engine* e, int device) {
   std::vector<int32_t> none;
   for (size_t g = 0; g < e->geoms.size(); g++) {
     const Geom& G = e->geoms[g];
-    int rc = append_geom(e, G.kind == G_MESH ? G_MESH : G_CLOUD, G.kind == G_MESH ? G.tri : G.sph, none, G.margin, e->dgeoms[g]);
+    int rc = append_geom(e, G.kind == G_MESH ? G_MESH : G_CLOUD, G.kind == G_MESH ? G.tri : G.sph, none, G.margin, e->dgeoms[g], true);
     if (rc) return rc;
     if (G.kind == G_EMPTY) e->dgeoms[g].empty = true;
   }
@@ -645,18 +834,34 @@ int kb_finalize(kb_engine* e, int device) {
     }
   }
   e->groups.resize(grp.size());
+  e->hgrids.assign(std::min<size_t>(grp.size(), KB_MAX_GRIDS), HostGrid());
   for (size_t g = 0; g < grp.size(); g++) {
-    int rc = append_geom(e, grp[g].kind, grp[g].elems, grp[g].owners, grp[g].margin, e->groups[g]);
+    int rc = append_geom(e, grp[g].kind, grp[g].elems, grp[g].owners, grp[g].margin, e->groups[g], false);
     if (rc) return rc;
+    if (g < KB_MAX_GRIDS && e->grid_res >= 8 && !e->groups[g].empty) {
+      // pad so that every covering sphere of the links that meet this group can be cleared outside the group's bounds
+      double need = 0;
+      for (int j = 0; j < L; j++) if (grp[g].sig[j] == '1') {
+        const DevGeom& lg = e->dgeoms[e->linkgeom[j]];
+        for (int c = 0; c < lg.ncover; c++) need = std::max(need, lg.cover[c][3] + lg.margin + grp[g].margin);
+      }
+      double ext = 0; for (int k = 0; k < 3; k++) ext = std::max(ext, e->groups[g].hi[k] - e->groups[g].lo[k]);
+      const double pad = 1.25 * need + 6.0 * (ext + 2.5 * need) / e->grid_res;
+      build_clear_grid(grp[g].kind, grp[g].elems, e->groups[g].lo, e->groups[g].hi, pad, e->grid_res, e->hgrids[g]);
+    }
     std::vector<double>().swap(grp[g].elems);
   }
   // ---- 3. work items per configuration: links vs groups (environment first, as CheckCollisionFree does), then self pairs
   e->feas_items = ItemSet(); e->env_items = ItemSet();
   e->feas_items.nxf = e->env_items.nxf = L;
+  struct ItemSrc { int item, link, group; };
+  std::vector<ItemSrc> item_src;
   for (size_t g = 0; g < grp.size(); g++)
     for (int j = 0; j < L; j++) if (grp[g].sig[j] == '1') {
       const DevGeom& lg = e->dgeoms[e->linkgeom[j]];
+      const size_t before = e->feas_items.items.size();
       int rc = add_item(e->feas_items, lg, j, link_id(e, j), e->groups[g], -1, -1, false); if (rc) return rc;
+      if (e->feas_items.items.size() > before) item_src.push_back({(int)before, j, (int)g});
       rc = add_item(e->env_items, lg, j, link_id(e, j), e->groups[g], -1, -1, false); if (rc) return rc;
     }
   for (int i = 0; i < L; i++) for (int j = i + 1; j < L; j++) {
@@ -679,6 +884,31 @@ int kb_finalize(kb_engine* e, int device) {
   double S = std::max(extent, reach + lmax) + lmax;
   if (!(S > 0)) S = 1;
   e->scene.eps_abs = (float)(8.0 * 5.9604645e-8 * S);
+  // ---- 4b. clearance probes of the (link, static group) items
+  {
+    ItemSet& fs = e->feas_items;
+    fs.probes.clear(); fs.always_on.assign((fs.items.size() + 31) / 32 + 1, 0u);
+    std::vector<char> probed(fs.items.size(), 0);
+    for (const ItemSrc& is : item_src) {
+      if (is.group >= (int)e->hgrids.size() || !(e->hgrids[is.group].h > 0)) continue;
+      const HostGrid& G = e->hgrids[is.group];
+      const DevGeom& lg = e->dgeoms[e->linkgeom[is.link]];
+      if (lg.ncover <= 0) continue;
+      probed[is.item] = 1;
+      for (int c = 0; c < lg.ncover; c++) {
+        KbProbe pr; memset(&pr, 0, sizeof pr);
+        for (int k = 0; k < 3; k++) pr.c[k] = (float)lg.cover[c][k];
+        // radius + threshold + fp32 slack (sphere centre rounded to fp32 and moved by fp32 transforms), in quarter voxels, rounded up
+        double lmaxc = std::fabs(lg.cover[c][0]) + std::fabs(lg.cover[c][1]) + std::fabs(lg.cover[c][2]);
+        const double reach_m = lg.cover[c][3] + fs.items[is.item].thr + 16.0 * (double)e->scene.eps_abs + 4e-7 * lmaxc;
+        const double qv = std::ceil(4.0 * reach_m / G.h) + 1.0;
+        pr.need = qv > 255.0 ? 256u : (uint32_t)qv;          // 256: can never be cleared by a u8 value
+        pr.item = is.item; pr.xf = is.link; pr.grid = is.group;
+        fs.probes.push_back(pr);
+      }
+    }
+    for (size_t i = 0; i < fs.items.size(); i++) if (!probed[i]) fs.always_on[i >> 5] |= 1u << (i & 31);
+  }
   // ---- 5. upload
   e->static_bytes = 0;
   int rc;
@@ -721,6 +951,15 @@ int kb_finalize(kb_engine* e, int device) {
   e->scene.triown = e->d_triown; e->scene.sphown = e->d_sphown;
   if ((rc = upload_itemset(e->feas_items, &e->static_bytes))) return rc;
   if ((rc = upload_itemset(e->env_items, &e->static_bytes))) return rc;
+  for (size_t g = 0; g < e->hgrids.size(); g++) {
+    const HostGrid& G = e->hgrids[g];
+    if (!(G.h > 0)) continue;
+    if ((rc = upload(e->d_grid[g], G.q.data(), G.q.size(), &e->static_bytes))) return rc;
+    KbClearGrid& D = e->scene.grids[g];
+    D.data = e->d_grid[g]; D.inv_h = (float)(1.0 / G.h);
+    for (int k = 0; k < 3; k++) { D.o[k] = (float)G.o[k]; D.dims[k] = G.dims[k]; }
+    std::vector<uint8_t>().swap(e->hgrids[g].q);
+  }
   KbRobotDev* R = new KbRobotDev(); memset(R, 0, sizeof(KbRobotDev));
   R->L = L; R->nj = (int)e->jtype.size(); R->ndrv = (int)e->drivers.size();
   for (int i = 0; i < L; i++) { R->parents[i] = e->parents[i]; R->linktype[i] = e->linktype[i]; R->qmin[i] = e->qmin[i]; R->qmax[i] = e->qmax[i]; }
@@ -737,7 +976,7 @@ int kb_finalize(kb_engine* e, int device) {
   if ((rc = upload(e->d_drv_link, dl.data(), dl.size() * 4, &e->static_bytes))) return rc;
   if ((rc = upload(e->d_drv_scale, ds.data(), ds.size() * 8, &e->static_bytes))) return rc;
   if ((rc = upload(e->d_drv_off, dofs.data(), dofs.size() * 8, &e->static_bytes))) return rc;
-  CK(cudaMalloc((void**)&e->d_work, 64)); CK(cudaMalloc((void**)&e->d_counters, 64)); CK(cudaMemset(e->d_counters, 0, 64));
+  CK(cudaMalloc((void**)&e->d_work, 64)); CK(cudaMalloc((void**)&e->d_counters, 128)); CK(cudaMemset(e->d_counters, 0, 128));
   CK(cudaMalloc((void**)&e->d_scalars, 64));
   // the host copies of the big arrays are no longer needed
   std::vector<float>().swap(e->h_tris32); std::vector<double>().swap(e->h_tris64); std::vector<float>().swap(e->h_sph32); std::vector<double>().swap(e->h_sph64);
@@ -763,6 +1002,13 @@ int kb_set_option(kb_engine* e, const char* name, int64_t value) {
   if (!strcmp(name, "time_kernels")) { e->time_kernels = value != 0; return KB_OK; }
   if (!strcmp(name, "pipeline")) { if (value != 0 && value != 1) return fail(KB_ERR_INVALID, "pipeline must be 0 (fused) or 1 (split)"); e->pipeline = (int)value; return KB_OK; }
   if (!strcmp(name, "leaf_budget")) { if (value < 1 || value > 100000) return fail(KB_ERR_INVALID, "leaf_budget out of range"); e->leaf_budget = (int)value; return KB_OK; }
+  if (!strcmp(name, "clear_grid")) { e->use_grids = value != 0; return KB_OK; }
+  if (!strcmp(name, "both_limit")) { e->both_limit = (int)value; return KB_OK; }
+  if (!strcmp(name, "grid_res")) {
+    if (e->finalized) return fail(KB_ERR_STATE, "grid_res must be set before kb_finalize");
+    if (value != 0 && (value < 8 || value > 512)) return fail(KB_ERR_INVALID, "grid_res must be 0 (no clearance grids) or in [8, 512]");
+    e->grid_res = (int)value; return KB_OK;
+  }
   if (!strcmp(name, "chunk")) {
     if (value < 256 || value > (1 << 22)) return fail(KB_ERR_INVALID, "chunk must be in [256, 4194304]");
     e->chunk = value; return KB_OK;
@@ -1023,9 +1269,9 @@ int kb_get_stats(kb_engine* e, kb_stats* out) {
   if (!e || !out) return fail(KB_ERR_INVALID, "null argument");
   if (e->finalized) {
     CK(cudaSetDevice(e->device)); CK(cudaStreamSynchronize(e->stream));
-    unsigned long long c[8]; CK(cudaMemcpy(c, e->d_counters, 64, cudaMemcpyDeviceToHost));
+    unsigned long long c[16]; CK(cudaMemcpy(c, e->d_counters, 128, cudaMemcpyDeviceToHost));
     e->stats.recheck_pairs = (int64_t)c[0]; e->stats.node_tests = (int64_t)c[1]; e->stats.elem_tests = (int64_t)c[2];
-    e->stats.configs_feasible = (int64_t)c[3]; e->stats.edges_visible = (int64_t)c[4];
+    e->stats.configs_feasible = (int64_t)c[3]; e->stats.edges_visible = (int64_t)c[4]; e->stats.items_dropped = (int64_t)c[7]; e->stats.node_iterations = (int64_t)c[8];
     fold_kernel_times(e);
   }
   *out = e->stats; return KB_OK;
@@ -1035,7 +1281,7 @@ int kb_reset_stats(kb_engine* e) {
   if (!e) return fail(KB_ERR_INVALID, "null argument");
   memset(&e->stats, 0, sizeof e->stats);
   e->tev_used = 0;
-  if (e->finalized) { CK(cudaSetDevice(e->device)); CK(cudaMemsetAsync(e->d_counters, 0, 64, e->stream)); }
+  if (e->finalized) { CK(cudaSetDevice(e->device)); CK(cudaMemsetAsync(e->d_counters, 0, 128, e->stream)); }
   return KB_OK;
 }
 

@@ -416,10 +416,19 @@ __device__ __forceinline__ void load_itc(const float* __restrict__ itc, int item
 
 // one popped frontier entry: fetch its item record + relative transform + both nodes, 6-axis SAT, and on overlap either
 // mark a leaf pair or produce the two child entries (descend the larger box)
+// KB_BOTH_MODE: 0 = a surviving inner pair always splits its larger box; 1 = pairs of comparable boxes split both boxes at
+// once (four child pairs: one level of each tree per iteration); 2 = like 1 but only while the frontier is at most option
+// both_limit entries (experiment knob).  KB_BOTH_RATIO bounds the ratio of the squared box diagonals that counts as comparable.
+#ifndef KB_BOTH_MODE
+#define KB_BOTH_MODE 1
+#endif
+#ifndef KB_BOTH_RATIO
+#define KB_BOTH_RATIO 4.f
+#endif
 template <bool ITC>
 __device__ __forceinline__ void node_test(const KbTraverseParams& p, const ItemS* __restrict__ s_items, const float* __restrict__ itc,
-                                          const float* __restrict__ xfw, float slack, const uint2 e,
-                                          bool& push2, bool& leafpair, uint2& c0e, uint2& c1e) {
+                                          const float* __restrict__ xfw, float slack, const uint2 e, const bool allow_both,
+                                          bool& push2, bool& push4, bool& leafpair, uint2& c0e, uint2& c1e) {
   const KbScene& sc = p.scene;
   const int item = (int)(e.x >> KB_NODEA_BITS);
   int nodeA, nodeB; float infl; XfF T;
@@ -442,7 +451,12 @@ __device__ __forceinline__ void node_test(const KbTraverseParams& p, const ItemS
     else {
       push2 = true;
       const float sa2 = a1.x * a1.x + a1.y * a1.y + a1.z * a1.z, sb2 = b1.x * b1.x + b1.y * b1.y + b1.z * b1.z;
-      if (lb < 0 || (la >= 0 && sa2 >= sb2)) {
+      if (KB_BOTH_MODE && allow_both && la >= 0 && lb >= 0 && sa2 < KB_BOTH_RATIO * sb2 && sb2 < KB_BOTH_RATIO * sa2) {
+        // comparable boxes and a narrow frontier: descend both trees at once (c0e = (a0, b0); the other three are derived at the push)
+        push4 = true;
+        c0e = make_uint2((e.x & ~(unsigned)(KB_MAX_NODES_A - 1)) | (unsigned)la, (unsigned)lb);
+        c1e = make_uint2(c0e.x + 1u, (unsigned)lb);
+      } else if (lb < 0 || (la >= 0 && sa2 >= sb2)) {
         c0e = make_uint2((e.x & ~(unsigned)(KB_MAX_NODES_A - 1)) | (unsigned)la, e.y);
         c1e = make_uint2(c0e.x + 1u, e.y);
       } else {
@@ -461,14 +475,18 @@ kb_traverse_kernel(const KbTraverseParams p) {
   const int xf_floats = (p.nxf * 12 + 3) & ~3;
   const int nit_c = ITC ? p.nitems : 0;
   ItemS* s_items = (ItemS*)smem_raw;
-  const size_t per_warp = (size_t)KB_STACK_CAP * 8 + (size_t)KB_LEAFQ_CAP * 8 + (size_t)KB_RQ_CAP * 16 + 16 + (size_t)xf_floats * 4 + (size_t)nit_c * 48;
-  unsigned char* base = smem_raw + (size_t)nit_c * 16 + warp * per_warp;
+  const int mask_words = p.nprobes > 0 ? (((p.nitems + 31) >> 5) + 3) & ~3 : 0;
+  const int nprobes_s = p.nprobes <= KB_PROBES_SMEM_MAX ? p.nprobes : 0;      // probes cached per CTA
+  const size_t per_warp = (size_t)KB_STACK_CAP * 8 + (size_t)KB_LEAFQ_CAP * 8 + (size_t)KB_RQ_CAP * 16 + 16 + (size_t)xf_floats * 4 + (size_t)nit_c * 48 + (size_t)mask_words * 4;
+  KbProbe* s_probes = (KbProbe*)(smem_raw + (size_t)nit_c * 16);
+  unsigned char* base = smem_raw + (size_t)nit_c * 16 + (size_t)nprobes_s * 32 + warp * per_warp;
   uint2* stack = (uint2*)base;
   uint2* leafq = (uint2*)(base + (size_t)KB_STACK_CAP * 8);
   uint4* rq = (uint4*)(base + (size_t)KB_STACK_CAP * 8 + (size_t)KB_LEAFQ_CAP * 8);
   int* rq_count = (int*)(rq + KB_RQ_CAP);
   float* xfw = (float*)(base + (size_t)KB_STACK_CAP * 8 + (size_t)KB_LEAFQ_CAP * 8 + (size_t)KB_RQ_CAP * 16 + 16);
   float* itc = xfw + xf_floats;
+  unsigned* amask = (unsigned*)(itc + (size_t)nit_c * 12);   // per configuration: bit i = item i must be traversed
   const KbScene& sc = p.scene;
   const float slack = 4.f * sc.eps_abs;
   if (ITC) {
@@ -479,11 +497,14 @@ kb_traverse_kernel(const KbTraverseParams p) {
       s_items[i] = s;
     }
   }
+  for (int i = threadIdx.x; i < nprobes_s * 2; i += blockDim.x) ((uint4*)s_probes)[i] = __ldg((const uint4*)p.probes + i);
   if (lane == 0) *rq_count = 0;
   __syncthreads();
   unsigned lt_mask;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
-  unsigned st_node = 0, st_leaf = 0, st_re = 0;   // only maintained when STATS
+  unsigned st_node = 0, st_leaf = 0, st_re = 0, st_drop = 0, st_iter = 0;   // only maintained when STATS
+  const bool use_probes = p.nprobes > 0;
+  const KbProbe* probes = nprobes_s ? s_probes : p.probes;
 
   // guided self-scheduling: 8 configurations per grab while work is plentiful, down to 1 near the end of the launch, so
   // the tail is one configuration long (configuration cost varies by two orders of magnitude)
@@ -515,13 +536,55 @@ kb_traverse_kernel(const KbTraverseParams p) {
         }
         __syncwarp();
       }
+      if (use_probes) {
+        // clearance-grid broad phase: an item whose covering spheres all have more clearance from the static group than
+        // radius + threshold cannot collide and is never fed to the traversal
+        for (int w = lane; w < ((p.nitems + 31) >> 5); w += 32) amask[w] = __ldg(p.always_on + w);
+        __syncwarp();
+        // four probes per lane per round: all grid bytes of a round are in flight together (one L2 round trip per 128 probes)
+        for (int s0 = 0; s0 < p.nprobes; s0 += 128) {
+          unsigned q[4], need[4]; int item[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int s = s0 + 32 * u + lane;
+            q[u] = 0xffffffffu; need[u] = 0u; item[u] = 0;
+            if (s < p.nprobes) {
+              const float4 pc = *(const float4*)(probes + s);
+              const int4 pi = *((const int4*)(probes + s) + 1);
+              const float* T = xfw + 12 * pi.y;
+              const float wx = T[0] * pc.x + T[1] * pc.y + T[2] * pc.z + T[9];
+              const float wy = T[3] * pc.x + T[4] * pc.y + T[5] * pc.z + T[10];
+              const float wz = T[6] * pc.x + T[7] * pc.y + T[8] * pc.z + T[11];
+              const KbClearGrid& g = sc.grids[pi.z];
+              // points outside the grid are clamped onto it: the projection onto a convex box never increases the distance
+              // to anything inside the box, and everything the grid measures lies inside
+              int ix = __float2int_rd((wx - g.o[0]) * g.inv_h), iy = __float2int_rd((wy - g.o[1]) * g.inv_h), iz = __float2int_rd((wz - g.o[2]) * g.inv_h);
+              ix = min(max(ix, 0), g.dims[0] - 1); iy = min(max(iy, 0), g.dims[1] - 1); iz = min(max(iz, 0), g.dims[2] - 1);
+              q[u] = __ldg(g.data + ((size_t)iz * g.dims[1] + iy) * g.dims[0] + ix);
+              need[u] = __float_as_uint(pc.w); item[u] = pi.x;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) if (q[u] < need[u]) atomicOr(amask + (item[u] >> 5), 1u << (item[u] & 31));
+        }
+        __syncwarp();
+      }
       int sp = 0, nleaf = 0, cursor = 0;
       int found = -1, found_ea = -1, found_eb = -1;
       for (;;) {
         if (sp < 32 && cursor < p.nitems) {          // feed root pairs of the next work items
           int k = p.nitems - cursor; if (k > 32) k = 32;
-          if (lane < k) stack[sp + lane] = make_uint2(((unsigned)(cursor + lane) << KB_NODEA_BITS), 0u);
-          sp += k; cursor += k;
+          if (use_probes) {
+            const bool on = lane < k && ((amask[(cursor + lane) >> 5] >> ((cursor + lane) & 31)) & 1u);
+            const unsigned om = __ballot_sync(FULL, on);
+            if (on) stack[sp + __popc(om & lt_mask)] = make_uint2(((unsigned)(cursor + lane) << KB_NODEA_BITS), 0u);
+            sp += __popc(om);
+            if (STATS) st_drop += (lane == 0) ? (unsigned)(k - __popc(om)) : 0u;
+          } else {
+            if (lane < k) stack[sp + lane] = make_uint2(((unsigned)(cursor + lane) << KB_NODEA_BITS), 0u);
+            sp += k;
+          }
+          cursor += k;
           __syncwarp();
         }
         if (sp == 0 && nleaf == 0) break;
@@ -587,16 +650,27 @@ kb_traverse_kernel(const KbTraverseParams p) {
         if (act) e = stack[sp_l - 1 - lane_l];
         sp_l -= m;
         __syncwarp();
-        bool push2 = false, leafpair = false;
+        bool push2 = false, push4 = false, leafpair = false;
         uint2 c0e = e, c1e = e;
         if (act) {
-          node_test<ITC>(p, s_items, itc_l, xfw, slack, e, push2, leafpair, c0e, c1e);
+          node_test<ITC>(p, s_items, itc_l, xfw, slack, e, KB_BOTH_MODE == 1 ? true : sp_l + m <= p.both_limit, push2, push4, leafpair, c0e, c1e);
           if (STATS) st_node++;
         }
+        if (STATS) st_iter += (lane_l == 0);
+#if KB_BOTH_MODE
+        const unsigned pm = __ballot_sync(FULL, push2), lm = __ballot_sync(FULL, leafpair), pm4 = __ballot_sync(FULL, push4);
+        if (push2) {
+          int off = sp_l + 2 * __popc(pm & lt_mask) + 2 * __popc(pm4 & lt_mask); stack[off] = c1e; stack[off + 1] = c0e;
+          if (push4) { stack[off + 2] = make_uint2(c1e.x, c1e.y + 1u); stack[off + 3] = make_uint2(c0e.x, c0e.y + 1u); }
+        }
+        if (leafpair) leafq[nleaf_l + __popc(lm & lt_mask)] = e;
+        sp_l += 2 * __popc(pm) + 2 * __popc(pm4); nleaf_l += __popc(lm);
+#else
         const unsigned pm = __ballot_sync(FULL, push2), lm = __ballot_sync(FULL, leafpair);
         if (push2) { int off = sp_l + 2 * __popc(pm & lt_mask); stack[off] = c1e; stack[off + 1] = c0e; }
         if (leafpair) leafq[nleaf_l + __popc(lm & lt_mask)] = e;
         sp_l += 2 * __popc(pm); nleaf_l += __popc(lm);
+#endif
         __syncwarp();
         } while (sp_l > 0 && nleaf_l < KB_LEAF_TRIGGER && !(sp_l < 32 && more_items));
         sp = sp_l; nleaf = nleaf_l;
@@ -609,8 +683,9 @@ kb_traverse_kernel(const KbTraverseParams p) {
         }
         if (lane == 0 && p.counters) {
           atomicAdd(p.counters + 0, (unsigned long long)st_re); atomicAdd(p.counters + 1, (unsigned long long)st_node); atomicAdd(p.counters + 2, (unsigned long long)st_leaf);
+          atomicAdd(p.counters + 7, (unsigned long long)st_drop); atomicAdd(p.counters + 8, (unsigned long long)st_iter);
         }
-        st_node = st_leaf = st_re = 0;
+        st_node = st_leaf = st_re = st_drop = st_iter = 0;
       }
       if (lane == 0) {
         p.hit[c] = found;
@@ -749,7 +824,8 @@ kb_allpairs_kernel(const KbTraverseParams p, int max_pairs, int32_t* __restrict_
           kb_order_pair(itp->flags, qa, qb);
           for (int k = 0; k < nfound && k < KB_AP_MAX; k++) skip |= (foundp[k].x == qa && foundp[k].y == qb);
         }
-        if (!skip) node_test<ITC>(p, s_items, itc, xfw, slack, e, push2, leafpair, c0e, c1e);
+        bool push4 = false;
+        if (!skip) node_test<ITC>(p, s_items, itc, xfw, slack, e, false, push2, push4, leafpair, c0e, c1e);
       }
       const unsigned pm = __ballot_sync(FULL, push2), lm = __ballot_sync(FULL, leafpair);
       if (push2) { const int off = sp + 2 * __popc(pm & lt_mask); stack[off] = c1e; stack[off + 1] = c0e; }
@@ -1365,10 +1441,12 @@ static cudaError_t launch_distance_t(const KbTraverseParams& p, double* out_dist
   return cudaGetLastError();
 }
 
-size_t kb_traverse_smem_bytes(int nxf, int nitems) {
+size_t kb_traverse_smem_bytes(int nxf, int nitems, int nprobes) {
   size_t xf_floats = ((size_t)nxf * 12 + 3) & ~(size_t)3;
   size_t nit = nitems <= KB_ITC_MAX_ITEMS ? (size_t)nitems : 0;
-  return nit * 16 + (size_t)KB_WARPS_PER_BLOCK * ((size_t)KB_STACK_CAP * 8 + (size_t)KB_LEAFQ_CAP * 8 + (size_t)KB_RQ_CAP * 16 + 16 + xf_floats * 4 + nit * 48);
+  size_t mask_words = nprobes > 0 ? ((((size_t)nitems + 31) >> 5) + 3) & ~(size_t)3 : 0;
+  size_t nps = nprobes <= KB_PROBES_SMEM_MAX ? (size_t)(nprobes > 0 ? nprobes : 0) : 0;
+  return nit * 16 + nps * 32 + (size_t)KB_WARPS_PER_BLOCK * ((size_t)KB_STACK_CAP * 8 + (size_t)KB_LEAFQ_CAP * 8 + (size_t)KB_RQ_CAP * 16 + 16 + xf_floats * 4 + nit * 48 + mask_words * 4);
 }
 
 cudaError_t kb_launch_fk(const KbRobotDev* robot, const KbDriverDev* drv, const int32_t* drv_link, const double* drv_scale,
@@ -1397,7 +1475,7 @@ static cudaError_t launch_traverse_t(const KbTraverseParams& p, int num_sms, siz
 
 cudaError_t kb_launch_traverse(const KbTraverseParams& p, int mode, double* out_dist, double upper_bound, int num_sms, cudaStream_t s) {
   if (p.N <= 0) return cudaSuccess;
-  const size_t smem = mode == 0 ? kb_traverse_smem_bytes(p.nxf, p.nitems) : kb_distance_smem_bytes(p.nxf, p.nitems);
+  const size_t smem = mode == 0 ? kb_traverse_smem_bytes(p.nxf, p.nitems, p.nprobes) : kb_distance_smem_bytes(p.nxf, p.nitems);
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
   cudaError_t e = cudaMemsetAsync(p.work_counter, 0, sizeof(uint32_t), s);
   if (e != cudaSuccess) return e;
@@ -1408,11 +1486,15 @@ cudaError_t kb_launch_traverse(const KbTraverseParams& p, int mode, double* out_
     return itc ? launch_distance_t<true, false>(p, out_dist, upper_bound, num_sms, smem, s) : launch_distance_t<false, false>(p, out_dist, upper_bound, num_sms, smem, s);
   }
   if (p.N > 0xfffffff0ll) return cudaErrorInvalidValue;
-  // two register budgets are compiled: 4 CTAs/SM (128 registers, a few spills) wins when the per-CTA shared memory is
-  // small (few work items per configuration, C2: 8.9 vs 9.2 ms), 3 CTAs/SM (168 registers, no spills) wins when the
-  // item cache is large (C3, 107 pairs: 10.5 vs 11.8 ms).  Measured on B200, profiles/r01_experiments.md.
+  // two register budgets are compiled: KB_BPS_HI = 5 CTAs/SM (20 warps, 102 registers, some spills in the element phase) wins
+  // when the per-CTA shared memory is small (few work items per configuration; C2: 7.33 ms at 5, 7.68 at 4, 8.07 at 6),
+  // 3 CTAs/SM (168 registers, no spills) wins when the item cache is large (C3, 107 pairs: 10.5 vs 11.8 ms at 4).
+  // Measured on B200, profiles/r01_experiments.md.
   const bool four = smem <= 40 * 1024;
-#define KB_LT(I, S) (four ? launch_traverse_t<I, S, 4>(p, num_sms, smem, s) : launch_traverse_t<I, S, 3>(p, num_sms, smem, s))
+#ifndef KB_BPS_HI
+#define KB_BPS_HI 5
+#endif
+#define KB_LT(I, S) (four ? launch_traverse_t<I, S, KB_BPS_HI>(p, num_sms, smem, s) : launch_traverse_t<I, S, 3>(p, num_sms, smem, s))
   if (p.collect_stats) return itc ? KB_LT(true, true) : KB_LT(false, true);
   return itc ? KB_LT(true, false) : KB_LT(false, false);
 #undef KB_LT

@@ -3,7 +3,7 @@
 #include "kb_types.h"
 #include <cuda_runtime.h>
 
-size_t kb_traverse_smem_bytes(int nxf, int nitems);
+size_t kb_traverse_smem_bytes(int nxf, int nitems, int nprobes);
 
 cudaError_t kb_launch_fk(const KbRobotDev* robot, const KbDriverDev* drv, const int32_t* drv_link, const double* drv_scale,
                          const double* drv_off, const double* Q, int64_t N, double* xf64, int nxf, uint8_t* state,

@@ -39,6 +39,30 @@
 
 enum { KB_ELEM_TRI = 0, KB_ELEM_SPHERE = 1 };
 
+// Clearance grids (broad phase of the boolean query).  For every merged static environment group a uniform voxel grid
+// over the group's bounds (+ a pad) stores, per voxel, a conservative lower bound on the distance from ANY point of the
+// voxel to the group's surface, in quarter-voxel units (u8).  A link whose covering spheres all have more clearance than
+// radius + threshold cannot touch the group, so its (link, group) work item is dropped before the BVH descent -- the
+// reference's per-object AABB pre-reject (Cpp/Planning/PlannerSettings.cpp:290-317) taken to an O(1) lookup.
+#define KB_MAX_GRIDS 4
+#define KB_COVER_MAX 8            // covering spheres per link geometry
+#define KB_PROBES_SMEM_MAX 512    // probe lists up to this size are cached in shared memory per CTA (32 B each)
+struct KbClearGrid {
+  const uint8_t* data;            // dims[0]*dims[1]*dims[2] bytes, x fastest
+  float o[3];                     // world position of voxel (0,0,0)'s lower corner
+  float inv_h;                    // 1 / voxel edge
+  int32_t dims[3];
+  int32_t pad_;
+};
+struct KbProbe {                  // one covering sphere of the moving side of a (link, static group) item: 32 bytes
+  float c[3];                     // centre in the link frame
+  uint32_t need;                  // quarter-voxels of clearance that rule a contact out: radius + threshold + slack, rounded up
+  int32_t item;                   // work item this probe belongs to
+  int32_t xf;                     // transform slot of the link
+  int32_t grid;                   // clearance grid of the static side
+  int32_t pad_;
+};
+
 struct KbItem {                   // 56 bytes
   int32_t nodeA, nodeB;           // global node index of the two roots
   int32_t elemA, elemB;           // global element base (into tris* or sph* according to kind)
@@ -78,6 +102,7 @@ struct KbScene {                  // device pointers to the static data
   const int32_t* sphown;
   float eps_abs;                  // absolute fp32 coordinate error bound for this scene (metres)
   float qo[3], qs[3];             // KB_QNODES builds only: origin and step of the 16-bit node quantisation grid
+  KbClearGrid grids[KB_MAX_GRIDS];
 };
 
 struct KbTraverseParams {
@@ -91,9 +116,13 @@ struct KbTraverseParams {
   int32_t* hit;                   // per configuration: -1 none, else item index of a colliding pair
   int32_t* hit_elem;              // per configuration: elemA / elemB (2 ints) of that pair; may be null
   uint32_t* work_counter;         // dynamic work distribution
-  unsigned long long* counters;   // [0] rechecks, [1] node tests, [2] leaf tests (optional statistics)
+  unsigned long long* counters;   // [0] rechecks, [1] node tests, [2] leaf tests, [7] items dropped by the clearance grids (optional statistics)
   int32_t wide_limit;             // stack size up to which 32-wide pops are allowed
   int32_t collect_stats;
+  int32_t both_limit;             // frontier size up to which comparable inner pairs push all four child pairs (0 = never)
+  const KbProbe* probes;          // clearance probes of this item set (boolean kernel only); null / 0 = no pre-filter
+  int32_t nprobes;
+  const uint32_t* always_on;      // bit i set: item i has no probes and is always traversed ((nitems + 31) / 32 words)
 };
 
 // split pipeline (node traversal kernel -> global leaf-pair list -> leaf kernel -> requeue for the fused kernel)

@@ -394,3 +394,21 @@ def test_all_colliding_pairs(c1):
     assert np.array_equal(c1_, count)
     for i in np.nonzero(count > 0)[0][:50]:
         assert (int(p1[i, 0, 0]), int(p1[i, 0, 1])) in {(int(a), int(b)) for a, b in pairs[i] if a >= 0}
+
+
+def test_clearance_grid_option_changes_nothing(c1, c2small):
+    """The clearance-grid broad phase (option clear_grid, SURVEY 8a row a8's AABB pre-reject as an O(1) lookup) is
+    conservative: results with the grids on equal the results with them off and the oracle's, and items are dropped."""
+    for w, eng, orc in (c1, c2small):
+        Q = synth.sample_configs(w.robot, 20000, 23)
+        eng.set_option("clear_grid", 0)
+        off = eng.feasible_batch(Q)
+        eng.set_option("clear_grid", 1)
+        eng.set_option("collect_stats", 1); eng.reset_stats()
+        on, pairs = eng.feasible_batch(Q, return_pairs=True)
+        st = eng.stats()
+        eng.set_option("collect_stats", 0); eng.set_option("clear_grid", 0)
+        assert np.array_equal(on, off)
+        assert st["items_dropped"] > 0
+        want = orc.feasible_batch(Q)
+        assert_bool_parity(on, want, Q, orc)
