@@ -583,7 +583,13 @@ KbTraverseParams make_params(kb_engine* e, const ItemSet& set, const double* xf,
   KbTraverseParams p; memset(&p, 0, sizeof p);
   p.scene = e->scene; p.items = set.d_items; p.nitems = (int)set.items.size(); p.nxf = set.nxf; p.xf64 = xf; p.N = n; p.state = state;
   p.hit = e->d_hit; p.hit_elem = e->d_hit_elem; p.work_counter = e->d_work; p.counters = e->d_counters;
-  p.wide_limit = KB_STACK_CAP - 32 - set.maxdepth - 2; p.collect_stats = e->collect_stats ? 1 : 0;
+  // Stack models.  Distance / all-pairs kernels: a 32-wide pop pushes at most 2 per entry, allowed while sp <= wide_limit; above it
+  // one entry is popped at a time, which grows the stack by at most the BVH depth sum.  Boolean kernel: an entry pushes at most 4
+  // (pairs of comparable boxes push all four child pairs), so m entries may be popped while sp + 3 m <= pop_room; single-entry
+  // pops grow the stack by at most 3 entries per two tree levels (1.5 x the depth sum).
+  p.wide_limit = KB_STACK_CAP - 32 - set.maxdepth - 2;
+  p.pop_room = KB_STACK_CAP - (3 * set.maxdepth + 1) / 2 - 4;
+  p.collect_stats = e->collect_stats ? 1 : 0;
   p.both_limit = e->both_limit;
   if (e->use_grids && set.d_probes && !set.probes.empty()) { p.probes = set.d_probes; p.nprobes = (int)set.probes.size(); p.always_on = set.d_always_on; }
   return p;
@@ -871,7 +877,7 @@ int kb_finalize(kb_engine* e, int device) {
     if (!(mask_en(e, link_id(e, i), link_id(e, j)) || mask_en(e, link_id(e, i), link_id(e, i)))) continue;
     int rc = add_item(e->feas_items, e->dgeoms[e->linkgeom[i]], i, link_id(e, i), e->dgeoms[e->linkgeom[j]], j, link_id(e, j), true); if (rc) return rc;
   }
-  if (e->feas_items.maxdepth + 64 + 34 > KB_STACK_CAP) return fail(KB_ERR_UNSUPPORTED, "BVH depth sum %d exceeds the traversal stack model", e->feas_items.maxdepth);
+  if (KB_STACK_CAP - (3 * e->feas_items.maxdepth + 1) / 2 - 4 < 160) return fail(KB_ERR_UNSUPPORTED, "BVH depth sum %d exceeds the traversal stack model", e->feas_items.maxdepth);
   // ---- 4. fp32 coordinate error bound: scene extent + robot reach
   double reach = 0;
   for (int j = 0; j < L; j++) {

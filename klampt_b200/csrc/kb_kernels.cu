@@ -642,9 +642,11 @@ kb_traverse_kernel(const KbTraverseParams p) {
         int sp_l = sp, nleaf_l = nleaf;
         const float* itc_l = itc;
         const bool more_items = cursor < p.nitems;
+        const int pop_room = p.pop_room;
         const int lane_l = lane;
         do {
-        int m = (sp_l <= p.wide_limit) ? (sp_l < KB_POP_WIDTH ? sp_l : KB_POP_WIDTH) : 1;
+        int m = sp_l < KB_POP_WIDTH ? sp_l : KB_POP_WIDTH;
+        { const int room = (pop_room - sp_l) / 3; m = m < room ? m : (room > 1 ? room : 1); }     // narrower pops as the stack fills up
         const bool act = lane_l < m;
         uint2 e = make_uint2(0u, 0u);
         if (act) e = stack[sp_l - 1 - lane_l];
@@ -1490,7 +1492,10 @@ cudaError_t kb_launch_traverse(const KbTraverseParams& p, int mode, double* out_
   // when the per-CTA shared memory is small (few work items per configuration; C2: 7.33 ms at 5, 7.68 at 4, 8.07 at 6),
   // 3 CTAs/SM (168 registers, no spills) wins when the item cache is large (C3, 107 pairs: 10.5 vs 11.8 ms at 4).
   // Measured on B200, profiles/r01_experiments.md.
-  const bool four = smem <= 40 * 1024;
+#ifndef KB_HI_SMEM_LIMIT
+#define KB_HI_SMEM_LIMIT (40 * 1024)
+#endif
+  const bool four = smem <= KB_HI_SMEM_LIMIT;
 #ifndef KB_BPS_HI
 #define KB_BPS_HI 5
 #endif

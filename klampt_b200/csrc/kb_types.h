@@ -20,7 +20,9 @@
 #include <stdint.h>
 
 #define KB_MAX_LINKS 128          // links per robot supported by the FK kernel's shared-memory model
-#define KB_STACK_CAP 512          // node-pair stack entries per warp
+#ifndef KB_STACK_CAP
+#define KB_STACK_CAP 448          // node-pair stack entries per warp (448: five CTAs of the boolean kernel fit the 164 KB shared-memory carve-out, leaving 92 KB of L1)
+#endif
 #define KB_LEAFQ_CAP 96           // leaf-pair queue entries per warp
 #define KB_ITEM_BITS 12
 #define KB_NODEA_BITS 20
@@ -119,6 +121,7 @@ struct KbTraverseParams {
   unsigned long long* counters;   // [0] rechecks, [1] node tests, [2] leaf tests, [7] items dropped by the clearance grids (optional statistics)
   int32_t wide_limit;             // stack size up to which 32-wide pops are allowed
   int32_t collect_stats;
+  int32_t pop_room;               // boolean kernel: m entries may be popped while sp + 3 m <= pop_room (see make_params)
   int32_t both_limit;             // frontier size up to which comparable inner pairs push all four child pairs (0 = never)
   const KbProbe* probes;          // clearance probes of this item set (boolean kernel only); null / 0 = no pre-filter
   int32_t nprobes;
