@@ -87,8 +87,12 @@ int kb_add_rigid_object(kb_engine* e, int geom, const double T[12]);
 int kb_robot_create(kb_engine* e, int L, const int32_t* parents, const uint8_t* linktype,
                     const double* axis, const double* T0_parent, const double* qmin, const double* qmax);
 int kb_robot_set_link_geometry(kb_engine* e, int link, int geom);
-/* RobotModel::joints; default = one Normal joint per link */
-int kb_robot_set_joints(kb_engine* e, int nj, const uint8_t* jtype, const int32_t* jlink);
+/* RobotModel::joints (type, linkIndex, baseIndex; Cpp/Modeling/Robot.h RobotModelJoint); default = one Normal joint per link.
+ * jbase (may be NULL when every joint drives one link) = the link a Floating / FloatingPlanar / BallAndSocket joint hangs
+ * from, -1 = world: the joint drives the chain base -> jlink (RobotModel::GetJointIndices, Cpp/Modeling/Robot.cpp:2120-2144),
+ * which must be 3 prismatic + 3 revolute (z, y, x) links for Floating, 3 revolute (z, y, x) for BallAndSocket, and end in a
+ * revolute link for FloatingPlanar -- the layout Klampt::Interpolate / Distance assert (Cpp/Modeling/Interpolate.cpp:24-26,231-236) */
+int kb_robot_set_joints(kb_engine* e, int nj, const uint8_t* jtype, const int32_t* jlink, const int32_t* jbase);
 /* RobotModelDriver limits as read by CheckJointLimits (Cpp/Modeling/Robot.cpp:2166-2187):
  * value = mean_k (q[links[k]] - offset[k]) / scale[k];  scale/offset may be NULL (1 / 0) */
 int kb_robot_add_driver(kb_engine* e, int n, const int32_t* links, const double* scale, const double* offset,

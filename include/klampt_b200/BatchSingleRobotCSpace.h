@@ -33,6 +33,7 @@ struct RobotDescription {
   std::vector<int32_t> parents; std::vector<uint8_t> linkType; std::vector<double> axis, T0Parent, qMin, qMax;
   std::vector<int> linkGeometry;                   // geometry index per link, -1 = none
   std::vector<uint8_t> jointType; std::vector<int32_t> jointLink;   // empty = one Normal joint per link
+  std::vector<int32_t> jointBase;                                     // RobotModelJoint::baseIndex per joint; only needed for Floating / FloatingPlanar / BallAndSocket joints
 };
 
 class WorldBuilder {
@@ -50,7 +51,7 @@ class WorldBuilder {
     const int L = (int)r.parents.size();
     kbCheck(kb_robot_create(e_, L, r.parents.data(), r.linkType.data(), r.axis.data(), r.T0Parent.data(), r.qMin.data(), r.qMax.data()));
     for (int i = 0; i < L; i++) kbCheck(kb_robot_set_link_geometry(e_, i, r.linkGeometry[i]));
-    if (!r.jointType.empty()) kbCheck(kb_robot_set_joints(e_, (int)r.jointType.size(), r.jointType.data(), r.jointLink.data()));
+    if (!r.jointType.empty()) kbCheck(kb_robot_set_joints(e_, (int)r.jointType.size(), r.jointType.data(), r.jointLink.data(), r.jointBase.empty() ? nullptr : r.jointBase.data()));
     robot_ = r;
   }
   // RobotModelDriver limits read by CheckJointLimits: value = mean_k (q[links[k]] - offset[k]) / scale[k]
@@ -96,14 +97,70 @@ class BatchSingleRobotCSpace {
   int NumDimensions() const { return (int)robot_.parents.size(); }
   bool IsFeasible(const Config& x) { uint8_t r = 0; IsFeasibleBatch(x.data(), 1, &r); lastConfig = x; return r != 0; }
   EdgePlannerPtr PathChecker(const Config& a, const Config& b) { return std::make_shared<BatchEdgeChecker>(this, a, b, collisionEpsilon); }
-  // RobotCSpace::Distance -> Klampt::Distance, L2 over joints (Interpolate.cpp:208-343, norm = 2)
+  // links a joint drives, root to tip (RobotModel::GetJointIndices, Cpp/Modeling/Robot.cpp:2120-2144)
+  int JointIndices(size_t j, int idx[6]) const {
+    int link = robot_.jointLink[j]; const int t = robot_.jointType[j];
+    if (t == KB_JOINT_WELD || t == KB_JOINT_NORMAL || t == KB_JOINT_SPIN || robot_.jointBase.empty()) { idx[0] = link; return 1; }
+    int n = 0, tmp[8];
+    while (link != robot_.jointBase[j] && link >= 0 && n < 6) { tmp[n++] = link; link = robot_.parents[link]; }
+    for (int i = 0; i < n; i++) idx[i] = tmp[n - 1 - i];
+    return n;
+  }
+  // Euler ZYX triplet <-> matrix, SO(3) log / exp: what EulerAngleRotation::getMatrixZYX / setMatrixZYX, interpolateRotation and
+  // AngleAxisRotation::angle compute for Floating / BallAndSocket joints (Interpolate.cpp:16-52,229-278)
+  static void EulerZYXToMatrix(const double e[3], double R[9]) {
+    const double ca = std::cos(e[0]), sa = std::sin(e[0]), cb = std::cos(e[1]), sb = std::sin(e[1]), cc = std::cos(e[2]), sc = std::sin(e[2]);
+    R[0] = ca * cb; R[1] = ca * sb * sc - sa * cc; R[2] = ca * sb * cc + sa * sc;
+    R[3] = sa * cb; R[4] = sa * sb * sc + ca * cc; R[5] = sa * sb * cc - ca * sc;
+    R[6] = -sb; R[7] = cb * sc; R[8] = cb * cc;
+  }
+  static double RotationAngle(const double R[9]) { return std::acos(std::min(1.0, std::max(-1.0, 0.5 * (R[0] + R[4] + R[8] - 1.0)))); }
+  static double EulerZYXAngleBetween(const double a[3], const double b[3]) {
+    double Ra[9], Rb[9], D[9]; EulerZYXToMatrix(a, Ra); EulerZYXToMatrix(b, Rb);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) D[3 * i + j] = Ra[3 * i] * Rb[3 * j] + Ra[3 * i + 1] * Rb[3 * j + 1] + Ra[3 * i + 2] * Rb[3 * j + 2];
+    return RotationAngle(D);
+  }
+  static void EulerZYXInterp(const double a[3], const double b[3], double u, double out[3]) {
+    double Ra[9], Rb[9], D[9], w[3], E[9], Ru[9];
+    EulerZYXToMatrix(a, Ra); EulerZYXToMatrix(b, Rb);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) D[3 * i + j] = Ra[i] * Rb[j] + Ra[3 + i] * Rb[3 + j] + Ra[6 + i] * Rb[6 + j];
+    const double th = RotationAngle(D), v[3] = {D[7] - D[5], D[2] - D[6], D[3] - D[1]};
+    if (th < 1e-9) for (int k = 0; k < 3; k++) w[k] = 0.5 * v[k];
+    else if (M_PI - th < 1e-6) {
+      double ax[3]; for (int k = 0; k < 3; k++) { const double d = 0.5 * (D[4 * k] + 1.0); ax[k] = d > 0 ? std::sqrt(d) : 0.0; }
+      int m = 0; for (int k = 1; k < 3; k++) if (ax[k] > ax[m]) m = k;
+      for (int k = 0; k < 3; k++) if (k != m && D[3 * m + k] + D[3 * k + m] < 0) ax[k] = -ax[k];
+      if (ax[0] * v[0] + ax[1] * v[1] + ax[2] * v[2] < 0) for (int k = 0; k < 3; k++) ax[k] = -ax[k];
+      const double n = std::sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]); for (int k = 0; k < 3; k++) w[k] = th * ax[k] / n;
+    } else { const double f = th / (2.0 * std::sin(th)); for (int k = 0; k < 3; k++) w[k] = f * v[k]; }
+    for (int k = 0; k < 3; k++) w[k] *= u;
+    const double t2 = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    if (t2 < 1e-12) { E[0] = 1; E[1] = -w[2]; E[2] = w[1]; E[3] = w[2]; E[4] = 1; E[5] = -w[0]; E[6] = -w[1]; E[7] = w[0]; E[8] = 1; }
+    else {
+      const double x = w[0] / t2, y = w[1] / t2, z = w[2] / t2, c = std::cos(t2), s = std::sin(t2), vv = 1.0 - c;
+      E[0] = c + vv * x * x; E[1] = vv * x * y - s * z; E[2] = vv * x * z + s * y;
+      E[3] = vv * y * x + s * z; E[4] = c + vv * y * y; E[5] = vv * y * z - s * x;
+      E[6] = vv * z * x - s * y; E[7] = vv * z * y + s * x; E[8] = c + vv * z * z;
+    }
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Ru[3 * i + j] = Ra[3 * i] * E[j] + Ra[3 * i + 1] * E[3 + j] + Ra[3 * i + 2] * E[6 + j];
+    out[1] = std::asin(std::min(1.0, std::max(-1.0, -Ru[6])));
+    if (std::fabs(Ru[6]) < 1.0 - 1e-12) { out[0] = std::atan2(Ru[3], Ru[0]); out[2] = std::atan2(Ru[7], Ru[8]); }
+    else { out[2] = 0.0; out[0] = std::atan2(-Ru[1], Ru[4]); }
+  }
+  // RobotCSpace::Distance -> Klampt::Distance, L2 over joints (Interpolate.cpp:208-343, norm = 2, floatingRotationWeight = 1)
   double Distance(const Config& x, const Config& y) const {
     double s = 0;
     for (size_t j = 0; j < robot_.jointType.size(); j++) {
-      const int k = robot_.jointLink[j]; const double w = jointWeights.empty() ? 1.0 : jointWeights[j]; double d;
-      if (robot_.jointType[j] == KB_JOINT_NORMAL) d = x[k] - y[k];
-      else if (robot_.jointType[j] == KB_JOINT_SPIN) d = AngleDiff(AngleNormalize(x[k]), AngleNormalize(y[k]));
-      else continue;
+      const int k = robot_.jointLink[j]; const double w = jointWeights.empty() ? 1.0 : jointWeights[j]; double d; int ix[6];
+      const int t = robot_.jointType[j];
+      if (t == KB_JOINT_NORMAL) d = x[k] - y[k];
+      else if (t == KB_JOINT_SPIN) d = AngleDiff(AngleNormalize(x[k]), AngleNormalize(y[k]));
+      else if (t == KB_JOINT_FLOATING || t == KB_JOINT_BALLANDSOCKET) {
+        const int n = JointIndices(j, ix);
+        if (t == KB_JOINT_FLOATING) for (int q = 0; q < 3; q++) { const double dt = x[ix[q]] - y[ix[q]]; s += w * dt * dt; }
+        const double ea[3] = {x[ix[n - 3]], x[ix[n - 2]], x[ix[n - 1]]}, eb[3] = {y[ix[n - 3]], y[ix[n - 2]], y[ix[n - 1]]};
+        d = EulerZYXAngleBetween(ea, eb);
+      } else continue;
       s += w * d * d;
     }
     return std::sqrt(s);
@@ -112,9 +169,18 @@ class BatchSingleRobotCSpace {
   void Interpolate(const Config& x, const Config& y, double u, Config& out) const {
     out.resize(x.size());
     for (size_t k = 0; k < x.size(); k++) { out[k] = x[k] * (1.0 - u); out[k] += y[k] * u; }
-    for (size_t j = 0; j < robot_.jointType.size(); j++) if (robot_.jointType[j] == KB_JOINT_SPIN) {
-      const int k = robot_.jointLink[j]; const double a = AngleNormalize(x[k]), b = AngleNormalize(y[k]);
-      out[k] = AngleNormalize(a + u * AngleDiff(b, a));
+    for (size_t j = 0; j < robot_.jointType.size(); j++) {
+      const int t = robot_.jointType[j]; int ix[6];
+      if (t == KB_JOINT_SPIN || t == KB_JOINT_FLOATINGPLANAR) {
+        int k = robot_.jointLink[j]; if (t == KB_JOINT_FLOATINGPLANAR) { JointIndices(j, ix); k = ix[2]; }
+        const double a = AngleNormalize(x[k]), b = AngleNormalize(y[k]);
+        out[k] = AngleNormalize(a + u * AngleDiff(b, a));
+      } else if (t == KB_JOINT_FLOATING || t == KB_JOINT_BALLANDSOCKET) {
+        const int n = JointIndices(j, ix);
+        const double ea[3] = {x[ix[n - 3]], x[ix[n - 2]], x[ix[n - 1]]}, eb[3] = {y[ix[n - 3]], y[ix[n - 2]], y[ix[n - 1]]}; double eu[3];
+        EulerZYXInterp(ea, eb, u, eu);
+        out[ix[n - 3]] = eu[0]; out[ix[n - 2]] = eu[1]; out[ix[n - 1]] = eu[2];
+      }
     }
   }
   void Sample(Config& x) {   // uniform in [qMin,qMax] (RobotCSpace.cpp:85-87)

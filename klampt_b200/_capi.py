@@ -40,7 +40,7 @@ SIGNATURES = {
     "kb_add_rigid_object": (C.c_int, [_VP, C.c_int, c_double_p]),
     "kb_robot_create": (C.c_int, [_VP, C.c_int, c_int32_p, c_uint8_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     "kb_robot_set_link_geometry": (C.c_int, [_VP, C.c_int, C.c_int]),
-    "kb_robot_set_joints": (C.c_int, [_VP, C.c_int, c_uint8_p, c_int32_p]),
+    "kb_robot_set_joints": (C.c_int, [_VP, C.c_int, c_uint8_p, c_int32_p, c_int32_p]),
     "kb_robot_add_driver": (C.c_int, [_VP, C.c_int, c_int32_p, c_double_p, c_double_p, C.c_double, C.c_double]),
     "kb_robot_set_self_collision": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int]),
     "kb_set_pair_mask": (C.c_int, [_VP, c_uint8_p, C.c_int]),

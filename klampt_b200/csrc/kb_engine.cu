@@ -311,7 +311,7 @@ struct kb_engine {
   int L = 0;
   std::vector<int32_t> parents; std::vector<uint8_t> linktype; std::vector<double> axis, T0, qmin, qmax;
   std::vector<int> linkgeom;
-  std::vector<uint8_t> jtype; std::vector<int32_t> jlink;
+  std::vector<uint8_t> jtype; std::vector<int32_t> jlink; std::vector<int16_t> jidx;
   std::vector<Driver> drivers;
   std::vector<uint8_t> selfcol; bool selfcol_default = true;
   std::vector<uint8_t> mask; int nids = 0; bool mask_user = false;
@@ -730,15 +730,41 @@ int kb_robot_set_link_geometry(kb_engine* e, int link, int geom) {
   e->linkgeom[link] = geom; return KB_OK;
 }
 
-int kb_robot_set_joints(kb_engine* e, int nj, const uint8_t* jtype, const int32_t* jlink) {
+// links a joint drives, root to tip: the chain from its base (exclusive) to its link (inclusive) -- RobotModel::GetJointIndices,
+// reference Cpp/Modeling/Robot.cpp:2120-2144
+static int joint_chain(const kb_engine* e, int link, int base, int idx[6]) {
+  int n = 0, tmp[8];
+  while (link != base) { if (link < 0 || n >= 6) return -1; tmp[n++] = link; link = e->parents[link]; }
+  for (int i = 0; i < n; i++) idx[i] = tmp[n - 1 - i];
+  return n;
+}
+
+int kb_robot_set_joints(kb_engine* e, int nj, const uint8_t* jtype, const int32_t* jlink, const int32_t* jbase) {
   if (!e || e->finalized) return fail(KB_ERR_STATE, "engine is null or already finalized");
   if (nj < 0 || nj > KB_MAX_LINKS) return fail(KB_ERR_INVALID, "bad joint count %d", nj);
+  std::vector<int16_t> jidx((size_t)nj * 6, 0);
   for (int i = 0; i < nj; i++) {
     if (jlink[i] < 0 || jlink[i] >= e->L) return fail(KB_ERR_INVALID, "joint %d references link %d", i, jlink[i]);
-    if (jtype[i] == KB_JOINT_FLOATING || jtype[i] == KB_JOINT_FLOATINGPLANAR || jtype[i] == KB_JOINT_BALLANDSOCKET)
-      return fail(KB_ERR_UNSUPPORTED, "floating / ball-and-socket joints are not supported by the batched metric and interpolation yet");
+    const int t = jtype[i];
+    if (t == KB_JOINT_CLOSED || t > KB_JOINT_CLOSED) return fail(KB_ERR_UNSUPPORTED, "joint %d: closed-chain joints are not supported", i);
+    if (t == KB_JOINT_FLOATING || t == KB_JOINT_FLOATINGPLANAR || t == KB_JOINT_BALLANDSOCKET) {
+      // the link layout the reference asserts (Cpp/Modeling/Interpolate.cpp:24-26,231-236): translations, then rotations about z, y, x
+      int idx[6]; const int base = jbase ? jbase[i] : -2;
+      if (base < -1) return fail(KB_ERR_INVALID, "joint %d spans several links and needs its base link (jbase)", i);
+      const int n = joint_chain(e, jlink[i], base, idx);
+      const int want = t == KB_JOINT_FLOATING ? 6 : 3;
+      if (n != want) return fail(KB_ERR_INVALID, "joint %d drives %d links from base %d; its type needs %d", i, n, base, want);
+      auto rev = [&](int l) { return e->linktype[l] == KB_REVOLUTE; };
+      auto ax = [&](int l, int k) { return e->axis[3 * l + k] == 1.0; };
+      bool ok = true;
+      if (t == KB_JOINT_FLOATING) ok = !rev(idx[0]) && !rev(idx[1]) && !rev(idx[2]) && rev(idx[3]) && rev(idx[4]) && rev(idx[5]) && ax(idx[3], 2) && ax(idx[4], 1) && ax(idx[5], 0);
+      else if (t == KB_JOINT_BALLANDSOCKET) ok = rev(idx[0]) && rev(idx[1]) && rev(idx[2]) && ax(idx[0], 2) && ax(idx[1], 1) && ax(idx[2], 0);
+      else ok = rev(idx[2]);
+      if (!ok) return fail(KB_ERR_INVALID, "joint %d: link types / axes do not match the layout its type requires (translations, then rotations about z, y, x)", i);
+      for (int k = 0; k < n; k++) jidx[(size_t)i * 6 + k] = (int16_t)idx[k];
+    }
   }
-  e->jtype.assign(jtype, jtype + nj); e->jlink.assign(jlink, jlink + nj); return KB_OK;
+  e->jtype.assign(jtype, jtype + nj); e->jlink.assign(jlink, jlink + nj); e->jidx = jidx; return KB_OK;
 }
 
 int kb_robot_add_driver(kb_engine* e, int n, const int32_t* links, const double* scale, const double* offset, double dmin, double dmax) {
@@ -970,7 +996,7 @@ int kb_finalize(kb_engine* e, int device) {
   R->L = L; R->nj = (int)e->jtype.size(); R->ndrv = (int)e->drivers.size();
   for (int i = 0; i < L; i++) { R->parents[i] = e->parents[i]; R->linktype[i] = e->linktype[i]; R->qmin[i] = e->qmin[i]; R->qmax[i] = e->qmax[i]; }
   memcpy(R->axis, e->axis.data(), sizeof(double) * 3 * L); memcpy(R->T0, e->T0.data(), sizeof(double) * 12 * L);
-  for (int i = 0; i < R->nj; i++) { R->jtype[i] = e->jtype[i]; R->jlink[i] = e->jlink[i]; }
+  for (int i = 0; i < R->nj; i++) { R->jtype[i] = e->jtype[i]; R->jlink[i] = e->jlink[i]; for (int k = 0; k < 6; k++) R->jidx[i][k] = (size_t)i * 6 + k < e->jidx.size() ? e->jidx[(size_t)i * 6 + k] : 0; }
   std::vector<KbDriverDev> dd; std::vector<int32_t> dl; std::vector<double> ds, dofs;
   for (const Driver& d : e->drivers) {
     KbDriverDev x; x.first = (int)dl.size(); x.n = (int)d.links.size(); x.dmin = d.dmin; x.dmax = d.dmax; dd.push_back(x);

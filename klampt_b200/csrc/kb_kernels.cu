@@ -307,7 +307,12 @@ __device__ __forceinline__ float fast_elem_distance(const KbScene& sc, const KbI
 // (configuration, item, elemA, elemB) that survives from one configuration to the next, and are re-run in fp64 32 at a
 // time so the slow path also runs on full warps.  A configuration whose traversal ended without a certain hit is
 // written as "no hit" and upgraded here if one of its parked pairs turns out to collide.
+#ifndef KB_RQ_CAP
 #define KB_RQ_CAP 96
+#endif
+#ifndef KB_BOOL_LEAFQ_CAP
+#define KB_BOOL_LEAFQ_CAP KB_LEAFQ_CAP   // leaf-pair queue of the boolean kernel (>= KB_LEAF_TRIGGER + 32)
+#endif
 __device__ __forceinline__ void drain_rechecks(const KbTraverseParams& p, uint4* rq, int* rq_count, int lane, int64_t cur_c,
                                                int& found, int& found_ea, int& found_eb, bool all) {
   __syncwarp();
@@ -477,14 +482,14 @@ kb_traverse_kernel(const KbTraverseParams p) {
   ItemS* s_items = (ItemS*)smem_raw;
   const int mask_words = p.nprobes > 0 ? (((p.nitems + 31) >> 5) + 3) & ~3 : 0;
   const int nprobes_s = p.nprobes <= KB_PROBES_SMEM_MAX ? p.nprobes : 0;      // probes cached per CTA
-  const size_t per_warp = (size_t)KB_STACK_CAP * 8 + (size_t)KB_LEAFQ_CAP * 8 + (size_t)KB_RQ_CAP * 16 + 16 + (size_t)xf_floats * 4 + (size_t)nit_c * 48 + (size_t)mask_words * 4;
+  const size_t per_warp = (size_t)KB_STACK_CAP * 8 + (size_t)KB_BOOL_LEAFQ_CAP * 8 + (size_t)KB_RQ_CAP * 16 + 16 + (size_t)xf_floats * 4 + (size_t)nit_c * 48 + (size_t)mask_words * 4;
   KbProbe* s_probes = (KbProbe*)(smem_raw + (size_t)nit_c * 16);
   unsigned char* base = smem_raw + (size_t)nit_c * 16 + (size_t)nprobes_s * 32 + warp * per_warp;
   uint2* stack = (uint2*)base;
   uint2* leafq = (uint2*)(base + (size_t)KB_STACK_CAP * 8);
-  uint4* rq = (uint4*)(base + (size_t)KB_STACK_CAP * 8 + (size_t)KB_LEAFQ_CAP * 8);
+  uint4* rq = (uint4*)(base + (size_t)KB_STACK_CAP * 8 + (size_t)KB_BOOL_LEAFQ_CAP * 8);
   int* rq_count = (int*)(rq + KB_RQ_CAP);
-  float* xfw = (float*)(base + (size_t)KB_STACK_CAP * 8 + (size_t)KB_LEAFQ_CAP * 8 + (size_t)KB_RQ_CAP * 16 + 16);
+  float* xfw = (float*)(base + (size_t)KB_STACK_CAP * 8 + (size_t)KB_BOOL_LEAFQ_CAP * 8 + (size_t)KB_RQ_CAP * 16 + 16);
   float* itc = xfw + xf_floats;
   unsigned* amask = (unsigned*)(itc + (size_t)nit_c * 12);   // per configuration: bit i = item i must be traversed
   const KbScene& sc = p.scene;
@@ -1316,6 +1321,66 @@ __global__ void kb_pair_ids_kernel(const int32_t* __restrict__ hit, const int32_
   pair[2 * c] = ia; pair[2 * c + 1] = ib;
 }
 
+// =============================================================================================== SO(3) for Floating / BallAndSocket joints
+// Klampt::Interpolate / Klampt::Distance (Cpp/Modeling/Interpolate.cpp:16-52,229-278) treat the last three links of a Floating
+// joint (and the three links of a BallAndSocket joint) as Euler angles about z, y, x: R = Rz(a) Ry(b) Rx(c); interpolation
+// follows the SO(3) geodesic Ra exp(u log(Ra^T Rb)) and the metric collects the geodesic angle acos((tr(Ra Rb^T) - 1) / 2).
+__device__ __forceinline__ void kb_euler_zyx_to_matrix(double a, double b, double c, double* R) {
+  double sa, ca, sb, cb, sc, cc; sincos(a, &sa, &ca); sincos(b, &sb, &cb); sincos(c, &sc, &cc);
+  R[0] = ca * cb; R[1] = ca * sb * sc - sa * cc; R[2] = ca * sb * cc + sa * sc;
+  R[3] = sa * cb; R[4] = sa * sb * sc + ca * cc; R[5] = sa * sb * cc - ca * sc;
+  R[6] = -sb;     R[7] = cb * sc;                R[8] = cb * cc;
+}
+__device__ __forceinline__ double kb_so3_angle(const double* R) { double c = 0.5 * (R[0] + R[4] + R[8] - 1.0); c = fmin(1.0, fmax(-1.0, c)); return acos(c); }
+__device__ double kb_euler_zyx_angle_between(const double* ea, const double* eb) {
+  double Ra[9], Rb[9], D[9]; kb_euler_zyx_to_matrix(ea[0], ea[1], ea[2], Ra); kb_euler_zyx_to_matrix(eb[0], eb[1], eb[2], Rb);
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) D[3 * i + j] = Ra[3 * i] * Rb[3 * j] + Ra[3 * i + 1] * Rb[3 * j + 1] + Ra[3 * i + 2] * Rb[3 * j + 2];
+  return kb_so3_angle(D);
+}
+__device__ void kb_euler_zyx_interp(const double* ea, const double* eb, double u, double* out) {
+  const double PI = 3.14159265358979323846;
+  double Ra[9], Rb[9], D[9], w[3], E[9], Ru[9];
+  kb_euler_zyx_to_matrix(ea[0], ea[1], ea[2], Ra); kb_euler_zyx_to_matrix(eb[0], eb[1], eb[2], Rb);
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) D[3 * i + j] = Ra[i] * Rb[j] + Ra[3 + i] * Rb[3 + j] + Ra[6 + i] * Rb[6 + j];      // Ra^T Rb
+  {   // log
+    const double th = kb_so3_angle(D);
+    const double v[3] = {D[7] - D[5], D[2] - D[6], D[3] - D[1]};
+    if (th < 1e-9) { for (int k = 0; k < 3; k++) w[k] = 0.5 * v[k]; }
+    else if (PI - th < 1e-6) {   // near a half turn: axis from the diagonal of (R + I) / 2, signs from the symmetric and skew parts
+      double ax[3]; for (int k = 0; k < 3; k++) { double d = 0.5 * (D[4 * k] + 1.0); ax[k] = d > 0 ? sqrt(d) : 0.0; }
+      int m = 0; for (int k = 1; k < 3; k++) if (ax[k] > ax[m]) m = k;
+      for (int k = 0; k < 3; k++) if (k != m) { double s2 = D[3 * m + k] + D[3 * k + m]; if (s2 < 0) ax[k] = -ax[k]; }
+      double sg = ax[0] * v[0] + ax[1] * v[1] + ax[2] * v[2]; if (sg < 0) for (int k = 0; k < 3; k++) ax[k] = -ax[k];
+      double n = sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]); for (int k = 0; k < 3; k++) w[k] = th * ax[k] / n;
+    } else { const double f = th / (2.0 * sin(th)); for (int k = 0; k < 3; k++) w[k] = f * v[k]; }
+  }
+  for (int k = 0; k < 3; k++) w[k] *= u;
+  {   // exp (Rodrigues)
+    const double th = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    if (th < 1e-12) { E[0] = 1; E[1] = -w[2]; E[2] = w[1]; E[3] = w[2]; E[4] = 1; E[5] = -w[0]; E[6] = -w[1]; E[7] = w[0]; E[8] = 1; }
+    else {
+      const double x = w[0] / th, y = w[1] / th, z = w[2] / th; double s, c; sincos(th, &s, &c); const double vv = 1.0 - c;
+      E[0] = c + vv * x * x;     E[1] = vv * x * y - s * z; E[2] = vv * x * z + s * y;
+      E[3] = vv * y * x + s * z; E[4] = c + vv * y * y;     E[5] = vv * y * z - s * x;
+      E[6] = vv * z * x - s * y; E[7] = vv * z * y + s * x; E[8] = c + vv * z * z;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) Ru[3 * i + j] = Ra[3 * i] * E[j] + Ra[3 * i + 1] * E[3 + j] + Ra[3 * i + 2] * E[6 + j];
+  double sb = fmin(1.0, fmax(-1.0, -Ru[6]));
+  out[1] = asin(sb);
+  if (fabs(Ru[6]) < 1.0 - 1e-12) { out[0] = atan2(Ru[3], Ru[0]); out[2] = atan2(Ru[7], Ru[8]); }
+  else { out[2] = 0.0; out[0] = atan2(-Ru[1], Ru[4]); }      // gimbal lock: the whole turn goes into the z angle
+}
+
 // =============================================================================================== edges (K8)
 // Edge e of C-space length len needs nlev = number of halvings until len/2^nlev <= eps.  Level l (1-based) holds the
 // 2^(l-1) odd multiples k/2^l.  All alive edges are expanded level by level; an edge dies at the first level that
@@ -1336,7 +1401,16 @@ __global__ void kb_edge_setup_kernel(const KbRobotDev* __restrict__ robot, const
       double y = fmod(B[e * L + k], 6.283185307179586476925286766559); if (y < 0) y += 6.283185307179586476925286766559;
       double dd = x - y; if (dd > 3.14159265358979323846) dd -= 6.283185307179586476925286766559; else if (dd < -3.14159265358979323846) dd += 6.283185307179586476925286766559;
       d = ExactD(dd);
-    } else continue;
+    } else if (t == 3) {          // Floating: three translations + the geodesic angle (floatingRotationWeight = 1)
+      const int16_t* ix = robot->jidx[j];
+      for (int q3 = 0; q3 < 3; q3++) { ExactD dt = ExactD(A[e * L + ix[q3]]) - ExactD(B[e * L + ix[q3]]); s = s + w * dt * dt; }
+      const double ea[3] = {A[e * L + ix[3]], A[e * L + ix[4]], A[e * L + ix[5]]}, eb[3] = {B[e * L + ix[3]], B[e * L + ix[4]], B[e * L + ix[5]]};
+      d = ExactD(kb_euler_zyx_angle_between(ea, eb));
+    } else if (t == 5) {          // BallAndSocket: the geodesic angle
+      const int16_t* ix = robot->jidx[j];
+      const double ea[3] = {A[e * L + ix[0]], A[e * L + ix[1]], A[e * L + ix[2]]}, eb[3] = {B[e * L + ix[0]], B[e * L + ix[1]], B[e * L + ix[2]]};
+      d = ExactD(kb_euler_zyx_angle_between(ea, eb));
+    } else continue;              // Weld; FloatingPlanar contributes nothing (Interpolate.cpp:338-340)
     s = s + w * d * d;
   }
   double len = kb_sqrt(s).v;
@@ -1374,8 +1448,17 @@ __global__ void kb_edge_expand_kernel(const KbRobotDev* __restrict__ robot, cons
   ExactD um = ExactD(1.0) - u;
   double* q = Q + s * L;
   for (int k = 0; k < L; k++) q[k] = (ExactD(A[e * L + k]) * um + ExactD(B[e * L + k]) * u).v;
-  for (int jn = 0; jn < robot->nj; jn++) if (robot->jtype[jn] == 2) {
-    int k = robot->jlink[jn];
+  for (int jn = 0; jn < robot->nj; jn++) {
+    const int jt = robot->jtype[jn];
+    if (jt == 3 || jt == 5) {     // Floating / BallAndSocket: Euler-ZYX triplet along the SO(3) geodesic
+      const int16_t* ix = robot->jidx[jn] + (jt == 3 ? 3 : 0);
+      const double ea[3] = {A[e * L + ix[0]], A[e * L + ix[1]], A[e * L + ix[2]]}, eb[3] = {B[e * L + ix[0]], B[e * L + ix[1]], B[e * L + ix[2]]};
+      double eu[3]; kb_euler_zyx_interp(ea, eb, u.v, eu);
+      q[ix[0]] = eu[0]; q[ix[1]] = eu[1]; q[ix[2]] = eu[2];
+      continue;
+    }
+    if (jt != 2 && jt != 4) continue;
+    int k = jt == 2 ? robot->jlink[jn] : robot->jidx[jn][2];      // Spin, or the angle of a FloatingPlanar joint: short arc
     const double tp = 6.283185307179586476925286766559;
     double x = fmod(A[e * L + k], tp); if (x < 0) x += tp;
     double y = fmod(B[e * L + k], tp); if (y < 0) y += tp;
@@ -1448,7 +1531,7 @@ size_t kb_traverse_smem_bytes(int nxf, int nitems, int nprobes) {
   size_t nit = nitems <= KB_ITC_MAX_ITEMS ? (size_t)nitems : 0;
   size_t mask_words = nprobes > 0 ? ((((size_t)nitems + 31) >> 5) + 3) & ~(size_t)3 : 0;
   size_t nps = nprobes <= KB_PROBES_SMEM_MAX ? (size_t)(nprobes > 0 ? nprobes : 0) : 0;
-  return nit * 16 + nps * 32 + (size_t)KB_WARPS_PER_BLOCK * ((size_t)KB_STACK_CAP * 8 + (size_t)KB_LEAFQ_CAP * 8 + (size_t)KB_RQ_CAP * 16 + 16 + xf_floats * 4 + nit * 48 + mask_words * 4);
+  return nit * 16 + nps * 32 + (size_t)KB_WARPS_PER_BLOCK * ((size_t)KB_STACK_CAP * 8 + (size_t)KB_BOOL_LEAFQ_CAP * 8 + (size_t)KB_RQ_CAP * 16 + 16 + xf_floats * 4 + nit * 48 + mask_words * 4);
 }
 
 cudaError_t kb_launch_fk(const KbRobotDev* robot, const KbDriverDev* drv, const int32_t* drv_link, const double* drv_scale,

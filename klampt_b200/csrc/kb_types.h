@@ -87,6 +87,7 @@ struct KbRobotDev {
   double qmin[KB_MAX_LINKS], qmax[KB_MAX_LINKS];
   uint8_t jtype[KB_MAX_LINKS];
   int32_t jlink[KB_MAX_LINKS];
+  int16_t jidx[KB_MAX_LINKS][6];  // links driven by a multi-link joint, root to tip (RobotModel::GetJointIndices): Floating 6, FloatingPlanar / BallAndSocket 3
 };
 
 struct KbDriverDev {              // flattened affine drivers: driver d covers terms [first, first+n)

@@ -89,7 +89,8 @@ class Engine:
         if r.joint_type is not None:
             jt = np.ascontiguousarray(r.joint_type, dtype=np.uint8)
             jl = np.ascontiguousarray(r.joint_link, dtype=np.int32)
-            check(lib.kb_robot_set_joints(h, len(jt), jt.ctypes.data_as(up), jl.ctypes.data_as(ip)))
+            jb = None if getattr(r, "joint_base", None) is None else np.ascontiguousarray(r.joint_base, dtype=np.int32)
+            check(lib.kb_robot_set_joints(h, len(jt), jt.ctypes.data_as(up), jl.ctypes.data_as(ip), None if jb is None else jb.ctypes.data_as(ip)))
         for d in r.drivers:
             li = np.ascontiguousarray(d.links, dtype=np.int32)
             sc, of = _f64(d.scale), _f64(d.offset)

@@ -332,6 +332,7 @@ class RobotModel(_Named):
         self._qmin, self._qmax = np.array(spec.qmin, dtype=np.float64), np.array(spec.qmax, dtype=np.float64)
         self._joint_type = np.full(L, JOINT_NORMAL, dtype=np.uint8) if spec.joint_type is None else np.array(spec.joint_type, dtype=np.uint8)
         self._joint_link = np.arange(L, dtype=np.int32) if spec.joint_link is None else np.array(spec.joint_link, dtype=np.int32)
+        self._joint_base = None if getattr(spec, "joint_base", None) is None else np.array(spec.joint_base, dtype=np.int32)
         self._drivers = list(spec.drivers)
         self._self_edits = list(spec.self_collision_edits)
         names = spec.names or ["link%d" % i for i in range(L)]
@@ -407,7 +408,8 @@ class RobotModel(_Named):
             link_geom.append(-1 if l._geom.empty() else world.add_geom(l._geom.to_spec()))
         return RobotSpec(parents=self._parents.copy(), linktype=self._linktype.copy(), axis=self._axis.copy(), T0=self._T0.copy(),
                          qmin=self._qmin.copy(), qmax=self._qmax.copy(), link_geom=link_geom, joint_type=self._joint_type.copy(),
-                         joint_link=self._joint_link.copy(), drivers=list(self._drivers), self_collision_edits=list(self._self_edits),
+                         joint_link=self._joint_link.copy(), joint_base=None if self._joint_base is None else self._joint_base.copy(),
+                         drivers=list(self._drivers), self_collision_edits=list(self._self_edits),
                          names=[l.getName() for l in self._links])
 
     def _self_engine(self):
@@ -455,29 +457,54 @@ class RobotModel(_Named):
         return self._nl_engine
 
     # ---- C-space helpers (RobotModel.interpolate / distance -> Klampt::Interpolate / Distance)
+    def _joint_indices(self, j: int) -> List[int]:
+        """RobotModel::GetJointIndices (reference Cpp/Modeling/Robot.cpp:2120-2144): links a joint drives, root to tip"""
+        link = int(self._joint_link[j])
+        if self._joint_type[j] in (0, 1, 2) or self._joint_base is None:
+            return [link]
+        out = []
+        while link != int(self._joint_base[j]):
+            out.append(link)
+            link = int(self._parents[link])
+        return out[::-1]
+
+    @staticmethod
+    def _short_arc(x, y):
+        x, y = x % (2 * np.pi), y % (2 * np.pi)
+        d = y - x
+        return x, d - 2 * np.pi if d > np.pi else (d + 2 * np.pi if d < -np.pi else d)
+
     def interpolate(self, a, b, u) -> List[float]:
+        """Klampt::Interpolate (reference Cpp/Modeling/Interpolate.cpp:10-71)"""
         a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
         out = a * (1.0 - u)
         out += b * u
-        for jt, k in zip(self._joint_type, self._joint_link):
-            if jt == 2:   # Spin: shortest arc
-                x, y = a[k] % (2 * np.pi), b[k] % (2 * np.pi)
-                d = y - x
-                d = d - 2 * np.pi if d > np.pi else (d + 2 * np.pi if d < -np.pi else d)
+        for j, (jt, k) in enumerate(zip(self._joint_type, self._joint_link)):
+            if jt == 2 or jt == 4:   # Spin / FloatingPlanar angle: shortest arc
+                if jt == 4:
+                    k = self._joint_indices(j)[2]
+                x, d = self._short_arc(a[k], b[k])
                 out[k] = (x + u * d) % (2 * np.pi)
+            elif jt == 3 or jt == 5:   # Floating / BallAndSocket: Euler ZYX triplet along the SO(3) geodesic
+                ix = self._joint_indices(j)[-3:]
+                out[ix] = so3.euler_zyx_interp(a[ix], b[ix], u)
         return list(out)
 
     def distance(self, a, b) -> float:
+        """Klampt::Distance, norm 2, floatingRotationWeight 1 (reference Cpp/Modeling/Interpolate.cpp:208-343)"""
         a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
         s = 0.0
-        for jt, k in zip(self._joint_type, self._joint_link):
+        for j, (jt, k) in enumerate(zip(self._joint_type, self._joint_link)):
             if jt == 1:
                 s += (a[k] - b[k]) ** 2
             elif jt == 2:
-                x, y = a[k] % (2 * np.pi), b[k] % (2 * np.pi)
-                d = x - y
-                d = d - 2 * np.pi if d > np.pi else (d + 2 * np.pi if d < -np.pi else d)
+                _, d = self._short_arc(b[k], a[k])
                 s += d * d
+            elif jt == 3 or jt == 5:
+                ix = self._joint_indices(j)
+                if jt == 3:
+                    s += float(((a[ix[:3]] - b[ix[:3]]) ** 2).sum())
+                s += so3.euler_zyx_angle_between(a[ix[-3:]], b[ix[-3:]]) ** 2
         return float(np.sqrt(s))
 
 

@@ -81,3 +81,62 @@ def to_rowmajor12(R: Sequence[float], t: Sequence[float]) -> np.ndarray:
 def from_rowmajor12(T12) -> Tuple[List[float], List[float]]:
     T12 = np.asarray(T12, dtype=np.float64)
     return from_matrix(T12[:9].reshape(3, 3)), list(T12[9:12])
+
+
+# ---- Euler ZYX triplets of Floating / BallAndSocket joints (row-major 3x3 numpy arrays here, not Klamp't 9-lists) ----------
+def euler_zyx_matrix(a: float, b: float, c: float) -> np.ndarray:
+    """EulerAngleRotation(a,b,c).getMatrixZYX = Rz(a) Ry(b) Rx(c) (the three links turn about z, y, x;
+    reference Cpp/Modeling/Interpolate.cpp:24-30)."""
+    ca, sa, cb, sb, cc, sc = math.cos(a), math.sin(a), math.cos(b), math.sin(b), math.cos(c), math.sin(c)
+    return np.array([[ca * cb, ca * sb * sc - sa * cc, ca * sb * cc + sa * sc],
+                     [sa * cb, sa * sb * sc + ca * cc, sa * sb * cc - ca * sc],
+                     [-sb, cb * sc, cb * cc]])
+
+
+def matrix_euler_zyx(R: np.ndarray) -> Tuple[float, float, float]:
+    b = math.asin(min(1.0, max(-1.0, -R[2, 0])))
+    if abs(R[2, 0]) < 1.0 - 1e-12:
+        return math.atan2(R[1, 0], R[0, 0]), b, math.atan2(R[2, 1], R[2, 2])
+    return math.atan2(-R[0, 1], R[1, 1]), b, 0.0      # gimbal lock: the whole turn goes into the z angle
+
+
+def angle(R: np.ndarray) -> float:
+    """AngleAxisRotation::angle of a rotation matrix"""
+    return math.acos(min(1.0, max(-1.0, 0.5 * (np.trace(R) - 1.0))))
+
+
+def log(R: np.ndarray) -> np.ndarray:
+    th = angle(R)
+    v = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    if th < 1e-9:
+        return 0.5 * v
+    if math.pi - th < 1e-6:      # near a half turn: axis from the diagonal of (R + I) / 2
+        ax = np.sqrt(np.maximum(0.5 * (np.diag(R) + 1.0), 0.0))
+        m = int(np.argmax(ax))
+        for k in range(3):
+            if k != m and R[m, k] + R[k, m] < 0:
+                ax[k] = -ax[k]
+        if ax @ v < 0:
+            ax = -ax
+        return th * ax / np.linalg.norm(ax)
+    return th / (2.0 * math.sin(th)) * v
+
+
+def exp(w: np.ndarray) -> np.ndarray:
+    th = float(np.linalg.norm(w))
+    K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    if th < 1e-12:
+        return np.eye(3) + K
+    x = np.asarray(w) / th
+    c, s = math.cos(th), math.sin(th)
+    return c * np.eye(3) + (1 - c) * np.outer(x, x) + s * K / th
+
+
+def euler_zyx_interp(ea, eb, u: float) -> Tuple[float, float, float]:
+    """interpolateRotation on two Euler ZYX triplets: Ra exp(u log(Ra^T Rb)), back to a triplet"""
+    Ra, Rb = euler_zyx_matrix(*ea), euler_zyx_matrix(*eb)
+    return matrix_euler_zyx(Ra @ exp(u * log(Ra.T @ Rb)))
+
+
+def euler_zyx_angle_between(ea, eb) -> float:
+    return angle(euler_zyx_matrix(*ea) @ euler_zyx_matrix(*eb).T)

@@ -18,7 +18,7 @@ from typing import Tuple
 
 import numpy as np
 
-from .worldspec import (GeomSpec, RobotSpec, WorldSpec, REVOLUTE, JOINT_NORMAL, JOINT_WELD, IDENTITY12)
+from .worldspec import (GeomSpec, RobotSpec, WorldSpec, REVOLUTE, JOINT_NORMAL, JOINT_WELD, JOINT_FLOATING, JOINT_BALLANDSOCKET, IDENTITY12)
 
 BASE_SEED = 20261017
 
@@ -274,6 +274,36 @@ def make_planar_nR(world: WorldSpec, n: int, link_length: float = 1.0) -> RobotS
                      joint_link=np.arange(n, dtype=np.int32))
 
 
+def make_floating_body(world: WorldSpec, with_ball_wrist: bool = True) -> RobotSpec:
+    """Free-flying body the way Klamp't models one (Cpp/docs/Manual-FileTypes.md "joint floating"): three prismatic
+    virtual links (x, y, z) and three revolute ones (z, y, x) with no geometry of their own, the body mesh on the
+    last; then a one-link arm on a Normal joint and, optionally, a tool on a ball-and-socket joint (three revolute
+    links about z, y, x).  Joints: Floating(link 5, base -1), Normal(6), BallAndSocket(link 9, base 6)."""
+    P, R = 1, 0
+    parents, ltype, axes, T0s, qmin, qmax, geoms = [], [], [], [], [], [], []
+    def add(parent, lt, axis, t, lo, hi, mesh):
+        parents.append(parent); ltype.append(lt); axes.append(axis); T0s.append(make_T(None, t)); qmin.append(lo); qmax.append(hi)
+        geoms.append(-1 if mesh is None else world.add_geom(GeomSpec.mesh(*mesh)))
+        return len(parents) - 1
+    l = add(-1, P, [1, 0, 0], (0, 0, 1.0), -1.0, 1.0, None)
+    l = add(l, P, [0, 1, 0], (0, 0, 0), -1.0, 1.0, None)
+    l = add(l, P, [0, 0, 1], (0, 0, 0), -0.6, 0.8, None)
+    l = add(l, R, [0, 0, 1], (0, 0, 0), -math.pi, math.pi, None)
+    l = add(l, R, [0, 1, 0], (0, 0, 0), -1.5, 1.5, None)
+    body = add(l, R, [1, 0, 0], (0, 0, 0), -math.pi, math.pi, box_mesh([-0.25, -0.15, -0.1], [0.25, 0.15, 0.1], div=6))
+    arm = add(body, R, [0, 1, 0], (0.25, 0, 0), -2.0, 2.0, capsule_mesh(0.05, 0.08, 0.40, nseg=16, ncap=4, nbody=6))
+    jt, jl, jb = [JOINT_FLOATING, JOINT_NORMAL], [body, arm], [-1, body]
+    if with_ball_wrist:
+        l = add(arm, R, [0, 0, 1], (0, 0, 0.47), -math.pi, math.pi, None)
+        l = add(l, R, [0, 1, 0], (0, 0, 0), -1.5, 1.5, None)
+        tool = add(l, R, [1, 0, 0], (0, 0, 0), -math.pi, math.pi, box_mesh([-0.03, -0.08, 0.02], [0.03, 0.08, 0.2], div=3))
+        jt.append(JOINT_BALLANDSOCKET); jl.append(tool); jb.append(arm)
+    return RobotSpec(parents=np.array(parents, dtype=np.int32), linktype=np.array(ltype, dtype=np.uint8),
+                     axis=np.array(axes, dtype=np.float64), T0=np.array(T0s), qmin=np.array(qmin), qmax=np.array(qmax),
+                     link_geom=geoms, joint_type=np.array(jt, dtype=np.uint8), joint_link=np.array(jl, dtype=np.int32),
+                     joint_base=np.array(jb, dtype=np.int32))
+
+
 # --------------------------------------------------------------------------------------- worlds
 def _ground(world: WorldSpec, half=2.0, div=8):
     v, t = box_mesh([-half, -half, -0.05], [half, half, 0.0], div=div)
@@ -331,6 +361,19 @@ def world_c2(seed_index: int = 2, n_obstacles: int = 200, fine_fraction: float =
         v, t = blob_mesh(rng, sub, r)
         w.objects.append((w.add_geom(GeomSpec.mesh(v, t)), make_T(_random_rotation(rng), c)))
     w.robot = make_arm6(w)
+    return w
+
+
+def world_floating(seed_index: int = 7, n_obstacles: int = 40) -> WorldSpec:
+    """Free-flying body + arm + ball-and-socket tool among blobs over the ground slab (exercises Floating /
+    BallAndSocket joints in the edge metric and interpolation)."""
+    rng = np.random.default_rng(BASE_SEED + seed_index)
+    w = WorldSpec()
+    _ground(w)
+    for c in _obstacle_centres(rng, n_obstacles, keepout=0.0):
+        v, t = blob_mesh(rng, 3, rng.uniform(0.05, 0.2))
+        w.objects.append((w.add_geom(GeomSpec.mesh(v, t)), make_T(_random_rotation(rng), c)))
+    w.robot = make_floating_body(w)
     return w
 
 

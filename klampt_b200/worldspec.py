@@ -88,6 +88,7 @@ class RobotSpec:
     link_geom: List[int]                     # geometry index per link, -1 = none
     joint_type: Optional[np.ndarray] = None  # (nj,) u8 ; default one Normal joint per link
     joint_link: Optional[np.ndarray] = None  # (nj,) i32
+    joint_base: Optional[np.ndarray] = None  # (nj,) i32 RobotModelJoint::baseIndex (-1 = world); default: the parent of joint_link
     drivers: List[DriverSpec] = field(default_factory=list)
     # edits applied after InitAllSelfCollisions (Cpp/Modeling/Robot.cpp:1274-1313): (i, j, enabled)
     self_collision_edits: List[Tuple[int, int, bool]] = field(default_factory=list)

@@ -98,7 +98,7 @@ struct ko_world {
   int* objects; xf_t* objT; int nobj;
   int L; int32_t* parents; uint8_t* linktype; double* axis; xf_t* T0; double* qmin; double* qmax;
   int* linkgeom;
-  int nj; uint8_t* jtype; int32_t* jlink;
+  int nj; uint8_t* jtype; int32_t* jlink; int32_t* jbase;
   driver_t* drivers; int ndrv;
   uint8_t* selfcol;     /* L*L upper triangular (i<j) */
   int selfcol_default;
@@ -319,7 +319,7 @@ void ko_destroy(ko_world* w) {
   for (int i=0;i<w->ngeoms;i++) geom_free(&w->geoms[i]);
   free(w->geoms); free(w->terrains); free(w->objects); free(w->objT);
   free(w->parents); free(w->linktype); free(w->axis); free(w->T0); free(w->qmin); free(w->qmax); free(w->linkgeom);
-  free(w->jtype); free(w->jlink);
+  free(w->jtype); free(w->jlink); free(w->jbase);
   for (int i=0;i<w->ndrv;i++) { free(w->drivers[i].links); free(w->drivers[i].scale); free(w->drivers[i].offset); }
   free(w->drivers); free(w->selfcol); free(w->mask);
   free(w);
@@ -366,17 +366,42 @@ int ko_robot_create(ko_world* w, int L, const int32_t* parents, const uint8_t* l
   w->qmax=(double*)malloc(sizeof(double)*L); memcpy(w->qmax,qmax,sizeof(double)*L);
   w->linkgeom=(int*)malloc(sizeof(int)*L); for (int i=0;i<L;i++) w->linkgeom[i]=-1;
   /* default joints: one Normal joint per link (Robot.cpp default when no "joint" lines) */
-  w->nj=L; w->jtype=(uint8_t*)malloc(L); w->jlink=(int32_t*)malloc(sizeof(int32_t)*L);
-  for (int i=0;i<L;i++) { w->jtype[i]=KO_JOINT_NORMAL; w->jlink[i]=i; }
+  w->nj=L; w->jtype=(uint8_t*)malloc(L); w->jlink=(int32_t*)malloc(sizeof(int32_t)*L); w->jbase=(int32_t*)malloc(sizeof(int32_t)*L);
+  for (int i=0;i<L;i++) { w->jtype[i]=KO_JOINT_NORMAL; w->jlink[i]=i; w->jbase[i]=parents[i]; }
   w->selfcol=(uint8_t*)calloc((size_t)L*L,1);
   for (int i=0;i<L;i++) if (parents[i]>=i) return -2;
   return 0;
 }
 int ko_robot_set_link_geometry(ko_world* w, int link, int geom) { if (link<0||link>=w->L) return -1; w->linkgeom[link]=geom; return 0; }
-int ko_robot_set_joints(ko_world* w, int nj, const uint8_t* jtype, const int32_t* jlink) {
-  free(w->jtype); free(w->jlink); w->nj=nj;
+/* links a joint drives: the chain from its base link (exclusive) down to its link (inclusive), in root-to-tip order
+ * (RobotModel::GetJointIndices, Cpp/Modeling/Robot.cpp:2120-2144).  Returns the count, or -1 if the chain never meets the base. */
+static int joint_indices(const ko_world* w, int j, int idx[6]) {
+  int t=w->jtype[j], n=0, tmp[8], link=w->jlink[j];
+  if (t==KO_JOINT_WELD||t==KO_JOINT_NORMAL||t==KO_JOINT_SPIN) { idx[0]=link; return 1; }
+  while (link!=w->jbase[j]) { if (link<0||n>=6) return -1; tmp[n++]=link; link=w->parents[link]; }
+  for (int i=0;i<n;i++) idx[i]=tmp[n-1-i];
+  return n;
+}
+int ko_robot_set_joints(ko_world* w, int nj, const uint8_t* jtype, const int32_t* jlink, const int32_t* jbase) {
+  free(w->jtype); free(w->jlink); free(w->jbase); w->nj=nj;
   w->jtype=(uint8_t*)malloc(nj>0?nj:1); memcpy(w->jtype,jtype,nj);
-  w->jlink=(int32_t*)malloc(sizeof(int32_t)*(nj>0?nj:1)); memcpy(w->jlink,jlink,sizeof(int32_t)*nj); return 0; }
+  w->jlink=(int32_t*)malloc(sizeof(int32_t)*(nj>0?nj:1)); memcpy(w->jlink,jlink,sizeof(int32_t)*nj);
+  w->jbase=(int32_t*)malloc(sizeof(int32_t)*(nj>0?nj:1));
+  for (int i=0;i<nj;i++) w->jbase[i]=jbase?jbase[i]:w->parents[jlink[i]];
+  /* the reference asserts the link layout of multi-link joints (Interpolate.cpp:24-26,231-236): translations first, then
+   * rotations about z, y, x */
+  for (int i=0;i<nj;i++) {
+    int idx[6], n=joint_indices(w,i,idx), t=jtype[i];
+    if (t==KO_JOINT_FLOATING) { if (n!=6) return -1;
+      for (int k=0;k<3;k++) if (w->linktype[idx[k]]!=KO_PRISMATIC || w->linktype[idx[3+k]]!=KO_REVOLUTE) return -1;
+      if (w->axis[3*idx[3]+2]!=1.0 || w->axis[3*idx[4]+1]!=1.0 || w->axis[3*idx[5]]!=1.0) return -1; }
+    else if (t==KO_JOINT_BALLANDSOCKET) { if (n!=3) return -1;
+      for (int k=0;k<3;k++) if (w->linktype[idx[k]]!=KO_REVOLUTE) return -1;
+      if (w->axis[3*idx[0]+2]!=1.0 || w->axis[3*idx[1]+1]!=1.0 || w->axis[3*idx[2]]!=1.0) return -1; }
+    else if (t==KO_JOINT_FLOATINGPLANAR) { if (n!=3 || w->linktype[idx[2]]!=KO_REVOLUTE) return -1; }
+    else if (t==KO_JOINT_CLOSED) return -1;
+  }
+  return 0; }
 int ko_robot_add_affine_driver(ko_world* w, int n, const int32_t* links, const double* scale, const double* offset, double dmin, double dmax) {
   w->drivers=(driver_t*)realloc(w->drivers,sizeof(driver_t)*(w->ndrv+1));
   driver_t* d=&w->drivers[w->ndrv++]; d->n=n; d->dmin=dmin; d->dmax=dmax;
@@ -761,26 +786,96 @@ void ko_feasible_batch(const ko_world* w, const double* Q, int64_t N, uint8_t* o
 static double angle_normalize(double a) { a=fmod(a,2*M_PI); if (a<0) a+=2*M_PI; return a; }
 static double angle_diff(double a, double b) { /* signed CCW difference a-b in (-pi,pi] */
   double d=a-b; if (d>M_PI) return d-2*M_PI; if (d<-M_PI) return d+2*M_PI; return d; }
-/* RobotCSpace::Distance -> Klampt::Distance, Interpolate.cpp:208-343, norm=2 (RobotCSpace.cpp:48).
- * Weld joints are skipped; Normal joints collect (a-b) (times weight).  Spin uses AngleDiff.
- * Floating / BallAndSocket bases are not part of this path's configs (C1-C5) and are rejected at build. */
+/* ---- SO(3) helpers for Floating / BallAndSocket joints.  KrisLibrary's EulerAngleRotation / interpolateRotation /
+ * AngleAxisRotation are absent; these restate their documented meaning: getMatrixZYX(a,b,c) = Rz(a) Ry(b) Rx(c) (the
+ * reference asserts the three links turn about z, y, x in that order, Interpolate.cpp:24-26), interpolateRotation = the
+ * SO(3) geodesic Rx exp(u log(Rx^T Ry)), AngleAxisRotation::angle = acos((tr - 1) / 2).  [unverified here: branch
+ * thresholds of the library's own log / Euler extraction near angle pi and gimbal lock] */
+static void euler_zyx_to_matrix(double a, double b, double c, double R[9]) {
+  double ca=cos(a), sa=sin(a), cb=cos(b), sb=sin(b), cc=cos(c), sc=sin(c);
+  R[0]=ca*cb; R[1]=ca*sb*sc-sa*cc; R[2]=ca*sb*cc+sa*sc;
+  R[3]=sa*cb; R[4]=sa*sb*sc+ca*cc; R[5]=sa*sb*cc-ca*sc;
+  R[6]=-sb;   R[7]=cb*sc;          R[8]=cb*cc;
+}
+static void matrix_to_euler_zyx(const double R[9], double* a, double* b, double* c) {
+  double sb=-R[6]; if (sb>1) sb=1; if (sb<-1) sb=-1;
+  *b=asin(sb);
+  if (fabs(R[6])<1.0-1e-12) { *a=atan2(R[3],R[0]); *c=atan2(R[7],R[8]); }
+  else { *c=0; *a=atan2(-R[1],R[4]); }          /* gimbal lock: put the whole turn into the z angle */
+}
+static void mat3_mul_tA(const double A[9], const double B[9], double C[9]) {   /* C = A^T B */
+  for (int i=0;i<3;i++) for (int j=0;j<3;j++) C[3*i+j]=A[i]*B[j]+A[3+i]*B[3+j]+A[6+i]*B[6+j]; }
+static void mat3_mul(const double A[9], const double B[9], double C[9]) {
+  for (int i=0;i<3;i++) for (int j=0;j<3;j++) C[3*i+j]=A[3*i]*B[j]+A[3*i+1]*B[3+j]+A[3*i+2]*B[6+j]; }
+static double so3_angle(const double R[9]) { double c=0.5*(R[0]+R[4]+R[8]-1.0); if (c>1) c=1; if (c<-1) c=-1; return acos(c); }
+static void so3_log(const double R[9], double w[3]) {
+  double th=so3_angle(R);
+  double v[3]={R[7]-R[5], R[2]-R[6], R[3]-R[1]};
+  if (th<1e-9) { for (int k=0;k<3;k++) w[k]=0.5*v[k]; return; }
+  if (M_PI-th<1e-6) {   /* near a half turn: axis from the diagonal of (R + I) / 2, sign from the skew part */
+    double ax[3]; for (int k=0;k<3;k++) { double d=0.5*(R[4*k]+1.0); ax[k]=d>0?sqrt(d):0; }
+    int m=0; for (int k=1;k<3;k++) if (ax[k]>ax[m]) m=k;
+    for (int k=0;k<3;k++) if (k!=m) { double s=R[3*m+k]+R[3*k+m]; if (s<0) ax[k]=-ax[k]; }
+    double sg=ax[0]*v[0]+ax[1]*v[1]+ax[2]*v[2]; if (sg<0) for (int k=0;k<3;k++) ax[k]=-ax[k];
+    double n=sqrt(ax[0]*ax[0]+ax[1]*ax[1]+ax[2]*ax[2]); for (int k=0;k<3;k++) w[k]=th*ax[k]/n; return; }
+  double f=th/(2.0*sin(th)); for (int k=0;k<3;k++) w[k]=f*v[k];
+}
+static void so3_exp(const double w[3], double R[9]) {   /* Rodrigues */
+  double th=sqrt(w[0]*w[0]+w[1]*w[1]+w[2]*w[2]);
+  if (th<1e-12) { R[0]=1; R[1]=-w[2]; R[2]=w[1]; R[3]=w[2]; R[4]=1; R[5]=-w[0]; R[6]=-w[1]; R[7]=w[0]; R[8]=1; return; }
+  double x=w[0]/th, y=w[1]/th, z=w[2]/th, c=cos(th), s=sin(th), v=1.0-c;
+  R[0]=c+v*x*x;   R[1]=v*x*y-s*z; R[2]=v*x*z+s*y;
+  R[3]=v*y*x+s*z; R[4]=c+v*y*y;   R[5]=v*y*z-s*x;
+  R[6]=v*z*x-s*y; R[7]=v*z*y+s*x; R[8]=c+v*z*z;
+}
+static double euler_zyx_angle_between(const double* ea, const double* eb) {   /* angle of Ra Rb^T */
+  double Ra[9], Rb[9], D[9]; euler_zyx_to_matrix(ea[0],ea[1],ea[2],Ra); euler_zyx_to_matrix(eb[0],eb[1],eb[2],Rb);
+  for (int i=0;i<3;i++) for (int j=0;j<3;j++) D[3*i+j]=Ra[3*i]*Rb[3*j]+Ra[3*i+1]*Rb[3*j+1]+Ra[3*i+2]*Rb[3*j+2];
+  return so3_angle(D); }
+static void euler_zyx_interp(const double* ea, const double* eb, double u, double* out) {
+  double Ra[9], Rb[9], D[9], w[3], E[9], Ru[9];
+  euler_zyx_to_matrix(ea[0],ea[1],ea[2],Ra); euler_zyx_to_matrix(eb[0],eb[1],eb[2],Rb);
+  mat3_mul_tA(Ra,Rb,D); so3_log(D,w); for (int k=0;k<3;k++) w[k]*=u; so3_exp(w,E); mat3_mul(Ra,E,Ru);
+  matrix_to_euler_zyx(Ru,&out[0],&out[1],&out[2]); }
+
+/* RobotCSpace::Distance -> Klampt::Distance, Interpolate.cpp:208-343, norm=2 (RobotCSpace.cpp:48), floatingRotationWeight=1
+ * (RobotCSpace.cpp:50).  Weld joints are skipped; Normal joints collect (a-b) (times weight); Spin uses AngleDiff; Floating
+ * collects the three translations and the geodesic angle; BallAndSocket the geodesic angle; FloatingPlanar contributes
+ * nothing (the weighted overload's default branch, :338-340; the unweighted one aborts on it, :270). */
 double ko_cspace_distance(const ko_world* w, const double* a, const double* b, const double* weights) {
   double s=0;
-  for (int i=0;i<w->nj;i++) { int k=w->jlink[i]; double wt=weights?weights[i]:1.0, d;
+  for (int i=0;i<w->nj;i++) { int k=w->jlink[i]; double wt=weights?weights[i]:1.0, d; int idx[6];
     switch (w->jtype[i]) {
       case KO_JOINT_WELD: continue;
       case KO_JOINT_NORMAL: d=a[k]-b[k]; break;
       case KO_JOINT_SPIN: d=angle_diff(angle_normalize(a[k]),angle_normalize(b[k])); break;
+      case KO_JOINT_FLOATING: { joint_indices(w,i,idx);
+        for (int t=0;t<3;t++) { double dt=a[idx[t]]-b[idx[t]]; s+=wt*dt*dt; }
+        double ea[3]={a[idx[3]],a[idx[4]],a[idx[5]]}, eb[3]={b[idx[3]],b[idx[4]],b[idx[5]]};
+        d=euler_zyx_angle_between(ea,eb); break; }
+      case KO_JOINT_BALLANDSOCKET: { joint_indices(w,i,idx);
+        double ea[3]={a[idx[0]],a[idx[1]],a[idx[2]]}, eb[3]={b[idx[0]],b[idx[1]],b[idx[2]]};
+        d=euler_zyx_angle_between(ea,eb); break; }
       default: continue; }
     s+=wt*d*d; }   /* NormAccumulator<Real>(2).collect(x,w): sum w*x^2, then sqrt */
   return sqrt(s);
 }
-/* Klampt::Interpolate, Interpolate.cpp:10-71: out = x*(1-u); out += y*u; Spin joints use the shortest arc */
+/* Klampt::Interpolate, Interpolate.cpp:10-71: out = x*(1-u); out += y*u; Spin and FloatingPlanar angles use the shortest arc;
+ * the Euler-ZYX triplet of Floating / BallAndSocket joints follows the SO(3) geodesic.  (The reference's BallAndSocket branch
+ * writes the result through indices[0], [2], [3] of a 3-element vector, :50 -- out of range; the intended [0], [1], [2] is used.) */
 void ko_interpolate(const ko_world* w, const double* a, const double* b, double u, double* out) {
   for (int k=0;k<w->L;k++) { out[k]=a[k]*(1.0-u); out[k]+=b[k]*u; }
-  for (int i=0;i<w->nj;i++) if (w->jtype[i]==KO_JOINT_SPIN) { int k=w->jlink[i];
-    double x=angle_normalize(a[k]), y=angle_normalize(b[k]); double d=angle_diff(y,x);
-    out[k]=angle_normalize(x+u*d); }
+  for (int i=0;i<w->nj;i++) { int t=w->jtype[i], idx[6];
+    if (t==KO_JOINT_SPIN || t==KO_JOINT_FLOATINGPLANAR) {
+      int k=w->jlink[i]; if (t==KO_JOINT_FLOATINGPLANAR) { joint_indices(w,i,idx); k=idx[2]; }
+      double x=angle_normalize(a[k]), y=angle_normalize(b[k]); double d=angle_diff(y,x);
+      out[k]=angle_normalize(x+u*d); }
+    else if (t==KO_JOINT_FLOATING || t==KO_JOINT_BALLANDSOCKET) {
+      joint_indices(w,i,idx); int o=t==KO_JOINT_FLOATING?3:0;
+      double ea[3]={a[idx[o]],a[idx[o+1]],a[idx[o+2]]}, eb[3]={b[idx[o]],b[idx[o+1]],b[idx[o+2]]}, eu[3];
+      euler_zyx_interp(ea,eb,u,eu);
+      out[idx[o]]=eu[0]; out[idx[o+1]]=eu[1]; out[idx[o+2]]=eu[2]; }
+  }
 }
 /* EpsilonEdgeChecker::IsVisible: bisect until segment length <= eps, midpoints in
  * coarse-to-fine order, endpoints not re-checked, false at the first infeasible midpoint. */

@@ -58,7 +58,8 @@ int ko_add_rigid_object(ko_world* w, int geom, const double T[12]);
 int ko_robot_create(ko_world* w, int L, const int32_t* parents, const uint8_t* linktype,
                     const double* axis, const double* T0, const double* qmin, const double* qmax);
 int ko_robot_set_link_geometry(ko_world* w, int link, int geom);
-int ko_robot_set_joints(ko_world* w, int nj, const uint8_t* jtype, const int32_t* jlink);
+/* jbase: per joint the link the joint hangs from (-1 = world; RobotModelJoint::baseIndex); NULL = the parent of jlink */
+int ko_robot_set_joints(ko_world* w, int nj, const uint8_t* jtype, const int32_t* jlink, const int32_t* jbase);
 int ko_robot_add_affine_driver(ko_world* w, int n, const int32_t* links, const double* scale,
                                const double* offset, double dmin, double dmax);
 int ko_robot_set_self_collision(ko_world* w, int i, int j, int enabled);

@@ -50,7 +50,7 @@ def lib():
     L.ko_add_rigid_object.argtypes = [vp, C.c_int, dp]
     L.ko_robot_create.argtypes = [vp, C.c_int, ip, u8p, dp, dp, dp, dp]
     L.ko_robot_set_link_geometry.argtypes = [vp, C.c_int, C.c_int]
-    L.ko_robot_set_joints.argtypes = [vp, C.c_int, u8p, ip]
+    L.ko_robot_set_joints.argtypes = [vp, C.c_int, u8p, ip, ip]
     L.ko_robot_add_affine_driver.argtypes = [vp, C.c_int, ip, dp, dp, C.c_double, C.c_double]
     L.ko_robot_set_self_collision.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.ko_set_pair_mask.argtypes = [vp, u8p, C.c_int]
@@ -176,7 +176,11 @@ class OracleWorld:
             if r.joint_type is not None:
                 jt, jtp = _u8(r.joint_type)
                 jl, jlp = _i(r.joint_link)
-                L.ko_robot_set_joints(self.h, len(jt), jtp, jlp)
+                jbp = None
+                if getattr(r, "joint_base", None) is not None:
+                    jb, jbp = _i(r.joint_base)
+                if L.ko_robot_set_joints(self.h, len(jt), jtp, jlp, jbp) != 0:
+                    raise ValueError("ko_robot_set_joints: a Floating / FloatingPlanar / BallAndSocket joint does not drive the link chain the reference asserts")
             for d in r.drivers:
                 li, lip = _i(d.links)
                 sc, scp = _d(d.scale)

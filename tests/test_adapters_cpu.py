@@ -100,3 +100,20 @@ def test_shard_arithmetic():
             assert sorted(idx) == list(range(n))
     with pytest.raises(ValueError):
         shard_range(10, 3, 2)
+
+
+def test_robot_model_metric_and_interpolation_match_the_oracle_for_multi_link_joints():
+    """RobotModel.interpolate / distance (the host-side scalar forms of Klampt::Interpolate / Distance,
+    Cpp/Modeling/Interpolate.cpp:10-71,208-343) agree with the oracle for Floating and BallAndSocket joints."""
+    spec = synth.world_floating()
+    world = WorldModel.from_spec(spec)
+    r = world.robot(0)
+    orc = OracleWorld(spec)
+    Q = synth.sample_configs(spec.robot, 80, 9)
+    rng = np.random.default_rng(2)
+    for i in range(40):
+        a, b, u = Q[2 * i], Q[2 * i + 1], rng.uniform()
+        assert abs(r.distance(a, b) - orc.cspace_distance(a, b)) < 1e-9
+        np.testing.assert_allclose(r.interpolate(a, b, u), orc.interpolate(a, b, u), atol=1e-9)
+    back = world.to_spec()
+    assert np.array_equal(back.robot.joint_base, spec.robot.joint_base)

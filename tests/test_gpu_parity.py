@@ -412,3 +412,33 @@ def test_clearance_grid_option_changes_nothing(c1, c2small):
         assert st["items_dropped"] > 0
         want = orc.feasible_batch(Q)
         assert_bool_parity(on, want, Q, orc)
+
+
+def test_edges_floating_base_and_ball_joint(built):
+    """Floating / BallAndSocket joints in the edge metric and interpolation (reference
+    Cpp/Modeling/Interpolate.cpp:16-52,229-278): same visibility and the same sequential check counts as the oracle."""
+    from klampt_b200.engine import Engine
+    from oracle.oracle import OracleWorld
+    w = synth.world_floating()
+    eng, orc = Engine(w), OracleWorld(w)
+    Q = synth.sample_configs(w.robot, 4000, 31)
+    assert_bool_parity(eng.feasible_batch(Q), orc.feasible_batch(Q), Q, orc)
+    A, B = synth.sample_edges(w.robot, lambda Q: orc.feasible_batch(Q), 600, 32, rmin=0.1, rmax=1.5)
+    vis, nchk = eng.edges_visible_batch(A, B, eps=0.02)
+    ovis, onchk = orc.edges_visible_batch(A, B, eps=0.02)
+    # midpoints agree to ~1e-15 (device vs host libm), so a disagreement needs a midpoint inside the margin band
+    assert (vis != ovis).sum() <= 1 and (nchk != onchk).sum() <= 1
+    assert 0.02 < vis.mean() < 0.98
+    wts = np.array([2.0, 0.5, 1.5])
+    vis, nchk = eng.edges_visible_batch(A[:200], B[:200], eps=0.05, weights=wts)
+    ovis, onchk = orc.edges_visible_batch(A[:200], B[:200], eps=0.05, weights=wts)
+    assert (vis != ovis).sum() <= 1 and (nchk != onchk).sum() <= 1
+
+
+def test_multi_link_joint_layout_is_validated_by_the_engine(built):
+    from klampt_b200.engine import Engine
+    from klampt_b200._capi import KbError
+    w = synth.world_floating()
+    w.robot.joint_base = None
+    with pytest.raises(KbError):
+        Engine(w)

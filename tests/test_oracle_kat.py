@@ -401,3 +401,41 @@ def test_robot_distance_with_margins_is_the_exact_minimum():
         T = o.fk(Q[i])
         best = min(o.geom_distance_brute(g, T[j], cloud, I12) for j, g in enumerate(w.robot.link_geom) if j > 0)
         assert d[i] == pytest.approx(best, abs=1e-13)
+
+
+def test_metric_and_interpolation_floating_and_ball_joints():
+    """Floating / BallAndSocket joints (reference Cpp/Modeling/Interpolate.cpp:16-52,229-278): Euler ZYX triplets are
+    compared by geodesic angle and interpolated along the SO(3) geodesic.  Second method: scipy Rotation / Slerp."""
+    from scipy.spatial.transform import Rotation as Rot, Slerp
+    w = synth.world_floating()
+    o = OracleWorld(w)
+    Q = synth.sample_configs(w.robot, 120, 3)
+    rng = np.random.default_rng(0)
+    T = o.fk_batch(Q[:8])
+    for i in range(8):     # the three revolute links of the floating joint compose to Rz(a) Ry(b) Rx(c)
+        np.testing.assert_allclose(T[i, 5, :9].reshape(3, 3), Rot.from_euler("ZYX", Q[i, 3:6]).as_matrix(), atol=1e-14)
+    for i in range(60):
+        a, b = Q[2 * i], Q[2 * i + 1]
+        Ra, Rb = Rot.from_euler("ZYX", a[3:6]), Rot.from_euler("ZYX", b[3:6])
+        Wa, Wb = Rot.from_euler("ZYX", a[7:10]), Rot.from_euler("ZYX", b[7:10])
+        want = math.sqrt(((a[:3] - b[:3]) ** 2).sum() + (Ra * Rb.inv()).magnitude() ** 2 + (a[6] - b[6]) ** 2 + (Wa * Wb.inv()).magnitude() ** 2)
+        assert abs(o.cspace_distance(a, b) - want) < 1e-9
+        u = rng.uniform()
+        m = o.interpolate(a, b, u)
+        Rm, Wm = Slerp([0, 1], Rot.concatenate([Ra, Rb]))(u), Slerp([0, 1], Rot.concatenate([Wa, Wb]))(u)
+        assert (Rot.from_euler("ZYX", m[3:6]) * Rm.inv()).magnitude() < 1e-7
+        assert (Rot.from_euler("ZYX", m[7:10]) * Wm.inv()).magnitude() < 1e-7
+        np.testing.assert_allclose(m[:3], a[:3] * (1 - u) + b[:3] * u, atol=1e-14)
+        assert abs(m[6] - (a[6] * (1 - u) + b[6] * u)) < 1e-14
+    # end points are reproduced as rotations, and a half-turn apart pair still interpolates on the geodesic
+    a = np.zeros(10); b = np.zeros(10); b[3] = math.pi - 1e-9
+    m = o.interpolate(a, b, 0.5)
+    assert abs(abs(m[3]) - math.pi / 2) < 1e-6 and abs(m[4]) < 1e-6 and abs(m[5]) < 1e-6
+
+
+def test_multi_link_joint_layout_is_validated():
+    """The reference asserts the link layout of Floating / BallAndSocket joints (Interpolate.cpp:24-26,231-236)."""
+    w = synth.world_floating()
+    w.robot.joint_base = np.array([0, 5, 6], dtype=np.int32)      # floating joint would drive only 5 links
+    with pytest.raises(ValueError):
+        OracleWorld(w)
