@@ -34,76 +34,99 @@ __device__ __forceinline__ void xf_mul(const Xf64& A, const Xf64& B, Xf64& C) {
   }
 }
 
-__global__ void __launch_bounds__(128)
+#define KB_FK_THREADS 128
+__global__ void __launch_bounds__(KB_FK_THREADS)
 kb_fk_kernel(const KbRobotDev* __restrict__ robot, const KbDriverDev* __restrict__ drv, const int32_t* __restrict__ drv_link,
              const double* __restrict__ drv_scale, const double* __restrict__ drv_off,
              const double* __restrict__ Q, int64_t N, double* __restrict__ xf64, int nxf,
              uint8_t* __restrict__ state, const uint8_t* __restrict__ alive, int32_t* __restrict__ hit) {
   __shared__ KbRobotDev R;
+  // per warp a staging tile of 32 configurations x 12 doubles (row stride 13: conflict-free): the transform of one link leaves
+  // as 96-byte runs (three full sectors per configuration) instead of 32 partial sectors per store instruction
+  __shared__ double stage_all[KB_FK_THREADS / 32][32 * 13];
   {
     const int* src = (const int*)robot; int* dst = (int*)&R;
     for (int i = threadIdx.x; i < (int)(sizeof(KbRobotDev) / 4); i += blockDim.x) dst[i] = src[i];
   }
   __syncthreads();
-  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= N) return;
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t c_warp = c - lane;
+  if (c_warp >= N) return;
+  double* stage = stage_all[threadIdx.x >> 5];
   const int L = R.L;
-  const double* q = Q + c * L;
-  if (hit) hit[c] = -1;
-  if (alive && !alive[c]) { if (state) state[c] = 0; return; }
-  // K2: joint limits (closed interval, Normal / Weld joints only) and driver limits
-  bool ok = true;
-  for (int j = 0; j < R.nj; j++) {
-    int t = R.jtype[j];
-    if (t == 1 || t == 0) { int k = R.jlink[j]; double v = q[k]; if (v < R.qmin[k] || v > R.qmax[k]) ok = false; }
+  const double* q = Q + (c < N ? c : 0) * L;
+  bool want_xf = false;
+  if (c < N) {
+    if (hit) hit[c] = -1;
+    if (alive && !alive[c]) { if (state) state[c] = 0; }
+    else {
+      // K2: joint limits (closed interval, Normal / Weld joints only) and driver limits
+      bool ok = true;
+      for (int j = 0; j < R.nj; j++) {
+        int t = R.jtype[j];
+        if (t == 1 || t == 0) { int k = R.jlink[j]; double v = q[k]; if (v < R.qmin[k] || v > R.qmax[k]) ok = false; }
+      }
+      for (int d = 0; d < R.ndrv; d++) {
+        ExactD v(0.0);
+        for (int k = drv[d].first; k < drv[d].first + drv[d].n; k++) v = v + (ExactD(q[drv_link[k]]) - ExactD(drv_off[k])) / ExactD(drv_scale[k]);
+        v = v / ExactD((double)drv[d].n);
+        if (v.v < drv[d].dmin || v.v > drv[d].dmax) ok = false;
+      }
+      if (state) state[c] = ok ? 1 : 0;
+      want_xf = ok || !state;          // infeasible by limits: the traversal skips it, no transforms needed
+    }
   }
-  for (int d = 0; d < R.ndrv; d++) {
-    ExactD v(0.0);
-    for (int k = drv[d].first; k < drv[d].first + drv[d].n; k++) v = v + (ExactD(q[drv_link[k]]) - ExactD(drv_off[k])) / ExactD(drv_scale[k]);
-    v = v / ExactD((double)drv[d].n);
-    if (v.v < drv[d].dmin || v.v > drv[d].dmax) ok = false;
-  }
-  if (state) state[c] = ok ? 1 : 0;
-  if (!ok && state) return;          // infeasible by limits: the traversal skips it, no transforms needed
+  const unsigned wm = __ballot_sync(FULL, want_xf);
+  if (!wm) return;
   // K1: T_World[i] = T_World[parent] * (T0_Parent[i] * T_loc(q_i))
-  double* out = xf64 + c * (int64_t)nxf * 12;
+  double* out = xf64 + (c < N ? c : 0) * (int64_t)nxf * 12;
+  double* out_warp = xf64 + c_warp * (int64_t)nxf * 12;
   Xf64 prev;                          // transform of link i-1 stays in registers (chains)
   for (int i = 0; i < L; i++) {
-    Xf64 T0, loc, rel, W;
+    if (want_xf) {
+      Xf64 T0, loc, rel, W;
 #pragma unroll
-    for (int k = 0; k < 9; k++) T0.r[k] = ExactD(R.T0[12 * i + k]);
+      for (int k = 0; k < 9; k++) T0.r[k] = ExactD(R.T0[12 * i + k]);
 #pragma unroll
-    for (int k = 0; k < 3; k++) T0.t[k] = ExactD(R.T0[12 * i + 9 + k]);
-    ExactD wx(R.axis[3 * i]), wy(R.axis[3 * i + 1]), wz(R.axis[3 * i + 2]), qi(q[i]);
-    if (R.linktype[i] == 1) {
-      loc.r[0] = loc.r[4] = loc.r[8] = ExactD(1.0);
-      loc.r[1] = loc.r[2] = loc.r[3] = loc.r[5] = loc.r[6] = loc.r[7] = ExactD(0.0);
-      loc.t[0] = qi * wx; loc.t[1] = qi * wy; loc.t[2] = qi * wz;
-    } else {
-      double sn, cs; sincos(qi.v, &sn, &cs);
-      ExactD s(sn), co(cs), v = ExactD(1.0) - co;
-      loc.r[0] = co + v * wx * wx;      loc.r[1] = v * wx * wy - s * wz; loc.r[2] = v * wx * wz + s * wy;
-      loc.r[3] = v * wy * wx + s * wz;  loc.r[4] = co + v * wy * wy;     loc.r[5] = v * wy * wz - s * wx;
-      loc.r[6] = v * wz * wx - s * wy;  loc.r[7] = v * wz * wy + s * wx; loc.r[8] = co + v * wz * wz;
-      loc.t[0] = loc.t[1] = loc.t[2] = ExactD(0.0);
+      for (int k = 0; k < 3; k++) T0.t[k] = ExactD(R.T0[12 * i + 9 + k]);
+      ExactD wx(R.axis[3 * i]), wy(R.axis[3 * i + 1]), wz(R.axis[3 * i + 2]), qi(q[i]);
+      if (R.linktype[i] == 1) {
+        loc.r[0] = loc.r[4] = loc.r[8] = ExactD(1.0);
+        loc.r[1] = loc.r[2] = loc.r[3] = loc.r[5] = loc.r[6] = loc.r[7] = ExactD(0.0);
+        loc.t[0] = qi * wx; loc.t[1] = qi * wy; loc.t[2] = qi * wz;
+      } else {
+        double sn, cs; sincos(qi.v, &sn, &cs);
+        ExactD s(sn), co(cs), v = ExactD(1.0) - co;
+        loc.r[0] = co + v * wx * wx;      loc.r[1] = v * wx * wy - s * wz; loc.r[2] = v * wx * wz + s * wy;
+        loc.r[3] = v * wy * wx + s * wz;  loc.r[4] = co + v * wy * wy;     loc.r[5] = v * wy * wz - s * wx;
+        loc.r[6] = v * wz * wx - s * wy;  loc.r[7] = v * wz * wy + s * wx; loc.r[8] = co + v * wz * wz;
+        loc.t[0] = loc.t[1] = loc.t[2] = ExactD(0.0);
+      }
+      xf_mul(T0, loc, rel);
+      int par = R.parents[i];
+      if (par < 0) W = rel;
+      else if (par == i - 1) xf_mul(prev, rel, W);
+      else {                            // branch: the parent's transform was written by this warp earlier in the loop
+        Xf64 P;
+#pragma unroll
+        for (int k = 0; k < 9; k++) P.r[k] = ExactD(__ldcg(out + 12 * par + k));
+#pragma unroll
+        for (int k = 0; k < 3; k++) P.t[k] = ExactD(__ldcg(out + 12 * par + 9 + k));
+        xf_mul(P, rel, W);
+      }
+#pragma unroll
+      for (int k = 0; k < 9; k++) stage[lane * 13 + k] = W.r[k].v;
+#pragma unroll
+      for (int k = 0; k < 3; k++) stage[lane * 13 + 9 + k] = W.t[k].v;
+      prev = W;
     }
-    xf_mul(T0, loc, rel);
-    int par = R.parents[i];
-    if (par < 0) W = rel;
-    else if (par == i - 1) xf_mul(prev, rel, W);
-    else {
-      Xf64 P;
-#pragma unroll
-      for (int k = 0; k < 9; k++) P.r[k] = ExactD(out[12 * par + k]);
-#pragma unroll
-      for (int k = 0; k < 3; k++) P.t[k] = ExactD(out[12 * par + 9 + k]);
-      xf_mul(P, rel, W);
+    __syncwarp();
+    for (int idx = lane; idx < 32 * 12; idx += 32) {
+      const int r = idx / 12, k2 = idx - 12 * r;
+      if ((wm >> r) & 1u) out_warp[(size_t)r * nxf * 12 + 12 * i + k2] = stage[r * 13 + k2];
     }
-#pragma unroll
-    for (int k = 0; k < 9; k++) out[12 * i + k] = W.r[k].v;
-#pragma unroll
-    for (int k = 0; k < 3; k++) out[12 * i + 9 + k] = W.t[k].v;
-    prev = W;
+    __syncwarp();
   }
 }
 
@@ -1538,7 +1561,7 @@ cudaError_t kb_launch_fk(const KbRobotDev* robot, const KbDriverDev* drv, const 
                          const double* drv_off, const double* Q, int64_t N, double* xf64, int nxf, uint8_t* state,
                          const uint8_t* alive, int32_t* hit, cudaStream_t s) {
   if (N <= 0) return cudaSuccess;
-  kb_fk_kernel<<<nblocks(N, 128), 128, 0, s>>>(robot, drv, drv_link, drv_scale, drv_off, Q, N, xf64, nxf, state, alive, hit);
+  kb_fk_kernel<<<nblocks(N, KB_FK_THREADS), KB_FK_THREADS, 0, s>>>(robot, drv, drv_link, drv_scale, drv_off, Q, N, xf64, nxf, state, alive, hit);
   return cudaGetLastError();
 }
 
