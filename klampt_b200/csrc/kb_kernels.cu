@@ -680,6 +680,38 @@ kb_traverse_kernel(const KbTraverseParams p) {
         if (act) e = stack[sp_l - 1 - lane_l];
         sp_l -= m;
         __syncwarp();
+#if KB_BOTH_MODE == 1 && !defined(KB_BRANCHY_NODE_TEST)
+        // Branch-free form: inactive lanes test entry (item 0, root, root) and discard the result, and the child entries are
+        // selected arithmetically -- no divergent regions inside the loop body.
+        const int item = (int)(e.x >> KB_NODEA_BITS);
+        int nodeA, nodeB; float infl; XfF T;
+        if (ITC) { const ItemS si = s_items[item]; nodeA = si.nodeA; nodeB = si.nodeB; infl = si.infl; load_itc(itc_l, item, T); }
+        else { const KbItem* itp = p.items + item; nodeA = itp->nodeA; nodeB = itp->nodeB; infl = (float)itp->thr + slack; rel_xf(xfw, itp->xfA, itp->xfB, T); }
+        float4 a0, a1, b0, b1;
+        load_node(sc.nodes, (size_t)(nodeA + (int)(e.x & (KB_MAX_NODES_A - 1))), a0, a1);
+        load_node(sc.nodes, (size_t)(nodeB + (int)e.y), b0, b1);
+        const bool ov = act & sat6_overlap(a0, a1, b0, b1, T, infl);
+        if (STATS) st_node += act;
+        if (STATS) st_iter += (lane_l == 0);
+        const int la = __float_as_int(a0.w), lb = __float_as_int(b0.w);
+        const bool leafpair = ov & ((la & lb) < 0);
+        const bool inner = ov & ((la & lb) >= 0);
+        const float sa2 = a1.x * a1.x + a1.y * a1.y + a1.z * a1.z, sb2 = b1.x * b1.x + b1.y * b1.y + b1.z * b1.z;
+        const bool both = inner & ((la | lb) >= 0) & (sa2 < KB_BOTH_RATIO * sb2) & (sb2 < KB_BOTH_RATIO * sa2);
+        const bool splitA = (lb < 0) | ((la >= 0) & (sa2 >= sb2));          // only meaningful when inner && !both
+        const bool useA = both | splitA, useB = both | !splitA;
+        const unsigned ax = useA ? ((e.x & ~(unsigned)(KB_MAX_NODES_A - 1)) | (unsigned)la) : e.x;
+        const unsigned by = useB ? (unsigned)lb : e.y;
+        const unsigned pm = __ballot_sync(FULL, inner), lm = __ballot_sync(FULL, leafpair), pm4 = __ballot_sync(FULL, both);
+        if (inner) {
+          const int off = sp_l + 2 * __popc(pm & lt_mask) + 2 * __popc(pm4 & lt_mask);
+          stack[off] = useA ? make_uint2(ax + 1u, by) : make_uint2(ax, by + 1u);
+          stack[off + 1] = make_uint2(ax, by);
+          if (both) { stack[off + 2] = make_uint2(ax + 1u, by + 1u); stack[off + 3] = make_uint2(ax, by + 1u); }
+        }
+        if (leafpair) leafq[nleaf_l + __popc(lm & lt_mask)] = e;
+        sp_l += 2 * __popc(pm) + 2 * __popc(pm4); nleaf_l += __popc(lm);
+#else
         bool push2 = false, push4 = false, leafpair = false;
         uint2 c0e = e, c1e = e;
         if (act) {
@@ -700,6 +732,7 @@ kb_traverse_kernel(const KbTraverseParams p) {
         if (push2) { int off = sp_l + 2 * __popc(pm & lt_mask); stack[off] = c1e; stack[off + 1] = c0e; }
         if (leafpair) leafq[nleaf_l + __popc(lm & lt_mask)] = e;
         sp_l += 2 * __popc(pm); nleaf_l += __popc(lm);
+#endif
 #endif
         __syncwarp();
         } while (sp_l > 0 && nleaf_l < KB_LEAF_TRIGGER && !(sp_l < 32 && more_items));
