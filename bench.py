@@ -102,21 +102,26 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def count(self, t0, t1=None):
+        """samples read inside the window [t0, t1] (host clock at the time the line arrived)"""
+        t1 = time.perf_counter() if t1 is None else t1
+        return sum(1 for t, r in self.rows if t0 <= t <= t1 and len(r) >= 8)
+
+    def stop(self, window=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        rows = [r for t, r in self.rows if len(r) >= 8 and (window is None or window[0] <= t <= window[1])]
+        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[k] for r in self.rows if len(r) >= 8 for k in range(4) if r[4 + k].lower().startswith("active")})
+        reasons = sorted({names[k] for r in rows for k in range(4) if r[4 + k].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
@@ -278,6 +283,7 @@ def main():
 
     # ---- device-resident throughput (value) with per-launch kernel timing for the roofline
     sampler = ClockSampler(local_rank)
+    sampler.start()                      # nvidia-smi needs a few hundred ms before its first line: start it ahead of the warm-up
     eng.reset_stats()
     eng.set_option("time_kernels", 1)
     # warm-up first so the timed region's statistics are clean
@@ -286,11 +292,21 @@ def main():
             step_device(k)
     barrier()
     eng.reset_stats()
-    sampler.start()
+    t_clk0 = time.perf_counter()
     ms_dev = timed(step_device, args.steps, 0)
-    clocks = sampler.stop()
     st = eng.stats()
     eng.set_option("time_kernels", 0)
+    # The timed region is a few tens of ms, shorter than nvidia-smi's sampling period: keep the same load running (untimed,
+    # not counted) until at least three clock samples were taken under it.
+    extra = 0
+    with torch.cuda.stream(stream):
+        while sampler.count(t_clk0) < 3 and time.perf_counter() - t_clk0 < 2.0:
+            step_device(extra); extra += 1
+            if extra % 4 == 0:
+                torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    clocks = sampler.stop(window=(t_clk0, time.perf_counter()))
+    clocks["window"] = "timed region + %d untimed trailing steps of the same load" % extra
     value = world * M * args.steps / (ms_dev * 1e-3)
     feas_frac = (st["configs_feasible"] / max(1, st["configs_checked"])) if not edges else (st["edges_visible"] / max(1, st["edges_checked"]))
     launches = st["kernel_launches"]
