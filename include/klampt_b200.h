@@ -39,7 +39,7 @@ enum { KB_REVOLUTE = 0, KB_PRISMATIC = 1 };
 enum { KB_JOINT_WELD = 0, KB_JOINT_NORMAL = 1, KB_JOINT_SPIN = 2, KB_JOINT_FLOATING = 3,
        KB_JOINT_FLOATINGPLANAR = 4, KB_JOINT_BALLANDSOCKET = 5, KB_JOINT_CLOSED = 6 };
 /* geometric primitives supported so far (subset of GeometricPrimitive3D, Cpp/docs/Manual-Geometry.md:22) */
-enum { KB_PRIM_POINT = 0, KB_PRIM_SPHERE = 1 };
+enum { KB_PRIM_POINT = 0, KB_PRIM_SPHERE = 1, KB_PRIM_TRIANGLE = 2 };   /* triangle: params = 9 doubles a,b,c */
 
 enum { KB_OK = 0, KB_ERR_INVALID = -1, KB_ERR_STATE = -2, KB_ERR_CUDA = -3, KB_ERR_UNSUPPORTED = -4,
        KB_ERR_NOMEM = -5 };

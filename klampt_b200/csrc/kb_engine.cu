@@ -695,7 +695,13 @@ int kb_add_pointcloud(kb_engine* e, const double* pts, int n, const double* radi
 
 int kb_add_primitive(kb_engine* e, int type, const double* params, double margin) {
   if (!e || e->finalized) return fail(KB_ERR_STATE, "engine is null or already finalized");
-  if (type != KB_PRIM_POINT && type != KB_PRIM_SPHERE) return fail(KB_ERR_UNSUPPORTED, "primitive type %d is not supported (point and sphere are)", type);
+  if (margin < 0 || !params) return fail(KB_ERR_INVALID, "negative margin or null parameters");
+  if (type == KB_PRIM_TRIANGLE) {       // a triangle primitive is a one-triangle mesh for every query of this path
+    Geom g; g.kind = G_MESH; g.margin = margin; g.tri.assign(params, params + 9);
+    e->geoms.push_back(std::move(g));
+    return (int)e->geoms.size() - 1;
+  }
+  if (type != KB_PRIM_POINT && type != KB_PRIM_SPHERE) return fail(KB_ERR_UNSUPPORTED, "primitive type %d is not supported (point, sphere and triangle are)", type);
   Geom g; g.kind = G_PRIM; g.margin = margin; g.sph = {params[0], params[1], params[2], type == KB_PRIM_SPHERE ? params[3] : 0.0};
   e->geoms.push_back(std::move(g));
   return (int)e->geoms.size() - 1;

@@ -47,6 +47,9 @@ class GeometricPrimitive:
     def setSphere(self, c, r):
         self.type, self.properties = "Sphere", [float(x) for x in c] + [float(r)]
 
+    def setTriangle(self, a, b, c):
+        self.type, self.properties = "Triangle", [float(x) for x in a] + [float(x) for x in b] + [float(x) for x in c]
+
 
 class DistanceQuerySettings:
     def __init__(self):
@@ -107,8 +110,8 @@ class Geometry3D:
         self._kind, self._data, self._version = "cloud", pc, self._version + 1
 
     def setGeometricPrimitive(self, p: GeometricPrimitive):
-        if p.type not in ("Point", "Sphere"):
-            raise ValueError("GeometricPrimitive type %r is not supported by the batched engine (Point and Sphere are)" % p.type)
+        if p.type not in ("Point", "Sphere", "Triangle"):
+            raise ValueError("GeometricPrimitive type %r is not supported by the batched engine (Point, Sphere and Triangle are)" % p.type)
         self._kind, self._data, self._version = "prim", p, self._version + 1
 
     def getTriangleMesh(self) -> TriangleMesh:
@@ -151,6 +154,8 @@ class Geometry3D:
             return GeomSpec.cloud(self._data.points, self._data.radius, self._margin)
         if self._kind == "prim":
             p = self._data
+            if p.type == "Triangle":
+                return GeomSpec.triangle(p.properties[:3], p.properties[3:6], p.properties[6:9], self._margin)
             return GeomSpec.point(p.properties[:3], self._margin) if p.type == "Point" else GeomSpec.sphere(p.properties[:3], p.properties[3], self._margin)
         return GeomSpec("empty")
 
@@ -160,7 +165,8 @@ class Geometry3D:
         if self._kind == "cloud":
             return self._data.points
         if self._kind == "prim":
-            return np.asarray(self._data.properties[:3], dtype=np.float64).reshape(1, 3)
+            n = 9 if self._data.type == "Triangle" else 3
+            return np.asarray(self._data.properties[:n], dtype=np.float64).reshape(-1, 3)
         return np.zeros((0, 3))
 
     def getBB(self):
@@ -227,12 +233,36 @@ class Geometry3D:
     def distance(self, other: "Geometry3D") -> DistanceQueryResult:
         return self.distance_ext(other, DistanceQuerySettings())
 
+    def distance_point(self, pt) -> DistanceQueryResult:
+        """Geometry3D.distance_point (reference Python/klampt/src/geometry.h:1011-1030): distance from this geometry, at its
+        current transform, to a world-space point (margins subtracted)."""
+        return self.distance_point_ext(pt, DistanceQuerySettings())
+
+    def distance_point_ext(self, pt, settings: DistanceQuerySettings) -> DistanceQueryResult:
+        return DistanceQueryResult(float(self.distance_points_batch([pt], settings.upperBound)[0]))
+
+    def distance_points_batch(self, pts, upper_bound: float = float("inf")) -> np.ndarray:
+        """distance_point for N world-space points in one launch: a point primitive at N translations"""
+        if self.empty():
+            raise RuntimeError("Distance queries not implemented yet for those types of geometry, or geometries are content-empty?")
+        pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+        probe = _POINT_PROBE
+        eng, ga, gb = self._pair_engine(probe)
+        Ta = np.tile(self._T12(), (len(pts), 1))
+        Tb = np.tile(IDENTITY12, (len(pts), 1))
+        Tb[:, 9:12] = pts
+        return eng.geom_distance_batch(ga, Ta, gb, Tb, upper_bound=upper_bound)
+
     def distance_ext(self, other: "Geometry3D", settings: DistanceQuerySettings) -> DistanceQueryResult:
         if self.empty() or other.empty():
             raise RuntimeError("Distance queries not implemented yet for those types of geometry, or geometries are content-empty?")
         eng, ga, gb = self._pair_engine(other)
         d = float(eng.geom_distance_batch(ga, self._T12(), gb, other._T12(), upper_bound=settings.upperBound)[0])
         return DistanceQueryResult(d)
+
+
+_POINT_PROBE = Geometry3D()
+_POINT_PROBE.setGeometricPrimitive(GeometricPrimitive("Point", [0.0, 0.0, 0.0]))
 
 
 class _Named:
@@ -344,8 +374,8 @@ class RobotModel(_Named):
                     self._links[i]._geom.setTriangleMesh(TriangleMesh(g.verts, g.tris))
                 elif g.kind == "cloud":
                     self._links[i]._geom.setPointCloud(PointCloud(g.points, g.radius))
-                elif g.kind in ("sphere", "point"):
-                    self._links[i]._geom.setGeometricPrimitive(GeometricPrimitive("Sphere" if g.kind == "sphere" else "Point", list(g.params)))
+                elif g.kind in ("sphere", "point", "triangle"):
+                    self._links[i]._geom.setGeometricPrimitive(GeometricPrimitive({"sphere": "Sphere", "point": "Point", "triangle": "Triangle"}[g.kind], list(g.params)))
                 self._links[i]._geom._margin = g.margin
         self._q = np.clip(np.zeros(L), self._qmin, self._qmax)
         self._selfcol = None
@@ -612,5 +642,5 @@ def _fill(geom: Geometry3D, g: Optional[GeomSpec]):
     elif g.kind == "cloud":
         geom.setPointCloud(PointCloud(g.points, g.radius))
     else:
-        geom.setGeometricPrimitive(GeometricPrimitive("Sphere" if g.kind == "sphere" else "Point", list(g.params)))
+        geom.setGeometricPrimitive(GeometricPrimitive({"sphere": "Sphere", "point": "Point", "triangle": "Triangle"}[g.kind], list(g.params)))
     geom._margin = g.margin

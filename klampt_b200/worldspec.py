@@ -23,7 +23,7 @@ import numpy as np
 
 REVOLUTE, PRISMATIC = 0, 1
 JOINT_WELD, JOINT_NORMAL, JOINT_SPIN, JOINT_FLOATING, JOINT_FLOATINGPLANAR, JOINT_BALLANDSOCKET, JOINT_CLOSED = range(7)
-PRIM_POINT, PRIM_SPHERE = 0, 1
+PRIM_POINT, PRIM_SPHERE, PRIM_TRIANGLE = 0, 1, 2
 
 IDENTITY12 = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], dtype=np.float64)
 
@@ -31,12 +31,12 @@ IDENTITY12 = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], dtype=np.float64)
 @dataclass
 class GeomSpec:
     """One collision geometry in its local frame (AnyCollisionGeometry3D minus the current transform)."""
-    kind: str = "empty"                      # 'mesh' | 'cloud' | 'sphere' | 'point' | 'empty'
+    kind: str = "empty"                      # 'mesh' | 'cloud' | 'sphere' | 'point' | 'triangle' | 'empty'
     verts: Optional[np.ndarray] = None       # (nv,3) f64   (mesh)
     tris: Optional[np.ndarray] = None        # (nt,3) i32   (mesh)
     points: Optional[np.ndarray] = None      # (n,3)  f64   (cloud)
     radius: Optional[np.ndarray] = None      # (n,)   f64 or None (cloud)
-    params: Optional[np.ndarray] = None      # sphere: cx,cy,cz,r ; point: x,y,z
+    params: Optional[np.ndarray] = None      # sphere: cx,cy,cz,r ; point: x,y,z ; triangle: a,b,c (9)
     margin: float = 0.0
 
     @staticmethod
@@ -57,6 +57,11 @@ class GeomSpec:
     @staticmethod
     def point(p, margin=0.0) -> "GeomSpec":
         return GeomSpec("point", params=np.array([p[0], p[1], p[2]], dtype=np.float64), margin=float(margin))
+
+    @staticmethod
+    def triangle(a, b, c, margin=0.0) -> "GeomSpec":
+        return GeomSpec("triangle", params=np.concatenate([np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64),
+                                                            np.asarray(c, dtype=np.float64)]), margin=float(margin))
 
     def num_elements(self) -> int:
         if self.kind == "mesh":

@@ -343,6 +343,7 @@ int ko_add_pointcloud(ko_world* w, const double* pts, int n, const double* radiu
   return w->ngeoms-1;
 }
 int ko_add_primitive(ko_world* w, int type, const double* params, double margin) {
+  if (type==KO_PRIM_TRIANGLE) { int32_t idx[3]={0,1,2}; return ko_add_trimesh(w,params,3,idx,1,margin); }   /* one-triangle mesh */
   double r = (type==KO_PRIM_SPHERE) ? params[3] : 0.0;
   if (type!=KO_PRIM_POINT && type!=KO_PRIM_SPHERE) return -1;
   int gi=ko_add_pointcloud(w,params,1,&r,margin);

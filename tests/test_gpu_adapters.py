@@ -169,3 +169,43 @@ def test_batch_roadmap_planner_on_the_engine(setup):
         st = plan.getStats()
         assert st["feasible_samples"] > 0 and st["edges_checked"] > 0
         plan.close()
+
+
+def test_triangle_primitive_and_distance_point(built):
+    """GeometricPrimitive "Triangle" (one of the common primitives of Cpp/docs/Manual-Geometry.md:241-250) and
+    Geometry3D.distance_point (Python/klampt/src/geometry.h:1011-1030), against the oracle and closed forms."""
+    from klampt_b200 import so3
+    from klampt_b200.robotsim import Geometry3D, GeometricPrimitive, TriangleMesh
+    from oracle import oracle as ko
+    rng = np.random.default_rng(5)
+    v, t = synth.unit_cube()
+    cube = Geometry3D(); cube.setTriangleMesh(TriangleMesh(v, t))
+    tri = Geometry3D(); p = GeometricPrimitive(); p.setTriangle([0, 0, 0], [1, 0, 0], [0, 1, 0]); tri.setGeometricPrimitive(p)
+    assert tri.type() == "GeometricPrimitive" and tri.numElements() == 1
+    # a triangle poking through the cube's top face collides; lifted clear of it, the distance is the gap
+    tri.setCurrentTransform(so3.identity(), [0.25, 0.25, 1.0 - 1e-3])
+    assert tri.collides(cube) and cube.collides(tri)
+    tri.setCurrentTransform(so3.identity(), [0.25, 0.25, 1.5])
+    assert not tri.collides(cube)
+    assert abs(tri.distance(cube).d - 0.5) < 1e-12 and tri.withinDistance(cube, 0.5 + 1e-9) and not tri.withinDistance(cube, 0.5 - 1e-9)
+    # random poses against the oracle's triangle-triangle routines
+    a = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], dtype=np.float64)
+    other = Geometry3D(); q = GeometricPrimitive(); q.setTriangle(*a); other.setGeometricPrimitive(q)
+    for _ in range(40):
+        R = synth._random_rotation(rng); tt = rng.uniform(-1.2, 1.2, size=3)
+        tri.setCurrentTransform(so3.from_matrix(R), list(tt))
+        other.setCurrentTransform(so3.identity(), [0, 0, 0])
+        b = a @ R.T + tt
+        want_hit = ko.tri_tri_intersect(b, a)
+        assert tri.collides(other) == want_hit
+        if not want_hit:
+            assert abs(tri.distance(other).d - ko.tri_tri_distance(b, a)) < 1e-9
+    # distance_point: outside the unit cube the distance to the surface has a closed form; batched = one by one
+    cube.setCurrentTransform(so3.identity(), [0, 0, 0])
+    P = rng.uniform(-1.5, 2.5, size=(200, 3))
+    outside = np.linalg.norm(np.maximum(np.maximum(-P, P - 1.0), 0.0), axis=1)
+    inside = np.minimum(P, 1.0 - P).min(axis=1)
+    want = np.where(outside > 0, outside, np.maximum(inside, 0.0))      # distance to the surface mesh, not a solid
+    got = cube.distance_points_batch(P)
+    np.testing.assert_allclose(got, want, atol=1e-12)
+    assert abs(cube.distance_point(list(P[0])).d - want[0]) < 1e-12

@@ -439,3 +439,20 @@ def test_multi_link_joint_layout_is_validated():
     w.robot.joint_base = np.array([0, 5, 6], dtype=np.int32)      # floating joint would drive only 5 links
     with pytest.raises(ValueError):
         OracleWorld(w)
+
+
+def test_triangle_primitive_is_a_one_triangle_mesh():
+    """GeometricPrimitive "Triangle" against the unit cube of the reference's tests/objects/cube.off"""
+    w = WorldSpec()
+    v, t = synth.unit_cube()
+    gc = w.add_geom(GeomSpec.mesh(v, t))
+    gt = w.add_geom(GeomSpec.triangle([0, 0, 0], [1, 0, 0], [0, 1, 0]))
+    w.robot = synth.make_planar_nR(w, 1)
+    o = OracleWorld(w)
+    I = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], dtype=np.float64)
+    T = I.copy(); T[9:] = [0.25, 0.25, 1.0 - 1e-3]
+    assert o.geom_collides(gt, T, gc, I)
+    T[11] = 1.5
+    assert not o.geom_collides(gt, T, gc, I)
+    assert abs(o.geom_distance(gt, T, gc, I) - 0.5) < 1e-12
+    assert o.geom_within_distance(gt, T, gc, I, 0.5 + 1e-9) and not o.geom_within_distance(gt, T, gc, I, 0.5 - 1e-9)
