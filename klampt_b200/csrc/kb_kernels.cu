@@ -365,6 +365,7 @@ __device__ __forceinline__ void drain_rechecks(const KbTraverseParams& p, uint4*
     }
     __syncwarp();
   }
+  __syncwarp();                       // every lane has read the counter before lane 0 rewrites it
   if (lane == 0) *rq_count = rqn;
   __syncwarp();
 }

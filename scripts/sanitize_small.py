@@ -18,4 +18,13 @@ w5 = synth.world_c5(n_points=20000, n_obstacles=20)
 e5 = Engine(w5)
 f5 = e5.feasible_batch(synth.sample_configs(w5.robot, 1500, 5))
 d5 = e5.distance_batch(synth.sample_configs(w5.robot, 200, 5), upper_bound=0.5)
+eng.set_option("clear_grid", 1)
+fg = eng.feasible_batch(Q)
+assert (fg == f).all()
+cp, cc = eng.colliding_pairs_batch(Q[:500], max_pairs=8)
+wf = synth.world_floating(n_obstacles=10)
+ef = Engine(wf)
+Qf = synth.sample_configs(wf.robot, 1500, 9)
+ff = ef.feasible_batch(Qf)
+vf, nf = ef.edges_visible_batch(Qf[ff == 1][:32], Qf[ff == 1][32:64], eps=0.05)
 print("ok", f.mean(), v.mean(), float(d.min()), f3.mean(), f5.mean(), float(d5.min()))
