@@ -1,14 +1,19 @@
 """Ingestion of the reference's data formats into the engine's plain world description, so the
 engine can be fed without a Klamp't install:
 
-  * triangle meshes: OFF (the format of the reference's ``tests/objects/cube.off``) and Wavefront OBJ
-    (``tests/objects/block.obj``), read and written;
+  * triangle meshes: OFF (the format of the reference's ``tests/objects/cube.off``), Wavefront OBJ
+    (``tests/objects/block.obj``) and STL (ascii / binary); point clouds: PCD (ascii / uncompressed binary, optional
+    ``radius`` field);
   * robots: the kinematic / geometric / joint subset of the ``.rob`` format documented in
     Cpp/docs/Manual-FileTypes.md:163-236 and parsed by Cpp/Modeling/Robot.cpp:216-1383 that the feasibility path reads:
     ``links parents jointtype tparent axis qmin/qmax(deg) q translation rotation scale geometry geomscale geommargin
     noselfcollision selfcollision joint driver``.  Inline geometry strings (``"{TriangleMesh\\nOFF ...}"`` as written by
     Python/klampt/model/create/planar_robot.py:20-70) are understood.  Dynamic items (mass, inertia, torque limits,
-    servo gains ...) are parsed over and ignored.  ``mount``, D-H parameters and URDF are not supported.
+    servo gains ...) are parsed over and ignored.  ``mount`` and D-H parameters are not supported;
+  * URDF with the ``<klampt>`` element (Manual-FileTypes.md:240-274), built the way RobotModel::LoadURDF builds its links
+    (Robot.cpp:2566-3300): fixed or floating base, revolute / continuous / prismatic / fixed joints, mimic joints as affine
+    drivers, box / cylinder / sphere / mesh collision geometry;
+  * world files (Manual-FileTypes.md:47-162): terrains, rigid objects and the robot.
 
 Root links get ``rotation`` / ``translation`` pre-multiplied into ``T0_Parent`` as Robot.cpp:971-975 does.
 """
@@ -77,14 +82,86 @@ def parse_obj(text: str) -> Tuple[np.ndarray, np.ndarray]:
     return np.array(verts, dtype=np.float64).reshape(-1, 3), np.array(tris, dtype=np.int32).reshape(-1, 3)
 
 
+def parse_stl(data: bytes) -> Tuple[np.ndarray, np.ndarray]:
+    """ASCII or binary STL -> (vertices, triangles); vertices are not merged (every triangle keeps its own three)."""
+    head = data[:512].lstrip().lower()
+    if head.startswith(b"solid") and b"facet" in data[:4096].lower():
+        toks = data.decode("ascii", "replace").split()
+        v = [float(toks[i + k]) for i, t in enumerate(toks) if t.lower() == "vertex" for k in (1, 2, 3)]
+        verts = np.array(v, dtype=np.float64).reshape(-1, 3)
+    else:
+        n = int(np.frombuffer(data[80:84], dtype="<u4")[0])
+        rec = np.frombuffer(data[84:84 + 50 * n], dtype=np.dtype([("n", "<f4", 3), ("v", "<f4", (3, 3)), ("a", "<u2")]))
+        verts = rec["v"].reshape(-1, 3).astype(np.float64)
+    return verts, np.arange(len(verts), dtype=np.int32).reshape(-1, 3)
+
+
+def parse_pcd(data: bytes) -> Tuple[np.ndarray, Optional[np.ndarray]]:
+    """Point Cloud Data file (ascii or uncompressed binary) -> (points (n,3), radius (n,) or None).  Only the x, y, z and
+    radius fields are read (the `radius` property makes every point a sphere, Cpp/docs/Manual-Geometry.md:25); rows with a
+    non-finite coordinate are dropped."""
+    hdr: Dict[str, List[str]] = {}
+    pos = 0
+    while True:
+        end = data.index(b"\n", pos)
+        line = data[pos:end].decode("ascii", "replace").strip()
+        pos = end + 1
+        if not line or line.startswith("#"):
+            continue
+        key, *vals = line.split()
+        hdr[key.upper()] = vals
+        if key.upper() == "DATA":
+            break
+    fields = hdr["FIELDS"]
+    sizes = [int(x) for x in hdr.get("SIZE", ["4"] * len(fields))]
+    types = hdr.get("TYPE", ["F"] * len(fields))
+    counts = [int(x) for x in hdr.get("COUNT", ["1"] * len(fields))]
+    npts = int(hdr["POINTS"][0]) if "POINTS" in hdr else int(hdr["WIDTH"][0]) * int(hdr.get("HEIGHT", ["1"])[0])
+    mode = hdr["DATA"][0].lower()
+    cols = {}
+    if mode == "ascii":
+        rows = np.array(data[pos:].decode("ascii", "replace").split(), dtype=np.float64).reshape(npts, -1)
+        c = 0
+        for f, k in zip(fields, counts):
+            cols[f] = rows[:, c]
+            c += k
+    elif mode == "binary":
+        dt = []
+        for f, sz, ty, k in zip(fields, sizes, types, counts):
+            code = {"F": "f", "I": "i", "U": "u"}[ty.upper()] + str(sz)
+            dt.append((f, "<" + code, (k,)) if k > 1 else (f, "<" + code))
+        rec = np.frombuffer(data[pos:pos + np.dtype(dt).itemsize * npts], dtype=np.dtype(dt))
+        for f in fields:
+            cols[f] = np.asarray(rec[f], dtype=np.float64).reshape(npts, -1)[:, 0]
+    else:
+        raise ValueError("PCD DATA mode %r is not supported (ascii and binary are)" % mode)
+    pts = np.stack([cols["x"], cols["y"], cols["z"]], axis=1)
+    ok = np.isfinite(pts).all(axis=1)
+    rad = np.asarray(cols["radius"], dtype=np.float64)[ok] if "radius" in cols else None
+    return np.ascontiguousarray(pts[ok]), rad
+
+
 def load_mesh(path: str) -> Tuple[np.ndarray, np.ndarray]:
-    text = open(path).read()
     ext = os.path.splitext(path)[1].lower()
+    if ext == ".stl":
+        return parse_stl(open(path, "rb").read())
+    text = open(path).read()
     if ext == ".off":
         return parse_off(text)
     if ext == ".obj":
         return parse_obj(text)
-    raise ValueError("unsupported mesh format %r (OFF and OBJ are)" % ext)
+    raise ValueError("unsupported mesh format %r (OFF, OBJ and STL are)" % ext)
+
+
+def load_geometry(path: str, scale=1.0, translate=(0.0, 0.0, 0.0), margin: float = 0.0) -> GeomSpec:
+    """any geometry file the path reads (.off / .obj / .stl mesh, .pcd point cloud) as a GeomSpec; `scale` may be a 3-vector"""
+    sc = np.broadcast_to(np.asarray(scale, dtype=np.float64), (3,))
+    tr = np.asarray(translate, dtype=np.float64)
+    if os.path.splitext(path)[1].lower() == ".pcd":
+        pts, rad = parse_pcd(open(path, "rb").read())
+        return GeomSpec.cloud(pts * sc + tr, None if rad is None else rad * float(sc.max()), margin)
+    v, t = load_mesh(path)
+    return GeomSpec.mesh(v * sc + tr, t, margin)
 
 
 def off_text(verts, tris) -> str:
@@ -221,8 +298,11 @@ def parse_rob(text: str, basedir: str = ".", world: Optional[WorldSpec] = None) 
     if joints:
         jt = np.array([j[0] for j in joints], dtype=np.uint8)
         jl = np.array([j[1] for j in joints], dtype=np.int32)
+        # "joint floating <link> <base>": the third field is RobotModelJoint::baseIndex (Robot.cpp:1152-1180); single-link joints hang
+        # from their link's parent
+        jb = np.array([j[2] if j[0] in (JOINT_FLOATING, JOINT_FLOATINGPLANAR, JOINT_BALLANDSOCKET) else int(parents[j[1]]) for j in joints], dtype=np.int32)
     else:
-        jt, jl = np.full(L, JOINT_NORMAL, dtype=np.uint8), np.arange(L, dtype=np.int32)
+        jt, jl, jb = np.full(L, JOINT_NORMAL, dtype=np.uint8), np.arange(L, dtype=np.int32), None
 
     def link_index(tok: str) -> int:
         try:
@@ -256,7 +336,7 @@ def parse_rob(text: str, basedir: str = ".", world: Optional[WorldSpec] = None) 
             rest = _floats(d[2 + 3 * n:])
             drv.append(DriverSpec(links, sc, of, rest[0] if len(rest) > 0 else -np.inf, rest[1] if len(rest) > 1 else np.inf))
     spec = RobotSpec(parents=parents, linktype=linktype, axis=axis, T0=T0, qmin=qmin, qmax=qmax, link_geom=link_geom, joint_type=jt, joint_link=jl,
-                     drivers=drv, self_collision_edits=edits, names=list(names))
+                     joint_base=jb, drivers=drv, self_collision_edits=edits, names=list(names))
     world.robot = spec
     return world, spec
 
@@ -284,9 +364,304 @@ def rob_text(spec: RobotSpec, world: WorldSpec) -> str:
     out.append("geommargin " + fmt(margins))
     inv = {v: k for k, v in _JOINT_TYPES.items()}
     if spec.joint_type is not None:
-        for t, k in zip(spec.joint_type, spec.joint_link):
-            out.append("joint %s %d" % (inv[int(t)], int(k)))
+        for n, (t, k) in enumerate(zip(spec.joint_type, spec.joint_link)):
+            if int(t) in (JOINT_FLOATING, JOINT_FLOATINGPLANAR, JOINT_BALLANDSOCKET) and spec.joint_base is not None:
+                out.append("joint %s %d %d" % (inv[int(t)], int(k), int(spec.joint_base[n])))
+            else:
+                out.append("joint %s %d" % (inv[int(t)], int(k)))
     dis = [(i, j) for (i, j, en) in spec.self_collision_edits if not en]
     if dis:
         out.append("noselfcollision " + " ".join("%d %d" % p for p in dis))
     return "\n".join(out) + "\n"
+
+
+# ============================================================================================== URDF
+def _rpy_matrix(r: float, p: float, y: float) -> np.ndarray:
+    """URDF fixed-axis roll-pitch-yaw: R = Rz(yaw) Ry(pitch) Rx(roll)"""
+    cr, sr, cp, sp, cy, sy = math.cos(r), math.sin(r), math.cos(p), math.sin(p), math.cos(y), math.sin(y)
+    return np.array([[cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr],
+                     [sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr],
+                     [-sp, cp * sr, cp * cr]])
+
+
+def _origin(el) -> Tuple[np.ndarray, np.ndarray]:
+    if el is None:
+        return np.eye(3), np.zeros(3)
+    xyz = np.array([float(x) for x in el.get("xyz", "0 0 0").split()], dtype=np.float64)
+    rpy = [float(x) for x in el.get("rpy", "0 0 0").split()]
+    return _rpy_matrix(*rpy), xyz
+
+
+def _cylinder_mesh(radius: float, length: float, nseg: int = 24) -> Tuple[np.ndarray, np.ndarray]:
+    ang = np.linspace(0, 2 * math.pi, nseg, endpoint=False)
+    ring = np.stack([radius * np.cos(ang), radius * np.sin(ang)], axis=1)
+    v = np.vstack([np.column_stack([ring, np.full(nseg, -length / 2)]), np.column_stack([ring, np.full(nseg, length / 2)]),
+                   [[0, 0, -length / 2]], [[0, 0, length / 2]]])
+    t = []
+    for i in range(nseg):
+        j = (i + 1) % nseg
+        t += [[i, j, nseg + j], [i, nseg + j, nseg + i], [2 * nseg, j, i], [2 * nseg + 1, nseg + i, nseg + j]]
+    return v, np.array(t, dtype=np.int32)
+
+
+def load_urdf(path: str, world: Optional[WorldSpec] = None) -> Tuple[WorldSpec, RobotSpec]:
+    return parse_urdf(open(path).read(), os.path.dirname(os.path.abspath(path)), world)
+
+
+def parse_urdf(text: str, basedir: str = ".", world: Optional[WorldSpec] = None) -> Tuple[WorldSpec, RobotSpec]:
+    """URDF -> RobotSpec the way RobotModel::LoadURDF builds its links (reference Cpp/Modeling/Robot.cpp:2566-3300):
+
+    * links in depth-first order from the root; a root link called ``world`` (``<klampt world_frame>``) is dropped and the
+      robot is fixed-base; any other root makes the robot floating: five virtual links base0..base4 (x, y, z prismatic; z, y
+      revolute) precede the root link, which turns about x, under one Floating joint (:2864-2998) -- unless
+      ``freeze_root_link``, which welds the six;
+    * ``T0_Parent`` = the joint's ``<origin>``; axis = ``<axis>`` (default x); revolute -> Normal, continuous -> Spin (limits
+      +-inf), prismatic -> Normal on a prismatic link, fixed -> Weld with limits 0 (:3086-3120); other joint types are errors;
+    * ``<mimic>`` joints become affine drivers (:3121-3135, 3180-3230): q_child = multiplier * q_parent + offset;
+    * collision geometry (visual with ``use_vis_geom``): meshes (OFF / OBJ / STL, ``package://`` relative to
+      ``package_root``, ``scale``; ``flip_yz`` swaps the mesh's y and z as the reference's default does), boxes, cylinders
+      and spheres tessellated; several ``<collision>`` elements of one link are merged; the element's ``<origin>`` is
+      baked into the vertices;
+    * ``<klampt><noselfcollision | selfcollision pairs= | group1= group2=>`` edit the default self-collision set."""
+    import xml.etree.ElementTree as ET
+    from . import synth
+    world = world if world is not None else WorldSpec()
+    root = ET.fromstring(text)
+    kl = root.find("klampt")
+    kattr = kl.attrib if kl is not None else {}
+    flag = lambda k, d: (kattr.get(k, d).strip().lower() not in ("0", "false")) if isinstance(kattr.get(k, d), str) else bool(d)
+    use_vis, flip_yz, freeze = flag("use_vis_geom", "0"), flag("flip_yz", "1"), flag("freeze_root_link", "0")
+    world_frame, pkg_root = kattr.get("world_frame", "world"), kattr.get("package_root", ".")
+    links = {l.get("name"): l for l in root.findall("link")}
+    joints = root.findall("joint")
+    child_of: Dict[str, list] = {}
+    parent_joint = {}
+    for j in joints:
+        pa, ch = j.find("parent").get("link"), j.find("child").get("link")
+        if ch not in links or pa not in links:
+            raise ValueError("URDF joint %r references an unknown link" % j.get("name"))
+        if ch in parent_joint:
+            raise ValueError("URDF link %r has multiple parents" % ch)
+        child_of.setdefault(pa, []).append(j)
+        parent_joint[ch] = j
+    roots = [n for n in links if n not in parent_joint]
+    if len(roots) != 1:
+        raise ValueError("URDF must have exactly one root link, found %r" % roots)
+    order, stack = [], [(roots[0], None)]
+    while stack:                                              # depth-first, children in file order
+        name, pj = stack.pop()
+        order.append((name, pj))
+        for j in reversed(child_of.get(name, [])):
+            stack.append((j.find("child").get("link"), j))
+    floating = roots[0] != world_frame
+    names: List[str] = []
+    parents: List[int] = []
+    ltype: List[int] = []
+    axes: List[List[float]] = []
+    T0: List[np.ndarray] = []
+    qmin: List[float] = []
+    qmax: List[float] = []
+    jt: List[int] = []
+    jl: List[int] = []
+    jb: List[int] = []
+    geoms: List[int] = []
+    index: Dict[str, int] = {}
+    mimic = []
+
+    def add(name, parent, lt, axis, T, lo, hi, g):
+        names.append(name); parents.append(parent); ltype.append(lt); axes.append(list(axis)); T0.append(T)
+        qmin.append(lo); qmax.append(hi); geoms.append(g)
+        return len(names) - 1
+
+    def link_geometry(lel) -> int:
+        parts = []
+        for c in lel.findall("visual" if use_vis else "collision"):
+            g = c.find("geometry")
+            if g is None or len(g) == 0:
+                continue
+            R, t = _origin(c.find("origin"))
+            shape = g[0]
+            if shape.tag == "mesh":
+                fn = shape.get("filename")
+                if fn.startswith("package://"):
+                    fn = os.path.join(pkg_root, fn[len("package://"):])
+                v, tr = load_mesh(fn if os.path.isabs(fn) else os.path.join(basedir, fn))
+                if flip_yz:
+                    v = np.stack([v[:, 0], -v[:, 2], v[:, 1]], axis=1)      # y-up asset -> z-up (a rotation about x, no mirroring)
+                v = v * np.array([float(x) for x in shape.get("scale", "1 1 1").split()], dtype=np.float64)
+            elif shape.tag == "box":
+                h = 0.5 * np.array([float(x) for x in shape.get("size").split()], dtype=np.float64)
+                v, tr = synth.box_mesh(-h, h, div=2)
+            elif shape.tag == "cylinder":
+                v, tr = _cylinder_mesh(float(shape.get("radius")), float(shape.get("length")))
+            elif shape.tag == "sphere":
+                v, tr = synth.icosphere(2)
+                v = v * float(shape.get("radius"))
+            else:
+                raise ValueError("URDF geometry <%s> is not supported" % shape.tag)
+            parts.append((v @ R.T + t, tr))
+        if not parts:
+            return -1
+        v, tr = synth.merge_meshes(parts)
+        return world.add_geom(GeomSpec.mesh(v, tr))
+
+    if floating:
+        for i, (lt, ax) in enumerate(((PRISMATIC, (1, 0, 0)), (PRISMATIC, (0, 1, 0)), (PRISMATIC, (0, 0, 1)), (REVOLUTE, (0, 0, 1)), (REVOLUTE, (0, 1, 0)))):
+            add("base%d" % i, i - 1, lt, ax, IDENTITY12.copy(), 0.0 if freeze else -np.inf, 0.0 if freeze else np.inf, -1)
+        if freeze:
+            for i in range(5):
+                jt.append(JOINT_WELD); jl.append(i); jb.append(i - 1)
+    for name, pj in order:
+        lel = links[name]
+        if pj is None:
+            if not floating:
+                continue                                      # the world link itself is not a robot link
+            k = add(name, 4, REVOLUTE, (1, 0, 0), IDENTITY12.copy(), 0.0 if freeze else -np.inf, 0.0 if freeze else np.inf, link_geometry(lel))
+            index[name] = k
+            if freeze:
+                jt.append(JOINT_WELD); jl.append(k); jb.append(4)
+            else:
+                jt.append(JOINT_FLOATING); jl.append(k); jb.append(-1)
+            continue
+        kind = pj.get("type")
+        R, t = _origin(pj.find("origin"))
+        T = np.concatenate([R.reshape(-1), t])
+        ax_el = pj.find("axis")
+        axis = [float(x) for x in ax_el.get("xyz").split()] if ax_el is not None else [1.0, 0.0, 0.0]
+        n = math.sqrt(sum(a * a for a in axis))
+        if kind != "fixed" and n < 0.1:
+            raise ValueError("URDF joint %r has a degenerate axis" % pj.get("name"))
+        axis = [a / n for a in axis] if n > 0 else [1.0, 0.0, 0.0]
+        lim = pj.find("limit")
+        lo, hi = (-np.inf, np.inf) if lim is None else (float(lim.get("lower", "0")), float(lim.get("upper", "0")))
+        if kind == "revolute":
+            jtype, lt = JOINT_NORMAL, REVOLUTE
+        elif kind == "continuous":
+            jtype, lt, lo, hi = JOINT_SPIN, REVOLUTE, -np.inf, np.inf
+        elif kind == "prismatic":
+            jtype, lt = JOINT_NORMAL, PRISMATIC
+        elif kind == "fixed":
+            jtype, lt, lo, hi = JOINT_WELD, REVOLUTE, 0.0, 0.0
+        else:
+            raise ValueError("URDF joint type %r is not supported" % kind)
+        parent_name = pj.find("parent").get("link")
+        par = index.get(parent_name, -1)
+        k = add(name, par, lt, axis, T, lo, hi, link_geometry(lel))
+        index[name] = k
+        jt.append(jtype); jl.append(k); jb.append(par)
+        m = pj.find("mimic")
+        if m is not None:
+            mimic.append((k, m.get("joint"), float(m.get("multiplier", "1")), float(m.get("offset", "0"))))
+    L = len(names)
+    if L == 0:
+        raise ValueError("URDF has no links besides the world frame")
+    jname_to_link = {j.get("name"): index[j.find("child").get("link")] for j in joints if j.find("child").get("link") in index}
+    drivers = []
+    for k, jn, mult, off in mimic:
+        if jn not in jname_to_link:
+            continue
+        src = jname_to_link[jn]
+        # q_k = mult * q_src + off: an affine driver over (src, k) with scales (1, mult) and offsets (0, off)
+        drivers.append(DriverSpec([src, k], [1.0, mult], [0.0, off], float(qmin[src]), float(qmax[src])))
+
+    def resolve(tok: str) -> int:
+        try:
+            return int(tok)
+        except ValueError:
+            return names.index(tok)
+
+    edits = []
+    if kl is not None:
+        if kl.findall("selfcollision"):
+            edits += [(i, j, False) for i in range(L) for j in range(i + 1, L)]
+        for tag, en in (("selfcollision", True), ("noselfcollision", False)):
+            for el in kl.findall(tag):
+                pairs = []
+                if el.get("pairs"):
+                    toks = el.get("pairs").split()
+                    if len(toks) % 2:
+                        raise ValueError("<%s pairs> holds link PAIRS" % tag)
+                    pairs = list(zip(toks[0::2], toks[1::2]))
+                elif el.get("group1") and el.get("group2"):
+                    pairs = [(a, b) for a in el.get("group1").split() for b in el.get("group2").split()]
+                else:
+                    raise ValueError("<%s> needs pairs or group1 + group2" % tag)
+                for a, b in pairs:
+                    i, j = resolve(a), resolve(b)
+                    if i != j:
+                        edits.append((min(i, j), max(i, j), en))
+    spec = RobotSpec(parents=np.array(parents, dtype=np.int32), linktype=np.array(ltype, dtype=np.uint8), axis=np.array(axes, dtype=np.float64),
+                     T0=np.array(T0, dtype=np.float64), qmin=np.array(qmin, dtype=np.float64), qmax=np.array(qmax, dtype=np.float64),
+                     link_geom=geoms, joint_type=np.array(jt, dtype=np.uint8), joint_link=np.array(jl, dtype=np.int32),
+                     joint_base=np.array(jb, dtype=np.int32), drivers=drivers, self_collision_edits=edits, names=names)
+    world.robot = spec
+    return world, spec
+
+
+# ============================================================================================== world XML
+def _vec(txt: Optional[str], n: int, default: float = 0.0) -> np.ndarray:
+    if txt is None:
+        return np.full(n, default, dtype=np.float64)
+    v = np.array([float(x) for x in txt.split()], dtype=np.float64)
+    return np.full(n, v[0]) if len(v) == 1 else v[:n]
+
+
+def _xml_rotation(el) -> np.ndarray:
+    """rotateRPY / rotateX / rotateY / rotateZ / rotateMoment attributes, applied in the order they are written
+    (Cpp/docs/Manual-FileTypes.md:66-72 "rotation attributes are applied in sequence")"""
+    from . import so3
+    R = np.eye(3)
+    for key, val in el.attrib.items():
+        if key == "rotateRPY":
+            r, p, y = _vec(val, 3)
+            R = _rpy_matrix(r, p, y) @ R
+        elif key in ("rotateX", "rotateY", "rotateZ"):
+            ax = {"rotateX": [1, 0, 0], "rotateY": [0, 1, 0], "rotateZ": [0, 0, 1]}[key]
+            R = so3.matrix(so3.from_axis_angle((ax, float(val)))) @ R
+        elif key == "rotateMoment":
+            R = so3.exp(_vec(val, 3)) @ R
+    return R
+
+
+def load_world_xml(path: str) -> WorldSpec:
+    return parse_world_xml(open(path).read(), os.path.dirname(os.path.abspath(path)))
+
+
+def parse_world_xml(text: str, basedir: str = ".") -> WorldSpec:
+    """The entities of a world file that the feasibility path reads (format: Cpp/docs/Manual-FileTypes.md:47-162; loader:
+    Cpp/IO/XmlWorld.cpp): ``<robot file=.rob|.urdf>`` (the first one is the engine's active robot, any further robot is
+    rejected -- one active robot per engine), ``<rigidObject>`` with ``<geometry file|mesh scale translate margin>`` and
+    ``position`` / ``rotate*``, ``<terrain file scale margin translation|position rotate*>``.  Display, physics and
+    simulation elements are parsed over.  A terrain's pose is baked into its geometry (terrains carry no transform)."""
+    import xml.etree.ElementTree as ET
+    root = ET.fromstring(text)
+    if root.tag != "world":
+        raise ValueError("not a world file: top-level element is <%s>" % root.tag)
+    w = WorldSpec()
+    resolve = lambda fn: fn if os.path.isabs(fn) else os.path.join(basedir, fn)
+    for el in root:
+        if el.tag == "terrain":
+            g = load_geometry(resolve(el.get("file")), _vec(el.get("scale"), 3, 1.0), (0, 0, 0), float(el.get("margin", "0")))
+            R, t = _xml_rotation(el), _vec(el.get("translation", el.get("position")), 3)
+            if g.kind == "mesh":
+                g.verts = g.verts @ R.T + t
+            else:
+                g.points = g.points @ R.T + t
+            w.terrains.append(w.add_geom(g))
+        elif el.tag == "rigidObject":
+            ge = el.find("geometry")
+            if ge is None:
+                raise ValueError("<rigidObject> without <geometry> (rigid object .obj description files are not read)")
+            fn = ge.get("file", ge.get("mesh"))
+            g = load_geometry(resolve(fn), _vec(ge.get("scale"), 3, 1.0), _vec(ge.get("translate"), 3), float(ge.get("margin", "0")))
+            T = np.concatenate([_xml_rotation(el).reshape(-1), _vec(el.get("position"), 3)])
+            w.objects.append((w.add_geom(g), T))
+        elif el.tag == "robot":
+            if w.robot is not None:
+                raise ValueError("more than one <robot>: the engine has one active robot (SingleRobotCSpace)")
+            fn = resolve(el.get("file"))
+            if fn.lower().endswith(".urdf"):
+                load_urdf(fn, w)
+            else:
+                load_rob(fn, w)
+    return w

@@ -117,3 +117,110 @@ def test_rob_base_transform_selfcollision_and_errors():
         kio.parse_rob("parents -1\nalpha 0\n")
     with pytest.raises(ValueError):
         kio.parse_rob("links a\n")
+
+
+URDF_ARM = """<robot name="two">
+ <link name="world"/>
+ <link name="base"><collision><origin xyz="0 0 0.05"/><geometry><box size="0.2 0.2 0.1"/></geometry></collision></link>
+ <link name="arm"><collision><origin xyz="0 0 0.25"/><geometry><cylinder radius="0.04" length="0.5"/></geometry></collision></link>
+ <link name="finger"><collision><geometry><sphere radius="0.03"/></geometry></collision></link>
+ <link name="finger2"/>
+ <joint name="fix" type="fixed"><parent link="world"/><child link="base"/><origin xyz="0 0 0.1"/></joint>
+ <joint name="j1" type="revolute"><parent link="base"/><child link="arm"/><origin xyz="0 0 0.1" rpy="0 0 1.5707963267948966"/><axis xyz="0 1 0"/><limit lower="-1" upper="2"/></joint>
+ <joint name="j2" type="prismatic"><parent link="arm"/><child link="finger"/><origin xyz="0 0 0.5"/><axis xyz="0 0 1"/><limit lower="0" upper="0.1"/></joint>
+ <joint name="j3" type="continuous"><parent link="arm"/><child link="finger2"/><origin xyz="0 0.1 0.5"/><axis xyz="0 0 2"/><mimic joint="j1" multiplier="2" offset="0.1"/></joint>
+ <klampt><noselfcollision pairs="base finger"/></klampt>
+</robot>"""
+
+
+def test_urdf_fixed_base_follows_the_reference_loader():
+    """RobotModel::LoadURDF (reference Cpp/Modeling/Robot.cpp:2864-3135): the world link is dropped, joint types, limits,
+    mimic -> affine driver, <klampt> self-collision edits; FK of the result through the oracle."""
+    from klampt_b200.worldspec import PRISMATIC, REVOLUTE
+    w, r = kio.parse_urdf(URDF_ARM)
+    assert r.names == ["base", "arm", "finger", "finger2"] and list(r.parents) == [-1, 0, 1, 1]
+    assert list(r.linktype) == [REVOLUTE, REVOLUTE, PRISMATIC, REVOLUTE]
+    assert list(r.joint_type) == [JOINT_WELD, JOINT_NORMAL, JOINT_NORMAL, JOINT_SPIN]
+    assert list(r.qmin) == [0, -1, 0, -np.inf] and list(r.qmax) == [0, 2, 0.1, np.inf]
+    assert np.allclose(r.axis[3], [0, 0, 1])                       # axes are normalised
+    assert r.self_collision_edits == [(0, 2, False)]
+    d = r.drivers[0]
+    assert d.links == [1, 3] and d.scale == [1.0, 2.0] and d.offset == [0.0, 0.1] and (d.qmin, d.qmax) == (-1.0, 2.0)
+    assert [w.geoms[g].tris.shape[0] for g in r.link_geom[:3]] == [48, 96, 320] and r.link_geom[3] == -1
+    o = OracleWorld(w)
+    q = np.array([0.0, 0.5, 0.05, 1.1])
+    T = o.fk(q)
+    # arm frame: base (0,0,0.1) + (0,0,0.1), yawed 90 deg, pitched 0.5 about its own y; finger 0.5 + 0.05 along the arm's z
+    Rz = np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1.0]]); c, s = math.cos(0.5), math.sin(0.5)
+    Ry = np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])
+    assert np.allclose(T[1, :9].reshape(3, 3), Rz @ Ry, atol=1e-12) and np.allclose(T[1, 9:], [0, 0, 0.2])
+    assert np.allclose(T[2, 9:], np.array([0, 0, 0.2]) + Rz @ Ry @ np.array([0, 0, 0.55]), atol=1e-12)
+    # mimic joint = affine driver: CheckJointLimits bounds the driver VALUE, the mean of q1 and (q3 - 0.1) / 2 (Robot.cpp:2166-2187)
+    assert o.check_joint_limits(q) and o.check_joint_limits(np.array([0.0, 2.0, 0.05, 4.1]))
+    assert not o.check_joint_limits(np.array([0.0, 2.0, 0.05, 6.1]))
+
+
+def test_urdf_floating_base_gets_six_virtual_links():
+    """a root link that is not the world frame makes the robot floating (Robot.cpp:2864-2998)"""
+    from klampt_b200.worldspec import JOINT_FLOATING
+    text = URDF_ARM.replace('<link name="world"/>', "").replace(
+        '<joint name="fix" type="fixed"><parent link="world"/><child link="base"/><origin xyz="0 0 0.1"/></joint>', "")
+    w, r = kio.parse_urdf(text)
+    assert r.names[:6] == ["base0", "base1", "base2", "base3", "base4", "base"] and list(r.parents[:7]) == [-1, 0, 1, 2, 3, 4, 5]
+    assert list(r.linktype[:6]) == [1, 1, 1, 0, 0, 0] and r.axis[3:6].tolist() == [[0, 0, 1], [0, 1, 0], [1, 0, 0]]
+    assert r.joint_type[0] == JOINT_FLOATING and r.joint_link[0] == 5 and r.joint_base[0] == -1
+    o = OracleWorld(w)                                             # the oracle validates the floating joint's layout
+    a = np.zeros(r.L); b = np.zeros(r.L); b[3] = 1.0; b[0] = 0.3
+    assert abs(o.cspace_distance(a, b) - math.sqrt(1.0 + 0.09)) < 1e-12
+    frozen = kio.parse_urdf(text.replace("<klampt>", '<klampt freeze_root_link="1">'))[1]
+    assert list(frozen.joint_type[:6]) == [JOINT_WELD] * 6 and (frozen.qmin[:6] == 0).all()
+
+
+def test_pcd_stl_and_world_xml(tmp_path):
+    """.pcd (ascii / binary), .stl (ascii / binary) and the world file entities the path reads
+    (Cpp/docs/Manual-FileTypes.md:47-162)"""
+    pcd = b"# .PCD v0.7\nVERSION 0.7\nFIELDS x y z radius\nSIZE 4 4 4 4\nTYPE F F F F\nCOUNT 1 1 1 1\nWIDTH 3\nHEIGHT 1\nPOINTS 3\nDATA ascii\n0 0 0 0.1\n1 2 3 0.2\nnan 0 0 0.3\n"
+    pts, rad = kio.parse_pcd(pcd)
+    assert pts.tolist() == [[0, 0, 0], [1, 2, 3]] and np.allclose(rad, [0.1, 0.2])
+    rec = np.zeros(2, dtype=[("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("rgb", "<u4")]); rec["x"] = [1, 2]; rec["z"] = [5, 6]
+    binp = b"VERSION 0.7\nFIELDS x y z rgb\nSIZE 4 4 4 4\nTYPE F F F U\nCOUNT 1 1 1 1\nWIDTH 2\nHEIGHT 1\nPOINTS 2\nDATA binary\n" + rec.tobytes()
+    pts2, rad2 = kio.parse_pcd(binp)
+    assert pts2.tolist() == [[1, 0, 5], [2, 0, 6]] and rad2 is None
+    v, t = synth.unit_cube()
+    ascii_stl = "solid c\n" + "".join("facet normal 0 0 0\nouter loop\n" + "".join("vertex %g %g %g\n" % tuple(v[i]) for i in tri) + "endloop\nendfacet\n" for tri in t) + "endsolid c\n"
+    sv, st = kio.parse_stl(ascii_stl.encode())
+    assert st.shape == (12, 3) and np.allclose(sv[st.reshape(-1)], v[t.reshape(-1)])
+    recs = np.zeros(12, dtype=[("n", "<f4", 3), ("v", "<f4", (3, 3)), ("a", "<u2")]); recs["v"] = v[t]
+    bv, bt = kio.parse_stl(b"\0" * 80 + np.uint32(12).tobytes() + recs.tobytes())
+    assert np.allclose(bv[bt.reshape(-1)], v[t.reshape(-1)])
+    # world file: terrain (scaled, lifted), rigid object from a point cloud with a pose, robot from a .rob file
+    (tmp_path / "cube.off").write_text(CUBE_OFF)
+    (tmp_path / "cloud.pcd").write_bytes(pcd)
+    spec0 = WorldSpec(); arm = synth.make_planar_nR(spec0, 2)
+    (tmp_path / "arm.rob").write_text(kio.rob_text(arm, spec0))
+    (tmp_path / "w.xml").write_text("""<?xml version="1.0"?>
+<world>
+  <terrain file="cube.off" scale="4 4 0.1" translation="-2 -2 -0.1" margin="0.01"><display color="1 0 0"/></terrain>
+  <rigidObject name="blob" position="1 0 0.5" rotateZ="1.5707963267948966">
+    <geometry file="cloud.pcd" scale="0.5" margin="0.02"/><physics mass="1"/>
+  </rigidObject>
+  <robot name="arm" file="arm.rob"/>
+  <simulation><globals maxContacts="20"/></simulation>
+</world>""")
+    w = kio.load_world_xml(str(tmp_path / "w.xml"))
+    assert len(w.terrains) == 1 and len(w.objects) == 1 and w.robot.L == 2
+    g = w.geoms[w.terrains[0]]
+    assert np.allclose(g.verts.min(0), [-2, -2, -0.1]) and np.allclose(g.verts.max(0), [2, 2, 0.0]) and g.margin == 0.01
+    go, T = w.objects[0]
+    assert w.geoms[go].kind == "cloud" and np.allclose(w.geoms[go].points, [[0, 0, 0], [0.5, 1.0, 1.5]]) and np.allclose(w.geoms[go].radius, [0.05, 0.1])
+    assert np.allclose(T[:9].reshape(3, 3), [[0, -1, 0], [1, 0, 0], [0, 0, 1]], atol=1e-12) and np.allclose(T[9:], [1, 0, 0.5])
+    o = OracleWorld(w)                                             # the whole description loads into the checker
+    assert o.num_ids() == 1 + 1 + 1 + 2
+
+
+def test_rob_floating_joint_base_round_trip():
+    w = synth.world_floating(n_obstacles=2)
+    text = kio.rob_text(w.robot, w)
+    assert "joint floating 5 -1" in text and "joint ballandsocket 9 6" in text
+    w2, r2 = kio.parse_rob(text)
+    assert list(r2.joint_base) == list(w.robot.joint_base) and list(r2.joint_type) == list(w.robot.joint_type)
