@@ -319,7 +319,7 @@ struct kb_engine {
   // ---- device
   int device = -1, num_sms = 148;
   cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
-  cudaEvent_t ev_copy0 = nullptr, ev_copy1 = nullptr;
+  cudaEvent_t ev_copy[4] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<float> h_nodes;               // 8 floats per node
   std::vector<float> h_tris32; std::vector<double> h_tris64; std::vector<int32_t> h_triown;
   std::vector<float> h_sph32; std::vector<double> h_sph64; std::vector<int32_t> h_sphown;
@@ -663,8 +663,7 @@ void kb_engine_destroy(kb_engine* e) {
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     for (cudaEvent_t ev : e->tev) cudaEventDestroy(ev);
-    if (e->ev_copy0) cudaEventDestroy(e->ev_copy0);
-    if (e->ev_copy1) cudaEventDestroy(e->ev_copy1);
+    for (int k = 0; k < 4; k++) if (e->ev_copy[k]) cudaEventDestroy(e->ev_copy[k]);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
   }
@@ -827,7 +826,7 @@ int kb_finalize(kb_engine* e, int device) {
   e->stream = e->own_stream;
   CK(cudaEventCreate(&e->ev0)); CK(cudaEventCreate(&e->ev1));
   CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-  CK(cudaEventCreateWithFlags(&e->ev_copy0, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&e->ev_copy1, cudaEventDisableTiming));
+  for (int k = 0; k < 4; k++) CK(cudaEventCreateWithFlags(&e->ev_copy[k], cudaEventDisableTiming));
 
   // ---- 1. per-geometry local-frame BVHs (links, and every geometry for explicit pair queries)
   e->dgeoms.resize(e->geoms.size());
@@ -1102,21 +1101,33 @@ int kb_feasible_batch(kb_engine* e, const double* Q, int64_t N, uint8_t* out, in
   if ((rc = grow(e->d_out, e->out_cap, N))) return rc;
   if (first_pair && (rc = grow(e->d_pair, e->pair_cap, 2 * N))) return rc;
   begin_timing(e);
-  // Two-stage upload: a small head batch goes up first and is checked while the rest of the configurations cross PCIe on the
-  // copy stream (1 M x 7 doubles = 56 MB is ~1 ms, 13 % of the step when it is not overlapped).  Two launches instead of one cost
-  // one extra launch tail, so small calls keep the single-stage path.
-  const int64_t n0 = N >= (1 << 17) ? std::max<int64_t>(1 << 15, (N / 8 / 1024) * 1024) : N;
-  CK(cudaMemcpyAsync(e->d_Q, Q, (size_t)n0 * e->L * 8, cudaMemcpyHostToDevice, e->stream));
-  if (n0 < N) {
-    CK(cudaEventRecord(e->ev_copy0, e->stream));                  // the copy stream must not run ahead of earlier work on the buffer
-    CK(cudaStreamWaitEvent(e->copy_stream, e->ev_copy0, 0));
-    CK(cudaMemcpyAsync(e->d_Q + n0 * e->L, Q + n0 * e->L, (size_t)(N - n0) * e->L * 8, cudaMemcpyHostToDevice, e->copy_stream));
-    CK(cudaEventRecord(e->ev_copy1, e->copy_stream));
+  // Staged upload: the batch crosses PCIe in up to four pieces of growing size (N/16, N/8, N/4, rest) on the copy stream, and
+  // piece k is checked while piece k+1 is in flight, so only the first, small copy is exposed (1 M x 7 doubles = 56 MB is ~1 ms,
+  // 19 links = 152 MB ~2.8 ms when not overlapped).  Every extra launch costs one launch tail, so small calls stay single-stage.
+  // Measured on B200: 7 links (56 B / configuration) 1.505e8 cfg/s with two pieces vs 1.46e8 with four; 19 links (152 B) 1.04e8
+  // vs 1.19e8 -- long rows take four pieces, short rows two (N/8, rest).
+  int64_t cut[5] = {0, N, N, N, N}; int nstage = 1;
+  if (N >= (1 << 17)) {
+    if (e->L >= 12) {
+      const int64_t unit = std::max<int64_t>(1 << 14, ((N / 16) / 1024) * 1024);
+      cut[1] = unit; cut[2] = 3 * unit; cut[3] = 7 * unit; cut[4] = N; nstage = 4;
+      if (cut[3] >= N) { cut[1] = N; nstage = 1; }
+    } else {
+      cut[1] = std::max<int64_t>(1 << 15, ((N / 8) / 1024) * 1024); cut[2] = N; nstage = 2;
+    }
   }
-  if ((rc = run_feasible_device(e, e->d_Q, n0, e->d_out, first_pair ? e->d_pair : nullptr, e->d_counters + 3))) return rc;
-  if (n0 < N) {
-    CK(cudaStreamWaitEvent(e->stream, e->ev_copy1, 0));
-    if ((rc = run_feasible_device(e, e->d_Q + n0 * e->L, N - n0, e->d_out + n0, first_pair ? e->d_pair + 2 * n0 : nullptr, e->d_counters + 3))) return rc;
+  CK(cudaMemcpyAsync(e->d_Q, Q, (size_t)cut[1] * e->L * 8, cudaMemcpyHostToDevice, e->stream));
+  if (nstage > 1) {
+    CK(cudaEventRecord(e->ev_copy[0], e->stream));                // the copy stream must not run ahead of earlier work on the buffer
+    CK(cudaStreamWaitEvent(e->copy_stream, e->ev_copy[0], 0));
+    for (int k = 1; k < nstage; k++) {
+      CK(cudaMemcpyAsync(e->d_Q + cut[k] * e->L, Q + cut[k] * e->L, (size_t)(cut[k + 1] - cut[k]) * e->L * 8, cudaMemcpyHostToDevice, e->copy_stream));
+      CK(cudaEventRecord(e->ev_copy[k], e->copy_stream));
+    }
+  }
+  for (int k = 0; k < nstage; k++) {
+    if (k > 0) CK(cudaStreamWaitEvent(e->stream, e->ev_copy[k], 0));
+    if ((rc = run_feasible_device(e, e->d_Q + cut[k] * e->L, cut[k + 1] - cut[k], e->d_out + cut[k], first_pair ? e->d_pair + 2 * cut[k] : nullptr, e->d_counters + 3))) return rc;
   }
   CK(cudaMemcpyAsync(out, e->d_out, (size_t)N, cudaMemcpyDeviceToHost, e->stream));
   if (first_pair) CK(cudaMemcpyAsync(first_pair, e->d_pair, (size_t)N * 8, cudaMemcpyDeviceToHost, e->stream));
