@@ -40,13 +40,15 @@ inline void xf_apply(const Xf& T, const double* p, double* o) {
   o[2] = T.R[6] * x + T.R[7] * y + T.R[8] * z + T.t[2];
 }
 
-enum { G_EMPTY = 0, G_MESH = 1, G_CLOUD = 2, G_PRIM = 3 };
+enum { G_EMPTY = 0, G_MESH = 1, G_CLOUD = 2, G_PRIM = 3, G_BOX = 4 };   // G_BOX: only as the element kind of solid-box hierarchies
 
 struct Geom {
   int kind = G_EMPTY;
   double margin = 0;
   std::vector<double> tri;     // 9 per triangle (expanded), local frame
   std::vector<double> sph;     // 4 per sphere (x,y,z,r), local frame
+  bool solid = false;          // box primitive: `tri` holds its 12 surface triangles and the interior counts as well
+  double box[15];              // solid box: centre(3), axes = columns of a row-major 3x3 (9), half dimensions(3)
   int nelem() const { return kind == G_MESH ? (int)(tri.size() / 9) : (int)(sph.size() / 4); }
   bool empty() const { return kind == G_EMPTY || nelem() == 0; }
 };
@@ -323,11 +325,14 @@ struct kb_engine {
   std::vector<float> h_nodes;               // 8 floats per node
   std::vector<float> h_tris32; std::vector<double> h_tris64; std::vector<int32_t> h_triown;
   std::vector<float> h_sph32; std::vector<double> h_sph64; std::vector<int32_t> h_sphown;
+  std::vector<float> h_box32; std::vector<double> h_box64; std::vector<int32_t> h_boxown;
+  std::vector<DevGeom> dsolid;              // per registered geometry: the solid of a box primitive (empty otherwise)
   std::vector<DevGeom> dgeoms;              // per registered geometry (local frame)
   std::vector<DevGeom> groups;              // merged environment groups (world frame)
   KbScene scene{};
   float4* d_nodes = nullptr; float4* d_tris32 = nullptr; double* d_tris64 = nullptr; float4* d_sph32 = nullptr; double* d_sph64 = nullptr;
   int32_t* d_triown = nullptr; int32_t* d_sphown = nullptr;
+  float4* d_box32 = nullptr; double* d_box64 = nullptr; int32_t* d_boxown = nullptr;
   KbRobotDev* d_robot = nullptr; KbDriverDev* d_drv = nullptr; int32_t* d_drv_link = nullptr; double* d_drv_scale = nullptr; double* d_drv_off = nullptr;
   ItemSet feas_items, env_items;            // env + self ; env only (distance without self)
   std::vector<HostGrid> hgrids; uint8_t* d_grid[KB_MAX_GRIDS] = {nullptr, nullptr, nullptr, nullptr};
@@ -394,23 +399,27 @@ inline bool mask_en(const kb_engine* e, int a, int b) { return e->mask[(size_t)a
 
 // appends one geometry (elements given in some frame) to the host arrays: builds its BVH, writes nodes + elements
 int append_geom(kb_engine* e, int kind, const std::vector<double>& elems, const std::vector<int32_t>& owners, double margin, DevGeom& dg, bool want_cover) {
-  const int stride = kind == G_MESH ? 9 : 4;
+  const int stride = kind == G_MESH ? 9 : (kind == G_BOX ? 15 : 4);
   const int n = (int)(elems.size() / stride);
-  dg = DevGeom(); dg.margin = margin; dg.kind = kind == G_MESH ? KB_ELEM_TRI : KB_ELEM_SPHERE; dg.nelem = n; dg.empty = n == 0;
+  dg = DevGeom(); dg.margin = margin; dg.kind = kind == G_MESH ? KB_ELEM_TRI : (kind == G_BOX ? KB_ELEM_BOX : KB_ELEM_SPHERE); dg.nelem = n; dg.empty = n == 0;
   if (n == 0) return KB_OK;
   std::vector<double> elo(3 * (size_t)n), ehi(3 * (size_t)n);
   for (int i = 0; i < n; i++) {
     const double* p = &elems[(size_t)stride * i];
     for (int k = 0; k < 3; k++) {
       if (kind == G_MESH) { elo[3 * (size_t)i + k] = std::min(p[k], std::min(p[3 + k], p[6 + k])); ehi[3 * (size_t)i + k] = std::max(p[k], std::max(p[3 + k], p[6 + k])); }
+      else if (kind == G_BOX) {      // extent of the oriented box along axis k: sum |R[k][j]| h_j (a hair up: the node box must contain it)
+        const double ext = (std::fabs(p[3 + 3 * k]) * p[12] + std::fabs(p[3 + 3 * k + 1]) * p[13] + std::fabs(p[3 + 3 * k + 2]) * p[14]) * (1 + 1e-12);
+        elo[3 * (size_t)i + k] = p[k] - ext; ehi[3 * (size_t)i + k] = p[k] + ext;
+      }
       else { elo[3 * (size_t)i + k] = p[k] - p[3]; ehi[3 * (size_t)i + k] = p[k] + p[3]; }
     }
-    if (kind != G_MESH) dg.rmax = std::max(dg.rmax, p[3]);
+    if (kind != G_MESH && kind != G_BOX) dg.rmax = std::max(dg.rmax, p[3]);
   }
   Bvh bvh; build_bvh(elo, ehi, n, kind == G_MESH ? 1 : 8, bvh);
   if ((e->h_nodes.size() / 8) & 1) e->h_nodes.insert(e->h_nodes.end(), 8, 0.f);                // even node base: sibling pairs share a 64 B line
   dg.node_base = (int)(e->h_nodes.size() / 8); dg.nnodes = (int)bvh.nodes.size(); dg.depth = bvh.depth;
-  dg.elem_base = kind == G_MESH ? (int)(e->h_tris64.size() / 9) : (int)(e->h_sph64.size() / 4);
+  dg.elem_base = kind == G_MESH ? (int)(e->h_tris64.size() / 9) : (kind == G_BOX ? (int)(e->h_box64.size() / 16) : (int)(e->h_sph64.size() / 4));
   memcpy(dg.lo, bvh.nodes[0].lo, 24); memcpy(dg.hi, bvh.nodes[0].hi, 24);
   for (const BNode& nd : bvh.nodes) {
     float v[8];
@@ -462,6 +471,11 @@ int append_geom(kb_engine* e, int kind, const std::vector<double>& elems, const 
       e->h_tris64.insert(e->h_tris64.end(), p, p + 9);
       for (int v = 0; v < 3; v++) { float f[4] = {(float)p[3 * v], (float)p[3 * v + 1], (float)p[3 * v + 2], v == 0 ? i2f(own) : 0.f}; e->h_tris32.insert(e->h_tris32.end(), f, f + 4); }
       e->h_triown.push_back(own);
+    } else if (kind == G_BOX) {      // {centre, hx} {axis0, hy} {axis1, hz} {axis2, 0}: axis j = column j of the row-major 3x3
+      double b[16] = {p[0], p[1], p[2], p[12], p[3], p[6], p[9], p[13], p[4], p[7], p[10], p[14], p[5], p[8], p[11], 0.0};
+      e->h_box64.insert(e->h_box64.end(), b, b + 16);
+      for (int k = 0; k < 16; k++) e->h_box32.push_back((float)b[k]);
+      e->h_boxown.push_back(own);
     } else {
       e->h_sph64.insert(e->h_sph64.end(), p, p + 4);
       float f[4] = {(float)p[0], (float)p[1], (float)p[2], (float)p[3]}; e->h_sph32.insert(e->h_sph32.end(), f, f + 4);
@@ -592,6 +606,7 @@ KbTraverseParams make_params(kb_engine* e, const ItemSet& set, const double* xf,
   p.pop_room = KB_STACK_CAP - (3 * set.maxdepth + 1) / 2 - 4;
   p.collect_stats = e->collect_stats ? 1 : 0;
   p.both_limit = e->both_limit;
+  for (const KbItem& it : set.items) if (it.kindA == KB_ELEM_BOX || it.kindB == KB_ELEM_BOX) { p.has_boxes = 1; break; }
   if (e->use_grids && set.d_probes && !set.probes.empty()) { p.probes = set.d_probes; p.nprobes = (int)set.probes.size(); p.always_on = set.d_always_on; }
   return p;
 }
@@ -618,7 +633,7 @@ int run_feasible_device(kb_engine* e, const double* dQ, int64_t N, uint8_t* d_ou
         e->stats.kernel_launches++;
       }
     }
-    CK(kb_launch_finish(e->d_state, e->d_hit, e->d_hit_elem, e->feas_items.d_items, e->d_triown, e->d_sphown, n, d_out + off,
+    CK(kb_launch_finish(e->d_state, e->d_hit, e->d_hit_elem, e->feas_items.d_items, e->d_triown, e->d_sphown, e->d_boxown, n, d_out + off,
                         d_first_pair ? d_first_pair + 2 * off : nullptr, d_nfeas, e->stream));
     e->stats.kernel_launches++;
   }
@@ -658,7 +673,7 @@ void kb_engine_destroy(kb_engine* e) {
                     e->d_drv_scale, e->d_drv_off, e->feas_items.d_items, e->env_items.d_items, e->d_xf, e->d_state, e->d_hit, e->d_hit_elem, e->d_leaf_list, e->d_flagged, e->d_state2, e->d_work,
                     e->d_counters, e->d_Q, e->d_out, e->d_pair, e->d_dist, e->d_A, e->d_B, e->d_nlev, e->d_alive, e->d_nchecks, e->d_firstbad, e->d_list,
                     e->d_eQ, e->d_efeas, e->d_scalars, e->d_weights, e->d_T, e->feas_items.d_probes, e->feas_items.d_always_on,
-                    e->d_grid[0], e->d_grid[1], e->d_grid[2], e->d_grid[3]};
+                    e->d_grid[0], e->d_grid[1], e->d_grid[2], e->d_grid[3], e->d_box32, e->d_box64, e->d_boxown};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -700,7 +715,27 @@ int kb_add_primitive(kb_engine* e, int type, const double* params, double margin
     e->geoms.push_back(std::move(g));
     return (int)e->geoms.size() - 1;
   }
-  if (type != KB_PRIM_POINT && type != KB_PRIM_SPHERE) return fail(KB_ERR_UNSUPPORTED, "primitive type %d is not supported (point, sphere and triangle are)", type);
+  if (type == KB_PRIM_BOX || type == KB_PRIM_AABB) {
+    // solid box: its surface as 12 triangles (vertex = R l + c, the same arithmetic and the same triangle list as the oracle's) plus
+    // the solid descriptor.  Vertex index = (x > 0) + 2 (y > 0) + 4 (z > 0).
+    double c[3], R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, h[3];
+    if (type == KB_PRIM_AABB) { for (int k = 0; k < 3; k++) { c[k] = 0.5 * (params[k] + params[3 + k]); h[k] = 0.5 * (params[3 + k] - params[k]); } }
+    else { memcpy(c, params, 24); memcpy(R, params + 3, 72); memcpy(h, params + 12, 24); }
+    for (int k = 0; k < 3; k++) if (!(h[k] >= 0)) return fail(KB_ERR_INVALID, "box half dimensions must be >= 0");
+    double v[24]; int nv = 0;
+    for (int sz = -1; sz <= 1; sz += 2) for (int sy = -1; sy <= 1; sy += 2) for (int sx = -1; sx <= 1; sx += 2) {
+      const double l[3] = {sx * h[0], sy * h[1], sz * h[2]};
+      for (int k = 0; k < 3; k++) v[3 * nv + k] = R[3 * k] * l[0] + R[3 * k + 1] * l[1] + R[3 * k + 2] * l[2] + c[k];
+      nv++;
+    }
+    static const int T[36] = {0, 2, 3, 0, 3, 1, 4, 5, 7, 4, 7, 6, 0, 1, 5, 0, 5, 4, 2, 6, 7, 2, 7, 3, 0, 4, 6, 0, 6, 2, 1, 3, 7, 1, 7, 5};
+    Geom g; g.kind = G_MESH; g.margin = margin; g.tri.resize(108); g.solid = true;
+    for (int t = 0; t < 36; t++) memcpy(&g.tri[3 * (size_t)t], v + 3 * T[t], 24);
+    memcpy(g.box, c, 24); memcpy(g.box + 3, R, 72); memcpy(g.box + 12, h, 24);
+    e->geoms.push_back(std::move(g));
+    return (int)e->geoms.size() - 1;
+  }
+  if (type != KB_PRIM_POINT && type != KB_PRIM_SPHERE) return fail(KB_ERR_UNSUPPORTED, "primitive type %d is not supported (point, sphere, triangle, box and aabb are)", type);
   Geom g; g.kind = G_PRIM; g.margin = margin; g.sph = {params[0], params[1], params[2], type == KB_PRIM_SPHERE ? params[3] : 0.0};
   e->geoms.push_back(std::move(g));
   return (int)e->geoms.size() - 1;
@@ -837,6 +872,12 @@ int kb_finalize(kb_engine* e, int device) {
     if (rc) return rc;
     if (G.kind == G_EMPTY) e->dgeoms[g].empty = true;
   }
+  e->dsolid.assign(e->geoms.size(), DevGeom());
+  for (size_t g = 0; g < e->geoms.size(); g++) if (e->geoms[g].solid) {
+    std::vector<double> b(e->geoms[g].box, e->geoms[g].box + 15);
+    int rc = append_geom(e, G_BOX, b, none, e->geoms[g].margin, e->dsolid[g], false);
+    if (rc) return rc;
+  }
   // ---- 2. merged world-frame environment groups: static objects with the same (element kind, margin, link mask)
   const int L = e->L, T = (int)e->terrains.size(), O = (int)e->objects.size();
   struct Grp { int kind; double margin; std::string sig; std::vector<double> elems; std::vector<int32_t> owners; };
@@ -855,8 +896,19 @@ int kb_finalize(kb_engine* e, int device) {
     std::string k = std::string(key) + sig;
     auto it = grp_index.find(k);
     if (it == grp_index.end()) { grp_index[k] = (int)grp.size(); grp.push_back({kind, G.margin, sig, {}, {}}); it = grp_index.find(k); }
-    Grp& gr = grp[it->second];
     Xf X; if (s < T) { memset(&X, 0, sizeof X); X.R[0] = X.R[4] = X.R[8] = 1; } else X = e->objT[s - T];
+    if (G.solid) {      // the solid of a static box primitive, baked into the world frame: centre X(c), axes X.R R
+      char bkey[64]; snprintf(bkey, sizeof bkey, "%d:%.17g:", (int)G_BOX, G.margin);
+      std::string bk = std::string(bkey) + sig;
+      auto bit = grp_index.find(bk);
+      if (bit == grp_index.end()) { grp_index[bk] = (int)grp.size(); grp.push_back({G_BOX, G.margin, sig, {}, {}}); bit = grp_index.find(bk); }
+      double w[15];
+      xf_apply(X, G.box, w);
+      for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) w[3 + 3 * i + j] = X.R[3 * i] * G.box[3 + j] + X.R[3 * i + 1] * G.box[6 + j] + X.R[3 * i + 2] * G.box[9 + j];
+      memcpy(w + 12, G.box + 12, 24);
+      grp[bit->second].elems.insert(grp[bit->second].elems.end(), w, w + 15); grp[bit->second].owners.push_back(s);
+    }
+    Grp& gr = grp[it->second];       // taken after the push_back above: a reference into `grp` would not survive it
     if (kind == G_MESH) {
       int nt = (int)(G.tri.size() / 9);
       for (int t = 0; t < nt; t++) {
@@ -881,7 +933,7 @@ int kb_finalize(kb_engine* e, int device) {
   for (size_t g = 0; g < grp.size(); g++) {
     int rc = append_geom(e, grp[g].kind, grp[g].elems, grp[g].owners, grp[g].margin, e->groups[g], false);
     if (rc) return rc;
-    if (g < KB_MAX_GRIDS && e->grid_res >= 8 && !e->groups[g].empty) {
+    if (g < KB_MAX_GRIDS && e->grid_res >= 8 && !e->groups[g].empty && grp[g].kind != G_BOX) {
       // pad so that every covering sphere of the links that meet this group can be cleared outside the group's bounds
       double need = 0;
       for (int j = 0; j < L; j++) if (grp[g].sig[j] == '1') {
@@ -906,6 +958,13 @@ int kb_finalize(kb_engine* e, int device) {
       int rc = add_item(e->feas_items, lg, j, link_id(e, j), e->groups[g], -1, -1, false); if (rc) return rc;
       if (e->feas_items.items.size() > before) item_src.push_back({(int)before, j, (int)g});
       rc = add_item(e->env_items, lg, j, link_id(e, j), e->groups[g], -1, -1, false); if (rc) return rc;
+      // a link that is a box primitive is solid: its interior against the group's elements (not against other solids --
+      // their surfaces are in the mesh groups)
+      const DevGeom& ls = e->dsolid[e->linkgeom[j]];
+      if (!ls.empty && grp[g].kind != G_BOX) {
+        rc = add_item(e->feas_items, ls, j, link_id(e, j), e->groups[g], -1, -1, false); if (rc) return rc;
+        rc = add_item(e->env_items, ls, j, link_id(e, j), e->groups[g], -1, -1, false); if (rc) return rc;
+      }
     }
   for (int i = 0; i < L; i++) for (int j = i + 1; j < L; j++) {
     if (geom_empty(e, e->linkgeom[i]) || geom_empty(e, e->linkgeom[j])) continue;
@@ -913,6 +972,8 @@ int kb_finalize(kb_engine* e, int device) {
     // for links under InitializeDefault, but honoured if a caller's mask sets it)
     if (!(mask_en(e, link_id(e, i), link_id(e, j)) || mask_en(e, link_id(e, i), link_id(e, i)))) continue;
     int rc = add_item(e->feas_items, e->dgeoms[e->linkgeom[i]], i, link_id(e, i), e->dgeoms[e->linkgeom[j]], j, link_id(e, j), true); if (rc) return rc;
+    if (!e->dsolid[e->linkgeom[i]].empty) { rc = add_item(e->feas_items, e->dsolid[e->linkgeom[i]], i, link_id(e, i), e->dgeoms[e->linkgeom[j]], j, link_id(e, j), true); if (rc) return rc; }
+    if (!e->dsolid[e->linkgeom[j]].empty) { rc = add_item(e->feas_items, e->dgeoms[e->linkgeom[i]], i, link_id(e, i), e->dsolid[e->linkgeom[j]], j, link_id(e, j), true); if (rc) return rc; }
   }
   if (KB_STACK_CAP - (3 * e->feas_items.maxdepth + 1) / 2 - 4 < 160) return fail(KB_ERR_UNSUPPORTED, "BVH depth sum %d exceeds the traversal stack model", e->feas_items.maxdepth);
   // ---- 4. fp32 coordinate error bound: scene extent + robot reach
@@ -988,10 +1049,14 @@ int kb_finalize(kb_engine* e, int device) {
   if ((rc = upload(e->d_tris64, e->h_tris64.data(), e->h_tris64.size() * 8, &e->static_bytes))) return rc;
   if ((rc = upload(e->d_sph32, e->h_sph32.data(), e->h_sph32.size() * 4, &e->static_bytes))) return rc;
   if ((rc = upload(e->d_sph64, e->h_sph64.data(), e->h_sph64.size() * 8, &e->static_bytes))) return rc;
+  if ((rc = upload(e->d_box32, e->h_box32.data(), e->h_box32.size() * 4, &e->static_bytes))) return rc;
+  if ((rc = upload(e->d_box64, e->h_box64.data(), e->h_box64.size() * 8, &e->static_bytes))) return rc;
+  if ((rc = upload(e->d_boxown, e->h_boxown.data(), e->h_boxown.size() * 4, &e->static_bytes))) return rc;
   if ((rc = upload(e->d_triown, e->h_triown.data(), e->h_triown.size() * 4, &e->static_bytes))) return rc;
   if ((rc = upload(e->d_sphown, e->h_sphown.data(), e->h_sphown.size() * 4, &e->static_bytes))) return rc;
   e->scene.nodes = e->d_nodes; e->scene.tris32 = e->d_tris32; e->scene.tris64 = e->d_tris64; e->scene.sph32 = e->d_sph32; e->scene.sph64 = e->d_sph64;
   e->scene.triown = e->d_triown; e->scene.sphown = e->d_sphown;
+  e->scene.box32 = e->d_box32; e->scene.box64 = e->d_box64; e->scene.boxown = e->d_boxown;
   if ((rc = upload_itemset(e->feas_items, &e->static_bytes))) return rc;
   if ((rc = upload_itemset(e->env_items, &e->static_bytes))) return rc;
   for (size_t g = 0; g < e->hgrids.size(); g++) {
@@ -1256,7 +1321,7 @@ int kb_distance_batch_device(kb_engine* e, const double* dQ, int64_t N, double u
     KbTraverseParams p = make_params(e, set, e->d_xf, n, nullptr);
     if (p.nitems > 0) { CK(timed_traverse(e, p, 1, d_out_d + off, upper_bound)); e->stats.kernel_launches++; }
     else return fail(KB_ERR_STATE, "no enabled geometry pairs to measure");
-    if (d_out_pair) { CK(kb_launch_pair_ids(e->d_hit, e->d_hit_elem, set.d_items, e->d_triown, e->d_sphown, n, d_out_pair + 2 * off, e->stream)); e->stats.kernel_launches++; }
+    if (d_out_pair) { CK(kb_launch_pair_ids(e->d_hit, e->d_hit_elem, set.d_items, e->d_triown, e->d_sphown, e->d_boxown, n, d_out_pair + 2 * off, e->stream)); e->stats.kernel_launches++; }
   }
   return KB_OK;
 }
@@ -1296,7 +1361,10 @@ static int geom_pair_query(kb_engine* e, int ga, const double* Ta, int gb, const
   }
   ItemSet set; set.nxf = 2;
   int rc = add_item(set, A, 0, ga, B, 1, gb, false); if (rc) return rc;
-  set.items[0].thr += tol;
+  // box primitives are solid: each solid against the other geometry's elements
+  if (!e->dsolid[ga].empty) { if ((rc = add_item(set, e->dsolid[ga], 0, ga, B, 1, gb, false))) return rc; }
+  if (!e->dsolid[gb].empty) { if ((rc = add_item(set, A, 0, ga, e->dsolid[gb], 1, gb, false))) return rc; }
+  for (KbItem& it : set.items) it.thr += tol;
   if ((rc = upload_itemset(set, nullptr))) return rc;
   std::vector<double> host((size_t)N * 24);
   for (int64_t i = 0; i < N; i++) { memcpy(&host[24 * (size_t)i], Ta + 12 * i, 96); memcpy(&host[24 * (size_t)i + 12], Tb + 12 * i, 96); }

@@ -194,9 +194,54 @@ __device__ __forceinline__ V3<ExactD> xform64(const double* __restrict__ xf, int
                      ExactD(T[6]) * x + ExactD(T[7]) * y + ExactD(T[8]) * z + ExactD(T[11]));
 }
 
+// ---- solid boxes (the interior of a box primitive; its surface is 12 ordinary triangles).  Every element of the other
+// geometry is measured against the solid through one reference point -- a triangle's first vertex, a sphere's centre:
+// d = dist(reference point, solid box) - radius, 0 for a point inside.  For a triangle outside the box the surface distance is
+// the true one and never larger than this term; for a triangle inside, the surfaces do not meet and this term is 0.
+__device__ __forceinline__ float point_box_dist32(const float4* __restrict__ bx, const V3<float>& p) {
+  const float4 c = __ldg(bx), u0 = __ldg(bx + 1), u1 = __ldg(bx + 2), u2 = __ldg(bx + 3);
+  const float dx = p.x - c.x, dy = p.y - c.y, dz = p.z - c.z;
+  const float g0 = fmaxf(fabsf(dx * u0.x + dy * u0.y + dz * u0.z) - c.w, 0.f);
+  const float g1 = fmaxf(fabsf(dx * u1.x + dy * u1.y + dz * u1.z) - u0.w, 0.f);
+  const float g2 = fmaxf(fabsf(dx * u2.x + dy * u2.y + dz * u2.z) - u1.w, 0.f);
+  return sqrtf(g0 * g0 + g1 * g1 + g2 * g2);
+}
+// squared fp64 distance from a world-frame point to the solid box `bi` whose frame is transform slot `slot`
+__device__ __noinline__ ExactD point_box_dist2_64(const KbScene& sc, const double* __restrict__ xf, int slot, int bi, const V3<ExactD>& pw) {
+  V3<ExactD> pl = pw;
+  if (slot >= 0) {
+    const double* T = xf + 12 * slot;
+    const V3<ExactD> d = mk3<ExactD>(pw.x - ExactD(T[9]), pw.y - ExactD(T[10]), pw.z - ExactD(T[11]));
+    pl = mk3<ExactD>(ExactD(T[0]) * d.x + ExactD(T[3]) * d.y + ExactD(T[6]) * d.z, ExactD(T[1]) * d.x + ExactD(T[4]) * d.y + ExactD(T[7]) * d.z,
+                     ExactD(T[2]) * d.x + ExactD(T[5]) * d.y + ExactD(T[8]) * d.z);
+  }
+  const double* b = sc.box64 + 16 * (size_t)bi;
+  const V3<ExactD> d = mk3<ExactD>(pl.x - ExactD(b[0]), pl.y - ExactD(b[1]), pl.z - ExactD(b[2]));
+  ExactD s(0.0);
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const ExactD q = ExactD(b[4 + 4 * k]) * d.x + ExactD(b[5 + 4 * k]) * d.y + ExactD(b[6 + 4 * k]) * d.z;
+    const ExactD g = kb_abs(q) - ExactD(b[3 + 4 * k]);
+    if (g.v > 0.0) s = s + g * g;
+  }
+  return s;
+}
+// reference point (world frame) and radius of element `el` of a TRI / SPHERE side
+__device__ __forceinline__ V3<ExactD> elem_ref_point64(const KbScene& sc, const double* __restrict__ xf, int kind, int slot, int el, double& radius) {
+  if (kind == KB_ELEM_TRI) { radius = 0.0; return xform64(xf, slot, sc.tris64 + 9 * (size_t)el); }
+  radius = sc.sph64[4 * (size_t)el + 3];
+  return xform64(xf, slot, sc.sph64 + 4 * (size_t)el);
+}
+
 // exact (fp64) distance between two elements in the world frame, minus sphere radii; 0 when triangles intersect
 __device__ __noinline__ double exact_elem_distance(const KbScene& sc, const KbItem& it, const double* __restrict__ xf,
                                                    int ea, int eb) {
+  if (it.kindA == KB_ELEM_BOX || it.kindB == KB_ELEM_BOX) {
+    const bool aBox = it.kindA == KB_ELEM_BOX;
+    double r;
+    const V3<ExactD> p = aBox ? elem_ref_point64(sc, xf, it.kindB, it.xfB, eb, r) : elem_ref_point64(sc, xf, it.kindA, it.xfA, ea, r);
+    return (kb_sqrt(point_box_dist2_64(sc, xf, aBox ? it.xfA : it.xfB, aBox ? ea : eb, p)) - ExactD(r)).v;
+  }
   if (it.kindA == KB_ELEM_TRI && it.kindB == KB_ELEM_TRI) {
     V3<ExactD> A[3], B[3];
 #pragma unroll
@@ -224,7 +269,14 @@ __device__ __noinline__ double exact_elem_distance(const KbScene& sc, const KbIt
 }
 
 // exact boolean: elements within thr of each other (thr == 0 and two triangles: surfaces intersect)
+template <bool BOXES>
 __device__ __noinline__ bool exact_elem_collide(const KbScene& sc, const KbItem& it, const double* __restrict__ xf, int ea, int eb) {
+  if (BOXES && (it.kindA == KB_ELEM_BOX || it.kindB == KB_ELEM_BOX)) {
+    const bool aBox = it.kindA == KB_ELEM_BOX;
+    double r;
+    const V3<ExactD> p = aBox ? elem_ref_point64(sc, xf, it.kindB, it.xfB, eb, r) : elem_ref_point64(sc, xf, it.kindA, it.xfA, ea, r);
+    return (kb_sqrt(point_box_dist2_64(sc, xf, aBox ? it.xfA : it.xfB, aBox ? ea : eb, p)) - ExactD(r)).v <= it.thr;
+  }
   if (it.kindA == KB_ELEM_TRI && it.kindB == KB_ELEM_TRI) {
     V3<ExactD> A[3], B[3];
 #pragma unroll
@@ -251,10 +303,32 @@ __device__ __noinline__ bool exact_elem_collide(const KbScene& sc, const KbItem&
   return dot(d, d).v <= (r * r).v;
 }
 
+// fp32 distance (radius subtracted) between the solid box on one side of an item and the reference point of the element on the
+// other side; T maps B's frame into A's.  (Inlined: as a separate function its XfF argument forced the relative transform of every
+// element phase through local memory -- C2 6.23 -> 6.99 ms.)
+__device__ __forceinline__ float fast_box_elem_distance(const KbScene& sc, const KbItem& it, const XfF& T, int ea, int eb) {
+  if (it.kindA == KB_ELEM_BOX) {           // box in A's frame, reference point of B's element mapped into it
+    float r = 0.f; V3<float> p;
+    if (it.kindB == KB_ELEM_TRI) p = xform(T, __ldg(sc.tris32 + 3 * (size_t)eb));
+    else { const float4 sp = __ldg(sc.sph32 + eb); r = sp.w; p = xform(T, sp); }
+    return point_box_dist32(sc.box32 + 4 * (size_t)ea, p) - r;
+  }
+  float r = 0.f; float4 q;                 // box in B's frame: A's reference point through the inverse of T
+  if (it.kindA == KB_ELEM_TRI) q = __ldg(sc.tris32 + 3 * (size_t)ea); else { q = __ldg(sc.sph32 + ea); r = q.w; }
+  const float dx = q.x - T.t[0], dy = q.y - T.t[1], dz = q.z - T.t[2];
+  const V3<float> p = mk3<float>(T.r[0] * dx + T.r[3] * dy + T.r[6] * dz, T.r[1] * dx + T.r[4] * dy + T.r[7] * dz, T.r[2] * dx + T.r[5] * dy + T.r[8] * dz);
+  return point_box_dist32(sc.box32 + 4 * (size_t)eb, p) - r;
+}
+
 // fp32 filtered boolean for one element pair in A's frame.  Returns KB_NO / KB_YES / KB_UNCERTAIN.
+template <bool BOXES>
 __device__ __forceinline__ int fast_elem_collide(const KbScene& sc, const KbItem& it, const XfF& T, int ea, int eb, float thr) {
   const float delta = sc.eps_abs;
   const float band = 16.f * delta;
+  if (BOXES && (it.kindA == KB_ELEM_BOX || it.kindB == KB_ELEM_BOX)) {
+    const float d = fast_box_elem_distance(sc, it, T, ea, eb);
+    return d < thr - band ? KB_YES : (d > thr + band ? KB_NO : KB_UNCERTAIN);
+  }
   if (it.kindA == KB_ELEM_TRI && it.kindB == KB_ELEM_TRI) {
     const float4* ta = sc.tris32 + 3 * (size_t)ea; const float4* tb = sc.tris32 + 3 * (size_t)eb;
     float4 a0 = __ldg(ta), a1 = __ldg(ta + 1), a2 = __ldg(ta + 2), b0 = __ldg(tb), b1 = __ldg(tb + 1), b2 = __ldg(tb + 2);
@@ -294,6 +368,7 @@ __device__ __forceinline__ int fast_elem_collide(const KbScene& sc, const KbItem
 // kernel to skip the fp64 evaluation of pairs that cannot improve the running minimum.  Point / sphere pairs: the distance
 // itself; triangle pairs: a plane-separation lower bound (80 flops instead of the 15-feature distance).
 __device__ __forceinline__ float fast_elem_distance(const KbScene& sc, const KbItem& it, const XfF& T, int ea, int eb) {
+  if (it.kindA == KB_ELEM_BOX || it.kindB == KB_ELEM_BOX) return fast_box_elem_distance(sc, it, T, ea, eb);
   if (it.kindA == KB_ELEM_TRI && it.kindB == KB_ELEM_TRI) {
     const float4* ta = sc.tris32 + 3 * (size_t)ea; const float4* tb = sc.tris32 + 3 * (size_t)eb;
     float4 a0 = __ldg(ta), a1 = __ldg(ta + 1), a2 = __ldg(ta + 2), b0 = __ldg(tb), b1 = __ldg(tb + 1), b2 = __ldg(tb + 2);
@@ -340,6 +415,7 @@ __device__ __forceinline__ float fast_elem_distance(const KbScene& sc, const KbI
 #ifndef KB_BOOL_LEAFQ_CAP
 #define KB_BOOL_LEAFQ_CAP KB_LEAFQ_CAP   // leaf-pair queue of the boolean kernel (>= KB_LEAF_TRIGGER + 32)
 #endif
+template <bool BOXES>
 __device__ __forceinline__ void drain_rechecks(const KbTraverseParams& p, uint4* rq, int* rq_count, int lane, int64_t cur_c,
                                                int& found, int& found_ea, int& found_eb, bool all) {
   __syncwarp();
@@ -355,7 +431,7 @@ __device__ __forceinline__ void drain_rechecks(const KbTraverseParams& p, uint4*
       const bool moot = (c == cur_c) ? (found >= 0) : (p.hit[c] >= 0);
       if (!moot) {
         const KbItem& it = p.items[e.y];
-        yes = exact_elem_collide(p.scene, it, p.xf64 + c * (int64_t)p.nxf * 12, (int)e.z, (int)e.w);
+        yes = exact_elem_collide<BOXES>(p.scene, it, p.xf64 + c * (int64_t)p.nxf * 12, (int)e.z, (int)e.w);
       }
     }
     rqn -= m;
@@ -500,7 +576,10 @@ __device__ __forceinline__ void node_test(const KbTraverseParams& p, const ItemS
   }
 }
 
-template <bool ITC, bool STATS, int BPS>
+// BOXES: the work list holds solid-box items.  The box predicates -- fp32 and the fp64 recheck -- are compiled only into that
+// instantiation so the common kernel keeps its register allocation: with the box branch inside the shared, not inlined
+// exact_elem_collide, its larger clobber set cost the calling kernel spills on the hot path (C2 6.23 -> 6.99 ms, C3 7.83 -> 9.59).
+template <bool ITC, bool STATS, int BPS, bool BOXES>
 __global__ void __launch_bounds__(KB_WARPS_PER_BLOCK * 32, BPS)
 kb_traverse_kernel(const KbTraverseParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -643,13 +722,13 @@ kb_traverse_kernel(const KbTraverseParams p) {
               const float thr = (float)it.thr;
               for (int i = 0; i < ca && res != KB_YES; i++)
                 for (int j = 0; j < cb && res != KB_YES; j++) {
-                  int r = fast_elem_collide(sc, it, T, fa + i, fb + j, thr);
+                  int r = fast_elem_collide<BOXES>(sc, it, T, fa + i, fb + j, thr);
                   if (STATS) st_leaf++;
                   if (r == KB_UNCERTAIN) {
                     if (STATS) st_re++;
                     const int slot = atomicAdd(rq_count, 1);
                     if (slot < KB_RQ_CAP) { rq[slot] = make_uint4((unsigned)c, (unsigned)item, (unsigned)(fa + i), (unsigned)(fb + j)); r = KB_NO; }
-                    else r = exact_elem_collide(sc, it, xf, fa + i, fb + j) ? KB_YES : KB_NO;   // queue full: recheck in place
+                    else r = exact_elem_collide<BOXES>(sc, it, xf, fa + i, fb + j) ? KB_YES : KB_NO;   // queue full: recheck in place
                   }
                   if (r == KB_YES) { res = KB_YES; ea = fa + i; eb = fb + j; }
                 }
@@ -663,7 +742,7 @@ kb_traverse_kernel(const KbTraverseParams p) {
               found = __shfl_sync(FULL, item, src); found_ea = __shfl_sync(FULL, ea, src); found_eb = __shfl_sync(FULL, eb, src);
               break;
             }
-            drain_rechecks(p, rq, rq_count, lane, (int64_t)c, found, found_ea, found_eb, false);
+            drain_rechecks<BOXES>(p, rq, rq_count, lane, (int64_t)c, found, found_ea, found_eb, false);
             if (found >= 0) break;
           }
           __syncwarp();
@@ -765,7 +844,7 @@ kb_traverse_kernel(const KbTraverseParams p) {
     }
   }
   // pairs still parked for the fp64 recheck belong to configurations already written as "no hit": resolve them now
-  { int f = 0, fa = 0, fb = 0; drain_rechecks(p, rq, rq_count, lane, (int64_t)-1, f, fa, fb, true); }
+  { int f = 0, fa = 0, fb = 0; drain_rechecks<BOXES>(p, rq, rq_count, lane, (int64_t)-1, f, fa, fb, true); }
 }
 
 // =============================================================================================== all colliding pairs
@@ -855,14 +934,14 @@ kb_allpairs_kernel(const KbTraverseParams p, int max_pairs, int32_t* __restrict_
           for (int i = 0; i < ca && !hit; i++)
             for (int j = 0; j < cb && !hit; j++) {
               int pa = it.idA, pb = it.idB;
-              if (pa < 0) pa = (it.kindA == KB_ELEM_TRI ? sc.triown : sc.sphown)[fa + i];
-              if (pb < 0) pb = (it.kindB == KB_ELEM_TRI ? sc.triown : sc.sphown)[fb + j];
+              if (pa < 0) pa = (it.kindA == KB_ELEM_TRI ? sc.triown : (it.kindA == KB_ELEM_BOX ? sc.boxown : sc.sphown))[fa + i];
+              if (pb < 0) pb = (it.kindB == KB_ELEM_TRI ? sc.triown : (it.kindB == KB_ELEM_BOX ? sc.boxown : sc.sphown))[fb + j];
               kb_order_pair(it.flags, pa, pb);
               bool known = false;
               for (int k = 0; k < nfound && k < KB_AP_MAX; k++) known |= (foundp[k].x == pa && foundp[k].y == pb);
               if (known) continue;
-              int r = fast_elem_collide(sc, it, T, fa + i, fb + j, thr);
-              if (r == KB_UNCERTAIN) r = exact_elem_collide(sc, it, xf, fa + i, fb + j) ? KB_YES : KB_NO;
+              int r = fast_elem_collide<true>(sc, it, T, fa + i, fb + j, thr);
+              if (r == KB_UNCERTAIN) r = exact_elem_collide<true>(sc, it, xf, fa + i, fb + j) ? KB_YES : KB_NO;
               if (r == KB_YES) { hit = true; ia = pa; ib = pb; }
             }
         }
@@ -1096,9 +1175,9 @@ kb_leaves_kernel(const KbTraverseParams p, const KbSplitParams q) {
     bool hit = false; int ea = -1, eb = -1;
     for (int ii = 0; ii < ca && !hit; ii++)
       for (int jj = 0; jj < cb && !hit; jj++) {
-        int r = fast_elem_collide(sc, it, T, fa + ii, fb + jj, thr);
+        int r = fast_elem_collide<true>(sc, it, T, fa + ii, fb + jj, thr);
         if (STATS) n_leaf++;
-        if (r == KB_UNCERTAIN) { if (STATS) n_re++; r = exact_elem_collide(sc, it, xf, fa + ii, fb + jj) ? KB_YES : KB_NO; }
+        if (r == KB_UNCERTAIN) { if (STATS) n_re++; r = exact_elem_collide<true>(sc, it, xf, fa + ii, fb + jj) ? KB_YES : KB_NO; }
         if (r == KB_YES) { hit = true; ea = fa + ii; eb = fb + jj; }
       }
     if (hit && atomicCAS(p.hit + c, -1, item) == -1 && p.hit_elem) { p.hit_elem[2 * (size_t)c] = ea; p.hit_elem[2 * (size_t)c + 1] = eb; }
@@ -1356,7 +1435,7 @@ kb_distance_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
 // =============================================================================================== result kernels
 // feasible[c] = limits ok && no hit ; first_pair = world ids of the reported pair
 __global__ void kb_finish_kernel(const uint8_t* __restrict__ state, const int32_t* __restrict__ hit, const int32_t* __restrict__ hit_elem,
-                                 const KbItem* __restrict__ items, const int32_t* __restrict__ triown, const int32_t* __restrict__ sphown,
+                                 const KbItem* __restrict__ items, const int32_t* __restrict__ triown, const int32_t* __restrict__ sphown, const int32_t* __restrict__ boxown,
                                  int64_t N, uint8_t* __restrict__ out, int32_t* __restrict__ first_pair, unsigned long long* nfeasible) {
   int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool feas = false;
@@ -1369,8 +1448,8 @@ __global__ void kb_finish_kernel(const uint8_t* __restrict__ state, const int32_
       if (state[c] != 0 && h >= 0) {
         const KbItem it = items[h];
         ia = it.idA; ib = it.idB;
-        if (ia < 0) ia = (it.kindA == KB_ELEM_TRI ? triown : sphown)[hit_elem[2 * c]];
-        if (ib < 0) ib = (it.kindB == KB_ELEM_TRI ? triown : sphown)[hit_elem[2 * c + 1]];
+        if (ia < 0) ia = (it.kindA == KB_ELEM_TRI ? triown : (it.kindA == KB_ELEM_BOX ? boxown : sphown))[hit_elem[2 * c]];
+        if (ib < 0) ib = (it.kindB == KB_ELEM_TRI ? triown : (it.kindB == KB_ELEM_BOX ? boxown : sphown))[hit_elem[2 * c + 1]];
     kb_order_pair(it.flags, ia, ib);
         kb_order_pair(it.flags, ia, ib);
       }
@@ -1384,15 +1463,15 @@ __global__ void kb_finish_kernel(const uint8_t* __restrict__ state, const int32_
 }
 
 __global__ void kb_pair_ids_kernel(const int32_t* __restrict__ hit, const int32_t* __restrict__ hit_elem, const KbItem* __restrict__ items,
-                                   const int32_t* __restrict__ triown, const int32_t* __restrict__ sphown, int64_t N, int32_t* __restrict__ pair) {
+                                   const int32_t* __restrict__ triown, const int32_t* __restrict__ sphown, const int32_t* __restrict__ boxown, int64_t N, int32_t* __restrict__ pair) {
   int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= N) return;
   int h = hit[c], ia = -1, ib = -1;
   if (h >= 0) {
     const KbItem it = items[h];
     ia = it.idA; ib = it.idB;
-    if (ia < 0) ia = (it.kindA == KB_ELEM_TRI ? triown : sphown)[hit_elem[2 * c]];
-    if (ib < 0) ib = (it.kindB == KB_ELEM_TRI ? triown : sphown)[hit_elem[2 * c + 1]];
+    if (ia < 0) ia = (it.kindA == KB_ELEM_TRI ? triown : (it.kindA == KB_ELEM_BOX ? boxown : sphown))[hit_elem[2 * c]];
+    if (ib < 0) ib = (it.kindB == KB_ELEM_TRI ? triown : (it.kindB == KB_ELEM_BOX ? boxown : sphown))[hit_elem[2 * c + 1]];
     kb_order_pair(it.flags, ia, ib);
   }
   pair[2 * c] = ia; pair[2 * c + 1] = ib;
@@ -1619,19 +1698,19 @@ cudaError_t kb_launch_fk(const KbRobotDev* robot, const KbDriverDev* drv, const 
   return cudaGetLastError();
 }
 
-template <bool ITC, bool STATS, int BPS>
+template <bool ITC, bool STATS, int BPS, bool BOXES>
 static cudaError_t launch_traverse_t(const KbTraverseParams& p, int num_sms, size_t smem, cudaStream_t s) {
   static bool attr_set[64] = {false};      // the attribute is per device
   int dev = 0; cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(kb_traverse_kernel<ITC, STATS, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(kb_traverse_kernel<ITC, STATS, BPS, BOXES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   int per_sm = (int)((224 * 1024) / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > BPS) per_sm = BPS;
   int64_t want = (p.N + 8 * KB_WARPS_PER_BLOCK - 1) / (8 * KB_WARPS_PER_BLOCK);
   int64_t grid = (int64_t)num_sms * per_sm; if (grid > want) grid = want; if (grid < 1) grid = 1;
-  kb_traverse_kernel<ITC, STATS, BPS><<<(unsigned)grid, KB_WARPS_PER_BLOCK * 32, smem, s>>>(p);
+  kb_traverse_kernel<ITC, STATS, BPS, BOXES><<<(unsigned)grid, KB_WARPS_PER_BLOCK * 32, smem, s>>>(p);
   return cudaGetLastError();
 }
 
@@ -1659,10 +1738,12 @@ cudaError_t kb_launch_traverse(const KbTraverseParams& p, int mode, double* out_
 #ifndef KB_BPS_HI
 #define KB_BPS_HI 5
 #endif
-#define KB_LT(I, S) (four ? launch_traverse_t<I, S, KB_BPS_HI>(p, num_sms, smem, s) : launch_traverse_t<I, S, 3>(p, num_sms, smem, s))
+#define KB_LT2(I, S, B) (four ? launch_traverse_t<I, S, KB_BPS_HI, B>(p, num_sms, smem, s) : launch_traverse_t<I, S, 3, B>(p, num_sms, smem, s))
+#define KB_LT(I, S) (p.has_boxes ? KB_LT2(I, S, true) : KB_LT2(I, S, false))
   if (p.collect_stats) return itc ? KB_LT(true, true) : KB_LT(false, true);
   return itc ? KB_LT(true, false) : KB_LT(false, false);
 #undef KB_LT
+#undef KB_LT2
 }
 
 size_t kb_nodes_smem_bytes(int nxf, int nitems, int stack_cap) {
@@ -1730,16 +1811,16 @@ cudaError_t kb_launch_allpairs(const KbTraverseParams& p, int max_pairs, int32_t
 }
 
 cudaError_t kb_launch_finish(const uint8_t* state, const int32_t* hit, const int32_t* hit_elem, const KbItem* items, const int32_t* triown,
-                             const int32_t* sphown, int64_t N, uint8_t* out, int32_t* first_pair, unsigned long long* nfeasible, cudaStream_t s) {
+                             const int32_t* sphown, const int32_t* boxown, int64_t N, uint8_t* out, int32_t* first_pair, unsigned long long* nfeasible, cudaStream_t s) {
   if (N <= 0) return cudaSuccess;
-  kb_finish_kernel<<<nblocks(N, 256), 256, 0, s>>>(state, hit, hit_elem, items, triown, sphown, N, out, first_pair, nfeasible);
+  kb_finish_kernel<<<nblocks(N, 256), 256, 0, s>>>(state, hit, hit_elem, items, triown, sphown, boxown, N, out, first_pair, nfeasible);
   return cudaGetLastError();
 }
 
-cudaError_t kb_launch_pair_ids(const int32_t* hit, const int32_t* hit_elem, const KbItem* items, const int32_t* triown, const int32_t* sphown,
+cudaError_t kb_launch_pair_ids(const int32_t* hit, const int32_t* hit_elem, const KbItem* items, const int32_t* triown, const int32_t* sphown, const int32_t* boxown,
                                int64_t N, int32_t* pair, cudaStream_t s) {
   if (N <= 0) return cudaSuccess;
-  kb_pair_ids_kernel<<<nblocks(N, 256), 256, 0, s>>>(hit, hit_elem, items, triown, sphown, N, pair);
+  kb_pair_ids_kernel<<<nblocks(N, 256), 256, 0, s>>>(hit, hit_elem, items, triown, sphown, boxown, N, pair);
   return cudaGetLastError();
 }
 

@@ -11,8 +11,8 @@ cudaError_t kb_launch_fk(const KbRobotDev* robot, const KbDriverDev* drv, const 
 // mode 0: boolean collide, mode 1: branch-and-bound distance (out_dist, upper_bound)
 cudaError_t kb_launch_traverse(const KbTraverseParams& p, int mode, double* out_dist, double upper_bound, int num_sms, cudaStream_t s);
 cudaError_t kb_launch_finish(const uint8_t* state, const int32_t* hit, const int32_t* hit_elem, const KbItem* items, const int32_t* triown,
-                             const int32_t* sphown, int64_t N, uint8_t* out, int32_t* first_pair, unsigned long long* nfeasible, cudaStream_t s);
-cudaError_t kb_launch_pair_ids(const int32_t* hit, const int32_t* hit_elem, const KbItem* items, const int32_t* triown, const int32_t* sphown,
+                             const int32_t* sphown, const int32_t* boxown, int64_t N, uint8_t* out, int32_t* first_pair, unsigned long long* nfeasible, cudaStream_t s);
+cudaError_t kb_launch_pair_ids(const int32_t* hit, const int32_t* hit_elem, const KbItem* items, const int32_t* triown, const int32_t* sphown, const int32_t* boxown,
                                int64_t N, int32_t* pair, cudaStream_t s);
 cudaError_t kb_launch_edge_setup(const KbRobotDev* robot, const double* A, const double* B, const double* w, int64_t N, double eps,
                                  int32_t* nlev, uint8_t* alive, int32_t* nchecks, int32_t* maxlev, cudaStream_t s);

@@ -11,6 +11,7 @@
 //   tris64   double[9*n]   the same triangles in fp64 for the exact recheck
 //   sph32    float4[n]     point-cloud points / sphere primitives: xyz, radius ; sph64 double[4*n]
 //   sphown   int[n]        owner world id per sphere element
+//   box32/64 float4[4n] / double[16n]  solid boxes of box primitives (centre, axes, half dimensions); boxown int[n]
 //   items    KbItem[]      the per-configuration work list: one entry per enabled geometry pair
 //                          (link vs merged environment group, link vs link)
 //   robot    KbRobotDev    SoA joint arrays for FK
@@ -39,7 +40,7 @@
 #define KB_BLOCKS_PER_SM 4         // resident CTAs per SM the traversal kernel is compiled for (register cap = 65536 / (128 * this))
 #endif
 
-enum { KB_ELEM_TRI = 0, KB_ELEM_SPHERE = 1 };
+enum { KB_ELEM_TRI = 0, KB_ELEM_SPHERE = 1, KB_ELEM_BOX = 2 };   // BOX: the solid of a box primitive (its surface is 12 TRI elements)
 
 // Clearance grids (broad phase of the boolean query).  For every merged static environment group a uniform voxel grid
 // over the group's bounds (+ a pad) stores, per voxel, a conservative lower bound on the distance from ANY point of the
@@ -103,6 +104,9 @@ struct KbScene {                  // device pointers to the static data
   const double* sph64;
   const int32_t* triown;
   const int32_t* sphown;
+  const float4* box32;            // solid boxes: 4 x float4 per box = {centre.xyz, hx} {axis0.xyz, hy} {axis1.xyz, hz} {axis2.xyz, -}
+  const double* box64;            // 16 doubles per box in the same order
+  const int32_t* boxown;
   float eps_abs;                  // absolute fp32 coordinate error bound for this scene (metres)
   float qo[3], qs[3];             // KB_QNODES builds only: origin and step of the 16-bit node quantisation grid
   KbClearGrid grids[KB_MAX_GRIDS];
@@ -122,6 +126,7 @@ struct KbTraverseParams {
   unsigned long long* counters;   // [0] rechecks, [1] node tests, [2] leaf tests, [7] items dropped by the clearance grids (optional statistics)
   int32_t wide_limit;             // stack size up to which 32-wide pops are allowed
   int32_t collect_stats;
+  int32_t has_boxes;              // the work list holds solid-box items (selects the kernel instantiation with the box predicates)
   int32_t pop_room;               // boolean kernel: m entries may be popped while sp + 3 m <= pop_room (see make_params)
   int32_t both_limit;             // frontier size up to which comparable inner pairs push all four child pairs (0 = never)
   const KbProbe* probes;          // clearance probes of this item set (boolean kernel only); null / 0 = no pre-filter

@@ -64,9 +64,9 @@ class Engine:
                 p = _f64(g.points)
                 r = None if g.radius is None else _f64(g.radius)
                 check(lib.kb_add_pointcloud(h, p.ctypes.data_as(dp), len(p), None if r is None else r.ctypes.data_as(dp), g.margin))
-            elif g.kind == "triangle":
+            elif g.kind in ("triangle", "box"):
                 p = _f64(g.params)
-                check(lib.kb_add_primitive(h, 2, p.ctypes.data_as(dp), g.margin))
+                check(lib.kb_add_primitive(h, 2 if g.kind == "triangle" else 3, p.ctypes.data_as(dp), g.margin))
             elif g.kind in ("sphere", "point"):
                 p = _f64(g.params)
                 check(lib.kb_add_primitive(h, 1 if g.kind == "sphere" else 0, p.ctypes.data_as(dp), g.margin))

@@ -47,6 +47,14 @@ class GeometricPrimitive:
     def setSphere(self, c, r):
         self.type, self.properties = "Sphere", [float(x) for x in c] + [float(r)]
 
+    def setAABB(self, bmin, bmax):
+        self.type, self.properties = "AABB", [float(x) for x in bmin] + [float(x) for x in bmax]
+
+    def setBox(self, ori, R, dims):
+        """Klamp't's convention (Python/klampt/src/geometry.h GeometricPrimitive.setBox): `ori` is the box's ORIGIN corner, `R`
+        a column-major so3 9-list whose columns are the box axes, `dims` the full edge lengths"""
+        self.type, self.properties = "Box", [float(x) for x in ori] + [float(x) for x in R] + [float(x) for x in dims]
+
     def setTriangle(self, a, b, c):
         self.type, self.properties = "Triangle", [float(x) for x in a] + [float(x) for x in b] + [float(x) for x in c]
 
@@ -110,8 +118,8 @@ class Geometry3D:
         self._kind, self._data, self._version = "cloud", pc, self._version + 1
 
     def setGeometricPrimitive(self, p: GeometricPrimitive):
-        if p.type not in ("Point", "Sphere", "Triangle"):
-            raise ValueError("GeometricPrimitive type %r is not supported by the batched engine (Point, Sphere and Triangle are)" % p.type)
+        if p.type not in ("Point", "Sphere", "Triangle", "AABB", "Box"):
+            raise ValueError("GeometricPrimitive type %r is not supported by the batched engine (Point, Sphere, Triangle, AABB and Box are)" % p.type)
         self._kind, self._data, self._version = "prim", p, self._version + 1
 
     def getTriangleMesh(self) -> TriangleMesh:
@@ -156,6 +164,11 @@ class Geometry3D:
             p = self._data
             if p.type == "Triangle":
                 return GeomSpec.triangle(p.properties[:3], p.properties[3:6], p.properties[6:9], self._margin)
+            if p.type == "AABB":
+                return GeomSpec.aabb(p.properties[:3], p.properties[3:6], self._margin)
+            if p.type == "Box":
+                ori, M, dims = np.asarray(p.properties[:3]), so3.matrix(p.properties[3:12]), np.asarray(p.properties[12:15])
+                return GeomSpec.box(ori + M @ (0.5 * dims), M, 0.5 * dims, self._margin)
             return GeomSpec.point(p.properties[:3], self._margin) if p.type == "Point" else GeomSpec.sphere(p.properties[:3], p.properties[3], self._margin)
         return GeomSpec("empty")
 
@@ -165,6 +178,11 @@ class Geometry3D:
         if self._kind == "cloud":
             return self._data.points
         if self._kind == "prim":
+            if self._data.type in ("AABB", "Box"):
+                g = self.to_spec()
+                c, M, h = g.params[:3], g.params[3:12].reshape(3, 3), g.params[12:15]
+                corners = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], dtype=np.float64) * h
+                return corners @ M.T + c
             n = 9 if self._data.type == "Triangle" else 3
             return np.asarray(self._data.properties[:n], dtype=np.float64).reshape(-1, 3)
         return np.zeros((0, 3))
@@ -259,6 +277,15 @@ class Geometry3D:
         eng, ga, gb = self._pair_engine(other)
         d = float(eng.geom_distance_batch(ga, self._T12(), gb, other._T12(), upper_bound=settings.upperBound)[0])
         return DistanceQueryResult(d)
+
+
+def _prim_from_spec(g: GeomSpec) -> GeometricPrimitive:
+    if g.kind == "box":
+        c, M, h = g.params[:3], g.params[3:12].reshape(3, 3), g.params[12:15]
+        p = GeometricPrimitive()
+        p.setBox(list(c - M @ h), so3.from_matrix(M), list(2.0 * h))
+        return p
+    return GeometricPrimitive({"sphere": "Sphere", "point": "Point", "triangle": "Triangle"}[g.kind], list(g.params))
 
 
 _POINT_PROBE = Geometry3D()
@@ -374,8 +401,8 @@ class RobotModel(_Named):
                     self._links[i]._geom.setTriangleMesh(TriangleMesh(g.verts, g.tris))
                 elif g.kind == "cloud":
                     self._links[i]._geom.setPointCloud(PointCloud(g.points, g.radius))
-                elif g.kind in ("sphere", "point", "triangle"):
-                    self._links[i]._geom.setGeometricPrimitive(GeometricPrimitive({"sphere": "Sphere", "point": "Point", "triangle": "Triangle"}[g.kind], list(g.params)))
+                elif g.kind in ("sphere", "point", "triangle", "box"):
+                    self._links[i]._geom.setGeometricPrimitive(_prim_from_spec(g))
                 self._links[i]._geom._margin = g.margin
         self._q = np.clip(np.zeros(L), self._qmin, self._qmax)
         self._selfcol = None
@@ -642,5 +669,5 @@ def _fill(geom: Geometry3D, g: Optional[GeomSpec]):
     elif g.kind == "cloud":
         geom.setPointCloud(PointCloud(g.points, g.radius))
     else:
-        geom.setGeometricPrimitive(GeometricPrimitive({"sphere": "Sphere", "point": "Point", "triangle": "Triangle"}[g.kind], list(g.params)))
+        geom.setGeometricPrimitive(_prim_from_spec(g))
     geom._margin = g.margin

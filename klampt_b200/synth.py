@@ -377,6 +377,26 @@ def world_floating(seed_index: int = 7, n_obstacles: int = 40) -> WorldSpec:
     return w
 
 
+def world_boxes(seed_index: int = 8, n_boxes: int = 14, n_blobs: int = 6) -> WorldSpec:
+    """arm6 whose pedestal and elbow are solid box primitives, among solid oriented boxes (some large enough to swallow a
+    whole link: only the solid semantics sees those), a few blobs, over a solid slab (AABB primitive) as the terrain."""
+    rng = np.random.default_rng(BASE_SEED + seed_index)
+    w = WorldSpec()
+    w.terrains.append(w.add_geom(GeomSpec.aabb([-2.0, -2.0, -0.05], [2.0, 2.0, 0.0])))
+    for i, c in enumerate(_obstacle_centres(rng, n_boxes, keepout=0.35)):
+        big = i % 4 == 0
+        h = rng.uniform(0.15, 0.3, size=3) if big else rng.uniform(0.03, 0.12, size=3)
+        g = w.add_geom(GeomSpec.box(rng.uniform(-0.02, 0.02, size=3), _random_rotation(rng), h))
+        w.objects.append((g, make_T(_random_rotation(rng), c)))
+    for c in _obstacle_centres(rng, n_blobs, keepout=0.4):
+        v, t = blob_mesh(rng, 3, rng.uniform(0.05, 0.15))
+        w.objects.append((w.add_geom(GeomSpec.mesh(v, t)), make_T(_random_rotation(rng), c)))
+    w.robot = make_arm6(w)
+    w.robot.link_geom[0] = w.add_geom(GeomSpec.aabb([-0.14, -0.14, 0.0], [0.14, 0.14, 0.22]))
+    w.robot.link_geom[3] = w.add_geom(GeomSpec.box([0.0, 0.0, 0.04], rot_axis_angle([0, 0, 1], 0.3), [0.07, 0.06, 0.08]))
+    return w
+
+
 def world_c3() -> WorldSpec:
     """C3: 15-DOF dual-arm torso, no environment (self-collision only)."""
     w = WorldSpec()

@@ -23,7 +23,7 @@ import numpy as np
 
 REVOLUTE, PRISMATIC = 0, 1
 JOINT_WELD, JOINT_NORMAL, JOINT_SPIN, JOINT_FLOATING, JOINT_FLOATINGPLANAR, JOINT_BALLANDSOCKET, JOINT_CLOSED = range(7)
-PRIM_POINT, PRIM_SPHERE, PRIM_TRIANGLE = 0, 1, 2
+PRIM_POINT, PRIM_SPHERE, PRIM_TRIANGLE, PRIM_BOX, PRIM_AABB = 0, 1, 2, 3, 4
 
 IDENTITY12 = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], dtype=np.float64)
 
@@ -31,12 +31,12 @@ IDENTITY12 = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], dtype=np.float64)
 @dataclass
 class GeomSpec:
     """One collision geometry in its local frame (AnyCollisionGeometry3D minus the current transform)."""
-    kind: str = "empty"                      # 'mesh' | 'cloud' | 'sphere' | 'point' | 'triangle' | 'empty'
+    kind: str = "empty"                      # 'mesh' | 'cloud' | 'sphere' | 'point' | 'triangle' | 'box' | 'empty'
     verts: Optional[np.ndarray] = None       # (nv,3) f64   (mesh)
     tris: Optional[np.ndarray] = None        # (nt,3) i32   (mesh)
     points: Optional[np.ndarray] = None      # (n,3)  f64   (cloud)
     radius: Optional[np.ndarray] = None      # (n,)   f64 or None (cloud)
-    params: Optional[np.ndarray] = None      # sphere: cx,cy,cz,r ; point: x,y,z ; triangle: a,b,c (9)
+    params: Optional[np.ndarray] = None      # sphere: cx,cy,cz,r ; point: x,y,z ; triangle: a,b,c (9) ; box: centre(3), row-major R whose columns are the axes (9), half dims(3)
     margin: float = 0.0
 
     @staticmethod
@@ -62,6 +62,18 @@ class GeomSpec:
     def triangle(a, b, c, margin=0.0) -> "GeomSpec":
         return GeomSpec("triangle", params=np.concatenate([np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64),
                                                             np.asarray(c, dtype=np.float64)]), margin=float(margin))
+
+    @staticmethod
+    def box(center, R, half, margin=0.0) -> "GeomSpec":
+        """solid oriented box (GeometricPrimitive3D Box3D): centre, 3x3 whose COLUMNS are the box axes, half dimensions"""
+        return GeomSpec("box", params=np.concatenate([np.asarray(center, dtype=np.float64).reshape(3), np.asarray(R, dtype=np.float64).reshape(9),
+                                                       np.asarray(half, dtype=np.float64).reshape(3)]), margin=float(margin))
+
+    @staticmethod
+    def aabb(lo, hi, margin=0.0) -> "GeomSpec":
+        """solid axis-aligned box (AABB3D) in the geometry's local frame"""
+        lo, hi = np.asarray(lo, dtype=np.float64), np.asarray(hi, dtype=np.float64)
+        return GeomSpec.box(0.5 * (lo + hi), np.eye(3), 0.5 * (hi - lo), margin)
 
     def num_elements(self) -> int:
         if self.kind == "mesh":

@@ -88,6 +88,8 @@ typedef struct {
   node_t* nodes; int nnodes;
   double lo[3], hi[3];  /* local AABB */
   double rmax;          /* largest element radius (0 for meshes) */
+  int solid;            /* box primitive: the mesh holds its 12 surface triangles, and the interior counts too */
+  double bc[3], bR[9], bh[3];   /* solid box: centre, axes (columns of the row-major bR), half dimensions, local frame */
 } geom_t;
 
 typedef struct { int n; int32_t* links; double* scale; double* offset; double dmin, dmax; } driver_t;
@@ -344,6 +346,25 @@ int ko_add_pointcloud(ko_world* w, const double* pts, int n, const double* radiu
 }
 int ko_add_primitive(ko_world* w, int type, const double* params, double margin) {
   if (type==KO_PRIM_TRIANGLE) { int32_t idx[3]={0,1,2}; return ko_add_trimesh(w,params,3,idx,1,margin); }   /* one-triangle mesh */
+  if (type==KO_PRIM_BOX || type==KO_PRIM_AABB) {
+    /* solid box (GeometricPrimitive3D Box3D / AABB3D; common primitives of Cpp/docs/Manual-Geometry.md:241-250): its surface
+     * as 12 triangles + the solid descriptor.  BOX params: centre(3), axes as the columns of a row-major 3x3 (9), half dims(3);
+     * AABB params: lo(3), hi(3). */
+    double c[3], R[9]={1,0,0,0,1,0,0,0,1}, h[3];
+    if (type==KO_PRIM_AABB) { for (int k=0;k<3;k++) { c[k]=0.5*(params[k]+params[3+k]); h[k]=0.5*(params[3+k]-params[k]); } }
+    else { memcpy(c,params,24); memcpy(R,params+3,72); memcpy(h,params+12,24); }
+    for (int k=0;k<3;k++) if (!(h[k]>=0)) return -1;
+    double v[24]; int nvv=0;
+    for (int sz=-1;sz<=1;sz+=2) for (int sy=-1;sy<=1;sy+=2) for (int sx=-1;sx<=1;sx+=2) {
+      double l[3]={sx*h[0],sy*h[1],sz*h[2]};
+      for (int k=0;k<3;k++) v[3*nvv+k]=R[3*k]*l[0]+R[3*k+1]*l[1]+R[3*k+2]*l[2]+c[k];
+      nvv++; }
+    /* vertex index = (x>0) + 2 (y>0) + 4 (z>0) */
+    static const int32_t T[36]={0,2,3, 0,3,1,  4,5,7, 4,7,6,  0,1,5, 0,5,4,  2,6,7, 2,7,3,  0,4,6, 0,6,2,  1,3,7, 1,7,5};
+    int gi=ko_add_trimesh(w,v,8,T,12,margin);
+    geom_t* g=&w->geoms[gi]; g->solid=1; memcpy(g->bc,c,24); memcpy(g->bR,R,72); memcpy(g->bh,h,24);
+    return gi;
+  }
   double r = (type==KO_PRIM_SPHERE) ? params[3] : 0.0;
   if (type!=KO_PRIM_POINT && type!=KO_PRIM_SPHERE) return -1;
   int gi=ko_add_pointcloud(w,params,1,&r,margin);
@@ -629,11 +650,38 @@ static void distance_rec(pairq_t* q, int ia, int ib, double* best) {
 static void pairq_init(pairq_t* q, const geom_t* A, const xf_t* Ta, const geom_t* B, const xf_t* Tb, double tol, ko_counts* cnt) {
   q->A=A; q->B=B; q->Ta=*Ta; q->Tb=*Tb; xf_mul_inv_a(Ta,Tb,&q->Tab); q->tol=tol; q->rsum=A->rmax+B->rmax; q->cnt=cnt; }
 
+/* ---- solid boxes.  A box primitive is solid: besides its surface (12 triangles, handled like any mesh) every element of the
+ * other geometry is measured against the solid through one reference point -- a triangle's first vertex, a sphere's centre:
+ *   d(element, solid) = dist(reference point, solid box) - radius        (0 for a point inside)
+ * For a triangle outside the box the surface distance is the true one and never larger than this; for a triangle inside, the
+ * surface test sees nothing and this term is 0.  For spheres it is the true signed distance by itself. */
+static double point_solid_box_dist(const geom_t* X, const xf_t* Tx, const double* pw) {
+  double pl[3], d[3], q[3]; v_sub(pw,Tx->t,d);
+  for (int k=0;k<3;k++) pl[k]=Tx->R[k]*d[0]+Tx->R[3+k]*d[1]+Tx->R[6+k]*d[2];        /* into X's local frame */
+  v_sub(pl,X->bc,d);
+  double s=0;
+  for (int k=0;k<3;k++) { q[k]=X->bR[k]*d[0]+X->bR[3+k]*d[1]+X->bR[6+k]*d[2];       /* onto the box axes (columns of bR) */
+    double g=fabs(q[k])-X->bh[k]; if (g>0) s+=g*g; }
+  return sqrt(s);
+}
+/* min over the elements of Y of d(element, solid X); stops early below `stop` (pass -DBL_MAX for the exact minimum) */
+static double solid_min_distance(const geom_t* X, const xf_t* Tx, const geom_t* Y, const xf_t* Ty, double stop) {
+  double best=DBL_MAX;
+  int n=(Y->kind==G_MESH)?Y->nt:Y->np;
+  for (int i=0;i<n;i++) { double pw[3], r=0;
+    if (Y->kind==G_MESH) xf_apply(Ty,Y->tv+9*(size_t)i,pw); else { xf_apply(Ty,Y->pts+3*(size_t)i,pw); r=Y->rad[i]; }
+    double d=point_solid_box_dist(X,Tx,pw)-r; if (d<best) { best=d; if (best<=stop) return best; } }
+  return best;
+}
+
 /* a11/a13: AnyCollisionQuery::Collide / WithinDistance(tol).  Margins add to the threshold (a12). */
 static int geom_pair_collide(const geom_t* A, const xf_t* Ta, const geom_t* B, const xf_t* Tb, double tol, ko_counts* cnt) {
   if (A->kind==G_EMPTY || B->kind==G_EMPTY) return 0;
   pairq_t q; pairq_init(&q,A,Ta,B,Tb,tol+A->margin+B->margin,cnt);
-  return collide_rec(&q,0,0);
+  if (collide_rec(&q,0,0)) return 1;
+  if (A->solid && solid_min_distance(A,Ta,B,Tb,q.tol)<=q.tol) return 1;
+  if (B->solid && solid_min_distance(B,Tb,A,Ta,q.tol)<=q.tol) return 1;
+  return 0;
 }
 /* AnyCollisionQuery::Distance(0,0,bound): geometric distance minus margins; returns bound if nothing closer */
 static double geom_pair_distance(const geom_t* A, const xf_t* Ta, const geom_t* B, const xf_t* Tb, double bound, ko_counts* cnt) {
@@ -643,6 +691,8 @@ static double geom_pair_distance(const geom_t* A, const xf_t* Ta, const geom_t* 
   double best = isinf(bound)? DBL_MAX : bound+m;
   double best0=best;
   distance_rec(&q,0,0,&best);
+  if (A->solid) { double d=solid_min_distance(A,Ta,B,Tb,-DBL_MAX); if (d<best) best=d; }
+  if (B->solid) { double d=solid_min_distance(B,Tb,A,Ta,-DBL_MAX); if (d<best) best=d; }
   if (best>=best0) return bound;
   return best-m;
 }
@@ -673,6 +723,8 @@ static double geom_pair_distance_brute(const geom_t* A, const xf_t* Ta, const ge
       if (d<best) best=d;
     }
   }
+  if (A->solid) { double d=solid_min_distance(A,Ta,B,Tb,-DBL_MAX); if (d<best) best=d; }
+  if (B->solid) { double d=solid_min_distance(B,Tb,A,Ta,-DBL_MAX); if (d<best) best=d; }
   return best-A->margin-B->margin;
 }
 double ko_geom_distance_brute(const ko_world* w, int ga, const double Ta[12], int gb, const double Tb[12]) {

@@ -151,9 +151,9 @@ class OracleWorld:
                 else:
                     r, rp = _d(g.radius)
                     L.ko_add_pointcloud(self.h, pp, len(p), rp, g.margin)
-            elif g.kind == "triangle":
+            elif g.kind in ("triangle", "box"):
                 p, pp = _d(g.params)
-                L.ko_add_primitive(self.h, 2, pp, g.margin)
+                L.ko_add_primitive(self.h, 2 if g.kind == "triangle" else 3, pp, g.margin)
             elif g.kind in ("sphere", "point"):
                 p, pp = _d(g.params)
                 L.ko_add_primitive(self.h, 1 if g.kind == "sphere" else 0, pp, g.margin)

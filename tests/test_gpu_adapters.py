@@ -209,3 +209,28 @@ def test_triangle_primitive_and_distance_point(built):
     got = cube.distance_points_batch(P)
     np.testing.assert_allclose(got, want, atol=1e-12)
     assert abs(cube.distance_point(list(P[0])).d - want[0]) < 1e-12
+
+
+def test_distance_query_state_machine_batch(built):
+    """DistanceQuery's Far / Close / Contact cycle (reference Cpp/Planning/DistanceQuery.cpp:15-76) over a batch of poses:
+    a unit cube approaching another along x."""
+    from klampt_b200 import so3
+    from klampt_b200.distancequery import DistanceQueryBatch, FAR, CLOSE, CONTACT
+    from klampt_b200.robotsim import Geometry3D, TriangleMesh
+    v, t = synth.unit_cube()
+    a = Geometry3D(); a.setTriangleMesh(TriangleMesh(v, t))
+    b = Geometry3D(); b.setTriangleMesh(TriangleMesh(v, t))
+    gaps = np.array([1.0, 0.5, 0.15, 0.05, -0.2, 0.35])
+    I = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], dtype=np.float64)
+    Ta = np.tile(I, (len(gaps), 1)); Tb = np.tile(I, (len(gaps), 1)); Tb[:, 9] = 1.0 + gaps
+    q = DistanceQueryBatch(a, b, len(gaps))
+    d = q.UpdateQuery(Ta, Tb)
+    assert list(q.s) == [FAR, FAR, CLOSE, CLOSE, CONTACT, FAR]
+    np.testing.assert_allclose(d, [0.2, 0.2, 0.15, 0.05, 0.0, 0.2], atol=1e-12)
+    assert q.launches == 2                                           # one within-distance launch, one distance launch
+    np.testing.assert_allclose(q.UpdateQuery(Ta, Tb), d)             # same cycle: cached
+    q.NextCycle()
+    Tb[:, 9] = 1.0 + gaps - 0.1                                      # everything moves 10 cm closer
+    d2 = q.UpdateQuery(Ta, Tb)
+    assert list(q.s) == [FAR, FAR, CLOSE, CONTACT, CONTACT, FAR]
+    np.testing.assert_allclose(d2, [0.2, 0.2, 0.05, 0.0, 0.0, 0.2], atol=1e-12)

@@ -442,3 +442,68 @@ def test_multi_link_joint_layout_is_validated_by_the_engine(built):
     w.robot.joint_base = None
     with pytest.raises(KbError):
         Engine(w)
+
+
+def test_solid_box_primitives_pair_queries(built):
+    """Box / AABB primitives are solid: explicit geometry-pair queries against the oracle for a box vs a
+    mesh (inside / crossing / outside), a point cloud, a sphere, and another box, at random poses."""
+    from klampt_b200.engine import Engine
+    from oracle.oracle import OracleWorld
+    rng = np.random.default_rng(41)
+    w = WorldSpec()
+    v, t = synth.unit_cube()
+    g_small = w.add_geom(GeomSpec.mesh((v - 0.5) * 0.25, t))
+    bv, bt = synth.blob_mesh(rng, 2, 0.3)
+    g_blob = w.add_geom(GeomSpec.mesh(bv, bt))
+    g_cloud = w.add_geom(GeomSpec.cloud(rng.uniform(-0.3, 0.3, size=(400, 3)), rng.uniform(0.0, 0.02, size=400)))
+    g_sph = w.add_geom(GeomSpec.sphere([0.05, 0, 0], 0.12))
+    g_box = w.add_geom(GeomSpec.box([0.05, -0.1, 0.0], synth.rot_axis_angle([1, 1, 0], 0.6), [0.5, 0.35, 0.25]))
+    g_aabb = w.add_geom(GeomSpec.aabb([-0.1, -0.15, -0.2], [0.1, 0.15, 0.2], margin=0.01))
+    w.robot = synth.make_planar_nR(w, 1)
+    eng, orc = Engine(w), OracleWorld(w)
+    N = 300
+    def poses(spread):
+        return np.stack([np.concatenate([synth._random_rotation(rng).reshape(-1), rng.uniform(-spread, spread, size=3)]) for _ in range(N)])
+    for ga, gb, spread in ((g_box, g_small, 0.5), (g_small, g_box, 0.5), (g_box, g_blob, 0.6), (g_box, g_cloud, 0.6), (g_sph, g_box, 0.6),
+                           (g_box, g_aabb, 0.5), (g_aabb, g_cloud, 0.4)):
+        Ta, Tb = poses(spread), poses(spread)
+        hit = eng.geom_collides_batch(ga, Ta, gb, Tb)
+        d = eng.geom_distance_batch(ga, Ta, gb, Tb)
+        near = eng.geom_collides_batch(ga, Ta, gb, Tb, tol=0.05)
+        want_hit = np.array([orc.geom_collides(ga, Ta[i], gb, Tb[i]) for i in range(N)])
+        want_d = np.array([orc.geom_distance(ga, Ta[i], gb, Tb[i]) for i in range(N)])
+        want_near = np.array([orc.geom_within_distance(ga, Ta[i], gb, Tb[i], 0.05) for i in range(N)])
+        assert 0.05 < want_hit.mean() < 0.98, (ga, gb, want_hit.mean())
+        bad = np.nonzero(hit != want_hit)[0]
+        assert all(abs(want_d[i]) <= BAND for i in bad)
+        bad = np.nonzero(near != want_near)[0]
+        assert all(abs(want_d[i] - 0.05) <= BAND for i in bad)
+        np.testing.assert_allclose(d, want_d, rtol=1e-5, atol=1e-9)
+
+
+def test_world_with_solid_boxes(built):
+    """a robot with box-primitive links among solid boxes, blobs and a solid slab: feasibility, first pairs, clearance and
+    edges against the oracle (a link of a chain cannot sit inside a box without a neighbour crossing its surface, so
+    containment itself is exercised by test_solid_box_primitives_pair_queries)"""
+    from klampt_b200.engine import Engine
+    from oracle.oracle import OracleWorld
+    w = synth.world_boxes()
+    eng, orc = Engine(w), OracleWorld(w)
+    Q = synth.sample_configs(w.robot, 20000, 43)
+    got, pairs = eng.feasible_batch(Q, return_pairs=True)
+    want = orc.feasible_batch(Q)
+    assert_bool_parity(got, want, Q, orc)
+    assert 0.1 < want.mean() < 0.9
+    assert ((pairs[:, 0] >= 0) == (got == 0)).all()
+    d = eng.distance_batch(Q[:1500], upper_bound=0.4, include_self=True)
+    do, _ = orc.distance_batch(Q[:1500], upper_bound=0.4, include_self=True)
+    np.testing.assert_allclose(d, do, rtol=1e-5, atol=1e-9)
+    A, B = synth.sample_edges(w.robot, lambda X: orc.feasible_batch(X), 300, 44)
+    vis, nchk = eng.edges_visible_batch(A, B, eps=0.02)
+    ovis, onchk = orc.edges_visible_batch(A, B, eps=0.02)
+    assert (vis == ovis).all() and (nchk == onchk).all()
+    eng.set_option("clear_grid", 1)
+    assert np.array_equal(eng.feasible_batch(Q), got)
+    eng.set_option("clear_grid", 0)
+    cp, cc = eng.colliding_pairs_batch(Q[:2000], max_pairs=8)
+    assert ((cc > 0) == (got[:2000] == 0)).all()

@@ -456,3 +456,51 @@ def test_triangle_primitive_is_a_one_triangle_mesh():
     assert not o.geom_collides(gt, T, gc, I)
     assert abs(o.geom_distance(gt, T, gc, I) - 0.5) < 1e-12
     assert o.geom_within_distance(gt, T, gc, I, 0.5 + 1e-9) and not o.geom_within_distance(gt, T, gc, I, 0.5 - 1e-9)
+
+
+def test_solid_box_primitive_semantics():
+    """Box / AABB primitives are solid (GeometricPrimitive3D Box3D / AABB3D; the common primitives of
+    Cpp/docs/Manual-Geometry.md:241-250): an element inside the box collides although no surfaces meet; outside, the
+    distance is the distance to the box surface.  Second method: closed-form point-to-box distance in numpy."""
+    w = WorldSpec()
+    v, t = synth.unit_cube()
+    gc = w.add_geom(GeomSpec.mesh(v * 0.2, t))
+    gb = w.add_geom(GeomSpec.aabb([0, 0, 0], [1, 1, 1]))
+    gs = w.add_geom(GeomSpec.sphere([0, 0, 0], 0.1))
+    R = synth.rot_axis_angle([1, 2, 3], 0.7)
+    go = w.add_geom(GeomSpec.box([0.1, -0.2, 0.3], R, [0.5, 0.25, 0.125]))
+    gp = w.add_geom(GeomSpec.point([0, 0, 0]))
+    w.robot = synth.make_planar_nR(w, 1)
+    o = OracleWorld(w)
+    I = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], dtype=np.float64)
+    T = I.copy(); T[9:] = [0.4, 0.4, 0.4]                       # the small cube is wholly inside the unit box
+    assert o.geom_collides(gc, T, gb, I) and o.geom_collides(gb, I, gc, T) and o.geom_distance(gc, T, gb, I) == 0.0
+    T[9:] = [1.5, 0.4, 0.4]
+    assert not o.geom_collides(gc, T, gb, I) and abs(o.geom_distance(gc, T, gb, I) - 0.5) < 1e-12
+    assert abs(o.geom_distance_brute(gc, T, gb, I) - 0.5) < 1e-12
+    T[9:] = [0.5, 0.5, 0.5]
+    assert o.geom_collides(gs, T, gb, I) and abs(o.geom_distance(gs, T, gb, I) + 0.1) < 1e-12     # centre inside: -radius
+    T[9:] = [1.3, 0.5, 0.5]
+    assert not o.geom_collides(gs, T, gb, I) and abs(o.geom_distance(gs, T, gb, I) - 0.2) < 1e-12
+    assert o.geom_within_distance(gs, T, gb, I, 0.2 + 1e-9) and not o.geom_within_distance(gs, T, gb, I, 0.2 - 1e-9)
+    # oriented box vs points at random poses of both
+    rng = np.random.default_rng(3)
+    c, h = np.array([0.1, -0.2, 0.3]), np.array([0.5, 0.25, 0.125])
+    for _ in range(200):
+        Tb = np.concatenate([synth._random_rotation(rng).reshape(-1), rng.uniform(-0.5, 0.5, size=3)])
+        Tp = I.copy(); Tp[9:] = rng.uniform(-1.2, 1.2, size=3)
+        pl = Tb[:9].reshape(3, 3).T @ (Tp[9:] - Tb[9:])            # the point in the box geometry's local frame
+        q = R.T @ (pl - c)
+        want = float(np.linalg.norm(np.maximum(np.abs(q) - h, 0.0)))
+        assert abs(o.geom_distance(go, Tb, gp, Tp) - want) < 1e-12
+        assert o.geom_collides(go, Tb, gp, Tp) == (want == 0.0)
+
+
+def test_world_with_solid_boxes_bvh_equals_brute_force():
+    w = synth.world_boxes(n_boxes=10, n_blobs=1)
+    o = OracleWorld(w)
+    Q = synth.sample_configs(w.robot, 300, 17)
+    f = o.feasible_batch(Q)
+    assert 0.05 < f.mean() < 0.95
+    for i in range(6):                                           # the all-pairs brute force costs seconds per configuration
+        assert bool(f[i]) == o.feasible_brute(Q[i])
