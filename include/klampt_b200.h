@@ -82,6 +82,14 @@ int kb_add_pointcloud(kb_engine* e, const double* pts, int n, const double* radi
 /* replaces Geometry3D.setGeometricPrimitive; params: point x,y,z / sphere cx,cy,cz,r */
 int kb_add_primitive(kb_engine* e, int type, const double* params, double margin);
 
+/* A point cloud whose points are replaced between batches -- sensor streams; the reference keeps such geometries as dynamic
+ * geometries (Cpp/Modeling/ManagedGeometry.h:49-52) and rebuilds their collision data on the CPU after Geometry3D.setPointCloud.
+ * Reserves room for `capacity` points of one `radius`; attach it with kb_add_terrain / kb_add_rigid_object (once).  It starts empty
+ * and forms its own environment group.  kb_update_pointcloud (after kb_finalize) uploads n <= capacity points given in the
+ * geometry's local frame and rebuilds the hierarchy on the GPU (linear BVH: Morton order, radix sort, Karras' parallel hierarchy). */
+int kb_add_dynamic_pointcloud(kb_engine* e, int capacity, double radius, double margin);
+int kb_update_pointcloud(kb_engine* e, int geom, const double* pts, int n);
+
 /* ---- world entities (WorldModel terrains / rigidObjects / robots, Cpp/Modeling/World.cpp:47-196) ------ */
 int kb_add_terrain(kb_engine* e, int geom);                         /* geom = -1: empty geometry */
 int kb_add_rigid_object(kb_engine* e, int geom, const double T[12]);

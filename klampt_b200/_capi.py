@@ -36,6 +36,8 @@ SIGNATURES = {
     "kb_add_trimesh": (C.c_int, [_VP, c_double_p, C.c_int, c_int32_p, C.c_int, C.c_double]),
     "kb_add_pointcloud": (C.c_int, [_VP, c_double_p, C.c_int, c_double_p, C.c_double]),
     "kb_add_primitive": (C.c_int, [_VP, C.c_int, c_double_p, C.c_double]),
+    "kb_add_dynamic_pointcloud": (C.c_int, [_VP, C.c_int, C.c_double, C.c_double]),
+    "kb_update_pointcloud": (C.c_int, [_VP, C.c_int, _VP, C.c_int]),
     "kb_add_terrain": (C.c_int, [_VP, C.c_int]),
     "kb_add_rigid_object": (C.c_int, [_VP, C.c_int, c_double_p]),
     "kb_robot_create": (C.c_int, [_VP, C.c_int, c_int32_p, c_uint8_p, c_double_p, c_double_p, c_double_p, c_double_p]),

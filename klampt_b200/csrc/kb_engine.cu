@@ -4,6 +4,7 @@
 // There is no CPU fallback: every query entry point runs the CUDA kernels or returns KB_ERR_CUDA.
 #include "../../include/klampt_b200.h"
 #include "kb_kernels.h"
+#include "kb_lbvh.h"
 #include "kb_types.h"
 #include <cuda_runtime.h>
 
@@ -50,7 +51,9 @@ struct Geom {
   bool solid = false;          // box primitive: `tri` holds its 12 surface triangles and the interior counts as well
   double box[15];              // solid box: centre(3), axes = columns of a row-major 3x3 (9), half dimensions(3)
   int nelem() const { return kind == G_MESH ? (int)(tri.size() / 9) : (int)(sph.size() / 4); }
-  bool empty() const { return kind == G_EMPTY || nelem() == 0; }
+  int dyn_cap = 0;             // > 0: a point cloud whose points are replaced between batches (kb_update_pointcloud); starts empty
+  double dyn_radius = 0;
+  bool empty() const { return kind == G_EMPTY || (nelem() == 0 && dyn_cap == 0); }
 };
 
 struct Driver { std::vector<int32_t> links; std::vector<double> scale, offset; double dmin, dmax; };
@@ -335,6 +338,10 @@ struct kb_engine {
   float4* d_box32 = nullptr; double* d_box64 = nullptr; int32_t* d_boxown = nullptr;
   KbRobotDev* d_robot = nullptr; KbDriverDev* d_drv = nullptr; int32_t* d_drv_link = nullptr; double* d_drv_scale = nullptr; double* d_drv_off = nullptr;
   ItemSet feas_items, env_items;            // env + self ; env only (distance without self)
+  struct DynCloud { int geom, group, owner, cap; double radius; double T[12]; };
+  std::vector<DynCloud> dyn;                // replaceable point clouds: their own environment groups, rebuilt on the GPU (kb_lbvh.cu)
+  double* d_dyn_pts = nullptr; double* d_dyn_T = nullptr; void* d_dyn_scratch = nullptr; int64_t dyn_pts_cap = 0; size_t dyn_scratch_bytes = 0;
+  double eps_extent = 0, eps_reach = 0, eps_lmax = 0;   // the parts of the fp32 error bound, kept so a new cloud can widen it
   std::vector<HostGrid> hgrids; uint8_t* d_grid[KB_MAX_GRIDS] = {nullptr, nullptr, nullptr, nullptr};
   int both_limit = 0;                        // experiment: frontier size up to which comparable inner pairs descend both trees at once
   int grid_res = 256; bool use_grids = false; // clearance-grid broad phase of the boolean query (options grid_res, clear_grid)
@@ -673,7 +680,7 @@ void kb_engine_destroy(kb_engine* e) {
                     e->d_drv_scale, e->d_drv_off, e->feas_items.d_items, e->env_items.d_items, e->d_xf, e->d_state, e->d_hit, e->d_hit_elem, e->d_leaf_list, e->d_flagged, e->d_state2, e->d_work,
                     e->d_counters, e->d_Q, e->d_out, e->d_pair, e->d_dist, e->d_A, e->d_B, e->d_nlev, e->d_alive, e->d_nchecks, e->d_firstbad, e->d_list,
                     e->d_eQ, e->d_efeas, e->d_scalars, e->d_weights, e->d_T, e->feas_items.d_probes, e->feas_items.d_always_on,
-                    e->d_grid[0], e->d_grid[1], e->d_grid[2], e->d_grid[3], e->d_box32, e->d_box64, e->d_boxown};
+                    e->d_grid[0], e->d_grid[1], e->d_grid[2], e->d_grid[3], e->d_box32, e->d_box64, e->d_boxown, e->d_dyn_pts, e->d_dyn_T, e->d_dyn_scratch};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -741,6 +748,40 @@ int kb_add_primitive(kb_engine* e, int type, const double* params, double margin
   return (int)e->geoms.size() - 1;
 }
 
+int kb_add_dynamic_pointcloud(kb_engine* e, int capacity, double radius, double margin) {
+  if (!e || e->finalized) return fail(KB_ERR_STATE, "engine is null or already finalized");
+  if (capacity < 1 || capacity > (1 << 27) || radius < 0 || margin < 0) return fail(KB_ERR_INVALID, "capacity must be in [1, 2^27], radius and margin >= 0");
+  Geom g; g.kind = G_CLOUD; g.margin = margin; g.dyn_cap = capacity; g.dyn_radius = radius;
+  e->geoms.push_back(std::move(g));
+  return (int)e->geoms.size() - 1;
+}
+
+int kb_update_pointcloud(kb_engine* e, int geom, const double* pts, int n) {
+  if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
+  const kb_engine::DynCloud* dc = nullptr;
+  for (const auto& d : e->dyn) if (d.geom == geom) dc = &d;
+  if (!dc) return fail(KB_ERR_INVALID, "geometry %d is not a dynamic point cloud attached to a terrain / rigid object with an enabled link pair", geom);
+  if (n < 0 || n > dc->cap || (n > 0 && !pts)) return fail(KB_ERR_INVALID, "n = %d outside [0, capacity %d]", n, dc->cap);
+  CK(cudaSetDevice(e->device));
+  int maxcap = 0; for (const auto& d : e->dyn) maxcap = std::max(maxcap, d.cap);
+  if (!e->d_dyn_scratch) {
+    e->dyn_scratch_bytes = kb_lbvh_scratch_bytes(maxcap);
+    CK(cudaMalloc(&e->d_dyn_scratch, e->dyn_scratch_bytes)); CK(cudaMalloc((void**)&e->d_dyn_pts, (size_t)maxcap * 24)); CK(cudaMalloc((void**)&e->d_dyn_T, 96));
+  }
+  const DevGeom& G = e->groups[dc->group];
+  CK(cudaMemcpyAsync(e->d_dyn_T, dc->T, 96, cudaMemcpyHostToDevice, e->stream));
+  if (n > 0) CK(cudaMemcpyAsync(e->d_dyn_pts, pts, (size_t)n * 24, cudaMemcpyHostToDevice, e->stream));
+  float maxabs = 0.f;
+  CK(kb_lbvh_build(e->d_dyn_pts, nullptr, dc->radius, n, e->d_dyn_T, dc->owner, e->d_sph64 + 4 * (size_t)G.elem_base, e->d_sph32 + G.elem_base,
+                   e->d_sphown + G.elem_base, e->d_nodes + 2 * (size_t)G.node_base, e->d_dyn_scratch, e->dyn_scratch_bytes, maxcap, &maxabs, e->stream));
+  e->stats.kernel_launches += 7;
+  // the fp32 error bound follows the scene extent: a cloud that reaches further out widens it (never narrows)
+  e->eps_extent = std::max(e->eps_extent, (double)maxabs + dc->radius);
+  double S = std::max(e->eps_extent, e->eps_reach + e->eps_lmax) + e->eps_lmax; if (!(S > 0)) S = 1;
+  e->scene.eps_abs = std::max(e->scene.eps_abs, (float)(8.0 * 5.9604645e-8 * S));
+  return KB_OK;
+}
+
 int kb_add_terrain(kb_engine* e, int geom) {
   if (!e || e->finalized) return fail(KB_ERR_STATE, "engine is null or already finalized");
   if (geom >= (int)e->geoms.size()) return fail(KB_ERR_INVALID, "unknown geometry %d", geom);
@@ -771,6 +812,7 @@ int kb_robot_create(kb_engine* e, int L, const int32_t* parents, const uint8_t* 
 int kb_robot_set_link_geometry(kb_engine* e, int link, int geom) {
   if (!e || e->finalized) return fail(KB_ERR_STATE, "engine is null or already finalized");
   if (link < 0 || link >= e->L || geom >= (int)e->geoms.size()) return fail(KB_ERR_INVALID, "bad link %d or geometry %d", link, geom);
+  if (geom >= 0 && e->geoms[geom].dyn_cap > 0) return fail(KB_ERR_UNSUPPORTED, "a dynamic point cloud can only be a terrain or a rigid object");
   e->linkgeom[link] = geom; return KB_OK;
 }
 
@@ -868,6 +910,7 @@ int kb_finalize(kb_engine* e, int device) {
   std::vector<int32_t> none;
   for (size_t g = 0; g < e->geoms.size(); g++) {
     const Geom& G = e->geoms[g];
+    if (G.dyn_cap > 0) { e->dgeoms[g] = DevGeom(); continue; }   // replaceable clouds live in their environment group only
     int rc = append_geom(e, G.kind == G_MESH ? G_MESH : G_CLOUD, G.kind == G_MESH ? G.tri : G.sph, none, G.margin, e->dgeoms[g], true);
     if (rc) return rc;
     if (G.kind == G_EMPTY) e->dgeoms[g].empty = true;
@@ -880,7 +923,7 @@ int kb_finalize(kb_engine* e, int device) {
   }
   // ---- 2. merged world-frame environment groups: static objects with the same (element kind, margin, link mask)
   const int L = e->L, T = (int)e->terrains.size(), O = (int)e->objects.size();
-  struct Grp { int kind; double margin; std::string sig; std::vector<double> elems; std::vector<int32_t> owners; };
+  struct Grp { int kind; double margin; std::string sig; std::vector<double> elems; std::vector<int32_t> owners; int dyn_geom = -1; int dyn_owner = -1; };
   std::vector<Grp> grp;
   std::map<std::string, int> grp_index;
   double extent = 0;
@@ -892,6 +935,12 @@ int kb_finalize(kb_engine* e, int device) {
     for (int j = 0; j < L; j++) if (!geom_empty(e, e->linkgeom[j]) && (mask_en(e, link_id(e, j), s) || mask_en(e, s, link_id(e, j)))) { sig[j] = '1'; any = true; }
     if (!any) continue;
     int kind = G.kind == G_MESH ? G_MESH : G_CLOUD;
+    if (G.dyn_cap > 0) {        // a replaceable cloud is a group of its own: its storage is reserved, its hierarchy built on the GPU
+      for (const Grp& other : grp) if (other.dyn_geom == gi) return fail(KB_ERR_UNSUPPORTED, "a dynamic point cloud can be attached to one terrain / rigid object only");
+      Grp dg; dg.kind = G_CLOUD; dg.margin = G.margin; dg.sig = sig; dg.dyn_geom = gi; dg.dyn_owner = s;
+      grp.push_back(dg);
+      continue;
+    }
     char key[64]; snprintf(key, sizeof key, "%d:%.17g:", kind, G.margin);
     std::string k = std::string(key) + sig;
     auto it = grp_index.find(k);
@@ -930,10 +979,34 @@ int kb_finalize(kb_engine* e, int device) {
   }
   e->groups.resize(grp.size());
   e->hgrids.assign(std::min<size_t>(grp.size(), KB_MAX_GRIDS), HostGrid());
+  e->dyn.clear();
   for (size_t g = 0; g < grp.size(); g++) {
+    if (grp[g].dyn_geom >= 0) {
+      const Geom& G = e->geoms[grp[g].dyn_geom];
+      DevGeom& dg = e->groups[g];
+      dg = DevGeom(); dg.margin = G.margin; dg.kind = KB_ELEM_SPHERE; dg.nelem = G.dyn_cap; dg.empty = false; dg.rmax = G.dyn_radius;
+      dg.depth = 64;                                              // bound for the stack model: 30 key bits + index bits of a linear BVH
+      for (int k = 0; k < 3; k++) dg.lo[k] = dg.hi[k] = 0;
+      if ((e->h_nodes.size() / 8) & 1) e->h_nodes.insert(e->h_nodes.end(), 8, 0.f);
+      dg.node_base = (int)(e->h_nodes.size() / 8); dg.nnodes = (int)kb_lbvh_nodes_for(G.dyn_cap);
+      {   // until the first update: a root leaf without elements whose box overlaps nothing
+        float v[8] = {0.f, 0.f, 0.f, i2f(~0), -1e30f, -1e30f, -1e30f, i2f(0)};
+        e->h_nodes.insert(e->h_nodes.end(), v, v + 8);
+        e->h_nodes.insert(e->h_nodes.end(), (size_t)(dg.nnodes - 1) * 8, 0.f);
+      }
+      dg.elem_base = (int)(e->h_sph64.size() / 4);
+      e->h_sph64.insert(e->h_sph64.end(), (size_t)G.dyn_cap * 4, 0.0); e->h_sph32.insert(e->h_sph32.end(), (size_t)G.dyn_cap * 4, 0.f);
+      e->h_sphown.insert(e->h_sphown.end(), (size_t)G.dyn_cap, grp[g].dyn_owner);
+      kb_engine::DynCloud dc; dc.geom = grp[g].dyn_geom; dc.group = (int)g; dc.owner = grp[g].dyn_owner; dc.cap = G.dyn_cap; dc.radius = G.dyn_radius;
+      const int so = grp[g].dyn_owner;
+      Xf X; if (so < T) { memset(&X, 0, sizeof X); X.R[0] = X.R[4] = X.R[8] = 1; } else X = e->objT[so - T];
+      memcpy(dc.T, X.R, 72); memcpy(dc.T + 9, X.t, 24);
+      e->dyn.push_back(dc);
+      continue;
+    }
     int rc = append_geom(e, grp[g].kind, grp[g].elems, grp[g].owners, grp[g].margin, e->groups[g], false);
     if (rc) return rc;
-    if (g < KB_MAX_GRIDS && e->grid_res >= 8 && !e->groups[g].empty && grp[g].kind != G_BOX) {
+    if (g < KB_MAX_GRIDS && e->grid_res >= 8 && !e->groups[g].empty && grp[g].kind != G_BOX && grp[g].dyn_geom < 0) {
       // pad so that every covering sphere of the links that meet this group can be cleared outside the group's bounds
       double need = 0;
       for (int j = 0; j < L; j++) if (grp[g].sig[j] == '1') {
@@ -988,6 +1061,7 @@ int kb_finalize(kb_engine* e, int device) {
   double S = std::max(extent, reach + lmax) + lmax;
   if (!(S > 0)) S = 1;
   e->scene.eps_abs = (float)(8.0 * 5.9604645e-8 * S);
+  e->eps_extent = extent; e->eps_reach = reach; e->eps_lmax = lmax;
   // ---- 4b. clearance probes of the (link, static group) items
   {
     ItemSet& fs = e->feas_items;

@@ -64,6 +64,8 @@ class Engine:
                 p = _f64(g.points)
                 r = None if g.radius is None else _f64(g.radius)
                 check(lib.kb_add_pointcloud(h, p.ctypes.data_as(dp), len(p), None if r is None else r.ctypes.data_as(dp), g.margin))
+            elif g.kind == "dyncloud":
+                check(lib.kb_add_dynamic_pointcloud(h, int(g.params[0]), float(g.params[1]), g.margin))
             elif g.kind in ("triangle", "box"):
                 p = _f64(g.params)
                 check(lib.kb_add_primitive(h, 2 if g.kind == "triangle" else 3, p.ctypes.data_as(dp), g.margin))
@@ -218,6 +220,12 @@ class Engine:
         out = np.empty(N, dtype=np.float64)
         check(self.lib.kb_geom_distance_batch(self.h, int(ga), _ptr(Ta), int(gb), _ptr(Tb), N, float(upper_bound), _ptr(out)))
         return out
+
+    def update_pointcloud(self, geom: int, points) -> None:
+        """Geometry3D.setPointCloud on a dynamic cloud (GeomSpec.dynamic_cloud): uploads the points (local frame) and rebuilds
+        the cloud's hierarchy on the GPU"""
+        p = _f64(points).reshape(-1, 3)
+        check(self.lib.kb_update_pointcloud(self.h, int(geom), _ptr(p) if len(p) else None, len(p)))
 
     # ------------------------------------------------------------------ hot path, device buffers
     def feasible_batch_device(self, dQ, N: int, d_out, d_first_pair=None):

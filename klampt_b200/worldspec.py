@@ -31,7 +31,7 @@ IDENTITY12 = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], dtype=np.float64)
 @dataclass
 class GeomSpec:
     """One collision geometry in its local frame (AnyCollisionGeometry3D minus the current transform)."""
-    kind: str = "empty"                      # 'mesh' | 'cloud' | 'sphere' | 'point' | 'triangle' | 'box' | 'empty'
+    kind: str = "empty"                      # 'mesh' | 'cloud' | 'dyncloud' | 'sphere' | 'point' | 'triangle' | 'box' | 'empty'
     verts: Optional[np.ndarray] = None       # (nv,3) f64   (mesh)
     tris: Optional[np.ndarray] = None        # (nt,3) i32   (mesh)
     points: Optional[np.ndarray] = None      # (n,3)  f64   (cloud)
@@ -49,6 +49,11 @@ class GeomSpec:
         r = None if radius is None else np.ascontiguousarray(radius, dtype=np.float64).reshape(-1)
         return GeomSpec("cloud", points=np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3), radius=r,
                         margin=float(margin))
+
+    @staticmethod
+    def dynamic_cloud(capacity: int, radius: float = 0.0, margin: float = 0.0) -> "GeomSpec":
+        """a point cloud whose points are replaced between batches (Engine.update_pointcloud); starts empty"""
+        return GeomSpec("dyncloud", params=np.array([float(capacity), float(radius)]), margin=float(margin))
 
     @staticmethod
     def sphere(center, r, margin=0.0) -> "GeomSpec":
@@ -80,6 +85,8 @@ class GeomSpec:
             return int(self.tris.shape[0])
         if self.kind == "cloud":
             return int(self.points.shape[0])
+        if self.kind == "dyncloud":
+            return int(self.params[0])
         return 0 if self.kind == "empty" else 1
 
 

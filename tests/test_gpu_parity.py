@@ -507,3 +507,54 @@ def test_world_with_solid_boxes(built):
     eng.set_option("clear_grid", 0)
     cp, cc = eng.colliding_pairs_batch(Q[:2000], max_pairs=8)
     assert ((cc > 0) == (got[:2000] == 0)).all()
+
+
+def test_dynamic_point_cloud_rebuilt_on_the_gpu(built):
+    """a point cloud obstacle replaced between batches (the reference's dynamic geometries, Cpp/Modeling/ManagedGeometry.h:49-52):
+    kb_update_pointcloud rebuilds its hierarchy on the GPU (linear BVH); every state is checked against the oracle built on
+    the same points as a static cloud"""
+    import copy
+    from klampt_b200.engine import Engine
+    from oracle.oracle import OracleWorld
+    rng = np.random.default_rng(51)
+    base = synth.world_c1()
+    T = synth.make_T(synth._random_rotation(rng), [0.1, -0.05, 0.2])
+    w = copy.deepcopy(base)
+    gdyn = w.add_geom(GeomSpec.dynamic_cloud(200000, radius=0.004, margin=0.002))
+    w.objects.append((gdyn, T))
+    w.robot = synth.make_arm6(w)                      # ids shift with the extra object: rebuild the robot on the new world
+    eng = Engine(w)
+    Q = synth.sample_configs(w.robot, 6000, 52)
+
+    def oracle_with(points):
+        wo = copy.deepcopy(base)
+        if points is not None and len(points):
+            wo.objects.append((wo.add_geom(GeomSpec.cloud(points, np.full(len(points), 0.004), margin=0.002)), T))
+        else:
+            wo.objects.append((-1, T))                # keeps the world ids aligned: an object with empty geometry
+        wo.robot = synth.make_arm6(wo)
+        return OracleWorld(wo)
+
+    def cloud(n, seed):
+        r2 = np.random.default_rng(seed)
+        c = r2.uniform([-0.9, -0.9, 0.1], [0.9, 0.9, 1.3], size=(12, 3))
+        p = c[r2.integers(0, 12, size=n)] + r2.normal(size=(n, 3)) * 0.05
+        return np.ascontiguousarray(p)
+
+    empty = oracle_with(None)
+    assert np.array_equal(eng.feasible_batch(Q), empty.feasible_batch(Q))          # before the first update the cloud is empty
+    for n, seed in ((150000, 1), (40, 2), (199999, 3), (1, 4), (8, 5)):
+        P = cloud(n, seed)
+        eng.update_pointcloud(gdyn, P)
+        orc = oracle_with(P)
+        got, want = eng.feasible_batch(Q), orc.feasible_batch(Q)
+        assert_bool_parity(got, want, Q, orc)
+        d = eng.distance_batch(Q[:500], upper_bound=0.3)
+        do, _ = orc.distance_batch(Q[:500], upper_bound=0.3)
+        np.testing.assert_allclose(d, do, rtol=1e-5, atol=1e-9)
+        if n > 1000:
+            assert (got != empty.feasible_batch(Q)).sum() > 0                      # the cloud matters
+    eng.update_pointcloud(gdyn, np.zeros((0, 3)))
+    assert np.array_equal(eng.feasible_batch(Q), empty.feasible_batch(Q))
+    with pytest.raises(Exception):
+        eng.update_pointcloud(gdyn, np.zeros((200001, 3)))
