@@ -234,9 +234,10 @@ __device__ __forceinline__ V3<ExactD> elem_ref_point64(const KbScene& sc, const 
 }
 
 // exact (fp64) distance between two elements in the world frame, minus sphere radii; 0 when triangles intersect
+template <bool BOXES>
 __device__ __noinline__ double exact_elem_distance(const KbScene& sc, const KbItem& it, const double* __restrict__ xf,
                                                    int ea, int eb) {
-  if (it.kindA == KB_ELEM_BOX || it.kindB == KB_ELEM_BOX) {
+  if (BOXES && (it.kindA == KB_ELEM_BOX || it.kindB == KB_ELEM_BOX)) {
     const bool aBox = it.kindA == KB_ELEM_BOX;
     double r;
     const V3<ExactD> p = aBox ? elem_ref_point64(sc, xf, it.kindB, it.xfB, eb, r) : elem_ref_point64(sc, xf, it.kindA, it.xfA, ea, r);
@@ -367,8 +368,9 @@ __device__ __forceinline__ int fast_elem_collide(const KbScene& sc, const KbItem
 // fp32 lower estimate of the element distance (radii subtracted) with absolute error <= 16*delta, used by the distance
 // kernel to skip the fp64 evaluation of pairs that cannot improve the running minimum.  Point / sphere pairs: the distance
 // itself; triangle pairs: a plane-separation lower bound (80 flops instead of the 15-feature distance).
+template <bool BOXES>
 __device__ __forceinline__ float fast_elem_distance(const KbScene& sc, const KbItem& it, const XfF& T, int ea, int eb) {
-  if (it.kindA == KB_ELEM_BOX || it.kindB == KB_ELEM_BOX) return fast_box_elem_distance(sc, it, T, ea, eb);
+  if (BOXES && (it.kindA == KB_ELEM_BOX || it.kindB == KB_ELEM_BOX)) return fast_box_elem_distance(sc, it, T, ea, eb);
   if (it.kindA == KB_ELEM_TRI && it.kindB == KB_ELEM_TRI) {
     const float4* ta = sc.tris32 + 3 * (size_t)ea; const float4* tb = sc.tris32 + 3 * (size_t)eb;
     float4 a0 = __ldg(ta), a1 = __ldg(ta + 1), a2 = __ldg(ta + 2), b0 = __ldg(tb), b1 = __ldg(tb + 1), b2 = __ldg(tb + 2);
@@ -1224,7 +1226,7 @@ __device__ __forceinline__ void classify_pair(unsigned itembits, int na, int nb,
   else e = make_uint2(itembits | (unsigned)na, (unsigned)lb | KB_SPLIT_B);                                // split B: slot B holds B's first child
 }
 
-template <bool ITC, bool STATS>
+template <bool ITC, bool STATS, bool BOXES>
 __global__ void __launch_bounds__(KB_WARPS_PER_BLOCK * 32, 3)
 kb_distance_kernel(const KbTraverseParams p, double* __restrict__ out_dist, double upper_bound) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1311,9 +1313,9 @@ kb_distance_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
                 for (int j = 0; j < cb; j++) {
                   if (STATS) st_leaf++;
                   // fp32 first: a pair whose estimate cannot beat the running minimum (nor this lane's own) skips the fp64 evaluation
-                  const float d32 = fast_elem_distance(sc, it, T, fa + i, fb + j) - margf - band;
+                  const float d32 = fast_elem_distance<BOXES>(sc, it, T, fa + i, fb + j) - margf - band;
                   if (d32 >= bestf || (double)d32 >= dmin) continue;
-                  const double d = exact_elem_distance(sc, it, xf, fa + i, fb + j) - marg;
+                  const double d = exact_elem_distance<BOXES>(sc, it, xf, fa + i, fb + j) - marg;
                   if (d < dmin) { dmin = d; ea = fa + i; eb = fb + j; }
                 }
             }
@@ -1666,19 +1668,19 @@ size_t kb_distance_smem_bytes(int nxf, int nitems) {
   return nit * 16 + (size_t)KB_WARPS_PER_BLOCK * ((size_t)KB_STACK_CAP * 12 + (size_t)KB_LEAFQ_CAP * 12 + xf_floats * 4 + nit * 48);
 }
 
-template <bool ITC, bool STATS>
+template <bool ITC, bool STATS, bool BOXES>
 static cudaError_t launch_distance_t(const KbTraverseParams& p, double* out_dist, double upper_bound, int num_sms, size_t smem, cudaStream_t s) {
   static bool attr_set[64] = {false};      // the attribute is per device
   int dev = 0; cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(kb_distance_kernel<ITC, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(kb_distance_kernel<ITC, STATS, BOXES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   int per_sm = (int)((224 * 1024) / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > 3) per_sm = 3;
   int64_t want = (p.N + KB_WARPS_PER_BLOCK - 1) / KB_WARPS_PER_BLOCK;
   int64_t grid = (int64_t)num_sms * per_sm; if (grid > want) grid = want; if (grid < 1) grid = 1;
-  kb_distance_kernel<ITC, STATS><<<(unsigned)grid, KB_WARPS_PER_BLOCK * 32, smem, s>>>(p, out_dist, upper_bound);
+  kb_distance_kernel<ITC, STATS, BOXES><<<(unsigned)grid, KB_WARPS_PER_BLOCK * 32, smem, s>>>(p, out_dist, upper_bound);
   return cudaGetLastError();
 }
 
@@ -1723,8 +1725,10 @@ cudaError_t kb_launch_traverse(const KbTraverseParams& p, int mode, double* out_
   const bool itc = p.nitems <= KB_ITC_MAX_ITEMS;
   if (p.N > 0xfffffff0ll) return cudaErrorInvalidValue;
   if (mode == 1) {
-    if (p.collect_stats) return itc ? launch_distance_t<true, true>(p, out_dist, upper_bound, num_sms, smem, s) : launch_distance_t<false, true>(p, out_dist, upper_bound, num_sms, smem, s);
-    return itc ? launch_distance_t<true, false>(p, out_dist, upper_bound, num_sms, smem, s) : launch_distance_t<false, false>(p, out_dist, upper_bound, num_sms, smem, s);
+#define KB_LD(I, S) (p.has_boxes ? launch_distance_t<I, S, true>(p, out_dist, upper_bound, num_sms, smem, s) : launch_distance_t<I, S, false>(p, out_dist, upper_bound, num_sms, smem, s))
+    if (p.collect_stats) return itc ? KB_LD(true, true) : KB_LD(false, true);
+    return itc ? KB_LD(true, false) : KB_LD(false, false);
+#undef KB_LD
   }
   if (p.N > 0xfffffff0ll) return cudaErrorInvalidValue;
   // two register budgets are compiled: KB_BPS_HI = 5 CTAs/SM (20 warps, 102 registers, some spills in the element phase) wins
