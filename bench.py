@@ -329,6 +329,28 @@ def main():
     h2d = (2 if edges or with_dist else 1) * M * L * 8
     d2h = M + (8 * M if with_dist else 0)
 
+    # ---- the same through the fp32-row entry point (kb_feasible_batch_f32: half the upload, values widened on the device); an extra
+    #      line item, not the headline: the reference's interface passes doubles
+    e2e_f32 = None
+    if not edges and not with_dist:
+        import ctypes as C
+        from klampt_b200._capi import check
+        hostQf = [q.to(torch.float32).pin_memory() for q in hostQ]
+
+        def step_host_f32(k):
+            check(eng.lib.kb_feasible_batch_f32(eng.h, C.c_void_p(hostQf[k % NB].data_ptr()), M, C.c_void_p(host_out.data_ptr()), None))
+        for k in range(args.warmup):
+            step_host_f32(k)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            step_host_f32(args.warmup + k)
+        torch.cuda.synchronize()
+        tf = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        e2e_f32 = {"value": world * M * args.steps / float(tf.item()), "unit": unit, "h2d_bytes_per_step": M * L * 4, "d2h_bytes_per_step": M}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -393,7 +415,7 @@ def main():
                                     % (NB, NB * M * L * 8 >> 20, eng.layout()["static_bytes"] >> 20),
                        "parallelism": "configs sharded, geometry replicated" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "e2e_f32_rows": e2e_f32, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu_baseline}
     print(json.dumps(line))
     if world > 1:

@@ -143,6 +143,9 @@ int kb_fk_batch(kb_engine* e, const double* Q, int64_t N, double* T_out);
  * traversal-order dependent in the reference as well). */
 int kb_feasible_batch(kb_engine* e, const double* Q, int64_t N, uint8_t* out, int32_t* first_pair);
 int kb_feasible_batch_device(kb_engine* e, const double* dQ, int64_t N, uint8_t* d_out, int32_t* d_first_pair);
+/* the same for configurations stored as floats (half the host-to-device bytes): every value is widened to fp64 on the device
+ * and checked exactly as kb_feasible_batch checks (double)q -- the answer is for the rounded configuration */
+int kb_feasible_batch_f32(kb_engine* e, const float* Q, int64_t N, uint8_t* out, int32_t* first_pair);
 
 /* SingleRobotCSpace::PathChecker(a,b)->IsVisible() = EpsilonEdgeChecker with RobotCSpace::Distance / Interpolate
  * (Cpp/Planning/RobotCSpace.cpp:835-838, Cpp/Modeling/Interpolate.cpp:10-71,208-343) for N edges.

@@ -54,6 +54,7 @@ SIGNATURES = {
     "kb_synchronize": (C.c_int, [_VP]),
     "kb_fk_batch": (C.c_int, [_VP, _VP, C.c_int64, _VP]),
     "kb_feasible_batch": (C.c_int, [_VP, _VP, C.c_int64, _VP, _VP]),
+    "kb_feasible_batch_f32": (C.c_int, [_VP, _VP, C.c_int64, _VP, _VP]),
     "kb_feasible_batch_device": (C.c_int, [_VP, _VP, C.c_int64, _VP, _VP]),
     "kb_edges_visible_batch": (C.c_int, [_VP, _VP, _VP, C.c_int64, C.c_double, _VP, _VP, _VP]),
     "kb_edges_visible_batch_device": (C.c_int, [_VP, _VP, _VP, C.c_int64, C.c_double, _VP, _VP, _VP]),

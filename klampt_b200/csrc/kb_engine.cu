@@ -356,6 +356,7 @@ struct kb_engine {
   int leaf_budget = 64; int leaf_slots = 40;
   uint32_t* d_work = nullptr; unsigned long long* d_counters = nullptr;   // counters: [0] recheck [1] node [2] leaf [3] feasible [4] visible
   double* d_Q = nullptr; int64_t q_cap = 0;             // staging for host entry points
+  float* d_Qf = nullptr; int64_t qf_cap = 0;            // fp32 configurations of kb_feasible_batch_f32, widened into d_Q
   uint8_t* d_out = nullptr; int64_t out_cap = 0;
   int32_t* d_pair = nullptr; int64_t pair_cap = 0;
   double* d_dist = nullptr; int64_t dist_cap = 0;
@@ -680,7 +681,7 @@ void kb_engine_destroy(kb_engine* e) {
                     e->d_drv_scale, e->d_drv_off, e->feas_items.d_items, e->env_items.d_items, e->d_xf, e->d_state, e->d_hit, e->d_hit_elem, e->d_leaf_list, e->d_flagged, e->d_state2, e->d_work,
                     e->d_counters, e->d_Q, e->d_out, e->d_pair, e->d_dist, e->d_A, e->d_B, e->d_nlev, e->d_alive, e->d_nchecks, e->d_firstbad, e->d_list,
                     e->d_eQ, e->d_efeas, e->d_scalars, e->d_weights, e->d_T, e->feas_items.d_probes, e->feas_items.d_always_on,
-                    e->d_grid[0], e->d_grid[1], e->d_grid[2], e->d_grid[3], e->d_box32, e->d_box64, e->d_boxown, e->d_dyn_pts, e->d_dyn_T, e->d_dyn_scratch};
+                    e->d_grid[0], e->d_grid[1], e->d_grid[2], e->d_grid[3], e->d_box32, e->d_box64, e->d_boxown, e->d_dyn_pts, e->d_dyn_T, e->d_dyn_scratch, e->d_Qf};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -1230,13 +1231,18 @@ int kb_feasible_batch_device(kb_engine* e, const double* dQ, int64_t N, uint8_t*
   return KB_OK;
 }
 
-int kb_feasible_batch(kb_engine* e, const double* Q, int64_t N, uint8_t* out, int32_t* first_pair) {
+// host-buffer feasibility for configurations given as doubles (esz 8) or floats (esz 4; widened to fp64 on the device)
+static int feasible_batch_host(kb_engine* e, const void* Qv, int esz, int64_t N, uint8_t* out, int32_t* first_pair) {
   if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
-  if (N < 0 || (N > 0 && (!Q || !out))) return fail(KB_ERR_INVALID, "bad arguments");
+  if (N < 0 || (N > 0 && (!Qv || !out))) return fail(KB_ERR_INVALID, "bad arguments");
   if (N == 0) return KB_OK;
   CK(cudaSetDevice(e->device));
   int rc;
+  const char* Q = (const char*)Qv;
+  if (esz == 4 && (rc = grow(e->d_Qf, e->qf_cap, N * e->L))) return rc;
+  char* d_in = esz == 4 ? (char*)e->d_Qf : nullptr;
   if ((rc = grow(e->d_Q, e->q_cap, N * e->L))) return rc;
+  if (esz == 8) d_in = (char*)e->d_Q;
   if ((rc = grow(e->d_out, e->out_cap, N))) return rc;
   if (first_pair && (rc = grow(e->d_pair, e->pair_cap, 2 * N))) return rc;
   begin_timing(e);
@@ -1255,17 +1261,19 @@ int kb_feasible_batch(kb_engine* e, const double* Q, int64_t N, uint8_t* out, in
       cut[1] = std::max<int64_t>(1 << 15, ((N / 8) / 1024) * 1024); cut[2] = N; nstage = 2;
     }
   }
-  CK(cudaMemcpyAsync(e->d_Q, Q, (size_t)cut[1] * e->L * 8, cudaMemcpyHostToDevice, e->stream));
+  const size_t row = (size_t)e->L * esz;
+  CK(cudaMemcpyAsync(d_in, Q, (size_t)cut[1] * row, cudaMemcpyHostToDevice, e->stream));
   if (nstage > 1) {
     CK(cudaEventRecord(e->ev_copy[0], e->stream));                // the copy stream must not run ahead of earlier work on the buffer
     CK(cudaStreamWaitEvent(e->copy_stream, e->ev_copy[0], 0));
     for (int k = 1; k < nstage; k++) {
-      CK(cudaMemcpyAsync(e->d_Q + cut[k] * e->L, Q + cut[k] * e->L, (size_t)(cut[k + 1] - cut[k]) * e->L * 8, cudaMemcpyHostToDevice, e->copy_stream));
+      CK(cudaMemcpyAsync(d_in + cut[k] * row, Q + cut[k] * row, (size_t)(cut[k + 1] - cut[k]) * row, cudaMemcpyHostToDevice, e->copy_stream));
       CK(cudaEventRecord(e->ev_copy[k], e->copy_stream));
     }
   }
   for (int k = 0; k < nstage; k++) {
     if (k > 0) CK(cudaStreamWaitEvent(e->stream, e->ev_copy[k], 0));
+    if (esz == 4) { CK(kb_launch_widen_f32(e->d_Qf + cut[k] * e->L, e->d_Q + cut[k] * e->L, (cut[k + 1] - cut[k]) * e->L, e->stream)); e->stats.kernel_launches++; }
     if ((rc = run_feasible_device(e, e->d_Q + cut[k] * e->L, cut[k + 1] - cut[k], e->d_out + cut[k], first_pair ? e->d_pair + 2 * cut[k] : nullptr, e->d_counters + 3))) return rc;
   }
   CK(cudaMemcpyAsync(out, e->d_out, (size_t)N, cudaMemcpyDeviceToHost, e->stream));
@@ -1275,6 +1283,9 @@ int kb_feasible_batch(kb_engine* e, const double* Q, int64_t N, uint8_t* out, in
   e->stats.configs_checked += N;
   return KB_OK;
 }
+
+int kb_feasible_batch(kb_engine* e, const double* Q, int64_t N, uint8_t* out, int32_t* first_pair) { return feasible_batch_host(e, Q, 8, N, out, first_pair); }
+int kb_feasible_batch_f32(kb_engine* e, const float* Q, int64_t N, uint8_t* out, int32_t* first_pair) { return feasible_batch_host(e, Q, 4, N, out, first_pair); }
 
 int kb_edges_visible_batch_device(kb_engine* e, const double* dA, const double* dB, int64_t N, double eps, const double* weights_host,
                                   uint8_t* d_out, int32_t* d_nchecks) {

@@ -1855,6 +1855,16 @@ cudaError_t kb_launch_edge_level_end(const int32_t* list, unsigned int nlist, in
   kb_edge_level_end_kernel<<<nblocks(nlist, 256), 256, 0, s>>>(list, nlist, lev, firstbad, alive, nchecks);
   return cudaGetLastError();
 }
+__global__ void kb_widen_f32_kernel(const float* __restrict__ src, double* __restrict__ dst, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (double)src[i];
+}
+cudaError_t kb_launch_widen_f32(const float* src, double* dst, int64_t n, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  kb_widen_f32_kernel<<<nblocks(n, 256), 256, 0, s>>>(src, dst, n);
+  return cudaGetLastError();
+}
+
 cudaError_t kb_launch_fill_i32(int32_t* p, int64_t n, int32_t v, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
   kb_fill_i32_kernel<<<nblocks(n, 256), 256, 0, s>>>(p, n, v);

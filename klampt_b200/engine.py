@@ -170,6 +170,14 @@ class Engine:
         return T
 
     def feasible_batch(self, Q, return_pairs: bool = False, out: Optional[np.ndarray] = None):
+        if isinstance(Q, np.ndarray) and Q.dtype == np.float32:      # fp32 rows travel as they are and are widened on the device
+            Qf = np.ascontiguousarray(Q).reshape(-1, self.L)
+            N = Qf.shape[0]
+            if out is None:
+                out = np.empty(N, dtype=np.uint8)
+            pairs = np.empty((N, 2), dtype=np.int32) if return_pairs else None
+            check(self.lib.kb_feasible_batch_f32(self.h, _ptr(Qf), N, _ptr(out), _ptr(pairs)))
+            return (out, pairs) if return_pairs else out
         Q = self._Q(Q)
         N = Q.shape[0]
         if out is None:

@@ -558,3 +558,15 @@ def test_dynamic_point_cloud_rebuilt_on_the_gpu(built):
     assert np.array_equal(eng.feasible_batch(Q), empty.feasible_batch(Q))
     with pytest.raises(Exception):
         eng.update_pointcloud(gdyn, np.zeros((200001, 3)))
+
+
+def test_fp32_configurations_entry_point(c1):
+    """kb_feasible_batch_f32: float rows are widened on the device; the answer is the fp64 answer for the rounded configuration"""
+    w, eng, orc = c1
+    Q = synth.sample_configs(w.robot, 300000, 61)          # large enough for the staged upload
+    Qf = Q.astype(np.float32)
+    got, pairs = eng.feasible_batch(Qf, return_pairs=True)
+    want = eng.feasible_batch(Qf.astype(np.float64))
+    assert np.array_equal(got, want)
+    assert_bool_parity(got[:5000], orc.feasible_batch(Qf[:5000].astype(np.float64)), Qf[:5000].astype(np.float64), orc)
+    assert ((pairs[:, 0] >= 0) == (got == 0)).all()
