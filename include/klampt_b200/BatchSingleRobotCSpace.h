@@ -45,6 +45,16 @@ class WorldBuilder {
   int AddPointCloud(const std::vector<double>& pts, const std::vector<double>* radius = nullptr, double margin = 0) {
     int g = kb_add_pointcloud(e_, pts.data(), (int)(pts.size() / 3), radius ? radius->data() : nullptr, margin); kbCheck(g); return g; }
   int AddSphere(const double c[3], double r, double margin = 0) { double p[4] = {c[0], c[1], c[2], r}; int g = kb_add_primitive(e_, KB_PRIM_SPHERE, p, margin); kbCheck(g); return g; }
+  int AddPoint(const double c[3], double margin = 0) { int g = kb_add_primitive(e_, KB_PRIM_POINT, c, margin); kbCheck(g); return g; }
+  int AddTriangle(const double abc[9], double margin = 0) { int g = kb_add_primitive(e_, KB_PRIM_TRIANGLE, abc, margin); kbCheck(g); return g; }
+  // solid boxes (GeometricPrimitive3D Box3D / AABB3D): centre, axes as the columns of a row-major 3x3, half dimensions / lo, hi
+  int AddBox(const double center[3], const double axes[9], const double half[3], double margin = 0) {
+    double p[15]; for (int k = 0; k < 3; k++) { p[k] = center[k]; p[12 + k] = half[k]; } for (int k = 0; k < 9; k++) p[3 + k] = axes[k];
+    int g = kb_add_primitive(e_, KB_PRIM_BOX, p, margin); kbCheck(g); return g; }
+  int AddAABB(const double lo[3], const double hi[3], double margin = 0) {
+    double p[6] = {lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]}; int g = kb_add_primitive(e_, KB_PRIM_AABB, p, margin); kbCheck(g); return g; }
+  // a point cloud replaced between batches (kb_update_pointcloud on the finished engine rebuilds its hierarchy on the GPU)
+  int AddDynamicPointCloud(int capacity, double radius = 0, double margin = 0) { int g = kb_add_dynamic_pointcloud(e_, capacity, radius, margin); kbCheck(g); return g; }
   int AddTerrain(int geom) { int i = kb_add_terrain(e_, geom); kbCheck(i); return i; }
   int AddRigidObject(int geom, const double T[12]) { int i = kb_add_rigid_object(e_, geom, T); kbCheck(i); return i; }
   void SetRobot(const RobotDescription& r) {
