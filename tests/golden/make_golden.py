@@ -19,6 +19,7 @@ from klampt_b200 import synth          # noqa: E402
 from oracle.oracle import OracleWorld  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+EDGE_EPS = {"floating": 0.02, "boxes": 0.02}
 
 
 def world_fixture(name, spec, n_cfg, n_edges, n_dist, seed):
@@ -29,7 +30,7 @@ def world_fixture(name, spec, n_cfg, n_edges, n_dist, seed):
                limits_ok=np.packbits(np.array([o.check_joint_limits(q) for q in Q], dtype=np.uint8)))
     if n_edges:
         A, B = synth.sample_edges(spec.robot, lambda X: o.feasible_batch(X), n_edges, seed)
-        vis, nchk = o.edges_visible_batch(A, B, eps=0.01)
+        vis, nchk = o.edges_visible_batch(A, B, eps=EDGE_EPS.get(name, 0.01))
         out.update(edge_seed=np.int64(seed), n_edges=np.int64(n_edges), edge_A=A, edge_B=B, edge_visible=np.packbits(vis), edge_nchecks=nchk.astype(np.int32))
     if n_dist:
         d, dp = o.distance_batch(Q[:n_dist], upper_bound=0.5, include_self=False)
@@ -43,3 +44,5 @@ if __name__ == "__main__":
     world_fixture("c1", synth.world_c1(), 4000, 300, 300, 1)
     world_fixture("c2_60", synth.world_c2(2, n_obstacles=60), 4000, 0, 200, 2)
     world_fixture("c3", synth.world_c3(), 4000, 150, 0, 3)
+    world_fixture("boxes", synth.world_boxes(), 4000, 100, 200, 8)          # solid box primitives (links, objects, terrain)
+    world_fixture("floating", synth.world_floating(), 4000, 150, 100, 7)    # Floating / BallAndSocket joints in the edge metric

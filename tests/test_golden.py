@@ -8,7 +8,9 @@ import pytest
 from klampt_b200 import synth
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-WORLDS = {"c1": lambda: synth.world_c1(), "c2_60": lambda: synth.world_c2(2, n_obstacles=60), "c3": lambda: synth.world_c3()}
+WORLDS = {"c1": lambda: synth.world_c1(), "c2_60": lambda: synth.world_c2(2, n_obstacles=60), "c3": lambda: synth.world_c3(),
+          "boxes": lambda: synth.world_boxes(), "floating": lambda: synth.world_floating()}
+EDGE_EPS = {"floating": 0.02, "boxes": 0.02}
 
 
 def load(name):
@@ -29,7 +31,7 @@ def test_oracle_reproduces_golden(name):
     np.testing.assert_allclose(o.fk_batch(Q[:16]), g["fk"], rtol=0, atol=1e-13)
     if "edge_A" in g.files:
         m = 60
-        vis, nchk = o.edges_visible_batch(g["edge_A"][:m], g["edge_B"][:m], eps=0.01)
+        vis, nchk = o.edges_visible_batch(g["edge_A"][:m], g["edge_B"][:m], eps=EDGE_EPS.get(name, 0.01))
         assert np.array_equal(vis, np.unpackbits(g["edge_visible"])[:m]) and np.array_equal(nchk, g["edge_nchecks"][:m])
     if "dist_env" in g.files:
         d, _ = o.distance_batch(Q[:50], upper_bound=0.5)
@@ -51,9 +53,11 @@ def test_gpu_matches_golden(name, built):
             assert o.distance(Q[i], upper_bound=1.0, include_self=True)[0] <= 1e-6
     np.testing.assert_allclose(eng.fk_batch(Q[:16]), g["fk"], rtol=0, atol=1e-12)
     if "edge_A" in g.files:
-        vis, nchk = eng.edges_visible_batch(g["edge_A"], g["edge_B"], eps=0.01)
-        assert np.array_equal(vis, np.unpackbits(g["edge_visible"])[:len(vis)])
-        assert np.array_equal(nchk, g["edge_nchecks"])
+        vis, nchk = eng.edges_visible_batch(g["edge_A"], g["edge_B"], eps=EDGE_EPS.get(name, 0.01))
+        # Floating / BallAndSocket midpoints go through device libm (sincos, acos, atan2): equal to ~1e-15, not bit for bit
+        slack = 1 if name == "floating" else 0
+        assert (vis != np.unpackbits(g["edge_visible"])[:len(vis)]).sum() <= slack
+        assert (nchk != g["edge_nchecks"]).sum() <= slack
     if "dist_env" in g.files:
         n = int(g["n_dist"])
         d, pr = eng.distance_batch(Q[:n], upper_bound=0.5, include_self=False, return_pairs=True)
