@@ -751,6 +751,9 @@ int kb_add_primitive(kb_engine* e, int type, const double* params, double margin
 
 int kb_add_dynamic_pointcloud(kb_engine* e, int capacity, double radius, double margin) {
   if (!e || e->finalized) return fail(KB_ERR_STATE, "engine is null or already finalized");
+#ifdef KB_QNODES
+  return fail(KB_ERR_UNSUPPORTED, "the experimental quantised-node build has no GPU hierarchy builder");
+#endif
   if (capacity < 1 || capacity > (1 << 27) || radius < 0 || margin < 0) return fail(KB_ERR_INVALID, "capacity must be in [1, 2^27], radius and margin >= 0");
   Geom g; g.kind = G_CLOUD; g.margin = margin; g.dyn_cap = capacity; g.dyn_radius = radius;
   e->geoms.push_back(std::move(g));
