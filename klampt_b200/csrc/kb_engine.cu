@@ -163,6 +163,8 @@ struct DevGeom {
   int ncover = 0; double cover[KB_COVER_MAX][4];   // covering spheres (local frame) for the clearance-grid broad phase
 };
 
+#define KB_GPU_CLOUD_MIN 4096      // clouds up to this size keep the host SAH build even with cloud_builder = 1
+
 struct ItemSet {
   std::vector<KbItem> items; KbItem* d_items = nullptr; int nxf = 0; int maxdepth = 0;
   std::vector<KbProbe> probes; std::vector<uint32_t> always_on; KbProbe* d_probes = nullptr; uint32_t* d_always_on = nullptr;
@@ -343,6 +345,9 @@ struct kb_engine {
   double* d_dyn_pts = nullptr; double* d_dyn_T = nullptr; void* d_dyn_scratch = nullptr; int64_t dyn_pts_cap = 0; size_t dyn_scratch_bytes = 0;
   double eps_extent = 0, eps_reach = 0, eps_lmax = 0;   // the parts of the fp32 error bound, kept so a new cloud can widen it
   std::vector<HostGrid> hgrids; uint8_t* d_grid[KB_MAX_GRIDS] = {nullptr, nullptr, nullptr, nullptr};
+  int cloud_builder = 0;                     // 0: point-cloud hierarchies by binned SAH on the host; 1: linear BVH on the GPU (kb_lbvh.cu)
+  struct PendingCloud { DevGeom* dg; std::vector<double> elems; std::vector<int32_t> owners; };
+  std::vector<PendingCloud> pending_clouds;   // clouds whose hierarchy is built on the GPU once the arrays are uploaded
   int both_limit = 0;                        // experiment: frontier size up to which comparable inner pairs descend both trees at once
   int grid_res = 256; bool use_grids = false; // clearance-grid broad phase of the boolean query (options grid_res, clear_grid)
   int64_t static_bytes = 0;
@@ -491,6 +496,31 @@ int append_geom(kb_engine* e, int kind, const std::vector<double>& elems, const 
     }
   }
   return KB_OK;
+}
+
+// reserves nodes / elements of a point cloud whose hierarchy the GPU builds after the upload (option cloud_builder = 1)
+void reserve_gpu_cloud(kb_engine* e, const std::vector<double>& elems, const std::vector<int32_t>& owners, double margin, DevGeom& dg) {
+  const int n = (int)(elems.size() / 4);
+  dg = DevGeom(); dg.margin = margin; dg.kind = KB_ELEM_SPHERE; dg.nelem = n; dg.empty = n == 0; dg.depth = 64;
+  for (int k = 0; k < 3; k++) { dg.lo[k] = 1e300; dg.hi[k] = -1e300; }
+  for (int i = 0; i < n; i++) {
+    const double* p = &elems[4 * (size_t)i];
+    dg.rmax = std::max(dg.rmax, p[3]);
+    for (int k = 0; k < 3; k++) { dg.lo[k] = std::min(dg.lo[k], p[k] - p[3]); dg.hi[k] = std::max(dg.hi[k], p[k] + p[3]); }
+  }
+  if ((e->h_nodes.size() / 8) & 1) e->h_nodes.insert(e->h_nodes.end(), 8, 0.f);
+  dg.node_base = (int)(e->h_nodes.size() / 8); dg.nnodes = (int)kb_lbvh_nodes_for(n);
+  const float v[8] = {0.f, 0.f, 0.f, i2f(~0), -1e30f, -1e30f, -1e30f, i2f(0)};
+  e->h_nodes.insert(e->h_nodes.end(), v, v + 8);
+  e->h_nodes.insert(e->h_nodes.end(), (size_t)(dg.nnodes - 1) * 8, 0.f);
+  dg.elem_base = (int)(e->h_sph64.size() / 4);
+  e->h_sph64.insert(e->h_sph64.end(), (size_t)n * 4, 0.0); e->h_sph32.insert(e->h_sph32.end(), (size_t)n * 4, 0.f);
+  e->h_sphown.insert(e->h_sphown.end(), (size_t)n, -1);
+  // covering spheres of the clearance-grid broad phase: one sphere round the bounds is enough for a cloud used as a link geometry
+  dg.ncover = 1;
+  double r2 = 0; for (int k = 0; k < 3; k++) { dg.cover[0][k] = 0.5 * (dg.lo[k] + dg.hi[k]); r2 += 0.25 * (dg.hi[k] - dg.lo[k]) * (dg.hi[k] - dg.lo[k]); }
+  dg.cover[0][3] = std::sqrt(r2) * (1 + 1e-12);
+  e->pending_clouds.push_back({&dg, elems, owners});
 }
 
 KbItem make_item(const DevGeom& A, int xfA, int idA, const DevGeom& B, int xfB, int idB, bool self) {
@@ -776,7 +806,7 @@ int kb_update_pointcloud(kb_engine* e, int geom, const double* pts, int n) {
   CK(cudaMemcpyAsync(e->d_dyn_T, dc->T, 96, cudaMemcpyHostToDevice, e->stream));
   if (n > 0) CK(cudaMemcpyAsync(e->d_dyn_pts, pts, (size_t)n * 24, cudaMemcpyHostToDevice, e->stream));
   float maxabs = 0.f;
-  CK(kb_lbvh_build(e->d_dyn_pts, nullptr, dc->radius, n, e->d_dyn_T, dc->owner, e->d_sph64 + 4 * (size_t)G.elem_base, e->d_sph32 + G.elem_base,
+  CK(kb_lbvh_build(e->d_dyn_pts, nullptr, dc->radius, n, e->d_dyn_T, dc->owner, nullptr, e->d_sph64 + 4 * (size_t)G.elem_base, e->d_sph32 + G.elem_base,
                    e->d_sphown + G.elem_base, e->d_nodes + 2 * (size_t)G.node_base, e->d_dyn_scratch, e->dyn_scratch_bytes, maxcap, &maxabs, e->stream));
   e->stats.kernel_launches += 7;
   // the fp32 error bound follows the scene extent: a cloud that reaches further out widens it (never narrows)
@@ -915,6 +945,7 @@ int kb_finalize(kb_engine* e, int device) {
   for (size_t g = 0; g < e->geoms.size(); g++) {
     const Geom& G = e->geoms[g];
     if (G.dyn_cap > 0) { e->dgeoms[g] = DevGeom(); continue; }   // replaceable clouds live in their environment group only
+    if (e->cloud_builder == 1 && G.kind == G_CLOUD && G.nelem() > KB_GPU_CLOUD_MIN) { reserve_gpu_cloud(e, G.sph, none, G.margin, e->dgeoms[g]); continue; }
     int rc = append_geom(e, G.kind == G_MESH ? G_MESH : G_CLOUD, G.kind == G_MESH ? G.tri : G.sph, none, G.margin, e->dgeoms[g], true);
     if (rc) return rc;
     if (G.kind == G_EMPTY) e->dgeoms[g].empty = true;
@@ -1008,8 +1039,12 @@ int kb_finalize(kb_engine* e, int device) {
       e->dyn.push_back(dc);
       continue;
     }
-    int rc = append_geom(e, grp[g].kind, grp[g].elems, grp[g].owners, grp[g].margin, e->groups[g], false);
-    if (rc) return rc;
+    if (e->cloud_builder == 1 && grp[g].kind == G_CLOUD && (int)(grp[g].elems.size() / 4) > KB_GPU_CLOUD_MIN) {
+      reserve_gpu_cloud(e, grp[g].elems, grp[g].owners, grp[g].margin, e->groups[g]);
+    } else {
+      int rc = append_geom(e, grp[g].kind, grp[g].elems, grp[g].owners, grp[g].margin, e->groups[g], false);
+      if (rc) return rc;
+    }
     if (g < KB_MAX_GRIDS && e->grid_res >= 8 && !e->groups[g].empty && grp[g].kind != G_BOX && grp[g].dyn_geom < 0) {
       // pad so that every covering sphere of the links that meet this group can be cleared outside the group's bounds
       double need = 0;
@@ -1162,6 +1197,28 @@ int kb_finalize(kb_engine* e, int device) {
   if ((rc = upload(e->d_drv_link, dl.data(), dl.size() * 4, &e->static_bytes))) return rc;
   if ((rc = upload(e->d_drv_scale, ds.data(), ds.size() * 8, &e->static_bytes))) return rc;
   if ((rc = upload(e->d_drv_off, dofs.data(), dofs.size() * 8, &e->static_bytes))) return rc;
+  if (!e->pending_clouds.empty()) {      // hierarchies of the large point clouds on the GPU (Morton order + Karras, kb_lbvh.cu)
+    size_t maxn = 0; for (const auto& pc : e->pending_clouds) maxn = std::max(maxn, pc.elems.size() / 4);
+    double* d_p = nullptr; double* d_r = nullptr; int32_t* d_o = nullptr; double* d_T = nullptr; void* d_s = nullptr;
+    const size_t sb = kb_lbvh_scratch_bytes((int)maxn);
+    CK(cudaMalloc((void**)&d_p, maxn * 24)); CK(cudaMalloc((void**)&d_r, maxn * 8)); CK(cudaMalloc((void**)&d_o, maxn * 4)); CK(cudaMalloc((void**)&d_T, 96)); CK(cudaMalloc(&d_s, sb));
+    const double I12[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+    CK(cudaMemcpy(d_T, I12, 96, cudaMemcpyHostToDevice));
+    std::vector<double> hp, hr;
+    for (auto& pc : e->pending_clouds) {
+      const size_t n = pc.elems.size() / 4;
+      hp.resize(3 * n); hr.resize(n);
+      for (size_t i = 0; i < n; i++) { hp[3 * i] = pc.elems[4 * i]; hp[3 * i + 1] = pc.elems[4 * i + 1]; hp[3 * i + 2] = pc.elems[4 * i + 2]; hr[i] = pc.elems[4 * i + 3]; }
+      CK(cudaMemcpy(d_p, hp.data(), n * 24, cudaMemcpyHostToDevice)); CK(cudaMemcpy(d_r, hr.data(), n * 8, cudaMemcpyHostToDevice));
+      if (!pc.owners.empty()) CK(cudaMemcpy(d_o, pc.owners.data(), n * 4, cudaMemcpyHostToDevice));
+      const DevGeom& G = *pc.dg;
+      CK(kb_lbvh_build(d_p, d_r, 0.0, (int)n, d_T, -1, pc.owners.empty() ? nullptr : d_o, e->d_sph64 + 4 * (size_t)G.elem_base, e->d_sph32 + G.elem_base,
+                       e->d_sphown + G.elem_base, e->d_nodes + 2 * (size_t)G.node_base, d_s, sb, (int)maxn, nullptr, e->stream));
+      CK(cudaStreamSynchronize(e->stream));
+    }
+    cudaFree(d_p); cudaFree(d_r); cudaFree(d_o); cudaFree(d_T); cudaFree(d_s);
+    e->pending_clouds.clear();
+  }
   CK(cudaMalloc((void**)&e->d_work, 64)); CK(cudaMalloc((void**)&e->d_counters, 128)); CK(cudaMemset(e->d_counters, 0, 128));
   CK(cudaMalloc((void**)&e->d_scalars, 64));
   // the host copies of the big arrays are no longer needed
@@ -1189,6 +1246,11 @@ int kb_set_option(kb_engine* e, const char* name, int64_t value) {
   if (!strcmp(name, "pipeline")) { if (value != 0 && value != 1) return fail(KB_ERR_INVALID, "pipeline must be 0 (fused) or 1 (split)"); e->pipeline = (int)value; return KB_OK; }
   if (!strcmp(name, "leaf_budget")) { if (value < 1 || value > 100000) return fail(KB_ERR_INVALID, "leaf_budget out of range"); e->leaf_budget = (int)value; return KB_OK; }
   if (!strcmp(name, "clear_grid")) { e->use_grids = value != 0; return KB_OK; }
+  if (!strcmp(name, "cloud_builder")) {
+    if (e->finalized) return fail(KB_ERR_STATE, "cloud_builder must be set before kb_finalize");
+    if (value != 0 && value != 1) return fail(KB_ERR_INVALID, "cloud_builder: 0 = binned SAH on the host (default), 1 = linear BVH on the GPU");
+    e->cloud_builder = (int)value; return KB_OK;
+  }
   if (!strcmp(name, "both_limit")) { e->both_limit = (int)value; return KB_OK; }
   if (!strcmp(name, "grid_res")) {
     if (e->finalized) return fail(KB_ERR_STATE, "grid_res must be set before kb_finalize");

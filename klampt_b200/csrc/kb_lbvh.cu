@@ -75,7 +75,7 @@ __global__ void lbvh_morton_kernel(const double* __restrict__ w64, int n, const 
 }
 
 // 2b. gather into BVH order
-__global__ void lbvh_gather_kernel(const double* __restrict__ w64, const int* __restrict__ sorted_idx, int n, int owner,
+__global__ void lbvh_gather_kernel(const double* __restrict__ w64, const int* __restrict__ sorted_idx, int n, int owner, const int32_t* __restrict__ owner_in,
                                    double* __restrict__ sph64, float4* __restrict__ sph32, int* __restrict__ sphown) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -83,7 +83,7 @@ __global__ void lbvh_gather_kernel(const double* __restrict__ w64, const int* __
   const double x = w64[4 * (size_t)s], y = w64[4 * (size_t)s + 1], z = w64[4 * (size_t)s + 2], r = w64[4 * (size_t)s + 3];
   sph64[4 * (size_t)i] = x; sph64[4 * (size_t)i + 1] = y; sph64[4 * (size_t)i + 2] = z; sph64[4 * (size_t)i + 3] = r;
   sph32[i] = make_float4((float)x, (float)y, (float)z, (float)r);
-  sphown[i] = owner;
+  sphown[i] = owner_in ? owner_in[s] : owner;
 }
 
 // 3. point boxes (fp64 extents rounded outwards to fp32): the leaves of the Karras tree are the single points
@@ -222,7 +222,7 @@ size_t kb_lbvh_scratch_bytes(int capacity) {
 }
 
 cudaError_t kb_lbvh_build(const double* d_pts_local, const double* d_radius, double uniform_radius, int n, const double* d_T12, int owner,
-                          double* sph64, float4* sph32, int32_t* sphown, float4* nodes, void* scratch, size_t scratch_bytes, int capacity, float* h_maxabs,
+                          const int32_t* d_owner_in, double* sph64, float4* sph32, int32_t* sphown, float4* nodes, void* scratch, size_t scratch_bytes, int capacity, float* h_maxabs,
                           cudaStream_t s) {
   if (n < 0 || n > capacity) return cudaErrorInvalidValue;
   if (scratch_bytes < kb_lbvh_scratch_bytes(capacity)) return cudaErrorInvalidValue;
@@ -249,7 +249,7 @@ cudaError_t kb_lbvh_build(const double* d_pts_local, const double* d_radius, dou
     size_t tb = tmp_bytes;
     e = cub::DeviceRadixSort::SortPairs(tmp, tb, keys, skeys, idx, sidx, n, 0, 30, s);
     if (e != cudaSuccess) return e;
-    lbvh_gather_kernel<<<nb(n, 256), 256, 0, s>>>(w64, sidx, n, owner, sph64, sph32, sphown);
+    lbvh_gather_kernel<<<nb(n, 256), 256, 0, s>>>(w64, sidx, n, owner, d_owner_in, sph64, sph32, sphown);
     lbvh_pointbox_kernel<<<nb(n, 256), 256, 0, s>>>(sph64, n, llo, lhi);
     if (n > 1) {
       e = cudaMemsetAsync(flags, 0, (size_t)n * 4, s);

@@ -10,6 +10,7 @@ size_t kb_lbvh_scratch_bytes(int capacity);
 // Builds the hierarchy of n points given in the geometry's local frame (device pointers; radius may be null = uniform_radius):
 // transforms them by d_T12 (row-major 3x3 + translation, device), writes them in BVH order to sph64 / sph32 / sphown (= owner) and the
 // nodes to `nodes`.  If h_maxabs is not null the stream is synchronised and the largest |world coordinate| is returned.
+// d_owner_in (may be null = `owner` for every point): owner id per input point, carried through the sort.
 cudaError_t kb_lbvh_build(const double* d_pts_local, const double* d_radius, double uniform_radius, int n, const double* d_T12, int owner,
-                          double* sph64, float4* sph32, int32_t* sphown, float4* nodes, void* scratch, size_t scratch_bytes, int capacity, float* h_maxabs,
+                          const int32_t* d_owner_in, double* sph64, float4* sph32, int32_t* sphown, float4* nodes, void* scratch, size_t scratch_bytes, int capacity, float* h_maxabs,
                           cudaStream_t s);

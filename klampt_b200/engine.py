@@ -37,13 +37,17 @@ def _f64(a, shape=None):
 class Engine:
     """One kb_engine handle = static world + one active robot, resident on one GPU."""
 
-    def __init__(self, spec: WorldSpec, device: int = 0):
+    def __init__(self, spec: WorldSpec, device: int = 0, options: Optional[dict] = None):
+        """options: kb_set_option values that must be in place before kb_finalize, e.g. {"cloud_builder": 1} (point-cloud
+        hierarchies built on the GPU) or {"grid_res": 0}"""
         self.lib = _capi.load()
         self.spec = spec
         self.h = C.c_void_p()
         check(self.lib.kb_engine_create(C.byref(self.h)))
         try:
             self._describe(spec)
+            for k, v in (options or {}).items():
+                check(self.lib.kb_set_option(self.h, k.encode(), int(v)))
             check(self.lib.kb_finalize(self.h, int(device)))
         except Exception:
             self.close()

@@ -570,3 +570,21 @@ def test_fp32_configurations_entry_point(c1):
     assert np.array_equal(got, want)
     assert_bool_parity(got[:5000], orc.feasible_batch(Qf[:5000].astype(np.float64)), Qf[:5000].astype(np.float64), orc)
     assert ((pairs[:, 0] >= 0) == (got == 0)).all()
+
+
+def test_static_clouds_built_on_the_gpu(c5small):
+    """option cloud_builder = 1: the hierarchies of static point clouds come from the GPU builder; same answers"""
+    from klampt_b200.engine import Engine
+    w, eng, orc = c5small
+    eg = Engine(w, options={"cloud_builder": 1})
+    Q = synth.sample_configs(w.robot, 8000, 71)
+    assert np.array_equal(eg.feasible_batch(Q), eng.feasible_batch(Q))
+    d, dg = eng.distance_batch(Q[:800], upper_bound=0.4), eg.distance_batch(Q[:800], upper_bound=0.4)
+    np.testing.assert_allclose(dg, d, rtol=1e-12, atol=1e-15)
+    # explicit pair queries use the per-geometry hierarchy, also built on the GPU
+    gi = [i for i, g in enumerate(w.geoms) if g.kind == "cloud"][0]
+    gl = w.robot.link_geom[4]
+    rng = np.random.default_rng(72)
+    Ta = np.tile(np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0.0]), (200, 1))
+    Tb = np.stack([np.concatenate([synth._random_rotation(rng).reshape(-1), rng.uniform(-1, 1, size=3) + [0, 0, 0.8]]) for _ in range(200)])
+    assert np.array_equal(eg.geom_collides_batch(gi, Ta, gl, Tb), eng.geom_collides_batch(gi, Ta, gl, Tb))
