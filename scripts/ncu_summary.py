@@ -54,12 +54,16 @@ def rep(path, out, title):
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}
         def val(r, k):
             return float(r[col[k]]) * scale.get(units[col[k]], 1.0)
-        if all(k in col for k in ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum")):
+        if all(k in col for k in ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum")):
             f.write("\n| derived | " + " | ".join("launch %d" % i for i in range(len(data))) + " |\n|---|" + "---|" * len(data) + "\n")
             f.write("| achieved HBM GB/s (of 6544.3 measured peak) | " + " | ".join("%.1f (%.1f %%)" % ((val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")) / val(r, "gpu__time_duration.sum") / 1e9,
                     100 * (val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")) / val(r, "gpu__time_duration.sum") / 6544.3e9) for r in data) + " |\n")
-            f.write("| achieved L2 GB/s | " + " | ".join("%.1f" % (val(r, "lts__t_bytes.sum") / val(r, "gpu__time_duration.sum") / 1e9) for r in data) + " |\n")
-
+            if "lts__t_bytes.sum" in col:
+                f.write("| achieved L2 GB/s | " + " | ".join("%.1f" % (val(r, "lts__t_bytes.sum") / val(r, "gpu__time_duration.sum") / 1e9) for r in data) + " |\n")
+            elif "lts__t_sectors.sum" in col:      # 32-byte sectors through the L2 tag stage
+                f.write("| achieved L2 GB/s (`lts__t_sectors.sum` x 32 B) | " + " | ".join("%.1f" % (float(r[col["lts__t_sectors.sum"]]) * 32 / val(r, "gpu__time_duration.sum") / 1e9) for r in data) + " |\n")
+            if "smsp__inst_executed.sum" in col:
+                f.write("| warp instructions issued per second (peak: 4 schedulers x 148 SMs x 1.965 GHz = 1163 G/s) | " + " | ".join("%.1f G/s" % (float(r[col["smsp__inst_executed.sum"]]) / val(r, "gpu__time_duration.sum") / 1e9) for r in data) + " |\n")
 
 def launches(path, out, title):
     rows = [r for r in csv.reader(open(path)) if len(r) > 10 and r[0].isdigit()]
