@@ -164,6 +164,7 @@ struct DevGeom {
 };
 
 #define KB_GPU_CLOUD_MIN 4096      // clouds up to this size keep the host SAH build even with cloud_builder = 1
+#define KB_GPU_MESH_MIN 16384      // meshes up to this size keep the host SAH build even with mesh_builder = 1 (link meshes: quality matters most)
 
 struct ItemSet {
   std::vector<KbItem> items; KbItem* d_items = nullptr; int nxf = 0; int maxdepth = 0;
@@ -346,7 +347,8 @@ struct kb_engine {
   double eps_extent = 0, eps_reach = 0, eps_lmax = 0;   // the parts of the fp32 error bound, kept so a new cloud can widen it
   std::vector<HostGrid> hgrids; uint8_t* d_grid[KB_MAX_GRIDS] = {nullptr, nullptr, nullptr, nullptr};
   int cloud_builder = 0;                     // 0: point-cloud hierarchies by binned SAH on the host; 1: linear BVH on the GPU (kb_lbvh.cu)
-  struct PendingCloud { DevGeom* dg; std::vector<double> elems; std::vector<int32_t> owners; };
+  int mesh_builder = 0;                      // the same choice for triangle meshes above KB_GPU_MESH_MIN triangles
+  struct PendingCloud { DevGeom* dg; std::vector<double> elems; std::vector<int32_t> owners; bool mesh = false; };
   std::vector<PendingCloud> pending_clouds;   // clouds whose hierarchy is built on the GPU once the arrays are uploaded
   int both_limit = 0;                        // experiment: frontier size up to which comparable inner pairs descend both trees at once
   int grid_res = 256; bool use_grids = false; // clearance-grid broad phase of the boolean query (options grid_res, clear_grid)
@@ -521,6 +523,26 @@ void reserve_gpu_cloud(kb_engine* e, const std::vector<double>& elems, const std
   double r2 = 0; for (int k = 0; k < 3; k++) { dg.cover[0][k] = 0.5 * (dg.lo[k] + dg.hi[k]); r2 += 0.25 * (dg.hi[k] - dg.lo[k]) * (dg.hi[k] - dg.lo[k]); }
   dg.cover[0][3] = std::sqrt(r2) * (1 + 1e-12);
   e->pending_clouds.push_back({&dg, elems, owners});
+}
+
+// the same for a large triangle mesh (option mesh_builder = 1)
+void reserve_gpu_mesh(kb_engine* e, const std::vector<double>& elems, const std::vector<int32_t>& owners, double margin, DevGeom& dg) {
+  const int n = (int)(elems.size() / 9);
+  dg = DevGeom(); dg.margin = margin; dg.kind = KB_ELEM_TRI; dg.nelem = n; dg.empty = n == 0; dg.depth = 64;
+  for (int k = 0; k < 3; k++) { dg.lo[k] = 1e300; dg.hi[k] = -1e300; }
+  for (size_t i = 0; i < elems.size(); i++) { const int k = (int)(i % 3); dg.lo[k] = std::min(dg.lo[k], elems[i]); dg.hi[k] = std::max(dg.hi[k], elems[i]); }
+  if ((e->h_nodes.size() / 8) & 1) e->h_nodes.insert(e->h_nodes.end(), 8, 0.f);
+  dg.node_base = (int)(e->h_nodes.size() / 8); dg.nnodes = (int)kb_lbvh_nodes_for(n);
+  const float v[8] = {0.f, 0.f, 0.f, i2f(~0), -1e30f, -1e30f, -1e30f, i2f(0)};
+  e->h_nodes.insert(e->h_nodes.end(), v, v + 8);
+  e->h_nodes.insert(e->h_nodes.end(), (size_t)(dg.nnodes - 1) * 8, 0.f);
+  dg.elem_base = (int)(e->h_tris64.size() / 9);
+  e->h_tris64.insert(e->h_tris64.end(), (size_t)n * 9, 0.0); e->h_tris32.insert(e->h_tris32.end(), (size_t)n * 12, 0.f);
+  e->h_triown.insert(e->h_triown.end(), (size_t)n, -1);
+  dg.ncover = 1;
+  double r2 = 0; for (int k = 0; k < 3; k++) { dg.cover[0][k] = 0.5 * (dg.lo[k] + dg.hi[k]); r2 += 0.25 * (dg.hi[k] - dg.lo[k]) * (dg.hi[k] - dg.lo[k]); }
+  dg.cover[0][3] = std::sqrt(r2) * (1 + 1e-12);
+  e->pending_clouds.push_back({&dg, elems, owners, true});
 }
 
 KbItem make_item(const DevGeom& A, int xfA, int idA, const DevGeom& B, int xfB, int idB, bool self) {
@@ -946,6 +968,7 @@ int kb_finalize(kb_engine* e, int device) {
     const Geom& G = e->geoms[g];
     if (G.dyn_cap > 0) { e->dgeoms[g] = DevGeom(); continue; }   // replaceable clouds live in their environment group only
     if (e->cloud_builder == 1 && G.kind == G_CLOUD && G.nelem() > KB_GPU_CLOUD_MIN) { reserve_gpu_cloud(e, G.sph, none, G.margin, e->dgeoms[g]); continue; }
+    if (e->mesh_builder == 1 && G.kind == G_MESH && G.nelem() > KB_GPU_MESH_MIN) { reserve_gpu_mesh(e, G.tri, none, G.margin, e->dgeoms[g]); continue; }
     int rc = append_geom(e, G.kind == G_MESH ? G_MESH : G_CLOUD, G.kind == G_MESH ? G.tri : G.sph, none, G.margin, e->dgeoms[g], true);
     if (rc) return rc;
     if (G.kind == G_EMPTY) e->dgeoms[g].empty = true;
@@ -1041,6 +1064,8 @@ int kb_finalize(kb_engine* e, int device) {
     }
     if (e->cloud_builder == 1 && grp[g].kind == G_CLOUD && (int)(grp[g].elems.size() / 4) > KB_GPU_CLOUD_MIN) {
       reserve_gpu_cloud(e, grp[g].elems, grp[g].owners, grp[g].margin, e->groups[g]);
+    } else if (e->mesh_builder == 1 && grp[g].kind == G_MESH && (int)(grp[g].elems.size() / 9) > KB_GPU_MESH_MIN) {
+      reserve_gpu_mesh(e, grp[g].elems, grp[g].owners, grp[g].margin, e->groups[g]);
     } else {
       int rc = append_geom(e, grp[g].kind, grp[g].elems, grp[g].owners, grp[g].margin, e->groups[g], false);
       if (rc) return rc;
@@ -1198,14 +1223,24 @@ int kb_finalize(kb_engine* e, int device) {
   if ((rc = upload(e->d_drv_scale, ds.data(), ds.size() * 8, &e->static_bytes))) return rc;
   if ((rc = upload(e->d_drv_off, dofs.data(), dofs.size() * 8, &e->static_bytes))) return rc;
   if (!e->pending_clouds.empty()) {      // hierarchies of the large point clouds on the GPU (Morton order + Karras, kb_lbvh.cu)
-    size_t maxn = 0; for (const auto& pc : e->pending_clouds) maxn = std::max(maxn, pc.elems.size() / 4);
+    size_t maxn = 0; for (const auto& pc : e->pending_clouds) maxn = std::max(maxn, pc.elems.size() / (pc.mesh ? 9 : 4));
     double* d_p = nullptr; double* d_r = nullptr; int32_t* d_o = nullptr; double* d_T = nullptr; void* d_s = nullptr;
     const size_t sb = kb_lbvh_scratch_bytes((int)maxn);
-    CK(cudaMalloc((void**)&d_p, maxn * 24)); CK(cudaMalloc((void**)&d_r, maxn * 8)); CK(cudaMalloc((void**)&d_o, maxn * 4)); CK(cudaMalloc((void**)&d_T, 96)); CK(cudaMalloc(&d_s, sb));
+    CK(cudaMalloc((void**)&d_p, maxn * 72)); CK(cudaMalloc((void**)&d_r, maxn * 8)); CK(cudaMalloc((void**)&d_o, maxn * 4)); CK(cudaMalloc((void**)&d_T, 96)); CK(cudaMalloc(&d_s, sb));
     const double I12[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
     CK(cudaMemcpy(d_T, I12, 96, cudaMemcpyHostToDevice));
     std::vector<double> hp, hr;
     for (auto& pc : e->pending_clouds) {
+      if (pc.mesh) {
+        const size_t nt = pc.elems.size() / 9;
+        CK(cudaMemcpy(d_p, pc.elems.data(), nt * 72, cudaMemcpyHostToDevice));
+        if (!pc.owners.empty()) CK(cudaMemcpy(d_o, pc.owners.data(), nt * 4, cudaMemcpyHostToDevice));
+        const DevGeom& G = *pc.dg;
+        CK(kb_lbvh_build_tris(d_p, (int)nt, -1, pc.owners.empty() ? nullptr : d_o, e->d_tris64 + 9 * (size_t)G.elem_base, e->d_tris32 + 3 * (size_t)G.elem_base,
+                              e->d_triown + G.elem_base, e->d_nodes + 2 * (size_t)G.node_base, d_s, sb, (int)maxn, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        continue;
+      }
       const size_t n = pc.elems.size() / 4;
       hp.resize(3 * n); hr.resize(n);
       for (size_t i = 0; i < n; i++) { hp[3 * i] = pc.elems[4 * i]; hp[3 * i + 1] = pc.elems[4 * i + 1]; hp[3 * i + 2] = pc.elems[4 * i + 2]; hr[i] = pc.elems[4 * i + 3]; }
@@ -1246,6 +1281,11 @@ int kb_set_option(kb_engine* e, const char* name, int64_t value) {
   if (!strcmp(name, "pipeline")) { if (value != 0 && value != 1) return fail(KB_ERR_INVALID, "pipeline must be 0 (fused) or 1 (split)"); e->pipeline = (int)value; return KB_OK; }
   if (!strcmp(name, "leaf_budget")) { if (value < 1 || value > 100000) return fail(KB_ERR_INVALID, "leaf_budget out of range"); e->leaf_budget = (int)value; return KB_OK; }
   if (!strcmp(name, "clear_grid")) { e->use_grids = value != 0; return KB_OK; }
+  if (!strcmp(name, "mesh_builder")) {
+    if (e->finalized) return fail(KB_ERR_STATE, "mesh_builder must be set before kb_finalize");
+    if (value != 0 && value != 1) return fail(KB_ERR_INVALID, "mesh_builder: 0 = binned SAH on the host (default), 1 = linear BVH on the GPU for large meshes");
+    e->mesh_builder = (int)value; return KB_OK;
+  }
   if (!strcmp(name, "cloud_builder")) {
     if (e->finalized) return fail(KB_ERR_STATE, "cloud_builder must be set before kb_finalize");
     if (value != 0 && value != 1) return fail(KB_ERR_INVALID, "cloud_builder: 0 = binned SAH on the host (default), 1 = linear BVH on the GPU");

@@ -109,7 +109,7 @@ __device__ __forceinline__ int lbvh_delta(const unsigned* __restrict__ k, int n,
 // worst leaves span metres and the traversal pays for them -- measured 20-45x slower queries).
 __global__ void lbvh_hierarchy_kernel(const unsigned* __restrict__ keys, int n, int* __restrict__ childL, int* __restrict__ childR,
                                       int* __restrict__ parentI, int* __restrict__ parentLeaf, int* __restrict__ first, int* __restrict__ count,
-                                      int* __restrict__ keep) {
+                                      int* __restrict__ keep, int leaf_max) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1) return;
   const int d = (lbvh_delta(keys, n, i, i + 1) - lbvh_delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
@@ -134,7 +134,7 @@ __global__ void lbvh_hierarchy_kernel(const unsigned* __restrict__ keys, int n, 
   if (cr >= 0) parentI[cr] = i; else parentLeaf[~cr] = i;
   if (i == 0) parentI[0] = -1;
   first[i] = lo; count[i] = hi - lo + 1;
-  keep[i] = (hi - lo + 1) > KB_LBVH_LEAF ? 1 : 0;
+  keep[i] = (hi - lo + 1) > leaf_max ? 1 : 0;
 }
 
 // 5. bottom-up boxes of the internal nodes
@@ -196,6 +196,63 @@ __global__ void lbvh_emit_kernel(int n, const int* __restrict__ childL, const in
   }
 }
 
+// ---- triangle meshes: keys from the centroids, one triangle per leaf
+__global__ void lbvh_tri_bounds_kernel(const double* __restrict__ tris, int n, int* __restrict__ bounds) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  if (i < n) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const double c = (tris[9 * (size_t)i + k] + tris[9 * (size_t)i + 3 + k] + tris[9 * (size_t)i + 6 + k]) * (1.0 / 3.0);
+      lo[k] = __double2float_rd(c); hi[k] = __double2float_ru(c);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o)); hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o)); }
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { atomicMin(bounds + k, f2ord(lo[k])); atomicMax(bounds + 3 + k, f2ord(hi[k])); }
+  }
+}
+__global__ void lbvh_tri_morton_kernel(const double* __restrict__ tris, int n, const int* __restrict__ bounds, unsigned* __restrict__ keys, int* __restrict__ idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned code = 0;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const float lo = ord2f(bounds[k]), hi = ord2f(bounds[3 + k]);
+    const float ext = fmaxf(hi - lo, 1e-30f);
+    const double c = (tris[9 * (size_t)i + k] + tris[9 * (size_t)i + 3 + k] + tris[9 * (size_t)i + 6 + k]) * (1.0 / 3.0);
+    float u = ((float)c - lo) / ext * 1024.f;
+    u = fminf(fmaxf(u, 0.f), 1023.f);
+    code |= expand10((unsigned)u) << (2 - k);
+  }
+  keys[i] = code; idx[i] = i;
+}
+// gather into BVH order (tris64, tris32 with the owner id in .w of vertex 0, triown) and the triangle boxes
+__global__ void lbvh_tri_gather_kernel(const double* __restrict__ tris, const int* __restrict__ sorted_idx, int n, int owner, const int32_t* __restrict__ owner_in,
+                                       double* __restrict__ tris64, float4* __restrict__ tris32, int* __restrict__ triown,
+                                       float* __restrict__ blo, float* __restrict__ bhi) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = sorted_idx[i];
+  const int own = owner_in ? owner_in[s] : owner;
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+#pragma unroll
+  for (int v = 0; v < 3; v++) {
+    const double x = tris[9 * (size_t)s + 3 * v], y = tris[9 * (size_t)s + 3 * v + 1], z = tris[9 * (size_t)s + 3 * v + 2];
+    tris64[9 * (size_t)i + 3 * v] = x; tris64[9 * (size_t)i + 3 * v + 1] = y; tris64[9 * (size_t)i + 3 * v + 2] = z;
+    tris32[3 * (size_t)i + v] = make_float4((float)x, (float)y, (float)z, v == 0 ? __int_as_float(own) : 0.f);
+    lo[0] = fmin(lo[0], x); lo[1] = fmin(lo[1], y); lo[2] = fmin(lo[2], z); hi[0] = fmax(hi[0], x); hi[1] = fmax(hi[1], y); hi[2] = fmax(hi[2], z);
+  }
+  triown[i] = own;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { blo[3 * (size_t)i + k] = __double2float_rd(lo[k]); bhi[3 * (size_t)i + k] = __double2float_ru(hi[k]); }
+}
+
 inline unsigned nb(int n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 }  // namespace
@@ -254,7 +311,7 @@ cudaError_t kb_lbvh_build(const double* d_pts_local, const double* d_radius, dou
     if (n > 1) {
       e = cudaMemsetAsync(flags, 0, (size_t)n * 4, s);
       if (e != cudaSuccess) return e;
-      lbvh_hierarchy_kernel<<<nb(n - 1, 256), 256, 0, s>>>(skeys, n, childL, childR, parentI, parentLeaf, first, count, keep);
+      lbvh_hierarchy_kernel<<<nb(n - 1, 256), 256, 0, s>>>(skeys, n, childL, childR, parentI, parentLeaf, first, count, keep, KB_LBVH_LEAF);
       lbvh_refit_kernel<<<nb(n, 256), 256, 0, s>>>(n, childL, childR, parentI, parentLeaf, llo, lhi, ilo, ihi, flags);
       tb = tmp_bytes;
       e = cub::DeviceScan::ExclusiveSum(tmp, tb, keep, rank, n - 1, s);      // dense numbering of the kept nodes (the root is 0)
@@ -275,4 +332,46 @@ cudaError_t kb_lbvh_build(const double* d_pts_local, const double* d_radius, dou
     *h_maxabs = m;
   }
   return cudaSuccess;
+}
+
+// the same for a triangle mesh (triangles already in the frame of the hierarchy, 9 doubles each): one triangle per leaf
+cudaError_t kb_lbvh_build_tris(const double* d_tris_in, int n, int owner, const int32_t* d_owner_in, double* tris64, float4* tris32, int32_t* triown,
+                               float4* nodes, void* scratch, size_t scratch_bytes, int capacity, cudaStream_t s) {
+  if (n < 0 || n > capacity) return cudaErrorInvalidValue;
+  if (scratch_bytes < kb_lbvh_scratch_bytes(capacity)) return cudaErrorInvalidValue;
+  const size_t cap = (size_t)capacity + 1;
+  unsigned char* p = (unsigned char*)scratch;
+  auto take = [&](size_t bytes) { void* r = p; p += (bytes + 255) & ~(size_t)255; return r; };
+  int* bounds = (int*)take(64);
+  (void)take(cap * 32);
+  unsigned* keys = (unsigned*)take(cap * 4); int* idx = (int*)take(cap * 4);
+  unsigned* skeys = (unsigned*)take(cap * 4); int* sidx = (int*)take(cap * 4);
+  float* llo = (float*)take(cap * 12); float* lhi = (float*)take(cap * 12); float* ilo = (float*)take(cap * 12); float* ihi = (float*)take(cap * 12);
+  int* childL = (int*)take(cap * 4); int* childR = (int*)take(cap * 4); int* parentI = (int*)take(cap * 4); int* parentLeaf = (int*)take(cap * 4); int* flags = (int*)take(cap * 4);
+  int* first = (int*)take(cap * 4); int* count = (int*)take(cap * 4); int* keep = (int*)take(cap * 4); int* rank = (int*)take(cap * 4);
+  size_t tmp_bytes = lbvh_sort_tmp(capacity);
+  void* tmp = take(tmp_bytes);
+  if ((size_t)(p - (unsigned char*)scratch) > scratch_bytes) return cudaErrorInvalidValue;
+  const int init[6] = {0x7f7fffff, 0x7f7fffff, 0x7f7fffff, INT_MIN, INT_MIN, INT_MIN};
+  cudaError_t e = cudaMemcpyAsync(bounds, init, sizeof init, cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return e;
+  if (n > 0) {
+    lbvh_tri_bounds_kernel<<<nb(n, 256), 256, 0, s>>>(d_tris_in, n, bounds);
+    lbvh_tri_morton_kernel<<<nb(n, 256), 256, 0, s>>>(d_tris_in, n, bounds, keys, idx);
+    size_t tb = tmp_bytes;
+    e = cub::DeviceRadixSort::SortPairs(tmp, tb, keys, skeys, idx, sidx, n, 0, 30, s);
+    if (e != cudaSuccess) return e;
+    lbvh_tri_gather_kernel<<<nb(n, 256), 256, 0, s>>>(d_tris_in, sidx, n, owner, d_owner_in, tris64, tris32, triown, llo, lhi);
+    if (n > 1) {
+      e = cudaMemsetAsync(flags, 0, (size_t)n * 4, s);
+      if (e != cudaSuccess) return e;
+      lbvh_hierarchy_kernel<<<nb(n - 1, 256), 256, 0, s>>>(skeys, n, childL, childR, parentI, parentLeaf, first, count, keep, 1);
+      lbvh_refit_kernel<<<nb(n, 256), 256, 0, s>>>(n, childL, childR, parentI, parentLeaf, llo, lhi, ilo, ihi, flags);
+      tb = tmp_bytes;
+      e = cub::DeviceScan::ExclusiveSum(tmp, tb, keep, rank, n - 1, s);
+      if (e != cudaSuccess) return e;
+    }
+  }
+  lbvh_emit_kernel<<<nb(n > 1 ? n - 1 : 1, 256), 256, 0, s>>>(n, childL, childR, first, count, keep, rank, llo, lhi, ilo, ihi, nodes);
+  return cudaGetLastError();
 }

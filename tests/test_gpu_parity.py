@@ -588,3 +588,18 @@ def test_static_clouds_built_on_the_gpu(c5small):
     Ta = np.tile(np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0.0]), (200, 1))
     Tb = np.stack([np.concatenate([synth._random_rotation(rng).reshape(-1), rng.uniform(-1, 1, size=3) + [0, 0, 0.8]]) for _ in range(200)])
     assert np.array_equal(eg.geom_collides_batch(gi, Ta, gl, Tb), eng.geom_collides_batch(gi, Ta, gl, Tb))
+
+
+def test_environment_mesh_built_on_the_gpu(c2small):
+    """option mesh_builder = 1: the merged environment mesh hierarchy comes from the GPU builder (Morton order of the triangle
+    centroids, one triangle per leaf); same answers as with the host SAH tree"""
+    from klampt_b200.engine import Engine
+    w, eng, orc = c2small
+    eg = Engine(w, options={"mesh_builder": 1})
+    assert eg.layout()["nodes"] > eng.layout()["nodes"]          # the reserved node range of the GPU-built tree (2 n + 4)
+    Q = synth.sample_configs(w.robot, 20000, 81)
+    got, pairs = eg.feasible_batch(Q, return_pairs=True)
+    assert np.array_equal(got, eng.feasible_batch(Q))
+    assert_bool_parity(got[:4000], orc.feasible_batch(Q[:4000]), Q[:4000], orc)
+    np.testing.assert_allclose(eg.distance_batch(Q[:1000], upper_bound=0.3, include_self=True), eng.distance_batch(Q[:1000], upper_bound=0.3, include_self=True),
+                               rtol=1e-12, atol=1e-15)
