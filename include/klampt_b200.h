@@ -129,7 +129,12 @@ int kb_synchronize(kb_engine* e);
  * "time_kernels" (0|1: bracket every traversal launch with CUDA events on the engine's stream, summed into kb_stats),
  * "chunk" (configurations per kernel launch, default up to 1 M within a 2 GB scratch budget),
  * "pipeline" (0 = fused traversal kernel, default; 1 = split pipeline: lean node kernel -> global leaf-pair list -> leaf kernel ->
- * fused kernel on requeued configurations; same results, measured slower on C2/C3), "leaf_budget" (split pipeline only) */
+ * fused kernel on requeued configurations; same results, measured slower on C2/C3), "leaf_budget" (split pipeline only),
+ * "clear_grid" (0|1, default 0: clearance-grid broad phase that drops (link, static group) pairs before the BVH descent; exact),
+ * "both_limit" (experiment knob of builds with KB_BOTH_MODE=2).
+ * Before kb_finalize only: "grid_res" (voxels along the longest axis of a clearance grid, 0 = none, default 256),
+ * "cloud_builder" / "mesh_builder" (0 = binned SAH on the host, default; 1 = linear BVH built on the GPU for point clouds above
+ * 4096 points / meshes above 16384 triangles: kb_finalize far faster, queries 7-13 % slower, identical answers). */
 int kb_set_option(kb_engine* e, const char* name, int64_t value);
 
 /* ---- the hot path ------------------------------------------------------------------------------------- */
