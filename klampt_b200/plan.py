@@ -8,6 +8,14 @@ module keeps the user-facing shape of ``klampt.plan.cspace.MotionPlan`` (referen
 
   'prm'       every round: sample a batch -> feasible_batch -> k nearest neighbours -> visible_batch on all candidate edges
   'lazyprm*'  same sampling, but edges are only checked (in batches) when they lie on the current best path
+  'rrt'       bidirectional, batch-synchronous RRT: a batch of random targets, each pulls the nearest vertex of the start or the
+              goal tree (alternating) one ``perturbationRadius`` step towards it; the new configurations go through
+              feasible_batch, their tree edges through visible_batch, and every new vertex then tries to bridge to the nearest
+              vertex of the other tree (``connectionThreshold``) with one more visible_batch
+  'sbl'       single-query bidirectional lazy planner: both trees grow by feasible samples drawn in the neighbourhood
+              (``perturbationRadius``) of random tree vertices WITHOUT checking the tree edges; bridges are proposed between
+              close vertices of the two trees; the edges of a candidate start-goal path are validated in one batch when the
+              path is asked for, and blocked edges are dropped
 
 Options (MotionPlan.setOptions keys that apply): ``knn``, ``connectionThreshold``; plus ``batch`` (samples per planMore
 iteration).  The planners need a space with ``feasible_batch(Q)`` and ``visible_batch(A, B)`` (``RobotCSpace``), and use
@@ -36,12 +44,14 @@ class MotionPlan:
         MotionPlan._next_options = {}
         self.space = space
         self.type = (type or "prm").lower()
-        if self.type not in ("prm", "prm*", "lazyprm*", "lazyprm"):
-            raise ValueError("planner type %r is not batched here; available: prm, prm*, lazyprm*" % type)
-        self.lazy = self.type.startswith("lazy")
+        if self.type not in ("prm", "prm*", "lazyprm*", "lazyprm", "rrt", "sbl"):
+            raise ValueError("planner type %r is not batched here; available: prm, prm*, lazyprm*, rrt, sbl" % type)
+        self.lazy = self.type.startswith("lazy") or self.type == "sbl"
+        self.tree: List[int] = []                          # rrt / sbl: 0 = vertex of the start tree, 1 = of the goal tree
         self.knn = int(opts.get("knn", 10))
         self.connectionThreshold = float(opts.get("connectionThreshold", float("inf")))
         self.batch = int(opts.get("batch", 2048))
+        self.perturbationRadius = float(opts.get("perturbationRadius", 0.25))
         self.rng = np.random.default_rng(int(opts.get("seed", 0)))
         lo, hi = np.array([b[0] for b in space.bound], dtype=np.float64), np.array([b[1] for b in space.bound], dtype=np.float64)
         self._lo, self._hi = lo, np.where(np.isfinite(hi), hi, 2 * np.pi)
@@ -72,6 +82,9 @@ class MotionPlan:
         if not ok[1]:
             raise RuntimeError("Goal configuration is infeasible")
         self.start, self.goal = self._add_vertices(ends)
+        if self.type in ("rrt", "sbl"):
+            self.tree = [0, 1]
+            return
         self._connect([self.start, self.goal])
 
     def _dist(self, A: np.ndarray, B: np.ndarray) -> np.ndarray:
@@ -114,7 +127,87 @@ class MotionPlan:
                 self.adj[j][int(i)] = (float(l), True)
 
     # ------------------------------------------------------------------ planning
+    # ------------------------------------------------------------------ tree planners
+    def _nearest_in_tree(self, t: int, Q: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        from scipy.spatial import cKDTree
+        ids = np.nonzero(np.asarray(self.tree) == t)[0]
+        d, k = cKDTree(self.V[ids]).query(Q)
+        return ids[k], d
+
+    def _edge(self, i: int, j: int, checked: bool):
+        l = float(self._dist(self.V[i], self.V[j]))
+        self.adj[i][j] = (l, checked)
+        self.adj[j][i] = (l, checked)
+
+    def _bridge(self, new: List[int]):
+        """every new vertex proposes an edge to the nearest vertex of the other tree within connectionThreshold"""
+        if not new:
+            return
+        new_arr = np.asarray(new)
+        cand = []
+        for t in (0, 1):
+            mine = new_arr[np.asarray(self.tree)[new_arr] == t]
+            if len(mine) == 0 or not any(x == 1 - t for x in self.tree):
+                continue
+            other, d = self._nearest_in_tree(1 - t, self.V[mine])
+            thr = self.connectionThreshold if np.isfinite(self.connectionThreshold) else (2 * self.perturbationRadius if self.type == "sbl" else np.inf)
+            cand += [(int(i), int(j)) for i, j, dd in zip(mine, other, d) if dd <= thr and int(j) not in self.adj[int(i)]]
+        if not cand:
+            return
+        if self.lazy:
+            for i, j in cand:
+                self._edge(i, j, False)
+            return
+        A, B = self.V[[i for i, _ in cand]], self.V[[j for _, j in cand]]
+        vis = np.asarray(self.space.visible_batch(A, B)).astype(bool)
+        self.stats["edges_checked"] += len(cand)
+        self.stats["edges_visible"] += int(vis.sum())
+        for (i, j), v in zip(cand, vis):
+            if v:
+                self._edge(i, j, True)
+
+    def _grow_trees(self):
+        if self.start is None:
+            raise RuntimeError("setEndpoints first")
+        n, dim = self.batch, len(self._lo)
+        side = (np.arange(n) + self.stats["iterations"]) % 2
+        if self.type == "rrt":
+            target = self.rng.uniform(self._lo, self._hi, size=(n, dim))
+            src = np.empty(n, dtype=np.int64)
+            Qn = np.empty((n, dim))
+            for t in (0, 1):
+                m = side == t
+                near, d = self._nearest_in_tree(t, target[m])
+                step = np.minimum(1.0, self.perturbationRadius / np.maximum(d, 1e-300))[:, None]
+                src[m] = near
+                Qn[m] = self.V[near] + step * (target[m] - self.V[near])
+        else:                                   # sbl: a sample in the neighbourhood of a random vertex of the tree
+            tree = np.asarray(self.tree)
+            src = np.array([self.rng.choice(np.nonzero(tree == t)[0]) for t in side], dtype=np.int64)
+            Qn = np.clip(self.V[src] + self.rng.uniform(-self.perturbationRadius, self.perturbationRadius, size=(n, dim)), self._lo, self._hi)
+        ok = np.asarray(self.space.feasible_batch(Qn)).astype(bool)
+        self.stats["samples"] += n
+        self.stats["feasible_samples"] += int(ok.sum())
+        keep = ok.copy()
+        if self.type == "rrt" and ok.any():      # rrt validates its tree edges now; sbl leaves them for getPath
+            vis = np.asarray(self.space.visible_batch(self.V[src[ok]], Qn[ok])).astype(bool)
+            self.stats["edges_checked"] += int(ok.sum())
+            self.stats["edges_visible"] += int(vis.sum())
+            keep[np.nonzero(ok)[0][~vis]] = False
+        if not keep.any():
+            return
+        new = self._add_vertices(Qn[keep])
+        self.tree.extend(int(t) for t in side[keep])
+        for v, u in zip(new, src[keep]):
+            self._edge(v, int(u), self.type == "rrt")
+        self._bridge(new)
+
     def planMore(self, iterations: int):
+        if self.type in ("rrt", "sbl"):
+            for _ in range(int(iterations)):
+                self._grow_trees()
+                self.stats["iterations"] += 1
+            return
         for _ in range(int(iterations)):
             Q = self.rng.uniform(self._lo, self._hi, size=(self.batch, len(self._lo)))
             ok = np.asarray(self.space.feasible_batch(Q)).astype(bool)

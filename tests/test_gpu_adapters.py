@@ -144,18 +144,19 @@ def test_cpp_batch_single_robot_cspace(built, tmp_path):
 
 
 def test_batch_roadmap_planner_on_the_engine(setup):
-    """klampt_b200.plan.MotionPlan (PRM / Lazy-PRM* over feasible_batch + visible_batch): the returned path is verified
+    """klampt_b200.plan.MotionPlan (PRM / Lazy-PRM* / RRT / SBL over feasible_batch + visible_batch): the returned path is verified
     milestone by milestone and edge by edge with the CPU oracle"""
     from klampt_b200.plan import MotionPlan
     spec, world, collider, space, orc = setup
     Q = synth.sample_configs(spec.robot, 400, 61)
     feas = Q[orc.feasible_batch(Q) == 1]
     start, goal = feas[0], feas[7]
-    for kind in ("prm", "lazyprm*"):
-        plan = MotionPlan(space, kind, knn=10, batch=1500, seed=5)
+    for kind in ("prm", "lazyprm*", "rrt", "sbl"):
+        tree = kind in ("rrt", "sbl")
+        plan = MotionPlan(space, kind, knn=10, batch=256 if tree else 1500, seed=5, perturbationRadius=0.5)
         plan.setEndpoints(list(start), list(goal))
         path = None
-        for _ in range(6):
+        for _ in range(60 if tree else 6):
             plan.planMore(1)
             path = plan.getPath()
             if path:

@@ -58,6 +58,34 @@ def test_endpoints_must_be_feasible_and_type_checked():
     with pytest.raises(RuntimeError, match="Goal"):
         plan.setEndpoints([0.1, 0.1], [0.5, 0.45])
     with pytest.raises(ValueError):
-        MotionPlan(sp, "rrt")
+        MotionPlan(sp, "fmm")
     with pytest.raises(TypeError):
         MotionPlan(object(), "prm")
+
+
+@pytest.mark.parametrize("kind", ["rrt", "sbl"])
+def test_tree_planners_find_a_valid_path(kind):
+    """batched bidirectional RRT / SBL (the planners the north star names next to Lazy-PRM*) on the disk world"""
+    sp = DiskSpace()
+    MotionPlan.setOptions(batch=64, seed=5, perturbationRadius=0.12)
+    plan = MotionPlan(sp, kind)
+    plan.setEndpoints([0.05, 0.5], [0.95, 0.5])
+    path = None
+    for _ in range(60):
+        plan.planMore(1)
+        path = plan.getPath()
+        if path:
+            break
+    assert path is not None and path[0] == [0.05, 0.5] and path[-1] == [0.95, 0.5]
+    P = np.array(path)
+    assert sp.visible_batch(P[:-1], P[1:]).all()
+    assert plan.pathCost(path) > 0.95
+    st = plan.getStats()
+    assert st["samples"] == 64 * st["iterations"] and st["milestones"] > 2
+    if kind == "sbl":
+        assert st["edges_checked"] < st["edges"]                  # tree edges off the answer were never validated
+    else:
+        V, E = plan.getRoadmap()
+        A, B = np.array(V)[[i for i, _ in E]], np.array(V)[[j for _, j in E]]
+        assert sp.visible_batch(A, B).all()                       # an RRT only keeps validated edges
+    plan.close()
