@@ -373,15 +373,16 @@ def main():
         per_launch_cfg = M * args.steps / tl
         avg_ms = tms / tl
         achieved = bytes_per_cfg * per_launch_cfg / (avg_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, ncu_extra = None, None
         try:   # DRAM bytes of one launch from the committed ncu --set full capture, if it was taken on this launch shape
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             if tj.get("workload") == args.workload and abs(tj["configs_per_launch"] - per_launch_cfg) < 1:
                 traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+                ncu_extra = {k: tj[k] for k in ("issue_active_pct", "l2_gbs", "dram_gbs", "warp_instructions") if k in tj}
         except Exception:
             pass
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                    "kernel": "kb_traverse_kernel<0>", "algorithmic_bytes_per_config": bytes_per_cfg, "configs_per_launch": per_launch_cfg,
+                    "ncu": ncu_extra, "kernel": "kb_traverse_kernel<0>", "algorithmic_bytes_per_config": bytes_per_cfg, "configs_per_launch": per_launch_cfg,
                     "avg_launch_ms": avg_ms, "kernel_share_of_step": tms / ms_dev, "peak_source": peak_src,
                     "counts_per_config": {k: float(cnt[k].mean()) for k in cnt.dtype.names}}
 
