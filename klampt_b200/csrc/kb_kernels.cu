@@ -639,6 +639,9 @@ kb_traverse_kernel(const KbTraverseParams p) {
       if (p.state && p.state[c] == 0) continue;
       const double* xf = p.xf64 + (size_t)c * (size_t)p.nxf * 12;
       __syncwarp();
+      // the transforms of the next configuration of this grab come from DRAM (FK wrote 96 L bytes x 1 M configurations): start them
+      // towards L2 now, one 128-byte line per lane.  Pays for long rows only (19 links: 7.83 -> 7.59 ms; 7 links: 6.22 -> 6.29).
+      if (p.nxf >= 12 && c + 1 < cend && lane * 16 < p.nxf * 12) asm volatile("prefetch.global.L2 [%0];" :: "l"(xf + (size_t)p.nxf * 12 + lane * 16));
       for (int i = lane; i < p.nxf * 12; i += 32) xfw[i] = (float)xf[i];
       __syncwarp();
       if (ITC) {
