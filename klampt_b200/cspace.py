@@ -72,6 +72,46 @@ class CSpace:
             return [] if self.inBounds(x) else ["bounds"]
         return [n for n, t in zip(self.feasibilityTestNames, self.feasibilityTests) if not t(x)]
 
+    def testFeasibility(self, name: str, x) -> bool:
+        """one named test (CSpaceInterface::testFeasibility, Python/klampt/src/motionplanning.h:124)"""
+        if self.feasibilityTests is None or name not in self.feasibilityTestNames:
+            raise ValueError("Invalid feasibility test name %r" % name)
+        return bool(self.feasibilityTests[self.feasibilityTestNames.index(name)](x))
+
+    def feasibilityQueryOrder(self) -> List[str]:
+        """the order in which isFeasible runs the named tests (CSpaceInterface::feasibilityQueryOrder): the order they were added
+        in -- the adaptive re-ordering of the reference (enableAdaptiveQueries) is not done, a batched test has no cheaper order"""
+        return list(self.feasibilityTestNames or [])
+
+    def feasibilityTestDependenciesOf(self, name: str) -> List[str]:
+        return [d for n, d in (self.feasibilityTestDependencies or []) if n == name]
+
+    def testVisibility(self, name: str, a, b) -> bool:
+        """visibility of the straight line under ONE named feasibility test (CSpaceInterface::testVisibility): the epsilon edge checker
+        restricted to that test"""
+        if self.feasibilityTests is None or name not in self.feasibilityTestNames:
+            raise ValueError("Invalid visibility test name %r" % name)
+        test = self.feasibilityTests[self.feasibilityTestNames.index(name)]
+        length, segs = self.distance(a, b), 1
+        while length > self.eps:
+            segs *= 2
+            length *= 0.5
+            for k in range(1, segs, 2):
+                if not test(self.interpolate(a, b, float(k) / segs)):
+                    return False
+        return True
+
+    def visibilityFailures(self, a, b) -> List[str]:
+        """names of the tests under which the line from a to b is not visible (CSpaceInterface::visibilityFailures)"""
+        if self.feasibilityTests is None:
+            return [] if self.isVisible(a, b) else ["visible"]
+        return [n for n in self.feasibilityTestNames if not self.testVisibility(n, a, b)]
+
+    def setVisibilityEpsilon(self, eps: float):
+        if not eps > 0:
+            raise ValueError("Invalid epsilon")          # motionplanning.cpp: PyException("Invalid epsilon")
+        self.eps = float(eps)
+
     def distance(self, a, b) -> float:
         return sum((p - q) ** 2 for p, q in zip(a, b)) ** 0.5
 

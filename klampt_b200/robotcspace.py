@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import math
 import random
-from typing import Optional
+from typing import List, Optional
 
 import numpy as np
 
@@ -130,6 +130,37 @@ class RobotCSpace(CSpace):
             if n not in names:
                 names.append(n)
         return names
+
+    def feasibilityTestNamesList(self) -> List[str]:
+        """the reference's test list for this world (plan/robotcspace.py:31-75): joint limits, self collision, one test per rigid
+        object and per terrain"""
+        names = ["joint limits", "self collision"]
+        if self.collider is not None:
+            w = self.collider.world
+            names += ["obj collision %d %s" % (i, w.rigidObject(i).getName()) for i in range(w.numRigidObjects())]
+            names += ["terrain collision %d %s" % (i, w.terrain(i).getName()) for i in range(w.numTerrains())]
+        return names
+
+    def testFeasibility(self, name: str, x) -> bool:
+        """one of the reference's named tests at x (CSpaceInterface::testFeasibility): evaluated from the all-pairs query, so any
+        number of names costs one launch"""
+        if name not in self.feasibilityTestNamesList():
+            raise ValueError("Invalid feasibility test name %r" % name)
+        if name == "joint limits":
+            return self.inJointLimits(x)
+        pairs, count = self.engine.colliding_pairs_batch(np.asarray(x, dtype=np.float64), max_pairs=32)
+        T, O = len(self.spec.terrains), len(self.spec.objects)
+        for a, b in pairs[0]:
+            if a < 0:
+                continue
+            lo = min(int(a), int(b))
+            if name == "self collision" and lo >= T + O:
+                return False
+            if name.startswith("terrain collision %d " % lo) and lo < T:
+                return False
+            if name.startswith("obj collision %d " % (lo - T)) and T <= lo < T + O:
+                return False
+        return True
 
     def interpolate(self, a, b, u):
         return self.robot.interpolate(a, b, u)

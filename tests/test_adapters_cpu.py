@@ -117,3 +117,26 @@ def test_robot_model_metric_and_interpolation_match_the_oracle_for_multi_link_jo
         np.testing.assert_allclose(r.interpolate(a, b, u), orc.interpolate(a, b, u), atol=1e-9)
     back = world.to_spec()
     assert np.array_equal(back.robot.joint_base, spec.robot.joint_base)
+
+
+def test_cspace_named_test_queries():
+    """CSpaceInterface's per-test queries (Python/klampt/src/motionplanning.h:122-171) on the host-side CSpace mirror"""
+    sp = CSpace()
+    sp.eps = 0.05
+    sp.setBounds([(0.0, 1.0), (0.0, 1.0)])
+    sp.addFeasibilityTest(lambda q: sp.inBounds(q), "bounds")
+    sp.addFeasibilityTest(lambda q: (q[0] - 0.5) ** 2 + (q[1] - 0.5) ** 2 > 0.04, "disk", dependencies="bounds")
+    sp.addFeasibilityTest(lambda q: q[1] < 0.9, "ceiling")
+    assert sp.feasibilityQueryOrder() == ["bounds", "disk", "ceiling"] and sp.feasibilityTestDependenciesOf("disk") == ["bounds"]
+    assert sp.testFeasibility("disk", [0.5, 0.5]) is False and sp.testFeasibility("ceiling", [0.5, 0.5]) is True
+    assert sp.feasibilityFailures([0.5, 0.95]) == ["ceiling"] and sp.feasibilityFailures([0.5, 0.5]) == ["disk"]
+    with pytest.raises(ValueError):
+        sp.testFeasibility("nope", [0, 0])
+    a, b = [0.1, 0.5], [0.9, 0.5]
+    assert not sp.testVisibility("disk", a, b) and sp.testVisibility("ceiling", a, b)
+    assert sp.visibilityFailures(a, b) == ["disk"] and sp.visibilityFailures([0.1, 0.1], [0.9, 0.1]) == []
+    assert not sp.isVisible(a, b) and sp.isVisible([0.1, 0.1], [0.9, 0.1])
+    with pytest.raises(ValueError):
+        sp.setVisibilityEpsilon(0.0)
+    sp.setVisibilityEpsilon(0.01)
+    assert sp.eps == 0.01

@@ -235,3 +235,20 @@ def test_distance_query_state_machine_batch(built):
     d2 = q.UpdateQuery(Ta, Tb)
     assert list(q.s) == [FAR, FAR, CLOSE, CONTACT, CONTACT, FAR]
     np.testing.assert_allclose(d2, [0.2, 0.2, 0.05, 0.0, 0.0, 0.2], atol=1e-12)
+
+
+def test_robot_cspace_named_tests(setup):
+    """RobotCSpace.testFeasibility / feasibilityFailures with the reference's test names (plan/robotcspace.py:31-75)"""
+    spec, world, collider, space, orc = setup
+    names = space.feasibilityTestNamesList()
+    assert names[:2] == ["joint limits", "self collision"] and sum(n.startswith("obj collision") for n in names) == 10
+    Q = synth.sample_configs(spec.robot, 300, 91)
+    want = orc.feasible_batch(Q)
+    for i in range(40):
+        x = list(Q[i])
+        fails = space.feasibilityFailures(x)
+        assert (len(fails) == 0) == bool(want[i])
+        for n in names:
+            assert space.testFeasibility(n, x) == (n not in fails)
+    with pytest.raises(ValueError):
+        space.testFeasibility("no such test", list(Q[0]))
