@@ -14,6 +14,7 @@
 #pragma once
 #include "../klampt_b200.h"
 
+#include <algorithm>
 #include <cmath>
 #include <map>
 #include <memory>
@@ -226,6 +227,56 @@ class BatchSingleRobotCSpace {
   double DistanceToObstacles(const Config& x, double upperBound, bool includeSelf = true) {
     double d = 0; kbCheck(kb_distance_batch(engine_, x.data(), 1, upperBound > 0 ? upperBound : 1e-12, includeSelf ? 1 : 0, &d, nullptr)); return d; }
 
+  // ---- named constraints (CSpace::constraints / constraintNames and IsFeasible(x, constraint); SingleRobotCSpace::Init,
+  // RobotCSpace.cpp:668-754): "<link>_joint_limit" for every link with a finite limit, "update_geometry", then one
+  // "coll[idA,idB]" per enabled (robot link, environment) pair and self pair, in world-id order.  The collision constraints of one
+  // configuration are all answered by ONE all-pairs launch (the reference evaluates its CollisionFreeSets one query at a time).
+  struct Constraint { int kind; int a, b; };           // kind 0: joint limit of link a; 1: update_geometry (always true); 2: collision pair of world ids a < b
+  std::vector<std::string> constraintNames;
+  void InitConstraints(const std::vector<std::string>* worldNames = nullptr) {
+    constraints_.clear(); constraintNames.clear();
+    const int L = NumDimensions();
+    auto idName = [&](int id) { return worldNames && id < (int)worldNames->size() ? (*worldNames)[id] : "id" + std::to_string(id); };
+    const int n = kb_num_ids(engine_), base = n - L;
+    for (int i = 0; i < L; i++) if (std::isfinite(robot_.qMin[i]) || std::isfinite(robot_.qMax[i])) {
+      constraints_.push_back({0, i, -1}); constraintNames.push_back(idName(base + i) + "_joint_limit"); }
+    constraints_.push_back({1, -1, -1}); constraintNames.push_back("update_geometry");
+    std::vector<uint8_t> mask((size_t)n * n); kbCheck(kb_get_pair_mask(engine_, mask.data()));
+    for (int i = base; i < n; i++) for (int j = 0; j < n; j++) {
+      if (j == base - 1 || (j >= base && j <= i)) continue;                    // the robot id itself; self pairs once, lower link first
+      if (robot_.linkGeometry[i - base] < 0 || (j >= base && robot_.linkGeometry[j - base] < 0)) continue;
+      if (!(mask[(size_t)i * n + j] || mask[(size_t)j * n + i])) continue;
+      constraints_.push_back({2, std::min(i, j), std::max(i, j)});
+      constraintNames.push_back("coll[" + idName(i) + "," + idName(j) + "]");
+    }
+  }
+  int NumConstraints() const { return (int)constraints_.size(); }
+  // indices of the constraints that fail at x (CSpace::FeasibilityFailures / CSpaceInterface::feasibilityFailures)
+  void FeasibilityFailures(const Config& x, std::vector<int>& failed) {
+    failed.clear();
+    int32_t pairs[64], count = 0;
+    bool limitsOk = true;
+    for (size_t c = 0; c < constraints_.size(); c++) if (constraints_[c].kind == 0) {
+      const int k = constraints_[c].a; if (x[k] < robot_.qMin[k] || x[k] > robot_.qMax[k]) { failed.push_back((int)c); limitsOk = false; } }
+    (void)limitsOk;
+    kbCheck(kb_colliding_pairs_batch(engine_, x.data(), 1, 32, pairs, &count));
+    // a configuration outside its limits is not traversed by the engine (count = -1): ask again with the limits ignored is not
+    // possible through this handle, so its collision constraints are reported as unknown = not failed
+    for (int k = 0; k < (count > 0 ? count : 0); k++) {
+      const int a = std::min(pairs[2 * k], pairs[2 * k + 1]), b = std::max(pairs[2 * k], pairs[2 * k + 1]);
+      for (size_t c = 0; c < constraints_.size(); c++) if (constraints_[c].kind == 2 && constraints_[c].a == a && constraints_[c].b == b) failed.push_back((int)c);
+    }
+    lastConfig = x;
+  }
+  bool IsFeasible(const Config& x, int constraint) {
+    if (constraint < 0 || constraint >= NumConstraints()) throw std::out_of_range("constraint index");
+    const Constraint& c = constraints_[constraint];
+    if (c.kind == 0) return x[c.a] >= robot_.qMin[c.a] && x[c.a] <= robot_.qMax[c.a];
+    if (c.kind == 1) return true;
+    std::vector<int> failed; FeasibilityFailures(x, failed);
+    return std::find(failed.begin(), failed.end(), constraint) == failed.end();
+  }
+
   // ---- batch entry points ---------------------------------------------------------------------------------------
   void IsFeasibleBatch(const double* Q, int64_t N, uint8_t* out, int32_t* firstPair = nullptr) { kbCheck(kb_feasible_batch(engine_, Q, N, out, firstPair)); }
   void IsVisibleBatch(const double* A, const double* B, int64_t N, double eps, uint8_t* out, int32_t* nchecks = nullptr) {
@@ -247,6 +298,7 @@ class BatchSingleRobotCSpace {
  private:
   kb_engine* engine_;
   RobotDescription robot_;
+  std::vector<Constraint> constraints_;
   std::mt19937_64 rng_;
 };
 

@@ -36,6 +36,16 @@ int main(int argc, char** argv) {
     auto e = space.PathChecker(a, b);
     if (e->IsVisible() != (vis[i] != 0) || e->numChecks != nchk[i]) return 5;
   }
+  // named constraints: a configuration is feasible iff none of its constraints fails; IsFeasible(x, c) agrees with the list
+  space.InitConstraints();
+  if (space.NumConstraints() < 3 || space.constraintNames.size() != (size_t)space.NumConstraints()) return 8;
+  for (int64_t i = 0; i < 30 && i < N; i++) {
+    Config x(Q.begin() + i * L, Q.begin() + (i + 1) * L);
+    std::vector<int> failed; space.FeasibilityFailures(x, failed);
+    if (failed.empty() != (feas[i] != 0)) return 9;
+    for (int c : failed) if (space.IsFeasible(x, c)) return 10;
+    if (!failed.empty() && space.constraintNames[failed[0]].rfind("coll[", 0) != 0 && space.constraintNames[failed[0]].find("_joint_limit") == std::string::npos) return 11;
+  }
   Config s; space.Sample(s); if (!space.CheckJointLimits(s)) return 6;
   std::map<std::string, std::string> props; space.Properties(props); if (props["geodesic"] != "1") return 7;
   FILE* o = fopen(argv[2], "wb"); fwrite(feas.data(), 1, feas.size(), o); fwrite(vis.data(), 1, vis.size(), o); fwrite(nchk.data(), 4, nchk.size(), o); fclose(o);
