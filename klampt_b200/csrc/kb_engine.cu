@@ -782,6 +782,8 @@ int kb_add_primitive(kb_engine* e, int type, const double* params, double margin
     if (type == KB_PRIM_AABB) { for (int k = 0; k < 3; k++) { c[k] = 0.5 * (params[k] + params[3 + k]); h[k] = 0.5 * (params[3 + k] - params[k]); } }
     else { memcpy(c, params, 24); memcpy(R, params + 3, 72); memcpy(h, params + 12, 24); }
     for (int k = 0; k < 3; k++) if (!(h[k] >= 0)) return fail(KB_ERR_INVALID, "box half dimensions must be >= 0");
+    const int nzero = (h[0] == 0) + (h[1] == 0) + (h[2] == 0);
+    if (nzero >= 2) return fail(KB_ERR_UNSUPPORTED, "a box with two zero dimensions is a segment or a point: not a supported primitive");
     double v[24]; int nv = 0;
     for (int sz = -1; sz <= 1; sz += 2) for (int sy = -1; sy <= 1; sy += 2) for (int sx = -1; sx <= 1; sx += 2) {
       const double l[3] = {sx * h[0], sy * h[1], sz * h[2]};
@@ -789,8 +791,14 @@ int kb_add_primitive(kb_engine* e, int type, const double* params, double margin
       nv++;
     }
     static const int T[36] = {0, 2, 3, 0, 3, 1, 4, 5, 7, 4, 7, 6, 0, 1, 5, 0, 5, 4, 2, 6, 7, 2, 7, 3, 0, 4, 6, 0, 6, 2, 1, 3, 7, 1, 7, 5};
-    Geom g; g.kind = G_MESH; g.margin = margin; g.tri.resize(108); g.solid = true;
-    for (int t = 0; t < 36; t++) memcpy(&g.tri[3 * (size_t)t], v + 3 * T[t], 24);
+    // face order of T: z-, z+, y-, y+, x-, x+ (two triangles each).  A flat box keeps only the two faces across its zero dimension:
+    // the other four have no area, and zero-area triangles have no place in the exact predicates.
+    Geom g; g.kind = G_MESH; g.margin = margin; g.solid = true;
+    for (int f = 0; f < 6; f++) {
+      const int axis = 2 - f / 2;
+      if (nzero == 1 && h[axis] != 0) continue;
+      for (int t = 6 * f; t < 6 * f + 6; t++) g.tri.insert(g.tri.end(), v + 3 * T[t], v + 3 * T[t] + 3);
+    }
     memcpy(g.box, c, 24); memcpy(g.box + 3, R, 72); memcpy(g.box + 12, h, 24);
     e->geoms.push_back(std::move(g));
     return (int)e->geoms.size() - 1;

@@ -354,6 +354,8 @@ int ko_add_primitive(ko_world* w, int type, const double* params, double margin)
     if (type==KO_PRIM_AABB) { for (int k=0;k<3;k++) { c[k]=0.5*(params[k]+params[3+k]); h[k]=0.5*(params[3+k]-params[k]); } }
     else { memcpy(c,params,24); memcpy(R,params+3,72); memcpy(h,params+12,24); }
     for (int k=0;k<3;k++) if (!(h[k]>=0)) return -1;
+    int nzero=(h[0]==0)+(h[1]==0)+(h[2]==0);
+    if (nzero>=2) return -1;            /* a segment or a point, not a box */
     double v[24]; int nvv=0;
     for (int sz=-1;sz<=1;sz+=2) for (int sy=-1;sy<=1;sy+=2) for (int sx=-1;sx<=1;sx+=2) {
       double l[3]={sx*h[0],sy*h[1],sz*h[2]};
@@ -361,7 +363,11 @@ int ko_add_primitive(ko_world* w, int type, const double* params, double margin)
       nvv++; }
     /* vertex index = (x>0) + 2 (y>0) + 4 (z>0) */
     static const int32_t T[36]={0,2,3, 0,3,1,  4,5,7, 4,7,6,  0,1,5, 0,5,4,  2,6,7, 2,7,3,  0,4,6, 0,6,2,  1,3,7, 1,7,5};
-    int gi=ko_add_trimesh(w,v,8,T,12,margin);
+    /* faces of T in the order z-, z+, y-, y+, x-, x+; a flat box keeps only the two faces across its zero dimension (the other
+     * four have no area) */
+    int32_t TT[36]; int ntt=0;
+    for (int f=0;f<6;f++) { int axis=2-f/2; if (nzero==1 && h[axis]!=0) continue; for (int k=6*f;k<6*f+6;k++) TT[ntt++]=T[k]; }
+    int gi=ko_add_trimesh(w,v,8,TT,ntt/3,margin);
     geom_t* g=&w->geoms[gi]; g->solid=1; memcpy(g->bc,c,24); memcpy(g->bR,R,72); memcpy(g->bh,h,24);
     return gi;
   }

@@ -459,13 +459,14 @@ def test_solid_box_primitives_pair_queries(built):
     g_sph = w.add_geom(GeomSpec.sphere([0.05, 0, 0], 0.12))
     g_box = w.add_geom(GeomSpec.box([0.05, -0.1, 0.0], synth.rot_axis_angle([1, 1, 0], 0.6), [0.5, 0.35, 0.25]))
     g_aabb = w.add_geom(GeomSpec.aabb([-0.1, -0.15, -0.2], [0.1, 0.15, 0.2], margin=0.01))
+    g_plate = w.add_geom(GeomSpec.aabb([-0.4, -0.3, 0.0], [0.4, 0.3, 0.0]))          # a flat box: only its two faces are surface
     w.robot = synth.make_planar_nR(w, 1)
     eng, orc = Engine(w), OracleWorld(w)
     N = 300
     def poses(spread):
         return np.stack([np.concatenate([synth._random_rotation(rng).reshape(-1), rng.uniform(-spread, spread, size=3)]) for _ in range(N)])
     for ga, gb, spread in ((g_box, g_small, 0.5), (g_small, g_box, 0.5), (g_box, g_blob, 0.6), (g_box, g_cloud, 0.6), (g_sph, g_box, 0.6),
-                           (g_box, g_aabb, 0.5), (g_aabb, g_cloud, 0.4)):
+                           (g_box, g_aabb, 0.5), (g_aabb, g_cloud, 0.4), (g_plate, g_blob, 0.5), (g_plate, g_cloud, 0.4)):
         Ta, Tb = poses(spread), poses(spread)
         hit = eng.geom_collides_batch(ga, Ta, gb, Tb)
         d = eng.geom_distance_batch(ga, Ta, gb, Tb)
@@ -479,6 +480,12 @@ def test_solid_box_primitives_pair_queries(built):
         bad = np.nonzero(near != want_near)[0]
         assert all(abs(want_d[i] - 0.05) <= BAND for i in bad)
         np.testing.assert_allclose(d, want_d, rtol=1e-5, atol=1e-9)
+    from klampt_b200._capi import KbError
+    bad = WorldSpec()
+    bad.add_geom(GeomSpec.aabb([0, 0, 0], [1, 0, 0]))                               # two zero dimensions: a segment, not a box
+    bad.robot = synth.make_planar_nR(bad, 1)
+    with pytest.raises(KbError):
+        Engine(bad)
 
 
 def test_world_with_solid_boxes(built):
