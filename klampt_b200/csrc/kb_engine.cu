@@ -754,6 +754,22 @@ int kb_add_trimesh(kb_engine* e, const double* verts, int nv, const int32_t* tri
     if (idx < 0 || idx >= nv) return fail(KB_ERR_INVALID, "triangle %d references vertex %d of %d", t, idx, nv);
     for (int k = 0; k < 3; k++) g.tri[9 * (size_t)t + 3 * v + k] = verts[3 * (size_t)idx + k];
   }
+  // A triangle whose area is below 1e-12 of its longest edge squared cannot be told from a segment in fp64 (the signs of the
+  // orientation tests against its "plane" are rounding noise): it becomes the segment between its two farthest vertices, written as
+  // the exactly degenerate triangle (p, q, q), which the predicates treat as a segment (degenerate_tri_tri).  The oracle applies
+  // the same rule.
+  for (int t = 0; t < nt; t++) {
+    double* T = &g.tri[9 * (size_t)t];
+    double e0[3], e1[3], e2[3];
+    for (int k = 0; k < 3; k++) { e0[k] = T[3 + k] - T[k]; e1[k] = T[6 + k] - T[k]; e2[k] = T[6 + k] - T[3 + k]; }
+    const double n[3] = {e0[1] * e1[2] - e0[2] * e1[1], e0[2] * e1[0] - e0[0] * e1[2], e0[0] * e1[1] - e0[1] * e1[0]};
+    const double l0 = e0[0] * e0[0] + e0[1] * e0[1] + e0[2] * e0[2], l1 = e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2], l2 = e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2];
+    const double L = std::max(l0, std::max(l1, l2));
+    if (n[0] * n[0] + n[1] * n[1] + n[2] * n[2] > 1e-24 * L * L) continue;
+    double p[3], q[3];
+    if (L == l0) { memcpy(p, T, 24); memcpy(q, T + 3, 24); } else if (L == l1) { memcpy(p, T, 24); memcpy(q, T + 6, 24); } else { memcpy(p, T + 3, 24); memcpy(q, T + 6, 24); }
+    memcpy(T, p, 24); memcpy(T + 3, q, 24); memcpy(T + 6, q, 24);
+  }
   e->geoms.push_back(std::move(g));
   return (int)e->geoms.size() - 1;
 }
@@ -771,9 +787,8 @@ int kb_add_primitive(kb_engine* e, int type, const double* params, double margin
   if (!e || e->finalized) return fail(KB_ERR_STATE, "engine is null or already finalized");
   if (margin < 0 || !params) return fail(KB_ERR_INVALID, "negative margin or null parameters");
   if (type == KB_PRIM_TRIANGLE) {       // a triangle primitive is a one-triangle mesh for every query of this path
-    Geom g; g.kind = G_MESH; g.margin = margin; g.tri.assign(params, params + 9);
-    e->geoms.push_back(std::move(g));
-    return (int)e->geoms.size() - 1;
+    const int32_t idx[3] = {0, 1, 2};
+    return kb_add_trimesh(e, params, 3, idx, 1, margin);
   }
   if (type == KB_PRIM_BOX || type == KB_PRIM_AABB) {
     // solid box: its surface as 12 triangles (vertex = R l + c, the same arithmetic and the same triangle list as the oracle's) plus

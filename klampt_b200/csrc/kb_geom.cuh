@@ -121,6 +121,24 @@ __device__ __noinline__ int coplanar_tri_tri(const V3<ExactD>* A, const V3<Exact
 __device__ __forceinline__ int coplanar_case(const V3<float>*, const V3<float>*) { return KB_UNCERTAIN; }
 __device__ __forceinline__ int coplanar_case(const V3<ExactD>* A, const V3<ExactD>* B) { return coplanar_tri_tri(A, B); }
 
+// One triangle has no area (repeated or collinear vertices): every orientation test against ITS plane vanishes although the other
+// triangle may be anywhere.  It is a segment: its edges are tested against the proper triangle P (closed segment vs closed
+// triangle; sd[] = signs of D's vertices against plane(P); an edge lying in the plane is covered by the coplanar case, which
+// needs all of D in the plane and was taken before this one).
+__device__ __noinline__ int degenerate_tri_tri(const V3<ExactD>* D, const V3<ExactD>* P, int sd0, int sd1, int sd2) {
+  const int sd[3] = {sd0, sd1, sd2};
+  const FiltE f;
+  for (int i = 0; i < 3; i++) {
+    const int j = (i + 1) % 3, sp = sd[i], sq = sd[j];
+    if ((sp > 0 && sq > 0) || (sp < 0 && sq < 0) || (sp == 0 && sq == 0)) continue;
+    const int s1 = side_sign(D[i], D[j], P[0], P[1], f), s2 = side_sign(D[i], D[j], P[1], P[2], f), s3 = side_sign(D[i], D[j], P[2], P[0], f);
+    if ((s1 >= 0 && s2 >= 0 && s3 >= 0) || (s1 <= 0 && s2 <= 0 && s3 <= 0)) return KB_YES;
+  }
+  return KB_NO;
+}
+__device__ __forceinline__ int degenerate_case(const V3<float>*, const V3<float>*, int, int, int) { return KB_UNCERTAIN; }
+__device__ __forceinline__ int degenerate_case(const V3<ExactD>* D, const V3<ExactD>* P, int s0, int s1, int s2) { return degenerate_tri_tri(D, P, s0, s1, s2); }
+
 // index of the vertex that is alone on its side of the other triangle's plane, and the side it is on.
 // s[i] in {-1,0,+1}; not all equal-nonzero, not all zero.
 __device__ __forceinline__ void lone_vertex(int s0, int s1, int s2, int& k, int& sigma) {
@@ -147,7 +165,12 @@ __device__ __forceinline__ int tri_tri_intersect(V3<T>* A, V3<T>* B, const F& f)
   if (sb0 == sb1 && sb1 == sb2 && (sb0 == 1 || sb0 == -1)) return KB_NO;
   if (sa0 == KB_UNCERTAIN || sa1 == KB_UNCERTAIN || sa2 == KB_UNCERTAIN || sb0 == KB_UNCERTAIN || sb1 == KB_UNCERTAIN || sb2 == KB_UNCERTAIN)
     return KB_UNCERTAIN;
-  if ((sa0 | sa1 | sa2) == 0 || (sb0 | sb1 | sb2) == 0) return coplanar_case(A, B);
+  {
+    const bool azero = (sa0 | sa1 | sa2) == 0, bzero = (sb0 | sb1 | sb2) == 0;
+    if (azero && bzero) return coplanar_case(A, B);        // each triangle lies in the other's plane (or both are segments)
+    if (azero) return degenerate_case(B, A, sb0, sb1, sb2);  // B has no area: its edges against A (sb = B's vertices against plane(A))
+    if (bzero) return degenerate_case(A, B, sa0, sa1, sa2);
+  }
   int ka, sga, kb, sgb;
   lone_vertex(sa0, sa1, sa2, ka, sga);
   lone_vertex(sb0, sb1, sb2, kb, sgb);
@@ -163,6 +186,16 @@ __device__ __forceinline__ int tri_tri_intersect(V3<T>* A, V3<T>* B, const F& f)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Is the face normal n = ab x ac (nn = |n|^2) usable?  fp64 (every product rounded separately, so a zero-area triangle
+// gives exactly n = 0 and its edge regions catch every point): any non-zero normal.  fp32 (products are contracted into
+// FMAs, so a zero-area triangle gives rounding noise instead of 0, and the direction of a thin triangle's normal is off by
+// ~1e-7 / sin(angle)): only when sin(angle at a) >= 0.01; otherwise the fp32 result is NaN, which every caller's
+// comparisons turn into "uncertain" / "evaluate in fp64".
+__device__ __forceinline__ bool kb_face_ok(float nn, float ab2, float ac2) { return nn >= 1e-4f * ab2 * ac2; }
+__device__ __forceinline__ bool kb_face_ok(ExactD nn, ExactD, ExactD) { return nn.v != 0.0; }
+__device__ __forceinline__ float kb_no_face(float, float) { return __int_as_float(0x7fc00000); }
+__device__ __forceinline__ ExactD kb_no_face(ExactD a, ExactD b) { return kb_min(a, b); }
+
 // squared distance point - triangle (Voronoi-region walk)
 template <class T>
 __device__ __forceinline__ T point_tri_dist2(const V3<T>& p, const V3<T>& a, const V3<T>& b, const V3<T>& c) {
@@ -185,7 +218,7 @@ __device__ __forceinline__ T point_tri_dist2(const V3<T>& p, const V3<T>& a, con
     T w = (d4 - d3) / ((d4 - d3) + (d5 - d6)); V3<T> q = madd(b, c - b, w) - p; return dot(q, q); }
   V3<T> n = cross(ab, ac);
   T nn = dot(n, n);
-  if (nn == zero) return kb_min(dot(ap, ap), kb_min(dot(bp, bp), dot(cp, cp)));
+  if (!kb_face_ok(nn, dot(ab, ab), dot(ac, ac))) return kb_no_face(dot(ap, ap), kb_min(dot(bp, bp), dot(cp, cp)));
   T h = dot(ap, n);
   return h * h / nn;
 }

@@ -340,6 +340,11 @@ __device__ __forceinline__ int fast_elem_collide(const KbScene& sc, const KbItem
     V3<float> A2[3] = {A[0], A[1], A[2]}, B2[3] = {B[0], B[1], B[2]};
     int r = tri_tri_intersect<float, FiltF>(A2, B2, f);
     if (r != KB_NO) return r;
+    {   // a thin triangle's fp32 face normal is not accurate enough for the vertex-face distances: leave the pair to fp64
+      const V3<float> ea1 = A[1] - A[0], ea2 = A[2] - A[0], eb1 = B[1] - B[0], eb2 = B[2] - B[0];
+      const V3<float> nA = cross(ea1, ea2), nB = cross(eb1, eb2);
+      if (!kb_face_ok(dot(nA, nA), dot(ea1, ea1), dot(ea2, ea2)) || !kb_face_ok(dot(nB, nB), dot(eb1, eb1), dot(eb2, eb2))) return KB_UNCERTAIN;
+    }
     float d = sqrtf(tri_tri_dist2_disjoint<float>(A, B));
     return d < thr - band ? KB_YES : (d > thr + band ? KB_NO : KB_UNCERTAIN);
   }
@@ -378,14 +383,22 @@ __device__ __forceinline__ float fast_elem_distance(const KbScene& sc, const KbI
     V3<float> B[3] = {xform(T, b0), xform(T, b1), xform(T, b2)};
     // cheap lower bound instead of the full 15-feature distance: if one triangle lies entirely on one side of the other's
     // plane, the distance is at least its smallest vertex-to-plane distance
-    const V3<float> nA = cross(A[1] - A[0], A[2] - A[0]), nB = cross(B[1] - B[0], B[2] - B[0]);
-    const float b0s = dot(nA, B[0] - A[0]), b1s = dot(nA, B[1] - A[0]), b2s = dot(nA, B[2] - A[0]);
-    const float a0s = dot(nB, A[0] - B[0]), a1s = dot(nB, A[1] - B[0]), a2s = dot(nB, A[2] - B[0]);
+    // The fp32 normal of a thin triangle points in a direction that is off by ~1e-7 / sin(angle), and that of a zero-area
+    // triangle is pure rounding noise (the products are contracted into FMAs, so cross(u, u) != 0): the signed values
+    // below carry an error of up to 4e-7 |e1| |e2| L (L = largest vertex offset), so 1e-6 |e1| |e2| L is taken off
+    // before they count as a separation.  A well-shaped triangle loses < 1e-6 L of its bound, a degenerate one gets none.
+    const V3<float> ea1 = A[1] - A[0], ea2 = A[2] - A[0], eb1 = B[1] - B[0], eb2 = B[2] - B[0];
+    const V3<float> nA = cross(ea1, ea2), nB = cross(eb1, eb2);
+    const V3<float> w0 = B[0] - A[0], w1 = B[1] - A[0], w2 = B[2] - A[0], u1 = A[1] - B[0], u2 = A[2] - B[0];
+    const float b0s = dot(nA, w0), b1s = dot(nA, w1), b2s = dot(nA, w2);
+    const float a0s = -dot(nB, w0), a1s = dot(nB, u1), a2s = dot(nB, u2);
+    const float slackA = 1e-6f * sqrtf(dot(ea1, ea1) * dot(ea2, ea2) * fmaxf(dot(w0, w0), fmaxf(dot(w1, w1), dot(w2, w2))));
+    const float slackB = 1e-6f * sqrtf(dot(eb1, eb1) * dot(eb2, eb2) * fmaxf(dot(w0, w0), fmaxf(dot(u1, u1), dot(u2, u2))));
     float lbA = 0.f, lbB = 0.f;
     if ((b0s > 0.f && b1s > 0.f && b2s > 0.f) || (b0s < 0.f && b1s < 0.f && b2s < 0.f))
-      lbA = fminf(fabsf(b0s), fminf(fabsf(b1s), fabsf(b2s))) * rsqrtf(fmaxf(dot(nA, nA), 1e-30f));
+      lbA = fmaxf(fminf(fabsf(b0s), fminf(fabsf(b1s), fabsf(b2s))) - slackA, 0.f) * rsqrtf(fmaxf(dot(nA, nA), 1e-30f));
     if ((a0s > 0.f && a1s > 0.f && a2s > 0.f) || (a0s < 0.f && a1s < 0.f && a2s < 0.f))
-      lbB = fminf(fabsf(a0s), fminf(fabsf(a1s), fabsf(a2s))) * rsqrtf(fmaxf(dot(nB, nB), 1e-30f));
+      lbB = fmaxf(fminf(fabsf(a0s), fminf(fabsf(a1s), fabsf(a2s))) - slackB, 0.f) * rsqrtf(fmaxf(dot(nB, nB), 1e-30f));
     return fmaxf(lbA, lbB) * (1.f - 1e-5f);
   }
   if (it.kindA == KB_ELEM_TRI) {

@@ -157,6 +157,8 @@ static int seg_tri(const double* p, const double* q, const double* a, const doub
   return (s1>=0&&s2>=0&&s3>=0)||(s1<=0&&s2<=0&&s3<=0);
 }
 
+static double seg_seg_dist2(const double* p1, const double* q1, const double* p2, const double* q2);
+
 /* Two closed triangles share a point?  Edge-vs-triangle formulation (any exact tri-tri overlap test is
  * acceptable because the boolean is a geometric fact). */
 int ko_tri_tri_intersect(const double A[9], const double B[9]) {
@@ -166,9 +168,17 @@ int ko_tri_tri_intersect(const double A[9], const double B[9]) {
   if ((da[0]>0&&da[1]>0&&da[2]>0)||(da[0]<0&&da[1]<0&&da[2]<0)) return 0;
   db[0]=orient3d(a0,a1,a2,b0); db[1]=orient3d(a0,a1,a2,b1); db[2]=orient3d(a0,a1,a2,b2);
   if ((db[0]>0&&db[1]>0&&db[2]>0)||(db[0]<0&&db[1]<0&&db[2]<0)) return 0;
-  if (da[0]==0&&da[1]==0&&da[2]==0) {
+  /* Coplanar only if EACH triangle lies in the other's plane.  A zero-area triangle (repeated or collinear vertices) makes every
+   * orient3d against it vanish without the other triangle being anywhere near its line: that case goes on to the edge tests,
+   * where its edges are tested against the proper triangle like any segment. */
+  if (da[0]==0&&da[1]==0&&da[2]==0 && db[0]==0&&db[1]==0&&db[2]==0) {
     double e1[3],e2[3],n[3]; v_sub(b1,b0,e1); v_sub(b2,b0,e2); v_cross(e1,e2,n);
     if (n[0]==0&&n[1]==0&&n[2]==0) { v_sub(a1,a0,e1); v_sub(a2,a0,e2); v_cross(e1,e2,n); }
+    if (n[0]==0&&n[1]==0&&n[2]==0) {   /* two zero-area triangles: segments in space, which meet only if some pair of edges touches */
+      const double* av[3]={a0,a1,a2}; const double* bv[3]={b0,b1,b2};
+      for (int i=0;i<3;i++) for (int j=0;j<3;j++) if (seg_seg_dist2(av[i],av[(i+1)%3],bv[j],bv[(j+1)%3])==0.0) return 1;
+      return 0;
+    }
     return tri_tri_coplanar(A,B,n);
   }
   /* edges of A against B */
@@ -275,6 +285,18 @@ static int build_rec(build_t* b, int first, int count) {
   return me;
 }
 
+/* A triangle whose area is below 1e-12 of its longest edge squared cannot be told from a segment in fp64: the signs of the
+ * orientation tests against its "plane" are rounding noise.  It is replaced by the segment between its two farthest vertices,
+ * written as the exactly degenerate triangle (p, q, q), which the predicates handle as a segment.  The engine applies the same
+ * rule when a mesh is added (kb_add_trimesh), so both sides see the same geometry. */
+static void snap_sliver(double* t) {
+  double e0[3],e1[3],e2[3],n[3]; v_sub(t+3,t,e0); v_sub(t+6,t,e1); v_sub(t+6,t+3,e2); v_cross(e0,e1,n);
+  double l0=v_dot(e0,e0), l1=v_dot(e1,e1), l2=v_dot(e2,e2), L=fmax(l0,fmax(l1,l2));
+  if (v_dot(n,n) > 1e-24*L*L) return;
+  double p[3],q[3];
+  if (L==l0) { memcpy(p,t,24); memcpy(q,t+3,24); } else if (L==l1) { memcpy(p,t,24); memcpy(q,t+6,24); } else { memcpy(p,t+3,24); memcpy(q,t+6,24); }
+  memcpy(t,p,24); memcpy(t+3,q,24); memcpy(t+6,q,24);
+}
 static void geom_build_bvh(geom_t* g) {
   int n = (g->kind==G_MESH) ? g->nt : g->np;
   if (n<=0) { g->nodes=NULL; g->nnodes=0; return; }
@@ -300,7 +322,8 @@ static void geom_build_bvh(geom_t* g) {
   if (g->kind==G_MESH) {
     g->tv=(double*)malloc(sizeof(double)*9*(size_t)n);
     for (int i=0;i<n;i++) { int e=g->perm[i];
-      for (int v=0;v<3;v++) for (int k=0;k<3;k++) g->tv[9*(size_t)i+3*v+k]=g->verts[3*g->tris[3*e+v]+k]; }
+      for (int v=0;v<3;v++) for (int k=0;k<3;k++) g->tv[9*(size_t)i+3*v+k]=g->verts[3*g->tris[3*e+v]+k];
+      snap_sliver(g->tv+9*(size_t)i); }
   } else {
     double* p2=(double*)malloc(sizeof(double)*3*(size_t)n); double* r2=(double*)malloc(sizeof(double)*n);
     for (int i=0;i<n;i++) { int e=g->perm[i]; memcpy(p2+3*(size_t)i,g->pts+3*(size_t)e,3*sizeof(double)); r2[i]=g->rad[e]; }

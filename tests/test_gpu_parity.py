@@ -610,3 +610,30 @@ def test_environment_mesh_built_on_the_gpu(c2small):
     assert_bool_parity(got[:4000], orc.feasible_batch(Q[:4000]), Q[:4000], orc)
     np.testing.assert_allclose(eg.distance_batch(Q[:1000], upper_bound=0.3, include_self=True), eng.distance_batch(Q[:1000], upper_bound=0.3, include_self=True),
                                rtol=1e-12, atol=1e-15)
+
+
+def test_degenerate_triangles_agree_with_the_oracle(built):
+    """meshes in the wild carry zero-area triangles (repeated or collinear vertices): whatever the predicates make of them, the
+    engine and the oracle must make the same thing"""
+    from klampt_b200.engine import Engine
+    from oracle.oracle import OracleWorld
+    rng = np.random.default_rng(97)
+    w = synth.world_c1()
+    extra_v, extra_t = [], []
+    for k in range(60):
+        a = rng.uniform([-0.8, -0.8, 0.1], [0.8, 0.8, 1.2]); d = rng.normal(size=3) * 0.15
+        b = a + d
+        c = b if k % 2 == 0 else a + 0.37 * d             # repeated vertex / three collinear vertices
+        base = 3 * k
+        extra_v += [a, b, c]; extra_t.append([base, base + 1, base + 2])
+    w.objects.append((w.add_geom(GeomSpec.mesh(np.array(extra_v), np.array(extra_t, dtype=np.int32))), synth.make_T(None, (0, 0, 0))))
+    w.robot = synth.make_arm6(w)
+    eng, orc = Engine(w), OracleWorld(w)
+    Q = synth.sample_configs(w.robot, 20000, 98)
+    got, want = eng.feasible_batch(Q), orc.feasible_batch(Q)
+    base = OracleWorld(synth.world_c1()).feasible_batch(Q)
+    assert (want != base).sum() > 0                        # the slivers do get hit
+    assert_bool_parity(got, want, Q, orc)
+    d = eng.distance_batch(Q[:1000], upper_bound=0.3)
+    do, _ = orc.distance_batch(Q[:1000], upper_bound=0.3)
+    np.testing.assert_allclose(d, do, rtol=1e-5, atol=1e-9)

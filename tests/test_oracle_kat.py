@@ -504,3 +504,25 @@ def test_world_with_solid_boxes_bvh_equals_brute_force():
     assert 0.05 < f.mean() < 0.95
     for i in range(6):                                           # the all-pairs brute force costs seconds per configuration
         assert bool(f[i]) == o.feasible_brute(Q[i])
+
+
+def test_zero_area_triangles_are_segments_not_planes():
+    """a triangle with repeated or collinear vertices makes every orientation test against it vanish; it must still behave as the
+    segment it is (an earlier version of the oracle sent it down the coplanar path and reported hits up to millimetres away --
+    found by the GPU parity test on slivers)"""
+    T = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], dtype=np.float64)
+    def sliver(p, q, collinear=False):
+        p, q = np.asarray(p, dtype=np.float64), np.asarray(q, dtype=np.float64)
+        return np.array([p, q, p + 0.37 * (q - p) if collinear else q])
+    for col in (False, True):
+        assert not ko.tri_tri_intersect(sliver([0.1, 0.1, 1e-3], [0.4, 0.3, 1e-3], col), T)      # hovering 1 mm above, parallel
+        assert not ko.tri_tri_intersect(T, sliver([0.1, 0.1, 1e-3], [0.4, 0.3, 2e-3], col))
+        assert ko.tri_tri_intersect(sliver([0.2, 0.2, -0.5], [0.2, 0.2, 0.5], col), T)           # piercing the interior
+        assert ko.tri_tri_intersect(T, sliver([0.2, 0.2, -0.5], [0.2, 0.2, 0.5], col))
+        assert not ko.tri_tri_intersect(sliver([0.8, 0.8, -0.5], [0.8, 0.8, 0.5], col), T)       # piercing the plane outside
+        assert ko.tri_tri_intersect(sliver([-0.5, 0.2, 0.0], [0.5, 0.2, 0.0], col), T)           # lying in the plane, crossing
+        assert not ko.tri_tri_intersect(sliver([-0.5, -0.2, 0.0], [0.5, -0.2, 0.0], col), T)     # in the plane, beside
+        assert abs(ko.tri_tri_distance(sliver([0.1, 0.1, 1e-3], [0.4, 0.3, 1e-3], col), T) - 1e-3) < 1e-15
+    # two slivers: segments in space
+    assert ko.tri_tri_intersect(sliver([0, 0, 0], [1, 1, 0]), sliver([0, 1, 0], [1, 0, 0]))
+    assert not ko.tri_tri_intersect(sliver([0, 0, 0], [1, 1, 0]), sliver([0, 1, 0.01], [1, 0, 0.01]))
