@@ -38,11 +38,12 @@ enum { KB_REVOLUTE = 0, KB_PRISMATIC = 1 };
 /* RobotModelJoint::Type (Cpp/Modeling/Robot.h:28) */
 enum { KB_JOINT_WELD = 0, KB_JOINT_NORMAL = 1, KB_JOINT_SPIN = 2, KB_JOINT_FLOATING = 3,
        KB_JOINT_FLOATINGPLANAR = 4, KB_JOINT_BALLANDSOCKET = 5, KB_JOINT_CLOSED = 6 };
-/* geometric primitives supported so far (the common ones of GeometricPrimitive3D: point, sphere, triangle, box;
+/* geometric primitives supported so far (GeometricPrimitive3D: point, sphere, segment, triangle, AABB, oriented box;
  * Cpp/docs/Manual-Geometry.md:22,241-250) */
-/* triangle: params = 9 doubles a,b,c.  BOX (solid oriented box): centre(3), axes as the columns of a row-major 3x3 (9), half
+/* segment: params = 6 doubles a,b (a != b; stored as the zero-area triangle a,b,b, which every predicate treats as the
+ * segment).  triangle: params = 9 doubles a,b,c.  BOX (solid oriented box): centre(3), axes as the columns of a row-major 3x3 (9), half
  * dimensions(3).  AABB (solid): lo(3), hi(3).  A box is solid: an element of the other geometry that lies inside it collides. */
-enum { KB_PRIM_POINT = 0, KB_PRIM_SPHERE = 1, KB_PRIM_TRIANGLE = 2, KB_PRIM_BOX = 3, KB_PRIM_AABB = 4 };
+enum { KB_PRIM_POINT = 0, KB_PRIM_SPHERE = 1, KB_PRIM_TRIANGLE = 2, KB_PRIM_BOX = 3, KB_PRIM_AABB = 4, KB_PRIM_SEGMENT = 5 };
 
 enum { KB_OK = 0, KB_ERR_INVALID = -1, KB_ERR_STATE = -2, KB_ERR_CUDA = -3, KB_ERR_UNSUPPORTED = -4,
        KB_ERR_NOMEM = -5 };

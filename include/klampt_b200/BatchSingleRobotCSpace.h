@@ -47,6 +47,7 @@ class WorldBuilder {
     int g = kb_add_pointcloud(e_, pts.data(), (int)(pts.size() / 3), radius ? radius->data() : nullptr, margin); kbCheck(g); return g; }
   int AddSphere(const double c[3], double r, double margin = 0) { double p[4] = {c[0], c[1], c[2], r}; int g = kb_add_primitive(e_, KB_PRIM_SPHERE, p, margin); kbCheck(g); return g; }
   int AddPoint(const double c[3], double margin = 0) { int g = kb_add_primitive(e_, KB_PRIM_POINT, c, margin); kbCheck(g); return g; }
+  int AddSegment(const double a[3], const double b[3], double margin = 0) { double p[6] = {a[0], a[1], a[2], b[0], b[1], b[2]}; int g = kb_add_primitive(e_, KB_PRIM_SEGMENT, p, margin); kbCheck(g); return g; }
   int AddTriangle(const double abc[9], double margin = 0) { int g = kb_add_primitive(e_, KB_PRIM_TRIANGLE, abc, margin); kbCheck(g); return g; }
   // solid boxes (GeometricPrimitive3D Box3D / AABB3D): centre, axes as the columns of a row-major 3x3, half dimensions / lo, hi
   int AddBox(const double center[3], const double axes[9], const double half[3], double margin = 0) {

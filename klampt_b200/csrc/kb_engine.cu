@@ -745,9 +745,17 @@ void kb_engine_destroy(kb_engine* e) {
   delete e;
 }
 
+// every coordinate that enters the scene must be a finite number: one NaN would poison the SAH build and every box above it
+static bool all_finite(const double* p, size_t n) {
+  for (size_t i = 0; i < n; i++) if (!std::isfinite(p[i])) return false;
+  return true;
+}
+
 int kb_add_trimesh(kb_engine* e, const double* verts, int nv, const int32_t* tris, int nt, double margin) {
   if (!e || e->finalized) return fail(KB_ERR_STATE, "engine is null or already finalized");
-  if (nt < 0 || nv < 0 || margin < 0) return fail(KB_ERR_INVALID, "negative size or margin");
+  if (nt < 0 || nv < 0 || !(margin >= 0) || !std::isfinite(margin)) return fail(KB_ERR_INVALID, "negative size or margin");
+  if (nt > 0 && (!verts || !tris)) return fail(KB_ERR_INVALID, "null vertex or triangle array");
+  if (nt > 0 && !all_finite(verts, 3 * (size_t)nv)) return fail(KB_ERR_INVALID, "mesh has a non-finite vertex coordinate");
   Geom g; g.kind = nt > 0 ? G_MESH : G_EMPTY; g.margin = margin; g.tri.resize(9 * (size_t)nt);
   for (int t = 0; t < nt; t++) for (int v = 0; v < 3; v++) {
     int idx = tris[3 * t + v];
@@ -776,7 +784,10 @@ int kb_add_trimesh(kb_engine* e, const double* verts, int nv, const int32_t* tri
 
 int kb_add_pointcloud(kb_engine* e, const double* pts, int n, const double* radius, double margin) {
   if (!e || e->finalized) return fail(KB_ERR_STATE, "engine is null or already finalized");
-  if (n < 0 || margin < 0) return fail(KB_ERR_INVALID, "negative size or margin");
+  if (n < 0 || !(margin >= 0) || !std::isfinite(margin)) return fail(KB_ERR_INVALID, "negative size or margin");
+  if (n > 0 && !pts) return fail(KB_ERR_INVALID, "null point array");
+  if (n > 0 && (!all_finite(pts, 3 * (size_t)n) || (radius && !all_finite(radius, (size_t)n)))) return fail(KB_ERR_INVALID, "point cloud has a non-finite coordinate or radius");
+  if (radius) for (int i = 0; i < n; i++) if (radius[i] < 0) return fail(KB_ERR_INVALID, "point %d has a negative radius", i);
   Geom g; g.kind = n > 0 ? G_CLOUD : G_EMPTY; g.margin = margin; g.sph.resize(4 * (size_t)n);
   for (int i = 0; i < n; i++) { for (int k = 0; k < 3; k++) g.sph[4 * (size_t)i + k] = pts[3 * (size_t)i + k]; g.sph[4 * (size_t)i + 3] = radius ? radius[i] : 0.0; }
   e->geoms.push_back(std::move(g));
@@ -785,10 +796,20 @@ int kb_add_pointcloud(kb_engine* e, const double* pts, int n, const double* radi
 
 int kb_add_primitive(kb_engine* e, int type, const double* params, double margin) {
   if (!e || e->finalized) return fail(KB_ERR_STATE, "engine is null or already finalized");
-  if (margin < 0 || !params) return fail(KB_ERR_INVALID, "negative margin or null parameters");
+  if (!(margin >= 0) || !std::isfinite(margin) || !params) return fail(KB_ERR_INVALID, "negative margin or null parameters");
+  {
+    static const int nparams[6] = {3, 4, 9, 15, 6, 6};      // point, sphere, triangle, box, aabb, segment
+    if (type >= 0 && type < 6 && !all_finite(params, nparams[type])) return fail(KB_ERR_INVALID, "primitive has a non-finite parameter");
+    if (type == KB_PRIM_SPHERE && params[3] < 0) return fail(KB_ERR_INVALID, "sphere has a negative radius");
+  }
   if (type == KB_PRIM_TRIANGLE) {       // a triangle primitive is a one-triangle mesh for every query of this path
     const int32_t idx[3] = {0, 1, 2};
     return kb_add_trimesh(e, params, 3, idx, 1, margin);
+  }
+  if (type == KB_PRIM_SEGMENT) {        // a segment is the zero-area triangle (a, b, b): the predicates give it segment semantics
+    if (params[0] == params[3] && params[1] == params[4] && params[2] == params[5]) return fail(KB_ERR_INVALID, "segment of zero length: use a point");
+    const int32_t idx[3] = {0, 1, 1};
+    return kb_add_trimesh(e, params, 2, idx, 1, margin);
   }
   if (type == KB_PRIM_BOX || type == KB_PRIM_AABB) {
     // solid box: its surface as 12 triangles (vertex = R l + c, the same arithmetic and the same triangle list as the oracle's) plus
@@ -798,7 +819,7 @@ int kb_add_primitive(kb_engine* e, int type, const double* params, double margin
     else { memcpy(c, params, 24); memcpy(R, params + 3, 72); memcpy(h, params + 12, 24); }
     for (int k = 0; k < 3; k++) if (!(h[k] >= 0)) return fail(KB_ERR_INVALID, "box half dimensions must be >= 0");
     const int nzero = (h[0] == 0) + (h[1] == 0) + (h[2] == 0);
-    if (nzero >= 2) return fail(KB_ERR_UNSUPPORTED, "a box with two zero dimensions is a segment or a point: not a supported primitive");
+    if (nzero >= 2) return fail(KB_ERR_UNSUPPORTED, "a box with two zero dimensions is a segment or a point: use those primitives");
     double v[24]; int nv = 0;
     for (int sz = -1; sz <= 1; sz += 2) for (int sy = -1; sy <= 1; sy += 2) for (int sx = -1; sx <= 1; sx += 2) {
       const double l[3] = {sx * h[0], sy * h[1], sz * h[2]};
@@ -818,7 +839,7 @@ int kb_add_primitive(kb_engine* e, int type, const double* params, double margin
     e->geoms.push_back(std::move(g));
     return (int)e->geoms.size() - 1;
   }
-  if (type != KB_PRIM_POINT && type != KB_PRIM_SPHERE) return fail(KB_ERR_UNSUPPORTED, "primitive type %d is not supported (point, sphere, triangle, box and aabb are)", type);
+  if (type != KB_PRIM_POINT && type != KB_PRIM_SPHERE) return fail(KB_ERR_UNSUPPORTED, "primitive type %d is not supported (point, sphere, segment, triangle, box and aabb are)", type);
   Geom g; g.kind = G_PRIM; g.margin = margin; g.sph = {params[0], params[1], params[2], type == KB_PRIM_SPHERE ? params[3] : 0.0};
   e->geoms.push_back(std::move(g));
   return (int)e->geoms.size() - 1;
@@ -863,13 +884,14 @@ int kb_update_pointcloud(kb_engine* e, int geom, const double* pts, int n) {
 
 int kb_add_terrain(kb_engine* e, int geom) {
   if (!e || e->finalized) return fail(KB_ERR_STATE, "engine is null or already finalized");
-  if (geom >= (int)e->geoms.size()) return fail(KB_ERR_INVALID, "unknown geometry %d", geom);
+  if (geom < 0 || geom >= (int)e->geoms.size()) return fail(KB_ERR_INVALID, "unknown geometry %d", geom);
   e->terrains.push_back(geom); return (int)e->terrains.size() - 1;
 }
 
 int kb_add_rigid_object(kb_engine* e, int geom, const double T[12]) {
   if (!e || e->finalized) return fail(KB_ERR_STATE, "engine is null or already finalized");
-  if (geom >= (int)e->geoms.size()) return fail(KB_ERR_INVALID, "unknown geometry %d", geom);
+  if (geom < 0 || geom >= (int)e->geoms.size()) return fail(KB_ERR_INVALID, "unknown geometry %d", geom);
+  if (!T || !all_finite(T, 12)) return fail(KB_ERR_INVALID, "rigid object needs a finite transform");
   Xf x; xf_from12(T, x); e->objects.push_back(geom); e->objT.push_back(x); return (int)e->objects.size() - 1;
 }
 
@@ -878,6 +900,12 @@ int kb_robot_create(kb_engine* e, int L, const int32_t* parents, const uint8_t* 
   if (!e || e->finalized) return fail(KB_ERR_STATE, "engine is null or already finalized");
   if (e->L) return fail(KB_ERR_STATE, "the engine already has its active robot");
   if (L <= 0 || L > KB_MAX_LINKS) return fail(KB_ERR_UNSUPPORTED, "robot has %d links; supported: 1..%d", L, KB_MAX_LINKS);
+  if (!parents || !linktype || !axis || !T0 || !qmin || !qmax) return fail(KB_ERR_INVALID, "null robot array");
+  if (!all_finite(axis, 3 * (size_t)L) || !all_finite(T0, 12 * (size_t)L)) return fail(KB_ERR_INVALID, "robot has a non-finite axis or parent transform");
+  for (int i = 0; i < L; i++) {
+    if (linktype[i] != KB_REVOLUTE && linktype[i] != KB_PRISMATIC) return fail(KB_ERR_INVALID, "link %d has type %d (0 = revolute, 1 = prismatic)", i, (int)linktype[i]);
+    if (std::isnan(qmin[i]) || std::isnan(qmax[i])) return fail(KB_ERR_INVALID, "link %d has a NaN joint limit (use +-inf for no limit)", i);
+  }
   for (int i = 0; i < L; i++) if (parents[i] >= i || parents[i] < -1) return fail(KB_ERR_INVALID, "parents[%d]=%d must be -1 or < %d", i, parents[i], i);
   e->L = L;
   e->parents.assign(parents, parents + L); e->linktype.assign(linktype, linktype + L);

@@ -101,9 +101,18 @@ __device__ inline bool pintri2(const ExactD* p, const ExactD* a, const ExactD* b
   double o1 = orient2(a, b, p).v, o2 = orient2(b, c, p).v, o3 = orient2(c, a, p).v;
   return (o1 >= 0 && o2 >= 0 && o3 >= 0) || (o1 <= 0 && o2 <= 0 && o3 <= 0);
 }
+template <class T> __device__ __forceinline__ T seg_seg_dist2(const V3<T>& p1, const V3<T>& q1, const V3<T>& p2, const V3<T>& q2);
 __device__ __noinline__ int coplanar_tri_tri(const V3<ExactD>* A, const V3<ExactD>* B) {
   V3<ExactD> n = cross(B[1] - B[0], B[2] - B[0]);
   if (n.x.v == 0 && n.y.v == 0 && n.z.v == 0) n = cross(A[1] - A[0], A[2] - A[0]);
+  if (n.x.v == 0 && n.y.v == 0 && n.z.v == 0) {   // two zero-area triangles: segments in space, which meet only if some pair of edges touches
+#pragma unroll 1
+    for (int i = 0; i < 3; i++)
+#pragma unroll 1
+      for (int j = 0; j < 3; j++)
+        if (seg_seg_dist2<ExactD>(A[i], A[(i + 1) % 3], B[j], B[(j + 1) % 3]).v == 0.0) return KB_YES;
+    return KB_NO;
+  }
   int ax = 0; double m = fabs(n.x.v);
   if (fabs(n.y.v) > m) { ax = 1; m = fabs(n.y.v); }
   if (fabs(n.z.v) > m) ax = 2;

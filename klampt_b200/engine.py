@@ -70,9 +70,9 @@ class Engine:
                 check(lib.kb_add_pointcloud(h, p.ctypes.data_as(dp), len(p), None if r is None else r.ctypes.data_as(dp), g.margin))
             elif g.kind == "dyncloud":
                 check(lib.kb_add_dynamic_pointcloud(h, int(g.params[0]), float(g.params[1]), g.margin))
-            elif g.kind in ("triangle", "box"):
+            elif g.kind in ("triangle", "box", "segment"):
                 p = _f64(g.params)
-                check(lib.kb_add_primitive(h, 2 if g.kind == "triangle" else 3, p.ctypes.data_as(dp), g.margin))
+                check(lib.kb_add_primitive(h, {"triangle": 2, "box": 3, "segment": 5}[g.kind], p.ctypes.data_as(dp), g.margin))
             elif g.kind in ("sphere", "point"):
                 p = _f64(g.params)
                 check(lib.kb_add_primitive(h, 1 if g.kind == "sphere" else 0, p.ctypes.data_as(dp), g.margin))

@@ -55,6 +55,9 @@ class GeometricPrimitive:
         a column-major so3 9-list whose columns are the box axes, `dims` the full edge lengths"""
         self.type, self.properties = "Box", [float(x) for x in ori] + [float(x) for x in R] + [float(x) for x in dims]
 
+    def setSegment(self, a, b):
+        self.type, self.properties = "Segment", [float(x) for x in a] + [float(x) for x in b]
+
     def setTriangle(self, a, b, c):
         self.type, self.properties = "Triangle", [float(x) for x in a] + [float(x) for x in b] + [float(x) for x in c]
 
@@ -118,8 +121,8 @@ class Geometry3D:
         self._kind, self._data, self._version = "cloud", pc, self._version + 1
 
     def setGeometricPrimitive(self, p: GeometricPrimitive):
-        if p.type not in ("Point", "Sphere", "Triangle", "AABB", "Box"):
-            raise ValueError("GeometricPrimitive type %r is not supported by the batched engine (Point, Sphere, Triangle, AABB and Box are)" % p.type)
+        if p.type not in ("Point", "Sphere", "Segment", "Triangle", "AABB", "Box"):
+            raise ValueError("GeometricPrimitive type %r is not supported by the batched engine (Point, Sphere, Segment, Triangle, AABB and Box are)" % p.type)
         self._kind, self._data, self._version = "prim", p, self._version + 1
 
     def getTriangleMesh(self) -> TriangleMesh:
@@ -162,6 +165,8 @@ class Geometry3D:
             return GeomSpec.cloud(self._data.points, self._data.radius, self._margin)
         if self._kind == "prim":
             p = self._data
+            if p.type == "Segment":
+                return GeomSpec.segment(p.properties[:3], p.properties[3:6], self._margin)
             if p.type == "Triangle":
                 return GeomSpec.triangle(p.properties[:3], p.properties[3:6], p.properties[6:9], self._margin)
             if p.type == "AABB":
@@ -183,7 +188,7 @@ class Geometry3D:
                 c, M, h = g.params[:3], g.params[3:12].reshape(3, 3), g.params[12:15]
                 corners = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], dtype=np.float64) * h
                 return corners @ M.T + c
-            n = 9 if self._data.type == "Triangle" else 3
+            n = {"Triangle": 9, "Segment": 6}.get(self._data.type, 3)
             return np.asarray(self._data.properties[:n], dtype=np.float64).reshape(-1, 3)
         return np.zeros((0, 3))
 
@@ -285,7 +290,7 @@ def _prim_from_spec(g: GeomSpec) -> GeometricPrimitive:
         p = GeometricPrimitive()
         p.setBox(list(c - M @ h), so3.from_matrix(M), list(2.0 * h))
         return p
-    return GeometricPrimitive({"sphere": "Sphere", "point": "Point", "triangle": "Triangle"}[g.kind], list(g.params))
+    return GeometricPrimitive({"sphere": "Sphere", "point": "Point", "triangle": "Triangle", "segment": "Segment"}[g.kind], list(g.params))
 
 
 _POINT_PROBE = Geometry3D()
@@ -401,7 +406,7 @@ class RobotModel(_Named):
                     self._links[i]._geom.setTriangleMesh(TriangleMesh(g.verts, g.tris))
                 elif g.kind == "cloud":
                     self._links[i]._geom.setPointCloud(PointCloud(g.points, g.radius))
-                elif g.kind in ("sphere", "point", "triangle", "box"):
+                elif g.kind in ("sphere", "point", "segment", "triangle", "box"):
                     self._links[i]._geom.setGeometricPrimitive(_prim_from_spec(g))
                 self._links[i]._geom._margin = g.margin
         self._q = np.clip(np.zeros(L), self._qmin, self._qmax)

@@ -31,7 +31,7 @@ IDENTITY12 = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], dtype=np.float64)
 @dataclass
 class GeomSpec:
     """One collision geometry in its local frame (AnyCollisionGeometry3D minus the current transform)."""
-    kind: str = "empty"                      # 'mesh' | 'cloud' | 'dyncloud' | 'sphere' | 'point' | 'triangle' | 'box' | 'empty'
+    kind: str = "empty"                      # 'mesh' | 'cloud' | 'dyncloud' | 'sphere' | 'point' | 'segment' | 'triangle' | 'box' | 'empty'
     verts: Optional[np.ndarray] = None       # (nv,3) f64   (mesh)
     tris: Optional[np.ndarray] = None        # (nt,3) i32   (mesh)
     points: Optional[np.ndarray] = None      # (n,3)  f64   (cloud)
@@ -62,6 +62,12 @@ class GeomSpec:
     @staticmethod
     def point(p, margin=0.0) -> "GeomSpec":
         return GeomSpec("point", params=np.array([p[0], p[1], p[2]], dtype=np.float64), margin=float(margin))
+
+    @staticmethod
+    def segment(a, b, margin=0.0) -> "GeomSpec":
+        """Segment3D a-b (a != b)"""
+        return GeomSpec("segment", params=np.concatenate([np.asarray(a, dtype=np.float64).reshape(3), np.asarray(b, dtype=np.float64).reshape(3)]),
+                        margin=float(margin))
 
     @staticmethod
     def triangle(a, b, c, margin=0.0) -> "GeomSpec":

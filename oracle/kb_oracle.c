@@ -369,6 +369,9 @@ int ko_add_pointcloud(ko_world* w, const double* pts, int n, const double* radiu
 }
 int ko_add_primitive(ko_world* w, int type, const double* params, double margin) {
   if (type==KO_PRIM_TRIANGLE) { int32_t idx[3]={0,1,2}; return ko_add_trimesh(w,params,3,idx,1,margin); }   /* one-triangle mesh */
+  if (type==KO_PRIM_SEGMENT) {          /* Segment3D = the zero-area triangle (a,b,b); ko_tri_tri_* treat it as the segment */
+    if (params[0]==params[3] && params[1]==params[4] && params[2]==params[5]) return -1;
+    int32_t idx[3]={0,1,1}; return ko_add_trimesh(w,params,2,idx,1,margin); }
   if (type==KO_PRIM_BOX || type==KO_PRIM_AABB) {
     /* solid box (GeometricPrimitive3D Box3D / AABB3D; common primitives of Cpp/docs/Manual-Geometry.md:241-250): its surface
      * as 12 triangles + the solid descriptor.  BOX params: centre(3), axes as the columns of a row-major 3x3 (9), half dims(3);

@@ -33,7 +33,7 @@ enum { KO_REVOLUTE = 0, KO_PRISMATIC = 1 };
 enum { KO_JOINT_WELD = 0, KO_JOINT_NORMAL = 1, KO_JOINT_SPIN = 2, KO_JOINT_FLOATING = 3,
        KO_JOINT_FLOATINGPLANAR = 4, KO_JOINT_BALLANDSOCKET = 5, KO_JOINT_CLOSED = 6 };
 /* primitive types (subset of GeometricPrimitive3D, Manual-Geometry.md:22) */
-enum { KO_PRIM_POINT = 0, KO_PRIM_SPHERE = 1, KO_PRIM_TRIANGLE = 2, KO_PRIM_BOX = 3, KO_PRIM_AABB = 4 };
+enum { KO_PRIM_POINT = 0, KO_PRIM_SPHERE = 1, KO_PRIM_TRIANGLE = 2, KO_PRIM_BOX = 3, KO_PRIM_AABB = 4, KO_PRIM_SEGMENT = 5 };
 
 /* per-config traversal counters of the canonical traversal */
 typedef struct {

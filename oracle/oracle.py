@@ -151,9 +151,10 @@ class OracleWorld:
                 else:
                     r, rp = _d(g.radius)
                     L.ko_add_pointcloud(self.h, pp, len(p), rp, g.margin)
-            elif g.kind in ("triangle", "box"):
+            elif g.kind in ("triangle", "box", "segment"):
                 p, pp = _d(g.params)
-                L.ko_add_primitive(self.h, 2 if g.kind == "triangle" else 3, pp, g.margin)
+                if L.ko_add_primitive(self.h, {"triangle": 2, "box": 3, "segment": 5}[g.kind], pp, g.margin) < 0:
+                    raise ValueError("the oracle rejected a %s primitive" % g.kind)
             elif g.kind in ("sphere", "point"):
                 p, pp = _d(g.params)
                 L.ko_add_primitive(self.h, 1 if g.kind == "sphere" else 0, pp, g.margin)

@@ -74,3 +74,46 @@ def test_argument_validation_without_gpu(built):
     assert lib.kb_add_trimesh(h, v.ctypes.data_as(_capi.c_double_p), 3, t.ctypes.data_as(_capi.c_int32_p), 1, 0.0) == -1
     assert lib.kb_add_primitive(h, 7, zd.ctypes.data_as(_capi.c_double_p), 0.0) == -4
     lib.kb_engine_destroy(h)
+
+
+def test_ingestion_rejects_non_finite_and_null_input_without_gpu(built):
+    """scene ingestion is host code: a NaN coordinate, a null array or a negative radius is refused with KB_ERR_INVALID and a
+    message instead of reaching the hierarchy builder"""
+    import numpy as np
+    lib = _capi.load()
+    h = ctypes.c_void_p()
+    assert lib.kb_engine_create(ctypes.byref(h)) == 0
+    dp, ip = _capi.c_double_p, _capi.c_int32_p
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, np.nan, 0]], dtype=np.float64); t = np.array([[0, 1, 2]], dtype=np.int32)
+    assert lib.kb_add_trimesh(h, v.ctypes.data_as(dp), 3, t.ctypes.data_as(ip), 1, 0.0) == -1 and b"non-finite" in lib.kb_last_error()
+    assert lib.kb_add_trimesh(h, None, 3, t.ctypes.data_as(ip), 1, 0.0) == -1 and b"null" in lib.kb_last_error()
+    v[2, 1] = 1.0
+    assert lib.kb_add_trimesh(h, v.ctypes.data_as(dp), 3, t.ctypes.data_as(ip), 1, float("nan")) == -1
+    g0 = lib.kb_add_trimesh(h, v.ctypes.data_as(dp), 3, t.ctypes.data_as(ip), 1, 0.0)
+    assert g0 == 0
+    p = np.array([[0, 0, 0], [np.inf, 0, 0]], dtype=np.float64); r = np.array([0.1, -0.1])
+    assert lib.kb_add_pointcloud(h, p.ctypes.data_as(dp), 2, None, 0.0) == -1 and b"non-finite" in lib.kb_last_error()
+    p[1, 0] = 1.0
+    assert lib.kb_add_pointcloud(h, p.ctypes.data_as(dp), 2, r.ctypes.data_as(dp), 0.0) == -1 and b"negative radius" in lib.kb_last_error()
+    assert lib.kb_add_pointcloud(h, None, 2, None, 0.0) == -1
+    s = np.array([0, 0, 0, -1.0])
+    assert lib.kb_add_primitive(h, 1, s.ctypes.data_as(dp), 0.0) == -1 and b"radius" in lib.kb_last_error()
+    seg = np.array([1.0, 2, 3, 1, 2, 3])
+    assert lib.kb_add_primitive(h, 5, seg.ctypes.data_as(dp), 0.0) == -1 and b"zero length" in lib.kb_last_error()
+    seg[3] = np.nan
+    assert lib.kb_add_primitive(h, 5, seg.ctypes.data_as(dp), 0.0) == -1 and b"non-finite" in lib.kb_last_error()
+    seg[3] = 2.0
+    assert lib.kb_add_primitive(h, 5, seg.ctypes.data_as(dp), 0.0) == 1
+    T = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, np.nan])
+    assert lib.kb_add_rigid_object(h, 0, T.ctypes.data_as(dp)) == -1 and b"finite" in lib.kb_last_error()
+    assert lib.kb_add_rigid_object(h, -1, T.ctypes.data_as(dp)) == -1
+    assert lib.kb_add_terrain(h, -3) == -1 and lib.kb_add_terrain(h, 0) == 0
+    par = np.array([-1, 0], dtype=np.int32); lt = np.array([0, 3], dtype=np.uint8)
+    ax = np.array([0, 0, 1, 0, 0, 1.0]); T0 = np.tile(np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0.0]), 2); q = np.zeros(2)
+    args = lambda lt_, q_: (h, 2, par.ctypes.data_as(ip), lt_.ctypes.data_as(_capi.c_uint8_p), ax.ctypes.data_as(dp), T0.ctypes.data_as(dp),
+                            q_.ctypes.data_as(dp), q_.ctypes.data_as(dp))
+    assert lib.kb_robot_create(*args(lt, q)) == -1 and b"type" in lib.kb_last_error()
+    lt[1] = 1; qn = np.array([0.0, np.nan])
+    assert lib.kb_robot_create(*args(lt, qn)) == -1 and b"NaN" in lib.kb_last_error()
+    assert lib.kb_robot_create(*args(lt, q)) == 0
+    lib.kb_engine_destroy(h)

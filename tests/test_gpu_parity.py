@@ -637,3 +637,41 @@ def test_degenerate_triangles_agree_with_the_oracle(built):
     d = eng.distance_batch(Q[:1000], upper_bound=0.3)
     do, _ = orc.distance_batch(Q[:1000], upper_bound=0.3)
     np.testing.assert_allclose(d, do, rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.gpu
+def test_segment_primitives_agree_with_the_oracle(built):
+    """GeometricPrimitive "Segment": bars with a margin (capsules) around the arm, and segment-vs-{segment, sphere, box, mesh} pair
+    queries; the margin sends every pair that involves the zero-area element through the fp64 path"""
+    from klampt_b200.engine import Engine
+    from oracle.oracle import OracleWorld
+    rng = np.random.default_rng(131)
+    w = synth.world_c1()
+    for k in range(30):
+        a = rng.uniform([-0.8, -0.8, 0.1], [0.8, 0.8, 1.2]); b = a + rng.normal(size=3) * 0.2
+        w.objects.append((w.add_geom(GeomSpec.segment(a, b, margin=0.0 if k % 3 == 0 else 0.01)), synth.make_T(synth._random_rotation(rng), rng.uniform(-0.1, 0.1, 3))))
+    gseg = [w.add_geom(GeomSpec.segment(rng.uniform(-0.3, 0.3, 3), rng.uniform(-0.3, 0.3, 3), margin=m)) for m in (0.0, 0.0, 0.02)]
+    gsph = w.add_geom(GeomSpec.sphere([0.05, 0, 0], 0.1))
+    gbox = w.add_geom(GeomSpec.box([0, 0, 0], synth._random_rotation(rng), [0.2, 0.1, 0.05]))
+    w.robot = synth.make_arm6(w)
+    glink = w.robot.link_geom[3]
+    eng, orc = Engine(w), OracleWorld(w)
+    Q = synth.sample_configs(w.robot, 20000, 132)
+    got, want = eng.feasible_batch(Q), orc.feasible_batch(Q)
+    assert (want != OracleWorld(synth.world_c1()).feasible_batch(Q)).sum() > 0          # the bars do get hit
+    assert_bool_parity(got, want, Q, orc)
+    d = eng.distance_batch(Q[:1000], upper_bound=0.3)
+    do, _ = orc.distance_batch(Q[:1000], upper_bound=0.3)
+    np.testing.assert_allclose(d, do, rtol=1e-5, atol=1e-9)
+    n = 400
+    Ta = np.stack([synth.make_T(synth._random_rotation(rng), rng.uniform(-0.25, 0.25, 3)) for _ in range(n)])
+    Tb = np.stack([synth.make_T(synth._random_rotation(rng), rng.uniform(-0.25, 0.25, 3)) for _ in range(n)])
+    for ga, gb in ((gseg[0], gseg[1]), (gseg[0], gseg[2]), (gseg[2], gsph), (gseg[1], gbox), (gseg[2], gbox), (gseg[0], glink), (glink, gseg[2])):
+        dg = eng.geom_distance_batch(ga, Ta, gb, Tb)
+        dw = np.array([orc.geom_distance(ga, Ta[i], gb, Tb[i]) for i in range(n)])
+        np.testing.assert_allclose(dg, dw, rtol=1e-5, atol=1e-9)
+        for tol in (0.0, 0.03):
+            cg = eng.geom_collides_batch(ga, Ta, gb, Tb, tol=tol).astype(bool)
+            cw = np.array([orc.geom_within_distance(ga, Ta[i], gb, Tb[i], tol) if tol > 0 else orc.geom_collides(ga, Ta[i], gb, Tb[i]) for i in range(n)])
+            near = np.abs(dw - tol) < 1e-6                                              # the stated band of the boolean parity
+            assert np.array_equal(cg[~near], cw[~near])

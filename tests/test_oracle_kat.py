@@ -526,3 +526,59 @@ def test_zero_area_triangles_are_segments_not_planes():
     # two slivers: segments in space
     assert ko.tri_tri_intersect(sliver([0, 0, 0], [1, 1, 0]), sliver([0, 1, 0], [1, 0, 0]))
     assert not ko.tri_tri_intersect(sliver([0, 0, 0], [1, 1, 0]), sliver([0, 1, 0.01], [1, 0, 0.01]))
+
+
+def _np_seg_seg_dist(p1, q1, p2, q2):
+    """second method: the squared distance is a convex quadratic in (s, t) on the unit square -- its minimum is the interior
+    stationary point if that lies inside, else the best of the four edges (each a clamped 1-D projection)"""
+    d1, d2, r = q1 - p1, q2 - p2, p1 - p2
+    def f(s, t):
+        v = r + s * d1 - t * d2
+        return float(v @ v)
+    best = min(f(0, 0), f(0, 1), f(1, 0), f(1, 1))
+    A = np.array([[d1 @ d1, -(d1 @ d2)], [-(d1 @ d2), d2 @ d2]]); b = -np.array([d1 @ r, -(d2 @ r)])
+    if abs(np.linalg.det(A)) > 1e-14 * A[0, 0] * A[1, 1]:
+        s, t = np.linalg.solve(A, b)
+        if 0 <= s <= 1 and 0 <= t <= 1:
+            best = min(best, f(s, t))
+    for s in (0.0, 1.0):
+        t = min(max(((r + s * d1) @ d2) / (d2 @ d2), 0.0), 1.0); best = min(best, f(s, t))
+    for t in (0.0, 1.0):
+        s = min(max(-((r - t * d2) @ d1) / (d1 @ d1), 0.0), 1.0); best = min(best, f(s, t))
+    return math.sqrt(best)
+
+
+def test_segment_primitive_semantics():
+    """GeometricPrimitive "Segment" (Segment3D; Cpp/docs/Manual-Geometry.md:22): closed-form answers against the unit cube of
+    tests/objects/cube.off, a sphere and other segments; margins widen it into a capsule"""
+    rng = np.random.default_rng(5)
+    w = WorldSpec()
+    v, t = synth.unit_cube()
+    gc = w.add_geom(GeomSpec.mesh(v, t))
+    gs = w.add_geom(GeomSpec.segment([0.5, 0.5, 1.25], [0.5, 0.5, 2.0]))
+    gsph = w.add_geom(GeomSpec.sphere([0, 0, 0], 0.1))
+    gcap = w.add_geom(GeomSpec.segment([0, 0, 0], [1, 0, 0], margin=0.05))
+    segs = [(rng.uniform(-1, 1, 3), rng.uniform(-1, 1, 3)) for _ in range(40)]
+    gr = [w.add_geom(GeomSpec.segment(a, b)) for a, b in segs]
+    w.robot = synth.make_planar_nR(w, 1)
+    o = OracleWorld(w)
+    I = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], dtype=np.float64)
+    assert abs(o.geom_distance(gs, I, gc, I) - 0.25) < 1e-15 and not o.geom_collides(gs, I, gc, I)
+    T = I.copy(); T[11] = -0.5                                        # now it pierces the top face
+    assert o.geom_collides(gs, T, gc, I) and o.geom_distance(gs, T, gc, I) == 0.0
+    T[11] = -1.125                                                    # wholly inside the cube's surface: a mesh is not a solid
+    assert not o.geom_collides(gs, T, gc, I) and abs(o.geom_distance(gs, T, gc, I) - 0.125) < 1e-15
+    # sphere beside the capsule's axis: distance = gap - radius - margin, signed
+    T = I.copy(); T[9:] = [0.5, 0.3, 0.0]
+    assert abs(o.geom_distance(gsph, T, gcap, I) - (0.3 - 0.1 - 0.05)) < 1e-15
+    T[10] = 0.12
+    assert o.geom_collides(gsph, T, gcap, I) and abs(o.geom_distance(gsph, T, gcap, I) - (0.12 - 0.15)) < 1e-15
+    with pytest.raises(ValueError):
+        w2 = WorldSpec(); w2.add_geom(GeomSpec.segment([1, 2, 3], [1, 2, 3])); w2.robot = synth.make_planar_nR(w2, 1); OracleWorld(w2)
+    # segment pairs at random poses against the numpy closed form
+    for k in range(0, 40, 2):
+        Ta, Tb = synth.make_T(synth._random_rotation(rng), rng.uniform(-0.5, 0.5, 3)), synth.make_T(synth._random_rotation(rng), rng.uniform(-0.5, 0.5, 3))
+        Ra, ta, Rb, tb = Ta[:9].reshape(3, 3), Ta[9:], Tb[:9].reshape(3, 3), Tb[9:]
+        want = _np_seg_seg_dist(Ra @ segs[k][0] + ta, Ra @ segs[k][1] + ta, Rb @ segs[k + 1][0] + tb, Rb @ segs[k + 1][1] + tb)
+        assert abs(o.geom_distance(gr[k], Ta, gr[k + 1], Tb) - want) < 1e-12
+        assert o.geom_within_distance(gr[k], Ta, gr[k + 1], Tb, want + 1e-9) and not o.geom_within_distance(gr[k], Ta, gr[k + 1], Tb, want - 1e-9)
