@@ -17,8 +17,13 @@ module keeps the user-facing shape of ``klampt.plan.cspace.MotionPlan`` (referen
               close vertices of the two trees; the edges of a candidate start-goal path are validated in one batch when the
               path is asked for, and blocked edges are dropped
 
-Options (MotionPlan.setOptions keys that apply): ``knn``, ``connectionThreshold``; plus ``batch`` (samples per planMore
-iteration).  The planners need a space with ``feasible_batch(Q)`` and ``visible_batch(A, B)`` (``RobotCSpace``), and use
+Option ``shortcut`` (the reference's ``MotionPlan.setOptions(shortcut=1)``, plan/cspace.py:254-256: "perform shortcutting after
+a first plan is found"): once a path exists every further planMore iteration is one batch-synchronous shortcutting round --
+``batch`` random pairs of points ON the current path (not only its vertices), all chords checked by one visible_batch, the
+visible ones applied greedily by saving as long as their spans do not overlap.
+
+Options (MotionPlan.setOptions keys that apply): ``knn``, ``connectionThreshold``, ``perturbationRadius``, ``shortcut``; plus
+``batch`` (samples per planMore iteration) and ``seed``.  The planners need a space with ``feasible_batch(Q)`` and ``visible_batch(A, B)`` (``RobotCSpace``), and use
 its ``distance`` metric restricted to the L2 form the engine implements.
 """
 from __future__ import annotations
@@ -52,6 +57,8 @@ class MotionPlan:
         self.connectionThreshold = float(opts.get("connectionThreshold", float("inf")))
         self.batch = int(opts.get("batch", 2048))
         self.perturbationRadius = float(opts.get("perturbationRadius", 0.25))
+        self.shortcut = bool(opts.get("shortcut", False))
+        self._best: Optional[np.ndarray] = None            # shortcut mode: the current solution, a polyline of configurations
         self.rng = np.random.default_rng(int(opts.get("seed", 0)))
         lo, hi = np.array([b[0] for b in space.bound], dtype=np.float64), np.array([b[1] for b in space.bound], dtype=np.float64)
         self._lo, self._hi = lo, np.where(np.isfinite(hi), hi, 2 * np.pi)
@@ -59,7 +66,8 @@ class MotionPlan:
         self.V = np.zeros((0, len(lo)))                    # milestones
         self.adj: List[Dict[int, Tuple[float, bool]]] = []  # neighbour -> (length, checked)
         self.start = self.goal = None
-        self.stats = {"samples": 0, "feasible_samples": 0, "edges_checked": 0, "edges_visible": 0, "iterations": 0}
+        self.stats = {"samples": 0, "feasible_samples": 0, "edges_checked": 0, "edges_visible": 0, "iterations": 0,
+                      "shortcuts_tried": 0, "shortcuts_applied": 0}
 
     # ------------------------------------------------------------------ roadmap primitives
     def addMilestone(self, q: Sequence[float]) -> int:
@@ -202,20 +210,74 @@ class MotionPlan:
             self._edge(v, int(u), self.type == "rrt")
         self._bridge(new)
 
+    def _shortcut_round(self) -> int:
+        """one batch of random chords across the current solution; returns how many were applied"""
+        P = self._best
+        seg = self._dist(P[:-1], P[1:])
+        s = np.concatenate([[0.0], np.cumsum(seg)])
+        if len(P) < 3 or not s[-1] > 0:
+            return 0
+        t = np.sort(self.rng.uniform(0.0, s[-1], size=(self.batch, 2)), axis=1)
+        ia = np.minimum(np.searchsorted(s, t[:, 0], side="right") - 1, len(seg) - 1)
+        ib = np.minimum(np.searchsorted(s, t[:, 1], side="right") - 1, len(seg) - 1)
+        def point(i, tt):
+            u = np.where(seg[i] > 0, (tt - s[i]) / np.where(seg[i] > 0, seg[i], 1.0), 0.0)[:, None]
+            return P[i] * (1.0 - u) + P[i + 1] * u
+        Xa, Xb = point(ia, t[:, 0]), point(ib, t[:, 1])
+        saving = (t[:, 1] - t[:, 0]) - self._dist(Xa, Xb)
+        cand = np.nonzero((ib > ia) & (saving > 1e-9 * s[-1]))[0]
+        if len(cand) == 0:
+            return 0
+        vis = np.asarray(self.space.visible_batch(Xa[cand], Xb[cand])).astype(bool)
+        self.stats["shortcuts_tried"] += len(cand)
+        self.stats["edges_checked"] += len(cand)
+        self.stats["edges_visible"] += int(vis.sum())
+        good = cand[vis]
+        chosen: List[int] = []
+        for k in good[np.argsort(-saving[good])]:           # largest saving first, spans must not overlap
+            if all(t[k, 1] <= t[c, 0] or t[k, 0] >= t[c, 1] for c in chosen):
+                chosen.append(int(k))
+        if not chosen:
+            return 0
+        chosen.sort(key=lambda k: t[k, 0])
+        out, nxt = [], 0                                     # nxt: first vertex of P not yet emitted
+        for k in chosen:
+            out.extend(P[nxt:ia[k] + 1]); out.append(Xa[k]); out.append(Xb[k])
+            nxt = ib[k] + 1
+        out.extend(P[nxt:])
+        Q = np.array(out)
+        keep = np.concatenate([[True], self._dist(Q[:-1], Q[1:]) > 0])      # a chord that starts on a vertex repeats it
+        self._best = Q[keep]
+        self.stats["shortcuts_applied"] += len(chosen)
+        return len(chosen)
+
     def planMore(self, iterations: int):
-        if self.type in ("rrt", "sbl"):
+        if self.shortcut:
             for _ in range(int(iterations)):
-                self._grow_trees()
-                self.stats["iterations"] += 1
+                if self._best is None:
+                    self._plan_once()
+                    path = self._search_path(self.start, self.goal) if self.start is not None else None
+                    if path is not None:
+                        self._best = np.array(path, dtype=np.float64)
+                else:
+                    self._shortcut_round()
+                    self.stats["iterations"] += 1
             return
         for _ in range(int(iterations)):
-            Q = self.rng.uniform(self._lo, self._hi, size=(self.batch, len(self._lo)))
-            ok = np.asarray(self.space.feasible_batch(Q)).astype(bool)
-            self.stats["samples"] += len(Q)
-            self.stats["feasible_samples"] += int(ok.sum())
+            self._plan_once()
+
+    def _plan_once(self):
+        if self.type in ("rrt", "sbl"):
+            self._grow_trees()
             self.stats["iterations"] += 1
-            if ok.any():
-                self._connect(self._add_vertices(Q[ok]))
+            return
+        Q = self.rng.uniform(self._lo, self._hi, size=(self.batch, len(self._lo)))
+        ok = np.asarray(self.space.feasible_batch(Q)).astype(bool)
+        self.stats["samples"] += len(Q)
+        self.stats["feasible_samples"] += int(ok.sum())
+        self.stats["iterations"] += 1
+        if ok.any():
+            self._connect(self._add_vertices(Q[ok]))
 
     def _shortest(self, src: int, dst: int) -> Optional[List[int]]:
         dist = {src: 0.0}
@@ -243,6 +305,11 @@ class MotionPlan:
         dst = self.goal if milestone2 is None else milestone2
         if src is None or dst is None:
             raise RuntimeError("setEndpoints (or two milestones) first")
+        if self.shortcut and self._best is not None and milestone1 is None and milestone2 is None:
+            return [list(q) for q in self._best]
+        return self._search_path(src, dst)
+
+    def _search_path(self, src: int, dst: int) -> Optional[List[List[float]]]:
         while True:
             path = self._shortest(src, dst)
             if path is None:
@@ -281,8 +348,11 @@ class MotionPlan:
         out = dict(self.stats)
         out["milestones"] = len(self.V)
         out["edges"] = sum(len(a) for a in self.adj) // 2
+        if self._best is not None:
+            out["path_cost"] = self.pathCost(self._best)
         return out
 
     def close(self):
         self.V = np.zeros((0, self.V.shape[1]))
         self.adj = []
+        self._best = None

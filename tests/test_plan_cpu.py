@@ -89,3 +89,36 @@ def test_tree_planners_find_a_valid_path(kind):
         A, B = np.array(V)[[i for i, _ in E]], np.array(V)[[j for _, j in E]]
         assert sp.visible_batch(A, B).all()                       # an RRT only keeps validated edges
     plan.close()
+
+
+@pytest.mark.parametrize("kind", ["rrt", "lazyprm*"])
+def test_shortcutting_after_the_first_plan(kind):
+    """MotionPlan.setOptions(shortcut=1) (reference plan/cspace.py): once a path exists, further iterations shorten it with batches of
+    chords between points ON the path; the result stays collision free and approaches the taut path round the disk"""
+    sp = DiskSpace()
+    MotionPlan.setOptions(batch=64, seed=11, perturbationRadius=0.12, knn=8, shortcut=1)
+    plan = MotionPlan(sp, kind)
+    plan.setEndpoints([0.05, 0.5], [0.95, 0.5])
+    for _ in range(80):
+        plan.planMore(1)
+        if plan.getPath():
+            break
+    first = plan.getPath()
+    assert first is not None
+    c0 = plan.pathCost(first)
+    costs = [c0]
+    for _ in range(15):
+        plan.planMore(1)
+        costs.append(plan.pathCost(plan.getPath()))
+    assert all(b <= a + 1e-12 for a, b in zip(costs[:-1], costs[1:]))      # never longer
+    path = plan.getPath()
+    P = np.array(path)
+    assert path[0] == [0.05, 0.5] and path[-1] == [0.95, 0.5]
+    assert sp.visible_batch(P[:-1], P[1:]).all()
+    # taut path: two tangents from the endpoints (0.45 from the centre) to the disk of radius 0.3 plus the arc between them
+    d, r = 0.45, 0.3
+    taut = 2 * np.sqrt(d * d - r * r) + r * (np.pi - 2 * np.arccos(r / d))
+    assert taut - 1e-9 <= costs[-1] < min(c0, 1.05 * taut)
+    st = plan.getStats()
+    assert st["shortcuts_applied"] > 0 and st["shortcuts_tried"] >= st["shortcuts_applied"] and abs(st["path_cost"] - costs[-1]) < 1e-12
+    plan.close()
