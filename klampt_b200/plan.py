@@ -7,6 +7,7 @@ module keeps the user-facing shape of ``klampt.plan.cspace.MotionPlan`` (referen
 ``getStats``, ``close``) but runs roadmap planners whose inner loops are the two batch calls:
 
   'prm'       every round: sample a batch -> feasible_batch -> k nearest neighbours -> visible_batch on all candidate edges
+  'prm*'      the same with k = e (1 + 1/d) log n neighbours (asymptotically optimal; an explicit ``knn`` is a lower limit)
   'lazyprm*'  same sampling, but edges are only checked (in batches) when they lie on the current best path
   'rrt'       bidirectional, batch-synchronous RRT: a batch of random targets, each pulls the nearest vertex of the start or the
               goal tree (alternating) one ``perturbationRadius`` step towards it; the new configurations go through
@@ -53,6 +54,7 @@ class MotionPlan:
             raise ValueError("planner type %r is not batched here; available: prm, prm*, lazyprm*, rrt, sbl" % type)
         self.lazy = self.type.startswith("lazy") or self.type == "sbl"
         self.tree: List[int] = []                          # rrt / sbl: 0 = vertex of the start tree, 1 = of the goal tree
+        self._user_opts = set(opts)
         self.knn = int(opts.get("knn", 10))
         self.connectionThreshold = float(opts.get("connectionThreshold", float("inf")))
         self.batch = int(opts.get("batch", 2048))
@@ -105,7 +107,12 @@ class MotionPlan:
         if len(self.V) < 2:
             return np.zeros((0, 2), dtype=np.int64)
         tree = cKDTree(self.V)
-        k = min(self.knn + 1, len(self.V))
+        knn = self.knn
+        if self.type.endswith("*"):      # PRM* / Lazy-PRM*: k grows as e (1 + 1/d) log n, the rate that keeps the roadmap asymptotically optimal
+            knn = max(1, int(np.ceil(np.e * (1.0 + 1.0 / self.V.shape[1]) * np.log(max(len(self.V), 2)))))
+            if "knn" in self._user_opts:
+                knn = max(knn, self.knn)
+        k = min(knn + 1, len(self.V))
         d, idx = tree.query(self.V[new], k=k)
         d, idx = np.atleast_2d(d), np.atleast_2d(idx)
         pairs = set()

@@ -122,3 +122,24 @@ def test_shortcutting_after_the_first_plan(kind):
     st = plan.getStats()
     assert st["shortcuts_applied"] > 0 and st["shortcuts_tried"] >= st["shortcuts_applied"] and abs(st["path_cost"] - costs[-1]) < 1e-12
     plan.close()
+
+
+def test_prm_star_neighbourhood_grows_and_cost_converges():
+    sp = DiskSpace()
+    MotionPlan.setOptions(batch=150, seed=2)
+    plan = MotionPlan(sp, "prm*")
+    plan.setEndpoints([0.05, 0.5], [0.95, 0.5])
+    costs = []
+    for _ in range(6):
+        plan.planMore(1)
+        p = plan.getPath()
+        if p:
+            costs.append(plan.pathCost(p))
+    d, r = 0.45, 0.3
+    taut = 2 * np.sqrt(d * d - r * r) + r * (np.pi - 2 * np.arccos(r / d))
+    assert len(costs) >= 4 and all(b <= a + 1e-12 for a, b in zip(costs[:-1], costs[1:]))       # a roadmap only gains edges
+    assert taut <= costs[-1] < 1.04 * taut
+    st = plan.getStats()
+    n = st["milestones"]
+    assert st["edges_checked"] > n * 4                      # k ~ e (1 + 1/2) log n > 10 neighbours were proposed per vertex
+    plan.close()
