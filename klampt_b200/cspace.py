@@ -23,6 +23,10 @@ class CSpace:
         self._stats = {"feasible_count": 0, "feasible_true": 0, "feasible_time": 0.0,
                        "visible_count": 0, "visible_true": 0, "visible_time": 0.0, "visible_length": 0.0}
         self._test_stats = {}
+        self._adaptive = False
+        self._prior = {"feasible": {}, "visible": {}}       # name -> [cost, probability, count] (AdaptiveCSpace::PredicateStats)
+        self._order = {"feasible": None, "visible": None}   # optimised test orders (lists of names) or None = as added
+        self._vis_deps: List[Tuple[str, str]] = []
 
     # ------------------------------------------------------------------ bounds / sampling
     def setBounds(self, bound: Sequence[Tuple[float, float]]):
@@ -80,8 +84,91 @@ class CSpace:
 
     def feasibilityQueryOrder(self) -> List[str]:
         """the order in which isFeasible runs the named tests (CSpaceInterface::feasibilityQueryOrder): the order they were added
-        in -- the adaptive re-ordering of the reference (enableAdaptiveQueries) is not done, a batched test has no cheaper order"""
-        return list(self.feasibilityTestNames or [])
+        in until optimizeQueryOrder has run"""
+        return list(self._order["feasible"] or self.feasibilityTestNames or [])
+
+    def visibilityQueryOrder(self) -> List[str]:
+        return list(self._order["visible"] or self.feasibilityTestNames or [])
+
+    # ------------------------------------------------------------------ adaptive queries (motionplanning.h:139-166)
+    # The reference keeps, per named test, a running (cost, success probability, evidence count) and can re-order the tests of the
+    # conjunction to minimise its expected cost.  The re-ordering itself is KrisLibrary's AdaptiveCSpace::OptimizeQueryOrder, which
+    # is not in the reference tree; the rule used here is the classical one for a conjunction of independent tests -- run them by
+    # increasing cost / (1 - p), p = probability of passing -- applied greedily among the tests whose prerequisites are placed.
+    def adaptiveQueriesEnabled(self) -> bool:
+        return self._adaptive
+
+    def enableAdaptiveQueries(self, enabled: bool = True):
+        self._adaptive = self._adaptive or bool(enabled)     # motionplanning.cpp:910-916 never switches it off again
+
+    def _need_adaptive(self):
+        if not self._adaptive:
+            raise RuntimeError("adaptive queries not enabled for this space")
+
+    def _pstats(self, kind: str, name: str) -> List[float]:
+        if self.feasibilityTestNames is None or name not in self.feasibilityTestNames:
+            raise ValueError("Invalid constraint name")
+        return self._prior[kind].setdefault(name, [0.0, 0.5, 0.0])      # PyCSpace's initial stats: cost 0, probability 0.5, count 0
+
+    @staticmethod
+    def _update_stats(s: List[float], cost: float, passed: bool, strength: float = 1.0):
+        n = s[2] + strength
+        s[0] += (cost - s[0]) * strength / n
+        s[1] += (float(passed) - s[1]) * strength / n
+        s[2] = n
+
+    def setFeasibilityDependency(self, name: str, precedingTest: str):
+        self._need_adaptive()
+        if name not in (self.feasibilityTestNames or []) or precedingTest not in (self.feasibilityTestNames or []) or name == precedingTest:
+            raise ValueError("Invalid dependency")
+        self.feasibilityTestDependencies.append((name, precedingTest))
+
+    def setVisibilityDependency(self, name: str, precedingTest: str):
+        self._need_adaptive()
+        if name not in (self.feasibilityTestNames or []) or precedingTest not in (self.feasibilityTestNames or []) or name == precedingTest:
+            raise ValueError("Invalid dependency")
+        self._vis_deps.append((name, precedingTest))
+
+    def setFeasibilityPrior(self, name: str, costPrior: float = 0.0, feasibilityProbability: float = 0.0, evidenceStrength: float = 1.0):
+        self._need_adaptive()
+        self._pstats("feasible", name)[:] = [float(costPrior), float(feasibilityProbability), float(evidenceStrength)]
+
+    def setVisibilityPrior(self, name: str, costPrior: float = 0.0, visibilityProbability: float = 0.0, evidenceStrength: float = 1.0):
+        self._need_adaptive()
+        self._pstats("visible", name)[:] = [float(costPrior), float(visibilityProbability), float(evidenceStrength)]
+
+    def feasibilityCost(self, name: str) -> float:
+        self._need_adaptive()
+        return self._pstats("feasible", name)[0]
+
+    def feasibilityProbability(self, name: str) -> float:
+        self._need_adaptive()
+        return self._pstats("feasible", name)[1]
+
+    def visibilityCost(self, name: str) -> float:
+        self._need_adaptive()
+        return self._pstats("visible", name)[0]
+
+    def visibilityProbability(self, name: str) -> float:
+        self._need_adaptive()
+        return self._pstats("visible", name)[1]
+
+    def optimizeQueryOrder(self):
+        self._need_adaptive()
+        names = list(self.feasibilityTestNames or [])
+        for kind, deps in (("feasible", self.feasibilityTestDependencies or []), ("visible", self._vis_deps)):
+            placed, order = set(), []
+            def key(n):
+                c, p, _ = self._pstats(kind, n)
+                return (c / (1.0 - p) if p < 1.0 else float("inf"), names.index(n))
+            while len(order) < len(names):
+                ready = [n for n in names if n not in placed and all(d in placed for m, d in deps if m == n)]
+                if not ready:
+                    raise ValueError("Invalid dependency")            # a cycle
+                best = min(ready, key=key)
+                order.append(best)
+                placed.add(best)
+            self._order[kind] = order
 
     def feasibilityTestDependenciesOf(self, name: str) -> List[str]:
         return [d for n, d in (self.feasibilityTestDependencies or []) if n == name]
@@ -131,13 +218,19 @@ class CSpace:
             ok = self.feasible(x)
         else:
             ok = True
-            for n, test in zip(self.feasibilityTestNames, self.feasibilityTests):
+            order = self._order["feasible"]
+            seq = zip(self.feasibilityTestNames, self.feasibilityTests) if order is None else \
+                ((n, self.feasibilityTests[self.feasibilityTestNames.index(n)]) for n in order)
+            for n, test in seq:
                 t1 = time.perf_counter()
                 r = bool(test(x))
+                dt = time.perf_counter() - t1
                 s = self._test_stats.setdefault(n, [0, 0, 0.0])
                 s[0] += 1
                 s[1] += int(r)
-                s[2] += time.perf_counter() - t1
+                s[2] += dt
+                if self._adaptive:
+                    self._update_stats(self._pstats("feasible", n), dt, r)
                 if not r:
                     ok = False
                     break

@@ -140,3 +140,43 @@ def test_cspace_named_test_queries():
         sp.setVisibilityEpsilon(0.0)
     sp.setVisibilityEpsilon(0.01)
     assert sp.eps == 0.01
+
+
+def test_adaptive_queries_reorder_the_conjunction():
+    """CSpaceInterface's adaptive-query face (motionplanning.h:139-166): per-test running cost / probability, priors, dependencies,
+    and an optimised order that runs cheap, selective tests first"""
+    from klampt_b200.cspace import CSpace
+    calls = []
+    sp = CSpace()
+    sp.bound = [(0.0, 1.0)]
+    sp.addFeasibilityTest(lambda x: calls.append("setup") or True, "setup")
+    sp.addFeasibilityTest(lambda x: calls.append("slow") or True, "slow", dependencies="setup")
+    sp.addFeasibilityTest(lambda x: calls.append("picky") or x[0] < 0.2, "picky")
+    with pytest.raises(RuntimeError, match="adaptive queries not enabled"):
+        sp.optimizeQueryOrder()
+    assert not sp.adaptiveQueriesEnabled() and sp.feasibilityQueryOrder() == ["setup", "slow", "picky"]
+    sp.enableAdaptiveQueries()
+    assert sp.adaptiveQueriesEnabled()
+    sp.setFeasibilityPrior("setup", 1.0, 0.99, 10.0)
+    sp.setFeasibilityPrior("slow", 50.0, 0.9, 10.0)
+    sp.setFeasibilityPrior("picky", 1.0, 0.2, 10.0)
+    assert sp.feasibilityCost("slow") == 50.0 and sp.feasibilityProbability("picky") == 0.2
+    sp.optimizeQueryOrder()
+    assert sp.feasibilityQueryOrder() == ["picky", "setup", "slow"]           # 1/0.8 < 1/0.01 < 50/0.1, and slow still follows setup
+    calls.clear()
+    assert not sp.isFeasible([0.7]) and calls == ["picky"]                    # the selective test fails first: nothing else runs
+    calls.clear()
+    assert sp.isFeasible([0.1]) and calls == ["picky", "setup", "slow"]
+    assert 0.2 < sp.feasibilityProbability("picky") < 0.3                     # (0.2 * 10 + 0 + 1) / 12
+    sp.setFeasibilityDependency("picky", "slow")                              # now picky may only run after slow
+    sp.optimizeQueryOrder()
+    assert sp.feasibilityQueryOrder() == ["setup", "slow", "picky"]
+    with pytest.raises(ValueError, match="Invalid dependency"):
+        sp.setFeasibilityDependency("picky", "nope")
+    with pytest.raises(ValueError, match="Invalid constraint name"):
+        sp.feasibilityCost("nope")
+    sp.setFeasibilityDependency("setup", "picky")                             # closes a cycle
+    with pytest.raises(ValueError, match="Invalid dependency"):
+        sp.optimizeQueryOrder()
+    sp.setVisibilityPrior("slow", 3.0, 0.5, 1.0)
+    assert sp.visibilityCost("slow") == 3.0 and sp.visibilityProbability("slow") == 0.5 and len(sp.visibilityQueryOrder()) == 3
