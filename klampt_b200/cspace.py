@@ -55,6 +55,7 @@ class CSpace:
         assert name is None or isinstance(name, str), "Name argument 'name' must be a string"
         assert callable(func), "Feasibility test 'func' must be a callable object"
         self.feasibilityTests.append(func)
+        self._order = {"feasible": None, "visible": None}     # an optimised order does not know the new test
         if name is None:
             name = "test_" + str(len(self.feasibilityTests) - 1)
         self.feasibilityTestNames.append(name)
