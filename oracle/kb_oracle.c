@@ -2,7 +2,9 @@
  * kb_oracle.c -- CPU oracle (plain C, fp64) for the batched configuration-feasibility path.
  *
  * TEST INFRASTRUCTURE ONLY -- see kb_oracle.h.  PARITY UNPINNED (KrisLibrary absent; no golden
- * vectors in the reference).  Deliberately simple: fp64 everywhere, median-split AABB trees with
+ * vectors in the reference) -- except the SO(3) arithmetic of Floating / BallAndSocket joints (z-y-x FK,
+ * geodesic interpolation, angle metric), which tests/test_reference_golden.py checks against outputs of
+ * the reference's own Python/klampt/math/so3.py (tests/golden/make_reference_so3.py).  Deliberately simple: fp64 everywhere, median-split AABB trees with
  * one element per leaf (8 for point clouds), exhaustive minima, no FMA contraction
  * (-ffp-contract=off in the Makefile).
  *

@@ -1,0 +1,95 @@
+"""Vectors produced by the reference's own pure-Python rotation code (tests/golden/make_reference_so3.py imports
+/root/reference/Python/klampt/math/so3.py and se3.py; the .npz travels) against this repo's mirror of those conventions, the URDF
+loader's roll-pitch-yaw, and the ORACLE's SO(3) arithmetic for Floating / BallAndSocket joints (FK of the z-y-x link triple,
+geodesic interpolation, angle metric) -- the one part of the oracle that real reference code can pin."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from klampt_b200 import io as kio, so3, synth
+from oracle.oracle import OracleWorld
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_so3.npz"))
+
+
+def M(R9):
+    """Klamp't column-major 9-list -> 3x3"""
+    return np.asarray(R9, dtype=np.float64).reshape(3, 3).T
+
+
+def test_so3_mirror_matches_reference_outputs():
+    for i in range(len(G["R"])):
+        R = list(G["R"][i])
+        np.testing.assert_allclose(so3.matrix(R), M(R), atol=0)
+        # the reference rounds rotation vectors shorter than its length threshold to the identity
+        np.testing.assert_allclose(so3.exp(G["w"][i]), M(R), atol=1e-14 if np.linalg.norm(G["w"][i]) > 1e-6 else 1e-8)
+        # equal as angles: the reference returns 2 pi where this mirror returns 0 (its acos branch maps sin = 0 to 2 pi - 0);
+        # acos near 1 costs the reference half its digits, hence 1e-7
+        d = np.asarray(so3.rpy(R)) - G["rpy"][i]
+        assert np.abs(np.arctan2(np.sin(d), np.cos(d))).max() < 1e-7
+        assert abs(so3.angle(M(R)) - G["angle"][i]) < 1e-7                    # acos near 0 / pi amplifies rounding
+        if 1e-6 < G["angle"][i] < math.pi - 1e-3:
+            np.testing.assert_allclose(so3.log(M(R)), G["moment"][i], atol=1e-9)
+        np.testing.assert_allclose(so3.from_quaternion(list(G["quat"][i])), R, atol=1e-12)
+        np.testing.assert_allclose(so3.inv(R), list(M(R).reshape(-1)), atol=0)                # inverse = transpose: row-major of R
+        w = G["w"][i]; th = np.linalg.norm(w)
+        if th > 1e-6:
+            np.testing.assert_allclose(so3.from_axis_angle((list(w / th), th)), R, atol=1e-12)
+    for k in range(len(G["ia"])):
+        Ra, Rb = list(G["R"][G["ia"][k]]), list(G["R"][G["ib"][k]])
+        np.testing.assert_allclose(so3.mul(Ra, Rb), G["mul"][k], atol=1e-14)
+        ta = G["t"][G["ia"][k]]
+        np.testing.assert_allclose(np.asarray(so3.apply(Ra, list(G["p"][k]))) + ta, G["applied"][k], atol=1e-14)
+        T12 = so3.to_rowmajor12(Ra, list(ta))                                               # the engine's transform layout
+        np.testing.assert_allclose(synth.transform_points(T12, G["p"][k][None])[0], G["applied"][k], atol=1e-14)
+        R2, t2 = so3.from_rowmajor12(T12)
+        np.testing.assert_allclose(R2, Ra, atol=0); np.testing.assert_allclose(t2, ta, atol=0)
+
+
+def test_urdf_rpy_matches_reference_from_rpy():
+    for i in range(len(G["rpy"])):
+        r, p, y = G["rpy"][i]
+        np.testing.assert_allclose(kio._rpy_matrix(r, p, y), M(G["R_from_rpy"][i]), atol=1e-14)
+        np.testing.assert_allclose(M(G["R_from_rpy"][i]), M(G["R"][i]), atol=1e-6)      # the reference's own round trip (its acos loses digits)
+
+
+@pytest.fixture(scope="module")
+def floating():
+    w = synth.world_floating()
+    return w, OracleWorld(w)
+
+
+def _zyx_of(R9):
+    """Euler ZYX triplet (a about z, b about y, c about x) of a reference rotation: rpy = (roll c, pitch b, yaw a)"""
+    r, p, y = so3.rpy(list(R9))
+    return np.array([y, p, r])
+
+
+def test_oracle_floating_fk_is_reference_from_rpy(floating):
+    """the z, y, x revolute links of a floating joint compose to the reference's from_rpy((c, b, a))"""
+    w, o = floating
+    q = np.zeros(w.robot.L)
+    for i in range(len(G["R"])):
+        q[3:6] = _zyx_of(G["R"][i])
+        T = o.fk(q)
+        np.testing.assert_allclose(T[5][:9].reshape(3, 3), M(G["R"][i]), atol=1e-9)
+
+
+def test_oracle_geodesic_interpolation_and_metric_match_reference_so3(floating):
+    """Interpolate.cpp:16-52 / :229-278 on the Euler triplets of a floating joint = so3.interpolate / so3.distance of the reference"""
+    w, o = floating
+    a, b = np.zeros(w.robot.L), np.zeros(w.robot.L)
+    checked = 0
+    for k in range(len(G["ia"])):
+        Ra, Rb = G["R"][G["ia"][k]], G["R"][G["ib"][k]]
+        a[3:6], b[3:6] = _zyx_of(Ra), _zyx_of(Rb)
+        assert abs(o.cspace_distance(a, b) - G["dist"][k]) < 1e-7
+        if G["dist"][k] > math.pi - 1e-3:
+            continue                                                   # antipodal pair: the geodesic is not unique
+        m = o.interpolate(a, b, float(G["u"][k]))
+        np.testing.assert_allclose(so3.euler_zyx_matrix(*m[3:6]), M(G["interp"][k]), atol=1e-8)
+        np.testing.assert_allclose(so3.euler_zyx_matrix(*so3.euler_zyx_interp(a[3:6], b[3:6], float(G["u"][k]))), M(G["interp"][k]), atol=1e-8)
+        checked += 1
+    assert checked > 150
