@@ -314,6 +314,10 @@ class TerrainModel(_Named):
         self.world, self.index = world, index
         self._geom = Geometry3D()
 
+    def getID(self) -> int:
+        """world ID (Cpp/Modeling/World.cpp:47-53: terrains, then rigid objects, then per robot its ID and its links)"""
+        return self.world.terrainID(self.index)
+
     def geometry(self) -> Geometry3D:
         return self._geom
 
@@ -323,6 +327,9 @@ class RigidObjectModel(_Named):
         super().__init__(name)
         self.world, self.index = world, index
         self._geom = Geometry3D()
+
+    def getID(self) -> int:
+        return self.world.rigidObjectID(self.index)
 
     def geometry(self) -> Geometry3D:
         return self._geom
@@ -338,10 +345,14 @@ class RobotModelLink(_Named):
     def __init__(self, robot: "RobotModel", index: int, name: str):
         super().__init__(name)
         self._robot, self.index = robot, index
+        self.world = getattr(robot, "world", None)
         self._geom = Geometry3D()
 
     def robot(self) -> "RobotModel":
         return self._robot
+
+    def getID(self) -> int:
+        return self.world.robotLinkID(self._robot.index, self.index)
 
     def getIndex(self) -> int:
         return self.index
@@ -384,6 +395,9 @@ class RobotModel(_Named):
         self._q = np.zeros(0)
         if spec is not None:
             self._from_spec(spec, geoms)
+
+    def getID(self) -> int:
+        return self.world.robotID(self.index)
 
     def _from_spec(self, spec: RobotSpec, geoms):
         L = spec.L

@@ -4,7 +4,9 @@
  * TEST INFRASTRUCTURE ONLY -- see kb_oracle.h.  PARITY UNPINNED (KrisLibrary absent; no golden
  * vectors in the reference) -- except the SO(3) arithmetic of Floating / BallAndSocket joints (z-y-x FK,
  * geodesic interpolation, angle metric), which tests/test_reference_golden.py checks against outputs of
- * the reference's own Python/klampt/math/so3.py (tests/golden/make_reference_so3.py).  Deliberately simple: fp64 everywhere, median-split AABB trees with
+ * the reference's own Python/klampt/math/so3.py (tests/golden/make_reference_so3.py), and the default pair
+ * mask, which is checked against the reference's own WorldCollider (tests/golden/make_reference_mask.py).
+ * Deliberately simple: fp64 everywhere, median-split AABB trees with
  * one element per leaf (8 for point clouds), exhaustive minima, no FMA contraction
  * (-ffp-contract=off in the Makefile).
  *

@@ -93,3 +93,71 @@ def test_oracle_geodesic_interpolation_and_metric_match_reference_so3(floating):
         np.testing.assert_allclose(so3.euler_zyx_matrix(*so3.euler_zyx_interp(a[3:6], b[3:6], float(G["u"][k]))), M(G["interp"][k]), atol=1e-8)
         checked += 1
     assert checked > 150
+
+
+# ------------------------------------------------------------------------------------------------ collision masks
+MASKS = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_masks.npz"))
+_KIND = {"TerrainModel": 0, "RigidObjectModel": 1, "RobotModelLink": 2}
+
+
+def _worlds():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_reference_mask", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_reference_mask.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.worlds()
+
+
+def _rows(col):
+    rows = set()
+    for i, s in enumerate(col.mask):
+        for j in s:
+            a, b = col.geomList[i][0], col.geomList[j][0]
+            rows.add((_KIND[type(a).__name__], a.index, _KIND[type(b).__name__], b.index))
+    return np.array(sorted(rows), dtype=np.int32).reshape(-1, 4)
+
+
+@pytest.mark.parametrize("name", ["c1", "c3", "boxes", "c1_empty"])
+def test_world_collider_mirror_equals_the_reference_world_collider(name):
+    """klampt_b200.collide.WorldCollider against the masks the reference's own WorldCollider.__init__ / ignoreCollision produced on the
+    same worlds (tests/golden/make_reference_mask.py)"""
+    from klampt_b200 import robotsim
+    from klampt_b200.collide import WorldCollider
+    world = robotsim.WorldModel.from_spec(_worlds()[name])
+    col = WorldCollider(world)
+    assert np.array_equal(_rows(col), MASKS[name])
+    robot = world.robot(0)
+    col.ignoreCollision(robot.link(robot.numLinks() - 1))
+    if world.numRigidObjects() > 0 and world.rigidObject(0).geometry().type() != "":
+        col.ignoreCollision((robot.link(1), world.rigidObject(0)))
+    assert np.array_equal(_rows(col), MASKS[name + "_ignored"])
+
+
+@pytest.mark.parametrize("name", ["c1", "c3", "boxes", "c1_empty"])
+def test_oracle_default_mask_agrees_with_the_reference_world_collider(name):
+    """the C++ side's InitializeDefault mask (PlannerSettings.cpp:16-41, restated in the oracle) and the Python side's WorldCollider
+    must enable the same (link, terrain), (link, object) and (link, link) pairs -- as far as the robot's feasibility test reads them:
+    CheckCollision tests collisionEnabled(i,j) || collisionEnabled(j,i) for the environment and (i<j) for self pairs, and only ever
+    reaches bodies with a non-empty geometry"""
+    spec = _worlds()[name]
+    o = OracleWorld(spec)
+    m = o.pair_mask()
+    T, O, L = len(spec.terrains), len(spec.objects), spec.robot.L
+    lid = lambda j: T + O + 1 + j
+    nonempty = lambda gi: gi >= 0 and spec.geoms[gi].kind != "empty"
+    want = set()
+    for j in range(L):
+        if not nonempty(spec.robot.link_geom[j]):
+            continue
+        for t in range(T):
+            if nonempty(spec.terrains[t]) and (m[lid(j), t] or m[t, lid(j)]):
+                want.add((2, j, 0, t)); want.add((0, t, 2, j))
+        for k in range(O):
+            if nonempty(spec.objects[k][0]) and (m[lid(j), T + k] or m[T + k, lid(j)]):
+                want.add((2, j, 1, k)); want.add((1, k, 2, j))
+        for k in range(j + 1, L):
+            if nonempty(spec.robot.link_geom[k]) and m[lid(j), lid(k)]:
+                want.add((2, j, 2, k)); want.add((2, k, 2, j))
+    ref = set(map(tuple, MASKS[name].tolist()))
+    ref_robot = {r for r in ref if r[0] == 2 or r[2] == 2}                # the robot's pairs (object-object / terrain-object ones are the world's)
+    assert want == ref_robot
