@@ -30,7 +30,8 @@ class RobotCSpace(CSpace):
         self.robot = robot
         self.collider = collider
         self.setBounds(list(zip(*robot.getJointLimits())))
-        self.eps = 1e-2                                  # robotplanning.make_space(edgeCheckResolution=1e-2)
+        # self.eps stays CSpace's 1e-3, as in the reference's RobotCSpace (tests/golden/ref_cspace.json); robotplanning.make_space
+        # is what sets edgeCheckResolution = 1e-2 there
         self.properties["geodesic"] = 1
         self.joint_limit_failures = [0] * len(self.bound)
         if collider is not None:
@@ -132,14 +133,24 @@ class RobotCSpace(CSpace):
         return names
 
     def feasibilityTestNamesList(self) -> List[str]:
-        """the reference's test list for this world (plan/robotcspace.py:31-75): joint limits, self collision, one test per rigid
-        object and per terrain"""
-        names = ["joint limits", "self collision"]
-        if self.collider is not None:
-            w = self.collider.world
-            names += ["obj collision %d %s" % (i, w.rigidObject(i).getName()) for i in range(w.numRigidObjects())]
-            names += ["terrain collision %d %s" % (i, w.terrain(i).getName()) for i in range(w.numTerrains())]
+        """the reference's test list for this world, in its order (plan/robotcspace.py:31-75; tests/golden/ref_cspace.json is what the
+        reference's own constructor produces): joint limits, the two bookkeeping tests setconfig / calcbb (always true: the engine
+        does FK and its own broad phase per configuration), self collision, one test per rigid object and per terrain"""
+        if self.collider is None:
+            return ["joint limits", "setconfig", "self collision"]
+        w = self.collider.world
+        names = ["joint limits", "setconfig", "calcbb", "self collision"]
+        names += ["obj collision %d %s" % (i, w.rigidObject(i).getName()) for i in range(w.numRigidObjects())]
+        names += ["terrain collision %d %s" % (i, w.terrain(i).getName()) for i in range(w.numTerrains())]
         return names
+
+    def feasibilityTestDependenciesList(self) -> List[tuple]:
+        """(test, prerequisite) pairs as the reference declares them (robotcspace.py:62-72)"""
+        if self.collider is None:
+            return [("self collision", "setconfig")]
+        deps = [("calcbb", "setconfig"), ("self collision", "setconfig")]
+        deps += [(n, "calcbb") for n in self.feasibilityTestNamesList() if n.startswith(("obj collision", "terrain collision"))]
+        return deps
 
     def testFeasibility(self, name: str, x) -> bool:
         """one of the reference's named tests at x (CSpaceInterface::testFeasibility): evaluated from the all-pairs query, so any
@@ -148,6 +159,8 @@ class RobotCSpace(CSpace):
             raise ValueError("Invalid feasibility test name %r" % name)
         if name == "joint limits":
             return self.inJointLimits(x)
+        if name in ("setconfig", "calcbb"):
+            return True
         pairs, count = self.engine.colliding_pairs_batch(np.asarray(x, dtype=np.float64), max_pairs=32)
         T, O = len(self.spec.terrains), len(self.spec.objects)
         for a, b in pairs[0]:

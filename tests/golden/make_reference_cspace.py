@@ -1,0 +1,66 @@
+"""Golden feasibility-test lists from the REFERENCE's own Python/klampt/plan/robotcspace.py + plan/cspace.py.
+
+``RobotCSpace.__init__`` (robotcspace.py:31-75) is pure Python.  It runs here UNMODIFIED on this repo's robotsim / collide mirror
+objects (the compiled ``motionplanning`` module is only needed by ``setup()``, which is not called): the names, order and
+dependencies of the feasibility tests, the bounds and the properties it derives are the reference's, and
+tests/test_reference_golden.py holds klampt_b200.robotcspace.RobotCSpace to them.
+
+Run in the build container (needs /root/reference):   python tests/golden/make_reference_cspace.py
+"""
+import importlib
+import json
+import os
+import sys
+import types
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("KLAMPT_REFERENCE", "/root/reference")
+
+
+def import_reference_robotcspace():
+    from klampt_b200 import robotsim as mirror
+    root = os.path.join(REF, "Python", "klampt")
+    for name, path in (("klampt", root), ("klampt.math", os.path.join(root, "math")), ("klampt.model", os.path.join(root, "model")),
+                       ("klampt.plan", os.path.join(root, "plan"))):
+        m = types.ModuleType(name)
+        m.__path__ = [path]
+        sys.modules[name] = m
+    rs = types.ModuleType("klampt.robotsim")                    # the mirror's names + the one extra name robotcspace.py imports
+    rs.__dict__.update({k: v for k, v in mirror.__dict__.items() if not k.startswith("__")})
+    rs.IKObjective = type("IKObjective", (), {})
+    sys.modules["klampt.robotsim"] = rs
+    sys.modules["klampt"].robotsim = rs
+    sys.modules["klampt.plan.motionplanning"] = types.ModuleType("klampt.plan.motionplanning")     # SWIG module: only setup() uses it
+    sys.modules["klampt.plan"].motionplanning = sys.modules["klampt.plan.motionplanning"]
+    collide = importlib.import_module("klampt.model.collide")
+    return importlib.import_module("klampt.plan.robotcspace"), collide
+
+
+def main():
+    from make_reference_mask import worlds
+    from klampt_b200 import robotsim as mirror
+    ref, collide = import_reference_robotcspace()
+    out = {}
+    for name, spec in worlds().items():
+        for with_collider in (True, False):
+            world = mirror.WorldModel.from_spec(spec)
+            robot = world.robot(0)
+            space = ref.RobotCSpace(robot, collide.WorldCollider(world) if with_collider else None)
+            out[name + ("" if with_collider else "_nocollider")] = {
+                "names": list(space.feasibilityTestNames),
+                "dependencies": [list(d) for d in space.feasibilityTestDependencies],
+                "bound": [[float(a), float(b)] for a, b in space.bound],
+                "properties": {k: (v if not isinstance(v, (list, tuple)) else [float(x) for x in v]) for k, v in space.properties.items()},
+                "eps": space.eps,
+                "in_limits": [bool(space.inJointLimits([b[0] for b in space.bound])), bool(space.inJointLimits([b[1] + 1e-9 for b in space.bound]))],
+            }
+            print(name, with_collider, len(space.feasibilityTestNames), "tests")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_cspace.json")
+    json.dump(out, open(path, "w"), indent=1, sort_keys=True)
+    print("wrote", path)
+
+
+if __name__ == "__main__":
+    main()

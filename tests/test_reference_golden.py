@@ -161,3 +161,44 @@ def test_oracle_default_mask_agrees_with_the_reference_world_collider(name):
     ref = set(map(tuple, MASKS[name].tolist()))
     ref_robot = {r for r in ref if r[0] == 2 or r[2] == 2}                # the robot's pairs (object-object / terrain-object ones are the world's)
     assert want == ref_robot
+
+
+# ------------------------------------------------------------------------------------------------ RobotCSpace test list
+import json
+
+CSPACE = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_cspace.json")))
+
+
+def _host_only_space(world, with_collider):
+    """RobotCSpace without its engine (no GPU here): the host-side members the reference's constructor also produces"""
+    from klampt_b200.collide import WorldCollider
+    from klampt_b200.cspace import CSpace
+    from klampt_b200.robotcspace import RobotCSpace
+    sp = RobotCSpace.__new__(RobotCSpace)
+    CSpace.__init__(sp)
+    sp.robot = world.robot(0)
+    sp.collider = WorldCollider(world) if with_collider else None
+    sp.setBounds(list(zip(*sp.robot.getJointLimits())))
+    sp.properties["geodesic"] = 1
+    sp.joint_limit_failures = [0] * len(sp.bound)
+    return sp
+
+
+@pytest.mark.parametrize("name", sorted(CSPACE))
+def test_robot_cspace_test_list_equals_the_reference_constructor(name):
+    """names, order and dependencies of the feasibility tests, bounds, properties and eps of the reference's own
+    RobotCSpace.__init__ run on the same worlds (tests/golden/make_reference_cspace.py)"""
+    from klampt_b200 import robotsim
+    want = CSPACE[name]
+    with_collider = not name.endswith("_nocollider")
+    world = robotsim.WorldModel.from_spec(_worlds()[name.replace("_nocollider", "")])
+    sp = _host_only_space(world, with_collider)
+    assert sp.feasibilityTestNamesList() == want["names"]
+    assert sorted(map(tuple, sp.feasibilityTestDependenciesList())) == sorted(map(tuple, want["dependencies"]))
+    np.testing.assert_allclose(np.array(sp.bound), np.array(want["bound"]), atol=0)
+    assert sp.eps == want["eps"]
+    assert set(sp.properties) == set(want["properties"])
+    for k, v in want["properties"].items():
+        np.testing.assert_allclose(np.asarray(sp.properties[k], dtype=np.float64), np.asarray(v, dtype=np.float64), rtol=1e-15)
+    lo, hi = [b[0] for b in sp.bound], [b[1] + 1e-9 for b in sp.bound]
+    assert [bool(sp.inJointLimits(lo)), bool(sp.inJointLimits(hi))] == want["in_limits"]
