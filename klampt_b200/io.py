@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import math
 import os
+import re
 import shlex
 from typing import Dict, List, Optional, Tuple
 
@@ -201,8 +202,28 @@ def _logical_lines(text: str) -> List[str]:
     return lines
 
 
+_NUM_PREFIX = re.compile(r"[+-]?(?:\d+\.?\d*|\.\d+)(?:[eE][+-]?\d+)?")
+
+
 def _floats(items, scale=1.0):
-    return [float("inf") if t.lower() == "inf" else (float("-inf") if t.lower() == "-inf" else float(t)) * scale for t in items]
+    """numbers of one .rob line with the semantics of the reference's ``while (ss >> ftemp)`` loops (Cpp/Modeling/Robot.cpp:409-431):
+    reading stops at the first token that is not a number, and a token that only STARTS with a number still yields that number.
+    The reference's own planar-robot generator depends on it: it ends its TParent line with a literal backslash-n
+    (model/create/planar_robot.py:44), which glues the following ``axis`` line onto it -- the reader takes the last translation
+    entry from the token ``0\\naxis`` and drops the rest, axes included (tests/golden/ref_planar_3R.rob)."""
+    out = []
+    for t in items:
+        low = t.lower()
+        if low in ("inf", "+inf", "-inf"):
+            out.append(float(low))
+            continue
+        m = _NUM_PREFIX.match(t)
+        if m is None:
+            break
+        out.append(float(m.group(0)) * scale)
+        if m.end() != len(t):
+            break
+    return out
 
 
 def _geometry_from_token(tok: str, basedir: str):
@@ -250,9 +271,12 @@ def parse_rob(text: str, basedir: str = ".", world: Optional[WorldSpec] = None) 
             raise NotImplementedError(".rob item %r is not supported by this loader" % key)
         else:
             items[key] = args
-    if "parents" not in items:
-        raise ValueError(".rob file has no 'parents' line")
-    parents = np.array([int(x) for x in items["parents"]], dtype=np.int32)
+    if "parents" in items:
+        parents = np.array([int(x) for x in items["parents"]], dtype=np.int32)
+    elif "tparent" in items:                 # no parents line: a serial chain, parents[i] = i - 1 (Robot.cpp:899-902)
+        parents = np.arange(-1, len(_floats(items["tparent"])) // 12 - 1, dtype=np.int32)
+    else:
+        raise ValueError(".rob file has neither a 'parents' nor a 'tparent' line")
     L = len(parents)
     names = items.get("links", ["link%d" % i for i in range(L)])
 

@@ -1,0 +1,45 @@
+"""A .rob file written by the REFERENCE's own generator, Python/klampt/model/create/planar_robot.py:3-77 (pure Python up to the
+``world.loadElement`` call, which a stub world intercepts): tests/golden/ref_planar_3R.rob is byte for byte what Klamp't writes and
+then loads.  tests/test_reference_golden.py feeds it to klampt_b200.io.parse_rob.
+
+Run in the build container (needs /root/reference):   python tests/golden/make_reference_rob.py
+"""
+import importlib.util
+import os
+import tempfile
+
+REF = os.environ.get("KLAMPT_REFERENCE", "/root/reference")
+
+
+class _StubWorld:
+    """captures the file the generator hands to WorldModel.loadElement; everything after that needs the compiled module"""
+    text = None
+
+    def loadElement(self, fn):
+        self.text = open(fn).read()
+        raise _Captured()
+
+
+class _Captured(Exception):
+    pass
+
+
+def main():
+    spec = importlib.util.spec_from_file_location("planar_robot", os.path.join(REF, "Python", "klampt", "model", "create", "planar_robot.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    here = os.path.dirname(os.path.abspath(__file__))
+    for n, length in ((3, 0.5),):
+        w = _StubWorld()
+        tmp = os.path.join(tempfile.mkdtemp(), "temp.rob")
+        try:
+            mod.make(n, w, link_length=length, tempname=tmp, debug=True)
+        except _Captured:
+            pass
+        out = os.path.join(here, "ref_planar_%dR.rob" % n)
+        open(out, "w").write(w.text)
+        print("wrote", out, len(w.text), "bytes")
+
+
+if __name__ == "__main__":
+    main()

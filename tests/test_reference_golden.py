@@ -202,3 +202,28 @@ def test_robot_cspace_test_list_equals_the_reference_constructor(name):
         np.testing.assert_allclose(np.asarray(sp.properties[k], dtype=np.float64), np.asarray(v, dtype=np.float64), rtol=1e-15)
     lo, hi = [b[0] for b in sp.bound], [b[1] + 1e-9 for b in sp.bound]
     assert [bool(sp.inJointLimits(lo)), bool(sp.inJointLimits(hi))] == want["in_limits"]
+
+
+# ------------------------------------------------------------------------------------------------ a .rob file the reference wrote
+def test_rob_loader_reads_the_file_the_reference_generator_writes():
+    """tests/golden/ref_planar_3R.rob is the output of the reference's model/create/planar_robot.py (make_reference_rob.py).  It has no
+    `parents` line (serial chain, Robot.cpp:899-902), and its TParent line ends in a literal backslash-n that glues the `axis` line
+    onto it, so -- as in the reference's reader (Robot.cpp:271-300, 409-416) -- the axes are never read and default to z
+    (Robot.cpp:953-954): the "planar" robot the reference actually loads turns in the x-y plane."""
+    text = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_planar_3R.rob")).read()
+    assert "0.5 0 0\\naxis" in text and "parents" not in text
+    world, r = kio.parse_rob(text)
+    assert r.L == 3 and list(r.parents) == [-1, 0, 1]
+    np.testing.assert_allclose(r.axis, [[0, 0, 1]] * 3)
+    np.testing.assert_allclose(r.T0[:, 9:], [[0, 0, 0], [0.5, 0, 0], [0.5, 0, 0]])
+    np.testing.assert_allclose(r.qmin, 0.0); np.testing.assert_allclose(r.qmax, 6.28319)
+    from klampt_b200.worldspec import JOINT_SPIN
+    assert (r.joint_type == JOINT_SPIN).all() and all(g >= 0 for g in r.link_geom)
+    g = world.geoms[r.link_geom[1]]
+    assert g.tris.shape == (12, 3) and g.verts[:, 0].max() == pytest.approx(0.5)       # geomscale 0.5 on the unit-length box
+    o = OracleWorld(world)
+    q = [0.3, -0.2, 0.5]
+    T = o.fk(q)
+    np.testing.assert_allclose(T[2][9:], [0.5 * math.cos(0.3) + 0.5 * math.cos(0.1), 0.5 * math.sin(0.3) + 0.5 * math.sin(0.1), 0.0], atol=1e-15)
+    c, s = math.cos(0.6), math.sin(0.6)
+    np.testing.assert_allclose(T[2][:9].reshape(3, 3), [[c, -s, 0], [s, c, 0], [0, 0, 1]], atol=1e-15)
