@@ -22,8 +22,83 @@ def bb_intersect(a, b) -> bool:
     return not any(q < u or v < p for (p, q, u, v) in zip(amin, amax, bmin, bmax))
 
 
+def bb_create(*ptlist):
+    """box of a set of points; no points: the empty box (+inf, -inf)"""
+    if not ptlist:
+        return [float("inf")] * 3, [float("-inf")] * 3
+    return [min(c) for c in zip(*ptlist)], [max(c) for c in zip(*ptlist)]
+
+
+def bb_empty(bb) -> bool:
+    return any(a > b for a, b in zip(bb[0], bb[1]))
+
+
+def bb_contains(bb, x) -> bool:
+    return all(p <= v <= q for p, q, v in zip(bb[0], bb[1], x))
+
+
+def bb_intersection(*bbs):
+    """may be empty (bb_empty)"""
+    return [max(x) for x in zip(*[b[0] for b in bbs])], [min(x) for x in zip(*[b[1] for b in bbs])]
+
+
 def bb_union(*bbs):
-    return [min(*x) for x in zip(*[b[0] for b in bbs])], [max(*x) for x in zip(*[b[1] for b in bbs])]
+    return [min(x) for x in zip(*[b[0] for b in bbs])], [max(x) for x in zip(*[b[1] for b in bbs])]
+
+
+def _wanted(pairs, i, j) -> bool:
+    return pairs == "all" or pairs(i, j)
+
+
+def self_collision_iter(geomlist, pairs="all") -> Iterator[Tuple[int, int]]:
+    """colliding pairs (i, j), i < j, within one list of geometries (reference collide.py:61-105: no box pre-reject here).
+    `pairs`: 'all', a predicate f(i, j), or an explicit list of index pairs"""
+    if pairs == "all" or callable(pairs):
+        cand = ((i, j) for i in range(len(geomlist)) for j in range(i + 1, len(geomlist)) if _wanted(pairs, i, j))
+    else:
+        cand = iter(pairs)
+    for i, j in cand:
+        if geomlist[i].collides(geomlist[j]):
+            yield (i, j)
+
+
+def _group_pairs(geoms1, geoms2, ids1, ids2, pairs):
+    """the broad phase the group iterators share (collide.py:131-136): a geometry takes part only if its box touches the union box
+    of the other group"""
+    bb1 = {i: geoms1[i].getBB() for i in ids1}
+    bb2 = {j: geoms2[j].getBB() for j in ids2}
+    u1, u2 = bb_union(*bb1.values()), bb_union(*bb2.values())
+    keep1 = [i for i in ids1 if bb_intersect(bb1[i], u2)]
+    keep2 = [j for j in ids2 if bb_intersect(bb2[j], u1)]
+    return ((i, j) for i in keep1 for j in keep2 if _wanted(pairs, i, j))
+
+
+def group_collision_iter(geomlist1, geomlist2, pairs="all") -> Iterator[Tuple[int, int]]:
+    """colliding pairs (i, j) between two lists (reference collide.py:107-157); an explicit pair list skips the box pre-reject"""
+    if len(geomlist1) == 0 or len(geomlist2) == 0:
+        return
+    if pairs == "all" or callable(pairs):
+        cand = _group_pairs(geomlist1, geomlist2, range(len(geomlist1)), range(len(geomlist2)), pairs)
+    else:
+        cand = iter(pairs)
+    for i, j in cand:
+        if geomlist1[i].collides(geomlist2[j]):
+            yield (i, j)
+
+
+def group_subset_collision_iter(geomlist, alist, blist, pairs="all") -> Iterator[Tuple[int, int]]:
+    """colliding pairs between two index subsets of one list (reference collide.py:159-216).  The reference only fills the boxes of
+    `blist` entries that are also in `alist` (`if bblist[id] is not None`, :191) and fails on the others; here every listed
+    geometry gets its box, which is what the docstring there describes."""
+    if pairs != "all" and not callable(pairs):
+        cand = iter(pairs)
+    elif len(alist) == 0 or len(blist) == 0:
+        return
+    else:
+        cand = _group_pairs(geomlist, geomlist, list(alist), list(blist), pairs)
+    for i, j in cand:
+        if geomlist[i].collides(geomlist[j]):
+            yield (i, j)
 
 
 class WorldCollider:

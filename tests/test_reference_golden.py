@@ -227,3 +227,38 @@ def test_rob_loader_reads_the_file_the_reference_generator_writes():
     np.testing.assert_allclose(T[2][9:], [0.5 * math.cos(0.3) + 0.5 * math.cos(0.1), 0.5 * math.sin(0.3) + 0.5 * math.sin(0.1), 0.0], atol=1e-15)
     c, s = math.cos(0.6), math.sin(0.6)
     np.testing.assert_allclose(T[2][:9].reshape(3, 3), [[c, -s, 0], [s, c, 0], [0, 0, 1]], atol=1e-15)
+
+
+# ------------------------------------------------------------------------------------------------ bb helpers / group iterators
+GROUPS = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_groupiter.json")))
+
+
+@pytest.mark.parametrize("name", ["dense", "sparse", "far_groups"])
+def test_group_iterators_and_bb_helpers_equal_the_reference(name):
+    """the module-level helpers of model/collide.py on stand-in box geometries: same pairs in the same order as the reference's own
+    functions produced (tests/golden/make_reference_groupiter.py)"""
+    import importlib.util
+    from klampt_b200 import collide as kc
+    spec = importlib.util.spec_from_file_location("make_reference_groupiter", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_reference_groupiter.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    want = GROUPS[name]
+    b, g1, g2 = gen.case_inputs(name)
+    G, G1, G2 = [gen.BoxGeom(*x, loose=0.01) for x in b], [gen.BoxGeom(*x, loose=0.01) for x in g1], [gen.BoxGeom(*x, loose=0.01) for x in g2]
+    even = lambda i, j: (i + j) % 2 == 0
+    L = lambda it: [list(p) for p in it]
+    assert L(kc.self_collision_iter(G)) == want["self_all"]
+    assert L(kc.self_collision_iter(G, even)) == want["self_even"]
+    assert L(kc.self_collision_iter(G, [(0, 1), (2, 5), (3, 4)])) == want["self_list"]
+    assert L(kc.group_collision_iter(G1, G2)) == want["group_all"]
+    assert L(kc.group_collision_iter(G1, G2, even)) == want["group_even"]
+    assert L(kc.group_collision_iter(G1, G2, [(0, 0), (1, 2)])) == want["group_list"]
+    assert L(kc.group_subset_collision_iter(G, *want["subset"])) == want["subset_all"]
+    assert L(kc.group_subset_collision_iter(G, [0, 1, 2], [5, 6, 7, 8])) == [[i, j] for i in (0, 1, 2) for j in (5, 6, 7, 8) if G[i].collides(G[j])]
+    assert list(map(list, kc.bb_union(*[g.getBB() for g in G]))) == want["bb_union"]
+    inter = kc.bb_intersection(G[0].getBB(), G[1].getBB())
+    assert list(map(list, inter)) == want["bb_intersection"] and kc.bb_empty(inter) == want["bb_empty"]
+    assert list(map(list, kc.bb_create(*[g.lo for g in G]))) == want["bb_create"]
+    assert [kc.bb_contains(G[0].getBB(), g.lo) for g in G] == want["bb_contains"]
+    assert list(map(list, kc.bb_create())) == GROUPS["bb_create_empty"] and kc.bb_empty(kc.bb_create())
+    assert list(map(list, kc.bb_union(G[0].getBB()))) == list(map(list, G[0].getBB()))      # one box: used to raise (min of a scalar)
