@@ -208,7 +208,11 @@ class CSpace:
 
     # ------------------------------------------------------------------ the CSpaceInterface face
     def setup(self, reinit: bool = False):
+        """the reference builds its CSpaceInterface here and, when the tests are named, enables adaptive queries and registers the
+        dependencies (plan/cspace.py:112-118); the host-side bookkeeping of this class plays that part"""
         self.cspace = self
+        if self.feasibilityTests is not None:
+            self.enableAdaptiveQueries()
 
     def close(self):
         self.cspace = None
@@ -264,7 +268,10 @@ class CSpace:
         return ok
 
     def getStats(self) -> dict:
-        """same keys as CSpaceInterface::getStats (motionplanning.cpp:1031-1055)"""
+        """same keys as CSpaceInterface::getStats (motionplanning.cpp:1031-1055); empty before setup(), as in the reference
+        (plan/cspace.py:195-199)"""
+        if self.cspace is None:
+            return {}
         s = self._stats
         out = {"feasible_count": s["feasible_count"],
                "feasible_probability": s["feasible_true"] / s["feasible_count"] if s["feasible_count"] else 0.0,

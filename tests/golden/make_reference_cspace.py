@@ -57,6 +57,17 @@ def main():
                 "in_limits": [bool(space.inJointLimits([b[0] for b in space.bound])), bool(space.inJointLimits([b[1] + 1e-9 for b in space.bound]))],
             }
             print(name, with_collider, len(space.feasibilityTestNames), "tests")
+    # the plain CSpace base class (plan/cspace.py:76-214), members that do not need the compiled CSpaceInterface
+    base = importlib.import_module("klampt.plan.cspace").CSpace()
+    base.setBounds([(0.0, 2.0), (1.0, 1.0), (-1.0, 3.0)])
+    base.addFeasibilityTest(lambda x: x[0] < 1.5)
+    base.addFeasibilityTest(lambda x: x[2] > 0.0, "positive z", dependencies=["test_0"])
+    base.addFeasibilityTest(lambda x: True, dependencies="positive z")
+    probes = [[0.5, 1.0, 1.0], [1.7, 1.0, 1.0], [0.5, 1.0, -0.5], [0.5, 1.2, 1.0], [2.0, 1.0, 3.0]]
+    out["plain_cspace"] = {"bound": [list(b) for b in base.bound], "properties": dict(base.properties), "eps": base.eps,
+                           "names": list(base.feasibilityTestNames), "dependencies": [list(d) for d in base.feasibilityTestDependencies],
+                           "probes": probes, "inBounds": [bool(base.inBounds(p)) for p in probes], "feasible": [bool(base.feasible(p)) for p in probes],
+                           "stats_before_setup": base.getStats()}
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_cspace.json")
     json.dump(out, open(path, "w"), indent=1, sort_keys=True)
     print("wrote", path)

@@ -184,7 +184,7 @@ def _host_only_space(world, with_collider):
     return sp
 
 
-@pytest.mark.parametrize("name", sorted(CSPACE))
+@pytest.mark.parametrize("name", sorted(k for k in CSPACE if k != "plain_cspace"))
 def test_robot_cspace_test_list_equals_the_reference_constructor(name):
     """names, order and dependencies of the feasibility tests, bounds, properties and eps of the reference's own
     RobotCSpace.__init__ run on the same worlds (tests/golden/make_reference_cspace.py)"""
@@ -262,3 +262,21 @@ def test_group_iterators_and_bb_helpers_equal_the_reference(name):
     assert [kc.bb_contains(G[0].getBB(), g.lo) for g in G] == want["bb_contains"]
     assert list(map(list, kc.bb_create())) == GROUPS["bb_create_empty"] and kc.bb_empty(kc.bb_create())
     assert list(map(list, kc.bb_union(G[0].getBB()))) == list(map(list, G[0].getBB()))      # one box: used to raise (min of a scalar)
+
+
+def test_plain_cspace_members_equal_the_reference_class():
+    """the pure-Python members of the reference's CSpace base class (plan/cspace.py:76-214) on the same calls"""
+    from klampt_b200.cspace import CSpace
+    want = CSPACE["plain_cspace"]
+    sp = CSpace()
+    sp.setBounds([(0.0, 2.0), (1.0, 1.0), (-1.0, 3.0)])
+    sp.addFeasibilityTest(lambda x: x[0] < 1.5)
+    sp.addFeasibilityTest(lambda x: x[2] > 0.0, "positive z", dependencies=["test_0"])
+    sp.addFeasibilityTest(lambda x: True, dependencies="positive z")
+    assert [list(b) for b in sp.bound] == want["bound"] and sp.properties == want["properties"] and sp.eps == want["eps"]
+    assert sp.feasibilityTestNames == want["names"] and [list(d) for d in sp.feasibilityTestDependencies] == want["dependencies"]
+    assert [sp.inBounds(p) for p in want["probes"]] == want["inBounds"]
+    assert [sp.feasible(p) for p in want["probes"]] == want["feasible"]          # named tests replace the bounds check
+    assert sp.getStats() == want["stats_before_setup"] == {}
+    sp.setup()
+    assert sp.adaptiveQueriesEnabled() and sp.getStats()["feasible_count"] == 0   # setup() enables adaptive queries for named tests
