@@ -1,8 +1,10 @@
 /*
  * kb_oracle.c -- CPU oracle (plain C, fp64) for the batched configuration-feasibility path.
  *
- * TEST INFRASTRUCTURE ONLY -- see kb_oracle.h.  PARITY UNPINNED (KrisLibrary absent; no golden
- * vectors in the reference) -- except the SO(3) arithmetic of Floating / BallAndSocket joints (z-y-x FK,
+ * TEST INFRASTRUCTURE ONLY -- see kb_oracle.h.  PARITY UNPINNED for the collision / distance arithmetic
+ * (KrisLibrary absent; no golden vectors in the reference).  Pinned by outputs of the reference's own Python
+ * code, generated here and committed under tests/golden/: forward kinematics (KinematicsBuilder of
+ * Python/klampt/math/autodiff/kinematics_ad.py:407-457, tests/golden/make_reference_fk.py), the SO(3) arithmetic of Floating / BallAndSocket joints (z-y-x FK,
  * geodesic interpolation, angle metric), which tests/test_reference_golden.py checks against outputs of
  * the reference's own Python/klampt/math/so3.py (tests/golden/make_reference_so3.py), and the default pair
  * mask, which is checked against the reference's own WorldCollider (tests/golden/make_reference_mask.py).

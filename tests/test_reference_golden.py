@@ -280,3 +280,40 @@ def test_plain_cspace_members_equal_the_reference_class():
     assert sp.getStats() == want["stats_before_setup"] == {}
     sp.setup()
     assert sp.adaptiveQueriesEnabled() and sp.getStats()["feasible_count"] == 0   # setup() enables adaptive queries for named tests
+
+
+# ------------------------------------------------------------------------------------------------ forward kinematics
+FK = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_fk.npz"))
+
+
+def _fk_robots():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_reference_fk", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_reference_fk.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.robots()
+
+
+@pytest.mark.parametrize("name", ["arm6", "dualarm15", "floating", "planar5R"])
+def test_oracle_fk_equals_the_reference_kinematics_builder(name):
+    """every link's world transform from the reference's own FK code (math/autodiff/kinematics_ad.py:407-457, run by
+    tests/golden/make_reference_fk.py) against the oracle's recurrence: revolute and prismatic links, branching trees, a floating base"""
+    spec = _fk_robots()[name]
+    o = OracleWorld(spec)
+    Q, want = FK[name + "_Q"], FK[name + "_T"]
+    got = o.fk_batch(Q)
+    assert got.shape == want.shape
+    np.testing.assert_allclose(got, want, rtol=0, atol=5e-15 * max(1.0, np.abs(want).max()) * spec.robot.L)
+    assert np.abs(want[1:] - want[0]).max() > 0.1                    # the configurations do move the links
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["arm6", "dualarm15", "floating", "planar5R"])
+def test_fk_kernel_equals_the_reference_kinematics_builder(name, built):
+    """the FK kernel (kb_fk_batch) against the same reference-computed transforms"""
+    from klampt_b200.engine import Engine
+    spec = _fk_robots()[name]
+    eng = Engine(spec)
+    Q, want = FK[name + "_Q"], FK[name + "_T"]
+    got = eng.fk_batch(Q)
+    np.testing.assert_allclose(got, want, rtol=0, atol=5e-15 * max(1.0, np.abs(want).max()) * spec.robot.L)
