@@ -216,24 +216,47 @@ class WorldCollider:
         return self.geomList[a][1].collides(self.geomList[b][1])
 
     def collisionTests(self, filter1=None, filter2=None, bb_reject=True) -> Iterator[Tuple[tuple, tuple]]:
-        for a, s in enumerate(self.mask):
-            for b in s:
-                if a < b:
-                    A, B = self.geomList[a], self.geomList[b]
-                    if filter1 is not None and not filter1(A[0]):
-                        continue
-                    if filter2 is not None and not filter2(B[0]):
-                        continue
-                    if bb_reject and not bb_intersect(A[1].getBB(), B[1].getBB()):
-                        continue
-                    yield A, B
+        """((object, geometry), (object, geometry)) pairs that should be tested, as the reference enumerates them (collide.py:429-499):
+        no filter -- every enabled pair once, lower geomList index first, boxes pre-rejected if `bb_reject`; filter1 only -- pairs
+        within the set filter1 accepts (no box pre-reject there: a TODO in the reference); both -- pairs between the two sets,
+        oriented (member of set 1, member of set 2).  Two deliberate differences: a body is never paired with itself (the
+        reference's mask holds (o, o) entries for rigid objects, see __init__, and its first branch lets them through), and with two
+        filters a pair is listed once (the reference lists it from both sides)."""
+        if filter1 is None:
+            bbs = [g[1].getBB() for g in self.geomList] if bb_reject else None
+            for a, s in enumerate(self.mask):
+                for b in s:
+                    if b > a and not (bb_reject and not bb_intersect(bbs[a], bbs[b])):
+                        yield self.geomList[a], self.geomList[b]
+        elif filter2 is None:
+            for a, s in enumerate(self.mask):
+                if filter1(self.geomList[a][0]):
+                    for b in s:
+                        if b > a and filter1(self.geomList[b][0]):
+                            yield self.geomList[a], self.geomList[b]
+        else:
+            for a, s in enumerate(self.mask):
+                A = self.geomList[a]
+                for b in s:
+                    if b > a:
+                        B = self.geomList[b]
+                        if filter1(A[0]) and filter2(B[0]):
+                            yield A, B
+                        elif filter1(B[0]) and filter2(A[0]):
+                            yield B, A
 
     def collisions(self, filter1=None, filter2=None):
         for A, B in self.collisionTests(filter1, filter2):
             if A[1].collides(B[1]):
                 yield A[0], B[0]
 
-    def robotSelfCollisions(self, robot=0):
+    def robotSelfCollisions(self, robot=None):
+        """colliding (RobotModelLink, RobotModelLink) pairs, the higher link first as in the reference (collide.py:531-560); robot =
+        None: every robot.  The box pre-reject is this mirror's (it cannot change the answer: getBB contains the geometry)."""
+        if robot is None:
+            for r in range(len(self.robots)):
+                yield from self.robotSelfCollisions(r)
+            return
         if isinstance(robot, RobotModel):
             robot = robot.index
         links = self.robots[robot]
@@ -241,7 +264,7 @@ class WorldCollider:
             for b in links[:i]:
                 if a >= 0 and b >= 0 and b in self.mask[a] and bb_intersect(self.geomList[a][1].getBB(), self.geomList[b][1].getBB()) \
                         and self._colliding(a, b):
-                    yield self.geomList[b][0], self.geomList[a][0]
+                    yield self.geomList[a][0], self.geomList[b][0]
 
     def robotObjectCollisions(self, robot, object=None):
         if isinstance(robot, RobotModel):
@@ -266,3 +289,24 @@ class WorldCollider:
             for a in self.robots[robot]:
                 if a >= 0 and b in self.mask[a] and bb_intersect(self.geomList[a][1].getBB(), self.geomList[b][1].getBB()) and self._colliding(a, b):
                     yield self.geomList[a][0], self.geomList[b][0]
+
+    def objectTerrainCollisions(self, object, terrain=None):
+        """colliding (RigidObjectModel, TerrainModel) pairs of one object (reference collide.py:632-664: no box pre-reject)"""
+        o = object.index if isinstance(object, RigidObjectModel) else object
+        ters = range(len(self.terrains)) if terrain is None else [terrain.index if isinstance(terrain, TerrainModel) else terrain]
+        a = self.rigidObjects[o]
+        for t in ters:
+            b = self.terrains[t]
+            if a >= 0 and b >= 0 and b in self.mask[a] and self._colliding(a, b):
+                yield self.geomList[a][0], self.geomList[b][0]
+
+    def objectObjectCollisions(self, object, object2=None):
+        """colliding (object, object2) pairs (reference collide.py:666-698).  With object2 = None the reference calls itself with the
+        same arguments and never returns (:687-689); here that case walks over all objects, which is what its comment intends."""
+        o = object.index if isinstance(object, RigidObjectModel) else object
+        others = range(len(self.rigidObjects)) if object2 is None else [object2.index if isinstance(object2, RigidObjectModel) else object2]
+        a = self.rigidObjects[o]
+        for o2 in others:
+            b = self.rigidObjects[o2]
+            if a >= 0 and b >= 0 and a in self.mask[b] and self._colliding(a, b):
+                yield self.geomList[a][0], self.geomList[b][0]

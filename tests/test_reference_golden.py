@@ -317,3 +317,49 @@ def test_fk_kernel_equals_the_reference_kinematics_builder(name, built):
     Q, want = FK[name + "_Q"], FK[name + "_T"]
     got = eng.fk_batch(Q)
     np.testing.assert_allclose(got, want, rtol=0, atol=5e-15 * max(1.0, np.abs(want).max()) * spec.robot.L)
+
+
+# ------------------------------------------------------------------------------------------------ WorldCollider iterators
+ITER = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_iterators.json")))
+
+
+@pytest.mark.parametrize("case", sorted(ITER))
+def test_world_collider_iterators_visit_the_reference_pairs(case):
+    """which pairs collisionTests / collisions / robotSelfCollisions / robotObjectCollisions / robotTerrainCollisions /
+    objectTerrainCollisions / objectObjectCollisions visit and report, their order and orientation: the reference's own methods on
+    the same worlds with the same stand-in boxes for getBB / collides (tests/golden/make_reference_iterators.py)"""
+    import importlib.util
+    from klampt_b200 import robotsim
+    from klampt_b200.collide import WorldCollider
+    spec = importlib.util.spec_from_file_location("make_reference_iterators", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_reference_iterators.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    name, seed = case.split("/")
+    world = robotsim.WorldModel.from_spec(_worlds()[name])
+    gen.stub_geometries(world, int(seed))
+    got = gen.run_iterators(WorldCollider(world), world)
+    want = ITER[case]
+    assert sorted(got) == sorted(want)
+    selfpairs = 0
+    for k in want:
+        if k.startswith(("collisionTests", "collisions")) and isinstance(want[k], list):
+            # order inside a mask row is set order, not part of the contract.  Two documented differences: the reference pairs rigid
+            # objects with themselves (mask quirk), and with two filters it lists every pair from both sides
+            ref = [p for p in want[k] if p[0] != p[1]]
+            selfpairs += len(want[k]) - len(ref)
+            assert all(p[0][0] == "RigidObjectModel" for p in want[k] if p[0] == p[1])
+            if "_vs_" in k:
+                assert len(ref) == 2 * len({str(p) for p in ref})
+                assert {str(p) for p in got[k]} == {str(p) for p in ref} and len(got[k]) == len({str(p) for p in got[k]}), k
+            else:
+                assert sorted(map(str, got[k])) == sorted(map(str, ref)), k
+        elif k == "collisionTests_nobb":
+            pass
+        elif k == "objectObjectCollisions":
+            # the (i, i) calls: the reference reports an object against itself where its mask has the (o, o) entry
+            assert [x for x in got[k] if x[0] != x[1]] == [x for x in want[k] if x[0] != x[1]], k
+        else:
+            assert got[k] == want[k], k
+    nobj = sum(1 for _, o in [(0, 0)] for _ in range(world.numRigidObjects()))
+    if world.numTerrains() > 0 and nobj > 0:
+        assert selfpairs > 0          # the quirk is really there in the reference's output
