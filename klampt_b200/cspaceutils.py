@@ -1,0 +1,86 @@
+"""Planning on a subset of the degrees of freedom: the mirror of ``klampt.plan.cspaceutils.EmbeddedCSpace`` (reference
+Python/klampt/plan/cspaceutils.py:108-203) -- the Python-side counterpart of ``SingleRobotCSpace::FixDof`` -- with the
+two batch entry points the batched planners (klampt_b200.plan.MotionPlan) call.
+
+An embedded configuration holds the values of the DOFs in ``mapping``; ``lift`` writes them into a copy of the ambient configuration
+``xinit`` (all other DOFs stay there), ``project`` reads them back.  Every query is answered by the ambient space on the lifted
+configurations, so ``feasible_batch`` / ``visible_batch`` on a ``RobotCSpace`` ambient space are still one launch per batch.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from .cspace import CSpace
+
+
+class EmbeddedCSpace(CSpace):
+    def __init__(self, ambientspace: CSpace, subset: Sequence[int], xinit: Optional[Sequence[float]] = None):
+        CSpace.__init__(self)
+        self.ambientspace = ambientspace
+        n = len(ambientspace.bound)
+        self.mapping = list(subset)
+        self.xinit = [0.0] * n if xinit is None else list(xinit)           # the zero configuration unless told otherwise
+        if len(self.xinit) != n:
+            raise ValueError("Invalid length of ambient space vector: %d should be %d" % (len(self.xinit), n))
+        self.eps = ambientspace.eps
+        self.bound = [ambientspace.bound[i] for i in self.mapping]
+        self.properties = ambientspace.properties                          # shared with the ambient space, as in the reference
+        if ambientspace.feasibilityTests is not None:
+            self.feasibilityTests = [(lambda x, f=f: f(self.lift(x))) for f in ambientspace.feasibilityTests]
+            self.feasibilityTestNames = list(ambientspace.feasibilityTestNames)
+            self.feasibilityTestDependencies = list(ambientspace.feasibilityTestDependencies)
+        if hasattr(ambientspace, "visible"):
+            self.visible = lambda a, b: ambientspace.visible(self.lift(a), self.lift(b))
+
+    # ------------------------------------------------------------------ embedding
+    def project(self, xamb) -> List[float]:
+        if len(xamb) != len(self.xinit):
+            raise ValueError("Invalid length of ambient space vector: %d should be %d" % (len(xamb), len(self.xinit)))
+        return [xamb[i] for i in self.mapping]
+
+    def lift(self, xemb) -> List[float]:
+        if len(xemb) != len(self.mapping):
+            raise ValueError("Invalid length of embedded space vector: %d should be %d" % (len(xemb), len(self.mapping)))
+        xamb = list(self.xinit)
+        for i, j in enumerate(self.mapping):
+            xamb[j] = xemb[i]
+        return xamb
+
+    def liftPath(self, path):
+        return [self.lift(q) for q in path]
+
+    def projectPath(self, path_amb):
+        return [self.project(q) for q in path_amb]
+
+    def lift_batch(self, X) -> np.ndarray:
+        X = np.asarray(X, dtype=np.float64).reshape(-1, len(self.mapping))
+        out = np.tile(np.asarray(self.xinit, dtype=np.float64), (len(X), 1))
+        out[:, self.mapping] = X
+        return out
+
+    def project_batch(self, Xamb) -> np.ndarray:
+        return np.ascontiguousarray(np.asarray(Xamb, dtype=np.float64).reshape(-1, len(self.xinit))[:, self.mapping])
+
+    # ------------------------------------------------------------------ queries, answered by the ambient space
+    def feasible(self, x) -> bool:
+        return self.ambientspace.feasible(self.lift(x))
+
+    def sample(self):
+        return self.project(self.ambientspace.sample())
+
+    def sampleneighborhood(self, c, r):
+        return self.project(self.ambientspace.sampleneighborhood(self.lift(c), r))
+
+    def distance(self, a, b) -> float:
+        return self.ambientspace.distance(self.lift(a), self.lift(b))
+
+    def interpolate(self, a, b, u):
+        return self.project(self.ambientspace.interpolate(self.lift(a), self.lift(b), u))
+
+    def feasible_batch(self, X, **kw):
+        return self.ambientspace.feasible_batch(self.lift_batch(X), **kw)
+
+    def visible_batch(self, A, B, **kw):
+        return self.ambientspace.visible_batch(self.lift_batch(A), self.lift_batch(B), **kw)

@@ -68,6 +68,20 @@ def main():
                            "names": list(base.feasibilityTestNames), "dependencies": [list(d) for d in base.feasibilityTestDependencies],
                            "probes": probes, "inBounds": [bool(base.inBounds(p)) for p in probes], "feasible": [bool(base.feasible(p)) for p in probes],
                            "stats_before_setup": base.getStats()}
+    # EmbeddedCSpace (plan/cspaceutils.py:108-203) over that plain space: DOFs 2 and 0 move, DOF 1 stays at xinit
+    utils = importlib.import_module("klampt.plan.cspaceutils")
+    base.distance = lambda a, b: sum(abs(p - q) for p, q in zip(a, b))                    # optional methods: a weighted-free L1 metric here
+    base.interpolate = lambda a, b, u: [p + u * (q - p) for p, q in zip(a, b)]
+    emb = utils.EmbeddedCSpace(base, [2, 0], xinit=[0.25, 1.0, 0.5])
+    eprobes = [[1.0, 0.5], [-0.5, 0.5], [1.0, 1.7], [3.0, 2.0]]
+    out["embedded_cspace"] = {"bound": [list(b) for b in emb.bound], "eps": emb.eps, "names": list(emb.feasibilityTestNames),
+                              "dependencies": [list(d) for d in emb.feasibilityTestDependencies], "probes": eprobes,
+                              "lift": [emb.lift(p) for p in eprobes], "project": emb.project([9.0, 8.0, 7.0]),
+                              "feasible": [bool(emb.feasible(p)) for p in eprobes],
+                              "tests": [[bool(f(p)) for f in emb.feasibilityTests] for p in eprobes],
+                              "distance": emb.distance(eprobes[0], eprobes[2]), "interpolate": emb.interpolate(eprobes[0], eprobes[2], 0.25),
+                              "liftPath": emb.liftPath(eprobes[:2]), "projectPath": emb.projectPath([[1.0, 2.0, 3.0], [4.0, 5.0, 6.0]]),
+                              "default_xinit_lift": utils.EmbeddedCSpace(base, [1]).lift([0.75])}
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_cspace.json")
     json.dump(out, open(path, "w"), indent=1, sort_keys=True)
     print("wrote", path)

@@ -184,7 +184,7 @@ def _host_only_space(world, with_collider):
     return sp
 
 
-@pytest.mark.parametrize("name", sorted(k for k in CSPACE if k != "plain_cspace"))
+@pytest.mark.parametrize("name", sorted(k for k in CSPACE if not k.endswith("_cspace")))
 def test_robot_cspace_test_list_equals_the_reference_constructor(name):
     """names, order and dependencies of the feasibility tests, bounds, properties and eps of the reference's own
     RobotCSpace.__init__ run on the same worlds (tests/golden/make_reference_cspace.py)"""
@@ -363,3 +363,75 @@ def test_world_collider_iterators_visit_the_reference_pairs(case):
     nobj = sum(1 for _, o in [(0, 0)] for _ in range(world.numRigidObjects()))
     if world.numTerrains() > 0 and nobj > 0:
         assert selfpairs > 0          # the quirk is really there in the reference's output
+
+
+def test_embedded_cspace_equals_the_reference_class():
+    """klampt_b200.cspaceutils.EmbeddedCSpace against the reference's own class on the same ambient space (plan/cspaceutils.py:108-203),
+    plus the batch forms the batched planners use"""
+    from klampt_b200.cspace import CSpace
+    from klampt_b200.cspaceutils import EmbeddedCSpace
+    want = CSPACE["embedded_cspace"]
+    base = CSpace()
+    base.setBounds([(0.0, 2.0), (1.0, 1.0), (-1.0, 3.0)])
+    base.addFeasibilityTest(lambda x: x[0] < 1.5)
+    base.addFeasibilityTest(lambda x: x[2] > 0.0, "positive z", dependencies=["test_0"])
+    base.addFeasibilityTest(lambda x: True, dependencies="positive z")
+    base.distance = lambda a, b: sum(abs(p - q) for p, q in zip(a, b))
+    base.interpolate = lambda a, b, u: [p + u * (q - p) for p, q in zip(a, b)]
+    emb = EmbeddedCSpace(base, [2, 0], xinit=[0.25, 1.0, 0.5])
+    P = want["probes"]
+    assert [list(b) for b in emb.bound] == want["bound"] and emb.eps == want["eps"]
+    assert emb.feasibilityTestNames == want["names"] and [list(d) for d in emb.feasibilityTestDependencies] == want["dependencies"]
+    assert [emb.lift(p) for p in P] == want["lift"] and emb.project([9.0, 8.0, 7.0]) == want["project"]
+    assert [emb.feasible(p) for p in P] == want["feasible"]
+    assert [[bool(f(p)) for f in emb.feasibilityTests] for p in P] == want["tests"]
+    assert emb.distance(P[0], P[2]) == want["distance"] and emb.interpolate(P[0], P[2], 0.25) == want["interpolate"]
+    assert emb.liftPath(P[:2]) == want["liftPath"] and emb.projectPath([[1.0, 2.0, 3.0], [4.0, 5.0, 6.0]]) == want["projectPath"]
+    assert EmbeddedCSpace(base, [1]).lift([0.75]) == want["default_xinit_lift"]
+    with pytest.raises(ValueError, match="Invalid length of embedded space vector"):
+        emb.lift([1.0])
+    with pytest.raises(ValueError, match="Invalid length of ambient space vector"):
+        emb.project([1.0])
+    np.testing.assert_array_equal(emb.lift_batch(P), np.array(want["lift"]))
+    np.testing.assert_array_equal(emb.project_batch(want["lift"]), np.array(P))
+
+
+def test_batched_planner_on_an_embedded_space():
+    """MotionPlan over EmbeddedCSpace: a 3-D ambient space whose middle DOF is fixed; the batch calls reach the ambient space lifted"""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_plan_cpu import DiskSpace
+    from klampt_b200.cspaceutils import EmbeddedCSpace
+    from klampt_b200.plan import MotionPlan
+
+    class Slab(DiskSpace):                      # the disk world in dims (0, 2); dim 1 must stay at 0.3
+        def __init__(self):
+            DiskSpace.__init__(self)
+            self.bound = [(0.0, 1.0), (0.0, 1.0), (0.0, 1.0)]
+            self.feasibilityTests, self.properties = None, {}
+            self.seen = []
+        def feasible_batch(self, Q):
+            Q = np.atleast_2d(Q)
+            self.seen.append(Q[:, 1].copy())
+            return (DiskSpace.feasible_batch(self, Q[:, [0, 2]]).astype(bool) & (Q[:, 1] == 0.3)).astype(np.uint8)
+        def visible_batch(self, A, B):
+            out = np.ones(len(A), dtype=np.uint8)
+            for u in np.linspace(0, 1, 101)[1:-1]:
+                out &= self.feasible_batch(A * (1 - u) + B * u)
+            return out
+
+    amb = Slab()
+    emb = EmbeddedCSpace(amb, [0, 2], xinit=[0.0, 0.3, 0.0])
+    MotionPlan.setOptions(knn=8, batch=200, seed=3)
+    plan = MotionPlan(emb, "prm")
+    plan.setEndpoints([0.05, 0.5], [0.95, 0.5])
+    path = None
+    for _ in range(10):
+        plan.planMore(1)
+        path = plan.getPath()
+        if path:
+            break
+    assert path is not None and len(path[0]) == 2
+    amb_path = np.array(emb.liftPath(path))
+    assert (amb_path[:, 1] == 0.3).all() and amb.visible_batch(amb_path[:-1], amb_path[1:]).all()
+    assert all((s == 0.3).all() for s in amb.seen)
