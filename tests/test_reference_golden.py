@@ -413,7 +413,7 @@ def test_batched_planner_on_an_embedded_space():
         def feasible_batch(self, Q):
             Q = np.atleast_2d(Q)
             self.seen.append(Q[:, 1].copy())
-            return (DiskSpace.feasible_batch(self, Q[:, [0, 2]]).astype(bool) & (Q[:, 1] == 0.3)).astype(np.uint8)
+            return (DiskSpace.feasible_batch(self, Q[:, [0, 2]]).astype(bool) & (np.abs(Q[:, 1] - 0.3) < 1e-12)).astype(np.uint8)
         def visible_batch(self, A, B):
             out = np.ones(len(A), dtype=np.uint8)
             for u in np.linspace(0, 1, 101)[1:-1]:
@@ -434,4 +434,4 @@ def test_batched_planner_on_an_embedded_space():
     assert path is not None and len(path[0]) == 2
     amb_path = np.array(emb.liftPath(path))
     assert (amb_path[:, 1] == 0.3).all() and amb.visible_batch(amb_path[:-1], amb_path[1:]).all()
-    assert all((s == 0.3).all() for s in amb.seen)
+    assert all((np.abs(s - 0.3) < 1e-12).all() for s in amb.seen)          # the fixed DOF never left its value
