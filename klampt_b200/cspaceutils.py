@@ -84,3 +84,44 @@ class EmbeddedCSpace(CSpace):
 
     def visible_batch(self, A, B, **kw):
         return self.ambientspace.visible_batch(self.lift_batch(A), self.lift_batch(B), **kw)
+
+
+class EmbeddedMotionPlan:
+    """MotionPlan over an EmbeddedCSpace that speaks ambient configurations (reference plan/cspaceutils.py:491-561): endpoints and
+    milestones are projected on the way in, paths and roadmap vertices lifted on the way out."""
+
+    def __init__(self, space, q0=None, type: Optional[str] = None, **options):
+        from .plan import MotionPlan
+        if not hasattr(space, "project") or not hasattr(space, "lift"):
+            raise ValueError("space argument must have the project and lift methods")
+        self.space = space
+        self.plan = MotionPlan(space, type, **options)
+
+    def setEndpoints(self, start, goal):
+        self.plan.setEndpoints(self.space.project(start), self.space.project(goal))
+
+    def addMilestone(self, x) -> int:
+        return self.plan.addMilestone(self.space.project(x))
+
+    def planMore(self, iterations: int):
+        self.plan.planMore(iterations)
+
+    def getPath(self, milestone1=None, milestone2=None):
+        p = self.plan.getPath(milestone1, milestone2)
+        return None if p is None else [self.space.lift(q) for q in p]
+
+    def getSolutionPath(self):
+        return self.getPath()
+
+    def getRoadmap(self):
+        V, E = self.plan.getRoadmap()
+        return [self.space.lift(v) for v in V], E
+
+    def pathCost(self, p) -> float:
+        return self.plan.pathCost([self.space.project(x) for x in p])
+
+    def getStats(self) -> dict:
+        return self.plan.getStats()
+
+    def close(self):
+        self.plan.close()

@@ -42,30 +42,65 @@ class RobotCSpace(CSpace):
             spec.robot = robot.to_spec(spec)
         self.spec = spec
         self.engine = Engine(spec, device=device)
+        self._extra: List = []                           # user constraints (addConstraint): host callables, one configuration at a time
         # the named tests of the reference, each answered by the engine for one configuration
         self.addFeasibilityTest(lambda x: self.inJointLimits(x), "joint limits")
         self.addFeasibilityTest(lambda x: bool(self.engine.feasible_batch(np.asarray(x, dtype=np.float64))[0]), "collision free")
 
     # ------------------------------------------------------------------ batch entry points
     def feasible_batch(self, Q, return_pairs: bool = False):
-        return self.engine.feasible_batch(Q, return_pairs=return_pairs)
+        """SingleRobotCSpace::IsFeasible per row.  Constraints added with addConstraint are host callables: they run only on the rows
+        the engine found feasible (a row they reject keeps first pair (-1, -1))"""
+        res = self.engine.feasible_batch(Q, return_pairs=return_pairs)
+        if not self._extra:
+            return res
+        ok = res[0] if return_pairs else res
+        Q2 = np.asarray(Q, dtype=np.float64).reshape(len(ok), -1)
+        for i in np.nonzero(ok)[0]:
+            if not self._extra_ok(Q2[i]):
+                ok[i] = 0
+        return res
+
+    def _extra_ok(self, q) -> bool:
+        x = list(map(float, q))
+        return all(c(x) for c in self._extra)
 
     def visible_batch(self, A, B, eps: Optional[float] = None, return_nchecks: bool = False):
-        return self.engine.edges_visible_batch(A, B, eps=self.eps if eps is None else eps, return_nchecks=return_nchecks)
+        """EpsilonEdgeChecker(a, b, eps).IsVisible per row.  With user constraints, the edges the engine found visible are walked
+        again on the host at the same resolution for those constraints alone (bisection order, robot.interpolate)"""
+        eps = self.eps if eps is None else eps
+        res = self.engine.edges_visible_batch(A, B, eps=eps, return_nchecks=return_nchecks)
+        if not self._extra:
+            return res
+        vis = res[0] if return_nchecks else res
+        A2, B2 = np.asarray(A, dtype=np.float64).reshape(len(vis), -1), np.asarray(B, dtype=np.float64).reshape(len(vis), -1)
+        for i in np.nonzero(vis)[0]:
+            a, b = list(A2[i]), list(B2[i])
+            length, segs = self.distance(a, b), 1
+            while length > eps and vis[i]:
+                segs *= 2
+                length *= 0.5
+                for k in range(1, segs, 2):
+                    if not self._extra_ok(self.interpolate(a, b, float(k) / segs)):
+                        vis[i] = 0
+                        break
+        return res
 
     def distance_batch(self, Q, upper_bound: float = float("inf"), include_self: bool = False):
         return self.engine.distance_batch(Q, upper_bound=upper_bound, include_self=include_self)
 
     # ------------------------------------------------------------------ single-configuration face
     def feasible(self, x) -> bool:
-        return bool(self.engine.feasible_batch(np.asarray(x, dtype=np.float64))[0])
+        return bool(self.feasible_batch(np.asarray(x, dtype=np.float64).reshape(1, -1))[0])
 
     def visible(self, a, b) -> bool:
-        return bool(self.engine.edges_visible_batch(np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64), eps=self.eps,
-                                                    return_nchecks=False)[0])
+        return bool(self.visible_batch(np.asarray(a, dtype=np.float64).reshape(1, -1), np.asarray(b, dtype=np.float64).reshape(1, -1))[0])
 
     def addConstraint(self, checker, name=None):
+        """an extra feasibility predicate f(q) -> bool (reference robotcspace.py:77-78); honoured by feasible / feasible_batch /
+        visible / visible_batch and listed among the named tests"""
         self.addFeasibilityTest(checker, name)
+        self._extra.append(checker)
 
     def sample(self):
         res = CSpace.sample(self)

@@ -57,6 +57,16 @@ def main():
                 "in_limits": [bool(space.inJointLimits([b[0] for b in space.bound])), bool(space.inJointLimits([b[1] + 1e-9 for b in space.bound]))],
             }
             print(name, with_collider, len(space.feasibilityTestNames), "tests")
+    # EmbeddedRobotCSpace.disableInactiveCollisions (plan/robotcspace.py:365-392) on the arm: which mask rows it rewrites
+    from make_reference_mask import mask_rows
+    for subset in ([1, 2], [4, 5, 6], [6], [0, 3]):
+        world = mirror.WorldModel.from_spec(worlds()["c1"])
+        robot = world.robot(0)
+        robot._q = __import__("numpy").zeros(robot.numLinks())
+        col = collide.WorldCollider(world)
+        sp = ref.EmbeddedRobotCSpace(ref.RobotCSpace(robot, col), subset, xinit=None)
+        sp.disableInactiveCollisions()
+        out["inactive_" + "_".join(map(str, subset))] = {"mask": mask_rows(col, mirror).tolist(), "xinit": list(map(float, sp.xinit)), "bound": [list(b) for b in sp.bound]}
     # the plain CSpace base class (plan/cspace.py:76-214), members that do not need the compiled CSpaceInterface
     base = importlib.import_module("klampt.plan.cspace").CSpace()
     base.setBounds([(0.0, 2.0), (1.0, 1.0), (-1.0, 3.0)])

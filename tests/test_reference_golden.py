@@ -184,7 +184,7 @@ def _host_only_space(world, with_collider):
     return sp
 
 
-@pytest.mark.parametrize("name", sorted(k for k in CSPACE if not k.endswith("_cspace")))
+@pytest.mark.parametrize("name", sorted(k for k in CSPACE if not k.endswith("_cspace") and not k.startswith("inactive_")))
 def test_robot_cspace_test_list_equals_the_reference_constructor(name):
     """names, order and dependencies of the feasibility tests, bounds, properties and eps of the reference's own
     RobotCSpace.__init__ run on the same worlds (tests/golden/make_reference_cspace.py)"""
@@ -435,3 +435,103 @@ def test_batched_planner_on_an_embedded_space():
     amb_path = np.array(emb.liftPath(path))
     assert (amb_path[:, 1] == 0.3).all() and amb.visible_batch(amb_path[:-1], amb_path[1:]).all()
     assert all((np.abs(s - 0.3) < 1e-12).all() for s in amb.seen)          # the fixed DOF never left its value
+
+
+@pytest.mark.parametrize("key", sorted(k for k in CSPACE if k.startswith("inactive_")))
+def test_disable_inactive_collisions_equals_the_reference(key):
+    """robotplanning.disable_inactive_collisions against EmbeddedRobotCSpace.disableInactiveCollisions of the reference
+    (plan/robotcspace.py:365-392) on the arm, for four moving subsets -- including its root-link lookup quirk"""
+    from klampt_b200 import robotsim
+    from klampt_b200.collide import WorldCollider
+    from klampt_b200.robotplanning import disable_inactive_collisions
+    subset = [int(x) for x in key.split("_")[1:]]
+    world = robotsim.WorldModel.from_spec(_worlds()["c1"])
+    col = WorldCollider(world)
+    before = len(_rows(col))
+    disable_inactive_collisions(col, world.robot(0), subset)
+    assert _rows(col).tolist() == CSPACE[key]["mask"]
+    # moving the base link moves everything; and through the reference's active[-1] lookup so does moving the LAST link
+    assert (len(_rows(col)) < before) == (0 not in subset and 6 not in subset)
+
+
+class _FakeEngine:
+    """stands in for the CUDA engine in host-logic tests: feasible iff q[0] < 1; an edge is visible iff both ends are feasible"""
+    def feasible_batch(self, Q, return_pairs=False):
+        Q = np.asarray(Q, dtype=np.float64).reshape(-1, 2)
+        ok = (Q[:, 0] < 1.0).astype(np.uint8)
+        return (ok, np.full((len(ok), 2), -1, dtype=np.int32)) if return_pairs else ok
+
+    def edges_visible_batch(self, A, B, eps=0.01, return_nchecks=False):
+        A, B = np.asarray(A, dtype=np.float64).reshape(-1, 2), np.asarray(B, dtype=np.float64).reshape(-1, 2)
+        vis = ((A[:, 0] < 1.0) & (B[:, 0] < 1.0)).astype(np.uint8)
+        return (vis, np.zeros(len(vis), dtype=np.int32)) if return_nchecks else vis
+
+
+def test_user_constraints_reach_the_batch_calls():
+    """RobotCSpace.addConstraint: the extra predicate is applied to the rows the engine passes, and walked along the edges the engine
+    found visible, at the space's resolution"""
+    from klampt_b200.cspace import CSpace
+    from klampt_b200.robotcspace import RobotCSpace
+    sp = RobotCSpace.__new__(RobotCSpace)
+    CSpace.__init__(sp)
+    sp.setBounds([(0.0, 2.0), (0.0, 2.0)])
+    sp.engine, sp._extra, sp.eps = _FakeEngine(), [], 0.05
+    sp.distance = lambda a, b: float(np.linalg.norm(np.asarray(a) - np.asarray(b)))
+    sp.interpolate = lambda a, b, u: [p + u * (q - p) for p, q in zip(a, b)]
+    Q = np.array([[0.5, 0.5], [0.5, 1.5], [1.5, 0.5]])
+    assert list(sp.feasible_batch(Q)) == [1, 1, 0]
+    calls = []
+    sp.addConstraint(lambda q: calls.append(tuple(q)) or not (0.9 < q[1] < 1.1), "no band")
+    assert list(sp.feasible_batch(Q)) == [1, 1, 0] and len(calls) == 2            # the infeasible row never reaches the callable
+    assert list(sp.feasible_batch(np.array([[0.5, 1.0]]))) == [0] and not sp.feasible([0.5, 1.0]) and sp.feasible([0.5, 0.2])
+    A = np.array([[0.2, 0.2], [0.2, 0.2], [0.2, 0.2]])
+    B = np.array([[0.8, 0.8], [0.8, 1.8], [1.8, 0.2]])
+    vis, n = sp.visible_batch(A, B, return_nchecks=True)
+    assert list(vis) == [1, 0, 0]                                                  # the second edge crosses the band, the third leaves the engine's set
+    assert sp.visible([0.2, 1.2], [0.8, 1.8]) and not sp.visible([0.2, 0.2], [0.2, 1.8])
+    assert "no band" in sp.feasibilityTestNames
+
+
+def test_plan_to_config_host_logic(monkeypatch):
+    """robotplanning.plan_to_config: 'auto' moving subset, the fixed-DOF error, the embedded plan speaking ambient configurations"""
+    from klampt_b200 import robotplanning, robotsim
+    from klampt_b200.cspace import CSpace
+    import klampt_b200.robotcspace as rcs
+
+    class HostSpace(CSpace):                       # RobotCSpace without the engine: everything is feasible inside the limits
+        def __init__(self, robot, collider=None, device=0):
+            CSpace.__init__(self)
+            self.robot, self.collider = robot, collider
+            self.setBounds(list(zip(*robot.getJointLimits())))
+        def addConstraint(self, c, name=None):
+            self.addFeasibilityTest(c, name)
+        def feasible_batch(self, Q):
+            Q = np.asarray(Q, dtype=np.float64).reshape(-1, len(self.bound))
+            lo, hi = np.array(self.bound).T
+            return ((Q >= lo) & (Q <= hi)).all(axis=1).astype(np.uint8)
+        def visible_batch(self, A, B):
+            return self.feasible_batch(A) & self.feasible_batch(B)
+    monkeypatch.setattr(rcs, "RobotCSpace", HostSpace)
+    world = robotsim.WorldModel.from_spec(_worlds()["c1"])
+    robot = world.robot(0)
+    q0 = np.zeros(robot.numLinks()); robot._q = q0.copy()
+    target = list(q0); target[2] = 0.7; target[4] = -0.4
+    plan = robotplanning.plan_to_config(world, robot, target, type="prm", batch=64, knn=6, seed=1)
+    assert plan.space.mapping == [2, 4] and plan.space.eps == 1e-2 and plan.space.xinit == list(q0)
+    path = None
+    for _ in range(5):
+        plan.planMore(1)
+        path = plan.getPath()
+        if path:
+            break
+    assert path is not None and path[0] == list(q0) and path[-1] == target and all(len(q) == robot.numLinks() for q in path)
+    assert all(q[k] == 0.0 for q in path for k in range(robot.numLinks()) if k not in (2, 4))
+    with pytest.raises(ValueError, match="fixed DOF"):
+        robotplanning.plan_to_config(world, robot, target, movingSubset=[2])
+    full = robotplanning.plan_to_config(world, robot, target, movingSubset="all", type="prm")
+    assert not hasattr(full.space, "lift") and len(full.space.bound) == robot.numLinks()
+    bad = list(q0); bad[1] = 100.0
+    with pytest.warns(UserWarning, match="Goal configuration fails"):
+        assert robotplanning.plan_to_config(world, robot, bad, type="prm") is None
+    with pytest.raises(NotImplementedError):
+        robotplanning.make_space(world, robot, equalityConstraints=[object()])
