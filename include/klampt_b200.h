@@ -80,14 +80,17 @@ const char* kb_version(void);
 int kb_add_trimesh(kb_engine* e, const double* verts, int nv, const int32_t* tris, int nt, double margin);
 /* replaces Geometry3D.setPointCloud; radius may be NULL (all zero) */
 int kb_add_pointcloud(kb_engine* e, const double* pts, int n, const double* radius, double margin);
-/* replaces Geometry3D.setGeometricPrimitive; params: point x,y,z / sphere cx,cy,cz,r */
+/* replaces Geometry3D.setGeometricPrimitive; params: point x,y,z / sphere cx,cy,cz,r / segment, triangle, box, aabb: see KB_PRIM_* */
 int kb_add_primitive(kb_engine* e, int type, const double* params, double margin);
 
 /* A point cloud whose points are replaced between batches -- sensor streams; the reference keeps such geometries as dynamic
  * geometries (Cpp/Modeling/ManagedGeometry.h:49-52) and rebuilds their collision data on the CPU after Geometry3D.setPointCloud.
  * Reserves room for `capacity` points of one `radius`; attach it with kb_add_terrain / kb_add_rigid_object (once).  It starts empty
  * and forms its own environment group.  kb_update_pointcloud (after kb_finalize) uploads n <= capacity points given in the
- * geometry's local frame and rebuilds the hierarchy on the GPU (linear BVH: Morton order, radix sort, Karras' parallel hierarchy). */
+ * geometry's local frame and rebuilds the hierarchy on the GPU (linear BVH: Morton order, radix sort, Karras' parallel hierarchy).
+ * The scene-building calls (kb_add_trimesh / _pointcloud / _primitive / _rigid_object, kb_robot_create) reject non-finite
+ * coordinates, null arrays and negative radii with KB_ERR_INVALID; kb_update_pointcloud is the per-batch path and does NOT scan its
+ * input: the caller drops invalid sensor returns (NaN / inf) before the call, as klampt_b200.io.parse_pcd does. */
 int kb_add_dynamic_pointcloud(kb_engine* e, int capacity, double radius, double margin);
 int kb_update_pointcloud(kb_engine* e, int geom, const double* pts, int n);
 
