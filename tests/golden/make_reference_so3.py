@@ -24,11 +24,11 @@ def import_reference_math():
         m.__path__ = [path]
         sys.modules[name] = m
     import importlib
-    return importlib.import_module("klampt.math.so3"), importlib.import_module("klampt.math.se3")
+    return importlib.import_module("klampt.math.so3"), importlib.import_module("klampt.math.se3"), importlib.import_module("klampt.math.so2")
 
 
 def main():
-    so3, se3 = import_reference_math()
+    so3, se3, so2 = import_reference_math()
     rng = np.random.default_rng(20261017)
     n = 96
     w = rng.normal(size=(n, 3))
@@ -52,8 +52,14 @@ def main():
     t = rng.normal(size=(n, 3))
     applied = np.array([se3.apply((list(R[a]), list(t[a])), list(x)) for a, x in zip(ia, p)])
     se3_mul = [se3.mul((list(R[a]), list(t[a])), (list(R[b]), list(t[b]))) for a, b in zip(ia, ib)]
+    # so2: the shortest-arc difference / interpolation that Spin joints and the angle of FloatingPlanar joints use
+    ang_a, ang_b, ang_u = rng.uniform(-7.0, 7.0, size=300), rng.uniform(-7.0, 7.0, size=300), rng.uniform(0, 1, size=300)
+    ang_a[:3], ang_b[:3] = [0.1, 6.2, -3.0], [6.2, 0.1, 3.0]
+    so2_diff = np.array([so2.diff(float(a), float(b)) for a, b in zip(ang_a, ang_b)])
+    so2_interp = np.array([so2.interp(float(a), float(b), float(t)) for a, b, t in zip(ang_a, ang_b, ang_u)])
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_so3.npz")
     np.savez_compressed(out, w=w, R=R, rpy=rpy, R_from_rpy=R_from_rpy, moment=moment, quat=quat, angle=ang, ia=ia, ib=ib, u=u,
+                        ang_a=ang_a, ang_b=ang_b, ang_u=ang_u, so2_diff=so2_diff, so2_interp=so2_interp,
                         interp=interp, dist=dist, mul=mul, p=p, t=t, applied=applied,
                         se3_mul_R=np.array([m[0] for m in se3_mul]), se3_mul_t=np.array([m[1] for m in se3_mul]))
     print("wrote", out, os.path.getsize(out), "bytes")

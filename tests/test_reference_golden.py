@@ -535,3 +535,27 @@ def test_plan_to_config_host_logic(monkeypatch):
         assert robotplanning.plan_to_config(world, robot, bad, type="prm") is None
     with pytest.raises(NotImplementedError):
         robotplanning.make_space(world, robot, equalityConstraints=[object()])
+
+
+def test_oracle_spin_joint_arithmetic_equals_reference_so2():
+    """Spin joints (and the angle of FloatingPlanar joints): Interpolate.cpp's AngleInterp / AngleDiff against the reference's own
+    math/so2.py interp / diff -- the oracle, and the robot-model mirror the planners' host side uses"""
+    from klampt_b200 import robotsim
+    from klampt_b200.worldspec import JOINT_SPIN, JOINT_NORMAL, WorldSpec
+    G2 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_so3.npz"))
+    w = WorldSpec()
+    r = synth.make_planar_nR(w, 2)
+    r.joint_type = np.array([JOINT_SPIN, JOINT_NORMAL], dtype=np.uint8)
+    r.qmin[:], r.qmax[:] = -10.0, 10.0
+    w.robot = r
+    o = OracleWorld(w)
+    robot = robotsim.WorldModel.from_spec(w).robot(0)
+    wrap = lambda d: math.atan2(math.sin(d), math.cos(d))
+    for a, b, u, dref, iref in zip(G2["ang_a"], G2["ang_b"], G2["ang_u"], G2["so2_diff"], G2["so2_interp"]):
+        qa, qb = np.array([a, 0.25]), np.array([b, 0.25])
+        assert abs(o.cspace_distance(qa, qb) - abs(dref)) < 1e-12                 # |so2.diff(a, b)|
+        m = o.interpolate(qa, qb, float(u))
+        if abs(abs(dref) - math.pi) > 1e-9:                                       # at exactly half a turn either way round is right
+            assert abs(wrap(m[0] - iref)) < 1e-12 and m[1] == 0.25
+            assert abs(wrap(robot.interpolate(list(qa), list(qb), float(u))[0] - iref)) < 1e-12
+        assert abs(robot.distance(list(qa), list(qb)) - abs(dref)) < 1e-12
