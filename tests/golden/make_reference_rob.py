@@ -4,9 +4,12 @@ then loads.  tests/test_reference_golden.py feeds it to klampt_b200.io.parse_rob
 
 Run in the build container (needs /root/reference):   python tests/golden/make_reference_rob.py
 """
+import importlib
 import importlib.util
 import os
+import sys
 import tempfile
+import types
 
 REF = os.environ.get("KLAMPT_REFERENCE", "/root/reference")
 
@@ -39,6 +42,25 @@ def main():
         out = os.path.join(here, "ref_planar_%dR.rob" % n)
         open(out, "w").write(w.text)
         print("wrote", out, len(w.text), "bytes")
+    # the free-floating base around a geometry file: model/create/moving_base_robot.py:12-137 (needs `klampt` names at import: stubs)
+    root = os.path.join(REF, "Python", "klampt")
+    for name, path in (("klampt", root), ("klampt.math", os.path.join(root, "math")), ("klampt.model", os.path.join(root, "model")),
+                       ("klampt.model.create", os.path.join(root, "model", "create"))):
+        m = types.ModuleType(name)
+        m.__path__ = [path]
+        sys.modules[name] = m
+    for cls in ("WorldModel", "RobotModel", "SimRobotController"):
+        setattr(sys.modules["klampt"], cls, type(cls, (), {}))
+    mb = importlib.import_module("klampt.model.create.moving_base_robot")
+    w = _StubWorld()
+    tmp = os.path.join(tempfile.mkdtemp(), "temp.rob")
+    try:
+        mb.make("cube.off", w, tempname=tmp, debug=True)
+    except _Captured:
+        pass
+    out = os.path.join(here, "ref_moving_base.rob")
+    open(out, "w").write(w.text)
+    print("wrote", out, len(w.text), "bytes")
 
 
 if __name__ == "__main__":

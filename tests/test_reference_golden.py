@@ -559,3 +559,28 @@ def test_oracle_spin_joint_arithmetic_equals_reference_so2():
             assert abs(wrap(m[0] - iref)) < 1e-12 and m[1] == 0.25
             assert abs(wrap(robot.interpolate(list(qa), list(qb), float(u))[0] - iref)) < 1e-12
         assert abs(robot.distance(list(qa), list(qb)) - abs(dref)) < 1e-12
+
+
+def test_rob_loader_reads_the_reference_moving_base_template(tmp_path):
+    """tests/golden/ref_moving_base.rob is what the reference's model/create/moving_base_robot.py:12-137 writes around a geometry
+    file (quoted link names, empty geometry strings, -inf / inf limits, continuation lines, a `property sensors <...>` line, one
+    accMax entry too many).  Loaded here, its configuration follows moving_base_robot.set_xform (:148-161): q = (t, yaw, pitch, roll)
+    places link 5 at (R, t) -- checked with rotations from the reference's so3."""
+    kio.save_off(str(tmp_path / "cube.off"), *synth.unit_cube())
+    text = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_moving_base.rob")).read()
+    world, r = kio.parse_rob(text, basedir=str(tmp_path))
+    from klampt_b200.worldspec import JOINT_NORMAL, JOINT_SPIN, PRISMATIC, REVOLUTE
+    assert r.L == 6 and list(r.parents) == [-1, 0, 1, 2, 3, 4] and r.names == ["tx", "ty", "tz", "rz", "ry", "rx"]
+    assert list(r.linktype) == [PRISMATIC] * 3 + [REVOLUTE] * 3
+    np.testing.assert_array_equal(r.axis, [[1, 0, 0], [0, 1, 0], [0, 0, 1], [0, 0, 1], [0, 1, 0], [1, 0, 0]])
+    assert list(r.joint_type) == [JOINT_NORMAL] * 3 + [JOINT_SPIN] * 3
+    assert list(r.qmin[:3]) == [-1, -1, -1] and np.isneginf(r.qmin[3:]).all() and np.isposinf(r.qmax[3:]).all()
+    assert r.link_geom[:5] == [-1] * 5 and r.link_geom[5] >= 0 and len(r.drivers) == 6
+    assert world.geoms[r.link_geom[5]].tris.shape == (12, 3)
+    o = OracleWorld(world)
+    for i in range(0, len(G["R"]), 7):
+        roll, pitch, yaw = so3.rpy(list(G["R"][i]))
+        t = np.clip(G["t"][i], -1, 1)
+        T = o.fk(np.array([t[0], t[1], t[2], yaw, pitch, roll]))
+        np.testing.assert_allclose(T[5][:9].reshape(3, 3), M(G["R"][i]), atol=1e-9)
+        np.testing.assert_allclose(T[5][9:], t, atol=1e-15)
