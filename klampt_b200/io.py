@@ -9,7 +9,8 @@ engine can be fed without a Klamp't install:
     ``links parents jointtype tparent axis qmin/qmax(deg) q translation rotation scale geometry geomscale geommargin
     noselfcollision selfcollision joint driver``.  Inline geometry strings (``"{TriangleMesh\\nOFF ...}"`` as written by
     Python/klampt/model/create/planar_robot.py:20-70) are understood.  Dynamic items (mass, inertia, torque limits,
-    servo gains ...) are parsed over and ignored.  ``mount`` and D-H parameters are not supported;
+    servo gains ...) are parsed over and ignored.  ``mount`` (geometry files and .rob / .urdf sub-chains) is supported, D-H
+    parameters are not;
   * URDF with the ``<klampt>`` element (Manual-FileTypes.md:240-274), built the way RobotModel::LoadURDF builds its links
     (Robot.cpp:2566-3300): fixed or floating base, revolute / continuous / prismatic / fixed joints, mimic joints as affine
     drivers, box / cylinder / sphere / mesh collision geometry;
@@ -249,6 +250,7 @@ def parse_rob(text: str, basedir: str = ".", world: Optional[WorldSpec] = None) 
     joints: List[Tuple[int, int, int]] = []
     drivers: List[List[str]] = []
     selfcol, noselfcol = [], []
+    mounts: List[List[str]] = []
     for line in _logical_lines(text):
         lex = shlex.shlex(line, posix=True)
         lex.whitespace_split = True
@@ -267,7 +269,9 @@ def parse_rob(text: str, basedir: str = ".", world: Optional[WorldSpec] = None) 
             selfcol += args
         elif key == "noselfcollision":
             noselfcol += args
-        elif key in ("mount", "alpha", "alphadeg", "a", "d", "theta", "thetadeg"):
+        elif key == "mount":
+            mounts.append(args)
+        elif key in ("alpha", "alphadeg", "a", "d", "theta", "thetadeg"):
             raise NotImplementedError(".rob item %r is not supported by this loader" % key)
         else:
             items[key] = args
@@ -361,8 +365,71 @@ def parse_rob(text: str, basedir: str = ".", world: Optional[WorldSpec] = None) 
             drv.append(DriverSpec(links, sc, of, rest[0] if len(rest) > 0 else -np.inf, rest[1] if len(rest) > 1 else np.inf))
     spec = RobotSpec(parents=parents, linktype=linktype, axis=axis, T0=T0, qmin=qmin, qmax=qmax, link_geom=link_geom, joint_type=jt, joint_link=jl,
                      joint_base=jb, drivers=drv, self_collision_edits=edits, names=list(names))
+    for m in mounts:
+        _mount(world, spec, m, basedir, link_index)
     world.robot = spec
     return world, spec
+
+
+def _mount(world: WorldSpec, spec: RobotSpec, args: List[str], basedir: str, link_index) -> None:
+    """``mount <link> "<file>" [R t] [as "<prefix>"]`` (Robot.cpp:648-690): a geometry file is merged into the link's geometry under the
+    transform (Robot.cpp:1213-1245, RobotModel::Mount :1860-1893); a .rob / .urdf file is appended as a sub-chain whose roots hang from
+    the link with `T * T0_Parent`, with links, joints and drivers renumbered and link names prefixed "prefix:" (:1895-2007).  Self
+    collisions between the old links and the new ones follow the default rule (all pairs but parent / child), which is what
+    InitSelfCollisionPair over all (i, j + norig) minus the mount link amounts to."""
+    if len(args) < 2:
+        raise ValueError("mount needs a link and a file")
+    link = -1 if args[0] == "-1" else link_index(args[0])
+    fn = args[1]
+    rest = args[2:]
+    T = np.array(IDENTITY12, dtype=np.float64)
+    nums = _floats(rest[:12])
+    if len(nums) == 12:
+        T, rest = np.array(nums), rest[12:]
+    prefix = rest[1] if len(rest) >= 2 and rest[0].lower() == "as" else None
+    path = fn if os.path.isabs(fn) else os.path.join(basedir, fn)
+    R, t = T[:9].reshape(3, 3), T[9:12]
+    if os.path.splitext(fn)[1].lower() not in (".rob", ".urdf"):
+        v, tr = load_mesh(path)
+        v = v @ R.T + t
+        if link < 0:
+            raise ValueError("a geometry can only be mounted on a link")
+        if spec.link_geom[link] >= 0 and world.geoms[spec.link_geom[link]].kind == "mesh":
+            g = world.geoms[spec.link_geom[link]]
+            v, tr = np.vstack([g.verts, v]), np.vstack([g.tris, tr + len(g.verts)]).astype(np.int32)
+            spec.link_geom[link] = world.add_geom(GeomSpec.mesh(v, tr, margin=g.margin))
+        else:
+            spec.link_geom[link] = world.add_geom(GeomSpec.mesh(v, tr))
+        return
+    keep = world.robot
+    _, sub = (load_urdf(path, world) if path.lower().endswith(".urdf") else load_rob(path, world))
+    world.robot = keep
+    n0 = spec.L
+    T0 = sub.T0.copy()
+    par = sub.parents.copy()
+    for i in range(sub.L):
+        if sub.parents[i] < 0:
+            Rs, ts = T0[i, :9].reshape(3, 3), T0[i, 9:12]
+            T0[i, :9], T0[i, 9:12] = (R @ Rs).reshape(-1), R @ ts + t
+            par[i] = link
+        else:
+            par[i] += n0
+    spec.parents = np.concatenate([spec.parents, par]).astype(np.int32)
+    spec.linktype = np.concatenate([spec.linktype, sub.linktype]).astype(np.uint8)
+    spec.axis, spec.T0 = np.vstack([spec.axis, sub.axis]), np.vstack([spec.T0, T0])
+    spec.qmin, spec.qmax = np.concatenate([spec.qmin, sub.qmin]), np.concatenate([spec.qmax, sub.qmax])
+    spec.link_geom = list(spec.link_geom) + list(sub.link_geom)
+    sub_names = sub.names or ["link%d" % i for i in range(sub.L)]
+    spec.names = list(spec.names or ["link%d" % i for i in range(n0)]) + [(prefix + ":" + s) if prefix else s for s in sub_names]
+    sjt = sub.joint_type if sub.joint_type is not None else np.full(sub.L, JOINT_NORMAL, dtype=np.uint8)
+    sjl = sub.joint_link if sub.joint_link is not None else np.arange(sub.L, dtype=np.int32)
+    sjb = sub.joint_base if sub.joint_base is not None else sub.parents[sjl]
+    jb0 = spec.joint_base if spec.joint_base is not None else spec.parents[:n0][spec.joint_link]
+    spec.joint_type = np.concatenate([spec.joint_type, sjt]).astype(np.uint8)
+    spec.joint_link = np.concatenate([spec.joint_link, sjl + n0]).astype(np.int32)
+    spec.joint_base = np.concatenate([jb0, np.where(np.asarray(sjb) < 0, link, np.asarray(sjb) + n0)]).astype(np.int32)
+    spec.drivers = list(spec.drivers) + [DriverSpec([k + n0 for k in d.links], list(d.scale), list(d.offset), d.qmin, d.qmax) for d in sub.drivers]
+    spec.self_collision_edits = list(spec.self_collision_edits) + [(i + n0, j + n0, en) for i, j, en in sub.self_collision_edits]
 
 
 def rob_text(spec: RobotSpec, world: WorldSpec) -> str:

@@ -61,6 +61,15 @@ def main():
     out = os.path.join(here, "ref_moving_base.rob")
     open(out, "w").write(w.text)
     print("wrote", out, len(w.text), "bytes")
+    # ... and around a robot file: the template with the `mount 5 "<file>" <T> as "<name>"` line
+    w = _StubWorld()
+    try:
+        mb.make("ref_planar_3R.rob", w, tempname=tmp, debug=True)
+    except _Captured:
+        pass
+    out = os.path.join(here, "ref_moving_base_mounted.rob")
+    open(out, "w").write(w.text)
+    print("wrote", out, len(w.text), "bytes")
 
 
 if __name__ == "__main__":

@@ -584,3 +584,34 @@ def test_rob_loader_reads_the_reference_moving_base_template(tmp_path):
         T = o.fk(np.array([t[0], t[1], t[2], yaw, pitch, roll]))
         np.testing.assert_allclose(T[5][:9].reshape(3, 3), M(G["R"][i]), atol=1e-9)
         np.testing.assert_allclose(T[5][9:], t, atol=1e-15)
+
+
+def test_rob_loader_mounts_a_robot_on_the_reference_moving_base(tmp_path):
+    """tests/golden/ref_moving_base_mounted.rob: the reference generator's template for a robot FILE -- a floating cube with
+    `mount 5 "ref_planar_3R.rob" <T> as "ref_planar_3R"` (Robot.cpp:648-690, RobotModel::Mount :1895-2007).  The mounted chain is the
+    other reference-written file, so both come from Klamp't's own generators."""
+    import shutil
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    shutil.copy(os.path.join(here, "ref_planar_3R.rob"), tmp_path / "ref_planar_3R.rob")
+    world, r = kio.parse_rob(open(os.path.join(here, "ref_moving_base_mounted.rob")).read(), basedir=str(tmp_path))
+    from klampt_b200.worldspec import JOINT_SPIN, JOINT_NORMAL
+    assert r.L == 9 and list(r.parents) == [-1, 0, 1, 2, 3, 4, 5, 6, 7]
+    assert r.names[5] == "rx" and r.names[6:] == ["ref_planar_3R:link0", "ref_planar_3R:link1", "ref_planar_3R:link2"]
+    assert list(r.joint_type) == [JOINT_NORMAL] * 3 + [JOINT_SPIN] * 6 and list(r.joint_link) == list(range(9))
+    assert r.link_geom[5] >= 0 and all(g >= 0 for g in r.link_geom[6:]) and len(r.drivers) == 6
+    assert world.robot is r and len(r.qmin) == 9 and r.T0.shape == (9, 12) and r.axis.shape == (9, 3)
+    np.testing.assert_allclose(r.T0[7, 9:], [0.5, 0, 0])
+    o = OracleWorld(world)
+    roll, pitch, yaw = so3.rpy(list(G["R"][9]))
+    t = np.array([0.3, -0.2, 0.5])
+    q = np.array([t[0], t[1], t[2], yaw, pitch, roll, 0.4, -0.3, 0.2])
+    T = o.fk(q)
+    Rb = M(G["R"][9])
+    np.testing.assert_allclose(T[5][:9].reshape(3, 3), Rb, atol=1e-9)
+    # the planar chain (axes z: see the planar test) rides on the base: link 8's origin in the base frame
+    p8 = np.array([0.5 * math.cos(0.4) + 0.5 * math.cos(0.1), 0.5 * math.sin(0.4) + 0.5 * math.sin(0.1), 0.0])
+    np.testing.assert_allclose(T[8][9:], Rb @ p8 + t, atol=1e-9)
+    # default self collisions: every old/new pair but the mount link with the chain's root (parent / child)
+    m = o.pair_mask()
+    lid = lambda j: 1 + j
+    assert not m[lid(5), lid(6)] and m[lid(5), lid(7)] and m[lid(5), lid(8)] and not m[lid(6), lid(7)] and m[lid(6), lid(8)]
