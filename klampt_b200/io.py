@@ -282,7 +282,7 @@ def parse_rob(text: str, basedir: str = ".", world: Optional[WorldSpec] = None) 
     else:
         raise ValueError(".rob file has neither a 'parents' nor a 'tparent' line")
     L = len(parents)
-    names = items.get("links", ["link%d" % i for i in range(L)])
+    names = items.get("links", ["Link_%d" % i for i in range(L)])          # the reference's default names (Robot.cpp:907-914)
 
     def per_link(key, default, width=1, scale=1.0):
         if key not in items:
@@ -419,8 +419,8 @@ def _mount(world: WorldSpec, spec: RobotSpec, args: List[str], basedir: str, lin
     spec.axis, spec.T0 = np.vstack([spec.axis, sub.axis]), np.vstack([spec.T0, T0])
     spec.qmin, spec.qmax = np.concatenate([spec.qmin, sub.qmin]), np.concatenate([spec.qmax, sub.qmax])
     spec.link_geom = list(spec.link_geom) + list(sub.link_geom)
-    sub_names = sub.names or ["link%d" % i for i in range(sub.L)]
-    spec.names = list(spec.names or ["link%d" % i for i in range(n0)]) + [(prefix + ":" + s) if prefix else s for s in sub_names]
+    sub_names = sub.names or ["Link_%d" % i for i in range(sub.L)]
+    spec.names = list(spec.names or ["Link_%d" % i for i in range(n0)]) + [(prefix + ":" + s) if prefix else s for s in sub_names]
     sjt = sub.joint_type if sub.joint_type is not None else np.full(sub.L, JOINT_NORMAL, dtype=np.uint8)
     sjl = sub.joint_link if sub.joint_link is not None else np.arange(sub.L, dtype=np.int32)
     sjb = sub.joint_base if sub.joint_base is not None else sub.parents[sjl]
@@ -435,7 +435,7 @@ def _mount(world: WorldSpec, spec: RobotSpec, args: List[str], basedir: str, lin
 def rob_text(spec: RobotSpec, world: WorldSpec) -> str:
     """Writes the kinematic / geometric subset back out with inline OFF geometry (round-trips through parse_rob)."""
     L = spec.L
-    names = spec.names or ["link%d" % i for i in range(L)]
+    names = spec.names or ["Link_%d" % i for i in range(L)]
     fmt = lambda a: " ".join("inf" if np.isposinf(x) else ("-inf" if np.isneginf(x) else "%.17g" % x) for x in np.asarray(a, dtype=np.float64).reshape(-1))
     out = ["links " + " ".join('"%s"' % n for n in names),
            "parents " + " ".join(str(int(p)) for p in spec.parents),

@@ -411,7 +411,7 @@ class RobotModel(_Named):
         self._joint_base = None if getattr(spec, "joint_base", None) is None else np.array(spec.joint_base, dtype=np.int32)
         self._drivers = list(spec.drivers)
         self._self_edits = list(spec.self_collision_edits)
-        names = spec.names or ["link%d" % i for i in range(L)]
+        names = spec.names or ["Link_%d" % i for i in range(L)]
         self._links = [RobotModelLink(self, i, names[i]) for i in range(L)]
         for i, gi in enumerate(spec.link_geom):
             if gi >= 0 and geoms is not None:

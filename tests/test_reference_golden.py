@@ -596,7 +596,7 @@ def test_rob_loader_mounts_a_robot_on_the_reference_moving_base(tmp_path):
     world, r = kio.parse_rob(open(os.path.join(here, "ref_moving_base_mounted.rob")).read(), basedir=str(tmp_path))
     from klampt_b200.worldspec import JOINT_SPIN, JOINT_NORMAL
     assert r.L == 9 and list(r.parents) == [-1, 0, 1, 2, 3, 4, 5, 6, 7]
-    assert r.names[5] == "rx" and r.names[6:] == ["ref_planar_3R:link0", "ref_planar_3R:link1", "ref_planar_3R:link2"]
+    assert r.names[5] == "rx" and r.names[6:] == ["ref_planar_3R:Link_0", "ref_planar_3R:Link_1", "ref_planar_3R:Link_2"]
     assert list(r.joint_type) == [JOINT_NORMAL] * 3 + [JOINT_SPIN] * 6 and list(r.joint_link) == list(range(9))
     assert r.link_geom[5] >= 0 and all(g >= 0 for g in r.link_geom[6:]) and len(r.drivers) == 6
     assert world.robot is r and len(r.qmin) == 9 and r.T0.shape == (9, 12) and r.axis.shape == (9, 3)
