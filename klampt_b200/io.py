@@ -14,7 +14,8 @@ engine can be fed without a Klamp't install:
   * URDF with the ``<klampt>`` element (Manual-FileTypes.md:240-274), built the way RobotModel::LoadURDF builds its links
     (Robot.cpp:2566-3300): fixed or floating base, revolute / continuous / prismatic / fixed joints, mimic joints as affine
     drivers, box / cylinder / sphere / mesh collision geometry;
-  * world files (Manual-FileTypes.md:47-162): terrains, rigid objects and the robot.
+  * world files (Manual-FileTypes.md:47-162): terrains, rigid objects and the robot;
+  * configurations and transforms: ``.config`` / ``.configs`` / ``.xform`` text as Python/klampt/io/loader.py writes it.
 
 Root links get ``rotation`` / ``translation`` pre-multiplied into ``T0_Parent`` as Robot.cpp:971-975 does.
 """
@@ -176,6 +177,64 @@ def off_text(verts, tris) -> str:
 def save_off(path: str, verts, tris):
     with open(path, "w") as f:
         f.write(off_text(verts, tris))
+
+
+# --------------------------------------------------------------------------------------- configurations / transforms
+# The reference's resource text formats (Python/klampt/io/loader.py:161-198,226-250; the same text the C++ bindings write):
+#   .config   "n<TAB>v1 v2 ... vn"        one configuration
+#   .configs  one such record after the other (any whitespace)  -> the N x L batch the engine takes
+#   .xform    "r11 r12 r13 r21 ... r33 t1 t2 t3"  row-major R then t = the 12-vector of the C ABI
+def write_config(q) -> str:
+    q = [float(v) for v in q]
+    return str(len(q)) + "\t" + " ".join(repr(v) for v in q)
+
+
+def read_config(text: str) -> np.ndarray:
+    items = text.split()
+    if len(items) == 0:
+        raise ValueError("Empty text")
+    if int(items[0]) + 1 != len(items):
+        raise ValueError("Invalid number of items")
+    return np.array([float(v) for v in items[1:]], dtype=np.float64)
+
+
+def write_configs(Q) -> str:
+    return "\n".join(write_config(q) for q in np.asarray(Q, dtype=np.float64).reshape(len(Q), -1))
+
+
+def read_configs(text: str) -> np.ndarray:
+    """all records of a .configs text as one (N, L) array; records of different lengths are an error (a batch is rectangular)"""
+    items, rows, pos = text.split(), [], 0
+    while pos < len(items):
+        n = int(items[pos])
+        if pos + 1 + n > len(items):
+            raise ValueError("Invalid number of items")
+        rows.append([float(v) for v in items[pos + 1:pos + 1 + n]])
+        pos += 1 + n
+    if rows and any(len(r) != len(rows[0]) for r in rows):
+        raise ValueError("configurations of different lengths cannot form a batch")
+    return np.array(rows, dtype=np.float64).reshape(len(rows), len(rows[0]) if rows else 0)
+
+
+def write_xform(T12) -> str:
+    T = np.asarray(T12, dtype=np.float64).reshape(12)
+    return "\t".join(" ".join(repr(float(v)) for v in T[3 * i:3 * i + 3]) for i in range(3)) + "\t" + " ".join(repr(float(v)) for v in T[9:])
+
+
+def read_xform(text: str) -> np.ndarray:
+    items = text.split()
+    if len(items) != 12:
+        raise ValueError("Invalid element of SE3, must have 12 elements")
+    return np.array([float(v) for v in items], dtype=np.float64)
+
+
+def load_configs(path: str) -> np.ndarray:
+    return read_configs(open(path).read())
+
+
+def save_configs(path: str, Q) -> None:
+    with open(path, "w") as f:
+        f.write(write_configs(Q) + "\n")
 
 
 # --------------------------------------------------------------------------------------- .rob

@@ -615,3 +615,25 @@ def test_rob_loader_mounts_a_robot_on_the_reference_moving_base(tmp_path):
     m = o.pair_mask()
     lid = lambda j: 1 + j
     assert not m[lid(5), lid(6)] and m[lid(5), lid(7)] and m[lid(5), lid(8)] and not m[lid(6), lid(7)] and m[lid(6), lid(8)]
+
+
+def test_config_and_xform_text_formats_equal_the_reference_loader(tmp_path):
+    """.config / .configs / .xform text as the reference's io/loader.py writes and reads it (tests/golden/make_reference_loader.py)"""
+    L = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_loader.json")))
+    Q = np.array(L["Q"])
+    assert kio.write_config(Q[0]) == L["config_text"] and kio.write_configs(Q) == L["configs_text"]
+    np.testing.assert_array_equal(kio.read_configs(L["configs_text"]), Q)
+    np.testing.assert_array_equal(kio.read_configs(L["configs_text"]), np.array(L["read_back_configs"]))
+    np.testing.assert_array_equal(kio.read_config(L["config_text"]), Q[0])
+    T12 = so3.to_rowmajor12(L["R"], L["t"])
+    assert kio.write_xform(T12) == L["xform_text"]
+    np.testing.assert_array_equal(kio.read_xform(L["xform_text"]), T12)
+    R2, t2 = so3.from_rowmajor12(kio.read_xform(L["xform_text"]))
+    np.testing.assert_allclose(R2, L["read_back_xform"][0], atol=0); np.testing.assert_allclose(t2, L["read_back_xform"][1], atol=0)
+    kio.save_configs(str(tmp_path / "batch.configs"), Q)
+    np.testing.assert_array_equal(kio.load_configs(str(tmp_path / "batch.configs")), Q)
+    with pytest.raises(ValueError, match="Invalid number of items"):
+        kio.read_config("3\t1.0 2.0")
+    with pytest.raises(ValueError, match="different lengths"):
+        kio.read_configs("2 1 2\n3 1 2 3")
+    assert kio.read_configs("").shape == (0, 0)
