@@ -3,14 +3,15 @@ Python/klampt/plan/robotplanning.py:23-265): ``make_space`` builds the robot's C
 extra constraints, edge resolution, optional moving subset) and ``plan_to_config`` sets up a planner from the robot's current
 configuration to a target -- here a batched planner (klampt_b200.plan.MotionPlan) over the GPU engine.
 
-Not mirrored: equality constraints (closed-loop / IK spaces) and the affine-driver embedding; both raise NotImplementedError.
+Robots with affine drivers get the driver-space embedding (AffineEmbeddedCSpace), as in the reference.  Not mirrored: equality
+constraints (closed-loop / IK spaces), which raise NotImplementedError.
 """
 from __future__ import annotations
 
 from typing import Callable, List, Optional, Sequence, Union
 
 from . import collide
-from .cspaceutils import EmbeddedCSpace, EmbeddedMotionPlan
+from .cspaceutils import AffineEmbeddedCSpace, EmbeddedCSpace, EmbeddedMotionPlan
 from .plan import MotionPlan
 
 
@@ -55,6 +56,15 @@ def make_space(world, robot, edgeCheckResolution: float = 1e-2, extraConstraints
     space.eps = edgeCheckResolution
     for c in extraConstraints:
         space.addConstraint(c)
+    # robots with affine drivers (coupled links: mimic joints, grippers) are planned in driver space (reference :94-142)
+    drivers = list(getattr(getattr(getattr(space, "spec", None), "robot", None), "drivers", []) or [])
+    moving = set(range(robot.numLinks()) if subset is None else subset)
+    if any(len(d.links) > 1 and moving.intersection(d.links) for d in drivers):
+        active = [k for k, d in enumerate(drivers) if moving.intersection(d.links)]
+        aff = AffineEmbeddedCSpace.from_drivers(space, drivers, robot.numLinks(), active)
+        aff.robot = robot
+        aff.setup()
+        return aff
     if embedded:
         space = EmbeddedCSpace(space, subset, xinit=robot.getConfig())
         space.robot = robot

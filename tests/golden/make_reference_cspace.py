@@ -92,6 +92,20 @@ def main():
                               "distance": emb.distance(eprobes[0], eprobes[2]), "interpolate": emb.interpolate(eprobes[0], eprobes[2], 0.25),
                               "liftPath": emb.liftPath(eprobes[:2]), "projectPath": emb.projectPath([[1.0, 2.0, 3.0], [4.0, 5.0, 6.0]]),
                               "default_xinit_lift": utils.EmbeddedCSpace(base, [1]).lift([0.75])}
+    # AffineEmbeddedCSpace (plan/cspaceutils.py:205-421): driver space of a 4-link chain -- link 0 alone, links 1 and 2 coupled
+    # (q1 = 2 v, q2 = -v + 0.1), link 3 not driven (stays at b)
+    import numpy as _np, io as _io, contextlib as _ctx
+    amb = importlib.import_module("klampt.plan.cspace").CSpace()
+    amb.setBounds([(-1.0, 1.0), (-2.0, 2.0), (-0.5, 0.5), (0.0, 1.0)])
+    A = _np.array([[1.0, 0.0], [0.0, 2.0], [0.0, -1.0], [0.0, 0.0]])
+    boff = [0.0, 0.0, 0.1, 0.25]
+    with _ctx.redirect_stdout(_io.StringIO()):
+        aff = utils.AffineEmbeddedCSpace(amb, A, boff)
+    xs = [[0.5, 0.2], [-1.0, -0.4], [0.0, 0.0]]
+    out["affine_cspace"] = {"lift": [list(map(float, aff.lift(x))) for x in xs],
+                            "project": [list(map(float, aff.project(aff.lift(x)))) for x in xs],
+                            "project_off_manifold": list(map(float, aff.project([0.3, 1.0, 0.2, 0.9]))),
+                            "bound_as_sets": [sorted(map(float, bd)) for bd in aff.bound], "eps": aff.eps}
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_cspace.json")
     json.dump(out, open(path, "w"), indent=1, sort_keys=True)
     print("wrote", path)

@@ -637,3 +637,79 @@ def test_config_and_xform_text_formats_equal_the_reference_loader(tmp_path):
     with pytest.raises(ValueError, match="different lengths"):
         kio.read_configs("2 1 2\n3 1 2 3")
     assert kio.read_configs("").shape == (0, 0)
+
+
+def test_affine_embedded_cspace_equals_the_reference_class():
+    """driver-space planning (q = A x + b): lift / least-squares project against the reference's AffineEmbeddedCSpace on the same
+    matrix; the bounds here are the exact interval (offset included, all coupled links considered), inside the reference's naive one"""
+    from klampt_b200.cspace import CSpace
+    from klampt_b200.cspaceutils import AffineEmbeddedCSpace
+    from klampt_b200.worldspec import DriverSpec
+    want = CSPACE["affine_cspace"]
+    amb = CSpace()
+    amb.setBounds([(-1.0, 1.0), (-2.0, 2.0), (-0.5, 0.5), (0.0, 1.0)])
+    A = np.array([[1.0, 0.0], [0.0, 2.0], [0.0, -1.0], [0.0, 0.0]])
+    aff = AffineEmbeddedCSpace(amb, A, [0.0, 0.0, 0.1, 0.25])
+    xs = [[0.5, 0.2], [-1.0, -0.4], [0.0, 0.0]]
+    np.testing.assert_allclose([aff.lift(x) for x in xs], want["lift"], atol=1e-15)
+    np.testing.assert_allclose([aff.project(aff.lift(x)) for x in xs], want["project"], atol=1e-12)
+    np.testing.assert_allclose(aff.project([0.3, 1.0, 0.2, 0.9]), want["project_off_manifold"], atol=1e-12)
+    assert aff.eps == want["eps"]
+    for (lo, hi), ref in zip(aff.bound, want["bound_as_sets"]):
+        assert ref[0] <= lo < hi <= ref[1]
+    np.testing.assert_allclose(aff.bound, [(-1.0, 1.0), (-0.4, 0.6)], atol=1e-15)
+    corners = aff.lift_batch([[lo, hi] for lo in aff.bound[0] for hi in aff.bound[1]])
+    assert all(amb.inBounds(list(c)) for c in corners)                    # the whole driver box maps inside the ambient bounds
+    np.testing.assert_allclose(aff.project_batch(aff.lift_batch(xs)), xs, atol=1e-12)
+    # the same space from driver records: a normal driver on link 0, an affine one over links 1 and 2
+    drv = [DriverSpec([0], [1.0], [0.0], -0.8, 0.8), DriverSpec([1, 2], [2.0, -1.0], [0.0, 0.1], -0.3, 5.0)]
+    aff2 = AffineEmbeddedCSpace.from_drivers(amb, drv, 4)
+    np.testing.assert_array_equal(aff2.A, A)
+    np.testing.assert_allclose(aff2.b, [0.0, 0.0, 0.1, 0.0])
+    np.testing.assert_allclose(aff2.bound, [(-0.8, 0.8), (-0.3, 0.6)], atol=1e-15)
+    with pytest.raises(ValueError, match="Invalid length of embedded space vector"):
+        aff.lift([1.0])
+
+
+def test_make_space_plans_in_driver_space_for_coupled_links(monkeypatch):
+    """robotplanning.make_space on a robot with an affine driver: the returned space is the driver-space embedding and a batched plan
+    over it keeps the coupled links coupled"""
+    from types import SimpleNamespace
+    from klampt_b200 import robotplanning, robotsim
+    from klampt_b200.cspace import CSpace
+    from klampt_b200.cspaceutils import AffineEmbeddedCSpace, EmbeddedMotionPlan
+    from klampt_b200.worldspec import DriverSpec
+    import klampt_b200.robotcspace as rcs
+    L = 7
+    drivers = [DriverSpec([k], [1.0], [0.0], -2.0, 2.0) for k in range(5)] + [DriverSpec([5, 6], [1.0, -1.0], [0.0, 0.0], -1.0, 1.0)]
+
+    class HostSpace(CSpace):
+        def __init__(self, robot, collider=None, device=0):
+            CSpace.__init__(self)
+            self.robot, self.collider = robot, collider
+            self.setBounds(list(zip(*robot.getJointLimits())))
+            self.spec = SimpleNamespace(robot=SimpleNamespace(drivers=drivers))
+        def addConstraint(self, c, name=None):
+            self.addFeasibilityTest(c, name)
+        def feasible_batch(self, Q):
+            Q = np.asarray(Q, dtype=np.float64).reshape(-1, L)
+            lo, hi = np.array(self.bound).T
+            return (((Q >= lo) & (Q <= hi)).all(axis=1) & (np.abs(Q[:, 5] + Q[:, 6]) < 1e-12)).astype(np.uint8)     # only coupled fingers are feasible
+        def visible_batch(self, A, B):
+            return self.feasible_batch(A) & self.feasible_batch(B)
+    monkeypatch.setattr(rcs, "RobotCSpace", HostSpace)
+    world = robotsim.WorldModel.from_spec(_worlds()["c1"])
+    robot = world.robot(0)
+    robot._q = np.zeros(L)
+    space = robotplanning.make_space(world, robot)
+    assert isinstance(space, AffineEmbeddedCSpace) and space.m == 6 and space.n == 7 and space.bound[5] == (-1.0, 1.0)
+    plan = EmbeddedMotionPlan(space, None, "prm", batch=128, knn=6, seed=2)
+    goal = [0.0, -0.3, 0.2, 0.1, 0.0, 0.4, -0.4]                     # link 0 is the fixed base
+    plan.setEndpoints([0.0] * L, goal)
+    path = None
+    for _ in range(6):
+        plan.planMore(1)
+        path = plan.getPath()
+        if path:
+            break
+    assert path is not None and np.allclose(path[-1], goal) and all(abs(q[5] + q[6]) < 1e-12 for q in path)
