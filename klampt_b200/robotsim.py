@@ -383,6 +383,32 @@ class RobotModelLink(_Named):
         return self._geom.getCurrentTransform()
 
 
+class RobotModelDriver:
+    """the part of RobotModelDriver the planning layer reads (Python/klampt/src/robotmodel.h; plan/cspaceutils.py:335-352): a normal
+    driver moves one link; an affine driver moves several with q_link = scale * value + offset"""
+
+    def __init__(self, robot: "RobotModel", index: int, spec):
+        self._robot, self.index, self._spec = robot, index, spec
+
+    def robot(self) -> "RobotModel":
+        return self._robot
+
+    def getType(self) -> str:
+        return "affine" if len(self._spec.links) > 1 else "normal"
+
+    def getAffectedLink(self) -> int:
+        return int(self._spec.links[0])
+
+    def getAffectedLinks(self) -> List[int]:
+        return [int(k) for k in self._spec.links]
+
+    def getAffineCoeffs(self):
+        return [float(s) for s in self._spec.scale], [float(o) for o in self._spec.offset]
+
+    def getLimits(self):
+        return [float(self._spec.qmin), float(self._spec.qmax)]
+
+
 class RobotModel(_Named):
     """RobotKinematics3D + RobotWithGeometry data model with the collision-relevant robotsim methods."""
 
@@ -433,6 +459,12 @@ class RobotModel(_Named):
             self.world._dirty()
 
     # ---- structure
+    def numDrivers(self) -> int:
+        return len(self._drivers)
+
+    def driver(self, i: int) -> RobotModelDriver:
+        return RobotModelDriver(self, i, self._drivers[i])
+
     def numLinks(self) -> int:
         return len(self._links)
 

@@ -106,6 +106,17 @@ def main():
                             "project": [list(map(float, aff.project(aff.lift(x)))) for x in xs],
                             "project_off_manifold": list(map(float, aff.project([0.3, 1.0, 0.2, 0.9]))),
                             "bound_as_sets": [sorted(map(float, bd)) for bd in aff.bound], "eps": aff.eps}
+    # AffineEmbeddedCSpace.fromRobotDrivers (:320-369) on a mirror robot whose last two links share an affine driver
+    from klampt_b200.worldspec import DriverSpec
+    spec = worlds()["c1"]
+    spec.robot.drivers = [DriverSpec([k], [1.0], [0.0], -2.0, 2.0) for k in range(1, 5)] + [DriverSpec([5, 6], [1.0, -0.5], [0.0, 0.2], -1.0, 1.0)]
+    world = mirror.WorldModel.from_spec(spec)
+    robot = world.robot(0)
+    robot._q = _np.zeros(robot.numLinks())
+    with _ctx.redirect_stdout(_io.StringIO()):
+        fr = utils.AffineEmbeddedCSpace.fromRobotDrivers(robot, ref.RobotCSpace(robot, None))
+    out["affine_from_drivers"] = {"A": _np.asarray(fr.A.todense() if hasattr(fr.A, "todense") else fr.A).tolist(), "b": list(map(float, fr.b)),
+                                  "lift": list(map(float, fr.lift([0.1, 0.2, 0.3, 0.4, 0.5])))}
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_cspace.json")
     json.dump(out, open(path, "w"), indent=1, sort_keys=True)
     print("wrote", path)

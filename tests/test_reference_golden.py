@@ -184,7 +184,7 @@ def _host_only_space(world, with_collider):
     return sp
 
 
-@pytest.mark.parametrize("name", sorted(k for k in CSPACE if not k.endswith("_cspace") and not k.startswith("inactive_")))
+@pytest.mark.parametrize("name", sorted(k for k in CSPACE if not k.endswith("_cspace") and not k.startswith(("inactive_", "affine_"))))
 def test_robot_cspace_test_list_equals_the_reference_constructor(name):
     """names, order and dependencies of the feasibility tests, bounds, properties and eps of the reference's own
     RobotCSpace.__init__ run on the same worlds (tests/golden/make_reference_cspace.py)"""
@@ -713,3 +713,24 @@ def test_make_space_plans_in_driver_space_for_coupled_links(monkeypatch):
         if path:
             break
     assert path is not None and np.allclose(path[-1], goal) and all(abs(q[5] + q[6]) < 1e-12 for q in path)
+
+
+def test_affine_space_from_drivers_equals_reference_from_robot_drivers():
+    """AffineEmbeddedCSpace.from_drivers against the reference's fromRobotDrivers run on a mirror robot with an affine driver
+    (plan/cspaceutils.py:320-369) -- and the mirror's driver accessors, which that reference code called"""
+    from klampt_b200 import robotsim
+    from klampt_b200.cspace import CSpace
+    from klampt_b200.cspaceutils import AffineEmbeddedCSpace
+    from klampt_b200.worldspec import DriverSpec
+    want = CSPACE["affine_from_drivers"]
+    spec = _worlds()["c1"]
+    spec.robot.drivers = [DriverSpec([k], [1.0], [0.0], -2.0, 2.0) for k in range(1, 5)] + [DriverSpec([5, 6], [1.0, -0.5], [0.0, 0.2], -1.0, 1.0)]
+    robot = robotsim.WorldModel.from_spec(spec).robot(0)
+    assert robot.numDrivers() == 5 and robot.driver(4).getType() == "affine" and robot.driver(0).getType() == "normal"
+    assert robot.driver(4).getAffectedLinks() == [5, 6] and robot.driver(4).getAffineCoeffs() == ([1.0, -0.5], [0.0, 0.2])
+    amb = CSpace()
+    amb.setBounds(list(zip(*robot.getJointLimits())))
+    aff = AffineEmbeddedCSpace.from_drivers(amb, spec.robot.drivers, robot.numLinks())
+    np.testing.assert_array_equal(aff.A, np.array(want["A"]))
+    np.testing.assert_array_equal(aff.b, want["b"])
+    np.testing.assert_allclose(aff.lift([0.1, 0.2, 0.3, 0.4, 0.5]), want["lift"], atol=1e-16)
