@@ -282,9 +282,46 @@ static int build_rec(build_t* b, int first, int count) {
   if (count<=b->leafsize) { nd->left=-1; nd->right=-1; return me; }
   int ax=0; double ext=nd->hi[0]-nd->lo[0];
   for (int k=1;k<3;k++) if (nd->hi[k]-nd->lo[k]>ext) { ext=nd->hi[k]-nd->lo[k]; ax=k; }
+  int half=count/2;
+#ifdef KO_SAH
+  /* CPU-baseline variant only (libkb_oracle_fast.so): binned surface-area heuristic, 16 bins x 3 axes over the centroid
+   * bounds, the split a production BVH builder would choose.  Falls back to the median split when the centroids coincide.
+   * The canonical tree of the checker (and of the roofline counts) stays the median split above. */
+  if (count>2) {
+    double clo[3]={DBL_MAX,DBL_MAX,DBL_MAX}, chi[3]={-DBL_MAX,-DBL_MAX,-DBL_MAX};
+    for (int i=first;i<first+count;i++) for (int k=0;k<3;k++) { double c=b->cents[i].c[k]; if (c<clo[k]) clo[k]=c; if (c>chi[k]) chi[k]=c; }
+    double bestc=DBL_MAX; int besta=-1, bestb=0;
+    for (int a=0;a<3;a++) {
+      double w=chi[a]-clo[a]; if (!(w>0)) continue;
+      enum { NB=16 };
+      int cnt[NB]; double blo[NB][3], bhi[NB][3];
+      for (int i=0;i<NB;i++) { cnt[i]=0; for (int k=0;k<3;k++) { blo[i][k]=DBL_MAX; bhi[i][k]=-DBL_MAX; } }
+      for (int i=first;i<first+count;i++) { int e=b->cents[i].idx; int bi=(int)((b->cents[i].c[a]-clo[a])/w*NB); if (bi>=NB) bi=NB-1;
+        cnt[bi]++; for (int k=0;k<3;k++) { if (b->elo[3*e+k]<blo[bi][k]) blo[bi][k]=b->elo[3*e+k]; if (b->ehi[3*e+k]>bhi[bi][k]) bhi[bi][k]=b->ehi[3*e+k]; } }
+      double ra[NB]; int rn[NB]; { double lo[3]={DBL_MAX,DBL_MAX,DBL_MAX}, hi[3]={-DBL_MAX,-DBL_MAX,-DBL_MAX}; int n=0;
+        for (int i=NB-1;i>0;i--) { n+=cnt[i]; for (int k=0;k<3;k++) { if (blo[i][k]<lo[k]) lo[k]=blo[i][k]; if (bhi[i][k]>hi[k]) hi[k]=bhi[i][k]; }
+          double d0=hi[0]-lo[0], d1=hi[1]-lo[1], d2=hi[2]-lo[2]; ra[i]= n? (d0*d1+d1*d2+d2*d0):0; rn[i]=n; } }
+      double lo[3]={DBL_MAX,DBL_MAX,DBL_MAX}, hi[3]={-DBL_MAX,-DBL_MAX,-DBL_MAX}; int n=0;
+      for (int i=0;i<NB-1;i++) { n+=cnt[i]; for (int k=0;k<3;k++) { if (blo[i][k]<lo[k]) lo[k]=blo[i][k]; if (bhi[i][k]>hi[k]) hi[k]=bhi[i][k]; }
+        if (!n || !rn[i+1]) continue;
+        double d0=hi[0]-lo[0], d1=hi[1]-lo[1], d2=hi[2]-lo[2];
+        double c=(d0*d1+d1*d2+d2*d0)*n+ra[i+1]*rn[i+1];
+        if (c<bestc) { bestc=c; besta=a; bestb=i; } }
+    }
+    if (besta>=0) {
+      double w=chi[besta]-clo[besta]; int i=first, j=first+count-1;
+      while (i<=j) { int bi=(int)((b->cents[i].c[besta]-clo[besta])/w*16); if (bi>=16) bi=15;
+        if (bi<=bestb) i++; else { cent_t t=b->cents[i]; b->cents[i]=b->cents[j]; b->cents[j]=t; j--; } }
+      half=i-first;
+      if (half<=0 || half>=count) { besta=-1; half=count/2; }
+    }
+    if (besta<0) { g_sort_axis=ax; qsort(b->cents+first,count,sizeof(cent_t),cent_cmp); }
+  } else
+#endif
+  {
   g_sort_axis=ax;
   qsort(b->cents+first,count,sizeof(cent_t),cent_cmp);
-  int half=count/2;
+  }
   int l=build_rec(b,first,half);
   int r=build_rec(b,first+half,count-half);
   b->nodes[me].left=l; b->nodes[me].right=r;
@@ -854,6 +891,90 @@ int ko_feasible_brute(const ko_world* w, const double* q) {
   free(T); free(s1); free(s2);
   return !hit;
 }
+/* ------------------------------------------------------------------ contact depth (test support for the 1e-6 m band)
+ * "Boolean results bit-exact outside a 1e-6 m margin band" needs a two-sided definition of the band.  A configuration the oracle
+ * calls FREE is inside the band when its clearance (ko_distance) is <= 1e-6.  A configuration the oracle calls COLLIDING is inside
+ * the band when its deepest contact is <= 1e-6: the largest, over all enabled geometry pairs and all element pairs within the
+ * pair's threshold, of (threshold - signed distance), where the signed distance of two intersecting triangles is minus their
+ * penetration depth -- the smallest translation that separates them = the smallest overlap of their projections on the 11
+ * candidate axes (two face normals, nine edge cross products: the face normals of the Minkowski difference of two triangles). */
+static double tri_tri_depth(const double* A, const double* B) {
+  double ax[11][3]; int na=0; double e[6][3];
+  for (int i=0;i<3;i++) { v_sub(A+3*((i+1)%3),A+3*i,e[i]); v_sub(B+3*((i+1)%3),B+3*i,e[3+i]); }
+  v_cross(e[0],e[1],ax[na++]); v_cross(e[3],e[4],ax[na++]);
+  for (int i=0;i<3;i++) for (int j=0;j<3;j++) v_cross(e[i],e[3+j],ax[na++]);
+  double best=DBL_MAX;
+  for (int k=0;k<na;k++) { double n2=v_dot(ax[k],ax[k]); if (!(n2>1e-300)) continue; double inv=1.0/sqrt(n2);
+    double amin=DBL_MAX,amax=-DBL_MAX,bmin=DBL_MAX,bmax=-DBL_MAX;
+    for (int v=0;v<3;v++) { double pa=v_dot(A+3*v,ax[k])*inv, pb=v_dot(B+3*v,ax[k])*inv;
+      amin=fmin(amin,pa); amax=fmax(amax,pa); bmin=fmin(bmin,pb); bmax=fmax(bmax,pb); }
+    double o=fmin(amax-bmin,bmax-amin); if (o<0) o=0; if (o<best) best=o; }
+  return best==DBL_MAX?0.0:best;
+}
+static void depth_leaf(pairq_t* q, const node_t* a, const node_t* b, double* worst) {
+  const geom_t *A=q->A, *B=q->B; double d;
+  if (A->kind==G_MESH && B->kind==G_MESH) {
+    double ta[9], tb[9];
+    for (int v=0;v<3;v++) { xf_apply(&q->Ta,A->tv+9*(size_t)a->first+3*v,ta+3*v); xf_apply(&q->Tb,B->tv+9*(size_t)b->first+3*v,tb+3*v); }
+    if (ko_tri_tri_intersect(ta,tb)) d=-tri_tri_depth(ta,tb); else d=sqrt(tri_tri_dist2(ta,tb));
+    if (d<=q->tol && q->tol-d>*worst) *worst=q->tol-d;
+    return;
+  }
+  if (A->kind==G_MESH || B->kind==G_MESH) {
+    const geom_t* M = A->kind==G_MESH?A:B; const geom_t* C = A->kind==G_MESH?B:A;
+    const node_t* mn = A->kind==G_MESH?a:b; const node_t* cn = A->kind==G_MESH?b:a;
+    const xf_t* Tm = A->kind==G_MESH?&q->Ta:&q->Tb; const xf_t* Tc = A->kind==G_MESH?&q->Tb:&q->Ta;
+    double t[9]; for (int v=0;v<3;v++) xf_apply(Tm,M->tv+9*(size_t)mn->first+3*v,t+3*v);
+    for (int i=cn->first;i<cn->first+cn->count;i++) { double p[3]; xf_apply(Tc,C->pts+3*(size_t)i,p);
+      d=sqrt(point_tri_dist2(p,t,t+3,t+6))-C->rad[i]; if (d<=q->tol && q->tol-d>*worst) *worst=q->tol-d; }
+    return;
+  }
+  for (int i=a->first;i<a->first+a->count;i++) { double p[3]; xf_apply(&q->Ta,A->pts+3*(size_t)i,p);
+    for (int j=b->first;j<b->first+b->count;j++) { double s[3]; xf_apply(&q->Tb,B->pts+3*(size_t)j,s);
+      d=sqrt(v_dist2(p,s))-A->rad[i]-B->rad[j]; if (d<=q->tol && q->tol-d>*worst) *worst=q->tol-d; } }
+}
+static void depth_rec(pairq_t* q, int ia, int ib, double* worst) {
+  const node_t* a=&q->A->nodes[ia]; const node_t* b=&q->B->nodes[ib];
+  if (!obb_overlap(a,b,&q->Tab,q->tol)) return;
+  int la=a->left<0, lb=b->left<0;
+  if (la && lb) { depth_leaf(q,a,b,worst); return; }
+  if (lb || (!la && node_size2(a)>=node_size2(b))) { depth_rec(q,a->left,ib,worst); depth_rec(q,node_right(q->A,ia),ib,worst); }
+  else { depth_rec(q,ia,b->left,worst); depth_rec(q,ia,node_right(q->B,ib),worst); }
+}
+static void geom_pair_depth(const geom_t* A, const xf_t* Ta, const geom_t* B, const xf_t* Tb, double* worst) {
+  if (A->kind==G_EMPTY || B->kind==G_EMPTY) return;
+  pairq_t q; pairq_init(&q,A,Ta,B,Tb,A->margin+B->margin,NULL);
+  depth_rec(&q,0,0,worst);
+  /* solids: an element reference point inside the box has no measurable depth here -> reported as 1 m (never inside the band) */
+  for (int side=0;side<2;side++) { const geom_t* X=side?B:A; const geom_t* Y=side?A:B; const xf_t* Tx=side?Tb:Ta; const xf_t* Ty=side?Ta:Tb;
+    if (!X->solid) continue;
+    int n=(Y->kind==G_MESH)?Y->nt:Y->np;
+    for (int i=0;i<n;i++) { double pw[3], r=0;
+      if (Y->kind==G_MESH) xf_apply(Ty,Y->tv+9*(size_t)i,pw); else { xf_apply(Ty,Y->pts+3*(size_t)i,pw); r=Y->rad[i]; }
+      double d0=point_solid_box_dist(X,Tx,pw), d=d0-r;
+      if (d<=q.tol) { double dep = d0==0.0 ? 1.0 : q.tol-d; if (dep>*worst) *worst=dep; } } }
+}
+/* deepest contact of configuration q (metres); -1 when nothing is in contact; joint limits are not looked at */
+double ko_penetration(const ko_world* w, const double* q, int include_self) {
+  int L=w->L; xf_t* T=(xf_t*)malloc(sizeof(xf_t)*L); fk_links(w,q,T);
+  active_t* s1=(active_t*)malloc(sizeof(active_t)*(L+1));
+  active_t* s2=(active_t*)malloc(sizeof(active_t)*(w->nterr+w->nobj+1));
+  int n1=gather_links(w,T,s1), n2=gather_env(w,s2);
+  double worst=-1.0;
+  for (int i=0;i<n1;i++) for (int j=0;j<n2;j++)
+    if (mask_en(w,s1[i].id,s2[j].id)||mask_en(w,s2[j].id,s1[i].id)) geom_pair_depth(s1[i].g,&s1[i].T,s2[j].g,&s2[j].T,&worst);
+  if (include_self) for (int i=0;i<n1;i++) for (int j=i+1;j<n1;j++)
+    if (mask_en(w,s1[i].id,s1[j].id)) geom_pair_depth(s1[i].g,&s1[i].T,s1[j].g,&s1[j].T,&worst);
+  free(T); free(s1); free(s2);
+  return worst;
+}
+double ko_tri_tri_depth(const double a[9], const double b[9]) { return tri_tri_depth(a,b); }
+/* the same for one geometry pair at explicit transforms with threshold margins + tol */
+double ko_geom_penetration(const ko_world* w, int ga, const double Ta[12], int gb, const double Tb[12], double tol) {
+  xf_t A,B; xf_from12(Ta,&A); xf_from12(Tb,&B);
+  geom_t a=w->geoms[ga], b=w->geoms[gb]; a.margin+=tol;      /* shallow copies: the threshold is margin_A + margin_B + tol */
+  double worst=-1.0; geom_pair_depth(&a,&A,&b,&B,&worst); return worst; }
+
 int ko_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

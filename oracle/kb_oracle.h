@@ -80,6 +80,12 @@ int ko_feasible_brute(const ko_world* w, const double* q);
 void ko_feasible_batch(const ko_world* w, const double* Q, int64_t N, uint8_t* out,
                        int32_t* first_pair, ko_counts* counts_per_config, int nthreads);
 
+/* test support for the two-sided 1e-6 m band: deepest contact of q over the enabled pairs (threshold - signed distance, with
+ * intersecting triangles measured by their separating-axis penetration depth); -1 when nothing is in contact */
+double ko_penetration(const ko_world* w, const double* q, int include_self);
+double ko_tri_tri_depth(const double a[9], const double b[9]);
+double ko_geom_penetration(const ko_world* w, int ga, const double Ta[12], int gb, const double Tb[12], double tol);
+
 /* a17/a18: EpsilonEdgeChecker with RobotCSpace::Distance / Interpolate */
 double ko_cspace_distance(const ko_world* w, const double* a, const double* b, const double* weights);
 void ko_interpolate(const ko_world* w, const double* a, const double* b, double u, double* out);

@@ -12,7 +12,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = None
+_LIBS = {}
 
 
 class Counts(C.Structure):
@@ -22,23 +22,25 @@ class Counts(C.Structure):
 COUNTS_DTYPE = np.dtype([("n_box", np.int64), ("n_node", np.int64), ("n_tri", np.int64), ("n_pt", np.int64)])
 
 
-def build(force: bool = False) -> str:
-    so = os.path.join(_HERE, "libkb_oracle.so")
+def build(force: bool = False, variant: str = "strict") -> str:
+    """strict: the checker (median-split tree, no FMA contraction, portable ISA).  fast: the CPU-baseline arm of bench.py (binned
+    SAH tree, -march=native, FMA allowed) -- always rebuilt on the machine that runs it, because -march=native does not travel."""
+    fast = variant == "fast"
+    so = os.path.join(_HERE, "libkb_oracle_fast.so" if fast else "libkb_oracle.so")
     src = os.path.join(_HERE, "kb_oracle.c")
     if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-C", _HERE, "-s", "clean", "all"])
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["cleanfast", "fast"] if fast else ["clean", "all"]))
     return so
 
 
-def lib():
-    global _LIB
-    if _LIB is not None:
-        return _LIB
-    so = build()
+def lib(variant: str = "strict"):
+    if variant in _LIBS:
+        return _LIBS[variant]
+    so = build(force=(variant == "fast"), variant=variant)
     try:
         L = C.CDLL(so)
     except OSError:
-        so = build(force=True)
+        so = build(force=True, variant=variant)
         L = C.CDLL(so)
     dp, ip, u8p, vp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_uint8), C.c_void_p
     L.ko_create.restype = vp
@@ -85,7 +87,13 @@ def lib():
     L.ko_seg_seg_distance.argtypes = [dp, dp, dp, dp]
     L.ko_seg_seg_distance.restype = C.c_double
     L.ko_max_threads.restype = C.c_int
-    _LIB = L
+    L.ko_penetration.argtypes = [vp, dp, C.c_int]
+    L.ko_penetration.restype = C.c_double
+    L.ko_tri_tri_depth.argtypes = [dp, dp]
+    L.ko_tri_tri_depth.restype = C.c_double
+    L.ko_geom_penetration.argtypes = [vp, C.c_int, dp, C.c_int, dp, C.c_double]
+    L.ko_geom_penetration.restype = C.c_double
+    _LIBS[variant] = L
     return L
 
 
@@ -127,6 +135,12 @@ def seg_seg_distance(p0, p1, q0, q1) -> float:
     return float(lib().ko_seg_seg_distance(*[x[1] for x in a]))
 
 
+def tri_tri_depth(a, b) -> float:
+    a_, ap = _d(np.asarray(a).reshape(9))
+    b_, bp = _d(np.asarray(b).reshape(9))
+    return float(lib().ko_tri_tri_depth(ap, bp))
+
+
 def max_threads() -> int:
     return int(lib().ko_max_threads())
 
@@ -134,9 +148,10 @@ def max_threads() -> int:
 class OracleWorld:
     """Builds the oracle's world from a klampt_b200.worldspec.WorldSpec."""
 
-    def __init__(self, spec):
-        L = lib()
+    def __init__(self, spec, variant: str = "strict"):
+        L = lib(variant)
         self.L = L
+        self.variant = variant
         self.spec = spec
         self.h = L.ko_create()
         for g in spec.geoms:
@@ -242,6 +257,11 @@ class OracleWorld:
             return ok, (int(pr[0]), int(pr[1])), cnt
         return ok
 
+    def penetration(self, q, include_self=True) -> float:
+        """deepest contact of q in metres (-1: nothing in contact); the colliding side of the two-sided 1e-6 m band"""
+        q_, qp = _d(q)
+        return float(self.L.ko_penetration(self.h, qp, int(include_self)))
+
     def feasible_brute(self, q) -> bool:
         q_, qp = _d(q)
         return bool(self.L.ko_feasible_brute(self.h, qp))
@@ -330,6 +350,11 @@ class OracleWorld:
         a_, ap = _d(Ta)
         b_, bp = _d(Tb)
         return float(self.L.ko_geom_distance_brute(self.h, ga, ap, gb, bp))
+
+    def geom_penetration(self, ga, Ta, gb, Tb, tol=0.0) -> float:
+        a_, ap = _d(Ta)
+        b_, bp = _d(Tb)
+        return float(self.L.ko_geom_penetration(self.h, ga, ap, gb, bp, float(tol)))
 
     def geom_aabb(self, g, T):
         T_, Tp = _d(T)

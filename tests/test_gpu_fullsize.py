@@ -16,11 +16,8 @@ def _check(world, n, seed, built):
     Q = synth.sample_configs(world.robot, n, seed)
     got = eng.feasible_batch(Q)
     want = orc.feasible_batch(Q, nthreads=0)
-    bad = np.nonzero(got != want)[0]
-    assert len(bad) <= 20, "%d mismatches in %d" % (len(bad), n)
-    for i in bad:                                   # only legal inside the 1e-6 m band
-        d, _ = orc.distance(Q[i], upper_bound=1.0, include_self=True)
-        assert d <= 1e-6
+    from parity import assert_bool_parity
+    assert_bool_parity(got, want, Q, orc, max_bad=0)   # mesh-mesh, margin 0: exact equality with the fp64 oracle
     return eng, orc, Q, got
 
 

@@ -11,7 +11,7 @@ from klampt_b200.worldspec import GeomSpec, WorldSpec
 
 pytestmark = pytest.mark.gpu
 
-BAND = 1e-6
+from parity import BAND, assert_bool_parity, assert_geom_bool_parity
 
 
 @pytest.fixture(scope="module")
@@ -36,14 +36,6 @@ def c3(built):
     from oracle.oracle import OracleWorld
     w = synth.world_c3()
     return w, Engine(w), OracleWorld(w)
-
-
-def assert_bool_parity(got, want, Q, orc, include_self=True):
-    bad = np.nonzero(np.asarray(got) != np.asarray(want))[0]
-    for i in bad:
-        d, _ = orc.distance(Q[i], upper_bound=1.0, include_self=include_self)
-        assert d <= BAND, "config %d: gpu=%d oracle=%d but oracle clearance is %g m (> band)" % (i, got[i], want[i], d)
-    return len(bad)
 
 
 def test_fk_matches_oracle(c1):
@@ -176,10 +168,7 @@ def test_margins_add_to_threshold(built):
     eng, orc = Engine(w), OracleWorld(w)
     Q = synth.sample_configs(w.robot, 6000, 9)
     got, want = eng.feasible_batch(Q), orc.feasible_batch(Q)
-    bad = np.nonzero(got != want)[0]
-    for i in bad:
-        d, _ = orc.distance(Q[i], upper_bound=1.0, include_self=True)
-        assert abs(d) <= BAND
+    assert_bool_parity(got, want, Q, orc, max_bad=len(Q) // 1000)     # fp32 distances with margins: in-band mismatches are legal
     w0 = synth.world_c1()
     base = OracleWorld(w0).feasible_batch(Q)
     assert want.sum() < base.sum()            # margins make the world strictly tighter
@@ -232,10 +221,7 @@ def test_point_cloud_collide_with_margin(c5small):
     w, eng, orc = c5small
     Q = synth.sample_configs(w.robot, 8000, 51)
     got, want = eng.feasible_batch(Q), orc.feasible_batch(Q)
-    bad = np.nonzero(got != want)[0]
-    for i in bad:
-        d, _ = orc.distance(Q[i], upper_bound=1.0, include_self=True)
-        assert abs(d) <= BAND
+    assert_bool_parity(got, want, Q, orc, max_bad=len(Q) // 1000)     # fp32 distances with margins: in-band mismatches are legal
     assert 0.2 < got.mean() < 0.9
 
 
@@ -355,7 +341,7 @@ def test_prismatic_spin_driver_and_custom_mask(built):
     Q = rng.uniform([-7, -2.1, -0.32, -2.1, -2.1, -2.1], [7, 2.1, 0.42, 2.1, 2.1, 2.1], size=(20000, 6))
     np.testing.assert_allclose(eng.fk_batch(Q[:200]), orc.fk_batch(Q[:200]), rtol=0, atol=1e-12)
     got, want = eng.feasible_batch(Q), orc.feasible_batch(Q)
-    assert_bool_parity(got, want, Q, orc)
+    assert_bool_parity(got, want, Q, orc, max_bad=max(2, len(Q) // 1000))   # distance-threshold elements: in-band mismatches are legal
     lim = np.array([orc.check_joint_limits(q) for q in Q[:2000]])
     assert 0.2 < lim.mean() < 0.9 and not got[:2000][~lim].any()
     ok = Q[want == 1]
@@ -475,10 +461,8 @@ def test_solid_box_primitives_pair_queries(built):
         want_d = np.array([orc.geom_distance(ga, Ta[i], gb, Tb[i]) for i in range(N)])
         want_near = np.array([orc.geom_within_distance(ga, Ta[i], gb, Tb[i], 0.05) for i in range(N)])
         assert 0.05 < want_hit.mean() < 0.98, (ga, gb, want_hit.mean())
-        bad = np.nonzero(hit != want_hit)[0]
-        assert all(abs(want_d[i]) <= BAND for i in bad)
-        bad = np.nonzero(near != want_near)[0]
-        assert all(abs(want_d[i] - 0.05) <= BAND for i in bad)
+        assert_geom_bool_parity(hit, want_hit, ga, Ta, gb, Tb, orc, 0.0, max_bad=2)
+        assert_geom_bool_parity(near, want_near, ga, Ta, gb, Tb, orc, 0.05, max_bad=2)
         np.testing.assert_allclose(d, want_d, rtol=1e-5, atol=1e-9)
     from klampt_b200._capi import KbError
     bad = WorldSpec()
@@ -499,7 +483,7 @@ def test_world_with_solid_boxes(built):
     Q = synth.sample_configs(w.robot, 20000, 43)
     got, pairs = eng.feasible_batch(Q, return_pairs=True)
     want = orc.feasible_batch(Q)
-    assert_bool_parity(got, want, Q, orc)
+    assert_bool_parity(got, want, Q, orc, max_bad=max(2, len(Q) // 1000))   # distance-threshold elements: in-band mismatches are legal
     assert 0.1 < want.mean() < 0.9
     assert ((pairs[:, 0] >= 0) == (got == 0)).all()
     d = eng.distance_batch(Q[:1500], upper_bound=0.4, include_self=True)
@@ -555,7 +539,7 @@ def test_dynamic_point_cloud_rebuilt_on_the_gpu(built):
         eng.update_pointcloud(gdyn, P)
         orc = oracle_with(P)
         got, want = eng.feasible_batch(Q), orc.feasible_batch(Q)
-        assert_bool_parity(got, want, Q, orc)
+        assert_bool_parity(got, want, Q, orc, max_bad=max(2, len(Q) // 1000))   # distance-threshold elements: in-band mismatches are legal
         d = eng.distance_batch(Q[:500], upper_bound=0.3)
         do, _ = orc.distance_batch(Q[:500], upper_bound=0.3)
         np.testing.assert_allclose(d, do, rtol=1e-5, atol=1e-9)
@@ -633,7 +617,7 @@ def test_degenerate_triangles_agree_with_the_oracle(built):
     got, want = eng.feasible_batch(Q), orc.feasible_batch(Q)
     base = OracleWorld(synth.world_c1()).feasible_batch(Q)
     assert (want != base).sum() > 0                        # the slivers do get hit
-    assert_bool_parity(got, want, Q, orc)
+    assert_bool_parity(got, want, Q, orc, max_bad=max(2, len(Q) // 1000))   # distance-threshold elements: in-band mismatches are legal
     d = eng.distance_batch(Q[:1000], upper_bound=0.3)
     do, _ = orc.distance_batch(Q[:1000], upper_bound=0.3)
     np.testing.assert_allclose(d, do, rtol=1e-5, atol=1e-9)
@@ -659,7 +643,7 @@ def test_segment_primitives_agree_with_the_oracle(built):
     Q = synth.sample_configs(w.robot, 20000, 132)
     got, want = eng.feasible_batch(Q), orc.feasible_batch(Q)
     assert (want != OracleWorld(synth.world_c1()).feasible_batch(Q)).sum() > 0          # the bars do get hit
-    assert_bool_parity(got, want, Q, orc)
+    assert_bool_parity(got, want, Q, orc, max_bad=max(2, len(Q) // 1000))   # distance-threshold elements: in-band mismatches are legal
     d = eng.distance_batch(Q[:1000], upper_bound=0.3)
     do, _ = orc.distance_batch(Q[:1000], upper_bound=0.3)
     np.testing.assert_allclose(d, do, rtol=1e-5, atol=1e-9)

@@ -582,3 +582,51 @@ def test_segment_primitive_semantics():
         want = _np_seg_seg_dist(Ra @ segs[k][0] + ta, Ra @ segs[k][1] + ta, Rb @ segs[k + 1][0] + tb, Rb @ segs[k + 1][1] + tb)
         assert abs(o.geom_distance(gr[k], Ta, gr[k + 1], Tb) - want) < 1e-12
         assert o.geom_within_distance(gr[k], Ta, gr[k + 1], Tb, want + 1e-9) and not o.geom_within_distance(gr[k], Ta, gr[k + 1], Tb, want - 1e-9)
+
+
+def test_contact_depth_known_answers(cubes):
+    """ko_penetration / ko_geom_penetration: the colliding side of the two-sided 1e-6 m band (tests/parity.py)"""
+    from oracle.oracle import tri_tri_depth
+    o, ga, gb, gm, gs = cubes
+    # two triangles crossing like a plus sign: A in the plane z = 0, B in the plane y = 0 dipping 0.01 below A
+    A = np.array([[-1, -1, 0], [1, -1, 0], [0, 1, 0]], float)
+    B = np.array([[-0.2, 0, -0.01], [0.2, 0, -0.01], [0, 0, 1.0]], float)
+    assert ko.tri_tri_intersect(A, B)
+    assert ko.tri_tri_depth(A, B) == pytest.approx(0.01, abs=1e-15)          # lift B by 0.01 along z and they separate
+    # unit cubes overlapping by delta along x: depth = delta (faces x = 1 of A and x = 0 of B cross the other cube's side faces)
+    for delta in (1e-3, 1e-7):
+        assert o.geom_penetration(ga, I12, gb, T_at(1.0 - delta, 0.25, 0.25)) == pytest.approx(delta, rel=1e-6)
+    assert o.geom_penetration(ga, I12, gb, T_at(1.5)) == -1.0            # nothing in contact
+    # margins: threshold 0.1, gap 0.05 -> depth 0.05; with tol the threshold grows
+    assert o.geom_penetration(ga, I12, gm, T_at(1.05)) == pytest.approx(0.05, abs=1e-12)
+    assert o.geom_penetration(ga, I12, gb, T_at(1.05), 0.08) == pytest.approx(0.03, abs=1e-12)
+    # sphere of radius 0.25 centred 0.2 outside the face x = 1: depth 0.05
+    assert o.geom_penetration(ga, I12, gs, T_at(1.2, 0.5, 0.5)) == pytest.approx(0.05, abs=1e-12)
+
+
+def test_contact_depth_of_a_robot_configuration():
+    w = synth.world_c1()
+    o = OracleWorld(w)
+    Q = synth.sample_configs(w.robot, 400, 77)
+    feas = o.feasible_batch(Q)
+    for i in range(len(Q)):
+        p = o.penetration(Q[i])
+        if feas[i]:
+            assert p == -1.0
+        elif o.check_joint_limits(Q[i]):
+            assert p >= 0.0
+
+
+def test_fast_baseline_variant_agrees_with_the_checker():
+    """libkb_oracle_fast.so (SAH tree, -march=native, FMA allowed) is the CPU arm bench.py times; it must answer like the checker"""
+    for w, n in ((synth.world_c1(), 3000), (synth.world_c2(2, n_obstacles=30), 3000), (synth.world_c3(), 1500)):
+        o, f = OracleWorld(w), OracleWorld(w, variant="fast")
+        Q = synth.sample_configs(w.robot, n, 5)
+        a, b = o.feasible_batch(Q), f.feasible_batch(Q)
+        bad = np.nonzero(a != b)[0]
+        for i in bad:                                  # FMA contraction may flip a contact that is exactly on the boundary
+            assert abs(o.distance(Q[i], upper_bound=1.0, include_self=True)[0]) <= 1e-9 or o.penetration(Q[i]) <= 1e-9
+        assert len(bad) <= 2
+        da, _ = o.distance_batch(Q[:200], upper_bound=0.5)
+        db, _ = f.distance_batch(Q[:200], upper_bound=0.5)
+        np.testing.assert_allclose(da, db, rtol=1e-9, atol=1e-12)
