@@ -155,6 +155,11 @@ int kb_feasible_batch_device(kb_engine* e, const double* dQ, int64_t N, uint8_t*
 /* the same for configurations stored as floats (half the host-to-device bytes): every value is widened to fp64 on the device
  * and checked exactly as kb_feasible_batch checks (double)q -- the answer is for the rounded configuration */
 int kb_feasible_batch_f32(kb_engine* e, const float* Q, int64_t N, uint8_t* out, int32_t* first_pair);
+/* the same with the result as a packed bitmask -- bit (c & 7) of byte (c >> 3) is configuration c, (N + 7) / 8 bytes: what a
+ * multi-GPU caller gathers ("only result bitmasks and distances are gathered").  The device form writes whole
+ * 32-bit words: d_out_bits must be 4-byte aligned and hold (N + 31) / 32 words. */
+int kb_feasible_batch_bits(kb_engine* e, const double* Q, int64_t N, uint8_t* out_bits);
+int kb_feasible_batch_bits_device(kb_engine* e, const double* dQ, int64_t N, uint8_t* d_out_bits);
 
 /* SingleRobotCSpace::PathChecker(a,b)->IsVisible() = EpsilonEdgeChecker with RobotCSpace::Distance / Interpolate
  * (Cpp/Planning/RobotCSpace.cpp:835-838, Cpp/Modeling/Interpolate.cpp:10-71,208-343) for N edges.
@@ -164,6 +169,9 @@ int kb_edges_visible_batch(kb_engine* e, const double* A, const double* B, int64
                            const double* weights, uint8_t* out, int32_t* nchecks);
 int kb_edges_visible_batch_device(kb_engine* e, const double* dA, const double* dB, int64_t N, double eps,
                                   const double* weights_host, uint8_t* d_out, int32_t* d_nchecks);
+/* visibility as a packed bitmask, (N + 7) / 8 bytes, bit order as kb_feasible_batch_bits */
+int kb_edges_visible_batch_bits(kb_engine* e, const double* A, const double* B, int64_t N, double eps,
+                                const double* weights, uint8_t* out_bits, int32_t* nchecks);
 
 /* Every colliding pair of each configuration: SingleRobotCSpace::Init's per-pair CollisionFreeSet constraints
  * (Cpp/Planning/RobotCSpace.cpp:697-747) evaluated together, as CSpaceInterface::feasibilityFailures needs them

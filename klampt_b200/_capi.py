@@ -56,6 +56,9 @@ SIGNATURES = {
     "kb_feasible_batch": (C.c_int, [_VP, _VP, C.c_int64, _VP, _VP]),
     "kb_feasible_batch_f32": (C.c_int, [_VP, _VP, C.c_int64, _VP, _VP]),
     "kb_feasible_batch_device": (C.c_int, [_VP, _VP, C.c_int64, _VP, _VP]),
+    "kb_feasible_batch_bits": (C.c_int, [_VP, _VP, C.c_int64, _VP]),
+    "kb_feasible_batch_bits_device": (C.c_int, [_VP, _VP, C.c_int64, _VP]),
+    "kb_edges_visible_batch_bits": (C.c_int, [_VP, _VP, _VP, C.c_int64, C.c_double, _VP, _VP, _VP]),
     "kb_edges_visible_batch": (C.c_int, [_VP, _VP, _VP, C.c_int64, C.c_double, _VP, _VP, _VP]),
     "kb_edges_visible_batch_device": (C.c_int, [_VP, _VP, _VP, C.c_int64, C.c_double, _VP, _VP, _VP]),
     "kb_colliding_pairs_batch": (C.c_int, [_VP, _VP, C.c_int64, C.c_int, _VP, _VP]),

@@ -365,6 +365,7 @@ struct kb_engine {
   double* d_Q = nullptr; int64_t q_cap = 0;             // staging for host entry points
   float* d_Qf = nullptr; int64_t qf_cap = 0;            // fp32 configurations of kb_feasible_batch_f32, widened into d_Q
   uint8_t* d_out = nullptr; int64_t out_cap = 0;
+  uint32_t* d_bits = nullptr; int64_t bits_cap = 0;   // packed result bitmask of the *_bits entry points
   int32_t* d_pair = nullptr; int64_t pair_cap = 0;
   double* d_dist = nullptr; int64_t dist_cap = 0;
   // edges
@@ -733,7 +734,7 @@ void kb_engine_destroy(kb_engine* e) {
                     e->d_drv_scale, e->d_drv_off, e->feas_items.d_items, e->env_items.d_items, e->d_xf, e->d_state, e->d_hit, e->d_hit_elem, e->d_leaf_list, e->d_flagged, e->d_state2, e->d_work,
                     e->d_counters, e->d_Q, e->d_out, e->d_pair, e->d_dist, e->d_A, e->d_B, e->d_nlev, e->d_alive, e->d_nchecks, e->d_firstbad, e->d_list,
                     e->d_eQ, e->d_efeas, e->d_scalars, e->d_weights, e->d_T, e->feas_items.d_probes, e->feas_items.d_always_on,
-                    e->d_grid[0], e->d_grid[1], e->d_grid[2], e->d_grid[3], e->d_box32, e->d_box64, e->d_boxown, e->d_dyn_pts, e->d_dyn_T, e->d_dyn_scratch, e->d_Qf};
+                    e->d_grid[0], e->d_grid[1], e->d_grid[2], e->d_grid[3], e->d_box32, e->d_box64, e->d_boxown, e->d_dyn_pts, e->d_dyn_T, e->d_dyn_scratch, e->d_Qf, e->d_bits};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -1388,7 +1389,7 @@ int kb_feasible_batch_device(kb_engine* e, const double* dQ, int64_t N, uint8_t*
 }
 
 // host-buffer feasibility for configurations given as doubles (esz 8) or floats (esz 4; widened to fp64 on the device)
-static int feasible_batch_host(kb_engine* e, const void* Qv, int esz, int64_t N, uint8_t* out, int32_t* first_pair) {
+static int feasible_batch_host(kb_engine* e, const void* Qv, int esz, int64_t N, uint8_t* out, int32_t* first_pair, bool bits = false) {
   if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
   if (N < 0 || (N > 0 && (!Qv || !out))) return fail(KB_ERR_INVALID, "bad arguments");
   if (N == 0) return KB_OK;
@@ -1400,6 +1401,7 @@ static int feasible_batch_host(kb_engine* e, const void* Qv, int esz, int64_t N,
   if ((rc = grow(e->d_Q, e->q_cap, N * e->L))) return rc;
   if (esz == 8) d_in = (char*)e->d_Q;
   if ((rc = grow(e->d_out, e->out_cap, N))) return rc;
+  if (bits && (rc = grow(e->d_bits, e->bits_cap, (N + 31) / 32))) return rc;
   if (first_pair && (rc = grow(e->d_pair, e->pair_cap, 2 * N))) return rc;
   begin_timing(e);
   // Staged upload: the batch crosses PCIe in up to four pieces of growing size (N/16, N/8, N/4, rest) on the copy stream, and
@@ -1432,7 +1434,10 @@ static int feasible_batch_host(kb_engine* e, const void* Qv, int esz, int64_t N,
     if (esz == 4) { CK(kb_launch_widen_f32(e->d_Qf + cut[k] * e->L, e->d_Q + cut[k] * e->L, (cut[k + 1] - cut[k]) * e->L, e->stream)); e->stats.kernel_launches++; }
     if ((rc = run_feasible_device(e, e->d_Q + cut[k] * e->L, cut[k + 1] - cut[k], e->d_out + cut[k], first_pair ? e->d_pair + 2 * cut[k] : nullptr, e->d_counters + 3))) return rc;
   }
-  CK(cudaMemcpyAsync(out, e->d_out, (size_t)N, cudaMemcpyDeviceToHost, e->stream));
+  if (bits) {
+    CK(kb_launch_pack_bits(e->d_out, N, e->d_bits, e->stream)); e->stats.kernel_launches++;
+    CK(cudaMemcpyAsync(out, e->d_bits, (size_t)((N + 7) / 8), cudaMemcpyDeviceToHost, e->stream));
+  } else CK(cudaMemcpyAsync(out, e->d_out, (size_t)N, cudaMemcpyDeviceToHost, e->stream));
   if (first_pair) CK(cudaMemcpyAsync(first_pair, e->d_pair, (size_t)N * 8, cudaMemcpyDeviceToHost, e->stream));
   end_timing(e, true);
   CK(cudaStreamSynchronize(e->stream));
@@ -1442,6 +1447,20 @@ static int feasible_batch_host(kb_engine* e, const void* Qv, int esz, int64_t N,
 
 int kb_feasible_batch(kb_engine* e, const double* Q, int64_t N, uint8_t* out, int32_t* first_pair) { return feasible_batch_host(e, Q, 8, N, out, first_pair); }
 int kb_feasible_batch_f32(kb_engine* e, const float* Q, int64_t N, uint8_t* out, int32_t* first_pair) { return feasible_batch_host(e, Q, 4, N, out, first_pair); }
+int kb_feasible_batch_bits(kb_engine* e, const double* Q, int64_t N, uint8_t* out_bits) { return feasible_batch_host(e, Q, 8, N, out_bits, nullptr, true); }
+int kb_feasible_batch_bits_device(kb_engine* e, const double* dQ, int64_t N, uint8_t* d_out_bits) {
+  if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
+  if (N < 0 || (N > 0 && (!dQ || !d_out_bits))) return fail(KB_ERR_INVALID, "bad arguments");
+  if (((uintptr_t)d_out_bits & 3) != 0) return fail(KB_ERR_INVALID, "d_out_bits must be 4-byte aligned (written as 32-bit words, (N + 31) / 32 of them)");
+  if (N == 0) return KB_OK;
+  CK(cudaSetDevice(e->device));
+  int rc;
+  if ((rc = grow(e->d_out, e->out_cap, N))) return rc;
+  if ((rc = run_feasible_device(e, dQ, N, e->d_out, nullptr, e->d_counters + 3))) return rc;
+  CK(kb_launch_pack_bits(e->d_out, N, (uint32_t*)d_out_bits, e->stream)); e->stats.kernel_launches++;
+  e->stats.configs_checked += N;
+  return KB_OK;
+}
 
 int kb_edges_visible_batch_device(kb_engine* e, const double* dA, const double* dB, int64_t N, double eps, const double* weights_host,
                                   uint8_t* d_out, int32_t* d_nchecks) {
@@ -1500,7 +1519,14 @@ int kb_edges_visible_batch_device(kb_engine* e, const double* dA, const double* 
   return KB_OK;
 }
 
+static int edges_visible_host(kb_engine* e, const double* A, const double* B, int64_t N, double eps, const double* weights, uint8_t* out, int32_t* nchecks, bool bits);
 int kb_edges_visible_batch(kb_engine* e, const double* A, const double* B, int64_t N, double eps, const double* weights, uint8_t* out, int32_t* nchecks) {
+  return edges_visible_host(e, A, B, N, eps, weights, out, nchecks, false);
+}
+int kb_edges_visible_batch_bits(kb_engine* e, const double* A, const double* B, int64_t N, double eps, const double* weights, uint8_t* out_bits, int32_t* nchecks) {
+  return edges_visible_host(e, A, B, N, eps, weights, out_bits, nchecks, true);
+}
+static int edges_visible_host(kb_engine* e, const double* A, const double* B, int64_t N, double eps, const double* weights, uint8_t* out, int32_t* nchecks, bool bits) {
   if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
   if (N < 0 || (N > 0 && (!A || !B || !out))) return fail(KB_ERR_INVALID, "bad arguments");
   if (N == 0) return KB_OK;
@@ -1516,6 +1542,11 @@ int kb_edges_visible_batch(kb_engine* e, const double* A, const double* B, int64
   CK(cudaMemcpyAsync(e->d_A, A, (size_t)N * e->L * 8, cudaMemcpyHostToDevice, e->stream));
   CK(cudaMemcpyAsync(e->d_B, B, (size_t)N * e->L * 8, cudaMemcpyHostToDevice, e->stream));
   if ((rc = kb_edges_visible_batch_device(e, e->d_A, e->d_B, N, eps, weights, e->d_out, nchecks ? e->d_pair : nullptr))) return rc;
+  if (bits) {
+    if ((rc = grow(e->d_bits, e->bits_cap, (N + 31) / 32))) return rc;
+    CK(kb_launch_pack_bits(e->d_out, N, e->d_bits, e->stream)); e->stats.kernel_launches++;
+    CK(cudaMemcpyAsync(out, e->d_bits, (size_t)((N + 7) / 8), cudaMemcpyDeviceToHost, e->stream));
+  } else
   CK(cudaMemcpyAsync(out, e->d_out, (size_t)N, cudaMemcpyDeviceToHost, e->stream));
   if (nchecks) CK(cudaMemcpyAsync(nchecks, e->d_pair, (size_t)N * 4, cudaMemcpyDeviceToHost, e->stream));
   end_timing(e, true);

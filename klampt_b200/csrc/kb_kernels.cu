@@ -1881,6 +1881,18 @@ cudaError_t kb_launch_widen_f32(const float* src, double* dst, int64_t n, cudaSt
   return cudaGetLastError();
 }
 
+// result bytes -> packed bitmask: bit (c & 7) of byte (c >> 3) = configuration c (the interface SURVEY 8b names: N / 8 bytes gathered)
+__global__ void kb_pack_bits_kernel(const uint8_t* __restrict__ src, int64_t n, uint32_t* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned m = __ballot_sync(FULL, i < n && src[i] != 0);
+  if ((threadIdx.x & 31) == 0 && (i - (i & 31)) < n) dst[i >> 5] = m;
+}
+cudaError_t kb_launch_pack_bits(const uint8_t* src, int64_t n, uint32_t* dst, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  kb_pack_bits_kernel<<<nblocks(n, 256), 256, 0, s>>>(src, n, dst);
+  return cudaGetLastError();
+}
+
 cudaError_t kb_launch_fill_i32(int32_t* p, int64_t n, int32_t v, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
   kb_fill_i32_kernel<<<nblocks(n, 256), 256, 0, s>>>(p, n, v);

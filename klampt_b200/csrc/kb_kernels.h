@@ -21,6 +21,7 @@ cudaError_t kb_launch_edge_expand(const KbRobotDev* robot, const double* A, cons
                                   int64_t nslots, int lev, double* Q, cudaStream_t s);
 cudaError_t kb_launch_edge_reduce(const uint8_t* feas, const int32_t* list, int64_t first_slot, int64_t nslots, int lev, int32_t* firstbad, cudaStream_t s);
 cudaError_t kb_launch_edge_level_end(const int32_t* list, unsigned int nlist, int lev, int32_t* firstbad, uint8_t* alive, int32_t* nchecks, cudaStream_t s);
+cudaError_t kb_launch_pack_bits(const uint8_t* src, int64_t n, uint32_t* dst, cudaStream_t s);   // dst: (n + 31) / 32 words
 cudaError_t kb_launch_fill_i32(int32_t* p, int64_t n, int32_t v, cudaStream_t s);
 cudaError_t kb_launch_widen_f32(const float* src, double* dst, int64_t n, cudaStream_t s);
 cudaError_t kb_launch_copy_u8(const uint8_t* src, uint8_t* dst, int64_t n, unsigned long long* ones, cudaStream_t s);

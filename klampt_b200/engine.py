@@ -190,6 +190,22 @@ class Engine:
         check(self.lib.kb_feasible_batch(self.h, _ptr(Q), N, _ptr(out), _ptr(pairs)))
         return (out, pairs) if return_pairs else out
 
+    def feasible_batch_bits(self, Q) -> np.ndarray:
+        """feasibility as a packed bitmask, (N + 7) // 8 bytes, little bit order: np.unpackbits(bits, bitorder="little")[:N]"""
+        Q = self._Q(Q)
+        N = Q.shape[0]
+        bits = np.zeros((N + 7) // 8, dtype=np.uint8)
+        check(self.lib.kb_feasible_batch_bits(self.h, _ptr(Q), N, _ptr(bits)))
+        return bits
+
+    def edges_visible_batch_bits(self, A, B, eps: float = 0.01, weights=None) -> np.ndarray:
+        A, B = self._Q(A), self._Q(B)
+        N = A.shape[0]
+        bits = np.zeros((N + 7) // 8, dtype=np.uint8)
+        w = None if weights is None else _f64(weights)
+        check(self.lib.kb_edges_visible_batch_bits(self.h, _ptr(A), _ptr(B), N, float(eps), _ptr(w), _ptr(bits), None))
+        return bits
+
     def edges_visible_batch(self, A, B, eps: float = 0.01, weights=None, return_nchecks: bool = True):
         A, B = self._Q(A), self._Q(B)
         if A.shape != B.shape:
@@ -242,6 +258,9 @@ class Engine:
     # ------------------------------------------------------------------ hot path, device buffers
     def feasible_batch_device(self, dQ, N: int, d_out, d_first_pair=None):
         check(self.lib.kb_feasible_batch_device(self.h, _ptr(dQ), int(N), _ptr(d_out), _ptr(d_first_pair)))
+
+    def feasible_batch_bits_device(self, dQ, N: int, d_bits):
+        check(self.lib.kb_feasible_batch_bits_device(self.h, _ptr(dQ), int(N), _ptr(d_bits)))
 
     def edges_visible_batch_device(self, dA, dB, N: int, eps: float, d_out, d_nchecks=None, weights=None):
         w = None if weights is None else _f64(weights)

@@ -54,3 +54,42 @@ def test_c4_edges_against_oracle(built):
     ovis, on = orc.edges_visible_batch(A, B, eps=0.01, nthreads=0)
     assert np.array_equal(vis, ovis) and np.array_equal(n, on)
     assert 0.4 < vis.mean() < 0.7 and n.max() >= 255
+
+
+def test_c4_one_hundred_thousand_edges(built):
+    """BASELINE config 4 at a size the oracle still finishes in seconds: visibility AND the sequential checker's nchecks, bit for bit"""
+    from klampt_b200.engine import Engine
+    from oracle.oracle import OracleWorld
+    w = synth.world_c2()
+    eng, orc = Engine(w), OracleWorld(w)
+    A, B = synth.sample_edges(w.robot, lambda Q: eng.feasible_batch(Q), 100_000, 44)
+    vis, n = eng.edges_visible_batch(A, B, eps=0.01)
+    ovis, on = orc.edges_visible_batch(A, B, eps=0.01, nthreads=0)
+    assert np.array_equal(vis, ovis) and np.array_equal(n, on)
+    bits = eng.edges_visible_batch_bits(A, B, eps=0.01)
+    assert np.array_equal(np.unpackbits(bits, bitorder="little")[:len(A)], vis)
+    assert 0.4 < vis.mean() < 0.7
+
+
+def test_c5_five_million_point_cloud(built):
+    """BASELINE config 5 at full cloud size (5M points): collide bit and min distance (upper bound 0.5 m) of 100k configurations
+    against the oracle -- booleans under the two-sided band rule, distances within 1e-5 relative"""
+    from klampt_b200.engine import Engine
+    from oracle.oracle import OracleWorld
+    from parity import assert_bool_parity
+    w = synth.world_c5()
+    eng, orc = Engine(w, options={"cloud_builder": 1}), OracleWorld(w)
+    n = 100_000
+    Q = synth.sample_configs(w.robot, n, 55)
+    got = eng.feasible_batch(Q)
+    want = orc.feasible_batch(Q, nthreads=0)
+    assert_bool_parity(got, want, Q, orc, max_bad=n // 1000)       # point spheres with a margin: a distance threshold in fp32 + fp64 recheck
+    assert 0.2 < got.mean() < 0.9
+    d = eng.distance_batch(Q, upper_bound=0.5, include_self=False)
+    od, _ = orc.distance_batch(Q, upper_bound=0.5, include_self=False, nthreads=0)
+    np.testing.assert_allclose(d, od, rtol=1e-5, atol=1e-9)
+    # consistency of the two query kinds: environment clearance <= 0 exactly where the environment collides (self pairs aside)
+    env_hit = d <= 0
+    assert not (env_hit & (got == 1)).any()
+    bits = eng.feasible_batch_bits(Q)
+    assert np.array_equal(np.unpackbits(bits, bitorder="little")[:n], got)
