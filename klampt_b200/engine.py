@@ -7,6 +7,7 @@ tensor) and enqueue on the engine's stream: PyTorch is only plumbing for device 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import numpy as np
@@ -46,7 +47,12 @@ class Engine:
         check(self.lib.kb_engine_create(C.byref(self.h)))
         try:
             self._describe(spec)
-            for k, v in (options or {}).items():
+            options = dict(options or {})
+            # experiment knob: KLAMPT_B200_OPTIONS="name=value,name=value" is applied to every engine of the process
+            for kv in filter(None, os.environ.get("KLAMPT_B200_OPTIONS", "").split(",")):
+                k, v = kv.split("=")
+                options[k.strip()] = int(v)
+            for k, v in options.items():
                 check(self.lib.kb_set_option(self.h, k.encode(), int(v)))
             check(self.lib.kb_finalize(self.h, int(device)))
         except Exception:
