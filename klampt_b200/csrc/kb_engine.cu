@@ -350,6 +350,7 @@ struct kb_engine {
   int mesh_builder = 0;                      // the same choice for triangle meshes above KB_GPU_MESH_MIN triangles
   struct PendingCloud { DevGeom* dg; std::vector<double> elems; std::vector<int32_t> owners; bool mesh = false; };
   std::vector<PendingCloud> pending_clouds;   // clouds whose hierarchy is built on the GPU once the arrays are uploaded
+  int cloud_leaf = 8;                        // points per leaf of a host-built point-cloud hierarchy (option cloud_leaf, 1..32)
   int both_limit = 0;                        // experiment: frontier size up to which comparable inner pairs descend both trees at once
   int grid_res = 256; bool use_grids = false; // clearance-grid broad phase of the boolean query (options grid_res, clear_grid)
   int64_t static_bytes = 0;
@@ -432,7 +433,7 @@ int append_geom(kb_engine* e, int kind, const std::vector<double>& elems, const 
     }
     if (kind != G_MESH && kind != G_BOX) dg.rmax = std::max(dg.rmax, p[3]);
   }
-  Bvh bvh; build_bvh(elo, ehi, n, kind == G_MESH ? 1 : 8, bvh);
+  Bvh bvh; build_bvh(elo, ehi, n, kind == G_MESH ? 1 : (kind == G_BOX ? 8 : e->cloud_leaf), bvh);
   if ((e->h_nodes.size() / 8) & 1) e->h_nodes.insert(e->h_nodes.end(), 8, 0.f);                // even node base: sibling pairs share a 64 B line
   dg.node_base = (int)(e->h_nodes.size() / 8); dg.nnodes = (int)bvh.nodes.size(); dg.depth = bvh.depth;
   dg.elem_base = kind == G_MESH ? (int)(e->h_tris64.size() / 9) : (kind == G_BOX ? (int)(e->h_box64.size() / 16) : (int)(e->h_sph64.size() / 4));
@@ -1344,6 +1345,11 @@ int kb_set_option(kb_engine* e, const char* name, int64_t value) {
     e->cloud_builder = (int)value; return KB_OK;
   }
   if (!strcmp(name, "both_limit")) { e->both_limit = (int)value; return KB_OK; }
+  if (!strcmp(name, "cloud_leaf")) {
+    if (e->finalized) return fail(KB_ERR_STATE, "cloud_leaf must be set before kb_finalize");
+    if (value < 1 || value > 32) return fail(KB_ERR_INVALID, "cloud_leaf must be in [1, 32]");
+    e->cloud_leaf = (int)value; return KB_OK;
+  }
   if (!strcmp(name, "grid_res")) {
     if (e->finalized) return fail(KB_ERR_STATE, "grid_res must be set before kb_finalize");
     if (value != 0 && (value < 8 || value > 512)) return fail(KB_ERR_INVALID, "grid_res must be 0 (no clearance grids) or in [8, 512]");

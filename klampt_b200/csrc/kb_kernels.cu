@@ -1242,24 +1242,161 @@ __device__ __forceinline__ void classify_pair(unsigned itembits, int na, int nb,
   else e = make_uint2(itembits | (unsigned)na, (unsigned)lb | KB_SPLIT_B);                                // split B: slot B holds B's first child
 }
 
+// ---- fp32 element distances with explicit bounds: lo <= (true element distance - radii) <= hi, hi = +inf when the fp32 value
+// cannot be trusted (thin / zero-area triangle, uncertain intersection).  `cut`: a pair whose cheap lower bound is already >= cut
+// is not worth the full evaluation (returns lo >= cut, hi = +inf).  lb_fallback: a lower bound the caller already has (leaf boxes).
+// squared distance point - triangle without the Voronoi-region walk: min over the three clamped edge projections, or the plane
+// distance when the projection falls inside (branch-free: the lanes of a warp hold unrelated pairs).  NaN for a triangle whose
+// fp32 normal cannot be trusted (kb_face_ok).
+__device__ __forceinline__ float point_tri_dist2_bf(const V3<float>& p, const V3<float>& a, const V3<float>& b, const V3<float>& c) {
+  const V3<float> ab = b - a, ac = c - a, bc = c - b, ap = p - a, bp = p - b;
+  const float ab2 = dot(ab, ab), ac2 = dot(ac, ac), bc2 = dot(bc, bc);
+  const float t1 = ab2 > 0.f ? __saturatef(__fdividef(dot(ab, ap), ab2)) : 0.f;
+  const float t2 = ac2 > 0.f ? __saturatef(__fdividef(dot(ac, ap), ac2)) : 0.f;
+  const float t3 = bc2 > 0.f ? __saturatef(__fdividef(dot(bc, bp), bc2)) : 0.f;
+  const V3<float> q1 = madd(ap, ab, -t1), q2 = madd(ap, ac, -t2), q3 = madd(bp, bc, -t3);
+  const float em = fminf(dot(q1, q1), fminf(dot(q2, q2), dot(q3, q3)));
+  const V3<float> n = cross(ab, ac);
+  const float nn = dot(n, n);
+  if (!kb_face_ok(nn, ab2, ac2)) return __int_as_float(0x7fc00000);
+  const float u = dot(cross(ab, ap), n), v = dot(cross(ap, ac), n), h = dot(ap, n);
+  const bool inside = (u >= 0.f) & (v >= 0.f) & (u + v <= nn);
+  return inside ? __fdividef(h * h, nn) : em;
+}
+
+template <bool BOXES>
+__device__ __forceinline__ void elem_bounds(const KbScene& sc, const KbItem& it, const XfF& T, int ea, int eb, float band, float cut, float lb_fallback,
+                                            float& lo, float& hi) {
+  const float INF = __int_as_float(0x7f800000);
+  if (BOXES && (it.kindA == KB_ELEM_BOX || it.kindB == KB_ELEM_BOX)) { const float d = fast_box_elem_distance(sc, it, T, ea, eb); lo = d - band; hi = d + band; return; }
+  if (it.kindA == KB_ELEM_TRI && it.kindB == KB_ELEM_TRI) {
+    const float4* ta = sc.tris32 + 3 * (size_t)ea; const float4* tb = sc.tris32 + 3 * (size_t)eb;
+    const float4 a0 = __ldg(ta), a1 = __ldg(ta + 1), a2 = __ldg(ta + 2), b0 = __ldg(tb), b1 = __ldg(tb + 1), b2 = __ldg(tb + 2);
+    V3<float> A[3] = {mk3<float>(a0.x, a0.y, a0.z), mk3<float>(a1.x, a1.y, a1.z), mk3<float>(a2.x, a2.y, a2.z)};
+    V3<float> B[3] = {xform(T, b0), xform(T, b1), xform(T, b2)};
+    // cheap plane-separation lower bound first (see fast_elem_distance): most pairs of a leaf phase cannot beat the running minimum
+    const V3<float> ea1 = A[1] - A[0], ea2 = A[2] - A[0], eb1 = B[1] - B[0], eb2 = B[2] - B[0];
+    const V3<float> nA = cross(ea1, ea2), nB = cross(eb1, eb2);
+    const V3<float> w0 = B[0] - A[0], w1 = B[1] - A[0], w2 = B[2] - A[0], u1 = A[1] - B[0], u2 = A[2] - B[0];
+    const float b0s = dot(nA, w0), b1s = dot(nA, w1), b2s = dot(nA, w2);
+    const float a0s = -dot(nB, w0), a1s = dot(nB, u1), a2s = dot(nB, u2);
+    const float slackA = 1e-6f * sqrtf(dot(ea1, ea1) * dot(ea2, ea2) * fmaxf(dot(w0, w0), fmaxf(dot(w1, w1), dot(w2, w2))));
+    const float slackB = 1e-6f * sqrtf(dot(eb1, eb1) * dot(eb2, eb2) * fmaxf(dot(w0, w0), fmaxf(dot(u1, u1), dot(u2, u2))));
+    float lbA = 0.f, lbB = 0.f;
+    if ((b0s > 0.f && b1s > 0.f && b2s > 0.f) || (b0s < 0.f && b1s < 0.f && b2s < 0.f))
+      lbA = fmaxf(fminf(fabsf(b0s), fminf(fabsf(b1s), fabsf(b2s))) - slackA, 0.f) * rsqrtf(fmaxf(dot(nA, nA), 1e-30f));
+    if ((a0s > 0.f && a1s > 0.f && a2s > 0.f) || (a0s < 0.f && a1s < 0.f && a2s < 0.f))
+      lbB = fmaxf(fminf(fabsf(a0s), fminf(fabsf(a1s), fabsf(a2s))) - slackB, 0.f) * rsqrtf(fmaxf(dot(nB, nB), 1e-30f));
+    const float lbt = fmaxf(fmaxf(lbA, lbB) * (1.f - 1e-5f) - band, 0.f);
+    lo = lbt; hi = INF;
+    if (lbt >= cut) return;
+    FiltF f; f.filt = 24.f * sc.eps_abs;
+    V3<float> A2[3] = {A[0], A[1], A[2]}, B2[3] = {B[0], B[1], B[2]};
+    const int r = tri_tri_intersect<float, FiltF>(A2, B2, f);
+    if (r == KB_YES) { lo = 0.f; hi = 0.f; return; }
+    if (r == KB_UNCERTAIN) { lo = 0.f; return; }
+    if (!kb_face_ok(dot(nA, nA), dot(ea1, ea1), dot(ea2, ea2)) || !kb_face_ok(dot(nB, nB), dot(eb1, eb1), dot(eb2, eb2))) return;
+    const float d = sqrtf(tri_tri_dist2_disjoint<float>(A, B));
+    lo = fmaxf(lbt, d - band); hi = d + band;
+    return;
+  }
+  float d;
+  if (it.kindA == KB_ELEM_TRI) {
+    const float4* ta = sc.tris32 + 3 * (size_t)ea;
+    const float4 a0 = __ldg(ta), a1 = __ldg(ta + 1), a2 = __ldg(ta + 2), s = __ldg(sc.sph32 + eb);
+    d = sqrtf(point_tri_dist2_bf(xform(T, s), mk3<float>(a0.x, a0.y, a0.z), mk3<float>(a1.x, a1.y, a1.z), mk3<float>(a2.x, a2.y, a2.z))) - s.w;
+  } else if (it.kindB == KB_ELEM_TRI) {
+    const float4* tb = sc.tris32 + 3 * (size_t)eb;
+    const float4 b0 = __ldg(tb), b1 = __ldg(tb + 1), b2 = __ldg(tb + 2), s = __ldg(sc.sph32 + ea);
+    d = sqrtf(point_tri_dist2_bf(mk3<float>(s.x, s.y, s.z), xform(T, b0), xform(T, b1), xform(T, b2))) - s.w;
+  } else {
+    const float4 sa = __ldg(sc.sph32 + ea), sb = __ldg(sc.sph32 + eb);
+    const V3<float> dv = xform(T, sb) - mk3<float>(sa.x, sa.y, sa.z);
+    d = sqrtf(dot(dv, dv)) - sa.w - sb.w;
+  }
+  if (d != d) { lo = lb_fallback; hi = INF; return; }      // NaN: a face normal fp32 cannot be trusted with -> the pair goes to fp64
+  lo = d - band; hi = d + band;
+}
+
+// kb_distance_kernel (v2).  One warp per configuration, branch and bound as before, re-organised after the round-1 profile
+// (166 registers, 13.9 active lanes, eager fp64 leaf distances inside the node loop):
+//   * the hot path is fp32 only.  Every element pair gets bounds lo <= d <= hi (elem_bounds); `bound` = the smallest hi seen is a
+//     valid upper bound of the answer and drives the pruning; a pair with lo < thr MAY be the minimum and is parked in a per-warp
+//     candidate list.  The list is evaluated in fp64 32 candidates at a time (exact_elem_distance, the same arithmetic as before, in
+//     one not-inlined cold path), which yields the exact minimum: the true closest pair p* always satisfies lo(p*) <= d(p*) <= bound.
+//   * node phase: a lane pops one pair, loads the two children of the split side (one 64-byte line) and the other node, and
+//     computes both box-gap bounds; the split side is chosen with selects, not branches.  Survivors are pushed farther first.
+//   * element phase: a lane owns one leaf pair and walks its (<= 8 x 8) element pairs with the branch-free point / triangle code.
+//   * relErr / absErr of AnyCollisionQuery::Distance: a pair is pruned when lb + absErr >= bound or lb + relErr |bound| >= bound,
+//     so the reported value is within that tolerance above the true minimum (0 / 0 = exact).
+struct KbDistArgs { double* out_dist; double* out_cp; double upper_bound; float rel_err, abs_err; };
+#ifndef KB_CAND_CAP
+#define KB_CAND_CAP 64
+#endif
+#ifndef KB_DIST_BPS
+#define KB_DIST_BPS 4
+#endif
+
+__device__ __forceinline__ float kb_thr_from(float bound, float rel_err, float abs_err) {
+  return fminf(bound - abs_err, bound - rel_err * fabsf(bound));
+}
+
+template <bool BOXES>
+__device__ __noinline__ void drain_candidates(const KbTraverseParams& p, const double* __restrict__ xf, uint4* cand, const float* cand_hi, int* cand_count, int lane,
+                                              float rel_err, float abs_err, double& best64, int& best_item, int& best_ea, int& best_eb, float& bound, float& thr) {
+  __syncwarp();
+  int n = *cand_count; if (n > KB_CAND_CAP) n = KB_CAND_CAP;
+  for (int base = 0; base < n; base += 32) {
+    const int k = base + lane;
+    double d = 1e300; int item = -1, ea = -1, eb = -1;
+    if (k < n) {
+      const uint4 c = cand[k];
+      // still able to be the answer (lo <= thr), or the pair whose fp32 upper bound IS the current bound: that one is always evaluated, so
+      // the bound the pruning used is backed by an exact value
+      if (__uint_as_float(c.w) <= thr || cand_hi[k] <= bound) {
+        item = (int)c.x; ea = (int)c.y; eb = (int)c.z;
+        const KbItem& it = p.items[item];
+        d = exact_elem_distance<BOXES>(p.scene, it, xf, ea, eb) - it.marg;
+      }
+    }
+    double wmin = d;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const double x = __shfl_xor_sync(FULL, wmin, o); wmin = x < wmin ? x : wmin; }
+    if (wmin < best64) {
+      const unsigned who = __ballot_sync(FULL, d == wmin);
+      const int src = __ffs(who) - 1;
+      best64 = wmin; best_item = __shfl_sync(FULL, item, src); best_ea = __shfl_sync(FULL, ea, src); best_eb = __shfl_sync(FULL, eb, src);
+      float bf = (float)best64; if ((double)bf < best64) bf = nextafterf(bf, INFINITY);
+      if (bf < bound) { bound = bf; thr = kb_thr_from(bound, rel_err, abs_err); }
+    }
+  }
+  __syncwarp();
+  if (lane == 0) *cand_count = 0;
+  __syncwarp();
+}
+
 template <bool ITC, bool STATS, bool BOXES>
-__global__ void __launch_bounds__(KB_WARPS_PER_BLOCK * 32, 3)
-kb_distance_kernel(const KbTraverseParams p, double* __restrict__ out_dist, double upper_bound) {
+__global__ void __launch_bounds__(KB_WARPS_PER_BLOCK * 32, KB_DIST_BPS)
+kb_distance_kernel(const KbTraverseParams p, const KbDistArgs da) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int xf_floats = (p.nxf * 12 + 3) & ~3;
   const int nit_c = ITC ? p.nitems : 0;
   ItemS* s_items = (ItemS*)smem_raw;
-  const size_t per_warp = (size_t)KB_STACK_CAP * 12 + (size_t)KB_LEAFQ_CAP * 12 + (size_t)xf_floats * 4 + (size_t)nit_c * 48;
+  const size_t per_warp = (size_t)KB_STACK_CAP * 12 + (size_t)KB_LEAFQ_CAP * 12 + (size_t)KB_CAND_CAP * 20 + 16 + (size_t)xf_floats * 4 + (size_t)nit_c * 48;
   unsigned char* base = smem_raw + (size_t)nit_c * 16 + warp * per_warp;
   uint2* stack = (uint2*)base;
   uint2* leafq = (uint2*)(base + (size_t)KB_STACK_CAP * 8);
   float* stack_lb = (float*)(base + (size_t)KB_STACK_CAP * 8 + (size_t)KB_LEAFQ_CAP * 8);
   float* leaf_lb = stack_lb + KB_STACK_CAP;
-  float* xfw = leaf_lb + KB_LEAFQ_CAP;
+  uint4* cand = (uint4*)(leaf_lb + KB_LEAFQ_CAP);
+  float* cand_hi = (float*)(cand + KB_CAND_CAP);
+  int* cand_count = (int*)(cand_hi + KB_CAND_CAP);
+  float* xfw = (float*)(cand_count + 4);
   float* itc = xfw + xf_floats;
   const KbScene& sc = p.scene;
   const float slack = 4.f * sc.eps_abs;
+  const float INF = __int_as_float(0x7f800000);
   if (ITC) {
     for (int i = threadIdx.x; i < p.nitems; i += blockDim.x) {
       const KbItem* it = p.items + i;
@@ -1268,10 +1405,11 @@ kb_distance_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
       s_items[i] = s;
     }
   }
+  if (lane == 0) *cand_count = 0;
   __syncthreads();
   unsigned lt_mask;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
-  unsigned st_node = 0, st_leaf = 0;
+  unsigned st_node = 0, st_leaf = 0, st_exact = 0, st_iter = 0;
   const unsigned total_warps = gridDim.x * KB_WARPS_PER_BLOCK;
   unsigned grab = 4;
   for (;;) {
@@ -1297,23 +1435,26 @@ kb_distance_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
         __syncwarp();
       }
       int sp = 0, nleaf = 0, cursor = 0;
-      double best = upper_bound;                       // running minimum, margins already subtracted
-      float bestf = (float)fmin(upper_bound, 3.0e38);  // fp32 copy rounded up, for the box tests
-      if ((double)bestf < best) bestf = nextafterf(bestf, INFINITY);
+      double best64 = da.upper_bound;                     // exact running minimum over the evaluated candidates, margins subtracted
       int best_item = -1, best_ea = -1, best_eb = -1;
-      bool have_bound = false;
+      float bound = (float)fmin(da.upper_bound, 3.0e38);  // fp32 upper bound of the answer (rounded up), drives the pruning
+      if ((double)bound < da.upper_bound) bound = nextafterf(bound, INFINITY);
+      const float bound0 = bound;
+      float thr = kb_thr_from(bound, da.rel_err, da.abs_err);
+      const float band = 16.f * sc.eps_abs;
       for (;;) {
         const bool feed = sp < 32 && nleaf < 32 && cursor < p.nitems;
         if (!feed) {
           if (sp == 0 && nleaf == 0) break;
-          if (nleaf >= 16 || sp == 0 || (nleaf > 0 && !have_bound)) {
-            // -------------------------------------------------------------- element phase (fp64)
+          if (nleaf >= 32 || sp == 0 || (nleaf > 0 && bound >= bound0)) {
+            // -------------------------------------------------------------- element phase (fp32 bounds, candidates parked)
             const int m = nleaf < 32 ? nleaf : 32;
-            int ea = -1, eb = -1, item = 0;
-            double dmin = 1e300;
-            if (lane < m && leaf_lb[nleaf - 1 - lane] < bestf) {
+            float bound_l = bound, thr_l = thr;
+            double dl = 1e300; int il = -1, eal = -1, ebl = -1;        // exact results of candidates that did not fit the list
+            if (lane < m && leaf_lb[nleaf - 1 - lane] <= thr) {
               const uint2 e = leafq[nleaf - 1 - lane];
-              item = (int)(e.x >> KB_NODEA_BITS);
+              const float lbq = leaf_lb[nleaf - 1 - lane];
+              const int item = (int)(e.x >> KB_NODEA_BITS);
               const KbItem& it = p.items[item];
               const int na = (int)(e.x & (KB_MAX_NODES_A - 1)), nb = (int)e.y;
               float4 a0, a1, b0, b1;
@@ -1321,32 +1462,47 @@ kb_distance_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
               load_node(sc.nodes, (size_t)(it.nodeB + nb), b0, b1);
               const int fa = it.elemA + ~__float_as_int(a0.w), ca = __float_as_int(a1.w);
               const int fb = it.elemB + ~__float_as_int(b0.w), cb = __float_as_int(b1.w);
-              const double marg = it.marg;
               XfF T;
               if (ITC) load_itc(itc, item, T); else rel_xf(xfw, it.xfA, it.xfB, T);
-              const float margf = (float)marg, band = 16.f * sc.eps_abs;
+              const float margf = (float)it.marg, bandm = band + 2e-7f * fabsf(margf);
               for (int i = 0; i < ca; i++)
                 for (int j = 0; j < cb; j++) {
                   if (STATS) st_leaf++;
-                  // fp32 first: a pair whose estimate cannot beat the running minimum (nor this lane's own) skips the fp64 evaluation
-                  const float d32 = fast_elem_distance<BOXES>(sc, it, T, fa + i, fb + j) - margf - band;
-                  if (d32 >= bestf || (double)d32 >= dmin) continue;
-                  const double d = exact_elem_distance<BOXES>(sc, it, xf, fa + i, fb + j) - marg;
-                  if (d < dmin) { dmin = d; ea = fa + i; eb = fb + j; }
+                  float lo, hi;
+                  elem_bounds<BOXES>(sc, it, T, fa + i, fb + j, bandm, thr_l + margf + bandm, lbq + margf, lo, hi);
+                  lo -= margf + bandm - band; hi -= margf - (bandm - band);
+                  if (lo <= thr_l || hi < bound_l) {
+                    const int slot = atomicAdd(cand_count, 1);
+                    if (slot < KB_CAND_CAP) { cand[slot] = make_uint4((unsigned)item, (unsigned)(fa + i), (unsigned)(fb + j), __float_as_uint(lo)); cand_hi[slot] = hi; }
+                    else {                                    // list full: evaluate in place (rare)
+                      if (STATS) st_exact++;
+                      const double d = exact_elem_distance<BOXES>(sc, it, xf, fa + i, fb + j) - it.marg;
+                      if (d < dl) { dl = d; il = item; eal = fa + i; ebl = fb + j; }
+                      float df = (float)d; if ((double)df < d) df = nextafterf(df, INFINITY);
+                      hi = fminf(hi, df);
+                    }
+                    if (hi < bound_l) { bound_l = hi; thr_l = kb_thr_from(bound_l, da.rel_err, da.abs_err); }
+                  }
                 }
             }
             nleaf -= m;
-            double wmin = dmin;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { const double x = __shfl_xor_sync(FULL, wmin, o); wmin = x < wmin ? x : wmin; }
-            if (wmin < best) {
-              const unsigned who = __ballot_sync(FULL, dmin == wmin);
-              const int src = __ffs(who) - 1;
-              best = wmin; best_item = __shfl_sync(FULL, item, src); best_ea = __shfl_sync(FULL, ea, src); best_eb = __shfl_sync(FULL, eb, src);
-              bestf = (float)best; if ((double)bestf < best) bestf = nextafterf(bestf, INFINITY);
-              have_bound = true;
+            for (int o = 16; o > 0; o >>= 1) bound_l = fminf(bound_l, __shfl_xor_sync(FULL, bound_l, o));
+            if (bound_l < bound) { bound = bound_l; thr = kb_thr_from(bound, da.rel_err, da.abs_err); }
+            if (__any_sync(FULL, dl < 1e300)) {
+              double wmin = dl;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) { const double x = __shfl_xor_sync(FULL, wmin, o); wmin = x < wmin ? x : wmin; }
+              if (wmin < best64) {
+                const int src = __ffs(__ballot_sync(FULL, dl == wmin)) - 1;
+                best64 = wmin; best_item = __shfl_sync(FULL, il, src); best_ea = __shfl_sync(FULL, eal, src); best_eb = __shfl_sync(FULL, ebl, src);
+              }
             }
             __syncwarp();
+            if (*cand_count >= KB_CAND_CAP / 2) {
+              if (STATS) st_exact += (lane == 0) ? (unsigned)min(*cand_count, KB_CAND_CAP) : 0u;
+              drain_candidates<BOXES>(p, xf, cand, cand_hi, cand_count, lane, da.rel_err, da.abs_err, best64, best_item, best_ea, best_eb, bound, thr);
+            }
             continue;
           }
         }
@@ -1356,12 +1512,13 @@ kb_distance_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
         bool live = false;
         if (feed) { m = p.nitems - cursor; if (m > 32) m = 32; live = lane < m; }
         else {
-          const int width = have_bound ? 32 : 8;
+          const int width = bound < bound0 ? 32 : 8;
           m = (sp <= p.wide_limit) ? (sp < width ? sp : width) : 1;
-          if (lane < m) { e = stack[sp - 1 - lane]; live = stack_lb[sp - 1 - lane] < bestf; }   // re-check against the current minimum
+          if (lane < m) { e = stack[sp - 1 - lane]; live = stack_lb[sp - 1 - lane] < thr; }   // re-check against the current bound
           sp -= m;
           __syncwarp();
         }
+        if (STATS) st_iter += (lane == 0);
         bool ok0 = false, ok1 = false, leaf0 = false, leaf1 = false;
         uint2 e0 = e, e1 = e;
         float lb0 = 0.f, lb1 = 0.f;
@@ -1380,36 +1537,34 @@ kb_distance_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
             rel_xf(xfw, itp->xfA, itp->xfB, T);
           }
           // conservative fp32 bound on (element distance - margins): box gap minus slack; touching boxes only bound by -radii
-          const float margu = marg * (1.f + 2.4e-7f) + 1e-30f;
+          const float margu = marg > 0.f ? marg * (1.f + 2.4e-7f) + 1e-30f : 0.f;
+          const float touch = -rsum * (1.f + 2.4e-7f) - margu;     // floor of the item: nothing is closer than -(radii + margins); == 0 for bare meshes,
+                                                                   // so once two triangles intersect (bound 0) every remaining pair is pruned
           if (feed) {
             float4 a0, a1, b0, b1;
             load_node(sc.nodes, (size_t)nodeA, a0, a1);
             load_node(sc.nodes, (size_t)nodeB, b0, b1);
             if (STATS) st_node++;
             const float g = box_dist_lb(a0, a1, b0, b1, T) - slack;
-            lb0 = (g > 0.f ? g * (1.f - 4e-7f) : -rsum * (1.f + 2.4e-7f)) - margu;
-            ok0 = lb0 < bestf;
+            lb0 = g > 0.f ? g * (1.f - 4e-7f) - margu : touch;
+            ok0 = lb0 < thr;
             if (ok0) classify_pair(itembits, 0, 0, a0, a1, b0, b1, leaf0, e0);
           } else {
             const bool splitB = (e.y & KB_SPLIT_B) != 0;
             const int ra = (int)(e.x & (KB_MAX_NODES_A - 1)), rb = (int)(e.y & ~KB_SPLIT_B);
+            // children of the split side (siblings: one 64-byte line) and the node of the other side; which is which by selects
             float4 c00, c01, c10, c11, o0, o1;
-            if (splitB) { load_node(sc.nodes, (size_t)(nodeB + rb), c00, c01); load_node(sc.nodes, (size_t)(nodeB + rb + 1), c10, c11); load_node(sc.nodes, (size_t)(nodeA + ra), o0, o1); }
-            else { load_node(sc.nodes, (size_t)(nodeA + ra), c00, c01); load_node(sc.nodes, (size_t)(nodeA + ra + 1), c10, c11); load_node(sc.nodes, (size_t)(nodeB + rb), o0, o1); }
+            const size_t ic = (size_t)(splitB ? nodeB + rb : nodeA + ra), io = (size_t)(splitB ? nodeA + ra : nodeB + rb);
+            load_node(sc.nodes, ic, c00, c01); load_node(sc.nodes, ic + 1, c10, c11); load_node(sc.nodes, io, o0, o1);
             if (STATS) st_node += 2;
-            float g0, g1;
-            if (splitB) { g0 = box_dist_lb(o0, o1, c00, c01, T) - slack; g1 = box_dist_lb(o0, o1, c10, c11, T) - slack; }
-            else { g0 = box_dist_lb(c00, c01, o0, o1, T) - slack; g1 = box_dist_lb(c10, c11, o0, o1, T) - slack; }
-            lb0 = (g0 > 0.f ? g0 * (1.f - 4e-7f) : -rsum * (1.f + 2.4e-7f)) - margu;
-            lb1 = (g1 > 0.f ? g1 * (1.f - 4e-7f) : -rsum * (1.f + 2.4e-7f)) - margu;
-            ok0 = lb0 < bestf; ok1 = lb1 < bestf;
-            if (splitB) {
-              if (ok0) classify_pair(itembits, ra, rb, o0, o1, c00, c01, leaf0, e0);
-              if (ok1) classify_pair(itembits, ra, rb + 1, o0, o1, c10, c11, leaf1, e1);
-            } else {
-              if (ok0) classify_pair(itembits, ra, rb, c00, c01, o0, o1, leaf0, e0);
-              if (ok1) classify_pair(itembits, ra + 1, rb, c10, c11, o0, o1, leaf1, e1);
-            }
+            const float4 A00 = splitB ? o0 : c00, A01 = splitB ? o1 : c01, B00 = splitB ? c00 : o0, B01 = splitB ? c01 : o1;
+            const float4 A10 = splitB ? o0 : c10, A11 = splitB ? o1 : c11, B10 = splitB ? c10 : o0, B11 = splitB ? c11 : o1;
+            const float g0 = box_dist_lb(A00, A01, B00, B01, T) - slack, g1 = box_dist_lb(A10, A11, B10, B11, T) - slack;
+            lb0 = g0 > 0.f ? g0 * (1.f - 4e-7f) - margu : touch;
+            lb1 = g1 > 0.f ? g1 * (1.f - 4e-7f) - margu : touch;
+            ok0 = lb0 < thr; ok1 = lb1 < thr;
+            if (ok0) classify_pair(itembits, ra, rb, A00, A01, B00, B01, leaf0, e0);
+            if (ok1) classify_pair(itembits, splitB ? ra : ra + 1, splitB ? rb + 1 : rb, A10, A11, B10, B11, leaf1, e1);
             if (ok0 && ok1 && lb0 < lb1) {              // candidate 1 is pushed last = on top: make it the nearer one
               const uint2 te = e0; e0 = e1; e1 = te; const bool tl = leaf0; leaf0 = leaf1; leaf1 = tl; const float tf = lb0; lb0 = lb1; lb1 = tf;
             }
@@ -1435,14 +1590,19 @@ kb_distance_kernel(const KbTraverseParams p, double* __restrict__ out_dist, doub
         sp += __popc(pm0) + __popc(pm1); nleaf += __popc(lm0) + __popc(lm1);
         __syncwarp();
       }
+      if (STATS) st_exact += (lane == 0) ? (unsigned)min(*cand_count, KB_CAND_CAP) : 0u;
+      drain_candidates<BOXES>(p, xf, cand, cand_hi, cand_count, lane, da.rel_err, da.abs_err, best64, best_item, best_ea, best_eb, bound, thr);
       if (STATS) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { st_node += __shfl_xor_sync(FULL, st_node, o); st_leaf += __shfl_xor_sync(FULL, st_leaf, o); }
-        if (lane == 0 && p.counters) { atomicAdd(p.counters + 1, (unsigned long long)st_node); atomicAdd(p.counters + 2, (unsigned long long)st_leaf); }
-        st_node = st_leaf = 0;
+        for (int o = 16; o > 0; o >>= 1) { st_node += __shfl_xor_sync(FULL, st_node, o); st_leaf += __shfl_xor_sync(FULL, st_leaf, o); st_exact += __shfl_xor_sync(FULL, st_exact, o); }
+        if (lane == 0 && p.counters) {
+          atomicAdd(p.counters + 1, (unsigned long long)st_node); atomicAdd(p.counters + 2, (unsigned long long)st_leaf);
+          atomicAdd(p.counters + 0, (unsigned long long)st_exact); atomicAdd(p.counters + 8, (unsigned long long)st_iter);
+        }
+        st_node = st_leaf = st_exact = st_iter = 0;
       }
       if (lane == 0) {
-        out_dist[c] = best;
+        da.out_dist[c] = best64;
         p.hit[c] = best_item;
         if (p.hit_elem) { p.hit_elem[2 * (size_t)c] = best_ea; p.hit_elem[2 * (size_t)c + 1] = best_eb; }
       }
@@ -1681,11 +1841,11 @@ static inline unsigned int nblocks(int64_t n, int bs) { return (unsigned int)((n
 size_t kb_distance_smem_bytes(int nxf, int nitems) {
   size_t xf_floats = ((size_t)nxf * 12 + 3) & ~(size_t)3;
   size_t nit = nitems <= KB_ITC_MAX_ITEMS ? (size_t)nitems : 0;
-  return nit * 16 + (size_t)KB_WARPS_PER_BLOCK * ((size_t)KB_STACK_CAP * 12 + (size_t)KB_LEAFQ_CAP * 12 + xf_floats * 4 + nit * 48);
+  return nit * 16 + (size_t)KB_WARPS_PER_BLOCK * ((size_t)KB_STACK_CAP * 12 + (size_t)KB_LEAFQ_CAP * 12 + (size_t)KB_CAND_CAP * 20 + 16 + xf_floats * 4 + nit * 48);
 }
 
 template <bool ITC, bool STATS, bool BOXES>
-static cudaError_t launch_distance_t(const KbTraverseParams& p, double* out_dist, double upper_bound, int num_sms, size_t smem, cudaStream_t s) {
+static cudaError_t launch_distance_t(const KbTraverseParams& p, const KbDistArgs& da, int num_sms, size_t smem, cudaStream_t s) {
   static bool attr_set[64] = {false};      // the attribute is per device
   int dev = 0; cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
@@ -1693,10 +1853,10 @@ static cudaError_t launch_distance_t(const KbTraverseParams& p, double* out_dist
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
-  int per_sm = (int)((224 * 1024) / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > 3) per_sm = 3;
+  int per_sm = (int)((224 * 1024) / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > KB_DIST_BPS) per_sm = KB_DIST_BPS;
   int64_t want = (p.N + KB_WARPS_PER_BLOCK - 1) / KB_WARPS_PER_BLOCK;
   int64_t grid = (int64_t)num_sms * per_sm; if (grid > want) grid = want; if (grid < 1) grid = 1;
-  kb_distance_kernel<ITC, STATS, BOXES><<<(unsigned)grid, KB_WARPS_PER_BLOCK * 32, smem, s>>>(p, out_dist, upper_bound);
+  kb_distance_kernel<ITC, STATS, BOXES><<<(unsigned)grid, KB_WARPS_PER_BLOCK * 32, smem, s>>>(p, da);
   return cudaGetLastError();
 }
 
@@ -1732,7 +1892,7 @@ static cudaError_t launch_traverse_t(const KbTraverseParams& p, int num_sms, siz
   return cudaGetLastError();
 }
 
-cudaError_t kb_launch_traverse(const KbTraverseParams& p, int mode, double* out_dist, double upper_bound, int num_sms, cudaStream_t s) {
+cudaError_t kb_launch_traverse(const KbTraverseParams& p, int mode, double* out_dist, double upper_bound, int num_sms, cudaStream_t s, double* out_cp, float rel_err, float abs_err) {
   if (p.N <= 0) return cudaSuccess;
   const size_t smem = mode == 0 ? kb_traverse_smem_bytes(p.nxf, p.nitems, p.nprobes) : kb_distance_smem_bytes(p.nxf, p.nitems);
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
@@ -1741,7 +1901,8 @@ cudaError_t kb_launch_traverse(const KbTraverseParams& p, int mode, double* out_
   const bool itc = p.nitems <= KB_ITC_MAX_ITEMS;
   if (p.N > 0xfffffff0ll) return cudaErrorInvalidValue;
   if (mode == 1) {
-#define KB_LD(I, S) (p.has_boxes ? launch_distance_t<I, S, true>(p, out_dist, upper_bound, num_sms, smem, s) : launch_distance_t<I, S, false>(p, out_dist, upper_bound, num_sms, smem, s))
+    KbDistArgs da; da.out_dist = out_dist; da.out_cp = out_cp; da.upper_bound = upper_bound; da.rel_err = rel_err; da.abs_err = abs_err;
+#define KB_LD(I, S) (p.has_boxes ? launch_distance_t<I, S, true>(p, da, num_sms, smem, s) : launch_distance_t<I, S, false>(p, da, num_sms, smem, s))
     if (p.collect_stats) return itc ? KB_LD(true, true) : KB_LD(false, true);
     return itc ? KB_LD(true, false) : KB_LD(false, false);
 #undef KB_LD

@@ -9,7 +9,9 @@ cudaError_t kb_launch_fk(const KbRobotDev* robot, const KbDriverDev* drv, const 
                          const double* drv_off, const double* Q, int64_t N, double* xf64, int nxf, uint8_t* state,
                          const uint8_t* alive, int32_t* hit, cudaStream_t s);
 // mode 0: boolean collide, mode 1: branch-and-bound distance (out_dist, upper_bound)
-cudaError_t kb_launch_traverse(const KbTraverseParams& p, int mode, double* out_dist, double upper_bound, int num_sms, cudaStream_t s);
+// out_cp (mode 1, optional): closest points, 6 doubles per configuration; rel_err / abs_err: tolerances of AnyCollisionQuery::Distance
+cudaError_t kb_launch_traverse(const KbTraverseParams& p, int mode, double* out_dist, double upper_bound, int num_sms, cudaStream_t s,
+                               double* out_cp = nullptr, float rel_err = 0.f, float abs_err = 0.f);
 cudaError_t kb_launch_finish(const uint8_t* state, const int32_t* hit, const int32_t* hit_elem, const KbItem* items, const int32_t* triown,
                              const int32_t* sphown, const int32_t* boxown, int64_t N, uint8_t* out, int32_t* first_pair, unsigned long long* nfeasible, cudaStream_t s);
 cudaError_t kb_launch_pair_ids(const int32_t* hit, const int32_t* hit_elem, const KbItem* items, const int32_t* triown, const int32_t* sphown, const int32_t* boxown,
