@@ -186,6 +186,16 @@ int kb_distance_batch(kb_engine* e, const double* Q, int64_t N, double upper_bou
                       double* out_d, int32_t* out_pair);
 int kb_distance_batch_device(kb_engine* e, const double* dQ, int64_t N, double upper_bound, int include_self,
                              double* d_out_d, int32_t* d_out_pair);
+/* The full AnyCollisionQuery::Distance(absErr, relErr, bound) (Cpp/Planning/PlannerSettings.cpp:109-115 passes eps as both, the
+ * Python binding DistanceQuerySettings, Python/klampt/src/geometry.h:605-629) with the rest of DistanceQueryResult
+ * (src/geometry.h:631-694).  abs_err / rel_err >= 0: a branch is abandoned once it cannot improve the running minimum by more
+ * than abs_err or rel_err * |minimum|, so the value is within that tolerance above the exact minimum (0, 0 = exact).
+ * out_cp (optional, N x 6): closest points in the world frame, first the point on the geometry of out_pair[0] then the one on
+ * out_pair[1], on the margin- and radius-inflated surfaces (|cp2 - cp1| = d when d > 0); NaN where the bound was returned.
+ * out_elem (optional, N x 2): index of the closest triangle / point in each geometry's own element order (0 for primitives), -1
+ * where the bound was returned. */
+int kb_distance_batch_ex(kb_engine* e, const double* Q, int64_t N, double abs_err, double rel_err, double upper_bound, int include_self,
+                         double* out_d, int32_t* out_pair, double* out_cp, int32_t* out_elem);
 
 /* AnyCollisionQuery between two registered geometries at explicit transforms, N transform pairs at once
  * (Geometry3D.collides / withinDistance / distance, Python/klampt/src/robotsim.cpp:1656-1819).
@@ -194,6 +204,10 @@ int kb_geom_collides_batch(kb_engine* e, int ga, const double* Ta, int gb, const
                            uint8_t* out);
 int kb_geom_distance_batch(kb_engine* e, int ga, const double* Ta, int gb, const double* Tb, int64_t N,
                            double upper_bound, double* out_d);
+/* Geometry3D.distance_ext(other, settings) -> DistanceQueryResult (Python/klampt/src/robotsim.cpp:1765-1819): distance with
+ * tolerances, closest points (cp1 on ga, cp2 on gb) and element indices, as kb_distance_batch_ex */
+int kb_geom_distance_batch_ex(kb_engine* e, int ga, const double* Ta, int gb, const double* Tb, int64_t N, double abs_err, double rel_err,
+                              double upper_bound, double* out_d, double* out_cp, int32_t* out_elem);
 
 /* ---- introspection ------------------------------------------------------------------------------------ */
 int kb_get_stats(kb_engine* e, kb_stats* out);

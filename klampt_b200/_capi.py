@@ -64,6 +64,8 @@ SIGNATURES = {
     "kb_colliding_pairs_batch": (C.c_int, [_VP, _VP, C.c_int64, C.c_int, _VP, _VP]),
     "kb_distance_batch": (C.c_int, [_VP, _VP, C.c_int64, C.c_double, C.c_int, _VP, _VP]),
     "kb_distance_batch_device": (C.c_int, [_VP, _VP, C.c_int64, C.c_double, C.c_int, _VP, _VP]),
+    "kb_distance_batch_ex": (C.c_int, [_VP, _VP, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_int, _VP, _VP, _VP, _VP]),
+    "kb_geom_distance_batch_ex": (C.c_int, [_VP, C.c_int, _VP, C.c_int, _VP, C.c_int64, C.c_double, C.c_double, C.c_double, _VP, _VP, _VP]),
     "kb_geom_collides_batch": (C.c_int, [_VP, C.c_int, _VP, C.c_int, _VP, C.c_int64, C.c_double, _VP]),
     "kb_geom_distance_batch": (C.c_int, [_VP, C.c_int, _VP, C.c_int, _VP, C.c_int64, C.c_double, _VP]),
     "kb_get_stats": (C.c_int, [_VP, C.POINTER(KbStats)]),

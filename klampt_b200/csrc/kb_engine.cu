@@ -329,15 +329,15 @@ struct kb_engine {
   cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev_copy[4] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<float> h_nodes;               // 8 floats per node
-  std::vector<float> h_tris32; std::vector<double> h_tris64; std::vector<int32_t> h_triown;
-  std::vector<float> h_sph32; std::vector<double> h_sph64; std::vector<int32_t> h_sphown;
+  std::vector<float> h_tris32; std::vector<double> h_tris64; std::vector<int32_t> h_triown, h_triorig;
+  std::vector<float> h_sph32; std::vector<double> h_sph64; std::vector<int32_t> h_sphown, h_sphorig;
   std::vector<float> h_box32; std::vector<double> h_box64; std::vector<int32_t> h_boxown;
   std::vector<DevGeom> dsolid;              // per registered geometry: the solid of a box primitive (empty otherwise)
   std::vector<DevGeom> dgeoms;              // per registered geometry (local frame)
   std::vector<DevGeom> groups;              // merged environment groups (world frame)
   KbScene scene{};
   float4* d_nodes = nullptr; float4* d_tris32 = nullptr; double* d_tris64 = nullptr; float4* d_sph32 = nullptr; double* d_sph64 = nullptr;
-  int32_t* d_triown = nullptr; int32_t* d_sphown = nullptr;
+  int32_t* d_triown = nullptr; int32_t* d_sphown = nullptr; int32_t* d_triorig = nullptr; int32_t* d_sphorig = nullptr;
   float4* d_box32 = nullptr; double* d_box64 = nullptr; int32_t* d_boxown = nullptr;
   KbRobotDev* d_robot = nullptr; KbDriverDev* d_drv = nullptr; int32_t* d_drv_link = nullptr; double* d_drv_scale = nullptr; double* d_drv_off = nullptr;
   ItemSet feas_items, env_items;            // env + self ; env only (distance without self)
@@ -348,7 +348,7 @@ struct kb_engine {
   std::vector<HostGrid> hgrids; uint8_t* d_grid[KB_MAX_GRIDS] = {nullptr, nullptr, nullptr, nullptr};
   int cloud_builder = 0;                     // 0: point-cloud hierarchies by binned SAH on the host; 1: linear BVH on the GPU (kb_lbvh.cu)
   int mesh_builder = 0;                      // the same choice for triangle meshes above KB_GPU_MESH_MIN triangles
-  struct PendingCloud { DevGeom* dg; std::vector<double> elems; std::vector<int32_t> owners; bool mesh = false; };
+  struct PendingCloud { DevGeom* dg; std::vector<double> elems; std::vector<int32_t> owners; bool mesh = false; std::vector<int32_t> origs; };
   std::vector<PendingCloud> pending_clouds;   // clouds whose hierarchy is built on the GPU once the arrays are uploaded
   int cloud_leaf = 8;                        // points per leaf of a host-built point-cloud hierarchy (option cloud_leaf, 1..32)
   int both_limit = 0;                        // experiment: frontier size up to which comparable inner pairs descend both trees at once
@@ -369,6 +369,7 @@ struct kb_engine {
   uint32_t* d_bits = nullptr; int64_t bits_cap = 0;   // packed result bitmask of the *_bits entry points
   int32_t* d_pair = nullptr; int64_t pair_cap = 0;
   double* d_dist = nullptr; int64_t dist_cap = 0;
+  double* d_cp = nullptr; int64_t cp_cap = 0;             // closest points of the *_ex distance entry points
   // edges
   double* d_A = nullptr; double* d_B = nullptr; int64_t ab_cap = 0;
   int32_t* d_nlev = nullptr; uint8_t* d_alive = nullptr; int32_t* d_nchecks = nullptr; int32_t* d_firstbad = nullptr; int32_t* d_list = nullptr; int64_t edge_cap = 0;
@@ -415,7 +416,8 @@ void init_default_mask(kb_engine* e) {
 inline bool mask_en(const kb_engine* e, int a, int b) { return e->mask[(size_t)a * e->nids + b] != 0; }
 
 // appends one geometry (elements given in some frame) to the host arrays: builds its BVH, writes nodes + elements
-int append_geom(kb_engine* e, int kind, const std::vector<double>& elems, const std::vector<int32_t>& owners, double margin, DevGeom& dg, bool want_cover) {
+int append_geom(kb_engine* e, int kind, const std::vector<double>& elems, const std::vector<int32_t>& owners, double margin, DevGeom& dg, bool want_cover,
+                const std::vector<int32_t>& origs = std::vector<int32_t>()) {
   const int stride = kind == G_MESH ? 9 : (kind == G_BOX ? 15 : 4);
   const int n = (int)(elems.size() / stride);
   dg = DevGeom(); dg.margin = margin; dg.kind = kind == G_MESH ? KB_ELEM_TRI : (kind == G_BOX ? KB_ELEM_BOX : KB_ELEM_SPHERE); dg.nelem = n; dg.empty = n == 0;
@@ -487,7 +489,7 @@ int append_geom(kb_engine* e, int kind, const std::vector<double>& elems, const 
     if (kind == G_MESH) {
       e->h_tris64.insert(e->h_tris64.end(), p, p + 9);
       for (int v = 0; v < 3; v++) { float f[4] = {(float)p[3 * v], (float)p[3 * v + 1], (float)p[3 * v + 2], v == 0 ? i2f(own) : 0.f}; e->h_tris32.insert(e->h_tris32.end(), f, f + 4); }
-      e->h_triown.push_back(own);
+      e->h_triown.push_back(own); e->h_triorig.push_back(origs.empty() ? src : origs[src]);
     } else if (kind == G_BOX) {      // {centre, hx} {axis0, hy} {axis1, hz} {axis2, 0}: axis j = column j of the row-major 3x3
       double b[16] = {p[0], p[1], p[2], p[12], p[3], p[6], p[9], p[13], p[4], p[7], p[10], p[14], p[5], p[8], p[11], 0.0};
       e->h_box64.insert(e->h_box64.end(), b, b + 16);
@@ -496,14 +498,15 @@ int append_geom(kb_engine* e, int kind, const std::vector<double>& elems, const 
     } else {
       e->h_sph64.insert(e->h_sph64.end(), p, p + 4);
       float f[4] = {(float)p[0], (float)p[1], (float)p[2], (float)p[3]}; e->h_sph32.insert(e->h_sph32.end(), f, f + 4);
-      e->h_sphown.push_back(own);
+      e->h_sphown.push_back(own); e->h_sphorig.push_back(origs.empty() ? src : origs[src]);
     }
   }
   return KB_OK;
 }
 
 // reserves nodes / elements of a point cloud whose hierarchy the GPU builds after the upload (option cloud_builder = 1)
-void reserve_gpu_cloud(kb_engine* e, const std::vector<double>& elems, const std::vector<int32_t>& owners, double margin, DevGeom& dg) {
+void reserve_gpu_cloud(kb_engine* e, const std::vector<double>& elems, const std::vector<int32_t>& owners, double margin, DevGeom& dg,
+                       const std::vector<int32_t>& origs = std::vector<int32_t>()) {
   const int n = (int)(elems.size() / 4);
   dg = DevGeom(); dg.margin = margin; dg.kind = KB_ELEM_SPHERE; dg.nelem = n; dg.empty = n == 0; dg.depth = 64;
   for (int k = 0; k < 3; k++) { dg.lo[k] = 1e300; dg.hi[k] = -1e300; }
@@ -519,16 +522,17 @@ void reserve_gpu_cloud(kb_engine* e, const std::vector<double>& elems, const std
   e->h_nodes.insert(e->h_nodes.end(), (size_t)(dg.nnodes - 1) * 8, 0.f);
   dg.elem_base = (int)(e->h_sph64.size() / 4);
   e->h_sph64.insert(e->h_sph64.end(), (size_t)n * 4, 0.0); e->h_sph32.insert(e->h_sph32.end(), (size_t)n * 4, 0.f);
-  e->h_sphown.insert(e->h_sphown.end(), (size_t)n, -1);
+  e->h_sphown.insert(e->h_sphown.end(), (size_t)n, -1); e->h_sphorig.insert(e->h_sphorig.end(), (size_t)n, -1);
   // covering spheres of the clearance-grid broad phase: one sphere round the bounds is enough for a cloud used as a link geometry
   dg.ncover = 1;
   double r2 = 0; for (int k = 0; k < 3; k++) { dg.cover[0][k] = 0.5 * (dg.lo[k] + dg.hi[k]); r2 += 0.25 * (dg.hi[k] - dg.lo[k]) * (dg.hi[k] - dg.lo[k]); }
   dg.cover[0][3] = std::sqrt(r2) * (1 + 1e-12);
-  e->pending_clouds.push_back({&dg, elems, owners});
+  e->pending_clouds.push_back({&dg, elems, owners, false, origs});
 }
 
 // the same for a large triangle mesh (option mesh_builder = 1)
-void reserve_gpu_mesh(kb_engine* e, const std::vector<double>& elems, const std::vector<int32_t>& owners, double margin, DevGeom& dg) {
+void reserve_gpu_mesh(kb_engine* e, const std::vector<double>& elems, const std::vector<int32_t>& owners, double margin, DevGeom& dg,
+                      const std::vector<int32_t>& origs = std::vector<int32_t>()) {
   const int n = (int)(elems.size() / 9);
   dg = DevGeom(); dg.margin = margin; dg.kind = KB_ELEM_TRI; dg.nelem = n; dg.empty = n == 0; dg.depth = 64;
   for (int k = 0; k < 3; k++) { dg.lo[k] = 1e300; dg.hi[k] = -1e300; }
@@ -540,11 +544,11 @@ void reserve_gpu_mesh(kb_engine* e, const std::vector<double>& elems, const std:
   e->h_nodes.insert(e->h_nodes.end(), (size_t)(dg.nnodes - 1) * 8, 0.f);
   dg.elem_base = (int)(e->h_tris64.size() / 9);
   e->h_tris64.insert(e->h_tris64.end(), (size_t)n * 9, 0.0); e->h_tris32.insert(e->h_tris32.end(), (size_t)n * 12, 0.f);
-  e->h_triown.insert(e->h_triown.end(), (size_t)n, -1);
+  e->h_triown.insert(e->h_triown.end(), (size_t)n, -1); e->h_triorig.insert(e->h_triorig.end(), (size_t)n, -1);
   dg.ncover = 1;
   double r2 = 0; for (int k = 0; k < 3; k++) { dg.cover[0][k] = 0.5 * (dg.lo[k] + dg.hi[k]); r2 += 0.25 * (dg.hi[k] - dg.lo[k]) * (dg.hi[k] - dg.lo[k]); }
   dg.cover[0][3] = std::sqrt(r2) * (1 + 1e-12);
-  e->pending_clouds.push_back({&dg, elems, owners, true});
+  e->pending_clouds.push_back({&dg, elems, owners, true, origs});
 }
 
 KbItem make_item(const DevGeom& A, int xfA, int idA, const DevGeom& B, int xfB, int idB, bool self) {
@@ -552,6 +556,7 @@ KbItem make_item(const DevGeom& A, int xfA, int idA, const DevGeom& B, int xfB, 
   it.nodeA = A.node_base; it.nodeB = B.node_base; it.elemA = A.elem_base; it.elemB = B.elem_base;
   it.xfA = (int16_t)xfA; it.xfB = (int16_t)xfB; it.kindA = (uint8_t)A.kind; it.kindB = (uint8_t)B.kind; it.flags = self ? 1 : 0;
   it.idA = idA; it.idB = idB; it.thr = A.margin + B.margin; it.marg = A.margin + B.margin; it.rsum = A.rmax + B.rmax;
+  it.margA = (float)A.margin; it.margB = (float)B.margin;
   return it;
 }
 // the A side of an item is limited to 2^20 nodes (stack entry packing); put the smaller hierarchy there
@@ -627,13 +632,13 @@ void fold_kernel_times(kb_engine* e) {
   }
   e->tev_used = 0;
 }
-cudaError_t timed_traverse(kb_engine* e, const KbTraverseParams& p, int mode, double* out_dist, double ub) {
-  if (!e->time_kernels) return kb_launch_traverse(p, mode, out_dist, ub, e->num_sms, e->stream);
+cudaError_t timed_traverse(kb_engine* e, const KbTraverseParams& p, int mode, double* out_dist, double ub, float rel_err = 0.f, float abs_err = 0.f) {
+  if (!e->time_kernels) return kb_launch_traverse(p, mode, out_dist, ub, e->num_sms, e->stream, nullptr, rel_err, abs_err);
   if (e->tev_used + 2 > 8192) fold_kernel_times(e);
   while (e->tev.size() < e->tev_used + 2) { cudaEvent_t ev; cudaError_t ce = cudaEventCreate(&ev); if (ce != cudaSuccess) return ce; e->tev.push_back(ev); }
   // the work-counter memset is part of kb_launch_traverse: keep it outside the bracket by issuing a no-op ordering point first
   cudaEventRecord(e->tev[e->tev_used], e->stream);
-  cudaError_t ce = kb_launch_traverse(p, mode, out_dist, ub, e->num_sms, e->stream);
+  cudaError_t ce = kb_launch_traverse(p, mode, out_dist, ub, e->num_sms, e->stream, nullptr, rel_err, abs_err);
   cudaEventRecord(e->tev[e->tev_used + 1], e->stream);
   e->tev_used += 2;
   return ce;
@@ -735,7 +740,7 @@ void kb_engine_destroy(kb_engine* e) {
                     e->d_drv_scale, e->d_drv_off, e->feas_items.d_items, e->env_items.d_items, e->d_xf, e->d_state, e->d_hit, e->d_hit_elem, e->d_leaf_list, e->d_flagged, e->d_state2, e->d_work,
                     e->d_counters, e->d_Q, e->d_out, e->d_pair, e->d_dist, e->d_A, e->d_B, e->d_nlev, e->d_alive, e->d_nchecks, e->d_firstbad, e->d_list,
                     e->d_eQ, e->d_efeas, e->d_scalars, e->d_weights, e->d_T, e->feas_items.d_probes, e->feas_items.d_always_on,
-                    e->d_grid[0], e->d_grid[1], e->d_grid[2], e->d_grid[3], e->d_box32, e->d_box64, e->d_boxown, e->d_dyn_pts, e->d_dyn_T, e->d_dyn_scratch, e->d_Qf, e->d_bits};
+                    e->d_grid[0], e->d_grid[1], e->d_grid[2], e->d_grid[3], e->d_box32, e->d_box64, e->d_boxown, e->d_dyn_pts, e->d_dyn_T, e->d_dyn_scratch, e->d_Qf, e->d_bits, e->d_triorig, e->d_sphorig, e->d_cp};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -875,7 +880,7 @@ int kb_update_pointcloud(kb_engine* e, int geom, const double* pts, int n) {
   if (n > 0) CK(cudaMemcpyAsync(e->d_dyn_pts, pts, (size_t)n * 24, cudaMemcpyHostToDevice, e->stream));
   float maxabs = 0.f;
   CK(kb_lbvh_build(e->d_dyn_pts, nullptr, dc->radius, n, e->d_dyn_T, dc->owner, nullptr, e->d_sph64 + 4 * (size_t)G.elem_base, e->d_sph32 + G.elem_base,
-                   e->d_sphown + G.elem_base, e->d_nodes + 2 * (size_t)G.node_base, e->d_dyn_scratch, e->dyn_scratch_bytes, maxcap, &maxabs, e->stream));
+                   e->d_sphown + G.elem_base, e->d_nodes + 2 * (size_t)G.node_base, e->d_dyn_scratch, e->dyn_scratch_bytes, maxcap, &maxabs, e->stream, nullptr, e->d_sphorig + G.elem_base));
   e->stats.kernel_launches += 7;
   // the fp32 error bound follows the scene extent: a cloud that reaches further out widens it (never narrows)
   e->eps_extent = std::max(e->eps_extent, (double)maxabs + dc->radius);
@@ -1034,7 +1039,7 @@ int kb_finalize(kb_engine* e, int device) {
   }
   // ---- 2. merged world-frame environment groups: static objects with the same (element kind, margin, link mask)
   const int L = e->L, T = (int)e->terrains.size(), O = (int)e->objects.size();
-  struct Grp { int kind; double margin; std::string sig; std::vector<double> elems; std::vector<int32_t> owners; int dyn_geom = -1; int dyn_owner = -1; };
+  struct Grp { int kind; double margin; std::string sig; std::vector<double> elems; std::vector<int32_t> owners; int dyn_geom = -1; int dyn_owner = -1; std::vector<int32_t> origs; };
   std::vector<Grp> grp;
   std::map<std::string, int> grp_index;
   double extent = 0;
@@ -1074,7 +1079,7 @@ int kb_finalize(kb_engine* e, int device) {
       for (int t = 0; t < nt; t++) {
         double w[9];
         for (int v = 0; v < 3; v++) { if (s < T) memcpy(w + 3 * v, &G.tri[9 * (size_t)t + 3 * v], 24); else xf_apply(X, &G.tri[9 * (size_t)t + 3 * v], w + 3 * v); }
-        gr.elems.insert(gr.elems.end(), w, w + 9); gr.owners.push_back(s);
+        gr.elems.insert(gr.elems.end(), w, w + 9); gr.owners.push_back(s); gr.origs.push_back(t);
         for (int k2 = 0; k2 < 9; k2++) extent = std::max(extent, std::fabs(w[k2]));
       }
     } else {
@@ -1083,7 +1088,7 @@ int kb_finalize(kb_engine* e, int device) {
         double w[4];
         if (s < T) memcpy(w, &G.sph[4 * (size_t)i], 24); else xf_apply(X, &G.sph[4 * (size_t)i], w);
         w[3] = G.sph[4 * (size_t)i + 3];
-        gr.elems.insert(gr.elems.end(), w, w + 4); gr.owners.push_back(s);
+        gr.elems.insert(gr.elems.end(), w, w + 4); gr.owners.push_back(s); gr.origs.push_back(i);
         for (int k2 = 0; k2 < 3; k2++) extent = std::max(extent, std::fabs(w[k2]) + w[3]);
       }
     }
@@ -1107,7 +1112,7 @@ int kb_finalize(kb_engine* e, int device) {
       }
       dg.elem_base = (int)(e->h_sph64.size() / 4);
       e->h_sph64.insert(e->h_sph64.end(), (size_t)G.dyn_cap * 4, 0.0); e->h_sph32.insert(e->h_sph32.end(), (size_t)G.dyn_cap * 4, 0.f);
-      e->h_sphown.insert(e->h_sphown.end(), (size_t)G.dyn_cap, grp[g].dyn_owner);
+      e->h_sphown.insert(e->h_sphown.end(), (size_t)G.dyn_cap, grp[g].dyn_owner); e->h_sphorig.insert(e->h_sphorig.end(), (size_t)G.dyn_cap, -1);
       kb_engine::DynCloud dc; dc.geom = grp[g].dyn_geom; dc.group = (int)g; dc.owner = grp[g].dyn_owner; dc.cap = G.dyn_cap; dc.radius = G.dyn_radius;
       const int so = grp[g].dyn_owner;
       Xf X; if (so < T) { memset(&X, 0, sizeof X); X.R[0] = X.R[4] = X.R[8] = 1; } else X = e->objT[so - T];
@@ -1116,11 +1121,11 @@ int kb_finalize(kb_engine* e, int device) {
       continue;
     }
     if (e->cloud_builder == 1 && grp[g].kind == G_CLOUD && (int)(grp[g].elems.size() / 4) > KB_GPU_CLOUD_MIN) {
-      reserve_gpu_cloud(e, grp[g].elems, grp[g].owners, grp[g].margin, e->groups[g]);
+      reserve_gpu_cloud(e, grp[g].elems, grp[g].owners, grp[g].margin, e->groups[g], grp[g].origs);
     } else if (e->mesh_builder == 1 && grp[g].kind == G_MESH && (int)(grp[g].elems.size() / 9) > KB_GPU_MESH_MIN) {
-      reserve_gpu_mesh(e, grp[g].elems, grp[g].owners, grp[g].margin, e->groups[g]);
+      reserve_gpu_mesh(e, grp[g].elems, grp[g].owners, grp[g].margin, e->groups[g], grp[g].origs);
     } else {
-      int rc = append_geom(e, grp[g].kind, grp[g].elems, grp[g].owners, grp[g].margin, e->groups[g], false);
+      int rc = append_geom(e, grp[g].kind, grp[g].elems, grp[g].owners, grp[g].margin, e->groups[g], false, grp[g].kind == G_BOX ? std::vector<int32_t>() : grp[g].origs);
       if (rc) return rc;
     }
     if (g < KB_MAX_GRIDS && e->grid_res >= 8 && !e->groups[g].empty && grp[g].kind != G_BOX && grp[g].dyn_geom < 0) {
@@ -1245,8 +1250,10 @@ int kb_finalize(kb_engine* e, int device) {
   if ((rc = upload(e->d_boxown, e->h_boxown.data(), e->h_boxown.size() * 4, &e->static_bytes))) return rc;
   if ((rc = upload(e->d_triown, e->h_triown.data(), e->h_triown.size() * 4, &e->static_bytes))) return rc;
   if ((rc = upload(e->d_sphown, e->h_sphown.data(), e->h_sphown.size() * 4, &e->static_bytes))) return rc;
+  if ((rc = upload(e->d_triorig, e->h_triorig.data(), e->h_triorig.size() * 4, &e->static_bytes))) return rc;
+  if ((rc = upload(e->d_sphorig, e->h_sphorig.data(), e->h_sphorig.size() * 4, &e->static_bytes))) return rc;
   e->scene.nodes = e->d_nodes; e->scene.tris32 = e->d_tris32; e->scene.tris64 = e->d_tris64; e->scene.sph32 = e->d_sph32; e->scene.sph64 = e->d_sph64;
-  e->scene.triown = e->d_triown; e->scene.sphown = e->d_sphown;
+  e->scene.triown = e->d_triown; e->scene.sphown = e->d_sphown; e->scene.triorig = e->d_triorig; e->scene.sphorig = e->d_sphorig;
   e->scene.box32 = e->d_box32; e->scene.box64 = e->d_box64; e->scene.boxown = e->d_boxown;
   if ((rc = upload_itemset(e->feas_items, &e->static_bytes))) return rc;
   if ((rc = upload_itemset(e->env_items, &e->static_bytes))) return rc;
@@ -1277,9 +1284,9 @@ int kb_finalize(kb_engine* e, int device) {
   if ((rc = upload(e->d_drv_off, dofs.data(), dofs.size() * 8, &e->static_bytes))) return rc;
   if (!e->pending_clouds.empty()) {      // hierarchies of the large point clouds on the GPU (Morton order + Karras, kb_lbvh.cu)
     size_t maxn = 0; for (const auto& pc : e->pending_clouds) maxn = std::max(maxn, pc.elems.size() / (pc.mesh ? 9 : 4));
-    double* d_p = nullptr; double* d_r = nullptr; int32_t* d_o = nullptr; double* d_T = nullptr; void* d_s = nullptr;
+    double* d_p = nullptr; double* d_r = nullptr; int32_t* d_o = nullptr; int32_t* d_g = nullptr; double* d_T = nullptr; void* d_s = nullptr;
     const size_t sb = kb_lbvh_scratch_bytes((int)maxn);
-    CK(cudaMalloc((void**)&d_p, maxn * 72)); CK(cudaMalloc((void**)&d_r, maxn * 8)); CK(cudaMalloc((void**)&d_o, maxn * 4)); CK(cudaMalloc((void**)&d_T, 96)); CK(cudaMalloc(&d_s, sb));
+    CK(cudaMalloc((void**)&d_p, maxn * 72)); CK(cudaMalloc((void**)&d_r, maxn * 8)); CK(cudaMalloc((void**)&d_o, maxn * 4)); CK(cudaMalloc((void**)&d_g, maxn * 4)); CK(cudaMalloc((void**)&d_T, 96)); CK(cudaMalloc(&d_s, sb));
     const double I12[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
     CK(cudaMemcpy(d_T, I12, 96, cudaMemcpyHostToDevice));
     std::vector<double> hp, hr;
@@ -1288,9 +1295,10 @@ int kb_finalize(kb_engine* e, int device) {
         const size_t nt = pc.elems.size() / 9;
         CK(cudaMemcpy(d_p, pc.elems.data(), nt * 72, cudaMemcpyHostToDevice));
         if (!pc.owners.empty()) CK(cudaMemcpy(d_o, pc.owners.data(), nt * 4, cudaMemcpyHostToDevice));
+        if (!pc.origs.empty()) CK(cudaMemcpy(d_g, pc.origs.data(), nt * 4, cudaMemcpyHostToDevice));
         const DevGeom& G = *pc.dg;
         CK(kb_lbvh_build_tris(d_p, (int)nt, -1, pc.owners.empty() ? nullptr : d_o, e->d_tris64 + 9 * (size_t)G.elem_base, e->d_tris32 + 3 * (size_t)G.elem_base,
-                              e->d_triown + G.elem_base, e->d_nodes + 2 * (size_t)G.node_base, d_s, sb, (int)maxn, e->stream));
+                              e->d_triown + G.elem_base, e->d_nodes + 2 * (size_t)G.node_base, d_s, sb, (int)maxn, e->stream, pc.origs.empty() ? nullptr : d_g, e->d_triorig + G.elem_base));
         CK(cudaStreamSynchronize(e->stream));
         continue;
       }
@@ -1299,12 +1307,13 @@ int kb_finalize(kb_engine* e, int device) {
       for (size_t i = 0; i < n; i++) { hp[3 * i] = pc.elems[4 * i]; hp[3 * i + 1] = pc.elems[4 * i + 1]; hp[3 * i + 2] = pc.elems[4 * i + 2]; hr[i] = pc.elems[4 * i + 3]; }
       CK(cudaMemcpy(d_p, hp.data(), n * 24, cudaMemcpyHostToDevice)); CK(cudaMemcpy(d_r, hr.data(), n * 8, cudaMemcpyHostToDevice));
       if (!pc.owners.empty()) CK(cudaMemcpy(d_o, pc.owners.data(), n * 4, cudaMemcpyHostToDevice));
+      if (!pc.origs.empty()) CK(cudaMemcpy(d_g, pc.origs.data(), n * 4, cudaMemcpyHostToDevice));
       const DevGeom& G = *pc.dg;
       CK(kb_lbvh_build(d_p, d_r, 0.0, (int)n, d_T, -1, pc.owners.empty() ? nullptr : d_o, e->d_sph64 + 4 * (size_t)G.elem_base, e->d_sph32 + G.elem_base,
-                       e->d_sphown + G.elem_base, e->d_nodes + 2 * (size_t)G.node_base, d_s, sb, (int)maxn, nullptr, e->stream));
+                       e->d_sphown + G.elem_base, e->d_nodes + 2 * (size_t)G.node_base, d_s, sb, (int)maxn, nullptr, e->stream, pc.origs.empty() ? nullptr : d_g, e->d_sphorig + G.elem_base));
       CK(cudaStreamSynchronize(e->stream));
     }
-    cudaFree(d_p); cudaFree(d_r); cudaFree(d_o); cudaFree(d_T); cudaFree(d_s);
+    cudaFree(d_p); cudaFree(d_r); cudaFree(d_o); cudaFree(d_g); cudaFree(d_T); cudaFree(d_s);
     e->pending_clouds.clear();
   }
   CK(cudaMalloc((void**)&e->d_work, 64)); CK(cudaMalloc((void**)&e->d_counters, 128)); CK(cudaMemset(e->d_counters, 0, 128));
@@ -1585,9 +1594,11 @@ int kb_colliding_pairs_batch(kb_engine* e, const double* Q, int64_t N, int max_p
   return KB_OK;
 }
 
-int kb_distance_batch_device(kb_engine* e, const double* dQ, int64_t N, double upper_bound, int include_self, double* d_out_d, int32_t* d_out_pair) {
+static int distance_device(kb_engine* e, const double* dQ, int64_t N, double abs_err, double rel_err, double upper_bound, int include_self,
+                           double* d_out_d, int32_t* d_out_pair, double* d_out_cp, int32_t* d_out_elem) {
   if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
   if (N < 0 || (N > 0 && (!dQ || !d_out_d))) return fail(KB_ERR_INVALID, "bad arguments");
+  if (!(abs_err >= 0) || !(rel_err >= 0)) return fail(KB_ERR_INVALID, "absErr and relErr must be >= 0");
   CK(cudaSetDevice(e->device));
   const ItemSet& set = include_self ? e->feas_items : e->env_items;
   int rc = ensure_cfg_scratch(e, set.nxf, N); if (rc) return rc;
@@ -1597,14 +1608,24 @@ int kb_distance_batch_device(kb_engine* e, const double* dQ, int64_t N, double u
     CK(kb_launch_fk(e->d_robot, e->d_drv, e->d_drv_link, e->d_drv_scale, e->d_drv_off, dQ + off * e->L, n, e->d_xf, set.nxf, nullptr, nullptr, e->d_hit, e->stream));
     e->stats.kernel_launches++;
     KbTraverseParams p = make_params(e, set, e->d_xf, n, nullptr);
-    if (p.nitems > 0) { CK(timed_traverse(e, p, 1, d_out_d + off, upper_bound)); e->stats.kernel_launches++; }
+    if (p.nitems > 0) { CK(timed_traverse(e, p, 1, d_out_d + off, upper_bound, (float)rel_err, (float)abs_err)); e->stats.kernel_launches++; }
     else return fail(KB_ERR_STATE, "no enabled geometry pairs to measure");
     if (d_out_pair) { CK(kb_launch_pair_ids(e->d_hit, e->d_hit_elem, set.d_items, e->d_triown, e->d_sphown, e->d_boxown, n, d_out_pair + 2 * off, e->stream)); e->stats.kernel_launches++; }
+    if (d_out_cp || d_out_elem) {
+      CK(kb_launch_closest_points(e->scene, set.d_items, e->d_xf, set.nxf, e->d_hit, e->d_hit_elem, n, d_out_cp ? d_out_cp + 6 * off : nullptr,
+                                  d_out_elem ? d_out_elem + 2 * off : nullptr, e->stream));
+      e->stats.kernel_launches++;
+    }
   }
   return KB_OK;
 }
 
-int kb_distance_batch(kb_engine* e, const double* Q, int64_t N, double upper_bound, int include_self, double* out_d, int32_t* out_pair) {
+int kb_distance_batch_device(kb_engine* e, const double* dQ, int64_t N, double upper_bound, int include_self, double* d_out_d, int32_t* d_out_pair) {
+  return distance_device(e, dQ, N, 0.0, 0.0, upper_bound, include_self, d_out_d, d_out_pair, nullptr, nullptr);
+}
+
+static int distance_host(kb_engine* e, const double* Q, int64_t N, double abs_err, double rel_err, double upper_bound, int include_self,
+                         double* out_d, int32_t* out_pair, double* out_cp, int32_t* out_elem) {
   if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
   if (N < 0 || (N > 0 && (!Q || !out_d))) return fail(KB_ERR_INVALID, "bad arguments");
   if (N == 0) return KB_OK;
@@ -1612,21 +1633,33 @@ int kb_distance_batch(kb_engine* e, const double* Q, int64_t N, double upper_bou
   int rc;
   if ((rc = grow(e->d_Q, e->q_cap, N * e->L))) return rc;
   if ((rc = grow(e->d_dist, e->dist_cap, N))) return rc;
-  if (out_pair && (rc = grow(e->d_pair, e->pair_cap, 2 * N))) return rc;
+  if ((out_pair || out_elem) && (rc = grow(e->d_pair, e->pair_cap, 4 * N))) return rc;      // pair ids, then element ids
+  if (out_cp && (rc = grow(e->d_cp, e->cp_cap, 6 * N))) return rc;
   begin_timing(e);
   CK(cudaMemcpyAsync(e->d_Q, Q, (size_t)N * e->L * 8, cudaMemcpyHostToDevice, e->stream));
-  if ((rc = kb_distance_batch_device(e, e->d_Q, N, upper_bound, include_self, e->d_dist, out_pair ? e->d_pair : nullptr))) return rc;
+  if ((rc = distance_device(e, e->d_Q, N, abs_err, rel_err, upper_bound, include_self, e->d_dist, out_pair ? e->d_pair : nullptr, out_cp ? e->d_cp : nullptr,
+                            out_elem ? e->d_pair + 2 * N : nullptr))) return rc;
   CK(cudaMemcpyAsync(out_d, e->d_dist, (size_t)N * 8, cudaMemcpyDeviceToHost, e->stream));
   if (out_pair) CK(cudaMemcpyAsync(out_pair, e->d_pair, (size_t)N * 8, cudaMemcpyDeviceToHost, e->stream));
+  if (out_elem) CK(cudaMemcpyAsync(out_elem, e->d_pair + 2 * N, (size_t)N * 8, cudaMemcpyDeviceToHost, e->stream));
+  if (out_cp) CK(cudaMemcpyAsync(out_cp, e->d_cp, (size_t)N * 48, cudaMemcpyDeviceToHost, e->stream));
   end_timing(e, true);
   CK(cudaStreamSynchronize(e->stream));
   if (std::isinf(upper_bound)) for (int64_t i = 0; i < N; i++) if (out_d[i] >= 1e300) out_d[i] = INFINITY;
   return KB_OK;
 }
 
+int kb_distance_batch(kb_engine* e, const double* Q, int64_t N, double upper_bound, int include_self, double* out_d, int32_t* out_pair) {
+  return distance_host(e, Q, N, 0.0, 0.0, upper_bound, include_self, out_d, out_pair, nullptr, nullptr);
+}
+int kb_distance_batch_ex(kb_engine* e, const double* Q, int64_t N, double abs_err, double rel_err, double upper_bound, int include_self,
+                         double* out_d, int32_t* out_pair, double* out_cp, int32_t* out_elem) {
+  return distance_host(e, Q, N, abs_err, rel_err, upper_bound, include_self, out_d, out_pair, out_cp, out_elem);
+}
+
 // explicit geometry pair at N transform pairs: a 1-item work list over a 2-slot transform table
 static int geom_pair_query(kb_engine* e, int ga, const double* Ta, int gb, const double* Tb, int64_t N, double tol, int mode, double upper_bound,
-                           uint8_t* out, double* out_d) {
+                           uint8_t* out, double* out_d, double abs_err = 0.0, double rel_err = 0.0, double* out_cp = nullptr, int32_t* out_elem = nullptr) {
   if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
   if (ga < 0 || gb < 0 || ga >= (int)e->dgeoms.size() || gb >= (int)e->dgeoms.size()) return fail(KB_ERR_INVALID, "unknown geometry");
   if (N < 0 || (N > 0 && (!Ta || !Tb))) return fail(KB_ERR_INVALID, "bad arguments");
@@ -1657,8 +1690,17 @@ static int geom_pair_query(kb_engine* e, int ga, const double* Ta, int gb, const
   if (ce == cudaSuccess) ce = kb_launch_fill_i32(e->d_hit, N, -1, e->stream);
   KbTraverseParams p = make_params(e, set, e->d_T, N, nullptr);
   if (std::isinf(upper_bound) || upper_bound > 1e300) upper_bound = 1e300;
-  if (ce == cudaSuccess) ce = kb_launch_traverse(p, mode, e->d_dist, upper_bound, e->num_sms, e->stream);
+  if (ce == cudaSuccess) ce = kb_launch_traverse(p, mode, e->d_dist, upper_bound, e->num_sms, e->stream, nullptr, (float)rel_err, (float)abs_err);
   e->stats.kernel_launches += 2;
+  if (ce == cudaSuccess && mode == 1 && (out_cp || out_elem)) {
+    // geometry ids of an explicit pair are (ga, gb): the first reported point belongs to ga
+    if (out_cp && grow(e->d_cp, e->cp_cap, 6 * N)) { cudaFree(set.d_items); return KB_ERR_CUDA; }
+    if (out_elem && grow(e->d_pair, e->pair_cap, 2 * N)) { cudaFree(set.d_items); return KB_ERR_CUDA; }
+    ce = kb_launch_closest_points(e->scene, set.d_items, e->d_T, 2, e->d_hit, e->d_hit_elem, N, out_cp ? e->d_cp : nullptr, out_elem ? e->d_pair : nullptr, e->stream);
+    if (ce == cudaSuccess && out_cp) ce = cudaMemcpyAsync(out_cp, e->d_cp, (size_t)N * 48, cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess && out_elem) ce = cudaMemcpyAsync(out_elem, e->d_pair, (size_t)N * 8, cudaMemcpyDeviceToHost, e->stream);
+    e->stats.kernel_launches++;
+  }
   std::vector<int32_t> hit((size_t)N);
   if (ce == cudaSuccess) ce = cudaMemcpyAsync(hit.data(), e->d_hit, (size_t)N * 4, cudaMemcpyDeviceToHost, e->stream);
   if (ce == cudaSuccess && out_d) ce = cudaMemcpyAsync(out_d, e->d_dist, (size_t)N * 8, cudaMemcpyDeviceToHost, e->stream);
@@ -1667,6 +1709,10 @@ static int geom_pair_query(kb_engine* e, int ga, const double* Ta, int gb, const
   if (ce != cudaSuccess) return fail(KB_ERR_CUDA, "geometry pair query: %s", cudaGetErrorString(ce));
   if (out) for (int64_t i = 0; i < N; i++) out[i] = hit[i] >= 0;
   if (out_d) for (int64_t i = 0; i < N; i++) if (out_d[i] >= 1e300) out_d[i] = INFINITY;
+  if (ga < gb) {   // the kernel orders a pair as (larger id, smaller id), the robot-vs-environment convention; here the first point belongs to ga
+    if (out_cp) for (int64_t i = 0; i < N; i++) for (int k = 0; k < 3; k++) std::swap(out_cp[6 * i + k], out_cp[6 * i + 3 + k]);
+    if (out_elem) for (int64_t i = 0; i < N; i++) std::swap(out_elem[2 * i], out_elem[2 * i + 1]);
+  }
   return KB_OK;
 }
 
@@ -1678,6 +1724,12 @@ int kb_geom_collides_batch(kb_engine* e, int ga, const double* Ta, int gb, const
 int kb_geom_distance_batch(kb_engine* e, int ga, const double* Ta, int gb, const double* Tb, int64_t N, double upper_bound, double* out_d) {
   if (!out_d) return fail(KB_ERR_INVALID, "bad arguments");
   return geom_pair_query(e, ga, Ta, gb, Tb, N, 0.0, 1, upper_bound, nullptr, out_d);
+}
+
+int kb_geom_distance_batch_ex(kb_engine* e, int ga, const double* Ta, int gb, const double* Tb, int64_t N, double abs_err, double rel_err, double upper_bound,
+                              double* out_d, double* out_cp, int32_t* out_elem) {
+  if (!out_d || !(abs_err >= 0) || !(rel_err >= 0)) return fail(KB_ERR_INVALID, "bad arguments");
+  return geom_pair_query(e, ga, Ta, gb, Tb, N, 0.0, 1, upper_bound, nullptr, out_d, abs_err, rel_err, out_cp, out_elem);
 }
 
 int kb_get_stats(kb_engine* e, kb_stats* out) {

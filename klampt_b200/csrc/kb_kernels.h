@@ -32,3 +32,8 @@ size_t kb_nodes_smem_bytes(int nxf, int nitems, int stack_cap);
 cudaError_t kb_launch_split(const KbTraverseParams& p, const KbSplitParams& q, int num_sms, cudaStream_t s);
 // every colliding world-id pair per configuration, up to max_pairs (<= 32); out_count = -1 where state == 0
 cudaError_t kb_launch_allpairs(const KbTraverseParams& p, int max_pairs, int32_t* out_pairs, int32_t* out_count, int num_sms, cudaStream_t s);
+
+// closest points (world frame, on the margin-inflated surfaces; 6 doubles: the point of the first reported id, then the second) and
+// element indices (in the geometries' own element order) of the pair each configuration's distance query ended with (kb_closest.cu)
+cudaError_t kb_launch_closest_points(const KbScene& sc, const KbItem* items, const double* xf64, int nxf, const int32_t* hit, const int32_t* hit_elem,
+                                     int64_t N, double* out_cp, int32_t* out_elem, cudaStream_t s);

@@ -76,7 +76,8 @@ __global__ void lbvh_morton_kernel(const double* __restrict__ w64, int n, const 
 
 // 2b. gather into BVH order
 __global__ void lbvh_gather_kernel(const double* __restrict__ w64, const int* __restrict__ sorted_idx, int n, int owner, const int32_t* __restrict__ owner_in,
-                                   double* __restrict__ sph64, float4* __restrict__ sph32, int* __restrict__ sphown) {
+                                   double* __restrict__ sph64, float4* __restrict__ sph32, int* __restrict__ sphown,
+                                   const int32_t* __restrict__ orig_in, int32_t* __restrict__ orig_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int s = sorted_idx[i];
@@ -84,6 +85,7 @@ __global__ void lbvh_gather_kernel(const double* __restrict__ w64, const int* __
   sph64[4 * (size_t)i] = x; sph64[4 * (size_t)i + 1] = y; sph64[4 * (size_t)i + 2] = z; sph64[4 * (size_t)i + 3] = r;
   sph32[i] = make_float4((float)x, (float)y, (float)z, (float)r);
   sphown[i] = owner_in ? owner_in[s] : owner;
+  if (orig_out) orig_out[i] = orig_in ? orig_in[s] : s;      // index of the point in the caller's array
 }
 
 // 3. point boxes (fp64 extents rounded outwards to fp32): the leaves of the Karras tree are the single points
@@ -235,11 +237,12 @@ __global__ void lbvh_tri_morton_kernel(const double* __restrict__ tris, int n, c
 // gather into BVH order (tris64, tris32 with the owner id in .w of vertex 0, triown) and the triangle boxes
 __global__ void lbvh_tri_gather_kernel(const double* __restrict__ tris, const int* __restrict__ sorted_idx, int n, int owner, const int32_t* __restrict__ owner_in,
                                        double* __restrict__ tris64, float4* __restrict__ tris32, int* __restrict__ triown,
-                                       float* __restrict__ blo, float* __restrict__ bhi) {
+                                       float* __restrict__ blo, float* __restrict__ bhi, const int32_t* __restrict__ orig_in, int32_t* __restrict__ orig_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int s = sorted_idx[i];
   const int own = owner_in ? owner_in[s] : owner;
+  if (orig_out) orig_out[i] = orig_in ? orig_in[s] : s;
   double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
 #pragma unroll
   for (int v = 0; v < 3; v++) {
@@ -280,7 +283,7 @@ size_t kb_lbvh_scratch_bytes(int capacity) {
 
 cudaError_t kb_lbvh_build(const double* d_pts_local, const double* d_radius, double uniform_radius, int n, const double* d_T12, int owner,
                           const int32_t* d_owner_in, double* sph64, float4* sph32, int32_t* sphown, float4* nodes, void* scratch, size_t scratch_bytes, int capacity, float* h_maxabs,
-                          cudaStream_t s) {
+                          cudaStream_t s, const int32_t* d_orig_in, int32_t* orig_out) {
   if (n < 0 || n > capacity) return cudaErrorInvalidValue;
   if (scratch_bytes < kb_lbvh_scratch_bytes(capacity)) return cudaErrorInvalidValue;
   const size_t cap = (size_t)capacity + 1;
@@ -306,7 +309,7 @@ cudaError_t kb_lbvh_build(const double* d_pts_local, const double* d_radius, dou
     size_t tb = tmp_bytes;
     e = cub::DeviceRadixSort::SortPairs(tmp, tb, keys, skeys, idx, sidx, n, 0, 30, s);
     if (e != cudaSuccess) return e;
-    lbvh_gather_kernel<<<nb(n, 256), 256, 0, s>>>(w64, sidx, n, owner, d_owner_in, sph64, sph32, sphown);
+    lbvh_gather_kernel<<<nb(n, 256), 256, 0, s>>>(w64, sidx, n, owner, d_owner_in, sph64, sph32, sphown, d_orig_in, orig_out);
     lbvh_pointbox_kernel<<<nb(n, 256), 256, 0, s>>>(sph64, n, llo, lhi);
     if (n > 1) {
       e = cudaMemsetAsync(flags, 0, (size_t)n * 4, s);
@@ -336,7 +339,7 @@ cudaError_t kb_lbvh_build(const double* d_pts_local, const double* d_radius, dou
 
 // the same for a triangle mesh (triangles already in the frame of the hierarchy, 9 doubles each): one triangle per leaf
 cudaError_t kb_lbvh_build_tris(const double* d_tris_in, int n, int owner, const int32_t* d_owner_in, double* tris64, float4* tris32, int32_t* triown,
-                               float4* nodes, void* scratch, size_t scratch_bytes, int capacity, cudaStream_t s) {
+                               float4* nodes, void* scratch, size_t scratch_bytes, int capacity, cudaStream_t s, const int32_t* d_orig_in, int32_t* orig_out) {
   if (n < 0 || n > capacity) return cudaErrorInvalidValue;
   if (scratch_bytes < kb_lbvh_scratch_bytes(capacity)) return cudaErrorInvalidValue;
   const size_t cap = (size_t)capacity + 1;
@@ -361,7 +364,7 @@ cudaError_t kb_lbvh_build_tris(const double* d_tris_in, int n, int owner, const 
     size_t tb = tmp_bytes;
     e = cub::DeviceRadixSort::SortPairs(tmp, tb, keys, skeys, idx, sidx, n, 0, 30, s);
     if (e != cudaSuccess) return e;
-    lbvh_tri_gather_kernel<<<nb(n, 256), 256, 0, s>>>(d_tris_in, sidx, n, owner, d_owner_in, tris64, tris32, triown, llo, lhi);
+    lbvh_tri_gather_kernel<<<nb(n, 256), 256, 0, s>>>(d_tris_in, sidx, n, owner, d_owner_in, tris64, tris32, triown, llo, lhi, d_orig_in, orig_out);
     if (n > 1) {
       e = cudaMemsetAsync(flags, 0, (size_t)n * 4, s);
       if (e != cudaSuccess) return e;

@@ -66,7 +66,7 @@ struct KbProbe {                  // one covering sphere of the moving side of a
   int32_t pad_;
 };
 
-struct KbItem {                   // 56 bytes
+struct KbItem {                   // 64 bytes
   int32_t nodeA, nodeB;           // global node index of the two roots
   int32_t elemA, elemB;           // global element base (into tris* or sph* according to kind)
   int16_t xfA, xfB;               // transform slot in the per-configuration table, -1 = identity (static world frame)
@@ -76,6 +76,7 @@ struct KbItem {                   // 56 bytes
   double thr;                     // collision threshold: margin_A + margin_B (+ tolerance); 0 = surfaces must intersect
   double marg;                    // margin_A + margin_B, subtracted from reported distances
   double rsum;                    // largest sphere radius of A + of B: bound on how far two touching boxes' elements can interpenetrate
+  float margA, margB;             // the two margins separately: closest points are reported on the margin-inflated surfaces
 };
 
 struct KbRobotDev {
@@ -107,6 +108,8 @@ struct KbScene {                  // device pointers to the static data
   const float4* box32;            // solid boxes: 4 x float4 per box = {centre.xyz, hx} {axis0.xyz, hy} {axis1.xyz, hz} {axis2.xyz, -}
   const double* box64;            // 16 doubles per box in the same order
   const int32_t* boxown;
+  const int32_t* triorig;         // per triangle / sphere element: its index in the geometry it came from (elements are stored in BVH leaf order)
+  const int32_t* sphorig;
   float eps_abs;                  // absolute fp32 coordinate error bound for this scene (metres)
   float qo[3], qs[3];             // KB_QNODES builds only: origin and step of the 16-bit node quantisation grid
   KbClearGrid grids[KB_MAX_GRIDS];

@@ -231,6 +231,30 @@ class Engine:
         check(self.lib.kb_distance_batch(self.h, _ptr(Q), N, float(upper_bound), int(include_self), _ptr(d), _ptr(pairs)))
         return (d, pairs) if return_pairs else d
 
+    def distance_batch_ex(self, Q, upper_bound: float = np.inf, include_self: bool = False, abs_err: float = 0.0, rel_err: float = 0.0):
+        """AnyCollisionQuery::Distance(absErr, relErr, bound) with the whole DistanceQueryResult: (d (N,), pairs (N, 2) world ids,
+        closest points (N, 2, 3) on the margin-inflated surfaces -- [:, 0] on pairs[:, 0]'s geometry --, element indices (N, 2))"""
+        Q = self._Q(Q)
+        N = Q.shape[0]
+        d = np.empty(N, dtype=np.float64)
+        pairs = np.empty((N, 2), dtype=np.int32)
+        cp = np.empty((N, 2, 3), dtype=np.float64)
+        elem = np.empty((N, 2), dtype=np.int32)
+        check(self.lib.kb_distance_batch_ex(self.h, _ptr(Q), N, float(abs_err), float(rel_err), float(upper_bound), int(include_self),
+                                            _ptr(d), _ptr(pairs), _ptr(cp), _ptr(elem)))
+        return d, pairs, cp, elem
+
+    def geom_distance_batch_ex(self, ga: int, Ta, gb: int, Tb, upper_bound: float = np.inf, abs_err: float = 0.0, rel_err: float = 0.0):
+        """Geometry3D.distance_ext for N transform pairs: (d, closest points (N, 2, 3): [:, 0] on ga, [:, 1] on gb, element indices (N, 2))"""
+        Ta, Tb = _f64(Ta).reshape(-1, 12), _f64(Tb).reshape(-1, 12)
+        N = Ta.shape[0]
+        d = np.empty(N, dtype=np.float64)
+        cp = np.empty((N, 2, 3), dtype=np.float64)
+        elem = np.empty((N, 2), dtype=np.int32)
+        check(self.lib.kb_geom_distance_batch_ex(self.h, int(ga), _ptr(Ta), int(gb), _ptr(Tb), N, float(abs_err), float(rel_err), float(upper_bound),
+                                                 _ptr(d), _ptr(cp), _ptr(elem)))
+        return d, cp, elem
+
     def colliding_pairs_batch(self, Q, max_pairs: int = 8):
         """every colliding (idA, idB) world-id pair per configuration: (pairs (N, max_pairs, 2) padded with -1, count (N,));
         count = -1 where the joint / driver limits already fail"""

@@ -70,14 +70,23 @@ class DistanceQuerySettings:
 
 
 class DistanceQueryResult:
-    """src/geometry.h:631-694; closest points / gradients are not produced by the batched kernel"""
+    """src/geometry.h:631-694: d, closest points (world frame, on the margin-inflated surfaces) and element indices; gradients:
+    the unit direction between the closest points when they are distinct (grad1 = d d / d cp1 = -(cp2 - cp1) / |..|, grad2 = -grad1)"""
 
-    def __init__(self, d):
+    def __init__(self, d, cp1=None, cp2=None, elem1=-1, elem2=-1):
         self.d = d
-        self.hasClosestPoints = False
+        self.hasClosestPoints = cp1 is not None and not any(x != x for x in cp1)
+        self.cp1 = [float(x) for x in cp1] if self.hasClosestPoints else []
+        self.cp2 = [float(x) for x in cp2] if self.hasClosestPoints else []
+        self.elem1, self.elem2 = (int(elem1), int(elem2)) if self.hasClosestPoints else (-1, -1)
         self.hasGradients = False
-        self.cp1 = self.cp2 = self.grad1 = self.grad2 = []
-        self.elem1 = self.elem2 = -1
+        self.grad1 = self.grad2 = []
+        if self.hasClosestPoints:
+            v = np.asarray(self.cp2) - np.asarray(self.cp1)
+            n = float(np.linalg.norm(v))
+            if n > 0 and d > 0:
+                self.hasGradients = True
+                self.grad1, self.grad2 = list(-v / n), list(v / n)
 
 
 _PAIR_ENGINES = {}
@@ -251,7 +260,9 @@ class Geometry3D:
         return bool(eng.geom_collides_batch(ga, self._T12(), gb, other._T12(), tol=tol)[0])
 
     def distance_simple(self, other: "Geometry3D", relErr: float = 0, absErr: float = 0) -> float:
-        return self.distance(other).d
+        st = DistanceQuerySettings()
+        st.relErr, st.absErr = relErr, absErr
+        return self.distance_ext(other, st).d
 
     def distance(self, other: "Geometry3D") -> DistanceQueryResult:
         return self.distance_ext(other, DistanceQuerySettings())
@@ -262,7 +273,13 @@ class Geometry3D:
         return self.distance_point_ext(pt, DistanceQuerySettings())
 
     def distance_point_ext(self, pt, settings: DistanceQuerySettings) -> DistanceQueryResult:
-        return DistanceQueryResult(float(self.distance_points_batch([pt], settings.upperBound)[0]))
+        if self.empty():
+            raise RuntimeError("Distance queries not implemented yet for those types of geometry, or geometries are content-empty?")
+        eng, ga, gb = self._pair_engine(_POINT_PROBE)
+        Tb = IDENTITY12.copy()
+        Tb[9:12] = np.asarray(pt, dtype=np.float64)
+        d, cp, el = eng.geom_distance_batch_ex(ga, self._T12(), gb, Tb, upper_bound=settings.upperBound, abs_err=settings.absErr, rel_err=settings.relErr)
+        return DistanceQueryResult(float(d[0]), cp[0, 0], cp[0, 1], el[0, 0], el[0, 1])
 
     def distance_points_batch(self, pts, upper_bound: float = float("inf")) -> np.ndarray:
         """distance_point for N world-space points in one launch: a point primitive at N translations"""
@@ -280,8 +297,9 @@ class Geometry3D:
         if self.empty() or other.empty():
             raise RuntimeError("Distance queries not implemented yet for those types of geometry, or geometries are content-empty?")
         eng, ga, gb = self._pair_engine(other)
-        d = float(eng.geom_distance_batch(ga, self._T12(), gb, other._T12(), upper_bound=settings.upperBound)[0])
-        return DistanceQueryResult(d)
+        d, cp, el = eng.geom_distance_batch_ex(ga, self._T12(), gb, other._T12(), upper_bound=settings.upperBound,
+                                               abs_err=settings.absErr, rel_err=settings.relErr)
+        return DistanceQueryResult(float(d[0]), cp[0, 0], cp[0, 1], el[0, 0], el[0, 1])
 
 
 def _prim_from_spec(g: GeomSpec) -> GeometricPrimitive:

@@ -659,3 +659,85 @@ def test_segment_primitives_agree_with_the_oracle(built):
             cw = np.array([orc.geom_within_distance(ga, Ta[i], gb, Tb[i], tol) if tol > 0 else orc.geom_collides(ga, Ta[i], gb, Tb[i]) for i in range(n)])
             near = np.abs(dw - tol) < 1e-6                                              # the stated band of the boolean parity
             assert np.array_equal(cg[~near], cw[~near])
+
+
+def test_closest_points_element_ids_and_tolerances(built):
+    """DistanceQueryResult beyond the scalar (src/geometry.h:631-694): closest points on the margin-inflated surfaces, element
+    indices in the geometries' own order, and the absErr / relErr contract of AnyCollisionQuery::Distance.  The points are not
+    compared with anything the oracle stores: they are RE-MEASURED by the oracle -- |cp2 - cp1| must be d, and each point must lie on
+    its geometry (oracle point-to-geometry distance = 0)."""
+    from klampt_b200.engine import Engine
+    from oracle.oracle import OracleWorld, point_tri_distance
+    rng = np.random.default_rng(11)
+    w = WorldSpec()
+    vb, tb = synth.blob_mesh(rng, 2, 0.4)
+    vc, tc = synth.unit_cube()
+    ga = w.add_geom(GeomSpec.mesh(vb, tb))
+    gb = w.add_geom(GeomSpec.mesh(vc, tc))
+    gm = w.add_geom(GeomSpec.mesh(vc, tc, margin=0.03))
+    pts = rng.uniform(-0.3, 0.3, size=(3000, 3))
+    gc = w.add_geom(GeomSpec.cloud(pts, None, margin=0.01))
+    gs = w.add_geom(GeomSpec.sphere([0.1, 0.0, 0.0], 0.2))
+    gp = w.add_geom(GeomSpec.point([0.0, 0.0, 0.0]))
+    w.robot = synth.make_planar_nR(w, 2)
+    eng, orc = Engine(w), OracleWorld(w)
+    N = 300
+    Ta = np.stack([synth.make_T(synth._random_rotation(rng), rng.uniform(-0.2, 0.2, size=3)) for _ in range(N)])
+    Tb = np.stack([synth.make_T(synth._random_rotation(rng), rng.uniform(-1.8, 1.8, size=3)) for _ in range(N)])
+    margin = {ga: 0.0, gb: 0.0, gm: 0.03, gc: 0.01, gs: 0.0}
+
+    def at(p):
+        T = synth.IDENTITY12.copy(); T[9:12] = p
+        return T
+    for g1, g2 in ((ga, gb), (ga, gm), (gb, gc), (gs, ga), (gc, gs), (gm, gc)):
+        d, cp, el = eng.geom_distance_batch_ex(g1, Ta, g2, Tb)
+        do = np.array([orc.geom_distance(g1, Ta[i], g2, Tb[i]) for i in range(N)])
+        np.testing.assert_allclose(d, do, rtol=1e-5, atol=1e-12)
+        far = d > 1e-9
+        assert far.sum() > 50
+        np.testing.assert_allclose(np.linalg.norm(cp[far, 1] - cp[far, 0], axis=1), d[far], rtol=1e-9, atol=1e-12)
+        for i in np.nonzero(far)[0][:60]:
+            # the oracle's distance from a point to the geometry subtracts the geometry's margin: 0 on the inflated surface
+            assert abs(orc.geom_distance(g1, Ta[i], gp, at(cp[i, 0]))) < 1e-9, (g1, g2, i)
+            assert abs(orc.geom_distance(g2, Tb[i], gp, at(cp[i, 1]))) < 1e-9, (g1, g2, i)
+        for i in np.nonzero(~far & (d == 0))[0][:40]:         # intersecting meshes: one common point, on both surfaces
+            assert np.array_equal(cp[i, 0], cp[i, 1])
+            assert abs(orc.geom_distance(g1, Ta[i], gp, at(cp[i, 0])) + margin[g1]) < 1e-9
+            assert abs(orc.geom_distance(g2, Tb[i], gp, at(cp[i, 1])) + margin[g2]) < 1e-9
+    # element indices refer to the caller's arrays: the reported triangle of the blob really is where cp1 lies
+    d, cp, el = eng.geom_distance_batch_ex(ga, Ta, gb, Tb)
+    for i in np.nonzero(d > 1e-9)[0][:80]:
+        tri = synth.transform_points(Ta[i], vb[tb[el[i, 0]]])
+        assert point_tri_distance(cp[i, 0], tri) < 1e-9
+        tri2 = synth.transform_points(Tb[i], vc[tc[el[i, 1]]])
+        assert point_tri_distance(cp[i, 1], tri2) < 1e-9
+    d, cp, el = eng.geom_distance_batch_ex(gb, Ta, gc, Tb)
+    for i in np.nonzero(d > 1e-9)[0][:80]:
+        p = synth.transform_points(Tb[i], pts[el[i, 1]][None])[0]
+        assert abs(np.linalg.norm(p - cp[i, 1]) - 0.01) < 1e-9          # the cloud's point, moved by the cloud's margin towards the cube
+    # tolerances: never below the exact value, never more than the tolerance above it; and cheaper
+    exact = eng.geom_distance_batch(ga, Ta, gb, Tb)
+    for ae, re_ in ((0.05, 0.0), (0.0, 0.2)):
+        dt, _, _ = eng.geom_distance_batch_ex(ga, Ta, gb, Tb, abs_err=ae, rel_err=re_)
+        assert (dt >= exact - 1e-12).all() and (dt <= exact + ae + re_ * np.abs(exact) + 1e-9).all()
+    # the robot query: same distances as the plain entry point, points on the reported link / obstacle
+    wc = synth.world_c1()
+    gp2 = wc.add_geom(GeomSpec.point([0.0, 0.0, 0.0]))
+    e2, o2 = Engine(wc), OracleWorld(wc)
+    Q = synth.sample_configs(wc.robot, 400, 5)
+    d, pairs, cp, el = e2.distance_batch_ex(Q, upper_bound=0.5, include_self=True)
+    d0, p0 = e2.distance_batch(Q, upper_bound=0.5, include_self=True, return_pairs=True)
+    assert np.array_equal(d, d0) and np.array_equal(pairs, p0)
+    nid = e2.num_ids(); L = wc.robot.L; base = nid - L
+    T = o2.fk_batch(Q)
+    seen = 0
+    for i in range(len(Q)):
+        if not (1e-9 < d[i] < 0.5):
+            assert d[i] <= 1e-9 or np.isnan(cp[i]).all()
+            continue
+        assert abs(np.linalg.norm(cp[i, 1] - cp[i, 0]) - d[i]) < 1e-9
+        a = pairs[i, 0]
+        assert a >= base                                          # first id: a robot link (CheckCollisionFree order)
+        assert abs(o2.geom_distance(wc.robot.link_geom[a - base], T[i, a - base], gp2, at(cp[i, 0]))) < 1e-9
+        seen += 1
+    assert seen > 100
