@@ -178,7 +178,7 @@ __global__ void kb_closest_points_kernel(const KbScene sc, const KbItem* __restr
   const double len = sqrt(dot(d, d));
   if (len > 0.0) {
     const D3 n = d * (1.0 / len);
-    pa = pa + n * (ra + (double)it.margA); pb = pb - n * (rb + (double)it.margB);
+    pa = pa + n * (ra + it.margA); pb = pb - n * (rb + it.margB);
   }
   int ia = it.idA, ib = it.idB;
   if (ia < 0) ia = (it.kindA == KB_ELEM_TRI ? sc.triown : (it.kindA == KB_ELEM_BOX ? sc.boxown : sc.sphown))[ea];

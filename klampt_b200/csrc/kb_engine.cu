@@ -556,7 +556,7 @@ KbItem make_item(const DevGeom& A, int xfA, int idA, const DevGeom& B, int xfB, 
   it.nodeA = A.node_base; it.nodeB = B.node_base; it.elemA = A.elem_base; it.elemB = B.elem_base;
   it.xfA = (int16_t)xfA; it.xfB = (int16_t)xfB; it.kindA = (uint8_t)A.kind; it.kindB = (uint8_t)B.kind; it.flags = self ? 1 : 0;
   it.idA = idA; it.idB = idB; it.thr = A.margin + B.margin; it.marg = A.margin + B.margin; it.rsum = A.rmax + B.rmax;
-  it.margA = (float)A.margin; it.margB = (float)B.margin;
+  it.margA = A.margin; it.margB = B.margin;
   return it;
 }
 // the A side of an item is limited to 2^20 nodes (stack entry packing); put the smaller hierarchy there

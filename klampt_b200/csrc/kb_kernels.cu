@@ -1264,27 +1264,6 @@ __device__ __forceinline__ float point_tri_dist2_bf(const V3<float>& p, const V3
   return inside ? __fdividef(h * h, nn) : em;
 }
 
-// the same with everything that depends on the triangle alone computed once: a leaf pair of the distance kernel tests up to 8
-// (cloud_leaf) points against one triangle
-struct TriPre { V3<float> a, b, ab, ac, bc, n; float iab2, iac2, ibc2, nn, inn; bool ok; };
-__device__ __forceinline__ void tri_pre(const V3<float>& a, const V3<float>& b, const V3<float>& c, TriPre& t) {
-  t.a = a; t.b = b; t.ab = b - a; t.ac = c - a; t.bc = c - b;
-  const float ab2 = dot(t.ab, t.ab), ac2 = dot(t.ac, t.ac), bc2 = dot(t.bc, t.bc);
-  t.iab2 = ab2 > 0.f ? __frcp_rn(ab2) : 0.f; t.iac2 = ac2 > 0.f ? __frcp_rn(ac2) : 0.f; t.ibc2 = bc2 > 0.f ? __frcp_rn(bc2) : 0.f;
-  t.n = cross(t.ab, t.ac); t.nn = dot(t.n, t.n);
-  t.ok = kb_face_ok(t.nn, ab2, ac2);
-  t.inn = t.ok ? __frcp_rn(t.nn) : 0.f;
-}
-__device__ __forceinline__ float point_tri_dist2_pre(const V3<float>& p, const TriPre& t) {
-  const V3<float> ap = p - t.a, bp = p - t.b;
-  const float t1 = __saturatef(dot(t.ab, ap) * t.iab2), t2 = __saturatef(dot(t.ac, ap) * t.iac2), t3 = __saturatef(dot(t.bc, bp) * t.ibc2);
-  const V3<float> q1 = madd(ap, t.ab, -t1), q2 = madd(ap, t.ac, -t2), q3 = madd(bp, t.bc, -t3);
-  const float em = fminf(dot(q1, q1), fminf(dot(q2, q2), dot(q3, q3)));
-  const float u = dot(cross(t.ab, ap), t.n), v = dot(cross(ap, t.ac), t.n), h = dot(ap, t.n);
-  const bool inside = (u >= 0.f) & (v >= 0.f) & (u + v <= t.nn);
-  return t.ok ? (inside ? h * h * t.inn : em) : __int_as_float(0x7fc00000);
-}
-
 template <bool BOXES>
 __device__ __forceinline__ void elem_bounds(const KbScene& sc, const KbItem& it, const XfF& T, int ea, int eb, float band, float cut, float lb_fallback,
                                             float& lo, float& hi) {
@@ -1348,7 +1327,7 @@ __device__ __forceinline__ void elem_bounds(const KbScene& sc, const KbItem& it,
 //   * node phase: a lane pops one pair, loads the two children of the split side (one 64-byte line) and the other node, and
 //     computes both box-gap bounds; the split side is chosen with selects, not branches.  Survivors are pushed farther first.
 //   * element phase: a lane owns one leaf pair and walks its (<= 8 x 8) element pairs with the branch-free point / triangle code.
-//   * relErr / absErr of AnyCollisionQuery::Distance: a pair is pruned when lb + absErr >= bound or lb + relErr |bound| >= bound,
+//   * relErr / absErr of AnyCollisionQuery::Distance: a pair is pruned when lb + absErr >= bound or lb (1 + relErr) >= bound,
 //     so the reported value is within that tolerance above the true minimum (0 / 0 = exact).
 struct KbDistArgs { double* out_dist; double* out_cp; double upper_bound; float rel_err, abs_err; };
 #ifndef KB_CAND_CAP
@@ -1358,8 +1337,11 @@ struct KbDistArgs { double* out_dist; double* out_cp; double upper_bound; float 
 #define KB_DIST_BPS 4
 #endif
 
+// pruning threshold below the current bound: a pair whose lower bound lb satisfies lb + absErr >= bound or lb (1 + relErr) >= bound
+// cannot improve the answer by more than the tolerance (PQP's rule), so value <= exact + absErr and value <= exact (1 + relErr)
 __device__ __forceinline__ float kb_thr_from(float bound, float rel_err, float abs_err) {
-  return fminf(bound - abs_err, bound - rel_err * fabsf(bound));
+  const float r = bound > 0.f ? __fdividef(bound, 1.f + rel_err) * (1.f - 2e-7f) : bound * (1.f + rel_err);
+  return fminf(bound - abs_err, rel_err > 0.f ? r : bound);
 }
 
 template <bool BOXES>
@@ -1486,22 +1468,10 @@ kb_distance_kernel(const KbTraverseParams p, const KbDistArgs da) {
               XfF T;
               if (ITC) load_itc(itc, item, T); else rel_xf(xfw, it.xfA, it.xfB, T);
               const float margf = (float)it.marg, bandm = band + 2e-7f * fabsf(margf);
-              const bool tri_cloud = it.kindA == KB_ELEM_TRI && it.kindB == KB_ELEM_SPHERE;     // link mesh vs point cloud: the whole of C5
               for (int i = 0; i < ca; i++) {
-                TriPre tp;
-                if (tri_cloud) {
-                  const float4* ta = sc.tris32 + 3 * (size_t)(fa + i);
-                  const float4 v0 = __ldg(ta), v1 = __ldg(ta + 1), v2 = __ldg(ta + 2);
-                  tri_pre(mk3<float>(v0.x, v0.y, v0.z), mk3<float>(v1.x, v1.y, v1.z), mk3<float>(v2.x, v2.y, v2.z), tp);
-                }
                 for (int j = 0; j < cb; j++) {
                   if (STATS) st_leaf++;
                   float lo, hi;
-                  if (tri_cloud) {
-                    const float4 sp4 = __ldg(sc.sph32 + fb + j);
-                    const float d = sqrtf(point_tri_dist2_pre(xform(T, sp4), tp)) - sp4.w;
-                    if (d != d) { lo = lbq + margf; hi = INF; } else { lo = d - bandm; hi = d + bandm; }
-                  } else
                   elem_bounds<BOXES>(sc, it, T, fa + i, fb + j, bandm, thr_l + margf + bandm, lbq + margf, lo, hi);
                   lo -= margf + bandm - band; hi -= margf - (bandm - band);
                   if (lo <= thr_l || hi < bound_l) {

@@ -66,7 +66,7 @@ struct KbProbe {                  // one covering sphere of the moving side of a
   int32_t pad_;
 };
 
-struct KbItem {                   // 64 bytes
+struct KbItem {                   // 72 bytes
   int32_t nodeA, nodeB;           // global node index of the two roots
   int32_t elemA, elemB;           // global element base (into tris* or sph* according to kind)
   int16_t xfA, xfB;               // transform slot in the per-configuration table, -1 = identity (static world frame)
@@ -76,7 +76,7 @@ struct KbItem {                   // 64 bytes
   double thr;                     // collision threshold: margin_A + margin_B (+ tolerance); 0 = surfaces must intersect
   double marg;                    // margin_A + margin_B, subtracted from reported distances
   double rsum;                    // largest sphere radius of A + of B: bound on how far two touching boxes' elements can interpenetrate
-  float margA, margB;             // the two margins separately: closest points are reported on the margin-inflated surfaces
+  double margA, margB;            // the two margins separately: closest points are reported on the margin-inflated surfaces
 };
 
 struct KbRobotDev {
