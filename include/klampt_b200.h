@@ -125,6 +125,14 @@ int kb_get_pair_mask(const kb_engine* e, uint8_t* mask_out);
 /* WorldModel::InitCollisions + SingleRobotCSpace::Init (Cpp/Modeling/World.cpp:266-274,
  * Cpp/Planning/RobotCSpace.cpp:668-754): builds the BVHs, flattens them and uploads everything to `device`. */
 int kb_finalize(kb_engine* e, int device);
+/* The same on several devices of one node (SURVEY 8b "kb_finalize(device_list)"): the hierarchies are built once, on devices[0], and
+ * replicated on the others by peer copies.  Afterwards every HOST-buffer entry point (kb_feasible_batch*, kb_edges_visible_batch*,
+ * kb_distance_batch*) cuts its batch into contiguous shards, one per device, runs them concurrently (one host thread, stream and
+ * scratch per device) and writes the results straight into the caller's buffers; batches below option "multi_min" (default 8192)
+ * stay on devices[0].  The *_device entry points, kb_fk_batch, kb_colliding_pairs_batch and the kb_geom_* queries use devices[0].
+ * A C++ planner thus drives 8 GPUs through one BatchSingleRobotCSpace without a process per GPU. */
+int kb_finalize_multi(kb_engine* e, const int* devices, int n_devices);
+int kb_num_devices(const kb_engine* e);
 /* use an existing CUDA stream (cudaStream_t) for all later work; NULL = the engine's own non-blocking stream.
  * The legacy default stream must be named explicitly as cudaStreamLegacy ((void*)0x1). */
 int kb_set_stream(kb_engine* e, void* cuda_stream);

@@ -73,6 +73,8 @@ class WorldBuilder {
   // WorldPlannerSettings::collisionEnabled over world ids (row-major n x n)
   void SetCollisionEnabled(const std::vector<uint8_t>& mask, int n) { kbCheck(kb_set_pair_mask(e_, mask.data(), n)); }
   kb_engine* Finalize(int device = 0) { kbCheck(kb_finalize(e_, device)); kb_engine* r = e_; e_ = nullptr; return r; }
+  // several GPUs behind one handle: IsFeasibleBatch / IsVisibleBatch shard their batches over `devices` (kb_finalize_multi)
+  kb_engine* Finalize(const std::vector<int>& devices) { kbCheck(kb_finalize_multi(e_, devices.data(), (int)devices.size())); kb_engine* r = e_; e_ = nullptr; return r; }
   const RobotDescription& robot() const { return robot_; }
  private:
   kb_engine* e_ = nullptr;

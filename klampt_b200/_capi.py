@@ -49,6 +49,8 @@ SIGNATURES = {
     "kb_num_ids": (C.c_int, [_VP]),
     "kb_get_pair_mask": (C.c_int, [_VP, c_uint8_p]),
     "kb_finalize": (C.c_int, [_VP, C.c_int]),
+    "kb_finalize_multi": (C.c_int, [_VP, c_int32_p, C.c_int]),
+    "kb_num_devices": (C.c_int, [_VP]),
     "kb_set_stream": (C.c_int, [_VP, _VP]),
     "kb_set_option": (C.c_int, [_VP, C.c_char_p, C.c_int64]),
     "kb_synchronize": (C.c_int, [_VP]),

@@ -309,6 +309,26 @@ void build_clear_grid(int kind, const std::vector<double>& elems, const double g
   });
 }
 
+// Multi-device handles (kb_finalize_multi): a host-buffer batch is cut into contiguous shards, one per device, each run by its own
+// host thread on that device's replica (own stream, own scratch, static data replicated) and written straight into the caller's
+// buffers -- SURVEY 8e: configurations shard naturally, no exchange step besides the results landing in one array.
+template <class F> static int run_sharded(kb_engine* e, int64_t N, int64_t align, F fn) {
+  const int nd = 1 + (int)e->replicas.size();
+  if (nd == 1 || N < e->multi_min) return fn(e, (int64_t)0, N);
+  int64_t per = (N + nd - 1) / nd; per = ((per + align - 1) / align) * align;
+  std::vector<int> rcs((size_t)nd, KB_OK); std::vector<std::string> errs((size_t)nd);
+  std::vector<std::thread> th;
+  for (int k = 0; k < nd; k++) {
+    const int64_t off = std::min(N, (int64_t)k * per), n = std::min(per, N - off);
+    if (n <= 0) break;
+    kb_engine* r = k == 0 ? e : e->replicas[(size_t)k - 1];
+    th.emplace_back([&, k, r, off, n]() { rcs[(size_t)k] = fn(r, off, n); if (rcs[(size_t)k]) errs[(size_t)k] = g_err; });
+  }
+  for (auto& t : th) t.join();
+  for (int k = 0; k < nd; k++) if (rcs[(size_t)k]) return fail(rcs[(size_t)k], "device %d: %s", k == 0 ? e->device : e->replicas[(size_t)k - 1]->device, errs[(size_t)k].c_str());
+  return KB_OK;
+}
+
 }  // namespace
 
 struct kb_engine {
@@ -324,6 +344,10 @@ struct kb_engine {
   std::vector<uint8_t> selfcol; bool selfcol_default = true;
   std::vector<uint8_t> mask; int nids = 0; bool mask_user = false;
   bool finalized = false;
+  struct StaticAlloc { size_t member_offset, bytes; };
+  std::vector<StaticAlloc> statics;          // device allocations of the read-only data, for replication (kb_finalize_multi)
+  std::vector<kb_engine*> replicas;          // further devices of a multi-device handle: full copies of the static data, own streams and scratch
+  int64_t multi_min = 8192;                  // host-buffer batches below this stay on the first device
   // ---- device
   int device = -1, num_sms = 148;
   cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
@@ -571,8 +595,11 @@ int add_item(ItemSet& set, const DevGeom& A, int xfA, int idA, const DevGeom& B,
   return KB_OK;
 }
 
-template <class T> int upload(T*& dptr, const void* src, size_t bytes, int64_t* total) {
+// rec: the engine whose member `dptr` is -- the allocation is remembered (member offset, size) so that kb_finalize_multi can replicate
+// the static data on further devices with peer copies instead of rebuilding it
+template <class T> int upload(T*& dptr, const void* src, size_t bytes, int64_t* total, kb_engine* rec = nullptr) {
   dptr = nullptr;
+  if (rec) rec->statics.push_back({(size_t)((char*)&dptr - (char*)rec), bytes ? bytes : 16});
   if (bytes == 0) { CK(cudaMalloc((void**)&dptr, 16)); return KB_OK; }
   CK(cudaMalloc((void**)&dptr, bytes));
   CK(cudaMemcpy(dptr, src, bytes, cudaMemcpyHostToDevice));
@@ -707,15 +734,15 @@ int run_feasible_device(kb_engine* e, const double* dQ, int64_t N, uint8_t* d_ou
   return KB_OK;
 }
 
-int upload_itemset(ItemSet& s, int64_t* total) {
+int upload_itemset(ItemSet& s, int64_t* total, kb_engine* rec = nullptr) {
   if (s.d_items) { cudaFree(s.d_items); s.d_items = nullptr; }
   if (s.d_probes) { cudaFree(s.d_probes); s.d_probes = nullptr; }
   if (s.d_always_on) { cudaFree(s.d_always_on); s.d_always_on = nullptr; }
   if (!s.probes.empty()) {
-    int rc = upload(s.d_probes, s.probes.data(), s.probes.size() * sizeof(KbProbe), total); if (rc) return rc;
-    if ((rc = upload(s.d_always_on, s.always_on.data(), s.always_on.size() * 4, total))) return rc;
+    int rc = upload(s.d_probes, s.probes.data(), s.probes.size() * sizeof(KbProbe), total, rec); if (rc) return rc;
+    if ((rc = upload(s.d_always_on, s.always_on.data(), s.always_on.size() * 4, total, rec))) return rc;
   }
-  return upload(s.d_items, s.items.data(), s.items.size() * sizeof(KbItem), total);
+  return upload(s.d_items, s.items.data(), s.items.size() * sizeof(KbItem), total, rec);
 }
 
 }  // namespace
@@ -734,6 +761,8 @@ int kb_engine_create(kb_engine** out) {
 
 void kb_engine_destroy(kb_engine* e) {
   if (!e) return;
+  for (kb_engine* r : e->replicas) kb_engine_destroy(r);
+  e->replicas.clear();
   if (e->device >= 0) {
     cudaSetDevice(e->device);
     void* ptrs[] = {e->d_nodes, e->d_tris32, e->d_tris64, e->d_sph32, e->d_sph64, e->d_triown, e->d_sphown, e->d_robot, e->d_drv, e->d_drv_link,
@@ -865,6 +894,7 @@ int kb_add_dynamic_pointcloud(kb_engine* e, int capacity, double radius, double 
 
 int kb_update_pointcloud(kb_engine* e, int geom, const double* pts, int n) {
   if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
+  for (kb_engine* r : e->replicas) { int rc = kb_update_pointcloud(r, geom, pts, n); if (rc) return rc; }      // every device rebuilds its own copy
   const kb_engine::DynCloud* dc = nullptr;
   for (const auto& d : e->dyn) if (d.geom == geom) dc = &d;
   if (!dc) return fail(KB_ERR_INVALID, "geometry %d is not a dynamic point cloud attached to a terrain / rigid object with an enabled link pair", geom);
@@ -1236,31 +1266,31 @@ int kb_finalize(kb_engine* e, int device) {
       if (left < 0) { const int32_t first = ~left; if (count < 1) count = 1; if (count > 8 || first >= (1 << 28)) return fail(KB_ERR_UNSUPPORTED, "leaf not encodable in a quantised node"); ref = -1 - (first * 8 + (count - 1)); }
       q[4 * i] = cq[0] | (cq[1] << 16); q[4 * i + 1] = cq[2] | (hq[0] << 16); q[4 * i + 2] = hq[1] | (hq[2] << 16); memcpy(&q[4 * i + 3], &ref, 4);
     }
-    if ((rc = upload(e->d_nodes, q.data(), q.size() * 4, &e->static_bytes))) return rc;
+    if ((rc = upload(e->d_nodes, q.data(), q.size() * 4, &e->static_bytes, e))) return rc;
   }
 #else
-  if ((rc = upload(e->d_nodes, e->h_nodes.data(), e->h_nodes.size() * 4, &e->static_bytes))) return rc;
+  if ((rc = upload(e->d_nodes, e->h_nodes.data(), e->h_nodes.size() * 4, &e->static_bytes, e))) return rc;
 #endif
-  if ((rc = upload(e->d_tris32, e->h_tris32.data(), e->h_tris32.size() * 4, &e->static_bytes))) return rc;
-  if ((rc = upload(e->d_tris64, e->h_tris64.data(), e->h_tris64.size() * 8, &e->static_bytes))) return rc;
-  if ((rc = upload(e->d_sph32, e->h_sph32.data(), e->h_sph32.size() * 4, &e->static_bytes))) return rc;
-  if ((rc = upload(e->d_sph64, e->h_sph64.data(), e->h_sph64.size() * 8, &e->static_bytes))) return rc;
-  if ((rc = upload(e->d_box32, e->h_box32.data(), e->h_box32.size() * 4, &e->static_bytes))) return rc;
-  if ((rc = upload(e->d_box64, e->h_box64.data(), e->h_box64.size() * 8, &e->static_bytes))) return rc;
-  if ((rc = upload(e->d_boxown, e->h_boxown.data(), e->h_boxown.size() * 4, &e->static_bytes))) return rc;
-  if ((rc = upload(e->d_triown, e->h_triown.data(), e->h_triown.size() * 4, &e->static_bytes))) return rc;
-  if ((rc = upload(e->d_sphown, e->h_sphown.data(), e->h_sphown.size() * 4, &e->static_bytes))) return rc;
-  if ((rc = upload(e->d_triorig, e->h_triorig.data(), e->h_triorig.size() * 4, &e->static_bytes))) return rc;
-  if ((rc = upload(e->d_sphorig, e->h_sphorig.data(), e->h_sphorig.size() * 4, &e->static_bytes))) return rc;
+  if ((rc = upload(e->d_tris32, e->h_tris32.data(), e->h_tris32.size() * 4, &e->static_bytes, e))) return rc;
+  if ((rc = upload(e->d_tris64, e->h_tris64.data(), e->h_tris64.size() * 8, &e->static_bytes, e))) return rc;
+  if ((rc = upload(e->d_sph32, e->h_sph32.data(), e->h_sph32.size() * 4, &e->static_bytes, e))) return rc;
+  if ((rc = upload(e->d_sph64, e->h_sph64.data(), e->h_sph64.size() * 8, &e->static_bytes, e))) return rc;
+  if ((rc = upload(e->d_box32, e->h_box32.data(), e->h_box32.size() * 4, &e->static_bytes, e))) return rc;
+  if ((rc = upload(e->d_box64, e->h_box64.data(), e->h_box64.size() * 8, &e->static_bytes, e))) return rc;
+  if ((rc = upload(e->d_boxown, e->h_boxown.data(), e->h_boxown.size() * 4, &e->static_bytes, e))) return rc;
+  if ((rc = upload(e->d_triown, e->h_triown.data(), e->h_triown.size() * 4, &e->static_bytes, e))) return rc;
+  if ((rc = upload(e->d_sphown, e->h_sphown.data(), e->h_sphown.size() * 4, &e->static_bytes, e))) return rc;
+  if ((rc = upload(e->d_triorig, e->h_triorig.data(), e->h_triorig.size() * 4, &e->static_bytes, e))) return rc;
+  if ((rc = upload(e->d_sphorig, e->h_sphorig.data(), e->h_sphorig.size() * 4, &e->static_bytes, e))) return rc;
   e->scene.nodes = e->d_nodes; e->scene.tris32 = e->d_tris32; e->scene.tris64 = e->d_tris64; e->scene.sph32 = e->d_sph32; e->scene.sph64 = e->d_sph64;
   e->scene.triown = e->d_triown; e->scene.sphown = e->d_sphown; e->scene.triorig = e->d_triorig; e->scene.sphorig = e->d_sphorig;
   e->scene.box32 = e->d_box32; e->scene.box64 = e->d_box64; e->scene.boxown = e->d_boxown;
-  if ((rc = upload_itemset(e->feas_items, &e->static_bytes))) return rc;
-  if ((rc = upload_itemset(e->env_items, &e->static_bytes))) return rc;
+  if ((rc = upload_itemset(e->feas_items, &e->static_bytes, e))) return rc;
+  if ((rc = upload_itemset(e->env_items, &e->static_bytes, e))) return rc;
   for (size_t g = 0; g < e->hgrids.size(); g++) {
     const HostGrid& G = e->hgrids[g];
     if (!(G.h > 0)) continue;
-    if ((rc = upload(e->d_grid[g], G.q.data(), G.q.size(), &e->static_bytes))) return rc;
+    if ((rc = upload(e->d_grid[g], G.q.data(), G.q.size(), &e->static_bytes, e))) return rc;
     KbClearGrid& D = e->scene.grids[g];
     D.data = e->d_grid[g]; D.inv_h = (float)(1.0 / G.h);
     for (int k = 0; k < 3; k++) { D.o[k] = (float)G.o[k]; D.dims[k] = G.dims[k]; }
@@ -1277,11 +1307,11 @@ int kb_finalize(kb_engine* e, int device) {
     dl.insert(dl.end(), d.links.begin(), d.links.end()); ds.insert(ds.end(), d.scale.begin(), d.scale.end()); dofs.insert(dofs.end(), d.offset.begin(), d.offset.end());
   }
   R->ndrv_terms = (int)dl.size();
-  rc = upload(e->d_robot, R, sizeof(KbRobotDev), &e->static_bytes); delete R; if (rc) return rc;
-  if ((rc = upload(e->d_drv, dd.data(), dd.size() * sizeof(KbDriverDev), &e->static_bytes))) return rc;
-  if ((rc = upload(e->d_drv_link, dl.data(), dl.size() * 4, &e->static_bytes))) return rc;
-  if ((rc = upload(e->d_drv_scale, ds.data(), ds.size() * 8, &e->static_bytes))) return rc;
-  if ((rc = upload(e->d_drv_off, dofs.data(), dofs.size() * 8, &e->static_bytes))) return rc;
+  rc = upload(e->d_robot, R, sizeof(KbRobotDev), &e->static_bytes, e); delete R; if (rc) return rc;
+  if ((rc = upload(e->d_drv, dd.data(), dd.size() * sizeof(KbDriverDev), &e->static_bytes, e))) return rc;
+  if ((rc = upload(e->d_drv_link, dl.data(), dl.size() * 4, &e->static_bytes, e))) return rc;
+  if ((rc = upload(e->d_drv_scale, ds.data(), ds.size() * 8, &e->static_bytes, e))) return rc;
+  if ((rc = upload(e->d_drv_off, dofs.data(), dofs.size() * 8, &e->static_bytes, e))) return rc;
   if (!e->pending_clouds.empty()) {      // hierarchies of the large point clouds on the GPU (Morton order + Karras, kb_lbvh.cu)
     size_t maxn = 0; for (const auto& pc : e->pending_clouds) maxn = std::max(maxn, pc.elems.size() / (pc.mesh ? 9 : 4));
     double* d_p = nullptr; double* d_r = nullptr; int32_t* d_o = nullptr; int32_t* d_g = nullptr; double* d_T = nullptr; void* d_s = nullptr;
@@ -1330,6 +1360,69 @@ int kb_finalize(kb_engine* e, int device) {
   return KB_OK;
 }
 
+// a replica of a finalized engine on another device: host-side description copied, every static device array copied peer to peer
+static int clone_to_device(const kb_engine* src, int device, kb_engine** out) {
+  kb_engine* r = new kb_engine(*src);
+  r->replicas.clear(); r->tev.clear(); r->tev_used = 0;
+  r->own_stream = r->stream = r->copy_stream = nullptr; r->ev0 = r->ev1 = nullptr;
+  for (int k = 0; k < 4; k++) r->ev_copy[k] = nullptr;
+  // per-batch scratch starts empty on the new device
+  r->d_xf = nullptr; r->xf_cap = 0; r->d_state = nullptr; r->d_hit = nullptr; r->d_hit_elem = nullptr; r->cfg_cap = 0;
+  r->d_leaf_list = nullptr; r->leaf_cap = 0; r->d_flagged = nullptr; r->d_state2 = nullptr; r->split_cap = 0;
+  r->d_work = nullptr; r->d_counters = nullptr; r->d_Q = nullptr; r->q_cap = 0; r->d_Qf = nullptr; r->qf_cap = 0; r->d_out = nullptr; r->out_cap = 0;
+  r->d_bits = nullptr; r->bits_cap = 0; r->d_pair = nullptr; r->pair_cap = 0; r->d_dist = nullptr; r->dist_cap = 0; r->d_cp = nullptr; r->cp_cap = 0;
+  r->d_A = r->d_B = nullptr; r->ab_cap = 0; r->d_nlev = r->d_nchecks = r->d_firstbad = r->d_list = nullptr; r->d_alive = nullptr; r->edge_cap = 0;
+  r->d_eQ = nullptr; r->d_efeas = nullptr; r->eq_cap = 0; r->d_scalars = nullptr; r->d_weights = nullptr; r->w_cap = 0; r->d_T = nullptr; r->t_cap = 0;
+  r->d_dyn_pts = nullptr; r->d_dyn_T = nullptr; r->d_dyn_scratch = nullptr; r->dyn_pts_cap = 0; r->dyn_scratch_bytes = 0;
+  memset(&r->stats, 0, sizeof r->stats);
+  // static arrays: null first so that a failure half way destroys cleanly
+  for (const auto& a : src->statics) *(void**)((char*)r + a.member_offset) = nullptr;
+  r->device = device;
+  *out = r;
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
+  r->num_sms = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&r->own_stream, cudaStreamNonBlocking)); r->stream = r->own_stream;
+  CK(cudaEventCreate(&r->ev0)); CK(cudaEventCreate(&r->ev1));
+  CK(cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking));
+  for (int k = 0; k < 4; k++) CK(cudaEventCreateWithFlags(&r->ev_copy[k], cudaEventDisableTiming));
+  for (const auto& a : src->statics) {
+    void* d = nullptr;
+    CK(cudaMalloc(&d, a.bytes));
+    *(void**)((char*)r + a.member_offset) = d;
+    CK(cudaMemcpyPeer(d, device, *(void* const*)((const char*)src + a.member_offset), src->device, a.bytes));
+  }
+  // the scene block holds device pointers: point it at this device's copies
+  r->scene.nodes = r->d_nodes; r->scene.tris32 = r->d_tris32; r->scene.tris64 = r->d_tris64; r->scene.sph32 = r->d_sph32; r->scene.sph64 = r->d_sph64;
+  r->scene.triown = r->d_triown; r->scene.sphown = r->d_sphown; r->scene.triorig = r->d_triorig; r->scene.sphorig = r->d_sphorig;
+  r->scene.box32 = r->d_box32; r->scene.box64 = r->d_box64; r->scene.boxown = r->d_boxown;
+  for (int g = 0; g < KB_MAX_GRIDS; g++) if (src->scene.grids[g].data) r->scene.grids[g].data = r->d_grid[g];
+  CK(cudaMalloc((void**)&r->d_work, 64)); CK(cudaMalloc((void**)&r->d_counters, 128)); CK(cudaMemset(r->d_counters, 0, 128));
+  CK(cudaMalloc((void**)&r->d_scalars, 64));
+  CK(cudaDeviceSynchronize());
+  return KB_OK;
+}
+
+int kb_finalize_multi(kb_engine* e, const int* devices, int n_devices) {
+  if (!e || e->finalized) return fail(KB_ERR_STATE, "engine is null or already finalized");
+  if (!devices || n_devices < 1 || n_devices > 64) return fail(KB_ERR_INVALID, "need 1..64 devices");
+  for (int i = 0; i < n_devices; i++) for (int j = 0; j < i; j++) if (devices[i] == devices[j]) return fail(KB_ERR_INVALID, "device %d listed twice", devices[i]);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(KB_ERR_CUDA, "no CUDA device available; this engine has no CPU fallback");
+  for (int i = 0; i < n_devices; i++) if (devices[i] < 0 || devices[i] >= ndev) return fail(KB_ERR_INVALID, "device %d out of range (0..%d)", devices[i], ndev - 1);
+  int rc = kb_finalize(e, devices[0]); if (rc) return rc;
+  CK(cudaSetDevice(e->device)); CK(cudaDeviceSynchronize());
+  for (int i = 1; i < n_devices; i++) {
+    kb_engine* r = nullptr;
+    rc = clone_to_device(e, devices[i], &r);
+    if (r) e->replicas.push_back(r);
+    if (rc) { cudaSetDevice(e->device); return rc; }
+  }
+  CK(cudaSetDevice(e->device));
+  return KB_OK;
+}
+int kb_num_devices(const kb_engine* e) { return e && e->finalized ? 1 + (int)e->replicas.size() : 0; }
+
 int kb_set_stream(kb_engine* e, void* s) {
   if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
   // NULL = the engine's own non-blocking stream; cudaStreamLegacy (0x1) / cudaStreamPerThread (0x2) select the default streams
@@ -1338,6 +1431,8 @@ int kb_set_stream(kb_engine* e, void* s) {
 
 int kb_set_option(kb_engine* e, const char* name, int64_t value) {
   if (!e || !name) return fail(KB_ERR_INVALID, "null argument");
+  for (kb_engine* r : e->replicas) { int rc = kb_set_option(r, name, value); if (rc) return rc; }
+  if (!strcmp(name, "multi_min")) { if (value < 1) return fail(KB_ERR_INVALID, "multi_min must be >= 1"); e->multi_min = value; return KB_OK; }
   if (!strcmp(name, "collect_stats")) { e->collect_stats = value != 0; return KB_OK; }
   if (!strcmp(name, "time_kernels")) { e->time_kernels = value != 0; return KB_OK; }
   if (!strcmp(name, "pipeline")) { if (value != 0 && value != 1) return fail(KB_ERR_INVALID, "pipeline must be 0 (fused) or 1 (split)"); e->pipeline = (int)value; return KB_OK; }
@@ -1373,6 +1468,7 @@ int kb_set_option(kb_engine* e, const char* name, int64_t value) {
 
 int kb_synchronize(kb_engine* e) {
   if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
+  for (kb_engine* r : e->replicas) { CK(cudaSetDevice(r->device)); CK(cudaStreamSynchronize(r->stream)); }
   CK(cudaSetDevice(e->device)); CK(cudaStreamSynchronize(e->stream)); return KB_OK;
 }
 
@@ -1404,7 +1500,7 @@ int kb_feasible_batch_device(kb_engine* e, const double* dQ, int64_t N, uint8_t*
 }
 
 // host-buffer feasibility for configurations given as doubles (esz 8) or floats (esz 4; widened to fp64 on the device)
-static int feasible_batch_host(kb_engine* e, const void* Qv, int esz, int64_t N, uint8_t* out, int32_t* first_pair, bool bits = false) {
+static int feasible_batch_host_one(kb_engine* e, const void* Qv, int esz, int64_t N, uint8_t* out, int32_t* first_pair, bool bits) {
   if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
   if (N < 0 || (N > 0 && (!Qv || !out))) return fail(KB_ERR_INVALID, "bad arguments");
   if (N == 0) return KB_OK;
@@ -1460,6 +1556,14 @@ static int feasible_batch_host(kb_engine* e, const void* Qv, int esz, int64_t N,
   return KB_OK;
 }
 
+static int feasible_batch_host(kb_engine* e, const void* Qv, int esz, int64_t N, uint8_t* out, int32_t* first_pair, bool bits = false) {
+  if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
+  if (N < 0 || (N > 0 && (!Qv || !out))) return fail(KB_ERR_INVALID, "bad arguments");
+  const size_t row = (size_t)e->L * esz;
+  return run_sharded(e, N, 32, [&](kb_engine* r, int64_t off, int64_t n) {
+    return feasible_batch_host_one(r, (const char*)Qv + off * row, esz, n, out + (bits ? off / 8 : off), first_pair ? first_pair + 2 * off : nullptr, bits);
+  });
+}
 int kb_feasible_batch(kb_engine* e, const double* Q, int64_t N, uint8_t* out, int32_t* first_pair) { return feasible_batch_host(e, Q, 8, N, out, first_pair); }
 int kb_feasible_batch_f32(kb_engine* e, const float* Q, int64_t N, uint8_t* out, int32_t* first_pair) { return feasible_batch_host(e, Q, 4, N, out, first_pair); }
 int kb_feasible_batch_bits(kb_engine* e, const double* Q, int64_t N, uint8_t* out_bits) { return feasible_batch_host(e, Q, 8, N, out_bits, nullptr, true); }
@@ -1535,6 +1639,7 @@ int kb_edges_visible_batch_device(kb_engine* e, const double* dA, const double* 
 }
 
 static int edges_visible_host(kb_engine* e, const double* A, const double* B, int64_t N, double eps, const double* weights, uint8_t* out, int32_t* nchecks, bool bits);
+static int edges_visible_host_one(kb_engine* e, const double* A, const double* B, int64_t N, double eps, const double* weights, uint8_t* out, int32_t* nchecks, bool bits);
 int kb_edges_visible_batch(kb_engine* e, const double* A, const double* B, int64_t N, double eps, const double* weights, uint8_t* out, int32_t* nchecks) {
   return edges_visible_host(e, A, B, N, eps, weights, out, nchecks, false);
 }
@@ -1542,6 +1647,14 @@ int kb_edges_visible_batch_bits(kb_engine* e, const double* A, const double* B, 
   return edges_visible_host(e, A, B, N, eps, weights, out_bits, nchecks, true);
 }
 static int edges_visible_host(kb_engine* e, const double* A, const double* B, int64_t N, double eps, const double* weights, uint8_t* out, int32_t* nchecks, bool bits) {
+  if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
+  if (N < 0 || (N > 0 && (!A || !B || !out))) return fail(KB_ERR_INVALID, "bad arguments");
+  const int64_t L = e->L;
+  return run_sharded(e, N, 32, [&](kb_engine* r, int64_t off, int64_t n) {
+    return edges_visible_host_one(r, A + off * L, B + off * L, n, eps, weights, out + (bits ? off / 8 : off), nchecks ? nchecks + off : nullptr, bits);
+  });
+}
+static int edges_visible_host_one(kb_engine* e, const double* A, const double* B, int64_t N, double eps, const double* weights, uint8_t* out, int32_t* nchecks, bool bits) {
   if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
   if (N < 0 || (N > 0 && (!A || !B || !out))) return fail(KB_ERR_INVALID, "bad arguments");
   if (N == 0) return KB_OK;
@@ -1624,8 +1737,20 @@ int kb_distance_batch_device(kb_engine* e, const double* dQ, int64_t N, double u
   return distance_device(e, dQ, N, 0.0, 0.0, upper_bound, include_self, d_out_d, d_out_pair, nullptr, nullptr);
 }
 
+static int distance_host_one(kb_engine* e, const double* Q, int64_t N, double abs_err, double rel_err, double upper_bound, int include_self,
+                             double* out_d, int32_t* out_pair, double* out_cp, int32_t* out_elem);
 static int distance_host(kb_engine* e, const double* Q, int64_t N, double abs_err, double rel_err, double upper_bound, int include_self,
                          double* out_d, int32_t* out_pair, double* out_cp, int32_t* out_elem) {
+  if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
+  if (N < 0 || (N > 0 && (!Q || !out_d))) return fail(KB_ERR_INVALID, "bad arguments");
+  const int64_t L = e->L;
+  return run_sharded(e, N, 1, [&](kb_engine* r, int64_t off, int64_t n) {
+    return distance_host_one(r, Q + off * L, n, abs_err, rel_err, upper_bound, include_self, out_d + off, out_pair ? out_pair + 2 * off : nullptr,
+                             out_cp ? out_cp + 6 * off : nullptr, out_elem ? out_elem + 2 * off : nullptr);
+  });
+}
+static int distance_host_one(kb_engine* e, const double* Q, int64_t N, double abs_err, double rel_err, double upper_bound, int include_self,
+                             double* out_d, int32_t* out_pair, double* out_cp, int32_t* out_elem) {
   if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
   if (N < 0 || (N > 0 && (!Q || !out_d))) return fail(KB_ERR_INVALID, "bad arguments");
   if (N == 0) return KB_OK;
@@ -1741,11 +1866,22 @@ int kb_get_stats(kb_engine* e, kb_stats* out) {
     e->stats.configs_feasible = (int64_t)c[3]; e->stats.edges_visible = (int64_t)c[4]; e->stats.items_dropped = (int64_t)c[7]; e->stats.node_iterations = (int64_t)c[8];
     fold_kernel_times(e);
   }
-  *out = e->stats; return KB_OK;
+  *out = e->stats;
+  for (kb_engine* r : e->replicas) {     // a multi-device handle reports the sum over its devices
+    kb_stats t; int rc = kb_get_stats(r, &t); if (rc) return rc;
+    out->configs_checked += t.configs_checked; out->configs_feasible += t.configs_feasible; out->edges_checked += t.edges_checked;
+    out->edges_visible += t.edges_visible; out->edge_config_checks += t.edge_config_checks; out->node_tests += t.node_tests;
+    out->elem_tests += t.elem_tests; out->recheck_pairs += t.recheck_pairs; out->kernel_launches += t.kernel_launches;
+    out->traverse_launches += t.traverse_launches; out->traverse_ms += t.traverse_ms; out->gpu_ms = std::max(out->gpu_ms, t.gpu_ms);
+    out->items_dropped += t.items_dropped; out->node_iterations += t.node_iterations;
+  }
+  if (!e->replicas.empty()) CK(cudaSetDevice(e->device));
+  return KB_OK;
 }
 
 int kb_reset_stats(kb_engine* e) {
   if (!e) return fail(KB_ERR_INVALID, "null argument");
+  for (kb_engine* r : e->replicas) { int rc = kb_reset_stats(r); if (rc) return rc; }
   memset(&e->stats, 0, sizeof e->stats);
   e->tev_used = 0;
   if (e->finalized) { CK(cudaSetDevice(e->device)); CK(cudaMemsetAsync(e->d_counters, 0, 128, e->stream)); }

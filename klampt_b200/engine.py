@@ -38,8 +38,9 @@ def _f64(a, shape=None):
 class Engine:
     """One kb_engine handle = static world + one active robot, resident on one GPU."""
 
-    def __init__(self, spec: WorldSpec, device: int = 0, options: Optional[dict] = None):
-        """options: kb_set_option values that must be in place before kb_finalize, e.g. {"cloud_builder": 1} (point-cloud
+    def __init__(self, spec: WorldSpec, device=0, options: Optional[dict] = None):
+        """device: one CUDA device index, or a list of them (kb_finalize_multi: host-buffer batches are sharded over the devices).
+        options: kb_set_option values that must be in place before kb_finalize, e.g. {"cloud_builder": 1} (point-cloud
         hierarchies built on the GPU) or {"grid_res": 0}"""
         self.lib = _capi.load()
         self.spec = spec
@@ -54,7 +55,12 @@ class Engine:
                 options[k.strip()] = int(v)
             for k, v in options.items():
                 check(self.lib.kb_set_option(self.h, k.encode(), int(v)))
-            check(self.lib.kb_finalize(self.h, int(device)))
+            if isinstance(device, (list, tuple)):
+                devs = np.ascontiguousarray(device, dtype=np.int32)
+                check(self.lib.kb_finalize_multi(self.h, devs.ctypes.data_as(_capi.c_int32_p), len(devs)))
+                device = int(devs[0])
+            else:
+                check(self.lib.kb_finalize(self.h, int(device)))
         except Exception:
             self.close()
             raise
@@ -141,6 +147,9 @@ class Engine:
 
     def set_option(self, name: str, value: int):
         check(self.lib.kb_set_option(self.h, name.encode(), int(value)))
+
+    def num_devices(self) -> int:
+        return int(self.lib.kb_num_devices(self.h))
 
     def num_ids(self) -> int:
         return int(self.lib.kb_num_ids(self.h))
