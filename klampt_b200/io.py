@@ -757,20 +757,27 @@ def _vec(txt: Optional[str], n: int, default: float = 0.0) -> np.ndarray:
 
 
 def _xml_rotation(el) -> np.ndarray:
-    """rotateRPY / rotateX / rotateY / rotateZ / rotateMoment attributes, applied in the order they are written
-    (Cpp/docs/Manual-FileTypes.md:66-72 "rotation attributes are applied in sequence")"""
+    """ReadTransform of the world loader (Cpp/IO/XmlWorld.cpp:97-160): rotateRPY sets the rotation, rotateMoment replaces it, then
+    rotateX, rotateY, rotateZ are pre-multiplied IN THAT FIXED ORDER -- whatever order the attributes are written in"""
     from . import so3
     R = np.eye(3)
-    for key, val in el.attrib.items():
-        if key == "rotateRPY":
-            r, p, y = _vec(val, 3)
-            R = _rpy_matrix(r, p, y) @ R
-        elif key in ("rotateX", "rotateY", "rotateZ"):
-            ax = {"rotateX": [1, 0, 0], "rotateY": [0, 1, 0], "rotateZ": [0, 0, 1]}[key]
-            R = so3.matrix(so3.from_axis_angle((ax, float(val)))) @ R
-        elif key == "rotateMoment":
-            R = so3.exp(_vec(val, 3)) @ R
+    if el.get("rotateRPY") is not None:
+        r, p, y = _vec(el.get("rotateRPY"), 3)
+        R = _rpy_matrix(r, p, y)
+    if el.get("rotateMoment") is not None:
+        R = so3.exp(_vec(el.get("rotateMoment"), 3))
+    for key, ax in (("rotateX", [1, 0, 0]), ("rotateY", [0, 1, 0]), ("rotateZ", [0, 0, 1])):
+        if el.get(key) is not None:
+            R = so3.matrix(so3.from_axis_angle((ax, float(el.get(key))))) @ R
     return R
+
+
+def _xml_translation(el, extra=()) -> np.ndarray:
+    """translation, else position (ReadTransform, XmlWorld.cpp:103-107); `extra`: further attribute names accepted after those"""
+    for key in ("translation", "position") + tuple(extra):
+        if el.get(key) is not None:
+            return _vec(el.get(key), 3)
+    return np.zeros(3)
 
 
 def load_world_xml(path: str) -> WorldSpec:
@@ -792,7 +799,7 @@ def parse_world_xml(text: str, basedir: str = ".") -> WorldSpec:
     for el in root:
         if el.tag == "terrain":
             g = load_geometry(resolve(el.get("file")), _vec(el.get("scale"), 3, 1.0), (0, 0, 0), float(el.get("margin", "0")))
-            R, t = _xml_rotation(el), _vec(el.get("translation", el.get("position")), 3)
+            R, t = _xml_rotation(el), _xml_translation(el)
             if g.kind == "mesh":
                 g.verts = g.verts @ R.T + t
             else:
@@ -803,8 +810,14 @@ def parse_world_xml(text: str, basedir: str = ".") -> WorldSpec:
             if ge is None:
                 raise ValueError("<rigidObject> without <geometry> (rigid object .obj description files are not read)")
             fn = ge.get("file", ge.get("mesh"))
-            g = load_geometry(resolve(fn), _vec(ge.get("scale"), 3, 1.0), _vec(ge.get("translate"), 3), float(ge.get("margin", "0")))
-            T = np.concatenate([_xml_rotation(el).reshape(-1), _vec(el.get("position"), 3)])
+            # <geometry> carries its own ReadTransform (XmlWorld.cpp:292-294): p -> R (s * p) + t, applied to the geometry itself
+            g = load_geometry(resolve(fn), _vec(ge.get("scale"), 3, 1.0), (0.0, 0.0, 0.0), float(ge.get("margin", "0")))
+            Rg, tg = _xml_rotation(ge), _xml_translation(ge, extra=("translate",))
+            if g.kind == "mesh":
+                g.verts = g.verts @ Rg.T + tg
+            else:
+                g.points = g.points @ Rg.T + tg
+            T = np.concatenate([_xml_rotation(el).reshape(-1), _xml_translation(el)])
             w.objects.append((w.add_geom(g), T))
         elif el.tag == "robot":
             if w.robot is not None:
@@ -814,4 +827,13 @@ def parse_world_xml(text: str, basedir: str = ".") -> WorldSpec:
                 load_urdf(fn, w)
             else:
                 load_rob(fn, w)
+            # XmlRobot::GetRobot (XmlWorld.cpp:251-257): the element's transform is pre-multiplied into T0_Parent of every root link
+            Rr, tr = _xml_rotation(el), _xml_translation(el)
+            if not (np.array_equal(Rr, np.eye(3)) and not tr.any()):
+                r = w.robot
+                for i in range(r.L):
+                    if r.parents[i] < 0:
+                        R0, t0 = r.T0[i, :9].reshape(3, 3).copy(), r.T0[i, 9:12].copy()
+                        r.T0[i, :9] = (Rr @ R0).reshape(-1)
+                        r.T0[i, 9:12] = Rr @ t0 + tr
     return w

@@ -52,10 +52,15 @@ class RobotCSpace(CSpace):
         """SingleRobotCSpace::IsFeasible per row.  Constraints added with addConstraint are host callables: they run only on the rows
         the engine found feasible (a row they reject keeps first pair (-1, -1))"""
         res = self.engine.feasible_batch(Q, return_pairs=return_pairs)
-        if not self._extra:
-            return res
         ok = res[0] if return_pairs else res
         Q2 = np.asarray(Q, dtype=np.float64).reshape(len(ok), -1)
+        # The reference's Python RobotCSpace tests EVERY dimension against self.bound ("joint limits", robotcspace.py:31-75), the engine
+        # only Normal / Weld joints and drivers (SingleRobotCSpace::CheckJointLimits).  One contract for isFeasible, feasible and the batch
+        # forms: the all-dimension check is ANDed in here (it also honours a setBounds() that tightened the box after construction;
+        # the engine keeps enforcing the robot's own limits, so widening the box beyond them has no effect -- as in the C++ space).
+        ok &= self._bounds_ok(Q2).astype(ok.dtype)
+        if not self._extra:
+            return res
         for i in np.nonzero(ok)[0]:
             if not self._extra_ok(Q2[i]):
                 ok[i] = 0
@@ -65,23 +70,34 @@ class RobotCSpace(CSpace):
         x = list(map(float, q))
         return all(c(x) for c in self._extra)
 
+    def _bounds_ok(self, Q2: np.ndarray) -> np.ndarray:
+        """vectorised inJointLimits over every dimension of self.bound (closed intervals), without the failure counters"""
+        lo = np.array([b[0] for b in self.bound], dtype=np.float64)
+        hi = np.array([b[1] for b in self.bound], dtype=np.float64)
+        return ((Q2 >= lo) & (Q2 <= hi)).all(axis=1)
+
     def visible_batch(self, A, B, eps: Optional[float] = None, return_nchecks: bool = False):
         """EpsilonEdgeChecker(a, b, eps).IsVisible per row.  With user constraints, the edges the engine found visible are walked
         again on the host at the same resolution for those constraints alone (bisection order, robot.interpolate)"""
         eps = self.eps if eps is None else eps
         res = self.engine.edges_visible_batch(A, B, eps=eps, return_nchecks=return_nchecks)
-        if not self._extra:
-            return res
         vis = res[0] if return_nchecks else res
         A2, B2 = np.asarray(A, dtype=np.float64).reshape(len(vis), -1), np.asarray(B, dtype=np.float64).reshape(len(vis), -1)
-        for i in np.nonzero(vis)[0]:
+        # all-dimension bounds (see feasible_batch): midpoints between two in-bound endpoints of a box stay in the box, so only edges
+        # with an endpoint outside self.bound need their midpoints looked at -- on the host, with the user constraints' walk
+        suspect = ~(self._bounds_ok(A2) & self._bounds_ok(B2))
+        if not self._extra and not suspect.any():
+            return res
+        rows = np.nonzero(vis)[0] if self._extra else np.nonzero(vis.astype(bool) & suspect)[0]
+        for i in rows:
             a, b = list(A2[i]), list(B2[i])
             length, segs = self.distance(a, b), 1
             while length > eps and vis[i]:
                 segs *= 2
                 length *= 0.5
                 for k in range(1, segs, 2):
-                    if not self._extra_ok(self.interpolate(a, b, float(k) / segs)):
+                    x = self.interpolate(a, b, float(k) / segs)
+                    if (suspect[i] and not self._bounds_ok(np.asarray(x, dtype=np.float64).reshape(1, -1))[0]) or not self._extra_ok(x):
                         vis[i] = 0
                         break
         return res

@@ -252,3 +252,40 @@ def test_robot_cspace_named_tests(setup):
             assert space.testFeasibility(n, x) == (n not in fails)
     with pytest.raises(ValueError):
         space.testFeasibility("no such test", list(Q[0]))
+
+
+def test_one_joint_limit_contract_for_single_and_batch_queries(built):
+    """The reference's Python RobotCSpace tests every dimension against `bound`; the C++ space (and the engine) only Normal / Weld joints.
+    The mirror answers isFeasible, feasible and feasible_batch / visible_batch by ONE rule: a floating base with a finite box is held to it
+    everywhere, and a box tightened with setBounds after construction is honoured by the batch forms too."""
+    from klampt_b200.collide import WorldCollider
+    from klampt_b200.robotcspace import RobotCSpace
+    from klampt_b200.robotsim import WorldModel
+    spec = synth.world_floating(n_obstacles=6)
+    world = WorldModel.from_spec(spec)
+    robot = world.robot(0)
+    qmin, qmax = robot.getJointLimits()
+    qmin, qmax = list(qmin), list(qmax)
+    for k in range(3):                                   # a finite box for the floating base's translation (the engine does not check it)
+        qmin[k], qmax[k] = -0.4, 0.4
+    robot.setJointLimits(qmin, qmax)
+    space = RobotCSpace(robot, WorldCollider(world))
+    rng = np.random.default_rng(2)
+    lo = np.array([b[0] if np.isfinite(b[0]) else -3.0 for b in space.bound]); hi = np.array([b[1] if np.isfinite(b[1]) else 3.0 for b in space.bound])
+    Q = rng.uniform(lo, hi, size=(3000, len(lo)))
+    Q[::3, 0] += 0.6                                      # a third of the rows leave the box along x
+    got = space.feasible_batch(Q)
+    inbox = ((Q >= np.array([b[0] for b in space.bound])) & (Q <= np.array([b[1] for b in space.bound]))).all(axis=1)
+    assert not got[~inbox].any() and got[inbox].any() and (~inbox).sum() > 300
+    for i in list(np.nonzero(~inbox)[0][:20]) + list(np.nonzero(inbox)[0][:40]):
+        assert bool(got[i]) == space.isFeasible(list(Q[i])) == space.feasible(list(Q[i]))
+    # an edge that starts outside the box is not visible although the engine alone would pass it
+    ok = Q[got == 1]
+    out = ok[:50].copy(); out[:, 0] = 0.9
+    vis = space.visible_batch(out, ok[50:100], eps=0.05)
+    assert not vis.any()
+    assert space.engine.edges_visible_batch(out, ok[50:100], eps=0.05, return_nchecks=False).any()       # the engine by itself ignores that box
+    # tightening the box after construction reaches the batch forms
+    b = list(space.bound); b[1] = (-0.1, 0.1); space.setBounds(b)
+    got2 = space.feasible_batch(Q)
+    assert not got2[np.abs(Q[:, 1]) > 0.1].any() and np.array_equal(got2[np.abs(Q[:, 1]) <= 0.1], got[np.abs(Q[:, 1]) <= 0.1])

@@ -224,3 +224,36 @@ def test_rob_floating_joint_base_round_trip():
     assert "joint floating 5 -1" in text and "joint ballandsocket 9 6" in text
     w2, r2 = kio.parse_rob(text)
     assert list(r2.joint_base) == list(w.robot.joint_base) and list(r2.joint_type) == list(w.robot.joint_type)
+
+
+def test_world_xml_places_the_robot_and_reads_transforms_like_the_reference(tmp_path):
+    """XmlRobot::GetRobot pre-multiplies the <robot> element's transform into T0_Parent of every root link (Cpp/IO/XmlWorld.cpp:251-257);
+    ReadTransform (:97-160) takes translation else position, and applies rotateRPY (set) -> rotateMoment (replace) -> rotateX -> rotateY
+    -> rotateZ in that fixed order whatever the attribute order; <geometry> has its own transform (:292-294)"""
+    (tmp_path / "cube.off").write_text(CUBE_OFF)
+    spec0 = WorldSpec(); arm = synth.make_planar_nR(spec0, 2)
+    (tmp_path / "arm.rob").write_text(kio.rob_text(arm, spec0))
+    (tmp_path / "w.xml").write_text("""<?xml version="1.0"?>
+<world>
+  <robot name="arm" file="arm.rob" position="1 2 0.5" rotateZ="1.5707963267948966"/>
+  <rigidObject name="box" rotateZ="0.3" rotateX="0.2" position="0 0 1">
+    <geometry file="cube.off" scale="2 1 1" rotateZ="1.5707963267948966" translation="0 0 3"/>
+  </rigidObject>
+</world>""")
+    w = kio.load_world_xml(str(tmp_path / "w.xml"))
+    base = kio.parse_rob(kio.rob_text(arm, spec0))[1]
+    Rz = np.array([[0.0, -1, 0], [1, 0, 0], [0, 0, 1]])
+    R0, t0 = base.T0[0, :9].reshape(3, 3), base.T0[0, 9:12]
+    assert np.allclose(w.robot.T0[0, :9].reshape(3, 3), Rz @ R0, atol=1e-12) and np.allclose(w.robot.T0[0, 9:12], Rz @ t0 + [1, 2, 0.5], atol=1e-12)
+    assert np.allclose(w.robot.T0[1], base.T0[1])                      # only root links move
+    # the displaced robot really is somewhere else for the feasibility path: link 0's world transform carries the offset
+    o = OracleWorld(w)
+    assert np.allclose(o.fk(np.zeros(2))[0, 9:12], Rz @ t0 + [1, 2, 0.5], atol=1e-12)
+    # fixed X-then-Z order although the file writes Z first:  R = Rz(0.3) Rx(0.2)
+    from klampt_b200 import so3
+    go, T = w.objects[0]
+    want = so3.matrix(so3.from_axis_angle(([0, 0, 1], 0.3))) @ so3.matrix(so3.from_axis_angle(([1, 0, 0], 0.2)))
+    assert np.allclose(T[:9].reshape(3, 3), want, atol=1e-12) and np.allclose(T[9:], [0, 0, 1])
+    # geometry: scale (2,1,1), then quarter turn about z, then lift by 3: the unit cube spans x in [-1,0], y in [0,2], z in [3,4]
+    v = w.geoms[go].verts
+    assert np.allclose(v.min(0), [-1, 0, 3], atol=1e-12) and np.allclose(v.max(0), [0, 2, 4], atol=1e-12)
