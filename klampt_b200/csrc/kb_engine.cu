@@ -374,6 +374,9 @@ struct kb_engine {
   int mesh_builder = 0;                      // the same choice for triangle meshes above KB_GPU_MESH_MIN triangles
   struct PendingCloud { DevGeom* dg; std::vector<double> elems; std::vector<int32_t> owners; bool mesh = false; std::vector<int32_t> origs; };
   std::vector<PendingCloud> pending_clouds;   // clouds whose hierarchy is built on the GPU once the arrays are uploaded
+  // small host-buffer batches (N <= graph_max): pinned staging + one CUDA graph per batch size (copy in, FK, traversal, finish, copy out)
+  struct SmallGraph { int64_t n = 0; cudaGraphExec_t exec = nullptr; const void* key[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; };
+  std::vector<SmallGraph> graphs; int64_t graph_max = 1024; double* h_pin_in = nullptr; uint8_t* h_pin_out = nullptr; double* g_dQ = nullptr; uint8_t* g_dout = nullptr;
   int cloud_leaf = 8;                        // points per leaf of a host-built point-cloud hierarchy (option cloud_leaf, 1..32)
   int both_limit = 0;                        // experiment: frontier size up to which comparable inner pairs descend both trees at once
   int grid_res = 256; bool use_grids = false; // clearance-grid broad phase of the boolean query (options grid_res, clear_grid)
@@ -773,6 +776,9 @@ void kb_engine_destroy(kb_engine* e) {
     for (void* p : ptrs) if (p) cudaFree(p);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
+    for (auto& x : e->graphs) if (x.exec) cudaGraphExecDestroy(x.exec);
+    if (e->h_pin_in) cudaFreeHost(e->h_pin_in); if (e->h_pin_out) cudaFreeHost(e->h_pin_out);
+    if (e->g_dQ) cudaFree(e->g_dQ); if (e->g_dout) cudaFree(e->g_dout);
     for (cudaEvent_t ev : e->tev) cudaEventDestroy(ev);
     for (int k = 0; k < 4; k++) if (e->ev_copy[k]) cudaEventDestroy(e->ev_copy[k]);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
@@ -1363,7 +1369,7 @@ int kb_finalize(kb_engine* e, int device) {
 // a replica of a finalized engine on another device: host-side description copied, every static device array copied peer to peer
 static int clone_to_device(const kb_engine* src, int device, kb_engine** out) {
   kb_engine* r = new kb_engine(*src);
-  r->replicas.clear(); r->tev.clear(); r->tev_used = 0;
+  r->replicas.clear(); r->tev.clear(); r->tev_used = 0; r->graphs.clear(); r->h_pin_in = nullptr; r->h_pin_out = nullptr; r->g_dQ = nullptr; r->g_dout = nullptr;
   r->own_stream = r->stream = r->copy_stream = nullptr; r->ev0 = r->ev1 = nullptr;
   for (int k = 0; k < 4; k++) r->ev_copy[k] = nullptr;
   // per-batch scratch starts empty on the new device
@@ -1449,6 +1455,7 @@ int kb_set_option(kb_engine* e, const char* name, int64_t value) {
     e->cloud_builder = (int)value; return KB_OK;
   }
   if (!strcmp(name, "both_limit")) { e->both_limit = (int)value; return KB_OK; }
+  if (!strcmp(name, "graph_max")) { if (value < 0 || value > 65536) return fail(KB_ERR_INVALID, "graph_max must be in [0, 65536]"); if (e->h_pin_in && value > e->graph_max) return fail(KB_ERR_STATE, "graph_max can only grow before the first small batch"); e->graph_max = value; return KB_OK; }
   if (!strcmp(name, "cloud_leaf")) {
     if (e->finalized) return fail(KB_ERR_STATE, "cloud_leaf must be set before kb_finalize");
     if (value < 1 || value > 32) return fail(KB_ERR_INVALID, "cloud_leaf must be in [1, 32]");
@@ -1499,6 +1506,59 @@ int kb_feasible_batch_device(kb_engine* e, const double* dQ, int64_t N, uint8_t*
   return KB_OK;
 }
 
+// Small batches -- the calls a planner makes between its own decisions (one configuration from RRT's extend step, a few hundred from a
+// batched PRM).  Their cost is fixed overhead, not kernels: N = 1 on C2 took 64 us of which the traversal was 15.  So the caller's
+// rows go through pinned staging and the whole sequence (copy in, FK, counter reset, traversal, finish, copy out) is ONE CUDA graph,
+// captured once per batch size and replayed: one launch call and one synchronisation per query.  A graph remembers the scratch pointers
+// it was captured with and is re-captured if a larger batch made the engine reallocate them.
+static int feasible_small(kb_engine* e, const double* Q, int64_t N, uint8_t* out) {
+  int rc;
+  if (!e->h_pin_in) {
+    const size_t cap = (size_t)std::max<int64_t>(1, e->graph_max);
+    CK(cudaMallocHost((void**)&e->h_pin_in, cap * e->L * 8)); CK(cudaMallocHost((void**)&e->h_pin_out, cap));
+    CK(cudaMalloc((void**)&e->g_dQ, cap * e->L * 8)); CK(cudaMalloc((void**)&e->g_dout, cap));
+  }
+  if ((rc = ensure_cfg_scratch(e, e->feas_items.nxf, N))) return rc;
+  const void* key[6] = {e->d_xf, e->d_state, e->d_hit, e->d_hit_elem, (const void*)e->stream, (const void*)(intptr_t)((e->use_grids ? 1 : 0) + 2 * e->chunk + ((int64_t)e->both_limit << 40))};
+  kb_engine::SmallGraph* g = nullptr;
+  for (auto& x : e->graphs) if (x.n == N) g = &x;
+  if (g && memcmp(g->key, key, sizeof key) != 0) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; }
+  if (!g) {
+    if (e->graphs.size() >= 32) { for (auto& x : e->graphs) if (x.exec) cudaGraphExecDestroy(x.exec); e->graphs.clear(); }
+    e->graphs.emplace_back(); g = &e->graphs.back(); g->n = N;
+  }
+  memcpy(e->h_pin_in, Q, (size_t)N * e->L * 8);
+  if (!g->exec) {
+    // one plain run first: it sets the kernels' attributes (not capturable) and leaves the answer for this very call
+    CK(cudaMemcpyAsync(e->g_dQ, e->h_pin_in, (size_t)N * e->L * 8, cudaMemcpyHostToDevice, e->stream));
+    if ((rc = run_feasible_device(e, e->g_dQ, N, e->g_dout, nullptr, e->d_counters + 3))) return rc;
+    CK(cudaMemcpyAsync(e->h_pin_out, e->g_dout, (size_t)N, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    memcpy(out, e->h_pin_out, (size_t)N);
+    e->stats.configs_checked += N;
+    cudaGraph_t graph = nullptr;
+    const int64_t launches_before = e->stats.kernel_launches;
+    CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    cudaError_t ce = cudaMemcpyAsync(e->g_dQ, e->h_pin_in, (size_t)N * e->L * 8, cudaMemcpyHostToDevice, e->stream);
+    rc = ce == cudaSuccess ? run_feasible_device(e, e->g_dQ, N, e->g_dout, nullptr, e->d_counters + 3) : KB_ERR_CUDA;
+    if (rc == KB_OK) ce = cudaMemcpyAsync(e->h_pin_out, e->g_dout, (size_t)N, cudaMemcpyDeviceToHost, e->stream);
+    cudaError_t ce2 = cudaStreamEndCapture(e->stream, &graph);
+    e->stats.kernel_launches = launches_before;                 // nothing ran during the capture
+    if (rc != KB_OK || ce != cudaSuccess || ce2 != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return KB_OK; }   // no graph: plain runs keep working
+    ce = cudaGraphInstantiate(&g->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) { g->exec = nullptr; cudaGetLastError(); return KB_OK; }
+    memcpy(g->key, key, sizeof key);
+    return KB_OK;
+  }
+  CK(cudaGraphLaunch(g->exec, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  memcpy(out, e->h_pin_out, (size_t)N);
+  e->stats.configs_checked += N;
+  e->stats.kernel_launches += 3;
+  return KB_OK;
+}
+
 // host-buffer feasibility for configurations given as doubles (esz 8) or floats (esz 4; widened to fp64 on the device)
 static int feasible_batch_host_one(kb_engine* e, const void* Qv, int esz, int64_t N, uint8_t* out, int32_t* first_pair, bool bits) {
   if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
@@ -1506,6 +1566,7 @@ static int feasible_batch_host_one(kb_engine* e, const void* Qv, int esz, int64_
   if (N == 0) return KB_OK;
   CK(cudaSetDevice(e->device));
   int rc;
+  if (N <= e->graph_max && esz == 8 && !first_pair && !bits && e->pipeline == 0 && !e->time_kernels && !e->collect_stats) return feasible_small(e, (const double*)Qv, N, out);
   const char* Q = (const char*)Qv;
   if (esz == 4 && (rc = grow(e->d_Qf, e->qf_cap, N * e->L))) return rc;
   char* d_in = esz == 4 ? (char*)e->d_Qf : nullptr;
@@ -1611,9 +1672,11 @@ int kb_edges_visible_batch_device(kb_engine* e, const double* dA, const double* 
   CK(cudaMemsetAsync(e->d_scalars, 0, 64, e->stream));
   CK(kb_launch_edge_setup(e->d_robot, dA, dB, d_w, N, eps, e->d_nlev, e->d_alive, e->d_nchecks, e->d_scalars, e->stream)); e->stats.kernel_launches++;
   CK(kb_launch_fill_i32(e->d_firstbad, N, 0x7fffffff, e->stream)); e->stats.kernel_launches++;
-  int32_t maxlev = 0;
-  CK(cudaMemcpyAsync(&maxlev, e->d_scalars, 4, cudaMemcpyDeviceToHost, e->stream));
+  int32_t head[3] = {0, 0, 0};
+  CK(cudaMemcpyAsync(head, e->d_scalars, 12, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
+  const int32_t maxlev = head[0];
+  if (head[2]) return fail(KB_ERR_UNSUPPORTED, "an edge is longer than 2^24 eps: it would need more than 16 M feasibility checks (eps = %g)", eps);
   int64_t cfg_checks = 0;
   for (int lev = 1; lev <= maxlev; lev++) {
     CK(cudaMemsetAsync(e->d_scalars + 1, 0, 4, e->stream));

@@ -1723,6 +1723,9 @@ __device__ void kb_euler_zyx_interp(const double* ea, const double* eb, double u
 // Edge e of C-space length len needs nlev = number of halvings until len/2^nlev <= eps.  Level l (1-based) holds the
 // 2^(l-1) odd multiples k/2^l.  All alive edges are expanded level by level; an edge dies at the first level that
 // holds an infeasible midpoint, and the sequential checker's check count is recovered from the lowest failing k.
+#ifndef KB_EDGE_MAX_LEVELS
+#define KB_EDGE_MAX_LEVELS 24    // an edge is bisected into at most 2^24 pieces (eps = 1e-7 of its length)
+#endif
 __global__ void kb_edge_setup_kernel(const KbRobotDev* __restrict__ robot, const double* __restrict__ A, const double* __restrict__ B,
                                      const double* __restrict__ weights, int64_t N, double eps, int32_t* __restrict__ nlev,
                                      uint8_t* __restrict__ alive, int32_t* __restrict__ nchecks, int32_t* maxlev) {
@@ -1752,8 +1755,13 @@ __global__ void kb_edge_setup_kernel(const KbRobotDev* __restrict__ robot, const
     s = s + w * d * d;
   }
   double len = kb_sqrt(s).v;
+  if (!(len == len) || len > 1.7e308) {       // NaN / inf coordinates: no path, and no 2^k midpoints to enumerate
+    nlev[e] = 0; alive[e] = 0; nchecks[e] = 0;
+    return;
+  }
   int n = 0;
-  while (len > eps && n < 30) { len *= 0.5; n++; }
+  while (len > eps && n < KB_EDGE_MAX_LEVELS) { len *= 0.5; n++; }
+  if (len > eps) atomicMax(maxlev + 2, 1);    // still longer than eps after 2^KB_EDGE_MAX_LEVELS pieces: reported as an error, never checked coarser than asked
   nlev[e] = n; alive[e] = 1; nchecks[e] = 0;
   if (n > 0) atomicMax(maxlev, n);
 }

@@ -37,3 +37,4 @@ cudaError_t kb_launch_allpairs(const KbTraverseParams& p, int max_pairs, int32_t
 // element indices (in the geometries' own element order) of the pair each configuration's distance query ended with (kb_closest.cu)
 cudaError_t kb_launch_closest_points(const KbScene& sc, const KbItem* items, const double* xf64, int nxf, const int32_t* hit, const int32_t* hit_elem,
                                      int64_t N, double* out_cp, int32_t* out_elem, cudaStream_t s);
+

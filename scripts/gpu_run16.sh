@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 400 python -m pytest tests/test_gpu_parity.py tests/test_gpu_adapters.py tests/test_golden.py -m gpu -q -x --timeout=120 > gpurun_out/pytest_16.log 2>&1; tail -6 gpurun_out/pytest_16.log
+timeout 120 python scripts/gpu_latency2.py c2 2>&1 | tee gpurun_out/latency_c2_graph.log
+timeout 120 python scripts/gpu_latency2.py c1 2>&1 | tee gpurun_out/latency_c1_graph.log

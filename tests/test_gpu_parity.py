@@ -741,3 +741,20 @@ def test_closest_points_element_ids_and_tolerances(built):
         assert abs(o2.geom_distance(wc.robot.link_geom[a - base], T[i, a - base], gp2, at(cp[i, 0]))) < 1e-9
         seen += 1
     assert seen > 100
+
+
+def test_edges_with_non_finite_or_absurd_length(c1):
+    """an edge with a NaN / inf coordinate is invisible without a single check; an edge that would need more than 2^24 pieces is an
+    error, never a coarser check than the caller asked for"""
+    from klampt_b200._capi import KbError
+    w, eng, orc = c1
+    Q = synth.sample_configs(w.robot, 64, 90)
+    ok = Q[orc.feasible_batch(Q) == 1]
+    A, B = ok[:8].copy(), ok[8:16].copy()
+    B[1, 2] = np.inf; A[3, 1] = np.nan
+    vis, n = eng.edges_visible_batch(A, B, eps=0.05)
+    ovis, on = orc.edges_visible_batch(np.delete(A, [1, 3], 0), np.delete(B, [1, 3], 0), eps=0.05)
+    assert vis[1] == 0 and vis[3] == 0 and n[1] == 0 and n[3] == 0
+    assert np.array_equal(np.delete(vis, [1, 3]), ovis) and np.array_equal(np.delete(n, [1, 3]), on)
+    with pytest.raises(KbError):
+        eng.edges_visible_batch(ok[:2], ok[2:4], eps=1e-9)
