@@ -401,12 +401,13 @@ struct kb_engine {
   double* d_A = nullptr; double* d_B = nullptr; int64_t ab_cap = 0;
   int32_t* d_nlev = nullptr; uint8_t* d_alive = nullptr; int32_t* d_nchecks = nullptr; int32_t* d_firstbad = nullptr; int32_t* d_list = nullptr; int64_t edge_cap = 0;
   double* d_eQ = nullptr; uint8_t* d_efeas = nullptr; int64_t eq_cap = 0;
+  uint8_t* d_eslot = nullptr; int64_t eslot_cap = 0; int64_t edge_flat_max = 1 << 18;   // small edge batches: all midpoints in one launch (option edge_flat_max, 0 = never)
   int32_t* d_scalars = nullptr;             // [0] maxlev, [1] list count
   double* d_weights = nullptr; int64_t w_cap = 0;
   // generic transform-pair queries
   double* d_T = nullptr; int64_t t_cap = 0;
   // ---- stats
-  kb_stats stats{};
+  kb_stats stats{}; int64_t edge_cfg_host = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool collect_stats = false, time_kernels = false;
   std::vector<cudaEvent_t> tev;             // event pairs around traversal launches (time_kernels)
@@ -709,11 +710,11 @@ KbTraverseParams make_params(kb_engine* e, const ItemSet& set, const double* xf,
 }
 
 // feasibility of n configurations resident on the device: FK -> traversal -> finish, chunk by chunk
-int run_feasible_device(kb_engine* e, const double* dQ, int64_t N, uint8_t* d_out, int32_t* d_first_pair, unsigned long long* d_nfeas) {
+int run_feasible_device(kb_engine* e, const double* dQ, int64_t N, uint8_t* d_out, int32_t* d_first_pair, unsigned long long* d_nfeas, const uint8_t* d_alive = nullptr) {
   int rc = ensure_cfg_scratch(e, e->feas_items.nxf, N); if (rc) return rc;
   for (int64_t off = 0; off < N; off += e->chunk) {
     int64_t n = std::min(e->chunk, N - off);
-    CK(kb_launch_fk(e->d_robot, e->d_drv, e->d_drv_link, e->d_drv_scale, e->d_drv_off, dQ + off * e->L, n, e->d_xf, e->feas_items.nxf, e->d_state, nullptr, e->d_hit, e->stream));
+    CK(kb_launch_fk(e->d_robot, e->d_drv, e->d_drv_link, e->d_drv_scale, e->d_drv_off, dQ + off * e->L, n, e->d_xf, e->feas_items.nxf, e->d_state, d_alive ? d_alive + off : nullptr, e->d_hit, e->stream));
     e->stats.kernel_launches++;
     if (!e->feas_items.items.empty()) {
       KbTraverseParams p = make_params(e, e->feas_items, e->d_xf, n, e->d_state);
@@ -772,7 +773,7 @@ void kb_engine_destroy(kb_engine* e) {
                     e->d_drv_scale, e->d_drv_off, e->feas_items.d_items, e->env_items.d_items, e->d_xf, e->d_state, e->d_hit, e->d_hit_elem, e->d_leaf_list, e->d_flagged, e->d_state2, e->d_work,
                     e->d_counters, e->d_Q, e->d_out, e->d_pair, e->d_dist, e->d_A, e->d_B, e->d_nlev, e->d_alive, e->d_nchecks, e->d_firstbad, e->d_list,
                     e->d_eQ, e->d_efeas, e->d_scalars, e->d_weights, e->d_T, e->feas_items.d_probes, e->feas_items.d_always_on,
-                    e->d_grid[0], e->d_grid[1], e->d_grid[2], e->d_grid[3], e->d_box32, e->d_box64, e->d_boxown, e->d_dyn_pts, e->d_dyn_T, e->d_dyn_scratch, e->d_Qf, e->d_bits, e->d_triorig, e->d_sphorig, e->d_cp};
+                    e->d_grid[0], e->d_grid[1], e->d_grid[2], e->d_grid[3], e->d_box32, e->d_box64, e->d_boxown, e->d_dyn_pts, e->d_dyn_T, e->d_dyn_scratch, e->d_Qf, e->d_bits, e->d_triorig, e->d_sphorig, e->d_cp, e->d_eslot};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -1378,7 +1379,7 @@ static int clone_to_device(const kb_engine* src, int device, kb_engine** out) {
   r->d_work = nullptr; r->d_counters = nullptr; r->d_Q = nullptr; r->q_cap = 0; r->d_Qf = nullptr; r->qf_cap = 0; r->d_out = nullptr; r->out_cap = 0;
   r->d_bits = nullptr; r->bits_cap = 0; r->d_pair = nullptr; r->pair_cap = 0; r->d_dist = nullptr; r->dist_cap = 0; r->d_cp = nullptr; r->cp_cap = 0;
   r->d_A = r->d_B = nullptr; r->ab_cap = 0; r->d_nlev = r->d_nchecks = r->d_firstbad = r->d_list = nullptr; r->d_alive = nullptr; r->edge_cap = 0;
-  r->d_eQ = nullptr; r->d_efeas = nullptr; r->eq_cap = 0; r->d_scalars = nullptr; r->d_weights = nullptr; r->w_cap = 0; r->d_T = nullptr; r->t_cap = 0;
+  r->d_eQ = nullptr; r->d_efeas = nullptr; r->eq_cap = 0; r->d_eslot = nullptr; r->eslot_cap = 0; r->d_scalars = nullptr; r->d_weights = nullptr; r->w_cap = 0; r->d_T = nullptr; r->t_cap = 0;
   r->d_dyn_pts = nullptr; r->d_dyn_T = nullptr; r->d_dyn_scratch = nullptr; r->dyn_pts_cap = 0; r->dyn_scratch_bytes = 0;
   memset(&r->stats, 0, sizeof r->stats);
   // static arrays: null first so that a failure half way destroys cleanly
@@ -1455,6 +1456,7 @@ int kb_set_option(kb_engine* e, const char* name, int64_t value) {
     e->cloud_builder = (int)value; return KB_OK;
   }
   if (!strcmp(name, "both_limit")) { e->both_limit = (int)value; return KB_OK; }
+  if (!strcmp(name, "edge_flat_max")) { if (value < 0) return fail(KB_ERR_INVALID, "edge_flat_max must be >= 0"); e->edge_flat_max = value; return KB_OK; }
   if (!strcmp(name, "graph_max")) { if (value < 0 || value > 65536) return fail(KB_ERR_INVALID, "graph_max must be in [0, 65536]"); if (e->h_pin_in && value > e->graph_max) return fail(KB_ERR_STATE, "graph_max can only grow before the first small batch"); e->graph_max = value; return KB_OK; }
   if (!strcmp(name, "cloud_leaf")) {
     if (e->finalized) return fail(KB_ERR_STATE, "cloud_leaf must be set before kb_finalize");
@@ -1678,6 +1680,15 @@ int kb_edges_visible_batch_device(kb_engine* e, const double* dA, const double* 
   const int32_t maxlev = head[0];
   if (head[2]) return fail(KB_ERR_UNSUPPORTED, "an edge is longer than 2^24 eps: it would need more than 16 M feasibility checks (eps = %g)", eps);
   int64_t cfg_checks = 0;
+  const int64_t per_max = maxlev >= 1 && maxlev <= 20 ? ((int64_t)1 << maxlev) - 1 : 0;
+  if (per_max > 0 && N * per_max <= std::min<int64_t>(e->edge_flat_max, e->chunk)) {
+    // small batch: every midpoint of every level at once (see kb_edge_flat_expand_kernel): one launch sequence, no read-back per level
+    const int64_t nslots = N * per_max;
+    if (!e->d_eslot || e->eslot_cap < e->chunk) { if (e->d_eslot) cudaFree(e->d_eslot); e->d_eslot = nullptr; CK(cudaMalloc((void**)&e->d_eslot, (size_t)e->chunk)); e->eslot_cap = e->chunk; }
+    CK(kb_launch_edge_flat_expand(e->d_robot, dA, dB, e->d_nlev, e->d_alive, nslots, (int)per_max, e->d_eQ, e->d_eslot, e->d_counters + 9, e->stream)); e->stats.kernel_launches++;
+    if ((rc = run_feasible_device(e, e->d_eQ, nslots, e->d_efeas, nullptr, nullptr, e->d_eslot))) return rc;
+    CK(kb_launch_edge_flat_finish(e->d_efeas, e->d_eslot, nslots, (int)per_max, e->d_nlev, e->d_firstbad, N, e->d_alive, e->d_nchecks, e->stream)); e->stats.kernel_launches += 2;
+  } else
   for (int lev = 1; lev <= maxlev; lev++) {
     CK(cudaMemsetAsync(e->d_scalars + 1, 0, 4, e->stream));
     CK(kb_launch_edge_count(e->d_nlev, e->d_alive, N, lev, e->d_list, (unsigned int*)(e->d_scalars + 1), e->stream)); e->stats.kernel_launches++;
@@ -1697,7 +1708,7 @@ int kb_edges_visible_batch_device(kb_engine* e, const double* dA, const double* 
   }
   CK(kb_launch_copy_u8(e->d_alive, d_out, N, e->d_counters + 4, e->stream)); e->stats.kernel_launches++;
   if (d_nchecks) CK(cudaMemcpyAsync(d_nchecks, e->d_nchecks, (size_t)N * 4, cudaMemcpyDeviceToDevice, e->stream));
-  e->stats.edges_checked += N; e->stats.edge_config_checks += cfg_checks;
+  e->stats.edges_checked += N; e->edge_cfg_host += cfg_checks; e->stats.edge_config_checks += cfg_checks;
   return KB_OK;
 }
 
@@ -1927,6 +1938,7 @@ int kb_get_stats(kb_engine* e, kb_stats* out) {
     unsigned long long c[16]; CK(cudaMemcpy(c, e->d_counters, 128, cudaMemcpyDeviceToHost));
     e->stats.recheck_pairs = (int64_t)c[0]; e->stats.node_tests = (int64_t)c[1]; e->stats.elem_tests = (int64_t)c[2];
     e->stats.configs_feasible = (int64_t)c[3]; e->stats.edges_visible = (int64_t)c[4]; e->stats.items_dropped = (int64_t)c[7]; e->stats.node_iterations = (int64_t)c[8];
+    e->stats.edge_config_checks = e->edge_cfg_host + (int64_t)c[9];
     fold_kernel_times(e);
   }
   *out = e->stats;
@@ -1945,7 +1957,7 @@ int kb_get_stats(kb_engine* e, kb_stats* out) {
 int kb_reset_stats(kb_engine* e) {
   if (!e) return fail(KB_ERR_INVALID, "null argument");
   for (kb_engine* r : e->replicas) { int rc = kb_reset_stats(r); if (rc) return rc; }
-  memset(&e->stats, 0, sizeof e->stats);
+  memset(&e->stats, 0, sizeof e->stats); e->edge_cfg_host = 0;
   e->tev_used = 0;
   if (e->finalized) { CK(cudaSetDevice(e->device)); CK(cudaMemsetAsync(e->d_counters, 0, 128, e->stream)); }
   return KB_OK;

@@ -1781,18 +1781,12 @@ __global__ void kb_edge_count_kernel(const int32_t* __restrict__ nlev, const uin
 
 // writes the midpoints of level `lev` for the listed edges: slot = i * per + j, k = 2j+1, u = k / 2^lev.
 // Klampt::Interpolate (Cpp/Modeling/Interpolate.cpp:10-71): out = x*(1-u); out += y*u; Spin joints take the short arc.
-__global__ void kb_edge_expand_kernel(const KbRobotDev* __restrict__ robot, const double* __restrict__ A, const double* __restrict__ B,
-                                      const int32_t* __restrict__ list, int64_t first_slot, int64_t nslots, int lev, double* __restrict__ Q) {
-  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= nslots) return;
+// Klampt::Interpolate(a, b, u) of edge e into q (Cpp/Modeling/Interpolate.cpp:10-71): out = x*(1-u); out += y*u; Spin joints and the
+// angle of FloatingPlanar joints take the short arc, Euler-ZYX triplets of Floating / BallAndSocket joints the SO(3) geodesic
+__device__ __forceinline__ void kb_edge_midpoint(const KbRobotDev* __restrict__ robot, const double* __restrict__ A, const double* __restrict__ B,
+                                                 int64_t e, ExactD u, double* __restrict__ q) {
   const int L = robot->L;
-  const int64_t per = (int64_t)1 << (lev - 1);
-  int64_t g = first_slot + s;
-  int64_t i = g / per, j = g % per;
-  int64_t e = list[i];
-  ExactD u((double)(2 * j + 1) / (double)((int64_t)1 << lev));
   ExactD um = ExactD(1.0) - u;
-  double* q = Q + s * L;
   for (int k = 0; k < L; k++) q[k] = (ExactD(A[e * L + k]) * um + ExactD(B[e * L + k]) * u).v;
   for (int jn = 0; jn < robot->nj; jn++) {
     const int jt = robot->jtype[jn];
@@ -1812,6 +1806,50 @@ __global__ void kb_edge_expand_kernel(const KbRobotDev* __restrict__ robot, cons
     double r = fmod((ExactD(x) + u * ExactD(d)).v, tp); if (r < 0) r += tp;
     q[k] = r;
   }
+}
+
+__global__ void kb_edge_expand_kernel(const KbRobotDev* __restrict__ robot, const double* __restrict__ A, const double* __restrict__ B,
+                                      const int32_t* __restrict__ list, int64_t first_slot, int64_t nslots, int lev, double* __restrict__ Q) {
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nslots) return;
+  const int64_t per = (int64_t)1 << (lev - 1);
+  int64_t g = first_slot + s;
+  int64_t i = g / per, j = g % per;
+  kb_edge_midpoint(robot, A, B, (int64_t)list[i], ExactD((double)(2 * j + 1) / (double)((int64_t)1 << lev)), Q + s * robot->L);
+}
+
+// ---- small edge batches: every midpoint of every level in ONE batch.  The level-by-level form stops an edge at the first level with an
+// infeasible midpoint, at the price of a launch sequence and a host read-back per level (0.7-1.3 ms for one edge at eps = 0.01).  When
+// N (2^maxlev - 1) midpoints fit one launch the machine is idle anyway: slot s = edge (s / per_max), midpoint j = s % per_max in the
+// sequential checker's order (level l = 1 + floor(log2(j + 1)), k = j + 1 - 2^(l-1), u = (2k + 1) / 2^l), all checked at once, and the
+// lowest failing j per edge gives the same visibility and the same nchecks (= j + 1) as the sequential early exit.
+__global__ void kb_edge_flat_expand_kernel(const KbRobotDev* __restrict__ robot, const double* __restrict__ A, const double* __restrict__ B,
+                                           const int32_t* __restrict__ nlev, const uint8_t* __restrict__ alive, int64_t nslots, int per_max,
+                                           double* __restrict__ Q, uint8_t* __restrict__ slot_on, unsigned long long* __restrict__ nactive) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool on = false;
+  if (s < nslots) {
+    const int64_t e = s / per_max; const int j = (int)(s % per_max);
+    on = alive[e] && j < (1 << nlev[e]) - 1;
+    slot_on[s] = on ? 1 : 0;
+    if (on) {
+      const int l = 32 - __clz(j + 1), k = j + 1 - (1 << (l - 1));
+      kb_edge_midpoint(robot, A, B, e, ExactD((double)(2 * k + 1) / (double)(1 << l)), Q + s * robot->L);
+    } else for (int k = 0; k < robot->L; k++) Q[s * robot->L + k] = 0.0;
+  }
+  const unsigned m = __ballot_sync(FULL, on);
+  if (nactive && (threadIdx.x & 31) == 0 && m) atomicAdd(nactive, (unsigned long long)__popc(m));
+}
+__global__ void kb_edge_flat_reduce_kernel(const uint8_t* __restrict__ feas, const uint8_t* __restrict__ slot_on, int64_t nslots, int per_max, int32_t* __restrict__ firstbad) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nslots || !slot_on[s] || feas[s]) return;
+  atomicMin(firstbad + s / per_max, (int32_t)(s % per_max));
+}
+__global__ void kb_edge_flat_end_kernel(const int32_t* __restrict__ nlev, const int32_t* __restrict__ firstbad, int64_t N, uint8_t* __restrict__ alive, int32_t* __restrict__ nchecks) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N || !alive[e]) return;
+  const int count = (1 << nlev[e]) - 1, fb = firstbad[e];
+  if (fb < count) { alive[e] = 0; nchecks[e] = fb + 1; } else nchecks[e] = count;
 }
 
 // folds the feasibility bytes of one level chunk back into the edges: lowest infeasible j per edge
@@ -2032,6 +2070,19 @@ cudaError_t kb_launch_edge_expand(const KbRobotDev* robot, const double* A, cons
                                   int64_t nslots, int lev, double* Q, cudaStream_t s) {
   if (nslots <= 0) return cudaSuccess;
   kb_edge_expand_kernel<<<nblocks(nslots, 256), 256, 0, s>>>(robot, A, B, list, first_slot, nslots, lev, Q);
+  return cudaGetLastError();
+}
+cudaError_t kb_launch_edge_flat_expand(const KbRobotDev* robot, const double* A, const double* B, const int32_t* nlev, const uint8_t* alive, int64_t nslots, int per_max,
+                                       double* Q, uint8_t* slot_on, unsigned long long* nactive, cudaStream_t s) {
+  if (nslots <= 0) return cudaSuccess;
+  kb_edge_flat_expand_kernel<<<nblocks(nslots, 256), 256, 0, s>>>(robot, A, B, nlev, alive, nslots, per_max, Q, slot_on, nactive);
+  return cudaGetLastError();
+}
+cudaError_t kb_launch_edge_flat_finish(const uint8_t* feas, const uint8_t* slot_on, int64_t nslots, int per_max, const int32_t* nlev, int32_t* firstbad, int64_t N,
+                                       uint8_t* alive, int32_t* nchecks, cudaStream_t s) {
+  if (nslots <= 0 || N <= 0) return cudaSuccess;
+  kb_edge_flat_reduce_kernel<<<nblocks(nslots, 256), 256, 0, s>>>(feas, slot_on, nslots, per_max, firstbad);
+  kb_edge_flat_end_kernel<<<nblocks(N, 256), 256, 0, s>>>(nlev, firstbad, N, alive, nchecks);
   return cudaGetLastError();
 }
 cudaError_t kb_launch_edge_reduce(const uint8_t* feas, const int32_t* list, int64_t first_slot, int64_t nslots, int lev, int32_t* firstbad, cudaStream_t s) {

@@ -38,3 +38,9 @@ cudaError_t kb_launch_allpairs(const KbTraverseParams& p, int max_pairs, int32_t
 cudaError_t kb_launch_closest_points(const KbScene& sc, const KbItem* items, const double* xf64, int nxf, const int32_t* hit, const int32_t* hit_elem,
                                      int64_t N, double* out_cp, int32_t* out_elem, cudaStream_t s);
 
+
+// small edge batches: all midpoints of all levels in one batch (slot = edge * per_max + sequential midpoint index)
+cudaError_t kb_launch_edge_flat_expand(const KbRobotDev* robot, const double* A, const double* B, const int32_t* nlev, const uint8_t* alive, int64_t nslots, int per_max,
+                                       double* Q, uint8_t* slot_on, unsigned long long* nactive, cudaStream_t s);
+cudaError_t kb_launch_edge_flat_finish(const uint8_t* feas, const uint8_t* slot_on, int64_t nslots, int per_max, const int32_t* nlev, int32_t* firstbad, int64_t N,
+                                       uint8_t* alive, int32_t* nchecks, cudaStream_t s);

@@ -758,3 +758,24 @@ def test_edges_with_non_finite_or_absurd_length(c1):
     assert np.array_equal(np.delete(vis, [1, 3]), ovis) and np.array_equal(np.delete(n, [1, 3]), on)
     with pytest.raises(KbError):
         eng.edges_visible_batch(ok[:2], ok[2:4], eps=1e-9)
+
+
+def test_small_edge_batches_all_levels_at_once(c1, c2small):
+    """a small edge batch is checked with every midpoint of every level in one launch (no early exit, no per-level read-back); visibility
+    and the sequential checker's nchecks must equal the level-by-level form and the oracle"""
+    for (w, eng, orc), eps in ((c1, 0.01), (c2small, 0.02)):
+        A, B = synth.sample_edges(w.robot, lambda Q: eng.feasible_batch(Q), 700, 17)
+        for n in (1, 5, 64, 700):
+            vis, nchk = eng.edges_visible_batch(A[:n], B[:n], eps=eps)
+            ovis, on = orc.edges_visible_batch(A[:n], B[:n], eps=eps)
+            assert np.array_equal(vis, ovis) and np.array_equal(nchk, on), n
+        eng.set_option("edge_flat_max", 0)
+        try:
+            v2, n2 = eng.edges_visible_batch(A, B, eps=eps)
+        finally:
+            eng.set_option("edge_flat_max", 1 << 18)
+        v1, n1 = eng.edges_visible_batch(A, B, eps=eps)
+        assert np.array_equal(v1, v2) and np.array_equal(n1, n2)
+        # degenerate edges: a == b needs no check at all
+        vis, nchk = eng.edges_visible_batch(A[:3], A[:3], eps=eps)
+        assert vis.all() and (nchk == 0).all()
