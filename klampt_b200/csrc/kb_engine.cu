@@ -704,6 +704,8 @@ KbTraverseParams make_params(kb_engine* e, const ItemSet& set, const double* xf,
   p.pop_room = KB_STACK_CAP - (3 * set.maxdepth + 1) / 2 - 4;
   p.collect_stats = e->collect_stats ? 1 : 0;
   p.both_limit = e->both_limit;
+  p.both_ratio = 16.f;
+  for (const KbItem& it : set.items) if (!(it.flags & 1)) { p.both_ratio = 4.f; break; }      // any link-vs-environment item: 4
   for (const KbItem& it : set.items) if (it.kindA == KB_ELEM_BOX || it.kindB == KB_ELEM_BOX) { p.has_boxes = 1; break; }
   if (e->use_grids && set.d_probes && !set.probes.empty()) { p.probes = set.d_probes; p.nprobes = (int)set.probes.size(); p.always_on = set.d_always_on; }
   return p;

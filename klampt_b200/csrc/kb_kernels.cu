@@ -777,6 +777,7 @@ kb_traverse_kernel(const KbTraverseParams p) {
         const int pop_room = p.pop_room;
         const int leaf_trig_l = leaf_trig;
         const int lane_l = lane;
+        const float both_ratio = p.both_ratio;
         do {
         int m = sp_l < KB_POP_WIDTH ? sp_l : KB_POP_WIDTH;
         { const int room = (pop_room - sp_l) / 3; m = m < room ? m : (room > 1 ? room : 1); }     // narrower pops as the stack fills up
@@ -802,7 +803,7 @@ kb_traverse_kernel(const KbTraverseParams p) {
         const bool leafpair = ov & ((la & lb) < 0);
         const bool inner = ov & ((la & lb) >= 0);
         const float sa2 = a1.x * a1.x + a1.y * a1.y + a1.z * a1.z, sb2 = b1.x * b1.x + b1.y * b1.y + b1.z * b1.z;
-        const bool both = inner & ((la | lb) >= 0) & (sa2 < KB_BOTH_RATIO * sb2) & (sb2 < KB_BOTH_RATIO * sa2);
+        const bool both = inner & ((la | lb) >= 0) & (sa2 < both_ratio * sb2) & (sb2 < both_ratio * sa2);
         const bool splitA = (lb < 0) | ((la >= 0) & (sa2 >= sb2));          // only meaningful when inner && !both
         const bool useA = both | splitA, useB = both | !splitA;
         const unsigned ax = useA ? ((e.x & ~(unsigned)(KB_MAX_NODES_A - 1)) | (unsigned)la) : e.x;

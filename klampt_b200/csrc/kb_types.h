@@ -132,6 +132,8 @@ struct KbTraverseParams {
   int32_t has_boxes;              // the work list holds solid-box items (selects the kernel instantiation with the box predicates)
   int32_t pop_room;               // boolean kernel: m entries may be popped while sp + 3 m <= pop_room (see make_params)
   int32_t both_limit;             // frontier size up to which comparable inner pairs push all four child pairs (0 = never)
+  float both_ratio;               // two inner nodes descend both trees at once while their squared diagonals are within this ratio (4: link vs
+                                  // environment, where the boxes differ in size; 16: link vs link only -- measured, profiles/r02_experiments.md)
   const KbProbe* probes;          // clearance probes of this item set (boolean kernel only); null / 0 = no pre-filter
   int32_t nprobes;
   const uint32_t* always_on;      // bit i set: item i has no probes and is always traversed ((nitems + 31) / 32 words)
