@@ -160,6 +160,7 @@ inline float i2f(int32_t i) { float f; memcpy(&f, &i, 4); return f; }
 // device-side geometry: a flattened BVH + elements in leaf order
 struct DevGeom {
   int node_base = 0, nnodes = 0, elem_base = 0, nelem = 0, kind = KB_ELEM_TRI, depth = 0; double margin = 0, rmax = 0; bool empty = true; double lo[3], hi[3];
+  int wide_base = -1, wide_slots = 0, wdepth = 0;   // 4-wide form of the same hierarchy (slot index into the wide array), -1 = none
   int ncover = 0; double cover[KB_COVER_MAX][4];   // covering spheres (local frame) for the clearance-grid broad phase
 };
 
@@ -167,7 +168,7 @@ struct DevGeom {
 #define KB_GPU_MESH_MIN 16384      // meshes up to this size keep the host SAH build even with mesh_builder = 1 (link meshes: quality matters most)
 
 struct ItemSet {
-  std::vector<KbItem> items; KbItem* d_items = nullptr; int nxf = 0; int maxdepth = 0;
+  std::vector<KbItem> items; KbItem* d_items = nullptr; int nxf = 0; int maxdepth = 0; bool all_wide = true; int wdepth = 0;
   std::vector<KbProbe> probes; std::vector<uint32_t> always_on; KbProbe* d_probes = nullptr; uint32_t* d_always_on = nullptr;
 };
 
@@ -309,26 +310,6 @@ void build_clear_grid(int kind, const std::vector<double>& elems, const double g
   });
 }
 
-// Multi-device handles (kb_finalize_multi): a host-buffer batch is cut into contiguous shards, one per device, each run by its own
-// host thread on that device's replica (own stream, own scratch, static data replicated) and written straight into the caller's
-// buffers -- SURVEY 8e: configurations shard naturally, no exchange step besides the results landing in one array.
-template <class F> static int run_sharded(kb_engine* e, int64_t N, int64_t align, F fn) {
-  const int nd = 1 + (int)e->replicas.size();
-  if (nd == 1 || N < e->multi_min) return fn(e, (int64_t)0, N);
-  int64_t per = (N + nd - 1) / nd; per = ((per + align - 1) / align) * align;
-  std::vector<int> rcs((size_t)nd, KB_OK); std::vector<std::string> errs((size_t)nd);
-  std::vector<std::thread> th;
-  for (int k = 0; k < nd; k++) {
-    const int64_t off = std::min(N, (int64_t)k * per), n = std::min(per, N - off);
-    if (n <= 0) break;
-    kb_engine* r = k == 0 ? e : e->replicas[(size_t)k - 1];
-    th.emplace_back([&, k, r, off, n]() { rcs[(size_t)k] = fn(r, off, n); if (rcs[(size_t)k]) errs[(size_t)k] = g_err; });
-  }
-  for (auto& t : th) t.join();
-  for (int k = 0; k < nd; k++) if (rcs[(size_t)k]) return fail(rcs[(size_t)k], "device %d: %s", k == 0 ? e->device : e->replicas[(size_t)k - 1]->device, errs[(size_t)k].c_str());
-  return KB_OK;
-}
-
 }  // namespace
 
 struct kb_engine {
@@ -353,6 +334,8 @@ struct kb_engine {
   cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev_copy[4] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<float> h_nodes;               // 8 floats per node
+  std::vector<float> h_wide;                // 8 floats per slot, 4 slots per wide node
+  float4* d_wide = nullptr; int wide = 1;     // option wide: 1 = the boolean query runs on the 4-wide hierarchies when every item has them
   std::vector<float> h_tris32; std::vector<double> h_tris64; std::vector<int32_t> h_triown, h_triorig;
   std::vector<float> h_sph32; std::vector<double> h_sph64; std::vector<int32_t> h_sphown, h_sphorig;
   std::vector<float> h_box32; std::vector<double> h_box64; std::vector<int32_t> h_boxown;
@@ -479,6 +462,41 @@ int append_geom(kb_engine* e, int kind, const std::vector<double>& elems, const 
     else { v[3] = i2f(~nd.first); v[7] = i2f(nd.count); }
     e->h_nodes.insert(e->h_nodes.end(), v, v + 8);
   }
+  if (kind != G_BOX) {
+    // ---- the same hierarchy 4 wide (kb_traverse_wide_kernel).  A wide node = 4 slots = 128 B = one cache line; a slot is a node's box
+    // plus a reference: >= 0 the wide node (index relative to this geometry, in wide nodes) that holds its grandchildren -- or children
+    // that are leaves --, < 0 a leaf (~first element, count in the second word).  Wide node 0 is a super root whose slot 0 is the root.
+    // Four lanes read the four slots of one node with one line fetch: the traversal touches 2 lines per 4 box tests instead of 2 per 1-2.
+    if ((e->h_wide.size() / 8) & 3) e->h_wide.insert(e->h_wide.end(), (4 - ((e->h_wide.size() / 8) & 3)) * 8, 0.f);
+    dg.wide_base = (int)(e->h_wide.size() / 8);
+    const size_t base = e->h_wide.size();
+    auto empty_slot = [&](size_t at) { float* v = &e->h_wide[at]; v[0] = v[1] = v[2] = 0.f; v[3] = i2f(~0); v[4] = v[5] = v[6] = -1e30f; v[7] = i2f(0); };
+    auto alloc_wide = [&]() { const size_t w = (e->h_wide.size() - base) / 32; e->h_wide.insert(e->h_wide.end(), 32, 0.f); for (int k = 0; k < 4; k++) empty_slot(base + w * 32 + 8 * k); return (int)w; };
+    struct Todo { int bnode; int wnode; int depth; };      // fill wide node `wnode` with the (grand)children of binary node `bnode`
+    std::vector<Todo> todo;
+    auto write_slot = [&](int wnode, int k, int bn, int depth) {
+      const BNode& nd = bvh.nodes[bn];
+      float v[8];
+      for (int a = 0; a < 3; a++) { const float c = (float)(0.5 * (nd.lo[a] + nd.hi[a])); v[a] = c; v[4 + a] = f_up(std::max(nd.hi[a] - (double)c, (double)c - nd.lo[a])); }
+      if (nd.left >= 0) { const int w = alloc_wide(); v[3] = i2f(w); v[7] = i2f(0); todo.push_back({bn, w, depth + 1}); }
+      else { v[3] = i2f(~nd.first); v[7] = i2f(nd.count); }
+      memcpy(&e->h_wide[base + (size_t)wnode * 32 + 8 * k], v, 32);       // (after alloc_wide: the vector may have moved)
+    };
+    const int w0 = alloc_wide();
+    write_slot(w0, 0, 0, 0);
+    dg.wdepth = 1;
+    while (!todo.empty()) {
+      const Todo t = todo.back(); todo.pop_back();
+      dg.wdepth = std::max(dg.wdepth, t.depth + 1);
+      int k = 0;
+      const int l = bvh.nodes[t.bnode].left;
+      for (int c = l; c <= l + 1; c++) {
+        if (bvh.nodes[c].left < 0) write_slot(t.wnode, k++, c, t.depth);
+        else { write_slot(t.wnode, k++, bvh.nodes[c].left, t.depth); write_slot(t.wnode, k++, bvh.nodes[c].left + 1, t.depth); }
+      }
+    }
+    dg.wide_slots = (int)((e->h_wide.size() - base) / 8);
+  }
   if (want_cover) {
     // up to KB_COVER_MAX spheres that together contain the geometry: a cut of the BVH grown by always splitting the
     // node with the largest sphere; sphere = box centre + the farthest element point
@@ -585,6 +603,7 @@ KbItem make_item(const DevGeom& A, int xfA, int idA, const DevGeom& B, int xfB, 
   it.xfA = (int16_t)xfA; it.xfB = (int16_t)xfB; it.kindA = (uint8_t)A.kind; it.kindB = (uint8_t)B.kind; it.flags = self ? 1 : 0;
   it.idA = idA; it.idB = idB; it.thr = A.margin + B.margin; it.marg = A.margin + B.margin; it.rsum = A.rmax + B.rmax;
   it.margA = A.margin; it.margB = B.margin;
+  it.wideA = A.wide_base; it.wideB = B.wide_base;
   return it;
 }
 // the A side of an item is limited to 2^20 nodes (stack entry packing); put the smaller hierarchy there
@@ -596,6 +615,8 @@ int add_item(ItemSet& set, const DevGeom& A, int xfA, int idA, const DevGeom& B,
   if ((int)set.items.size() >= KB_MAX_ITEMS) return fail(KB_ERR_UNSUPPORTED, "more than %d geometry pairs per configuration", KB_MAX_ITEMS);
   set.items.push_back(swap ? make_item(B, xfB, idB, A, xfA, idA, self) : make_item(A, xfA, idA, B, xfB, idB, self));
   set.maxdepth = std::max(set.maxdepth, a.depth + b.depth);
+  if (a.wide_base < 0 || b.wide_base < 0 || a.wide_slots >= KB_MAX_NODES_A) set.all_wide = false;
+  set.wdepth = std::max(set.wdepth, a.wdepth + b.wdepth);
   return KB_OK;
 }
 
@@ -704,6 +725,10 @@ KbTraverseParams make_params(kb_engine* e, const ItemSet& set, const double* xf,
   p.pop_room = KB_STACK_CAP - (3 * set.maxdepth + 1) / 2 - 4;
   p.collect_stats = e->collect_stats ? 1 : 0;
   p.both_limit = e->both_limit;
+  // 4-wide traversal: 8 entries (32 lanes) per pop while the stack has room for their <= 32 children plus a depth-first tail of
+  // <= 3 entries per wide level; one entry per pop above that
+  p.use_wide = (e->wide && set.all_wide && !e->use_grids && 3 * set.wdepth + 48 <= KB_STACK_CAP) ? 1 : 0;
+  p.wide_room = KB_STACK_CAP - 32 - 3 * set.wdepth - 4;
   p.both_ratio = 16.f;
   for (const KbItem& it : set.items) if (!(it.flags & 1)) { p.both_ratio = 4.f; break; }      // any link-vs-environment item: 4
   for (const KbItem& it : set.items) if (it.kindA == KB_ELEM_BOX || it.kindB == KB_ELEM_BOX) { p.has_boxes = 1; break; }
@@ -751,6 +776,27 @@ int upload_itemset(ItemSet& s, int64_t* total, kb_engine* rec = nullptr) {
   return upload(s.d_items, s.items.data(), s.items.size() * sizeof(KbItem), total, rec);
 }
 
+// Multi-device handles (kb_finalize_multi): a host-buffer batch is cut into contiguous shards, one per device, each run by its own
+// host thread on that device's replica (own stream, own scratch, static data replicated) and written straight into the caller's
+// buffers -- SURVEY 8e: configurations shard naturally, no exchange step besides the results landing in one array.
+template <class F> static int run_sharded(kb_engine* e, int64_t N, int64_t align, F fn) {
+  const int nd = 1 + (int)e->replicas.size();
+  if (nd == 1 || N < e->multi_min) return fn(e, (int64_t)0, N);
+  int64_t per = (N + nd - 1) / nd; per = ((per + align - 1) / align) * align;
+  std::vector<int> rcs((size_t)nd, KB_OK); std::vector<std::string> errs((size_t)nd);
+  std::vector<std::thread> th;
+  for (int k = 0; k < nd; k++) {
+    const int64_t off = std::min(N, (int64_t)k * per), n = std::min(per, N - off);
+    if (n <= 0) break;
+    kb_engine* r = k == 0 ? e : e->replicas[(size_t)k - 1];
+    th.emplace_back([&, k, r, off, n]() { rcs[(size_t)k] = fn(r, off, n); if (rcs[(size_t)k]) errs[(size_t)k] = g_err; });
+  }
+  for (auto& t : th) t.join();
+  for (int k = 0; k < nd; k++) if (rcs[(size_t)k]) return fail(rcs[(size_t)k], "device %d: %s", k == 0 ? e->device : e->replicas[(size_t)k - 1]->device, errs[(size_t)k].c_str());
+  return KB_OK;
+}
+
+
 }  // namespace
 
 // =================================================================================================== C ABI
@@ -775,7 +821,7 @@ void kb_engine_destroy(kb_engine* e) {
                     e->d_drv_scale, e->d_drv_off, e->feas_items.d_items, e->env_items.d_items, e->d_xf, e->d_state, e->d_hit, e->d_hit_elem, e->d_leaf_list, e->d_flagged, e->d_state2, e->d_work,
                     e->d_counters, e->d_Q, e->d_out, e->d_pair, e->d_dist, e->d_A, e->d_B, e->d_nlev, e->d_alive, e->d_nchecks, e->d_firstbad, e->d_list,
                     e->d_eQ, e->d_efeas, e->d_scalars, e->d_weights, e->d_T, e->feas_items.d_probes, e->feas_items.d_always_on,
-                    e->d_grid[0], e->d_grid[1], e->d_grid[2], e->d_grid[3], e->d_box32, e->d_box64, e->d_boxown, e->d_dyn_pts, e->d_dyn_T, e->d_dyn_scratch, e->d_Qf, e->d_bits, e->d_triorig, e->d_sphorig, e->d_cp, e->d_eslot};
+                    e->d_grid[0], e->d_grid[1], e->d_grid[2], e->d_grid[3], e->d_box32, e->d_box64, e->d_boxown, e->d_dyn_pts, e->d_dyn_T, e->d_dyn_scratch, e->d_Qf, e->d_bits, e->d_triorig, e->d_sphorig, e->d_cp, e->d_eslot, e->d_wide};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -1280,6 +1326,7 @@ int kb_finalize(kb_engine* e, int device) {
 #else
   if ((rc = upload(e->d_nodes, e->h_nodes.data(), e->h_nodes.size() * 4, &e->static_bytes, e))) return rc;
 #endif
+  if ((rc = upload(e->d_wide, e->h_wide.data(), e->h_wide.size() * 4, &e->static_bytes, e))) return rc;
   if ((rc = upload(e->d_tris32, e->h_tris32.data(), e->h_tris32.size() * 4, &e->static_bytes, e))) return rc;
   if ((rc = upload(e->d_tris64, e->h_tris64.data(), e->h_tris64.size() * 8, &e->static_bytes, e))) return rc;
   if ((rc = upload(e->d_sph32, e->h_sph32.data(), e->h_sph32.size() * 4, &e->static_bytes, e))) return rc;
@@ -1291,7 +1338,7 @@ int kb_finalize(kb_engine* e, int device) {
   if ((rc = upload(e->d_sphown, e->h_sphown.data(), e->h_sphown.size() * 4, &e->static_bytes, e))) return rc;
   if ((rc = upload(e->d_triorig, e->h_triorig.data(), e->h_triorig.size() * 4, &e->static_bytes, e))) return rc;
   if ((rc = upload(e->d_sphorig, e->h_sphorig.data(), e->h_sphorig.size() * 4, &e->static_bytes, e))) return rc;
-  e->scene.nodes = e->d_nodes; e->scene.tris32 = e->d_tris32; e->scene.tris64 = e->d_tris64; e->scene.sph32 = e->d_sph32; e->scene.sph64 = e->d_sph64;
+  e->scene.nodes = e->d_nodes; e->scene.wide = e->d_wide; e->scene.tris32 = e->d_tris32; e->scene.tris64 = e->d_tris64; e->scene.sph32 = e->d_sph32; e->scene.sph64 = e->d_sph64;
   e->scene.triown = e->d_triown; e->scene.sphown = e->d_sphown; e->scene.triorig = e->d_triorig; e->scene.sphorig = e->d_sphorig;
   e->scene.box32 = e->d_box32; e->scene.box64 = e->d_box64; e->scene.boxown = e->d_boxown;
   if ((rc = upload_itemset(e->feas_items, &e->static_bytes, e))) return rc;
@@ -1359,7 +1406,7 @@ int kb_finalize(kb_engine* e, int device) {
   CK(cudaMalloc((void**)&e->d_scalars, 64));
   // the host copies of the big arrays are no longer needed
   std::vector<float>().swap(e->h_tris32); std::vector<double>().swap(e->h_tris64); std::vector<float>().swap(e->h_sph32); std::vector<double>().swap(e->h_sph64);
-  std::vector<float>().swap(e->h_nodes);
+  std::vector<float>().swap(e->h_nodes); std::vector<float>().swap(e->h_wide);
   // Configurations per launch.  Configuration cost varies by two orders of magnitude, so every launch ends with a tail of
   // idle SMs; measured on C2 a 71 k chunk (transforms L2-resident) runs 26 % slower than a 1 M chunk (transforms through
   // HBM: 2 x 96 L bytes per configuration, ~2 % of the step).  Use up to 1 M per launch within a 2 GB scratch budget.
@@ -1402,7 +1449,7 @@ static int clone_to_device(const kb_engine* src, int device, kb_engine** out) {
     CK(cudaMemcpyPeer(d, device, *(void* const*)((const char*)src + a.member_offset), src->device, a.bytes));
   }
   // the scene block holds device pointers: point it at this device's copies
-  r->scene.nodes = r->d_nodes; r->scene.tris32 = r->d_tris32; r->scene.tris64 = r->d_tris64; r->scene.sph32 = r->d_sph32; r->scene.sph64 = r->d_sph64;
+  r->scene.nodes = r->d_nodes; r->scene.wide = r->d_wide; r->scene.tris32 = r->d_tris32; r->scene.tris64 = r->d_tris64; r->scene.sph32 = r->d_sph32; r->scene.sph64 = r->d_sph64;
   r->scene.triown = r->d_triown; r->scene.sphown = r->d_sphown; r->scene.triorig = r->d_triorig; r->scene.sphorig = r->d_sphorig;
   r->scene.box32 = r->d_box32; r->scene.box64 = r->d_box64; r->scene.boxown = r->d_boxown;
   for (int g = 0; g < KB_MAX_GRIDS; g++) if (src->scene.grids[g].data) r->scene.grids[g].data = r->d_grid[g];
@@ -1458,6 +1505,7 @@ int kb_set_option(kb_engine* e, const char* name, int64_t value) {
     e->cloud_builder = (int)value; return KB_OK;
   }
   if (!strcmp(name, "both_limit")) { e->both_limit = (int)value; return KB_OK; }
+  if (!strcmp(name, "wide")) { e->wide = value != 0; return KB_OK; }
   if (!strcmp(name, "edge_flat_max")) { if (value < 0) return fail(KB_ERR_INVALID, "edge_flat_max must be >= 0"); e->edge_flat_max = value; return KB_OK; }
   if (!strcmp(name, "graph_max")) { if (value < 0 || value > 65536) return fail(KB_ERR_INVALID, "graph_max must be in [0, 65536]"); if (e->h_pin_in && value > e->graph_max) return fail(KB_ERR_STATE, "graph_max can only grow before the first small batch"); e->graph_max = value; return KB_OK; }
   if (!strcmp(name, "cloud_leaf")) {

@@ -866,6 +866,271 @@ kb_traverse_kernel(const KbTraverseParams p) {
   { int f = 0, fa = 0, fb = 0; drain_rechecks<BOXES>(p, rq, rq_count, lane, (int64_t)-1, f, fa, fb, true); }
 }
 
+// =============================================================================================== traversal (boolean, 4-wide hierarchies)
+// kb_traverse_wide_kernel -- kb_traverse_kernel on the 4-wide form of the hierarchies (KbScene::wide).  Same warp-per-configuration
+// frontier, same element phase, same deferred fp64 rechecks; what changes is the node step.  The binary kernel is bound by the number
+// of distinct 128-byte lines its two node loads touch per iteration (profiles/r02_experiments.md): 32 lanes test 32 pairs and fetch
+// 8-16+ lines per load.  Here a popped entry is (item, wide node of the side to expand, slot of the other side's box) and FOUR lanes
+// test the node's four child slots against that box: one line on the expanded side, one 32-byte slot on the other, per four tests.
+// The side to expand is always the larger box (decided when the entry is pushed, where both boxes are in registers), i.e. the
+// descend-larger rule two levels at a time -- no descend-both step, whose extra tests cost C2 more than they saved.
+template <bool ITC, bool STATS, int BPS, bool BOXES>
+__global__ void __launch_bounds__(KB_WARPS_PER_BLOCK * 32, BPS)
+kb_traverse_wide_kernel(const KbTraverseParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int xf_floats = (p.nxf * 12 + 3) & ~3;
+  const int nit_c = ITC ? p.nitems : 0;
+  ItemS* s_items = (ItemS*)smem_raw;
+  const int mask_words = p.nprobes > 0 ? (((p.nitems + 31) >> 5) + 3) & ~3 : 0;
+  const int nprobes_s = p.nprobes <= KB_PROBES_SMEM_MAX ? p.nprobes : 0;      // probes cached per CTA
+  const size_t per_warp = (size_t)KB_STACK_CAP * 8 + (size_t)KB_BOOL_LEAFQ_CAP * 8 + (size_t)KB_RQ_CAP * 16 + 16 + (size_t)xf_floats * 4 + (size_t)nit_c * 48 + (size_t)mask_words * 4;
+  KbProbe* s_probes = (KbProbe*)(smem_raw + (size_t)nit_c * 16);
+  unsigned char* base = smem_raw + (size_t)nit_c * 16 + (size_t)nprobes_s * 32 + warp * per_warp;
+  uint2* stack = (uint2*)base;
+  uint2* leafq = (uint2*)(base + (size_t)KB_STACK_CAP * 8);
+  uint4* rq = (uint4*)(base + (size_t)KB_STACK_CAP * 8 + (size_t)KB_BOOL_LEAFQ_CAP * 8);
+  int* rq_count = (int*)(rq + KB_RQ_CAP);
+  float* xfw = (float*)(base + (size_t)KB_STACK_CAP * 8 + (size_t)KB_BOOL_LEAFQ_CAP * 8 + (size_t)KB_RQ_CAP * 16 + 16);
+  float* itc = xfw + xf_floats;
+  unsigned* amask = (unsigned*)(itc + (size_t)nit_c * 12);   // per configuration: bit i = item i must be traversed
+  const KbScene& sc = p.scene;
+  const float slack = 4.f * sc.eps_abs;
+  if (ITC) {
+    for (int i = threadIdx.x; i < p.nitems; i += blockDim.x) {
+      const KbItem* it = p.items + i;
+      ItemS s; s.nodeA = it->wideA; s.nodeB = it->wideB; s.infl = (float)it->thr + slack;      // slot bases of the two 4-wide hierarchies
+      s.xf = (int)((unsigned)(unsigned short)it->xfA | ((unsigned)(unsigned short)it->xfB << 16));
+      s_items[i] = s;
+    }
+  }
+  for (int i = threadIdx.x; i < nprobes_s * 2; i += blockDim.x) ((uint4*)s_probes)[i] = __ldg((const uint4*)p.probes + i);
+  if (lane == 0) *rq_count = 0;
+  __syncthreads();
+  unsigned lt_mask;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
+  unsigned st_node = 0, st_leaf = 0, st_re = 0, st_drop = 0, st_iter = 0;   // only maintained when STATS
+  const bool use_probes = p.nprobes > 0;
+  const KbProbe* probes = nprobes_s ? s_probes : p.probes;
+
+  // guided self-scheduling: 8 configurations per grab while work is plentiful, down to 1 near the end of the launch, so
+  // the tail is one configuration long (configuration cost varies by two orders of magnitude)
+  const unsigned total_warps = gridDim.x * KB_WARPS_PER_BLOCK;
+  unsigned grab = 8;
+  for (;;) {
+    unsigned int c0 = 0;
+    if (lane == 0) c0 = atomicAdd(p.work_counter, grab);
+    c0 = __shfl_sync(FULL, c0, 0);
+    if ((int64_t)c0 >= p.N) break;
+    const unsigned nN = (unsigned)p.N;
+    const unsigned cend = (c0 + grab < nN) ? c0 + grab : nN;
+    {
+      const unsigned g = (nN - cend) / (4u * total_warps);
+      grab = g >= 8u ? 8u : (g < 1u ? 1u : g);
+    }
+    for (unsigned c = c0; c < cend; c++) {
+      if (p.state && p.state[c] == 0) continue;
+      const double* xf = p.xf64 + (size_t)c * (size_t)p.nxf * 12;
+      __syncwarp();
+      // the transforms of the next configuration of this grab come from DRAM (FK wrote 96 L bytes x 1 M configurations): start them
+      // towards L2 now, one 128-byte line per lane.  Pays for long rows only (19 links: 7.83 -> 7.59 ms; 7 links: 6.22 -> 6.29).
+      if (p.nxf >= 12 && c + 1 < cend && lane * 16 < p.nxf * 12) asm volatile("prefetch.global.L2 [%0];" :: "l"(xf + (size_t)p.nxf * 12 + lane * 16));
+      for (int i = lane; i < p.nxf * 12; i += 32) xfw[i] = (float)xf[i];
+      __syncwarp();
+      if (ITC) {
+        for (int i = lane; i < p.nitems; i += 32) {
+          const int xfp = s_items[i].xf;
+          XfF T; rel_xf(xfw, (int)(short)(xfp & 0xffff), (int)(short)(xfp >> 16), T);
+          float4* q = (float4*)(itc + 12 * i);
+          q[0] = make_float4(T.r[0], T.r[1], T.r[2], T.r[3]); q[1] = make_float4(T.r[4], T.r[5], T.r[6], T.r[7]); q[2] = make_float4(T.r[8], T.t[0], T.t[1], T.t[2]);
+        }
+        __syncwarp();
+      }
+      if (use_probes) {
+        // clearance-grid broad phase: an item whose covering spheres all have more clearance from the static group than
+        // radius + threshold cannot collide and is never fed to the traversal
+        for (int w = lane; w < ((p.nitems + 31) >> 5); w += 32) amask[w] = __ldg(p.always_on + w);
+        __syncwarp();
+        // four probes per lane per round: all grid bytes of a round are in flight together (one L2 round trip per 128 probes)
+        for (int s0 = 0; s0 < p.nprobes; s0 += 128) {
+          unsigned q[4], need[4]; int item[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int s = s0 + 32 * u + lane;
+            q[u] = 0xffffffffu; need[u] = 0u; item[u] = 0;
+            if (s < p.nprobes) {
+              const float4 pc = *(const float4*)(probes + s);
+              const int4 pi = *((const int4*)(probes + s) + 1);
+              const float* T = xfw + 12 * pi.y;
+              const float wx = T[0] * pc.x + T[1] * pc.y + T[2] * pc.z + T[9];
+              const float wy = T[3] * pc.x + T[4] * pc.y + T[5] * pc.z + T[10];
+              const float wz = T[6] * pc.x + T[7] * pc.y + T[8] * pc.z + T[11];
+              const KbClearGrid& g = sc.grids[pi.z];
+              // points outside the grid are clamped onto it: the projection onto a convex box never increases the distance
+              // to anything inside the box, and everything the grid measures lies inside
+              int ix = __float2int_rd((wx - g.o[0]) * g.inv_h), iy = __float2int_rd((wy - g.o[1]) * g.inv_h), iz = __float2int_rd((wz - g.o[2]) * g.inv_h);
+              ix = min(max(ix, 0), g.dims[0] - 1); iy = min(max(iy, 0), g.dims[1] - 1); iz = min(max(iz, 0), g.dims[2] - 1);
+              q[u] = __ldg(g.data + ((size_t)iz * g.dims[1] + iy) * g.dims[0] + ix);
+              need[u] = __float_as_uint(pc.w); item[u] = pi.x;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) if (q[u] < need[u]) atomicOr(amask + (item[u] >> 5), 1u << (item[u] & 31));
+        }
+        __syncwarp();
+      }
+      int sp = 0, nleaf = 0, cursor = 0;
+      int leaf_trig = KB_LEAF_FIRST;                 // the first element phase of a configuration runs on a smaller batch
+      int found = -1, found_ea = -1, found_eb = -1;
+      for (;;) {
+        if (sp < 32 && nleaf <= KB_BOOL_LEAFQ_CAP - 32 && cursor < p.nitems) {
+          // root pairs of the next work items, one lane each: the two root boxes (slot 0 of each super root) are tested right here and
+          // only the pairs that overlap enter the frontier, already knowing which side to expand
+          int kf = p.nitems - cursor; if (kf > 32) kf = 32;
+          const bool act = lane < kf;
+          const int item = act ? cursor + lane : 0;
+          int baseA, baseB; float infl; XfF T;
+          if (ITC) { const ItemS si = s_items[item]; baseA = si.nodeA; baseB = si.nodeB; infl = si.infl; load_itc(itc, item, T); }
+          else { const KbItem* itp = p.items + item; baseA = itp->wideA; baseB = itp->wideB; infl = (float)itp->thr + slack; rel_xf(xfw, itp->xfA, itp->xfB, T); }
+          float4 a0, a1, b0, b1;
+          load_node(sc.wide, (size_t)baseA, a0, a1);
+          load_node(sc.wide, (size_t)baseB, b0, b1);
+          const bool ov = act & sat6_overlap(a0, a1, b0, b1, T, infl);
+          if (STATS) st_node += act;
+          if (STATS) st_iter += (lane == 0);
+          const int la = __float_as_int(a0.w), lb = __float_as_int(b0.w);
+          const bool leafpair = ov & ((la & lb) < 0);
+          const bool inner = ov & ((la & lb) >= 0);
+          const float sa2 = a1.x * a1.x + a1.y * a1.y + a1.z * a1.z, sb2 = b1.x * b1.x + b1.y * b1.y + b1.z * b1.z;
+          const bool nextA = (lb < 0) | ((la >= 0) & (sa2 >= sb2));
+          const unsigned itembits = (unsigned)item << KB_NODEA_BITS;
+          const unsigned pm = __ballot_sync(FULL, inner), lm = __ballot_sync(FULL, leafpair);
+          if (inner) stack[sp + __popc(pm & lt_mask)] = make_uint2(itembits | (unsigned)(nextA ? 4 * la : 0), nextA ? 0u : (0x80000000u | (unsigned)(4 * lb)));
+          if (leafpair) leafq[nleaf + __popc(lm & lt_mask)] = make_uint2(itembits, 0u);
+          sp += __popc(pm); nleaf += __popc(lm);
+          cursor += kf;
+          __syncwarp();
+        }
+        if (sp == 0 && nleaf == 0) { if (cursor < p.nitems) continue; break; }
+        if (nleaf >= leaf_trig || sp == 0) {
+          leaf_trig = KB_LEAF_TRIGGER;
+          // ---------------------------------------------------------------- element phase
+          int m = nleaf < 32 ? nleaf : 32;
+          int res = KB_NO, ea = -1, eb = -1, item = 0;
+          if (lane < m) {
+            uint2 e = leafq[nleaf - 1 - lane];
+            item = (int)(e.x >> KB_NODEA_BITS);
+            const KbItem& it = p.items[item];
+            int na = (int)(e.x & (KB_MAX_NODES_A - 1)), nb = (int)e.y;
+            float4 a0, a1, b0, b1;
+            load_node(sc.wide, (size_t)(it.wideA + na), a0, a1);
+            load_node(sc.wide, (size_t)(it.wideB + nb), b0, b1);
+            int fa = it.elemA + ~__float_as_int(a0.w), ca = __float_as_int(a1.w);
+            int fb = it.elemB + ~__float_as_int(b0.w), cb = __float_as_int(b1.w);
+            {
+              XfF T;
+              if (ITC) load_itc(itc, item, T); else rel_xf(xfw, it.xfA, it.xfB, T);
+              const float thr = (float)it.thr;
+              for (int i = 0; i < ca && res != KB_YES; i++)
+                for (int j = 0; j < cb && res != KB_YES; j++) {
+                  int r = fast_elem_collide<BOXES>(sc, it, T, fa + i, fb + j, thr);
+                  if (STATS) st_leaf++;
+                  if (r == KB_UNCERTAIN) {
+                    if (STATS) st_re++;
+                    const int slot = atomicAdd(rq_count, 1);
+                    if (slot < KB_RQ_CAP) { rq[slot] = make_uint4((unsigned)c, (unsigned)item, (unsigned)(fa + i), (unsigned)(fb + j)); r = KB_NO; }
+                    else r = exact_elem_collide<BOXES>(sc, it, xf, fa + i, fb + j) ? KB_YES : KB_NO;   // queue full: recheck in place
+                  }
+                  if (r == KB_YES) { res = KB_YES; ea = fa + i; eb = fb + j; }
+                }
+            }
+          }
+          nleaf -= m;
+          {
+            unsigned hm = __ballot_sync(FULL, res == KB_YES);
+            if (hm) {
+              int src = __ffs(hm) - 1;
+              found = __shfl_sync(FULL, item, src); found_ea = __shfl_sync(FULL, ea, src); found_eb = __shfl_sync(FULL, eb, src);
+              break;
+            }
+            drain_rechecks<BOXES>(p, rq, rq_count, lane, (int64_t)c, found, found_ea, found_eb, false);
+            if (found >= 0) break;
+          }
+          __syncwarp();
+          continue;
+        }
+        // ------------------------------------------------------------------ node phase: a tight inner loop that runs until leaf pairs
+        // are due, the stack runs dry or new root pairs must be fed (keeps the loop state in registers)
+        {
+        // loop state in fresh variables: the allocator keeps them in registers for the loop instead of in the spill slots the
+        // element phase forces on the outer copies
+        int sp_l = sp, nleaf_l = nleaf;
+        const float* itc_l = itc;
+        const bool more_items = cursor < p.nitems;
+        const int leaf_trig_l = leaf_trig;
+        const int lane_l = lane;
+        const int wide_room = p.wide_room;
+        do {
+        // Eight entries per iteration, four lanes each.  An entry = (item, side to expand, the wide node of that side, the slot of the
+        // other side's box); lane t of a group tests child slot t of the wide node against that box: the four lanes read ONE 128-byte
+        // line on the expanded side and the same 32 bytes on the other.
+        int m = sp_l < 8 ? sp_l : 8;
+        if (sp_l > wide_room) m = 1;                                  // nearly full: depth-first, one entry at a time
+        const int g = lane_l >> 2, t = lane_l & 3;
+        const bool act = g < m;
+        uint2 e = make_uint2(0u, 0u);
+        if (act) e = stack[sp_l - 1 - g];
+        sp_l -= m;
+        __syncwarp();
+        const int item = (int)(e.x >> KB_NODEA_BITS);
+        int baseA, baseB; float infl; XfF T;
+        if (ITC) { const ItemS si = s_items[item]; baseA = si.nodeA; baseB = si.nodeB; infl = si.infl; load_itc(itc_l, item, T); }
+        else { const KbItem* itp = p.items + item; baseA = itp->wideA; baseB = itp->wideB; infl = (float)itp->thr + slack; rel_xf(xfw, itp->xfA, itp->xfB, T); }
+        const bool expB = (e.y >> 31) != 0;
+        const int sa = (int)(e.x & (KB_MAX_NODES_A - 1)) + (expB ? 0 : t), sb = (int)(e.y & 0x7fffffffu) + (expB ? t : 0);
+        float4 a0, a1, b0, b1;
+        load_node(sc.wide, (size_t)(baseA + sa), a0, a1);
+        load_node(sc.wide, (size_t)(baseB + sb), b0, b1);
+        const bool ov = act & sat6_overlap(a0, a1, b0, b1, T, infl);
+        if (STATS) st_node += act;
+        if (STATS) st_iter += (lane_l == 0);
+        const int la = __float_as_int(a0.w), lb = __float_as_int(b0.w);
+        const bool leafpair = ov & ((la & lb) < 0);
+        const bool inner = ov & ((la & lb) >= 0);
+        const float sa2 = a1.x * a1.x + a1.y * a1.y + a1.z * a1.z, sb2 = b1.x * b1.x + b1.y * b1.y + b1.z * b1.z;
+        const bool nextA = (lb < 0) | ((la >= 0) & (sa2 >= sb2));          // expand the larger box next (the only inner one if the other is a leaf)
+        const unsigned ex = (e.x & ~(unsigned)(KB_MAX_NODES_A - 1)) | (unsigned)(nextA ? 4 * la : sa);
+        const unsigned ey = nextA ? (unsigned)sb : (0x80000000u | (unsigned)(4 * lb));
+        const unsigned pm = __ballot_sync(FULL, inner), lm = __ballot_sync(FULL, leafpair);
+        if (inner) stack[sp_l + __popc(pm & lt_mask)] = make_uint2(ex, ey);
+        if (leafpair) leafq[nleaf_l + __popc(lm & lt_mask)] = make_uint2((e.x & ~(unsigned)(KB_MAX_NODES_A - 1)) | (unsigned)sa, (unsigned)sb);
+        sp_l += __popc(pm); nleaf_l += __popc(lm);
+        __syncwarp();
+        } while (sp_l > 0 && nleaf_l < leaf_trig_l && !(sp_l < 32 && more_items));
+        sp = sp_l; nleaf = nleaf_l;
+        }
+      }
+      if (STATS) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          st_node += __shfl_xor_sync(FULL, st_node, o); st_leaf += __shfl_xor_sync(FULL, st_leaf, o); st_re += __shfl_xor_sync(FULL, st_re, o);
+        }
+        if (lane == 0 && p.counters) {
+          atomicAdd(p.counters + 0, (unsigned long long)st_re); atomicAdd(p.counters + 1, (unsigned long long)st_node); atomicAdd(p.counters + 2, (unsigned long long)st_leaf);
+          atomicAdd(p.counters + 7, (unsigned long long)st_drop); atomicAdd(p.counters + 8, (unsigned long long)st_iter);
+        }
+        st_node = st_leaf = st_re = st_drop = st_iter = 0;
+      }
+      if (lane == 0) {
+        p.hit[c] = found;
+        if (p.hit_elem) { p.hit_elem[2 * (size_t)c] = found_ea; p.hit_elem[2 * (size_t)c + 1] = found_eb; }
+      }
+    }
+  }
+  // pairs still parked for the fp64 recheck belong to configurations already written as "no hit": resolve them now
+  { int f = 0, fa = 0, fb = 0; drain_rechecks<BOXES>(p, rq, rq_count, lane, (int64_t)-1, f, fa, fb, true); }
+}
+
 // =============================================================================================== all colliding pairs
 // kb_allpairs_kernel -- no early exit: lists every colliding (idA, idB) world-id pair of a configuration, up to max_pairs.
 // Replaces evaluating SingleRobotCSpace's per-pair CollisionFreeSet constraints one by one (reference
@@ -1933,13 +2198,15 @@ static cudaError_t launch_traverse_t(const KbTraverseParams& p, int num_sms, siz
   int dev = 0; cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kb_traverse_kernel<ITC, STATS, BPS, BOXES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess && !BOXES) e = cudaFuncSetAttribute(kb_traverse_wide_kernel<ITC, STATS, BPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   int per_sm = (int)((224 * 1024) / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > BPS) per_sm = BPS;
   int64_t want = (p.N + 8 * KB_WARPS_PER_BLOCK - 1) / (8 * KB_WARPS_PER_BLOCK);
   int64_t grid = (int64_t)num_sms * per_sm; if (grid > want) grid = want; if (grid < 1) grid = 1;
-  kb_traverse_kernel<ITC, STATS, BPS, BOXES><<<(unsigned)grid, KB_WARPS_PER_BLOCK * 32, smem, s>>>(p);
+  if (p.use_wide && !BOXES) kb_traverse_wide_kernel<ITC, STATS, BPS, false><<<(unsigned)grid, KB_WARPS_PER_BLOCK * 32, smem, s>>>(p);
+  else kb_traverse_kernel<ITC, STATS, BPS, BOXES><<<(unsigned)grid, KB_WARPS_PER_BLOCK * 32, smem, s>>>(p);
   return cudaGetLastError();
 }
 

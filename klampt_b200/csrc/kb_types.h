@@ -66,7 +66,7 @@ struct KbProbe {                  // one covering sphere of the moving side of a
   int32_t pad_;
 };
 
-struct KbItem {                   // 72 bytes
+struct KbItem {                   // 80 bytes
   int32_t nodeA, nodeB;           // global node index of the two roots
   int32_t elemA, elemB;           // global element base (into tris* or sph* according to kind)
   int16_t xfA, xfB;               // transform slot in the per-configuration table, -1 = identity (static world frame)
@@ -77,6 +77,7 @@ struct KbItem {                   // 72 bytes
   double marg;                    // margin_A + margin_B, subtracted from reported distances
   double rsum;                    // largest sphere radius of A + of B: bound on how far two touching boxes' elements can interpenetrate
   double margA, margB;            // the two margins separately: closest points are reported on the margin-inflated surfaces
+  int32_t wideA, wideB;           // slot base of each side's 4-wide hierarchy in KbScene::wide, -1 = that geometry has none (GPU-built trees)
 };
 
 struct KbRobotDev {
@@ -99,6 +100,7 @@ struct KbDriverDev {              // flattened affine drivers: driver d covers t
 
 struct KbScene {                  // device pointers to the static data
   const float4* nodes;
+  const float4* wide;             // 4-wide hierarchies (kb_traverse_wide_kernel): slot = {centre.xyz, ref} {half.xyz, count}, 4 slots = one 128 B node
   const float4* tris32;
   const double* tris64;
   const float4* sph32;
@@ -130,6 +132,8 @@ struct KbTraverseParams {
   int32_t wide_limit;             // stack size up to which 32-wide pops are allowed
   int32_t collect_stats;
   int32_t has_boxes;              // the work list holds solid-box items (selects the kernel instantiation with the box predicates)
+  int32_t use_wide;               // every item has both 4-wide hierarchies and the option is on: kb_traverse_wide_kernel
+  int32_t wide_room;              // wide kernel: entries may be popped 8 at a time while sp <= wide_room, one at a time above
   int32_t pop_room;               // boolean kernel: m entries may be popped while sp + 3 m <= pop_room (see make_params)
   int32_t both_limit;             // frontier size up to which comparable inner pairs push all four child pairs (0 = never)
   float both_ratio;               // two inner nodes descend both trees at once while their squared diagonals are within this ratio (4: link vs
