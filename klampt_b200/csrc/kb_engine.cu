@@ -312,6 +312,7 @@ void build_clear_grid(int kind, const std::vector<double>& elems, const double g
 
 }  // namespace
 
+#define KB_STAGES 8          // pieces a large host batch is uploaded / checked in (feasible_batch_host_one)
 struct kb_engine {
   // ---- description
   std::vector<Geom> geoms;
@@ -331,7 +332,8 @@ struct kb_engine {
   int64_t multi_min = 8192;                  // host-buffer batches below this stay on the first device
   // ---- device
   int device = -1, num_sms = 148;
-  cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+  cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr, aux_stream = nullptr;
+  cudaEvent_t ev_stage[KB_STAGES] = {};
   cudaEvent_t ev_copy[4] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<float> h_nodes;               // 8 floats per node
   std::vector<float> h_wide;                // 8 floats per slot, 4 slots per wide node
@@ -765,6 +767,27 @@ int run_feasible_device(kb_engine* e, const double* dQ, int64_t N, uint8_t* d_ou
   return KB_OK;
 }
 
+// One PIECE of a batch whose per-configuration scratch (transforms, limit bytes, hit records) was already sized for the whole batch:
+// rows [soff, soff + n) of the scratch, its own work counter (wslot) and the stream it runs on.  Pieces of one batch on two alternating
+// streams overlap where it matters: the next piece's CTAs fill the SMs the previous launch's tail (its few hardest configurations) has
+// left idle -- every launch of the persistent traversal kernel ends with such a tail, ~0.1 ms on C2.
+int run_feasible_piece(kb_engine* e, const double* dQ, int64_t soff, int64_t n, uint8_t* d_out, int32_t* d_first_pair, unsigned long long* d_nfeas, cudaStream_t st, int wslot) {
+  const int nxf = e->feas_items.nxf;
+  double* xf = e->d_xf + soff * nxf * 12;
+  CK(kb_launch_fk(e->d_robot, e->d_drv, e->d_drv_link, e->d_drv_scale, e->d_drv_off, dQ, n, xf, nxf, e->d_state + soff, nullptr, e->d_hit + soff, st));
+  e->stats.kernel_launches++;
+  if (!e->feas_items.items.empty()) {
+    KbTraverseParams p = make_params(e, e->feas_items, xf, n, e->d_state + soff);
+    p.hit = e->d_hit + soff; p.hit_elem = e->d_hit_elem + 2 * soff; p.work_counter = e->d_work + wslot;
+    CK(kb_launch_traverse(p, 0, nullptr, 0.0, e->num_sms, st));
+    e->stats.kernel_launches++;
+  }
+  CK(kb_launch_finish(e->d_state + soff, e->d_hit + soff, e->d_hit_elem + 2 * soff, e->feas_items.d_items, e->d_triown, e->d_sphown, e->d_boxown, n, d_out,
+                      d_first_pair, d_nfeas, st));
+  e->stats.kernel_launches++;
+  return KB_OK;
+}
+
 int upload_itemset(ItemSet& s, int64_t* total, kb_engine* rec = nullptr) {
   if (s.d_items) { cudaFree(s.d_items); s.d_items = nullptr; }
   if (s.d_probes) { cudaFree(s.d_probes); s.d_probes = nullptr; }
@@ -830,7 +853,9 @@ void kb_engine_destroy(kb_engine* e) {
     if (e->g_dQ) cudaFree(e->g_dQ); if (e->g_dout) cudaFree(e->g_dout);
     for (cudaEvent_t ev : e->tev) cudaEventDestroy(ev);
     for (int k = 0; k < 4; k++) if (e->ev_copy[k]) cudaEventDestroy(e->ev_copy[k]);
+    for (int k = 0; k < KB_STAGES; k++) if (e->ev_stage[k]) cudaEventDestroy(e->ev_stage[k]);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
   }
   delete e;
@@ -1101,8 +1126,9 @@ int kb_finalize(kb_engine* e, int device) {
   CK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
   e->stream = e->own_stream;
   CK(cudaEventCreate(&e->ev0)); CK(cudaEventCreate(&e->ev1));
-  CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&e->aux_stream, cudaStreamNonBlocking));
   for (int k = 0; k < 4; k++) CK(cudaEventCreateWithFlags(&e->ev_copy[k], cudaEventDisableTiming));
+  for (int k = 0; k < KB_STAGES; k++) CK(cudaEventCreateWithFlags(&e->ev_stage[k], cudaEventDisableTiming));
 
   // ---- 1. per-geometry local-frame BVHs (links, and every geometry for explicit pair queries)
   e->dgeoms.resize(e->geoms.size());
@@ -1420,7 +1446,8 @@ int kb_finalize(kb_engine* e, int device) {
 static int clone_to_device(const kb_engine* src, int device, kb_engine** out) {
   kb_engine* r = new kb_engine(*src);
   r->replicas.clear(); r->tev.clear(); r->tev_used = 0; r->graphs.clear(); r->h_pin_in = nullptr; r->h_pin_out = nullptr; r->g_dQ = nullptr; r->g_dout = nullptr;
-  r->own_stream = r->stream = r->copy_stream = nullptr; r->ev0 = r->ev1 = nullptr;
+  r->own_stream = r->stream = r->copy_stream = r->aux_stream = nullptr; r->ev0 = r->ev1 = nullptr;
+  for (int k = 0; k < KB_STAGES; k++) r->ev_stage[k] = nullptr;
   for (int k = 0; k < 4; k++) r->ev_copy[k] = nullptr;
   // per-batch scratch starts empty on the new device
   r->d_xf = nullptr; r->xf_cap = 0; r->d_state = nullptr; r->d_hit = nullptr; r->d_hit_elem = nullptr; r->cfg_cap = 0;
@@ -1440,8 +1467,9 @@ static int clone_to_device(const kb_engine* src, int device, kb_engine** out) {
   r->num_sms = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&r->own_stream, cudaStreamNonBlocking)); r->stream = r->own_stream;
   CK(cudaEventCreate(&r->ev0)); CK(cudaEventCreate(&r->ev1));
-  CK(cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&r->aux_stream, cudaStreamNonBlocking));
   for (int k = 0; k < 4; k++) CK(cudaEventCreateWithFlags(&r->ev_copy[k], cudaEventDisableTiming));
+  for (int k = 0; k < KB_STAGES; k++) CK(cudaEventCreateWithFlags(&r->ev_stage[k], cudaEventDisableTiming));
   for (const auto& a : src->statics) {
     void* d = nullptr;
     CK(cudaMalloc(&d, a.bytes));
@@ -1628,35 +1656,38 @@ static int feasible_batch_host_one(kb_engine* e, const void* Qv, int esz, int64_
   if (bits && (rc = grow(e->d_bits, e->bits_cap, (N + 31) / 32))) return rc;
   if (first_pair && (rc = grow(e->d_pair, e->pair_cap, 2 * N))) return rc;
   begin_timing(e);
-  // Staged upload: the batch crosses PCIe in up to four pieces of growing size (N/16, N/8, N/4, rest) on the copy stream, and
-  // piece k is checked while piece k+1 is in flight, so only the first, small copy is exposed (1 M x 7 doubles = 56 MB is ~1 ms,
-  // 19 links = 152 MB ~2.8 ms when not overlapped).  Every extra launch costs one launch tail, so small calls stay single-stage.
-  // Measured on B200: 7 links (56 B / configuration) 1.505e8 cfg/s with two pieces vs 1.46e8 with four; 19 links (152 B) 1.04e8
-  // vs 1.19e8 -- long rows take four pieces, short rows two (N/8, rest).
-  int64_t cut[5] = {0, N, N, N, N}; int nstage = 1;
-  if (N >= (1 << 17)) {
-    if (e->L >= 12) {
-      const int64_t unit = std::max<int64_t>(1 << 14, ((N / 16) / 1024) * 1024);
-      cut[1] = unit; cut[2] = 3 * unit; cut[3] = 7 * unit; cut[4] = N; nstage = 4;
-      if (cut[3] >= N) { cut[1] = N; nstage = 1; }
-    } else {
-      cut[1] = std::max<int64_t>(1 << 15, ((N / 8) / 1024) * 1024); cut[2] = N; nstage = 2;
-    }
-  }
+  // Staged upload.  A large batch crosses PCIe in KB_STAGES equal pieces on the copy stream; piece k is checked while piece k + 1 is in
+  // flight, and consecutive pieces run on two alternating streams with their own scratch rows and work counters, so a piece starts
+  // filling the SMs that the previous launch's tail has left idle.  Cost ~ copy(N / KB_STAGES) + max(copy, compute): one GPU on its own
+  // x16 link is compute bound (56 MB in ~1.1 ms against 5 ms of checking); eight ranks sharing one host's memory are close to copy bound,
+  // where two pieces (round 1) left the GPU waiting for the second one.  Small batches stay single-stage.
   const size_t row = (size_t)e->L * esz;
-  CK(cudaMemcpyAsync(d_in, Q, (size_t)cut[1] * row, cudaMemcpyHostToDevice, e->stream));
-  if (nstage > 1) {
-    CK(cudaEventRecord(e->ev_copy[0], e->stream));                // the copy stream must not run ahead of earlier work on the buffer
+  const bool staged = N >= (1 << 17) && N <= e->chunk && e->pipeline == 0 && !e->time_kernels && !e->collect_stats;
+  if (!staged) {
+    CK(cudaMemcpyAsync(d_in, Q, (size_t)N * row, cudaMemcpyHostToDevice, e->stream));
+    if (esz == 4) { CK(kb_launch_widen_f32(e->d_Qf, e->d_Q, N * e->L, e->stream)); e->stats.kernel_launches++; }
+    if ((rc = run_feasible_device(e, e->d_Q, N, e->d_out, first_pair ? e->d_pair : nullptr, e->d_counters + 3))) return rc;
+  } else {
+    if ((rc = ensure_cfg_scratch(e, e->feas_items.nxf, N))) return rc;
+    const int K = KB_STAGES;
+    int64_t cut[KB_STAGES + 1];
+    for (int k = 0; k <= K; k++) cut[k] = k == K ? N : ((N * k / K) / 1024) * 1024;
+    CK(cudaEventRecord(e->ev_copy[0], e->stream));                  // neither the copies nor the second stream may run ahead of earlier work
     CK(cudaStreamWaitEvent(e->copy_stream, e->ev_copy[0], 0));
-    for (int k = 1; k < nstage; k++) {
+    CK(cudaStreamWaitEvent(e->aux_stream, e->ev_copy[0], 0));
+    for (int k = 0; k < K; k++) {
       CK(cudaMemcpyAsync(d_in + cut[k] * row, Q + cut[k] * row, (size_t)(cut[k + 1] - cut[k]) * row, cudaMemcpyHostToDevice, e->copy_stream));
-      CK(cudaEventRecord(e->ev_copy[k], e->copy_stream));
+      CK(cudaEventRecord(e->ev_stage[k], e->copy_stream));
     }
-  }
-  for (int k = 0; k < nstage; k++) {
-    if (k > 0) CK(cudaStreamWaitEvent(e->stream, e->ev_copy[k], 0));
-    if (esz == 4) { CK(kb_launch_widen_f32(e->d_Qf + cut[k] * e->L, e->d_Q + cut[k] * e->L, (cut[k + 1] - cut[k]) * e->L, e->stream)); e->stats.kernel_launches++; }
-    if ((rc = run_feasible_device(e, e->d_Q + cut[k] * e->L, cut[k + 1] - cut[k], e->d_out + cut[k], first_pair ? e->d_pair + 2 * cut[k] : nullptr, e->d_counters + 3))) return rc;
+    for (int k = 0; k < K; k++) {
+      cudaStream_t st = (k & 1) ? e->aux_stream : e->stream;
+      const int64_t n = cut[k + 1] - cut[k];
+      CK(cudaStreamWaitEvent(st, e->ev_stage[k], 0));
+      if (esz == 4) { CK(kb_launch_widen_f32(e->d_Qf + cut[k] * e->L, e->d_Q + cut[k] * e->L, n * e->L, st)); e->stats.kernel_launches++; }
+      if ((rc = run_feasible_piece(e, e->d_Q + cut[k] * e->L, cut[k], n, e->d_out + cut[k], first_pair ? e->d_pair + 2 * cut[k] : nullptr, e->d_counters + 3, st, k & 1))) return rc;
+    }
+    CK(cudaEventRecord(e->ev_copy[1], e->aux_stream));                // results are read back on e->stream: wait for the other stream's pieces
+    CK(cudaStreamWaitEvent(e->stream, e->ev_copy[1], 0));
   }
   if (bits) {
     CK(kb_launch_pack_bits(e->d_out, N, e->d_bits, e->stream)); e->stats.kernel_launches++;

@@ -343,10 +343,12 @@ def parse_rob(text: str, basedir: str = ".", world: Optional[WorldSpec] = None) 
     L = len(parents)
     names = items.get("links", ["Link_%d" % i for i in range(L)])          # the reference's default names (Robot.cpp:907-914)
 
-    def per_link(key, default, width=1, scale=1.0):
+    def per_link(key, default, width=1, scale=1.0, broadcast=False):
         if key not in items:
             return np.tile(np.asarray(default, dtype=np.float64), (L, 1)) if width > 1 else np.full(L, default, dtype=np.float64)
         v = np.array(_floats(items[key], scale), dtype=np.float64)
+        if broadcast and v.size == 1 and width == 1:       # one value for every link (geomscale / geommargin, Robot.cpp:882-887,1024-1051)
+            return np.full(L, v[0], dtype=np.float64)
         if v.size != L * width:
             raise ValueError("'%s' needs %d values, got %d" % (key, L * width, v.size))
         return v.reshape(L, width) if width > 1 else v
@@ -371,8 +373,8 @@ def parse_rob(text: str, basedir: str = ".", world: Optional[WorldSpec] = None) 
             T0[i, :9] = (Rb @ R).reshape(-1)
             T0[i, 9:12] = Rb @ t + tb
     # geometry
-    gscale = per_link("geomscale", 1.0)
-    gmargin = per_link("geommargin", 0.0)
+    gscale = per_link("geomscale", 1.0, broadcast=True)
+    gmargin = per_link("geommargin", 0.0, broadcast=True)
     link_geom = [-1] * L
     cache: Dict[Tuple[str, float], int] = {}
     for i, tok in enumerate(items.get("geometry", [""] * L)):
@@ -398,6 +400,7 @@ def parse_rob(text: str, basedir: str = ".", world: Optional[WorldSpec] = None) 
             return names.index(tok)
 
     edits = []
+    residual = []        # pairs that name links of a sub-chain mounted further down: resolved after the mounts (Robot.cpp:1297-1313,1344-1380)
     for lst, en in ((selfcol, True), (noselfcol, False)):
         if len(lst) % 2:
             raise ValueError("self-collision lists hold link PAIRS")
@@ -405,7 +408,13 @@ def parse_rob(text: str, basedir: str = ".", world: Optional[WorldSpec] = None) 
             # an explicit selfcollision list replaces the default set (Robot.cpp:1277-1296): start from nothing
             edits += [(i, j, False) for i in range(L) for j in range(i + 1, L)]
         for a, b in zip(lst[0::2], lst[1::2]):
-            i, j = link_index(a), link_index(b)
+            try:
+                i, j = link_index(a), link_index(b)
+            except ValueError:
+                if not mounts:
+                    raise ValueError("self-collision pair names an unknown link: %s, %s" % (a, b))
+                residual.append((a, b, en))
+                continue
             if i == j:
                 raise ValueError("Invalid self collision pair %s, %s" % (a, b))
             edits.append((min(i, j), max(i, j), en))
@@ -426,6 +435,19 @@ def parse_rob(text: str, basedir: str = ".", world: Optional[WorldSpec] = None) 
                      joint_base=jb, drivers=drv, self_collision_edits=edits, names=list(names))
     for m in mounts:
         _mount(world, spec, m, basedir, link_index)
+    for a, b, en in residual:
+        def late(tok):
+            try:
+                return int(tok)
+            except ValueError:
+                return list(spec.names).index(tok)
+        try:
+            i, j = late(a), late(b)
+        except ValueError:
+            raise ValueError("self-collision pair names an unknown link (also after the mounts): %s, %s" % (a, b))
+        if i == j:
+            raise ValueError("Invalid self collision pair %s, %s" % (a, b))
+        spec.self_collision_edits.append((min(i, j), max(i, j), en))
     world.robot = spec
     return world, spec
 

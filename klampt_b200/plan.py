@@ -63,8 +63,15 @@ class MotionPlan:
         self._best: Optional[np.ndarray] = None            # shortcut mode: the current solution, a polyline of configurations
         self.rng = np.random.default_rng(int(opts.get("seed", 0)))
         lo, hi = np.array([b[0] for b in space.bound], dtype=np.float64), np.array([b[1] for b in space.bound], dtype=np.float64)
-        self._lo, self._hi = lo, np.where(np.isfinite(hi), hi, 2 * np.pi)
-        self._lo = np.where(np.isfinite(lo), lo, 0.0)
+        # sampling box: an unbounded side is replaced by one turn next to the bounded one (lo + [0, 2 pi) / hi - [0, 2 pi)), or [0, 2 pi)
+        self._lo = np.where(np.isfinite(lo), lo, np.where(np.isfinite(hi), hi - 2 * np.pi, 0.0))
+        self._hi = np.where(np.isfinite(hi), hi, self._lo + 2 * np.pi)
+        # Metric and interpolation.  The engine checks edges along Klampt::Interpolate geodesics (Spin: short arc, Floating / BallAndSocket:
+        # SO(3)); for robots with only Normal / Weld joints those are straight lines and the Euclidean forms below are exact and
+        # vectorised.  Otherwise every distance / interpolation goes through space.distance / space.interpolate, row by row, so that
+        # nearest neighbours, steering, shortcut end points and path costs live on the same curves the edge checker verifies.
+        jt = getattr(getattr(getattr(space, "spec", None), "robot", None), "joint_type", None)
+        self._geodesic = jt is not None and any(int(t) not in (0, 1) for t in jt)
         self.V = np.zeros((0, len(lo)))                    # milestones
         self.adj: List[Dict[int, Tuple[float, bool]]] = []  # neighbour -> (length, checked)
         self.start = self.goal = None
@@ -98,7 +105,18 @@ class MotionPlan:
         self._connect([self.start, self.goal])
 
     def _dist(self, A: np.ndarray, B: np.ndarray) -> np.ndarray:
-        return np.sqrt(((A - B) ** 2).sum(axis=-1))
+        if not self._geodesic:
+            return np.sqrt(((A - B) ** 2).sum(axis=-1))
+        A2, B2 = np.broadcast_arrays(np.atleast_2d(A), np.atleast_2d(B))
+        d = np.array([self.space.distance(list(a), list(b)) for a, b in zip(A2, B2)])
+        return d if np.ndim(A) > 1 or np.ndim(B) > 1 else d[0]
+
+    def _interp(self, A: np.ndarray, B: np.ndarray, u) -> np.ndarray:
+        """Klampt::Interpolate(A[i], B[i], u[i]) per row"""
+        u = np.broadcast_to(np.asarray(u, dtype=np.float64).reshape(-1), (len(A),))
+        if not self._geodesic:
+            return A * (1.0 - u[:, None]) + B * u[:, None]
+        return np.array([self.space.interpolate(list(a), list(b), float(t)) for a, b, t in zip(A, B, u)])
 
     def _candidates(self, new: List[int]) -> np.ndarray:
         """k nearest neighbours of every new vertex among all vertices (brute-force on the host: the roadmap is small next to
@@ -118,9 +136,14 @@ class MotionPlan:
         pairs = set()
         for row, i in enumerate(new):
             for dist, j in zip(d[row], idx[row]):
-                if j != i and np.isfinite(dist) and dist <= self.connectionThreshold and int(j) not in self.adj[i]:
+                if j != i and np.isfinite(dist) and int(j) not in self.adj[i]:
                     pairs.add((min(i, int(j)), max(i, int(j))))
-        return np.array(sorted(pairs), dtype=np.int64).reshape(-1, 2)
+        cand = np.array(sorted(pairs), dtype=np.int64).reshape(-1, 2)
+        # The k-d tree ranks by Euclidean distance -- a candidate generator only.  The connection threshold is applied in the space's own
+        # metric (identical for Normal-joint robots; for Spin / Floating joints the geodesic can be shorter than the chord in R^n).
+        if len(cand) and np.isfinite(self.connectionThreshold):
+            cand = cand[self._dist(self.V[cand[:, 0]], self.V[cand[:, 1]]) <= self.connectionThreshold]
+        return cand
 
     def _connect(self, new: List[int]):
         cand = self._candidates(new)
@@ -146,7 +169,9 @@ class MotionPlan:
     def _nearest_in_tree(self, t: int, Q: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
         from scipy.spatial import cKDTree
         ids = np.nonzero(np.asarray(self.tree) == t)[0]
-        d, k = cKDTree(self.V[ids]).query(Q)
+        d, k = cKDTree(self.V[ids]).query(Q)          # Euclidean ranking picks the tree vertex; the step length below uses the space's metric
+        if self._geodesic:
+            d = self._dist(self.V[ids[k]], Q)
         return ids[k], d
 
     def _edge(self, i: int, j: int, checked: bool):
@@ -195,7 +220,7 @@ class MotionPlan:
                 near, d = self._nearest_in_tree(t, target[m])
                 step = np.minimum(1.0, self.perturbationRadius / np.maximum(d, 1e-300))[:, None]
                 src[m] = near
-                Qn[m] = self.V[near] + step * (target[m] - self.V[near])
+                Qn[m] = self._interp(self.V[near], target[m], step[:, 0])
         else:                                   # sbl: a sample in the neighbourhood of a random vertex of the tree
             tree = np.asarray(self.tree)
             src = np.array([self.rng.choice(np.nonzero(tree == t)[0]) for t in side], dtype=np.int64)
@@ -228,8 +253,8 @@ class MotionPlan:
         ia = np.minimum(np.searchsorted(s, t[:, 0], side="right") - 1, len(seg) - 1)
         ib = np.minimum(np.searchsorted(s, t[:, 1], side="right") - 1, len(seg) - 1)
         def point(i, tt):
-            u = np.where(seg[i] > 0, (tt - s[i]) / np.where(seg[i] > 0, seg[i], 1.0), 0.0)[:, None]
-            return P[i] * (1.0 - u) + P[i + 1] * u
+            u = np.where(seg[i] > 0, (tt - s[i]) / np.where(seg[i] > 0, seg[i], 1.0), 0.0)
+            return self._interp(P[i], P[i + 1], u)
         Xa, Xb = point(ia, t[:, 0]), point(ib, t[:, 1])
         saving = (t[:, 1] - t[:, 0]) - self._dist(Xa, Xb)
         cand = np.nonzero((ib > ia) & (saving > 1e-9 * s[-1]))[0]

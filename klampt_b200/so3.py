@@ -57,14 +57,20 @@ def from_quaternion(q: Sequence[float]) -> List[float]:
 def rpy(R: Sequence[float]) -> Tuple[float, float, float]:
     """roll, pitch, yaw with R = Rz(yaw) Ry(pitch) Rx(roll).  Ranges follow the reference
     (Python/klampt/math/so3.py:84-116): roll and yaw in [0, 2 pi) away from the singularity; at pitch = +-pi/2 the
-    roll is fixed to 0 and yaw = -asin(m01), reflected to pi - yaw when cos(yaw) and m11 disagree in sign."""
+    roll is fixed to 0 and yaw = -asin(m01), reflected to pi - yaw when cos(yaw) and m11 disagree in sign.
+
+    One stated deviation: the reference takes acos of the cosine and returns 2 pi - acos(..) whenever the sine's sign differs from
+    cos(pitch)'s, a zero sine included, so it answers (2 pi, 0, 2 pi) for the identity and 2 pi wherever m10 or m21 is exactly 0.  This
+    one uses atan2 (better conditioned near 0 and pi) folded into [0, 2 pi), so those cases answer 0.  The rotation is the same;
+    only the representative of the angle modulo 2 pi differs (tests/test_oracle_kat.py pins both facts)."""
     M = matrix(R)
     pitch = -math.asin(min(1.0, max(M[2, 0], -1.0)))
     cp = math.cos(pitch)
     two_pi = 2.0 * math.pi
     if abs(cp) > 1e-7:
-        yaw = math.atan2(M[1, 0] / cp, M[0, 0] / cp) % two_pi
-        roll = math.atan2(M[2, 1] / cp, M[2, 2] / cp) % two_pi
+        fold = lambda a: 0.0 if (a % two_pi) >= two_pi else a % two_pi      # -1e-17 % 2 pi rounds up to 2 pi itself
+        yaw = fold(math.atan2(M[1, 0] / cp, M[0, 0] / cp))
+        roll = fold(math.atan2(M[2, 1] / cp, M[2, 2] / cp))
         return roll, pitch, yaw
     yaw = -math.asin(min(1.0, max(M[0, 1], -1.0)))
     sgn = lambda x: int(x > 0) - int(x < 0)

@@ -257,3 +257,23 @@ def test_world_xml_places_the_robot_and_reads_transforms_like_the_reference(tmp_
     # geometry: scale (2,1,1), then quarter turn about z, then lift by 3: the unit cube spans x in [-1,0], y in [0,2], z in [3,4]
     v = w.geoms[go].verts
     assert np.allclose(v.min(0), [-1, 0, 3], atol=1e-12) and np.allclose(v.max(0), [0, 2, 4], atol=1e-12)
+
+
+def test_rob_single_value_broadcast_and_selfcollision_names_of_mounted_links(tmp_path):
+    """geomscale / geommargin with one value apply to every link (Robot.cpp:882-887,1024-1051); self-collision pairs naming links
+    of a sub-chain mounted further down are resolved after the mounts (Robot.cpp:1297-1313,1344-1380)"""
+    (tmp_path / "tri.off").write_text("OFF\n3 1 0\n0 0 0\n1 0 0\n0 1 0\n3 0 1 2\n")
+    (tmp_path / "hand.rob").write_text('links palm finger\nparents -1 0\ntparent 1 0 0 0 1 0 0 0 1 0 0 0  1 0 0 0 1 0 0 0 1 0.1 0 0\n'
+                                       'qmin -1 -1\nqmax 1 1\ngeometry "tri.off" "tri.off"\n')
+    text = ('links a b\nparents -1 0\ntparent 1 0 0 0 1 0 0 0 1 0 0 0  1 0 0 0 1 0 0 0 1 1 0 0\nqmin -1 -1\nqmax 1 1\n'
+            'geometry "tri.off" "tri.off"\ngeomscale 2\ngeommargin 0.01\nnoselfcollision a hand:finger\nmount 1 "hand.rob" as "hand"\n')
+    world, r = kio.parse_rob(text, basedir=str(tmp_path))
+    assert r.L == 4 and list(r.names) == ["a", "b", "hand:palm", "hand:finger"]
+    assert (0, 3, False) in r.self_collision_edits
+    for i in (0, 1):
+        g = world.geoms[r.link_geom[i]]
+        assert np.isclose(g.verts.max(), 2.0) and np.isclose(g.margin, 0.01)
+    with pytest.raises(ValueError):
+        kio.parse_rob(text.replace("hand:finger", "hand:thumb"), basedir=str(tmp_path))
+    with pytest.raises(ValueError):
+        kio.parse_rob("links a b\nparents -1 0\nnoselfcollision a zz\n")

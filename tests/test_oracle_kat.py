@@ -23,6 +23,17 @@ def test_so3_rpy_reference_kat():
     assert y == pytest.approx(3.141592653589793, abs=5e-8)
 
 
+def test_so3_rpy_branch_representative():
+    """the stated deviation of so3.rpy: angles are folded into [0, 2 pi) with atan2, so the identity answers (0, 0, 0) where the
+    reference's acos / sign branches (math/so3.py:95-106) answer (2 pi, 0, 2 pi); the rotation is the same either way"""
+    assert so3.rpy(so3.identity()) == (0.0, 0.0, 0.0)
+    for trip in ((2 * math.pi, 0.0, 2 * math.pi), (0.3, -0.4, 6.0), (5.0, 1.2, 0.0)):
+        R = so3.from_matrix(so3.euler_zyx_matrix(trip[2], trip[1], trip[0]))        # Rz(yaw) Ry(pitch) Rx(roll)
+        r, p, y = so3.rpy(R)
+        assert np.allclose(so3.euler_zyx_matrix(y, p, r), so3.matrix(R), atol=1e-12)
+        assert 0.0 <= r < 2 * math.pi and 0.0 <= y < 2 * math.pi
+
+
 def test_so3_column_major_convention():
     R = so3.from_axis_angle(((0, 0, 1), math.pi / 2))
     # column-major: first three entries are the first COLUMN = image of the x axis = +y
