@@ -532,7 +532,7 @@ def main():
                 except Exception:
                     pass
                 res["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                                   "ncu": ncu_extra, "kernel": {"feas": "kb_traverse_kernel", "edges": "kb_traverse_kernel (edge midpoints)",
+                                   "ncu": ncu_extra, "kernel": {"feas": "kb_traverse_wide_kernel", "edges": "kb_traverse_wide_kernel (edge midpoints)",
                                                                 "dist": "kb_traverse_kernel + kb_distance_kernel"}[kind],
                                    "algorithmic_bytes_per_unit": bytes_per_unit, "units_per_launch": units_rank / tl, "avg_launch_ms": tms / tl,
                                    "kernel_share_of_step": tms / ms_dev, "peak_source": peak_src, "counts_per_unit": counts}
