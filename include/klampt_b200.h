@@ -65,6 +65,7 @@ typedef struct {
   double  gpu_ms;               /* device time of the host-buffer entry points, copies included         */
   int64_t items_dropped;        /* (link, static group) pairs ruled out by the clearance grids ("collect_stats") */
   int64_t node_iterations;      /* warp-wide iterations of the node loop ("collect_stats")              */
+  int64_t rays_cast;            /* rays through kb_raycast_batch / kb_geom_raycast_batch                */
 } kb_stats;
 
 /* ---- lifetime ---------------------------------------------------------------------------------------- */
@@ -216,6 +217,26 @@ int kb_geom_distance_batch(kb_engine* e, int ga, const double* Ta, int gb, const
  * tolerances, closest points (cp1 on ga, cp2 on gb) and element indices, as kb_distance_batch_ex */
 int kb_geom_distance_batch_ex(kb_engine* e, int ga, const double* Ta, int gb, const double* Tb, int64_t N, double abs_err, double rel_err,
                               double upper_bound, double* out_d, double* out_cp, int32_t* out_elem);
+
+/* ---- ray casting --------------------------------------------------------------------- */
+/* WorldModel::RayCast / RayCastIgnore (Cpp/Modeling/World.cpp:465-588) for N rays at once -- what the camera sensor's fallback
+ * calls per pixel (Cpp/Sensing/VisualSensors.cpp:430-475), the laser sensor per measurement (:113-134) and WorldCollider.rayCast
+ * per query (Python/klampt/model/collide.py:700-748).  q: the robot's configuration (L doubles, host), NULL = the robot is left
+ * out.  rays: N x 6 = source xyz, direction xyz (any length > 0; normalised internally, as the sensors do).  ignore_ids: one byte
+ * per world id (kb_num_ids), 1 = rays pass through that body; NULL = none.  out_id: world id of the nearest body hit or -1;
+ * out_dist: distance from the source along the direction (+inf when nothing is hit; the hit point is source + dist * unit
+ * direction); out_elem (optional): triangle / point index within the body's geometry.  Every link, rigid object and terrain with a
+ * geometry is seen, whatever the collision mask says.  A triangle mesh reports its nearest two-sided intersection minus its
+ * collision margin, a point cloud where the ray enters the first sphere of radius (point radius + margin); ties in distance keep
+ * the body the reference visits first (links in order, rigid objects, terrains). */
+int kb_raycast_batch(kb_engine* e, const double* q, const double* rays, int64_t N, const uint8_t* ignore_ids,
+                     int32_t* out_id, double* out_dist, int32_t* out_elem);
+/* the same with the rays and the results device-resident on the engine's stream (q and ignore_ids stay host pointers) */
+int kb_raycast_batch_device(kb_engine* e, const double* q, const double* d_rays, int64_t N, const uint8_t* ignore_ids,
+                            int32_t* d_out_id, double* d_out_dist, int32_t* d_out_elem);
+/* Geometry3D::rayCast_ext (Python/klampt/src/geometry.cpp:1837-1852) of one registered geometry at transform T (12 doubles, NULL =
+ * identity): out_elem = element hit or -1, out_dist as above */
+int kb_geom_raycast_batch(kb_engine* e, int geom, const double* T, const double* rays, int64_t N, int32_t* out_elem, double* out_dist);
 
 /* ---- introspection ------------------------------------------------------------------------------------ */
 int kb_get_stats(kb_engine* e, kb_stats* out);

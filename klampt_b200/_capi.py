@@ -23,7 +23,7 @@ class KbStats(C.Structure):
                 ("edges_visible", C.c_int64), ("edge_config_checks", C.c_int64), ("node_tests", C.c_int64),
                 ("elem_tests", C.c_int64), ("recheck_pairs", C.c_int64), ("kernel_launches", C.c_int64),
                 ("traverse_launches", C.c_int64), ("traverse_ms", C.c_double), ("gpu_ms", C.c_double),
-                ("items_dropped", C.c_int64), ("node_iterations", C.c_int64)]
+                ("items_dropped", C.c_int64), ("node_iterations", C.c_int64), ("rays_cast", C.c_int64)]
 
 
 # every symbol include/klampt_b200.h declares: name -> (restype, argtypes)
@@ -68,6 +68,9 @@ SIGNATURES = {
     "kb_distance_batch_device": (C.c_int, [_VP, _VP, C.c_int64, C.c_double, C.c_int, _VP, _VP]),
     "kb_distance_batch_ex": (C.c_int, [_VP, _VP, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_int, _VP, _VP, _VP, _VP]),
     "kb_geom_distance_batch_ex": (C.c_int, [_VP, C.c_int, _VP, C.c_int, _VP, C.c_int64, C.c_double, C.c_double, C.c_double, _VP, _VP, _VP]),
+    "kb_raycast_batch": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP, _VP, _VP, _VP]),
+    "kb_raycast_batch_device": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP, _VP, _VP, _VP]),
+    "kb_geom_raycast_batch": (C.c_int, [_VP, C.c_int, _VP, _VP, C.c_int64, _VP, _VP]),
     "kb_geom_collides_batch": (C.c_int, [_VP, C.c_int, _VP, C.c_int, _VP, C.c_int64, C.c_double, _VP]),
     "kb_geom_distance_batch": (C.c_int, [_VP, C.c_int, _VP, C.c_int, _VP, C.c_int64, C.c_double, _VP]),
     "kb_get_stats": (C.c_int, [_VP, C.POINTER(KbStats)]),

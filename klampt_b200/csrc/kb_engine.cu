@@ -312,6 +312,7 @@ void build_clear_grid(int kind, const std::vector<double>& elems, const double g
 
 }  // namespace
 
+#define KB_RAY_TLAS_DEPTH 36   // depth bound of the top-level ray hierarchy (kb_raycast.cu keeps a 40-entry stack for it)
 #define KB_STAGES 8          // pieces a large host batch is uploaded / checked in (feasible_batch_host_one)
 struct kb_engine {
   // ---- description
@@ -391,6 +392,11 @@ struct kb_engine {
   double* d_weights = nullptr; int64_t w_cap = 0;
   // generic transform-pair queries
   double* d_T = nullptr; int64_t t_cap = 0;
+  // ray casting (kb_raycast.cu): bodies + top-level hierarchy are static data, the rest per-call scratch
+  std::vector<KbRayBody> ray_bodies; int ray_nlink = 0, ray_nstatic = 0; std::vector<float> h_tlas; float tlas_ext = 0; double ray_max_margin = 0;
+  KbRayBody* d_raybodies = nullptr; float4* d_tlas = nullptr;
+  double* d_rays = nullptr; int32_t* d_rid = nullptr; double* d_rdist = nullptr; int32_t* d_relem = nullptr; int64_t ray_cap = 0;
+  uint8_t* d_ignore = nullptr; double* d_rayq = nullptr; KbRayBody* d_onebody = nullptr;
   // ---- stats
   kb_stats stats{}; int64_t edge_cfg_host = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -844,7 +850,8 @@ void kb_engine_destroy(kb_engine* e) {
                     e->d_drv_scale, e->d_drv_off, e->feas_items.d_items, e->env_items.d_items, e->d_xf, e->d_state, e->d_hit, e->d_hit_elem, e->d_leaf_list, e->d_flagged, e->d_state2, e->d_work,
                     e->d_counters, e->d_Q, e->d_out, e->d_pair, e->d_dist, e->d_A, e->d_B, e->d_nlev, e->d_alive, e->d_nchecks, e->d_firstbad, e->d_list,
                     e->d_eQ, e->d_efeas, e->d_scalars, e->d_weights, e->d_T, e->feas_items.d_probes, e->feas_items.d_always_on,
-                    e->d_grid[0], e->d_grid[1], e->d_grid[2], e->d_grid[3], e->d_box32, e->d_box64, e->d_boxown, e->d_dyn_pts, e->d_dyn_T, e->d_dyn_scratch, e->d_Qf, e->d_bits, e->d_triorig, e->d_sphorig, e->d_cp, e->d_eslot, e->d_wide};
+                    e->d_grid[0], e->d_grid[1], e->d_grid[2], e->d_grid[3], e->d_box32, e->d_box64, e->d_boxown, e->d_dyn_pts, e->d_dyn_T, e->d_dyn_scratch, e->d_Qf, e->d_bits, e->d_triorig, e->d_sphorig, e->d_cp, e->d_eslot, e->d_wide,
+                    e->d_raybodies, e->d_tlas, e->d_rays, e->d_rid, e->d_rdist, e->d_relem, e->d_ignore, e->d_rayq, e->d_onebody};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -1320,6 +1327,64 @@ int kb_finalize(kb_engine* e, int device) {
     }
     for (size_t i = 0; i < fs.items.size(); i++) if (!probed[i]) fs.always_on[i >> 5] |= 1u << (i & 31);
   }
+  // ---- 4c. ray casting: one body per link / rigid object / terrain that has a geometry, whatever the collision mask says (a ray
+  // sees every body: WorldModel::RayCast, World.cpp:465-516), static ones under a top-level hierarchy of their world boxes
+  {
+    e->ray_bodies.clear(); e->h_tlas.clear(); e->ray_max_margin = 0; e->tlas_ext = 0;
+    auto body_of = [&](const DevGeom& dg, int id, int rank, int xf, const Xf* X) {
+      KbRayBody b; memset(&b, 0, sizeof b);
+      b.margin = dg.margin; b.node_base = dg.node_base; b.elem_base = dg.elem_base; b.kind = dg.kind; b.id = id; b.rank = rank; b.xf = xf;
+      b.T[0] = b.T[4] = b.T[8] = 1;
+      if (X) { memcpy(b.T, X->R, 72); memcpy(b.T + 9, X->t, 24); b.has_T = 1; }
+      double ext = 0; for (int k = 0; k < 3; k++) ext = std::max(ext, std::max(std::fabs(dg.lo[k]), std::fabs(dg.hi[k])));
+      b.ext = (float)(3.0 * ext * (1 + 1e-6));
+      return b;
+    };
+    for (int j = 0; j < L; j++) {
+      if (geom_empty(e, e->linkgeom[j])) continue;
+      const DevGeom& dg = e->dgeoms[e->linkgeom[j]];
+      if (dg.empty || dg.depth >= 90) continue;
+      e->ray_bodies.push_back(body_of(dg, link_id(e, j), j, j, nullptr));
+    }
+    for (const auto& dc : e->dyn) {      // replaceable clouds: world-frame groups whose boxes change with every update -> not under the hierarchy
+      KbRayBody b = body_of(e->groups[dc.group], dc.owner, dc.owner < T ? L + O + dc.owner : L + (dc.owner - T), -1, nullptr);
+      b.ext = 1e6f;                      // extent unknown ahead of the updates: a pad that is safe for any cloud within a kilometre
+      e->ray_bodies.push_back(b);
+    }
+    e->ray_nlink = (int)e->ray_bodies.size();
+    std::vector<KbRayBody> st; std::vector<double> blo, bhi;
+    for (int s2 = 0; s2 < T + O; s2++) {
+      const int gi = s2 < T ? e->terrains[s2] : e->objects[s2 - T];
+      if (geom_empty(e, gi) || e->geoms[gi].dyn_cap > 0) continue;
+      const DevGeom& dg = e->dgeoms[gi];
+      if (dg.empty || dg.depth >= 90) continue;
+      const Xf* X = s2 < T ? nullptr : &e->objT[s2 - T];
+      st.push_back(body_of(dg, s2, s2 < T ? L + O + s2 : L + (s2 - T), -1, X));
+      double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+      for (int c = 0; c < 8; c++) {
+        double pl[3] = {(c & 1) ? dg.hi[0] : dg.lo[0], (c & 2) ? dg.hi[1] : dg.lo[1], (c & 4) ? dg.hi[2] : dg.lo[2]}, pw[3];
+        if (X) xf_apply(*X, pl, pw); else memcpy(pw, pl, 24);
+        for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], pw[k]); hi[k] = std::max(hi[k], pw[k]); }
+      }
+      const double grow = dg.margin + 1e-9 * (1 + std::fabs(lo[0]) + std::fabs(lo[1]) + std::fabs(lo[2]) + std::fabs(hi[0]) + std::fabs(hi[1]) + std::fabs(hi[2]));
+      for (int k = 0; k < 3; k++) { blo.push_back(lo[k] - grow); e->tlas_ext = std::max(e->tlas_ext, (float)std::fabs(lo[k] - grow)); }
+      for (int k = 0; k < 3; k++) { bhi.push_back(hi[k] + grow); e->tlas_ext = std::max(e->tlas_ext, (float)std::fabs(hi[k] + grow)); }
+      if (dg.kind == KB_ELEM_TRI) e->ray_max_margin = std::max(e->ray_max_margin, dg.margin);
+    }
+    e->tlas_ext *= 3.f;
+    e->ray_nstatic = (int)st.size();
+    if (!st.empty()) {
+      Bvh tb; build_bvh(blo, bhi, (int)st.size(), 2, tb);
+      if (tb.depth >= KB_RAY_TLAS_DEPTH) return fail(KB_ERR_UNSUPPORTED, "top-level ray hierarchy is %d deep", tb.depth);
+      for (int i = 0; i < (int)st.size(); i++) e->ray_bodies.push_back(st[tb.perm[i]]);
+      for (const BNode& nd : tb.nodes) {
+        float v[8];
+        for (int k = 0; k < 3; k++) { const float c = (float)(0.5 * (nd.lo[k] + nd.hi[k])); v[k] = c; v[4 + k] = f_up(std::max(nd.hi[k] - (double)c, (double)c - nd.lo[k])); }
+        if (nd.left >= 0) { v[3] = i2f(nd.left); v[7] = i2f(0); } else { v[3] = i2f(~nd.first); v[7] = i2f(nd.count); }
+        e->h_tlas.insert(e->h_tlas.end(), v, v + 8);
+      }
+    }
+  }
   // ---- 5. upload
   e->static_bytes = 0;
   int rc;
@@ -1364,6 +1429,8 @@ int kb_finalize(kb_engine* e, int device) {
   if ((rc = upload(e->d_sphown, e->h_sphown.data(), e->h_sphown.size() * 4, &e->static_bytes, e))) return rc;
   if ((rc = upload(e->d_triorig, e->h_triorig.data(), e->h_triorig.size() * 4, &e->static_bytes, e))) return rc;
   if ((rc = upload(e->d_sphorig, e->h_sphorig.data(), e->h_sphorig.size() * 4, &e->static_bytes, e))) return rc;
+  if ((rc = upload(e->d_raybodies, e->ray_bodies.data(), e->ray_bodies.size() * sizeof(KbRayBody), &e->static_bytes, e))) return rc;
+  if ((rc = upload(e->d_tlas, e->h_tlas.data(), e->h_tlas.size() * 4, &e->static_bytes, e))) return rc;
   e->scene.nodes = e->d_nodes; e->scene.wide = e->d_wide; e->scene.tris32 = e->d_tris32; e->scene.tris64 = e->d_tris64; e->scene.sph32 = e->d_sph32; e->scene.sph64 = e->d_sph64;
   e->scene.triown = e->d_triown; e->scene.sphown = e->d_sphown; e->scene.triorig = e->d_triorig; e->scene.sphorig = e->d_sphorig;
   e->scene.box32 = e->d_box32; e->scene.box64 = e->d_box64; e->scene.boxown = e->d_boxown;
@@ -1457,6 +1524,7 @@ static int clone_to_device(const kb_engine* src, int device, kb_engine** out) {
   r->d_A = r->d_B = nullptr; r->ab_cap = 0; r->d_nlev = r->d_nchecks = r->d_firstbad = r->d_list = nullptr; r->d_alive = nullptr; r->edge_cap = 0;
   r->d_eQ = nullptr; r->d_efeas = nullptr; r->eq_cap = 0; r->d_eslot = nullptr; r->eslot_cap = 0; r->d_scalars = nullptr; r->d_weights = nullptr; r->w_cap = 0; r->d_T = nullptr; r->t_cap = 0;
   r->d_dyn_pts = nullptr; r->d_dyn_T = nullptr; r->d_dyn_scratch = nullptr; r->dyn_pts_cap = 0; r->dyn_scratch_bytes = 0;
+  r->d_rays = nullptr; r->d_rid = nullptr; r->d_rdist = nullptr; r->d_relem = nullptr; r->ray_cap = 0; r->d_ignore = nullptr; r->d_rayq = nullptr; r->d_onebody = nullptr;
   memset(&r->stats, 0, sizeof r->stats);
   // static arrays: null first so that a failure half way destroys cleanly
   for (const auto& a : src->statics) *(void**)((char*)r + a.member_offset) = nullptr;
@@ -2012,6 +2080,107 @@ int kb_geom_distance_batch_ex(kb_engine* e, int ga, const double* Ta, int gb, co
   return geom_pair_query(e, ga, Ta, gb, Tb, N, 0.0, 1, upper_bound, nullptr, out_d, abs_err, rel_err, out_cp, out_elem);
 }
 
+// ---- ray casting --------------------------------------------------------------------------------------------------------------
+static int raycast_run(kb_engine* e, const double* q_host, const double* d_rays, int64_t N, const uint8_t* ignore_host, const KbRayBody* one_body_host,
+                       int32_t* d_id, double* d_dist, int32_t* d_elem) {
+  KbRayParams p; memset(&p, 0, sizeof p);
+  p.scene = e->scene; p.rays = d_rays; p.N = N; p.out_id = d_id; p.out_dist = d_dist; p.out_elem = d_elem;
+  if (one_body_host) {          // Geometry3D::rayCast: one geometry at an explicit transform
+    if (!e->d_onebody) CK(cudaMalloc((void**)&e->d_onebody, sizeof(KbRayBody)));
+    CK(cudaMemcpyAsync(e->d_onebody, one_body_host, sizeof(KbRayBody), cudaMemcpyHostToDevice, e->stream));
+    p.bodies = e->d_onebody; p.nlinkbodies = 1; p.nstatic = 0;
+  } else {
+    p.bodies = e->d_raybodies; p.nstatic = e->ray_nstatic; p.tlas = e->d_tlas; p.tlas_ext = e->tlas_ext; p.max_margin = e->ray_max_margin;
+    const int nl = e->ray_nlink;
+    if (q_host) {
+      int rc = ensure_cfg_scratch(e, e->L, 1); if (rc) return rc;
+      if (!e->d_rayq) CK(cudaMalloc((void**)&e->d_rayq, (size_t)KB_MAX_LINKS * 8));
+      CK(cudaMemcpyAsync(e->d_rayq, q_host, (size_t)e->L * 8, cudaMemcpyHostToDevice, e->stream));
+      CK(kb_launch_fk(e->d_robot, e->d_drv, e->d_drv_link, e->d_drv_scale, e->d_drv_off, e->d_rayq, 1, e->d_xf, e->L, nullptr, nullptr, nullptr, e->stream));
+      e->stats.kernel_launches++;
+      p.xf64 = e->d_xf; p.nlinkbodies = nl;
+    } else {
+      // no configuration: the robot is left out; only the replaceable clouds of the first section remain (they follow the links there)
+      int nrobot = 0; for (int b = 0; b < nl; b++) if (e->ray_bodies[b].xf >= 0) nrobot++;
+      p.bodies = e->d_raybodies + nrobot; p.nlinkbodies = nl - nrobot;
+    }
+    if (ignore_host) {
+      if (!e->d_ignore) CK(cudaMalloc((void**)&e->d_ignore, (size_t)std::max(16, e->nids)));
+      CK(cudaMemcpyAsync(e->d_ignore, ignore_host, (size_t)e->nids, cudaMemcpyHostToDevice, e->stream));
+      p.ignore = e->d_ignore;
+    }
+  }
+  CK(kb_launch_raycast(p, e->stream));
+  e->stats.kernel_launches++;
+  return KB_OK;
+}
+
+int kb_raycast_batch_device(kb_engine* e, const double* q, const double* d_rays, int64_t N, const uint8_t* ignore_ids, int32_t* d_out_id, double* d_out_dist, int32_t* d_out_elem) {
+  if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
+  if (N < 0 || (N > 0 && (!d_rays || !d_out_id || !d_out_dist))) return fail(KB_ERR_INVALID, "bad arguments");
+  if (q && !all_finite(q, (size_t)e->L)) return fail(KB_ERR_INVALID, "non-finite configuration");
+  if (N == 0) return KB_OK;
+  CK(cudaSetDevice(e->device));
+  return raycast_run(e, q, d_rays, N, ignore_ids, nullptr, d_out_id, d_out_dist, d_out_elem);
+}
+
+static int raycast_host(kb_engine* e, const double* q, const double* rays, int64_t N, const uint8_t* ignore_ids, const KbRayBody* one, int32_t* out_id, double* out_dist, int32_t* out_elem) {
+  CK(cudaSetDevice(e->device));
+  int rc;
+  const int64_t chunk = 1 << 22;
+  if (std::min(N, chunk) > e->ray_cap) {
+    void* olds[] = {e->d_rays, e->d_rid, e->d_rdist, e->d_relem};
+    for (void* o : olds) if (o) cudaFree(o);
+    e->d_rays = nullptr; e->d_rid = nullptr; e->d_rdist = nullptr; e->d_relem = nullptr; e->ray_cap = 0;
+    const int64_t cap = std::min(N, chunk);
+    CK(cudaMalloc((void**)&e->d_rays, (size_t)cap * 48)); CK(cudaMalloc((void**)&e->d_rid, (size_t)cap * 4));
+    CK(cudaMalloc((void**)&e->d_rdist, (size_t)cap * 8)); CK(cudaMalloc((void**)&e->d_relem, (size_t)cap * 4));
+    e->ray_cap = cap;
+  }
+  begin_timing(e);
+  for (int64_t off = 0; off < N; off += chunk) {
+    const int64_t n = std::min(chunk, N - off);
+    CK(cudaMemcpyAsync(e->d_rays, rays + 6 * off, (size_t)n * 48, cudaMemcpyHostToDevice, e->stream));
+    if ((rc = raycast_run(e, q, e->d_rays, n, ignore_ids, one, e->d_rid, e->d_rdist, e->d_relem))) return rc;
+    if (out_id) CK(cudaMemcpyAsync(out_id + off, e->d_rid, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(out_dist + off, e->d_rdist, (size_t)n * 8, cudaMemcpyDeviceToHost, e->stream));
+    if (out_elem) CK(cudaMemcpyAsync(out_elem + off, e->d_relem, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (off + chunk < N) CK(cudaStreamSynchronize(e->stream));      // the scratch is reused by the next piece
+  }
+  end_timing(e, true);
+  CK(cudaStreamSynchronize(e->stream));
+  e->stats.rays_cast += N;
+  return KB_OK;
+}
+
+int kb_raycast_batch(kb_engine* e, const double* q, const double* rays, int64_t N, const uint8_t* ignore_ids, int32_t* out_id, double* out_dist, int32_t* out_elem) {
+  if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
+  if (N < 0 || (N > 0 && (!rays || !out_id || !out_dist))) return fail(KB_ERR_INVALID, "bad arguments");
+  if (q && !all_finite(q, (size_t)e->L)) return fail(KB_ERR_INVALID, "non-finite configuration");
+  if (N == 0) return KB_OK;
+  return raycast_host(e, q, rays, N, ignore_ids, nullptr, out_id, out_dist, out_elem);
+}
+
+int kb_geom_raycast_batch(kb_engine* e, int geom, const double* T, const double* rays, int64_t N, int32_t* out_elem, double* out_dist) {
+  if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
+  if (geom < 0 || geom >= (int)e->geoms.size()) return fail(KB_ERR_INVALID, "unknown geometry %d", geom);
+  if (N < 0 || (N > 0 && (!rays || !out_elem || !out_dist)) || (T && !all_finite(T, 12))) return fail(KB_ERR_INVALID, "bad arguments");
+  if (N == 0) return KB_OK;
+  const DevGeom& dg = e->dgeoms[geom];
+  if (e->geoms[geom].dyn_cap > 0) return fail(KB_ERR_UNSUPPORTED, "a replaceable point cloud is cast through kb_raycast_batch (it lives in the world frame only)");
+  if (dg.empty) {
+    for (int64_t i = 0; i < N; i++) { out_elem[i] = -1; out_dist[i] = std::numeric_limits<double>::infinity(); }
+    return KB_OK;
+  }
+  if (dg.depth >= 90) return fail(KB_ERR_UNSUPPORTED, "hierarchy of geometry %d is %d deep; the ray kernel's stack holds 96", geom, dg.depth);
+  KbRayBody b; memset(&b, 0, sizeof b);
+  b.margin = dg.margin; b.node_base = dg.node_base; b.elem_base = dg.elem_base; b.kind = dg.kind; b.id = 0; b.rank = 0; b.xf = -1; b.has_T = T ? 1 : 0;
+  b.T[0] = b.T[4] = b.T[8] = 1; if (T) memcpy(b.T, T, 96);
+  double ext = 0; for (int k = 0; k < 3; k++) ext = std::max(ext, std::max(std::fabs(dg.lo[k]), std::fabs(dg.hi[k])));
+  b.ext = (float)(3.0 * ext * (1 + 1e-6));
+  return raycast_host(e, nullptr, rays, N, nullptr, &b, nullptr, out_dist, out_elem);
+}
+
 int kb_get_stats(kb_engine* e, kb_stats* out) {
   if (!e || !out) return fail(KB_ERR_INVALID, "null argument");
   if (e->finalized) {
@@ -2029,7 +2198,7 @@ int kb_get_stats(kb_engine* e, kb_stats* out) {
     out->edges_visible += t.edges_visible; out->edge_config_checks += t.edge_config_checks; out->node_tests += t.node_tests;
     out->elem_tests += t.elem_tests; out->recheck_pairs += t.recheck_pairs; out->kernel_launches += t.kernel_launches;
     out->traverse_launches += t.traverse_launches; out->traverse_ms += t.traverse_ms; out->gpu_ms = std::max(out->gpu_ms, t.gpu_ms);
-    out->items_dropped += t.items_dropped; out->node_iterations += t.node_iterations;
+    out->items_dropped += t.items_dropped; out->node_iterations += t.node_iterations; out->rays_cast += t.rays_cast;
   }
   if (!e->replicas.empty()) CK(cudaSetDevice(e->device));
   return KB_OK;

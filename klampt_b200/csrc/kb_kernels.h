@@ -44,3 +44,6 @@ cudaError_t kb_launch_edge_flat_expand(const KbRobotDev* robot, const double* A,
                                        double* Q, uint8_t* slot_on, unsigned long long* nactive, cudaStream_t s);
 cudaError_t kb_launch_edge_flat_finish(const uint8_t* feas, const uint8_t* slot_on, int64_t nslots, int per_max, const int32_t* nlev, int32_t* firstbad, int64_t N,
                                        uint8_t* alive, int32_t* nchecks, cudaStream_t s);
+
+// kb_raycast.cu: nearest hit of N rays with the world (links at one configuration + static bodies)
+cudaError_t kb_launch_raycast(const KbRayParams& p, cudaStream_t s);

@@ -1,0 +1,218 @@
+// kb_raycast.cu -- batched ray casting against the world.
+//
+// Replaces WorldModel::RayCast / RayCastIgnore called once per ray (reference Cpp/Modeling/World.cpp:465-588): the camera sensor's
+// fallback renders a depth image with one call per pixel (Cpp/Sensing/VisualSensors.cpp:430-475), the laser sensor one per
+// measurement (:113-134), and Python's WorldCollider.rayCast / collide.ray_cast loop over Geometry3D.rayCast
+// (Python/klampt/model/collide.py:225-243,700-748; Python/klampt/src/geometry.cpp:1821-1852).  Semantics kept: the closest hit over
+// the robot's links at one configuration, the rigid objects and the terrains; a tie keeps the body the reference visits first
+// (links in order, then objects, then terrains); a triangle mesh reports its nearest two-sided ray / triangle intersection minus
+// its collision margin; a point cloud is the union of spheres of radius (point radius + margin).
+//
+// One thread per ray (neighbouring pixels of an image share most of their path, so a warp's node loads fall into the same lines).
+// Bodies are the per-geometry local-frame hierarchies every registered geometry already has; static bodies sit under a small
+// top-level hierarchy of their world boxes, links are tested one by one in the frames FK gives.  Node boxes are tested in fp32 with
+// the box padded by a bound on the rounding of the ray, elements in fp64: the reported distance is the fp64 one.
+#include "kb_types.h"
+#include "kb_kernels.h"
+#include <cuda_runtime.h>
+#include <math.h>
+#include <float.h>
+
+namespace {
+
+#define KB_RAY_STACK 96
+#define KB_RAY_TSTACK 40
+
+__device__ __forceinline__ void ld_node(const float4* __restrict__ nodes, size_t idx, float4& n0, float4& n1) {
+  const float4* p = nodes + 2 * idx;
+  n0 = __ldg(p); n1 = __ldg(p + 1);
+}
+
+struct RayF { float ox, oy, oz, ix, iy, iz; };
+
+// slab test of a padded box; tn = entry parameter (<= 0 when the source is inside).  Conservative: pad covers the rounding of the
+// fp32 ray and box, the relative slack the rounding of the products.
+__device__ __forceinline__ bool slab(const float4& n0, const float4& n1, const RayF& r, float pad, float tlim, float& tn) {
+  const float cx = n0.x - r.ox, cy = n0.y - r.oy, cz = n0.z - r.oz;
+  const float hx = n1.x + pad, hy = n1.y + pad, hz = n1.z + pad;
+  const float ax = (cx - hx) * r.ix, bx = (cx + hx) * r.ix;
+  const float ay = (cy - hy) * r.iy, by = (cy + hy) * r.iy;
+  const float az = (cz - hz) * r.iz, bz = (cz + hz) * r.iz;
+  const float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+  const float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+  tn = t0;
+  return (t0 - 2e-6f * fabsf(t0) <= t1 + 2e-6f * fabsf(t1)) && (t1 >= 0.f) && (t0 - 2e-6f * fabsf(t0) <= tlim);
+}
+
+// two-sided ray / triangle intersection in fp64 (the oracle's statement, same operation order)
+__device__ __forceinline__ bool ray_tri(const double* s, const double* d, const double* __restrict__ T, double& t) {
+  const double e1x = T[3] - T[0], e1y = T[4] - T[1], e1z = T[5] - T[2];
+  const double e2x = T[6] - T[0], e2y = T[7] - T[1], e2z = T[8] - T[2];
+  const double px = d[1] * e2z - d[2] * e2y, py = d[2] * e2x - d[0] * e2z, pz = d[0] * e2y - d[1] * e2x;
+  const double det = e1x * px + e1y * py + e1z * pz;
+  if (!(det != 0.0)) return false;
+  const double tx = s[0] - T[0], ty = s[1] - T[1], tz = s[2] - T[2];
+  const double u = (tx * px + ty * py + tz * pz) / det;
+  if (!(u >= 0.0 && u <= 1.0)) return false;
+  const double qx = ty * e1z - tz * e1y, qy = tz * e1x - tx * e1z, qz = tx * e1y - ty * e1x;
+  const double v = (d[0] * qx + d[1] * qy + d[2] * qz) / det;
+  if (!(v >= 0.0 && u + v <= 1.0)) return false;
+  const double tt = (e2x * qx + e2y * qy + e2z * qz) / det;
+  if (!(tt >= 0.0)) return false;
+  t = tt; return true;
+}
+
+__device__ __forceinline__ bool ray_sphere(const double* s, const double* d, const double* __restrict__ c, double r, double& t) {
+  if (!(r > 0.0)) return false;
+  const double mx = s[0] - c[0], my = s[1] - c[1], mz = s[2] - c[2];
+  const double b = mx * d[0] + my * d[1] + mz * d[2], cc = mx * mx + my * my + mz * mz - r * r;
+  if (cc <= 0.0) { t = 0.0; return true; }
+  if (b > 0.0) return false;
+  const double disc = b * b - cc;
+  if (disc < 0.0) return false;
+  t = -b - sqrt(disc); if (t < 0.0) t = 0.0;
+  return true;
+}
+
+struct Best { double d; int rank, id, elem; };
+
+// nearest hit of the world-frame ray (s, d) with one body whose frame is T (world <- local, 12 doubles, null = world frame)
+__device__ void cast_body(const KbScene& sc, const KbRayBody& B, const double* __restrict__ T, const double* s, const double* d, Best& best) {
+  double sl[3], dl[3];
+  if (T) {
+    const double mx = s[0] - T[9], my = s[1] - T[10], mz = s[2] - T[11];
+    sl[0] = T[0] * mx + T[3] * my + T[6] * mz; sl[1] = T[1] * mx + T[4] * my + T[7] * mz; sl[2] = T[2] * mx + T[5] * my + T[8] * mz;
+    dl[0] = T[0] * d[0] + T[3] * d[1] + T[6] * d[2]; dl[1] = T[1] * d[0] + T[4] * d[1] + T[7] * d[2]; dl[2] = T[2] * d[0] + T[5] * d[1] + T[8] * d[2];
+  } else { sl[0] = s[0]; sl[1] = s[1]; sl[2] = s[2]; dl[0] = d[0]; dl[1] = d[1]; dl[2] = d[2]; }
+  const bool mesh = B.kind == KB_ELEM_TRI;
+  const double shift = mesh ? B.margin : 0.0;                 // a mesh reports t - margin; a cloud's margin is part of its spheres
+  double tbest = best.d + shift;                              // raw parameter this body has to beat (ties resolved by rank below)
+  if (!(tbest >= 0.0)) return;
+  RayF r;
+  r.ox = (float)sl[0]; r.oy = (float)sl[1]; r.oz = (float)sl[2];
+  {
+    const float fx = (float)dl[0], fy = (float)dl[1], fz = (float)dl[2];
+    r.ix = 1.f / (fabsf(fx) > 1e-30f ? fx : copysignf(1e-30f, fx));
+    r.iy = 1.f / (fabsf(fy) > 1e-30f ? fy : copysignf(1e-30f, fy));
+    r.iz = 1.f / (fabsf(fz) > 1e-30f ? fz : copysignf(1e-30f, fz));
+  }
+  const float pad = (mesh ? 0.f : (float)B.margin * 1.000001f) + 8.f * sc.eps_abs + 4e-6f * (fabsf(r.ox) + fabsf(r.oy) + fabsf(r.oz) + B.ext);
+  float tlim = tbest < 3e38 ? __double2float_ru(tbest) * 1.00001f + 1e-30f : FLT_MAX;
+  const float4* __restrict__ nodes = sc.nodes + 2 * (size_t)B.node_base;
+  int stack_n[KB_RAY_STACK]; float stack_t[KB_RAY_STACK];
+  int sp = 0, node = 0, elem = -1;
+  bool hit = false;
+  float4 n0, n1; float tn;
+  ld_node(nodes, 0, n0, n1);
+  if (!slab(n0, n1, r, pad, tlim, tn)) return;
+  for (;;) {
+    const int ref = __float_as_int(n0.w);
+    if (ref < 0) {
+      const int first = ~ref, cnt = __float_as_int(n1.w);
+      for (int i = 0; i < cnt; i++) {
+        const int e = B.elem_base + first + i;
+        double t; bool h;
+        if (mesh) h = ray_tri(sl, dl, sc.tris64 + 9 * (size_t)e, t);
+        else h = ray_sphere(sl, dl, sc.sph64 + 4 * (size_t)e, sc.sph64[4 * (size_t)e + 3] + B.margin, t);
+        if (h) {
+          const int orig = mesh ? sc.triorig[e] : sc.sphorig[e];
+          if (t < tbest || (t == tbest && hit && orig < elem) || (t == tbest && !hit)) {
+            tbest = t; elem = orig; hit = true;
+            tlim = __double2float_ru(tbest) * 1.00001f + 1e-30f;
+          }
+        }
+      }
+    } else {
+      float4 a0, a1, b0, b1; float ta, tb;
+      ld_node(nodes, (size_t)ref, a0, a1);
+      ld_node(nodes, (size_t)ref + 1, b0, b1);
+      const bool ha = slab(a0, a1, r, pad, tlim, ta), hb = slab(b0, b1, r, pad, tlim, tb);
+      if (ha | hb) {
+        const bool afirst = ha && (!hb || ta <= tb);
+        if (ha & hb && sp < KB_RAY_STACK) { stack_n[sp] = afirst ? ref + 1 : ref; stack_t[sp] = afirst ? tb : ta; sp++; }
+        node = afirst ? ref : ref + 1;
+        if (afirst) { n0 = a0; n1 = a1; } else { n0 = b0; n1 = b1; }
+        continue;
+      }
+    }
+    // pop the nearest deferred subtree that can still beat the best hit
+    bool got = false;
+    while (sp > 0) {
+      sp--;
+      if (stack_t[sp] - 2e-6f * fabsf(stack_t[sp]) <= tlim) { node = stack_n[sp]; got = true; break; }
+    }
+    if (!got) break;
+    ld_node(nodes, (size_t)node, n0, n1);
+  }
+  if (!hit) return;
+  const double dist = tbest - shift;
+  if (dist < best.d || (dist == best.d && B.rank < best.rank)) { best.d = dist; best.rank = B.rank; best.id = B.id; best.elem = elem; }
+}
+
+__global__ void __launch_bounds__(128)
+kb_raycast_kernel(const KbRayParams p) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.N) return;
+  const double* __restrict__ ray = p.rays + 6 * i;
+  double s[3] = {ray[0], ray[1], ray[2]}, d[3] = {ray[3], ray[4], ray[5]};
+  Best best; best.d = INFINITY; best.rank = 0x7fffffff; best.id = -1; best.elem = -1;
+  const double n2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+  const bool ok = n2 > 0.0 && isfinite(n2) && isfinite(s[0]) && isfinite(s[1]) && isfinite(s[2]);
+  if (ok) {
+    const double n = sqrt(n2);
+    d[0] /= n; d[1] /= n; d[2] /= n;
+    // ---- the robot's links in the frames of this call's configuration
+    for (int b = 0; b < p.nlinkbodies; b++) {
+      const KbRayBody& B = p.bodies[b];
+      if (p.ignore && p.ignore[B.id]) continue;
+      cast_body(p.scene, B, B.xf >= 0 ? p.xf64 + 12 * (size_t)B.xf : (B.has_T ? B.T : nullptr), s, d, best);
+    }
+    // ---- static bodies under the top-level hierarchy (world boxes, already grown by each body's margin)
+    if (p.nstatic > 0) {
+      RayF r;
+      r.ox = (float)s[0]; r.oy = (float)s[1]; r.oz = (float)s[2];
+      const float fx = (float)d[0], fy = (float)d[1], fz = (float)d[2];
+      r.ix = 1.f / (fabsf(fx) > 1e-30f ? fx : copysignf(1e-30f, fx));
+      r.iy = 1.f / (fabsf(fy) > 1e-30f ? fy : copysignf(1e-30f, fy));
+      r.iz = 1.f / (fabsf(fz) > 1e-30f ? fz : copysignf(1e-30f, fz));
+      const float pad = 8.f * p.scene.eps_abs + 4e-6f * (fabsf(r.ox) + fabsf(r.oy) + fabsf(r.oz) + p.tlas_ext);
+      int tstack[KB_RAY_TSTACK]; int tsp = 0;
+      tstack[tsp++] = 0;
+      while (tsp > 0) {
+        const int node = tstack[--tsp];
+        float4 n0, n1; float tn;
+        ld_node(p.tlas, (size_t)node, n0, n1);
+        const double lim = best.d + p.max_margin;
+        const float tlim = lim < 3e38 ? __double2float_ru(lim) * 1.00001f + 1e-30f : FLT_MAX;
+        if (!slab(n0, n1, r, pad, tlim, tn)) continue;
+        const int ref = __float_as_int(n0.w);
+        if (ref < 0) {
+          const int first = ~ref, cnt = __float_as_int(n1.w);
+          for (int k = 0; k < cnt; k++) {
+            const KbRayBody& B = p.bodies[p.nlinkbodies + first + k];
+            if (p.ignore && p.ignore[B.id]) continue;
+            cast_body(p.scene, B, B.has_T ? B.T : nullptr, s, d, best);
+          }
+        } else if (tsp + 2 <= KB_RAY_TSTACK) {
+          // nearer child on top: its hits shorten the ray before the farther one is looked at
+          float4 a0, a1, b0, b1; float ta, tb;
+          ld_node(p.tlas, (size_t)ref, a0, a1); ld_node(p.tlas, (size_t)ref + 1, b0, b1);
+          slab(a0, a1, r, pad, tlim, ta); slab(b0, b1, r, pad, tlim, tb);
+          if (ta <= tb) { tstack[tsp++] = ref + 1; tstack[tsp++] = ref; } else { tstack[tsp++] = ref; tstack[tsp++] = ref + 1; }
+        }
+      }
+    }
+  }
+  p.out_id[i] = best.id;
+  p.out_dist[i] = best.d;
+  if (p.out_elem) p.out_elem[i] = best.elem;
+}
+
+}  // namespace
+
+cudaError_t kb_launch_raycast(const KbRayParams& p, cudaStream_t s) {
+  if (p.N <= 0) return cudaSuccess;
+  const int64_t blocks = (p.N + 127) / 128;
+  kb_raycast_kernel<<<(unsigned)blocks, 128, 0, s>>>(p);
+  return cudaGetLastError();
+}

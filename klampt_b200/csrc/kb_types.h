@@ -143,6 +143,34 @@ struct KbTraverseParams {
   const uint32_t* always_on;      // bit i set: item i has no probes and is always traversed ((nitems + 31) / 32 words)
 };
 
+// ray casting (kb_raycast.cu): one entry per body a ray can hit -- a robot link, a rigid object, a terrain
+struct KbRayBody {                // 144 bytes
+  double T[12];                   // world <- local of a static body (has_T); links take theirs from the FK table (xf >= 0)
+  double margin;
+  int32_t node_base, elem_base;   // the geometry's local-frame hierarchy / elements
+  int32_t kind;                   // KB_ELEM_TRI / KB_ELEM_SPHERE
+  int32_t id;                     // world id reported for a hit
+  int32_t rank;                   // order in which WorldModel::RayCast visits the bodies: a tie in distance keeps the lower rank
+  int32_t xf;                     // transform slot of a link, -1 = static
+  int32_t has_T;                  // static body with a transform other than the identity
+  float ext;                      // largest |coordinate| of the geometry's local box (bounds the fp32 rounding of its node tests)
+};
+struct KbRayParams {
+  KbScene scene;
+  const KbRayBody* bodies;        // [0, nlinkbodies): tested one by one; then nstatic bodies in the leaf order of the top-level hierarchy
+  int32_t nlinkbodies, nstatic;
+  const float4* tlas;             // top-level hierarchy over the static bodies' world boxes (same node format; leaf = body range)
+  float tlas_ext;                 // largest |coordinate| of its root box
+  double max_margin;              // largest mesh margin among the static bodies (a body reports t - margin)
+  const double* xf64;             // link transforms of this call's configuration (nxf x 12), null when there is no link body
+  const double* rays;             // N x 6: source, direction (any length > 0)
+  int64_t N;
+  const uint8_t* ignore;          // per world id: 1 = rays pass through (RayCastIgnore); may be null
+  int32_t* out_id;                // world id of the nearest hit, -1 = none
+  double* out_dist;               // distance along the normalised direction, +inf = none
+  int32_t* out_elem;              // element index within the body's geometry; may be null
+};
+
 // split pipeline (node traversal kernel -> global leaf-pair list -> leaf kernel -> requeue for the fused kernel)
 struct KbSplitParams {
   uint4* leaf_list;               // (configuration, item | nodeA, nodeB, 0)

@@ -264,6 +264,36 @@ class Engine:
                                                  _ptr(d), _ptr(cp), _ptr(elem)))
         return d, cp, elem
 
+    def raycast_batch(self, q, rays, ignore_ids=None):
+        """WorldModel::RayCast / RayCastIgnore (World.cpp:465-588) for N rays (rows of source xyz, direction xyz) with the robot at q
+        (None: the robot is left out): (world id or -1, distance along the normalised direction or inf, element index or -1).
+        ignore_ids: world ids the rays pass through (an iterable of ids, or one byte per id)."""
+        rays = _f64(rays).reshape(-1, 6)
+        N = rays.shape[0]
+        ids, dist, elem = np.empty(N, dtype=np.int32), np.empty(N, dtype=np.float64), np.empty(N, dtype=np.int32)
+        qa = None if q is None else _f64(q).reshape(self.L)
+        ig = None
+        if ignore_ids is not None:
+            ig = np.asarray(ignore_ids)
+            nids = self.num_ids()
+            if ig.dtype != np.uint8 or ig.shape != (nids,):
+                m = np.zeros(nids, dtype=np.uint8)
+                m[np.asarray(list(ignore_ids), dtype=np.int64)] = 1
+                ig = m
+            ig = np.ascontiguousarray(ig)
+        check(self.lib.kb_raycast_batch(self.h, None if qa is None else _ptr(qa), _ptr(rays), N, None if ig is None else _ptr(ig),
+                                        _ptr(ids), _ptr(dist), _ptr(elem)))
+        return ids, dist, elem
+
+    def geom_raycast_batch(self, geom: int, T, rays):
+        """Geometry3D.rayCast_ext of one registered geometry at transform T (12 doubles or None) for N rays: (element or -1, distance or inf)"""
+        rays = _f64(rays).reshape(-1, 6)
+        N = rays.shape[0]
+        elem, dist = np.empty(N, dtype=np.int32), np.empty(N, dtype=np.float64)
+        Ta = None if T is None else _f64(T).reshape(12)
+        check(self.lib.kb_geom_raycast_batch(self.h, int(geom), None if Ta is None else _ptr(Ta), _ptr(rays), N, _ptr(elem), _ptr(dist)))
+        return elem, dist
+
     def colliding_pairs_batch(self, Q, max_pairs: int = 8):
         """every colliding (idA, idB) world-id pair per configuration: (pairs (N, max_pairs, 2) padded with -1, count (N,));
         count = -1 where the joint / driver limits already fail"""

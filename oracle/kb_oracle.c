@@ -975,6 +975,104 @@ double ko_geom_penetration(const ko_world* w, int ga, const double Ta[12], int g
   geom_t a=w->geoms[ga], b=w->geoms[gb]; a.margin+=tol;      /* shallow copies: the threshold is margin_A + margin_B + tol */
   double worst=-1.0; geom_pair_depth(&a,&A,&b,&B,&worst); return worst; }
 
+/* ------------------------------------------------------------------ ray casting
+ * WorldModel::RayCast / RayCastIgnore (reference Cpp/Modeling/World.cpp:465-588): the closest hit over the robot's links at q, the
+ * rigid objects and the terrains, visited in that order with a strict '<' (a tie keeps the earlier body); each body answers through
+ * AnyCollisionGeometry3D::RayCast(ray, &dist) and the world point is source + dist * direction.  Geometry3D::rayCast / rayCast_ext
+ * (Python/klampt/src/geometry.cpp:1821-1852) is the one-geometry form.  The per-geometry arithmetic lives in KrisLibrary (absent:
+ * parity unpinned); restated here from its published behaviour: a triangle mesh reports the nearest two-sided ray / triangle
+ * intersection and takes its collision margin off the distance; a point cloud is the union of spheres of radius (point radius +
+ * margin) and reports where the ray enters the first one (nothing when that radius is 0).  The direction is normalised on entry, so
+ * dist is a length. */
+static int ray_tri(const double* s, const double* d, const double* a, const double* b, const double* c, double* t) {
+  double e1[3],e2[3],p[3],tv[3],qv[3]; v_sub(b,a,e1); v_sub(c,a,e2); v_cross(d,e2,p);
+  double det=v_dot(e1,p); if (!(det!=0)) return 0;            /* parallel to the plane, or no plane (segment triangles) */
+  v_sub(s,a,tv); double u=v_dot(tv,p)/det; if (!(u>=0 && u<=1)) return 0;
+  v_cross(tv,e1,qv); double v=v_dot(d,qv)/det; if (!(v>=0 && u+v<=1)) return 0;
+  double tt=v_dot(e2,qv)/det; if (!(tt>=0)) return 0;
+  *t=tt; return 1;
+}
+static int ray_sphere(const double* s, const double* d, const double* c, double r, double* t) {   /* |d| = 1 */
+  if (!(r>0)) return 0;
+  double m[3]; v_sub(s,c,m); double b=v_dot(m,d), cc=v_dot(m,m)-r*r;
+  if (cc<=0) { *t=0; return 1; }                              /* the source is inside */
+  if (b>0) return 0;
+  double disc=b*b-cc; if (disc<0) return 0;
+  *t=-b-sqrt(disc); if (*t<0) *t=0; return 1;
+}
+static int ray_box(const double* s, const double* d, const double* lo, const double* hi, double pad, double tmax, double* tnear) {
+  double t0=0, t1=tmax;
+  for (int k=0;k<3;k++) {
+    if (d[k]==0) { if (s[k]<lo[k]-pad || s[k]>hi[k]+pad) return 0; continue; }
+    double a=(lo[k]-pad-s[k])/d[k], b=(hi[k]+pad-s[k])/d[k];
+    double mn=a<b?a:b, mx=a<b?b:a;
+    if (mn>t0) t0=mn;
+    if (mx<t1) t1=mx;
+  }
+  *tnear=t0; return t0<=t1;
+}
+/* nearest hit of the local-frame ray with geometry g: t (before the margin is taken off) and the element in the caller's order */
+static int geom_ray_local(const geom_t* g, const double* s, const double* d, double tmax, double* tbest, int* elem, int brute) {
+  int hit=0; *tbest=tmax;
+  if (g->kind==G_EMPTY || g->nnodes<=0) return 0;
+  if (brute) {
+    int n=(g->kind==G_MESH)?g->nt:g->np;
+    for (int i=0;i<n;i++) { double t; int h=(g->kind==G_MESH) ? ray_tri(s,d,g->tv+9*(size_t)i,g->tv+9*(size_t)i+3,g->tv+9*(size_t)i+6,&t)
+                                                              : ray_sphere(s,d,g->pts+3*(size_t)i,g->rad[i]+g->margin,&t);
+      if (h && (!hit || t<*tbest || (t==*tbest && g->perm[i]<*elem))) { *tbest=t; *elem=g->perm[i]; hit=1; } }
+    return hit;
+  }
+  double pad=(g->kind==G_MESH)?0.0:g->margin;                 /* node boxes hold the point radii, not the margin */
+  int stack[128], sp=0; stack[sp++]=0;
+  while (sp>0) {
+    int i=stack[--sp]; const node_t* n=&g->nodes[i]; double tn;
+    if (!ray_box(s,d,n->lo,n->hi,pad+1e-12,*tbest,&tn)) continue;
+    if (n->left<0) {
+      for (int e=n->first;e<n->first+n->count;e++) { double t; int h=(g->kind==G_MESH) ? ray_tri(s,d,g->tv+9*(size_t)e,g->tv+9*(size_t)e+3,g->tv+9*(size_t)e+6,&t)
+                                                                                    : ray_sphere(s,d,g->pts+3*(size_t)e,g->rad[e]+g->margin,&t);
+        if (h && (!hit || t<*tbest || (t==*tbest && g->perm[e]<*elem))) { *tbest=t; *elem=g->perm[e]; hit=1; } }
+    } else if (sp+2<=128) { stack[sp++]=n->left; stack[sp++]=n->right; }
+  }
+  return hit;
+}
+static int geom_raycast(const geom_t* g, const xf_t* T, const double* s, const double* d, double* dist, int* elem, int brute) {
+  double sl[3],dl[3],m[3]; v_sub(s,T->t,m);
+  for (int k=0;k<3;k++) { sl[k]=T->R[k]*m[0]+T->R[3+k]*m[1]+T->R[6+k]*m[2]; dl[k]=T->R[k]*d[0]+T->R[3+k]*d[1]+T->R[6+k]*d[2]; }   /* R^T */
+  double t; if (!geom_ray_local(g,sl,dl,DBL_MAX,&t,elem,brute)) return 0;
+  *dist = (g->kind==G_MESH) ? t-g->margin : t;
+  return 1;
+}
+static int ray_unit(const double* d, double* u) { double n=sqrt(v_dot(d,d)); if (!(n>0) || !isfinite(n)) return 0; u[0]=d[0]/n; u[1]=d[1]/n; u[2]=d[2]/n; return 1; }
+int ko_geom_raycast(const ko_world* w, int g, const double T12[12], const double s[3], const double d[3], double* dist, int32_t* elem, int brute) {
+  xf_t T; xf_from12(T12,&T); double u[3]; int el=-1; *dist=INFINITY; if (elem) *elem=-1;
+  if (g<0||g>=w->ngeoms||!ray_unit(d,u)) return 0;
+  if (!geom_raycast(&w->geoms[g],&T,s,u,dist,&el,brute)) { *dist=INFINITY; return 0; }
+  if (elem) *elem=el;
+  return 1;
+}
+int ko_raycast(const ko_world* w, const double* q, const double s[3], const double d[3], const uint8_t* ignore_ids, double* dist, int32_t* elem) {
+  double u[3]; int best=-1, bel=-1; double bd=INFINITY;
+  if (ray_unit(d,u)) {
+    if (q && w->L) {
+      xf_t* T=(xf_t*)malloc(sizeof(xf_t)*w->L); fk_links(w,q,T);
+      for (int j=0;j<w->L;j++) { int g=w->linkgeom[j]; if (geom_empty(w,g) || (ignore_ids && ignore_ids[id_link(w,j)])) continue;
+        double dd; int el; if (geom_raycast(&w->geoms[g],&T[j],s,u,&dd,&el,0) && dd<bd) { bd=dd; best=id_link(w,j); bel=el; } }
+      free(T);
+    }
+    for (int i=0;i<w->nobj;i++) { int g=w->objects[i]; if (geom_empty(w,g) || (ignore_ids && ignore_ids[w->nterr+i])) continue;
+      double dd; int el; if (geom_raycast(&w->geoms[g],&w->objT[i],s,u,&dd,&el,0) && dd<bd) { bd=dd; best=w->nterr+i; bel=el; } }
+    xf_t I; xf_identity(&I);
+    for (int i=0;i<w->nterr;i++) { int g=w->terrains[i]; if (geom_empty(w,g) || (ignore_ids && ignore_ids[i])) continue;
+      double dd; int el; if (geom_raycast(&w->geoms[g],&I,s,u,&dd,&el,0) && dd<bd) { bd=dd; best=i; bel=el; } }
+  }
+  *dist=bd; if (elem) *elem=bel; return best;
+}
+void ko_raycast_batch(const ko_world* w, const double* q, const double* rays, int64_t N, const uint8_t* ignore_ids, int32_t* ids, double* dist, int32_t* elem, int nthreads) {
+  if (nthreads<=0) nthreads=ko_max_threads();
+  #pragma omp parallel for schedule(dynamic,256) num_threads(nthreads)
+  for (int64_t i=0;i<N;i++) { int32_t el; ids[i]=ko_raycast(w,q,rays+6*i,rays+6*i+3,ignore_ids,dist+i,&el); if (elem) elem[i]=el; }
+}
+
 int ko_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

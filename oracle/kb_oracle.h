@@ -113,6 +113,15 @@ double ko_tri_tri_distance(const double a[9], const double b[9]);
 double ko_point_tri_distance(const double p[3], const double t[9]);
 double ko_seg_seg_distance(const double p0[3], const double p1[3], const double q0[3], const double q1[3]);
 
+/* f4: WorldModel::RayCast / RayCastIgnore (World.cpp:465-588) with the robot at q (NULL: robot left out); returns the world id hit
+ * or -1, *dist = length along the (normalised) direction or +inf, *elem = element index within the body's geometry.
+ * ko_geom_raycast: Geometry3D::rayCast_ext (Python/klampt/src/geometry.cpp:1837-1852) of geometry g at transform T; brute = 1
+ * tests every element without the hierarchy (cross-check). */
+int ko_raycast(const ko_world* w, const double* q, const double s[3], const double d[3], const uint8_t* ignore_ids, double* dist, int32_t* elem);
+void ko_raycast_batch(const ko_world* w, const double* q, const double* rays, int64_t N, const uint8_t* ignore_ids,
+                      int32_t* ids, double* dist, int32_t* elem, int nthreads);
+int ko_geom_raycast(const ko_world* w, int g, const double T[12], const double s[3], const double d[3], double* dist, int32_t* elem, int brute);
+
 int ko_max_threads(void);
 
 #ifdef __cplusplus

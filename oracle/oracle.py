@@ -93,6 +93,9 @@ def lib(variant: str = "strict"):
     L.ko_tri_tri_depth.restype = C.c_double
     L.ko_geom_penetration.argtypes = [vp, C.c_int, dp, C.c_int, dp, C.c_double]
     L.ko_geom_penetration.restype = C.c_double
+    L.ko_raycast.argtypes = [vp, dp, dp, dp, u8p, dp, ip]
+    L.ko_raycast_batch.argtypes = [vp, dp, dp, C.c_int64, u8p, ip, dp, ip, C.c_int]
+    L.ko_geom_raycast.argtypes = [vp, C.c_int, dp, dp, dp, dp, ip, C.c_int]
     _LIBS[variant] = L
     return L
 
@@ -355,6 +358,27 @@ class OracleWorld:
         a_, ap = _d(Ta)
         b_, bp = _d(Tb)
         return float(self.L.ko_geom_penetration(self.h, ga, ap, gb, bp, float(tol)))
+
+    def raycast_batch(self, q, rays, ignore_ids=None, nthreads=0):
+        """WorldModel::RayCast / RayCastIgnore (World.cpp:465-588) of N rays (source xyz, direction xyz) with the robot at q (None: robot
+        left out): (world id or -1, distance along the normalised direction or inf, element index)"""
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)
+        N = rays.shape[0]
+        ids, dist, elem = np.zeros(N, dtype=np.int32), np.zeros(N), np.zeros(N, dtype=np.int32)
+        q_, qp = (None, None) if q is None else _d(q)
+        ig_, igp = (None, None) if ignore_ids is None else _u8(ignore_ids)
+        self.L.ko_raycast_batch(self.h, qp, rays.ctypes.data_as(C.POINTER(C.c_double)), N, igp, ids.ctypes.data_as(C.POINTER(C.c_int32)),
+                                dist.ctypes.data_as(C.POINTER(C.c_double)), elem.ctypes.data_as(C.POINTER(C.c_int32)), int(nthreads))
+        return ids, dist, elem
+
+    def geom_raycast(self, g, T, s, d, brute=False):
+        """Geometry3D::rayCast_ext (Python/klampt/src/geometry.cpp:1837-1852): (hit, distance, element)"""
+        T_, Tp = _d(T)
+        s_, sp = _d(s)
+        d_, dp_ = _d(d)
+        dist, el = C.c_double(0), C.c_int32(-1)
+        hit = self.L.ko_geom_raycast(self.h, int(g), Tp, sp, dp_, C.byref(dist), C.byref(el), int(brute))
+        return bool(hit), float(dist.value), int(el.value)
 
     def geom_aabb(self, g, T):
         T_, Tp = _d(T)

@@ -1,0 +1,135 @@
+"""Ray casting against the CPU oracle: WorldModel::RayCast / RayCastIgnore semantics (World.cpp:465-588) through
+kb_raycast_batch, Geometry3D::rayCast_ext through kb_geom_raycast_batch.  Hit / miss and the body hit must be equal; distances
+within 1e-9 relative (both sides evaluate the same fp64 ray / triangle statement; only the hierarchy differs); the reported element
+must reproduce the distance when it is cast alone (two triangles sharing the edge a ray crosses tie)."""
+import numpy as np
+import pytest
+
+from klampt_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def camera_rays(eye, target, up, fov_deg, w, h):
+    """pinhole camera rays the way the camera sensor's fallback builds them (VisualSensors.cpp:430-450): unit directions"""
+    eye, target, up = (np.asarray(v, dtype=np.float64) for v in (eye, target, up))
+    f = target - eye
+    f /= np.linalg.norm(f)
+    r = np.cross(f, up)
+    r /= np.linalg.norm(r)
+    u = np.cross(r, f)
+    fx = 0.5 * w / np.tan(0.5 * np.radians(fov_deg))
+    ii, jj = np.meshgrid(np.arange(w) - 0.5 * (w - 1), 0.5 * (h - 1) - np.arange(h))
+    d = f[None, None, :] + (ii / fx)[..., None] * r + (jj / fx)[..., None] * u
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    return np.concatenate([np.broadcast_to(eye, d.shape), d], axis=-1).reshape(-1, 6)
+
+
+def check_against_oracle(eng, orc, q, rays, ignore=None, rtol=1e-9):
+    ids, dist, elem = eng.raycast_batch(q, rays, ignore)
+    ig = None
+    if ignore is not None:
+        ig = np.zeros(orc.num_ids(), dtype=np.uint8)
+        ig[list(ignore)] = 1
+    oid, odist, oelem = orc.raycast_batch(q, rays, ig)
+    assert np.array_equal(ids >= 0, oid >= 0), "hit / miss differs on %d rays" % int(((ids >= 0) != (oid >= 0)).sum())
+    hit = ids >= 0
+    assert np.all(np.isinf(dist[~hit])) and np.all(elem[~hit] == -1)
+    np.testing.assert_allclose(dist[hit], odist[hit], rtol=rtol, atol=1e-12)
+    assert np.array_equal(ids, oid)
+    return ids, dist, elem, oelem
+
+
+def test_camera_image_of_the_c2_world(built):
+    from klampt_b200.engine import Engine
+    from oracle.oracle import OracleWorld
+    w = synth.world_c2(2, n_obstacles=40)
+    eng, orc = Engine(w), OracleWorld(w)
+    q = synth.sample_configs(w.robot, 1, 3)[0]
+    rays = camera_rays((2.6, 0.4, 1.4), (0, 0, 0.5), (0, 0, 1), 70, 160, 120)
+    ids, dist, elem, oelem = check_against_oracle(eng, orc, q, rays)
+    assert 0.3 < (ids >= 0).mean() < 1.0
+    assert len(np.unique(ids[ids >= 0])) > 5                       # links and several obstacles are in view
+    agree = (elem == oelem)[ids >= 0].mean()
+    assert agree > 0.999                                           # ties across a shared edge aside
+    # the robot left out, and single links ignored (RayCastIgnore, the laser sensor's use)
+    ids2, _, _, _ = check_against_oracle(eng, orc, None, rays)
+    assert not np.any(ids2 >= w.robot_id())
+    link_ids = [w.robot_link_id(j) for j in range(w.robot.L)]
+    ids3, _, _, _ = check_against_oracle(eng, orc, q, rays, ignore=link_ids[2:5])
+    assert not np.isin(ids3, link_ids[2:5]).any()
+    # idempotent, independent of the batch split
+    a = eng.raycast_batch(q, rays[:5000])
+    b = eng.raycast_batch(q, rays)
+    assert all(np.array_equal(x, y[:5000]) for x, y in zip(a, b))
+
+
+def test_random_rays_and_degenerate_input(built):
+    from klampt_b200.engine import Engine
+    from oracle.oracle import OracleWorld
+    w = synth.world_c2(5, n_obstacles=25)
+    eng, orc = Engine(w), OracleWorld(w)
+    q = synth.sample_configs(w.robot, 1, 8)[0]
+    rng = np.random.default_rng(0)
+    N = 20000
+    src = rng.uniform([-3, -3, -0.5], [3, 3, 3], (N, 3))
+    tgt = rng.uniform([-1, -1, 0], [1, 1, 1.5], (N, 3))
+    rays = np.hstack([src, (tgt - src) * rng.uniform(0.1, 5.0, (N, 1))])          # directions of any length
+    rays[:50, 3:] = np.eye(3)[rng.integers(0, 3, 50)] * rng.choice([-1.0, 1.0], (50, 1))     # axis-parallel: zero direction components
+    check_against_oracle(eng, orc, q, rays)
+    bad = rays[:4].copy()
+    bad[0, 3:] = 0.0
+    bad[1, 3] = np.nan
+    bad[2, 0] = np.inf
+    ids, dist, elem = eng.raycast_batch(q, bad)
+    assert list(ids[:3]) == [-1, -1, -1] and np.all(np.isinf(dist[:3]))
+    ids0, dist0, _ = eng.raycast_batch(q, np.zeros((0, 6)))
+    assert ids0.shape == (0,)
+
+
+def test_point_clouds_margins_and_primitives(built):
+    from klampt_b200.engine import Engine
+    from klampt_b200.worldspec import GeomSpec
+    from oracle.oracle import OracleWorld
+    w = synth.world_c5(n_points=30000, n_obstacles=12)
+    eng, orc = Engine(w), OracleWorld(w)
+    q = synth.sample_configs(w.robot, 1, 1)[0]
+    rays = camera_rays((2.4, -0.6, 1.2), (0, 0, 0.4), (0, 0, 1), 60, 128, 96)
+    ids, dist, elem, oelem = check_against_oracle(eng, orc, q, rays)
+    assert (ids >= 0).mean() > 0.05
+    # the same cloud through the GPU-built hierarchy
+    eng2 = Engine(w, options={"cloud_builder": 1})
+    ids2, dist2, _ = eng2.raycast_batch(q, rays)
+    assert np.array_equal(ids2, ids)
+    np.testing.assert_allclose(dist2[ids >= 0], dist[ids >= 0], rtol=1e-9, atol=1e-12)
+    # boxes, spheres, a mesh with a margin
+    wb = synth.world_boxes(n_boxes=8, n_blobs=2)
+    eb, ob = Engine(wb), OracleWorld(wb)
+    qb = synth.sample_configs(wb.robot, 1, 2)[0]
+    rb = camera_rays((2.2, 0.9, 1.5), (0, 0, 0.4), (0, 0, 1), 75, 96, 96)
+    check_against_oracle(eb, ob, qb, rb)
+
+
+def test_geometry_raycast_ext(built):
+    from klampt_b200.engine import Engine
+    from oracle.oracle import OracleWorld
+    w = synth.world_c2(2, n_obstacles=6)
+    eng, orc = Engine(w), OracleWorld(w)
+    rng = np.random.default_rng(5)
+    T = synth.make_T(None, (0.3, -0.2, 0.1))
+    for g in (0, w.robot.link_geom[2], len(w.geoms) - 1):
+        lo, hi = orc.geom_aabb(g, T)
+        c, ext = 0.5 * (lo + hi), np.linalg.norm(hi - lo)
+        N = 3000
+        src = c + rng.normal(size=(N, 3)) * ext
+        tgt = rng.uniform(lo, hi, (N, 3))
+        rays = np.hstack([src, tgt - src])
+        elem, dist = eng.geom_raycast_batch(g, T, rays)
+        nhit = 0
+        for i in range(0, N, 7):
+            h, d, el = orc.geom_raycast(g, T, rays[i, :3], rays[i, 3:], brute=True)
+            assert h == (elem[i] >= 0)
+            if h:
+                nhit += 1
+                assert abs(d - dist[i]) <= 1e-9 * max(1.0, d)
+        assert nhit > 20

@@ -641,3 +641,76 @@ def test_fast_baseline_variant_agrees_with_the_checker():
         da, _ = o.distance_batch(Q[:200], upper_bound=0.5)
         db, _ = f.distance_batch(Q[:200], upper_bound=0.5)
         np.testing.assert_allclose(da, db, rtol=1e-9, atol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------ ray casting
+def test_raycast_known_answers(cubes):
+    """Geometry3D::rayCast_ext on the unit cube [0,1]^3 and a sphere: analytic distances, margin taken off a mesh's distance, a moved
+    geometry, rays that miss, start inside or point away; the hierarchy against every-element brute force"""
+    o, ga, gb, gm, gs = cubes
+    hit, d, el = o.geom_raycast(ga, I12, [0.25, 0.5, 3.0], [0, 0, -1])
+    assert hit and d == pytest.approx(2.0, abs=1e-15) and el >= 0
+    hit, d, _ = o.geom_raycast(ga, I12, [0.25, 0.5, 3.0], [0, 0, -7.5])                      # direction of any length: dist is a length
+    assert hit and d == pytest.approx(2.0, abs=1e-15)
+    assert not o.geom_raycast(ga, I12, [0.25, 0.5, 3.0], [0, 0, 1])[0]                       # pointing away
+    assert not o.geom_raycast(ga, I12, [1.5, 0.5, 3.0], [0, 0, -1])[0]                       # passes beside the cube
+    hit, d, _ = o.geom_raycast(ga, I12, [0.5, 0.5, 0.5], [1, 0, 0])                          # from inside: the far face (surface mesh, two-sided)
+    assert hit and d == pytest.approx(0.5, abs=1e-15)
+    hit, d, _ = o.geom_raycast(gm, I12, [0.25, 0.5, 3.0], [0, 0, -1])                        # margin 0.1 comes off the distance
+    assert hit and d == pytest.approx(1.9, abs=1e-15)
+    hit, d, _ = o.geom_raycast(ga, T_at(0.0, 0.0, -2.0), [0.25, 0.5, 3.0], [0, 0, -1])       # cube moved down by 2
+    assert hit and d == pytest.approx(4.0, abs=1e-15)
+    s = 1 / math.sqrt(3)
+    hit, d, _ = o.geom_raycast(gs, I12, [2.0, 2.0, 2.0], [-s, -s, -s])                       # sphere of radius 0.25 at the origin
+    assert hit and d == pytest.approx(2 * math.sqrt(3) - 0.25, abs=1e-14)
+    assert not o.geom_raycast(gs, I12, [2.0, 2.0, 2.0], [-1, 0, 0])[0]
+    hit, d, _ = o.geom_raycast(gs, I12, [0.1, 0.0, 0.0], [1, 0, 0])                          # source inside the sphere
+    assert hit and d == 0.0
+    assert not o.geom_raycast(ga, I12, [0.25, 0.5, 3.0], [0, 0, 0])[0]                       # no direction
+    rng = np.random.default_rng(2)
+    w = synth.world_c1()
+    ow = OracleWorld(w)
+    for g in range(min(4, len(w.geoms))):
+        lo, hi = ow.geom_aabb(g, I12)
+        for _ in range(200):
+            src = 0.5 * (lo + hi) + rng.normal(size=3) * np.linalg.norm(hi - lo)
+            dirn = rng.uniform(lo, hi) - src
+            a, b = ow.geom_raycast(g, I12, src, dirn), ow.geom_raycast(g, I12, src, dirn, brute=True)
+            assert a[0] == b[0] and (not a[0] or (abs(a[1] - b[1]) < 1e-12 and a[2] == b[2]))
+
+
+def test_world_raycast_order_ignore_and_robot():
+    """WorldModel::RayCast (World.cpp:465-516): nearest body wins, ids follow the world numbering; RayCastIgnore skips ids; the robot is
+    cast at the given configuration"""
+    w = WorldSpec()
+    v, t = synth.unit_cube()
+    g = w.add_geom(GeomSpec.mesh(v, t))
+    w.terrains.append(g)                                             # id 0: cube at [0,1]^3
+    w.objects.append((g, T_at(3.0)))                                 # id 1: cube at x in [3,4]
+    w.objects.append((g, T_at(6.0)))                                 # id 2: cube at x in [6,7]
+    w.robot = synth.make_planar_nR(w, 2)
+    o = OracleWorld(w)
+    rays = np.array([[10.0, 0.5, 0.5, -1, 0, 0], [-5.0, 0.5, 0.5, 1, 0, 0], [4.5, 0.5, 0.5, 1, 0, 0], [4.5, 0.5, 5.0, 0, 0, 1]])
+    ids, dist, _ = o.raycast_batch(None, rays)
+    assert list(ids) == [2, 0, 2, -1]
+    np.testing.assert_allclose(dist[:3], [3.0, 5.0, 1.5], atol=1e-14)
+    assert np.isinf(dist[3])
+    ig = np.zeros(o.num_ids(), dtype=np.uint8)
+    ig[2] = 1
+    ids, dist, _ = o.raycast_batch(None, rays, ig)
+    assert list(ids) == [1, 0, -1, -1] and dist[0] == pytest.approx(6.0, abs=1e-14)
+    q = np.zeros(w.robot.L)
+    ids_r, dist_r, _ = o.raycast_batch(q, rays)
+    T = o.fk(q)
+    for j in range(w.robot.L):                                       # every link geometry is hit by a ray aimed at its box centre from above
+        gj = w.robot.link_geom[j]
+        if gj < 0:
+            continue
+        lo, hi = o.geom_aabb(gj, T[j])
+        c = 0.5 * (lo + hi)
+        i1, d1, _ = o.raycast_batch(q, [[c[0], c[1], hi[2] + 1.0, 0, 0, -1]])
+        if i1[0] == w.robot_link_id(j):
+            assert d1[0] <= 1.0 + (hi[2] - lo[2]) + 1e-12
+            break
+    else:
+        pytest.fail("no link was hit")
