@@ -8,7 +8,7 @@ object-link; links of different robots; self pairs from ``selfCollisionEnabled``
 """
 from __future__ import annotations
 
-from typing import Iterator, List, Tuple
+from typing import Iterator, List, Optional, Tuple
 
 import numpy as np
 
@@ -99,6 +99,20 @@ def group_subset_collision_iter(geomlist, alist, blist, pairs="all") -> Iterator
     for i, j in cand:
         if geomlist[i].collides(geomlist[j]):
             yield (i, j)
+
+
+def ray_cast(geomlist, s, d):
+    """first hit of the ray (s, d) with a list of geometries: (index, point) or None (reference collide.py:219-243: the nearest by
+    dot(d, pt - s), a strict '<' so that a tie keeps the earlier geometry)"""
+    res = None
+    dmin = 1e300
+    for i, g in enumerate(geomlist):
+        (coll, pt) = g.rayCast(s, d)
+        if coll:
+            dist = float(np.dot(d, np.subtract(pt, s)))
+            if dist < dmin:
+                dmin, res = dist, (i, pt)
+    return res
 
 
 class WorldCollider:
@@ -310,3 +324,61 @@ class WorldCollider:
             b = self.rigidObjects[o2]
             if a >= 0 and b >= 0 and a in self.mask[b] and self._colliding(a, b):
                 yield self.geomList[a][0], self.geomList[b][0]
+
+    # ------------------------------------------------------------------ ray casts (reference collide.py:700-748)
+    def _ray_engine(self):
+        """one engine over the whole world (worlds with exactly one robot), rebuilt when the world, a geometry or an object's transform
+        changes; None otherwise (callers fall back to one launch per geometry)"""
+        w = self.world
+        if w.numRobots() != 1:
+            return None
+        key = (w._version, tuple((g._version, g._T12().tobytes()) for (o, g) in self.geomList if not isinstance(o, RobotModelLink)),
+               tuple(g._version for (o, g) in self.geomList if isinstance(o, RobotModelLink)))
+        if getattr(self, "_ray_key", None) != key:
+            from .engine import Engine
+            self._ray_eng, self._ray_key = Engine(w.to_spec()), key
+        return self._ray_eng
+
+    def rayCastBatch(self, rays, indices: Optional[List[int]] = None):
+        """N rays (rows of source xyz, direction xyz) against the geometries of geomList (all, or those at `indices`) in one launch:
+        (geomList index of the nearest hit or -1, distance along the normalised direction or inf, hit points (N, 3))"""
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)
+        N = len(rays)
+        unit = rays[:, 3:] / np.linalg.norm(rays[:, 3:], axis=1, keepdims=True)
+        eng = self._ray_engine()
+        if eng is not None:
+            nids = eng.num_ids()
+            ignore = None
+            if indices is not None:
+                ignore = np.ones(nids, dtype=np.uint8)
+                ignore[[self._ids[i] for i in indices if i >= 0]] = 0
+            ids, dist, _ = eng.raycast_batch(self.world.robot(0).getConfig(), rays, ignore)
+            back = np.full(nids + 1, -1, dtype=np.int64)
+            back[np.asarray(self._ids, dtype=np.int64)] = np.arange(len(self._ids))
+            which = back[ids]                      # id -1 reads the spare last slot
+        else:
+            which, dist = np.full(N, -1, dtype=np.int64), np.full(N, np.inf)
+            for i in (range(len(self.geomList)) if indices is None else indices):
+                if i < 0:
+                    continue
+                el, di = self.geomList[i][1].rayCastBatch(rays)
+                better = (el >= 0) & (di < dist)
+                which[better], dist[better] = i, di[better]
+        pts = rays[:, :3] + np.where(np.isfinite(dist), dist, 0.0)[:, None] * unit
+        return which, dist, pts
+
+    def rayCast(self, s, d, indices: Optional[List[int]] = None):
+        """first hit of the ray with the world's geometries (or those at `indices`): (object, point) or None"""
+        which, dist, pts = self.rayCastBatch(np.concatenate([np.asarray(s, dtype=np.float64), np.asarray(d, dtype=np.float64)])[None, :], indices)
+        if which[0] < 0:
+            return None
+        return self.geomList[int(which[0])][0], list(pts[0])
+
+    def rayCastRobot(self, robot, s, d):
+        """first hit of the ray with the links of one robot: (link, point) or None"""
+        if isinstance(robot, RobotModel):
+            found = [r for r in range(self.world.numRobots()) if self.world.robot(r) is robot]
+            if not found:
+                raise RuntimeError("Robot " + robot.getName() + " is not found in the world!")
+            robot = found[0]
+        return self.rayCast(s, d, [i for i in self.robots[robot] if i >= 0])

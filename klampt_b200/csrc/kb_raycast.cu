@@ -5,8 +5,8 @@
 // measurement (:113-134), and Python's WorldCollider.rayCast / collide.ray_cast loop over Geometry3D.rayCast
 // (Python/klampt/model/collide.py:225-243,700-748; Python/klampt/src/geometry.cpp:1821-1852).  Semantics kept: the closest hit over
 // the robot's links at one configuration, the rigid objects and the terrains; a tie keeps the body the reference visits first
-// (links in order, then objects, then terrains); a triangle mesh reports its nearest two-sided ray / triangle intersection minus
-// its collision margin; a point cloud is the union of spheres of radius (point radius + margin).
+// (links in order, then objects, then terrains); a triangle mesh reports its nearest two-sided ray / triangle intersection
+// (watertight: no ray slips between two triangles that share an edge) minus its collision margin; a point cloud is the union of spheres of radius (point radius + margin).
 //
 // One thread per ray (neighbouring pixels of an image share most of their path, so a warp's node loads fall into the same lines).
 // Bodies are the per-geometry local-frame hierarchies every registered geometry already has; static bodies sit under a small
@@ -44,20 +44,38 @@ __device__ __forceinline__ bool slab(const float4& n0, const float4& n1, const R
   return (t0 - 2e-6f * fabsf(t0) <= t1 + 2e-6f * fabsf(t1)) && (t1 >= 0.f) && (t0 - 2e-6f * fabsf(t0) <= tlim);
 }
 
-// two-sided ray / triangle intersection in fp64 (the oracle's statement, same operation order)
-__device__ __forceinline__ bool ray_tri(const double* s, const double* d, const double* __restrict__ T, double& t) {
-  const double e1x = T[3] - T[0], e1y = T[4] - T[1], e1z = T[5] - T[2];
-  const double e2x = T[6] - T[0], e2y = T[7] - T[1], e2z = T[8] - T[2];
-  const double px = d[1] * e2z - d[2] * e2y, py = d[2] * e2x - d[0] * e2z, pz = d[0] * e2y - d[1] * e2x;
-  const double det = e1x * px + e1y * py + e1z * pz;
+// Two-sided, watertight ray / triangle intersection in fp64 -- the oracle's statement operation by operation (no contraction: every
+// product and sum is rounded on its own, so a static body answers bit for bit like the strict CPU build).  The triangle is sheared
+// into the ray's frame and tested with three 2-D edge functions whose sign is exact (difference of two products evaluated with
+// its rounding error) and antisymmetric in the edge's vertices: a ray through an edge or vertex shared by two triangles hits at
+// least one of them (Woop, Benthin, Wald 2013).
+struct RayShear { int kx, ky, kz; double Sx, Sy, Sz; };
+__device__ __forceinline__ void ray_shear(const double* d, RayShear& r) {
+  int kz = 0; if (fabs(d[1]) > fabs(d[kz])) kz = 1; if (fabs(d[2]) > fabs(d[kz])) kz = 2;
+  int kx = kz == 2 ? 0 : kz + 1, ky = kx == 2 ? 0 : kx + 1;
+  const double dz = kz == 0 ? d[0] : (kz == 1 ? d[1] : d[2]);
+  if (dz < 0.0) { const int t = kx; kx = ky; ky = t; }
+  const double dx = kx == 0 ? d[0] : (kx == 1 ? d[1] : d[2]), dy = ky == 0 ? d[0] : (ky == 1 ? d[1] : d[2]);
+  r.kx = kx; r.ky = ky; r.kz = kz; r.Sx = __ddiv_rn(dx, dz); r.Sy = __ddiv_rn(dy, dz); r.Sz = __ddiv_rn(1.0, dz);
+}
+__device__ __forceinline__ double pick(const double* __restrict__ v, int k) { return k == 0 ? v[0] : (k == 1 ? v[1] : v[2]); }
+__device__ __forceinline__ double diff_of_products(double a, double b, double c, double d) {
+  const double p1 = __dmul_rn(a, b), e1 = __fma_rn(a, b, -p1), p2 = __dmul_rn(c, d), e2 = __fma_rn(c, d, -p2);
+  return __dadd_rn(__dsub_rn(p1, p2), __dsub_rn(e1, e2));
+}
+__device__ __forceinline__ bool ray_tri(const double* s, const RayShear& r, const double* __restrict__ T, double& t) {
+  const double sx = pick(s, r.kx), sy = pick(s, r.ky), sz = pick(s, r.kz);
+  const double Az = __dsub_rn(pick(T, r.kz), sz), Bz = __dsub_rn(pick(T + 3, r.kz), sz), Cz = __dsub_rn(pick(T + 6, r.kz), sz);
+  const double Ax = __dsub_rn(__dsub_rn(pick(T, r.kx), sx), __dmul_rn(r.Sx, Az)), Ay = __dsub_rn(__dsub_rn(pick(T, r.ky), sy), __dmul_rn(r.Sy, Az));
+  const double Bx = __dsub_rn(__dsub_rn(pick(T + 3, r.kx), sx), __dmul_rn(r.Sx, Bz)), By = __dsub_rn(__dsub_rn(pick(T + 3, r.ky), sy), __dmul_rn(r.Sy, Bz));
+  const double Cx = __dsub_rn(__dsub_rn(pick(T + 6, r.kx), sx), __dmul_rn(r.Sx, Cz)), Cy = __dsub_rn(__dsub_rn(pick(T + 6, r.ky), sy), __dmul_rn(r.Sy, Cz));
+  const double U = diff_of_products(Cx, By, Cy, Bx), V = diff_of_products(Ax, Cy, Ay, Cx), W = diff_of_products(Bx, Ay, By, Ax);
+  if ((U < 0.0 || V < 0.0 || W < 0.0) && (U > 0.0 || V > 0.0 || W > 0.0)) return false;
+  const double det = __dadd_rn(__dadd_rn(U, V), W);
   if (!(det != 0.0)) return false;
-  const double tx = s[0] - T[0], ty = s[1] - T[1], tz = s[2] - T[2];
-  const double u = (tx * px + ty * py + tz * pz) / det;
-  if (!(u >= 0.0 && u <= 1.0)) return false;
-  const double qx = ty * e1z - tz * e1y, qy = tz * e1x - tx * e1z, qz = tx * e1y - ty * e1x;
-  const double v = (d[0] * qx + d[1] * qy + d[2] * qz) / det;
-  if (!(v >= 0.0 && u + v <= 1.0)) return false;
-  const double tt = (e2x * qx + e2y * qy + e2z * qz) / det;
+  const double Tn = __dadd_rn(__dadd_rn(__dmul_rn(U, __dmul_rn(r.Sz, Az)), __dmul_rn(V, __dmul_rn(r.Sz, Bz))), __dmul_rn(W, __dmul_rn(r.Sz, Cz)));
+  if ((det < 0.0 && Tn > 0.0) || (det > 0.0 && Tn < 0.0)) return false;
+  const double tt = __ddiv_rn(Tn, det);
   if (!(tt >= 0.0)) return false;
   t = tt; return true;
 }
@@ -80,11 +98,16 @@ struct Best { double d; int rank, id, elem; };
 __device__ void cast_body(const KbScene& sc, const KbRayBody& B, const double* __restrict__ T, const double* s, const double* d, Best& best) {
   double sl[3], dl[3];
   if (T) {
-    const double mx = s[0] - T[9], my = s[1] - T[10], mz = s[2] - T[11];
-    sl[0] = T[0] * mx + T[3] * my + T[6] * mz; sl[1] = T[1] * mx + T[4] * my + T[7] * mz; sl[2] = T[2] * mx + T[5] * my + T[8] * mz;
-    dl[0] = T[0] * d[0] + T[3] * d[1] + T[6] * d[2]; dl[1] = T[1] * d[0] + T[4] * d[1] + T[7] * d[2]; dl[2] = T[2] * d[0] + T[5] * d[1] + T[8] * d[2];
+    // R^T (s - t) and R^T d, every product and sum rounded on its own (the oracle's order: bit-identical local rays)
+    const double mx = __dsub_rn(s[0], T[9]), my = __dsub_rn(s[1], T[10]), mz = __dsub_rn(s[2], T[11]);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      sl[k] = __dadd_rn(__dadd_rn(__dmul_rn(T[k], mx), __dmul_rn(T[3 + k], my)), __dmul_rn(T[6 + k], mz));
+      dl[k] = __dadd_rn(__dadd_rn(__dmul_rn(T[k], d[0]), __dmul_rn(T[3 + k], d[1])), __dmul_rn(T[6 + k], d[2]));
+    }
   } else { sl[0] = s[0]; sl[1] = s[1]; sl[2] = s[2]; dl[0] = d[0]; dl[1] = d[1]; dl[2] = d[2]; }
   const bool mesh = B.kind == KB_ELEM_TRI;
+  RayShear sh; ray_shear(dl, sh);
   const double shift = mesh ? B.margin : 0.0;                 // a mesh reports t - margin; a cloud's margin is part of its spheres
   double tbest = best.d + shift;                              // raw parameter this body has to beat (ties resolved by rank below)
   if (!(tbest >= 0.0)) return;
@@ -112,7 +135,7 @@ __device__ void cast_body(const KbScene& sc, const KbRayBody& B, const double* _
       for (int i = 0; i < cnt; i++) {
         const int e = B.elem_base + first + i;
         double t; bool h;
-        if (mesh) h = ray_tri(sl, dl, sc.tris64 + 9 * (size_t)e, t);
+        if (mesh) h = ray_tri(sl, sh, sc.tris64 + 9 * (size_t)e, t);
         else h = ray_sphere(sl, dl, sc.sph64 + 4 * (size_t)e, sc.sph64[4 * (size_t)e + 3] + B.margin, t);
         if (h) {
           const int orig = mesh ? sc.triorig[e] : sc.sphorig[e];
@@ -156,11 +179,11 @@ kb_raycast_kernel(const KbRayParams p) {
   const double* __restrict__ ray = p.rays + 6 * i;
   double s[3] = {ray[0], ray[1], ray[2]}, d[3] = {ray[3], ray[4], ray[5]};
   Best best; best.d = INFINITY; best.rank = 0x7fffffff; best.id = -1; best.elem = -1;
-  const double n2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+  const double n2 = __dadd_rn(__dadd_rn(__dmul_rn(d[0], d[0]), __dmul_rn(d[1], d[1])), __dmul_rn(d[2], d[2]));
   const bool ok = n2 > 0.0 && isfinite(n2) && isfinite(s[0]) && isfinite(s[1]) && isfinite(s[2]);
   if (ok) {
-    const double n = sqrt(n2);
-    d[0] /= n; d[1] /= n; d[2] /= n;
+    const double n = __dsqrt_rn(n2);
+    d[0] = __ddiv_rn(d[0], n); d[1] = __ddiv_rn(d[1], n); d[2] = __ddiv_rn(d[2], n);
     // ---- the robot's links in the frames of this call's configuration
     for (int b = 0; b < p.nlinkbodies; b++) {
       const KbRayBody& B = p.bodies[b];

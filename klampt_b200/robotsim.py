@@ -302,6 +302,30 @@ class Geometry3D:
         return DistanceQueryResult(float(d[0]), cp[0, 0], cp[0, 1], el[0, 0], el[0, 1])
 
 
+    # ---- ray casts (GPU; reference Python/klampt/src/geometry.h:1106-1140, src/geometry.cpp:1821-1852)
+    def rayCastBatch(self, rays):
+        """rayCast_ext for N rays (rows of source xyz, direction xyz) in one launch: (element index or -1, distance along the
+        normalised direction or inf).  The hit point is source + distance * direction / |direction|."""
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)
+        if self.empty():
+            return np.full(len(rays), -1, dtype=np.int32), np.full(len(rays), np.inf)
+        eng, ga, _ = self._pair_engine(_POINT_PROBE)
+        return eng.geom_raycast_batch(ga, self._T12(), rays)
+
+    def rayCast_ext(self, s, d):
+        """(hit_element, pt): the element hit (-1: none) and the hit point in world coordinates"""
+        s, d = np.asarray(s, dtype=np.float64), np.asarray(d, dtype=np.float64)
+        el, dist = self.rayCastBatch(np.concatenate([s, d])[None, :])
+        if el[0] < 0:
+            return -1, [0.0, 0.0, 0.0]
+        return int(el[0]), list(s + dist[0] * d / np.linalg.norm(d))
+
+    def rayCast(self, s, d):
+        """(hit, pt): whether the ray from s along d hits the geometry, and where (world coordinates)"""
+        el, pt = self.rayCast_ext(s, d)
+        return el >= 0, pt
+
+
 def _prim_from_spec(g: GeomSpec) -> GeometricPrimitive:
     if g.kind == "box":
         c, M, h = g.params[:3], g.params[3:12].reshape(3, 3), g.params[12:15]

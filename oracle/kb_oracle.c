@@ -981,18 +981,45 @@ double ko_geom_penetration(const ko_world* w, int ga, const double Ta[12], int g
  * AnyCollisionGeometry3D::RayCast(ray, &dist) and the world point is source + dist * direction.  Geometry3D::rayCast / rayCast_ext
  * (Python/klampt/src/geometry.cpp:1821-1852) is the one-geometry form.  The per-geometry arithmetic lives in KrisLibrary (absent:
  * parity unpinned); restated here from its published behaviour: a triangle mesh reports the nearest two-sided ray / triangle
- * intersection and takes its collision margin off the distance; a point cloud is the union of spheres of radius (point radius +
+ * intersection (watertight form, see ray_tri) and takes its collision margin off the distance; a point cloud is the union of spheres of radius (point radius +
  * margin) and reports where the ray enters the first one (nothing when that radius is 0).  The direction is normalised on entry, so
  * dist is a length. */
-static int ray_tri(const double* s, const double* d, const double* a, const double* b, const double* c, double* t) {
-  double e1[3],e2[3],p[3],tv[3],qv[3]; v_sub(b,a,e1); v_sub(c,a,e2); v_cross(d,e2,p);
-  double det=v_dot(e1,p); if (!(det!=0)) return 0;            /* parallel to the plane, or no plane (segment triangles) */
-  v_sub(s,a,tv); double u=v_dot(tv,p)/det; if (!(u>=0 && u<=1)) return 0;
-  v_cross(tv,e1,qv); double v=v_dot(d,qv)/det; if (!(v>=0 && u+v<=1)) return 0;
-  double tt=v_dot(e2,qv)/det; if (!(tt>=0)) return 0;
+static __thread ko_counts* ray_cnt = NULL;      /* set by ko_raycast_counts: box / triangle / sphere tests of the calling thread */
+/* Ray vs triangle, two-sided, watertight: the triangle is sheared into the ray's frame (largest direction component along z) and
+ * tested with three 2-D edge functions whose sign is exact -- each a difference of two products evaluated with its rounding error
+ * (fma) -- and antisymmetric in the edge's two vertices, so a ray through an edge or a vertex shared by two triangles always hits
+ * at least one of them and never slips between (Woop, Benthin, Wald 2013).  KrisLibrary's own test (absent) is the plain plane /
+ * barycentric form; results differ only for rays that pass exactly through an edge.  t = distance along d. */
+typedef struct { int kx, ky, kz; double Sx, Sy, Sz; } rayshear_t;
+static void ray_shear(const double* d, rayshear_t* r) {
+  int kz=0; if (fabs(d[1])>fabs(d[kz])) kz=1; if (fabs(d[2])>fabs(d[kz])) kz=2;
+  int kx=(kz+1)%3, ky=(kx+1)%3;
+  if (d[kz]<0) { int t=kx; kx=ky; ky=t; }
+  r->kx=kx; r->ky=ky; r->kz=kz; r->Sx=d[kx]/d[kz]; r->Sy=d[ky]/d[kz]; r->Sz=1.0/d[kz];
+}
+static inline double diff_of_products(double a, double b, double c, double d) {   /* a*b - c*d with an exact sign */
+  double p1=a*b, e1=fma(a,b,-p1), p2=c*d, e2=fma(c,d,-p2);
+  return (p1-p2)+(e1-e2);
+}
+static int ray_tri(const double* s, const rayshear_t* r, const double* a, const double* b, const double* c, double* t) {
+  if (ray_cnt) ray_cnt->n_tri++;
+  const int kx=r->kx, ky=r->ky, kz=r->kz;
+  const double Az=a[kz]-s[kz], Bz=b[kz]-s[kz], Cz=c[kz]-s[kz];
+  const double Ax=(a[kx]-s[kx])-r->Sx*Az, Ay=(a[ky]-s[ky])-r->Sy*Az;
+  const double Bx=(b[kx]-s[kx])-r->Sx*Bz, By=(b[ky]-s[ky])-r->Sy*Bz;
+  const double Cx=(c[kx]-s[kx])-r->Sx*Cz, Cy=(c[ky]-s[ky])-r->Sy*Cz;
+  const double U=diff_of_products(Cx,By,Cy,Bx), V=diff_of_products(Ax,Cy,Ay,Cx), W=diff_of_products(Bx,Ay,By,Ax);
+  if ((U<0||V<0||W<0) && (U>0||V>0||W>0)) return 0;
+  const double det=U+V+W;
+  if (!(det!=0)) return 0;                                   /* edge-on, or no area (segment triangles) */
+  const double T=(U*(r->Sz*Az)+V*(r->Sz*Bz))+W*(r->Sz*Cz);
+  if ((det<0 && T>0) || (det>0 && T<0)) return 0;            /* behind the source */
+  const double tt=T/det;
+  if (!(tt>=0)) return 0;
   *t=tt; return 1;
 }
 static int ray_sphere(const double* s, const double* d, const double* c, double r, double* t) {   /* |d| = 1 */
+  if (ray_cnt) ray_cnt->n_pt++;
   if (!(r>0)) return 0;
   double m[3]; v_sub(s,c,m); double b=v_dot(m,d), cc=v_dot(m,m)-r*r;
   if (cc<=0) { *t=0; return 1; }                              /* the source is inside */
@@ -1002,6 +1029,7 @@ static int ray_sphere(const double* s, const double* d, const double* c, double 
 }
 static int ray_box(const double* s, const double* d, const double* lo, const double* hi, double pad, double tmax, double* tnear) {
   double t0=0, t1=tmax;
+  if (ray_cnt) ray_cnt->n_node++;
   for (int k=0;k<3;k++) {
     if (d[k]==0) { if (s[k]<lo[k]-pad || s[k]>hi[k]+pad) return 0; continue; }
     double a=(lo[k]-pad-s[k])/d[k], b=(hi[k]+pad-s[k])/d[k];
@@ -1014,10 +1042,11 @@ static int ray_box(const double* s, const double* d, const double* lo, const dou
 /* nearest hit of the local-frame ray with geometry g: t (before the margin is taken off) and the element in the caller's order */
 static int geom_ray_local(const geom_t* g, const double* s, const double* d, double tmax, double* tbest, int* elem, int brute) {
   int hit=0; *tbest=tmax;
+  rayshear_t sh; ray_shear(d,&sh);
   if (g->kind==G_EMPTY || g->nnodes<=0) return 0;
   if (brute) {
     int n=(g->kind==G_MESH)?g->nt:g->np;
-    for (int i=0;i<n;i++) { double t; int h=(g->kind==G_MESH) ? ray_tri(s,d,g->tv+9*(size_t)i,g->tv+9*(size_t)i+3,g->tv+9*(size_t)i+6,&t)
+    for (int i=0;i<n;i++) { double t; int h=(g->kind==G_MESH) ? ray_tri(s,&sh,g->tv+9*(size_t)i,g->tv+9*(size_t)i+3,g->tv+9*(size_t)i+6,&t)
                                                               : ray_sphere(s,d,g->pts+3*(size_t)i,g->rad[i]+g->margin,&t);
       if (h && (!hit || t<*tbest || (t==*tbest && g->perm[i]<*elem))) { *tbest=t; *elem=g->perm[i]; hit=1; } }
     return hit;
@@ -1028,7 +1057,7 @@ static int geom_ray_local(const geom_t* g, const double* s, const double* d, dou
     int i=stack[--sp]; const node_t* n=&g->nodes[i]; double tn;
     if (!ray_box(s,d,n->lo,n->hi,pad+1e-12,*tbest,&tn)) continue;
     if (n->left<0) {
-      for (int e=n->first;e<n->first+n->count;e++) { double t; int h=(g->kind==G_MESH) ? ray_tri(s,d,g->tv+9*(size_t)e,g->tv+9*(size_t)e+3,g->tv+9*(size_t)e+6,&t)
+      for (int e=n->first;e<n->first+n->count;e++) { double t; int h=(g->kind==G_MESH) ? ray_tri(s,&sh,g->tv+9*(size_t)e,g->tv+9*(size_t)e+3,g->tv+9*(size_t)e+6,&t)
                                                                                     : ray_sphere(s,d,g->pts+3*(size_t)e,g->rad[e]+g->margin,&t);
         if (h && (!hit || t<*tbest || (t==*tbest && g->perm[e]<*elem))) { *tbest=t; *elem=g->perm[e]; hit=1; } }
     } else if (sp+2<=128) { stack[sp++]=n->left; stack[sp++]=n->right; }
@@ -1066,6 +1095,12 @@ int ko_raycast(const ko_world* w, const double* q, const double s[3], const doub
       double dd; int el; if (geom_raycast(&w->geoms[g],&I,s,u,&dd,&el,0) && dd<bd) { bd=dd; best=i; bel=el; } }
   }
   *dist=bd; if (elem) *elem=bel; return best;
+}
+/* traversal counts of the per-body loop above, summed over N rays (single thread): n_node = box tests, n_tri / n_pt = element tests */
+void ko_raycast_counts(const ko_world* w, const double* q, const double* rays, int64_t N, ko_counts* total) {
+  memset(total,0,sizeof(*total)); ray_cnt=total;
+  for (int64_t i=0;i<N;i++) { double dd; int32_t el; ko_raycast(w,q,rays+6*i,rays+6*i+3,NULL,&dd,&el); }
+  ray_cnt=NULL;
 }
 void ko_raycast_batch(const ko_world* w, const double* q, const double* rays, int64_t N, const uint8_t* ignore_ids, int32_t* ids, double* dist, int32_t* elem, int nthreads) {
   if (nthreads<=0) nthreads=ko_max_threads();

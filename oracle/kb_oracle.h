@@ -120,6 +120,7 @@ double ko_seg_seg_distance(const double p0[3], const double p1[3], const double 
 int ko_raycast(const ko_world* w, const double* q, const double s[3], const double d[3], const uint8_t* ignore_ids, double* dist, int32_t* elem);
 void ko_raycast_batch(const ko_world* w, const double* q, const double* rays, int64_t N, const uint8_t* ignore_ids,
                       int32_t* ids, double* dist, int32_t* elem, int nthreads);
+void ko_raycast_counts(const ko_world* w, const double* q, const double* rays, int64_t N, ko_counts* total);
 int ko_geom_raycast(const ko_world* w, int g, const double T[12], const double s[3], const double d[3], double* dist, int32_t* elem, int brute);
 
 int ko_max_threads(void);

@@ -96,6 +96,7 @@ def lib(variant: str = "strict"):
     L.ko_raycast.argtypes = [vp, dp, dp, dp, u8p, dp, ip]
     L.ko_raycast_batch.argtypes = [vp, dp, dp, C.c_int64, u8p, ip, dp, ip, C.c_int]
     L.ko_geom_raycast.argtypes = [vp, C.c_int, dp, dp, dp, dp, ip, C.c_int]
+    L.ko_raycast_counts.argtypes = [vp, dp, dp, C.c_int64, C.POINTER(Counts)]
     _LIBS[variant] = L
     return L
 
@@ -370,6 +371,14 @@ class OracleWorld:
         self.L.ko_raycast_batch(self.h, qp, rays.ctypes.data_as(C.POINTER(C.c_double)), N, igp, ids.ctypes.data_as(C.POINTER(C.c_int32)),
                                 dist.ctypes.data_as(C.POINTER(C.c_double)), elem.ctypes.data_as(C.POINTER(C.c_int32)), int(nthreads))
         return ids, dist, elem
+
+    def raycast_counts(self, q, rays):
+        """box / triangle / sphere tests of the per-body ray loop, averaged per ray (roofline of bench.py's ray workload)"""
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)
+        q_, qp = (None, None) if q is None else _d(q)
+        c = Counts()
+        self.L.ko_raycast_counts(self.h, qp, rays.ctypes.data_as(C.POINTER(C.c_double)), len(rays), C.byref(c))
+        return {k: getattr(c, k) / max(1, len(rays)) for k in ("n_box", "n_node", "n_tri", "n_pt")}
 
     def geom_raycast(self, g, T, s, d, brute=False):
         """Geometry3D::rayCast_ext (Python/klampt/src/geometry.cpp:1837-1852): (hit, distance, element)"""

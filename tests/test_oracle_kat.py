@@ -714,3 +714,20 @@ def test_world_raycast_order_ignore_and_robot():
             break
     else:
         pytest.fail("no link was hit")
+
+
+def test_raycast_is_watertight_on_shared_edges_and_vertices(cubes):
+    """rays aimed exactly at vertices, edge points and face diagonals of the unit cube (each face is two triangles) never slip between
+    the triangles: the edge functions of the watertight test are exact in sign and antisymmetric in an edge's two vertices"""
+    o, ga, gb, gm, gs = cubes
+    targets = [(x, y) for x in (0.0, 0.25, 0.5, 1.0) for y in (0.0, 0.25, 0.5, 1.0)] + [(t, t) for t in np.linspace(0, 1, 23)] + [(t, 1 - t) for t in np.linspace(0, 1, 23)]
+    rng = np.random.default_rng(4)
+    for (x, y) in targets:
+        hit, d, _ = o.geom_raycast(ga, I12, [x, y, 3.0], [0, 0, -1])                     # straight down onto the top face z = 1
+        assert hit and d == pytest.approx(2.0, abs=1e-15), (x, y)
+        if not (0.0 < x < 1.0 and 0.0 < y < 1.0):
+            continue                                                                   # the cube's own edges are silhouettes: grazing them may miss
+        for _ in range(4):                                                             # from a random source through the same point of the face diagonal
+            src = np.array([x, y, 1.0]) + rng.uniform([-2, -2, 0.5], [2, 2, 3.0])
+            hit, d, _ = o.geom_raycast(ga, I12, src, np.array([x, y, 1.0]) - src)
+            assert hit and d <= np.linalg.norm(np.array([x, y, 1.0]) - src) + 1e-12, (x, y)

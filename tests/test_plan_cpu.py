@@ -143,3 +143,32 @@ def test_prm_star_neighbourhood_grows_and_cost_converges():
     n = st["milestones"]
     assert st["edges_checked"] > n * 4                      # k ~ e (1 + 1/2) log n > 10 neighbours were proposed per vertex
     plan.close()
+
+
+def test_sensor_ray_construction_follows_the_reference():
+    """CameraSensor::GetViewport / the ray-cast fallback (VisualSensors.cpp:424-449,865-897) and LaserRangeSensor's sweep (:57-126):
+    rays only, no GPU"""
+    import math
+    from klampt_b200 import sensing
+    cam = sensing.CameraSensor(xres=64, yres=48, xfov=math.radians(90), yfov=math.radians(60), zmin=0.5, zmax=4.0)
+    fx, fy, cx, cy = cam.viewport()
+    assert fx == pytest.approx(32.0) and fy == pytest.approx(24.0 / math.tan(math.radians(30))) and (cx, cy) == (32.0, 24.0)
+    rays, eye, fwd = cam.rays()
+    assert rays.shape == (64 * 48, 6) and np.allclose(eye, 0) and np.allclose(fwd, [0, 0, 1])
+    k = 24 * 64 + 32                                  # pixel (i, j) = (cx, cy) looks straight ahead and starts zmin along it
+    assert np.allclose(rays[k], [0, 0, 0.5, 0, 0, 1])
+    k = 24 * 64 + 63                                  # right edge: +x; image rows grow downwards: row 0 looks up = -y of the camera frame
+    assert rays[k, 3] > 0.69 and abs(rays[k, 4]) < 1e-12
+    assert rays[0, 4] < 0 and rays[47 * 64, 4] > 0
+    assert np.allclose(np.linalg.norm(rays[:, 3:], axis=1), 1.0)
+    d0 = np.array([0, 0, 1.0]) + (0 - cx) * np.array([1.0, 0, 0]) / fx + (cy - 0) * np.array([0, -1.0, 0]) / fy
+    assert np.allclose(rays[0, :3], d0 * 0.5) and np.allclose(rays[0, 3:], d0 / np.linalg.norm(d0))
+    las = sensing.LaserRangeSensor(measurementCount=181, depthMinimum=0.1)
+    r = las.rays()
+    xt, yt = las.angles()
+    assert xt[0] == pytest.approx(-math.pi / 2) and xt[90] == pytest.approx(0.0, abs=1e-12) and np.all(yt == 0)
+    assert xt[-1] == pytest.approx(-math.pi / 2)      # the sawtooth wraps at u = 1 when the sensor has not been advanced (reference behaviour)
+    assert np.allclose(r[90], [0, 0, 0.1, 0, 0, 1])
+    las.advance(0.1)
+    xt2, _ = las.angles()
+    assert xt2[-1] == pytest.approx(math.pi / 2, abs=0.02) and np.all(np.diff(xt2) > 0)
