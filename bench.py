@@ -566,7 +566,7 @@ def main():
         q = synth.sample_configs(spec.robot, 1, 77)[0]
         qc = np.ascontiguousarray(q)
         per_step, W, H = 4, 640, 480
-        host, dev = [], []
+        host, dev, cams = [], [], []
         for k in range(8):
             a = 2.0 * math.pi * (k + 8 * rank) / (8 * world)
             eye = np.array([3.2 * math.cos(a), 3.2 * math.sin(a), 1.3])
@@ -575,6 +575,7 @@ def main():
             right = np.cross(fwd, [0.0, 0.0, 1.0]); right /= np.linalg.norm(right)
             down = np.cross(fwd, right)
             cam = sensing.CameraSensor(W, H, zmin=0.1, zmax=8.0, Tsensor=synth.make_T(np.stack([right, down, fwd], axis=1), eye))
+            cams.append(cam)
             r, _, _ = cam.rays()
             host.append(torch.from_numpy(np.ascontiguousarray(r)).pin_memory())
             dev.append(host[-1].cuda(non_blocking=True))
@@ -592,6 +593,19 @@ def main():
             for j in range(per_step):
                 check(eng.lib.kb_raycast_batch(eng.h, qp, C.c_void_p(host[(k * per_step + j) % 8].data_ptr()), n, None,
                                                C.c_void_p(h_id.data_ptr()), C.c_void_p(h_dist.data_ptr()), None))
+        from klampt_b200._capi import KbCamera
+        kcams = []
+        for cam in cams:
+            kc = KbCamera()
+            kc.pose[:] = list(cam.Tsensor)
+            kc.fx, kc.fy, kc.cx, kc.cy = cam.viewport()
+            kc.zmin, kc.zmax, kc.xres, kc.yres = cam.zmin, cam.zmax, W, H
+            kcams.append(kc)
+        h_depth = torch.empty(n, dtype=torch.float32).pin_memory()
+
+        def step_camera(k):
+            for j in range(per_step):
+                check(eng.lib.kb_camera_depth(eng.h, qp, C.byref(kcams[(k * per_step + j) % 8]), None, C.c_void_p(h_depth.data_ptr()), C.c_void_p(h_id.data_ptr())))
         with torch.cuda.stream(stream):
             for k in range(warm):
                 step_device(k)
@@ -602,12 +616,15 @@ def main():
         units_all = world * per_step * n
         value = units_all * steps / (ms_dev * 1e-3)
         dt = timed_host(step_host, steps, warm)
+        dt_cam = timed_host(step_camera, steps, warm)
         hit_frac = float((h_id >= 0).float().mean())
         res = {"workload": "C6 depth images of the C2 world (arm6 at one configuration + 200 blob obstacles, ~500k triangles): 640 x 480 rays per image "
                            "from a camera circling the scene, nearest hit + world id per ray (WorldModel::RayCast per pixel)",
                "metric": "rays/sec", "value": value, "unit": "rays/s", "ms_per_step": ms_dev / steps, "steps": steps, "warmup": warm,
                "units_per_step_all_gpus": int(units_all), "scaling": "weak",
                "e2e": {"value": units_all * steps / dt, "unit": "rays/s", "h2d_bytes_per_step": per_step * n * 48, "d2h_bytes_per_step": per_step * n * 12},
+               "e2e_camera": {"value": units_all * steps / dt_cam, "unit": "rays/s", "h2d_bytes_per_step": per_step * 176, "d2h_bytes_per_step": per_step * n * 8,
+                              "what": "kb_camera_depth: the rays are built on the device from the camera's pose and intrinsics; float depth + world id per pixel come back"},
                "ones_fraction": hit_frac, "gpu_launches": launches,
                "l2_policy": "8 distinct images (118 MB of rays) rotate; the static data (258 MB) is larger than L2"}
         if rank == 0:

@@ -234,6 +234,20 @@ int kb_raycast_batch(kb_engine* e, const double* q, const double* rays, int64_t 
 /* the same with the rays and the results device-resident on the engine's stream (q and ignore_ids stay host pointers) */
 int kb_raycast_batch_device(kb_engine* e, const double* q, const double* d_rays, int64_t N, const uint8_t* ignore_ids,
                             int32_t* d_out_id, double* d_out_dist, int32_t* d_out_elem);
+/* CameraSensor's ray-cast rendering (Cpp/Sensing/VisualSensors.cpp:413-475) in one call: the rays of an xres x yres pinhole image are
+ * built on the device exactly as the reference builds them per pixel -- pixel (i, j) looks along fwd + (i - cx) right / fx +
+ * (cy - j) up / fy, starts zmin along that vector -- and cast as kb_raycast_batch does.  pose: the camera's world pose, 12 doubles
+ * (row-major R then t), camera frame x right, y down, z forward (Klamp't's sensor convention; for a camera on a link: the link's
+ * transform from kb_fk_batch times the sensor's Tsensor).  out_depth (optional, yres x xres floats, row j = image row j): depth along
+ * the viewing direction, fwd . (pt - eye); readings below zmin and pixels that see nothing report zmax.  out_id (optional): world
+ * id seen by each pixel, -1 = background (the reference colours the pixel by that body's appearance). */
+typedef struct {
+  double pose[12];
+  double fx, fy, cx, cy;          /* CameraSensor::GetViewport (:865-889): fx = xres / 2 / tan(xfov / 2), cx = xres / 2, ... */
+  double zmin, zmax;
+  int32_t xres, yres;
+} kb_camera;
+int kb_camera_depth(kb_engine* e, const double* q, const kb_camera* cam, const uint8_t* ignore_ids, float* out_depth, int32_t* out_id);
 /* Geometry3D::rayCast_ext (Python/klampt/src/geometry.cpp:1837-1852) of one registered geometry at transform T (12 doubles, NULL =
  * identity): out_elem = element hit or -1, out_dist as above */
 int kb_geom_raycast_batch(kb_engine* e, int geom, const double* T, const double* rays, int64_t N, int32_t* out_elem, double* out_dist);

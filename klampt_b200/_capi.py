@@ -26,6 +26,11 @@ class KbStats(C.Structure):
                 ("items_dropped", C.c_int64), ("node_iterations", C.c_int64), ("rays_cast", C.c_int64)]
 
 
+class KbCamera(C.Structure):
+    _fields_ = [("pose", C.c_double * 12), ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("zmin", C.c_double), ("zmax", C.c_double), ("xres", C.c_int32), ("yres", C.c_int32)]
+
+
 # every symbol include/klampt_b200.h declares: name -> (restype, argtypes)
 _VP = C.c_void_p
 SIGNATURES = {
@@ -71,6 +76,7 @@ SIGNATURES = {
     "kb_raycast_batch": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP, _VP, _VP, _VP]),
     "kb_raycast_batch_device": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP, _VP, _VP, _VP]),
     "kb_geom_raycast_batch": (C.c_int, [_VP, C.c_int, _VP, _VP, C.c_int64, _VP, _VP]),
+    "kb_camera_depth": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
     "kb_geom_collides_batch": (C.c_int, [_VP, C.c_int, _VP, C.c_int, _VP, C.c_int64, C.c_double, _VP]),
     "kb_geom_distance_batch": (C.c_int, [_VP, C.c_int, _VP, C.c_int, _VP, C.c_int64, C.c_double, _VP]),
     "kb_get_stats": (C.c_int, [_VP, C.POINTER(KbStats)]),

@@ -2082,9 +2082,10 @@ int kb_geom_distance_batch_ex(kb_engine* e, int ga, const double* Ta, int gb, co
 
 // ---- ray casting --------------------------------------------------------------------------------------------------------------
 static int raycast_run(kb_engine* e, const double* q_host, const double* d_rays, int64_t N, const uint8_t* ignore_host, const KbRayBody* one_body_host,
-                       int32_t* d_id, double* d_dist, int32_t* d_elem) {
+                       int32_t* d_id, double* d_dist, int32_t* d_elem, const KbRayParams* cam = nullptr, float* d_depth = nullptr) {
   KbRayParams p; memset(&p, 0, sizeof p);
-  p.scene = e->scene; p.rays = d_rays; p.N = N; p.out_id = d_id; p.out_dist = d_dist; p.out_elem = d_elem;
+  if (cam) p = *cam;
+  p.scene = e->scene; p.rays = d_rays; p.N = N; p.out_id = d_id; p.out_dist = d_dist; p.out_elem = d_elem; p.out_depth = d_depth;
   if (one_body_host) {          // Geometry3D::rayCast: one geometry at an explicit transform
     if (!e->d_onebody) CK(cudaMalloc((void**)&e->d_onebody, sizeof(KbRayBody)));
     CK(cudaMemcpyAsync(e->d_onebody, one_body_host, sizeof(KbRayBody), cudaMemcpyHostToDevice, e->stream));
@@ -2159,6 +2160,43 @@ int kb_raycast_batch(kb_engine* e, const double* q, const double* rays, int64_t 
   if (q && !all_finite(q, (size_t)e->L)) return fail(KB_ERR_INVALID, "non-finite configuration");
   if (N == 0) return KB_OK;
   return raycast_host(e, q, rays, N, ignore_ids, nullptr, out_id, out_dist, out_elem);
+}
+
+int kb_camera_depth(kb_engine* e, const double* q, const kb_camera* cam, const uint8_t* ignore_ids, float* out_depth, int32_t* out_id) {
+  if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
+  if (!cam || (!out_depth && !out_id)) return fail(KB_ERR_INVALID, "bad arguments");
+  if (cam->xres <= 0 || cam->yres <= 0 || (int64_t)cam->xres * cam->yres > (1ll << 28)) return fail(KB_ERR_INVALID, "image of %d x %d pixels", cam->xres, cam->yres);
+  if (!all_finite(cam->pose, 12) || !(cam->fx > 0) || !(cam->fy > 0) || !std::isfinite(cam->cx) || !std::isfinite(cam->cy) || !(cam->zmin >= 0) || !(cam->zmax >= cam->zmin))
+    return fail(KB_ERR_INVALID, "camera needs a finite pose, fx, fy > 0 and 0 <= zmin <= zmax");
+  if (q && !all_finite(q, (size_t)e->L)) return fail(KB_ERR_INVALID, "non-finite configuration");
+  CK(cudaSetDevice(e->device));
+  const int64_t N = (int64_t)cam->xres * cam->yres;
+  if (N > e->ray_cap) {
+    void* olds[] = {e->d_rays, e->d_rid, e->d_rdist, e->d_relem};
+    for (void* o : olds) if (o) cudaFree(o);
+    e->d_rays = nullptr; e->d_rid = nullptr; e->d_rdist = nullptr; e->d_relem = nullptr; e->ray_cap = 0;
+    CK(cudaMalloc((void**)&e->d_rays, (size_t)N * 48)); CK(cudaMalloc((void**)&e->d_rid, (size_t)N * 4));
+    CK(cudaMalloc((void**)&e->d_rdist, (size_t)N * 8)); CK(cudaMalloc((void**)&e->d_relem, (size_t)N * 4));
+    e->ray_cap = N;
+  }
+  // camera frame: x right, y down, z forward (the sensor convention; CameraSensor::GetViewport flips y and z into OpenGL's, :890-897)
+  KbRayParams cp; memset(&cp, 0, sizeof cp);
+  cp.cam_on = 1; cp.xres = cam->xres; cp.cx = cam->cx; cp.cy = cam->cy; cp.zmin = cam->zmin; cp.zmax = cam->zmax;
+  const double ifx = 1.0 / cam->fx, ify = 1.0 / cam->fy;
+  for (int k = 0; k < 3; k++) {
+    cp.eye[k] = cam->pose[9 + k]; cp.fwd[k] = cam->pose[3 * k + 2];
+    cp.dx[k] = cam->pose[3 * k] * ifx; cp.dy[k] = -cam->pose[3 * k + 1] * ify;
+  }
+  begin_timing(e);
+  float* d_depth = (float*)e->d_rdist;             // the distance scratch doubles as the float image
+  int rc = raycast_run(e, q, nullptr, N, ignore_ids, nullptr, out_id ? e->d_rid : nullptr, nullptr, nullptr, &cp, out_depth ? d_depth : nullptr);
+  if (rc) return rc;
+  if (out_depth) CK(cudaMemcpyAsync(out_depth, d_depth, (size_t)N * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (out_id) CK(cudaMemcpyAsync(out_id, e->d_rid, (size_t)N * 4, cudaMemcpyDeviceToHost, e->stream));
+  end_timing(e, true);
+  CK(cudaStreamSynchronize(e->stream));
+  e->stats.rays_cast += N;
+  return KB_OK;
 }
 
 int kb_geom_raycast_batch(kb_engine* e, int geom, const double* T, const double* rays, int64_t N, int32_t* out_elem, double* out_dist) {

@@ -176,8 +176,20 @@ __global__ void __launch_bounds__(128)
 kb_raycast_kernel(const KbRayParams p) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.N) return;
-  const double* __restrict__ ray = p.rays + 6 * i;
-  double s[3] = {ray[0], ray[1], ray[2]}, d[3] = {ray[3], ray[4], ray[5]};
+  double s[3], d[3];
+  if (p.cam_on) {
+    // pixel (ii, jj): direction fwd + (ii - cx) dx + (cy - jj) dy, source zmin along that unnormalised vector (the reference's order)
+    const int jj = (int)(i / p.xres), ii = (int)(i - (int64_t)jj * p.xres);
+    const double u = (double)ii - p.cx, v = p.cy - (double)jj;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      d[k] = __dadd_rn(__dadd_rn(p.fwd[k], __dmul_rn(u, p.dx[k])), __dmul_rn(v, p.dy[k]));
+      s[k] = __dadd_rn(p.eye[k], __dmul_rn(d[k], p.zmin));
+    }
+  } else {
+    const double* __restrict__ ray = p.rays + 6 * i;
+    s[0] = ray[0]; s[1] = ray[1]; s[2] = ray[2]; d[0] = ray[3]; d[1] = ray[4]; d[2] = ray[5];
+  }
   Best best; best.d = INFINITY; best.rank = 0x7fffffff; best.id = -1; best.elem = -1;
   const double n2 = __dadd_rn(__dadd_rn(__dmul_rn(d[0], d[0]), __dmul_rn(d[1], d[1])), __dmul_rn(d[2], d[2]));
   const bool ok = n2 > 0.0 && isfinite(n2) && isfinite(s[0]) && isfinite(s[1]) && isfinite(s[2]);
@@ -226,9 +238,20 @@ kb_raycast_kernel(const KbRayParams p) {
       }
     }
   }
-  p.out_id[i] = best.id;
-  p.out_dist[i] = best.d;
+  if (p.out_id) p.out_id[i] = best.id;
+  if (p.out_dist) p.out_dist[i] = best.d;
   if (p.out_elem) p.out_elem[i] = best.elem;
+  if (p.out_depth) {
+    // depth along the viewing direction: fwd . (pt - eye); below zmin = not sensed, beyond zmax = zmax (VisualSensors.cpp:461-466)
+    double z = p.zmax;
+    if (best.id >= 0) {
+      z = 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; k++) z += p.fwd[k] * (s[k] + best.d * d[k] - p.eye[k]);
+      z = z < p.zmin ? p.zmax : fmin(z, p.zmax);
+    }
+    p.out_depth[i] = (float)z;
+  }
 }
 
 }  // namespace

@@ -169,6 +169,12 @@ struct KbRayParams {
   int32_t* out_id;                // world id of the nearest hit, -1 = none
   double* out_dist;               // distance along the normalised direction, +inf = none
   int32_t* out_elem;              // element index within the body's geometry; may be null
+  // camera mode (kb_camera_depth): rays == null, ray k = pixel (k % xres, k / xres) of a pinhole camera, built the way the camera
+  // sensor's ray-cast path builds them (VisualSensors.cpp:424-449)
+  int32_t cam_on, xres;
+  double eye[3], fwd[3], dx[3], dy[3];   // dx = right / fx, dy = up / fy
+  double cx, cy, zmin, zmax;
+  float* out_depth;               // forward depth per pixel, zmax where nothing is seen; may be null
 };
 
 // split pipeline (node traversal kernel -> global leaf-pair list -> leaf kernel -> requeue for the fused kernel)

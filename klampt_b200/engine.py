@@ -264,6 +264,15 @@ class Engine:
                                                  _ptr(d), _ptr(cp), _ptr(elem)))
         return d, cp, elem
 
+    def _ignore_mask(self, ignore_ids) -> np.ndarray:
+        ig = np.asarray(ignore_ids)
+        nids = self.num_ids()
+        if ig.dtype != np.uint8 or ig.shape != (nids,):
+            m = np.zeros(nids, dtype=np.uint8)
+            m[np.asarray(list(ignore_ids), dtype=np.int64)] = 1
+            ig = m
+        return np.ascontiguousarray(ig)
+
     def raycast_batch(self, q, rays, ignore_ids=None):
         """WorldModel::RayCast / RayCastIgnore (World.cpp:465-588) for N rays (rows of source xyz, direction xyz) with the robot at q
         (None: the robot is left out): (world id or -1, distance along the normalised direction or inf, element index or -1).
@@ -272,18 +281,25 @@ class Engine:
         N = rays.shape[0]
         ids, dist, elem = np.empty(N, dtype=np.int32), np.empty(N, dtype=np.float64), np.empty(N, dtype=np.int32)
         qa = None if q is None else _f64(q).reshape(self.L)
-        ig = None
-        if ignore_ids is not None:
-            ig = np.asarray(ignore_ids)
-            nids = self.num_ids()
-            if ig.dtype != np.uint8 or ig.shape != (nids,):
-                m = np.zeros(nids, dtype=np.uint8)
-                m[np.asarray(list(ignore_ids), dtype=np.int64)] = 1
-                ig = m
-            ig = np.ascontiguousarray(ig)
+        ig = None if ignore_ids is None else self._ignore_mask(ignore_ids)
         check(self.lib.kb_raycast_batch(self.h, None if qa is None else _ptr(qa), _ptr(rays), N, None if ig is None else _ptr(ig),
                                         _ptr(ids), _ptr(dist), _ptr(elem)))
         return ids, dist, elem
+
+    def camera_depth(self, q, pose, fx, fy, cx, cy, zmin, zmax, xres, yres, ignore_ids=None, want_ids=True):
+        """CameraSensor's ray-cast rendering in one call (rays built on the device): (depth (yres, xres) float32, world ids (yres, xres)
+        int32 or None).  pose: the camera's world pose (12 doubles; x right, y down, z forward)."""
+        from ._capi import KbCamera
+        cam = KbCamera()
+        cam.pose[:] = list(_f64(pose).reshape(12))
+        cam.fx, cam.fy, cam.cx, cam.cy, cam.zmin, cam.zmax, cam.xres, cam.yres = fx, fy, cx, cy, zmin, zmax, int(xres), int(yres)
+        depth = np.empty((int(yres), int(xres)), dtype=np.float32)
+        ids = np.empty((int(yres), int(xres)), dtype=np.int32) if want_ids else None
+        qa = None if q is None else _f64(q).reshape(self.L)
+        ig = None if ignore_ids is None else self._ignore_mask(ignore_ids)
+        check(self.lib.kb_camera_depth(self.h, None if qa is None else _ptr(qa), C.byref(cam), None if ig is None else _ptr(ig), _ptr(depth),
+                                       None if ids is None else _ptr(ids)))
+        return depth, ids
 
     def geom_raycast_batch(self, geom: int, T, rays):
         """Geometry3D.rayCast_ext of one registered geometry at transform T (12 doubles or None) for N rays: (element or -1, distance or inf)"""

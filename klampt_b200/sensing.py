@@ -60,13 +60,21 @@ class CameraSensor:
         fx, fy, cx, cy = self.viewport()
         u = (np.arange(self.xres, dtype=np.float64) - cx)[None, :, None]
         v = (cy - np.arange(self.yres, dtype=np.float64))[:, None, None]
-        d = fwd[None, None, :] + u * (right / fx)[None, None, :] + v * (up / fy)[None, None, :]
+        d = fwd[None, None, :] + u * (right * (1.0 / fx))[None, None, :] + v * (up * (1.0 / fy))[None, None, :]
         src = eye[None, None, :] + d * self.zmin
         d = d / np.linalg.norm(d, axis=-1, keepdims=True)
         return np.concatenate([src, d], axis=-1).reshape(-1, 6), eye, fwd
 
     def simulate(self, engine, q, ignore_ids=None):
-        """(depth image (yres, xres) float32, id image (yres, xres) int32: world id seen by each pixel, -1 = background)"""
+        """(depth image (yres, xres) float32, id image (yres, xres) int32: world id seen by each pixel, -1 = background); the rays are
+        built on the device (kb_camera_depth): nothing but the pose goes up, only the two images come back"""
+        T = engine.fk_batch(np.asarray(q, dtype=np.float64)[None, :])[0] if self.link >= 0 else None
+        R, eye = self.pose(T)
+        fx, fy, cx, cy = self.viewport()
+        return engine.camera_depth(q, np.concatenate([R.reshape(-1), eye]), fx, fy, cx, cy, self.zmin, self.zmax, self.xres, self.yres, ignore_ids)
+
+    def simulate_from_rays(self, engine, q, ignore_ids=None):
+        """the same reading with the rays built on the host and cast through kb_raycast_batch (cross-check of the device-side builder)"""
         T = engine.fk_batch(np.asarray(q, dtype=np.float64)[None, :])[0] if self.link >= 0 else None
         rays, eye, fwd = self.rays(T)
         ids, dist, _ = engine.raycast_batch(q, rays, ignore_ids)

@@ -166,6 +166,15 @@ def test_camera_and_laser_sensors_follow_the_per_ray_statement(built):
             want[j, i] = z
     np.testing.assert_allclose(depth, want, rtol=1e-6, atol=1e-6)
     assert (depth < cam.zmax).mean() > 0.2 and (ids >= 0).any()
+    depth2, ids2 = cam.simulate_from_rays(eng, q)                  # host-built rays through kb_raycast_batch: the same image
+    assert np.array_equal(ids2, ids)
+    np.testing.assert_allclose(depth2, depth, rtol=1e-6, atol=1e-6)
+    cam3 = sensing.CameraSensor(xres=40, yres=30, zmin=0.05, zmax=4.0, link=5, Tsensor=synth.make_T(None, (0.0, 0.0, 0.12)))     # camera riding on a link
+    own = [w.robot_link_id(5), w.robot_link_id(6)]          # the wrist and the tool sphere the camera sits in (a source inside a sphere reads zmin exactly)
+    d3, i3 = cam3.simulate(eng, q, ignore_ids=own)
+    d4, i4 = cam3.simulate_from_rays(eng, q, ignore_ids=own)
+    assert np.array_equal(i3, i4) and not np.isin(i3, own).any() and (i3 >= 0).mean() > 0.1
+    np.testing.assert_allclose(d3, d4, rtol=1e-6, atol=1e-6)
     # laser on link 3, sweeping 90 degrees: its own link is ignored
     # (mounted at a generic angle: rays lying exactly in a symmetry plane of the link meshes graze silhouette edges, where hit or miss
     # is a matter of the last bit of FK)
