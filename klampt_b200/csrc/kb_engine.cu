@@ -1160,6 +1160,7 @@ int kb_finalize(kb_engine* e, int device) {
   struct Grp { int kind; double margin; std::string sig; std::vector<double> elems; std::vector<int32_t> owners; int dyn_geom = -1; int dyn_owner = -1; std::vector<int32_t> origs; };
   std::vector<Grp> grp;
   std::map<std::string, int> grp_index;
+  std::vector<int> static_grp((size_t)(T + O), -1);     // merged group that holds a static body's elements in the world frame (ray casting reuses it)
   double extent = 0;
   for (int s = 0; s < T + O; s++) {
     int gi = s < T ? e->terrains[s] : e->objects[s - T];
@@ -1192,6 +1193,7 @@ int kb_finalize(kb_engine* e, int device) {
       grp[bit->second].elems.insert(grp[bit->second].elems.end(), w, w + 15); grp[bit->second].owners.push_back(s);
     }
     Grp& gr = grp[it->second];       // taken after the push_back above: a reference into `grp` would not survive it
+    static_grp[s] = it->second;
     if (kind == G_MESH) {
       int nt = (int)(G.tri.size() / 9);
       for (int t = 0; t < nt; t++) {
@@ -1353,23 +1355,39 @@ int kb_finalize(kb_engine* e, int device) {
     }
     e->ray_nlink = (int)e->ray_bodies.size();
     std::vector<KbRayBody> st; std::vector<double> blo, bhi;
+    auto add_static = [&](const KbRayBody& b, const double* lo, const double* hi, double margin, bool mesh) {
+      st.push_back(b);
+      const double grow = margin + 1e-9 * (1 + std::fabs(lo[0]) + std::fabs(lo[1]) + std::fabs(lo[2]) + std::fabs(hi[0]) + std::fabs(hi[1]) + std::fabs(hi[2]));
+      for (int k = 0; k < 3; k++) { blo.push_back(lo[k] - grow); e->tlas_ext = std::max(e->tlas_ext, (float)std::fabs(lo[k] - grow)); }
+      for (int k = 0; k < 3; k++) { bhi.push_back(hi[k] + grow); e->tlas_ext = std::max(e->tlas_ext, (float)std::fabs(hi[k] + grow)); }
+      if (mesh) e->ray_max_margin = std::max(e->ray_max_margin, margin);
+    };
+    // static bodies whose elements already sit in a merged world-frame group are cast through that group (one hierarchy for the
+    // whole environment, no per-body transform; owner id and rank come from the element), the others one by one in their own frames
+    std::vector<char> group_used(e->groups.size(), 0);
     for (int s2 = 0; s2 < T + O; s2++) {
       const int gi = s2 < T ? e->terrains[s2] : e->objects[s2 - T];
       if (geom_empty(e, gi) || e->geoms[gi].dyn_cap > 0) continue;
+      const int gidx = static_grp[s2];
+      if (gidx >= 0 && !e->groups[gidx].empty && e->groups[gidx].depth < 90 && e->groups[gidx].kind != KB_ELEM_BOX) {
+        if (!group_used[gidx]) {
+          group_used[gidx] = 1;
+          const DevGeom& G = e->groups[gidx];
+          KbRayBody b = body_of(G, -1, -1, -1, nullptr);
+          add_static(b, G.lo, G.hi, G.margin, G.kind == KB_ELEM_TRI);
+        }
+        continue;
+      }
       const DevGeom& dg = e->dgeoms[gi];
       if (dg.empty || dg.depth >= 90) continue;
       const Xf* X = s2 < T ? nullptr : &e->objT[s2 - T];
-      st.push_back(body_of(dg, s2, s2 < T ? L + O + s2 : L + (s2 - T), -1, X));
       double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
       for (int c = 0; c < 8; c++) {
         double pl[3] = {(c & 1) ? dg.hi[0] : dg.lo[0], (c & 2) ? dg.hi[1] : dg.lo[1], (c & 4) ? dg.hi[2] : dg.lo[2]}, pw[3];
         if (X) xf_apply(*X, pl, pw); else memcpy(pw, pl, 24);
         for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], pw[k]); hi[k] = std::max(hi[k], pw[k]); }
       }
-      const double grow = dg.margin + 1e-9 * (1 + std::fabs(lo[0]) + std::fabs(lo[1]) + std::fabs(lo[2]) + std::fabs(hi[0]) + std::fabs(hi[1]) + std::fabs(hi[2]));
-      for (int k = 0; k < 3; k++) { blo.push_back(lo[k] - grow); e->tlas_ext = std::max(e->tlas_ext, (float)std::fabs(lo[k] - grow)); }
-      for (int k = 0; k < 3; k++) { bhi.push_back(hi[k] + grow); e->tlas_ext = std::max(e->tlas_ext, (float)std::fabs(hi[k] + grow)); }
-      if (dg.kind == KB_ELEM_TRI) e->ray_max_margin = std::max(e->ray_max_margin, dg.margin);
+      add_static(body_of(dg, s2, s2 < T ? L + O + s2 : L + (s2 - T), -1, X), lo, hi, dg.margin, dg.kind == KB_ELEM_TRI);
     }
     e->tlas_ext *= 3.f;
     e->ray_nstatic = (int)st.size();
@@ -2092,6 +2110,7 @@ static int raycast_run(kb_engine* e, const double* q_host, const double* d_rays,
     p.bodies = e->d_onebody; p.nlinkbodies = 1; p.nstatic = 0;
   } else {
     p.bodies = e->d_raybodies; p.nstatic = e->ray_nstatic; p.tlas = e->d_tlas; p.tlas_ext = e->tlas_ext; p.max_margin = e->ray_max_margin;
+    p.nterr = (int)e->terrains.size(); p.nobj = (int)e->objects.size(); p.nlinks = e->L;
     const int nl = e->ray_nlink;
     if (q_host) {
       int rc = ensure_cfg_scratch(e, e->L, 1); if (rc) return rc;

@@ -94,8 +94,15 @@ __device__ __forceinline__ bool ray_sphere(const double* s, const double* d, con
 
 struct Best { double d; int rank, id, elem; };
 
-// nearest hit of the world-frame ray (s, d) with one body whose frame is T (world <- local, 12 doubles, null = world frame)
-__device__ void cast_body(const KbScene& sc, const KbRayBody& B, const double* __restrict__ T, const double* s, const double* d, Best& best) {
+struct WorldCounts { int nterr, nobj, nlinks; };
+// order in which WorldModel::RayCast visits a static body with world id `own`: the links come first, then the rigid objects, then the terrains
+__device__ __forceinline__ int rank_of_owner(int own, const WorldCounts& wc) { return own < wc.nterr ? wc.nlinks + wc.nobj + own : wc.nlinks + (own - wc.nterr); }
+
+// nearest hit of the world-frame ray (s, d) with one body whose frame is T (world <- local, 12 doubles, null = world frame).
+// Two nested loops (Aila & Laine's while-while form): descend through inner nodes until a leaf is reached, then test its elements --
+// the lanes of a warp stay together in the cheap fp32 node loop instead of waiting for the one lane that is in an fp64 element test.
+__device__ void cast_body(const KbScene& sc, const KbRayBody& B, const double* __restrict__ T, const double* s, const double* d, Best& best,
+                          const uint8_t* __restrict__ ignore, const WorldCounts& wc) {
   double sl[3], dl[3];
   if (T) {
     // R^T (s - t) and R^T d, every product and sum rounded on its own (the oracle's order: bit-identical local rays)
@@ -107,9 +114,10 @@ __device__ void cast_body(const KbScene& sc, const KbRayBody& B, const double* _
     }
   } else { sl[0] = s[0]; sl[1] = s[1]; sl[2] = s[2]; dl[0] = d[0]; dl[1] = d[1]; dl[2] = d[2]; }
   const bool mesh = B.kind == KB_ELEM_TRI;
+  const bool grouped = B.id < 0;                              // merged environment group: owner id (and rank) per element
   RayShear sh; ray_shear(dl, sh);
   const double shift = mesh ? B.margin : 0.0;                 // a mesh reports t - margin; a cloud's margin is part of its spheres
-  double tbest = best.d + shift;                              // raw parameter this body has to beat (ties resolved by rank below)
+  double tbest = best.d + shift;                              // raw parameter this body has to beat (ties resolved by rank)
   if (!(tbest >= 0.0)) return;
   RayF r;
   r.ox = (float)sl[0]; r.oy = (float)sl[1]; r.oz = (float)sl[2];
@@ -123,29 +131,16 @@ __device__ void cast_body(const KbScene& sc, const KbRayBody& B, const double* _
   float tlim = tbest < 3e38 ? __double2float_ru(tbest) * 1.00001f + 1e-30f : FLT_MAX;
   const float4* __restrict__ nodes = sc.nodes + 2 * (size_t)B.node_base;
   int stack_n[KB_RAY_STACK]; float stack_t[KB_RAY_STACK];
-  int sp = 0, node = 0, elem = -1;
+  int sp = 0, elem = -1, rank = best.rank, id = -1;
   bool hit = false;
   float4 n0, n1; float tn;
   ld_node(nodes, 0, n0, n1);
   if (!slab(n0, n1, r, pad, tlim, tn)) return;
   for (;;) {
-    const int ref = __float_as_int(n0.w);
-    if (ref < 0) {
-      const int first = ~ref, cnt = __float_as_int(n1.w);
-      for (int i = 0; i < cnt; i++) {
-        const int e = B.elem_base + first + i;
-        double t; bool h;
-        if (mesh) h = ray_tri(sl, sh, sc.tris64 + 9 * (size_t)e, t);
-        else h = ray_sphere(sl, dl, sc.sph64 + 4 * (size_t)e, sc.sph64[4 * (size_t)e + 3] + B.margin, t);
-        if (h) {
-          const int orig = mesh ? sc.triorig[e] : sc.sphorig[e];
-          if (t < tbest || (t == tbest && hit && orig < elem) || (t == tbest && !hit)) {
-            tbest = t; elem = orig; hit = true;
-            tlim = __double2float_ru(tbest) * 1.00001f + 1e-30f;
-          }
-        }
-      }
-    } else {
+    // ---- node loop: nearer child first, the farther one deferred with its entry distance
+    bool alive = true;
+    int ref;
+    while ((ref = __float_as_int(n0.w)) >= 0) {
       float4 a0, a1, b0, b1; float ta, tb;
       ld_node(nodes, (size_t)ref, a0, a1);
       ld_node(nodes, (size_t)ref + 1, b0, b1);
@@ -153,23 +148,51 @@ __device__ void cast_body(const KbScene& sc, const KbRayBody& B, const double* _
       if (ha | hb) {
         const bool afirst = ha && (!hb || ta <= tb);
         if (ha & hb && sp < KB_RAY_STACK) { stack_n[sp] = afirst ? ref + 1 : ref; stack_t[sp] = afirst ? tb : ta; sp++; }
-        node = afirst ? ref : ref + 1;
         if (afirst) { n0 = a0; n1 = a1; } else { n0 = b0; n1 = b1; }
         continue;
       }
+      // both children missed: the nearest deferred subtree that can still beat the best hit
+      alive = false;
+      while (sp > 0) {
+        sp--;
+        if (stack_t[sp] - 2e-6f * fabsf(stack_t[sp]) <= tlim) { ld_node(nodes, (size_t)stack_n[sp], n0, n1); alive = true; break; }
+      }
+      if (!alive) break;
     }
-    // pop the nearest deferred subtree that can still beat the best hit
+    if (!alive) break;
+    // ---- element loop of the leaf in n0 / n1
+    {
+      const int first = ~ref, cnt = __float_as_int(n1.w);
+      for (int i = 0; i < cnt; i++) {
+        const int e = B.elem_base + first + i;
+        double t; bool h;
+        if (mesh) h = ray_tri(sl, sh, sc.tris64 + 9 * (size_t)e, t);
+        else h = ray_sphere(sl, dl, sc.sph64 + 4 * (size_t)e, sc.sph64[4 * (size_t)e + 3] + B.margin, t);
+        if (h && t <= tbest) {
+          const int orig = mesh ? sc.triorig[e] : sc.sphorig[e];
+          int own = B.id, rk = B.rank;
+          if (grouped) {
+            own = mesh ? sc.triown[e] : sc.sphown[e];
+            if (ignore && ignore[own]) continue;
+            rk = rank_of_owner(own, wc);
+          }
+          // nearer wins; at equal distance the body the reference visits first, then the lower element index
+          if (t < tbest || rk < rank || (rk == rank && (!hit || orig < elem))) {
+            tbest = t; elem = orig; rank = rk; id = own; hit = true;
+            tlim = __double2float_ru(tbest) * 1.00001f + 1e-30f;
+          }
+        }
+      }
+    }
     bool got = false;
     while (sp > 0) {
       sp--;
-      if (stack_t[sp] - 2e-6f * fabsf(stack_t[sp]) <= tlim) { node = stack_n[sp]; got = true; break; }
+      if (stack_t[sp] - 2e-6f * fabsf(stack_t[sp]) <= tlim) { ld_node(nodes, (size_t)stack_n[sp], n0, n1); got = true; break; }
     }
     if (!got) break;
-    ld_node(nodes, (size_t)node, n0, n1);
   }
   if (!hit) return;
-  const double dist = tbest - shift;
-  if (dist < best.d || (dist == best.d && B.rank < best.rank)) { best.d = dist; best.rank = B.rank; best.id = B.id; best.elem = elem; }
+  best.d = tbest - shift; best.rank = rank; best.id = id; best.elem = elem;
 }
 
 __global__ void __launch_bounds__(128)
@@ -191,6 +214,7 @@ kb_raycast_kernel(const KbRayParams p) {
     s[0] = ray[0]; s[1] = ray[1]; s[2] = ray[2]; d[0] = ray[3]; d[1] = ray[4]; d[2] = ray[5];
   }
   Best best; best.d = INFINITY; best.rank = 0x7fffffff; best.id = -1; best.elem = -1;
+  WorldCounts wc; wc.nterr = p.nterr; wc.nobj = p.nobj; wc.nlinks = p.nlinks;
   const double n2 = __dadd_rn(__dadd_rn(__dmul_rn(d[0], d[0]), __dmul_rn(d[1], d[1])), __dmul_rn(d[2], d[2]));
   const bool ok = n2 > 0.0 && isfinite(n2) && isfinite(s[0]) && isfinite(s[1]) && isfinite(s[2]);
   if (ok) {
@@ -199,8 +223,8 @@ kb_raycast_kernel(const KbRayParams p) {
     // ---- the robot's links in the frames of this call's configuration
     for (int b = 0; b < p.nlinkbodies; b++) {
       const KbRayBody& B = p.bodies[b];
-      if (p.ignore && p.ignore[B.id]) continue;
-      cast_body(p.scene, B, B.xf >= 0 ? p.xf64 + 12 * (size_t)B.xf : (B.has_T ? B.T : nullptr), s, d, best);
+      if (B.id >= 0 && p.ignore && p.ignore[B.id]) continue;
+      cast_body(p.scene, B, B.xf >= 0 ? p.xf64 + 12 * (size_t)B.xf : (B.has_T ? B.T : nullptr), s, d, best, p.ignore, wc);
     }
     // ---- static bodies under the top-level hierarchy (world boxes, already grown by each body's margin)
     if (p.nstatic > 0) {
@@ -225,8 +249,8 @@ kb_raycast_kernel(const KbRayParams p) {
           const int first = ~ref, cnt = __float_as_int(n1.w);
           for (int k = 0; k < cnt; k++) {
             const KbRayBody& B = p.bodies[p.nlinkbodies + first + k];
-            if (p.ignore && p.ignore[B.id]) continue;
-            cast_body(p.scene, B, B.has_T ? B.T : nullptr, s, d, best);
+            if (B.id >= 0 && p.ignore && p.ignore[B.id]) continue;
+            cast_body(p.scene, B, B.has_T ? B.T : nullptr, s, d, best, p.ignore, wc);
           }
         } else if (tsp + 2 <= KB_RAY_TSTACK) {
           // nearer child on top: its hits shorten the ray before the farther one is looked at

@@ -149,8 +149,8 @@ struct KbRayBody {                // 144 bytes
   double margin;
   int32_t node_base, elem_base;   // the geometry's local-frame hierarchy / elements
   int32_t kind;                   // KB_ELEM_TRI / KB_ELEM_SPHERE
-  int32_t id;                     // world id reported for a hit
-  int32_t rank;                   // order in which WorldModel::RayCast visits the bodies: a tie in distance keeps the lower rank
+  int32_t id;                     // world id reported for a hit; -1 = a merged environment group: the owner id comes with the element
+  int32_t rank;                   // order in which WorldModel::RayCast visits the bodies: a tie in distance keeps the lower rank (groups: from the owner)
   int32_t xf;                     // transform slot of a link, -1 = static
   int32_t has_T;                  // static body with a transform other than the identity
   float ext;                      // largest |coordinate| of the geometry's local box (bounds the fp32 rounding of its node tests)
@@ -159,6 +159,7 @@ struct KbRayParams {
   KbScene scene;
   const KbRayBody* bodies;        // [0, nlinkbodies): tested one by one; then nstatic bodies in the leaf order of the top-level hierarchy
   int32_t nlinkbodies, nstatic;
+  int32_t nterr, nobj, nlinks;    // world counts: rank of an owner id inside a merged group (links, then objects, then terrains)
   const float4* tlas;             // top-level hierarchy over the static bodies' world boxes (same node format; leaf = body range)
   float tlas_ext;                 // largest |coordinate| of its root box
   double max_margin;              // largest mesh margin among the static bodies (a body reports t - margin)
