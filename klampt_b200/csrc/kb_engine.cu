@@ -397,6 +397,7 @@ struct kb_engine {
   KbRayBody* d_raybodies = nullptr; float4* d_tlas = nullptr;
   double* d_rays = nullptr; int32_t* d_rid = nullptr; double* d_rdist = nullptr; int32_t* d_relem = nullptr; int64_t ray_cap = 0;
   uint8_t* d_ignore = nullptr; double* d_rayq = nullptr; KbRayBody* d_onebody = nullptr;
+  int ray_variant = 0, ray_tile = 1;      // experiment knobs of the ray kernel (options ray_variant, ray_tile)
   // ---- stats
   kb_stats stats{}; int64_t edge_cfg_host = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1608,6 +1609,8 @@ int kb_set_option(kb_engine* e, const char* name, int64_t value) {
   if (!strcmp(name, "pipeline")) { if (value != 0 && value != 1) return fail(KB_ERR_INVALID, "pipeline must be 0 (fused) or 1 (split)"); e->pipeline = (int)value; return KB_OK; }
   if (!strcmp(name, "leaf_budget")) { if (value < 1 || value > 100000) return fail(KB_ERR_INVALID, "leaf_budget out of range"); e->leaf_budget = (int)value; return KB_OK; }
   if (!strcmp(name, "clear_grid")) { e->use_grids = value != 0; return KB_OK; }
+  if (!strcmp(name, "ray_variant")) { e->ray_variant = (int)value; for (kb_engine* r : e->replicas) r->ray_variant = (int)value; return KB_OK; }
+  if (!strcmp(name, "ray_tile")) { e->ray_tile = value != 0; for (kb_engine* r : e->replicas) r->ray_tile = value != 0; return KB_OK; }
   if (!strcmp(name, "mesh_builder")) {
     if (e->finalized) return fail(KB_ERR_STATE, "mesh_builder must be set before kb_finalize");
     if (value != 0 && value != 1) return fail(KB_ERR_INVALID, "mesh_builder: 0 = binned SAH on the host (default), 1 = linear BVH on the GPU for large meshes");
@@ -2130,7 +2133,8 @@ static int raycast_run(kb_engine* e, const double* q_host, const double* d_rays,
       p.ignore = e->d_ignore;
     }
   }
-  CK(kb_launch_raycast(p, e->stream));
+  if (p.cam_on) p.tile = e->ray_tile;
+  CK(kb_launch_raycast(p, e->stream, e->ray_variant));
   e->stats.kernel_launches++;
   return KB_OK;
 }
@@ -2200,7 +2204,7 @@ int kb_camera_depth(kb_engine* e, const double* q, const kb_camera* cam, const u
   }
   // camera frame: x right, y down, z forward (the sensor convention; CameraSensor::GetViewport flips y and z into OpenGL's, :890-897)
   KbRayParams cp; memset(&cp, 0, sizeof cp);
-  cp.cam_on = 1; cp.xres = cam->xres; cp.cx = cam->cx; cp.cy = cam->cy; cp.zmin = cam->zmin; cp.zmax = cam->zmax;
+  cp.cam_on = 1; cp.xres = cam->xres; cp.yres = cam->yres; cp.cx = cam->cx; cp.cy = cam->cy; cp.zmin = cam->zmin; cp.zmax = cam->zmax;
   const double ifx = 1.0 / cam->fx, ify = 1.0 / cam->fy;
   for (int k = 0; k < 3; k++) {
     cp.eye[k] = cam->pose[9 + k]; cp.fwd[k] = cam->pose[3 * k + 2];

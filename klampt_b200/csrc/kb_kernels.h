@@ -46,4 +46,4 @@ cudaError_t kb_launch_edge_flat_finish(const uint8_t* feas, const uint8_t* slot_
                                        uint8_t* alive, int32_t* nchecks, cudaStream_t s);
 
 // kb_raycast.cu: nearest hit of N rays with the world (links at one configuration + static bodies)
-cudaError_t kb_launch_raycast(const KbRayParams& p, cudaStream_t s);
+cudaError_t kb_launch_raycast(const KbRayParams& p, cudaStream_t s, int variant = 0);

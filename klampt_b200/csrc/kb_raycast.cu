@@ -115,7 +115,7 @@ __device__ void cast_body(const KbScene& sc, const KbRayBody& B, const double* _
   } else { sl[0] = s[0]; sl[1] = s[1]; sl[2] = s[2]; dl[0] = d[0]; dl[1] = d[1]; dl[2] = d[2]; }
   const bool mesh = B.kind == KB_ELEM_TRI;
   const bool grouped = B.id < 0;                              // merged environment group: owner id (and rank) per element
-  RayShear sh; ray_shear(dl, sh);
+  RayShear sh; bool have_shear = false;         // three fp64 divisions: only once a leaf is reached (most bodies are missed at their root box)
   const double shift = mesh ? B.margin : 0.0;                 // a mesh reports t - margin; a cloud's margin is part of its spheres
   double tbest = best.d + shift;                              // raw parameter this body has to beat (ties resolved by rank)
   if (!(tbest >= 0.0)) return;
@@ -163,6 +163,7 @@ __device__ void cast_body(const KbScene& sc, const KbRayBody& B, const double* _
     // ---- element loop of the leaf in n0 / n1
     {
       const int first = ~ref, cnt = __float_as_int(n1.w);
+      if (mesh && !have_shear) { ray_shear(dl, sh); have_shear = true; }
       for (int i = 0; i < cnt; i++) {
         const int e = B.elem_base + first + i;
         double t; bool h;
@@ -195,9 +196,19 @@ __device__ void cast_body(const KbScene& sc, const KbRayBody& B, const double* _
   best.d = tbest - shift; best.rank = rank; best.id = id; best.elem = elem;
 }
 
-__global__ void __launch_bounds__(128)
+template <int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
 kb_raycast_kernel(const KbRayParams p) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (p.cam_on && p.tile) {
+    // camera mode: a warp renders an 8 x 4 pixel tile instead of 32 pixels of one row (its rays share more of their path)
+    const int64_t w = i >> 5; const int l = (int)(i & 31);
+    const int tiles_x = (p.xres + 7) >> 3;
+    const int64_t ty = w / tiles_x; const int tx = (int)(w - ty * tiles_x);
+    const int px = tx * 8 + (l & 7); const int64_t py = ty * 4 + (l >> 3);
+    if (px >= p.xres || py >= p.yres) return;
+    i = py * p.xres + px;
+  }
   if (i >= p.N) return;
   double s[3], d[3];
   if (p.cam_on) {
@@ -280,9 +291,13 @@ kb_raycast_kernel(const KbRayParams p) {
 
 }  // namespace
 
-cudaError_t kb_launch_raycast(const KbRayParams& p, cudaStream_t s) {
+// 64-thread blocks, 8 per SM: measured best of {128 x 4, 128 x 5 / 6 (spills), 64 x 8, 64 x 10 (spills), 32 x 16} on 640 x 480 images of the C2
+// world (profiles/r02_experiments.md); variant 1 keeps the 128 x 4 shape for comparison
+cudaError_t kb_launch_raycast(const KbRayParams& p, cudaStream_t s, int variant) {
   if (p.N <= 0) return cudaSuccess;
-  const int64_t blocks = (p.N + 127) / 128;
-  kb_raycast_kernel<<<(unsigned)blocks, 128, 0, s>>>(p);
+  int64_t threads = p.N;
+  if (p.cam_on && p.tile) threads = (int64_t)((p.xres + 7) / 8) * ((p.yres + 3) / 4) * 32;
+  if (variant == 1) kb_raycast_kernel<128, 4><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(p);
+  else kb_raycast_kernel<64, 8><<<(unsigned)((threads + 63) / 64), 64, 0, s>>>(p);
   return cudaGetLastError();
 }

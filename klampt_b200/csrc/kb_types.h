@@ -172,7 +172,7 @@ struct KbRayParams {
   int32_t* out_elem;              // element index within the body's geometry; may be null
   // camera mode (kb_camera_depth): rays == null, ray k = pixel (k % xres, k / xres) of a pinhole camera, built the way the camera
   // sensor's ray-cast path builds them (VisualSensors.cpp:424-449)
-  int32_t cam_on, xres;
+  int32_t cam_on, xres, yres, tile;     // tile: a warp renders 8 x 4 pixels instead of 32 pixels of one row
   double eye[3], fwd[3], dx[3], dy[3];   // dx = right / fx, dy = up / fy
   double cx, cy, zmin, zmax;
   float* out_depth;               // forward depth per pixel, zmax where nothing is seen; may be null
