@@ -1745,7 +1745,7 @@ static int feasible_batch_host_one(kb_engine* e, const void* Qv, int esz, int64_
   if (bits && (rc = grow(e->d_bits, e->bits_cap, (N + 31) / 32))) return rc;
   if (first_pair && (rc = grow(e->d_pair, e->pair_cap, 2 * N))) return rc;
   begin_timing(e);
-  // Staged upload.  A large batch crosses PCIe in KB_STAGES equal pieces on the copy stream; piece k is checked while piece k + 1 is in
+  // Staged upload.  A large batch crosses PCIe in KB_STAGES pieces on the copy stream; piece k is checked while piece k + 1 is in
   // flight, and consecutive pieces run on two alternating streams with their own scratch rows and work counters, so a piece starts
   // filling the SMs that the previous launch's tail has left idle.  Cost ~ copy(N / KB_STAGES) + max(copy, compute): one GPU on its own
   // x16 link is compute bound (56 MB in ~1.1 ms against 5 ms of checking); eight ranks sharing one host's memory are close to copy bound,
@@ -1760,7 +1760,9 @@ static int feasible_batch_host_one(kb_engine* e, const void* Qv, int esz, int64_
     if ((rc = ensure_cfg_scratch(e, e->feas_items.nxf, N))) return rc;
     const int K = KB_STAGES;
     int64_t cut[KB_STAGES + 1];
-    for (int k = 0; k <= K; k++) cut[k] = k == K ? N : ((N * k / K) / 1024) * 1024;
+    // a small first piece (1/32 of the batch: the only upload nothing overlaps with), then eighths, a quarter at the end
+    static const int frac32[KB_STAGES + 1] = {0, 1, 4, 8, 12, 16, 20, 24, 32};
+    for (int k = 0; k <= K; k++) cut[k] = k == K ? N : ((N * frac32[k] / 32) / 1024) * 1024;
     CK(cudaEventRecord(e->ev_copy[0], e->stream));                  // neither the copies nor the second stream may run ahead of earlier work
     CK(cudaStreamWaitEvent(e->copy_stream, e->ev_copy[0], 0));
     CK(cudaStreamWaitEvent(e->aux_stream, e->ev_copy[0], 0));
