@@ -2184,7 +2184,10 @@ int kb_raycast_batch(kb_engine* e, const double* q, const double* rays, int64_t 
   if (N < 0 || (N > 0 && (!rays || !out_id || !out_dist))) return fail(KB_ERR_INVALID, "bad arguments");
   if (q && !all_finite(q, (size_t)e->L)) return fail(KB_ERR_INVALID, "non-finite configuration");
   if (N == 0) return KB_OK;
-  return raycast_host(e, q, rays, N, ignore_ids, nullptr, out_id, out_dist, out_elem);
+  // a multi-device handle casts contiguous blocks of the rays on its devices (every replica runs FK for q itself)
+  return run_sharded(e, N, 1, [&](kb_engine* r, int64_t off, int64_t n) {
+    return raycast_host(r, q, rays + 6 * off, n, ignore_ids, nullptr, out_id + off, out_dist + off, out_elem ? out_elem + off : nullptr);
+  });
 }
 
 int kb_camera_depth(kb_engine* e, const double* q, const kb_camera* cam, const uint8_t* ignore_ids, float* out_depth, int32_t* out_id) {

@@ -93,3 +93,31 @@ def test_c5_five_million_point_cloud(built):
     assert not (env_hit & (got == 1)).any()
     bits = eng.feasible_batch_bits(Q)
     assert np.array_equal(np.unpackbits(bits, bitorder="little")[:n], got)
+
+
+def test_c6_depth_images_at_full_world_size(built):
+    """the ray-cast row at BASELINE's world sizes: a 640 x 480 image of the full C2 world (200 obstacles, 505 k triangles) and one of
+    the 5 M-point cloud world, every pixel against the oracle's per-body loop: same body, distance to 1e-9"""
+    import math
+    from klampt_b200 import sensing
+    from klampt_b200.engine import Engine
+    from oracle.oracle import OracleWorld
+    for world, opts in ((synth.world_c2(), None), (synth.world_c5(), {"cloud_builder": 1})):
+        eng, orc = Engine(world, options=opts), OracleWorld(world)
+        q = synth.sample_configs(world.robot, 1, 77)[0]
+        eye = np.array([3.2 * math.cos(0.4), 3.2 * math.sin(0.4), 1.3])
+        fwd = np.array([0.0, 0.0, 0.5]) - eye
+        fwd /= np.linalg.norm(fwd)
+        right = np.cross(fwd, [0.0, 0.0, 1.0])
+        right /= np.linalg.norm(right)
+        cam = sensing.CameraSensor(640, 480, zmin=0.1, zmax=8.0, Tsensor=synth.make_T(np.stack([right, np.cross(fwd, right), fwd], axis=1), eye))
+        rays, _, _ = cam.rays()
+        ids, dist, elem = eng.raycast_batch(q, rays)
+        oid, od, oel = orc.raycast_batch(q, rays, nthreads=0)
+        assert np.array_equal(ids, oid)
+        hit = ids >= 0
+        assert 0.3 < hit.mean() <= 1.0
+        np.testing.assert_allclose(dist[hit], od[hit], rtol=1e-9, atol=1e-12)
+        assert (elem == oel)[hit].mean() > 0.999                      # ties across a shared edge / coincident points aside
+        depth, idimg = cam.simulate(eng, q)                            # the device-built rays give the same picture
+        assert (idimg.reshape(-1) == ids).mean() > 0.9999             # (host-normalised directions differ from the device's in the last bit)

@@ -37,6 +37,12 @@ def test_sharded_batches_equal_one_device(built):
     d2 = two.distance_batch_ex(Q[:30_000], upper_bound=0.3, include_self=True)
     assert np.array_equal(d1[0], d2[0]) and np.array_equal(d1[1], d2[1])
     np.testing.assert_array_equal(d1[2], d2[2])
+    # rays are cast in contiguous blocks on the two devices (every replica runs FK for the configuration itself)
+    rng = np.random.default_rng(3)
+    src = rng.uniform([-3, -3, 0.2], [3, 3, 3], (60_001, 3))
+    rays = np.hstack([src, rng.uniform([-1, -1, 0], [1, 1, 1.5], (60_001, 3)) - src])
+    r1, r2 = one.raycast_batch(Q[0], rays), two.raycast_batch(Q[0], rays)
+    assert all(np.array_equal(a, b) for a, b in zip(r1, r2)) and (r1[0] >= 0).mean() > 0.3
     # small batches stay on the first device; the threshold is an option
     two.set_option("multi_min", 16)
     assert np.array_equal(two.feasible_batch(Q[:1000]), f1[:1000])
