@@ -10,9 +10,10 @@ from klampt_b200._capi import check
 
 maxd = int(sys.argv[1]) if len(sys.argv) > 1 else torch.cuda.device_count()
 per = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
+only = [int(c) for c in sys.argv[3]] if len(sys.argv) > 3 else [1, 2, 4, 8]          # e.g. "18": one and eight devices
 w = synth.world_c2()
 base = None
-for nd in [n for n in (1, 2, 4, 8) if n <= maxd]:
+for nd in [n for n in only if n <= maxd]:
     t0 = time.time()
     eng = Engine(w, device=list(range(nd)))
     tf = time.time() - t0
