@@ -362,6 +362,7 @@ struct kb_engine {
   std::vector<PendingCloud> pending_clouds;   // clouds whose hierarchy is built on the GPU once the arrays are uploaded
   // small host-buffer batches (N <= graph_max): pinned staging + one CUDA graph per batch size (copy in, FK, traversal, finish, copy out)
   struct SmallGraph { int64_t n = 0; cudaGraphExec_t exec = nullptr; const void* key[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; };
+  int64_t zero_copy_max = 64;                // small batches up to this size read / write the pinned staging buffers directly (option zero_copy_max)
   std::vector<SmallGraph> graphs; int64_t graph_max = 1024; double* h_pin_in = nullptr; uint8_t* h_pin_out = nullptr; double* g_dQ = nullptr; uint8_t* g_dout = nullptr;
   int cloud_leaf = 8;                        // points per leaf of a host-built point-cloud hierarchy (option cloud_leaf, 1..32)
   int both_limit = 0;                        // experiment: frontier size up to which comparable inner pairs descend both trees at once
@@ -1624,6 +1625,7 @@ int kb_set_option(kb_engine* e, const char* name, int64_t value) {
   if (!strcmp(name, "both_limit")) { e->both_limit = (int)value; return KB_OK; }
   if (!strcmp(name, "wide")) { e->wide = value != 0; return KB_OK; }
   if (!strcmp(name, "edge_flat_max")) { if (value < 0) return fail(KB_ERR_INVALID, "edge_flat_max must be >= 0"); e->edge_flat_max = value; return KB_OK; }
+  if (!strcmp(name, "zero_copy_max")) { if (value < 0) return fail(KB_ERR_INVALID, "zero_copy_max must be >= 0"); e->zero_copy_max = value; return KB_OK; }
   if (!strcmp(name, "graph_max")) { if (value < 0 || value > 65536) return fail(KB_ERR_INVALID, "graph_max must be in [0, 65536]"); if (e->h_pin_in && value > e->graph_max) return fail(KB_ERR_STATE, "graph_max can only grow before the first small batch"); e->graph_max = value; return KB_OK; }
   if (!strcmp(name, "cloud_leaf")) {
     if (e->finalized) return fail(KB_ERR_STATE, "cloud_leaf must be set before kb_finalize");
@@ -1688,7 +1690,13 @@ static int feasible_small(kb_engine* e, const double* Q, int64_t N, uint8_t* out
     CK(cudaMalloc((void**)&e->g_dQ, cap * e->L * 8)); CK(cudaMalloc((void**)&e->g_dout, cap));
   }
   if ((rc = ensure_cfg_scratch(e, e->feas_items.nxf, N))) return rc;
-  const void* key[6] = {e->d_xf, e->d_state, e->d_hit, e->d_hit_elem, (const void*)e->stream, (const void*)(intptr_t)((e->use_grids ? 1 : 0) + 2 * e->chunk + ((int64_t)e->both_limit << 40))};
+  // The smallest batches skip both copies: FK reads the rows from the pinned staging buffer and the finish kernel writes the result
+  // bytes into the pinned result buffer directly (pinned host memory is device-addressable under unified addressing) -- two graph
+  // nodes fewer on a path that is all fixed overhead.
+  const bool zc = N <= e->zero_copy_max;
+  const double* dQ = zc ? e->h_pin_in : e->g_dQ;
+  uint8_t* dout = zc ? e->h_pin_out : e->g_dout;
+  const void* key[6] = {e->d_xf, e->d_state, e->d_hit, e->d_hit_elem, (const void*)e->stream, (const void*)(intptr_t)((e->use_grids ? 1 : 0) + 2 * e->chunk + ((int64_t)e->both_limit << 40) + ((int64_t)(zc ? 1 : 0) << 50))};
   kb_engine::SmallGraph* g = nullptr;
   for (auto& x : e->graphs) if (x.n == N) g = &x;
   if (g && memcmp(g->key, key, sizeof key) != 0) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; }
@@ -1699,18 +1707,18 @@ static int feasible_small(kb_engine* e, const double* Q, int64_t N, uint8_t* out
   memcpy(e->h_pin_in, Q, (size_t)N * e->L * 8);
   if (!g->exec) {
     // one plain run first: it sets the kernels' attributes (not capturable) and leaves the answer for this very call
-    CK(cudaMemcpyAsync(e->g_dQ, e->h_pin_in, (size_t)N * e->L * 8, cudaMemcpyHostToDevice, e->stream));
-    if ((rc = run_feasible_device(e, e->g_dQ, N, e->g_dout, nullptr, e->d_counters + 3))) return rc;
-    CK(cudaMemcpyAsync(e->h_pin_out, e->g_dout, (size_t)N, cudaMemcpyDeviceToHost, e->stream));
+    if (!zc) CK(cudaMemcpyAsync(e->g_dQ, e->h_pin_in, (size_t)N * e->L * 8, cudaMemcpyHostToDevice, e->stream));
+    if ((rc = run_feasible_device(e, dQ, N, dout, nullptr, e->d_counters + 3))) return rc;
+    if (!zc) CK(cudaMemcpyAsync(e->h_pin_out, e->g_dout, (size_t)N, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     memcpy(out, e->h_pin_out, (size_t)N);
     e->stats.configs_checked += N;
     cudaGraph_t graph = nullptr;
     const int64_t launches_before = e->stats.kernel_launches;
     CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
-    cudaError_t ce = cudaMemcpyAsync(e->g_dQ, e->h_pin_in, (size_t)N * e->L * 8, cudaMemcpyHostToDevice, e->stream);
-    rc = ce == cudaSuccess ? run_feasible_device(e, e->g_dQ, N, e->g_dout, nullptr, e->d_counters + 3) : KB_ERR_CUDA;
-    if (rc == KB_OK) ce = cudaMemcpyAsync(e->h_pin_out, e->g_dout, (size_t)N, cudaMemcpyDeviceToHost, e->stream);
+    cudaError_t ce = zc ? cudaSuccess : cudaMemcpyAsync(e->g_dQ, e->h_pin_in, (size_t)N * e->L * 8, cudaMemcpyHostToDevice, e->stream);
+    rc = ce == cudaSuccess ? run_feasible_device(e, dQ, N, dout, nullptr, e->d_counters + 3) : KB_ERR_CUDA;
+    if (rc == KB_OK && !zc) ce = cudaMemcpyAsync(e->h_pin_out, e->g_dout, (size_t)N, cudaMemcpyDeviceToHost, e->stream);
     cudaError_t ce2 = cudaStreamEndCapture(e->stream, &graph);
     e->stats.kernel_launches = launches_before;                 // nothing ran during the capture
     if (rc != KB_OK || ce != cudaSuccess || ce2 != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return KB_OK; }   // no graph: plain runs keep working
