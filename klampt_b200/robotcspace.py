@@ -161,6 +161,22 @@ class RobotCSpace(CSpace):
         """all colliding world-id pairs per configuration (no early exit); see Engine.colliding_pairs_batch"""
         return self.engine.colliding_pairs_batch(Q, max_pairs=max_pairs)
 
+    def _counts(self):
+        """(terrains, rigid objects of the world, all engine objects): the engine's objects beyond the world's own are the links of
+        other robots, which ride along as rigid bodies (WorldModel.to_spec)"""
+        T = len(self.spec.terrains)
+        O = self.collider.world.numRigidObjects() if self.collider is not None else len(self.spec.objects)
+        return T, O, len(self.spec.objects)
+
+    def _other_robot_of(self, k: int):
+        """engine object k >= O belongs to another robot: (robot index, name)"""
+        w = self.collider.world
+        wid = int(self.spec.world_ids[len(self.spec.terrains) + k])
+        for r in range(w.numRobots()):
+            if w.robotID(r) < wid <= w.robotID(r) + w.robot(r).numLinks():
+                return r, w.robot(r).getName()
+        return -1, ""
+
     def feasibilityFailures(self, x):
         """names of the reference's feasibility tests that fail at x (CSpaceInterface::feasibilityFailures with the test names of
         plan/robotcspace.py:62-75): 'joint limits', 'self collision', 'obj collision i name', 'terrain collision i name'"""
@@ -168,7 +184,7 @@ class RobotCSpace(CSpace):
             return ["joint limits"]
         pairs, count = self.engine.colliding_pairs_batch(np.asarray(x, dtype=np.float64), max_pairs=32)
         names = []
-        T, O = len(self.spec.terrains), len(self.spec.objects)
+        T, O, Oall = self._counts()
         for a, b in pairs[0]:
             if a < 0:
                 continue
@@ -177,6 +193,8 @@ class RobotCSpace(CSpace):
                 n = "terrain collision %d %s" % (lo, self.collider.world.terrain(lo).getName() if self.collider else "")
             elif lo < T + O:
                 n = "obj collision %d %s" % (lo - T, self.collider.world.rigidObject(lo - T).getName() if self.collider else "")
+            elif lo < T + Oall:
+                n = "robot collision %d %s" % self._other_robot_of(lo - T)
             else:
                 n = "self collision"
             if n not in names:
@@ -193,6 +211,8 @@ class RobotCSpace(CSpace):
         names = ["joint limits", "setconfig", "calcbb", "self collision"]
         names += ["obj collision %d %s" % (i, w.rigidObject(i).getName()) for i in range(w.numRigidObjects())]
         names += ["terrain collision %d %s" % (i, w.terrain(i).getName()) for i in range(w.numTerrains())]
+        # not in the reference's Python list (its RobotCSpace never looks at other robots); the C++ space does (RobotCSpace.cpp:806-809)
+        names += ["robot collision %d %s" % (r, w.robot(r).getName()) for r in range(w.numRobots()) if w.robot(r) is not self.robot]
         return names
 
     def feasibilityTestDependenciesList(self) -> List[tuple]:
@@ -200,7 +220,7 @@ class RobotCSpace(CSpace):
         if self.collider is None:
             return [("self collision", "setconfig")]
         deps = [("calcbb", "setconfig"), ("self collision", "setconfig")]
-        deps += [(n, "calcbb") for n in self.feasibilityTestNamesList() if n.startswith(("obj collision", "terrain collision"))]
+        deps += [(n, "calcbb") for n in self.feasibilityTestNamesList() if n.startswith(("obj collision", "terrain collision", "robot collision"))]
         return deps
 
     def testFeasibility(self, name: str, x) -> bool:
@@ -213,12 +233,14 @@ class RobotCSpace(CSpace):
         if name in ("setconfig", "calcbb"):
             return True
         pairs, count = self.engine.colliding_pairs_batch(np.asarray(x, dtype=np.float64), max_pairs=32)
-        T, O = len(self.spec.terrains), len(self.spec.objects)
+        T, O, Oall = self._counts()
         for a, b in pairs[0]:
             if a < 0:
                 continue
             lo = min(int(a), int(b))
-            if name == "self collision" and lo >= T + O:
+            if name == "self collision" and lo >= T + Oall:
+                return False
+            if name.startswith("robot collision ") and T + O <= lo < T + Oall and name == "robot collision %d %s" % self._other_robot_of(lo - T):
                 return False
             if name.startswith("terrain collision %d " % lo) and lo < T:
                 return False

@@ -739,17 +739,38 @@ class WorldModel:
         return self.robotID(r) + 1 + j
 
     def to_spec(self, robot_index: int = 0, pair_mask: Optional[np.ndarray] = None) -> WorldSpec:
-        """the single-robot world the engine works on (SingleRobotCSpace holds one active robot)"""
-        if len(self._robots) != 1:
-            raise NotImplementedError("the batched engine takes worlds with exactly one robot (other robots would have to be "
-                                      "added as rigid objects at their current configuration)")
+        """the world the engine works on: ONE active robot (SingleRobotCSpace holds one), the terrains, the rigid objects, and -- as
+        SingleRobotCSpace::CheckCollisionFree checks the robot against "all other robots" too (RobotCSpace.cpp:794-823) -- the links of
+        every other robot as rigid bodies at their current transforms.  The engine numbers those links after the rigid objects;
+        ``spec.world_ids[engine id]`` gives the id of the reference's scheme (World.cpp:47-53: terrains, rigid objects, then per
+        robot its id and its links), and ``pair_mask`` (reference numbering) is permuted accordingly."""
+        if not self._robots:
+            raise NotImplementedError("the batched engine needs a robot")
         w = WorldSpec()
-        for t in self._terrains:
+        ids: List[int] = []
+        for i, t in enumerate(self._terrains):
             w.terrains.append(-1 if t._geom.empty() else w.add_geom(t._geom.to_spec()))
-        for o in self._objects:
+            ids.append(self.terrainID(i))
+        for i, o in enumerate(self._objects):
             gi = -1 if o._geom.empty() else w.add_geom(o._geom.to_spec())
             w.objects.append((gi, o._geom._T12()))
-        w.robot = self._robots[robot_index].to_spec(w)
+            ids.append(self.rigidObjectID(i))
+        for r, rob in enumerate(self._robots):
+            if r == robot_index:
+                continue
+            for j in range(rob.numLinks()):
+                g = rob.link(j)._geom
+                w.objects.append((-1 if g.empty() else w.add_geom(g.to_spec()), g._T12()))
+                ids.append(self.robotLinkID(r, j))
+        active = self._robots[robot_index]
+        w.robot = active.to_spec(w)
+        ids.append(self.robotID(robot_index))
+        ids += [self.robotLinkID(robot_index, j) for j in range(active.numLinks())]
+        multi = len(self._robots) > 1
+        w.world_ids = np.asarray(ids, dtype=np.int32) if multi else None
+        if pair_mask is not None and multi:
+            pm = np.asarray(pair_mask, dtype=np.uint8)
+            pair_mask = np.ascontiguousarray(pm[np.ix_(ids, ids)])
         w.pair_mask = pair_mask
         return w
 

@@ -136,6 +136,7 @@ class WorldSpec:
     objects: List[Tuple[int, np.ndarray]] = field(default_factory=list)  # (geometry index, T12) per rigid object
     robot: Optional[RobotSpec] = None
     pair_mask: Optional[np.ndarray] = None                           # (n_ids,n_ids) u8 overrides InitializeDefault
+    world_ids: Optional[np.ndarray] = None                           # engine id -> id in the caller's world (set when other robots' links ride along as rigid objects)
 
     def add_geom(self, g: GeomSpec) -> int:
         self.geoms.append(g)

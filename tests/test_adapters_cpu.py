@@ -180,3 +180,42 @@ def test_adaptive_queries_reorder_the_conjunction():
         sp.optimizeQueryOrder()
     sp.setVisibilityPrior("slow", 3.0, 0.5, 1.0)
     assert sp.visibilityCost("slow") == 3.0 and sp.visibilityProbability("slow") == 0.5 and len(sp.visibilityQueryOrder()) == 3
+
+
+def test_other_robots_ride_along_as_rigid_bodies():
+    """SingleRobotCSpace::CheckCollisionFree checks the robot against all OTHER robots too (RobotCSpace.cpp:794-823): WorldModel.to_spec
+    hands their links to the engine as rigid objects at their current transforms and keeps the id translation"""
+    from klampt_b200 import so3
+    spec = synth.world_c1()
+    world = WorldModel.from_spec(spec)
+    other = world.addRobot("second", spec.robot, spec.geoms)
+    T_other = synth.make_T(None, (0.9, 0.25, 0.0))
+    for j in range(other.numLinks()):                     # (setConfig needs the GPU: place the second arm's links by hand)
+        other.link(j).geometry().setCurrentTransform(*so3.from_rowmajor12(T_other))
+    T, O, L = world.numTerrains(), world.numRigidObjects(), spec.robot.L
+    n_geo = sum(1 for j in range(L) if not other.link(j).geometry().empty())
+    w0 = world.to_spec(0)
+    assert len(w0.terrains) == T and len(w0.objects) == O + L
+    assert sum(1 for gi, _ in w0.objects[O:] if gi >= 0) == n_geo
+    assert all(np.allclose(Tm, T_other) for _, Tm in w0.objects[O:])
+    ids = list(w0.world_ids)
+    assert ids[:T + O] == list(range(T + O))
+    assert ids[T + O:T + O + L] == [world.robotLinkID(1, j) for j in range(L)]
+    assert ids[T + O + L] == world.robotID(0) and ids[T + O + L + 1:] == [world.robotLinkID(0, j) for j in range(L)]
+    # the second robot as the active one: the first one's links ride along
+    w1 = world.to_spec(1)
+    assert list(w1.world_ids[T + O:T + O + L]) == [world.robotLinkID(0, j) for j in range(L)] and w1.world_ids[T + O + L] == world.robotID(1)
+    # a reference-numbered mask is permuted into the engine's numbering
+    wc = WorldCollider(world)
+    m = wc.to_pair_mask()
+    w0m = world.to_spec(0, pair_mask=m)
+    a, b = world.robotLinkID(0, 3), world.robotLinkID(1, 2)
+    ea, eb = ids.index(a), ids.index(b)
+    assert m[min(a, b), max(a, b)] == 1 and (w0m.pair_mask[ea, eb] == 1 or w0m.pair_mask[eb, ea] == 1)
+    assert w0m.pair_mask.shape == (len(ids), len(ids))
+    # the oracle agrees that a link of the first arm placed inside the second arm collides with it (and names an object id)
+    single = WorldModel.from_spec(spec).to_spec(0)
+    assert single.world_ids is None and len(single.objects) == O
+    Q = synth.sample_configs(spec.robot, 3000, 5)
+    f_two, f_one = OracleWorld(world.to_spec(0)).feasible_batch(Q), OracleWorld(single).feasible_batch(Q)
+    assert np.all(f_two <= f_one) and (f_two < f_one).sum() > 0          # the second arm only takes feasible configurations away

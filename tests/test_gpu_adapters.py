@@ -289,3 +289,37 @@ def test_one_joint_limit_contract_for_single_and_batch_queries(built):
     b = list(space.bound); b[1] = (-0.1, 0.1); space.setBounds(b)
     got2 = space.feasible_batch(Q)
     assert not got2[np.abs(Q[:, 1]) > 0.1].any() and np.array_equal(got2[np.abs(Q[:, 1]) <= 0.1], got[np.abs(Q[:, 1]) <= 0.1])
+
+
+def test_two_robots_the_other_one_is_an_obstacle(built):
+    """SingleRobotCSpace checks its robot against every other robot of the world (RobotCSpace.cpp:794-823): a second arm, standing
+    0.9 m away at its own configuration, takes feasible configurations away from the first; the oracle on the same description
+    agrees bit for bit, and the named tests report the other robot"""
+    from klampt_b200.collide import WorldCollider
+    from klampt_b200.robotcspace import RobotCSpace
+    from klampt_b200.robotsim import WorldModel
+    from oracle.oracle import OracleWorld
+    spec = synth.world_c1()
+    world = WorldModel.from_spec(spec)
+    base = spec.robot.T0.copy()
+    second = synth.world_c1().robot
+    second.T0 = base.copy()
+    second.T0[0, 9:12] += np.array([0.9, 0.25, 0.0])                 # the second arm's base stands beside the first
+    other = world.addRobot("second", second, spec.geoms)
+    other.setConfig(list(synth.sample_configs(second, 1, 3)[0]))      # FK on the GPU places its links
+    space = RobotCSpace(world.robot(0), WorldCollider(world))
+    alone = RobotCSpace(WorldModel.from_spec(spec).robot(0), WorldCollider(WorldModel.from_spec(spec)))
+    Q = synth.sample_configs(spec.robot, 20000, 31)
+    f2, f1 = space.feasible_batch(Q), alone.feasible_batch(Q)
+    assert np.all(f2 <= f1) and (f2 < f1).sum() > 50
+    assert np.array_equal(f2, OracleWorld(space.spec).feasible_batch(Q))
+    lost = np.flatnonzero(f2 < f1)[:5]
+    for i in lost:
+        assert "robot collision 1 second" in space.feasibilityFailures(list(Q[i]))
+        assert not space.testFeasibility("robot collision 1 second", list(Q[i]))
+    assert "robot collision 1 second" in space.feasibilityTestNamesList()
+    # the id translation: first colliding pairs named in the world's numbering point at links of the second robot
+    ok, pairs = space.engine.feasible_batch(Q[lost], return_pairs=True)
+    wid = space.spec.world_ids[pairs]
+    lo1, hi1 = world.robotLinkID(1, 0), world.robotLinkID(1, second.L - 1)
+    assert any(any(lo1 <= int(x) <= hi1 for x in row) for row in wid)
