@@ -363,7 +363,7 @@ struct kb_engine {
   // small host-buffer batches (N <= graph_max): pinned staging + one CUDA graph per batch size (copy in, FK, traversal, finish, copy out)
   struct SmallGraph { int64_t n = 0; cudaGraphExec_t exec = nullptr; const void* key[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; };
   int64_t zero_copy_max = 64;                // small batches up to this size read / write the pinned staging buffers directly (option zero_copy_max)
-  std::vector<SmallGraph> graphs; int64_t graph_max = 1024; double* h_pin_in = nullptr; uint8_t* h_pin_out = nullptr; double* g_dQ = nullptr; uint8_t* g_dout = nullptr;
+  std::vector<SmallGraph> graphs; int64_t graph_max = 16384; double* h_pin_in = nullptr; uint8_t* h_pin_out = nullptr; double* g_dQ = nullptr; uint8_t* g_dout = nullptr;
   int cloud_leaf = 8;                        // points per leaf of a host-built point-cloud hierarchy (option cloud_leaf, 1..32)
   int both_limit = 0;                        // experiment: frontier size up to which comparable inner pairs descend both trees at once
   int grid_res = 256; bool use_grids = false; // clearance-grid broad phase of the boolean query (options grid_res, clear_grid)
@@ -772,6 +772,24 @@ int run_feasible_device(kb_engine* e, const double* dQ, int64_t N, uint8_t* d_ou
                         d_first_pair ? d_first_pair + 2 * off : nullptr, d_nfeas, e->stream));
     e->stats.kernel_launches++;
   }
+  return KB_OK;
+}
+
+// Small batches: FK, then the traversal with one warp per configuration, which writes the result bytes itself (no counter reset, no
+// finish kernel): two kernels per call.  Split-pipeline / statistics runs do not come here (feasible_small's caller checks).
+int run_feasible_small(kb_engine* e, const double* dQ, int64_t n, uint8_t* d_out, unsigned long long* d_nfeas) {
+  const int nxf = e->feas_items.nxf;
+  CK(kb_launch_fk(e->d_robot, e->d_drv, e->d_drv_link, e->d_drv_scale, e->d_drv_off, dQ, n, e->d_xf, nxf, e->d_state, nullptr, e->d_hit, e->stream));
+  e->stats.kernel_launches++;
+  if (e->feas_items.items.empty()) {
+    CK(kb_launch_finish(e->d_state, e->d_hit, e->d_hit_elem, e->feas_items.d_items, e->d_triown, e->d_sphown, e->d_boxown, n, d_out, nullptr, d_nfeas, e->stream));
+    e->stats.kernel_launches++;
+    return KB_OK;
+  }
+  KbTraverseParams p = make_params(e, e->feas_items, e->d_xf, n, e->d_state);
+  p.static_sched = 1; p.out_bytes = d_out; p.nfeasible = d_nfeas;
+  CK(kb_launch_traverse(p, 0, nullptr, 0.0, e->num_sms, e->stream));
+  e->stats.kernel_launches++;
   return KB_OK;
 }
 
@@ -1708,7 +1726,7 @@ static int feasible_small(kb_engine* e, const double* Q, int64_t N, uint8_t* out
   if (!g->exec) {
     // one plain run first: it sets the kernels' attributes (not capturable) and leaves the answer for this very call
     if (!zc) CK(cudaMemcpyAsync(e->g_dQ, e->h_pin_in, (size_t)N * e->L * 8, cudaMemcpyHostToDevice, e->stream));
-    if ((rc = run_feasible_device(e, dQ, N, dout, nullptr, e->d_counters + 3))) return rc;
+    if ((rc = run_feasible_small(e, dQ, N, dout, e->d_counters + 3))) return rc;
     if (!zc) CK(cudaMemcpyAsync(e->h_pin_out, e->g_dout, (size_t)N, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     memcpy(out, e->h_pin_out, (size_t)N);
@@ -1717,7 +1735,7 @@ static int feasible_small(kb_engine* e, const double* Q, int64_t N, uint8_t* out
     const int64_t launches_before = e->stats.kernel_launches;
     CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
     cudaError_t ce = zc ? cudaSuccess : cudaMemcpyAsync(e->g_dQ, e->h_pin_in, (size_t)N * e->L * 8, cudaMemcpyHostToDevice, e->stream);
-    rc = ce == cudaSuccess ? run_feasible_device(e, dQ, N, dout, nullptr, e->d_counters + 3) : KB_ERR_CUDA;
+    rc = ce == cudaSuccess ? run_feasible_small(e, dQ, N, dout, e->d_counters + 3) : KB_ERR_CUDA;
     if (rc == KB_OK && !zc) ce = cudaMemcpyAsync(e->h_pin_out, e->g_dout, (size_t)N, cudaMemcpyDeviceToHost, e->stream);
     cudaError_t ce2 = cudaStreamEndCapture(e->stream, &graph);
     e->stats.kernel_launches = launches_before;                 // nothing ran during the capture
@@ -1732,7 +1750,7 @@ static int feasible_small(kb_engine* e, const double* Q, int64_t N, uint8_t* out
   CK(cudaStreamSynchronize(e->stream));
   memcpy(out, e->h_pin_out, (size_t)N);
   e->stats.configs_checked += N;
-  e->stats.kernel_launches += 3;
+  e->stats.kernel_launches += 2;
   return KB_OK;
 }
 

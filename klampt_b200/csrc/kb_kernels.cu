@@ -594,7 +594,7 @@ __device__ __forceinline__ void node_test(const KbTraverseParams& p, const ItemS
 // BOXES: the work list holds solid-box items.  The box predicates -- fp32 and the fp64 recheck -- are compiled only into that
 // instantiation so the common kernel keeps its register allocation: with the box branch inside the shared, not inlined
 // exact_elem_collide, its larger clobber set cost the calling kernel spills on the hot path (C2 6.23 -> 6.99 ms, C3 7.83 -> 9.59).
-template <bool ITC, bool STATS, int BPS, bool BOXES>
+template <bool ITC, bool STATS, int BPS, bool BOXES, bool STATIC>
 __global__ void __launch_bounds__(KB_WARPS_PER_BLOCK * 32, BPS)
 kb_traverse_kernel(const KbTraverseParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -637,10 +637,18 @@ kb_traverse_kernel(const KbTraverseParams p) {
   // the tail is one configuration long (configuration cost varies by two orders of magnitude)
   const unsigned total_warps = gridDim.x * KB_WARPS_PER_BLOCK;
   unsigned grab = 8;
+  bool static_done = false;
   for (;;) {
     unsigned int c0 = 0;
-    if (lane == 0) c0 = atomicAdd(p.work_counter, grab);
-    c0 = __shfl_sync(FULL, c0, 0);
+    if (STATIC) {                     // one configuration per warp, by warp index (small batches; a compile-time variant: the
+                                      // batch kernel's register allocation stays what it was)
+      if (static_done) break;
+      static_done = true; grab = 1;
+      c0 = blockIdx.x * KB_WARPS_PER_BLOCK + warp;
+    } else {
+      if (lane == 0) c0 = atomicAdd(p.work_counter, grab);
+      c0 = __shfl_sync(FULL, c0, 0);
+    }
     if ((int64_t)c0 >= p.N) break;
     const unsigned nN = (unsigned)p.N;
     const unsigned cend = (c0 + grab < nN) ? c0 + grab : nN;
@@ -864,6 +872,15 @@ kb_traverse_kernel(const KbTraverseParams p) {
   }
   // pairs still parked for the fp64 recheck belong to configurations already written as "no hit": resolve them now
   { int f = 0, fa = 0, fb = 0; drain_rechecks<BOXES>(p, rq, rq_count, lane, (int64_t)-1, f, fa, fb, true); }
+  if (STATIC) {
+    // the result byte of this warp's configuration, after every pair it parked for the fp64 recheck was resolved
+    const int64_t c = (int64_t)blockIdx.x * KB_WARPS_PER_BLOCK + warp;
+    if (c < p.N && lane == 0) {
+      const bool feas = (!p.state || p.state[c] != 0) && p.hit[c] < 0;
+      p.out_bytes[c] = feas ? 1 : 0;
+      if (feas && p.nfeasible) atomicAdd(p.nfeasible, 1ull);
+    }
+  }
 }
 
 // =============================================================================================== traversal (boolean, 4-wide hierarchies)
@@ -874,7 +891,7 @@ kb_traverse_kernel(const KbTraverseParams p) {
 // test the node's four child slots against that box: one line on the expanded side, one 32-byte slot on the other, per four tests.
 // The side to expand is always the larger box (decided when the entry is pushed, where both boxes are in registers), i.e. the
 // descend-larger rule two levels at a time -- no descend-both step, whose extra tests cost C2 more than they saved.
-template <bool ITC, bool STATS, int BPS, bool BOXES>
+template <bool ITC, bool STATS, int BPS, bool BOXES, bool STATIC>
 __global__ void __launch_bounds__(KB_WARPS_PER_BLOCK * 32, BPS)
 kb_traverse_wide_kernel(const KbTraverseParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -917,10 +934,18 @@ kb_traverse_wide_kernel(const KbTraverseParams p) {
   // the tail is one configuration long (configuration cost varies by two orders of magnitude)
   const unsigned total_warps = gridDim.x * KB_WARPS_PER_BLOCK;
   unsigned grab = 8;
+  bool static_done = false;
   for (;;) {
     unsigned int c0 = 0;
-    if (lane == 0) c0 = atomicAdd(p.work_counter, grab);
-    c0 = __shfl_sync(FULL, c0, 0);
+    if (STATIC) {                     // one configuration per warp, by warp index (small batches; a compile-time variant: the
+                                      // batch kernel's register allocation stays what it was)
+      if (static_done) break;
+      static_done = true; grab = 1;
+      c0 = blockIdx.x * KB_WARPS_PER_BLOCK + warp;
+    } else {
+      if (lane == 0) c0 = atomicAdd(p.work_counter, grab);
+      c0 = __shfl_sync(FULL, c0, 0);
+    }
     if ((int64_t)c0 >= p.N) break;
     const unsigned nN = (unsigned)p.N;
     const unsigned cend = (c0 + grab < nN) ? c0 + grab : nN;
@@ -1129,6 +1154,15 @@ kb_traverse_wide_kernel(const KbTraverseParams p) {
   }
   // pairs still parked for the fp64 recheck belong to configurations already written as "no hit": resolve them now
   { int f = 0, fa = 0, fb = 0; drain_rechecks<BOXES>(p, rq, rq_count, lane, (int64_t)-1, f, fa, fb, true); }
+  if (STATIC) {
+    // the result byte of this warp's configuration, after every pair it parked for the fp64 recheck was resolved
+    const int64_t c = (int64_t)blockIdx.x * KB_WARPS_PER_BLOCK + warp;
+    if (c < p.N && lane == 0) {
+      const bool feas = (!p.state || p.state[c] != 0) && p.hit[c] < 0;
+      p.out_bytes[c] = feas ? 1 : 0;
+      if (feas && p.nfeasible) atomicAdd(p.nfeasible, 1ull);
+    }
+  }
 }
 
 // =============================================================================================== all colliding pairs
@@ -2197,16 +2231,23 @@ static cudaError_t launch_traverse_t(const KbTraverseParams& p, int num_sms, siz
   static bool attr_set[64] = {false};      // the attribute is per device
   int dev = 0; cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(kb_traverse_kernel<ITC, STATS, BPS, BOXES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e == cudaSuccess && !BOXES) e = cudaFuncSetAttribute(kb_traverse_wide_kernel<ITC, STATS, BPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(kb_traverse_kernel<ITC, STATS, BPS, BOXES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess && !BOXES) e = cudaFuncSetAttribute(kb_traverse_wide_kernel<ITC, STATS, BPS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess && !STATS) e = cudaFuncSetAttribute(kb_traverse_kernel<ITC, false, 3, BOXES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess && !STATS && !BOXES) e = cudaFuncSetAttribute(kb_traverse_wide_kernel<ITC, false, 3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   int per_sm = (int)((224 * 1024) / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > BPS) per_sm = BPS;
   int64_t want = (p.N + 8 * KB_WARPS_PER_BLOCK - 1) / (8 * KB_WARPS_PER_BLOCK);
   int64_t grid = (int64_t)num_sms * per_sm; if (grid > want) grid = want; if (grid < 1) grid = 1;
-  if (p.use_wide && !BOXES) kb_traverse_wide_kernel<ITC, STATS, BPS, false><<<(unsigned)grid, KB_WARPS_PER_BLOCK * 32, smem, s>>>(p);
-  else kb_traverse_kernel<ITC, STATS, BPS, BOXES><<<(unsigned)grid, KB_WARPS_PER_BLOCK * 32, smem, s>>>(p);
+  if (p.static_sched) grid = (p.N + KB_WARPS_PER_BLOCK - 1) / KB_WARPS_PER_BLOCK;      // one warp per configuration
+  if (p.static_sched && !STATS) {      // small batches: the 168-register build (occupancy is irrelevant at one warp per configuration)
+    if (p.use_wide && !BOXES) kb_traverse_wide_kernel<ITC, false, 3, false, true><<<(unsigned)grid, KB_WARPS_PER_BLOCK * 32, smem, s>>>(p);
+    else kb_traverse_kernel<ITC, false, 3, BOXES, true><<<(unsigned)grid, KB_WARPS_PER_BLOCK * 32, smem, s>>>(p);
+  }
+  else if (p.use_wide && !BOXES) kb_traverse_wide_kernel<ITC, STATS, BPS, false, false><<<(unsigned)grid, KB_WARPS_PER_BLOCK * 32, smem, s>>>(p);
+  else kb_traverse_kernel<ITC, STATS, BPS, BOXES, false><<<(unsigned)grid, KB_WARPS_PER_BLOCK * 32, smem, s>>>(p);
   return cudaGetLastError();
 }
 
@@ -2214,7 +2255,7 @@ cudaError_t kb_launch_traverse(const KbTraverseParams& p, int mode, double* out_
   if (p.N <= 0) return cudaSuccess;
   const size_t smem = mode == 0 ? kb_traverse_smem_bytes(p.nxf, p.nitems, p.nprobes) : kb_distance_smem_bytes(p.nxf, p.nitems);
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
-  cudaError_t e = cudaMemsetAsync(p.work_counter, 0, sizeof(uint32_t), s);
+  cudaError_t e = (mode == 0 && p.static_sched) ? cudaSuccess : cudaMemsetAsync(p.work_counter, 0, sizeof(uint32_t), s);
   if (e != cudaSuccess) return e;
   const bool itc = p.nitems <= KB_ITC_MAX_ITEMS;
   if (p.N > 0xfffffff0ll) return cudaErrorInvalidValue;

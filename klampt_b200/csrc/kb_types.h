@@ -141,6 +141,11 @@ struct KbTraverseParams {
   const KbProbe* probes;          // clearance probes of this item set (boolean kernel only); null / 0 = no pre-filter
   int32_t nprobes;
   const uint32_t* always_on;      // bit i set: item i has no probes and is always traversed ((nitems + 31) / 32 words)
+  // small batches (kb_feasible_batch, N <= graph_max): warp w checks configuration w and nothing else -- no work counter to reset, no
+  // finish kernel: the warp writes the result byte itself once its parked fp64 rechecks are resolved
+  int32_t static_sched;
+  uint8_t* out_bytes;             // static_sched: 1 = feasible, 0 = not (limits or collision)
+  unsigned long long* nfeasible;  // static_sched: feasible configurations are counted here (statistics)
 };
 
 // ray casting (kb_raycast.cu): one entry per body a ray can hit -- a robot link, a rigid object, a terrain
