@@ -777,9 +777,10 @@ int run_feasible_device(kb_engine* e, const double* dQ, int64_t N, uint8_t* d_ou
 
 // Small batches: FK, then the traversal with one warp per configuration, which writes the result bytes itself (no counter reset, no
 // finish kernel): two kernels per call.  Split-pipeline / statistics runs do not come here (feasible_small's caller checks).
-int run_feasible_small(kb_engine* e, const double* dQ, int64_t n, uint8_t* d_out, unsigned long long* d_nfeas) {
+int run_feasible_small(kb_engine* e, const double* dQ, int64_t n, uint8_t* d_out, unsigned long long* d_nfeas, const uint8_t* d_alive = nullptr) {
   const int nxf = e->feas_items.nxf;
-  CK(kb_launch_fk(e->d_robot, e->d_drv, e->d_drv_link, e->d_drv_scale, e->d_drv_off, dQ, n, e->d_xf, nxf, e->d_state, nullptr, e->d_hit, e->stream));
+  int rc = ensure_cfg_scratch(e, nxf, n); if (rc) return rc;
+  CK(kb_launch_fk(e->d_robot, e->d_drv, e->d_drv_link, e->d_drv_scale, e->d_drv_off, dQ, n, e->d_xf, nxf, e->d_state, d_alive, e->d_hit, e->stream));
   e->stats.kernel_launches++;
   if (e->feas_items.items.empty()) {
     CK(kb_launch_finish(e->d_state, e->d_hit, e->d_hit_elem, e->feas_items.d_items, e->d_triown, e->d_sphown, e->d_boxown, n, d_out, nullptr, d_nfeas, e->stream));
@@ -1884,7 +1885,10 @@ int kb_edges_visible_batch_device(kb_engine* e, const double* dA, const double* 
     const int64_t nslots = N * per_max;
     if (!e->d_eslot || e->eslot_cap < e->chunk) { if (e->d_eslot) cudaFree(e->d_eslot); e->d_eslot = nullptr; CK(cudaMalloc((void**)&e->d_eslot, (size_t)e->chunk)); e->eslot_cap = e->chunk; }
     CK(kb_launch_edge_flat_expand(e->d_robot, dA, dB, e->d_nlev, e->d_alive, nslots, (int)per_max, e->d_eQ, e->d_eslot, e->d_counters + 9, e->stream)); e->stats.kernel_launches++;
-    if ((rc = run_feasible_device(e, e->d_eQ, nslots, e->d_efeas, nullptr, nullptr, e->d_eslot))) return rc;
+    // the midpoints of a small edge batch are a small configuration batch: one warp per midpoint (run_feasible_small)
+    const bool small = nslots <= 16384 && e->pipeline == 0 && !e->time_kernels && !e->collect_stats;
+    if ((rc = small ? run_feasible_small(e, e->d_eQ, nslots, e->d_efeas, nullptr, e->d_eslot)
+                    : run_feasible_device(e, e->d_eQ, nslots, e->d_efeas, nullptr, nullptr, e->d_eslot))) return rc;
     CK(kb_launch_edge_flat_finish(e->d_efeas, e->d_eslot, nslots, (int)per_max, e->d_nlev, e->d_firstbad, N, e->d_alive, e->d_nchecks, e->stream)); e->stats.kernel_launches += 2;
   } else
   for (int lev = 1; lev <= maxlev; lev++) {
