@@ -747,7 +747,11 @@ KbTraverseParams make_params(kb_engine* e, const ItemSet& set, const double* xf,
 }
 
 // feasibility of n configurations resident on the device: FK -> traversal -> finish, chunk by chunk
+int run_feasible_small(kb_engine* e, const double* dQ, int64_t n, uint8_t* d_out, unsigned long long* d_nfeas, const uint8_t* d_alive);
+#define KB_SMALL_MAX 16384      // batches up to this size are checked one warp per configuration (run_feasible_small)
+
 int run_feasible_device(kb_engine* e, const double* dQ, int64_t N, uint8_t* d_out, int32_t* d_first_pair, unsigned long long* d_nfeas, const uint8_t* d_alive = nullptr) {
+  if (N <= KB_SMALL_MAX && !d_first_pair && e->pipeline == 0 && !e->collect_stats) return run_feasible_small(e, dQ, N, d_out, d_nfeas, d_alive);
   int rc = ensure_cfg_scratch(e, e->feas_items.nxf, N); if (rc) return rc;
   for (int64_t off = 0; off < N; off += e->chunk) {
     int64_t n = std::min(e->chunk, N - off);
@@ -777,7 +781,7 @@ int run_feasible_device(kb_engine* e, const double* dQ, int64_t N, uint8_t* d_ou
 
 // Small batches: FK, then the traversal with one warp per configuration, which writes the result bytes itself (no counter reset, no
 // finish kernel): two kernels per call.  Split-pipeline / statistics runs do not come here (feasible_small's caller checks).
-int run_feasible_small(kb_engine* e, const double* dQ, int64_t n, uint8_t* d_out, unsigned long long* d_nfeas, const uint8_t* d_alive = nullptr) {
+int run_feasible_small(kb_engine* e, const double* dQ, int64_t n, uint8_t* d_out, unsigned long long* d_nfeas, const uint8_t* d_alive) {
   const int nxf = e->feas_items.nxf;
   int rc = ensure_cfg_scratch(e, nxf, n); if (rc) return rc;
   CK(kb_launch_fk(e->d_robot, e->d_drv, e->d_drv_link, e->d_drv_scale, e->d_drv_off, dQ, n, e->d_xf, nxf, e->d_state, d_alive, e->d_hit, e->stream));
@@ -789,7 +793,7 @@ int run_feasible_small(kb_engine* e, const double* dQ, int64_t n, uint8_t* d_out
   }
   KbTraverseParams p = make_params(e, e->feas_items, e->d_xf, n, e->d_state);
   p.static_sched = 1; p.out_bytes = d_out; p.nfeasible = d_nfeas;
-  CK(kb_launch_traverse(p, 0, nullptr, 0.0, e->num_sms, e->stream));
+  CK(timed_traverse(e, p, 0, nullptr, 0.0));
   e->stats.kernel_launches++;
   return KB_OK;
 }
@@ -1727,7 +1731,7 @@ static int feasible_small(kb_engine* e, const double* Q, int64_t N, uint8_t* out
   if (!g->exec) {
     // one plain run first: it sets the kernels' attributes (not capturable) and leaves the answer for this very call
     if (!zc) CK(cudaMemcpyAsync(e->g_dQ, e->h_pin_in, (size_t)N * e->L * 8, cudaMemcpyHostToDevice, e->stream));
-    if ((rc = run_feasible_small(e, dQ, N, dout, e->d_counters + 3))) return rc;
+    if ((rc = run_feasible_small(e, dQ, N, dout, e->d_counters + 3, nullptr))) return rc;
     if (!zc) CK(cudaMemcpyAsync(e->h_pin_out, e->g_dout, (size_t)N, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     memcpy(out, e->h_pin_out, (size_t)N);
@@ -1736,7 +1740,7 @@ static int feasible_small(kb_engine* e, const double* Q, int64_t N, uint8_t* out
     const int64_t launches_before = e->stats.kernel_launches;
     CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
     cudaError_t ce = zc ? cudaSuccess : cudaMemcpyAsync(e->g_dQ, e->h_pin_in, (size_t)N * e->L * 8, cudaMemcpyHostToDevice, e->stream);
-    rc = ce == cudaSuccess ? run_feasible_small(e, dQ, N, dout, e->d_counters + 3) : KB_ERR_CUDA;
+    rc = ce == cudaSuccess ? run_feasible_small(e, dQ, N, dout, e->d_counters + 3, nullptr) : KB_ERR_CUDA;
     if (rc == KB_OK && !zc) ce = cudaMemcpyAsync(e->h_pin_out, e->g_dout, (size_t)N, cudaMemcpyDeviceToHost, e->stream);
     cudaError_t ce2 = cudaStreamEndCapture(e->stream, &graph);
     e->stats.kernel_launches = launches_before;                 // nothing ran during the capture
@@ -1885,10 +1889,8 @@ int kb_edges_visible_batch_device(kb_engine* e, const double* dA, const double* 
     const int64_t nslots = N * per_max;
     if (!e->d_eslot || e->eslot_cap < e->chunk) { if (e->d_eslot) cudaFree(e->d_eslot); e->d_eslot = nullptr; CK(cudaMalloc((void**)&e->d_eslot, (size_t)e->chunk)); e->eslot_cap = e->chunk; }
     CK(kb_launch_edge_flat_expand(e->d_robot, dA, dB, e->d_nlev, e->d_alive, nslots, (int)per_max, e->d_eQ, e->d_eslot, e->d_counters + 9, e->stream)); e->stats.kernel_launches++;
-    // the midpoints of a small edge batch are a small configuration batch: one warp per midpoint (run_feasible_small)
-    const bool small = nslots <= 16384 && e->pipeline == 0 && !e->time_kernels && !e->collect_stats;
-    if ((rc = small ? run_feasible_small(e, e->d_eQ, nslots, e->d_efeas, nullptr, e->d_eslot)
-                    : run_feasible_device(e, e->d_eQ, nslots, e->d_efeas, nullptr, nullptr, e->d_eslot))) return rc;
+    // (the midpoints of a small edge batch are a small configuration batch: run_feasible_device checks them one warp per midpoint)
+    if ((rc = run_feasible_device(e, e->d_eQ, nslots, e->d_efeas, nullptr, nullptr, e->d_eslot))) return rc;
     CK(kb_launch_edge_flat_finish(e->d_efeas, e->d_eslot, nslots, (int)per_max, e->d_nlev, e->d_firstbad, N, e->d_alive, e->d_nchecks, e->stream)); e->stats.kernel_launches += 2;
   } else
   for (int lev = 1; lev <= maxlev; lev++) {
