@@ -636,7 +636,8 @@ kb_traverse_kernel(const KbTraverseParams p) {
   // guided self-scheduling: 8 configurations per grab while work is plentiful, down to 1 near the end of the launch, so
   // the tail is one configuration long (configuration cost varies by two orders of magnitude)
   const unsigned total_warps = gridDim.x * KB_WARPS_PER_BLOCK;
-  unsigned grab = 8;
+  unsigned grab;                      // first grab by the same rule as the later ones: a mid-size batch must not sit on an eighth of the warps
+  { const unsigned g0 = (unsigned)p.N / (4u * total_warps); grab = g0 >= 8u ? 8u : (g0 < 1u ? 1u : g0); }
   bool static_done = false;
   for (;;) {
     unsigned int c0 = 0;
@@ -933,7 +934,8 @@ kb_traverse_wide_kernel(const KbTraverseParams p) {
   // guided self-scheduling: 8 configurations per grab while work is plentiful, down to 1 near the end of the launch, so
   // the tail is one configuration long (configuration cost varies by two orders of magnitude)
   const unsigned total_warps = gridDim.x * KB_WARPS_PER_BLOCK;
-  unsigned grab = 8;
+  unsigned grab;                      // first grab by the same rule as the later ones: a mid-size batch must not sit on an eighth of the warps
+  { const unsigned g0 = (unsigned)p.N / (4u * total_warps); grab = g0 >= 8u ? 8u : (g0 < 1u ? 1u : g0); }
   bool static_done = false;
   for (;;) {
     unsigned int c0 = 0;
@@ -1714,7 +1716,8 @@ kb_distance_kernel(const KbTraverseParams p, const KbDistArgs da) {
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
   unsigned st_node = 0, st_leaf = 0, st_exact = 0, st_iter = 0;
   const unsigned total_warps = gridDim.x * KB_WARPS_PER_BLOCK;
-  unsigned grab = 4;
+  unsigned grab;
+  { const unsigned g0 = (unsigned)p.N / (4u * total_warps); grab = g0 >= 4u ? 4u : (g0 < 1u ? 1u : g0); }
   for (;;) {
     unsigned int c0 = 0;
     if (lane == 0) c0 = atomicAdd(p.work_counter, grab);
@@ -2239,7 +2242,7 @@ static cudaError_t launch_traverse_t(const KbTraverseParams& p, int num_sms, siz
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   int per_sm = (int)((224 * 1024) / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > BPS) per_sm = BPS;
-  int64_t want = (p.N + 8 * KB_WARPS_PER_BLOCK - 1) / (8 * KB_WARPS_PER_BLOCK);
+  int64_t want = (p.N + KB_WARPS_PER_BLOCK - 1) / KB_WARPS_PER_BLOCK;      // at most one warp per configuration
   int64_t grid = (int64_t)num_sms * per_sm; if (grid > want) grid = want; if (grid < 1) grid = 1;
   if (p.static_sched) grid = (p.N + KB_WARPS_PER_BLOCK - 1) / KB_WARPS_PER_BLOCK;      // one warp per configuration
   if (p.static_sched && !STATS) {      // small batches: the 168-register build (occupancy is irrelevant at one warp per configuration)

@@ -9,7 +9,7 @@ which = sys.argv[1] if len(sys.argv) > 1 else "c2"
 w = synth.world_c2() if which == "c2" else synth.world_c1()
 eng = Engine(w)
 Q = synth.sample_configs(w.robot, 1 << 17, 3)
-for n in (1, 8, 32, 256, 1024, 4096, 10000):
+for n in (1, 1024, 10000, 20000, 32768, 50000, 100000):
     q = np.ascontiguousarray(Q[:n]); out = np.empty(n, dtype=np.uint8)
     qp, op = C.c_void_p(q.ctypes.data), C.c_void_p(out.ctypes.data)
     for _ in range(30):
