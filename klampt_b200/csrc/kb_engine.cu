@@ -1375,7 +1375,7 @@ int kb_finalize(kb_engine* e, int device) {
     }
     for (const auto& dc : e->dyn) {      // replaceable clouds: world-frame groups whose boxes change with every update -> not under the hierarchy
       KbRayBody b = body_of(e->groups[dc.group], dc.owner, dc.owner < T ? L + O + dc.owner : L + (dc.owner - T), -1, nullptr);
-      b.ext = 1e6f;                      // extent unknown ahead of the updates: a pad that is safe for any cloud within a kilometre
+      b.ext = -1.f;                      // extent unknown ahead of the updates: the kernel derives it from the scene's error bound, which every update widens
       e->ray_bodies.push_back(b);
     }
     e->ray_nlink = (int)e->ray_bodies.size();

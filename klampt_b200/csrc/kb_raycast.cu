@@ -127,7 +127,9 @@ __device__ void cast_body(const KbScene& sc, const KbRayBody& B, const double* _
     r.iy = 1.f / (fabsf(fy) > 1e-30f ? fy : copysignf(1e-30f, fy));
     r.iz = 1.f / (fabsf(fz) > 1e-30f ? fz : copysignf(1e-30f, fz));
   }
-  const float pad = (mesh ? 0.f : (float)B.margin * 1.000001f) + 8.f * sc.eps_abs + 4e-6f * (fabsf(r.ox) + fabsf(r.oy) + fabsf(r.oz) + B.ext);
+  // (a replaceable cloud has no fixed extent: eps_abs = 8 * 2^-24 * scene extent, and every update of the cloud widens it)
+  const float ext = B.ext >= 0.f ? B.ext : 3.f * sc.eps_abs * 2.1e6f;
+  const float pad = (mesh ? 0.f : (float)B.margin * 1.000001f) + 8.f * sc.eps_abs + 4e-6f * (fabsf(r.ox) + fabsf(r.oy) + fabsf(r.oz) + ext);
   float tlim = tbest < 3e38 ? __double2float_ru(tbest) * 1.00001f + 1e-30f : FLT_MAX;
   const float4* __restrict__ nodes = sc.nodes + 2 * (size_t)B.node_base;
   int stack_n[KB_RAY_STACK]; float stack_t[KB_RAY_STACK];

@@ -158,7 +158,7 @@ struct KbRayBody {                // 144 bytes
   int32_t rank;                   // order in which WorldModel::RayCast visits the bodies: a tie in distance keeps the lower rank (groups: from the owner)
   int32_t xf;                     // transform slot of a link, -1 = static
   int32_t has_T;                  // static body with a transform other than the identity
-  float ext;                      // largest |coordinate| of the geometry's local box (bounds the fp32 rounding of its node tests)
+  float ext;                      // largest |coordinate| of the geometry's local box (bounds the fp32 rounding of its node tests); < 0: from eps_abs
 };
 struct KbRayParams {
   KbScene scene;

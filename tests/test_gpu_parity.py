@@ -545,6 +545,16 @@ def test_dynamic_point_cloud_rebuilt_on_the_gpu(built):
         np.testing.assert_allclose(d, do, rtol=1e-5, atol=1e-9)
         if n > 1000:
             assert (got != empty.feasible_batch(Q)).sum() > 0                      # the cloud matters
+        # rays see the cloud of the moment too (it is cast through its world-frame group)
+        rr = np.random.default_rng(seed)
+        src = rr.uniform([-2.5, -2.5, 0.2], [2.5, 2.5, 2.5], (3000, 3))
+        rays = np.hstack([src, rr.uniform([-0.9, -0.9, 0.1], [0.9, 0.9, 1.3], (3000, 3)) - src])
+        ri, rd, _ = eng.raycast_batch(Q[0], rays)
+        oi, od, _ = orc.raycast_batch(Q[0], rays)
+        assert np.array_equal(ri, oi)
+        np.testing.assert_allclose(rd[ri >= 0], od[oi >= 0], rtol=1e-9, atol=1e-12)
+        if n > 1000:
+            assert (ri == 11).sum() > 10                                           # the cloud object (world id 11: ground + 10 boxes before it)
     eng.update_pointcloud(gdyn, np.zeros((0, 3)))
     assert np.array_equal(eng.feasible_batch(Q), empty.feasible_batch(Q))
     with pytest.raises(Exception):
