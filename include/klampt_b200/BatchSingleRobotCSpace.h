@@ -287,6 +287,16 @@ class BatchSingleRobotCSpace {
   // every colliding (idA, idB) pair per configuration: the per-pair CollisionFreeSet constraints of Init() evaluated together
   void CollidingPairsBatch(const double* Q, int64_t N, int maxPairs, int32_t* outPairs, int32_t* outCount) { kbCheck(kb_colliding_pairs_batch(engine_, Q, N, maxPairs, outPairs, outCount)); }
   void DistanceBatch(const double* Q, int64_t N, double upperBound, bool includeSelf, double* out) { kbCheck(kb_distance_batch(engine_, Q, N, upperBound, includeSelf ? 1 : 0, out, nullptr)); }
+  // WorldModel::RayCast / RayCastIgnore (Cpp/Modeling/World.cpp:465-588) for N rays (source xyz, direction xyz per row) with the robot
+  // at x: ids[i] = world id hit or -1, dist[i] = distance along the unit direction (inf = nothing); ignoreIDs as RayCastIgnore's list
+  void RayCastBatch(const Config& x, const double* rays, int64_t N, int32_t* ids, double* dist, const std::vector<int>* ignoreIDs = nullptr, int32_t* elems = nullptr) {
+    std::vector<uint8_t> ig;
+    if (ignoreIDs) { ig.assign((size_t)kb_num_ids(engine_), 0); for (int id : *ignoreIDs) if (id >= 0 && (size_t)id < ig.size()) ig[(size_t)id] = 1; }
+    kbCheck(kb_raycast_batch(engine_, x.data(), rays, N, ignoreIDs ? ig.data() : nullptr, ids, dist, elems));
+  }
+  // the camera sensor's ray-cast rendering (Cpp/Sensing/VisualSensors.cpp:413-475) in one call: depth along the viewing direction per
+  // pixel (zmax where nothing is seen) and the world id per pixel
+  void CameraDepth(const Config& x, const kb_camera& cam, float* depth, int32_t* ids = nullptr) { kbCheck(kb_camera_depth(engine_, x.data(), &cam, nullptr, depth, ids)); }
   kb_stats GetStats() { kb_stats s; kbCheck(kb_get_stats(engine_, &s)); return s; }
   kb_engine* engine() { return engine_; }
 

@@ -3,6 +3,7 @@
 #include "klampt_b200/BatchSingleRobotCSpace.h"
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 using namespace klampt_b200;
 
 template <class T> static std::vector<T> rd(FILE* f) { int64_t n = 0; if (fread(&n, 8, 1, f) != 1) exit(3); std::vector<T> v((size_t)n); if (n && fread(v.data(), sizeof(T), (size_t)n, f) != (size_t)n) exit(3); return v; }
@@ -48,7 +49,22 @@ int main(int argc, char** argv) {
   }
   Config s; space.Sample(s); if (!space.CheckJointLimits(s)) return 6;
   std::map<std::string, std::string> props; space.Properties(props); if (props["geodesic"] != "1") return 7;
-  FILE* o = fopen(argv[2], "wb"); fwrite(feas.data(), 1, feas.size(), o); fwrite(vis.data(), 1, vis.size(), o); fwrite(nchk.data(), 4, nchk.size(), o); fclose(o);
+  // ray casts: a fan of rays from above the scene, with the robot at the first configuration; the second pass ignores whatever the first ray hit
+  const int R = 400;
+  std::vector<double> rays((size_t)R * 6);
+  for (int i = 0; i < R; i++) {
+    const double a = 2.0 * M_PI * i / R, rad = 0.2 + 1.3 * ((i * 37) % R) / (double)R;
+    rays[6 * i] = 0.3; rays[6 * i + 1] = -0.2; rays[6 * i + 2] = 3.0;
+    rays[6 * i + 3] = rad * std::cos(a) - 0.3; rays[6 * i + 4] = rad * std::sin(a) + 0.2; rays[6 * i + 5] = -3.0;
+  }
+  Config x0(Q.begin(), Q.begin() + L);
+  std::vector<int32_t> rid((size_t)R), rid2((size_t)R); std::vector<double> rdist((size_t)R), rdist2((size_t)R);
+  space.RayCastBatch(x0, rays.data(), R, rid.data(), rdist.data());
+  std::vector<int> ign; if (rid[0] >= 0) ign.push_back(rid[0]);
+  space.RayCastBatch(x0, rays.data(), R, rid2.data(), rdist2.data(), &ign);
+  if (!ign.empty()) for (int i = 0; i < R; i++) if (rid2[i] == ign[0]) return 12;
+  FILE* o = fopen(argv[2], "wb"); fwrite(feas.data(), 1, feas.size(), o); fwrite(vis.data(), 1, vis.size(), o); fwrite(nchk.data(), 4, nchk.size(), o);
+  fwrite(rays.data(), 8, rays.size(), o); fwrite(rid.data(), 4, rid.size(), o); fwrite(rdist.data(), 8, rdist.size(), o); fclose(o);
   kb_stats st = space.GetStats();
   printf("ok N=%lld E=%lld launches=%lld\n", (long long)N, (long long)E, (long long)st.kernel_launches);
   return 0;

@@ -137,10 +137,17 @@ def test_cpp_batch_single_robot_cspace(built, tmp_path):
     raw = open(tmp_path / "out.bin", "rb").read()
     feas = np.frombuffer(raw[:2000], dtype=np.uint8)
     vis = np.frombuffer(raw[2000:2200], dtype=np.uint8)
-    nchk = np.frombuffer(raw[2200:], dtype=np.int32)
+    nchk = np.frombuffer(raw[2200:3000], dtype=np.int32)
     assert np.array_equal(feas, orc.feasible_batch(Q))
     ovis, on = orc.edges_visible_batch(A, B, eps=0.01)
     assert np.array_equal(vis, ovis) and np.array_equal(nchk, on)
+    # the ray casts of the C++ face (RayCastBatch): 400 rays it built itself, robot at Q[0]
+    rays = np.frombuffer(raw[3000:3000 + 400 * 48], dtype=np.float64).reshape(400, 6)
+    rid = np.frombuffer(raw[3000 + 400 * 48:3000 + 400 * 52], dtype=np.int32)
+    rdist = np.frombuffer(raw[3000 + 400 * 52:], dtype=np.float64)
+    oid, od, _ = orc.raycast_batch(Q[0], rays)
+    assert np.array_equal(rid, oid) and (rid >= 0).sum() > 100
+    np.testing.assert_allclose(rdist[rid >= 0], od[oid >= 0], rtol=1e-9, atol=1e-12)
 
 
 def test_batch_roadmap_planner_on_the_engine(setup):
