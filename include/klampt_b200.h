@@ -231,6 +231,9 @@ int kb_geom_distance_batch_ex(kb_engine* e, int ga, const double* Ta, int gb, co
  * the body the reference visits first (links in order, rigid objects, terrains). */
 int kb_raycast_batch(kb_engine* e, const double* q, const double* rays, int64_t N, const uint8_t* ignore_ids,
                      int32_t* out_id, double* out_dist, int32_t* out_elem);
+/* rays given as floats (N x 6): half the upload, widened to fp64 on the device -- the answer is the fp64 answer for the rounded rays */
+int kb_raycast_batch_f32(kb_engine* e, const double* q, const float* rays, int64_t N, const uint8_t* ignore_ids,
+                         int32_t* out_id, double* out_dist, int32_t* out_elem);
 /* the same with the rays and the results device-resident on the engine's stream (q and ignore_ids stay host pointers) */
 int kb_raycast_batch_device(kb_engine* e, const double* q, const double* d_rays, int64_t N, const uint8_t* ignore_ids,
                             int32_t* d_out_id, double* d_out_dist, int32_t* d_out_elem);

@@ -74,6 +74,7 @@ SIGNATURES = {
     "kb_distance_batch_ex": (C.c_int, [_VP, _VP, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_int, _VP, _VP, _VP, _VP]),
     "kb_geom_distance_batch_ex": (C.c_int, [_VP, C.c_int, _VP, C.c_int, _VP, C.c_int64, C.c_double, C.c_double, C.c_double, _VP, _VP, _VP]),
     "kb_raycast_batch": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP, _VP, _VP, _VP]),
+    "kb_raycast_batch_f32": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP, _VP, _VP, _VP]),
     "kb_raycast_batch_device": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP, _VP, _VP, _VP]),
     "kb_geom_raycast_batch": (C.c_int, [_VP, C.c_int, _VP, _VP, C.c_int64, _VP, _VP]),
     "kb_camera_depth": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),

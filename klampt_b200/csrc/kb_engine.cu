@@ -2182,7 +2182,8 @@ int kb_raycast_batch_device(kb_engine* e, const double* q, const double* d_rays,
   return raycast_run(e, q, d_rays, N, ignore_ids, nullptr, d_out_id, d_out_dist, d_out_elem);
 }
 
-static int raycast_host(kb_engine* e, const double* q, const double* rays, int64_t N, const uint8_t* ignore_ids, const KbRayBody* one, int32_t* out_id, double* out_dist, int32_t* out_elem) {
+static int raycast_host(kb_engine* e, const double* q, const void* rays_v, int esz, int64_t N, const uint8_t* ignore_ids, const KbRayBody* one, int32_t* out_id, double* out_dist, int32_t* out_elem) {
+  const char* rays = (const char*)rays_v;
   CK(cudaSetDevice(e->device));
   int rc;
   const int64_t chunk = 1 << 22;
@@ -2191,14 +2192,20 @@ static int raycast_host(kb_engine* e, const double* q, const double* rays, int64
     for (void* o : olds) if (o) cudaFree(o);
     e->d_rays = nullptr; e->d_rid = nullptr; e->d_rdist = nullptr; e->d_relem = nullptr; e->ray_cap = 0;
     const int64_t cap = std::min(N, chunk);
-    CK(cudaMalloc((void**)&e->d_rays, (size_t)cap * 48)); CK(cudaMalloc((void**)&e->d_rid, (size_t)cap * 4));
+    // 48 B per fp64 ray + 24 B per fp32 ray behind them (kb_raycast_batch_f32)
+    CK(cudaMalloc((void**)&e->d_rays, (size_t)cap * 72)); CK(cudaMalloc((void**)&e->d_rid, (size_t)cap * 4));
     CK(cudaMalloc((void**)&e->d_rdist, (size_t)cap * 8)); CK(cudaMalloc((void**)&e->d_relem, (size_t)cap * 4));
     e->ray_cap = cap;
   }
   begin_timing(e);
   for (int64_t off = 0; off < N; off += chunk) {
     const int64_t n = std::min(chunk, N - off);
-    CK(cudaMemcpyAsync(e->d_rays, rays + 6 * off, (size_t)n * 48, cudaMemcpyHostToDevice, e->stream));
+    if (esz == 8) CK(cudaMemcpyAsync(e->d_rays, rays + (size_t)off * 48, (size_t)n * 48, cudaMemcpyHostToDevice, e->stream));
+    else {      // fp32 rays: half the upload, widened on the device (they land behind the fp64 rows of the ray scratch)
+      float* d_rf = (float*)((char*)e->d_rays + (size_t)e->ray_cap * 48);
+      CK(cudaMemcpyAsync(d_rf, rays + (size_t)off * 24, (size_t)n * 24, cudaMemcpyHostToDevice, e->stream));
+      CK(kb_launch_widen_f32(d_rf, e->d_rays, n * 6, e->stream)); e->stats.kernel_launches++;
+    }
     if ((rc = raycast_run(e, q, e->d_rays, n, ignore_ids, one, e->d_rid, e->d_rdist, e->d_relem))) return rc;
     if (out_id) CK(cudaMemcpyAsync(out_id + off, e->d_rid, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaMemcpyAsync(out_dist + off, e->d_rdist, (size_t)n * 8, cudaMemcpyDeviceToHost, e->stream));
@@ -2218,7 +2225,17 @@ int kb_raycast_batch(kb_engine* e, const double* q, const double* rays, int64_t 
   if (N == 0) return KB_OK;
   // a multi-device handle casts contiguous blocks of the rays on its devices (every replica runs FK for q itself)
   return run_sharded(e, N, 1, [&](kb_engine* r, int64_t off, int64_t n) {
-    return raycast_host(r, q, rays + 6 * off, n, ignore_ids, nullptr, out_id + off, out_dist + off, out_elem ? out_elem + off : nullptr);
+    return raycast_host(r, q, rays + 6 * off, 8, n, ignore_ids, nullptr, out_id + off, out_dist + off, out_elem ? out_elem + off : nullptr);
+  });
+}
+
+int kb_raycast_batch_f32(kb_engine* e, const double* q, const float* rays, int64_t N, const uint8_t* ignore_ids, int32_t* out_id, double* out_dist, int32_t* out_elem) {
+  if (!e || !e->finalized) return fail(KB_ERR_STATE, "engine is not finalized");
+  if (N < 0 || (N > 0 && (!rays || !out_id || !out_dist))) return fail(KB_ERR_INVALID, "bad arguments");
+  if (q && !all_finite(q, (size_t)e->L)) return fail(KB_ERR_INVALID, "non-finite configuration");
+  if (N == 0) return KB_OK;
+  return run_sharded(e, N, 1, [&](kb_engine* r, int64_t off, int64_t n) {
+    return raycast_host(r, q, rays + 6 * off, 4, n, ignore_ids, nullptr, out_id + off, out_dist + off, out_elem ? out_elem + off : nullptr);
   });
 }
 
@@ -2235,7 +2252,7 @@ int kb_camera_depth(kb_engine* e, const double* q, const kb_camera* cam, const u
     void* olds[] = {e->d_rays, e->d_rid, e->d_rdist, e->d_relem};
     for (void* o : olds) if (o) cudaFree(o);
     e->d_rays = nullptr; e->d_rid = nullptr; e->d_rdist = nullptr; e->d_relem = nullptr; e->ray_cap = 0;
-    CK(cudaMalloc((void**)&e->d_rays, (size_t)N * 48)); CK(cudaMalloc((void**)&e->d_rid, (size_t)N * 4));
+    CK(cudaMalloc((void**)&e->d_rays, (size_t)N * 72)); CK(cudaMalloc((void**)&e->d_rid, (size_t)N * 4));
     CK(cudaMalloc((void**)&e->d_rdist, (size_t)N * 8)); CK(cudaMalloc((void**)&e->d_relem, (size_t)N * 4));
     e->ray_cap = N;
   }
@@ -2276,7 +2293,7 @@ int kb_geom_raycast_batch(kb_engine* e, int geom, const double* T, const double*
   b.T[0] = b.T[4] = b.T[8] = 1; if (T) memcpy(b.T, T, 96);
   double ext = 0; for (int k = 0; k < 3; k++) ext = std::max(ext, std::max(std::fabs(dg.lo[k]), std::fabs(dg.hi[k])));
   b.ext = (float)(3.0 * ext * (1 + 1e-6));
-  return raycast_host(e, nullptr, rays, N, nullptr, &b, nullptr, out_dist, out_elem);
+  return raycast_host(e, nullptr, rays, 8, N, nullptr, &b, nullptr, out_dist, out_elem);
 }
 
 int kb_get_stats(kb_engine* e, kb_stats* out) {

@@ -277,12 +277,13 @@ class Engine:
         """WorldModel::RayCast / RayCastIgnore (World.cpp:465-588) for N rays (rows of source xyz, direction xyz) with the robot at q
         (None: the robot is left out): (world id or -1, distance along the normalised direction or inf, element index or -1).
         ignore_ids: world ids the rays pass through (an iterable of ids, or one byte per id)."""
-        rays = _f64(rays).reshape(-1, 6)
+        f32 = isinstance(rays, np.ndarray) and rays.dtype == np.float32       # fp32 rays travel as they are and are widened on the device
+        rays = np.ascontiguousarray(rays).reshape(-1, 6) if f32 else _f64(rays).reshape(-1, 6)
         N = rays.shape[0]
         ids, dist, elem = np.empty(N, dtype=np.int32), np.empty(N, dtype=np.float64), np.empty(N, dtype=np.int32)
         qa = None if q is None else _f64(q).reshape(self.L)
         ig = None if ignore_ids is None else self._ignore_mask(ignore_ids)
-        check(self.lib.kb_raycast_batch(self.h, None if qa is None else _ptr(qa), _ptr(rays), N, None if ig is None else _ptr(ig),
+        check((self.lib.kb_raycast_batch_f32 if f32 else self.lib.kb_raycast_batch)(self.h, None if qa is None else _ptr(qa), _ptr(rays), N, None if ig is None else _ptr(ig),
                                         _ptr(ids), _ptr(dist), _ptr(elem)))
         return ids, dist, elem
 

@@ -90,6 +90,10 @@ def test_random_rays_and_degenerate_input(built):
     ids2, _, _, _ = check_against_oracle(eng2, orc2, q, rays)
     assert np.isin(ids2, off).sum() > 20
     assert np.array_equal(ids2, eng.raycast_batch(q, rays)[0])
+    # fp32 rays: the fp64 answer for the rounded rays
+    rf = rays.astype(np.float32)
+    a32, b32 = eng.raycast_batch(q, rf), eng.raycast_batch(q, rf.astype(np.float64))
+    assert all(np.array_equal(x, y) for x, y in zip(a32, b32))
     bad = rays[:4].copy()
     bad[0, 3:] = 0.0
     bad[1, 3] = np.nan
