@@ -144,8 +144,14 @@ int kb_synchronize(kb_engine* e);
  * "pipeline" (0 = fused traversal kernel, default; 1 = split pipeline: lean node kernel -> global leaf-pair list -> leaf kernel ->
  * fused kernel on requeued configurations; same results, measured slower on C2/C3), "leaf_budget" (split pipeline only),
  * "clear_grid" (0|1, default 0: clearance-grid broad phase that drops (link, static group) pairs before the BVH descent; exact),
- * "both_limit" (experiment knob of builds with KB_BOTH_MODE=2).
- * Before kb_finalize only: "grid_res" (voxels along the longest axis of a clearance grid, 0 = none, default 256),
+ * "both_limit" (experiment knob of builds with KB_BOTH_MODE=2), "wide" (0|1, default 1: the boolean query runs on the 4-wide
+ * hierarchies when every work item has them), "graph_max" (default 16384: host-buffer batches up to this size take the small-batch
+ * path -- pinned staging, one CUDA graph per batch size, one warp per configuration; can only grow before the first small batch),
+ * "zero_copy_max" (default 64: small batches up to this size are read from / written to pinned host memory by the kernels
+ * themselves), "edge_flat_max" (default 262144: edge batches with at most this many midpoints are checked all levels at once),
+ * "multi_min" (default 8192: smaller host batches of a multi-device handle stay on its first device), "ray_tile" (0|1, default 1:
+ * kb_camera_depth renders 8 x 4 pixel tiles per warp), "ray_variant" (launch shape of the ray kernel, experiment knob).
+ * Before kb_finalize only: "cloud_leaf" (points per leaf of a host-built point-cloud hierarchy, 1..32, default 8), "grid_res" (voxels along the longest axis of a clearance grid, 0 = none, default 256),
  * "cloud_builder" / "mesh_builder" (0 = binned SAH on the host, default; 1 = linear BVH built on the GPU for point clouds above
  * 4096 points / meshes above 16384 triangles: kb_finalize far faster, queries 7-13 % slower, identical answers). */
 int kb_set_option(kb_engine* e, const char* name, int64_t value);
