@@ -361,7 +361,7 @@ struct kb_engine {
   struct PendingCloud { DevGeom* dg; std::vector<double> elems; std::vector<int32_t> owners; bool mesh = false; std::vector<int32_t> origs; };
   std::vector<PendingCloud> pending_clouds;   // clouds whose hierarchy is built on the GPU once the arrays are uploaded
   // small host-buffer batches (N <= graph_max): pinned staging + one CUDA graph per batch size (copy in, FK, traversal, finish, copy out)
-  struct SmallGraph { int64_t n = 0; cudaGraphExec_t exec = nullptr; const void* key[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; };
+  struct SmallGraph { int64_t n = 0; int seen = 0; cudaGraphExec_t exec = nullptr; const void* key[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; };
   int64_t zero_copy_max = 64;                // small batches up to this size read / write the pinned staging buffers directly (option zero_copy_max)
   std::vector<SmallGraph> graphs; int64_t graph_max = 16384; double* h_pin_in = nullptr; uint8_t* h_pin_out = nullptr; double* g_dQ = nullptr; uint8_t* g_dout = nullptr;
   int cloud_leaf = 8;                        // points per leaf of a host-built point-cloud hierarchy (option cloud_leaf, 1..32)
@@ -1722,7 +1722,7 @@ static int feasible_small(kb_engine* e, const double* Q, int64_t N, uint8_t* out
   const void* key[6] = {e->d_xf, e->d_state, e->d_hit, e->d_hit_elem, (const void*)e->stream, (const void*)(intptr_t)((e->use_grids ? 1 : 0) + 2 * e->chunk + ((int64_t)e->both_limit << 40) + ((int64_t)(zc ? 1 : 0) << 50))};
   kb_engine::SmallGraph* g = nullptr;
   for (auto& x : e->graphs) if (x.n == N) g = &x;
-  if (g && memcmp(g->key, key, sizeof key) != 0) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; }
+  if (g && g->exec && memcmp(g->key, key, sizeof key) != 0) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; }
   if (!g) {
     if (e->graphs.size() >= 32) { for (auto& x : e->graphs) if (x.exec) cudaGraphExecDestroy(x.exec); e->graphs.clear(); }
     e->graphs.emplace_back(); g = &e->graphs.back(); g->n = N;
@@ -1736,6 +1736,9 @@ static int feasible_small(kb_engine* e, const double* Q, int64_t N, uint8_t* out
     CK(cudaStreamSynchronize(e->stream));
     memcpy(out, e->h_pin_out, (size_t)N);
     e->stats.configs_checked += N;
+    // a batch size is captured the second time it is seen: a planner whose batch sizes never repeat must not pay a capture and an
+    // instantiation (hundreds of microseconds) on every call
+    if (g->seen++ == 0) return KB_OK;
     cudaGraph_t graph = nullptr;
     const int64_t launches_before = e->stats.kernel_launches;
     CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));

@@ -108,6 +108,21 @@ def test_empty_and_ragged_batches(c1):
         assert (eng.feasible_batch(Q) == orc.feasible_batch(Q)).all()
 
 
+def test_small_batches_plain_captured_and_replayed(c1):
+    """the small-batch path of kb_feasible_batch: a size is run plainly the first time, captured into a CUDA graph the second time and
+    replayed afterwards -- every call with different rows, all equal to the oracle; many distinct sizes (more than the graph cache
+    holds) stay correct; the zero-copy sizes (<= 64) and the copied ones (> 64) both"""
+    w, eng, orc = c1
+    for n in (1, 5, 64, 65, 300, 5000):
+        for rep in range(4):
+            Q = synth.sample_configs(w.robot, n, 1000 * n + rep)
+            assert np.array_equal(eng.feasible_batch(Q), orc.feasible_batch(Q)), (n, rep)
+    for n in range(2, 42):                                  # 40 distinct sizes, each seen twice: the cache (32 entries) is recycled
+        for rep in range(2):
+            Q = synth.sample_configs(w.robot, n, 7 * n + rep)
+            assert np.array_equal(eng.feasible_batch(Q), orc.feasible_batch(Q)), (n, rep)
+
+
 def test_idempotent_and_order_independent(c1):
     w, eng, orc = c1
     Q = synth.sample_configs(w.robot, 5000, 5)
